@@ -1,0 +1,134 @@
+"""Host-side analysis bookkeeping shared by the CUDA engine and the test oracle.
+
+Nothing here is arithmetic of the hot path: it decides WHICH right-hand sides exist
+(load cases + combinations, pydantic_models.py:2171-2174), which geometry each one is solved
+on (imperfection cases, pydantic_models.py:2036-2040) and a few scalar conventions.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import wire
+
+# stiffness multiplier of a tension-/compression-only member that is switched off by the
+# active-set loop (keeps nodes that hang only on inactive members non-singular)
+INACTIVE_SCALE = 1.0e-9
+# rigid members (RigidStrategy "RigidMember", pydantic_models.py:1047-1049) are modelled as
+# members RIGID_FACTOR times stiffer than the stiffest section of the model
+RIGID_FACTOR = 1.0e6
+
+
+@dataclass
+class RhsGroup:
+    imperfection: dict | None        # raw imperfection case or None (perfect geometry)
+    columns: list                    # rhs column indices solved on this geometry
+
+
+@dataclass
+class RhsPlan:
+    kinds: list                      # "Loadcase" | "Loadcombination" per column
+    ids: list                        # wire id per column
+    names: list                      # result key per column
+    factors: np.ndarray              # [n_rhs, Nlc] load-case factors per column
+    groups: list = field(default_factory=list)
+
+    @property
+    def n_rhs(self) -> int:
+        return len(self.kinds)
+
+
+def rhs_plan(model: wire.ModelArrays) -> RhsPlan:
+    """Columns = load cases (when ``solve_loadcases``) followed by combinations, wire order."""
+    nlc = len(model.load_cases)
+    kinds, ids, names, rows = [], [], [], []
+    if model.options.solve_loadcases:
+        for i, lc in enumerate(model.load_cases):
+            kinds.append("Loadcase"); ids.append(lc.id); names.append(lc.name)
+            r = np.zeros(nlc); r[i] = 1.0
+            rows.append(r)
+    for ci in range(model.combo_ids.shape[0]):
+        kinds.append("Loadcombination"); ids.append(int(model.combo_ids[ci])); names.append(model.combo_names[ci])
+        rows.append(model.combo_factors[ci].copy())
+    factors = np.array(rows, np.float64).reshape(len(rows), nlc)
+    plan = RhsPlan(kinds, ids, names, factors)
+    # group columns by imperfection case (first case listing a combination wins)
+    imp_of = {}
+    for case in model.imperfections:
+        for cid in case.get("load_combinations") or []:
+            cid = cid["id"] if isinstance(cid, dict) else cid
+            imp_of.setdefault(int(cid), case)
+    by_case: dict = {}
+    order: list = []
+    for col in range(plan.n_rhs):
+        case = imp_of.get(ids[col]) if kinds[col] == "Loadcombination" else None
+        key = id(case) if case is not None else None
+        if key not in by_case:
+            by_case[key] = RhsGroup(case, [])
+            order.append(key)
+        by_case[key].columns.append(col)
+    plan.groups = [by_case[k] for k in order]
+    return plan
+
+
+def _unit(v, default):
+    a = np.asarray(default if v is None else v, np.float64)
+    n = np.linalg.norm(a)
+    return a / n if n > 0 else np.asarray(default, np.float64)
+
+
+def imperfect_coordinates(model: wire.ModelArrays, case: dict) -> np.ndarray:
+    """Node coordinates perturbed by one imperfection case.
+
+    Sway (pydantic_models.py:1970-1985): lean angle ``magnitude`` [rad] about ``axis``; a node's
+    offset is magnitude * h * (axis x height_direction) with h its height above
+    ``reference_point`` along ``height_direction``.  Translation (1988-1991): nodes of the listed
+    member sets are shifted by magnitude * axis.
+    """
+    xyz = model.xyz.copy()
+    for sw in case.get("sway_imperfections") or []:
+        hd = _unit(sw.get("height_direction"), (0.0, 1.0, 0.0))
+        ax = _unit(sw.get("axis"), (0.0, 0.0, 1.0))
+        ref = np.asarray(sw.get("reference_point") or (0.0, 0.0, 0.0), np.float64)
+        sway_dir = np.cross(ax, hd)
+        n = np.linalg.norm(sway_dir)
+        if n == 0.0:
+            continue
+        sway_dir /= n
+        h = (model.xyz - ref) @ hd
+        xyz += float(sw["magnitude"]) * h[:, None] * sway_dir[None, :]
+    for tr in case.get("translation_imperfections") or []:
+        sets = tr.get("memberset_ids") or tr.get("memberset") or []
+        ax = np.asarray(tr.get("axis") or (0.0, 0.0, 0.0), np.float64)
+        nodes = set()
+        for sid in sets:
+            sid = sid["id"] if isinstance(sid, dict) else sid
+            for mi in model.member_sets.get(int(sid), []):
+                nodes.add(int(model.m_n1[mi])); nodes.add(int(model.m_n2[mi]))
+        if nodes:
+            idx = np.fromiter(nodes, np.int64)
+            xyz[idx] += float(tr["magnitude"]) * ax[None, :]
+    return xyz
+
+
+def rigid_property_row(prop: np.ndarray) -> np.ndarray:
+    """Property row [EA EIy EIz GJ GAsy GAsz ..] used for MemberType.Rigid members."""
+    row = np.zeros(wire.NPROP)
+    if prop.size:
+        ea = float(prop[:, wire.P_EA].max())
+        ei = float(max(prop[:, wire.P_EIY].max(), prop[:, wire.P_EIZ].max()))
+    else:
+        ea, ei = 2.1e11 * 1e-2, 2.1e11 * 1e-4
+    row[wire.P_EA] = RIGID_FACTOR * ea
+    row[wire.P_EIY] = row[wire.P_EIZ] = row[wire.P_GJ] = RIGID_FACTOR * ei
+    return row
+
+
+def pdelta_suppressed_axes(model: wire.ModelArrays) -> tuple:
+    """Global translational axes (0,1,2) excluded from P-Delta (pydantic_models.py:1374-1384)."""
+    o = model.options
+    if o.pdelta_mode == "IN_PLANE_ONLY" and model.n_nodes:
+        ext = np.ptp(model.xyz, axis=0)
+        return (int(np.argmin(ext)),)
+    return tuple("XYZ".index(a) for a in o.pdelta_suppress_axes if a in ("X", "Y", "Z"))

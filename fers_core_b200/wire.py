@@ -1,0 +1,550 @@
+"""Wire-format parser: reference JSON document -> structure-of-arrays model.
+
+The reference front end (``FERS.to_dict``, /root/reference/fers_core/fers/fers.py:315-361)
+serialises its object graph to the document described by the generated schema
+``fers_core/types/pydantic_models.py`` (``FERS`` 2241-2258).  This module is the host-side
+half of the drop-in boundary: it turns that document into flat numpy arrays (the layout the
+CUDA path consumes, see DESIGN.md "Data layout") and nothing else -- no arithmetic of the
+analysis itself happens here.
+
+Accepted spelling drifts: legacy enum values ``"Linear"``/
+``"Nonlinear"``, ``"Rigid_Member"``/``"Linear_MPC"``; ``"Positive-only"``/``"Negative-only"``;
+``memberset`` for ``memberset_ids``; unknown extra keys are ignored.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+
+# member_type codes (pydantic_models.py:592-598)
+MT_NORMAL, MT_TRUSS, MT_TENSION, MT_COMPRESSION, MT_RIGID, MT_CABLE = range(6)
+_MEMBER_TYPES = {
+    "normal": MT_NORMAL, "truss": MT_TRUSS, "tension": MT_TENSION,
+    "compression": MT_COMPRESSION, "rigid": MT_RIGID, "cable": MT_CABLE,
+}
+# boundary-condition codes per DOF (pydantic_models.py:1232-1237)
+BC_FREE, BC_FIXED, BC_SPRING, BC_POS_ONLY, BC_NEG_ONLY = range(5)
+_BC_TYPES = {
+    "free": BC_FREE, "fixed": BC_FIXED, "spring": BC_SPRING,
+    "positiveonly": BC_POS_ONLY, "positive-only": BC_POS_ONLY,
+    "negativeonly": BC_NEG_ONLY, "negative-only": BC_NEG_ONLY,
+}
+DOF_NAMES = ("X", "Y", "Z", "RX", "RY", "RZ")
+
+# columns of the per-section property table (one row per distinct section x option set)
+P_EA, P_EIY, P_EIZ, P_GJ, P_GASY, P_GASZ, P_WPL, P_SPARE = range(8)
+NPROP = 8
+# local release order = local DOF order [u v w rx ry rz]
+_HINGE_FIELDS = (
+    "translational_release_vx", "translational_release_vy", "translational_release_vz",
+    "rotational_release_mx", "rotational_release_my", "rotational_release_mz",
+)
+RIGID_RELEASE = -1.0  # sentinel: DOF rigidly connected (no hinge spring)
+
+
+class WireError(ValueError):
+    """Malformed input document (maps to the reference's RuntimeError at fers.py:301-302)."""
+
+
+@dataclass
+class LoadCaseArrays:
+    """One load case flattened to arrays (pydantic_models.py:2048-2059)."""
+    id: int
+    name: str
+    # nodal forces+moments: (node index, 6-vector)
+    nod_node: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    nod_vec: np.ndarray = field(default_factory=lambda: np.zeros((0, 6)))
+    # distributed (trapezoid) member loads, global direction; row = [q1(3), q2(3), a, b]
+    dl_member: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    dl_data: np.ndarray = field(default_factory=lambda: np.zeros((0, 8)))
+    # member point loads / moments; row = [F(3), M(3), position, is_local]
+    pl_member: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    pl_data: np.ndarray = field(default_factory=lambda: np.zeros((0, 8)))
+    # plate pressures resolved to elements: (plate index, global traction vector per area)
+    pp_plate: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    pp_vec: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
+
+
+@dataclass
+class Options:
+    """analysis.options (pydantic_models.py:1334-1398; defaults anlysis_options.py:15-28)."""
+    order: str = "NONLINEAR"            # LINEAR | NONLINEAR
+    nonlinear_method: str = "COROTATIONAL"  # engine default (anlysis_options.py:53-55)
+    pdelta_formulation: str = "CONSISTENT"
+    pdelta_mode: str = "FULL"
+    pdelta_suppress_axes: tuple = ()
+    tolerance: float = 0.01
+    max_iterations: int = 30
+    dimensionality: str = "3D"
+    rigid_strategy: str = "RigidMember"
+    axial_slack: float = 500.0
+    include_shear_deformation: bool = True
+    include_warping: bool = True
+    include_shear_center_coupling: bool = True
+    solve_loadcases: bool = True
+    enable_self_weight: bool = False
+    gravity_direction: tuple = (0.0, -1.0, 0.0)
+    gravity_factor: float = -9.81
+    self_weight_load_case_id: int | None = None
+
+
+@dataclass
+class ModelArrays:
+    """Structure-of-arrays view of one wire document."""
+    node_ids: np.ndarray          # int64 [Nn]      wire ids, wire order
+    xyz: np.ndarray               # f64   [Nn,3]
+    node_support_id: np.ndarray   # int64 [Nn]      nodal_support id or -1
+    bc_code: np.ndarray           # uint8 [Nn,6]    BC_* per DOF
+    bc_k: np.ndarray              # f64   [Nn,6]    spring stiffness where BC_SPRING
+    m_ids: np.ndarray             # int64 [Nm]
+    m_n1: np.ndarray              # int32 [Nm]      start node INDEX
+    m_n2: np.ndarray              # int32 [Nm]
+    m_type: np.ndarray            # int32 [Nm]      MT_*
+    m_roll: np.ndarray            # f64   [Nm]      roll angle, radians
+    m_prop: np.ndarray            # int32 [Nm]      row of `prop` (-1: rigid member without section)
+    m_rel: np.ndarray             # int32 [Nm]      row of `rel` or -1
+    prop: np.ndarray              # f64   [Np,8]    EA EIy EIz GJ GAsy GAsz Wpl spare
+    prop_rho_a: np.ndarray        # f64   [Np]      density*area (self weight)
+    rel: np.ndarray               # f64   [Nr,12]   hinge spring stiffness per local end DOF (-1 rigid)
+    # plates (TRI3): node indices, thickness, E, nu, behaviour code
+    p_ids: np.ndarray             # int64 [Npl]
+    p_nodes: np.ndarray           # int32 [Npl,3]
+    p_data: np.ndarray            # f64   [Npl,4]  thickness, E, nu, spare
+    p_flags: np.ndarray           # int32 [Npl]    bit0 membrane, bit1 bending
+    load_cases: list              # [LoadCaseArrays]
+    combo_ids: np.ndarray         # int64 [Nc]
+    combo_names: list
+    combo_factors: np.ndarray     # f64 [Nc,Nlc]
+    imperfections: list           # raw imperfection_cases (resolved by analysis host code)
+    member_sets: dict             # id -> [member index]
+    options: Options
+    warnings: list = field(default_factory=list)
+
+    @property
+    def n_nodes(self) -> int:
+        return int(self.node_ids.shape[0])
+
+    @property
+    def n_members(self) -> int:
+        return int(self.m_ids.shape[0])
+
+    @property
+    def n_plates(self) -> int:
+        return int(self.p_ids.shape[0])
+
+    @property
+    def n_dof(self) -> int:
+        return 6 * self.n_nodes
+
+
+def _norm_enum(v: Any) -> str:
+    return str(v).strip().lower().replace("_", "").replace(" ", "")
+
+
+def parse_options(raw: dict | None) -> Options:
+    raw = raw or {}
+    o = Options()
+    order = _norm_enum(raw.get("order", "NONLINEAR"))
+    o.order = "LINEAR" if order in ("linear", "firstorder") else "NONLINEAR"
+    nm = raw.get("nonlinear_method")
+    if nm is not None:
+        o.nonlinear_method = "P_DELTA" if _norm_enum(nm) in ("pdelta",) else "COROTATIONAL"
+    pf = raw.get("pdelta_formulation")
+    if pf is not None:
+        o.pdelta_formulation = "SIMPLIFIED" if _norm_enum(pf) == "simplified" else "CONSISTENT"
+    pm = raw.get("pdelta_mode")
+    if pm is not None:
+        o.pdelta_mode = "IN_PLANE_ONLY" if _norm_enum(pm) == "inplaneonly" else "FULL"
+    o.pdelta_suppress_axes = tuple(str(a).upper() for a in (raw.get("pdelta_suppress_axes") or ()))
+    if raw.get("tolerance") is not None:
+        o.tolerance = float(raw["tolerance"])
+    if raw.get("max_iterations") is not None:
+        o.max_iterations = int(raw["max_iterations"])
+    dim = _norm_enum(raw.get("dimensionality", "3D"))
+    o.dimensionality = "2D" if dim in ("2d", "twodimensional") else "3D"
+    rs = _norm_enum(raw.get("rigid_strategy", "RigidMember"))
+    o.rigid_strategy = "LinearMpc" if rs == "linearmpc" else "RigidMember"
+    if raw.get("axial_slack") is not None:
+        o.axial_slack = float(raw["axial_slack"])
+    for k in ("include_shear_deformation", "include_warping", "include_shear_center_coupling",
+              "solve_loadcases", "enable_self_weight"):
+        if raw.get(k) is not None:
+            setattr(o, k, bool(raw[k]))
+    if raw.get("gravity_direction") is not None:
+        o.gravity_direction = tuple(float(x) for x in raw["gravity_direction"])
+    if raw.get("gravity_factor") is not None:
+        o.gravity_factor = float(raw["gravity_factor"])
+    if raw.get("self_weight_load_case_id") is not None:
+        o.self_weight_load_case_id = int(raw["self_weight_load_case_id"])
+    return o
+
+
+def _vec3(v, what: str) -> np.ndarray:
+    if isinstance(v, dict):
+        v = [v.get("X", v.get("x", 0.0)), v.get("Y", v.get("y", 0.0)), v.get("Z", v.get("z", 0.0))]
+    a = np.asarray(v, dtype=np.float64).reshape(-1)
+    if a.shape[0] != 3:
+        raise WireError(f"{what}: expected a 3-vector, got {v!r}")
+    return a
+
+
+def _index_map(ids: np.ndarray, what: str) -> dict:
+    m = {int(v): i for i, v in enumerate(ids.tolist())}
+    if len(m) != ids.shape[0]:
+        raise WireError(f"duplicate {what} ids")
+    return m
+
+
+def parse_document(doc: dict) -> ModelArrays:
+    """Flatten a wire document (dict) into :class:`ModelArrays`."""
+    if not isinstance(doc, dict) or "model" not in doc or "analysis" not in doc:
+        raise WireError("document must contain 'model' and 'analysis'")
+    model, analysis = doc["model"], doc["analysis"]
+    opts = parse_options(analysis.get("options"))
+    warnings: list = []
+
+    # ---- nodes (pydantic_models.py:Node; wire order = DOF numbering order) ----------------
+    nodes = model.get("nodes") or []
+    nn = len(nodes)
+    node_ids = np.fromiter((int(n["id"]) for n in nodes), np.int64, nn)
+    xyz = np.array([[float(n["X"]), float(n["Y"]), float(n["Z"])] for n in nodes], np.float64).reshape(nn, 3)
+    node_index = _index_map(node_ids, "node")
+
+    # ---- supports (pydantic_models.py:2104-2115; default all-Fixed nodalsupport.py:29-41) --
+    supports = {int(s["id"]): s for s in (model.get("nodal_supports") or [])}
+    bc_code = np.zeros((nn, 6), np.uint8)
+    bc_k = np.zeros((nn, 6), np.float64)
+    node_support_id = np.full(nn, -1, np.int64)
+    for i, n in enumerate(nodes):
+        sid = n.get("nodal_support")
+        if sid is None:
+            continue
+        if isinstance(sid, dict):
+            sup, sid = sid, int(sid.get("id", 0))
+        else:
+            sid = int(sid)
+            if sid not in supports:
+                raise WireError(f"node {n['id']}: unknown nodal_support {sid}")
+            sup = supports[sid]
+        node_support_id[i] = sid
+        for d, name in enumerate(DOF_NAMES):
+            cond = sup.get(name)
+            if cond is None:
+                continue  # absent = free
+            ctype = _BC_TYPES.get(_norm_enum(cond.get("condition_type", "Fixed")).replace("-", ""))
+            if ctype is None:
+                ctype = _BC_TYPES.get(str(cond.get("condition_type")).strip().lower())
+            if ctype is None:
+                raise WireError(f"support {sid}.{name}: unknown condition {cond.get('condition_type')!r}")
+            bc_code[i, d] = ctype
+            if ctype == BC_SPRING:
+                k = cond.get("stiffness")
+                if k is None:
+                    curve = cond.get("stiffness_curve")
+                    if curve and curve.get("points"):
+                        k = curve["points"][0][1]
+                        warnings.append(("W_SUPPORT_CURVE", f"support {sid}.{name}: stiffness curve linearised at first point"))
+                    else:
+                        raise WireError(f"support {sid}.{name}: Spring without stiffness")
+                bc_k[i, d] = float(k)
+    if opts.dimensionality == "2D":
+        # out-of-plane DOFs restrained for every node (reference builders.py:108-110)
+        for d in (2, 3, 4):
+            free = bc_code[:, d] == BC_FREE
+            bc_code[free, d] = BC_FIXED
+
+    # ---- materials / sections -> property table ---------------------------------------
+    mats = {int(m["id"]): m for m in (model.get("materials") or [])}
+    secs = {int(s["id"]): s for s in (model.get("sections") or [])}
+    prop_rows: list = []
+    prop_rho_a: list = []
+    sec_row: dict = {}
+    for sid, s in secs.items():
+        mid = s.get("material")
+        if isinstance(mid, dict):
+            mat = mid
+        else:
+            if int(mid) not in mats:
+                raise WireError(f"section {sid}: unknown material {mid}")
+            mat = mats[int(mid)]
+        E, G = float(mat["e_mod"]), float(mat["g_mod"])
+        A, Iy, Iz, J = float(s["area"]), float(s["i_y"]), float(s["i_z"]), float(s["j"])
+        asy = s.get("a_sy") if opts.include_shear_deformation else None
+        asz = s.get("a_sz") if opts.include_shear_deformation else None
+        row = [E * A, E * Iy, E * Iz, G * J,
+               G * float(asy) if asy else 0.0, G * float(asz) if asz else 0.0,
+               float(s.get("wpl_y") or 0.0), 0.0]
+        sec_row[sid] = len(prop_rows)
+        prop_rows.append(row)
+        prop_rho_a.append(float(mat.get("density") or 0.0) * A)
+        if s.get("i_w") and opts.include_warping:
+            warnings.append(("W_WARPING_IGNORED", f"section {sid}: warping DOF not modelled (St-Venant torsion only)"))
+    prop = np.array(prop_rows, np.float64).reshape(len(prop_rows), NPROP)
+
+    # ---- hinges (pydantic_models.py:2062-2087; release fields are spring stiffnesses) ----
+    hinges = {int(h["id"]): h for h in (model.get("member_hinges") or [])}
+
+    def hinge_row(hid) -> np.ndarray:
+        r = np.full(6, RIGID_RELEASE)
+        if hid is None:
+            return r
+        if int(hid) not in hinges:
+            raise WireError(f"unknown member hinge {hid}")
+        h = hinges[int(hid)]
+        for d, f in enumerate(_HINGE_FIELDS):
+            v = h.get(f)
+            if v is not None:
+                r[d] = max(float(v), 0.0)
+        return r
+
+    # ---- members (pydantic_models.py:1507-1549) ----------------------------------------
+    members = model.get("members") or []
+    nm = len(members)
+    m_ids = np.fromiter((int(m["id"]) for m in members), np.int64, nm)
+    member_index = _index_map(m_ids, "member")
+    m_n1 = np.zeros(nm, np.int32)
+    m_n2 = np.zeros(nm, np.int32)
+    m_type = np.zeros(nm, np.int32)
+    m_roll = np.zeros(nm, np.float64)
+    m_prop = np.full(nm, -1, np.int32)
+    m_rel = np.full(nm, -1, np.int32)
+    rel_rows: list = []
+    for i, m in enumerate(members):
+        try:
+            m_n1[i] = node_index[int(m["start_node_id"])]
+            m_n2[i] = node_index[int(m["end_node_id"])]
+        except KeyError as e:
+            raise WireError(f"member {m['id']}: unknown node {e}") from None
+        t = _MEMBER_TYPES.get(_norm_enum(m.get("member_type", "Normal")))
+        if t is None:
+            raise WireError(f"member {m['id']}: unknown member_type {m.get('member_type')!r}")
+        m_type[i] = t
+        m_roll[i] = np.radians(float(m.get("rotation_angle") or 0.0))
+        sid = m.get("section")
+        if sid is not None:
+            if int(sid) not in sec_row:
+                raise WireError(f"member {m['id']}: unknown section {sid}")
+            m_prop[i] = sec_row[int(sid)]
+        elif t != MT_RIGID:
+            raise WireError(f"member {m['id']}: non-rigid member without section")
+        if m.get("start_hinge") is not None or m.get("end_hinge") is not None:
+            m_rel[i] = len(rel_rows)
+            rel_rows.append(np.concatenate([hinge_row(m.get("start_hinge")), hinge_row(m.get("end_hinge"))]))
+        if t == MT_CABLE:
+            warnings.append(("W_CABLE_AS_TENSION", f"member {m['id']}: cable treated as tension-only straight member"))
+        if m.get("start_offset") or m.get("end_offset"):
+            warnings.append(("W_OFFSET_IGNORED", f"member {m['id']}: end offsets not modelled"))
+    rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), 12)
+    member_sets = {}
+    for ms in (model.get("member_sets") or []):
+        idx = []
+        for mid in (ms.get("member_ids") or ms.get("members") or []):
+            mid = mid["id"] if isinstance(mid, dict) else mid
+            if int(mid) in member_index:
+                idx.append(member_index[int(mid)])
+        member_sets[int(ms["id"])] = idx
+
+    # ---- plate elements (pydantic_models.py:1700-1726) ---------------------------------
+    plates = model.get("plate_elements") or []
+    p_ids_l, p_nodes_l, p_data_l, p_flags_l = [], [], [], []
+    for p in plates:
+        nids = [nid["id"] if isinstance(nid, dict) else nid for nid in p["node_ids"]]
+        mat = mats.get(int(p["material"])) if not isinstance(p.get("material"), dict) else p["material"]
+        if mat is None:
+            raise WireError(f"plate {p['id']}: unknown material")
+        E, G = float(mat["e_mod"]), float(mat["g_mod"])
+        nu = E / (2.0 * G) - 1.0
+        beh = _norm_enum(p.get("behavior") or "Shell")
+        flags = {"shell": 3, "membrane": 1, "plate": 2, "bending": 2}.get(beh, 3)
+        tris = [nids] if len(nids) == 3 else [[nids[0], nids[1], nids[2]], [nids[0], nids[2], nids[3]]]
+        if len(nids) == 4:
+            warnings.append(("W_QUAD_SPLIT", f"plate {p['id']}: QUAD4 split into two TRI3"))
+        for t3 in tris:
+            try:
+                p_nodes_l.append([node_index[int(v)] for v in t3])
+            except KeyError as e:
+                raise WireError(f"plate {p['id']}: unknown node {e}") from None
+            p_ids_l.append(int(p["id"]))
+            p_data_l.append([float(p["thickness"]), E, nu, 0.0])
+            p_flags_l.append(flags)
+    p_ids = np.array(p_ids_l, np.int64)
+    p_nodes = np.array(p_nodes_l, np.int32).reshape(len(p_ids_l), 3)
+    p_data = np.array(p_data_l, np.float64).reshape(len(p_ids_l), 4)
+    p_flags = np.array(p_flags_l, np.int32)
+    plate_index = {}
+    for i, pid in enumerate(p_ids_l):
+        plate_index.setdefault(pid, []).append(i)
+
+    # ---- load cases (pydantic_models.py:2048-2059) -------------------------------------
+    load_cases = []
+    raw_cases = list(analysis.get("load_cases") or [])
+    sw_case_id = None
+    if opts.enable_self_weight:
+        sw_case_id = opts.self_weight_load_case_id
+        if sw_case_id is None or all(int(c["id"]) != sw_case_id for c in raw_cases):
+            sw_case_id = (max([int(c["id"]) for c in raw_cases], default=0) + 1) if sw_case_id is None else sw_case_id
+            raw_cases.append({"id": sw_case_id, "name": "Self weight"})
+    for c in raw_cases:
+        lca = LoadCaseArrays(id=int(c["id"]), name=str(c.get("name", c["id"])))
+        nod_node, nod_vec = [], []
+        for nl in (c.get("nodal_loads") or []):
+            v = np.zeros(6)
+            v[:3] = float(nl["magnitude"]) * _vec3(nl["direction"], "nodal_load.direction")
+            nod_node.append(_node_of(nl, node_index)); nod_vec.append(v)
+        for nmo in (c.get("nodal_moments") or []):
+            v = np.zeros(6)
+            v[3:] = float(nmo["magnitude"]) * _vec3(nmo["direction"], "nodal_moment.direction")
+            nod_node.append(_node_of(nmo, node_index)); nod_vec.append(v)
+        dl_member, dl_data = [], []
+        for dl in (c.get("distributed_loads") or []):
+            mi = _member_of(dl, member_index)
+            d = _vec3(dl["direction"], "distributed_load.direction")
+            q1 = float(dl["magnitude"])
+            q2 = float(dl["end_magnitude"]) if dl.get("end_magnitude") is not None else q1
+            a = float(dl.get("start_frac", 0.0) or 0.0)
+            b = float(dl.get("end_frac", 1.0) if dl.get("end_frac") is not None else 1.0)
+            if not (0.0 <= a <= b <= 1.0):
+                raise WireError(f"distributed load {dl.get('id')}: need 0<=start_frac<=end_frac<=1")
+            dl_member.append(mi)
+            dl_data.append(np.concatenate([q1 * d, q2 * d, [a, b]]))
+        if opts.enable_self_weight and int(c["id"]) == sw_case_id:
+            g = np.asarray(opts.gravity_direction, np.float64)
+            g = g / (np.linalg.norm(g) or 1.0)
+            for i, m in enumerate(members):
+                if m_prop[i] < 0 or m_type[i] == MT_CABLE:
+                    continue
+                w = float(m.get("weight") or 0.0)
+                if w == 0.0:
+                    w = prop_rho_a[m_prop[i]] * abs(opts.gravity_factor)
+                if w != 0.0:
+                    dl_member.append(i)
+                    dl_data.append(np.concatenate([w * g, w * g, [0.0, 1.0]]))
+        pl_member, pl_data = [], []
+        for pl in (c.get("member_point_loads") or []):
+            row = np.zeros(8)
+            row[:3] = float(pl["magnitude"]) * _vec3(pl["direction"], "member_point_load.direction")
+            row[6] = float(pl["position"])
+            row[7] = 1.0 if _norm_enum(pl.get("axes") or "global") == "local" else 0.0
+            pl_member.append(_member_of(pl, member_index)); pl_data.append(row)
+        for pm_ in (c.get("member_point_moments") or []):
+            row = np.zeros(8)
+            row[3:6] = float(pm_["magnitude"]) * _vec3(pm_["direction"], "member_point_moment.direction")
+            row[6] = float(pm_["position"])
+            row[7] = 1.0 if _norm_enum(pm_.get("axes") or "global") == "local" else 0.0
+            pl_member.append(_member_of(pm_, member_index)); pl_data.append(row)
+        pp_plate, pp_vec = [], []
+        for pp in (c.get("plate_pressures") or []):
+            tgt = pp.get("target") or {}
+            d = _vec3(pp["direction"], "plate_pressure.direction")
+            ids = []
+            # tagged union {"kind": "Element", "plate_element_id"} | {"kind": "Surface", "surface_id"}
+            # (pydantic_models.py:763-787)
+            if tgt.get("plate_element_id") is not None:
+                ids += plate_index.get(int(tgt["plate_element_id"]), [])
+            if tgt.get("surface_id") is not None:
+                sid_ = int(tgt["surface_id"])
+                ids += [i for i, p in enumerate(plates_flat_surface(plates, p_ids_l)) if p == sid_]
+            for i in ids:
+                pp_plate.append(i); pp_vec.append(float(pp["magnitude"]) * d)
+        for sl in (c.get("surface_loads") or []):
+            _surface_load_to_plates(sl, xyz, p_nodes, pp_plate, pp_vec, warnings)
+        lca.nod_node = np.array(nod_node, np.int32)
+        lca.nod_vec = np.array(nod_vec, np.float64).reshape(len(nod_node), 6)
+        lca.dl_member = np.array(dl_member, np.int32)
+        lca.dl_data = np.array(dl_data, np.float64).reshape(len(dl_member), 8)
+        lca.pl_member = np.array(pl_member, np.int32)
+        lca.pl_data = np.array(pl_data, np.float64).reshape(len(pl_member), 8)
+        lca.pp_plate = np.array(pp_plate, np.int32)
+        lca.pp_vec = np.array(pp_vec, np.float64).reshape(len(pp_plate), 3)
+        load_cases.append(lca)
+
+    # ---- combinations (pydantic_models.py:491-505) --------------------------------------
+    lc_index = {lc.id: i for i, lc in enumerate(load_cases)}
+    combos = analysis.get("load_combinations") or []
+    combo_ids = np.fromiter((int(c["id"]) for c in combos), np.int64, len(combos))
+    combo_names = [str(c.get("name", c["id"])) for c in combos]
+    combo_factors = np.zeros((len(combos), len(load_cases)), np.float64)
+    for ci, c in enumerate(combos):
+        lcf = c.get("load_case_factors") or c.get("load_cases_factors") or []
+        if isinstance(lcf, dict):
+            lcf = [{"load_case_id": k, "factor": v} for k, v in lcf.items()]
+        for f in lcf:
+            lid = int(f["load_case_id"])
+            if lid not in lc_index:
+                raise WireError(f"combination {c['id']}: unknown load case {lid}")
+            combo_factors[ci, lc_index[lid]] += float(f["factor"])
+
+    return ModelArrays(
+        node_ids=node_ids, xyz=xyz, node_support_id=node_support_id, bc_code=bc_code, bc_k=bc_k,
+        m_ids=m_ids, m_n1=m_n1, m_n2=m_n2, m_type=m_type, m_roll=m_roll, m_prop=m_prop, m_rel=m_rel,
+        prop=prop, prop_rho_a=np.array(prop_rho_a, np.float64), rel=rel,
+        p_ids=p_ids, p_nodes=p_nodes, p_data=p_data, p_flags=p_flags,
+        load_cases=load_cases, combo_ids=combo_ids, combo_names=combo_names, combo_factors=combo_factors,
+        imperfections=list(analysis.get("imperfection_cases") or []), member_sets=member_sets,
+        options=opts, warnings=warnings,
+    )
+
+
+def plates_flat_surface(plates, p_ids_l):
+    """source_surface_id per flattened TRI3 row (quads contribute two rows)."""
+    by_id = {int(p["id"]): p.get("source_surface_id") for p in plates}
+    return [(-1 if by_id[pid] is None else int(by_id[pid])) for pid in p_ids_l]
+
+
+def _node_of(item: dict, node_index: dict) -> int:
+    nid = item.get("node")
+    nid = nid["id"] if isinstance(nid, dict) else nid
+    if int(nid) not in node_index:
+        raise WireError(f"load {item.get('id')}: unknown node {nid}")
+    return node_index[int(nid)]
+
+
+def _member_of(item: dict, member_index: dict) -> int:
+    mid = item.get("member")
+    mid = mid["id"] if isinstance(mid, dict) else mid
+    if int(mid) not in member_index:
+        raise WireError(f"load {item.get('id')}: unknown member {mid}")
+    return member_index[int(mid)]
+
+
+def _surface_load_to_plates(sl, xyz, p_nodes, pp_plate, pp_vec, warnings):
+    """SurfaceLoad polygon -> per-plate traction (pydantic_models.py:1962-1967).
+
+    A plate receives the full pressure when its centroid lies inside the polygon (evaluated in
+    the polygon's own plane); plates cut by the polygon edge are not split (SURVEY.md A.9 [G]).
+    """
+    if p_nodes.shape[0] == 0:
+        warnings.append(("W_SURFACE_LOAD_NO_PLATES", f"surface load {sl.get('id')}: no plate elements to load"))
+        return
+    poly = np.array([_vec3(v, "surface_load.polygon") for v in sl["polygon"]])
+    d = _vec3(sl["direction"], "surface_load.direction")
+    q = float(sl["magnitude"])
+    o = poly[0]
+    nrm = np.zeros(3)
+    for i in range(len(poly)):
+        nrm += np.cross(poly[i] - o, poly[(i + 1) % len(poly)] - o)
+    nn = np.linalg.norm(nrm)
+    if nn == 0.0:
+        raise WireError(f"surface load {sl.get('id')}: degenerate polygon")
+    nrm /= nn
+    e1 = poly[1] - o
+    e1 /= np.linalg.norm(e1)
+    e2 = np.cross(nrm, e1)
+    p2 = np.stack([(poly - o) @ e1, (poly - o) @ e2], 1)
+    cen = xyz[p_nodes].mean(axis=1)
+    c2 = np.stack([(cen - o) @ e1, (cen - o) @ e2], 1)
+    off = np.abs((cen - o) @ nrm)
+    span = max(np.ptp(p2[:, 0]), np.ptp(p2[:, 1]), 1e-12)
+    inside = np.zeros(len(cen), bool)
+    x, y = c2[:, 0], c2[:, 1]
+    j = len(p2) - 1
+    for i in range(len(p2)):
+        xi, yi, xj, yj = p2[i, 0], p2[i, 1], p2[j, 0], p2[j, 1]
+        cond = ((yi > y) != (yj > y)) & (x < (xj - xi) * (y - yi) / (yj - yi + 1e-300) + xi)
+        inside ^= cond
+        j = i
+    inside &= off <= 1e-6 * span + 1e-9
+    for i in np.nonzero(inside)[0]:
+        pp_plate.append(int(i)); pp_vec.append(q * d)

@@ -1,0 +1,790 @@
+"""CPU ORACLE for the FERS analysis hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
+reference`` leg may import this module.  The product path (``fers_calculations`` ->
+``fers_core_b200.engine`` -> ``libfers_b200.so``) never does.
+
+What it restates.  The reference (``/root/reference``, Jeroen124/FERS_core) holds no solver
+source: the arithmetic lives in the third-party Rust wheel ``fers_calculations==0.2.43``
+(pyproject.toml:26, requirements.txt:6), absent from the reference tree and not installable
+here.  This file therefore restates the *published* algorithm that the reference's call sites
+(fers_core/fers/fers.py:260,300; tests/nafems/nafems_harness.py:38), schema docstrings
+(fers_core/types/pydantic_models.py), tests and golden numbers pin:
+
+* 3D Euler-Bernoulli/Timoshenko frame element (pydantic_models.py:1052-1114, shear pairing per
+  SURVEY.md A.5), local axes of fers_core/members/member.py:309-354, T^T k T assembly;
+* supports by elimination, springs on the diagonal (pydantic_models.py:2104-2115, 1956-1959);
+* consistent equivalent nodal loads for trapezoid partial member loads and member point
+  loads/moments (pydantic_models.py:1438-1445, 1562-1591);
+* combinations as factored load vectors (pydantic_models.py:491-505);
+* P-Delta iteration with consistent (Przemieniecki) / simplified geometric stiffness and sway /
+  translation imperfections (pydantic_models.py:1370-1398, 1970-1991);
+* CST membrane + DSG3 Mindlin TRI3 plate (pinned by
+  tests/nafems/benchmarks/LE1_result.json and LE6_result.json);
+* result recovery in the reference's conventions (golden
+  fers_core/examples/json_input_solver/805_JSON_Import_Export_with_results.json).
+
+Pinning status: pinned against the reference's closed-form test-suite
+(tests/beam_equation_checks, tests/functionality) and the NAFEMS LE1/LE6 known-answer numbers
+(see tests/test_oracle_*.py).  Parity against the Rust engine at 1e-9 is otherwise UNPINNED
+(no runnable reference; see DESIGN.md "Oracle").
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from fers_core_b200 import wire
+from fers_core_b200.results import ResultArrays, SECTION_FRACS
+from fers_core_b200.hostlogic import (
+    rhs_plan, imperfect_coordinates, rigid_property_row, pdelta_suppressed_axes, INACTIVE_SCALE,
+)
+
+GAUSS3_X = np.array([-np.sqrt(3.0 / 5.0), 0.0, np.sqrt(3.0 / 5.0)])
+GAUSS3_W = np.array([5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0])
+
+
+# --------------------------------------------------------------------------------------
+# element geometry  (fers_core/members/member.py:309-354)
+# --------------------------------------------------------------------------------------
+def member_frames(xyz, n1, n2, roll):
+    """Rotation matrices R [Nm,3,3] (rows = local x,y,z in global coordinates) and lengths."""
+    d = xyz[n2] - xyz[n1]
+    L = np.sqrt((d * d).sum(1))
+    if np.any(L < 1e-12):
+        raise ValueError("zero-length member")
+    lx = d / L[:, None]
+    ref = np.tile(np.array([0.0, 1.0, 0.0]), (len(L), 1))
+    vertical = np.abs(lx[:, 1]) > 1.0 - 1e-6
+    ref[vertical] = np.array([0.0, 0.0, 1.0])
+    lz = np.cross(lx, ref)
+    lz /= np.sqrt((lz * lz).sum(1))[:, None]
+    ly = np.cross(lz, lx)
+    ly /= np.sqrt((ly * ly).sum(1))[:, None]
+    c, s = np.cos(roll)[:, None], np.sin(roll)[:, None]
+    rolled = roll != 0.0
+    ly2 = np.where(rolled[:, None], c * ly + s * lz, ly)
+    lz2 = np.where(rolled[:, None], -s * ly + c * lz, lz)
+    return np.stack([lx, ly2, lz2], 1), L
+
+
+def member_props(model: wire.ModelArrays):
+    """Per-member [EA EIy EIz GJ GAsy GAsz]; rigid members get the stiff stand-in row."""
+    prop = model.prop
+    rigid = rigid_property_row(prop)
+    table = np.vstack([prop, rigid[None, :]]) if prop.size else rigid[None, :]
+    idx = np.where(model.m_prop >= 0, model.m_prop, table.shape[0] - 1)
+    idx = np.where(model.m_type == wire.MT_RIGID, table.shape[0] - 1, idx)
+    return table[idx]
+
+
+def shear_phis(P, L, mtype):
+    """(phi_y, phi_z): phi_y couples v/theta_z bending (EIz with G*a_sz)."""
+    EIy, EIz, GAsy, GAsz = P[:, 1], P[:, 2], P[:, 4], P[:, 5]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        phi_y = np.where(GAsz > 0.0, 12.0 * EIz / (GAsz * L * L), 0.0)
+        phi_z = np.where(GAsy > 0.0, 12.0 * EIy / (GAsy * L * L), 0.0)
+    return phi_y, phi_z
+
+
+def local_stiffness(P, L, mtype):
+    """12x12 local stiffness per member, DOF order [u v w rx ry rz] x 2 nodes."""
+    nm = len(L)
+    k = np.zeros((nm, 12, 12))
+    EA, EIy, EIz, GJ = P[:, 0], P[:, 1], P[:, 2], P[:, 3]
+    phi_y, phi_z = shear_phis(P, L, mtype)
+    axial_only = mtype == wire.MT_TRUSS
+    a = EA / L
+    t = np.where(axial_only, 0.0, GJ / L)
+    for (i, j, s) in ((0, 0, 1), (0, 6, -1), (6, 0, -1), (6, 6, 1)):
+        k[:, i, j] = s * a
+    for (i, j, s) in ((3, 3, 1), (3, 9, -1), (9, 3, -1), (9, 9, 1)):
+        k[:, i, j] = s * t
+    # bending about local z: v (1,7), theta_z (5,11)
+    bz = np.where(axial_only, 0.0, EIz / (1.0 + phi_y))
+    k12, k6, k4, k2 = 12 * bz / L**3, 6 * bz / L**2, (4 + phi_y) * bz / L, (2 - phi_y) * bz / L
+    v1, r1, v2, r2 = 1, 5, 7, 11
+    blk = ((v1, v1, k12), (v1, r1, k6), (v1, v2, -k12), (v1, r2, k6),
+           (r1, r1, k4), (r1, v2, -k6), (r1, r2, k2),
+           (v2, v2, k12), (v2, r2, -k6), (r2, r2, k4))
+    for (i, j, val) in blk:
+        k[:, i, j] = val
+        k[:, j, i] = val
+    # bending about local y: w (2,8), theta_y (4,10)
+    by = np.where(axial_only, 0.0, EIy / (1.0 + phi_z))
+    k12, k6, k4, k2 = 12 * by / L**3, 6 * by / L**2, (4 + phi_z) * by / L, (2 - phi_z) * by / L
+    w1, q1, w2, q2 = 2, 4, 8, 10
+    blk = ((w1, w1, k12), (w1, q1, -k6), (w1, w2, -k12), (w1, q2, -k6),
+           (q1, q1, k4), (q1, w2, k6), (q1, q2, k2),
+           (w2, w2, k12), (w2, q2, k6), (q2, q2, k4))
+    for (i, j, val) in blk:
+        k[:, i, j] = val
+        k[:, j, i] = val
+    return k
+
+
+def geometric_stiffness(N, L, formulation, mtype=None):
+    """Local geometric stiffness for axial force N (tension positive).
+
+    CONSISTENT = Przemieniecki string+bending terms; SIMPLIFIED = N/L on the transverse
+    translations only (pydantic_models.py:1377-1380).
+    """
+    nm = len(L)
+    g = np.zeros((nm, 12, 12))
+    if formulation == "SIMPLIFIED":
+        c = N / L
+        for (i, j) in ((1, 7), (2, 8)):
+            g[:, i, i] = c; g[:, j, j] = c; g[:, i, j] = -c; g[:, j, i] = -c
+        return g
+    c = N / (30.0 * L)
+    v1, r1, v2, r2 = 1, 5, 7, 11
+    for (i, j, val) in ((v1, v1, 36.0), (v1, r1, 3 * L), (v1, v2, -36.0), (v1, r2, 3 * L),
+                        (r1, r1, 4 * L * L), (r1, v2, -3 * L), (r1, r2, -L * L),
+                        (v2, v2, 36.0), (v2, r2, -3 * L), (r2, r2, 4 * L * L)):
+        g[:, i, j] = c * val
+        g[:, j, i] = c * val
+    w1, q1, w2, q2 = 2, 4, 8, 10
+    for (i, j, val) in ((w1, w1, 36.0), (w1, q1, -3 * L), (w1, w2, -36.0), (w1, q2, -3 * L),
+                        (q1, q1, 4 * L * L), (q1, w2, 3 * L), (q1, q2, -L * L),
+                        (w2, w2, 36.0), (w2, q2, 3 * L), (q2, q2, 4 * L * L)):
+        g[:, i, j] = c * val
+        g[:, j, i] = c * val
+    if mtype is not None:
+        # truss members keep only the string terms (no rotational stiffness to couple to)
+        tr = mtype == wire.MT_TRUSS
+        if np.any(tr):
+            gs = geometric_stiffness(N[tr], L[tr], "SIMPLIFIED")
+            g[tr] = gs
+    return g
+
+
+def condense_releases(k, p, rel):
+    """Static condensation of end-release springs (pydantic_models.py:2062-2087).
+
+    For each local end DOF d with release spring ks >= 0 (ks = 0: full release) the member end
+    is connected to the node through ks:  k <- k - k[:,d] k[d,:] / (k[d,d] + ks), same for p.
+    ``p`` is [nrhs,12] equivalent nodal load rows (may be empty).
+    """
+    k = k.copy()
+    p = p.copy()
+    for d in range(12):
+        ks = rel[d]
+        if ks < 0.0:
+            continue
+        den = k[d, d] + ks
+        if den <= 0.0:
+            continue
+        col = k[:, d].copy()
+        if p.size:
+            p -= np.outer(p[:, d] / den, col)
+        k -= np.outer(col, col) / den
+    return k, p
+
+
+def expand_T(R):
+    """[Nm,12,12] block-diagonal transformation from R [Nm,3,3]."""
+    nm = R.shape[0]
+    T = np.zeros((nm, 12, 12))
+    for b in range(4):
+        T[:, 3 * b:3 * b + 3, 3 * b:3 * b + 3] = R
+    return T
+
+
+# --------------------------------------------------------------------------------------
+# plate element: CST membrane + DSG3 Mindlin bending
+# --------------------------------------------------------------------------------------
+def plate_frame(x3):
+    """Local frame of a flat triangle: rows = local x,y,z.  x3 [3,3] corner coordinates.
+
+    local z = normal (right-hand rule over the wire node order); local x = global X projected
+    into the plane (global Y when the normal is parallel to X), so an XY-plane plate has local =
+    global as in every pinned case.
+    """
+    n = np.cross(x3[1] - x3[0], x3[2] - x3[0])
+    nn = np.linalg.norm(n)
+    if nn < 1e-300:
+        raise ValueError("degenerate plate element")
+    ez = n / nn
+    gx = np.array([1.0, 0.0, 0.0])
+    if abs(ez @ gx) > 1.0 - 1e-6:
+        gx = np.array([0.0, 1.0, 0.0])
+    ex = gx - (gx @ ez) * ez
+    ex /= np.linalg.norm(ex)
+    ey = np.cross(ez, ex)
+    return np.stack([ex, ey, ez])
+
+
+def plate_local_matrices(xl, t, E, nu, flags):
+    """18x18 local stiffness of a TRI3 shell, plus (Bm, Bb, Bs, Dm, Db, Ds, area).
+
+    Local DOFs per node [u v w rx ry rz]; DSG3 uses (w, bx, by) with bx = +ry, by = -rx
+    (SURVEY.md B.3 note).  Drilling rz gets a small stabilising stiffness.
+    """
+    (x1, y1), (x2, y2), (x3, y3) = xl
+    a_, b_, c_, d_ = x2 - x1, y2 - y1, y3 - y1, x3 - x1
+    A = 0.5 * (a_ * c_ - b_ * d_)
+    twoA = 2.0 * A
+    k = np.zeros((18, 18))
+    # ---- CST membrane (B.1)
+    bb = np.array([y2 - y3, y3 - y1, y1 - y2])
+    cc = np.array([x3 - x2, x1 - x3, x2 - x1])
+    Bm = np.zeros((3, 6))
+    Bm[0, 0::2] = bb
+    Bm[1, 1::2] = cc
+    Bm[2, 0::2] = cc
+    Bm[2, 1::2] = bb
+    Bm /= twoA
+    Dm = E / (1.0 - nu * nu) * np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]])
+    mdof = np.array([0, 1, 6, 7, 12, 13])
+    if flags & 1:
+        km = t * abs(A) * Bm.T @ Dm @ Bm
+        k[np.ix_(mdof, mdof)] += km
+    # ---- DSG3 bending (B.3), dofs (w, bx, by) per node
+    Bb = np.array([[0, b_ - c_, 0, 0, c_, 0, 0, -b_, 0],
+                   [0, 0, d_ - a_, 0, 0, -d_, 0, 0, a_],
+                   [0, d_ - a_, b_ - c_, 0, -d_, c_, 0, a_, -b_]]) / twoA
+    Bs = np.array([[b_ - c_, A, 0, c_, a_ * c_ / 2, b_ * c_ / 2, -b_, -b_ * d_ / 2, -b_ * c_ / 2],
+                   [d_ - a_, 0, A, -d_, -a_ * d_ / 2, -b_ * d_ / 2, a_, a_ * d_ / 2, a_ * c_ / 2]]) / twoA
+    Db = E * t**3 / (12.0 * (1.0 - nu * nu)) * np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]])
+    G = E / (2.0 * (1.0 + nu))
+    Ds = (5.0 / 6.0) * G * t * np.eye(2)
+    if flags & 2:
+        kb = abs(A) * (Bb.T @ Db @ Bb + Bs.T @ Ds @ Bs)
+        # map (w, bx, by) -> (w, rx, ry): bx = ry, by = -rx
+        S = np.zeros((9, 18))
+        for n in range(3):
+            S[3 * n + 0, 6 * n + 2] = 1.0
+            S[3 * n + 1, 6 * n + 4] = 1.0
+            S[3 * n + 2, 6 * n + 3] = -1.0
+        k += S.T @ kb @ S
+    # ---- drilling stabilisation: small fraction of the membrane shear stiffness
+    kd = 1e-6 * E * t * abs(A)
+    for n in range(3):
+        k[6 * n + 5, 6 * n + 5] += kd
+    return k, (Bm, Bb, Bs, Dm, Db, Ds, A)
+
+
+def plate_stiffness_global(model, xyz):
+    """Per-plate (18x18 global stiffness, frame R, local corner coords)."""
+    out = []
+    for e in range(model.n_plates):
+        x3 = xyz[model.p_nodes[e]]
+        R = plate_frame(x3)
+        xl = (x3 - x3[0]) @ R.T
+        t, E, nu, _ = model.p_data[e]
+        k, mats = plate_local_matrices(xl[:, :2], t, E, nu, int(model.p_flags[e]))
+        T = np.zeros((18, 18))
+        for b in range(6):
+            T[3 * b:3 * b + 3, 3 * b:3 * b + 3] = R
+        out.append((T.T @ k @ T, R, xl[:, :2], mats, T))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# symbolic pattern (bit-exact contract with the CUDA path)
+# --------------------------------------------------------------------------------------
+def bsr_pattern(model: wire.ModelArrays):
+    """Node-block sparsity: sorted unique (row,col) node pairs, every diagonal present.
+
+    Returns (rowptr int32 [Nn+1], colidx int32 [nnzb]).
+    """
+    nn = model.n_nodes
+    rows = [np.arange(nn, dtype=np.int64)]
+    cols = [np.arange(nn, dtype=np.int64)]
+    a, b = model.m_n1.astype(np.int64), model.m_n2.astype(np.int64)
+    rows += [a, b]
+    cols += [b, a]
+    if model.n_plates:
+        pn = model.p_nodes.astype(np.int64)
+        for i in range(3):
+            for j in range(3):
+                if i != j:
+                    rows.append(pn[:, i]); cols.append(pn[:, j])
+    key = np.unique(np.concatenate(rows) * nn + np.concatenate(cols))
+    r, c = key // nn, key % nn
+    rowptr = np.zeros(nn + 1, np.int64)
+    np.add.at(rowptr, r + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    return rowptr.astype(np.int32), c.astype(np.int32)
+
+
+def bc_masks(model: wire.ModelArrays):
+    """(fixed mask uint8 [Ndof], free-DOF numbering int32 [Ndof] (-1 constrained))."""
+    code = model.bc_code.reshape(-1)
+    fixed = (code == wire.BC_FIXED).astype(np.uint8)
+    free_index = np.where(fixed == 0, np.cumsum(1 - fixed.astype(np.int64)) - 1, -1).astype(np.int32)
+    return fixed, free_index
+
+
+# --------------------------------------------------------------------------------------
+# assembly
+# --------------------------------------------------------------------------------------
+class Assembly:
+    """Everything geometry-dependent for one coordinate set (one imperfection case)."""
+
+    def __init__(self, model: wire.ModelArrays, xyz=None, m_scale=None):
+        self.model = model
+        self.xyz = model.xyz if xyz is None else xyz
+        nm = model.n_members
+        self.m_scale = np.ones(nm) if m_scale is None else m_scale
+        if nm:
+            self.R, self.L = member_frames(self.xyz, model.m_n1, model.m_n2, model.m_roll)
+            self.P = member_props(model)
+            self.k_local = local_stiffness(self.P, self.L, model.m_type)
+            self.phi_y, self.phi_z = shear_phis(self.P, self.L, model.m_type)
+        else:
+            self.R = np.zeros((0, 3, 3)); self.L = np.zeros(0); self.P = np.zeros((0, 8))
+            self.k_local = np.zeros((0, 12, 12)); self.phi_y = self.phi_z = np.zeros(0)
+        self.T = expand_T(self.R)
+        self.k_cond = self.k_local.copy()       # after release condensation
+        for i in np.nonzero(model.m_rel >= 0)[0]:
+            self.k_cond[i], _ = condense_releases(self.k_local[i], np.zeros((0, 12)), model.rel[model.m_rel[i]])
+        self.plates = plate_stiffness_global(model, self.xyz) if model.n_plates else []
+        self.edof = np.concatenate([6 * model.m_n1[:, None] + np.arange(6), 6 * model.m_n2[:, None] + np.arange(6)], 1) if nm else np.zeros((0, 12), np.int64)
+
+    def K_elastic(self, kg_local=None):
+        """Global stiffness (no supports, no springs) as CSR [Ndof,Ndof]."""
+        model = self.model
+        nd = model.n_dof
+        rows, cols, vals = [], [], []
+        if model.n_members:
+            kl = self.k_cond * self.m_scale[:, None, None]
+            if kg_local is not None:
+                kl = kl + kg_local
+            kg = np.einsum("mji,mjk,mkl->mil", self.T, kl, self.T)
+            rows.append(np.repeat(self.edof, 12, axis=1).reshape(-1))
+            cols.append(np.tile(self.edof, (1, 12)).reshape(-1))
+            vals.append(kg.reshape(-1))
+        for e, (kge, *_rest) in enumerate(self.plates):
+            ed = (6 * model.p_nodes[e][:, None] + np.arange(6)).reshape(-1)
+            rows.append(np.repeat(ed, 18)); cols.append(np.tile(ed, 18)); vals.append(kge.reshape(-1))
+        if not rows:
+            return sp.csr_matrix((nd, nd))
+        K = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nd, nd))
+        return K.tocsr()
+
+
+def shape_integrals(a, b, q1, q2, phi, L):
+    """Integrals of a linear load q(xi) (q1 at a, q2 at b) against the Timoshenko shapes.
+
+    Returns (S1, S2, S3, S4, lin0, lin1): int N_i q L dxi and int (1-xi) q L dxi, int xi q L dxi.
+    3-point Gauss is exact (integrand degree 4).
+    """
+    half = 0.5 * (b - a)
+    mid = 0.5 * (a + b)
+    out = np.zeros(6)
+    if half <= 0.0:
+        return out
+    for gx, gw in zip(GAUSS3_X, GAUSS3_W):
+        xi = mid + half * gx
+        q = q1 + (q2 - q1) * (xi - a) / (b - a)
+        w = gw * half * L * q
+        n1, n2, n3, n4 = hermite(xi, phi, L)
+        out += w * np.array([n1, n2, n3, n4, 1.0 - xi, xi])
+    return out
+
+
+def hermite(xi, phi, L):
+    d = 1.0 + phi
+    n1 = (1 - 3 * xi**2 + 2 * xi**3 + phi * (1 - xi)) / d
+    n2 = L * (xi - 2 * xi**2 + xi**3 + phi * (xi - xi**2) / 2) / d
+    n3 = (3 * xi**2 - 2 * xi**3 + phi * xi) / d
+    n4 = L * (-xi**2 + xi**3 - phi * (xi - xi**2) / 2) / d
+    return n1, n2, n3, n4
+
+
+def hermite_rot(xi, phi, L):
+    d = 1.0 + phi
+    g1 = 6 * (xi**2 - xi) / (L * d)
+    g2 = (1 - 4 * xi + 3 * xi**2 + phi * (1 - xi)) / d
+    g3 = -g1
+    g4 = (3 * xi**2 - 2 * xi + phi * xi) / d
+    return g1, g2, g3, g4
+
+
+def equivalent_loads(asm: Assembly, lc: wire.LoadCaseArrays):
+    """Local equivalent nodal loads p_eq [Nm,12] of one load case (before release condensation)."""
+    model = asm.model
+    p = np.zeros((model.n_members, 12))
+    for mi, row in zip(lc.dl_member, lc.dl_data):
+        R, L = asm.R[mi], asm.L[mi]
+        q1, q2, a, b = R @ row[0:3], R @ row[3:6], row[6], row[7]
+        truss = model.m_type[mi] == wire.MT_TRUSS
+        # axial
+        s = shape_integrals(a, b, q1[0], q2[0], 0.0, L)
+        p[mi, 0] += s[4]; p[mi, 6] += s[5]
+        sy = shape_integrals(a, b, q1[1], q2[1], asm.phi_y[mi], L)
+        sz = shape_integrals(a, b, q1[2], q2[2], asm.phi_z[mi], L)
+        if truss:
+            p[mi, 1] += sy[4]; p[mi, 7] += sy[5]; p[mi, 2] += sz[4]; p[mi, 8] += sz[5]
+        else:
+            p[mi, 1] += sy[0]; p[mi, 5] += sy[1]; p[mi, 7] += sy[2]; p[mi, 11] += sy[3]
+            p[mi, 2] += sz[0]; p[mi, 4] -= sz[1]; p[mi, 8] += sz[2]; p[mi, 10] -= sz[3]
+    for mi, row in zip(lc.pl_member, lc.pl_data):
+        R, L = asm.R[mi], asm.L[mi]
+        F, M, xi, is_local = row[0:3], row[3:6], row[6], row[7] != 0.0
+        if not is_local:
+            F, M = R @ F, R @ M
+        truss = model.m_type[mi] == wire.MT_TRUSS
+        p[mi, 0] += (1 - xi) * F[0]; p[mi, 6] += xi * F[0]
+        p[mi, 3] += (1 - xi) * M[0]; p[mi, 9] += xi * M[0]
+        if truss:
+            p[mi, 1] += (1 - xi) * F[1]; p[mi, 7] += xi * F[1]
+            p[mi, 2] += (1 - xi) * F[2]; p[mi, 8] += xi * F[2]
+            continue
+        n = hermite(xi, asm.phi_y[mi], L); g = hermite_rot(xi, asm.phi_y[mi], L)
+        for dof, nv, gv in zip((1, 5, 7, 11), n, g):
+            p[mi, dof] += nv * F[1] + gv * M[2]
+        n = hermite(xi, asm.phi_z[mi], L); g = hermite_rot(xi, asm.phi_z[mi], L)
+        for dof, nv, gv, sg in zip((2, 4, 8, 10), n, g, (1.0, -1.0, 1.0, -1.0)):
+            # w = N1 w1 - N2 ry1 + N3 w2 - N4 ry2 ; ry = -G1 w1 + G2 ry1 - G3 w2 + G4 ry2
+            p[mi, dof] += sg * nv * F[2] + (-sg) * gv * M[1]
+    return p
+
+
+def plate_loads(asm: Assembly, lc: wire.LoadCaseArrays, F):
+    """Lump plate pressures: q*A/3 on each corner's translations."""
+    model = asm.model
+    for e, vec in zip(lc.pp_plate, lc.pp_vec):
+        A = abs(asm.plates[e][3][6])
+        for n in model.p_nodes[e]:
+            F[6 * n:6 * n + 3] += vec * A / 3.0
+
+
+def load_vectors(asm: Assembly):
+    """Per load case: global nodal load vector F [Nlc,Ndof] and local p_eq [Nlc,Nm,12]
+    (p_eq already condensed for end releases)."""
+    model = asm.model
+    nlc = len(model.load_cases)
+    F = np.zeros((nlc, model.n_dof))
+    peq = np.zeros((nlc, model.n_members, 12))
+    for li, lc in enumerate(model.load_cases):
+        for n, v in zip(lc.nod_node, lc.nod_vec):
+            F[li, 6 * n:6 * n + 6] += v
+        p = equivalent_loads(asm, lc)
+        for i in np.nonzero(model.m_rel >= 0)[0]:
+            _, pc = condense_releases(asm.k_local[i], p[i][None, :], model.rel[model.m_rel[i]])
+            p[i] = pc[0]
+        p *= 1.0  # member scale does not apply to loads
+        peq[li] = p
+        if model.n_members:
+            pg = np.einsum("mji,mj->mi", asm.T, p)
+            np.add.at(F[li], asm.edof.reshape(-1), pg.reshape(-1))
+        if len(lc.pp_plate):
+            plate_loads(asm, lc, F[li])
+    return F, peq
+
+
+# --------------------------------------------------------------------------------------
+# solve + recovery
+# --------------------------------------------------------------------------------------
+def constrain(K, model, extra_fixed=None):
+    """Add support springs, eliminate fixed DOFs. Returns (K_ff factor-ready csc, free idx)."""
+    nd = model.n_dof
+    code = model.bc_code.reshape(-1)
+    kspring = np.where(code == wire.BC_SPRING, model.bc_k.reshape(-1), 0.0)
+    fixed = code == wire.BC_FIXED
+    if extra_fixed is not None:
+        fixed = fixed | extra_fixed
+    Ks = K + sp.diags(kspring)
+    # zero-stiffness free DOFs (e.g. rotations of truss-only nodes) are restrained automatically
+    diag = Ks.diagonal()
+    dead = (~fixed) & (diag == 0.0)
+    fixed = fixed | dead
+    free = np.nonzero(~fixed)[0]
+    return Ks[free][:, free].tocsc(), free, dead
+
+
+def solve_sym(Kff, B):
+    """Direct solve of K_ff X = B (B [n,nrhs])."""
+    if Kff.shape[0] == 0:
+        return np.zeros_like(B)
+    if Kff.shape[0] <= 3000:
+        import scipy.linalg as sla
+        A = Kff.toarray()
+        try:
+            c = sla.cho_factor(A, lower=True, check_finite=False)
+            return sla.cho_solve(c, B, check_finite=False)
+        except np.linalg.LinAlgError:
+            return np.linalg.solve(A, B)
+    lu = spla.splu(Kff, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    return lu.solve(B)
+
+
+def recover_members(asm: Assembly, U, peq, kg_local=None):
+    """Member forces for displacement columns U [nrhs,Ndof], p_eq [nrhs,Nm,12].
+
+    Returns dict of arrays (see fers_core_b200.results.ResultArrays).
+    """
+    model = asm.model
+    nrhs, nm = U.shape[0], model.n_members
+    out = {}
+    if nm == 0:
+        z = lambda *s: np.zeros((nrhs, 0) + s)
+        return dict(f_local=z(12), f_global=z(12), u_local=z(12), sec=z(len(SECTION_FRACS), 6),
+                    lmax=z(6), lmin=z(6), gmax=z(6), gmin=z(6))
+    ue = U[:, asm.edof]                                   # [nrhs,Nm,12]
+    ul = np.einsum("mij,rmj->rmi", asm.T, ue)
+    kl = asm.k_cond * asm.m_scale[:, None, None]
+    if kg_local is not None:
+        kl = kl[None] + kg_local                          # [nrhs,Nm,12,12]
+        fl = np.einsum("rmij,rmj->rmi", kl, ul) - peq
+    else:
+        fl = np.einsum("mij,rmj->rmi", kl, ul) - peq
+    fg = np.einsum("mji,rmj->rmi", asm.T, fl)
+    out["f_local"], out["f_global"], out["u_local"] = fl, fg, ul
+    return out
+
+
+def span_load_tables(asm: Assembly):
+    """Per load case, per member: list of local span loads for section-force transport."""
+    model = asm.model
+    tabs = []
+    for lc in model.load_cases:
+        per = {}
+        for mi, row in zip(lc.dl_member, lc.dl_data):
+            R = asm.R[mi]
+            per.setdefault(int(mi), []).append(("d", R @ row[0:3], R @ row[3:6], row[6], row[7]))
+        for mi, row in zip(lc.pl_member, lc.pl_data):
+            R = asm.R[mi]
+            F, M = row[0:3], row[3:6]
+            if row[7] == 0.0:
+                F, M = R @ F, R @ M
+            per.setdefault(int(mi), []).append(("p", F, M, row[6]))
+        tabs.append(per)
+    return tabs
+
+
+def span_resultant(loads, L, x):
+    """Resultant (force[3], moment[3] about the section point) of span loads on [0, x*L]."""
+    f = np.zeros(3); m = np.zeros(3)
+    for ld in loads:
+        if ld[0] == "d":
+            _, q1, q2, a, b = ld
+            hi = min(b, x)
+            if hi <= a:
+                continue
+            half, mid = 0.5 * (hi - a), 0.5 * (hi + a)
+            for gx, gw in zip(GAUSS3_X, GAUSS3_W):
+                xi = mid + half * gx
+                q = q1 + (q2 - q1) * ((xi - a) / (b - a))
+                w = gw * half * L
+                d = (x - xi) * L
+                f += w * q
+                m += w * np.array([0.0, d * q[2], -d * q[1]])
+        else:
+            _, F, M, pos = ld
+            if pos <= x:
+                d = (x - pos) * L
+                f += F
+                m += M + np.array([0.0, d * F[2], -d * F[1]])
+    return f, m
+
+
+def section_forces(asm: Assembly, fl, span_by_rhs):
+    """Internal forces at SECTION_FRACS: start force transported along the member.
+
+    fl [nrhs,Nm,12]; span_by_rhs: per rhs a list of (factor, span table) pairs.
+    """
+    nrhs, nm = fl.shape[:2]
+    ns = len(SECTION_FRACS)
+    sec = np.zeros((nrhs, nm, ns, 6))
+    for si, x in enumerate(SECTION_FRACS):
+        d = x * asm.L
+        sec[:, :, si, 0:3] = fl[:, :, 0:3]
+        sec[:, :, si, 3] = fl[:, :, 3]
+        sec[:, :, si, 4] = fl[:, :, 4] + d[None, :] * fl[:, :, 2]
+        sec[:, :, si, 5] = fl[:, :, 5] - d[None, :] * fl[:, :, 1]
+    for r in range(nrhs):
+        for fac, tab in span_by_rhs[r]:
+            if fac == 0.0:
+                continue
+            for mi, loads in tab.items():
+                for si, x in enumerate(SECTION_FRACS):
+                    f, m = span_resultant(loads, asm.L[mi], x)
+                    sec[r, mi, si, 0:3] += fac * f
+                    sec[r, mi, si, 3:6] += fac * m
+    return sec
+
+
+def min_max(asm: Assembly, fl, fg, sec):
+    """Per-component extrema over {start, end (nodal convention), interior sections}."""
+    loc = np.concatenate([fl[:, :, None, 0:6], fl[:, :, None, 6:12], sec], axis=2)
+    secg = np.concatenate([np.einsum("mji,rmsj->rmsi", asm.R, sec[..., 0:3]),
+                           np.einsum("mji,rmsj->rmsi", asm.R, sec[..., 3:6])], axis=-1)
+    glo = np.concatenate([fg[:, :, None, 0:6], fg[:, :, None, 6:12], secg], axis=2)
+    return loc.max(2), loc.min(2), glo.max(2), glo.min(2)
+
+
+def recover_plates(asm: Assembly, U):
+    """Plate resultants at the centroid + corner forces.  Returns dict of arrays."""
+    model = asm.model
+    nrhs, npl = U.shape[0], model.n_plates
+    res = np.zeros((nrhs, npl, 8))        # nx ny nxy mx my mxy qx qy
+    nod = np.zeros((nrhs, npl, 3, 6))
+    cdg = np.zeros((nrhs, npl, 6)); cdl = np.zeros((nrhs, npl, 6))
+    cen = np.zeros((npl, 3))
+    for e, (kge, R, xl, mats, T) in enumerate(asm.plates):
+        Bm, Bb, Bs, Dm, Db, Ds, A = mats
+        ed = (6 * model.p_nodes[e][:, None] + np.arange(6)).reshape(-1)
+        cen[e] = asm.xyz[model.p_nodes[e]].mean(0)
+        t = model.p_data[e, 0]
+        for r in range(nrhs):
+            ug = U[r, ed]
+            ul = T @ ug
+            um = ul[[0, 1, 6, 7, 12, 13]]
+            ub = np.zeros(9)
+            for n in range(3):
+                ub[3 * n] = ul[6 * n + 2]; ub[3 * n + 1] = ul[6 * n + 4]; ub[3 * n + 2] = -ul[6 * n + 3]
+            flags = int(model.p_flags[e])
+            Nm_ = t * Dm @ (Bm @ um) if flags & 1 else np.zeros(3)
+            Mb = -Db @ (Bb @ ub) if flags & 2 else np.zeros(3)
+            Qs = Ds @ (Bs @ ub) if flags & 2 else np.zeros(2)
+            res[r, e] = np.concatenate([Nm_, Mb, Qs])
+            nod[r, e] = (kge @ ug).reshape(3, 6)
+            cdg[r, e] = ug.reshape(3, 6).mean(0)
+            cdl[r, e] = ul.reshape(3, 6).mean(0)
+    return dict(p_res=res, p_nodal=nod, p_cdg=cdg, p_cdl=cdl, p_centroid=cen)
+
+
+def analyze(model: wire.ModelArrays, timings: dict | None = None) -> ResultArrays:
+    """Full analysis of one document: the oracle twin of fers_core_b200.engine.analyze."""
+    opts = model.options
+    plan = rhs_plan(model)              # list of RhsGroup(imperfection case, rhs columns ...)
+    nn, nm, nd = model.n_nodes, model.n_members, model.n_dof
+    nrhs = plan.n_rhs
+    ns = len(SECTION_FRACS)
+    out = ResultArrays.empty(model, plan)
+    second_order = opts.order == "NONLINEAR"
+    unilateral_members = np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE))
+    t0 = time.perf_counter()
+    for grp in plan.groups:
+        xyz = imperfect_coordinates(model, grp.imperfection) if grp.imperfection is not None else model.xyz
+        asm = Assembly(model, xyz)
+        F_lc, peq_lc = load_vectors(asm)
+        spans = span_load_tables(asm)
+        fac = plan.factors[grp.columns]                         # [ng,Nlc]
+        F = fac @ F_lc
+        peq = np.einsum("rl,lmk->rmk", fac, peq_lc)
+        cols = list(grp.columns)
+        needs_own = second_order or np.any(unilateral_members)
+        if not needs_own:
+            # ---- linear: one factorisation, all right-hand sides
+            K = asm.K_elastic()
+            Kff, free, dead = constrain(K, model)
+            Uf = solve_sym(Kff, F[:, free].T).T
+            U = np.zeros((len(cols), nd)); U[:, free] = Uf
+            _store(out, asm, model, cols, U, F, peq, K, None, spans, fac, iters=None)
+        else:
+            for ci, col in enumerate(cols):
+                U1, K1, kg1, scale1, it, conv, resn = _solve_nonlinear(asm, model, F[ci], peq[ci], second_order)
+                asm_c = asm
+                if scale1 is not None:
+                    asm_c = Assembly(model, xyz, scale1)
+                _store(out, asm_c, model, [col], U1[None], F[ci:ci + 1], peq[ci:ci + 1], K1,
+                       None if kg1 is None else kg1[None], spans, fac[ci:ci + 1], iters=(it, conv, resn))
+    if timings is not None:
+        timings["total_s"] = time.perf_counter() - t0
+    return out
+
+
+def _axial_forces(asm, U, peq, kg_local=None):
+    rec = recover_members(asm, U[None], peq[None], None if kg_local is None else kg_local[None])
+    return rec["f_local"][0][:, 6]
+
+
+def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
+    """Active-set (tension/compression-only) outer loop around the P-Delta fixed point."""
+    opts = model.options
+    nd = model.n_dof
+    uni = np.nonzero(np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)))[0]
+    scale = np.ones(model.n_members)
+    asm = asm0
+    total_it, conv, resn = 0, True, 0.0
+    suppressed = pdelta_suppressed_axes(model)
+    for _outer in range(max(1, 2 * len(uni) + 2)):
+        K0 = asm.K_elastic()
+        Kff, free, _ = constrain(K0, model)
+        U = np.zeros(nd); U[free] = solve_sym(Kff, F[free][:, None])[:, 0]
+        kg = None
+        K = K0
+        if second_order and model.n_members:
+            conv = False
+            for it in range(max(1, opts.max_iterations)):
+                N = _axial_forces(asm, U, peq, kg)
+                kg = geometric_stiffness(N, asm.L, opts.pdelta_formulation, model.m_type)
+                kg = _suppress_kg(asm, kg, suppressed)
+                K = asm.K_elastic(kg)
+                Kff, free, _ = constrain(K, model)
+                Un = np.zeros(nd); Un[free] = solve_sym(Kff, F[free][:, None])[:, 0]
+                total_it += 1
+                den = np.linalg.norm(Un)
+                resn = np.linalg.norm(Un - U) / den if den > 0 else 0.0
+                U = Un
+                if resn < opts.tolerance:
+                    conv = True
+                    break
+            # geometric stiffness consistent with the converged displacement
+            N = _axial_forces(asm, U, peq, kg)
+        if len(uni) == 0:
+            break
+        N = _axial_forces(asm, U, peq, kg)
+        # elongation decides re-activation of inactive members
+        ue = U[asm.edof[uni]]
+        ul = np.einsum("mij,mj->mi", asm.T[uni], ue)
+        elong = ul[:, 6] - ul[:, 0]
+        tens = np.isin(model.m_type[uni], (wire.MT_TENSION, wire.MT_CABLE))
+        want_active = np.where(tens, elong >= 0.0, elong <= 0.0)
+        new_scale = scale.copy()
+        new_scale[uni] = np.where(want_active, 1.0, INACTIVE_SCALE)
+        if np.array_equal(new_scale, scale):
+            break
+        scale = new_scale
+        asm = Assembly(model, asm0.xyz, scale)
+    return U, K, kg, (scale if len(uni) else None), (total_it if second_order else None), conv, resn
+
+
+def _suppress_kg(asm, kg, suppressed):
+    """pdelta_suppress_axes: zero the global translational rows/cols of the element K_g
+    (pydantic_models.py:1381-1384)."""
+    if not suppressed:
+        return kg
+    kgg = np.einsum("mji,mjk,mkl->mil", asm.T, kg, asm.T)
+    for ax in suppressed:
+        for d in (ax, ax + 6):
+            kgg[:, d, :] = 0.0
+            kgg[:, :, d] = 0.0
+    return np.einsum("mij,mjk,mlk->mil", asm.T, kgg, asm.T)
+
+
+def _store(out: ResultArrays, asm, model, cols, U, F, peq, K, kg, spans, fac, iters):
+    """Fill result arrays for the given rhs columns."""
+    nn = model.n_nodes
+    cols = np.asarray(cols)
+    out.U[cols] = U.reshape(len(cols), nn, 6)
+    # reactions R = K u - F at supported nodes; springs excluded from K
+    Rfull = (K @ U.T).T - F
+    sup = model.node_support_id >= 0
+    Rn = Rfull.reshape(len(cols), nn, 6) * sup[None, :, None]
+    out.R[cols] = Rn
+    rec = recover_members(asm, U, peq, kg)
+    out.f_local[cols] = rec["f_local"]; out.f_global[cols] = rec["f_global"]; out.u_local[cols] = rec["u_local"]
+    if model.n_members:
+        span_by_rhs = [[(fac[r, li], spans[li]) for li in range(fac.shape[1])] for r in range(len(cols))]
+        sec = section_forces(asm, rec["f_local"], span_by_rhs)
+        out.sec[cols] = sec
+        lmax, lmin, gmax, gmin = min_max(asm, rec["f_local"], rec["f_global"], sec)
+        out.lmax[cols], out.lmin[cols], out.gmax[cols], out.gmin[cols] = lmax, lmin, gmax, gmin
+    if model.n_plates:
+        pr = recover_plates(asm, U)
+        out.p_res[cols] = pr["p_res"]; out.p_nodal[cols] = pr["p_nodal"]
+        out.p_cdg[cols] = pr["p_cdg"]; out.p_cdl[cols] = pr["p_cdl"]; out.p_centroid = pr["p_centroid"]
+    if iters is not None:
+        it, conv, resn = iters
+        for c in cols:
+            out.iterations[c] = -1 if it is None else it
+            out.converged[c] = bool(conv)
+            out.residual[c] = resn
