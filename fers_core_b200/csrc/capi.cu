@@ -1,0 +1,46 @@
+// capi.cu -- library-level entry points of libfers_b200 (include/fers_b200.h).
+#include "common.cuh"
+
+namespace fers {
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+    }
+    return cached;
+}
+}  // namespace fers
+
+extern "C" {
+
+const char* fers_b200_version(void) { return "fers_b200 0.1.0 (sm_100a, abi 1)"; }
+const char* fers_b200_last_error(void) { return fers::g_error.c_str(); }
+
+int fers_b200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+    cudaDeviceProp p;
+    FERS_CK(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    FERS_REQUIRE(p.major == 10, "libfers_b200 is built for sm_100a only; device is not compute capability 10.x");
+    return 0;
+}
+
+int fers_b200_set_device(int device) {
+    FERS_CK(cudaSetDevice(device));
+    return 0;
+}
+
+int fers_b200_zero(void* ptr, size_t bytes, void* stream) {
+    if (bytes == 0) return 0;
+    FERS_CK(cudaMemsetAsync(ptr, 0, bytes, fers::as_stream(stream)));
+    return 0;
+}
+
+}  // extern "C"

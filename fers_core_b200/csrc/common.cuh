@@ -1,0 +1,44 @@
+// common.cuh -- error plumbing and small device helpers shared by the libfers_b200 translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/fers_b200.h"
+#include "fers_elem.cuh"
+
+namespace fers {
+
+void set_error(const std::string& msg);
+
+#define FERS_CK(expr)                                                                               \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            fers::set_error(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                            ":" + std::to_string(__LINE__) + ")");                                  \
+            return 1;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+#define FERS_LAUNCH_CHECK() FERS_CK(cudaGetLastError())
+
+#define FERS_REQUIRE(cond, msg)          \
+    do {                                 \
+        if (!(cond)) {                   \
+            fers::set_error(msg);        \
+            return 2;                    \
+        }                                \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+int sm_count();   // SMs of the current device (cached)
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// 128-bit read-only load of two doubles
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+}  // namespace fers

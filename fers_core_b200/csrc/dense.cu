@@ -1,0 +1,223 @@
+// dense.cu -- dense direct path for small models and batches of small models
+// (BASELINE.json configs[0..2] and the per-frame systems of configs[4]).
+//
+// Blocked right-looking Cholesky with 32x32 tiles, batched over blockIdx.z; row-major storage,
+// lower triangle holds L on exit.  Three kernels per block column (diagonal factor, panel solve,
+// trailing update), two per block column and direction for the multi-RHS substitution.
+// The matrices of this path live in L2 (n <= ~4k), so the kernels are latency/FP64-pipe bound,
+// not HBM bound; the HBM-bound large-model path is solve_pcg.cu.
+#include "common.cuh"
+
+namespace fers {
+
+constexpr int NB = 32;
+constexpr int NBP = NB + 1;   // padded shared-memory stride
+
+// expand block-CSR to dense with constrained DOFs replaced by identity rows/cols
+__global__ void k_dense_expand(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                               const double* __restrict__ vals, const uint8_t* __restrict__ fixed,
+                               const double* __restrict__ kspring, double* __restrict__ a) {
+    const int n = 6 * n_nodes;
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_nodes) return;
+    for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) {
+        const int col = colidx[k];
+        for (int e = lane; e < 36; e += 32) {
+            const int r = e / 6, c = e % 6;
+            const int gi = 6 * row + r, gj = 6 * col + c;
+            double v = vals[(size_t)k * 36 + e];
+            const bool fx = (fixed[gi] != 0) || (fixed[gj] != 0);
+            if (fx) v = (gi == gj) ? 1.0 : 0.0;
+            else if (gi == gj && kspring != nullptr) v += kspring[gi];
+            a[(size_t)gi * n + gj] = v;
+        }
+    }
+}
+
+// factor the diagonal tile [j0, j0+nb)
+__global__ void __launch_bounds__(NB* NB) k_potrf_diag(double* __restrict__ a_all, int n, int j0, int* __restrict__ info) {
+    __shared__ double t[NB][NBP];
+    double* a = a_all + (size_t)blockIdx.z * n * n;
+    const int tx = threadIdx.x % NB, ty = threadIdx.x / NB;
+    const int nb = min(NB, n - j0);
+    const bool in = (ty < nb && tx < nb);
+    t[ty][tx] = (in && tx <= ty) ? a[(size_t)(j0 + ty) * n + j0 + tx] : ((ty == tx) ? 1.0 : 0.0);
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {
+        if (tx == k && ty == k) {
+            double d = t[k][k];
+            if (!(d > 0.0)) {
+                if (info && info[blockIdx.z] == 0) info[blockIdx.z] = j0 + k + 1;
+                d = 1.0;
+            }
+            t[k][k] = sqrt(d);
+        }
+        __syncthreads();
+        if (tx == k && ty > k && ty < nb) t[ty][k] /= t[k][k];
+        __syncthreads();
+        if (tx > k && tx <= ty && ty < nb) t[ty][tx] -= t[ty][k] * t[tx][k];
+        __syncthreads();
+    }
+    if (in && tx <= ty) a[(size_t)(j0 + ty) * n + j0 + tx] = t[ty][tx];
+}
+
+// panel: rows below the diagonal tile, X * L_jj^T = A_panel
+__global__ void __launch_bounds__(NB* NB) k_trsm_panel(double* __restrict__ a_all, int n, int j0) {
+    __shared__ double l[NB][NBP];
+    __shared__ double b[NB][NBP];
+    double* a = a_all + (size_t)blockIdx.z * n * n;
+    const int tx = threadIdx.x % NB, ty = threadIdx.x / NB;
+    const int nb = min(NB, n - j0);
+    const int i0 = j0 + NB + blockIdx.x * NB;
+    const int rows = min(NB, n - i0);
+    l[ty][tx] = (ty < nb && tx < nb && tx <= ty) ? a[(size_t)(j0 + ty) * n + j0 + tx] : ((ty == tx) ? 1.0 : 0.0);
+    b[ty][tx] = (ty < rows && tx < nb) ? a[(size_t)(i0 + ty) * n + j0 + tx] : 0.0;
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {
+        if (tx == k) b[ty][k] /= l[k][k];
+        __syncthreads();
+        if (tx > k && tx < nb) b[ty][tx] -= b[ty][k] * l[tx][k];
+        __syncthreads();
+    }
+    if (ty < rows && tx < nb) a[(size_t)(i0 + ty) * n + j0 + tx] = b[ty][tx];
+}
+
+// trailing update: A[ti][tk] -= P_ti P_tk^T for tiles ti >= tk below/right of the panel
+__global__ void __launch_bounds__(NB* NB) k_syrk_update(double* __restrict__ a_all, int n, int j0) {
+    if (blockIdx.y > blockIdx.x) return;
+    __shared__ double pi[NB][NBP];
+    __shared__ double pk[NB][NBP];
+    double* a = a_all + (size_t)blockIdx.z * n * n;
+    const int tx = threadIdx.x % NB, ty = threadIdx.x / NB;
+    const int nb = min(NB, n - j0);
+    const int i0 = j0 + NB + blockIdx.x * NB, k0 = j0 + NB + blockIdx.y * NB;
+    const int ri = min(NB, n - i0), rk = min(NB, n - k0);
+    pi[ty][tx] = (ty < ri && tx < nb) ? a[(size_t)(i0 + ty) * n + j0 + tx] : 0.0;
+    pk[ty][tx] = (ty < rk && tx < nb) ? a[(size_t)(k0 + ty) * n + j0 + tx] : 0.0;
+    __syncthreads();
+    if (ty < ri && tx < rk && (k0 + tx) <= (i0 + ty)) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int q = 0; q < NB; ++q) s = fma(pi[ty][q], pk[tx][q], s);
+        a[(size_t)(i0 + ty) * n + k0 + tx] -= s;
+    }
+}
+
+// ---- multi-RHS substitution; bx [batch][n][nrhs] -----------------------------------------------
+// diagonal solve of block j: forward (L) or backward (L^T); one CTA per 32 rhs columns
+__global__ void __launch_bounds__(NB* NB) k_trsv_diag(const double* __restrict__ a_all, double* __restrict__ bx_all, int n,
+                                                      int nrhs, int j0, int backward) {
+    __shared__ double l[NB][NBP];
+    __shared__ double b[NB][NBP];
+    const double* a = a_all + (size_t)blockIdx.z * n * n;
+    double* bx = bx_all + (size_t)blockIdx.z * n * nrhs;
+    const int tx = threadIdx.x % NB, ty = threadIdx.x / NB;
+    const int nb = min(NB, n - j0);
+    const int c0 = blockIdx.x * NB;
+    const int col = c0 + tx;
+    l[ty][tx] = (ty < nb && tx < nb && tx <= ty) ? a[(size_t)(j0 + ty) * n + j0 + tx] : ((ty == tx) ? 1.0 : 0.0);
+    b[ty][tx] = (ty < nb && col < nrhs) ? bx[(size_t)(j0 + ty) * nrhs + col] : 0.0;
+    __syncthreads();
+    if (!backward) {
+        for (int k = 0; k < nb; ++k) {
+            if (ty == k) b[k][tx] /= l[k][k];
+            __syncthreads();
+            if (ty > k && ty < nb) b[ty][tx] -= l[ty][k] * b[k][tx];
+            __syncthreads();
+        }
+    } else {
+        for (int k = nb - 1; k >= 0; --k) {
+            if (ty == k) b[k][tx] /= l[k][k];
+            __syncthreads();
+            if (ty < k) b[ty][tx] -= l[k][ty] * b[k][tx];
+            __syncthreads();
+        }
+    }
+    if (ty < nb && col < nrhs) bx[(size_t)(j0 + ty) * nrhs + col] = b[ty][tx];
+}
+
+// forward: b_i -= L_ij x_j (i > j);  backward: b_k -= L_jk^T x_j (k < j)
+__global__ void __launch_bounds__(NB* NB) k_subst_update(const double* __restrict__ a_all, double* __restrict__ bx_all, int n,
+                                                         int nrhs, int j0, int backward) {
+    __shared__ double l[NB][NBP];
+    __shared__ double xj[NB][NBP];
+    const double* a = a_all + (size_t)blockIdx.z * n * n;
+    double* bx = bx_all + (size_t)blockIdx.z * n * nrhs;
+    const int tx = threadIdx.x % NB, ty = threadIdx.x / NB;
+    const int nb = min(NB, n - j0);
+    const int col = blockIdx.x * NB + tx;
+    const int i0 = backward ? blockIdx.y * NB : j0 + NB + blockIdx.y * NB;
+    const int rows = backward ? min(NB, j0 - i0) : min(NB, n - i0);
+    // l[ty][tx] = coefficient of x_j[tx] in row i0+ty
+    if (!backward) l[ty][tx] = (ty < rows && tx < nb) ? a[(size_t)(i0 + ty) * n + j0 + tx] : 0.0;
+    else l[ty][tx] = (ty < rows && tx < nb) ? a[(size_t)(j0 + tx) * n + i0 + ty] : 0.0;
+    xj[ty][tx] = (ty < nb && col < nrhs) ? bx[(size_t)(j0 + ty) * nrhs + col] : 0.0;
+    __syncthreads();
+    if (ty < rows && col < nrhs) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int q = 0; q < NB; ++q) s = fma(l[ty][q], xj[q][tx], s);
+        bx[(size_t)(i0 + ty) * nrhs + col] -= s;
+    }
+}
+
+}  // namespace fers
+
+using namespace fers;
+
+extern "C" {
+
+int fers_b200_dense_expand(int n_nodes, const int* rowptr, const int* colidx, const double* vals,
+                           const uint8_t* fixed, const double* kspring, double* a, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    const size_t n = 6 * (size_t)n_nodes;
+    FERS_CK(cudaMemsetAsync(a, 0, n * n * sizeof(double), st));
+    const int T = 256;
+    int grid = (n_nodes * 32 + T - 1) / T;
+    k_dense_expand<<<grid, T, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, a);
+    FERS_LAUNCH_CHECK();
+    return 0;
+}
+
+int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* info_out, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    FERS_REQUIRE(n > 0 && batch > 0, "dense_cholesky: empty problem");
+    FERS_REQUIRE(batch <= 65535, "dense_cholesky: batch exceeds gridDim.z");
+    if (info_dev) FERS_CK(cudaMemsetAsync(info_dev, 0, sizeof(int) * batch, st));
+    for (int j0 = 0; j0 < n; j0 += NB) {
+        k_potrf_diag<<<dim3(1, 1, batch), NB * NB, 0, st>>>(a, n, j0, info_dev);
+        const int rem = n - j0 - NB;
+        if (rem > 0) {
+            const int nt = (rem + NB - 1) / NB;
+            k_trsm_panel<<<dim3(nt, 1, batch), NB * NB, 0, st>>>(a, n, j0);
+            k_syrk_update<<<dim3(nt, nt, batch), NB * NB, 0, st>>>(a, n, j0);
+        }
+    }
+    FERS_LAUNCH_CHECK();
+    if (info_dev && info_out) {
+        FERS_CK(cudaMemcpyAsync(info_out, info_dev, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+        FERS_CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* bx, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    FERS_REQUIRE(n > 0 && nrhs > 0 && batch > 0, "dense_solve: empty problem");
+    const int nc = (nrhs + NB - 1) / NB;
+    for (int j0 = 0; j0 < n; j0 += NB) {
+        k_trsv_diag<<<dim3(nc, 1, batch), NB * NB, 0, st>>>(a, bx, n, nrhs, j0, 0);
+        const int rem = n - j0 - NB;
+        if (rem > 0) k_subst_update<<<dim3(nc, (rem + NB - 1) / NB, batch), NB * NB, 0, st>>>(a, bx, n, nrhs, j0, 0);
+    }
+    const int last = ((n - 1) / NB) * NB;
+    for (int j0 = last; j0 >= 0; j0 -= NB) {
+        k_trsv_diag<<<dim3(nc, 1, batch), NB * NB, 0, st>>>(a, bx, n, nrhs, j0, 1);
+        if (j0 > 0) k_subst_update<<<dim3(nc, j0 / NB, batch), NB * NB, 0, st>>>(a, bx, n, nrhs, j0, 1);
+    }
+    FERS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,478 @@
+// fers_elem.cuh -- element-level arithmetic of the FERS hot path (fp64), shared by every kernel.
+//
+// All functions are FERS_HD (= __host__ __device__ under nvcc, plain inline under g++) so the
+// same code is exercised on the CPU by tests/test_elem_host.py against the oracle before it
+// ever runs on a GPU.  Nothing in the product path calls the host instantiation.
+//
+// Reference semantics restated here (the reference ships no solver source):
+//   local axes ............ fers_core/members/member.py:309-354
+//   section properties .... fers_core/types/pydantic_models.py:1052-1114 (shear pairing: SURVEY.md A.5)
+//   member types .......... pydantic_models.py:592-598
+//   P-Delta K_g ........... pydantic_models.py:1377-1380
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define FERS_HD __host__ __device__ __forceinline__
+#else
+#define FERS_HD inline
+#endif
+
+namespace fers {
+
+enum MemberType { MT_NORMAL = 0, MT_TRUSS = 1, MT_TENSION = 2, MT_COMPRESSION = 3, MT_RIGID = 4, MT_CABLE = 5 };
+enum { P_EA = 0, P_EIY = 1, P_EIZ = 2, P_GJ = 3, P_GASY = 4, P_GASZ = 5, NPROP = 8 };
+
+// Local frame of a member: R rows = local x, y, z expressed in global coordinates.
+struct Frame {
+    double r[3][3];
+    double L;
+};
+
+FERS_HD Frame member_frame(const double a[3], const double b[3], double roll) {
+    Frame f;
+    double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
+    double L = sqrt(dx * dx + dy * dy + dz * dz);
+    f.L = L;
+    double inv = 1.0 / L;
+    double lx0 = dx * inv, lx1 = dy * inv, lx2 = dz * inv;
+    // reference vector: +Y, or +Z for (near-)vertical members
+    double rf0 = 0.0, rf1 = 1.0, rf2 = 0.0;
+    if (fabs(lx1) > 1.0 - 1e-6) { rf1 = 0.0; rf2 = 1.0; }
+    // lz = lx x ref
+    double z0 = lx1 * rf2 - lx2 * rf1, z1 = lx2 * rf0 - lx0 * rf2, z2 = lx0 * rf1 - lx1 * rf0;
+    double zn = 1.0 / sqrt(z0 * z0 + z1 * z1 + z2 * z2);
+    z0 *= zn; z1 *= zn; z2 *= zn;
+    // ly = lz x lx
+    double y0 = z1 * lx2 - z2 * lx1, y1 = z2 * lx0 - z0 * lx2, y2 = z0 * lx1 - z1 * lx0;
+    double yn = 1.0 / sqrt(y0 * y0 + y1 * y1 + y2 * y2);
+    y0 *= yn; y1 *= yn; y2 *= yn;
+    if (roll != 0.0) {
+        double c = cos(roll), s = sin(roll);
+        double ny0 = c * y0 + s * z0, ny1 = c * y1 + s * z1, ny2 = c * y2 + s * z2;
+        double nz0 = -s * y0 + c * z0, nz1 = -s * y1 + c * z1, nz2 = -s * y2 + c * z2;
+        y0 = ny0; y1 = ny1; y2 = ny2; z0 = nz0; z1 = nz1; z2 = nz2;
+    }
+    f.r[0][0] = lx0; f.r[0][1] = lx1; f.r[0][2] = lx2;
+    f.r[1][0] = y0;  f.r[1][1] = y1;  f.r[1][2] = y2;
+    f.r[2][0] = z0;  f.r[2][1] = z1;  f.r[2][2] = z2;
+    return f;
+}
+
+// Closed-form coefficients of the 12x12 local stiffness (Euler-Bernoulli / Timoshenko).
+struct BeamCoef {
+    double a;                    // EA/L
+    double t;                    // GJ/L
+    double z12, z6, z4, z2;      // bending about local z (v, theta_z): 12EIz/L^3(1+phi_y) ...
+    double y12, y6, y4, y2;      // bending about local y (w, theta_y)
+    double phi_y, phi_z;
+};
+
+FERS_HD BeamCoef beam_coef(const double* P, double L, int mtype, double scale) {
+    BeamCoef c;
+    double EA = P[P_EA], EIy = P[P_EIY], EIz = P[P_EIZ], GJ = P[P_GJ], GAsy = P[P_GASY], GAsz = P[P_GASZ];
+    double L2 = L * L, L3 = L2 * L;
+    c.phi_y = (GAsz > 0.0) ? 12.0 * EIz / (GAsz * L2) : 0.0;
+    c.phi_z = (GAsy > 0.0) ? 12.0 * EIy / (GAsy * L2) : 0.0;
+    bool axial_only = (mtype == MT_TRUSS);
+    c.a = scale * (EA / L);
+    c.t = axial_only ? 0.0 : scale * (GJ / L);
+    double bz = axial_only ? 0.0 : EIz / (1.0 + c.phi_y);
+    double by = axial_only ? 0.0 : EIy / (1.0 + c.phi_z);
+    c.z12 = scale * (12.0 * bz / L3); c.z6 = scale * (6.0 * bz / L2);
+    c.z4 = scale * ((4.0 + c.phi_y) * bz / L); c.z2 = scale * ((2.0 - c.phi_y) * bz / L);
+    c.y12 = scale * (12.0 * by / L3); c.y6 = scale * (6.0 * by / L2);
+    c.y4 = scale * ((4.0 + c.phi_z) * by / L); c.y2 = scale * ((2.0 - c.phi_z) * by / L);
+    return c;
+}
+
+// Dense 12x12 local stiffness, row-major, DOF order [u v w rx ry rz] x {start, end}.
+FERS_HD void beam_local_k(const BeamCoef& c, double* k /*144*/) {
+    for (int i = 0; i < 144; ++i) k[i] = 0.0;
+#define KS(i, j, v) { k[(i) * 12 + (j)] = (v); k[(j) * 12 + (i)] = (v); }
+    KS(0, 0, c.a) KS(0, 6, -c.a) KS(6, 6, c.a)
+    KS(3, 3, c.t) KS(3, 9, -c.t) KS(9, 9, c.t)
+    KS(1, 1, c.z12) KS(1, 5, c.z6) KS(1, 7, -c.z12) KS(1, 11, c.z6)
+    KS(5, 5, c.z4) KS(5, 7, -c.z6) KS(5, 11, c.z2)
+    KS(7, 7, c.z12) KS(7, 11, -c.z6) KS(11, 11, c.z4)
+    KS(2, 2, c.y12) KS(2, 4, -c.y6) KS(2, 8, -c.y12) KS(2, 10, -c.y6)
+    KS(4, 4, c.y4) KS(4, 8, c.y6) KS(4, 10, c.y2)
+    KS(8, 8, c.y12) KS(8, 10, c.y6) KS(10, 10, c.y4)
+#undef KS
+}
+
+// Local geometric stiffness added into k (tension-positive axial force N).
+// consistent != 0: Przemieniecki string+bending terms; else N/L on transverse translations.
+FERS_HD void beam_add_kg(double* k /*144*/, double N, double L, int consistent, int mtype) {
+#define KA(i, j, v) { k[(i) * 12 + (j)] += (v); if ((i) != (j)) k[(j) * 12 + (i)] += (v); }
+    if (!consistent || mtype == MT_TRUSS) {
+        double c = N / L;
+        KA(1, 1, c) KA(7, 7, c) KA(1, 7, -c)
+        KA(2, 2, c) KA(8, 8, c) KA(2, 8, -c)
+    } else {
+        double c = N / (30.0 * L), L2 = L * L;
+        KA(1, 1, 36.0 * c) KA(1, 5, 3.0 * L * c) KA(1, 7, -36.0 * c) KA(1, 11, 3.0 * L * c)
+        KA(5, 5, 4.0 * L2 * c) KA(5, 7, -3.0 * L * c) KA(5, 11, -L2 * c)
+        KA(7, 7, 36.0 * c) KA(7, 11, -3.0 * L * c) KA(11, 11, 4.0 * L2 * c)
+        KA(2, 2, 36.0 * c) KA(2, 4, -3.0 * L * c) KA(2, 8, -36.0 * c) KA(2, 10, -3.0 * L * c)
+        KA(4, 4, 4.0 * L2 * c) KA(4, 8, 3.0 * L * c) KA(4, 10, -L2 * c)
+        KA(8, 8, 36.0 * c) KA(8, 10, 3.0 * L * c) KA(10, 10, 4.0 * L2 * c)
+    }
+#undef KA
+}
+
+// Static condensation of end-release springs (pydantic_models.py:2062-2087): for each local
+// end DOF d with spring ks >= 0 (ks < 0: rigid connection):  k -= k[:,d] k[d,:] / (k[d,d]+ks),
+// p -= k[:,d] p[d] / (k[d,d]+ks)  for each of the np load rows p (stride 12).
+FERS_HD void beam_condense(double* k /*144*/, const double* rel /*12*/, double* p, int np) {
+    for (int d = 0; d < 12; ++d) {
+        double ks = rel[d];
+        if (ks < 0.0) continue;
+        double den = k[d * 12 + d] + ks;
+        if (!(den > 0.0)) continue;
+        double col[12];
+        for (int i = 0; i < 12; ++i) col[i] = k[i * 12 + d];
+        double inv = 1.0 / den;
+        for (int q = 0; q < np; ++q) {
+            double s = p[q * 12 + d] * inv;
+            for (int i = 0; i < 12; ++i) p[q * 12 + i] -= s * col[i];
+        }
+        for (int i = 0; i < 12; ++i) {
+            double s = col[i] * inv;
+            for (int j = 0; j < 12; ++j) k[i * 12 + j] -= s * col[j];
+        }
+    }
+}
+
+// G = T^T k T for one 6x6 node block (bi, bj in {0,1}) of the 12x12 local matrix.
+// out[36] row-major.  T = blockdiag(R,R,R,R).
+FERS_HD void beam_rotate_block(const double* k /*144*/, const Frame& f, int bi, int bj, double* out /*36*/) {
+    for (int si = 0; si < 2; ++si)
+        for (int sj = 0; sj < 2; ++sj) {
+            const int r0 = 6 * bi + 3 * si, c0 = 6 * bj + 3 * sj;
+            double m[3][3];   // m = K_sub * R
+            for (int a = 0; a < 3; ++a)
+                for (int c = 0; c < 3; ++c)
+                    m[a][c] = k[(r0 + a) * 12 + c0] * f.r[0][c] + k[(r0 + a) * 12 + c0 + 1] * f.r[1][c] +
+                              k[(r0 + a) * 12 + c0 + 2] * f.r[2][c];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    out[(3 * si + r) * 6 + 3 * sj + c] = f.r[0][r] * m[0][c] + f.r[1][r] * m[1][c] + f.r[2][r] * m[2][c];
+        }
+}
+
+// Closed-form global 6x6 block for an un-released member (no dense 12x12 needed).
+// Each 3x3 sub-block is  cxx x x^T + cyy y y^T + czz z z^T + cyz y z^T + czy z y^T.
+FERS_HD void beam_block_closed(const BeamCoef& c, const Frame& f, int bi, int bj, double* out /*36*/) {
+    const double* x = f.r[0];
+    const double* y = f.r[1];
+    const double* z = f.r[2];
+    const double sgn = (bi == bj) ? 1.0 : -1.0;          // translational coupling sign
+    // translation-translation
+    {
+        double cxx = sgn * c.a, cyy = sgn * c.z12, czz = sgn * c.y12;
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) out[r * 6 + q] = cxx * x[r] * x[q] + cyy * y[r] * y[q] + czz * z[r] * z[q];
+    }
+    // rotation-rotation
+    {
+        double cxx = sgn * c.t;
+        double cyy = (bi == bj) ? c.y4 : c.y2;
+        double czz = (bi == bj) ? c.z4 : c.z2;
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q)
+                out[(3 + r) * 6 + 3 + q] = cxx * x[r] * x[q] + cyy * y[r] * y[q] + czz * z[r] * z[q];
+    }
+    // translation(bi)-rotation(bj): local entries k[v_i][rz_j] and k[w_i][ry_j]
+    {
+        // k[v1][rz1]=z6 k[v1][rz2]=z6 k[v2][rz1]=-z6 k[v2][rz2]=-z6 ; k[w1][ry*]=-y6 k[w2][ry*]=+y6
+        double cyz = (bi == 0) ? c.z6 : -c.z6;   // y (v) row, z (rz) col
+        double czy = (bi == 0) ? -c.y6 : c.y6;   // z (w) row, y (ry) col
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) out[r * 6 + 3 + q] = cyz * y[r] * z[q] + czy * z[r] * y[q];
+    }
+    // rotation(bi)-translation(bj): transpose of the (bj, bi) translation-rotation block
+    {
+        double cyz = (bj == 0) ? c.z6 : -c.z6;
+        double czy = (bj == 0) ? -c.y6 : c.y6;
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) out[(3 + r) * 6 + q] = cyz * z[r] * y[q] + czy * y[r] * z[q];
+    }
+}
+
+// f = k u for the closed-form (un-released) local stiffness.
+FERS_HD void beam_k_times_u(const BeamCoef& c, const double* u /*12*/, double* f /*12*/) {
+    double du = u[0] - u[6], dt = u[3] - u[9], dv = u[1] - u[7], dw = u[2] - u[8];
+    f[0] = c.a * du; f[6] = -f[0];
+    f[3] = c.t * dt; f[9] = -f[3];
+    f[1] = c.z12 * dv + c.z6 * (u[5] + u[11]); f[7] = -f[1];
+    f[5] = c.z6 * dv + c.z4 * u[5] + c.z2 * u[11];
+    f[11] = c.z6 * dv + c.z2 * u[5] + c.z4 * u[11];
+    f[2] = c.y12 * dw - c.y6 * (u[4] + u[10]); f[8] = -f[2];
+    f[4] = -c.y6 * dw + c.y4 * u[4] + c.y2 * u[10];
+    f[10] = -c.y6 * dw + c.y2 * u[4] + c.y4 * u[10];
+}
+
+// f += k_g(N) u, closed form of beam_add_kg.
+FERS_HD void beam_kg_times_u(double N, double L, int consistent, int mtype, const double* u /*12*/, double* f /*12*/) {
+    double dv = u[1] - u[7], dw = u[2] - u[8];
+    if (!consistent || mtype == MT_TRUSS) {
+        double c = N / L;
+        f[1] += c * dv; f[7] -= c * dv;
+        f[2] += c * dw; f[8] -= c * dw;
+    } else {
+        double c = N / (30.0 * L), L2 = L * L;
+        double fv = c * (36.0 * dv + 3.0 * L * (u[5] + u[11]));
+        f[1] += fv; f[7] -= fv;
+        f[5] += c * (3.0 * L * dv + 4.0 * L2 * u[5] - L2 * u[11]);
+        f[11] += c * (3.0 * L * dv - L2 * u[5] + 4.0 * L2 * u[11]);
+        double fw = c * (36.0 * dw - 3.0 * L * (u[4] + u[10]));
+        f[2] += fw; f[8] -= fw;
+        f[4] += c * (-3.0 * L * dw + 4.0 * L2 * u[4] - L2 * u[10]);
+        f[10] += c * (-3.0 * L * dw - L2 * u[4] + 4.0 * L2 * u[10]);
+    }
+}
+
+// local = R * global (each 3-vector of a 6-vector pair) and its transpose
+FERS_HD void rot_to_local(const Frame& f, const double* g, double* l) {
+    for (int i = 0; i < 3; ++i) l[i] = f.r[i][0] * g[0] + f.r[i][1] * g[1] + f.r[i][2] * g[2];
+}
+FERS_HD void rot_to_global(const Frame& f, const double* l, double* g) {
+    for (int i = 0; i < 3; ++i) g[i] = f.r[0][i] * l[0] + f.r[1][i] * l[1] + f.r[2][i] * l[2];
+}
+
+// ---- Timoshenko-exact shape functions (phi = 0: Hermite cubics) ----------------------
+FERS_HD void shape_n(double xi, double phi, double L, double n[4]) {
+    double d = 1.0 / (1.0 + phi), x2 = xi * xi, x3 = x2 * xi;
+    n[0] = (1.0 - 3.0 * x2 + 2.0 * x3 + phi * (1.0 - xi)) * d;
+    n[1] = L * (xi - 2.0 * x2 + x3 + 0.5 * phi * (xi - x2)) * d;
+    n[2] = (3.0 * x2 - 2.0 * x3 + phi * xi) * d;
+    n[3] = L * (-x2 + x3 - 0.5 * phi * (xi - x2)) * d;
+}
+FERS_HD void shape_g(double xi, double phi, double L, double g[4]) {
+    double d = 1.0 / (1.0 + phi), x2 = xi * xi;
+    g[0] = 6.0 * (x2 - xi) * d / L;
+    g[1] = (1.0 - 4.0 * xi + 3.0 * x2 + phi * (1.0 - xi)) * d;
+    g[2] = -g[0];
+    g[3] = (3.0 * x2 - 2.0 * xi + phi * xi) * d;
+}
+
+// Equivalent nodal loads (local, 12) of a linearly varying load (global vectors q1 at fraction a,
+// q2 at fraction b) -- pydantic_models.py:1438-1445.  Accumulates into p.
+FERS_HD void beam_dist_load(const Frame& f, const BeamCoef& c, int mtype, const double* row /*q1[3] q2[3] a b*/,
+                            double* p /*12*/) {
+    const double gx[3] = {-0.7745966692414834, 0.0, 0.7745966692414834};
+    const double gw[3] = {5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0};
+    double a = row[6], b = row[7];
+    double half = 0.5 * (b - a), mid = 0.5 * (a + b);
+    if (!(half > 0.0)) return;
+    double q1[3], q2[3];
+    for (int i = 0; i < 3; ++i) {
+        q1[i] = f.r[i][0] * row[0] + f.r[i][1] * row[1] + f.r[i][2] * row[2];
+        q2[i] = f.r[i][0] * row[3] + f.r[i][1] * row[4] + f.r[i][2] * row[5];
+    }
+    bool truss = (mtype == MT_TRUSS);
+    for (int g = 0; g < 3; ++g) {
+        double xi = mid + half * gx[g];
+        double s = (xi - a) / (b - a);
+        double w = gw[g] * half * f.L;
+        double qx = (q1[0] + (q2[0] - q1[0]) * s) * w;
+        double qy = (q1[1] + (q2[1] - q1[1]) * s) * w;
+        double qz = (q1[2] + (q2[2] - q1[2]) * s) * w;
+        p[0] += (1.0 - xi) * qx; p[6] += xi * qx;
+        if (truss) {
+            p[1] += (1.0 - xi) * qy; p[7] += xi * qy;
+            p[2] += (1.0 - xi) * qz; p[8] += xi * qz;
+        } else {
+            double n[4];
+            shape_n(xi, c.phi_y, f.L, n);
+            p[1] += n[0] * qy; p[5] += n[1] * qy; p[7] += n[2] * qy; p[11] += n[3] * qy;
+            shape_n(xi, c.phi_z, f.L, n);
+            p[2] += n[0] * qz; p[4] -= n[1] * qz; p[8] += n[2] * qz; p[10] -= n[3] * qz;
+        }
+    }
+}
+
+// Equivalent nodal loads of a member point load / moment (pydantic_models.py:1562-1591).
+// row = F[3] M[3] position is_local.
+FERS_HD void beam_point_load(const Frame& f, const BeamCoef& c, int mtype, const double* row, double* p /*12*/) {
+    double F[3], M[3];
+    if (row[7] != 0.0) {
+        for (int i = 0; i < 3; ++i) { F[i] = row[i]; M[i] = row[3 + i]; }
+    } else {
+        for (int i = 0; i < 3; ++i) {
+            F[i] = f.r[i][0] * row[0] + f.r[i][1] * row[1] + f.r[i][2] * row[2];
+            M[i] = f.r[i][0] * row[3] + f.r[i][1] * row[4] + f.r[i][2] * row[5];
+        }
+    }
+    double xi = row[6];
+    p[0] += (1.0 - xi) * F[0]; p[6] += xi * F[0];
+    p[3] += (1.0 - xi) * M[0]; p[9] += xi * M[0];
+    if (mtype == MT_TRUSS) {
+        p[1] += (1.0 - xi) * F[1]; p[7] += xi * F[1];
+        p[2] += (1.0 - xi) * F[2]; p[8] += xi * F[2];
+        return;
+    }
+    double n[4], g[4];
+    shape_n(xi, c.phi_y, f.L, n); shape_g(xi, c.phi_y, f.L, g);
+    p[1] += n[0] * F[1] + g[0] * M[2]; p[5] += n[1] * F[1] + g[1] * M[2];
+    p[7] += n[2] * F[1] + g[2] * M[2]; p[11] += n[3] * F[1] + g[3] * M[2];
+    shape_n(xi, c.phi_z, f.L, n); shape_g(xi, c.phi_z, f.L, g);
+    p[2] += n[0] * F[2] - g[0] * M[1]; p[4] += -n[1] * F[2] + g[1] * M[1];
+    p[8] += n[2] * F[2] - g[2] * M[1]; p[10] += -n[3] * F[2] + g[3] * M[1];
+}
+
+// Resultant of a distributed load on [0, x] about the section at fraction x (local frame):
+// adds force into s[0..2] and moment into s[3..5], scaled by `fac`.
+FERS_HD void span_dist_resultant(const Frame& f, const double* row, double x, double fac, double* s /*6*/) {
+    const double gx[3] = {-0.7745966692414834, 0.0, 0.7745966692414834};
+    const double gw[3] = {5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0};
+    double a = row[6], b = row[7];
+    double hi = b < x ? b : x;
+    if (!(hi > a)) return;
+    double q1[3], q2[3];
+    for (int i = 0; i < 3; ++i) {
+        q1[i] = f.r[i][0] * row[0] + f.r[i][1] * row[1] + f.r[i][2] * row[2];
+        q2[i] = f.r[i][0] * row[3] + f.r[i][1] * row[4] + f.r[i][2] * row[5];
+    }
+    double half = 0.5 * (hi - a), mid = 0.5 * (hi + a);
+    for (int g = 0; g < 3; ++g) {
+        double xi = mid + half * gx[g];
+        double t = (xi - a) / (b - a);
+        double w = fac * gw[g] * half * f.L;
+        double d = (x - xi) * f.L;
+        double qx = q1[0] + (q2[0] - q1[0]) * t, qy = q1[1] + (q2[1] - q1[1]) * t, qz = q1[2] + (q2[2] - q1[2]) * t;
+        s[0] += w * qx; s[1] += w * qy; s[2] += w * qz;
+        s[4] += w * d * qz; s[5] -= w * d * qy;
+    }
+}
+
+FERS_HD void span_point_resultant(const Frame& f, const double* row, double x, double fac, double* s /*6*/) {
+    double pos = row[6];
+    if (pos > x) return;
+    double F[3], M[3];
+    if (row[7] != 0.0) {
+        for (int i = 0; i < 3; ++i) { F[i] = row[i]; M[i] = row[3 + i]; }
+    } else {
+        for (int i = 0; i < 3; ++i) {
+            F[i] = f.r[i][0] * row[0] + f.r[i][1] * row[1] + f.r[i][2] * row[2];
+            M[i] = f.r[i][0] * row[3] + f.r[i][1] * row[4] + f.r[i][2] * row[5];
+        }
+    }
+    double d = (x - pos) * f.L;
+    s[0] += fac * F[0]; s[1] += fac * F[1]; s[2] += fac * F[2];
+    s[3] += fac * M[0]; s[4] += fac * (M[1] + d * F[2]); s[5] += fac * (M[2] - d * F[1]);
+}
+
+// ---- TRI3 shell: CST membrane + DSG3 Mindlin bending --------
+struct PlateGeom {
+    double r[3][3];     // rows = local x, y, z
+    double xl[3][2];    // local corner coordinates (corner 0 at origin)
+    double A;           // signed area
+};
+
+FERS_HD PlateGeom plate_geom(const double p0[3], const double p1[3], const double p2[3]) {
+    PlateGeom g;
+    double e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+    double e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+    double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    double nn = 1.0 / sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    double ez[3] = {n[0] * nn, n[1] * nn, n[2] * nn};
+    double gx[3] = {1.0, 0.0, 0.0};
+    if (fabs(ez[0]) > 1.0 - 1e-6) { gx[0] = 0.0; gx[1] = 1.0; }
+    double dot = gx[0] * ez[0] + gx[1] * ez[1] + gx[2] * ez[2];
+    double ex[3] = {gx[0] - dot * ez[0], gx[1] - dot * ez[1], gx[2] - dot * ez[2]};
+    double en = 1.0 / sqrt(ex[0] * ex[0] + ex[1] * ex[1] + ex[2] * ex[2]);
+    ex[0] *= en; ex[1] *= en; ex[2] *= en;
+    double ey[3] = {ez[1] * ex[2] - ez[2] * ex[1], ez[2] * ex[0] - ez[0] * ex[2], ez[0] * ex[1] - ez[1] * ex[0]};
+    for (int c = 0; c < 3; ++c) { g.r[0][c] = ex[c]; g.r[1][c] = ey[c]; g.r[2][c] = ez[c]; }
+    g.xl[0][0] = 0.0; g.xl[0][1] = 0.0;
+    g.xl[1][0] = e1[0] * ex[0] + e1[1] * ex[1] + e1[2] * ex[2];
+    g.xl[1][1] = e1[0] * ey[0] + e1[1] * ey[1] + e1[2] * ey[2];
+    g.xl[2][0] = e2[0] * ex[0] + e2[1] * ex[1] + e2[2] * ex[2];
+    g.xl[2][1] = e2[0] * ey[0] + e2[1] * ey[1] + e2[2] * ey[2];
+    double a_ = g.xl[1][0], b_ = g.xl[1][1], c_ = g.xl[2][1], d_ = g.xl[2][0];
+    g.A = 0.5 * (a_ * c_ - b_ * d_);
+    return g;
+}
+
+// Strain-displacement rows in LOCAL shell DOFs (18 = 3 nodes x [u v w rx ry rz]).
+// Bm[3][18] membrane, Bb[3][18] curvature, Bs[2][18] transverse shear (DSG3, bx=+ry, by=-rx).
+FERS_HD void plate_B(const PlateGeom& g, double Bm[3][18], double Bb[3][18], double Bs[2][18]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 18; ++j) { Bm[i][j] = 0.0; Bb[i][j] = 0.0; if (i < 2) Bs[i][j] = 0.0; }
+    double x1 = g.xl[0][0], y1 = g.xl[0][1], x2 = g.xl[1][0], y2 = g.xl[1][1], x3 = g.xl[2][0], y3 = g.xl[2][1];
+    double A = g.A, i2A = 1.0 / (2.0 * A);
+    double bb[3] = {y2 - y3, y3 - y1, y1 - y2};
+    double cc[3] = {x3 - x2, x1 - x3, x2 - x1};
+    for (int n = 0; n < 3; ++n) {
+        Bm[0][6 * n + 0] = bb[n] * i2A;
+        Bm[1][6 * n + 1] = cc[n] * i2A;
+        Bm[2][6 * n + 0] = cc[n] * i2A;
+        Bm[2][6 * n + 1] = bb[n] * i2A;
+    }
+    double a_ = x2 - x1, b_ = y2 - y1, c_ = y3 - y1, d_ = x3 - x1;
+    // columns in (w, bx, by) per node
+    double bbm[3][9] = {{0, b_ - c_, 0, 0, c_, 0, 0, -b_, 0},
+                        {0, 0, d_ - a_, 0, 0, -d_, 0, 0, a_},
+                        {0, d_ - a_, b_ - c_, 0, -d_, c_, 0, a_, -b_}};
+    double bsm[2][9] = {{b_ - c_, A, 0, c_, a_ * c_ / 2, b_ * c_ / 2, -b_, -b_ * d_ / 2, -b_ * c_ / 2},
+                        {d_ - a_, 0, A, -d_, -a_ * d_ / 2, -b_ * d_ / 2, a_, a_ * d_ / 2, a_ * c_ / 2}};
+    for (int n = 0; n < 3; ++n) {
+        for (int i = 0; i < 3; ++i) {
+            Bb[i][6 * n + 2] = bbm[i][3 * n + 0] * i2A;      // w
+            Bb[i][6 * n + 4] = bbm[i][3 * n + 1] * i2A;      // bx = +ry
+            Bb[i][6 * n + 3] = -bbm[i][3 * n + 2] * i2A;     // by = -rx
+        }
+        for (int i = 0; i < 2; ++i) {
+            Bs[i][6 * n + 2] = bsm[i][3 * n + 0] * i2A;
+            Bs[i][6 * n + 4] = bsm[i][3 * n + 1] * i2A;
+            Bs[i][6 * n + 3] = -bsm[i][3 * n + 2] * i2A;
+        }
+    }
+}
+
+// 18x18 local stiffness (row-major).  data = thickness, E, nu ; flags bit0 membrane bit1 bending.
+FERS_HD void plate_local_k(const PlateGeom& g, const double* data, int flags, double* k /*324*/) {
+    double Bm[3][18], Bb[3][18], Bs[2][18];
+    plate_B(g, Bm, Bb, Bs);
+    double t = data[0], E = data[1], nu = data[2];
+    double A = fabs(g.A);
+    double dm = E / (1.0 - nu * nu);
+    double D[3][3] = {{dm, dm * nu, 0.0}, {dm * nu, dm, 0.0}, {0.0, 0.0, dm * (1.0 - nu) / 2.0}};
+    double cm = (flags & 1) ? t * A : 0.0;
+    double cb = (flags & 2) ? A * t * t * t / 12.0 : 0.0;
+    double cs = (flags & 2) ? A * (5.0 / 6.0) * (E / (2.0 * (1.0 + nu))) * t : 0.0;
+    for (int i = 0; i < 18; ++i)
+        for (int j = 0; j < 18; ++j) {
+            double sm = 0.0, sb = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                double dmj = D[a][0] * Bm[0][j] + D[a][1] * Bm[1][j] + D[a][2] * Bm[2][j];
+                double dbj = D[a][0] * Bb[0][j] + D[a][1] * Bb[1][j] + D[a][2] * Bb[2][j];
+                sm += Bm[a][i] * dmj;
+                sb += Bb[a][i] * dbj;
+            }
+            double ss = Bs[0][i] * Bs[0][j] + Bs[1][i] * Bs[1][j];
+            k[i * 18 + j] = cm * sm + cb * sb + cs * ss;
+        }
+    double kd = 1e-6 * E * t * A;     // drilling stabilisation
+    for (int n = 0; n < 3; ++n) k[(6 * n + 5) * 18 + 6 * n + 5] += kd;
+}
+
+// Global 6x6 block (node bi, node bj) of T^T k T for a plate.
+FERS_HD void plate_rotate_block(const double* k /*324*/, const PlateGeom& g, int bi, int bj, double* out /*36*/) {
+    for (int si = 0; si < 2; ++si)
+        for (int sj = 0; sj < 2; ++sj) {
+            const int r0 = 6 * bi + 3 * si, c0 = 6 * bj + 3 * sj;
+            double m[3][3];
+            for (int a = 0; a < 3; ++a)
+                for (int c = 0; c < 3; ++c)
+                    m[a][c] = k[(r0 + a) * 18 + c0] * g.r[0][c] + k[(r0 + a) * 18 + c0 + 1] * g.r[1][c] +
+                              k[(r0 + a) * 18 + c0 + 2] * g.r[2][c];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    out[(3 * si + r) * 6 + 3 * sj + c] = g.r[0][r] * m[0][c] + g.r[1][r] * m[1][c] + g.r[2][r] * m[2][c];
+        }
+}
+
+}  // namespace fers

@@ -1,0 +1,460 @@
+// solve_pcg.cu -- block-CSR (6x6) SpMM / SpMV, block-Jacobi preconditioner and the batched
+// multi-right-hand-side preconditioned CG (the reference engine's
+// "batch first-order solve ... across many load cases", pydantic_models.py:1216-1219).
+//
+// Layout: multi-vectors are [n_dof][NR] with the right-hand-side index fastest, so a warp
+// reading one DOF row touches NR*8 contiguous bytes.  Thread mapping of every multi-vector
+// kernel: a group of CP = NR/2 lanes owns one node (six DOF rows), each lane two adjacent
+// columns (one 16-byte access per row); G = 32/CP node groups share a warp.  A 6x6 matrix block
+// is read through the read-only path as a broadcast (all lanes of a group load the same 16
+// bytes), six x rows of the neighbour node are read once per block, 72 DFMA per lane follow.
+// HBM-bound by design: 0.23 GB of matrix + 2 * n_dof * NR * 8 bytes of vectors per product
+// (DESIGN.md "SpMM").  Reductions are deterministic: per-CTA partials + ordered final sum.
+#include "common.cuh"
+
+namespace fers {
+
+constexpr int SPMM_THREADS = 256;
+constexpr int SPMM_WARPS = SPMM_THREADS / 32;
+constexpr int CTAS_PER_SM = 3;
+
+__device__ __forceinline__ void fma2(double2& a, double k, const double2& x) {
+    a.x = fma(k, x.x, a.x);
+    a.y = fma(k, x.y, a.y);
+}
+
+// NS partial sums per column are reduced over the node groups of a warp, then over the warps of
+// the CTA, and written to partial[blockIdx.x][NS][NR].
+template <int NR, int NS>
+__device__ __forceinline__ void cta_reduce_store(double2 (&v)[NS], double* __restrict__ partial) {
+    constexpr int CP = NR / 2;
+    __shared__ double2 s_red[SPMM_WARPS][NS][CP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+#pragma unroll
+        for (int off = CP; off < 32; off <<= 1) {
+            v[s].x += __shfl_xor_sync(FULL, v[s].x, off);
+            v[s].y += __shfl_xor_sync(FULL, v[s].y, off);
+        }
+        if (lane < CP) s_red[warp][s][lane] = v[s];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < NS * CP; t += SPMM_THREADS) {
+        const int s = t / CP, cp = t % CP;
+        double2 a = s_red[0][s][cp];
+#pragma unroll
+        for (int w = 1; w < SPMM_WARPS; ++w) { a.x += s_red[w][s][cp].x; a.y += s_red[w][s][cp].y; }
+        reinterpret_cast<double2*>(partial + ((size_t)blockIdx.x * NS + s) * NR)[cp] = a;
+    }
+}
+
+template <int NR, bool DOT>
+__global__ void __launch_bounds__(SPMM_THREADS, CTAS_PER_SM)
+k_spmm(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
+       const uint8_t* __restrict__ fixed, const double* __restrict__ kspring, const double* __restrict__ x,
+       double* __restrict__ y, double* __restrict__ partial) {
+    constexpr int CP = NR / 2, G = 32 / CP;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / CP, cp = lane % CP;
+    const int per_cta = (n_nodes + gridDim.x - 1) / gridDim.x;
+    const int row0 = blockIdx.x * per_cta;
+    const int row1 = min(n_nodes, row0 + per_cta);
+    double2 dot[1];
+    dot[0] = make_double2(0.0, 0.0);
+    for (int row = row0 + warp * G + g; row < row1; row += SPMM_WARPS * G) {
+        double2 acc[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[r] = make_double2(0.0, 0.0);
+        const int kb = rowptr[row], ke = rowptr[row + 1];
+        for (int k = kb; k < ke; ++k) {
+            const int col = __ldg(colidx + k);
+            const double* xb = x + (size_t)col * 6 * NR + 2 * cp;
+            double2 xv[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) xv[c] = ldg2(xb + (size_t)c * NR);
+            const double* blk = vals + (size_t)k * 36;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                for (int c = 0; c < 6; c += 2) {
+                    const double2 kk = ldg2(blk + r * 6 + c);
+                    fma2(acc[r], kk.x, xv[c]);
+                    fma2(acc[r], kk.y, xv[c + 1]);
+                }
+            }
+        }
+        const size_t d0 = (size_t)row * 6;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const size_t d = d0 + r;
+            double2 xo = make_double2(0.0, 0.0);
+            if (kspring != nullptr || DOT) xo = ldg2(x + d * NR + 2 * cp);
+            if (fixed != nullptr && fixed[d]) {
+                acc[r] = make_double2(0.0, 0.0);
+            } else if (kspring != nullptr) {
+                const double ks = kspring[d];
+                acc[r].x = fma(ks, xo.x, acc[r].x);
+                acc[r].y = fma(ks, xo.y, acc[r].y);
+            }
+            reinterpret_cast<double2*>(y + d * NR)[cp] = acc[r];
+            if (DOT) { dot[0].x = fma(xo.x, acc[r].x, dot[0].x); dot[0].y = fma(xo.y, acc[r].y, dot[0].y); }
+        }
+    }
+    if (DOT) cta_reduce_store<NR, 1>(dot, partial);
+}
+
+// single right-hand side: one warp per block row, lanes stride over the row's 36*nb values
+__global__ void __launch_bounds__(SPMM_THREADS)
+k_spmv1(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
+        const uint8_t* __restrict__ fixed, const double* __restrict__ kspring, const double* __restrict__ x,
+        double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int wglobal = (blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * SPMM_THREADS) >> 5;
+    for (int row = wglobal; row < n_nodes; row += nw) {
+        const int kb = rowptr[row], ke = rowptr[row + 1];
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        const int total = (ke - kb) * 36;
+        const double* base = vals + (size_t)kb * 36;
+        for (int v = lane; v < total; v += 32) {
+            const int k = v / 36, rem = v - k * 36, r = rem / 6, c = rem - r * 6;
+            const double t = __ldg(base + v) * __ldg(x + (size_t)__ldg(colidx + kb + k) * 6 + c);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc[q] += (q == r) ? t : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_xor_sync(FULL, acc[q], off);
+        if (lane < 6) {
+            double out = 0.0;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) out = (q == lane) ? acc[q] : out;
+            const size_t d = (size_t)row * 6 + lane;
+            if (fixed != nullptr && fixed[d]) out = 0.0;
+            else if (kspring != nullptr) out = fma(kspring[d], x[d], out);
+            y[d] = out;
+        }
+    }
+}
+
+// Inverse of each node's diagonal block restricted to the free DOFs (constrained rows/cols ->
+// identity).  Gauss-Jordan without pivoting: the restricted block is symmetric positive definite.
+__global__ void k_block_jacobi(int n_nodes, const double* __restrict__ vals, const int* __restrict__ diag_slot,
+                               const uint8_t* __restrict__ fixed, const double* __restrict__ kspring,
+                               double* __restrict__ minv) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    double a[6][6], b[6][6];
+    const double* blk = vals + (size_t)diag_slot[n] * 36;
+    bool fx[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) fx[r] = fixed[(size_t)n * 6 + r] != 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double v = blk[r * 6 + c];
+            if (fx[r] || fx[c]) v = (r == c) ? 1.0 : 0.0;
+            else if (r == c && kspring != nullptr) v += kspring[(size_t)n * 6 + r];
+            a[r][c] = v;
+            b[r][c] = (r == c) ? 1.0 : 0.0;
+        }
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        double piv = a[p][p];
+        double inv = (piv != 0.0) ? 1.0 / piv : 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { a[p][c] *= inv; b[p][c] *= inv; }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            if (r == p) continue;
+            const double f = a[r][p];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { a[r][c] -= f * a[p][c]; b[r][c] -= f * b[p][c]; }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) minv[(size_t)n * 36 + r * 6 + c] = (fx[r] || fx[c]) ? 0.0 : b[r][c];
+}
+
+// z = Minv r for one node / two columns
+__device__ __forceinline__ void apply_minv(const double* __restrict__ mb, const double2 (&rv)[6], double2 (&z)[6]) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        z[r] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int c = 0; c < 6; c += 2) {
+            const double2 kk = ldg2(mb + r * 6 + c);
+            fma2(z[r], kk.x, rv[c]);
+            fma2(z[r], kk.y, rv[c + 1]);
+        }
+    }
+}
+
+// r = mask (b - ax), p = Minv r; partial sums: [0] r.z  [1] r.r  [2] (mask b).(mask b)
+template <int NR>
+__global__ void __launch_bounds__(SPMM_THREADS, CTAS_PER_SM)
+k_pcg_init(int n_nodes, const uint8_t* __restrict__ fixed, const double* __restrict__ minv,
+           const double* __restrict__ b, const double* __restrict__ ax, double* __restrict__ r,
+           double* __restrict__ p, double* __restrict__ partial) {
+    constexpr int CP = NR / 2, G = 32 / CP;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / CP, cp = lane % CP;
+    const int per_cta = (n_nodes + gridDim.x - 1) / gridDim.x;
+    const int row0 = blockIdx.x * per_cta, row1 = min(n_nodes, row0 + per_cta);
+    double2 s[3];
+    s[0] = s[1] = s[2] = make_double2(0.0, 0.0);
+    for (int row = row0 + warp * G + g; row < row1; row += SPMM_WARPS * G) {
+        double2 rv[6], z[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const size_t d = (size_t)row * 6 + q;
+            double2 bv = ldg2(b + d * NR + 2 * cp);
+            if (fixed[d]) bv = make_double2(0.0, 0.0);
+            s[2].x = fma(bv.x, bv.x, s[2].x); s[2].y = fma(bv.y, bv.y, s[2].y);
+            if (ax != nullptr) {
+                const double2 av = ldg2(ax + d * NR + 2 * cp);
+                bv.x -= av.x; bv.y -= av.y;
+                if (fixed[d]) bv = make_double2(0.0, 0.0);
+            }
+            rv[q] = bv;
+            reinterpret_cast<double2*>(r + d * NR)[cp] = bv;
+            s[1].x = fma(bv.x, bv.x, s[1].x); s[1].y = fma(bv.y, bv.y, s[1].y);
+        }
+        apply_minv(minv + (size_t)row * 36, rv, z);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            reinterpret_cast<double2*>(p + ((size_t)row * 6 + q) * NR)[cp] = z[q];
+            s[0].x = fma(rv[q].x, z[q].x, s[0].x); s[0].y = fma(rv[q].y, z[q].y, s[0].y);
+        }
+    }
+    cta_reduce_store<NR, 3>(s, partial);
+}
+
+// alpha = rz / pAp ; x += alpha p ; r -= alpha Ap ; partial sums: [0] r.(Minv r)  [1] r.r
+template <int NR>
+__global__ void __launch_bounds__(SPMM_THREADS, CTAS_PER_SM)
+k_pcg_update(int n_nodes, const double* __restrict__ minv, const double* __restrict__ rz,
+             const double* __restrict__ pAp, const double* __restrict__ p, const double* __restrict__ Ap,
+             double* __restrict__ x, double* __restrict__ r, double* __restrict__ partial) {
+    constexpr int CP = NR / 2, G = 32 / CP;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / CP, cp = lane % CP;
+    const int per_cta = (n_nodes + gridDim.x - 1) / gridDim.x;
+    const int row0 = blockIdx.x * per_cta, row1 = min(n_nodes, row0 + per_cta);
+    const double2 num = ldg2(rz + 2 * cp), den = ldg2(pAp + 2 * cp);
+    double2 alpha;
+    alpha.x = (den.x > 0.0 && num.x > 0.0) ? num.x / den.x : 0.0;
+    alpha.y = (den.y > 0.0 && num.y > 0.0) ? num.y / den.y : 0.0;
+    double2 s[2];
+    s[0] = s[1] = make_double2(0.0, 0.0);
+    for (int row = row0 + warp * G + g; row < row1; row += SPMM_WARPS * G) {
+        double2 rv[6], z[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const size_t o = ((size_t)row * 6 + q) * NR + 2 * cp;
+            const double2 pv = ldg2(p + o), av = ldg2(Ap + o);
+            double2 xv = *reinterpret_cast<const double2*>(x + o);
+            double2 rr = *reinterpret_cast<const double2*>(r + o);
+            xv.x = fma(alpha.x, pv.x, xv.x); xv.y = fma(alpha.y, pv.y, xv.y);
+            rr.x = fma(-alpha.x, av.x, rr.x); rr.y = fma(-alpha.y, av.y, rr.y);
+            *reinterpret_cast<double2*>(x + o) = xv;
+            *reinterpret_cast<double2*>(r + o) = rr;
+            rv[q] = rr;
+            s[1].x = fma(rr.x, rr.x, s[1].x); s[1].y = fma(rr.y, rr.y, s[1].y);
+        }
+        apply_minv(minv + (size_t)row * 36, rv, z);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { s[0].x = fma(rv[q].x, z[q].x, s[0].x); s[0].y = fma(rv[q].y, z[q].y, s[0].y); }
+    }
+    cta_reduce_store<NR, 2>(s, partial);
+}
+
+// beta = rz_new / rz_old ; p = Minv r + beta p
+template <int NR>
+__global__ void __launch_bounds__(SPMM_THREADS, CTAS_PER_SM)
+k_pcg_direction(int n_nodes, const double* __restrict__ minv, const double* __restrict__ rz_new,
+                const double* __restrict__ rz_old, const double* __restrict__ r, double* __restrict__ p) {
+    constexpr int CP = NR / 2, G = 32 / CP;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / CP, cp = lane % CP;
+    const int per_cta = (n_nodes + gridDim.x - 1) / gridDim.x;
+    const int row0 = blockIdx.x * per_cta, row1 = min(n_nodes, row0 + per_cta);
+    const double2 num = ldg2(rz_new + 2 * cp), den = ldg2(rz_old + 2 * cp);
+    double2 beta;
+    beta.x = (den.x > 0.0) ? num.x / den.x : 0.0;
+    beta.y = (den.y > 0.0) ? num.y / den.y : 0.0;
+    for (int row = row0 + warp * G + g; row < row1; row += SPMM_WARPS * G) {
+        double2 rv[6], z[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) rv[q] = ldg2(r + ((size_t)row * 6 + q) * NR + 2 * cp);
+        apply_minv(minv + (size_t)row * 36, rv, z);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const size_t o = ((size_t)row * 6 + q) * NR + 2 * cp;
+            double2 pv = *reinterpret_cast<const double2*>(p + o);
+            pv.x = fma(beta.x, pv.x, z[q].x); pv.y = fma(beta.y, pv.y, z[q].y);
+            *reinterpret_cast<double2*>(p + o) = pv;
+        }
+    }
+}
+
+// out[j] = sum_b partial[b][j], fixed order (deterministic)
+__global__ void k_reduce_partials(int n_blocks, int width, const double* __restrict__ partial, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= width) return;
+    double a = 0.0;
+    for (int b = 0; b < n_blocks; ++b) a += partial[(size_t)b * width + j];
+    out[j] = a;
+}
+
+static int persistent_grid(int n_nodes, int nr) {
+    const int groups_per_cta = SPMM_WARPS * (32 / (nr / 2));
+    int need = (n_nodes + groups_per_cta - 1) / groups_per_cta;
+    int cap = sm_count() * CTAS_PER_SM;
+    return need < cap ? (need > 0 ? need : 1) : cap;
+}
+
+template <int NR>
+static int run_spmm(int n_nodes, const int* rowptr, const int* colidx, const double* vals, const uint8_t* fixed,
+                    const double* kspring, const double* x, double* y, double* partial, bool dot, cudaStream_t st) {
+    // plain products use one node group per warp slot (fine-grained grid), PCG uses the persistent grid
+    const int groups_per_cta = SPMM_WARPS * (32 / (NR / 2));
+    int grid = dot ? persistent_grid(n_nodes, NR) : (n_nodes + groups_per_cta - 1) / groups_per_cta;
+    if (grid < 1) grid = 1;
+    if (dot) k_spmm<NR, true><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
+    else k_spmm<NR, false><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
+    FERS_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int NR>
+static int run_pcg(int n_nodes, const int* rowptr, const int* colidx, const double* vals, const uint8_t* fixed,
+                   const double* kspring, const double* minv, const double* b, double* x, int warm_start, double tol,
+                   int max_iter, int check_every, int* iters_out, double* relres_out, void* workspace, cudaStream_t st) {
+    const size_t nv = (size_t)n_nodes * 6 * NR;
+    const int grid = persistent_grid(n_nodes, NR);
+    char* w = (char*)workspace;
+    double* r = (double*)w; w += align_up(nv * 8);
+    double* p = (double*)w; w += align_up(nv * 8);
+    double* Ap = (double*)w; w += align_up(nv * 8);
+    double* partial = (double*)w; w += align_up((size_t)sm_count() * CTAS_PER_SM * 3 * NR * 8);
+    // device scalars, NR wide each: [0] pAp | [1..3] init sums (r.z, r.r, b.b) | [4,5] and [6,7] update sums
+    double* scal = (double*)w;
+    double* s_pAp = scal;
+    double* s_init = scal + NR;
+    double* s_pair[2] = {scal + 4 * NR, scal + 6 * NR};
+    const double* s_bb = scal + 3 * NR;
+    const double* rz_cur = s_init;
+    const double* rr_cur = s_init + NR;
+    double host[2 * 64];
+    if (!warm_start) FERS_CK(cudaMemsetAsync(x, 0, nv * 8, st));
+    const double* ax = nullptr;
+    if (warm_start) {
+        if (run_spmm<NR>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, Ap, partial, false, st)) return 1;
+        ax = Ap;
+    }
+    k_pcg_init<NR><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, fixed, minv, b, ax, r, p, partial);
+    FERS_LAUNCH_CHECK();
+    k_reduce_partials<<<(3 * NR + 127) / 128, 128, 0, st>>>(grid, 3 * NR, partial, s_init);
+    FERS_LAUNCH_CHECK();
+    int it = 0;
+    bool converged = false;
+    auto check = [&]() -> int {
+        FERS_CK(cudaMemcpyAsync(host, rr_cur, NR * 8, cudaMemcpyDeviceToHost, st));
+        FERS_CK(cudaMemcpyAsync(host + NR, s_bb, NR * 8, cudaMemcpyDeviceToHost, st));
+        FERS_CK(cudaStreamSynchronize(st));
+        converged = true;
+        for (int c = 0; c < NR; ++c) {
+            const double bb = host[NR + c], rr = host[c];
+            const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+            relres_out[c] = rel;
+            if (!(rel <= tol)) converged = false;
+        }
+        return 0;
+    };
+    if (check()) return 1;
+    while (!converged && it < max_iter) {
+        const int burst = (max_iter - it) < check_every ? (max_iter - it) : check_every;
+        for (int q = 0; q < burst; ++q, ++it) {
+            double* pair = s_pair[it & 1];
+            k_spmm<NR, true><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, p, Ap, partial);
+            k_reduce_partials<<<(NR + 127) / 128, 128, 0, st>>>(grid, NR, partial, s_pAp);
+            k_pcg_update<NR><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, minv, rz_cur, s_pAp, p, Ap, x, r, partial);
+            k_reduce_partials<<<(2 * NR + 127) / 128, 128, 0, st>>>(grid, 2 * NR, partial, pair);   // r.z, r.r
+            k_pcg_direction<NR><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, minv, pair, rz_cur, r, p);
+            FERS_LAUNCH_CHECK();
+            rz_cur = pair;
+            rr_cur = pair + NR;
+        }
+        if (check()) return 1;
+    }
+    *iters_out = it;
+    return 0;
+}
+
+}  // namespace fers
+
+using namespace fers;
+
+#define FERS_DISPATCH_NR(nr, CALL)                                                         \
+    switch (nr) {                                                                          \
+        case 8: { constexpr int NR = 8; CALL; break; }                                     \
+        case 16: { constexpr int NR = 16; CALL; break; }                                   \
+        case 32: { constexpr int NR = 32; CALL; break; }                                   \
+        case 64: { constexpr int NR = 64; CALL; break; }                                   \
+        default: fers::set_error("nrhs must be one of 8, 16, 32, 64 (pad the right-hand sides)"); return 2; \
+    }
+
+extern "C" {
+
+int fers_b200_spmm(int n_nodes, int nrhs, const int* rowptr, const int* colidx, const double* vals,
+                   const uint8_t* fixed, const double* kspring, const double* x, double* y, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    if (n_nodes <= 0) return 0;
+    if (nrhs == 1) {
+        int grid = (n_nodes + SPMM_WARPS - 1) / SPMM_WARPS;
+        int cap = sm_count() * 8;
+        if (grid > cap) grid = cap;
+        k_spmv1<<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y);
+        FERS_LAUNCH_CHECK();
+        return 0;
+    }
+    int rc = 0;
+    FERS_DISPATCH_NR(nrhs, rc = run_spmm<NR>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, nullptr, false, st));
+    return rc;
+}
+
+int fers_b200_block_jacobi(int n_nodes, const double* vals, const int* diag_slot, const uint8_t* fixed,
+                           const double* kspring, double* minv, void* stream) {
+    if (n_nodes <= 0) return 0;
+    const int T = 128;
+    k_block_jacobi<<<(n_nodes + T - 1) / T, T, 0, as_stream(stream)>>>(n_nodes, vals, diag_slot, fixed, kspring, minv);
+    FERS_LAUNCH_CHECK();
+    return 0;
+}
+
+size_t fers_b200_pcg_workspace(int n_nodes, int nrhs) {
+    const size_t nv = (size_t)n_nodes * 6 * nrhs;
+    return 3 * align_up(nv * 8) + align_up((size_t)sm_count() * CTAS_PER_SM * 3 * nrhs * 8) + align_up(16 * (size_t)nrhs * 8) + 1024;
+}
+
+int fers_b200_pcg_solve(int n_nodes, int nrhs, const int* rowptr, const int* colidx, const double* vals,
+                        const uint8_t* fixed, const double* kspring, const double* minv, const double* b, double* x,
+                        int warm_start, double tol, int max_iter, int check_every, int* iters_out, double* relres_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    FERS_REQUIRE(n_nodes > 0, "pcg_solve: empty system");
+    FERS_REQUIRE(workspace_bytes >= fers_b200_pcg_workspace(n_nodes, nrhs), "pcg_solve: workspace too small");
+    FERS_REQUIRE(fixed != nullptr && minv != nullptr, "pcg_solve: fixed mask and preconditioner are required");
+    if (check_every < 1) check_every = 25;
+    int rc = 0;
+    FERS_DISPATCH_NR(nrhs, rc = run_pcg<NR>(n_nodes, rowptr, colidx, vals, fixed, kspring, minv, b, x, warm_start, tol,
+                                            max_iter, check_every, iters_out, relres_out, workspace, as_stream(stream)));
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,471 @@
+"""CUDA engine: drives libfers_b200.so through its C ABI for one analysis.
+
+Host-side mirror of the reference boundary ``fers_calculations.calculate_from_json`` /
+``calculate_from_file`` (fers_core/fers/fers.py:300, :260).  PyTorch is used only for device
+memory, streams and host<->device copies; every arithmetic step of the path is a kernel of
+``libfers_b200.so`` (include/fers_b200.h).  There is no CPU fallback: without a CUDA device or
+without the built library every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import time
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, wire
+from .hostlogic import (
+    INACTIVE_SCALE, imperfect_coordinates, pdelta_suppressed_axes, rhs_plan, rigid_property_row,
+)
+from .results import ResultArrays, SECTION_FRACS, results_to_wire
+
+DENSE_MAX_DOF = 8192          # models up to this many DOFs use the dense Cholesky path
+PCG_TOL = 1e-12               # relative residual ||r|| / ||b|| per right-hand side
+PCG_MAX_ITER = 200000
+NR_CHOICES = (8, 16, 32, 64)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise EngineError("fers_core_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return dev
+
+
+def _pad_nr(n: int) -> int:
+    for c in NR_CHOICES:
+        if n <= c:
+            return c
+    return NR_CHOICES[-1]
+
+
+@dataclass
+class SolveStats:
+    method: str = "dense"
+    iterations: int = 0
+    relres: float = 0.0
+    n_free: int = 0
+    n_dead: int = 0
+    nnzb: int = 0
+
+
+class Engine:
+    """One model resident on one GPU."""
+
+    def __init__(self, model: wire.ModelArrays, device=None, assembly_variant: int = 0):
+        self.model = model
+        self.dev = _require_cuda(device)
+        self.lib = _lib.load()
+        torch.cuda.set_device(self.dev)
+        _lib.check(self.lib.fers_b200_set_device(self.dev.index or 0), "set_device")
+        sm, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        _lib.check(self.lib.fers_b200_device_info(self.dev.index or 0, C.byref(sm), C.byref(maj), C.byref(mnr),
+                                                  C.byref(mem)), "device_info")
+        self.assembly_variant = assembly_variant
+        self.stats = SolveStats()
+        self.timings: dict = {}
+        self._upload_static()
+        self._build_pattern()
+
+    # ---- helpers ---------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _t(self, a: np.ndarray, dtype) -> torch.Tensor:
+        """Host array -> device tensor (through pinned memory for large arrays)."""
+        a = np.ascontiguousarray(a, dtype=dtype)
+        t = torch.from_numpy(a)
+        if a.nbytes >= (1 << 20):
+            t = t.pin_memory()
+        return t.to(self.dev, non_blocking=True)
+
+    def _empty(self, shape, dtype=torch.float64) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.dev)
+
+    def _zeros(self, shape, dtype=torch.float64) -> torch.Tensor:
+        return torch.zeros(shape, dtype=dtype, device=self.dev)
+
+    # ---- set-up ----------------------------------------------------------------------------
+    def _upload_static(self) -> None:
+        m = self.model
+        rigid = rigid_property_row(m.prop)
+        table = np.vstack([m.prop, rigid[None, :]]) if m.prop.size else rigid[None, :]
+        idx = np.where(m.m_prop >= 0, m.m_prop, table.shape[0] - 1)
+        idx = np.where(m.m_type == wire.MT_RIGID, table.shape[0] - 1, idx).astype(np.int32)
+        self.n_prop = int(table.shape[0])
+        self.d_prop = self._t(table, np.float64)
+        self.d_m_prop = self._t(idx, np.int32)
+        self.d_n1 = self._t(m.m_n1, np.int32)
+        self.d_n2 = self._t(m.m_n2, np.int32)
+        self.d_type = self._t(m.m_type, np.int32)
+        self.d_roll = self._t(m.m_roll, np.float64)
+        self.has_rel = bool(np.any(m.m_rel >= 0))
+        self.d_rel_idx = self._t(m.m_rel, np.int32) if self.has_rel else None
+        self.d_rel = self._t(m.rel, np.float64) if self.has_rel else None
+        unilateral = np.isin(m.bc_code, (wire.BC_POS_ONLY, wire.BC_NEG_ONLY))
+        if unilateral.any():
+            m.warnings.append(("W_UNILATERAL_SUPPORT", "Positive/Negative-only supports treated as fixed"))
+        code = np.where(unilateral, wire.BC_FIXED, m.bc_code).astype(np.uint8)
+        self.d_bc_code = self._t(code.reshape(-1), np.uint8)
+        self.d_bc_k = self._t(m.bc_k.reshape(-1), np.float64)
+        self.d_supported = self._t((m.node_support_id >= 0).astype(np.uint8), np.uint8)
+        self.d_p_nodes = self._t(m.p_nodes, np.int32) if m.n_plates else None
+        self.d_p_data = self._t(m.p_data, np.float64) if m.n_plates else None
+        self.d_p_flags = self._t(m.p_flags, np.int32) if m.n_plates else None
+        self.d_xyz0 = self._t(m.xyz, np.float64)
+
+    def _build_pattern(self) -> None:
+        m, lib = self.model, self.lib
+        nn, nm, npl = m.n_nodes, m.n_members, m.n_plates
+        cap = nn + 2 * nm + 6 * npl
+        self.d_rowptr = self._empty(nn + 1, torch.int32)
+        self.d_colidx = self._empty(cap, torch.int32)
+        self.d_m_slot = self._empty(max(nm, 1) * 4, torch.int32)
+        self.d_p_slot = self._empty(max(npl, 1) * 9, torch.int32)
+        self.d_diag_slot = self._empty(nn, torch.int32)
+        ws_bytes = lib.fers_b200_pattern_workspace(nn, nm, npl)
+        ws = self._empty(ws_bytes, torch.uint8)
+        nnzb = C.c_int()
+        _lib.check(lib.fers_b200_pattern_build(
+            nn, nm, _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), npl, _lib.ptr(self.d_p_nodes),
+            _lib.ptr(self.d_rowptr), _lib.ptr(self.d_colidx), cap, _lib.ptr(self.d_m_slot), _lib.ptr(self.d_p_slot),
+            _lib.ptr(self.d_diag_slot), C.byref(nnzb), _lib.ptr(ws), ws_bytes, self.stream), "pattern_build")
+        self.nnzb = nnzb.value
+        self.stats.nnzb = self.nnzb
+        self.d_colidx = self.d_colidx[: self.nnzb]
+        self.d_vals = self._empty(self.nnzb * 36)
+        nd = m.n_dof
+        self.d_fixed = self._empty(nd, torch.uint8)
+        self.d_free_index = self._empty(nd, torch.int32)
+        self.d_kspring = self._empty(nd)
+        self._bc_ws_bytes = lib.fers_b200_bc_workspace(nd)
+        self._bc_ws = self._empty(self._bc_ws_bytes, torch.uint8)
+
+    # ---- stages ----------------------------------------------------------------------------
+    def assemble(self, d_xyz, d_scale=None, d_axial=None, kg_mode=0, kg_suppress=0) -> None:
+        """Element stiffness + assembly + boundary conditions for one geometry / state."""
+        m, lib, st = self.model, self.lib, self.stream
+        _lib.check(lib.fers_b200_zero(_lib.ptr(self.d_vals), self.d_vals.numel() * 8, st), "zero")
+        _lib.check(lib.fers_b200_assemble_beams(
+            m.n_members, _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_prop),
+            _lib.ptr(self.d_type), _lib.ptr(self.d_roll), _lib.ptr(d_scale), _lib.ptr(self.d_rel_idx),
+            _lib.ptr(self.d_prop), self.n_prop, _lib.ptr(self.d_rel), 0 if self.d_rel is None else self.d_rel.shape[0],
+            _lib.ptr(d_axial), kg_mode, kg_suppress, _lib.ptr(self.d_m_slot), _lib.ptr(self.d_vals),
+            self.assembly_variant, st), "assemble_beams")
+        if m.n_plates:
+            _lib.check(lib.fers_b200_assemble_plates(
+                m.n_plates, _lib.ptr(d_xyz), _lib.ptr(self.d_p_nodes), _lib.ptr(self.d_p_data), _lib.ptr(self.d_p_flags),
+                _lib.ptr(self.d_p_slot), _lib.ptr(self.d_vals), st), "assemble_plates")
+        n_free, n_dead = C.c_int(), C.c_int()
+        _lib.check(lib.fers_b200_bc_build(
+            m.n_nodes, _lib.ptr(self.d_bc_code), _lib.ptr(self.d_bc_k), _lib.ptr(self.d_vals), _lib.ptr(self.d_diag_slot),
+            _lib.ptr(self.d_fixed), _lib.ptr(self.d_free_index), _lib.ptr(self.d_kspring), C.byref(n_free),
+            C.byref(n_dead), _lib.ptr(self._bc_ws), self._bc_ws_bytes, st), "bc_build")
+        self.stats.n_free, self.stats.n_dead = n_free.value, n_dead.value
+
+    def load_cases(self, d_xyz, d_scale=None):
+        """Per load case: nodal load vector [Nlc,Ndof] and local equivalent loads [Nlc,Nm*12]."""
+        m, lib, st = self.model, self.lib, self.stream
+        nlc = len(m.load_cases)
+        f = self._zeros((max(nlc, 1), m.n_dof))
+        peq = self._zeros((max(nlc, 1), max(m.n_members, 1) * 12))
+        for li, lc in enumerate(m.load_cases):
+            t = {k: (self._t(getattr(lc, k), dt) if len(getattr(lc, k)) else None)
+                 for k, dt in (("nod_node", np.int32), ("nod_vec", np.float64), ("dl_member", np.int32),
+                               ("dl_data", np.float64), ("pl_member", np.int32), ("pl_data", np.float64),
+                               ("pp_plate", np.int32), ("pp_vec", np.float64))}
+            _lib.check(lib.fers_b200_load_case(
+                m.n_nodes, m.n_members, _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_prop),
+                _lib.ptr(self.d_type), _lib.ptr(self.d_roll), _lib.ptr(d_scale), _lib.ptr(self.d_rel_idx),
+                _lib.ptr(self.d_prop), _lib.ptr(self.d_rel),
+                len(lc.nod_node), _lib.ptr(t["nod_node"]), _lib.ptr(t["nod_vec"]),
+                len(lc.dl_member), _lib.ptr(t["dl_member"]), _lib.ptr(t["dl_data"]),
+                len(lc.pl_member), _lib.ptr(t["pl_member"]), _lib.ptr(t["pl_data"]),
+                len(lc.pp_plate), _lib.ptr(t["pp_plate"]), _lib.ptr(t["pp_vec"]), _lib.ptr(self.d_p_nodes),
+                _lib.ptr(f[li]), _lib.ptr(peq[li]), st), "load_case")
+        return f, peq
+
+    def combine(self, per_case: torch.Tensor, factors: np.ndarray, nr: int) -> torch.Tensor:
+        """[Nlc,rows] -> [rows,nr] with factors [ncols<=nr, Nlc] (zero-padded columns)."""
+        nlc = per_case.shape[0]
+        fac = np.zeros((nr, nlc))
+        fac[: factors.shape[0]] = factors
+        d_fac = self._t(fac, np.float64)
+        out = self._empty((per_case.shape[1], nr))
+        _lib.check(self.lib.fers_b200_combine(per_case.shape[1], nlc, nr, _lib.ptr(per_case), _lib.ptr(d_fac),
+                                              _lib.ptr(out), self.stream), "combine")
+        return out
+
+    def solve(self, d_f: torch.Tensor, x0: torch.Tensor | None = None) -> torch.Tensor:
+        """K_ff u = f for all columns of d_f [Ndof,nr]; returns u [Ndof,nr]."""
+        m, lib, st = self.model, self.lib, self.stream
+        nd, nr = d_f.shape
+        if nd <= DENSE_MAX_DOF:
+            a = self._empty((nd, nd))
+            _lib.check(lib.fers_b200_dense_expand(m.n_nodes, _lib.ptr(self.d_rowptr), _lib.ptr(self.d_colidx),
+                                                  _lib.ptr(self.d_vals), _lib.ptr(self.d_fixed), _lib.ptr(self.d_kspring),
+                                                  _lib.ptr(a), st), "dense_expand")
+            info_dev = self._zeros(1, torch.int32)
+            info = C.c_int()
+            _lib.check(lib.fers_b200_dense_cholesky(nd, 1, _lib.ptr(a), _lib.ptr(info_dev), C.byref(info), st),
+                       "dense_cholesky")
+            if info.value != 0:
+                raise EngineError(f"stiffness matrix is not positive definite (leading minor {info.value}): "
+                                  "the structure is a mechanism or insufficiently supported")
+            u = d_f * (1 - self.d_fixed.to(torch.float64))[:, None]     # zero load rows of constrained DOFs
+            u = u.contiguous()
+            _lib.check(lib.fers_b200_dense_solve(nd, nr, 1, _lib.ptr(a), _lib.ptr(u), st), "dense_solve")
+            self.stats.method = "dense"
+            return u
+        if nr not in NR_CHOICES:
+            raise EngineError(f"PCG path needs nrhs in {NR_CHOICES}, got {nr}")
+        minv = self._empty(m.n_nodes * 36)
+        _lib.check(lib.fers_b200_block_jacobi(m.n_nodes, _lib.ptr(self.d_vals), _lib.ptr(self.d_diag_slot),
+                                              _lib.ptr(self.d_fixed), _lib.ptr(self.d_kspring), _lib.ptr(minv), st),
+                   "block_jacobi")
+        ws_bytes = lib.fers_b200_pcg_workspace(m.n_nodes, nr)
+        ws = self._empty(ws_bytes, torch.uint8)
+        u = x0 if x0 is not None else self._empty((nd, nr))
+        iters = C.c_int()
+        relres = (C.c_double * nr)()
+        _lib.check(lib.fers_b200_pcg_solve(
+            m.n_nodes, nr, _lib.ptr(self.d_rowptr), _lib.ptr(self.d_colidx), _lib.ptr(self.d_vals), _lib.ptr(self.d_fixed),
+            _lib.ptr(self.d_kspring), _lib.ptr(minv), _lib.ptr(d_f), _lib.ptr(u), 1 if x0 is not None else 0,
+            PCG_TOL, PCG_MAX_ITER, 50, C.byref(iters), relres, _lib.ptr(ws), ws_bytes, st), "pcg_solve")
+        self.stats.method = "pcg"
+        self.stats.iterations = iters.value
+        self.stats.relres = max(relres)
+        if not (self.stats.relres <= PCG_TOL * 10):
+            raise EngineError(f"PCG did not converge: relative residual {self.stats.relres:.3e} after "
+                              f"{iters.value} iterations")
+        return u
+
+    def recover(self, d_xyz, d_u, d_f, d_peq, factors_pad, span, d_scale=None, d_axial_rhs=None, kg_mode=0,
+                kg_suppress=0, detail=True) -> dict:
+        """All recovery kernels for displacement columns d_u [Ndof,nr]."""
+        m, lib, st = self.model, self.lib, self.stream
+        nr = d_u.shape[1]
+        nm = m.n_members
+        out = {}
+        r = self._empty((m.n_dof, nr))
+        _lib.check(lib.fers_b200_reactions(m.n_nodes, nr, _lib.ptr(self.d_rowptr), _lib.ptr(self.d_colidx),
+                                           _lib.ptr(self.d_vals), _lib.ptr(self.d_supported), _lib.ptr(d_u),
+                                           _lib.ptr(d_f), _lib.ptr(r), st), "reactions")
+        out["R"] = r
+        if nm:
+            fl = self._empty((nm, 12, nr)); fg = self._empty((nm, 12, nr)); ul = self._empty((nm, 12, nr))
+            _lib.check(lib.fers_b200_recover_members(
+                nm, nr, _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_prop),
+                _lib.ptr(self.d_type), _lib.ptr(self.d_roll), _lib.ptr(d_scale), _lib.ptr(self.d_rel_idx),
+                _lib.ptr(self.d_prop), _lib.ptr(self.d_rel), _lib.ptr(d_axial_rhs), kg_mode, kg_suppress,
+                _lib.ptr(d_u), _lib.ptr(d_peq), _lib.ptr(fl), _lib.ptr(fg), _lib.ptr(ul), st), "recover_members")
+            out.update(f_local=fl, f_global=fg, u_local=ul)
+            if detail:
+                sp_ptr, sp_rows = span
+                sec = self._empty((nm, 18, nr))
+                mm = [self._empty((nm, 6, nr)) for _ in range(4)]
+                d_fac = self._t(factors_pad, np.float64)
+                _lib.check(lib.fers_b200_recover_sections(
+                    nm, nr, factors_pad.shape[1], _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2),
+                    _lib.ptr(self.d_roll), _lib.ptr(sp_ptr), _lib.ptr(sp_rows), _lib.ptr(d_fac), _lib.ptr(fl), _lib.ptr(fg),
+                    _lib.ptr(sec), _lib.ptr(mm[0]), _lib.ptr(mm[1]), _lib.ptr(mm[2]), _lib.ptr(mm[3]), st),
+                    "recover_sections")
+                out.update(sec=sec, lmax=mm[0], lmin=mm[1], gmax=mm[2], gmin=mm[3])
+        if m.n_plates:
+            npl = m.n_plates
+            pres = self._empty((npl, 8, nr)); pnod = self._empty((npl, 18, nr)); pcd = self._empty((npl, 12, nr))
+            _lib.check(lib.fers_b200_recover_plates(npl, nr, _lib.ptr(d_xyz), _lib.ptr(self.d_p_nodes),
+                                                    _lib.ptr(self.d_p_data), _lib.ptr(self.d_p_flags), _lib.ptr(d_u),
+                                                    _lib.ptr(pres), _lib.ptr(pnod), _lib.ptr(pcd), st), "recover_plates")
+            out.update(p_res=pres, p_nodal=pnod, p_cd=pcd)
+        return out
+
+    def span_tables(self):
+        """Span loads per load case as CSR over members: (sp_ptr [Nlc*(Nm+1)] int32, sp_rows [*,9])."""
+        m = self.model
+        nm, nlc = m.n_members, len(m.load_cases)
+        ptr = np.zeros((max(nlc, 1), nm + 1), np.int32)
+        rows = []
+        base = 0
+        for li, lc in enumerate(m.load_cases):
+            mem = np.concatenate([lc.dl_member, lc.pl_member]).astype(np.int64)
+            dat = np.concatenate([np.concatenate([np.zeros((len(lc.dl_member), 1)), lc.dl_data], 1),
+                                  np.concatenate([np.ones((len(lc.pl_member), 1)), lc.pl_data], 1)], 0)
+            order = np.argsort(mem, kind="stable")
+            cnt = np.bincount(mem, minlength=nm) if len(mem) else np.zeros(nm, np.int64)
+            ptr[li, 1:] = base + np.cumsum(cnt)
+            ptr[li, 0] = base
+            base += len(mem)
+            rows.append(dat[order])
+        rows = np.concatenate(rows, 0) if rows else np.zeros((0, 9))
+        if rows.shape[0] == 0:
+            rows = np.zeros((1, 9))
+        return self._t(ptr.reshape(-1), np.int32), self._t(rows, np.float64)
+
+
+# ---------------------------------------------------------------------------------------------
+def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_variant: int = 0,
+            stats_out: dict | None = None) -> ResultArrays:
+    """Full analysis of one document on the GPU (twin of oracle.fers_oracle.analyze)."""
+    t_start = time.perf_counter()
+    eng = Engine(model, device, assembly_variant)
+    opts = model.options
+    plan = rhs_plan(model)
+    out = ResultArrays.empty(model, plan)
+    if plan.n_rhs == 0:
+        return out
+    second_order = opts.order == "NONLINEAR"
+    unilateral = np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE))
+    span = eng.span_tables()
+    for grp in plan.groups:
+        xyz = imperfect_coordinates(model, grp.imperfection) if grp.imperfection is not None else model.xyz
+        d_xyz = eng._t(xyz, np.float64) if grp.imperfection is not None else eng.d_xyz0
+        cols = list(grp.columns)
+        fac = plan.factors[cols]
+        if not (second_order or unilateral.any()):
+            f_case, peq_case = eng.load_cases(d_xyz)
+            eng.assemble(d_xyz)
+            for c0 in range(0, len(cols), 64):
+                sub = cols[c0:c0 + 64]
+                nr = _pad_nr(len(sub))
+                facp = np.zeros((nr, fac.shape[1])); facp[: len(sub)] = fac[c0:c0 + 64]
+                d_f = eng.combine(f_case, fac[c0:c0 + 64], nr)
+                d_peq = eng.combine(peq_case, fac[c0:c0 + 64], nr)
+                d_u = eng.solve(d_f)
+                rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, detail=detail)
+                _store(out, model, sub, d_u, rec, xyz)
+        else:
+            for ci, col in enumerate(cols):
+                _solve_nonlinear(eng, out, model, d_xyz, xyz, col, fac[ci:ci + 1], span, second_order, detail)
+    out.method = "Linear" if not second_order else "P_DELTA"
+    if second_order and opts.nonlinear_method == "COROTATIONAL":
+        out.warnings.append(("W_COROTATIONAL_AS_PDELTA",
+                             "corotational Newton-Raphson is not implemented; second-order effects use P-Delta"))
+    torch.cuda.synchronize(eng.dev)
+    out.solve_ms = (time.perf_counter() - t_start) * 1e3
+    if stats_out is not None:
+        stats_out.update(vars(eng.stats))
+    return out
+
+
+def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second_order, detail):
+    """Active-set (tension/compression-only members) around the P-Delta fixed point, one column."""
+    opts = model.options
+    nm = model.n_members
+    uni = np.nonzero(np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)))[0]
+    scale = np.ones(nm)
+    kg_mode = (1 if opts.pdelta_formulation == "CONSISTENT" else 2) if second_order else 0
+    sup = 0
+    for ax in pdelta_suppressed_axes(model):
+        sup |= 1 << ax
+    nr = 8 if model.n_dof > DENSE_MAX_DOF else 1
+    facp = np.zeros((nr, fac.shape[1])); facp[0] = fac[0]
+    total_it, conv, resn = 0, True, 0.0
+    d_axial = None
+    rec = None
+    for _outer in range(max(1, 2 * len(uni) + 2)):
+        d_scale = eng._t(scale, np.float64) if len(uni) else None
+        f_case, peq_case = eng.load_cases(d_xyz, d_scale)
+        d_f = eng.combine(f_case, fac, nr)
+        d_peq = eng.combine(peq_case, fac, nr)
+        eng.assemble(d_xyz, d_scale)
+        d_u = eng.solve(d_f)
+        d_axial = None
+        if second_order and nm:
+            conv = False
+            for _it in range(max(1, opts.max_iterations)):
+                rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, d_scale, d_axial, kg_mode, sup, detail=False)
+                ax_rhs = eng._empty((nm, nr))
+                _lib.check(eng.lib.fers_b200_member_axial(nm, nr, _lib.ptr(rec["f_local"]), _lib.ptr(ax_rhs), eng.stream),
+                           "member_axial")
+                d_axial = ax_rhs
+                d_ax1 = ax_rhs[:, 0].contiguous()
+                eng.assemble(d_xyz, d_scale, d_ax1, kg_mode, sup)
+                d_un = eng.solve(d_f)
+                total_it += 1
+                den = float(torch.linalg.norm(d_un[:, 0]))
+                resn = float(torch.linalg.norm(d_un[:, 0] - d_u[:, 0])) / den if den > 0 else 0.0
+                d_u = d_un
+                if resn < opts.tolerance:
+                    conv = True
+                    break
+        if len(uni) == 0:
+            break
+        # elongation decides the active set
+        u = d_u[:, 0].cpu().numpy().reshape(model.n_nodes, 6)
+        d = xyz[model.m_n2[uni]] - xyz[model.m_n1[uni]]
+        lx = d / np.linalg.norm(d, axis=1)[:, None]
+        elong = ((u[model.m_n2[uni], :3] - u[model.m_n1[uni], :3]) * lx).sum(1)
+        tens = np.isin(model.m_type[uni], (wire.MT_TENSION, wire.MT_CABLE))
+        want = np.where(tens, elong >= 0.0, elong <= 0.0)
+        new_scale = scale.copy()
+        new_scale[uni] = np.where(want, 1.0, INACTIVE_SCALE)
+        if np.array_equal(new_scale, scale):
+            break
+        scale = new_scale
+    d_scale = eng._t(scale, np.float64) if len(uni) else None
+    rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, d_scale, d_axial, kg_mode, sup, detail=detail)
+    _store(out, model, [col], d_u, rec, xyz)
+    if second_order:
+        out.iterations[col] = total_it
+        out.converged[col] = bool(conv)
+        out.residual[col] = resn
+
+
+def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:
+    """Device results [.., nr] -> host result arrays for the given rhs columns."""
+    n = len(cols)
+    cols = np.asarray(cols)
+    nn, nm = model.n_nodes, model.n_members
+
+    def host(t, shape):
+        a = t.cpu().numpy()
+        a = a.reshape(shape + (a.shape[-1],))
+        return np.moveaxis(a, -1, 0)[:n]
+
+    out.U[cols] = host(d_u, (nn, 6))
+    out.R[cols] = host(rec["R"], (nn, 6))
+    if nm:
+        out.f_local[cols] = host(rec["f_local"], (nm, 12))
+        out.f_global[cols] = host(rec["f_global"], (nm, 12))
+        out.u_local[cols] = host(rec["u_local"], (nm, 12))
+        if "sec" in rec:
+            out.sec[cols] = host(rec["sec"], (nm, len(SECTION_FRACS), 6))
+            out.lmax[cols] = host(rec["lmax"], (nm, 6)); out.lmin[cols] = host(rec["lmin"], (nm, 6))
+            out.gmax[cols] = host(rec["gmax"], (nm, 6)); out.gmin[cols] = host(rec["gmin"], (nm, 6))
+    if model.n_plates:
+        npl = model.n_plates
+        out.p_res[cols] = host(rec["p_res"], (npl, 8))
+        out.p_nodal[cols] = host(rec["p_nodal"], (npl, 3, 6))
+        cd = host(rec["p_cd"], (npl, 12))
+        out.p_cdg[cols] = cd[..., :6]; out.p_cdl[cols] = cd[..., 6:]
+        out.p_centroid = xyz[model.p_nodes].mean(axis=1)
+
+
+# ---- the drop-in boundary ---------------------------------------------------------------------
+def solve_document(doc: dict, device=None) -> dict:
+    """dict in -> dict out (input document with ``results`` filled)."""
+    model = wire.parse_document(doc)
+    res = analyze(model, device)
+    out = dict(doc)
+    out["results"] = results_to_wire(model, res)
+    return out
+
+
+def calculate_from_json(input_json: str) -> str:
+    """Drop-in for ``fers_calculations.calculate_from_json`` (fers_core/fers/fers.py:300)."""
+    return json.dumps(solve_document(json.loads(input_json)))
+
+
+def calculate_from_file(file_path: str) -> str:
+    """Drop-in for ``fers_calculations.calculate_from_file`` (fers_core/fers/fers.py:260)."""
+    with open(file_path, "r", encoding="utf-8") as fh:
+        return calculate_from_json(fh.read())

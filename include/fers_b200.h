@@ -1,0 +1,162 @@
+/* fers_b200.h -- C ABI of libfers_b200.so, the sm_100a implementation of the FERS analysis hot path.
+ *
+ * What this boundary replaces.  The reference front end (Jeroen124/FERS_core) hands the whole
+ * analysis to one native call, `fers_calculations.calculate_from_json(str) -> str`
+ * (fers_core/fers/fers.py:300; file variant fers.py:260; direct use tests/nafems/nafems_harness.py:38).
+ * The Python module `fers_calculations/` in this repo keeps exactly that signature; below it the
+ * work is split into the stages the reference engine documents (element stiffness -> assembly ->
+ * boundary conditions -> "batch first-order solve that shares one factorization across many load
+ * cases" -> recovery; fers_core/types/pydantic_models.py:1200-1219, 1334-1398, 1594-1635) and
+ * each stage is one entry point here.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; fers_b200_last_error() gives the
+ *     message of the last failure on the calling thread;
+ *   - pointers are DEVICE pointers unless the parameter is marked [host];
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); calls are asynchronous on
+ *     that stream unless they return a value to the host (documented per function);
+ *   - no allocation happens inside the library except cub scratch carved from caller workspace;
+ *   - multi-vector layout is [n_dof][nrhs] (right-hand side index fastest), n_dof = 6 * n_nodes,
+ *     DOF order per node = X Y Z RX RY RZ (fers_core/supports/nodalsupport.py:146-159);
+ *   - the stiffness matrix is block-CSR with 6x6 node blocks, row-major inside a block.
+ */
+#ifndef FERS_B200_H
+#define FERS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FERS_B200_ABI_VERSION 1
+
+/* ---- library -------------------------------------------------------------------------------- */
+const char* fers_b200_version(void);
+const char* fers_b200_last_error(void);
+/* [host] outputs.  Fails when `device` is not a CUDA device of compute capability 10.x. */
+int fers_b200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* Make `device` current for this library's CUDA runtime (one process per GPU: call once with
+ * LOCAL_RANK before any other entry point). */
+int fers_b200_set_device(int device);
+
+/* ---- symbolic pattern (replaces the engine's DOF numbering / sparsity set-up; contract
+ *      SURVEY.md 8a row A7, pydantic_models.py:2104-2115) ------------------------------------- */
+size_t fers_b200_pattern_workspace(int n_nodes, int n_members, int n_plates);
+/* Sorted unique node pairs (every diagonal present) -> rowptr[n_nodes+1], colidx[<=cap];
+ * per-element block slots: m_slot[n_members*4] = (s,s)(s,e)(e,s)(e,e), p_slot[n_plates*9],
+ * diag_slot[n_nodes].  *nnzb_out [host] receives the block count (synchronises the stream). */
+int fers_b200_pattern_build(int n_nodes, int n_members, const int* m_n1, const int* m_n2,
+                            int n_plates, const int* p_nodes,
+                            int* rowptr, int* colidx, int cap,
+                            int* m_slot, int* p_slot, int* diag_slot, int* nnzb_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- boundary conditions (pydantic_models.py:1956-1959, 1232-1237) -------------------------- */
+/* bc_code[n_dof] (0 free, 1 fixed, 2 spring) -> fixed[n_dof] (uint8 0/1) and
+ * free_index[n_dof] (running number of free DOFs, -1 when constrained).  DOFs whose diagonal
+ * stiffness (vals + spring) is exactly zero are restrained too ("dead" DOFs, e.g. rotations of
+ * truss-only nodes).  *n_free_out, *n_dead_out [host] (synchronises the stream). */
+size_t fers_b200_bc_workspace(int n_dof);
+int fers_b200_bc_build(int n_nodes, const uint8_t* bc_code, const double* bc_k, const double* vals,
+                       const int* diag_slot, uint8_t* fixed, int* free_index, double* kspring,
+                       int* n_free_out, int* n_dead_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- element stiffness + assembly --------------------------------- */
+/* Beam members: 12x12 local stiffness (Euler-Bernoulli / Timoshenko), optional end-release
+ * condensation and geometric stiffness, T^T k T, scatter-add into vals[nnzb*36].
+ *   m_scale  : per-member stiffness multiplier or NULL (active-set switch of tension-only members)
+ *   m_rel    : per-member row of rel[n_rel*12] or -1; NULL = no releases
+ *   m_axial  : per-member axial force (tension +) for K_g or NULL; kg_mode 0 none, 1 consistent,
+ *              2 simplified; kg_suppress = bit mask of global axes removed from K_g (bit0 X..)
+ *   variant  : 0 = warp-aggregated atomic scatter-add, 1 = plain atomic scatter-add
+ * vals must be zeroed by the caller (fers_b200_zero).                                           */
+int fers_b200_assemble_beams(int n_members, const double* xyz, const int* m_n1, const int* m_n2,
+                             const int* m_prop, const int* m_type, const double* m_roll,
+                             const double* m_scale, const int* m_rel, const double* prop, int n_prop,
+                             const double* rel, int n_rel, const double* m_axial, int kg_mode, int kg_suppress,
+                             const int* m_slot, double* vals, int variant, void* stream);
+/* TRI3 shell elements: CST membrane + DSG3 Mindlin bending (pydantic_models.py:1700-1726). */
+int fers_b200_assemble_plates(int n_plates, const double* xyz, const int* p_nodes, const double* p_data,
+                              const int* p_flags, const int* p_slot, double* vals, void* stream);
+int fers_b200_zero(void* ptr, size_t bytes, void* stream);
+
+/* ---- load vectors (pydantic_models.py:2048-2059, 491-505) ---------- */
+/* One load case: nodal loads, member span loads (-> consistent equivalent nodal loads) and plate
+ * pressures accumulate into f_case[n_dof] and peq_case[n_members*12] (local frame, after release
+ * condensation).  Both must be zeroed by the caller. */
+int fers_b200_load_case(int n_nodes, int n_members, const double* xyz, const int* m_n1, const int* m_n2,
+                        const int* m_prop, const int* m_type, const double* m_roll, const double* m_scale,
+                        const int* m_rel, const double* prop, const double* rel,
+                        int n_nod, const int* nod_node, const double* nod_vec,
+                        int n_dl, const int* dl_member, const double* dl_data,
+                        int n_pl, const int* pl_member, const double* pl_data,
+                        int n_pp, const int* pp_plate, const double* pp_vec, const int* p_nodes,
+                        double* f_case, double* peq_case, void* stream);
+/* out[n_rows][nrhs] = sum_l factors[rhs][l] * in[l][n_rows]   (factors [nrhs][n_cases], row-major) */
+int fers_b200_combine(int n_rows, int n_cases, int nrhs, const double* in, const double* factors,
+                      double* out, void* stream);
+
+/* ---- solve ------------------------------------------------------- */
+/* y = K x on the free DOFs (rows of constrained DOFs give 0), springs included; nrhs in
+ * {1,8,16,32,64}.  fixed == NULL: plain product with the unconstrained matrix (used for
+ * reactions R = K u - F). */
+int fers_b200_spmm(int n_nodes, int nrhs, const int* rowptr, const int* colidx, const double* vals,
+                   const uint8_t* fixed, const double* kspring, const double* x, double* y, void* stream);
+/* Block-Jacobi preconditioner: inverse of each node's 6x6 diagonal block restricted to its free
+ * DOFs -> minv[n_nodes*36]. */
+int fers_b200_block_jacobi(int n_nodes, const double* vals, const int* diag_slot, const uint8_t* fixed,
+                           const double* kspring, double* minv, void* stream);
+size_t fers_b200_pcg_workspace(int n_nodes, int nrhs);
+/* Batched preconditioned CG, one independent recurrence per right-hand side column.
+ * b, x: [n_dof][nrhs]; x holds the initial guess when warm_start != 0, else it is zeroed.
+ * Stops when every column has ||r|| <= tol * ||b|| or after max_iter iterations.
+ * [host] outputs: *iters_out, relres_out[nrhs].  Returns 0 also when not converged (caller
+ * inspects relres_out).  Synchronises the stream. */
+int fers_b200_pcg_solve(int n_nodes, int nrhs, const int* rowptr, const int* colidx, const double* vals,
+                        const uint8_t* fixed, const double* kspring, const double* minv,
+                        const double* b, double* x, int warm_start, double tol, int max_iter, int check_every,
+                        int* iters_out, double* relres_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Dense direct path for small models and batches of small models: expand block-CSR to dense
+ * (constrained DOFs -> identity rows), Cholesky, multi-RHS substitution.
+ * a: [batch][n][n] column-major lower factor on exit; bx: [batch][n][nrhs] in: b, out: x.
+ * info_out [host][batch]: 0 ok, k>0 = leading minor k not positive definite. Synchronises. */
+int fers_b200_dense_expand(int n_nodes, const int* rowptr, const int* colidx, const double* vals,
+                           const uint8_t* fixed, const double* kspring, double* a, void* stream);
+int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* info_out, void* stream);
+int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* bx, void* stream);
+
+/* ---- recovery (pydantic_models.py:1594-1635) --------------------------- */
+/* Member end forces f = k_local (T u_e) - p_eq for every (member, rhs):
+ *   f_local, f_global, u_local : [n_members][12][nrhs]
+ * peq: [n_members*12][nrhs] or NULL.  m_axial_rhs: [n_members][nrhs] axial forces for K_g or NULL. */
+int fers_b200_recover_members(int n_members, int nrhs, const double* xyz, const int* m_n1, const int* m_n2,
+                              const int* m_prop, const int* m_type, const double* m_roll, const double* m_scale,
+                              const int* m_rel, const double* prop, const double* rel,
+                              const double* m_axial_rhs, int kg_mode, int kg_suppress,
+                              const double* u, const double* peq,
+                              double* f_local, double* f_global, double* u_local, void* stream);
+/* Interior section forces at x_frac 0.25/0.5/0.75 and per-component extrema:
+ *   sec [n_members][18][nrhs]; lmax,lmin,gmax,gmin [n_members][6][nrhs].
+ * Span loads are given per load case as CSR over members (sp_ptr[n_cases*(n_members+1)] into
+ * rows sp_rows[*][9] = kind(0 dist,1 point) + 8 data); factors [nrhs][n_cases]. */
+int fers_b200_recover_sections(int n_members, int nrhs, int n_cases, const double* xyz, const int* m_n1,
+                               const int* m_n2, const double* m_roll, const int* sp_ptr, const double* sp_rows,
+                               const double* factors, const double* f_local, const double* f_global,
+                               double* sec, double* lmax, double* lmin, double* gmax, double* gmin, void* stream);
+/* r[n_dof][nrhs] = supported(node) ? (K u - f) : 0, K WITHOUT support springs. */
+int fers_b200_reactions(int n_nodes, int nrhs, const int* rowptr, const int* colidx, const double* vals,
+                        const uint8_t* supported, const double* u, const double* f, double* r, void* stream);
+/* Plate resultants at the centroid (nx ny nxy mx my mxy qx qy), corner forces and centroid
+ * displacements:  p_res [n_plates][8][nrhs], p_nodal [n_plates][18][nrhs], p_cd [n_plates][12][nrhs]. */
+int fers_b200_recover_plates(int n_plates, int nrhs, const double* xyz, const int* p_nodes, const double* p_data,
+                             const int* p_flags, const double* u, double* p_res, double* p_nodal, double* p_cd,
+                             void* stream);
+/* axial[n_members][nrhs] = f_local[m][6][rhs] (tension +), used between P-Delta iterations. */
+int fers_b200_member_axial(int n_members, int nrhs, const double* f_local, double* axial, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FERS_B200_H */

@@ -333,7 +333,8 @@ class Assembly:
         if nm:
             self.R, self.L = member_frames(self.xyz, model.m_n1, model.m_n2, model.m_roll)
             self.P = member_props(model)
-            self.k_local = local_stiffness(self.P, self.L, model.m_type)
+            # the per-member multiplier (active-set switch) scales the stiffness BEFORE release condensation
+            self.k_local = local_stiffness(self.P, self.L, model.m_type) * self.m_scale[:, None, None]
             self.phi_y, self.phi_z = shear_phis(self.P, self.L, model.m_type)
         else:
             self.R = np.zeros((0, 3, 3)); self.L = np.zeros(0); self.P = np.zeros((0, 8))
@@ -351,7 +352,7 @@ class Assembly:
         nd = model.n_dof
         rows, cols, vals = [], [], []
         if model.n_members:
-            kl = self.k_cond * self.m_scale[:, None, None]
+            kl = self.k_cond
             if kg_local is not None:
                 kl = kl + kg_local
             kg = np.einsum("mji,mjk,mkl->mil", self.T, kl, self.T)
@@ -528,7 +529,7 @@ def recover_members(asm: Assembly, U, peq, kg_local=None):
                     lmax=z(6), lmin=z(6), gmax=z(6), gmin=z(6))
     ue = U[:, asm.edof]                                   # [nrhs,Nm,12]
     ul = np.einsum("mij,rmj->rmi", asm.T, ue)
-    kl = asm.k_cond * asm.m_scale[:, None, None]
+    kl = asm.k_cond
     if kg_local is not None:
         kl = kl[None] + kg_local                          # [nrhs,Nm,12,12]
         fl = np.einsum("rmij,rmj->rmi", kl, ul) - peq

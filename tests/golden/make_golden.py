@@ -1,0 +1,387 @@
+"""Generate tests/golden/wire_cases.json.gz with the reference's OWN front end.
+
+Run in the build container only (needs /root/reference):
+
+    PYTHONPATH=tests/refshim:/root/reference python tests/golden/make_golden.py
+
+Every case is a model built through the unmodified ``fers_core`` objects (Node, Member,
+Section, NodalSupport, loads, imperfections, plates ...), serialised by ``FERS.to_dict()``
+(fers_core/fers/fers.py:315-361) -- i.e. the exact wire document the reference would hand to
+``fers_calculations.calculate_from_json`` -- plus the expectations the reference's tests hold
+for that model: closed-form beam theory (tests/common_functions.py:90-246,
+tests/beam_equation_checks/test_beam_equations.py, tests/functionality/test_functionality.py)
+and the NAFEMS known-answer numbers (tests/nafems/benchmarks/LE1_result.json, LE6_result.json).
+The GPU box has no /root/reference, so the documents travel as this fixture.
+"""
+import gzip
+import json
+import math
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, "/root/reference/tests/nafems")
+sys.path.insert(0, "/root/reference/tests/nafems/benchmarks")
+
+from fers_core import (  # noqa: E402
+    FERS, Member, MemberHinge, MemberSet, Material, NodalLoad, NodalSupport, Node, Section, SupportCondition,
+    DistributedLoad,
+)
+from fers_core.settings.enums import AnalysisOrder  # noqa: E402
+
+E, G = 210e9, 80.769e9
+IZ, IY, A, J = 13.21e-6, 1.01e-6, 0.00196, 0.027e-6
+
+
+def steel():
+    return Material(name="Steel", e_mod=E, g_mod=G, density=7850.0, yield_stress=235e6)
+
+
+def ipe180(mat, shear=False):
+    kw = dict(name="IPE 180", material=mat, i_y=IY, i_z=IZ, j=J, area=A)
+    s = Section(**kw)
+    if shear:
+        s.a_sy, s.a_sz = 1.1e-3, 0.9e-3
+    return s
+
+
+def reset():
+    for cls in (Node, Member, Section, Material, NodalSupport, MemberSet, MemberHinge):
+        for name in dir(cls):
+            if name.startswith("reset_counter"):
+                getattr(cls, name)()
+    try:
+        from fers_core.loads.loadcase import LoadCase
+        from fers_core.loads.loadcombination import LoadCombination
+        from fers_core.loads.nodalload import NodalLoad as NL
+        LoadCase.reset_counter(); LoadCombination.reset_counter()
+        if hasattr(NL, "reset_counter"):
+            NL.reset_counter()
+    except Exception:
+        pass
+
+
+CASES = []
+
+
+def emit(name, calc, expect, mutate=None):
+    d = calc.to_dict()
+    d["results"] = None
+    if mutate:
+        mutate(d)
+    CASES.append({"name": name, "doc": d, "expect": expect})
+
+
+def X(path, value, abs_tol, rel_tol=1e-5):
+    return {"path": path, "value": value, "abs": abs_tol, "rel": rel_tol}
+
+
+def linear(calc):
+    calc.settings.analysis_options.order = AnalysisOrder.LINEAR
+
+
+# 1 cantilever, tip load (default NONLINEAR order, as the reference test runs it)
+reset()
+c = FERS(); s = ipe180(steel())
+n1, n2 = Node(0, 0, 0), Node(5.0, 0, 0); n1.nodal_support = NodalSupport()
+m = Member(start_node=n1, end_node=n2, section=s); c.add_member_set(MemberSet(members=[m]))
+lc = c.create_load_case(name="End Load")
+NodalLoad(node=n2, load_case=lc, magnitude=1000.0, direction=(0, -1, 0))
+emit("cantilever_end_load", c, [
+    X("loadcases/End Load/displacement_nodes/2/dy", -1000 * 125 / (3 * E * IZ), 1e-6),
+    X("loadcases/End Load/reaction_nodes/1/nodal_forces/mz", 5000.0, 1e-3),
+    X("loadcases/End Load/reaction_nodes/1/nodal_forces/fy", 1000.0, 1e-6),
+    X("loadcases/End Load/member_results/1/section_forces/1/forces/mz", 2500.0, 1e-3),
+])
+
+# 2 cantilever, partial UDL 0.4-0.7 L
+reset()
+c = FERS(); linear(c); s = ipe180(steel())
+n1, n2 = Node(0, 0, 0), Node(5.0, 0, 0); n1.nodal_support = NodalSupport()
+m = Member(start_node=n1, end_node=n2, section=s); c.add_member_set(MemberSet(members=[m]))
+lc = c.create_load_case(name="Partial")
+DistributedLoad(member=m, load_case=lc, magnitude=1000.0, direction=(0, -1, 0), start_frac=0.4, end_frac=0.7)
+W = 1000.0 * 0.3 * 5.0
+emit("cantilever_partial_udl", c, [
+    X("loadcases/Partial/reaction_nodes/1/nodal_forces/fy", W, 1e-6),
+    X("loadcases/Partial/reaction_nodes/1/nodal_forces/mz", W * 0.55 * 5.0, 1e-3),
+])
+
+# 3 cantilever, partial triangular 0 -> 1000 over 0.3-0.7 L
+reset()
+c = FERS(); linear(c); s = ipe180(steel())
+n1, n2 = Node(0, 0, 0), Node(5.0, 0, 0); n1.nodal_support = NodalSupport()
+m = Member(start_node=n1, end_node=n2, section=s); c.add_member_set(MemberSet(members=[m]))
+lc = c.create_load_case(name="Tri")
+DistributedLoad(member=m, load_case=lc, magnitude=0.0, end_magnitude=1000.0, direction=(0, -1, 0),
+                start_frac=0.3, end_frac=0.7)
+W = 0.5 * 1000.0 * 0.4 * 5.0
+xbar = (0.3 + 0.4 * 2.0 / 3.0) * 5.0
+emit("cantilever_partial_triangular", c, [
+    X("loadcases/Tri/reaction_nodes/1/nodal_forces/fy", W, 1e-6),
+    X("loadcases/Tri/reaction_nodes/1/nodal_forces/mz", W * xbar, 1e-3),
+])
+
+# 4 cantilever, end moment about +Z
+reset()
+from fers_core import NodalMoment  # noqa: E402
+c = FERS(); linear(c); s = ipe180(steel())
+n1, n2 = Node(0, 0, 0), Node(5.0, 0, 0); n1.nodal_support = NodalSupport()
+m = Member(start_node=n1, end_node=n2, section=s); c.add_member_set(MemberSet(members=[m]))
+lc = c.create_load_case(name="Moment")
+NodalMoment(node=n2, load_case=lc, magnitude=500.0, direction=(0, 0, 1))
+emit("cantilever_end_moment", c, [
+    X("loadcases/Moment/displacement_nodes/2/dy", 500.0 * 25 / (2 * E * IZ), 1e-6),
+    X("loadcases/Moment/displacement_nodes/2/rz", 500.0 * 5 / (E * IZ), 1e-9),
+])
+
+# 5 simply supported, UDL, two members
+reset()
+c = FERS(); linear(c); s = ipe180(steel())
+L = 6.0
+n1, n2, n3 = Node(0, 0, 0), Node(L / 2, 0, 0), Node(L, 0, 0)
+n1.nodal_support = NodalSupport(rotation_conditions={"X": SupportCondition.fixed(), "Y": SupportCondition.free(),
+                                                     "Z": SupportCondition.free()})
+n3.nodal_support = NodalSupport(displacement_conditions={"X": SupportCondition.free(), "Y": SupportCondition.fixed(),
+                                                         "Z": SupportCondition.fixed()},
+                                rotation_conditions={"X": SupportCondition.free(), "Y": SupportCondition.free(),
+                                                     "Z": SupportCondition.free()})
+m1 = Member(start_node=n1, end_node=n2, section=s); m2 = Member(start_node=n2, end_node=n3, section=s)
+c.add_member_set(MemberSet(members=[m1, m2]))
+lc = c.create_load_case(name="UDL")
+w = 2000.0
+DistributedLoad(member=m1, load_case=lc, magnitude=w, direction=(0, -1, 0))
+DistributedLoad(member=m2, load_case=lc, magnitude=w, direction=(0, -1, 0))
+emit("simply_supported_udl", c, [
+    X("loadcases/UDL/displacement_nodes/2/dy", -5 * w * L**4 / (384 * E * IZ), 1e-6),
+    X("loadcases/UDL/member_results/1/end_node_forces/mz", w * L * L / 8, 1e-3),
+    X("loadcases/UDL/reaction_nodes/1/nodal_forces/fy", w * L / 2, 1e-6),
+])
+
+# 6 fixed-fixed, centre load, Timoshenko section (shear pairing SURVEY.md A.5)
+reset()
+c = FERS(); linear(c); s = ipe180(steel(), shear=True)
+L = 6.0; P = 20000.0
+n1, n2, n3 = Node(0, 0, 0), Node(L / 2, 0, 0), Node(L, 0, 0)
+n1.nodal_support = NodalSupport(); n3.nodal_support = NodalSupport()
+m1 = Member(start_node=n1, end_node=n2, section=s); m2 = Member(start_node=n2, end_node=n3, section=s)
+c.add_member_set(MemberSet(members=[m1, m2]))
+lc = c.create_load_case(name="Centre")
+NodalLoad(node=n2, load_case=lc, magnitude=P, direction=(0, -1, 0))
+emit("fixed_fixed_timoshenko", c, [
+    X("loadcases/Centre/displacement_nodes/2/dy", -(P * L**3 / (192 * E * IZ) + P * L / (4 * G * 0.9e-3)), 1e-7),
+    X("loadcases/Centre/reaction_nodes/1/nodal_forces/mz", P * L / 8, 1e-3),
+])
+
+# 7 rigid link (reference test_041)
+reset()
+c = FERS(); s = ipe180(steel())
+n1, n2, n3 = Node(0, 0, 0), Node(5, 0, 0), Node(10, 0, 0); n1.nodal_support = NodalSupport()
+me = Member(start_node=n1, end_node=n2, section=s); mr = Member(start_node=n2, end_node=n3, member_type="RIGID")
+c.add_member_set(MemberSet(members=[me, mr]))
+lc = c.create_load_case(name="End Load")
+NodalLoad(node=n2, load_case=lc, magnitude=1000.0, direction=(0, -1, 0))
+rz = -1000.0 * 25 / (2 * E * IZ)
+emit("rigid_link", c, [
+    X("loadcases/End Load/displacement_nodes/2/rz", rz, 1e-9),
+    X("loadcases/End Load/displacement_nodes/3/rz", rz, 1e-9),
+    X("loadcases/End Load/displacement_nodes/3/dy", -1000 * 125 / (3 * E * IZ) + rz * 5.0, 1e-6),
+])
+
+# 8 hinge with rotational spring (reference test_051)
+reset()
+c = FERS(); s = ipe180(steel())
+n1, n2, n3 = Node(0, 0, 0), Node(2.5, 0, 0), Node(5, 0, 0); n1.nodal_support = NodalSupport()
+kphi = 1000.0 * 2.5 / 0.1
+hinge = MemberHinge(hinge_type="SPRING_Z", rotational_release_mz=kphi)
+mr = Member(start_node=n1, end_node=n2, member_type="RIGID")
+mf = Member(start_node=n2, end_node=n3, section=s, start_hinge=hinge)
+c.add_member_set(MemberSet(members=[mr, mf]))
+lc = c.create_load_case(name="End Load")
+NodalLoad(node=n3, load_case=lc, magnitude=1000.0, direction=(0, -1, 0))
+emit("hinge_spring", c, [
+    X("loadcases/End Load/displacement_nodes/3/dy", -(1000 * 2.5**3 / (3 * E * IZ) + 0.1 * 2.5), 1e-6),
+    X("loadcases/End Load/displacement_nodes/3/rz", -(1000 * 2.5**2 / (2 * E * IZ) + 0.1), 1e-6),
+    X("loadcases/End Load/reaction_nodes/1/nodal_forces/mz", 5000.0, 1e-3),
+])
+
+# 9 tension-only members (reference test_061)
+reset()
+c = FERS(); s = ipe180(steel())
+n1, n2, n3 = Node(0, 0, 0), Node(2.5, 0, 0), Node(5, 0, 0)
+n1.nodal_support = NodalSupport(); n3.nodal_support = NodalSupport()
+n2.nodal_support = NodalSupport(displacement_conditions={"X": SupportCondition.free(), "Y": SupportCondition.fixed(),
+                                                         "Z": SupportCondition.fixed()})
+ml = Member(start_node=n1, end_node=n2, section=s, member_type="TENSION")
+mr = Member(start_node=n2, end_node=n3, section=s, member_type="TENSION")
+c.add_member_set(MemberSet(members=[ml, mr]))
+lc = c.create_load_case(name="Mid Load")
+NodalLoad(node=n2, load_case=lc, magnitude=10000.0, direction=(1, 0, 0))
+emit("tension_only", c, [
+    X("loadcases/Mid Load/displacement_nodes/2/dx", 10000.0 * 2.5 / (A * E), 1e-6),
+    X("loadcases/Mid Load/reaction_nodes/1/nodal_forces/fx", -10000.0, 1e-3, 1e-4),
+    X("loadcases/Mid Load/reaction_nodes/3/nodal_forces/fx", 0.0, 1e-3),
+])
+
+# 10 3D frame: skew members, roll angle, several load cases + combinations, local-axis member loads
+reset()
+c = FERS(); linear(c); mat = steel(); s = ipe180(mat, shear=True); s2 = ipe180(mat)
+nodes = [Node(0, 0, 0), Node(0, 3.2, 0), Node(4.0, 3.5, 0.8), Node(4.0, 0, 0.8), Node(2.0, 5.0, 3.0), Node(0, 3.2, 3.0),
+         Node(0, 0, 3.0)]
+for i in (0, 3, 6):
+    nodes[i].nodal_support = NodalSupport()
+mem = [Member(start_node=nodes[0], end_node=nodes[1], section=s),
+       Member(start_node=nodes[1], end_node=nodes[2], section=s2, rotation_angle=30.0),
+       Member(start_node=nodes[3], end_node=nodes[2], section=s),
+       Member(start_node=nodes[2], end_node=nodes[4], section=s2, rotation_angle=-75.0),
+       Member(start_node=nodes[1], end_node=nodes[4], section=s),
+       Member(start_node=nodes[5], end_node=nodes[4], section=s2),
+       Member(start_node=nodes[6], end_node=nodes[5], section=s),
+       Member(start_node=nodes[1], end_node=nodes[5], section=s2, rotation_angle=12.0)]
+c.add_member_set(MemberSet(members=mem))
+lc1 = c.create_load_case(name="G"); lc2 = c.create_load_case(name="W"); lc3 = c.create_load_case(name="P")
+for mm in (mem[1], mem[3], mem[4], mem[5], mem[7]):
+    DistributedLoad(member=mm, load_case=lc1, magnitude=3000.0, direction=(0, -1, 0))
+DistributedLoad(member=mem[0], load_case=lc2, magnitude=800.0, end_magnitude=1500.0, direction=(1, 0, 0.3),
+                start_frac=0.1, end_frac=0.9)
+NodalLoad(node=nodes[4], load_case=lc2, magnitude=2500.0, direction=(0.6, 0, 0.8))
+NodalMoment(node=nodes[2], load_case=lc3, magnitude=700.0, direction=(0, 1, 0))
+NodalLoad(node=nodes[5], load_case=lc3, magnitude=-4000.0, direction=(0, 1, 0))
+c.create_load_combination(name="ULS", load_cases_factors={lc1: 1.35, lc2: 1.5, lc3: 1.05}, situation="ULS", check="ALL")
+c.create_load_combination(name="SLS", load_cases_factors={lc1: 1.0, lc2: 0.7}, situation="SLS", check="ALL")
+
+
+def add_member_point_loads(d):
+    d["analysis"]["load_cases"][2]["member_point_loads"] = [
+        {"id": 1, "member": 2, "magnitude": 1200.0, "direction": [0, -1, 0], "position": 0.35, "axes": "global"},
+        {"id": 2, "member": 4, "magnitude": 900.0, "direction": [0, 0, 1], "position": 0.6, "axes": "local"}]
+    d["analysis"]["load_cases"][2]["member_point_moments"] = [
+        {"id": 1, "member": 5, "magnitude": 300.0, "direction": [0, 1, 0], "position": 0.5, "axes": "local"}]
+
+
+emit("space_frame_3d", c, [], add_member_point_loads)
+
+# 11 2D portal frame, load cases + combinations (BASELINE.json configs[1])
+reset()
+c = FERS(); linear(c); mat = steel(); s = ipe180(mat)
+from fers_core.settings.enums import Dimensionality  # noqa: E402
+c.settings.analysis_options.dimensionality = Dimensionality.TWO_DIMENSIONAL
+h, b = 4.0, 8.0
+p = [Node(0, 0, 0), Node(0, h, 0), Node(b / 2, h + 1.0, 0), Node(b, h, 0), Node(b, 0, 0)]
+pin = dict(rotation_conditions={"X": SupportCondition.fixed(), "Y": SupportCondition.fixed(), "Z": SupportCondition.free()})
+p[0].nodal_support = NodalSupport(**pin); p[4].nodal_support = NodalSupport(**pin)
+pm = [Member(start_node=p[0], end_node=p[1], section=s), Member(start_node=p[1], end_node=p[2], section=s),
+      Member(start_node=p[2], end_node=p[3], section=s), Member(start_node=p[4], end_node=p[3], section=s)]
+c.add_member_set(MemberSet(members=pm))
+g = c.create_load_case(name="G"); sn = c.create_load_case(name="S"); wd = c.create_load_case(name="W")
+for mm in pm[1:3]:
+    DistributedLoad(member=mm, load_case=g, magnitude=1500.0, direction=(0, -1, 0))
+    DistributedLoad(member=mm, load_case=sn, magnitude=2200.0, direction=(0, -1, 0))
+DistributedLoad(member=pm[0], load_case=wd, magnitude=900.0, direction=(1, 0, 0))
+NodalLoad(node=p[1], load_case=wd, magnitude=1800.0, direction=(1, 0, 0))
+c.create_load_combination(name="ULS1", load_cases_factors={g: 1.35, sn: 1.5}, situation="ULS", check="ALL")
+c.create_load_combination(name="ULS2", load_cases_factors={g: 1.35, sn: 0.75, wd: 1.5}, situation="ULS", check="ALL")
+c.create_load_combination(name="SLS", load_cases_factors={g: 1.0, sn: 1.0}, situation="SLS", check="ALL")
+tot = 1500.0 * 2 * math.hypot(b / 2, 1.0)
+emit("portal_2d_combinations", c, [
+    X("loadcases/G/reaction_nodes/1/nodal_forces/fy", tot / 2, 1e-6),
+    X("loadcases/G/reaction_nodes/5/nodal_forces/fy", tot / 2, 1e-6),
+])
+
+# 12 3D portal, sway imperfection, P-Delta (consistent and simplified / suppressed axis)
+for variant in ("consistent", "simplified_suppress_z"):
+    reset()
+    from fers_core import ImperfectionCase, SwayImperfection  # noqa: E402
+    c = FERS(); mat = steel(); s = ipe180(mat)
+    q = [Node(0, 0, 0), Node(0, 4, 0), Node(5, 4, 0), Node(5, 0, 0), Node(0, 0, 4), Node(0, 4, 4), Node(5, 4, 4), Node(5, 0, 4)]
+    for i in (0, 3, 4, 7):
+        q[i].nodal_support = NodalSupport()
+    qm = [Member(start_node=q[0], end_node=q[1], section=s), Member(start_node=q[1], end_node=q[2], section=s),
+          Member(start_node=q[3], end_node=q[2], section=s), Member(start_node=q[4], end_node=q[5], section=s),
+          Member(start_node=q[5], end_node=q[6], section=s), Member(start_node=q[7], end_node=q[6], section=s),
+          Member(start_node=q[1], end_node=q[5], section=s), Member(start_node=q[2], end_node=q[6], section=s)]
+    c.add_member_set(MemberSet(members=qm))
+    gv = c.create_load_case(name="V"); hh = c.create_load_case(name="H")
+    for nd_ in (q[1], q[2], q[5], q[6]):
+        NodalLoad(node=nd_, load_case=gv, magnitude=60000.0, direction=(0, -1, 0))
+    NodalLoad(node=q[1], load_case=hh, magnitude=3000.0, direction=(1, 0, 0))
+    NodalLoad(node=q[5], load_case=hh, magnitude=1000.0, direction=(0, 0, 1))
+    combo = c.create_load_combination(name="VH", load_cases_factors={gv: 1.0, hh: 1.0}, situation="ULS", check="ALL")
+    combo2 = c.create_load_combination(name="V2H", load_cases_factors={gv: 1.35, hh: 0.5}, situation="ULS", check="ALL")
+    imp = ImperfectionCase(loadcombinations=[combo])
+    imp.add_sway_imperfection(SwayImperfection(magnitude=1.0 / 200.0, axis=(0, 0, 1), height_direction=(0, 1, 0),
+                                               reference_point=(0, 0, 0)))
+    c.add_imperfection_case(imp)
+
+    def mut(d, variant=variant):
+        o = d["analysis"]["options"]
+        o["order"] = "NONLINEAR"; o["nonlinear_method"] = "P_DELTA"; o["tolerance"] = 1e-10; o["max_iterations"] = 50
+        if variant != "consistent":
+            o["pdelta_formulation"] = "SIMPLIFIED"; o["pdelta_suppress_axes"] = ["Z"]
+    emit("portal_pdelta_" + variant, c, [], mut)
+
+# 13 spring support + truss members (auto-restrained rotations)
+reset()
+c = FERS(); linear(c); mat = steel(); s = ipe180(mat)
+t = [Node(0, 0, 0), Node(4, 0, 0), Node(2, 3, 0)]
+t[0].nodal_support = NodalSupport(rotation_conditions={k: SupportCondition.free() for k in "XYZ"})
+t[1].nodal_support = NodalSupport(displacement_conditions={"X": SupportCondition.spring(2.0e6), "Y": SupportCondition.fixed(),
+                                                           "Z": SupportCondition.fixed()},
+                                  rotation_conditions={k: SupportCondition.free() for k in "XYZ"})
+t[2].nodal_support = NodalSupport(displacement_conditions={"X": SupportCondition.free(), "Y": SupportCondition.free(),
+                                                           "Z": SupportCondition.fixed()},
+                                  rotation_conditions={k: SupportCondition.free() for k in "XYZ"})
+tm = [Member(start_node=t[0], end_node=t[1], section=s, member_type="TRUSS"),
+      Member(start_node=t[1], end_node=t[2], section=s, member_type="TRUSS"),
+      Member(start_node=t[0], end_node=t[2], section=s, member_type="TRUSS")]
+c.add_member_set(MemberSet(members=tm))
+lc = c.create_load_case(name="Apex")
+NodalLoad(node=t[2], load_case=lc, magnitude=50000.0, direction=(0.2, -1, 0))
+emit("truss_spring_support", c, [X("loadcases/Apex/reaction_nodes/2/nodal_forces/fx", None, 0.0)])
+
+# 14 plate strip under a surface load (reference tests/functionality/test_plate_results.py, nx = 10)
+reset()
+from fers_core import LoadCase, Plate, SurfaceLoad  # noqa: E402
+c = FERS(); linear(c); mat = steel(); sup = NodalSupport()
+length, width, thick, nx = 2.0, 0.20, 0.03, 10
+cols = []
+for ix in range(nx + 1):
+    x = length * ix / nx
+    cols.append((Node(X=x, Y=0.0, Z=0.0, nodal_support=sup if ix == 0 else None),
+                 Node(X=x, Y=width, Z=0.0, nodal_support=sup if ix == 0 else None)))
+for ix in range(nx):
+    a0, a1 = cols[ix]; b0, b1 = cols[ix + 1]
+    c.add_plate(Plate(nodes=[a0, b0, b1], material=mat, thickness=thick, classification="Strip", local_x_direction=(1, 0, 0)),
+                Plate(nodes=[a0, b1, a1], material=mat, thickness=thick, classification="Strip", local_x_direction=(1, 0, 0)))
+lc = LoadCase(name="Pressure")
+SurfaceLoad(load_case=lc, polygon=[(0, 0, 0), (length, 0, 0), (length, width, 0), (0, width, 0)], magnitude=1000.0,
+            direction=(0, 0, -1))
+c.add_load_case(lc)
+emit("plate_strip_surface_load", c, [X("loadcases/Pressure/__sum_reaction_fz", 1000.0 * length * width, 1e-6)])
+
+# 15 NAFEMS LE1 (CST membrane) and LE6 (DSG3 Mindlin): the reference's own builders + known answers
+import LE1_build  # noqa: E402
+import LE6_build  # noqa: E402
+
+
+def nafems_emit(name, calc, kind, point, thickness, value, abs_tol):
+    d = calc.to_dict(include_results=False)
+    d["results"] = None
+    CASES.append({"name": name, "doc": d,
+                  "expect": [{"nafems": kind, "point": list(point), "thickness": thickness, "value": value,
+                              "abs": abs_tol, "rel": 0.0}]})
+
+
+for (nth, ns, val, tol) in ((24, 4, 79129730.5, 0.06), (72, 8, 90160401.4, 0.06)):
+    reset()
+    calc, nd = LE1_build.build(nth, ns)
+    nafems_emit(f"nafems_LE1_{nth}x{ns}", calc, "LE1", LE1_build.D_PT, LE1_build.T, val, tol)
+for (n, val, tol) in ((8, 396102.7, 0.06), (32, 741737.1, 0.06)):
+    reset()
+    calc = LE6_build.build(n)
+    nafems_emit(f"nafems_LE6_{n}x{n}", calc, "LE6", LE6_build.E_CENTRE, LE6_build.T, val, tol)
+
+out = os.path.join(HERE, "wire_cases.json.gz")
+with gzip.open(out, "wt", encoding="utf-8") as fh:
+    json.dump(CASES, fh)
+print(f"wrote {len(CASES)} cases -> {out} ({os.path.getsize(out)} bytes)")

@@ -1,0 +1,162 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): bit-exact block-CSR pattern, DOF numbering and BC masks; fp64
+displacements, reactions and member forces within 1e-9 relative (per result column, relative to
+the column's largest magnitude)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from fers_core_b200 import synth, wire
+from oracle import fers_oracle
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def engine_mod():
+    from fers_core_b200 import engine
+    return engine
+
+
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_golden_documents_match_oracle(engine_mod, name):
+    case = helpers.golden(name)
+    model = wire.parse_document(case["doc"])
+    want = fers_oracle.analyze(model)
+    got = engine_mod.analyze(wire.parse_document(case["doc"]))
+    rtol = RTOL if "rigid" not in name and "hinge" not in name else 1e-7   # 1e6-stiff rigid links: cond ~1e13
+    helpers.assert_results_close(got, want, rtol, label=name)
+    assert np.array_equal(got.iterations, want.iterations), (got.iterations, want.iterations)
+
+
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_golden_documents_meet_reference_expectations(engine_mod, name):
+    """Same closed-form / known-answer expectations as the oracle, through calculate_from_json."""
+    import json
+    case = helpers.golden(name)
+    out = json.loads(engine_mod.calculate_from_json(json.dumps(case["doc"])))
+    helpers.check_expectations(out["results"], case["expect"])
+
+
+@pytest.mark.parametrize("name", ["space_frame_3d", "plate_strip_surface_load", "truss_spring_support",
+                                  "portal_2d_combinations", "nafems_LE6_8x8"])
+def test_pattern_numbering_and_masks_bit_exact(engine_mod, name):
+    model = wire.parse_document(helpers.golden(name)["doc"])
+    eng = engine_mod.Engine(model)
+    eng.assemble(eng.d_xyz0)
+    rowptr, colidx = fers_oracle.bsr_pattern(model)
+    assert np.array_equal(eng.d_rowptr.cpu().numpy(), rowptr)
+    assert np.array_equal(eng.d_colidx.cpu().numpy(), colidx)
+    asm = fers_oracle.Assembly(model)
+    _, free, dead = fers_oracle.constrain(asm.K_elastic(), model)
+    fixed = np.ones(model.n_dof, np.uint8); fixed[free] = 0
+    free_index = np.where(fixed == 0, np.cumsum(1 - fixed.astype(np.int64)) - 1, -1).astype(np.int32)
+    assert np.array_equal(eng.d_fixed.cpu().numpy(), fixed)
+    assert np.array_equal(eng.d_free_index.cpu().numpy(), free_index)
+    assert eng.stats.n_free == len(free) and eng.stats.n_dead == int(dead.sum())
+
+
+def _bsr_to_scipy(eng, n_nodes):
+    import scipy.sparse as sp
+    vals = eng.d_vals.cpu().numpy().reshape(-1, 6, 6)
+    return sp.bsr_matrix((vals, eng.d_colidx.cpu().numpy(), eng.d_rowptr.cpu().numpy()), shape=(6 * n_nodes, 6 * n_nodes))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_assembled_values_match_oracle(engine_mod, variant):
+    """Every assembly variant (aggregated/plain atomics x TMA-staged/global section table)."""
+    model = synth.grid_frame(5, 4, 3, timoshenko=True)
+    eng = engine_mod.Engine(model, assembly_variant=variant)
+    eng.assemble(eng.d_xyz0)
+    K = _bsr_to_scipy(eng, model.n_nodes).toarray()
+    want = fers_oracle.Assembly(model).K_elastic().toarray()
+    assert np.abs(K - want).max() <= 1e-13 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("nrhs", [1, 8, 16, 32, 64])
+def test_spmm_matches_scipy(engine_mod, nrhs):
+    import torch
+    from fers_core_b200 import _lib
+    model = synth.grid_frame(6, 5, 4)
+    eng = engine_mod.Engine(model)
+    eng.assemble(eng.d_xyz0)
+    K = _bsr_to_scipy(eng, model.n_nodes).tocsr()
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(model.n_dof, nrhs))
+    fixed = eng.d_fixed.cpu().numpy().astype(bool)
+    d_x = torch.from_numpy(x).to(eng.dev)
+    d_y = torch.empty_like(d_x)
+    for masked in (False, True):
+        _lib.check(eng.lib.fers_b200_spmm(model.n_nodes, nrhs, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx),
+                                          _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed) if masked else None,
+                                          _lib.ptr(eng.d_kspring) if masked else None, _lib.ptr(d_x), _lib.ptr(d_y),
+                                          eng.stream), "spmm")
+        want = K @ x
+        if masked:
+            want[fixed] = 0.0
+        got = d_y.cpu().numpy()
+        assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("dims,force_pcg", [((4, 4, 4), False), ((4, 4, 4), True), ((9, 8, 6), False),
+                                            ((12, 12, 10), True)])
+def test_synthetic_frame_matches_oracle(engine_mod, monkeypatch, dims, force_pcg):
+    """configs[3]-shaped frames at oracle-sized scale, dense and PCG solve paths."""
+    if force_pcg:
+        monkeypatch.setattr(engine_mod, "DENSE_MAX_DOF", 0)
+    model = synth.grid_frame(*dims, n_combos=11, timoshenko=(dims[0] == 9), solve_loadcases=True)
+    want = fers_oracle.analyze(model)
+    stats = {}
+    got = engine_mod.analyze(model, stats_out=stats)
+    assert stats["method"] == ("pcg" if force_pcg else "dense")
+    helpers.assert_results_close(got, want, RTOL, label=str(dims))
+
+
+def test_midsize_frame_properties(engine_mod):
+    """Size-independent properties on a frame too large for the oracle's comfort: global
+    equilibrium, true residual, linearity of combinations."""
+    import torch
+    from fers_core_b200.hostlogic import rhs_plan
+    model = synth.grid_frame(24, 24, 12, n_combos=8, solve_loadcases=True)
+    got = engine_mod.analyze(model, detail=False)
+    plan = rhs_plan(model)
+    nlc = len(model.load_cases)
+    for col in range(nlc, plan.n_rhs):
+        want = np.einsum("l,lnd->nd", plan.factors[col], got.U[:nlc])
+        assert np.abs(got.U[col] - want).max() <= 1e-8 * np.abs(want).max()
+    asm = fers_oracle.Assembly(model)
+    F, _ = fers_oracle.load_vectors(asm)
+    for li in range(nlc):
+        tot = F[li].reshape(-1, 6)[:, :3].sum(0) + got.R[li][:, :3].sum(0)
+        assert np.abs(tot).max() <= 1e-7 * np.abs(F[li]).sum()
+    K = asm.K_elastic()
+    _, free, _ = fers_oracle.constrain(K, model)
+    for li in range(nlc):
+        r = (K @ got.U[li].reshape(-1) - F[li])[free]
+        assert np.linalg.norm(r) <= 1e-9 * np.linalg.norm(F[li][free])
+
+
+def test_dense_cholesky_batched(engine_mod):
+    """Batched dense factor/solve used for batches of small frames (configs[4])."""
+    import torch
+    from fers_core_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    batch, n, nrhs = 5, 77, 3
+    A = rng.normal(size=(batch, n, n)); A = A @ A.transpose(0, 2, 1) + n * np.eye(n)
+    B = rng.normal(size=(batch, n, nrhs))
+    dev = torch.device("cuda", 0)
+    dA = torch.from_numpy(A.copy()).to(dev); dB = torch.from_numpy(B.copy()).to(dev)
+    info_dev = torch.zeros(batch, dtype=torch.int32, device=dev)
+    info = (C.c_int * batch)()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.fers_b200_dense_cholesky(n, batch, _lib.ptr(dA), _lib.ptr(info_dev), info, st), "chol")
+    assert list(info) == [0] * batch
+    _lib.check(lib.fers_b200_dense_solve(n, nrhs, batch, _lib.ptr(dA), _lib.ptr(dB), st), "solve")
+    X = dB.cpu().numpy()
+    want = np.linalg.solve(A, B)
+    assert np.abs(X - want).max() <= 1e-11 * np.abs(want).max()

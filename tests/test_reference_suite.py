@@ -1,0 +1,33 @@
+"""Run the reference's OWN engine-dependent tests against the CPU oracle (build container only).
+
+This is how the oracle is pinned on the reference's closed-form suite: the unmodified tests under
+/root/reference/tests call ``FERS.run_analysis()`` -> ``fers_calculations.calculate_from_json``,
+which tests/refshim routes to oracle/oracle_engine.py.  Skipped where /root/reference is absent
+(the GPU box); the same models travel there as tests/golden/wire_cases.json.gz."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests.conftest import HAVE_REFERENCE, REFERENCE, ROOT
+
+pytestmark = pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference not present")
+
+SUITES = [
+    "tests/beam_equation_checks/test_beam_equations.py",
+    "tests/functionality/test_functionality.py",
+    "tests/functionality/test_plate_results.py",
+    "tests/nafems/test_nafems_benchmarks.py::test_LE1_elliptic_membrane_converges",
+    "tests/nafems/test_nafems_benchmarks.py::test_LE6_skew_plate_converges",
+]
+
+
+@pytest.mark.parametrize("suite", SUITES)
+def test_reference_suite_against_oracle(suite):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "refshim"), REFERENCE, ROOT])
+    env["FERS_SHIM_BACKEND"] = "oracle"
+    p = subprocess.run([sys.executable, "-m", "pytest", "-p", "no:cacheprovider", "-x", "-q", suite], cwd=REFERENCE,
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
