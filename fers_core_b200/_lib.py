@@ -18,6 +18,8 @@ SIGNATURES = {
     "fers_b200_last_error": (C.c_char_p, []),
     "fers_b200_device_info": (_i, [_i, _ip, _ip, _ip, C.POINTER(_sz)]),
     "fers_b200_set_device": (_i, [_i]),
+    "fers_b200_launch_count": (C.c_longlong, []),
+    "fers_b200_pcg_profile": (_i, [_dp]),
     "fers_b200_pattern_workspace": (_sz, [_i, _i, _i]),
     "fers_b200_pattern_build": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _ip, _vp, _sz, _vp]),
     "fers_b200_bc_workspace": (_sz, [_i]),

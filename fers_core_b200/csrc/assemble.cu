@@ -272,6 +272,7 @@ int fers_b200_assemble_beams(int n_members, const double* xyz, const int* m_n1, 
     if (general) k_assemble_beams<true><<<grid, ASM_THREADS, smem, as_stream(stream)>>>(A);
     else k_assemble_beams<false><<<grid, ASM_THREADS, smem, as_stream(stream)>>>(A);
     FERS_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 
@@ -281,6 +282,7 @@ int fers_b200_assemble_plates(int n_plates, const double* xyz, const int* p_node
     int grid = (n_plates + ASM_THREADS - 1) / ASM_THREADS;
     k_assemble_plates<<<grid, ASM_THREADS, 0, as_stream(stream)>>>(n_plates, xyz, p_nodes, p_data, p_flags, p_slot, vals);
     FERS_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 

@@ -1,8 +1,13 @@
 // capi.cu -- library-level entry points of libfers_b200 (include/fers_b200.h).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace fers {
 static thread_local std::string g_error;
+static std::atomic<long long> g_launches{0};
+void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches_total() { return g_launches.load(std::memory_order_relaxed); }
 void set_error(const std::string& msg) { g_error = msg; }
 int sm_count() {
     static int cached = 0;
@@ -31,6 +36,8 @@ int fers_b200_device_info(int device, int* sm_count, int* cc_major, int* cc_mino
     FERS_REQUIRE(p.major == 10, "libfers_b200 is built for sm_100a only; device is not compute capability 10.x");
     return 0;
 }
+
+long long fers_b200_launch_count(void) { return fers::launches_total(); }
 
 int fers_b200_set_device(int device) {
     FERS_CK(cudaSetDevice(device));

@@ -35,6 +35,7 @@ void set_error(const std::string& msg);
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 int sm_count();   // SMs of the current device (cached)
+void count_launches(long long n);   // bookkeeping for fers_b200_launch_count()
 
 constexpr unsigned FULL = 0xffffffffu;
 

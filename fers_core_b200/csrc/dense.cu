@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(NB* NB) k_subst_update(const double* __restric
 
 using namespace fers;
 
+static inline int rem_count(int n, int j0) { return (n - j0 - NB) > 0 ? 2 : 1; }
+
 extern "C" {
 
 int fers_b200_dense_expand(int n_nodes, const int* rowptr, const int* colidx, const double* vals,
@@ -177,6 +179,7 @@ int fers_b200_dense_expand(int n_nodes, const int* rowptr, const int* colidx, co
     int grid = (n_nodes * 32 + T - 1) / T;
     k_dense_expand<<<grid, T, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, a);
     FERS_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 
@@ -187,11 +190,13 @@ int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* in
     if (info_dev) FERS_CK(cudaMemsetAsync(info_dev, 0, sizeof(int) * batch, st));
     for (int j0 = 0; j0 < n; j0 += NB) {
         k_potrf_diag<<<dim3(1, 1, batch), NB * NB, 0, st>>>(a, n, j0, info_dev);
+        count_launches(1);
         const int rem = n - j0 - NB;
         if (rem > 0) {
             const int nt = (rem + NB - 1) / NB;
             k_trsm_panel<<<dim3(nt, 1, batch), NB * NB, 0, st>>>(a, n, j0);
             k_syrk_update<<<dim3(nt, nt, batch), NB * NB, 0, st>>>(a, n, j0);
+            count_launches(2);
         }
     }
     FERS_LAUNCH_CHECK();
@@ -208,12 +213,14 @@ int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* b
     const int nc = (nrhs + NB - 1) / NB;
     for (int j0 = 0; j0 < n; j0 += NB) {
         k_trsv_diag<<<dim3(nc, 1, batch), NB * NB, 0, st>>>(a, bx, n, nrhs, j0, 0);
+        count_launches(rem_count(n, j0));
         const int rem = n - j0 - NB;
         if (rem > 0) k_subst_update<<<dim3(nc, (rem + NB - 1) / NB, batch), NB * NB, 0, st>>>(a, bx, n, nrhs, j0, 0);
     }
     const int last = ((n - 1) / NB) * NB;
     for (int j0 = last; j0 >= 0; j0 -= NB) {
         k_trsv_diag<<<dim3(nc, 1, batch), NB * NB, 0, st>>>(a, bx, n, nrhs, j0, 1);
+        count_launches(j0 > 0 ? 2 : 1);
         if (j0 > 0) k_subst_update<<<dim3(nc, j0 / NB, batch), NB * NB, 0, st>>>(a, bx, n, nrhs, j0, 1);
     }
     FERS_LAUNCH_CHECK();

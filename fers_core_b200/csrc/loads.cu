@@ -154,11 +154,13 @@ int fers_b200_load_case(int n_nodes, int n_members, const double* xyz, const int
         int grid = (int)((total + T - 1) / T);
         k_load_records<<<grid, T, 0, st>>>(A);
         FERS_LAUNCH_CHECK();
+        count_launches(1);
     }
     if (n_members > 0 && (n_dl + n_pl) > 0) {
         int grid = (n_members + T - 1) / T;
         k_load_members<<<grid, T, 0, st>>>(A);
         FERS_LAUNCH_CHECK();
+        count_launches(1);
     }
     return 0;
 }
@@ -174,6 +176,7 @@ int fers_b200_combine(int n_rows, int n_cases, int nrhs, const double* in, const
     if (grid > cap) grid = cap;
     k_combine<<<grid, T, (size_t)nrhs * n_cases * 8, as_stream(stream)>>>(n_rows, n_cases, nrhs, in, factors, out);
     FERS_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 

@@ -166,6 +166,7 @@ int fers_b200_pattern_build(int n_nodes, int n_members, const int* m_n1, const i
     k_pattern_slots<<<grid, T, 0, st>>>(n_nodes, n_members, m_n1, m_n2, n_plates, p_nodes, rowptr, colidx, m_slot,
                                         p_slot, diag_slot);
     FERS_LAUNCH_CHECK();
+    count_launches(3 + 6);   // keys, rows, slots + cub sort/unique passes
     if (nnzb_out) *nnzb_out = nnzb;
     return 0;
 }
@@ -203,6 +204,7 @@ int fers_b200_bc_build(int n_nodes, const uint8_t* bc_code, const double* bc_k, 
     FERS_CK(cudaMemcpyAsync(&last_flag, flag + n_dof - 1, 4, cudaMemcpyDeviceToHost, st));
     FERS_CK(cudaMemcpyAsync(&dead, d_cnt, 4, cudaMemcpyDeviceToHost, st));
     FERS_CK(cudaStreamSynchronize(st));
+    count_launches(2 + 2);
     if (n_free_out) *n_free_out = last_scan + last_flag;
     if (n_dead_out) *n_dead_out = dead;
     return 0;

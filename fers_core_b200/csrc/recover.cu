@@ -332,6 +332,7 @@ int fers_b200_recover_members(int n_members, int nrhs, const double* xyz, const 
     int grid = (n_members + REC_WARPS - 1) / REC_WARPS;
     k_recover_members<<<grid, REC_THREADS, 0, as_stream(stream)>>>(A);
     FERS_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 
@@ -347,6 +348,7 @@ int fers_b200_recover_sections(int n_members, int nrhs, int n_cases, const doubl
     int grid = (n_members + REC_WARPS - 1) / REC_WARPS;
     k_recover_sections<<<grid, REC_THREADS, 0, as_stream(stream)>>>(A);
     FERS_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 
@@ -361,6 +363,7 @@ int fers_b200_reactions(int n_nodes, int nrhs, const int* rowptr, const int* col
     size_t cap = (size_t)sm_count() * 16;
     k_reaction_finish<<<(int)(g < cap ? g : cap), T, 0, as_stream(stream)>>>(total, nrhs, supported, f, r);
     FERS_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 
@@ -372,6 +375,7 @@ int fers_b200_recover_plates(int n_plates, int nrhs, const double* xyz, const in
     k_recover_plates<<<grid, REC_THREADS, 0, as_stream(stream)>>>(n_plates, nrhs, xyz, p_nodes, p_data, p_flags, u, p_res,
                                                                   p_nodal, p_cd);
     FERS_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 
@@ -383,6 +387,7 @@ int fers_b200_member_axial(int n_members, int nrhs, const double* f_local, doubl
     size_t cap = (size_t)sm_count() * 16;
     k_member_axial<<<(int)(g < cap ? g : cap), T, 0, as_stream(stream)>>>(total, nrhs, f_local, axial);
     FERS_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 

@@ -312,6 +312,36 @@ __global__ void k_reduce_partials(int n_blocks, int width, const double* __restr
     out[j] = a;
 }
 
+// Device-time profile of the last PCG solve (fers_b200_pcg_profile).
+constexpr int PROFILE_STRIDE = 16;
+constexpr int PROFILE_MAX = 64;
+struct Profile {
+    cudaEvent_t ev[6 * PROFILE_MAX];
+    bool have_events = false;
+    double spmm_ms = 0, update_ms = 0, direction_ms = 0, iter_ms = 0;
+    int samples = 0, iterations = 0;
+    int ensure_events() {
+        if (have_events) return 0;
+        for (int i = 0; i < 6 * PROFILE_MAX; ++i) FERS_CK(cudaEventCreate(&ev[i]));
+        have_events = true;
+        return 0;
+    }
+    // call after the stream has been synchronised
+    void collect(int n, int iters) {
+        double a = 0, b = 0, c = 0, d = 0;
+        for (int s = 0; s < n; ++s) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ev[6 * s + 0], ev[6 * s + 1]); a += t;
+            cudaEventElapsedTime(&t, ev[6 * s + 2], ev[6 * s + 3]); b += t;
+            cudaEventElapsedTime(&t, ev[6 * s + 4], ev[6 * s + 5]); c += t;
+            cudaEventElapsedTime(&t, ev[6 * s + 0], ev[6 * s + 5]); d += t;
+        }
+        samples = n; iterations = iters;
+        spmm_ms = n ? a / n : 0; update_ms = n ? b / n : 0; direction_ms = n ? c / n : 0; iter_ms = n ? d / n : 0;
+    }
+};
+static Profile g_profile;
+
 static int persistent_grid(int n_nodes, int nr) {
     const int groups_per_cta = SPMM_WARPS * (32 / (nr / 2));
     int need = (n_nodes + groups_per_cta - 1) / groups_per_cta;
@@ -362,6 +392,7 @@ static int run_pcg(int n_nodes, const int* rowptr, const int* colidx, const doub
     FERS_LAUNCH_CHECK();
     k_reduce_partials<<<(3 * NR + 127) / 128, 128, 0, st>>>(grid, 3 * NR, partial, s_init);
     FERS_LAUNCH_CHECK();
+    count_launches(2);
     int it = 0;
     bool converged = false;
     auto check = [&]() -> int {
@@ -378,21 +409,35 @@ static int run_pcg(int n_nodes, const int* rowptr, const int* colidx, const doub
         return 0;
     };
     if (check()) return 1;
+    Profile& prof = g_profile;
+    if (prof.ensure_events()) return 1;
+    int n_samples = 0;
     while (!converged && it < max_iter) {
         const int burst = (max_iter - it) < check_every ? (max_iter - it) : check_every;
         for (int q = 0; q < burst; ++q, ++it) {
             double* pair = s_pair[it & 1];
+            // every PROFILE_STRIDE-th iteration is bracketed by CUDA events on this stream
+            const bool sample = (it % PROFILE_STRIDE == PROFILE_STRIDE / 2) && n_samples < PROFILE_MAX;
+            cudaEvent_t* ev = sample ? prof.ev + 6 * n_samples : nullptr;
+            if (sample) cudaEventRecord(ev[0], st);
             k_spmm<NR, true><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, p, Ap, partial);
+            if (sample) cudaEventRecord(ev[1], st);
             k_reduce_partials<<<(NR + 127) / 128, 128, 0, st>>>(grid, NR, partial, s_pAp);
+            if (sample) cudaEventRecord(ev[2], st);
             k_pcg_update<NR><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, minv, rz_cur, s_pAp, p, Ap, x, r, partial);
+            if (sample) cudaEventRecord(ev[3], st);
             k_reduce_partials<<<(2 * NR + 127) / 128, 128, 0, st>>>(grid, 2 * NR, partial, pair);   // r.z, r.r
+            if (sample) cudaEventRecord(ev[4], st);
             k_pcg_direction<NR><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, minv, pair, rz_cur, r, p);
+            if (sample) { cudaEventRecord(ev[5], st); ++n_samples; }
             FERS_LAUNCH_CHECK();
             rz_cur = pair;
             rr_cur = pair + NR;
         }
+        count_launches(5LL * burst);
         if (check()) return 1;
     }
+    prof.collect(n_samples, it);
     *iters_out = it;
     return 0;
 }
@@ -422,10 +467,12 @@ int fers_b200_spmm(int n_nodes, int nrhs, const int* rowptr, const int* colidx, 
         if (grid > cap) grid = cap;
         k_spmv1<<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y);
         FERS_LAUNCH_CHECK();
+        count_launches(1);
         return 0;
     }
     int rc = 0;
     FERS_DISPATCH_NR(nrhs, rc = run_spmm<NR>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, nullptr, false, st));
+    count_launches(1);
     return rc;
 }
 
@@ -435,6 +482,14 @@ int fers_b200_block_jacobi(int n_nodes, const double* vals, const int* diag_slot
     const int T = 128;
     k_block_jacobi<<<(n_nodes + T - 1) / T, T, 0, as_stream(stream)>>>(n_nodes, vals, diag_slot, fixed, kspring, minv);
     FERS_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int fers_b200_pcg_profile(double* out6) {
+    const Profile& p = g_profile;
+    out6[0] = p.spmm_ms; out6[1] = p.update_ms; out6[2] = p.direction_ms;
+    out6[3] = p.samples; out6[4] = p.iterations; out6[5] = p.iter_ms;
     return 0;
 }
 

@@ -71,7 +71,9 @@ class Engine:
         self.assembly_variant = assembly_variant
         self.stats = SolveStats()
         self.timings: dict = {}
+        self.h2d_bytes = 0
         self._upload_static()
+        self._upload_load_cases()
         self._build_pattern()
 
     # ---- helpers ---------------------------------------------------------------------------
@@ -83,7 +85,8 @@ class Engine:
         """Host array -> device tensor (through pinned memory for large arrays)."""
         a = np.ascontiguousarray(a, dtype=dtype)
         t = torch.from_numpy(a)
-        if a.nbytes >= (1 << 20):
+        self.h2d_bytes += a.nbytes
+        if a.nbytes >= (1 << 20) and not t.is_pinned():
             t = t.pin_memory()
         return t.to(self.dev, non_blocking=True)
 
@@ -121,6 +124,15 @@ class Engine:
         self.d_p_data = self._t(m.p_data, np.float64) if m.n_plates else None
         self.d_p_flags = self._t(m.p_flags, np.int32) if m.n_plates else None
         self.d_xyz0 = self._t(m.xyz, np.float64)
+
+    def _upload_load_cases(self) -> None:
+        """Load records of every case, resident on the device (inputs of fers_b200_load_case)."""
+        self.d_lc = []
+        for lc in self.model.load_cases:
+            self.d_lc.append({k: (self._t(getattr(lc, k), dt) if len(getattr(lc, k)) else None)
+                              for k, dt in (("nod_node", np.int32), ("nod_vec", np.float64), ("dl_member", np.int32),
+                                            ("dl_data", np.float64), ("pl_member", np.int32), ("pl_data", np.float64),
+                                            ("pp_plate", np.int32), ("pp_vec", np.float64))})
 
     def _build_pattern(self) -> None:
         m, lib = self.model, self.lib
@@ -178,10 +190,7 @@ class Engine:
         f = self._zeros((max(nlc, 1), m.n_dof))
         peq = self._zeros((max(nlc, 1), max(m.n_members, 1) * 12))
         for li, lc in enumerate(m.load_cases):
-            t = {k: (self._t(getattr(lc, k), dt) if len(getattr(lc, k)) else None)
-                 for k, dt in (("nod_node", np.int32), ("nod_vec", np.float64), ("dl_member", np.int32),
-                               ("dl_data", np.float64), ("pl_member", np.int32), ("pl_data", np.float64),
-                               ("pp_plate", np.int32), ("pp_vec", np.float64))}
+            t = self.d_lc[li]
             _lib.check(lib.fers_b200_load_case(
                 m.n_nodes, m.n_members, _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_prop),
                 _lib.ptr(self.d_type), _lib.ptr(self.d_roll), _lib.ptr(d_scale), _lib.ptr(self.d_rel_idx),
@@ -287,6 +296,26 @@ class Engine:
                                                     _lib.ptr(pres), _lib.ptr(pnod), _lib.ptr(pcd), st), "recover_plates")
             out.update(p_res=pres, p_nodal=pnod, p_cd=pcd)
         return out
+
+    def run_linear(self, factors: np.ndarray, detail: bool = False, span=None) -> dict:
+        """One pass of the linear hot path for the right-hand sides ``factors`` [ncols<=64, Nlc]:
+        load vectors -> element stiffness + assembly + BC -> multi-RHS solve -> recovery.
+        Everything stays on the device; returns the result tensors (layout [.., nr])."""
+        nr = _pad_nr(factors.shape[0])
+        if factors.shape[0] > 64:
+            raise EngineError("run_linear handles at most 64 right-hand sides per pass")
+        f_case, peq_case = self.load_cases(self.d_xyz0)
+        self.assemble(self.d_xyz0)
+        d_f = self.combine(f_case, factors, nr)
+        d_peq = self.combine(peq_case, factors, nr)
+        d_u = self.solve(d_f)
+        facp = np.zeros((nr, factors.shape[1]))
+        facp[: factors.shape[0]] = factors
+        if detail and span is None:
+            span = self.span_tables()
+        rec = self.recover(self.d_xyz0, d_u, d_f, d_peq, facp, span, detail=detail)
+        rec["U"] = d_u
+        return rec
 
     def span_tables(self):
         """Span loads per load case as CSR over members: (sp_ptr [Nlc*(Nm+1)] int32, sp_rows [*,9])."""

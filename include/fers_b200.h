@@ -40,6 +40,8 @@ int fers_b200_device_info(int device, int* sm_count, int* cc_major, int* cc_mino
 /* Make `device` current for this library's CUDA runtime (one process per GPU: call once with
  * LOCAL_RANK before any other entry point). */
 int fers_b200_set_device(int device);
+/* Number of kernels this library has launched in this process (monotonic). */
+long long fers_b200_launch_count(void);
 
 /* ---- symbolic pattern (replaces the engine's DOF numbering / sparsity set-up; contract
  *      SURVEY.md 8a row A7, pydantic_models.py:2104-2115) ------------------------------------- */
@@ -109,6 +111,11 @@ int fers_b200_spmm(int n_nodes, int nrhs, const int* rowptr, const int* colidx, 
 int fers_b200_block_jacobi(int n_nodes, const double* vals, const int* diag_slot, const uint8_t* fixed,
                            const double* kspring, double* minv, void* stream);
 size_t fers_b200_pcg_workspace(int n_nodes, int nrhs);
+/* [host] Device-side timing of the last fers_b200_pcg_solve, from CUDA events recorded on its
+ * stream around a sample of the iterations: out[0..2] = mean ms of the SpMM, update and direction
+ * kernels, out[3] = sampled iterations, out[4] = total iterations, out[5] = mean ms of one whole
+ * iteration (all five launches). */
+int fers_b200_pcg_profile(double* out6);
 /* Batched preconditioned CG, one independent recurrence per right-hand side column.
  * b, x: [n_dof][nrhs]; x holds the initial guess when warm_start != 0, else it is zeroed.
  * Stops when every column has ||r|| <= tol * ||b|| or after max_iter iterations.

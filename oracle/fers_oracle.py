@@ -651,8 +651,9 @@ def recover_plates(asm: Assembly, U):
     return dict(p_res=res, p_nodal=nod, p_cdg=cdg, p_cdl=cdl, p_centroid=cen)
 
 
-def analyze(model: wire.ModelArrays, timings: dict | None = None) -> ResultArrays:
-    """Full analysis of one document: the oracle twin of fers_core_b200.engine.analyze."""
+def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool = True) -> ResultArrays:
+    """Full analysis of one document: the oracle twin of fers_core_b200.engine.analyze.
+    detail=False skips interior section forces / extrema (as the engine's detail=False)."""
     opts = model.options
     plan = rhs_plan(model)              # list of RhsGroup(imperfection case, rhs columns ...)
     nn, nm, nd = model.n_nodes, model.n_members, model.n_dof
@@ -678,7 +679,7 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None) -> ResultArray
             Kff, free, dead = constrain(K, model)
             Uf = solve_sym(Kff, F[:, free].T).T
             U = np.zeros((len(cols), nd)); U[:, free] = Uf
-            _store(out, asm, model, cols, U, F, peq, K, None, spans, fac, iters=None)
+            _store(out, asm, model, cols, U, F, peq, K, None, spans, fac, iters=None, detail=detail)
         else:
             for ci, col in enumerate(cols):
                 U1, K1, kg1, scale1, it, conv, resn = _solve_nonlinear(asm, model, F[ci], peq[ci], second_order)
@@ -686,7 +687,7 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None) -> ResultArray
                 if scale1 is not None:
                     asm_c = Assembly(model, xyz, scale1)
                 _store(out, asm_c, model, [col], U1[None], F[ci:ci + 1], peq[ci:ci + 1], K1,
-                       None if kg1 is None else kg1[None], spans, fac[ci:ci + 1], iters=(it, conv, resn))
+                       None if kg1 is None else kg1[None], spans, fac[ci:ci + 1], iters=(it, conv, resn), detail=detail)
     if timings is not None:
         timings["total_s"] = time.perf_counter() - t0
     return out
@@ -761,7 +762,7 @@ def _suppress_kg(asm, kg, suppressed):
     return np.einsum("mij,mjk,mlk->mil", asm.T, kgg, asm.T)
 
 
-def _store(out: ResultArrays, asm, model, cols, U, F, peq, K, kg, spans, fac, iters):
+def _store(out: ResultArrays, asm, model, cols, U, F, peq, K, kg, spans, fac, iters, detail=True):
     """Fill result arrays for the given rhs columns."""
     nn = model.n_nodes
     cols = np.asarray(cols)
@@ -773,7 +774,7 @@ def _store(out: ResultArrays, asm, model, cols, U, F, peq, K, kg, spans, fac, it
     out.R[cols] = Rn
     rec = recover_members(asm, U, peq, kg)
     out.f_local[cols] = rec["f_local"]; out.f_global[cols] = rec["f_global"]; out.u_local[cols] = rec["u_local"]
-    if model.n_members:
+    if model.n_members and detail:
         span_by_rhs = [[(fac[r, li], spans[li]) for li in range(fac.shape[1])] for r in range(len(cols))]
         sec = section_forces(asm, rec["f_local"], span_by_rhs)
         out.sec[cols] = sec
