@@ -49,6 +49,8 @@ def parse_args():
     p.add_argument("--assembly-variant", type=int, default=0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--profile-iters", type=int, default=0,
+                   help="cap PCG at this many iterations and accept the unconverged result (ncu captures only)")
     return p.parse_args()
 
 
@@ -182,6 +184,9 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     n_dof, n_comb = model.n_dof, factors.shape[0]
     units = n_dof * n_comb
 
+    if args.profile_iters > 0:
+        engine.PCG_MAX_ITER = args.profile_iters
+        engine.PCG_ALLOW_UNCONVERGED = True
     eng = engine.Engine(model, dev, args.assembly_variant)
 
     def barrier():

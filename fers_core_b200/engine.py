@@ -25,6 +25,7 @@ from .results import ResultArrays, SECTION_FRACS, results_to_wire
 DENSE_MAX_DOF = 8192          # models up to this many DOFs use the dense Cholesky path
 PCG_TOL = 1e-12               # relative residual ||r|| / ||b|| per right-hand side
 PCG_MAX_ITER = 200000
+PCG_ALLOW_UNCONVERGED = False  # profiling captures only (bench.py --profile-iters)
 NR_CHOICES = (8, 16, 32, 64)
 
 
@@ -252,7 +253,7 @@ class Engine:
         self.stats.method = "pcg"
         self.stats.iterations = iters.value
         self.stats.relres = max(relres)
-        if not (self.stats.relres <= PCG_TOL * 10):
+        if not (self.stats.relres <= PCG_TOL * 10) and not PCG_ALLOW_UNCONVERGED:
             raise EngineError(f"PCG did not converge: relative residual {self.stats.relres:.3e} after "
                               f"{iters.value} iterations")
         return u
