@@ -47,6 +47,7 @@ def parse_args():
     p.add_argument("--ny", type=int, default=30)
     p.add_argument("--combos", type=int, default=64)
     p.add_argument("--assembly-variant", type=int, default=0)
+    p.add_argument("--spmm-variant", type=int, default=-1, help="0 register/LDG, 1 TMA-staged (default: library default)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--profile-iters", type=int, default=0,
@@ -179,6 +180,8 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    if args.spmm_variant >= 0:
+        _lib.check(lib.fers_b200_set_spmm_variant(args.spmm_variant), "set_spmm_variant")
     model = pin_model(build_model(args, rank))
     factors = model.combo_factors
     n_dof, n_comb = model.n_dof, factors.shape[0]

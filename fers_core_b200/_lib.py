@@ -31,6 +31,7 @@ SIGNATURES = {
     "fers_b200_load_case": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_combine": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "fers_b200_set_spmm_variant": (_i, [_i]),
     "fers_b200_spmm": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_block_jacobi": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_pcg_workspace": (_sz, [_i, _i]),

@@ -10,6 +10,8 @@
 // bytes), six x rows of the neighbour node are read once per block, 72 DFMA per lane follow.
 // HBM-bound by design: 0.23 GB of matrix + 2 * n_dof * NR * 8 bytes of vectors per product
 // (DESIGN.md "SpMM").  Reductions are deterministic: per-CTA partials + ordered final sum.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fers {
@@ -57,12 +59,12 @@ k_spmm(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ coli
     constexpr int CP = NR / 2, G = 32 / CP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / CP, cp = lane % CP;
-    const int per_cta = (n_nodes + gridDim.x - 1) / gridDim.x;
-    const int row0 = blockIdx.x * per_cta;
-    const int row1 = min(n_nodes, row0 + per_cta);
     double2 dot[1];
     dot[0] = make_double2(0.0, 0.0);
-    for (int row = row0 + warp * G + g; row < row1; row += SPMM_WARPS * G) {
+    // interleaved row groups: at any instant all CTAs work inside one narrow window of consecutive
+    // rows, so the x rows of neighbouring nodes are shared through L2 (ncu r1: chunked mapping gave
+    // 8 % L2 hit rate and 2.4x the algorithmic DRAM traffic)
+    for (int row = (blockIdx.x * SPMM_WARPS + warp) * G + g; row < n_nodes; row += gridDim.x * SPMM_WARPS * G) {
         double2 acc[6];
 #pragma unroll
         for (int r = 0; r < 6; ++r) acc[r] = make_double2(0.0, 0.0);
@@ -102,6 +104,133 @@ k_spmm(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ coli
         }
     }
     if (DOT) cta_reduce_store<NR, 1>(dot, partial);
+}
+
+// ---- TMA-staged variant for NR = 64 ------------------------------------------------------------
+// Each warp owns a ring of STAGES shared-memory slots; one slot holds one 6x6 matrix block (288 B)
+// and the six x rows of its column node (6*64*8 = 3072 contiguous bytes).  Lane 0 issues two bulk
+// copies (cp.async.bulk, completion on an mbarrier) per block, STAGES blocks ahead of the FMA loop,
+// so the DFMA pipe never waits on an L2/HBM round trip; the FMA loop reads 16 B per lane per x row
+// (conflict-free) and the matrix block as shared-memory broadcasts.
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_KB = 36 * 8;
+constexpr int TMA_XB = 6 * 64 * 8;
+constexpr int TMA_SLOT = TMA_KB + TMA_XB;
+constexpr size_t TMA_SMEM = (size_t)SPMM_WARPS * TMA_STAGES * TMA_SLOT + (size_t)SPMM_WARPS * TMA_STAGES * 8;
+
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool DOT>
+__global__ void __launch_bounds__(SPMM_THREADS, 2)
+k_spmm64_tma(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
+             const uint8_t* __restrict__ fixed, const double* __restrict__ kspring, const double* __restrict__ x,
+             double* __restrict__ y, double* __restrict__ partial) {
+    constexpr int NR = 64;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* ring = smem_dyn + (size_t)warp * TMA_STAGES * TMA_SLOT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + (size_t)SPMM_WARPS * TMA_STAGES * TMA_SLOT) + warp * TMA_STAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_addr(&bars[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int first = blockIdx.x * SPMM_WARPS + warp, stride = gridDim.x * SPMM_WARPS;
+    // producer cursor (meaningful on lane 0 only)
+    int prow = first, pk = 0, pke = 0;
+    if (prow < n_nodes) { pk = rowptr[prow]; pke = rowptr[prow + 1]; }
+    auto issue = [&](int stage) {
+        if (prow >= n_nodes) return;
+        const int col = __ldg(colidx + pk);
+        const uint32_t bar = s_addr(&bars[stage]);
+        const uint32_t dk = s_addr(ring + (size_t)stage * TMA_SLOT), dx = dk + TMA_KB;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TMA_SLOT) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dk),
+                     "l"(vals + (size_t)pk * 36), "r"((uint32_t)TMA_KB), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dx),
+                     "l"(x + (size_t)col * 6 * NR), "r"((uint32_t)TMA_XB), "r"(bar)
+                     : "memory");
+        if (++pk == pke) {
+            prow += stride;
+            if (prow < n_nodes) { pk = rowptr[prow]; pke = rowptr[prow + 1]; }
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; ++s) issue(s);
+    }
+    double2 dot[1];
+    dot[0] = make_double2(0.0, 0.0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int row = first; row < n_nodes; row += stride) {
+        double2 acc[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[r] = make_double2(0.0, 0.0);
+        const int kb = rowptr[row], ke = rowptr[row + 1];
+        for (int k = kb; k < ke; ++k) {
+            {   // wait for this slot's bytes
+                const uint32_t bar = s_addr(&bars[stage]);
+                uint32_t done = 0;
+                while (!done) {
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                        "selp.u32 %0, 1, 0, p;\n\t}"
+                        : "=r"(done)
+                        : "r"(bar), "r"(phase)
+                        : "memory");
+                }
+            }
+            const double* sk = reinterpret_cast<const double*>(ring + (size_t)stage * TMA_SLOT);
+            const double* sx = sk + 36;
+            double2 xv[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) xv[c] = *reinterpret_cast<const double2*>(sx + c * NR + 2 * lane);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                for (int c = 0; c < 6; c += 2) {
+                    const double2 kk = *reinterpret_cast<const double2*>(sk + r * 6 + c);
+                    fma2(acc[r], kk.x, xv[c]);
+                    fma2(acc[r], kk.y, xv[c + 1]);
+                }
+            }
+            __syncwarp();                       // every lane has consumed the slot
+            if (lane == 0) issue(stage);        // refill it with the block TMA_STAGES ahead
+            if (++stage == TMA_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        const size_t d0 = (size_t)row * 6;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const size_t d = d0 + r;
+            double2 xo = make_double2(0.0, 0.0);
+            if (kspring != nullptr || DOT) xo = ldg2(x + d * NR + 2 * lane);
+            if (fixed != nullptr && fixed[d]) {
+                acc[r] = make_double2(0.0, 0.0);
+            } else if (kspring != nullptr) {
+                const double ks = kspring[d];
+                acc[r].x = fma(ks, xo.x, acc[r].x);
+                acc[r].y = fma(ks, xo.y, acc[r].y);
+            }
+            reinterpret_cast<double2*>(y + d * NR)[lane] = acc[r];
+            if (DOT) { dot[0].x = fma(xo.x, acc[r].x, dot[0].x); dot[0].y = fma(xo.y, acc[r].y, dot[0].y); }
+        }
+    }
+    if (DOT) cta_reduce_store<NR, 1>(dot, partial);
+}
+
+// 0 = register/LDG variant, 1 = TMA-staged variant (NR = 64 only); FERS_SPMM_VARIANT overrides
+static int g_spmm_variant = -1;
+static int spmm_variant() {
+    if (g_spmm_variant < 0) {
+        const char* e = getenv("FERS_SPMM_VARIANT");
+        g_spmm_variant = e ? atoi(e) : 0;
+    }
+    return g_spmm_variant;
 }
 
 // single right-hand side: one warp per block row, lanes stride over the row's 36*nb values
@@ -349,15 +478,50 @@ static int persistent_grid(int n_nodes, int nr) {
     return need < cap ? (need > 0 ? need : 1) : cap;
 }
 
+// Launch y = K x with fused x.y partials (PCG); returns the grid size used (= rows of `partial`).
+template <int NR>
+static int launch_spmm_dot(int n_nodes, const int* rowptr, const int* colidx, const double* vals, const uint8_t* fixed,
+                           const double* kspring, const double* x, double* y, double* partial, cudaStream_t st) {
+    if (NR == 64 && spmm_variant() == 1) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(k_spmm64_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
+            cudaFuncSetAttribute(k_spmm64_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
+            attr = true;
+        }
+        int grid = sm_count() * 2;
+        const int need = (n_nodes + SPMM_WARPS - 1) / SPMM_WARPS;
+        if (grid > need) grid = need;
+        k_spmm64_tma<true><<<grid, SPMM_THREADS, TMA_SMEM, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
+        return grid;
+    }
+    const int grid = persistent_grid(n_nodes, NR);
+    k_spmm<NR, true><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
+    return grid;
+}
+
 template <int NR>
 static int run_spmm(int n_nodes, const int* rowptr, const int* colidx, const double* vals, const uint8_t* fixed,
                     const double* kspring, const double* x, double* y, double* partial, bool dot, cudaStream_t st) {
-    // plain products use one node group per warp slot (fine-grained grid), PCG uses the persistent grid
-    const int groups_per_cta = SPMM_WARPS * (32 / (NR / 2));
-    int grid = dot ? persistent_grid(n_nodes, NR) : (n_nodes + groups_per_cta - 1) / groups_per_cta;
-    if (grid < 1) grid = 1;
-    if (dot) k_spmm<NR, true><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
-    else k_spmm<NR, false><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
+    if (dot) {
+        launch_spmm_dot<NR>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial, st);
+    } else if (NR == 64 && spmm_variant() == 1) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(k_spmm64_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
+            attr = true;
+        }
+        int grid = sm_count() * 2;
+        const int need = (n_nodes + SPMM_WARPS - 1) / SPMM_WARPS;
+        if (grid > need) grid = need;
+        k_spmm64_tma<false><<<grid, SPMM_THREADS, TMA_SMEM, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
+    } else {
+        // plain products: one node group per warp slot (fine-grained grid)
+        const int groups_per_cta = SPMM_WARPS * (32 / (NR / 2));
+        int grid = (n_nodes + groups_per_cta - 1) / groups_per_cta;
+        if (grid < 1) grid = 1;
+        k_spmm<NR, false><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
+    }
     FERS_LAUNCH_CHECK();
     return 0;
 }
@@ -420,9 +584,9 @@ static int run_pcg(int n_nodes, const int* rowptr, const int* colidx, const doub
             const bool sample = (it % PROFILE_STRIDE == PROFILE_STRIDE / 2) && n_samples < PROFILE_MAX;
             cudaEvent_t* ev = sample ? prof.ev + 6 * n_samples : nullptr;
             if (sample) cudaEventRecord(ev[0], st);
-            k_spmm<NR, true><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, p, Ap, partial);
+            const int sgrid = launch_spmm_dot<NR>(n_nodes, rowptr, colidx, vals, fixed, kspring, p, Ap, partial, st);
             if (sample) cudaEventRecord(ev[1], st);
-            k_reduce_partials<<<(NR + 127) / 128, 128, 0, st>>>(grid, NR, partial, s_pAp);
+            k_reduce_partials<<<(NR + 127) / 128, 128, 0, st>>>(sgrid, NR, partial, s_pAp);
             if (sample) cudaEventRecord(ev[2], st);
             k_pcg_update<NR><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, minv, rz_cur, s_pAp, p, Ap, x, r, partial);
             if (sample) cudaEventRecord(ev[3], st);
@@ -483,6 +647,12 @@ int fers_b200_block_jacobi(int n_nodes, const double* vals, const int* diag_slot
     k_block_jacobi<<<(n_nodes + T - 1) / T, T, 0, as_stream(stream)>>>(n_nodes, vals, diag_slot, fixed, kspring, minv);
     FERS_LAUNCH_CHECK();
     count_launches(1);
+    return 0;
+}
+
+int fers_b200_set_spmm_variant(int variant) {
+    FERS_REQUIRE(variant == 0 || variant == 1, "set_spmm_variant: 0 (register/LDG) or 1 (TMA-staged, nrhs = 64)");
+    g_spmm_variant = variant;
     return 0;
 }
 

@@ -77,12 +77,13 @@ def test_assembled_values_match_oracle(engine_mod, variant):
     assert np.abs(K - want).max() <= 1e-13 * np.abs(want).max()
 
 
-@pytest.mark.parametrize("nrhs", [1, 8, 16, 32, 64])
-def test_spmm_matches_scipy(engine_mod, nrhs):
+@pytest.mark.parametrize("nrhs,variant", [(1, 0), (8, 0), (16, 0), (32, 0), (64, 0), (64, 1)])
+def test_spmm_matches_scipy(engine_mod, nrhs, variant):
     import torch
     from fers_core_b200 import _lib
     model = synth.grid_frame(6, 5, 4)
     eng = engine_mod.Engine(model)
+    _lib.check(eng.lib.fers_b200_set_spmm_variant(variant), "set_spmm_variant")
     eng.assemble(eng.d_xyz0)
     K = _bsr_to_scipy(eng, model.n_nodes).tocsr()
     rng = np.random.default_rng(3)
@@ -100,18 +101,23 @@ def test_spmm_matches_scipy(engine_mod, nrhs):
             want[fixed] = 0.0
         got = d_y.cpu().numpy()
         assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+    eng.lib.fers_b200_set_spmm_variant(0)
 
 
-@pytest.mark.parametrize("dims,force_pcg", [((4, 4, 4), False), ((4, 4, 4), True), ((9, 8, 6), False),
-                                            ((12, 12, 10), True)])
-def test_synthetic_frame_matches_oracle(engine_mod, monkeypatch, dims, force_pcg):
-    """configs[3]-shaped frames at oracle-sized scale, dense and PCG solve paths."""
+@pytest.mark.parametrize("dims,force_pcg,variant", [((4, 4, 4), False, 0), ((4, 4, 4), True, 0), ((9, 8, 6), False, 0),
+                                                    ((12, 12, 10), True, 0), ((12, 12, 10), True, 1)])
+def test_synthetic_frame_matches_oracle(engine_mod, monkeypatch, dims, force_pcg, variant):
+    """configs[3]-shaped frames at oracle-sized scale, dense and PCG solve paths (both SpMM kernels)."""
+    from fers_core_b200 import _lib
     if force_pcg:
         monkeypatch.setattr(engine_mod, "DENSE_MAX_DOF", 0)
-    model = synth.grid_frame(*dims, n_combos=11, timoshenko=(dims[0] == 9), solve_loadcases=True)
+    _lib.load().fers_b200_set_spmm_variant(variant)
+    n_combos = 60 if variant == 1 else 11      # 8 cases + 60 combinations -> one 64-wide and one 8-wide pass
+    model = synth.grid_frame(*dims, n_combos=n_combos, timoshenko=(dims[0] == 9), solve_loadcases=True)
     want = fers_oracle.analyze(model)
     stats = {}
     got = engine_mod.analyze(model, stats_out=stats)
+    _lib.load().fers_b200_set_spmm_variant(0)
     assert stats["method"] == ("pcg" if force_pcg else "dense")
     helpers.assert_results_close(got, want, RTOL, label=str(dims))
 
