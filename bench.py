@@ -234,7 +234,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     d_f = eng.combine(f_case, factors, nr)
     ku = torch.empty_like(rec["U"])
     _lib.check(lib.fers_b200_spmm(model.n_nodes, nr, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals),
-                                  _lib.ptr(eng.d_fixed), _lib.ptr(eng.d_kspring), _lib.ptr(rec["U"]), _lib.ptr(ku),
+                                  _lib.ptr(eng.d_fixed), _lib.ptr(eng.d_ks), _lib.ptr(rec["U"]), _lib.ptr(ku),
                                   eng.stream), "spmm")
     free = (eng.d_fixed == 0).to(torch.float64)[:, None]
     resid = float((torch.linalg.norm((ku - d_f) * free, dim=0) / torch.linalg.norm(d_f * free, dim=0))[:n_comb].max())

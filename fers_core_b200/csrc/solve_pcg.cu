@@ -115,11 +115,15 @@ k_spmm(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ coli
 constexpr int TMA_STAGES = 3;
 constexpr int TMA_KB = 36 * 8;
 constexpr int TMA_XB = 6 * 64 * 8;
-constexpr int TMA_SLOT = TMA_KB + TMA_XB;
+constexpr int TMA_SLOT = TMA_KB + TMA_XB + 16;       // + 16-byte header holding the block's column node
 constexpr size_t TMA_SMEM = (size_t)SPMM_WARPS * TMA_STAGES * TMA_SLOT + (size_t)SPMM_WARPS * TMA_STAGES * 8;
 
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// No global load sits on the critical path of the FMA loop: row pointers and the BC mask of the NEXT
+// row are fetched while the current row is processed, the producer lane keeps the next column index
+// prefetched, and the row's own x (needed for the fused p.Ap and the support springs) is taken from
+// the shared-memory slot of its diagonal block.
 template <bool DOT>
 __global__ void __launch_bounds__(SPMM_THREADS, 2)
 k_spmm64_tma(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
@@ -138,39 +142,63 @@ k_spmm64_tma(int n_nodes, const int* __restrict__ rowptr, const int* __restrict_
     }
     __syncwarp();
     const int first = blockIdx.x * SPMM_WARPS + warp, stride = gridDim.x * SPMM_WARPS;
-    // producer cursor (meaningful on lane 0 only)
-    int prow = first, pk = 0, pke = 0;
-    if (prow < n_nodes) { pk = rowptr[prow]; pke = rowptr[prow + 1]; }
+
+    // ---- producer cursor (lane 0): block pk of row prow, its column prefetched in pcol; the
+    //      pointers of the following row prefetched in (nkb, nke)
+    int prow = first, pk = 0, pke = 0, pcol = 0, nkb = 0, nke = 0;
+    if (lane == 0 && prow < n_nodes) {
+        pk = rowptr[prow]; pke = rowptr[prow + 1];
+        pcol = __ldg(colidx + pk);
+        if (prow + stride < n_nodes) { nkb = rowptr[prow + stride]; nke = rowptr[prow + stride + 1]; }
+    }
     auto issue = [&](int stage) {
         if (prow >= n_nodes) return;
-        const int col = __ldg(colidx + pk);
         const uint32_t bar = s_addr(&bars[stage]);
         const uint32_t dk = s_addr(ring + (size_t)stage * TMA_SLOT), dx = dk + TMA_KB;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TMA_SLOT) : "memory");
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(dk + TMA_KB + TMA_XB), "r"(pcol) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(TMA_KB + TMA_XB))
+                     : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dk),
                      "l"(vals + (size_t)pk * 36), "r"((uint32_t)TMA_KB), "r"(bar)
                      : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dx),
-                     "l"(x + (size_t)col * 6 * NR), "r"((uint32_t)TMA_XB), "r"(bar)
+                     "l"(x + (size_t)pcol * 6 * NR), "r"((uint32_t)TMA_XB), "r"(bar)
                      : "memory");
         if (++pk == pke) {
             prow += stride;
-            if (prow < n_nodes) { pk = rowptr[prow]; pke = rowptr[prow + 1]; }
+            pk = nkb; pke = nke;
+            if (prow + stride < n_nodes) { nkb = rowptr[prow + stride]; nke = rowptr[prow + stride + 1]; }
         }
+        if (prow < n_nodes) pcol = __ldg(colidx + pk);      // consumed at the next issue
     };
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < TMA_STAGES; ++s) issue(s);
     }
+
+    // ---- consumer: current row state + prefetched next row state (uniform across the warp)
+    auto load_mask = [&](int r) -> uint32_t {
+        if (fixed == nullptr) return 0u;
+        uint32_t m = 0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) m |= (uint32_t)(fixed[(size_t)r * 6 + q] != 0) << q;
+        return m;
+    };
+    int row = first, kb = 0, ke = 0;
+    uint32_t fx = 0;
+    if (row < n_nodes) { kb = rowptr[row]; ke = rowptr[row + 1]; fx = load_mask(row); }
     double2 dot[1];
     dot[0] = make_double2(0.0, 0.0);
     int stage = 0;
     uint32_t phase = 0;
-    for (int row = first; row < n_nodes; row += stride) {
-        double2 acc[6];
+    while (row < n_nodes) {
+        const int next = row + stride;
+        int nkb2 = 0, nke2 = 0;
+        uint32_t nfx = 0;
+        if (next < n_nodes) { nkb2 = rowptr[next]; nke2 = rowptr[next + 1]; nfx = load_mask(next); }
+        double2 acc[6], xo[6];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) acc[r] = make_double2(0.0, 0.0);
-        const int kb = rowptr[row], ke = rowptr[row + 1];
+        for (int r = 0; r < 6; ++r) { acc[r] = make_double2(0.0, 0.0); xo[r] = make_double2(0.0, 0.0); }
         for (int k = kb; k < ke; ++k) {
             {   // wait for this slot's bytes
                 const uint32_t bar = s_addr(&bars[stage]);
@@ -187,9 +215,14 @@ k_spmm64_tma(int n_nodes, const int* __restrict__ rowptr, const int* __restrict_
             }
             const double* sk = reinterpret_cast<const double*>(ring + (size_t)stage * TMA_SLOT);
             const double* sx = sk + 36;
+            const int col = *reinterpret_cast<const int*>(ring + (size_t)stage * TMA_SLOT + TMA_KB + TMA_XB);
             double2 xv[6];
 #pragma unroll
             for (int c = 0; c < 6; ++c) xv[c] = *reinterpret_cast<const double2*>(sx + c * NR + 2 * lane);
+            if (col == row) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) xo[c] = xv[c];
+            }
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
 #pragma unroll
@@ -207,18 +240,17 @@ k_spmm64_tma(int n_nodes, const int* __restrict__ rowptr, const int* __restrict_
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
             const size_t d = d0 + r;
-            double2 xo = make_double2(0.0, 0.0);
-            if (kspring != nullptr || DOT) xo = ldg2(x + d * NR + 2 * lane);
-            if (fixed != nullptr && fixed[d]) {
+            if (fx & (1u << r)) {
                 acc[r] = make_double2(0.0, 0.0);
             } else if (kspring != nullptr) {
                 const double ks = kspring[d];
-                acc[r].x = fma(ks, xo.x, acc[r].x);
-                acc[r].y = fma(ks, xo.y, acc[r].y);
+                acc[r].x = fma(ks, xo[r].x, acc[r].x);
+                acc[r].y = fma(ks, xo[r].y, acc[r].y);
             }
             reinterpret_cast<double2*>(y + d * NR)[lane] = acc[r];
-            if (DOT) { dot[0].x = fma(xo.x, acc[r].x, dot[0].x); dot[0].y = fma(xo.y, acc[r].y, dot[0].y); }
+            if (DOT) { dot[0].x = fma(xo[r].x, acc[r].x, dot[0].x); dot[0].y = fma(xo[r].y, acc[r].y, dot[0].y); }
         }
+        row = next; kb = nkb2; ke = nke2; fx = nfx;
     }
     if (DOT) cta_reduce_store<NR, 1>(dot, partial);
 }

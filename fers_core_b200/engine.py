@@ -79,6 +79,12 @@ class Engine:
 
     # ---- helpers ---------------------------------------------------------------------------
     @property
+    def d_ks(self):
+        """Support-spring diagonal for the solve kernels, or None when the model has no springs
+        (saves one dependent load per DOF row in the SpMM epilogue)."""
+        return self.d_kspring if self.has_springs else None
+
+    @property
     def stream(self) -> int:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
@@ -118,6 +124,7 @@ class Engine:
         if unilateral.any():
             m.warnings.append(("W_UNILATERAL_SUPPORT", "Positive/Negative-only supports treated as fixed"))
         code = np.where(unilateral, wire.BC_FIXED, m.bc_code).astype(np.uint8)
+        self.has_springs = bool((code == wire.BC_SPRING).any())
         self.d_bc_code = self._t(code.reshape(-1), np.uint8)
         self.d_bc_k = self._t(m.bc_k.reshape(-1), np.float64)
         self.d_supported = self._t((m.node_support_id >= 0).astype(np.uint8), np.uint8)
@@ -221,7 +228,7 @@ class Engine:
         if nd <= DENSE_MAX_DOF:
             a = self._empty((nd, nd))
             _lib.check(lib.fers_b200_dense_expand(m.n_nodes, _lib.ptr(self.d_rowptr), _lib.ptr(self.d_colidx),
-                                                  _lib.ptr(self.d_vals), _lib.ptr(self.d_fixed), _lib.ptr(self.d_kspring),
+                                                  _lib.ptr(self.d_vals), _lib.ptr(self.d_fixed), _lib.ptr(self.d_ks),
                                                   _lib.ptr(a), st), "dense_expand")
             info_dev = self._zeros(1, torch.int32)
             info = C.c_int()
@@ -239,7 +246,7 @@ class Engine:
             raise EngineError(f"PCG path needs nrhs in {NR_CHOICES}, got {nr}")
         minv = self._empty(m.n_nodes * 36)
         _lib.check(lib.fers_b200_block_jacobi(m.n_nodes, _lib.ptr(self.d_vals), _lib.ptr(self.d_diag_slot),
-                                              _lib.ptr(self.d_fixed), _lib.ptr(self.d_kspring), _lib.ptr(minv), st),
+                                              _lib.ptr(self.d_fixed), _lib.ptr(self.d_ks), _lib.ptr(minv), st),
                    "block_jacobi")
         ws_bytes = lib.fers_b200_pcg_workspace(m.n_nodes, nr)
         ws = self._empty(ws_bytes, torch.uint8)
@@ -248,7 +255,7 @@ class Engine:
         relres = (C.c_double * nr)()
         _lib.check(lib.fers_b200_pcg_solve(
             m.n_nodes, nr, _lib.ptr(self.d_rowptr), _lib.ptr(self.d_colidx), _lib.ptr(self.d_vals), _lib.ptr(self.d_fixed),
-            _lib.ptr(self.d_kspring), _lib.ptr(minv), _lib.ptr(d_f), _lib.ptr(u), 1 if x0 is not None else 0,
+            _lib.ptr(self.d_ks), _lib.ptr(minv), _lib.ptr(d_f), _lib.ptr(u), 1 if x0 is not None else 0,
             PCG_TOL, PCG_MAX_ITER, 50, C.byref(iters), relres, _lib.ptr(ws), ws_bytes, st), "pcg_solve")
         self.stats.method = "pcg"
         self.stats.iterations = iters.value
