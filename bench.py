@@ -174,6 +174,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     import torch
     import torch.distributed as dist
     from fers_core_b200 import _lib, engine
+    from fers_core_b200 import dist as fdist
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -213,10 +214,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     barrier()
     launches = lib.fers_b200_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_step = float(ms_total.item()) / args.steps
+    ms_step = fdist.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     value = world * units / (ms_step / 1e3)
     prof = (C.c_double * 6)()
     lib.fers_b200_pcg_profile(prof)
@@ -224,9 +222,8 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
 
     # summary gather over NVLink: per-combination max |u| from every rank
     summ = rec["U"].abs().amax(dim=0)[:n_comb].contiguous()
-    if world > 1:
-        gathered = [torch.empty_like(summ) for _ in range(world)]
-        dist.all_gather(gathered, summ)
+    all_summ = fdist.gather_summary(summ)            # [world * n_comb] over NCCL / NVLink
+    assert all_summ.shape[0] == world * n_comb
 
     # true residual of the last step (free DOFs), on the device through the C ABI
     nr = rec["U"].shape[1]
@@ -301,12 +298,10 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             t_e2e.append(time.perf_counter() - t0)
             h2d = eng.h2d_bytes
             del out
-        te = torch.tensor([min(t_e2e)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * units / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        te = fdist.max_over_ranks(min(t_e2e), dev)
+        e2e = {"value": world * units / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(h_u.numel() * 8 + h_r.numel() * 8 + h_f.numel() * 8),
-               "ms_per_step": 1e3 * float(te.item()),
+               "ms_per_step": 1e3 * te,
                "api": "fers_core_b200.engine.Engine(model_arrays).run_linear(factors) + D2H of U, R, f_local"}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------

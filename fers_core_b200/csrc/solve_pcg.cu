@@ -255,12 +255,12 @@ k_spmm64_tma(int n_nodes, const int* __restrict__ rowptr, const int* __restrict_
     if (DOT) cta_reduce_store<NR, 1>(dot, partial);
 }
 
-// 0 = register/LDG variant, 1 = TMA-staged variant (NR = 64 only); FERS_SPMM_VARIANT overrides
+// 0 = register/LDG variant, 1 = TMA-staged variant (NR = 64 only, default); FERS_SPMM_VARIANT overrides
 static int g_spmm_variant = -1;
 static int spmm_variant() {
     if (g_spmm_variant < 0) {
         const char* e = getenv("FERS_SPMM_VARIANT");
-        g_spmm_variant = e ? atoi(e) : 0;
+        g_spmm_variant = e ? atoi(e) : 1;   // TMA-staged kernel is the default for nrhs = 64 (profiles/r1_*)
     }
     return g_spmm_variant;
 }
@@ -464,13 +464,31 @@ k_pcg_direction(int n_nodes, const double* __restrict__ minv, const double* __re
     }
 }
 
-// out[j] = sum_b partial[b][j], fixed order (deterministic)
-__global__ void k_reduce_partials(int n_blocks, int width, const double* __restrict__ partial, double* __restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= width) return;
+// out[j] = sum_b partial[b][j] in a fixed order (deterministic).  One CTA of 32 x RED_GROUPS threads
+// per 32 outputs: thread (j, g) sums blocks g, g+RED_GROUPS, ... (independent, coalesced loads), the
+// groups are then combined through shared memory in index order.
+constexpr int RED_GROUPS = 16;
+__global__ void __launch_bounds__(32 * RED_GROUPS)
+k_reduce_partials(int n_blocks, int width, const double* __restrict__ partial, double* __restrict__ out) {
+    __shared__ double s[RED_GROUPS][33];
+    const int tj = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tj;
     double a = 0.0;
-    for (int b = 0; b < n_blocks; ++b) a += partial[(size_t)b * width + j];
-    out[j] = a;
+    if (j < width) {
+#pragma unroll 4
+        for (int b = g; b < n_blocks; b += RED_GROUPS) a += partial[(size_t)b * width + j];
+    }
+    s[g][tj] = a;
+    __syncthreads();
+    if (g == 0 && j < width) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < RED_GROUPS; ++q) t += s[q][tj];
+        out[j] = t;
+    }
+}
+static inline void launch_reduce(int n_blocks, int width, const double* partial, double* out, cudaStream_t st) {
+    k_reduce_partials<<<(width + 31) / 32, 32 * RED_GROUPS, 0, st>>>(n_blocks, width, partial, out);
 }
 
 // Device-time profile of the last PCG solve (fers_b200_pcg_profile).
@@ -586,7 +604,7 @@ static int run_pcg(int n_nodes, const int* rowptr, const int* colidx, const doub
     }
     k_pcg_init<NR><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, fixed, minv, b, ax, r, p, partial);
     FERS_LAUNCH_CHECK();
-    k_reduce_partials<<<(3 * NR + 127) / 128, 128, 0, st>>>(grid, 3 * NR, partial, s_init);
+    launch_reduce(grid, 3 * NR, partial, s_init, st);
     FERS_LAUNCH_CHECK();
     count_launches(2);
     int it = 0;
@@ -618,11 +636,11 @@ static int run_pcg(int n_nodes, const int* rowptr, const int* colidx, const doub
             if (sample) cudaEventRecord(ev[0], st);
             const int sgrid = launch_spmm_dot<NR>(n_nodes, rowptr, colidx, vals, fixed, kspring, p, Ap, partial, st);
             if (sample) cudaEventRecord(ev[1], st);
-            k_reduce_partials<<<(NR + 127) / 128, 128, 0, st>>>(sgrid, NR, partial, s_pAp);
+            launch_reduce(sgrid, NR, partial, s_pAp, st);
             if (sample) cudaEventRecord(ev[2], st);
             k_pcg_update<NR><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, minv, rz_cur, s_pAp, p, Ap, x, r, partial);
             if (sample) cudaEventRecord(ev[3], st);
-            k_reduce_partials<<<(2 * NR + 127) / 128, 128, 0, st>>>(grid, 2 * NR, partial, pair);   // r.z, r.r
+            launch_reduce(grid, 2 * NR, partial, pair, st);   // r.z, r.r
             if (sample) cudaEventRecord(ev[4], st);
             k_pcg_direction<NR><<<grid, SPMM_THREADS, 0, st>>>(n_nodes, minv, pair, rz_cur, r, p);
             if (sample) { cudaEventRecord(ev[5], st); ++n_samples; }

@@ -105,7 +105,7 @@ int fers_b200_combine(int n_rows, int n_cases, int nrhs, const double* in, const
  * {1,8,16,32,64}.  fixed == NULL: plain product with the unconstrained matrix (used for
  * reactions R = K u - F). */
 /* SpMM kernel variant: 0 = register/LDG kernel (all nrhs), 1 = TMA-staged shared-memory pipeline
- * (nrhs = 64 only; other nrhs fall back to 0).  Default from env FERS_SPMM_VARIANT, else 0. */
+ * (nrhs = 64 only; other nrhs fall back to 0).  Default from env FERS_SPMM_VARIANT, else 1. */
 int fers_b200_set_spmm_variant(int variant);
 int fers_b200_spmm(int n_nodes, int nrhs, const int* rowptr, const int* colidx, const double* vals,
                    const uint8_t* fixed, const double* kspring, const double* x, double* y, void* stream);
