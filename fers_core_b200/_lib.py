@@ -38,6 +38,7 @@ SIGNATURES = {
     "fers_b200_pcg_solve": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _i, _ip, _dp,
                                  _vp, _sz, _vp]),
     "fers_b200_dense_expand": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fers_b200_dense_expand_batched": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_dense_cholesky": (_i, [_i, _i, _vp, _vp, _ip, _vp]),
     "fers_b200_dense_solve": (_i, [_i, _i, _i, _vp, _vp, _vp]),
     "fers_b200_recover_members": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i,

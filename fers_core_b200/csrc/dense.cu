@@ -35,6 +35,36 @@ __global__ void k_dense_expand(int n_nodes, const int* __restrict__ rowptr, cons
     }
 }
 
+// batched variant: the model is a set of `batch` disconnected frames of nodes_per_frame nodes each
+// (numbered frame by frame); frame f is expanded into its own dense matrix a[f][n][n], n = 6*npf
+__global__ void k_dense_expand_batched(int npf, int batch, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                       const double* __restrict__ vals, const uint8_t* __restrict__ fixed,
+                                       const double* __restrict__ kspring, double* __restrict__ a, int* __restrict__ bad) {
+    const int n = 6 * npf;
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= npf * batch) return;
+    const int f = row / npf, lr = row - f * npf;
+    double* af = a + (size_t)f * n * n;
+    for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) {
+        const int col = colidx[k];
+        const int lc = col - f * npf;
+        if (lc < 0 || lc >= npf) {           // a member crosses frames: not a block-diagonal batch
+            if (lane == 0) atomicExch(bad, 1);
+            continue;
+        }
+        for (int e = lane; e < 36; e += 32) {
+            const int r = e / 6, c = e % 6;
+            const int gi = 6 * row + r, gj = 6 * col + c;
+            double v = vals[(size_t)k * 36 + e];
+            const bool fx = (fixed[gi] != 0) || (fixed[gj] != 0);
+            if (fx) v = (gi == gj) ? 1.0 : 0.0;
+            else if (gi == gj && kspring != nullptr) v += kspring[gi];
+            af[(size_t)(6 * lr + r) * n + 6 * lc + c] = v;
+        }
+    }
+}
+
 // factor the diagonal tile [j0, j0+nb)
 __global__ void __launch_bounds__(NB* NB) k_potrf_diag(double* __restrict__ a_all, int n, int j0, int* __restrict__ info) {
     __shared__ double t[NB][NBP];
@@ -180,6 +210,27 @@ int fers_b200_dense_expand(int n_nodes, const int* rowptr, const int* colidx, co
     k_dense_expand<<<grid, T, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, a);
     FERS_LAUNCH_CHECK();
     count_launches(1);
+    return 0;
+}
+
+int fers_b200_dense_expand_batched(int nodes_per_frame, int batch, const int* rowptr, const int* colidx,
+                                   const double* vals, const uint8_t* fixed, const double* kspring, double* a,
+                                   int* flag_dev, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    FERS_REQUIRE(nodes_per_frame > 0 && batch > 0 && flag_dev != nullptr, "dense_expand_batched: bad arguments");
+    const size_t n = 6 * (size_t)nodes_per_frame;
+    FERS_CK(cudaMemsetAsync(a, 0, (size_t)batch * n * n * sizeof(double), st));
+    FERS_CK(cudaMemsetAsync(flag_dev, 0, sizeof(int), st));
+    const int T = 256;
+    const long long rows = (long long)nodes_per_frame * batch;
+    int grid = (int)((rows * 32 + T - 1) / T);
+    k_dense_expand_batched<<<grid, T, 0, st>>>(nodes_per_frame, batch, rowptr, colidx, vals, fixed, kspring, a, flag_dev);
+    FERS_LAUNCH_CHECK();
+    count_launches(1);
+    int bad = 0;
+    FERS_CK(cudaMemcpyAsync(&bad, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FERS_CK(cudaStreamSynchronize(st));
+    FERS_REQUIRE(bad == 0, "dense_expand_batched: the model is not a batch of disconnected equal-sized frames");
     return 0;
 }
 

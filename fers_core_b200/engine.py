@@ -487,6 +487,104 @@ def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:
         out.p_centroid = xyz[model.p_nodes].mean(axis=1)
 
 
+def analyze_frame_batch(model: wire.ModelArrays, nodes_per_frame: int, device=None, detail: bool = False,
+                        stats_out: dict | None = None) -> ResultArrays:
+    """BASELINE.json configs[4]: a batch of independent equal-sized frames (one concatenated,
+    block-diagonal model, nodes numbered frame by frame), one combination, linear or P-Delta.
+    Every frame is factorised by the batched dense Cholesky; the P-Delta fixed point runs for all
+    frames at once and each frame stops at ITS OWN convergence (converged frames are frozen), so the
+    result equals analysing the frames one by one."""
+    eng = Engine(model, device)
+    opts = model.options
+    plan = rhs_plan(model)
+    if plan.n_rhs != 1:
+        raise EngineError("analyze_frame_batch expects exactly one right-hand side (one combination, no load cases)")
+    if model.n_nodes % nodes_per_frame or model.n_plates:
+        raise EngineError("analyze_frame_batch: model is not a batch of equal-sized beam frames")
+    nf = model.n_nodes // nodes_per_frame
+    n = 6 * nodes_per_frame
+    nm = model.n_members
+    if nm % nf:
+        raise EngineError("analyze_frame_batch: members are not evenly distributed over the frames")
+    nmf = nm // nf
+    out = ResultArrays.empty(model, plan)
+    grp = plan.groups[0]
+    xyz = imperfect_coordinates(model, grp.imperfection) if grp.imperfection is not None else model.xyz
+    d_xyz = eng._t(xyz, np.float64) if grp.imperfection is not None else eng.d_xyz0
+    lib, st = eng.lib, eng.stream
+    fac = plan.factors[[0]]
+    f_case, peq_case = eng.load_cases(d_xyz)
+    d_f = eng.combine(f_case, fac, 1)
+    d_peq = eng.combine(peq_case, fac, 1)
+    a = eng._empty((nf, n, n))
+    flag = eng._zeros(1, torch.int32)
+    info_dev = eng._zeros(nf, torch.int32)
+    info = (C.c_int * nf)()
+    free = (1 - eng.d_fixed.to(torch.float64))[:, None]
+
+    def factor_solve():
+        _lib.check(lib.fers_b200_dense_expand_batched(
+            nodes_per_frame, nf, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
+            _lib.ptr(eng.d_ks), _lib.ptr(a), _lib.ptr(flag), st), "dense_expand_batched")
+        _lib.check(lib.fers_b200_dense_cholesky(n, nf, _lib.ptr(a), _lib.ptr(info_dev), info, st), "dense_cholesky")
+        bad = [i for i in range(nf) if info[i] != 0]
+        if bad:
+            raise EngineError(f"{len(bad)} frame(s) of the batch are not positive definite (first: frame {bad[0]}): "
+                              "buckled under the applied load or insufficiently supported")
+        u = (d_f * ((1 - eng.d_fixed.to(torch.float64))[:, None])).contiguous()
+        _lib.check(lib.fers_b200_dense_solve(n, 1, nf, _lib.ptr(a), _lib.ptr(u), st), "dense_solve")
+        return u
+
+    second_order = opts.order == "NONLINEAR"
+    kg_mode = (1 if opts.pdelta_formulation == "CONSISTENT" else 2) if second_order else 0
+    sup = 0
+    for ax in pdelta_suppressed_axes(model):
+        sup |= 1 << ax
+    facp = np.zeros((1, fac.shape[1])); facp[0] = fac[0]
+    eng.assemble(d_xyz)
+    d_u = factor_solve()
+    d_axial = None
+    iters = torch.zeros(nf, dtype=torch.int64, device=eng.dev)
+    resid = torch.zeros(nf, dtype=torch.float64, device=eng.dev)
+    active = torch.ones(nf, dtype=torch.bool, device=eng.dev)
+    if second_order and nm:
+        for _it in range(max(1, opts.max_iterations)):
+            rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, None, None, d_axial, kg_mode, sup, detail=False)
+            ax_new = eng._empty((nm, 1))
+            _lib.check(lib.fers_b200_member_axial(nm, 1, _lib.ptr(rec["f_local"]), _lib.ptr(ax_new), st), "member_axial")
+            if d_axial is not None:      # frozen frames keep the axial forces of their last iteration
+                am = active.repeat_interleave(nmf)[:, None]
+                ax_new = torch.where(am, ax_new, d_axial).contiguous()
+            d_axial = ax_new
+            eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup)
+            d_un = factor_solve()
+            un_f, u_f = d_un.view(nf, n), d_u.view(nf, n)
+            den = torch.linalg.norm(un_f, dim=1)
+            r = torch.where(den > 0, torch.linalg.norm(un_f - u_f, dim=1) / den, torch.zeros_like(den))
+            iters += active.to(torch.int64)
+            resid = torch.where(active, r, resid)
+            d_u = torch.where(active.repeat_interleave(n)[:, None], d_un, d_u).contiguous()
+            active = active & ~(r < opts.tolerance)
+            if not bool(active.any()):
+                break
+        # the matrix in eng.d_vals must be the tangent of the frozen state for the reactions
+        eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup)
+    span = eng.span_tables() if detail else None
+    rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, None, d_axial, kg_mode, sup, detail=detail)
+    _store(out, model, [0], d_u, rec, xyz)
+    out.method = "Linear" if not second_order else "P_DELTA"
+    it_host = iters.cpu().numpy()
+    out.iterations[0] = int(it_host.max()) if second_order else -1
+    out.converged[0] = not bool(active.any()) if second_order else True
+    out.residual[0] = float(resid.max()) if second_order else 0.0
+    if stats_out is not None:
+        stats_out.update(vars(eng.stats))
+        stats_out["frame_iterations"] = it_host
+        stats_out["frame_residual"] = resid.cpu().numpy()
+        stats_out["frames"] = nf
+    return out
+
+
 # ---- the drop-in boundary ---------------------------------------------------------------------
 def solve_document(doc: dict, device=None) -> dict:
     """dict in -> dict out (input document with ``results`` filled)."""

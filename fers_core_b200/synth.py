@@ -180,3 +180,123 @@ def to_wire_document(model: wire.ModelArrays) -> dict:
                      "load_cases": cases, "load_combinations": combos, "imperfection_cases": [], "unity_checks": []},
         "results": None,
     }
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: batch of parametric frames, sway imperfection, second-order P-Delta
+# ---------------------------------------------------------------------------------------------
+# A, Iy, Iz, J of a few catalogue sections (fers_core/sections/steel_sections.generated.json)
+BATCH_SECTIONS = (
+    (0.0078, 2.0e-05, 5.7e-05, 6.0e-07),     # HEB200-like column
+    (0.0106, 3.9e-05, 1.13e-04, 1.0e-06),    # HEB240-like column
+    HEB300[:4],
+    (0.0039, 2.8e-06, 3.9e-05, 1.3e-07),     # IPE240-like beam
+    (0.0054, 6.0e-06, 8.4e-05, 2.0e-07),     # IPE300-like beam
+    (0.0073, 1.0e-05, 1.63e-04, 3.7e-07),    # IPE360-like beam
+)
+BATCH_SEED = 7
+PORTAL_NODES = 45            # 3 x 3 plan x 5 levels
+
+
+def portal_frame(bay: float, storey: float, col_sec: int, beam_sec: int, gravity: float, wind: float,
+                 tolerance: float = 1e-8, order: str = "NONLINEAR") -> wire.ModelArrays:
+    """One 2x2-bay, 4-storey 3D frame (45 nodes, 270 DOF) with a 1/200 sway imperfection about Z and a
+    single combination (gravity UDL on the beams + lateral nodal loads), P-Delta consistent."""
+    px = pz = 3
+    py = 5
+    nn = px * pz * py
+    i, k, j = np.meshgrid(np.arange(px), np.arange(pz), np.arange(py), indexing="ij")
+    idx = (i + px * (k + pz * j)).reshape(-1)
+    xyz = np.zeros((nn, 3))
+    xyz[idx, 0] = (i * bay).reshape(-1); xyz[idx, 1] = (j * storey).reshape(-1); xyz[idx, 2] = (k * bay).reshape(-1)
+
+    def nid(ii, kk, jj):
+        return ii + px * (kk + pz * jj)
+    ii, kk, jj = np.meshgrid(np.arange(px), np.arange(pz), np.arange(py - 1), indexing="ij")
+    c1, c2 = nid(ii, kk, jj).reshape(-1), nid(ii, kk, jj + 1).reshape(-1)
+    ii, kk, jj = np.meshgrid(np.arange(px - 1), np.arange(pz), np.arange(1, py), indexing="ij")
+    bx1, bx2 = nid(ii, kk, jj).reshape(-1), nid(ii + 1, kk, jj).reshape(-1)
+    ii, kk, jj = np.meshgrid(np.arange(px), np.arange(pz - 1), np.arange(1, py), indexing="ij")
+    bz1, bz2 = nid(ii, kk, jj).reshape(-1), nid(ii, kk + 1, jj).reshape(-1)
+    n1 = np.concatenate([c1, bx1, bz1]); n2 = np.concatenate([c2, bx2, bz2])
+    is_beam = np.concatenate([np.zeros(len(c1), bool), np.ones(len(bx1) + len(bz1), bool)])
+    o = np.lexsort((n2, n1))
+    n1, n2, is_beam = n1[o], n2[o], is_beam[o]
+    nm = len(n1)
+    bc = np.zeros((nn, 6), np.uint8); bc[: px * pz] = wire.BC_FIXED
+    sup = np.full(nn, -1, np.int64); sup[: px * pz] = 1
+    prop = np.array([[E_STEEL * s[0], E_STEEL * s[1], E_STEEL * s[2], G_STEEL * s[3], 0, 0, 0, 0] for s in BATCH_SECTIONS])
+    m_prop = np.where(is_beam, beam_sec, col_sec).astype(np.int32)
+    lc = wire.LoadCaseArrays(id=1, name="Design")
+    beams = np.nonzero(is_beam)[0].astype(np.int32)
+    lc.dl_member = beams
+    q = -20e3 * gravity
+    lc.dl_data = np.tile(np.array([0.0, q, 0.0, 0.0, q, 0.0, 0.0, 1.0]), (len(beams), 1))
+    lvl = idx // (px * pz)
+    top = idx[(lvl >= 1) & (idx % px == 0)]
+    lc.nod_node = top.astype(np.int32)
+    lc.nod_vec = np.tile(np.array([wind, 0, 0.3 * wind, 0, 0, 0.0]), (len(top), 1))
+    opts = wire.Options(order=order, nonlinear_method="P_DELTA", pdelta_formulation="CONSISTENT", tolerance=tolerance,
+                        max_iterations=30, solve_loadcases=False)
+    imp = [{"imperfection_case_id": 1, "load_combinations": [1],
+            "sway_imperfections": [{"magnitude": 1.0 / 200.0, "axis": [0, 0, 1], "height_direction": [0, 1, 0],
+                                    "reference_point": [0, 0, 0]}], "translation_imperfections": []}]
+    return wire.ModelArrays(
+        node_ids=np.arange(1, nn + 1, dtype=np.int64), xyz=xyz, node_support_id=sup, bc_code=bc, bc_k=np.zeros((nn, 6)),
+        m_ids=np.arange(1, nm + 1, dtype=np.int64), m_n1=n1.astype(np.int32), m_n2=n2.astype(np.int32),
+        m_type=np.zeros(nm, np.int32), m_roll=np.zeros(nm), m_prop=m_prop, m_rel=np.full(nm, -1, np.int32), prop=prop,
+        prop_rho_a=np.array([RHO_STEEL * s[0] for s in BATCH_SECTIONS]), rel=np.zeros((0, 12)),
+        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 4)),
+        p_flags=np.zeros(0, np.int32), load_cases=[lc], combo_ids=np.array([1], np.int64), combo_names=["ULS"],
+        combo_factors=np.ones((1, 1)), imperfections=imp, member_sets={}, options=opts)
+
+
+def portal_params(n_frames: int, seed: int = BATCH_SEED) -> list:
+    """Parameters of the batch: bay 4-8 m, storey 3-4 m, section indices, gravity factor 0.5-1.5."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_frames):
+        out.append(dict(bay=float(rng.uniform(4.0, 8.0)), storey=float(rng.uniform(3.0, 4.0)),
+                        col_sec=int(rng.integers(0, 3)), beam_sec=int(rng.integers(3, 6)),
+                        gravity=float(rng.uniform(0.5, 1.5)), wind=float(rng.uniform(2e3, 8e3))))
+    return out
+
+
+def concat_models(models: list) -> wire.ModelArrays:
+    """Concatenate equally-shaped models into one block-diagonal model (frame-major numbering).
+    All models must share the section table, options, load-case layout and imperfection case."""
+    m0 = models[0]
+    nn, nm = m0.n_nodes, m0.n_members
+    nf = len(models)
+
+    def cat(name, node_offset=False, member_offset=False):
+        parts = []
+        for f, m in enumerate(models):
+            a = getattr(m, name)
+            parts.append(a + (f * nn if node_offset else 0) if node_offset else a)
+        return np.concatenate(parts, 0)
+    cases = []
+    for li, lc0 in enumerate(m0.load_cases):
+        lc = wire.LoadCaseArrays(id=lc0.id, name=lc0.name)
+        lc.nod_node = np.concatenate([m.load_cases[li].nod_node + f * nn for f, m in enumerate(models)]).astype(np.int32)
+        lc.nod_vec = np.concatenate([m.load_cases[li].nod_vec for m in models], 0)
+        lc.dl_member = np.concatenate([m.load_cases[li].dl_member + f * nm for f, m in enumerate(models)]).astype(np.int32)
+        lc.dl_data = np.concatenate([m.load_cases[li].dl_data for m in models], 0)
+        lc.pl_member = np.concatenate([m.load_cases[li].pl_member + f * nm for f, m in enumerate(models)]).astype(np.int32)
+        lc.pl_data = np.concatenate([m.load_cases[li].pl_data for m in models], 0)
+        cases.append(lc)
+    return wire.ModelArrays(
+        node_ids=np.arange(1, nf * nn + 1, dtype=np.int64), xyz=cat("xyz"),
+        node_support_id=cat("node_support_id"), bc_code=cat("bc_code"), bc_k=cat("bc_k"),
+        m_ids=np.arange(1, nf * nm + 1, dtype=np.int64), m_n1=cat("m_n1", node_offset=True).astype(np.int32),
+        m_n2=cat("m_n2", node_offset=True).astype(np.int32), m_type=cat("m_type"), m_roll=cat("m_roll"),
+        m_prop=cat("m_prop"), m_rel=cat("m_rel"), prop=m0.prop.copy(), prop_rho_a=m0.prop_rho_a.copy(), rel=m0.rel.copy(),
+        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 4)),
+        p_flags=np.zeros(0, np.int32), load_cases=cases, combo_ids=m0.combo_ids.copy(), combo_names=list(m0.combo_names),
+        combo_factors=m0.combo_factors.copy(), imperfections=list(m0.imperfections), member_sets={}, options=m0.options)
+
+
+def portal_batch(n_frames: int, seed: int = BATCH_SEED, tolerance: float = 1e-8):
+    """(concatenated model, list of per-frame models) for configs[4]."""
+    frames = [portal_frame(tolerance=tolerance, **p) for p in portal_params(n_frames, seed)]
+    return concat_models(frames), frames

@@ -134,6 +134,12 @@ int fers_b200_pcg_solve(int n_nodes, int nrhs, const int* rowptr, const int* col
  * info_out [host][batch]: 0 ok, k>0 = leading minor k not positive definite. Synchronises. */
 int fers_b200_dense_expand(int n_nodes, const int* rowptr, const int* colidx, const double* vals,
                            const uint8_t* fixed, const double* kspring, double* a, void* stream);
+/* Batch of `batch` disconnected frames with nodes_per_frame nodes each (nodes numbered frame by
+ * frame): frame f -> a[f][n][n], n = 6*nodes_per_frame.  flag_dev: one device int of scratch.
+ * Fails when a block couples two frames.  Synchronises the stream. */
+int fers_b200_dense_expand_batched(int nodes_per_frame, int batch, const int* rowptr, const int* colidx,
+                                   const double* vals, const uint8_t* fixed, const double* kspring, double* a,
+                                   int* flag_dev, void* stream);
 int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* info_out, void* stream);
 int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* bx, void* stream);
 

@@ -166,3 +166,22 @@ def test_dense_cholesky_batched(engine_mod):
     X = dB.cpu().numpy()
     want = np.linalg.solve(A, B)
     assert np.abs(X - want).max() <= 1e-11 * np.abs(want).max()
+
+
+def test_frame_batch_pdelta_matches_per_frame_oracle(engine_mod):
+    """configs[4] at oracle scale: a batch of parametric frames with sway imperfection and P-Delta,
+    solved at once on the GPU (batched dense Cholesky), against the oracle run frame by frame."""
+    n_frames = 12
+    big, frames = synth.portal_batch(n_frames, tolerance=1e-10)
+    stats = {}
+    got = engine_mod.analyze_frame_batch(big, synth.PORTAL_NODES, detail=True, stats_out=stats)
+    nn, nm = frames[0].n_nodes, frames[0].n_members
+    for f, fm in enumerate(frames):
+        want = fers_oracle.analyze(fm)
+        assert stats["frame_iterations"][f] == want.iterations[0], (f, stats["frame_iterations"][f], want.iterations)
+        for name, lo, hi in (("U", f * nn, (f + 1) * nn), ("R", f * nn, (f + 1) * nn),
+                             ("f_local", f * nm, (f + 1) * nm), ("f_global", f * nm, (f + 1) * nm),
+                             ("sec", f * nm, (f + 1) * nm), ("lmax", f * nm, (f + 1) * nm)):
+            a, b = getattr(got, name)[0, lo:hi], getattr(want, name)[0]
+            scale = np.abs(getattr(want, "f_local" if name not in ("U", "R") else name)[0]).max()
+            assert np.abs(a - b).max() <= 1e-9 * scale, (f, name, np.abs(a - b).max() / scale)
