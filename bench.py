@@ -51,7 +51,7 @@ def parse_args():
                         "parametric frames, sway imperfection, P-Delta")
     p.add_argument("--frames", type=int, default=1024, help="cfg5: frames per GPU")
     p.add_argument("--assembly-variant", type=int, default=0)
-    p.add_argument("--spmm-variant", type=int, default=-1, help="0 register/LDG, 1 TMA-staged (default: library default)")
+    p.add_argument("--spmm-variant", type=int, default=-1, help="0 register/LDG, 1 TMA-staged, 2 TMA warp-specialised (default: library default)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--profile-iters", type=int, default=0,

@@ -119,6 +119,11 @@ constexpr int TMA_SLOT = TMA_KB + TMA_XB + 16;       // + 16-byte header holding
 constexpr size_t TMA_SMEM = (size_t)SPMM_WARPS * TMA_STAGES * TMA_SLOT + (size_t)SPMM_WARPS * TMA_STAGES * 8;
 
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// 16-byte shared-memory load at base + compile-time offset (keeps the address math out of the loop)
+template <int OFFSET>
+__device__ __forceinline__ void lds_f64x2(double2& v, uint32_t base) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(base), "n"(OFFSET));
+}
 
 // No global load sits on the critical path of the FMA loop: row pointers and the BC mask of the NEXT
 // row are fetched while the current row is processed, the producer lane keeps the next column index
@@ -187,6 +192,8 @@ k_spmm64_tma(int n_nodes, const int* __restrict__ rowptr, const int* __restrict_
     int row = first, kb = 0, ke = 0;
     uint32_t fx = 0;
     if (row < n_nodes) { kb = rowptr[row]; ke = rowptr[row + 1]; fx = load_mask(row); }
+    const uint32_t ring_addr = s_addr(ring);
+    const uint32_t lane16 = (uint32_t)lane * 16u;
     double2 dot[1];
     dot[0] = make_double2(0.0, 0.0);
     int stage = 0;
@@ -213,25 +220,31 @@ k_spmm64_tma(int n_nodes, const int* __restrict__ rowptr, const int* __restrict_
                         : "memory");
                 }
             }
-            const double* sk = reinterpret_cast<const double*>(ring + (size_t)stage * TMA_SLOT);
-            const double* sx = sk + 36;
-            const int col = *reinterpret_cast<const int*>(ring + (size_t)stage * TMA_SLOT + TMA_KB + TMA_XB);
+            // explicit 32-bit shared addressing: one base per slot, every load is base + immediate
+            const uint32_t kbase = ring_addr + (uint32_t)stage * TMA_SLOT;
+            const uint32_t xbase = kbase + TMA_KB + lane16;
+            int col;
+            asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(col) : "r"(kbase), "n"(TMA_KB + TMA_XB));
             double2 xv[6];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) xv[c] = *reinterpret_cast<const double2*>(sx + c * NR + 2 * lane);
+#define FERS_LDSX(c) lds_f64x2<(c) * 64 * 8>(xv[c], xbase);
+            FERS_LDSX(0) FERS_LDSX(1) FERS_LDSX(2) FERS_LDSX(3) FERS_LDSX(4) FERS_LDSX(5)
+#undef FERS_LDSX
             if (col == row) {
 #pragma unroll
                 for (int c = 0; c < 6; ++c) xo[c] = xv[c];
             }
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-#pragma unroll
-                for (int c = 0; c < 6; c += 2) {
-                    const double2 kk = *reinterpret_cast<const double2*>(sk + r * 6 + c);
-                    fma2(acc[r], kk.x, xv[c]);
-                    fma2(acc[r], kk.y, xv[c + 1]);
-                }
-            }
+#define FERS_ROW(r)                                                                              \
+    {                                                                                            \
+        double2 k0, k1, k2;                                                                      \
+        lds_f64x2<((r) * 6 + 0) * 8>(k0, kbase);                                                 \
+        lds_f64x2<((r) * 6 + 2) * 8>(k1, kbase);                                                 \
+        lds_f64x2<((r) * 6 + 4) * 8>(k2, kbase);                                                 \
+        fma2(acc[r], k0.x, xv[0]); fma2(acc[r], k0.y, xv[1]);                                    \
+        fma2(acc[r], k1.x, xv[2]); fma2(acc[r], k1.y, xv[3]);                                    \
+        fma2(acc[r], k2.x, xv[4]); fma2(acc[r], k2.y, xv[5]);                                    \
+    }
+            FERS_ROW(0) FERS_ROW(1) FERS_ROW(2) FERS_ROW(3) FERS_ROW(4) FERS_ROW(5)
+#undef FERS_ROW
             __syncwarp();                       // every lane has consumed the slot
             if (lane == 0) issue(stage);        // refill it with the block TMA_STAGES ahead
             if (++stage == TMA_STAGES) { stage = 0; phase ^= 1u; }
@@ -256,6 +269,198 @@ k_spmm64_tma(int n_nodes, const int* __restrict__ rowptr, const int* __restrict_
 }
 
 // 0 = register/LDG variant, 1 = TMA-staged variant (NR = 64 only, default); FERS_SPMM_VARIANT overrides
+// ---- warp-specialised TMA variant (variant 2) ----------------------------------------------------
+// 8 consumer warps + 2 producer warps per CTA.  Producer lane l of warp 8 (9) feeds the ring of
+// consumer warp l (4 + l): it waits on the slot's "empty" mbarrier, then issues the two bulk copies
+// that complete on the slot's "full" mbarrier.  Consumers never execute copy-issue code: per block they
+// wait on "full", read the slot (25 shared loads), run 72 DFMA and arrive on "empty".
+constexpr int WS_CONSUMERS = 8;
+constexpr int WS_PRODUCERS = 2;
+constexpr int WS_THREADS = (WS_CONSUMERS + WS_PRODUCERS) * 32;
+constexpr int WS_STAGES = 3;
+constexpr int WS_XO = 6 * 64 * 8;                       // per-consumer copy of the row's own x
+constexpr size_t WS_SMEM = (size_t)WS_CONSUMERS * (WS_STAGES * TMA_SLOT + WS_XO) + (size_t)WS_CONSUMERS * WS_STAGES * 16;
+
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ uint32_t mbar_test_parity(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(WS_THREADS, 2)
+k_spmm64_ws(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
+            const uint8_t* __restrict__ fixed, const double* __restrict__ kspring, const double* __restrict__ x,
+            double* __restrict__ y, double* __restrict__ partial) {
+    constexpr int NR = 64;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t smem0 = s_addr(smem_dyn);
+    constexpr uint32_t RING = WS_STAGES * TMA_SLOT + WS_XO;              // bytes per consumer
+    const uint32_t bars0 = smem0 + WS_CONSUMERS * RING;                  // [consumer][stage] {full, empty}
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < WS_CONSUMERS * WS_STAGES * 2; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars0 + 8u * i));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int stride = gridDim.x * WS_CONSUMERS;
+
+    if (warp >= WS_CONSUMERS) {
+        // ================= producer warps =================
+        const int cw = (warp - WS_CONSUMERS) * (WS_CONSUMERS / WS_PRODUCERS) + lane;    // consumer served by this lane
+        const bool mine = lane < (WS_CONSUMERS / WS_PRODUCERS);
+        int prow = mine ? blockIdx.x * WS_CONSUMERS + cw : n_nodes;
+        int pk = 0, pke = 0, pcol = 0, nkb = 0, nke = 0, stage = 0;
+        uint32_t phase = 0;
+        if (prow < n_nodes) {
+            pk = rowptr[prow]; pke = rowptr[prow + 1];
+            pcol = __ldg(colidx + pk);
+            if (prow + stride < n_nodes) { nkb = rowptr[prow + stride]; nke = rowptr[prow + stride + 1]; }
+        }
+        const uint32_t ring = smem0 + (uint32_t)cw * RING;
+        const uint32_t bars = bars0 + (uint32_t)cw * WS_STAGES * 16u;
+        while (__any_sync(FULL, prow < n_nodes)) {
+            bool issued = false;
+            if (prow < n_nodes) {
+                const uint32_t full = bars + (uint32_t)stage * 16u, empty = full + 8u;
+                if (mbar_test_parity(empty, phase ^ 1u)) {
+                    const uint32_t dk = ring + (uint32_t)stage * TMA_SLOT, dx = dk + TMA_KB;
+                    asm volatile("st.shared.s32 [%0], %1;" ::"r"(dk + TMA_KB + TMA_XB), "r"(pcol) : "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full),
+                                 "r"((uint32_t)(TMA_KB + TMA_XB))
+                                 : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dk),
+                                 "l"(vals + (size_t)pk * 36), "r"((uint32_t)TMA_KB), "r"(full)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dx),
+                                 "l"(x + (size_t)pcol * 6 * NR), "r"((uint32_t)TMA_XB), "r"(full)
+                                 : "memory");
+                    if (++pk == pke) {
+                        prow += stride;
+                        pk = nkb; pke = nke;
+                        if (prow + stride < n_nodes) { nkb = rowptr[prow + stride]; nke = rowptr[prow + stride + 1]; }
+                    }
+                    if (prow < n_nodes) pcol = __ldg(colidx + pk);
+                    if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
+                    issued = true;
+                }
+            }
+            if (!__any_sync(FULL, issued)) __nanosleep(64);
+        }
+        return;
+    }
+
+    // ================= consumer warps =================
+    const uint32_t ring = smem0 + (uint32_t)warp * RING;
+    const uint32_t xo_addr = ring + WS_STAGES * TMA_SLOT + (uint32_t)lane * 16u;
+    const uint32_t bars = bars0 + (uint32_t)warp * WS_STAGES * 16u;
+    const uint32_t lane16 = (uint32_t)lane * 16u;
+    auto load_mask = [&](int r) -> uint32_t {
+        if (fixed == nullptr) return 0u;
+        uint32_t m = 0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) m |= (uint32_t)(fixed[(size_t)r * 6 + q] != 0) << q;
+        return m;
+    };
+    int row = blockIdx.x * WS_CONSUMERS + warp, kb = 0, ke = 0;
+    uint32_t fx = 0;
+    if (row < n_nodes) { kb = rowptr[row]; ke = rowptr[row + 1]; fx = load_mask(row); }
+    double2 dot = make_double2(0.0, 0.0);
+    int stage = 0;
+    uint32_t phase = 0;
+    while (row < n_nodes) {
+        const int next = row + stride;
+        int nkb2 = 0, nke2 = 0;
+        uint32_t nfx = 0;
+        if (next < n_nodes) { nkb2 = rowptr[next]; nke2 = rowptr[next + 1]; nfx = load_mask(next); }
+        double2 acc[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[r] = make_double2(0.0, 0.0);
+        for (int k = kb; k < ke; ++k) {
+            const uint32_t full = bars + (uint32_t)stage * 16u;
+            mbar_wait_parity(full, phase);
+            const uint32_t kbase = ring + (uint32_t)stage * TMA_SLOT;
+            const uint32_t xbase = kbase + TMA_KB + lane16;
+            int col;
+            asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(col) : "r"(kbase), "n"(TMA_KB + TMA_XB));
+            double2 xv[6];
+#define FERS_LDSX(c) lds_f64x2<(c) * 64 * 8>(xv[c], xbase);
+            FERS_LDSX(0) FERS_LDSX(1) FERS_LDSX(2) FERS_LDSX(3) FERS_LDSX(4) FERS_LDSX(5)
+#undef FERS_LDSX
+            if (col == row) {            // diagonal block: keep the row's own x for the epilogue
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(xo_addr + (uint32_t)c * 512u), "d"(xv[c].x), "d"(xv[c].y)
+                                 : "memory");
+            }
+#define FERS_ROW(r)                                                                              \
+    {                                                                                            \
+        double2 k0, k1, k2;                                                                      \
+        lds_f64x2<((r) * 6 + 0) * 8>(k0, kbase);                                                 \
+        lds_f64x2<((r) * 6 + 2) * 8>(k1, kbase);                                                 \
+        lds_f64x2<((r) * 6 + 4) * 8>(k2, kbase);                                                 \
+        fma2(acc[r], k0.x, xv[0]); fma2(acc[r], k0.y, xv[1]);                                    \
+        fma2(acc[r], k1.x, xv[2]); fma2(acc[r], k1.y, xv[3]);                                    \
+        fma2(acc[r], k2.x, xv[4]); fma2(acc[r], k2.y, xv[5]);                                    \
+    }
+            FERS_ROW(0) FERS_ROW(1) FERS_ROW(2) FERS_ROW(3) FERS_ROW(4) FERS_ROW(5)
+#undef FERS_ROW
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full + 8u) : "memory");
+            if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        const size_t d0 = (size_t)row * 6;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const size_t d = d0 + r;
+            double2 xo = make_double2(0.0, 0.0);
+            if (kspring != nullptr || DOT)
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xo.x), "=d"(xo.y) : "r"(xo_addr + (uint32_t)r * 512u));
+            if (fx & (1u << r)) {
+                acc[r] = make_double2(0.0, 0.0);
+            } else if (kspring != nullptr) {
+                const double ks = kspring[d];
+                acc[r].x = fma(ks, xo.x, acc[r].x);
+                acc[r].y = fma(ks, xo.y, acc[r].y);
+            }
+            reinterpret_cast<double2*>(y + d * NR)[lane] = acc[r];
+            if (DOT) { dot.x = fma(xo.x, acc[r].x, dot.x); dot.y = fma(xo.y, acc[r].y, dot.y); }
+        }
+        row = next; kb = nkb2; ke = nke2; fx = nfx;
+    }
+    if (DOT) {
+        // consumers only: reduce over the 8 consumer warps through shared memory (named barrier 1)
+        __shared__ double2 s_red[WS_CONSUMERS][32];
+        s_red[warp][lane] = dot;
+        asm volatile("bar.sync 1, %0;" ::"n"(WS_CONSUMERS * 32));
+        if (warp == 0) {
+            double2 a = s_red[0][lane];
+#pragma unroll
+            for (int w = 1; w < WS_CONSUMERS; ++w) { a.x += s_red[w][lane].x; a.y += s_red[w][lane].y; }
+            reinterpret_cast<double2*>(partial + (size_t)blockIdx.x * NR)[lane] = a;
+        }
+    }
+}
+
 static int g_spmm_variant = -1;
 static int spmm_variant() {
     if (g_spmm_variant < 0) {
@@ -532,6 +737,19 @@ static int persistent_grid(int n_nodes, int nr) {
 template <int NR>
 static int launch_spmm_dot(int n_nodes, const int* rowptr, const int* colidx, const double* vals, const uint8_t* fixed,
                            const double* kspring, const double* x, double* y, double* partial, cudaStream_t st) {
+    if (NR == 64 && spmm_variant() == 2) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(k_spmm64_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
+            cudaFuncSetAttribute(k_spmm64_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
+            attr = true;
+        }
+        int grid = sm_count() * 2;
+        const int need = (n_nodes + WS_CONSUMERS - 1) / WS_CONSUMERS;
+        if (grid > need) grid = need;
+        k_spmm64_ws<true><<<grid, WS_THREADS, WS_SMEM, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
+        return grid;
+    }
     if (NR == 64 && spmm_variant() == 1) {
         static bool attr = false;
         if (!attr) {
@@ -555,6 +773,16 @@ static int run_spmm(int n_nodes, const int* rowptr, const int* colidx, const dou
                     const double* kspring, const double* x, double* y, double* partial, bool dot, cudaStream_t st) {
     if (dot) {
         launch_spmm_dot<NR>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial, st);
+    } else if (NR == 64 && spmm_variant() == 2) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(k_spmm64_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
+            attr = true;
+        }
+        int grid = sm_count() * 2;
+        const int need = (n_nodes + WS_CONSUMERS - 1) / WS_CONSUMERS;
+        if (grid > need) grid = need;
+        k_spmm64_ws<false><<<grid, WS_THREADS, WS_SMEM, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
     } else if (NR == 64 && spmm_variant() == 1) {
         static bool attr = false;
         if (!attr) {
@@ -701,7 +929,8 @@ int fers_b200_block_jacobi(int n_nodes, const double* vals, const int* diag_slot
 }
 
 int fers_b200_set_spmm_variant(int variant) {
-    FERS_REQUIRE(variant == 0 || variant == 1, "set_spmm_variant: 0 (register/LDG) or 1 (TMA-staged, nrhs = 64)");
+    FERS_REQUIRE(variant >= 0 && variant <= 2,
+                 "set_spmm_variant: 0 (register/LDG), 1 (TMA-staged) or 2 (TMA, warp-specialised); 1 and 2 need nrhs = 64");
     g_spmm_variant = variant;
     return 0;
 }

@@ -104,8 +104,8 @@ int fers_b200_combine(int n_rows, int n_cases, int nrhs, const double* in, const
 /* y = K x on the free DOFs (rows of constrained DOFs give 0), springs included; nrhs in
  * {1,8,16,32,64}.  fixed == NULL: plain product with the unconstrained matrix (used for
  * reactions R = K u - F). */
-/* SpMM kernel variant: 0 = register/LDG kernel (all nrhs), 1 = TMA-staged shared-memory pipeline
- * (nrhs = 64 only; other nrhs fall back to 0).  Default from env FERS_SPMM_VARIANT, else 1. */
+/* SpMM kernel variant: 0 = register/LDG kernel (all nrhs), 1 = TMA-staged shared-memory pipeline,
+ * 2 = TMA-staged with dedicated producer warps (1 and 2: nrhs = 64 only; other nrhs fall back to 0).  Default from env FERS_SPMM_VARIANT, else 1. */
 int fers_b200_set_spmm_variant(int variant);
 int fers_b200_spmm(int n_nodes, int nrhs, const int* rowptr, const int* colidx, const double* vals,
                    const uint8_t* fixed, const double* kspring, const double* x, double* y, void* stream);

@@ -77,7 +77,7 @@ def test_assembled_values_match_oracle(engine_mod, variant):
     assert np.abs(K - want).max() <= 1e-13 * np.abs(want).max()
 
 
-@pytest.mark.parametrize("nrhs,variant", [(1, 0), (8, 0), (16, 0), (32, 0), (64, 0), (64, 1)])
+@pytest.mark.parametrize("nrhs,variant", [(1, 0), (8, 0), (16, 0), (32, 0), (64, 0), (64, 1), (64, 2)])
 def test_spmm_matches_scipy(engine_mod, nrhs, variant):
     import torch
     from fers_core_b200 import _lib
@@ -105,14 +105,14 @@ def test_spmm_matches_scipy(engine_mod, nrhs, variant):
 
 
 @pytest.mark.parametrize("dims,force_pcg,variant", [((4, 4, 4), False, 0), ((4, 4, 4), True, 0), ((9, 8, 6), False, 0),
-                                                    ((12, 12, 10), True, 0), ((12, 12, 10), True, 1)])
+                                                    ((12, 12, 10), True, 0), ((12, 12, 10), True, 1), ((12, 12, 10), True, 2)])
 def test_synthetic_frame_matches_oracle(engine_mod, monkeypatch, dims, force_pcg, variant):
     """configs[3]-shaped frames at oracle-sized scale, dense and PCG solve paths (both SpMM kernels)."""
     from fers_core_b200 import _lib
     if force_pcg:
         monkeypatch.setattr(engine_mod, "DENSE_MAX_DOF", 0)
     _lib.load().fers_b200_set_spmm_variant(variant)
-    n_combos = 60 if variant == 1 else 11      # 8 cases + 60 combinations -> one 64-wide and one 8-wide pass
+    n_combos = 60 if variant >= 1 else 11      # 8 cases + 60 combinations -> one 64-wide and one 8-wide pass
     model = synth.grid_frame(*dims, n_combos=n_combos, timoshenko=(dims[0] == 9), solve_loadcases=True)
     want = fers_oracle.analyze(model)
     stats = {}
