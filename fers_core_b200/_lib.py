@@ -48,6 +48,13 @@ SIGNATURES = {
     "fers_b200_reactions": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_recover_plates": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_member_axial": (_i, [_i, _i, _vp, _vp, _vp]),
+    # sparse multifrontal Cholesky: host plan ([host] pointers are passed as integers / ctypes arrays)
+    "fers_b200_chol_plan_create": (_i, [_i, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
+    "fers_b200_chol_plan_destroy": (None, [_vp]),
+    "fers_b200_chol_plan_info": (_i, [_vp, C.POINTER(C.c_longlong), _i]),
+    "fers_b200_chol_plan_perm": (_i, [_vp, _vp]),
+    "fers_b200_chol_plan_levels": (_i, [_vp, C.POINTER(C.c_longlong), _i]),
+    "fers_b200_chol_plan_export": (_i, [_vp, _vp, C.POINTER(C.c_longlong), _vp, _vp]),
 }
 
 

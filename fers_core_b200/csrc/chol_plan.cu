@@ -1,0 +1,419 @@
+// chol_plan.cu -- host side of the sparse multifrontal Cholesky: nested-dissection ordering on the node
+// coordinates, elimination tree of fronts, symbolic factorisation (front boundaries), the index maps
+// of the extend-add and the memory plan.  Pure host code (no CUDA call except the index upload).
+//
+// Ordering.  A node set is split at the median coordinate of one axis; the vertex separator is the
+// smaller of the two one-sided boundary layers of the edge cut; all three axes are tried and the
+// smallest separator wins.  Sets of at most `leaf_nodes` nodes become leaves.  Fronts of equal tree
+// depth are independent and are processed as one batch ("level") by the numeric kernels.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <string.h>
+
+#include "chol.cuh"
+#include "common.cuh"
+
+namespace fers {
+namespace {
+
+struct FrontBuild {
+    int parent = -1;
+    int depth = 0;
+    std::vector<int> own;
+    std::vector<int> children;
+};
+
+struct Dissector {
+    int n;
+    const int* rp;
+    const int* ci;
+    const double* xyz;
+    int leaf;
+    std::vector<uint8_t> part;
+    std::vector<FrontBuild> fronts;
+
+    int new_front(int parent, std::vector<int>&& own) {
+        FrontBuild f;
+        f.parent = parent;
+        f.depth = parent < 0 ? 0 : fronts[parent].depth + 1;
+        f.own = std::move(own);
+        fronts.push_back(std::move(f));
+        const int id = (int)fronts.size() - 1;
+        if (parent >= 0) fronts[parent].children.push_back(id);
+        return id;
+    }
+
+    // split `nodes` along `axis` at the median; returns false when the axis cannot separate the set
+    bool split_axis(const std::vector<int>& nodes, int axis, std::vector<int>& a, std::vector<int>& b) const {
+        std::vector<double> c(nodes.size());
+        for (size_t i = 0; i < nodes.size(); ++i) c[i] = xyz[(size_t)nodes[i] * 3 + axis];
+        std::vector<double> tmp(c);
+        const size_t mid = tmp.size() / 2;
+        std::nth_element(tmp.begin(), tmp.begin() + mid, tmp.end());
+        const double thr = tmp[mid];
+        a.clear(); b.clear();
+        for (size_t i = 0; i < nodes.size(); ++i) (c[i] < thr ? a : b).push_back(nodes[i]);
+        if (a.empty()) {
+            a.clear(); b.clear();
+            for (size_t i = 0; i < nodes.size(); ++i) (c[i] <= thr ? a : b).push_back(nodes[i]);
+        }
+        return !a.empty() && !b.empty();
+    }
+
+    // one-sided boundary layers of the cut (part: 1 = a, 2 = b)
+    void separators(const std::vector<int>& a, const std::vector<int>& b, std::vector<int>& sa, std::vector<int>& sb) {
+        for (int v : a) part[v] = 1;
+        for (int v : b) part[v] = 2;
+        sa.clear(); sb.clear();
+        for (int v : a)
+            for (int k = rp[v]; k < rp[v + 1]; ++k)
+                if (part[ci[k]] == 2) { sa.push_back(v); break; }
+        for (int v : b)
+            for (int k = rp[v]; k < rp[v + 1]; ++k)
+                if (part[ci[k]] == 1) { sb.push_back(v); break; }
+        for (int v : a) part[v] = 0;
+        for (int v : b) part[v] = 0;
+    }
+
+    void dissect(std::vector<int>&& nodes, int parent) {
+        if ((int)nodes.size() <= leaf) {
+            if (!nodes.empty()) new_front(parent, std::move(nodes));
+            return;
+        }
+        std::vector<int> best_a, best_b, best_sep;
+        bool have = false, best_from_a = true;
+        double best_score = 0.0;
+        std::vector<int> a, b, sa, sb;
+        for (int axis = 0; axis < 3; ++axis) {
+            if (!split_axis(nodes, axis, a, b)) continue;
+            separators(a, b, sa, sb);
+            const bool from_a = sa.size() <= sb.size();
+            const std::vector<int>& sep = from_a ? sa : sb;
+            // balance guard: a median split is balanced unless many nodes share the median coordinate
+            const size_t small = std::min(a.size(), b.size());
+            const bool balanced = small * 5 >= nodes.size();
+            const double score = (double)sep.size() * (balanced ? 1.0 : 4.0);
+            if (!have || score < best_score) {
+                have = true; best_from_a = from_a; best_score = score;
+                best_a = a; best_b = b; best_sep = sep;
+            }
+        }
+        if (!have) {   // coincident coordinates: split by position in the list
+            const size_t mid = nodes.size() / 2;
+            best_a.assign(nodes.begin(), nodes.begin() + mid);
+            best_b.assign(nodes.begin() + mid, nodes.end());
+            separators(best_a, best_b, sa, sb);
+            best_from_a = sa.size() <= sb.size();
+            best_sep = best_from_a ? sa : sb;
+        }
+        nodes.clear(); nodes.shrink_to_fit();
+        if (best_sep.empty()) {   // the two halves are not connected: no separator front
+            dissect(std::move(best_a), parent);
+            dissect(std::move(best_b), parent);
+            return;
+        }
+        // remove the separator from the side it was taken from
+        for (int v : best_sep) part[v] = 3;
+        std::vector<int>& side = best_from_a ? best_a : best_b;
+        side.erase(std::remove_if(side.begin(), side.end(), [&](int v) { return part[v] == 3; }), side.end());
+        for (int v : best_sep) part[v] = 0;
+        const int f = new_front(parent, std::move(best_sep));
+        dissect(std::move(best_a), f);
+        dissect(std::move(best_b), f);
+    }
+};
+
+}  // namespace
+
+static int build_plan(int n_nodes, const int* rp, const int* ci, const double* xyz, int leaf_nodes, CholPlanHost& P) {
+    Dissector D;
+    D.n = n_nodes; D.rp = rp; D.ci = ci; D.xyz = xyz; D.leaf = leaf_nodes < 1 ? 1 : leaf_nodes;
+    D.part.assign(n_nodes, 0);
+    {
+        std::vector<int> all(n_nodes);
+        std::iota(all.begin(), all.end(), 0);
+        D.dissect(std::move(all), -1);
+    }
+    std::vector<FrontBuild>& B = D.fronts;
+    const int nf = (int)B.size();
+    // post-order (children before parents), iterative
+    std::vector<int> order; order.reserve(nf);
+    {
+        std::vector<std::pair<int, int>> stack;
+        for (int r = 0; r < nf; ++r) {
+            if (B[r].parent >= 0) continue;
+            stack.push_back({r, 0});
+            while (!stack.empty()) {
+                auto& top = stack.back();
+                if (top.second < (int)B[top.first].children.size()) {
+                    const int c = B[top.first].children[top.second++];
+                    stack.push_back({c, 0});
+                } else {
+                    order.push_back(top.first);
+                    stack.pop_back();
+                }
+            }
+        }
+    }
+    std::vector<int> new_id(nf);
+    for (int i = 0; i < nf; ++i) new_id[order[i]] = i;
+
+    P.n_nodes = n_nodes;
+    P.n_fronts = nf;
+    P.perm.clear(); P.perm.reserve(n_nodes);
+    P.pos.assign(n_nodes, -1);
+    P.fronts.assign(nf, FrontDev{});
+    P.front_first.assign(nf, 0);
+    int max_depth = 0;
+    for (int i = 0; i < nf; ++i) {
+        FrontBuild& fb = B[order[i]];
+        std::sort(fb.own.begin(), fb.own.end());
+        P.front_first[i] = (int)P.perm.size();
+        for (int v : fb.own) { P.pos[v] = (int)P.perm.size(); P.perm.push_back(v); }
+        P.fronts[i].n1 = (int)fb.own.size();
+        P.fronts[i].parent = fb.parent < 0 ? -1 : new_id[fb.parent];
+        max_depth = std::max(max_depth, fb.depth);
+    }
+    if ((int)P.perm.size() != n_nodes) { set_error("chol_plan: ordering lost nodes"); return 3; }
+
+    // symbolic factorisation: boundaries in post-order
+    std::vector<std::vector<int>> bnd(nf);
+    std::vector<int> stamp(n_nodes, -1);
+    P.child.clear(); P.inv_off.clear();
+    for (int i = 0; i < nf; ++i) {
+        const FrontBuild& fb = B[order[i]];
+        const int first = P.front_first[i], last = first + P.fronts[i].n1;
+        std::vector<int>& out = bnd[i];
+        for (int v : fb.own)
+            for (int k = rp[v]; k < rp[v + 1]; ++k) {
+                const int w = ci[k];
+                if (P.pos[w] >= last && stamp[w] != i) { stamp[w] = i; out.push_back(w); }
+            }
+        for (int c : fb.children)
+            for (int w : bnd[new_id[c]])
+                if (P.pos[w] >= last && stamp[w] != i) { stamp[w] = i; out.push_back(w); }
+        std::sort(out.begin(), out.end(), [&](int x, int y) { return P.pos[x] < P.pos[y]; });
+        P.fronts[i].n2 = (int)out.size();
+    }
+
+    // node lists, child lists and inverse maps
+    P.nodes.clear(); P.inv.clear();
+    std::vector<int> loc(n_nodes, -1);
+    long long factor = 0, rhs_rows = 0;
+    P.flops = 0; P.nnz_l = 0; P.max_front_nodes = 0;
+    std::vector<int> depth_of(nf);
+    for (int i = 0; i < nf; ++i) {
+        FrontDev& f = P.fronts[i];
+        const FrontBuild& fb = B[order[i]];
+        depth_of[i] = fb.depth;
+        f.nodes_off = (int)P.nodes.size();
+        for (int v : fb.own) P.nodes.push_back(v);
+        for (int v : bnd[i]) P.nodes.push_back(v);
+        const int nt = f.n1 + f.n2;
+        P.max_front_nodes = std::max(P.max_front_nodes, nt);
+        for (int q = 0; q < nt; ++q) loc[P.nodes[f.nodes_off + q]] = q;
+        f.child_begin = (int)P.child.size();
+        for (int c : fb.children) {
+            const int cid = new_id[c];
+            P.child.push_back(cid);
+            P.inv_off.push_back((long long)P.inv.size());
+            const size_t base = P.inv.size();
+            P.inv.resize(base + nt, -1);
+            const std::vector<int>& cb = bnd[cid];
+            for (int q = 0; q < (int)cb.size(); ++q) {
+                const int l = loc[cb[q]];
+                if (l < 0) { set_error("chol_plan: child boundary node missing from parent front"); return 3; }
+                P.inv[base + l] = q;
+            }
+        }
+        f.child_end = (int)P.child.size();
+        for (int q = 0; q < nt; ++q) loc[P.nodes[f.nodes_off + q]] = -1;
+        const long long m = 6LL * nt, k1 = 6LL * f.n1, m2 = 6LL * f.n2;
+        f.panel_off = factor;
+        factor += m * k1;
+        f.dinv_off = factor;
+        factor += ((k1 + CHOL_NB - 1) / CHOL_NB) * (long long)(CHOL_NB * CHOL_NB);
+        f.rhs_off = rhs_rows;
+        rhs_rows += m;
+        P.flops += (double)k1 * k1 * k1 / 3.0 + (double)k1 * k1 * m2 + (double)k1 * m2 * m2;
+        P.nnz_l += k1 * (k1 + 1) / 2 + m2 * k1;
+    }
+    P.factor_doubles = factor;
+    P.rhs_rows = rhs_rows;
+
+    // levels: deepest depth first; the parent of a front of level l is in level l + 1
+    P.n_levels = max_depth + 1;
+    P.level_ptr.assign(P.n_levels + 1, 0);
+    for (int i = 0; i < nf; ++i) P.level_ptr[max_depth - depth_of[i] + 1]++;
+    for (int l = 0; l < P.n_levels; ++l) P.level_ptr[l + 1] += P.level_ptr[l];
+    P.level_fronts.assign(nf, 0);
+    {
+        std::vector<int> cur(P.level_ptr.begin(), P.level_ptr.end() - 1);
+        for (int i = 0; i < nf; ++i) P.level_fronts[cur[max_depth - depth_of[i]]++] = i;
+    }
+    P.level_max_n1.assign(P.n_levels, 0);
+    P.level_max_n.assign(P.n_levels, 0);
+    P.schur_doubles[0] = P.schur_doubles[1] = 0;
+    for (int l = 0; l < P.n_levels; ++l) {
+        long long s = 0;
+        for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; ++q) {
+            FrontDev& f = P.fronts[P.level_fronts[q]];
+            f.schur_off = s;
+            s += 36LL * f.n2 * f.n2;
+            P.level_max_n1[l] = std::max(P.level_max_n1[l], f.n1);
+            P.level_max_n[l] = std::max(P.level_max_n[l], f.n1 + f.n2);
+        }
+        P.schur_doubles[l & 1] = std::max(P.schur_doubles[l & 1], s);
+    }
+
+    // K blocks of the lower triangle (in elimination order) -> panel positions, grouped by level
+    std::vector<int> front_of_node(n_nodes);
+    for (int i = 0; i < nf; ++i)
+        for (int q = 0; q < P.fronts[i].n1; ++q) front_of_node[P.nodes[P.fronts[i].nodes_off + q]] = i;
+    std::vector<int> level_of(nf);
+    for (int l = 0; l < P.n_levels; ++l)
+        for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; ++q) level_of[P.level_fronts[q]] = l;
+    std::vector<long long> cnt(P.n_levels + 1, 0);
+    for (int v = 0; v < n_nodes; ++v)
+        for (int k = rp[v]; k < rp[v + 1]; ++k)
+            if (P.pos[v] >= P.pos[ci[k]]) cnt[level_of[front_of_node[ci[k]]] + 1]++;
+    for (int l = 0; l < P.n_levels; ++l) cnt[l + 1] += cnt[l];
+    P.kscatter_ptr = cnt;
+    P.kscatter.assign((size_t)cnt[P.n_levels], KScatter{});
+    {
+        std::vector<long long> cur(cnt.begin(), cnt.end() - 1);
+        // local index of a node inside a front: own nodes by position, boundary nodes by search
+        for (int i = 0; i < nf; ++i) {
+            const FrontDev& f = P.fronts[i];
+            const int nt = f.n1 + f.n2;
+            for (int q = 0; q < nt; ++q) loc[P.nodes[f.nodes_off + q]] = q;
+            for (int q = 0; q < f.n1; ++q) {
+                const int c = P.nodes[f.nodes_off + q];          // column node (own)
+                for (int k = rp[c]; k < rp[c + 1]; ++k) {
+                    const int r = ci[k];                          // row node; block (r, c) = transpose slot of (c, r)
+                    if (P.pos[r] < P.pos[c]) continue;
+                    if (loc[r] < 0) { set_error("chol_plan: matrix entry outside its front"); return 3; }
+                    // we need the block stored at row r, column c: find it in row r
+                    const int* b = std::lower_bound(ci + rp[r], ci + rp[r + 1], c);
+                    if (b == ci + rp[r + 1] || *b != c) { set_error("chol_plan: pattern is not structurally symmetric"); return 3; }
+                    KScatter e; e.front = i; e.k = (int)(b - ci); e.bi = loc[r]; e.bj = q;
+                    P.kscatter[(size_t)cur[level_of[i]]++] = e;
+                }
+            }
+            for (int q = 0; q < nt; ++q) loc[P.nodes[f.nodes_off + q]] = -1;
+        }
+    }
+
+    // device index buffer layout
+    size_t o = 0;
+    auto place = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes); return at; };
+    P.off_fronts = place(sizeof(FrontDev) * (size_t)nf);
+    P.off_nodes = place(sizeof(int) * P.nodes.size());
+    P.off_child = place(sizeof(int) * P.child.size());
+    P.off_inv_off = place(sizeof(long long) * P.inv_off.size());
+    P.off_inv = place(sizeof(int) * P.inv.size());
+    P.off_level_fronts = place(sizeof(int) * P.level_fronts.size());
+    P.off_kscatter = place(sizeof(KScatter) * P.kscatter.size());
+    P.index_bytes = o;
+    return 0;
+}
+
+}  // namespace fers
+
+using namespace fers;
+
+extern "C" {
+
+int fers_b200_chol_plan_create(int n_nodes, const int* rowptr, const int* colidx, const double* xyz, int leaf_nodes,
+                               void** plan_out) {
+    FERS_REQUIRE(n_nodes > 0 && rowptr && colidx && xyz && plan_out, "chol_plan_create: bad arguments");
+    CholPlanHost* P = new CholPlanHost();
+    const int rc = build_plan(n_nodes, rowptr, colidx, xyz, leaf_nodes, *P);
+    if (rc) { delete P; return rc; }
+    *plan_out = P;
+    return 0;
+}
+
+void fers_b200_chol_plan_destroy(void* plan) { delete static_cast<CholPlanHost*>(plan); }
+
+int fers_b200_chol_plan_info(void* plan, long long* out, int n_out) {
+    FERS_REQUIRE(plan && out && n_out >= 12, "chol_plan_info: need 12 outputs");
+    const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    out[0] = P.n_fronts;
+    out[1] = P.n_levels;
+    out[2] = P.max_front_nodes;
+    out[3] = P.factor_doubles;
+    out[4] = P.schur_doubles[0];
+    out[5] = P.schur_doubles[1];
+    out[6] = P.rhs_rows;
+    out[7] = (long long)P.index_bytes;
+    out[8] = (long long)(P.flops / 1e6);   // Mflop
+    out[9] = P.nnz_l;
+    out[10] = (long long)P.kscatter.size();
+    out[11] = P.n_levels ? P.fronts[P.level_fronts[P.level_ptr[P.n_levels - 1]]].n1 : 0;   // root separator nodes
+    return 0;
+}
+
+int fers_b200_chol_plan_perm(void* plan, int* perm_out) {
+    FERS_REQUIRE(plan && perm_out, "chol_plan_perm: bad arguments");
+    const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    std::copy(P.perm.begin(), P.perm.end(), perm_out);
+    return 0;
+}
+
+/* per-level statistics: out[level*4 + {0,1,2,3}] = fronts, max own nodes, max front nodes, Mflop */
+int fers_b200_chol_plan_levels(void* plan, long long* out, int n_levels_cap) {
+    FERS_REQUIRE(plan && out, "chol_plan_levels: bad arguments");
+    const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    FERS_REQUIRE(n_levels_cap >= P.n_levels, "chol_plan_levels: output too small");
+    for (int l = 0; l < P.n_levels; ++l) {
+        double fl = 0;
+        for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; ++q) {
+            const FrontDev& f = P.fronts[P.level_fronts[q]];
+            const double k1 = 6.0 * f.n1, m2 = 6.0 * f.n2;
+            fl += k1 * k1 * k1 / 3.0 + k1 * k1 * m2 + k1 * m2 * m2;
+        }
+        out[l * 4 + 0] = P.level_ptr[l + 1] - P.level_ptr[l];
+        out[l * 4 + 1] = P.level_max_n1[l];
+        out[l * 4 + 2] = P.level_max_n[l];
+        out[l * 4 + 3] = (long long)(fl / 1e6);
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+namespace fers {
+// serialise the index arrays into one buffer laid out as CholPlanHost::off_* describe
+void chol_plan_serialise(const CholPlanHost& P, unsigned char* out) {
+    memcpy(out + P.off_fronts, P.fronts.data(), sizeof(FrontDev) * P.fronts.size());
+    memcpy(out + P.off_nodes, P.nodes.data(), sizeof(int) * P.nodes.size());
+    memcpy(out + P.off_child, P.child.data(), sizeof(int) * P.child.size());
+    memcpy(out + P.off_inv_off, P.inv_off.data(), sizeof(long long) * P.inv_off.size());
+    memcpy(out + P.off_inv, P.inv.data(), sizeof(int) * P.inv.size());
+    memcpy(out + P.off_level_fronts, P.level_fronts.data(), sizeof(int) * P.level_fronts.size());
+    memcpy(out + P.off_kscatter, P.kscatter.data(), sizeof(KScatter) * P.kscatter.size());
+}
+}  // namespace fers
+
+extern "C" {
+
+/* [host] copy of the index buffer (index_bytes of chol_plan_info) and of its section offsets:
+ * offsets_out[8] = fronts, nodes, child, inv_off, inv, level_fronts, kscatter, n_child_entries;
+ * level_ptr_out[n_levels+1], kscatter_ptr_out[n_levels+1]. */
+int fers_b200_chol_plan_export(void* plan, void* index_out, long long* offsets_out, int* level_ptr_out,
+                               long long* kscatter_ptr_out) {
+    FERS_REQUIRE(plan && index_out && offsets_out && level_ptr_out && kscatter_ptr_out, "chol_plan_export: bad arguments");
+    const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    chol_plan_serialise(P, static_cast<unsigned char*>(index_out));
+    offsets_out[0] = (long long)P.off_fronts; offsets_out[1] = (long long)P.off_nodes; offsets_out[2] = (long long)P.off_child;
+    offsets_out[3] = (long long)P.off_inv_off; offsets_out[4] = (long long)P.off_inv;
+    offsets_out[5] = (long long)P.off_level_fronts; offsets_out[6] = (long long)P.off_kscatter;
+    offsets_out[7] = (long long)P.child.size();
+    std::copy(P.level_ptr.begin(), P.level_ptr.end(), level_ptr_out);
+    std::copy(P.kscatter_ptr.begin(), P.kscatter_ptr.end(), kscatter_ptr_out);
+    return 0;
+}
+
+}  // extern "C"
