@@ -55,6 +55,14 @@ SIGNATURES = {
     "fers_b200_chol_plan_perm": (_i, [_vp, _vp]),
     "fers_b200_chol_plan_levels": (_i, [_vp, C.POINTER(C.c_longlong), _i]),
     "fers_b200_chol_plan_export": (_i, [_vp, _vp, C.POINTER(C.c_longlong), _vp, _vp]),
+    "fers_b200_chol_factor_bytes": (_sz, [_vp]),
+    "fers_b200_chol_work_bytes": (_sz, [_vp, _i]),
+    "fers_b200_chol_upload": (_i, [_vp, _vp, _vp]),
+    "fers_b200_chol_factor": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _ip, _vp]),
+    "fers_b200_chol_solve": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]),
+    "fers_b200_residual": (_i, [C.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fers_b200_chol_set_profile": (_i, [_i]),
+    "fers_b200_chol_profile": (_i, [_dp, _i]),
 }
 
 

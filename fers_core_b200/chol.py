@@ -107,3 +107,53 @@ class CholPlan:
             kscatter=np.frombuffer(buf, KSCATTER_DTYPE, self.info.n_kscatter, offs[6]),
             level_ptr=lp, kscatter_ptr=kp, raw=buf,
         )
+
+
+class CholSolver:
+    """Device side of the sparse direct solve: owns index / factor / work buffers (torch tensors) and
+    calls the numeric kernels.  One instance per (plan, device)."""
+
+    def __init__(self, plan: CholPlan, device, max_nrhs: int = 64):
+        import torch
+        self.torch = torch
+        self.plan = plan
+        self.lib = plan.lib
+        self.dev = device
+        self.max_nrhs = max_nrhs
+        self.index = torch.empty(plan.info.index_bytes, dtype=torch.uint8, device=device)
+        self.factor_bytes = self.lib.fers_b200_chol_factor_bytes(plan.handle)
+        self.work_bytes = self.lib.fers_b200_chol_work_bytes(plan.handle, max_nrhs)
+        self.factor = torch.empty(self.factor_bytes, dtype=torch.uint8, device=device)
+        self.work = torch.empty(self.work_bytes, dtype=torch.uint8, device=device)
+        self.info_dev = torch.zeros(1, dtype=torch.int32, device=device)
+        st = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(self.lib.fers_b200_chol_upload(plan.handle, self.index.data_ptr(), st), "chol_upload")
+        self.factored = False
+
+    @property
+    def stream(self) -> int:
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def factorize(self, d_vals, d_diag_slot, d_fixed, d_kspring=None, check: bool = True) -> int:
+        """Numeric factorisation; returns info (0 = positive definite)."""
+        info = C.c_int(0)
+        _lib.check(self.lib.fers_b200_chol_factor(
+            self.plan.handle, self.index.data_ptr(), d_vals.data_ptr(), d_diag_slot.data_ptr(), d_fixed.data_ptr(),
+            None if d_kspring is None else d_kspring.data_ptr(), self.factor.data_ptr(), self.work.data_ptr(),
+            self.work_bytes, self.info_dev.data_ptr(), C.byref(info) if check else None, self.stream), "chol_factor")
+        self.factored = True
+        return info.value
+
+    def solve(self, d_b, d_x, d_fixed, accumulate: bool = False) -> None:
+        """x (+)= K^-1 b for [n_dof, nrhs] device tensors (nrhs even, <= max_nrhs)."""
+        nrhs = int(d_b.shape[1])
+        _lib.check(self.lib.fers_b200_chol_solve(
+            self.plan.handle, self.index.data_ptr(), self.factor.data_ptr(), d_fixed.data_ptr(), nrhs, d_b.data_ptr(),
+            d_x.data_ptr(), 1 if accumulate else 0, self.work.data_ptr(), self.work_bytes, self.stream), "chol_solve")
+
+    def profile(self) -> dict:
+        out = (C.c_double * 10)()
+        _lib.check(self.lib.fers_b200_chol_profile(out, 10), "chol_profile")
+        keys = ["init_ms", "scatter_ms", "potrf_ms", "trsm_ms", "update_ms", "syrk_ms", "factor_ms", "solve_ms",
+                "factor_launches", "solve_launches"]
+        return dict(zip(keys, out[:]))

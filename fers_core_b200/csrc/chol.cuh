@@ -24,7 +24,8 @@ struct FrontDev {
     int child_begin;      // into child[] (front ids) and inv_off[]
     int child_end;
     int parent;           // front id or -1
-    int pad0, pad1;
+    int pad0;             // elimination position of the first own node (row 6*pad0 of the permuted solution)
+    int pad1;
     long long panel_off;  // doubles into the factor store: panel [6(n1+n2)] x [6 n1], column-major
     long long schur_off;  // doubles into the Schur arena of this front's level parity: [6 n2] x [6 n2]
     long long dinv_off;   // doubles into the factor store: ceil(6 n1 / NB) inverted diagonal tiles NB x NB
@@ -63,7 +64,8 @@ struct CholPlanHost {
     int max_front_nodes = 0;
     // device index buffer layout (bytes), filled by layout()
     size_t off_fronts = 0, off_nodes = 0, off_child = 0, off_inv_off = 0, off_inv = 0, off_level_fronts = 0,
-           off_kscatter = 0, index_bytes = 0;
+           off_kscatter = 0, off_pos = 0, index_bytes = 0;
+    std::vector<unsigned char> staging;   // serialised index buffer (filled on first upload)
 };
 
 }  // namespace fers

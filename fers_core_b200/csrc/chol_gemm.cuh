@@ -1,0 +1,159 @@
+// chol_gemm.cuh -- fp64 tile GEMM core of the multifrontal Cholesky (C -= A * op(B)).
+//
+// All matrices are column-major.  A is M x K with rows contiguous; B is either N x K with rows
+// contiguous ("NT": C -= A B^T, the form of every factorisation update and of the forward
+// substitution) or K x N with K contiguous ("NN": the backward substitution, which multiplies by L^T).
+// One CTA of 256 threads computes a (16 TM) x (16 TN) tile; a thread owns TM x TN accumulators laid
+// out as 2-wide row / column pairs every 32 rows / columns, so that
+//   - the A fragment of a warp is 16 consecutive 16-byte words (conflict-free LDS.128, the two
+//     column groups of the warp read the same words = broadcast),
+//   - a C column segment written by a warp is 256 contiguous bytes.
+// Operand tiles move global -> shared with cp.async (16 B, zero-fill outside the matrix) through a
+// STAGES-deep ring; the fp64 pipe is the intended limiter (64 DFMA per 8 shared loads per thread).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fers {
+
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_BKP = GEMM_BK + 2;   // padded K extent of the K-major B tile
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int TM, int TN, bool B_KMAJOR>
+struct GemmTile {
+    static constexpr int BM = 16 * TM, BN = 16 * TN;
+    static constexpr int A_STAGE = GEMM_BK * BM;                                   // doubles
+    static constexpr int B_STAGE = B_KMAJOR ? BN * GEMM_BKP : GEMM_BK * BN;        // doubles
+    static constexpr size_t SMEM = (size_t)GEMM_STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+
+    // stage loader: k-tile kt (columns kt*BK .. ) of A (mrem x K, lda) and B into ring slot `slot`
+    __device__ static __forceinline__ void load_stage(double* smem, int slot, int kt, const double* __restrict__ A, int lda,
+                                                      int mrem, const double* __restrict__ B, int ldb, int nrem, int K) {
+        const int tid = threadIdx.x;
+        const int k0 = kt * GEMM_BK;
+        double* as = smem + (size_t)slot * (A_STAGE + B_STAGE);
+        double* bs = as + A_STAGE;
+        const uint32_t as_addr = (uint32_t)__cvta_generic_to_shared(as);
+        const uint32_t bs_addr = (uint32_t)__cvta_generic_to_shared(bs);
+        constexpr int A_CHUNKS = GEMM_BK * BM / 2;
+#pragma unroll
+        for (int c = tid; c < A_CHUNKS; c += GEMM_THREADS) {
+            const int k = c / (BM / 2), i = 2 * (c % (BM / 2));
+            const bool ok = (i < mrem) && (k0 + k < K);
+            const double* src = ok ? A + (size_t)(k0 + k) * lda + i : A;
+            cp_async16(as_addr + (uint32_t)(k * BM + i) * 8u, src, ok);
+        }
+        if (!B_KMAJOR) {
+            constexpr int B_CHUNKS = GEMM_BK * BN / 2;
+#pragma unroll
+            for (int c = tid; c < B_CHUNKS; c += GEMM_THREADS) {
+                const int k = c / (BN / 2), j = 2 * (c % (BN / 2));
+                const bool ok = (j < nrem) && (k0 + k < K);
+                const double* src = ok ? B + (size_t)(k0 + k) * ldb + j : B;
+                cp_async16(bs_addr + (uint32_t)(k * BN + j) * 8u, src, ok);
+            }
+        } else {
+            constexpr int B_CHUNKS = BN * GEMM_BK / 2;
+#pragma unroll
+            for (int c = tid; c < B_CHUNKS; c += GEMM_THREADS) {
+                const int j = c / (GEMM_BK / 2), k = 2 * (c % (GEMM_BK / 2));
+                const bool ok = (j < nrem) && (k0 + k < K);
+                const double* src = ok ? B + (size_t)j * ldb + k0 + k : B;
+                cp_async16(bs_addr + (uint32_t)(j * GEMM_BKP + k) * 8u, src, ok);
+            }
+        }
+    }
+
+    // acc += A(mrem x K) * op(B)(K x nrem) for this CTA's tile (pointers at the tile origin)
+    __device__ static __forceinline__ void mainloop(double (&acc)[TM][TN], double* smem, const double* __restrict__ A, int lda,
+                                                    int mrem, const double* __restrict__ B, int ldb, int nrem, int K) {
+        const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
+        const int nk = (K + GEMM_BK - 1) / GEMM_BK;
+#pragma unroll
+        for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+            if (s < nk) load_stage(smem, s, s, A, lda, mrem, B, ldb, nrem, K);
+            cp_async_commit();
+        }
+        for (int kt = 0; kt < nk; ++kt) {
+            cp_async_wait<GEMM_STAGES - 2>();
+            __syncthreads();
+            {
+                const int nxt = kt + GEMM_STAGES - 1;
+                if (nxt < nk) load_stage(smem, nxt % GEMM_STAGES, nxt, A, lda, mrem, B, ldb, nrem, K);
+                cp_async_commit();
+            }
+            const double* as = smem + (size_t)(kt % GEMM_STAGES) * (A_STAGE + B_STAGE);
+            const double* bs = as + A_STAGE;
+#pragma unroll
+            for (int kk = 0; kk < GEMM_BK; ++kk) {
+                double a[TM], b[TN];
+#pragma unroll
+                for (int q = 0; q < TM / 2; ++q) {
+                    const double2 v = *reinterpret_cast<const double2*>(as + kk * BM + 32 * q + 2 * tx);
+                    a[2 * q] = v.x; a[2 * q + 1] = v.y;
+                }
+                if (!B_KMAJOR) {
+#pragma unroll
+                    for (int q = 0; q < TN / 2; ++q) {
+                        const double2 v = *reinterpret_cast<const double2*>(bs + kk * BN + 32 * q + 2 * ty);
+                        b[2 * q] = v.x; b[2 * q + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < TN / 2; ++q) {
+                        b[2 * q] = bs[(32 * q + 2 * ty) * GEMM_BKP + kk];
+                        b[2 * q + 1] = bs[(32 * q + 2 * ty + 1) * GEMM_BKP + kk];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+    // C = C - acc (SET == false) or C = acc (SET == true) on the valid part of the tile
+    template <bool SET>
+    __device__ static __forceinline__ void store(const double (&acc)[TM][TN], double* __restrict__ C, size_t ldc, int mrem,
+                                                 int nrem) {
+        const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int col = 32 * (j / 2) + 2 * ty + (j & 1);
+            if (col >= nrem) continue;
+#pragma unroll
+            for (int q = 0; q < TM / 2; ++q) {
+                const int row = 32 * q + 2 * tx;
+                if (row >= mrem) continue;
+                double2* p = reinterpret_cast<double2*>(C + (size_t)col * ldc + row);
+                double2 v;
+                if (SET) {
+                    v.x = acc[2 * q][j]; v.y = acc[2 * q + 1][j];
+                } else {
+                    v = *p;
+                    v.x -= acc[2 * q][j]; v.y -= acc[2 * q + 1][j];
+                }
+                *p = v;
+            }
+        }
+    }
+};
+
+}  // namespace fers

@@ -1,0 +1,764 @@
+// chol_numeric.cu -- numeric phase of the sparse multifrontal Cholesky on the GPU (SURVEY.md 8a row
+// A10: "a batch first-order solve that shares one factorization across many load cases",
+// fers_core/types/pydantic_models.py:1216-1219).
+//
+// Fronts of one tree level are independent and processed as a batch (blockIdx.z = front).  Per level:
+//   k_front_init    gather the children's Schur complements into the panel [F11;F21] and into F22
+//   k_scatter_k     add the (equilibrated, BC-masked) stiffness blocks of the own nodes
+//   per 64-column step s:  k_potrf_inv (diagonal tile: Cholesky + inverse)
+//                          k_trsm      (rows below: X = B * inv(D)^T, tile GEMM)
+//                          k_update    (trailing columns of the panel: C -= X X^T, tile GEMM)
+//   k_syrk          F22 -= L21 L21^T  (tile GEMM, K = all own columns)  -> Schur complement for the parent
+// The substitution runs the same level schedule with front-local right-hand-side blocks (forward:
+// children -> parent, backward: parent -> children); all its products are tile GEMMs with the
+// right-hand-side index as the contiguous dimension.  No atomics anywhere: results are deterministic.
+#include <vector>
+
+#include "chol.cuh"
+#include "chol_gemm.cuh"
+#include "common.cuh"
+
+namespace fers {
+
+void chol_plan_serialise(const CholPlanHost& P, unsigned char* out);
+
+struct LevelCtx {
+    const FrontDev* fronts;
+    const int* level_fronts;   // fronts of this level
+    const int* nodes;
+    const int* child;
+    const long long* inv_off;
+    const int* inv;
+    double* factor;
+    double* schur_cur;         // arena of this level
+    const double* schur_child; // arena of the children's level
+};
+
+// ---- front initialisation: children's Schur complements -> panel + F22 (lower triangle) -----------
+constexpr int INIT_ROWS = 192;
+constexpr int INIT_COLS = 24;
+
+__global__ void __launch_bounds__(INIT_ROWS)
+k_front_init(LevelCtx L) {
+    const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
+    const int nt = f.n1 + f.n2, m = 6 * nt, k1 = 6 * f.n1, m2 = 6 * f.n2;
+    const int r0 = blockIdx.x * INIT_ROWS, c0 = blockIdx.y * INIT_COLS;
+    if (r0 >= m || c0 >= m || c0 > r0 + INIT_ROWS - 1) return;
+    const int r = r0 + threadIdx.x;
+    if (r >= m) return;
+    const int bi = r / 6, a = r - 6 * bi;
+    double v[INIT_COLS];
+#pragma unroll
+    for (int q = 0; q < INIT_COLS; ++q) v[q] = 0.0;
+    for (int ce = f.child_begin; ce < f.child_end; ++ce) {
+        const int* mp = L.inv + L.inv_off[ce];
+        const int ci = mp[bi];
+        if (ci < 0) continue;
+        const FrontDev fc = L.fronts[L.child[ce]];
+        const size_t ldc = 6 * (size_t)fc.n2;
+        const double* s = L.schur_child + fc.schur_off + 6 * ci + a;
+#pragma unroll
+        for (int q = 0; q < INIT_COLS; ++q) {
+            const int c = c0 + q;
+            if (c > r || c >= m) continue;
+            const int bj = c / 6, b = c - 6 * bj;
+            const int cj = mp[bj];
+            if (cj >= 0) v[q] += s[(size_t)(6 * cj + b) * ldc];
+        }
+    }
+    double* panel = L.factor + f.panel_off;
+    double* schur = L.schur_cur + f.schur_off;
+#pragma unroll
+    for (int q = 0; q < INIT_COLS; ++q) {
+        const int c = c0 + q;
+        if (c > r || c >= m) continue;
+        if (c < k1) panel[(size_t)c * m + r] = v[q];
+        else schur[(size_t)(c - k1) * m2 + (r - k1)] = v[q];
+    }
+}
+
+// ---- equilibration: sc[d] = 1 / sqrt(K_dd) (1 for constrained DOFs and non-positive diagonals) ----
+__global__ void k_chol_scale(int n_nodes, const double* __restrict__ vals, const int* __restrict__ diag_slot,
+                             const uint8_t* __restrict__ fixed, const double* __restrict__ kspring, double* __restrict__ sc) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= 6 * n_nodes) return;
+    const int n = d / 6, a = d - 6 * n;
+    double k = vals[(size_t)diag_slot[n] * 36 + a * 7];
+    if (kspring != nullptr) k += kspring[d];
+    sc[d] = (fixed[d] || !(k > 0.0)) ? 1.0 : rsqrt(k);
+}
+
+// ---- stiffness blocks -> panel (one warp per block) ----------------------------------------------
+__global__ void __launch_bounds__(256)
+k_scatter_k(LevelCtx L, const KScatter* __restrict__ ks, long long n_entries, const double* __restrict__ vals,
+            const uint8_t* __restrict__ fixed, const double* __restrict__ kspring, const double* __restrict__ sc) {
+    const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= n_entries) return;
+    const int lane = threadIdx.x & 31;
+    const KScatter e = ks[w];
+    const FrontDev f = L.fronts[e.front];
+    const int m = 6 * (f.n1 + f.n2);
+    const int gi = L.nodes[f.nodes_off + e.bi], gj = L.nodes[f.nodes_off + e.bj];
+    double* panel = L.factor + f.panel_off;
+    for (int t = lane; t < 36; t += 32) {
+        const int a = t / 6, b = t - 6 * a;
+        if (e.bi == e.bj && a < b) continue;      // upper triangle is never read
+        const int dr = 6 * gi + a, dc = 6 * gj + b;
+        double v;
+        if (fixed[dr] || fixed[dc]) {
+            v = (dr == dc) ? 1.0 : 0.0;
+        } else {
+            v = vals[(size_t)e.k * 36 + t];
+            if (dr == dc && kspring != nullptr) v += kspring[dr];
+            v *= sc[dr] * sc[dc];
+        }
+        panel[(size_t)(6 * e.bj + b) * m + 6 * e.bi + a] += v;
+    }
+}
+
+// ---- diagonal tile: Cholesky + explicit inverse of the factor --------------------------------------
+constexpr int NB = CHOL_NB;
+constexpr int TP = NB + 1;
+constexpr size_t POTRF_SMEM = 2 * NB * TP * sizeof(double);
+
+__global__ void __launch_bounds__(256)
+k_potrf_inv(LevelCtx L, int s, int* __restrict__ info) {
+    const int fid = L.level_fronts[blockIdx.x];
+    const FrontDev f = L.fronts[fid];
+    const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
+    const int c0 = s * NB;
+    if (c0 >= k1) return;
+    const int nb = min(NB, k1 - c0);
+    extern __shared__ __align__(16) double potrf_smem[];
+    double* T = potrf_smem;
+    double* X = potrf_smem + NB * TP;
+    __shared__ int s_bad;
+    double* panel = L.factor + f.panel_off;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_bad = 0;
+    for (int t = tid; t < NB * NB; t += 256) {
+        const int i = t % NB, j = t / NB;
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < nb && j < nb && i >= j) v = panel[(size_t)(c0 + j) * m + c0 + i];
+        T[i * TP + j] = v;
+    }
+    const int ti = tid & 63, tq = tid >> 6;
+    for (int j = 0; j < NB; ++j) {
+        __syncthreads();
+        const double d = T[j * TP + j];
+        const bool bad = !(d > 0.0);
+        const double rt = bad ? 1.0 : sqrt(d);
+        const double rinv = 1.0 / rt;
+        __syncthreads();
+        if (tq == 0) {
+            if (ti == j) { T[j * TP + j] = rt; if (bad && s_bad == 0) s_bad = j + 1; }
+            else if (ti > j) T[ti * TP + j] *= rinv;
+        }
+        __syncthreads();
+        const double lij = T[ti * TP + j];
+        for (int k = j + 1 + tq; k < NB; k += 4)
+            if (ti >= k) T[ti * TP + k] -= lij * T[k * TP + j];
+    }
+    __syncthreads();
+    // inverse, one thread per column: X[:, c] = L^-1 e_c by forward substitution
+    if (tid < NB) {
+        const int c = tid;
+        for (int i = 0; i < NB; ++i) {
+            double acc = (i == c) ? 1.0 : 0.0;
+            for (int k = c; k < i; ++k) acc -= T[i * TP + k] * X[k * TP + c];
+            X[i * TP + c] = (i < c) ? 0.0 : acc / T[i * TP + i];
+        }
+    }
+    __syncthreads();
+    double* dinv = L.factor + f.dinv_off + (size_t)s * NB * NB;
+    for (int t = tid; t < NB * NB; t += 256) {
+        const int i = t % NB, j = t / NB;
+        dinv[t] = X[i * TP + j];                                  // column-major NB x NB
+        if (i < nb && j < nb && i >= j) panel[(size_t)(c0 + j) * m + c0 + i] = T[i * TP + j];
+    }
+    if (tid == 0 && s_bad) atomicMax(info, 6 * f.pad0 + c0 + s_bad);   // 1-based elimination-order DOF
+}
+
+// ---- tile GEMM kernels of the factorisation --------------------------------------------------------
+using G88 = GemmTile<8, 8, false>;
+using G84 = GemmTile<8, 4, false>;
+
+// rows below the diagonal tile of step s:  X = B * inv(D)^T   (in place)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_trsm(LevelCtx L, int s) {
+    extern __shared__ __align__(16) double smem[];
+    const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
+    const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
+    const int c0 = s * NB;
+    if (c0 >= k1) return;
+    const int nb = min(NB, k1 - c0);
+    const int r0 = c0 + nb + blockIdx.x * G84::BM;
+    if (r0 >= m) return;
+    double* A = L.factor + f.panel_off + (size_t)c0 * m + r0;
+    const double* B = L.factor + f.dinv_off + (size_t)s * NB * NB;
+    double acc[8][4];
+    G84::mainloop(acc, smem, A, m, m - r0, B, NB, nb, nb);
+    G84::store<true>(acc, A, (size_t)m, m - r0, nb);
+}
+
+// trailing columns of the panel after step s:  C -= X X^T on the lower tiles
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_update(LevelCtx L, int s) {
+    extern __shared__ __align__(16) double smem[];
+    const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
+    const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
+    const int c0 = (s + 1) * NB;
+    if (c0 >= k1) return;
+    const int ti = blockIdx.x, tj = blockIdx.y;
+    if (tj > ti) return;
+    const int r = c0 + ti * G88::BM, c = c0 + tj * G88::BN;
+    if (r >= m || c >= k1) return;
+    const double* X = L.factor + f.panel_off + (size_t)(s * NB) * m;
+    double acc[8][8];
+    G88::mainloop(acc, smem, X + r, m, m - r, X + c, m, k1 - c, NB);
+    G88::store<false>(acc, L.factor + f.panel_off + (size_t)c * m + r, (size_t)m, m - r, k1 - c);
+}
+
+// Schur complement: F22 -= L21 L21^T on the lower tiles
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_syrk(LevelCtx L) {
+    extern __shared__ __align__(16) double smem[];
+    const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
+    const int k1 = 6 * f.n1, m2 = 6 * f.n2, m = k1 + m2;
+    const int ti = blockIdx.x, tj = blockIdx.y;
+    if (tj > ti) return;
+    const int r = ti * G88::BM, c = tj * G88::BN;
+    if (r >= m2 || c >= m2) return;
+    const double* L21 = L.factor + f.panel_off + k1;
+    double acc[8][8];
+    G88::mainloop(acc, smem, L21 + r, m, m2 - r, L21 + c, m, m2 - c, k1);
+    G88::store<false>(acc, L.schur_cur + f.schur_off + (size_t)c * m2 + r, (size_t)m2, m2 - r, m2 - c);
+}
+
+// ---- substitution ------------------------------------------------------------------------------------
+struct SolveCtx {
+    const FrontDev* fronts;
+    const int* level_fronts;
+    const int* nodes;
+    const int* child;
+    const long long* inv_off;
+    const int* inv;
+    const int* pos;            // node -> elimination position
+    const double* factor;
+    double* W;                 // front-local right-hand sides [rhs_rows][nrhs]
+    double* Y;                 // solution in elimination order [n_dof][nrhs]
+    int nrhs;
+};
+
+// W_f = [ sc * b(own) ; 0 ] + sum over children of their updated boundary rows
+__global__ void __launch_bounds__(256)
+k_fwd_gather(SolveCtx S, const double* __restrict__ b, const uint8_t* __restrict__ fixed, const double* __restrict__ sc) {
+    const FrontDev f = S.fronts[S.level_fronts[blockIdx.y]];
+    const int m = 6 * (f.n1 + f.n2);
+    const int nr = S.nrhs;
+    const long long total = (long long)m * nr;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int row = (int)(idx / nr), r = (int)(idx - (long long)row * nr);
+        const int q = row / 6, a = row - 6 * q;
+        double v = 0.0;
+        if (q < f.n1) {
+            const int g = 6 * S.nodes[f.nodes_off + q] + a;
+            v = fixed[g] ? 0.0 : b[(size_t)g * nr + r] * sc[g];
+        }
+        for (int ce = f.child_begin; ce < f.child_end; ++ce) {
+            const int ci = S.inv[S.inv_off[ce] + q];
+            if (ci < 0) continue;
+            const FrontDev fc = S.fronts[S.child[ce]];
+            v += S.W[(size_t)(fc.rhs_off + 6 * (fc.n1 + ci) + a) * nr + r];
+        }
+        S.W[(size_t)(f.rhs_off + row) * nr + r] = v;
+    }
+}
+
+// boundary rows of W_f <- solved values of the ancestors
+__global__ void __launch_bounds__(256)
+k_bwd_gather(SolveCtx S) {
+    const FrontDev f = S.fronts[S.level_fronts[blockIdx.y]];
+    const int k1 = 6 * f.n1, m2 = 6 * f.n2;
+    const int nr = S.nrhs;
+    const long long total = (long long)m2 * nr;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int row = (int)(idx / nr), r = (int)(idx - (long long)row * nr);
+        const int q = row / 6, a = row - 6 * q;
+        const int node = S.nodes[f.nodes_off + f.n1 + q];
+        S.W[(size_t)(f.rhs_off + k1 + row) * nr + r] = S.Y[(size_t)(6 * S.pos[node] + a) * nr + r];
+    }
+}
+
+// x[node dof] = sc * Y[elimination dof]; constrained DOFs -> 0
+__global__ void __launch_bounds__(256)
+k_chol_unpermute(int n_nodes, int nr, const int* __restrict__ pos, const uint8_t* __restrict__ fixed,
+                 const double* __restrict__ sc, const double* __restrict__ Y, double* __restrict__ x, int accumulate) {
+    const long long total = (long long)n_nodes * 6 * nr;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int d = (int)(idx / nr), r = (int)(idx - (long long)d * nr);
+        const int n = d / 6, a = d - 6 * n;
+        const double v = fixed[d] ? 0.0 : sc[d] * Y[(size_t)(6 * pos[n] + a) * nr + r];
+        if (accumulate) x[idx] += v; else x[idx] = v;
+    }
+}
+
+using G44 = GemmTile<4, 4, false>;
+using G48 = GemmTile<4, 8, false>;
+using G44N = GemmTile<4, 4, true>;
+using G48N = GemmTile<4, 8, true>;
+
+// forward, diagonal tile of step s:  y_s = inv(D_s) w_s  -> Y
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_fwd_diag(SolveCtx S, int s) {
+    extern __shared__ __align__(16) double smem[];
+    const FrontDev f = S.fronts[S.level_fronts[blockIdx.x]];
+    const int k1 = 6 * f.n1;
+    const int c0 = s * NB;
+    if (c0 >= k1) return;
+    const int nb = min(NB, k1 - c0), nr = S.nrhs;
+    const double* A = S.W + (size_t)(f.rhs_off + c0) * nr;
+    const double* B = S.factor + f.dinv_off + (size_t)s * NB * NB;
+    double acc[4][4];
+    G44::mainloop(acc, smem, A, nr, nr, B, NB, nb, nb);
+    G44::store<true>(acc, S.Y + (size_t)(6 * f.pad0 + c0) * nr, (size_t)nr, nr, nb);
+}
+
+// forward, rows below step s:  w_rest -= L[rest, s] y_s
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_fwd_update(SolveCtx S, int s) {
+    extern __shared__ __align__(16) double smem[];
+    const FrontDev f = S.fronts[S.level_fronts[blockIdx.y]];
+    const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
+    const int c0 = s * NB;
+    if (c0 >= k1) return;
+    const int nb = min(NB, k1 - c0), nr = S.nrhs;
+    const int r0 = c0 + nb + blockIdx.x * G48::BN;
+    if (r0 >= m) return;
+    const double* A = S.Y + (size_t)(6 * f.pad0 + c0) * nr;
+    const double* B = S.factor + f.panel_off + (size_t)c0 * m + r0;
+    double acc[4][8];
+    G48::mainloop(acc, smem, A, nr, nr, B, m, m - r0, nb);
+    G48::store<false>(acc, S.W + (size_t)(f.rhs_off + r0) * nr, (size_t)nr, nr, m - r0);
+}
+
+// backward, boundary coupling:  y_own -= L21^T x_bnd
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_bwd_bnd(SolveCtx S) {
+    extern __shared__ __align__(16) double smem[];
+    const FrontDev f = S.fronts[S.level_fronts[blockIdx.y]];
+    const int k1 = 6 * f.n1, m2 = 6 * f.n2, m = k1 + m2;
+    const int c = blockIdx.x * G44N::BN;
+    if (c >= k1 || m2 == 0) return;
+    const int nr = S.nrhs;
+    const double* A = S.W + (size_t)(f.rhs_off + k1) * nr;
+    const double* B = S.factor + f.panel_off + (size_t)c * m + k1;
+    double acc[4][4];
+    G44N::mainloop(acc, smem, A, nr, nr, B, m, k1 - c, m2);
+    G44N::store<false>(acc, S.Y + (size_t)(6 * f.pad0 + c) * nr, (size_t)nr, nr, k1 - c);
+}
+
+// backward, diagonal tile of step s:  x_s = inv(D_s)^T y_s   (in place in Y)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_bwd_diag(SolveCtx S, int s) {
+    extern __shared__ __align__(16) double smem[];
+    const FrontDev f = S.fronts[S.level_fronts[blockIdx.x]];
+    const int k1 = 6 * f.n1;
+    const int c0 = s * NB;
+    if (c0 >= k1) return;
+    const int nb = min(NB, k1 - c0), nr = S.nrhs;
+    double* A = S.Y + (size_t)(6 * f.pad0 + c0) * nr;
+    const double* B = S.factor + f.dinv_off + (size_t)s * NB * NB;
+    double acc[4][4];
+    G44N::mainloop(acc, smem, A, nr, nr, B, NB, nb, nb);
+    G44N::store<true>(acc, A, (size_t)nr, nr, nb);
+}
+
+// backward, columns before step s:  y_before -= L[s, before]^T x_s
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_bwd_update(SolveCtx S, int s) {
+    extern __shared__ __align__(16) double smem[];
+    const FrontDev f = S.fronts[S.level_fronts[blockIdx.y]];
+    const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
+    const int c0 = s * NB;
+    if (c0 >= k1 || s == 0) return;
+    const int nb = min(NB, k1 - c0), nr = S.nrhs;
+    const int c = blockIdx.x * G48N::BN;
+    if (c >= c0) return;
+    const double* A = S.Y + (size_t)(6 * f.pad0 + c0) * nr;
+    const double* B = S.factor + f.panel_off + (size_t)c * m + c0;
+    double acc[4][8];
+    G48N::mainloop(acc, smem, A, nr, nr, B, m, c0 - c, nb);
+    G48N::store<false>(acc, S.Y + (size_t)(6 * f.pad0 + c) * nr, (size_t)nr, nr, c0 - c);
+}
+
+// r = mask (f - Kx); norms2[0][c] += r_c . r_c, norms2[1][c] += (mask f_c) . (mask f_c)  (diagnostics)
+__global__ void __launch_bounds__(256)
+k_chol_residual(long long n_dof, int nr, const double* __restrict__ f, const double* __restrict__ kx,
+                const uint8_t* __restrict__ fixed, double* __restrict__ r, double* __restrict__ norms2) {
+    __shared__ double s_r[64], s_f[64];
+    if (threadIdx.x < 64) { s_r[threadIdx.x] = 0.0; s_f[threadIdx.x] = 0.0; }
+    __syncthreads();
+    // thread -> fixed column (256 is a multiple of every supported nr), rows strided
+    const int c = threadIdx.x % nr;
+    const int rows_per_pass = 256 / nr;
+    double ar = 0.0, af = 0.0;
+    for (long long d = (long long)blockIdx.x * rows_per_pass + threadIdx.x / nr; d < n_dof; d += (long long)gridDim.x * rows_per_pass) {
+        const size_t o = (size_t)d * nr + c;
+        double fv = f[o], rv = 0.0;
+        if (fixed[d]) fv = 0.0; else rv = fv - kx[o];
+        r[o] = rv;
+        ar = fma(rv, rv, ar); af = fma(fv, fv, af);
+    }
+    atomicAdd(&s_r[c], ar); atomicAdd(&s_f[c], af);
+    __syncthreads();
+    if (threadIdx.x < nr) { atomicAdd(&norms2[threadIdx.x], s_r[threadIdx.x]); atomicAdd(&norms2[nr + threadIdx.x], s_f[threadIdx.x]); }
+}
+
+// ---- host driver ---------------------------------------------------------------------------------------
+struct CholProfile {
+    // ms per kernel class of the last profiled factorisation / substitution
+    double init = 0, scatter = 0, potrf = 0, trsm = 0, update = 0, syrk = 0, factor_total = 0;
+    double solve_total = 0;
+    long long launches_factor = 0, launches_solve = 0;
+};
+static CholProfile g_chol_profile;
+static bool g_chol_profile_on = false;
+
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    cudaEvent_t get() {
+        if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+        return ev[used++];
+    }
+    void reset() { used = 0; }
+};
+static EventPool g_pool;
+
+struct Timed {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[6];
+    void clear() { for (auto& s : spans) s.clear(); }
+};
+static Timed g_timed;
+
+static int set_smem_attrs() {
+    static bool done = false;
+    if (done) return 0;
+    FERS_CK(cudaFuncSetAttribute(k_potrf_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G84::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G88::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G88::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_fwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_fwd_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G48::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_bwd_bnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_bwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_bwd_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G48N::SMEM));
+    done = true;
+    return 0;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+struct IndexPtrs {
+    const FrontDev* fronts;
+    const int* nodes;
+    const int* child;
+    const long long* inv_off;
+    const int* inv;
+    const int* level_fronts;
+    const KScatter* kscatter;
+    const int* pos;
+};
+static IndexPtrs index_ptrs(const CholPlanHost& P, const void* index_dev) {
+    const unsigned char* b = static_cast<const unsigned char*>(index_dev);
+    IndexPtrs I;
+    I.fronts = reinterpret_cast<const FrontDev*>(b + P.off_fronts);
+    I.nodes = reinterpret_cast<const int*>(b + P.off_nodes);
+    I.child = reinterpret_cast<const int*>(b + P.off_child);
+    I.inv_off = reinterpret_cast<const long long*>(b + P.off_inv_off);
+    I.inv = reinterpret_cast<const int*>(b + P.off_inv);
+    I.level_fronts = reinterpret_cast<const int*>(b + P.off_level_fronts);
+    I.kscatter = reinterpret_cast<const KScatter*>(b + P.off_kscatter);
+    I.pos = reinterpret_cast<const int*>(b + P.off_pos);
+    return I;
+}
+
+static size_t chol_work_bytes(const CholPlanHost& P, int nrhs) {
+    const size_t schur = (size_t)(P.schur_doubles[0] + P.schur_doubles[1]) * 8 + 512;
+    const size_t solve = ((size_t)P.rhs_rows + 6 * (size_t)P.n_nodes) * (size_t)nrhs * 8 + 512;
+    return align_up(schur > solve ? schur : solve) + 256;
+}
+
+static int chol_factor(const CholPlanHost& P, const void* index_dev, const double* vals, const int* diag_slot,
+                       const uint8_t* fixed, const double* kspring, double* factor, void* work, int* info_dev,
+                       cudaStream_t st) {
+    if (set_smem_attrs()) return 1;
+    const IndexPtrs I = index_ptrs(P, index_dev);
+    double* sc = factor + P.factor_doubles;
+    double* arena[2];
+    arena[0] = static_cast<double*>(work);
+    arena[1] = arena[0] + P.schur_doubles[0];
+    const bool prof = g_chol_profile_on;
+    if (prof) { g_pool.reset(); g_timed.clear(); }
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    if (prof) { ev_begin = g_pool.get(); cudaEventRecord(ev_begin, st); }
+    long long launches = 0;
+    auto span_begin = [&](int cls) -> cudaEvent_t {
+        if (!prof) return nullptr;
+        cudaEvent_t e = g_pool.get();
+        cudaEventRecord(e, st);
+        (void)cls;
+        return e;
+    };
+    auto span_end = [&](int cls, cudaEvent_t b) {
+        if (!prof) return;
+        cudaEvent_t e = g_pool.get();
+        cudaEventRecord(e, st);
+        g_timed.spans[cls].push_back({b, e});
+    };
+    FERS_CK(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
+    k_chol_scale<<<cdiv(6 * P.n_nodes, 256), 256, 0, st>>>(P.n_nodes, vals, diag_slot, fixed, kspring, sc);
+    FERS_LAUNCH_CHECK();
+    ++launches;
+    for (int l = 0; l < P.n_levels; ++l) {
+        const int nf = P.level_ptr[l + 1] - P.level_ptr[l];
+        if (nf == 0) continue;
+        LevelCtx L;
+        L.fronts = I.fronts; L.level_fronts = I.level_fronts + P.level_ptr[l]; L.nodes = I.nodes; L.child = I.child;
+        L.inv_off = I.inv_off; L.inv = I.inv; L.factor = factor;
+        L.schur_cur = arena[l & 1]; L.schur_child = arena[(l & 1) ^ 1];
+        const int max_m = 6 * P.level_max_n[l], max_k1 = 6 * P.level_max_n1[l];
+        cudaEvent_t e0 = span_begin(0);
+        {
+            dim3 grid(cdiv(max_m, INIT_ROWS), cdiv(max_m, INIT_COLS), nf);
+            k_front_init<<<grid, INIT_ROWS, 0, st>>>(L);
+            FERS_LAUNCH_CHECK();
+            ++launches;
+        }
+        span_end(0, e0);
+        const long long ks0 = P.kscatter_ptr[l], ks1 = P.kscatter_ptr[l + 1];
+        if (ks1 > ks0) {
+            e0 = span_begin(1);
+            k_scatter_k<<<(unsigned)((ks1 - ks0 + 7) / 8), 256, 0, st>>>(L, I.kscatter + ks0, ks1 - ks0, vals, fixed, kspring, sc);
+            FERS_LAUNCH_CHECK();
+            ++launches;
+            span_end(1, e0);
+        }
+        const int steps = cdiv(max_k1, NB);
+        for (int s = 0; s < steps; ++s) {
+            e0 = span_begin(2);
+            k_potrf_inv<<<nf, 256, POTRF_SMEM, st>>>(L, s, info_dev);
+            span_end(2, e0);
+            const int rows_below = max_m - s * NB;          // upper bound on rows below the diagonal tile
+            if (rows_below > 0) {
+                e0 = span_begin(3);
+                dim3 grid(cdiv(rows_below, G84::BM), 1, nf);
+                k_trsm<<<grid, GEMM_THREADS, G84::SMEM, st>>>(L, s);
+                span_end(3, e0);
+                ++launches;
+            }
+            const int trail_cols = max_k1 - (s + 1) * NB;
+            if (trail_cols > 0) {
+                e0 = span_begin(4);
+                dim3 grid(cdiv(max_m - (s + 1) * NB, G88::BM), cdiv(trail_cols, G88::BN), nf);
+                k_update<<<grid, GEMM_THREADS, G88::SMEM, st>>>(L, s);
+                span_end(4, e0);
+                ++launches;
+            }
+            FERS_LAUNCH_CHECK();
+            ++launches;
+        }
+        const int max_m2 = max_m;   // upper bound on 6 * n2
+        if (l + 1 < P.n_levels) {
+            e0 = span_begin(5);
+            dim3 grid(cdiv(max_m2, G88::BM), cdiv(max_m2, G88::BN), nf);
+            k_syrk<<<grid, GEMM_THREADS, G88::SMEM, st>>>(L);
+            FERS_LAUNCH_CHECK();
+            span_end(5, e0);
+            ++launches;
+        }
+    }
+    if (prof) { ev_end = g_pool.get(); cudaEventRecord(ev_end, st); }
+    count_launches(launches);
+    if (prof) {
+        FERS_CK(cudaStreamSynchronize(st));
+        double t[6] = {0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < 6; ++c)
+            for (auto& sp : g_timed.spans[c]) { float ms = 0; cudaEventElapsedTime(&ms, sp.first, sp.second); t[c] += ms; }
+        float tot = 0;
+        cudaEventElapsedTime(&tot, ev_begin, ev_end);
+        g_chol_profile.init = t[0]; g_chol_profile.scatter = t[1]; g_chol_profile.potrf = t[2];
+        g_chol_profile.trsm = t[3]; g_chol_profile.update = t[4]; g_chol_profile.syrk = t[5];
+        g_chol_profile.factor_total = tot;
+        g_chol_profile.launches_factor = launches;
+    }
+    return 0;
+}
+
+static int chol_solve(const CholPlanHost& P, const void* index_dev, const double* factor, const uint8_t* fixed, int nrhs,
+                      const double* b, double* x, int accumulate, void* work, cudaStream_t st) {
+    if (set_smem_attrs()) return 1;
+    const IndexPtrs I = index_ptrs(P, index_dev);
+    const double* sc = factor + P.factor_doubles;
+    SolveCtx S;
+    S.fronts = I.fronts; S.nodes = I.nodes; S.child = I.child; S.inv_off = I.inv_off; S.inv = I.inv; S.pos = I.pos;
+    S.factor = factor;
+    S.W = static_cast<double*>(work);
+    S.Y = S.W + (size_t)P.rhs_rows * nrhs;
+    S.nrhs = nrhs;
+    long long launches = 0;
+    const bool prof = g_chol_profile_on;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    if (prof) { cudaEventCreate(&ev_begin); cudaEventCreate(&ev_end); cudaEventRecord(ev_begin, st); }
+    for (int l = 0; l < P.n_levels; ++l) {                // forward: children -> parents
+        const int nf = P.level_ptr[l + 1] - P.level_ptr[l];
+        if (nf == 0) continue;
+        S.level_fronts = I.level_fronts + P.level_ptr[l];
+        const int max_m = 6 * P.level_max_n[l], max_k1 = 6 * P.level_max_n1[l];
+        {
+            const long long total = (long long)max_m * nrhs;
+            dim3 grid((unsigned)std::min<long long>((total + 255) / 256, 1024), nf);
+            k_fwd_gather<<<grid, 256, 0, st>>>(S, b, fixed, sc);
+            ++launches;
+        }
+        const int steps = cdiv(max_k1, NB);
+        for (int s = 0; s < steps; ++s) {
+            k_fwd_diag<<<nf, GEMM_THREADS, G44::SMEM, st>>>(S, s);
+            ++launches;
+            const int rows_below = max_m - s * NB;
+            if (rows_below > 0) {
+                dim3 grid(cdiv(rows_below, G48::BN), nf);
+                k_fwd_update<<<grid, GEMM_THREADS, G48::SMEM, st>>>(S, s);
+                ++launches;
+            }
+        }
+        FERS_LAUNCH_CHECK();
+    }
+    for (int l = P.n_levels - 1; l >= 0; --l) {           // backward: parents -> children
+        const int nf = P.level_ptr[l + 1] - P.level_ptr[l];
+        if (nf == 0) continue;
+        S.level_fronts = I.level_fronts + P.level_ptr[l];
+        const int max_m = 6 * P.level_max_n[l], max_k1 = 6 * P.level_max_n1[l];
+        if (l + 1 < P.n_levels) {
+            const long long total = (long long)max_m * nrhs;
+            dim3 grid((unsigned)std::min<long long>((total + 255) / 256, 1024), nf);
+            k_bwd_gather<<<grid, 256, 0, st>>>(S);
+            dim3 grid2(cdiv(max_k1, G44N::BN), nf);
+            k_bwd_bnd<<<grid2, GEMM_THREADS, G44N::SMEM, st>>>(S);
+            launches += 2;
+        }
+        const int steps = cdiv(max_k1, NB);
+        for (int s = steps - 1; s >= 0; --s) {
+            k_bwd_diag<<<nf, GEMM_THREADS, G44N::SMEM, st>>>(S, s);
+            ++launches;
+            if (s > 0) {
+                dim3 grid(cdiv(s * NB, G48N::BN), nf);
+                k_bwd_update<<<grid, GEMM_THREADS, G48N::SMEM, st>>>(S, s);
+                ++launches;
+            }
+        }
+        FERS_LAUNCH_CHECK();
+    }
+    {
+        const long long total = (long long)P.n_nodes * 6 * nrhs;
+        k_chol_unpermute<<<(unsigned)std::min<long long>((total + 255) / 256, 65535), 256, 0, st>>>(
+            P.n_nodes, nrhs, I.pos, fixed, sc, S.Y, x, accumulate);
+        FERS_LAUNCH_CHECK();
+        ++launches;
+    }
+    count_launches(launches);
+    if (prof) {
+        cudaEventRecord(ev_end, st);
+        FERS_CK(cudaStreamSynchronize(st));
+        float tot = 0;
+        cudaEventElapsedTime(&tot, ev_begin, ev_end);
+        g_chol_profile.solve_total = tot;
+        g_chol_profile.launches_solve = launches;
+        cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
+    }
+    return 0;
+}
+
+}  // namespace fers
+
+using namespace fers;
+
+extern "C" {
+
+size_t fers_b200_chol_factor_bytes(void* plan) {
+    if (!plan) return 0;
+    const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    return align_up(((size_t)P.factor_doubles + 6 * (size_t)P.n_nodes) * 8);
+}
+
+size_t fers_b200_chol_work_bytes(void* plan, int nrhs) {
+    if (!plan) return 0;
+    return chol_work_bytes(*static_cast<CholPlanHost*>(plan), nrhs < 1 ? 1 : nrhs);
+}
+
+int fers_b200_chol_upload(void* plan, void* index_dev, void* stream) {
+    FERS_REQUIRE(plan && index_dev, "chol_upload: bad arguments");
+    CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    if (P.staging.size() != P.index_bytes) {
+        P.staging.assign(P.index_bytes, 0);
+        chol_plan_serialise(P, P.staging.data());
+    }
+    FERS_CK(cudaMemcpyAsync(index_dev, P.staging.data(), P.index_bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    FERS_CK(cudaStreamSynchronize(as_stream(stream)));
+    return 0;
+}
+
+int fers_b200_chol_factor(void* plan, const void* index_dev, const double* vals, const int* diag_slot,
+                          const uint8_t* fixed, const double* kspring, double* factor, void* work, size_t work_bytes,
+                          int* info_dev, int* info_out, void* stream) {
+    FERS_REQUIRE(plan && index_dev && vals && diag_slot && fixed && factor && work && info_dev, "chol_factor: bad arguments");
+    const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    FERS_REQUIRE(work_bytes >= chol_work_bytes(P, 1), "chol_factor: workspace too small");
+    const int rc = chol_factor(P, index_dev, vals, diag_slot, fixed, kspring, factor, work, info_dev, as_stream(stream));
+    if (rc) return rc;
+    if (info_out) {
+        FERS_CK(cudaMemcpyAsync(info_out, info_dev, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
+        FERS_CK(cudaStreamSynchronize(as_stream(stream)));
+    }
+    return 0;
+}
+
+int fers_b200_chol_solve(void* plan, const void* index_dev, const double* factor, const uint8_t* fixed, int nrhs,
+                         const double* b, double* x, int accumulate, void* work, size_t work_bytes, void* stream) {
+    FERS_REQUIRE(plan && index_dev && factor && fixed && b && x && work, "chol_solve: bad arguments");
+    FERS_REQUIRE(nrhs >= 2 && nrhs <= 64 && (nrhs % 2) == 0, "chol_solve: nrhs must be even and in 2..64 (pad the right-hand sides)");
+    const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    FERS_REQUIRE(work_bytes >= chol_work_bytes(P, nrhs), "chol_solve: workspace too small");
+    return chol_solve(P, index_dev, factor, fixed, nrhs, b, x, accumulate, work, as_stream(stream));
+}
+
+int fers_b200_residual(long long n_dof, int nrhs, const double* f, const double* kx, const uint8_t* fixed, double* r,
+                       double* norms2, void* stream) {
+    FERS_REQUIRE(f && kx && fixed && r && norms2, "residual: bad arguments");
+    FERS_REQUIRE(nrhs >= 1 && nrhs <= 64 && 256 % nrhs == 0, "residual: nrhs must divide 256 and be <= 64");
+    cudaStream_t st = as_stream(stream);
+    FERS_CK(cudaMemsetAsync(norms2, 0, 2 * (size_t)nrhs * sizeof(double), st));
+    const int rows_per_pass = 256 / nrhs;
+    long long grid = (n_dof + rows_per_pass - 1) / rows_per_pass;
+    const long long cap = (long long)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    k_chol_residual<<<(unsigned)grid, 256, 0, st>>>(n_dof, nrhs, f, kx, fixed, r, norms2);
+    FERS_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int fers_b200_chol_set_profile(int on) { g_chol_profile_on = on != 0; return 0; }
+
+/* out[10]: ms of init, scatter, potrf, trsm, update, syrk, factor total, solve total; launches factor, solve */
+int fers_b200_chol_profile(double* out, int n_out) {
+    FERS_REQUIRE(out && n_out >= 10, "chol_profile: need 10 outputs");
+    const CholProfile& p = g_chol_profile;
+    out[0] = p.init; out[1] = p.scatter; out[2] = p.potrf; out[3] = p.trsm; out[4] = p.update; out[5] = p.syrk;
+    out[6] = p.factor_total; out[7] = p.solve_total; out[8] = (double)p.launches_factor; out[9] = (double)p.launches_solve;
+    return 0;
+}
+
+}  // extern "C"

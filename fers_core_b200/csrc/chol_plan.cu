@@ -172,6 +172,7 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
         P.front_first[i] = (int)P.perm.size();
         for (int v : fb.own) { P.pos[v] = (int)P.perm.size(); P.perm.push_back(v); }
         P.fronts[i].n1 = (int)fb.own.size();
+        P.fronts[i].pad0 = P.front_first[i];
         P.fronts[i].parent = fb.parent < 0 ? -1 : new_id[fb.parent];
         max_depth = std::max(max_depth, fb.depth);
     }
@@ -315,6 +316,7 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
     P.off_inv = place(sizeof(int) * P.inv.size());
     P.off_level_fronts = place(sizeof(int) * P.level_fronts.size());
     P.off_kscatter = place(sizeof(KScatter) * P.kscatter.size());
+    P.off_pos = place(sizeof(int) * P.pos.size());
     P.index_bytes = o;
     return 0;
 }
@@ -394,6 +396,7 @@ void chol_plan_serialise(const CholPlanHost& P, unsigned char* out) {
     memcpy(out + P.off_inv, P.inv.data(), sizeof(int) * P.inv.size());
     memcpy(out + P.off_level_fronts, P.level_fronts.data(), sizeof(int) * P.level_fronts.size());
     memcpy(out + P.off_kscatter, P.kscatter.data(), sizeof(KScatter) * P.kscatter.size());
+    memcpy(out + P.off_pos, P.pos.data(), sizeof(int) * P.pos.size());
 }
 }  // namespace fers
 

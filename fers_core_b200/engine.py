@@ -16,13 +16,16 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from . import _lib, wire
+from . import _lib, chol, wire
 from .hostlogic import (
     INACTIVE_SCALE, imperfect_coordinates, pdelta_suppressed_axes, rhs_plan, rigid_property_row,
 )
 from .results import ResultArrays, SECTION_FRACS, results_to_wire
 
 DENSE_MAX_DOF = 8192          # models up to this many DOFs use the dense Cholesky path
+SOLVERS = ("auto", "dense", "cholesky", "pcg")   # auto: dense up to DENSE_MAX_DOF, sparse Cholesky above
+CHOL_REFINE_STEPS = 1         # iterative-refinement passes after the direct substitution
+CHOL_RESIDUAL_LIMIT = 1e-8    # relative residual above which the direct solve is reported as failed
 PCG_TOL = 1e-12               # relative residual ||r|| / ||b|| per right-hand side
 PCG_MAX_ITER = 200000
 PCG_ALLOW_UNCONVERGED = False  # profiling captures only (bench.py --profile-iters)
@@ -60,7 +63,13 @@ class SolveStats:
 class Engine:
     """One model resident on one GPU."""
 
-    def __init__(self, model: wire.ModelArrays, device=None, assembly_variant: int = 0):
+    def __init__(self, model: wire.ModelArrays, device=None, assembly_variant: int = 0, solver: str = "auto"):
+        if solver not in SOLVERS:
+            raise EngineError(f"solver must be one of {SOLVERS}, got {solver!r}")
+        self.solver = solver
+        self._chol = None
+        self._k_version = 0
+        self._chol_version = -1
         self.model = model
         self.dev = _require_cuda(device)
         self.lib = _lib.load()
@@ -173,6 +182,7 @@ class Engine:
     def assemble(self, d_xyz, d_scale=None, d_axial=None, kg_mode=0, kg_suppress=0) -> None:
         """Element stiffness + assembly + boundary conditions for one geometry / state."""
         m, lib, st = self.model, self.lib, self.stream
+        self._k_version += 1
         _lib.check(lib.fers_b200_zero(_lib.ptr(self.d_vals), self.d_vals.numel() * 8, st), "zero")
         _lib.check(lib.fers_b200_assemble_beams(
             m.n_members, _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_prop),
@@ -225,7 +235,12 @@ class Engine:
         """K_ff u = f for all columns of d_f [Ndof,nr]; returns u [Ndof,nr]."""
         m, lib, st = self.model, self.lib, self.stream
         nd, nr = d_f.shape
-        if nd <= DENSE_MAX_DOF:
+        method = self.solver
+        if method == "auto":
+            method = "dense" if nd <= DENSE_MAX_DOF else "cholesky"
+        if method == "cholesky" and nr >= 2 and nr % 2 == 0:
+            return self._solve_cholesky(d_f)
+        if method == "dense" or (method == "cholesky" and nd <= DENSE_MAX_DOF):
             a = self._empty((nd, nd))
             _lib.check(lib.fers_b200_dense_expand(m.n_nodes, _lib.ptr(self.d_rowptr), _lib.ptr(self.d_colidx),
                                                   _lib.ptr(self.d_vals), _lib.ptr(self.d_fixed), _lib.ptr(self.d_ks),
@@ -263,6 +278,52 @@ class Engine:
         if not (self.stats.relres <= PCG_TOL * 10) and not PCG_ALLOW_UNCONVERGED:
             raise EngineError(f"PCG did not converge: relative residual {self.stats.relres:.3e} after "
                               f"{iters.value} iterations")
+        return u
+
+    def _solve_cholesky(self, d_f: torch.Tensor) -> torch.Tensor:
+        """Sparse multifrontal Cholesky (chol_plan.cu / chol_numeric.cu) + iterative refinement with
+        the block-CSR SpMM.  The plan (ordering + symbolic) is built once per engine; the numeric
+        factorisation is redone only when the matrix was reassembled."""
+        m, lib, st = self.model, self.lib, self.stream
+        nd, nr = d_f.shape
+        if self._chol is None:
+            t0 = time.perf_counter()
+            rowptr = self.d_rowptr.cpu().numpy()
+            colidx = self.d_colidx.cpu().numpy()
+            plan = chol.CholPlan(rowptr, colidx, m.xyz)
+            self._chol = chol.CholSolver(plan, self.dev, max_nrhs=64)
+            self.timings["chol_plan_ms"] = (time.perf_counter() - t0) * 1e3
+        sol = self._chol
+        if self._chol_version != self._k_version:
+            info = sol.factorize(self.d_vals, self.d_diag_slot, self.d_fixed, self.d_ks)
+            if info != 0:
+                raise EngineError(f"stiffness matrix is not positive definite (pivot {info} in elimination order): "
+                                  "the structure is a mechanism, insufficiently supported or buckled")
+            self._chol_version = self._k_version
+        u = self._empty((nd, nr))
+        sol.solve(d_f, u, self.d_fixed)
+        r = self._empty((nd, nr))
+        ku = self._empty((nd, nr))
+        norms = self._empty((2, nr))
+        relres = float("nan")
+        for step in range(CHOL_REFINE_STEPS + 1):
+            _lib.check(lib.fers_b200_spmm(m.n_nodes, nr, _lib.ptr(self.d_rowptr), _lib.ptr(self.d_colidx),
+                                          _lib.ptr(self.d_vals), _lib.ptr(self.d_fixed), _lib.ptr(self.d_ks), _lib.ptr(u),
+                                          _lib.ptr(ku), st), "spmm")
+            _lib.check(lib.fers_b200_residual(nd, nr, _lib.ptr(d_f), _lib.ptr(ku), _lib.ptr(self.d_fixed), _lib.ptr(r),
+                                              _lib.ptr(norms), st), "residual")
+            if step == CHOL_REFINE_STEPS:
+                break
+            sol.solve(r, u, self.d_fixed, accumulate=True)
+        nh = norms.cpu().numpy()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rel = np.sqrt(np.where(nh[1] > 0, nh[0] / np.where(nh[1] > 0, nh[1], 1.0), 0.0))
+        relres = float(rel.max())
+        self.stats.method = "cholesky"
+        self.stats.iterations = CHOL_REFINE_STEPS
+        self.stats.relres = relres
+        if not (relres <= CHOL_RESIDUAL_LIMIT):
+            raise EngineError(f"sparse Cholesky solve failed: relative residual {relres:.3e} after refinement")
         return u
 
     def recover(self, d_xyz, d_u, d_f, d_peq, factors_pad, span, d_scale=None, d_axial_rhs=None, kg_mode=0,
@@ -350,10 +411,10 @@ class Engine:
 
 # ---------------------------------------------------------------------------------------------
 def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_variant: int = 0,
-            stats_out: dict | None = None) -> ResultArrays:
+            stats_out: dict | None = None, solver: str = "auto") -> ResultArrays:
     """Full analysis of one document on the GPU (twin of oracle.fers_oracle.analyze)."""
     t_start = time.perf_counter()
-    eng = Engine(model, device, assembly_variant)
+    eng = Engine(model, device, assembly_variant, solver)
     opts = model.options
     plan = rhs_plan(model)
     out = ResultArrays.empty(model, plan)

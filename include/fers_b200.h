@@ -143,6 +143,55 @@ int fers_b200_dense_expand_batched(int nodes_per_frame, int batch, const int* ro
 int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* info_out, void* stream);
 int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* bx, void* stream);
 
+/* ---- sparse direct solve: multifrontal Cholesky (the reference engine's
+ *      "batch first-order solve that shares one factorization across many load cases",
+ *      pydantic_models.py:1216-1219) -------------------------------------------------------------
+ * Analysis phase, host only (no CUDA call): nested dissection on the node coordinates, front tree,
+ * symbolic factorisation.  rowptr/colidx [host]: the block-CSR node pattern (structurally symmetric,
+ * diagonal present, columns sorted); xyz [host][n_nodes*3].  leaf_nodes: largest undivided node set.
+ * *plan_out receives an opaque host handle (free with fers_b200_chol_plan_destroy). */
+int fers_b200_chol_plan_create(int n_nodes, const int* rowptr, const int* colidx, const double* xyz, int leaf_nodes,
+                               void** plan_out);
+void fers_b200_chol_plan_destroy(void* plan);
+/* [host] out[12]: fronts, levels, largest front (nodes), factor doubles, Schur arena doubles (even
+ * levels, odd levels), front-local rhs rows, index bytes, factorisation Mflop, nnz(L), K blocks
+ * scattered, root separator nodes. */
+int fers_b200_chol_plan_info(void* plan, long long* out, int n_out);
+/* [host] perm_out[n_nodes]: elimination position -> node. */
+int fers_b200_chol_plan_perm(void* plan, int* perm_out);
+/* [host] out[level*4 + {0,1,2,3}] = fronts, max own nodes, max front nodes, Mflop of the level. */
+int fers_b200_chol_plan_levels(void* plan, long long* out, int n_levels_cap);
+/* [host] copy of the device index buffer and its section offsets (tests, diagnostics). */
+int fers_b200_chol_plan_export(void* plan, void* index_out, long long* offsets_out, int* level_ptr_out,
+                               long long* kscatter_ptr_out);
+/* Device buffers the caller provides: index (index bytes of plan_info), factor (factor_bytes),
+ * work (work_bytes; shared by factorisation and substitution). */
+size_t fers_b200_chol_factor_bytes(void* plan);
+size_t fers_b200_chol_work_bytes(void* plan, int nrhs);
+/* Copy the index arrays to index_dev (synchronises the stream). */
+int fers_b200_chol_upload(void* plan, void* index_dev, void* stream);
+/* Numeric factorisation K_ff = L L^T of the block-CSR values (constrained DOFs -> identity rows,
+ * support springs added, symmetric diagonal equilibration).  info_dev: one device int; info_out
+ * [host] or NULL: 0 ok, d > 0 = the d-th unknown in elimination order has a non-positive pivot
+ * (mechanism / buckled).  Synchronises the stream when info_out != NULL. */
+int fers_b200_chol_factor(void* plan, const void* index_dev, const double* vals, const int* diag_slot,
+                          const uint8_t* fixed, const double* kspring, double* factor, void* work, size_t work_bytes,
+                          int* info_dev, int* info_out, void* stream);
+/* x = K_ff^-1 b (accumulate == 0) or x += K_ff^-1 b (accumulate != 0, iterative refinement);
+ * b, x: [n_dof][nrhs], nrhs even, 2..64; rows of constrained DOFs give 0. */
+int fers_b200_chol_solve(void* plan, const void* index_dev, const double* factor, const uint8_t* fixed, int nrhs,
+                         const double* b, double* x, int accumulate, void* work, size_t work_bytes, void* stream);
+/* Iterative refinement helper: r = f - kx on the free DOFs (0 on constrained rows); norms2
+ * [2][nrhs] (device) receives ||r_c||^2 and ||f_c||^2 per column (diagnostics; atomics). */
+int fers_b200_residual(long long n_dof, int nrhs, const double* f, const double* kx, const uint8_t* fixed, double* r,
+                       double* norms2, void* stream);
+/* Per-kernel-class device timing of the next factorisations / substitutions (CUDA events on their
+ * stream; makes both calls synchronise).  out[10] [host]: ms of front init, K scatter, diagonal
+ * tiles, trsm, panel updates, Schur updates, whole factorisation, whole substitution; launches of
+ * the factorisation and of the substitution. */
+int fers_b200_chol_set_profile(int on);
+int fers_b200_chol_profile(double* out, int n_out);
+
 /* ---- recovery (pydantic_models.py:1594-1635) --------------------------- */
 /* Member end forces f = k_local (T u_e) - p_eq for every (member, rhs):
  *   f_local, f_global, u_local : [n_members][12][nrhs]
