@@ -35,6 +35,7 @@ struct GemmTile {
     static constexpr int A_STAGE = GEMM_BK * BM;                                   // doubles
     static constexpr int B_STAGE = B_KMAJOR ? BN * GEMM_BKP : GEMM_BK * BN;        // doubles
     static constexpr size_t SMEM = (size_t)GEMM_STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+    struct Acc { double v[TM][TN]; };
 
     // stage loader: k-tile kt (columns kt*BK .. ) of A (mrem x K, lda) and B into ring slot `slot`
     __device__ static __forceinline__ void load_stage(double* smem, int slot, int kt, const double* __restrict__ A, int lda,
@@ -75,9 +76,10 @@ struct GemmTile {
     }
 
     // acc += A(mrem x K) * op(B)(K x nrem) for this CTA's tile (pointers at the tile origin)
-    __device__ static __forceinline__ void mainloop(double (&acc)[TM][TN], double* smem, const double* __restrict__ A, int lda,
+    __device__ static __forceinline__ void mainloop(Acc& acc_, double* smem, const double* __restrict__ A, int lda,
                                                     int mrem, const double* __restrict__ B, int ldb, int nrem, int K) {
         const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+        double (&acc)[TM][TN] = acc_.v;
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -131,9 +133,10 @@ struct GemmTile {
 
     // C = C - acc (SET == false) or C = acc (SET == true) on the valid part of the tile
     template <bool SET>
-    __device__ static __forceinline__ void store(const double (&acc)[TM][TN], double* __restrict__ C, size_t ldc, int mrem,
+    __device__ static __forceinline__ void store(const Acc& acc_, double* __restrict__ C, size_t ldc, int mrem,
                                                  int nrem) {
         const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+        const double (&acc)[TM][TN] = acc_.v;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             const int col = 32 * (j / 2) + 2 * ty + (j & 1);
@@ -149,6 +152,143 @@ struct GemmTile {
                 } else {
                     v = *p;
                     v.x -= acc[2 * q][j]; v.y -= acc[2 * q + 1][j];
+                }
+                *p = v;
+            }
+        }
+    }
+};
+
+// ---- DMMA variant -------------------------------------------------------------------------------
+// Same interface, products on the fp64 tensor pipe (mma.sync m8n8k4 = SASS DMMA.8x8x4).  Measured on
+// B200 (tools/micro/fp64_peak.cu): DFMA and DMMA both peak at 37.0 TFLOP/s, but one DMMA replaces
+// eight DFMA per lane and a 64 x 32 warp tile needs 12 shared loads per 32 DMMA instead of 8 per 64
+// DFMA, so the shared-memory pipe and the issue slots stop being co-limiters (ncu r1d: the DFMA
+// kernel kept the fp64 pipe 65 % busy).  The MMA "A" operand is fed from the B tile and the MMA "B"
+// operand from the A tile: a lane then owns two consecutive ROWS of C per 8x8 block and the epilogue
+// uses 16-byte accesses along the contiguous dimension of the column-major C.
+// Shared tiles are padded (+4 doubles per k row, 20 doubles per column of the K-major B tile) so that
+// the fragment loads of a half-warp (4 k x 4 consecutive elements) hit 32 distinct banks.
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
+
+constexpr int MMA_BKP = GEMM_BK + 4;   // padded K extent of the K-major B tile
+
+template <int BM_, int BN_, int WARPS_M, int WARPS_N, bool B_KMAJOR>
+struct GemmMma {
+    static_assert(WARPS_M * WARPS_N * 32 == GEMM_THREADS, "8 warps per CTA");
+    static constexpr int BM = BM_, BN = BN_;
+    static constexpr int MT = BM / WARPS_M / 8, NT = BN / WARPS_N / 8;   // 8x8 blocks per warp
+    static constexpr int LDA = BM + 4;
+    static constexpr int LDB = B_KMAJOR ? MMA_BKP : BN + 4;
+    static constexpr int A_STAGE = GEMM_BK * LDA;
+    static constexpr int B_STAGE = B_KMAJOR ? BN * MMA_BKP : GEMM_BK * LDB;
+    static constexpr size_t SMEM = (size_t)GEMM_STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+    struct Acc { double v[NT][MT][2]; };
+
+    __device__ static __forceinline__ void load_stage(double* smem, int slot, int kt, const double* __restrict__ A, int lda,
+                                                      int mrem, const double* __restrict__ B, int ldb, int nrem, int K) {
+        const int tid = threadIdx.x;
+        const int k0 = kt * GEMM_BK;
+        double* as = smem + (size_t)slot * (A_STAGE + B_STAGE);
+        const uint32_t as_addr = (uint32_t)__cvta_generic_to_shared(as);
+        const uint32_t bs_addr = as_addr + A_STAGE * 8u;
+        constexpr int A_CHUNKS = GEMM_BK * BM / 2;
+#pragma unroll
+        for (int c = tid; c < A_CHUNKS; c += GEMM_THREADS) {
+            const int k = c / (BM / 2), i = 2 * (c % (BM / 2));
+            const bool ok = (i < mrem) && (k0 + k < K);
+            const double* src = ok ? A + (size_t)(k0 + k) * lda + i : A;
+            cp_async16(as_addr + (uint32_t)(k * LDA + i) * 8u, src, ok);
+        }
+        if (!B_KMAJOR) {
+            constexpr int B_CHUNKS = GEMM_BK * BN / 2;
+#pragma unroll
+            for (int c = tid; c < B_CHUNKS; c += GEMM_THREADS) {
+                const int k = c / (BN / 2), j = 2 * (c % (BN / 2));
+                const bool ok = (j < nrem) && (k0 + k < K);
+                const double* src = ok ? B + (size_t)(k0 + k) * ldb + j : B;
+                cp_async16(bs_addr + (uint32_t)(k * LDB + j) * 8u, src, ok);
+            }
+        } else {
+            constexpr int B_CHUNKS = BN * GEMM_BK / 2;
+#pragma unroll
+            for (int c = tid; c < B_CHUNKS; c += GEMM_THREADS) {
+                const int j = c / (GEMM_BK / 2), k = 2 * (c % (GEMM_BK / 2));
+                const bool ok = (j < nrem) && (k0 + k < K);
+                const double* src = ok ? B + (size_t)j * ldb + k0 + k : B;
+                cp_async16(bs_addr + (uint32_t)(j * MMA_BKP + k) * 8u, src, ok);
+            }
+        }
+    }
+
+    __device__ static __forceinline__ void mainloop(Acc& acc, double* smem, const double* __restrict__ A, int lda, int mrem,
+                                                    const double* __restrict__ B, int ldb, int nrem, int K) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int wm0 = (warp % WARPS_M) * (MT * 8), wn0 = (warp / WARPS_M) * (NT * 8);
+        const int lk = lane & 3, lr = lane >> 2;
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int i = 0; i < MT; ++i) acc.v[j][i][0] = acc.v[j][i][1] = 0.0;
+        const int nk = (K + GEMM_BK - 1) / GEMM_BK;
+#pragma unroll
+        for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+            if (s < nk) load_stage(smem, s, s, A, lda, mrem, B, ldb, nrem, K);
+            cp_async_commit();
+        }
+        const int a_off = lk * LDA + wm0 + lr;
+        const int b_off = B_KMAJOR ? (wn0 + lr) * MMA_BKP + lk : lk * LDB + wn0 + lr;
+        for (int kt = 0; kt < nk; ++kt) {
+            cp_async_wait<GEMM_STAGES - 2>();
+            __syncthreads();
+            {
+                const int nxt = kt + GEMM_STAGES - 1;
+                if (nxt < nk) load_stage(smem, nxt % GEMM_STAGES, nxt, A, lda, mrem, B, ldb, nrem, K);
+                cp_async_commit();
+            }
+            const double* as = smem + (size_t)(kt % GEMM_STAGES) * (A_STAGE + B_STAGE) + a_off;
+            const double* bs = smem + (size_t)(kt % GEMM_STAGES) * (A_STAGE + B_STAGE) + A_STAGE + b_off;
+#pragma unroll
+            for (int k4 = 0; k4 < GEMM_BK; k4 += 4) {
+                double am[MT], bn[NT];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) am[i] = as[k4 * LDA + 8 * i];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) bn[j] = B_KMAJOR ? bs[8 * j * MMA_BKP + k4] : bs[k4 * LDB + 8 * j];
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) dmma884(acc.v[j][i], bn[j], am[i]);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+    template <bool SET>
+    __device__ static __forceinline__ void store(const Acc& acc, double* __restrict__ C, size_t ldc, int mrem, int nrem) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int wm0 = (warp % WARPS_M) * (MT * 8), wn0 = (warp / WARPS_M) * (NT * 8);
+        const int lk = lane & 3, lr = lane >> 2;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int col = wn0 + 8 * j + lr;
+            if (col >= nrem) continue;
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const int row = wm0 + 8 * i + 2 * lk;
+                if (row >= mrem) continue;
+                double2* p = reinterpret_cast<double2*>(C + (size_t)col * ldc + row);
+                double2 v;
+                if (SET) {
+                    v.x = acc.v[j][i][0]; v.y = acc.v[j][i][1];
+                } else {
+                    v = *p;
+                    v.x -= acc.v[j][i][0]; v.y -= acc.v[j][i][1];
                 }
                 *p = v;
             }

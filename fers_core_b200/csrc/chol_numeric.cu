@@ -118,9 +118,14 @@ k_scatter_k(LevelCtx L, const KScatter* __restrict__ ks, long long n_entries, co
 
 // ---- diagonal tile: Cholesky + explicit inverse of the factor --------------------------------------
 constexpr int NB = CHOL_NB;
+constexpr int CHOL_OUTER = 4;           // 64-column steps per outer block of the two-level blocked panel update
 constexpr int TP = NB + 1;
 constexpr size_t POTRF_SMEM = 2 * NB * TP * sizeof(double);
 
+// Blocked in 8-column panels: the 8x8 diagonal block is factorised redundantly in the registers of every
+// row thread (no barrier inside a panel), each row below solves its 8 entries against it, then all 256
+// threads apply the rank-8 update to the trailing columns.  The inverse is built block row by block
+// row, one thread per column with 8 independent accumulators (a thread only re-reads its own column).
 __global__ void __launch_bounds__(256)
 k_potrf_inv(LevelCtx L, int s, int* __restrict__ info) {
     const int fid = L.level_fronts[blockIdx.x];
@@ -133,6 +138,7 @@ k_potrf_inv(LevelCtx L, int s, int* __restrict__ info) {
     double* T = potrf_smem;
     double* X = potrf_smem + NB * TP;
     __shared__ int s_bad;
+    __shared__ double s_rdiag[NB];
     double* panel = L.factor + f.panel_off;
     const int tid = threadIdx.x;
     if (tid == 0) s_bad = 0;
@@ -142,31 +148,101 @@ k_potrf_inv(LevelCtx L, int s, int* __restrict__ info) {
         if (i < nb && j < nb && i >= j) v = panel[(size_t)(c0 + j) * m + c0 + i];
         T[i * TP + j] = v;
     }
-    const int ti = tid & 63, tq = tid >> 6;
-    for (int j = 0; j < NB; ++j) {
-        __syncthreads();
-        const double d = T[j * TP + j];
-        const bool bad = !(d > 0.0);
-        const double rt = bad ? 1.0 : sqrt(d);
-        const double rinv = 1.0 / rt;
-        __syncthreads();
-        if (tq == 0) {
-            if (ti == j) { T[j * TP + j] = rt; if (bad && s_bad == 0) s_bad = j + 1; }
-            else if (ti > j) T[ti * TP + j] *= rinv;
+    __syncthreads();
+    const int r = tid & 63, tq = tid >> 6;
+    for (int jb = 0; jb < NB / 8; ++jb) {
+        const int j0 = jb * 8;
+        const bool row_thread = (tq == 0 && r >= j0);
+        double d[8][8];
+        if (row_thread) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b) d[a][b] = T[(j0 + a) * TP + j0 + b];
+        }
+        __syncthreads();       // every copy of the diagonal block is loaded before its rows are overwritten
+        if (row_thread) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                double p = d[b][b];
+                if (!(p > 0.0)) {
+                    if (r == j0 && s_bad == 0) s_bad = j0 + b + 1;
+                    p = 1.0;
+                }
+                const double ri = rsqrt(p);
+                d[b][b] = ri;                      // reciprocal of the diagonal entry of L
+#pragma unroll
+                for (int a = b + 1; a < 8; ++a) d[a][b] *= ri;
+#pragma unroll
+                for (int c = b + 1; c < 8; ++c)
+#pragma unroll
+                    for (int a = c; a < 8; ++a) d[a][c] = fma(-d[a][b], d[c][b], d[a][c]);
+            }
+            if (r < j0 + 8) {
+                // a diagonal row: write row (r - j0) of the factored block
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    if (a == r - j0) {
+#pragma unroll
+                        for (int b = 0; b < a; ++b) T[r * TP + j0 + b] = d[a][b];
+                        T[r * TP + j0 + a] = 1.0 / d[a][a];
+                    }
+            } else {
+                double x[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    double v = T[r * TP + j0 + b];
+#pragma unroll
+                    for (int c = 0; c < b; ++c) v = fma(-x[c], d[b][c], v);
+                    x[b] = v * d[b][b];
+                }
+#pragma unroll
+                for (int b = 0; b < 8; ++b) T[r * TP + j0 + b] = x[b];
+            }
         }
         __syncthreads();
-        const double lij = T[ti * TP + j];
-        for (int k = j + 1 + tq; k < NB; k += 4)
-            if (ti >= k) T[ti * TP + k] -= lij * T[k * TP + j];
+        if (r >= j0 + 8) {
+            double lrow[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) lrow[j] = T[r * TP + j0 + j];
+            for (int k = j0 + 8 + tq; k <= r; k += 4) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc = fma(lrow[j], T[k * TP + j0 + j], acc);
+                T[r * TP + k] -= acc;
+            }
+        }
+        __syncthreads();
     }
+    if (tid < NB) s_rdiag[tid] = 1.0 / T[tid * TP + tid];
     __syncthreads();
-    // inverse, one thread per column: X[:, c] = L^-1 e_c by forward substitution
     if (tid < NB) {
-        const int c = tid;
-        for (int i = 0; i < NB; ++i) {
-            double acc = (i == c) ? 1.0 : 0.0;
-            for (int k = c; k < i; ++k) acc -= T[i * TP + k] * X[k * TP + c];
-            X[i * TP + c] = (i < c) ? 0.0 : acc / T[i * TP + i];
+        const int c = tid, cb = c >> 3;
+        for (int I = 0; I < NB / 8; ++I) {
+            const int i0 = 8 * I;
+            if (I < cb) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) X[(i0 + a) * TP + c] = 0.0;
+                continue;
+            }
+            double t[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) t[a] = (i0 + a == c) ? 1.0 : 0.0;
+            for (int k = 8 * cb; k < i0; ++k) {
+                const double xk = X[k * TP + c];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) t[a] = fma(-T[(i0 + a) * TP + k], xk, t[a]);
+            }
+            double x[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                double v = t[a];
+#pragma unroll
+                for (int b = 0; b < a; ++b) v = fma(-T[(i0 + a) * TP + i0 + b], x[b], v);
+                x[a] = v * s_rdiag[i0 + a];
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) X[(i0 + a) * TP + c] = x[a];
         }
     }
     __syncthreads();
@@ -180,8 +256,21 @@ k_potrf_inv(LevelCtx L, int s, int* __restrict__ info) {
 }
 
 // ---- tile GEMM kernels of the factorisation --------------------------------------------------------
+#ifdef FERS_CHOL_DFMA     // vector-FMA tile core (kept for A/B measurements)
 using G88 = GemmTile<8, 8, false>;
 using G84 = GemmTile<8, 4, false>;
+using G44 = GemmTile<4, 4, false>;
+using G48 = GemmTile<4, 8, false>;
+using G44N = GemmTile<4, 4, true>;
+using G48N = GemmTile<4, 8, true>;
+#else                     // fp64 tensor-pipe tile core (default)
+using G88 = GemmMma<128, 128, 2, 4, false>;
+using G84 = GemmMma<128, 64, 2, 4, false>;
+using G44 = GemmMma<64, 64, 2, 4, false>;
+using G48 = GemmMma<64, 128, 2, 4, false>;
+using G44N = GemmMma<64, 64, 2, 4, true>;
+using G48N = GemmMma<64, 128, 2, 4, true>;
+#endif
 
 // rows below the diagonal tile of step s:  X = B * inv(D)^T   (in place)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -196,27 +285,30 @@ k_trsm(LevelCtx L, int s) {
     if (r0 >= m) return;
     double* A = L.factor + f.panel_off + (size_t)c0 * m + r0;
     const double* B = L.factor + f.dinv_off + (size_t)s * NB * NB;
-    double acc[8][4];
+    G84::Acc acc;
     G84::mainloop(acc, smem, A, m, m - r0, B, NB, nb, nb);
     G84::store<true>(acc, A, (size_t)m, m - r0, nb);
 }
 
-// trailing columns of the panel after step s:  C -= X X^T on the lower tiles
+// panel update: columns [cbeg, min(cend, k1)) of the panel, rows >= column, get C -= X X^T with
+// X = panel columns [kc0, kc0 + kw).  Used twice (two-level blocking): after every 64-column step for
+// the columns of the current 256-column block (kw = 64), and once per block for all later columns
+// (kw = 256), so that most of the trailing matrix is read and written once per 256 eliminated columns.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_update(LevelCtx L, int s) {
+k_update(LevelCtx L, int kc0, int kw, int cbeg, int cend) {
     extern __shared__ __align__(16) double smem[];
     const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
     const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
-    const int c0 = (s + 1) * NB;
-    if (c0 >= k1) return;
+    if (cend > k1) cend = k1;
+    if (cbeg >= cend) return;
     const int ti = blockIdx.x, tj = blockIdx.y;
     if (tj > ti) return;
-    const int r = c0 + ti * G88::BM, c = c0 + tj * G88::BN;
-    if (r >= m || c >= k1) return;
-    const double* X = L.factor + f.panel_off + (size_t)(s * NB) * m;
-    double acc[8][8];
-    G88::mainloop(acc, smem, X + r, m, m - r, X + c, m, k1 - c, NB);
-    G88::store<false>(acc, L.factor + f.panel_off + (size_t)c * m + r, (size_t)m, m - r, k1 - c);
+    const int r = cbeg + ti * G88::BM, c = cbeg + tj * G88::BN;
+    if (r >= m || c >= cend) return;
+    const double* X = L.factor + f.panel_off + (size_t)kc0 * m;
+    G88::Acc acc;
+    G88::mainloop(acc, smem, X + r, m, m - r, X + c, m, cend - c, kw);
+    G88::store<false>(acc, L.factor + f.panel_off + (size_t)c * m + r, (size_t)m, m - r, cend - c);
 }
 
 // Schur complement: F22 -= L21 L21^T on the lower tiles
@@ -230,7 +322,7 @@ k_syrk(LevelCtx L) {
     const int r = ti * G88::BM, c = tj * G88::BN;
     if (r >= m2 || c >= m2) return;
     const double* L21 = L.factor + f.panel_off + k1;
-    double acc[8][8];
+    G88::Acc acc;
     G88::mainloop(acc, smem, L21 + r, m, m2 - r, L21 + c, m, m2 - c, k1);
     G88::store<false>(acc, L.schur_cur + f.schur_off + (size_t)c * m2 + r, (size_t)m2, m2 - r, m2 - c);
 }
@@ -303,11 +395,6 @@ k_chol_unpermute(int n_nodes, int nr, const int* __restrict__ pos, const uint8_t
     }
 }
 
-using G44 = GemmTile<4, 4, false>;
-using G48 = GemmTile<4, 8, false>;
-using G44N = GemmTile<4, 4, true>;
-using G48N = GemmTile<4, 8, true>;
-
 // forward, diagonal tile of step s:  y_s = inv(D_s) w_s  -> Y
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 k_fwd_diag(SolveCtx S, int s) {
@@ -319,7 +406,7 @@ k_fwd_diag(SolveCtx S, int s) {
     const int nb = min(NB, k1 - c0), nr = S.nrhs;
     const double* A = S.W + (size_t)(f.rhs_off + c0) * nr;
     const double* B = S.factor + f.dinv_off + (size_t)s * NB * NB;
-    double acc[4][4];
+    G44::Acc acc;
     G44::mainloop(acc, smem, A, nr, nr, B, NB, nb, nb);
     G44::store<true>(acc, S.Y + (size_t)(6 * f.pad0 + c0) * nr, (size_t)nr, nr, nb);
 }
@@ -337,7 +424,7 @@ k_fwd_update(SolveCtx S, int s) {
     if (r0 >= m) return;
     const double* A = S.Y + (size_t)(6 * f.pad0 + c0) * nr;
     const double* B = S.factor + f.panel_off + (size_t)c0 * m + r0;
-    double acc[4][8];
+    G48::Acc acc;
     G48::mainloop(acc, smem, A, nr, nr, B, m, m - r0, nb);
     G48::store<false>(acc, S.W + (size_t)(f.rhs_off + r0) * nr, (size_t)nr, nr, m - r0);
 }
@@ -353,7 +440,7 @@ k_bwd_bnd(SolveCtx S) {
     const int nr = S.nrhs;
     const double* A = S.W + (size_t)(f.rhs_off + k1) * nr;
     const double* B = S.factor + f.panel_off + (size_t)c * m + k1;
-    double acc[4][4];
+    G44N::Acc acc;
     G44N::mainloop(acc, smem, A, nr, nr, B, m, k1 - c, m2);
     G44N::store<false>(acc, S.Y + (size_t)(6 * f.pad0 + c) * nr, (size_t)nr, nr, k1 - c);
 }
@@ -369,7 +456,7 @@ k_bwd_diag(SolveCtx S, int s) {
     const int nb = min(NB, k1 - c0), nr = S.nrhs;
     double* A = S.Y + (size_t)(6 * f.pad0 + c0) * nr;
     const double* B = S.factor + f.dinv_off + (size_t)s * NB * NB;
-    double acc[4][4];
+    G44N::Acc acc;
     G44N::mainloop(acc, smem, A, nr, nr, B, NB, nb, nb);
     G44N::store<true>(acc, A, (size_t)nr, nr, nb);
 }
@@ -387,7 +474,7 @@ k_bwd_update(SolveCtx S, int s) {
     if (c >= c0) return;
     const double* A = S.Y + (size_t)(6 * f.pad0 + c0) * nr;
     const double* B = S.factor + f.panel_off + (size_t)c * m + c0;
-    double acc[4][8];
+    G48N::Acc acc;
     G48N::mainloop(acc, smem, A, nr, nr, B, m, c0 - c, nb);
     G48N::store<false>(acc, S.Y + (size_t)(6 * f.pad0 + c) * nr, (size_t)nr, nr, c0 - c);
 }
@@ -558,11 +645,21 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
                 span_end(3, e0);
                 ++launches;
             }
-            const int trail_cols = max_k1 - (s + 1) * NB;
-            if (trail_cols > 0) {
+            // two-level blocking: inner update inside the current OUTER-column block, outer update once per block
+            const int cbeg = (s + 1) * NB;
+            const int blk_end = (s / CHOL_OUTER + 1) * CHOL_OUTER * NB;
+            const int in_end = std::min(blk_end, max_k1);
+            if (cbeg < in_end) {
                 e0 = span_begin(4);
-                dim3 grid(cdiv(max_m - (s + 1) * NB, G88::BM), cdiv(trail_cols, G88::BN), nf);
-                k_update<<<grid, GEMM_THREADS, G88::SMEM, st>>>(L, s);
+                dim3 grid(cdiv(max_m - cbeg, G88::BM), cdiv(in_end - cbeg, G88::BN), nf);
+                k_update<<<grid, GEMM_THREADS, G88::SMEM, st>>>(L, s * NB, NB, cbeg, blk_end);
+                span_end(4, e0);
+                ++launches;
+            }
+            if (cbeg == blk_end && blk_end < max_k1) {
+                e0 = span_begin(4);
+                dim3 grid(cdiv(max_m - blk_end, G88::BM), cdiv(max_k1 - blk_end, G88::BN), nf);
+                k_update<<<grid, GEMM_THREADS, G88::SMEM, st>>>(L, blk_end - CHOL_OUTER * NB, CHOL_OUTER * NB, blk_end, 1 << 30);
                 span_end(4, e0);
                 ++launches;
             }
