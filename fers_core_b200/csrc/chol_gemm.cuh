@@ -175,52 +175,47 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-constexpr int MMA_BKP = GEMM_BK + 4;   // padded K extent of the K-major B tile
-
-template <int BM_, int BN_, int WARPS_M, int WARPS_N, bool B_KMAJOR>
+template <int BM_, int BN_, int WARPS_M, int WARPS_N, bool B_KMAJOR, int BK_ = 32, int STAGES_ = 3, int MIN_CTAS_ = 1>
 struct GemmMma {
+    static constexpr int MIN_CTAS = MIN_CTAS_;                           // CTAs per SM the register budget is set for
     static_assert(WARPS_M * WARPS_N * 32 == GEMM_THREADS, "8 warps per CTA");
-    static constexpr int BM = BM_, BN = BN_;
+    static constexpr int BM = BM_, BN = BN_, BK = BK_, STAGES = STAGES_;
     static constexpr int MT = BM / WARPS_M / 8, NT = BN / WARPS_N / 8;   // 8x8 blocks per warp
+    static constexpr int BKP = BK + 4;                                   // padded K extent of the K-major B tile
     static constexpr int LDA = BM + 4;
-    static constexpr int LDB = B_KMAJOR ? MMA_BKP : BN + 4;
-    static constexpr int A_STAGE = GEMM_BK * LDA;
-    static constexpr int B_STAGE = B_KMAJOR ? BN * MMA_BKP : GEMM_BK * LDB;
-    static constexpr size_t SMEM = (size_t)GEMM_STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+    static constexpr int LDB = B_KMAJOR ? BKP : BN + 4;
+    static constexpr int A_STAGE = BK * LDA;
+    static constexpr int B_STAGE = B_KMAJOR ? BN * BKP : BK * LDB;
+    static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+    static constexpr int A_CHUNKS = BK * BM / 2 / GEMM_THREADS;          // 16-byte chunks per thread and stage
+    static constexpr int B_CHUNKS = BK * BN / 2 / GEMM_THREADS;
+    static constexpr int KSTEPS = BK / 4;
+    static_assert((BK * BM / 2) % GEMM_THREADS == 0 && (BK * BN / 2) % GEMM_THREADS == 0, "whole chunks per thread");
     struct Acc { double v[NT][MT][2]; };
 
-    __device__ static __forceinline__ void load_stage(double* smem, int slot, int kt, const double* __restrict__ A, int lda,
+    // chunk `q` (0 .. A_CHUNKS + B_CHUNKS - 1) of this thread for k-tile kt -> ring slot
+    __device__ static __forceinline__ void load_chunk(int q, uint32_t stage_addr, int k0, const double* __restrict__ A, int lda,
                                                       int mrem, const double* __restrict__ B, int ldb, int nrem, int K) {
         const int tid = threadIdx.x;
-        const int k0 = kt * GEMM_BK;
-        double* as = smem + (size_t)slot * (A_STAGE + B_STAGE);
-        const uint32_t as_addr = (uint32_t)__cvta_generic_to_shared(as);
-        const uint32_t bs_addr = as_addr + A_STAGE * 8u;
-        constexpr int A_CHUNKS = GEMM_BK * BM / 2;
-#pragma unroll
-        for (int c = tid; c < A_CHUNKS; c += GEMM_THREADS) {
+        if (q < A_CHUNKS) {
+            const int c = tid + q * GEMM_THREADS;
             const int k = c / (BM / 2), i = 2 * (c % (BM / 2));
             const bool ok = (i < mrem) && (k0 + k < K);
             const double* src = ok ? A + (size_t)(k0 + k) * lda + i : A;
-            cp_async16(as_addr + (uint32_t)(k * LDA + i) * 8u, src, ok);
-        }
-        if (!B_KMAJOR) {
-            constexpr int B_CHUNKS = GEMM_BK * BN / 2;
-#pragma unroll
-            for (int c = tid; c < B_CHUNKS; c += GEMM_THREADS) {
+            cp_async16(stage_addr + (uint32_t)(k * LDA + i) * 8u, src, ok);
+        } else {
+            const int c = tid + (q - A_CHUNKS) * GEMM_THREADS;
+            const uint32_t bs_addr = stage_addr + A_STAGE * 8u;
+            if (!B_KMAJOR) {
                 const int k = c / (BN / 2), j = 2 * (c % (BN / 2));
                 const bool ok = (j < nrem) && (k0 + k < K);
                 const double* src = ok ? B + (size_t)(k0 + k) * ldb + j : B;
                 cp_async16(bs_addr + (uint32_t)(k * LDB + j) * 8u, src, ok);
-            }
-        } else {
-            constexpr int B_CHUNKS = BN * GEMM_BK / 2;
-#pragma unroll
-            for (int c = tid; c < B_CHUNKS; c += GEMM_THREADS) {
-                const int j = c / (GEMM_BK / 2), k = 2 * (c % (GEMM_BK / 2));
+            } else {
+                const int j = c / (BK / 2), k = 2 * (c % (BK / 2));
                 const bool ok = (j < nrem) && (k0 + k < K);
                 const double* src = ok ? B + (size_t)j * ldb + k0 + k : B;
-                cp_async16(bs_addr + (uint32_t)(j * MMA_BKP + k) * 8u, src, ok);
+                cp_async16(bs_addr + (uint32_t)(j * BKP + k) * 8u, src, ok);
             }
         }
     }
@@ -234,36 +229,59 @@ struct GemmMma {
         for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int i = 0; i < MT; ++i) acc.v[j][i][0] = acc.v[j][i][1] = 0.0;
-        const int nk = (K + GEMM_BK - 1) / GEMM_BK;
+        const int nk = (K + BK - 1) / BK;
+        const uint32_t smem_addr = (uint32_t)__cvta_generic_to_shared(smem);
+        constexpr uint32_t STAGE_BYTES = (A_STAGE + B_STAGE) * 8u;
 #pragma unroll
-        for (int s = 0; s < GEMM_STAGES - 1; ++s) {
-            if (s < nk) load_stage(smem, s, s, A, lda, mrem, B, ldb, nrem, K);
+        for (int s = 0; s < STAGES - 1; ++s) {
+            if (s < nk) {
+#pragma unroll
+                for (int q = 0; q < A_CHUNKS + B_CHUNKS; ++q)
+                    load_chunk(q, smem_addr + s * STAGE_BYTES, s * BK, A, lda, mrem, B, ldb, nrem, K);
+            }
             cp_async_commit();
         }
         const int a_off = lk * LDA + wm0 + lr;
-        const int b_off = B_KMAJOR ? (wn0 + lr) * MMA_BKP + lk : lk * LDB + wn0 + lr;
+        const int b_off = B_KMAJOR ? (wn0 + lr) * BKP + lk : lk * LDB + wn0 + lr;
+        int slot = 0, nslot = STAGES - 1;       // ring slot being computed / being filled
         for (int kt = 0; kt < nk; ++kt) {
-            cp_async_wait<GEMM_STAGES - 2>();
+            cp_async_wait<STAGES - 2>();
             __syncthreads();
-            {
-                const int nxt = kt + GEMM_STAGES - 1;
-                if (nxt < nk) load_stage(smem, nxt % GEMM_STAGES, nxt, A, lda, mrem, B, ldb, nrem, K);
-                cp_async_commit();
-            }
-            const double* as = smem + (size_t)(kt % GEMM_STAGES) * (A_STAGE + B_STAGE) + a_off;
-            const double* bs = smem + (size_t)(kt % GEMM_STAGES) * (A_STAGE + B_STAGE) + A_STAGE + b_off;
+            const int nxt = kt + STAGES - 1;
+            const bool do_load = nxt < nk;
+            const uint32_t fill_addr = smem_addr + nslot * STAGE_BYTES;
+            const double* as = smem + (size_t)slot * (A_STAGE + B_STAGE) + a_off;
+            const double* bs = smem + (size_t)slot * (A_STAGE + B_STAGE) + A_STAGE + b_off;
+            double am[2][MT], bn[2][NT];
 #pragma unroll
-            for (int k4 = 0; k4 < GEMM_BK; k4 += 4) {
-                double am[MT], bn[NT];
+            for (int i = 0; i < MT; ++i) am[0][i] = as[8 * i];
 #pragma unroll
-                for (int i = 0; i < MT; ++i) am[i] = as[k4 * LDA + 8 * i];
+            for (int j = 0; j < NT; ++j) bn[0][j] = B_KMAJOR ? bs[8 * j * BKP] : bs[8 * j];
 #pragma unroll
-                for (int j = 0; j < NT; ++j) bn[j] = B_KMAJOR ? bs[8 * j * MMA_BKP + k4] : bs[k4 * LDB + 8 * j];
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const int cur = ks & 1;
+                if (ks + 1 < KSTEPS) {          // fragments of the next k4 step
+                    const int k4 = 4 * (ks + 1);
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) am[cur ^ 1][i] = as[k4 * LDA + 8 * i];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) bn[cur ^ 1][j] = B_KMAJOR ? bs[8 * j * BKP + k4] : bs[k4 * LDB + 8 * j];
+                }
 #pragma unroll
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
-                    for (int i = 0; i < MT; ++i) dmma884(acc.v[j][i], bn[j], am[i]);
+                    for (int i = 0; i < MT; ++i) dmma884(acc.v[j][i], bn[cur][j], am[cur][i]);
+                // this step's share of the next stage's copies, issued while the tensor pipe drains the DMMAs
+                if (do_load) {
+                    constexpr int TOTAL = A_CHUNKS + B_CHUNKS;
+#pragma unroll
+                    for (int q = ks * TOTAL / KSTEPS; q < (ks + 1) * TOTAL / KSTEPS; ++q)
+                        load_chunk(q, fill_addr, nxt * BK, A, lda, mrem, B, ldb, nrem, K);
+                }
             }
+            cp_async_commit();
+            slot = (slot + 1 == STAGES) ? 0 : slot + 1;
+            nslot = (nslot + 1 == STAGES) ? 0 : nslot + 1;
         }
         cp_async_wait<0>();
         __syncthreads();

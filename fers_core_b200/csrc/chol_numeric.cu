@@ -12,6 +12,8 @@
 // The substitution runs the same level schedule with front-local right-hand-side blocks (forward:
 // children -> parent, backward: parent -> children); all its products are tile GEMMs with the
 // right-hand-side index as the contiguous dimension.  No atomics anywhere: results are deterministic.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "chol.cuh"
@@ -258,6 +260,7 @@ k_potrf_inv(LevelCtx L, int s, int* __restrict__ info) {
 // ---- tile GEMM kernels of the factorisation --------------------------------------------------------
 #ifdef FERS_CHOL_DFMA     // vector-FMA tile core (kept for A/B measurements)
 using G88 = GemmTile<8, 8, false>;
+using G86 = GemmTile<8, 8, false>;
 using G84 = GemmTile<8, 4, false>;
 using G44 = GemmTile<4, 4, false>;
 using G48 = GemmTile<4, 8, false>;
@@ -265,11 +268,12 @@ using G44N = GemmTile<4, 4, true>;
 using G48N = GemmTile<4, 8, true>;
 #else                     // fp64 tensor-pipe tile core (default)
 using G88 = GemmMma<128, 128, 2, 4, false>;
+using G86 = GemmMma<128, 64, 4, 2, false, 16, 3, 2>;    // two CTAs per SM: one tile's epilogue overlaps the other's products
 using G84 = GemmMma<128, 64, 2, 4, false>;
-using G44 = GemmMma<64, 64, 2, 4, false>;
-using G48 = GemmMma<64, 128, 2, 4, false>;
-using G44N = GemmMma<64, 64, 2, 4, true>;
-using G48N = GemmMma<64, 128, 2, 4, true>;
+using G44 = GemmMma<64, 64, 2, 4, false, 16>;
+using G48 = GemmMma<64, 128, 2, 4, false, 16>;
+using G44N = GemmMma<64, 64, 2, 4, true, 16>;
+using G48N = GemmMma<64, 128, 2, 4, true, 16>;
 #endif
 
 // rows below the diagonal tile of step s:  X = B * inv(D)^T   (in place)
@@ -294,37 +298,35 @@ k_trsm(LevelCtx L, int s) {
 // X = panel columns [kc0, kc0 + kw).  Used twice (two-level blocking): after every 64-column step for
 // the columns of the current 256-column block (kw = 64), and once per block for all later columns
 // (kw = 256), so that most of the trailing matrix is read and written once per 256 eliminated columns.
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <class G>
+__global__ void __launch_bounds__(GEMM_THREADS, G::MIN_CTAS)
 k_update(LevelCtx L, int kc0, int kw, int cbeg, int cend) {
     extern __shared__ __align__(16) double smem[];
     const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
     const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
     if (cend > k1) cend = k1;
     if (cbeg >= cend) return;
-    const int ti = blockIdx.x, tj = blockIdx.y;
-    if (tj > ti) return;
-    const int r = cbeg + ti * G88::BM, c = cbeg + tj * G88::BN;
-    if (r >= m || c >= cend) return;
+    const int r = cbeg + blockIdx.x * G::BM, c = cbeg + blockIdx.y * G::BN;
+    if (r >= m || c >= cend || c >= r + G::BM) return;       // outside the panel or entirely above the diagonal
     const double* X = L.factor + f.panel_off + (size_t)kc0 * m;
-    G88::Acc acc;
-    G88::mainloop(acc, smem, X + r, m, m - r, X + c, m, cend - c, kw);
-    G88::store<false>(acc, L.factor + f.panel_off + (size_t)c * m + r, (size_t)m, m - r, cend - c);
+    typename G::Acc acc;
+    G::mainloop(acc, smem, X + r, m, m - r, X + c, m, cend - c, kw);
+    G::template store<false>(acc, L.factor + f.panel_off + (size_t)c * m + r, (size_t)m, m - r, cend - c);
 }
 
 // Schur complement: F22 -= L21 L21^T on the lower tiles
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <class G>
+__global__ void __launch_bounds__(GEMM_THREADS, G::MIN_CTAS)
 k_syrk(LevelCtx L) {
     extern __shared__ __align__(16) double smem[];
     const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
     const int k1 = 6 * f.n1, m2 = 6 * f.n2, m = k1 + m2;
-    const int ti = blockIdx.x, tj = blockIdx.y;
-    if (tj > ti) return;
-    const int r = ti * G88::BM, c = tj * G88::BN;
-    if (r >= m2 || c >= m2) return;
+    const int r = blockIdx.x * G::BM, c = blockIdx.y * G::BN;
+    if (r >= m2 || c >= m2 || c >= r + G::BM) return;
     const double* L21 = L.factor + f.panel_off + k1;
-    G88::Acc acc;
-    G88::mainloop(acc, smem, L21 + r, m, m2 - r, L21 + c, m, m2 - c, k1);
-    G88::store<false>(acc, L.schur_cur + f.schur_off + (size_t)c * m2 + r, (size_t)m2, m2 - r, m2 - c);
+    typename G::Acc acc;
+    G::mainloop(acc, smem, L21 + r, m, m2 - r, L21 + c, m, m2 - c, k1);
+    G::template store<false>(acc, L.schur_cur + f.schur_off + (size_t)c * m2 + r, (size_t)m2, m2 - r, m2 - c);
 }
 
 // ---- substitution ------------------------------------------------------------------------------------
@@ -510,6 +512,9 @@ struct CholProfile {
     long long launches_factor = 0, launches_solve = 0;
 };
 static CholProfile g_chol_profile;
+// tile-shape selection (A/B measurements): bit 0 = panel updates, bit 1 = Schur update;
+// set = 128x128 tile, one CTA per SM; clear = 128x64 tile, two CTAs per SM.  FERS_CHOL_VARIANT overrides.
+static int g_chol_variant = getenv("FERS_CHOL_VARIANT") ? atoi(getenv("FERS_CHOL_VARIANT")) : 0;
 static bool g_chol_profile_on = false;
 
 struct EventPool {
@@ -534,8 +539,10 @@ static int set_smem_attrs() {
     if (done) return 0;
     FERS_CK(cudaFuncSetAttribute(k_potrf_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
     FERS_CK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G84::SMEM));
-    FERS_CK(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G88::SMEM));
-    FERS_CK(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G88::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_update<G88>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G88::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_syrk<G88>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G88::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_update<G86>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G86::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_syrk<G86>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G86::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_fwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_fwd_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G48::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_bwd_bnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
@@ -651,15 +658,25 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
             const int in_end = std::min(blk_end, max_k1);
             if (cbeg < in_end) {
                 e0 = span_begin(4);
-                dim3 grid(cdiv(max_m - cbeg, G88::BM), cdiv(in_end - cbeg, G88::BN), nf);
-                k_update<<<grid, GEMM_THREADS, G88::SMEM, st>>>(L, s * NB, NB, cbeg, blk_end);
+                if (g_chol_variant & 1) {
+                    dim3 grid(cdiv(max_m - cbeg, G88::BM), cdiv(in_end - cbeg, G88::BN), nf);
+                    k_update<G88><<<grid, GEMM_THREADS, G88::SMEM, st>>>(L, s * NB, NB, cbeg, blk_end);
+                } else {
+                    dim3 grid(cdiv(max_m - cbeg, G86::BM), cdiv(in_end - cbeg, G86::BN), nf);
+                    k_update<G86><<<grid, GEMM_THREADS, G86::SMEM, st>>>(L, s * NB, NB, cbeg, blk_end);
+                }
                 span_end(4, e0);
                 ++launches;
             }
             if (cbeg == blk_end && blk_end < max_k1) {
                 e0 = span_begin(4);
-                dim3 grid(cdiv(max_m - blk_end, G88::BM), cdiv(max_k1 - blk_end, G88::BN), nf);
-                k_update<<<grid, GEMM_THREADS, G88::SMEM, st>>>(L, blk_end - CHOL_OUTER * NB, CHOL_OUTER * NB, blk_end, 1 << 30);
+                if (g_chol_variant & 1) {
+                    dim3 grid(cdiv(max_m - blk_end, G88::BM), cdiv(max_k1 - blk_end, G88::BN), nf);
+                    k_update<G88><<<grid, GEMM_THREADS, G88::SMEM, st>>>(L, blk_end - CHOL_OUTER * NB, CHOL_OUTER * NB, blk_end, 1 << 30);
+                } else {
+                    dim3 grid(cdiv(max_m - blk_end, G86::BM), cdiv(max_k1 - blk_end, G86::BN), nf);
+                    k_update<G86><<<grid, GEMM_THREADS, G86::SMEM, st>>>(L, blk_end - CHOL_OUTER * NB, CHOL_OUTER * NB, blk_end, 1 << 30);
+                }
                 span_end(4, e0);
                 ++launches;
             }
@@ -669,8 +686,13 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
         const int max_m2 = max_m;   // upper bound on 6 * n2
         if (l + 1 < P.n_levels) {
             e0 = span_begin(5);
-            dim3 grid(cdiv(max_m2, G88::BM), cdiv(max_m2, G88::BN), nf);
-            k_syrk<<<grid, GEMM_THREADS, G88::SMEM, st>>>(L);
+            if (g_chol_variant & 2) {
+                dim3 grid(cdiv(max_m2, G88::BM), cdiv(max_m2, G88::BN), nf);
+                k_syrk<G88><<<grid, GEMM_THREADS, G88::SMEM, st>>>(L);
+            } else {
+                dim3 grid(cdiv(max_m2, G86::BM), cdiv(max_m2, G86::BN), nf);
+                k_syrk<G86><<<grid, GEMM_THREADS, G86::SMEM, st>>>(L);
+            }
             FERS_LAUNCH_CHECK();
             span_end(5, e0);
             ++launches;
@@ -844,6 +866,12 @@ int fers_b200_residual(long long n_dof, int nrhs, const double* f, const double*
     k_chol_residual<<<(unsigned)grid, 256, 0, st>>>(n_dof, nrhs, f, kx, fixed, r, norms2);
     FERS_LAUNCH_CHECK();
     count_launches(1);
+    return 0;
+}
+
+int fers_b200_chol_set_variant(int variant) {
+    FERS_REQUIRE(variant >= 0 && variant <= 3, "chol_set_variant: bit 0 = panel updates, bit 1 = Schur update use the 128x128 tile");
+    g_chol_variant = variant;
     return 0;
 }
 

@@ -190,6 +190,9 @@ int fers_b200_residual(long long n_dof, int nrhs, const double* f, const double*
  * tiles, trsm, panel updates, Schur updates, whole factorisation, whole substitution; launches of
  * the factorisation and of the substitution. */
 int fers_b200_chol_set_profile(int on);
+/* Tile shape of the factorisation GEMMs: bit 0 = panel updates, bit 1 = Schur update; bit set =
+ * 128x128 tile with one CTA per SM, clear (default) = 128x64 tile with two CTAs per SM. */
+int fers_b200_chol_set_variant(int variant);
 int fers_b200_chol_profile(double* out, int n_out);
 
 /* ---- recovery (pydantic_models.py:1594-1635) --------------------------- */

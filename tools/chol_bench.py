@@ -24,7 +24,10 @@ print(f"dof {model.n_dof} fronts {plan.info.n_fronts} levels {plan.info.n_levels
       f"factor GB {plan.info.factor_doubles*8/1e9:.2f} plan {t_plan*1e3:.0f} ms", flush=True)
 sol = chol.CholSolver(plan, eng.dev, max_nrhs=nrhs)
 lib.fers_b200_chol_set_profile(1)
-for rep in range(2):
+import os
+variants = [int(v) for v in os.environ.get("CHOL_VARIANTS", "0").split(",")]
+for rep in variants:
+    lib.fers_b200_chol_set_variant(rep)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     info = sol.factorize(eng.d_vals, eng.d_diag_slot, eng.d_fixed, eng.d_ks)
@@ -36,7 +39,7 @@ for rep in range(2):
     torch.cuda.synchronize()
     t_s = time.perf_counter() - t0
     p = sol.profile()
-    print(f"rep {rep}: info {info} factor {t_f*1e3:.1f} ms ({plan.info.flops/t_f/1e12:.2f} TF/s) solve {t_s*1e3:.1f} ms", flush=True)
+    print(f"variant {rep}: info {info} factor {t_f*1e3:.1f} ms ({plan.info.flops/t_f/1e12:.2f} TF/s) solve {t_s*1e3:.1f} ms", flush=True)
     print("   ", {k: round(v, 2) for k, v in p.items()}, flush=True)
     gemm_ms = p["update_ms"] + p["syrk_ms"]
     print(f"    gemm share {gemm_ms/p['factor_ms']:.2f}  gemm TF/s (all flops / gemm time) {plan.info.flops/gemm_ms/1e9:.2f}", flush=True)
