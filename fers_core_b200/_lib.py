@@ -20,6 +20,7 @@ SIGNATURES = {
     "fers_b200_set_device": (_i, [_i]),
     "fers_b200_launch_count": (C.c_longlong, []),
     "fers_b200_pcg_profile": (_i, [_dp]),
+    "fers_b200_fp64_peak": (_i, [_d, _dp, _dp, _vp, _sz, _vp]),
     "fers_b200_pattern_workspace": (_sz, [_i, _i, _i]),
     "fers_b200_pattern_build": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _ip, _vp, _sz, _vp]),
     "fers_b200_bc_workspace": (_sz, [_i]),

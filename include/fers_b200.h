@@ -43,6 +43,12 @@ int fers_b200_set_device(int device);
 /* Number of kernels this library has launched in this process (monotonic). */
 long long fers_b200_launch_count(void);
 
+/* Live fp64 roofline denominators (bench.py): register-resident throughput of the fp64 tensor pipe
+ * (DMMA.8x8x4) and of the vector pipe (DFMA) in TFLOP/s, each the best of bursts lasting at least
+ * min_ms.  scratch: device buffer of >= 8 * 1024 * SM-count bytes.  Synchronises the stream. */
+int fers_b200_fp64_peak(double min_ms, double* dmma_tflops, double* dfma_tflops, double* scratch, size_t scratch_bytes,
+                        void* stream);
+
 /* ---- symbolic pattern (replaces the engine's DOF numbering / sparsity set-up; contract
  *      SURVEY.md 8a row A7, pydantic_models.py:2104-2115) ------------------------------------- */
 size_t fers_b200_pattern_workspace(int n_nodes, int n_members, int n_plates);
