@@ -52,6 +52,8 @@ def parse_args():
     p.add_argument("--frames", type=int, default=1024, help="cfg5: frames per GPU")
     p.add_argument("--assembly-variant", type=int, default=0)
     p.add_argument("--spmm-variant", type=int, default=-1, help="0 register/LDG, 1 TMA-staged, 2 TMA warp-specialised (default: library default)")
+    p.add_argument("--solver", default="auto", choices=["auto", "cholesky", "pcg"],
+                   help="auto = sparse multifrontal Cholesky above 8 192 DOF (default); pcg = block-Jacobi PCG")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--profile-iters", type=int, default=0,
@@ -195,7 +197,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     if args.profile_iters > 0:
         engine.PCG_MAX_ITER = args.profile_iters
         engine.PCG_ALLOW_UNCONVERGED = True
-    eng = engine.Engine(model, dev, args.assembly_variant)
+    eng = engine.Engine(model, dev, args.assembly_variant, args.solver)
 
     def barrier():
         if world > 1:
@@ -205,7 +207,10 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     # ---- device-resident steps -----------------------------------------------------------------
     for _ in range(args.warmup):
         rec = eng.run_linear(factors)
+    direct = eng.stats.method == "cholesky"
     sampler = ClockSampler(local_rank)
+    if direct:
+        lib.fers_b200_chol_set_profile(2)       # events around the Schur-update launches + totals only
     barrier()
     if rank == 0:
         sampler.start()
@@ -220,9 +225,12 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     clocks = sampler.stop() if rank == 0 else None
     ms_step = fdist.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     value = world * units / (ms_step / 1e3)
+    timed_prof = eng._chol.profile() if direct else None
+    lib.fers_b200_chol_set_profile(0)
     prof = (C.c_double * 6)()
     lib.fers_b200_pcg_profile(prof)
     iters = int(prof[4])
+    relres_solver = eng.stats.relres
 
     # summary gather over NVLink: per-combination max |u| from every rank
     summ = rec["U"].abs().amax(dim=0)[:n_comb].contiguous()
@@ -240,44 +248,111 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     free = (eng.d_fixed == 0).to(torch.float64)[:, None]
     resid = float((torch.linalg.norm((ku - d_f) * free, dim=0) / torch.linalg.norm(d_f * free, dim=0))[:n_comb].max())
 
-    # ---- kernel roofline numbers (CUDA events inside the timed PCG loop, see fers_b200_pcg_profile) ---
+    # ---- kernel roofline numbers ------------------------------------------------------------------
     peaks = measured_peaks()
     peak = float(peaks["hbm_gbs"])
     nnzb, nn = eng.nnzb, model.n_nodes
     V = n_dof * nr * 8
     spmm_bytes = nnzb * (36 * 8 + 4) + (nn + 1) * 4 + 2 * V
-    upd_bytes = 6 * V + nn * 36 * 8
-    dir_bytes = 3 * V + nn * 36 * 8
     kern = []
-    for name, b, ms in (("k_spmm<64,dot>", spmm_bytes, prof[0]), ("k_pcg_update<64>", upd_bytes, prof[1]),
-                        ("k_pcg_direction<64>", dir_bytes, prof[2])):
+
+    def timed_launches(fn, reps=5, pre=None):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out = []
+        for _ in range(reps):
+            if pre is not None:
+                pre()
+            a0.record()
+            fn()
+            a1.record()
+            torch.cuda.synchronize(dev)
+            out.append(a0.elapsed_time(a1))
+        return float(np.median(out))
+
+    def hbm_row(name, b, ms, launches_per_step):
         gbs = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        kern.append({"kernel": name, "algorithmic_bytes": int(b), "ms": ms, "GB/s": gbs, "frac": gbs / peak,
-                     "share_of_step": ms * iters / ms_step if ms_step > 0 else 0.0})
-    # assembly kernel timed on its own (one launch per step): events around a dedicated launch
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    asm_ms = []
-    for _ in range(5):
-        lib.fers_b200_zero(_lib.ptr(eng.d_vals), eng.d_vals.numel() * 8, eng.stream)
-        a0.record()
-        _lib.check(lib.fers_b200_assemble_beams(
-            model.n_members, _lib.ptr(eng.d_xyz0), _lib.ptr(eng.d_n1), _lib.ptr(eng.d_n2), _lib.ptr(eng.d_m_prop),
-            _lib.ptr(eng.d_type), _lib.ptr(eng.d_roll), None, None, _lib.ptr(eng.d_prop), eng.n_prop, None, 0, None, 0, 0,
-            _lib.ptr(eng.d_m_slot), _lib.ptr(eng.d_vals), args.assembly_variant, eng.stream), "assemble")
-        a1.record()
-        torch.cuda.synchronize(dev)
-        asm_ms.append(a0.elapsed_time(a1))
+        return {"kernel": name, "bound": "hbm", "algorithmic_bytes": int(b), "ms": ms, "GB/s": gbs, "frac": gbs / peak,
+                "share_of_step": ms * launches_per_step / ms_step if ms_step > 0 else 0.0}
+
+    # assembly and SpMM kernels timed on their own (few launches per step): events around dedicated launches
+    am = timed_launches(lambda: _lib.check(lib.fers_b200_assemble_beams(
+        model.n_members, _lib.ptr(eng.d_xyz0), _lib.ptr(eng.d_n1), _lib.ptr(eng.d_n2), _lib.ptr(eng.d_m_prop),
+        _lib.ptr(eng.d_type), _lib.ptr(eng.d_roll), None, None, _lib.ptr(eng.d_prop), eng.n_prop, None, 0, None, 0, 0,
+        _lib.ptr(eng.d_m_slot), _lib.ptr(eng.d_vals), args.assembly_variant, eng.stream), "assemble"),
+        pre=lambda: lib.fers_b200_zero(_lib.ptr(eng.d_vals), eng.d_vals.numel() * 8, eng.stream))
     asm_bytes = model.n_members * (64 + 4 * 36 * 8)
-    am = float(np.median(asm_ms))
-    kern.append({"kernel": "k_assemble_beams", "algorithmic_bytes": int(asm_bytes), "ms": am,
-                 "GB/s": asm_bytes / (am * 1e-3) / 1e9, "frac": asm_bytes / (am * 1e-3) / 1e9 / peak,
-                 "share_of_step": am / ms_step})
-    dom = max(kern[:3], key=lambda k: k["share_of_step"])
-    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GB/s"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": None, "peak_source": peaks["_source"] + " (MEASURED_PEAKS.json hbm_gbs)",
-                "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "ms_per_launch": dom["ms"],
-                "timing": f"CUDA events on the launch stream around {int(prof[3])} sampled PCG iterations inside the timed region",
-                "kernels": kern}
+    if direct:
+        sm = timed_launches(lambda: _lib.check(lib.fers_b200_spmm(
+            model.n_nodes, nr, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
+            _lib.ptr(eng.d_ks), _lib.ptr(rec["U"]), _lib.ptr(ku), eng.stream), "spmm"))
+        kern.append(hbm_row("k_spmm<64> (residual of the refinement)", spmm_bytes, sm, engine.CHOL_REFINE_STEPS + 1))
+        kern.append(hbm_row("k_assemble_beams", asm_bytes, am, 1))
+        # fp64 pipe peak measured live by the library (register-resident DMMA.8x8x4 / DFMA bursts)
+        scratch = torch.empty(8 * 1024 * 160, dtype=torch.uint8, device=dev)
+        dmma, dfma = C.c_double(), C.c_double()
+        _lib.check(lib.fers_b200_fp64_peak(50.0, C.byref(dmma), C.byref(dfma), _lib.ptr(scratch), scratch.numel(),
+                                           eng.stream), "fp64_peak")
+        fr = eng._chol.plan.export()["fronts"]
+        k1 = 6.0 * fr["n1"].astype(np.float64)
+        m2 = 6.0 * fr["n2"].astype(np.float64)
+        cls_flops = {"potrf": float((k1 ** 3 / 3).sum()), "panel": float((k1 * k1 * m2).sum()),
+                     "syrk": float((k1 * m2 * (m2 + 1)).sum())}
+        n_fac = max(timed_prof["n_factor"], 1.0)
+        syrk_ms_per_fac = timed_prof["syrk_sum_ms"] / n_fac
+        syrk_launches = max(timed_prof["n_syrk_launches"], 1.0)
+        tf = cls_flops["syrk"] / (syrk_ms_per_fac * 1e-3) / 1e12 if syrk_ms_per_fac > 0 else 0.0
+        # one more step with events around every kernel class (outside the timed region) for the breakdown
+        lib.fers_b200_chol_set_profile(1)
+        eng.run_linear(factors)
+        full = eng._chol.profile()
+        lib.fers_b200_chol_set_profile(0)
+        breakdown = {k: full[k] for k in ("init_ms", "scatter_ms", "potrf_ms", "trsm_ms", "update_ms", "syrk_ms",
+                                           "factor_ms", "solve_ms", "factor_launches", "solve_launches")}
+        upd_flops = cls_flops["panel"] + cls_flops["potrf"]
+        kern.insert(0, {"kernel": "k_syrk<128x64 DMMA> (Schur complement F22 -= L21 L21^T)", "bound": "tensor",
+                        "algorithmic_flops": cls_flops["syrk"], "ms": syrk_ms_per_fac, "TFLOP/s": tf,
+                        "frac": tf / dmma.value if dmma.value > 0 else None,
+                        "share_of_step": syrk_ms_per_fac / ms_step})
+        um = full["update_ms"] + full["trsm_ms"] + full["potrf_ms"]
+        kern.insert(1, {"kernel": "panel factorisation (k_potrf_inv + k_trsm + k_update<128x64 DMMA>)", "bound": "tensor",
+                        "algorithmic_flops": upd_flops, "ms": um, "TFLOP/s": upd_flops / (um * 1e-3) / 1e12 if um > 0 else 0.0,
+                        "frac": upd_flops / (um * 1e-3) / 1e12 / dmma.value if um > 0 and dmma.value > 0 else None,
+                        "share_of_step": um / ms_step, "timing": "profiled extra step (events around every launch)"})
+        roofline = {"bound": "tensor", "kernel": kern[0]["kernel"], "achieved": tf, "peak": dmma.value, "unit": "TFLOP/s",
+                    "frac": kern[0]["frac"], "traffic": None,
+                    "peak_source": "fp64 tensor pipe (DMMA.8x8x4) measured live by fers_b200_fp64_peak on this device, "
+                                   f">=50 ms bursts (DFMA vector pipe: {dfma.value:.2f} TFLOP/s); MEASURED_PEAKS.json holds "
+                                   "no fp64 figure",
+                    "algorithmic_flops_per_launch": cls_flops["syrk"] / (syrk_launches / n_fac),
+                    "ms_per_launch": timed_prof["syrk_sum_ms"] / syrk_launches,
+                    "launches_per_step": syrk_launches / n_fac,
+                    "timing": "CUDA events on the launch stream around every Schur-update launch of the "
+                              f"{int(n_fac)} factorisations inside the timed region",
+                    "factor_tflops_all_kernels": float(sum(cls_flops.values())) / (timed_prof["factor_sum_ms"] / n_fac * 1e-3) / 1e12,
+                    "factor_ms": timed_prof["factor_sum_ms"] / n_fac,
+                    "substitution_ms": timed_prof["solve_sum_ms"] / max(timed_prof["n_solve"], 1.0),
+                    "substitutions_per_step": timed_prof["n_solve"] / n_fac,
+                    "class_ms_profiled_step": breakdown, "hbm_peak": peak, "kernels": kern}
+        solver_cfg = {"solver": "sparse multifrontal Cholesky (nested dissection, fp64 DMMA tile GEMMs) + "
+                                f"{engine.CHOL_REFINE_STEPS} refinement pass, 64 RHS",
+                      "fronts": int(len(fr)), "factor_gb": eng._chol.plan.info.factor_doubles * 8 / 1e9,
+                      "factor_tflop": float(sum(cls_flops.values())) / 1e12, "solver_rel_residual": relres_solver}
+        cache_note = "factor (16 GB) and multi-vectors (354 MB each) >> 126 MB L2; no flush needed"
+    else:
+        upd_bytes = 6 * V + nn * 36 * 8
+        dir_bytes = 3 * V + nn * 36 * 8
+        for name, b, ms in (("k_spmm<64,dot>", spmm_bytes, prof[0]), ("k_pcg_update<64>", upd_bytes, prof[1]),
+                            ("k_pcg_direction<64>", dir_bytes, prof[2])):
+            kern.append(hbm_row(name, b, ms, iters))
+        kern.append(hbm_row("k_assemble_beams", asm_bytes, am, 1))
+        dom = max(kern[:3], key=lambda k: k["share_of_step"])
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GB/s"], "peak": peak, "unit": "GB/s",
+                    "frac": dom["frac"], "traffic": None, "peak_source": peaks["_source"] + " (MEASURED_PEAKS.json hbm_gbs)",
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "ms_per_launch": dom["ms"],
+                    "timing": f"CUDA events on the launch stream around {int(prof[3])} sampled PCG iterations inside the timed region",
+                    "kernels": kern}
+        solver_cfg = {"solver": "block-Jacobi PCG, 64 RHS, tol 1e-12", "pcg_iterations": iters}
+        cache_note = "working set (5 multi-vectors x 354 MB + 227 MB matrix) >> 126 MB L2; no flush needed"
 
     # ---- end-to-end through the public array API with HOST buffers -------------------------------
     e2e = None
@@ -294,7 +369,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             del eng
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            eng = engine.Engine(model, dev, args.assembly_variant)        # H2D of the model + symbolic pattern
+            eng = engine.Engine(model, dev, args.assembly_variant, args.solver)   # H2D of the model + symbolic pattern / plan
             out = eng.run_linear(factors)
             h_u.copy_(out["U"], non_blocking=True); h_r.copy_(out["R"], non_blocking=True)
             h_f.copy_(out["f_local"], non_blocking=True)
@@ -331,9 +406,8 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                                    f"linear static, {n_comb} combinations per GPU",
                        "nodes": model.n_nodes, "members": model.n_members, "dof": n_dof, "free_dof": eng.stats.n_free,
                        "nnz_blocks": nnzb, "load_cases": len(model.load_cases), "combinations_per_gpu": n_comb,
-                       "solver": "block-Jacobi PCG, 64 RHS, tol 1e-12", "pcg_iterations": iters,
-                       "max_rel_residual": resid, "parallelism": f"combination batches x{world}",
-                       "cache": "working set (5 multi-vectors x 354 MB + 227 MB matrix) >> 126 MB L2; no flush needed"},
+                       **solver_cfg, "max_rel_residual": resid, "parallelism": f"combination batches x{world}",
+                       "cache": cache_note},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
         }))
     if world > 1:

@@ -152,8 +152,9 @@ class CholSolver:
             d_x.data_ptr(), 1 if accumulate else 0, self.work.data_ptr(), self.work_bytes, self.stream), "chol_solve")
 
     def profile(self) -> dict:
-        out = (C.c_double * 10)()
-        _lib.check(self.lib.fers_b200_chol_profile(out, 10), "chol_profile")
+        out = (C.c_double * 16)()
+        _lib.check(self.lib.fers_b200_chol_profile(out, 16), "chol_profile")
         keys = ["init_ms", "scatter_ms", "potrf_ms", "trsm_ms", "update_ms", "syrk_ms", "factor_ms", "solve_ms",
-                "factor_launches", "solve_launches"]
+                "factor_launches", "solve_launches", "syrk_sum_ms", "factor_sum_ms", "solve_sum_ms", "n_factor",
+                "n_solve", "n_syrk_launches"]
         return dict(zip(keys, out[:]))

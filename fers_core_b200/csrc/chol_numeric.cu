@@ -510,12 +510,15 @@ struct CholProfile {
     double init = 0, scatter = 0, potrf = 0, trsm = 0, update = 0, syrk = 0, factor_total = 0;
     double solve_total = 0;
     long long launches_factor = 0, launches_solve = 0;
+    // accumulated since the last fers_b200_chol_set_profile call
+    double syrk_sum = 0, factor_sum = 0, solve_sum = 0;
+    long long n_factor = 0, n_solve = 0, n_syrk_launches = 0;
 };
 static CholProfile g_chol_profile;
 // tile-shape selection (A/B measurements): bit 0 = panel updates, bit 1 = Schur update;
 // set = 128x128 tile, one CTA per SM; clear = 128x64 tile, two CTAs per SM.  FERS_CHOL_VARIANT overrides.
 static int g_chol_variant = getenv("FERS_CHOL_VARIANT") ? atoi(getenv("FERS_CHOL_VARIANT")) : 0;
-static bool g_chol_profile_on = false;
+static int g_chol_profile_on = 0;      // 0 off, 1 every kernel class, 2 Schur-update spans + totals only
 
 struct EventPool {
     std::vector<cudaEvent_t> ev;
@@ -593,20 +596,20 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
     double* arena[2];
     arena[0] = static_cast<double*>(work);
     arena[1] = arena[0] + P.schur_doubles[0];
-    const bool prof = g_chol_profile_on;
+    const bool prof = g_chol_profile_on != 0;
+    const bool prof_all = g_chol_profile_on == 1;
     if (prof) { g_pool.reset(); g_timed.clear(); }
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     if (prof) { ev_begin = g_pool.get(); cudaEventRecord(ev_begin, st); }
     long long launches = 0;
     auto span_begin = [&](int cls) -> cudaEvent_t {
-        if (!prof) return nullptr;
+        if (!prof || !(prof_all || cls == 5)) return nullptr;
         cudaEvent_t e = g_pool.get();
         cudaEventRecord(e, st);
-        (void)cls;
         return e;
     };
     auto span_end = [&](int cls, cudaEvent_t b) {
-        if (!prof) return;
+        if (b == nullptr) return;
         cudaEvent_t e = g_pool.get();
         cudaEventRecord(e, st);
         g_timed.spans[cls].push_back({b, e});
@@ -711,6 +714,8 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
         g_chol_profile.trsm = t[3]; g_chol_profile.update = t[4]; g_chol_profile.syrk = t[5];
         g_chol_profile.factor_total = tot;
         g_chol_profile.launches_factor = launches;
+        g_chol_profile.syrk_sum += t[5]; g_chol_profile.factor_sum += tot; g_chol_profile.n_factor += 1;
+        g_chol_profile.n_syrk_launches += (long long)g_timed.spans[5].size();
     }
     return 0;
 }
@@ -727,7 +732,7 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
     S.Y = S.W + (size_t)P.rhs_rows * nrhs;
     S.nrhs = nrhs;
     long long launches = 0;
-    const bool prof = g_chol_profile_on;
+    const bool prof = g_chol_profile_on != 0;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     if (prof) { cudaEventCreate(&ev_begin); cudaEventCreate(&ev_end); cudaEventRecord(ev_begin, st); }
     for (int l = 0; l < P.n_levels; ++l) {                // forward: children -> parents
@@ -794,6 +799,7 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
         cudaEventElapsedTime(&tot, ev_begin, ev_end);
         g_chol_profile.solve_total = tot;
         g_chol_profile.launches_solve = launches;
+        g_chol_profile.solve_sum += tot; g_chol_profile.n_solve += 1;
         cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
     }
     return 0;
@@ -875,14 +881,24 @@ int fers_b200_chol_set_variant(int variant) {
     return 0;
 }
 
-int fers_b200_chol_set_profile(int on) { g_chol_profile_on = on != 0; return 0; }
+int fers_b200_chol_set_profile(int on) {
+    g_chol_profile_on = on < 0 ? 0 : (on > 2 ? 1 : on);
+    g_chol_profile.syrk_sum = g_chol_profile.factor_sum = g_chol_profile.solve_sum = 0;
+    g_chol_profile.n_factor = g_chol_profile.n_solve = g_chol_profile.n_syrk_launches = 0;
+    return 0;
+}
 
-/* out[10]: ms of init, scatter, potrf, trsm, update, syrk, factor total, solve total; launches factor, solve */
+/* out[10]: ms of init, scatter, potrf, trsm, update, syrk, factor total, solve total; launches factor, solve;
+ * n_out >= 16 adds sums since the last set_profile: syrk ms, factor ms, solve ms, factorisations, substitutions, syrk launches */
 int fers_b200_chol_profile(double* out, int n_out) {
     FERS_REQUIRE(out && n_out >= 10, "chol_profile: need 10 outputs");
     const CholProfile& p = g_chol_profile;
     out[0] = p.init; out[1] = p.scatter; out[2] = p.potrf; out[3] = p.trsm; out[4] = p.update; out[5] = p.syrk;
     out[6] = p.factor_total; out[7] = p.solve_total; out[8] = (double)p.launches_factor; out[9] = (double)p.launches_solve;
+    if (n_out >= 16) {
+        out[10] = p.syrk_sum; out[11] = p.factor_sum; out[12] = p.solve_sum;
+        out[13] = (double)p.n_factor; out[14] = (double)p.n_solve; out[15] = (double)p.n_syrk_launches;
+    }
     return 0;
 }
 

@@ -194,11 +194,15 @@ int fers_b200_residual(long long n_dof, int nrhs, const double* f, const double*
 /* Per-kernel-class device timing of the next factorisations / substitutions (CUDA events on their
  * stream; makes both calls synchronise).  out[10] [host]: ms of front init, K scatter, diagonal
  * tiles, trsm, panel updates, Schur updates, whole factorisation, whole substitution; launches of
- * the factorisation and of the substitution. */
+ * the factorisation and of the substitution.  on = 1: every kernel class; on = 2: only the Schur-update
+ * spans and the two totals (a few events per tree level: cheap enough for a timed region); 0 = off. */
 int fers_b200_chol_set_profile(int on);
 /* Tile shape of the factorisation GEMMs: bit 0 = panel updates, bit 1 = Schur update; bit set =
  * 128x128 tile with one CTA per SM, clear (default) = 128x64 tile with two CTAs per SM. */
 int fers_b200_chol_set_variant(int variant);
+/* n_out >= 16 additionally returns sums since the last fers_b200_chol_set_profile call: out[10..12] = ms
+ * of the Schur updates, of whole factorisations, of whole substitutions; out[13..15] = factorisations,
+ * substitutions, Schur-update launches. */
 int fers_b200_chol_profile(double* out, int n_out);
 
 /* ---- recovery (pydantic_models.py:1594-1635) --------------------------- */

@@ -109,14 +109,12 @@ def test_spmm_matches_scipy(engine_mod, nrhs, variant):
 def test_synthetic_frame_matches_oracle(engine_mod, monkeypatch, dims, force_pcg, variant):
     """configs[3]-shaped frames at oracle-sized scale, dense and PCG solve paths (both SpMM kernels)."""
     from fers_core_b200 import _lib
-    if force_pcg:
-        monkeypatch.setattr(engine_mod, "DENSE_MAX_DOF", 0)
     _lib.load().fers_b200_set_spmm_variant(variant)
     n_combos = 60 if variant >= 1 else 11      # 8 cases + 60 combinations -> one 64-wide and one 8-wide pass
     model = synth.grid_frame(*dims, n_combos=n_combos, timoshenko=(dims[0] == 9), solve_loadcases=True)
     want = fers_oracle.analyze(model)
     stats = {}
-    got = engine_mod.analyze(model, stats_out=stats)
+    got = engine_mod.analyze(model, stats_out=stats, solver="pcg" if force_pcg else "auto")
     _lib.load().fers_b200_set_spmm_variant(0)
     assert stats["method"] == ("pcg" if force_pcg else "dense")
     helpers.assert_results_close(got, want, RTOL, label=str(dims))
