@@ -50,7 +50,8 @@ def parse_args():
                    help="cfg4 = configs[3] space frame x 64 combinations (headline); cfg5 = configs[4] batch of "
                         "parametric frames, sway imperfection, P-Delta")
     p.add_argument("--frames", type=int, default=1024, help="cfg5: frames per GPU")
-    p.add_argument("--assembly-variant", type=int, default=0)
+    p.add_argument("--assembly-variant", type=int, default=4,
+                   help="4 = gather kernel (default, no atomics); 0-3 = atomic scatter-add variants")
     p.add_argument("--spmm-variant", type=int, default=-1, help="0 register/LDG, 1 TMA-staged, 2 TMA warp-specialised (default: library default)")
     p.add_argument("--solver", default="auto", choices=["auto", "cholesky", "pcg"],
                    help="auto = sparse multifrontal Cholesky above 8 192 DOF (default); pcg = block-Jacobi PCG")
@@ -231,6 +232,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     lib.fers_b200_pcg_profile(prof)
     iters = int(prof[4])
     relres_solver = eng.stats.relres
+    refine_passes = eng.stats.iterations if direct else 0
 
     # summary gather over NVLink: per-combination max |u| from every rank
     summ = rec["U"].abs().amax(dim=0)[:n_comb].contiguous()
@@ -275,18 +277,36 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                 "share_of_step": ms * launches_per_step / ms_step if ms_step > 0 else 0.0}
 
     # assembly and SpMM kernels timed on their own (few launches per step): events around dedicated launches
-    am = timed_launches(lambda: _lib.check(lib.fers_b200_assemble_beams(
-        model.n_members, _lib.ptr(eng.d_xyz0), _lib.ptr(eng.d_n1), _lib.ptr(eng.d_n2), _lib.ptr(eng.d_m_prop),
-        _lib.ptr(eng.d_type), _lib.ptr(eng.d_roll), None, None, _lib.ptr(eng.d_prop), eng.n_prop, None, 0, None, 0, 0,
-        _lib.ptr(eng.d_m_slot), _lib.ptr(eng.d_vals), args.assembly_variant, eng.stream), "assemble"),
-        pre=lambda: lib.fers_b200_zero(_lib.ptr(eng.d_vals), eng.d_vals.numel() * 8, eng.stream))
-    asm_bytes = model.n_members * (64 + 4 * 36 * 8)
+    if args.assembly_variant == engine.ASSEMBLY_GATHER:
+        am = timed_launches(lambda: _lib.check(lib.fers_b200_assemble_beams_gather(
+            model.n_nodes, model.n_members, _lib.ptr(eng.d_xyz0), _lib.ptr(eng.d_n1), _lib.ptr(eng.d_n2),
+            _lib.ptr(eng.d_m_prop), _lib.ptr(eng.d_type), _lib.ptr(eng.d_roll), None, None, _lib.ptr(eng.d_prop), eng.n_prop,
+            None, 0, None, 0, 0, _lib.ptr(eng.d_m_slot), _lib.ptr(eng.d_hm_ptr), _lib.ptr(eng.d_hm_list),
+            eng.n_dup_half_members, _lib.ptr(eng.d_diag_slot), _lib.ptr(eng.d_vals), eng.stream), "assemble_gather"))
+        asm_name = "k_assemble_gather"
+        # unique bytes: member records in, every block of K out once (the gather kernel has no zero pass, no atomics)
+        asm_bytes = model.n_members * 64 + nnzb * 36 * 8
+    else:
+        am = timed_launches(lambda: _lib.check(lib.fers_b200_assemble_beams(
+            model.n_members, _lib.ptr(eng.d_xyz0), _lib.ptr(eng.d_n1), _lib.ptr(eng.d_n2), _lib.ptr(eng.d_m_prop),
+            _lib.ptr(eng.d_type), _lib.ptr(eng.d_roll), None, None, _lib.ptr(eng.d_prop), eng.n_prop, None, 0, None, 0, 0,
+            _lib.ptr(eng.d_m_slot), _lib.ptr(eng.d_vals), args.assembly_variant, eng.stream), "assemble"),
+            pre=lambda: lib.fers_b200_zero(_lib.ptr(eng.d_vals), eng.d_vals.numel() * 8, eng.stream))
+        asm_name = "k_assemble_beams (atomic scatter-add)"
+        asm_bytes = model.n_members * (64 + 4 * 36 * 8)      # 4 blocks per member, RMW not counted
     if direct:
         sm = timed_launches(lambda: _lib.check(lib.fers_b200_spmm(
             model.n_nodes, nr, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
             _lib.ptr(eng.d_ks), _lib.ptr(rec["U"]), _lib.ptr(ku), eng.stream), "spmm"))
-        kern.append(hbm_row("k_spmm<64> (residual of the refinement)", spmm_bytes, sm, engine.CHOL_REFINE_STEPS + 1))
-        kern.append(hbm_row("k_assemble_beams", asm_bytes, am, 1))
+        kern.append(hbm_row("k_spmm64_tma (64 RHS; residual check / refinement)", spmm_bytes, sm, refine_passes + 1))
+        x1 = rec["U"][:, 0].contiguous()
+        y1 = torch.empty_like(x1)
+        sv = timed_launches(lambda: _lib.check(lib.fers_b200_spmm(
+            model.n_nodes, 1, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
+            _lib.ptr(eng.d_ks), _lib.ptr(x1), _lib.ptr(y1), eng.stream), "spmv"))
+        spmv_bytes = nnzb * (36 * 8 + 4) + (nn + 1) * 4 + 2 * n_dof * 8 + n_dof      # BSR-6 values + indices, x, y, BC mask
+        kern.append(hbm_row("k_spmv (1 RHS, not on the step path)", spmv_bytes, sv, 0))
+        kern.append(hbm_row(asm_name, asm_bytes, am, 1))
         # fp64 pipe peak measured live by the library (register-resident DMMA.8x8x4 / DFMA bursts)
         scratch = torch.empty(8 * 1024 * 160, dtype=torch.uint8, device=dev)
         dmma, dfma = C.c_double(), C.c_double()
@@ -317,7 +337,9 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         kern.insert(1, {"kernel": "panel factorisation (k_potrf_inv + k_trsm + k_update<128x64 DMMA>)", "bound": "tensor",
                         "algorithmic_flops": upd_flops, "ms": um, "TFLOP/s": upd_flops / (um * 1e-3) / 1e12 if um > 0 else 0.0,
                         "frac": upd_flops / (um * 1e-3) / 1e12 / dmma.value if um > 0 and dmma.value > 0 else None,
-                        "share_of_step": um / ms_step, "timing": "profiled extra step (events around every launch)"})
+                        "share_of_step": um / ms_step,
+                        "timing": "profiled extra step (events around every launch, look-ahead off: the timed steps overlap "
+                                  "the panel chain with the trailing updates)"})
         roofline = {"bound": "tensor", "kernel": kern[0]["kernel"], "achieved": tf, "peak": dmma.value, "unit": "TFLOP/s",
                     "frac": kern[0]["frac"], "traffic": None,
                     "peak_source": "fp64 tensor pipe (DMMA.8x8x4) measured live by fers_b200_fp64_peak on this device, "
@@ -334,7 +356,8 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                     "substitutions_per_step": timed_prof["n_solve"] / n_fac,
                     "class_ms_profiled_step": breakdown, "hbm_peak": peak, "kernels": kern}
         solver_cfg = {"solver": "sparse multifrontal Cholesky (nested dissection, fp64 DMMA tile GEMMs) + "
-                                f"{engine.CHOL_REFINE_STEPS} refinement pass, 64 RHS",
+                                f"residual check, iterative refinement while rel. residual > {engine.CHOL_REFINE_TOL:g} "
+                                f"({refine_passes} pass(es) taken), 64 RHS",
                       "fronts": int(len(fr)), "factor_gb": eng._chol.plan.info.factor_doubles * 8 / 1e9,
                       "factor_tflop": float(sum(cls_flops.values())) / 1e12, "solver_rel_residual": relres_solver}
         cache_note = "factor (16 GB) and multi-vectors (354 MB each) >> 126 MB L2; no flush needed"
@@ -344,7 +367,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         for name, b, ms in (("k_spmm<64,dot>", spmm_bytes, prof[0]), ("k_pcg_update<64>", upd_bytes, prof[1]),
                             ("k_pcg_direction<64>", dir_bytes, prof[2])):
             kern.append(hbm_row(name, b, ms, iters))
-        kern.append(hbm_row("k_assemble_beams", asm_bytes, am, 1))
+        kern.append(hbm_row(asm_name, asm_bytes, am, 1))
         dom = max(kern[:3], key=lambda k: k["share_of_step"])
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GB/s"], "peak": peak, "unit": "GB/s",
                     "frac": dom["frac"], "traffic": None, "peak_source": peaks["_source"] + " (MEASURED_PEAKS.json hbm_gbs)",

@@ -29,6 +29,10 @@ SIGNATURES = {
                                       _vp, _vp, _i, _vp]),
     "fers_b200_assemble_plates": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_zero": (_i, [_vp, _sz, _vp]),
+    "fers_b200_gather_map_workspace": (_sz, [_i, _i]),
+    "fers_b200_gather_map_build": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _ip, _vp, _sz, _vp]),
+    "fers_b200_assemble_beams_gather": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i,
+                                             _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "fers_b200_load_case": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_combine": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -50,7 +54,7 @@ SIGNATURES = {
     "fers_b200_recover_plates": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_member_axial": (_i, [_i, _i, _vp, _vp, _vp]),
     # sparse multifrontal Cholesky: host plan ([host] pointers are passed as integers / ctypes arrays)
-    "fers_b200_chol_plan_create": (_i, [_i, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
+    "fers_b200_chol_plan_create": (_i, [_i, _vp, _vp, _vp, _i, _vp, C.POINTER(_vp)]),
     "fers_b200_chol_plan_destroy": (None, [_vp]),
     "fers_b200_chol_plan_info": (_i, [_vp, C.POINTER(C.c_longlong), _i]),
     "fers_b200_chol_plan_perm": (_i, [_vp, _vp]),

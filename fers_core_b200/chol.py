@@ -40,15 +40,21 @@ class PlanInfo:
 class CholPlan:
     """Nested-dissection ordering + symbolic factorisation of a block-CSR node pattern."""
 
-    def __init__(self, rowptr: np.ndarray, colidx: np.ndarray, xyz: np.ndarray, leaf_nodes: int = DEFAULT_LEAF_NODES):
+    def __init__(self, rowptr: np.ndarray, colidx: np.ndarray, xyz: np.ndarray, leaf_nodes: int = DEFAULT_LEAF_NODES,
+                 node_restrained: np.ndarray | None = None):
         self.lib = _lib.load()
         self.n_nodes = int(len(rowptr) - 1)
         rp = np.ascontiguousarray(rowptr, np.int32)
         ci = np.ascontiguousarray(colidx, np.int32)
         xy = np.ascontiguousarray(xyz, np.float64)
         h = C.c_void_p()
+        mask = None
+        if node_restrained is not None and np.any(node_restrained):
+            mask = np.ascontiguousarray(node_restrained, np.uint8)
+            assert mask.shape == (self.n_nodes,)
         _lib.check(self.lib.fers_b200_chol_plan_create(self.n_nodes, rp.ctypes.data, ci.ctypes.data, xy.ctypes.data,
-                                                       int(leaf_nodes), C.byref(h)), "chol_plan_create")
+                                                       int(leaf_nodes), None if mask is None else mask.ctypes.data,
+                                                       C.byref(h)), "chol_plan_create")
         self.handle = h
         out = (C.c_longlong * 12)()
         _lib.check(self.lib.fers_b200_chol_plan_info(self.handle, out, 12), "chol_plan_info")

@@ -14,6 +14,8 @@
 // in shared memory first and only the group leader issues the atomic ("warp-aggregated").
 // The section/material table is staged into shared memory with one TMA bulk copy
 // (cp.async.bulk + mbarrier) while the threads fetch their coordinates.
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 
 namespace fers {
@@ -50,6 +52,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
             : "r"(smem_u32(bar)), "r"(phase)
             : "memory");
     }
+}
+
+// 256-bit global store (sm_100+): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
 struct BeamArgs {
@@ -195,6 +202,231 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_beams(BeamArgs A) {
     }
 }
 
+// ---- gather formulation (default): no atomics, no zero pass, bit-reproducible ---------------------
+// Work unit = "half-member" (member, end): the thread forms the member's frame and coefficients and
+// the two 6x6 blocks that live in the block row of its own node: the off-diagonal block (own, other),
+// which has exactly one contributor and is stored straight from registers, and the member's
+// contribution to the diagonal block (own, own).  Half-members are sorted by block slot (= by node),
+// a CTA owns GA_NODES consecutive nodes, the diagonal contributions meet in shared memory and are
+// summed in list order by fixed (node, entry) owners, so every value of K is written exactly once.
+// Duplicate members between the same node pair (flagged at map-build time) are summed by the first
+// of them.  Element arithmetic is the same as in k_assemble_beams (each member is formed twice, two
+// blocks each time, instead of once with four blocks).
+constexpr int GA_THREADS = 128;
+constexpr int GA_NODES = 16;
+constexpr int GA_STRIDE = 37;
+constexpr int GA_PAIRS = (GA_NODES * 36 + GA_THREADS - 1) / GA_THREADS;
+
+struct GatherArgs {
+    BeamArgs B;
+    int n_nodes;
+    const int* hm_ptr;     // [n_nodes + 1]
+    const int* hm_list;    // [2 * n_members]  member << 2 | dup << 1 | end
+    const int* diag_slot;  // [n_nodes]
+};
+
+// one 6x6 block (bi, bj) of member m, self-contained (duplicate-member path)
+template <bool GENERAL>
+__device__ __noinline__ void member_block(const BeamArgs& A, const double* prop_tab, int m, int bi, int bj, double* blk) {
+    const int a = A.n1[m], b = A.n2[m];
+    double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
+    double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+    const Frame f = member_frame(pa, pb, A.m_roll[m]);
+    const int mtype = A.m_type[m];
+    const double scale = A.m_scale ? A.m_scale[m] : 1.0;
+    const int ri = A.m_rel ? A.m_rel[m] : -1;
+    const double axial = (A.m_axial && A.kg_mode) ? A.m_axial[m] : 0.0;
+    double Pr[NPROP];
+    const double* P = prop_tab + (size_t)A.m_prop[m] * NPROP;
+#pragma unroll
+    for (int i = 0; i < NPROP; ++i) Pr[i] = P[i];
+    const BeamCoef c = beam_coef(Pr, f.L, mtype, scale);
+    if (GENERAL && ((ri >= 0) || (axial != 0.0))) {
+        double kE[144];
+        beam_local_k(c, kE);
+        if (ri >= 0) beam_condense(kE, A.rel + (size_t)ri * 12, nullptr, 0);
+        beam_rotate_block(kE, f, bi, bj, blk);
+        if (axial != 0.0) {
+            for (int i = 0; i < 144; ++i) kE[i] = 0.0;
+            beam_add_kg(kE, axial, f.L, A.kg_mode == 1, mtype);
+            double g[36];
+            beam_rotate_block(kE, f, bi, bj, g);
+            if (A.kg_suppress) suppress_block(g, A.kg_suppress);
+#pragma unroll
+            for (int e = 0; e < 36; ++e) blk[e] += g[e];
+        }
+    } else {
+        beam_block_closed(c, f, bi, bj, blk);
+    }
+}
+
+template <bool GENERAL>
+__global__ void __launch_bounds__(GA_THREADS, GENERAL ? 1 : 4) k_assemble_gather(GatherArgs G) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const BeamArgs& A = G.B;
+    double* s_stage = reinterpret_cast<double*>(smem_raw);
+    double* s_prop = s_stage + GA_THREADS * GA_STRIDE;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_prop + (size_t)(A.use_tma ? A.n_prop : 0) * NPROP);
+    __shared__ int s_hp[GA_NODES + 1];
+
+    const int tid = threadIdx.x;
+    if (A.use_tma) {
+        if (tid == 0) mbar_init(s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t prop_bytes = (uint32_t)A.n_prop * NPROP * sizeof(double);
+            mbar_expect_tx(s_bar, prop_bytes);
+            tma_bulk_g2s(s_prop, A.prop, prop_bytes, s_bar);
+        }
+    }
+    const int node_a = blockIdx.x * GA_NODES;
+    const int nn = min(GA_NODES, G.n_nodes - node_a);
+    if (tid <= nn) s_hp[tid] = G.hm_ptr[node_a + tid];
+    __syncthreads();
+    const int h_begin = s_hp[0], h_end = s_hp[nn];
+    const double* prop_tab = A.use_tma ? s_prop : A.prop;
+    bool prop_ready = !A.use_tma;
+
+    double acc[GA_PAIRS];
+#pragma unroll
+    for (int q = 0; q < GA_PAIRS; ++q) acc[q] = 0.0;
+
+    for (int chunk0 = h_begin; chunk0 < h_end; chunk0 += GA_THREADS) {
+        const int h = chunk0 + tid;
+        const bool valid = h < h_end;
+        if (valid) {
+            const int code = G.hm_list[h];
+            const int m = code >> 2, end = code & 1;
+            const bool dup = (code & 2) != 0;
+            const int a = A.n1[m], b = A.n2[m];
+            double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
+            double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+            const Frame f = member_frame(pa, pb, A.m_roll[m]);
+            const int mtype = A.m_type[m];
+            const int pi = A.m_prop[m];
+            const double scale = A.m_scale ? A.m_scale[m] : 1.0;
+            const int ri = A.m_rel ? A.m_rel[m] : -1;
+            const double axial = (A.m_axial && A.kg_mode) ? A.m_axial[m] : 0.0;
+            const int4 slots = reinterpret_cast<const int4*>(A.m_slot)[m];
+            const int off_slot = end ? slots.z : slots.y, dg_slot = end ? slots.w : slots.x;
+            if (!prop_ready) { mbar_wait(s_bar, 0); prop_ready = true; }
+            double Pr[NPROP];
+#pragma unroll
+            for (int i = 0; i < NPROP; ++i) Pr[i] = prop_tab[(size_t)pi * NPROP + i];
+            const BeamCoef c = beam_coef(Pr, f.L, mtype, scale);
+            const bool general = GENERAL && ((ri >= 0) || (axial != 0.0));
+            double kE[GENERAL ? 144 : 1], kG[GENERAL ? 144 : 1];
+            if (GENERAL && general) {
+                beam_local_k(c, kE);
+                if (axial != 0.0) {
+                    for (int i = 0; i < 144; ++i) kG[i] = 0.0;
+                    beam_add_kg(kG, axial, f.L, A.kg_mode == 1, mtype);
+                }
+                if (ri >= 0) beam_condense(kE, A.rel + (size_t)ri * 12, nullptr, 0);
+            }
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {          // 0: diagonal contribution, 1: off-diagonal block
+                const int bi = end, bj = pass ? 1 - end : end;
+                double blk[36];
+                if (!GENERAL || !general) {
+                    beam_block_closed(c, f, bi, bj, blk);
+                } else {
+                    beam_rotate_block(kE, f, bi, bj, blk);
+                    if (axial != 0.0) {
+                        double g[36];
+                        beam_rotate_block(kG, f, bi, bj, g);
+                        if (A.kg_suppress) suppress_block(g, A.kg_suppress);
+#pragma unroll
+                        for (int e = 0; e < 36; ++e) blk[e] += g[e];
+                    }
+                }
+                if (pass == 0) {
+#pragma unroll
+                    for (int e = 0; e < 36; ++e) s_stage[tid * GA_STRIDE + e] = blk[e];
+                } else if (!dup && off_slot != dg_slot) {       // duplicated node pairs: k_gather_dups
+                    // 288-byte block = nine full 32-byte sectors: 256-bit stores, no partial-sector writes
+                    double* dst = A.vals + (size_t)off_slot * 36;
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) st_global_v4(dst + 4 * e, blk[4 * e], blk[4 * e + 1], blk[4 * e + 2], blk[4 * e + 3]);
+                }
+            }
+        }
+        __syncthreads();
+        // fixed owners sum the diagonal contributions of this chunk in list order
+#pragma unroll
+        for (int q = 0; q < GA_PAIRS; ++q) {
+            const int p = tid + q * GA_THREADS;
+            const int nl = p / 36, e = p - nl * 36;
+            if (nl < nn) {
+                const int lo = max(s_hp[nl], chunk0), hi = min(s_hp[nl + 1], chunk0 + GA_THREADS);
+                for (int hh = lo; hh < hi; ++hh) acc[q] += s_stage[(hh - chunk0) * GA_STRIDE + e];
+            }
+        }
+        __syncthreads();
+    }
+    if (!prop_ready) mbar_wait(s_bar, 0);     // never leave the CTA with a bulk copy in flight
+#pragma unroll
+    for (int q = 0; q < GA_PAIRS; ++q) {
+        const int p = tid + q * GA_THREADS;
+        const int nl = p / 36, e = p - nl * 36;
+        if (nl < nn) A.vals[(size_t)G.diag_slot[node_a + nl] * 36 + e] = acc[q];
+    }
+}
+
+// Off-diagonal blocks shared by several members (flagged dup): the first half-member of each run of
+// equal slots forms every contribution of the run and stores the sum.  Launched only when the map has
+// duplicates.
+template <bool GENERAL>
+__global__ void __launch_bounds__(128) k_gather_dups(GatherArgs G) {
+    const BeamArgs& A = G.B;
+    const int n_half = 2 * A.n_members;
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_half) return;
+    const int code = G.hm_list[h];
+    if (!(code & 2)) return;
+    const int m = code >> 2, end = code & 1;
+    const int4 sl = reinterpret_cast<const int4*>(A.m_slot)[m];
+    const int off_slot = end ? sl.z : sl.y, dg_slot = end ? sl.w : sl.x;
+    if (off_slot == dg_slot) return;
+    auto slot_of = [&](int hh) {
+        const int c2 = G.hm_list[hh];
+        const int4 s2 = reinterpret_cast<const int4*>(A.m_slot)[c2 >> 2];
+        return (c2 & 1) ? s2.z : s2.y;
+    };
+    if (h > 0 && slot_of(h - 1) == off_slot) return;          // not the first of its run
+    double sum[36], blk[36];
+    member_block<GENERAL>(A, A.prop, m, end, 1 - end, sum);
+    for (int h2 = h + 1; h2 < n_half && slot_of(h2) == off_slot; ++h2) {
+        const int c2 = G.hm_list[h2];
+        member_block<GENERAL>(A, A.prop, c2 >> 2, c2 & 1, 1 - (c2 & 1), blk);
+        for (int e = 0; e < 36; ++e) sum[e] += blk[e];
+    }
+    for (int e = 0; e < 36; ++e) A.vals[(size_t)off_slot * 36 + e] = sum[e];
+}
+
+// ---- gather map: half-members sorted by the block slot of their off-diagonal block ---------------
+__global__ void k_gather_keys(int n_members, const int* __restrict__ n1, const int* __restrict__ n2,
+                              const int* __restrict__ m_slot, unsigned long long* __restrict__ keys, int* __restrict__ count) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 2 * n_members; k += gridDim.x * blockDim.x) {
+        const int m = k >> 1, end = k & 1;
+        const int4 s = reinterpret_cast<const int4*>(m_slot)[m];
+        const unsigned long long slot = (unsigned)(end ? s.z : s.y);
+        keys[k] = (slot << 32) | (unsigned)k;
+        atomicAdd(count + (end ? n2[m] : n1[m]), 1);
+    }
+}
+
+__global__ void k_gather_list(int n_half, const unsigned long long* __restrict__ sorted, int* __restrict__ hm_list,
+                              int* __restrict__ n_dup) {
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < n_half; h += gridDim.x * blockDim.x) {
+        const unsigned long long key = sorted[h];
+        const unsigned slot = (unsigned)(key >> 32), k = (unsigned)(key & 0xffffffffull);
+        const bool dup = (h > 0 && (unsigned)(sorted[h - 1] >> 32) == slot) || (h + 1 < n_half && (unsigned)(sorted[h + 1] >> 32) == slot);
+        hm_list[h] = (int)(((k >> 1) << 2) | (dup ? 2u : 0u) | (k & 1u));
+        if (dup) atomicAdd(n_dup, 1);
+    }
+}
+
 // ---- plates: one thread per TRI3, nine 6x6 blocks, same staged scatter -------------------------
 __global__ void __launch_bounds__(ASM_THREADS) k_assemble_plates(int n_plates, const double* __restrict__ xyz,
                                                                  const int* __restrict__ pn,
@@ -273,6 +505,95 @@ int fers_b200_assemble_beams(int n_members, const double* xyz, const int* m_n1, 
     else k_assemble_beams<false><<<grid, ASM_THREADS, smem, as_stream(stream)>>>(A);
     FERS_LAUNCH_CHECK();
     count_launches(1);
+    return 0;
+}
+
+size_t fers_b200_gather_map_workspace(int n_nodes, int n_members) {
+    size_t sort_tmp = 0, scan_tmp = 0;
+    const int nh = 2 * (n_members > 0 ? n_members : 1);
+    cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (unsigned long long*)nullptr, (unsigned long long*)nullptr, nh);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (int*)nullptr, (int*)nullptr, n_nodes + 1);
+    const size_t tmp = sort_tmp > scan_tmp ? sort_tmp : scan_tmp;
+    return 2 * align_up((size_t)nh * 8) + align_up(((size_t)n_nodes + 1) * 4) + align_up(tmp) + 512;
+}
+
+int fers_b200_gather_map_build(int n_nodes, int n_members, int nnzb, const int* m_n1, const int* m_n2, const int* m_slot,
+                               int* hm_ptr, int* hm_list, int* n_dup_out, void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    FERS_REQUIRE(n_nodes > 0 && hm_ptr, "gather_map_build: bad arguments");
+    FERS_REQUIRE(n_members < (1 << 29), "gather_map_build: too many members for the packed half-member code");
+    FERS_REQUIRE(workspace_bytes >= fers_b200_gather_map_workspace(n_nodes, n_members), "gather_map_build: workspace too small");
+    if (n_members <= 0) {
+        FERS_CK(cudaMemsetAsync(hm_ptr, 0, ((size_t)n_nodes + 1) * 4, st));
+        if (n_dup_out) *n_dup_out = 0;
+        return 0;
+    }
+    const int nh = 2 * n_members;
+    char* w = (char*)workspace;
+    unsigned long long* keys = (unsigned long long*)w;   w += align_up((size_t)nh * 8);
+    unsigned long long* sorted = (unsigned long long*)w; w += align_up((size_t)nh * 8);
+    int* count = (int*)w;                                w += align_up(((size_t)n_nodes + 1) * 4);
+    int* d_dup = (int*)w;                                w += 256;
+    size_t tmp_bytes = workspace_bytes - (size_t)(w - (char*)workspace);
+    FERS_CK(cudaMemsetAsync(count, 0, ((size_t)n_nodes + 1) * 4, st));
+    FERS_CK(cudaMemsetAsync(d_dup, 0, 4, st));
+    const int T = 256, grid = (nh + T - 1) / T;
+    k_gather_keys<<<grid, T, 0, st>>>(n_members, m_n1, m_n2, m_slot, keys, count);
+    FERS_LAUNCH_CHECK();
+    int bits = 1;
+    while ((1ll << bits) < (long long)(nnzb > 1 ? nnzb : 2)) ++bits;
+    size_t t1 = tmp_bytes;
+    FERS_CK(cub::DeviceRadixSort::SortKeys(w, t1, keys, sorted, nh, 0, 32 + bits, st));
+    size_t t2 = tmp_bytes;
+    FERS_CK(cub::DeviceScan::ExclusiveSum(w, t2, count, hm_ptr, n_nodes + 1, st));
+    k_gather_list<<<grid, T, 0, st>>>(nh, sorted, hm_list, d_dup);
+    FERS_LAUNCH_CHECK();
+    count_launches(2 + 5);
+    int n_dup = 0;
+    FERS_CK(cudaMemcpyAsync(&n_dup, d_dup, 4, cudaMemcpyDeviceToHost, st));
+    FERS_CK(cudaStreamSynchronize(st));
+    if (n_dup_out) *n_dup_out = n_dup;
+    return 0;
+}
+
+int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xyz, const int* m_n1, const int* m_n2,
+                                    const int* m_prop, const int* m_type, const double* m_roll, const double* m_scale,
+                                    const int* m_rel, const double* prop, int n_prop, const double* rel, int n_rel,
+                                    const double* m_axial, int kg_mode, int kg_suppress, const int* m_slot,
+                                    const int* hm_ptr, const int* hm_list, int n_dup, const int* diag_slot, double* vals,
+                                    void* stream) {
+    (void)n_rel;
+    FERS_REQUIRE(n_nodes > 0 && hm_ptr && diag_slot && vals, "assemble_beams_gather: bad arguments");
+    FERS_REQUIRE(n_members <= 0 || (n_prop > 0 && hm_list && m_slot), "assemble_beams_gather: empty property table or missing maps");
+    GatherArgs G;
+    BeamArgs& A = G.B;
+    A.n_members = n_members; A.xyz = xyz; A.n1 = m_n1; A.n2 = m_n2; A.m_prop = m_prop; A.m_type = m_type;
+    A.m_roll = m_roll; A.m_scale = m_scale; A.m_rel = m_rel; A.prop = prop; A.n_prop = n_prop; A.rel = rel;
+    A.m_axial = m_axial; A.kg_mode = kg_mode; A.kg_suppress = kg_suppress; A.m_slot = m_slot; A.vals = vals;
+    A.aggregate = 0;
+    A.use_tma = (n_members > 0 && n_prop <= MAX_PROP_SMEM_ROWS && (((uintptr_t)prop) & 15) == 0) ? 1 : 0;
+    G.n_nodes = n_nodes; G.hm_ptr = hm_ptr; G.hm_list = hm_list; G.diag_slot = diag_slot;
+    const size_t smem = (size_t)GA_THREADS * GA_STRIDE * sizeof(double) + (A.use_tma ? (size_t)n_prop * NPROP * sizeof(double) : 0) + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const int max_smem = (int)((size_t)GA_THREADS * GA_STRIDE * 8 + MAX_PROP_SMEM_ROWS * NPROP * 8 + 16);
+        FERS_CK(cudaFuncSetAttribute(k_assemble_gather<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        FERS_CK(cudaFuncSetAttribute(k_assemble_gather<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_set = true;
+    }
+    const int grid = (n_nodes + GA_NODES - 1) / GA_NODES;
+    const bool general = (m_rel != nullptr) || (m_axial != nullptr && kg_mode != 0);
+    if (general) k_assemble_gather<true><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
+    else k_assemble_gather<false><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
+    FERS_LAUNCH_CHECK();
+    count_launches(1);
+    if (n_dup > 0 && n_members > 0) {
+        const int g2 = (2 * n_members + 127) / 128;
+        if (general) k_gather_dups<true><<<g2, 128, 0, as_stream(stream)>>>(G);
+        else k_gather_dups<false><<<g2, 128, 0, as_stream(stream)>>>(G);
+        FERS_LAUNCH_CHECK();
+        count_launches(1);
+    }
     return 0;
 }
 

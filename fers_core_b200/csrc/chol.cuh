@@ -41,10 +41,11 @@ struct KScatter {
 
 struct CholPlanHost {
     int n_nodes = 0;
+    int n_active = 0;               // nodes taking part in the elimination (n_nodes minus fully restrained ones)
     int n_fronts = 0;
     int n_levels = 0;
     std::vector<int> perm;          // elimination position -> node
-    std::vector<int> pos;           // node -> elimination position
+    std::vector<int> pos;           // node -> elimination position (-1: fully restrained node, left out)
     std::vector<FrontDev> fronts;   // in elimination (post-)order
     std::vector<int> front_first;   // elimination position of a front's first own node
     std::vector<int> nodes;         // concatenated front node lists

@@ -37,21 +37,26 @@ struct LevelCtx {
 };
 
 // ---- front initialisation: children's Schur complements -> panel + F22 (lower triangle) -----------
-constexpr int INIT_ROWS = 192;
+// One thread owns two consecutive rows (the even/odd DOF pair of one node: 16-byte loads and stores
+// along the contiguous dimension of the column-major fronts) and INIT_COLS columns (four whole nodes,
+// so the child index of a column node is looked up once per six columns).
+constexpr int INIT_THREADS = 192;
+constexpr int INIT_ROWS = 2 * INIT_THREADS;
 constexpr int INIT_COLS = 24;
 
-__global__ void __launch_bounds__(INIT_ROWS)
+__global__ void __launch_bounds__(INIT_THREADS)
 k_front_init(LevelCtx L) {
     const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
     const int nt = f.n1 + f.n2, m = 6 * nt, k1 = 6 * f.n1, m2 = 6 * f.n2;
     const int r0 = blockIdx.x * INIT_ROWS, c0 = blockIdx.y * INIT_COLS;
     if (r0 >= m || c0 >= m || c0 > r0 + INIT_ROWS - 1) return;
-    const int r = r0 + threadIdx.x;
-    if (r >= m) return;
+    const int r = r0 + 2 * threadIdx.x;                       // rows r, r + 1 (m is even)
+    if (r >= m || c0 > r + 1) return;
     const int bi = r / 6, a = r - 6 * bi;
-    double v[INIT_COLS];
+    const int bj0 = c0 / 6;
+    double2 v[INIT_COLS];
 #pragma unroll
-    for (int q = 0; q < INIT_COLS; ++q) v[q] = 0.0;
+    for (int q = 0; q < INIT_COLS; ++q) v[q] = make_double2(0.0, 0.0);
     for (int ce = f.child_begin; ce < f.child_end; ++ce) {
         const int* mp = L.inv + L.inv_off[ce];
         const int ci = mp[bi];
@@ -60,12 +65,17 @@ k_front_init(LevelCtx L) {
         const size_t ldc = 6 * (size_t)fc.n2;
         const double* s = L.schur_child + fc.schur_off + 6 * ci + a;
 #pragma unroll
-        for (int q = 0; q < INIT_COLS; ++q) {
-            const int c = c0 + q;
-            if (c > r || c >= m) continue;
-            const int bj = c / 6, b = c - 6 * bj;
+        for (int qn = 0; qn < INIT_COLS / 6; ++qn) {
+            const int bj = bj0 + qn;
+            if (bj > bi) break;                                // column node after the row node: upper triangle
             const int cj = mp[bj];
-            if (cj >= 0) v[q] += s[(size_t)(6 * cj + b) * ldc];
+            if (cj < 0) continue;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                if (6 * bj + b > r + 1) continue;
+                const double2 t = *reinterpret_cast<const double2*>(s + (size_t)(6 * cj + b) * ldc);
+                v[6 * qn + b].x += t.x; v[6 * qn + b].y += t.y;
+            }
         }
     }
     double* panel = L.factor + f.panel_off;
@@ -73,9 +83,11 @@ k_front_init(LevelCtx L) {
 #pragma unroll
     for (int q = 0; q < INIT_COLS; ++q) {
         const int c = c0 + q;
-        if (c > r || c >= m) continue;
-        if (c < k1) panel[(size_t)c * m + r] = v[q];
-        else schur[(size_t)(c - k1) * m2 + (r - k1)] = v[q];
+        if (c > r + 1 || c >= m) continue;
+        double2 t = v[q];
+        if (c > r) t.x = 0.0;                                  // (r, r + 1) lies above the diagonal: never read
+        if (c < k1) *reinterpret_cast<double2*>(panel + (size_t)c * m + r) = t;
+        else *reinterpret_cast<double2*>(schur + (size_t)(c - k1) * m2 + (r - k1)) = t;
     }
 }
 
@@ -392,7 +404,8 @@ k_chol_unpermute(int n_nodes, int nr, const int* __restrict__ pos, const uint8_t
     for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
         const int d = (int)(idx / nr), r = (int)(idx - (long long)d * nr);
         const int n = d / 6, a = d - 6 * n;
-        const double v = fixed[d] ? 0.0 : sc[d] * Y[(size_t)(6 * pos[n] + a) * nr + r];
+        const int pn = pos[n];
+        const double v = (fixed[d] || pn < 0) ? 0.0 : sc[d] * Y[(size_t)(6 * pn + a) * nr + r];
         if (accumulate) x[idx] += v; else x[idx] = v;
     }
 }
@@ -518,6 +531,8 @@ static CholProfile g_chol_profile;
 // tile-shape selection (A/B measurements): bit 0 = panel updates, bit 1 = Schur update;
 // set = 128x128 tile, one CTA per SM; clear = 128x64 tile, two CTAs per SM.  FERS_CHOL_VARIANT overrides.
 static int g_chol_variant = getenv("FERS_CHOL_VARIANT") ? atoi(getenv("FERS_CHOL_VARIANT")) : 0;
+static cudaStream_t g_side_stream = nullptr;   // low-priority stream of the overlapped (look-ahead) panel updates
+static cudaStream_t g_main_stream = nullptr;   // high-priority stream of the factorisation when look-ahead is on
 static int g_chol_profile_on = 0;      // 0 off, 1 every kernel class, 2 Schur-update spans + totals only
 
 struct EventPool {
@@ -589,7 +604,7 @@ static size_t chol_work_bytes(const CholPlanHost& P, int nrhs) {
 
 static int chol_factor(const CholPlanHost& P, const void* index_dev, const double* vals, const int* diag_slot,
                        const uint8_t* fixed, const double* kspring, double* factor, void* work, int* info_dev,
-                       cudaStream_t st) {
+                       cudaStream_t caller) {
     if (set_smem_attrs()) return 1;
     const IndexPtrs I = index_ptrs(P, index_dev);
     double* sc = factor + P.factor_doubles;
@@ -600,7 +615,27 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
     const bool prof_all = g_chol_profile_on == 1;
     if (prof) { g_pool.reset(); g_timed.clear(); }
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    if (prof) { ev_begin = g_pool.get(); cudaEventRecord(ev_begin, st); }
+    if (prof) { ev_begin = g_pool.get(); cudaEventRecord(ev_begin, caller); }
+    // look-ahead needs two internal streams (high priority: the panel chain and everything else; low priority:
+    // the overlapped panel updates); per-class profiling (mode 1) keeps everything on the caller's stream
+    const bool lookahead = !(g_chol_variant & 4) && !prof_all;
+    static cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_fork = nullptr;
+    if (lookahead && g_side_stream == nullptr) {
+        int lo = 0, hi = 0;
+        FERS_CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        FERS_CK(cudaStreamCreateWithPriority(&g_side_stream, cudaStreamNonBlocking, lo));
+        FERS_CK(cudaStreamCreateWithPriority(&g_main_stream, cudaStreamNonBlocking, hi));
+        FERS_CK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+        FERS_CK(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
+        FERS_CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    }
+    cudaStream_t st = caller;
+    if (lookahead) {
+        FERS_CK(cudaEventRecord(ev_fork, caller));
+        FERS_CK(cudaStreamWaitEvent(g_main_stream, ev_fork, 0));
+        st = g_main_stream;
+    }
+    bool side_pending = false;
     long long launches = 0;
     auto span_begin = [&](int cls) -> cudaEvent_t {
         if (!prof || !(prof_all || cls == 5)) return nullptr;
@@ -629,7 +664,7 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
         cudaEvent_t e0 = span_begin(0);
         {
             dim3 grid(cdiv(max_m, INIT_ROWS), cdiv(max_m, INIT_COLS), nf);
-            k_front_init<<<grid, INIT_ROWS, 0, st>>>(L);
+            k_front_init<<<grid, INIT_THREADS, 0, st>>>(L);
             FERS_LAUNCH_CHECK();
             ++launches;
         }
@@ -672,20 +707,43 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
                 ++launches;
             }
             if (cbeg == blk_end && blk_end < max_k1) {
-                e0 = span_begin(4);
-                if (g_chol_variant & 1) {
-                    dim3 grid(cdiv(max_m - blk_end, G88::BM), cdiv(max_k1 - blk_end, G88::BN), nf);
-                    k_update<G88><<<grid, GEMM_THREADS, G88::SMEM, st>>>(L, blk_end - CHOL_OUTER * NB, CHOL_OUTER * NB, blk_end, 1 << 30);
+                const int kc0 = blk_end - CHOL_OUTER * NB, kw = CHOL_OUTER * NB;
+                auto outer = [&](cudaStream_t q, int c_from, int c_to_grid, int c_to) {
+                    if (g_chol_variant & 1) {
+                        dim3 grid(cdiv(max_m - c_from, G88::BM), cdiv(c_to_grid - c_from, G88::BN), nf);
+                        k_update<G88><<<grid, GEMM_THREADS, G88::SMEM, q>>>(L, kc0, kw, c_from, c_to);
+                    } else {
+                        dim3 grid(cdiv(max_m - c_from, G86::BM), cdiv(c_to_grid - c_from, G86::BN), nf);
+                        k_update<G86><<<grid, GEMM_THREADS, G86::SMEM, q>>>(L, kc0, kw, c_from, c_to);
+                    }
+                    ++launches;
+                };
+                if (!lookahead) {
+                    e0 = span_begin(4);
+                    outer(st, blk_end, max_k1, 1 << 30);
+                    span_end(4, e0);
                 } else {
-                    dim3 grid(cdiv(max_m - blk_end, G86::BM), cdiv(max_k1 - blk_end, G86::BN), nf);
-                    k_update<G86><<<grid, GEMM_THREADS, G86::SMEM, st>>>(L, blk_end - CHOL_OUTER * NB, CHOL_OUTER * NB, blk_end, 1 << 30);
+                    // look-ahead: the columns of the next outer block are updated first, on the main stream, so
+                    // that its chain of diagonal tiles / trsm / inner updates overlaps the update of all later
+                    // columns, which runs on the side stream.  Both touch disjoint columns; successive side
+                    // updates are ordered by the side stream, and the urgent update of block b+1 waits for the
+                    // side update of block b (same columns).
+                    const int next_end = std::min(blk_end + kw, max_k1);
+                    if (side_pending) { FERS_CK(cudaStreamWaitEvent(st, ev_side, 0)); side_pending = false; }
+                    outer(st, blk_end, next_end, next_end);
+                    if (next_end < max_k1) {
+                        FERS_CK(cudaEventRecord(ev_main, st));
+                        FERS_CK(cudaStreamWaitEvent(g_side_stream, ev_main, 0));
+                        outer(g_side_stream, next_end, max_k1, 1 << 30);
+                        FERS_CK(cudaEventRecord(ev_side, g_side_stream));
+                        side_pending = true;
+                    }
                 }
-                span_end(4, e0);
-                ++launches;
             }
             FERS_LAUNCH_CHECK();
             ++launches;
         }
+        if (side_pending) { FERS_CK(cudaStreamWaitEvent(st, ev_side, 0)); side_pending = false; }
         const int max_m2 = max_m;   // upper bound on 6 * n2
         if (l + 1 < P.n_levels) {
             e0 = span_begin(5);
@@ -701,10 +759,14 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
             ++launches;
         }
     }
-    if (prof) { ev_end = g_pool.get(); cudaEventRecord(ev_end, st); }
+    if (lookahead) {                       // join: the caller's stream continues after the internal one
+        FERS_CK(cudaEventRecord(ev_fork, st));
+        FERS_CK(cudaStreamWaitEvent(caller, ev_fork, 0));
+    }
+    if (prof) { ev_end = g_pool.get(); cudaEventRecord(ev_end, caller); }
     count_launches(launches);
     if (prof) {
-        FERS_CK(cudaStreamSynchronize(st));
+        FERS_CK(cudaStreamSynchronize(caller));
         double t[6] = {0, 0, 0, 0, 0, 0};
         for (int c = 0; c < 6; ++c)
             for (auto& sp : g_timed.spans[c]) { float ms = 0; cudaEventElapsedTime(&ms, sp.first, sp.second); t[c] += ms; }
@@ -876,7 +938,7 @@ int fers_b200_residual(long long n_dof, int nrhs, const double* f, const double*
 }
 
 int fers_b200_chol_set_variant(int variant) {
-    FERS_REQUIRE(variant >= 0 && variant <= 3, "chol_set_variant: bit 0 = panel updates, bit 1 = Schur update use the 128x128 tile");
+    FERS_REQUIRE(variant >= 0 && variant <= 7, "chol_set_variant: bit 0 = panel updates, bit 1 = Schur update use the 128x128 tile, bit 2 = no look-ahead");
     g_chol_variant = variant;
     return 0;
 }

@@ -126,13 +126,19 @@ struct Dissector {
 
 }  // namespace
 
-static int build_plan(int n_nodes, const int* rp, const int* ci, const double* xyz, int leaf_nodes, CholPlanHost& P) {
+static int build_plan(int n_nodes, const int* rp, const int* ci, const double* xyz, int leaf_nodes, const uint8_t* drop,
+                      CholPlanHost& P) {
     Dissector D;
     D.n = n_nodes; D.rp = rp; D.ci = ci; D.xyz = xyz; D.leaf = leaf_nodes < 1 ? 1 : leaf_nodes;
     D.part.assign(n_nodes, 0);
     {
-        std::vector<int> all(n_nodes);
-        std::iota(all.begin(), all.end(), 0);
+        // nodes whose six DOFs are all restrained by supports take no part in the elimination
+        std::vector<int> all;
+        all.reserve(n_nodes);
+        for (int v = 0; v < n_nodes; ++v)
+            if (!drop || !drop[v]) all.push_back(v);
+        if (all.empty()) { set_error("chol_plan: every node is fully restrained, nothing to factorise"); return 3; }
+        P.n_active = (int)all.size();
         D.dissect(std::move(all), -1);
     }
     std::vector<FrontBuild>& B = D.fronts;
@@ -176,7 +182,7 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
         P.fronts[i].parent = fb.parent < 0 ? -1 : new_id[fb.parent];
         max_depth = std::max(max_depth, fb.depth);
     }
-    if ((int)P.perm.size() != n_nodes) { set_error("chol_plan: ordering lost nodes"); return 3; }
+    if ((int)P.perm.size() != P.n_active) { set_error("chol_plan: ordering lost nodes"); return 3; }
 
     // symbolic factorisation: boundaries in post-order
     std::vector<std::vector<int>> bnd(nf);
@@ -269,16 +275,18 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
     }
 
     // K blocks of the lower triangle (in elimination order) -> panel positions, grouped by level
-    std::vector<int> front_of_node(n_nodes);
+    std::vector<int> front_of_node(n_nodes, -1);
     for (int i = 0; i < nf; ++i)
         for (int q = 0; q < P.fronts[i].n1; ++q) front_of_node[P.nodes[P.fronts[i].nodes_off + q]] = i;
     std::vector<int> level_of(nf);
     for (int l = 0; l < P.n_levels; ++l)
         for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; ++q) level_of[P.level_fronts[q]] = l;
     std::vector<long long> cnt(P.n_levels + 1, 0);
-    for (int v = 0; v < n_nodes; ++v)
+    for (int v = 0; v < n_nodes; ++v) {
+        if (P.pos[v] < 0) continue;
         for (int k = rp[v]; k < rp[v + 1]; ++k)
-            if (P.pos[v] >= P.pos[ci[k]]) cnt[level_of[front_of_node[ci[k]]] + 1]++;
+            if (P.pos[ci[k]] >= 0 && P.pos[v] >= P.pos[ci[k]]) cnt[level_of[front_of_node[ci[k]]] + 1]++;
+    }
     for (int l = 0; l < P.n_levels; ++l) cnt[l + 1] += cnt[l];
     P.kscatter_ptr = cnt;
     P.kscatter.assign((size_t)cnt[P.n_levels], KScatter{});
@@ -328,10 +336,10 @@ using namespace fers;
 extern "C" {
 
 int fers_b200_chol_plan_create(int n_nodes, const int* rowptr, const int* colidx, const double* xyz, int leaf_nodes,
-                               void** plan_out) {
+                               const uint8_t* node_restrained, void** plan_out) {
     FERS_REQUIRE(n_nodes > 0 && rowptr && colidx && xyz && plan_out, "chol_plan_create: bad arguments");
     CholPlanHost* P = new CholPlanHost();
-    const int rc = build_plan(n_nodes, rowptr, colidx, xyz, leaf_nodes, *P);
+    const int rc = build_plan(n_nodes, rowptr, colidx, xyz, leaf_nodes, node_restrained, *P);
     if (rc) { delete P; return rc; }
     *plan_out = P;
     return 0;
@@ -360,6 +368,7 @@ int fers_b200_chol_plan_info(void* plan, long long* out, int n_out) {
 int fers_b200_chol_plan_perm(void* plan, int* perm_out) {
     FERS_REQUIRE(plan && perm_out, "chol_plan_perm: bad arguments");
     const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    std::fill(perm_out, perm_out + P.n_nodes, -1);          // fully restrained nodes are not eliminated
     std::copy(P.perm.begin(), P.perm.end(), perm_out);
     return 0;
 }

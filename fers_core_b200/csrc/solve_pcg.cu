@@ -470,38 +470,47 @@ static int spmm_variant() {
     return g_spmm_variant;
 }
 
-// single right-hand side: one warp per block row, lanes stride over the row's 36*nb values
+// single right-hand side: one thread per scalar row.  Lanes 6g..6g+5 of a warp own the six DOF rows of
+// one node (five nodes per warp, two lanes idle); a thread streams its 48-byte row of every 6x6 block
+// of the node's block row (three 16-byte streaming loads; a group reads the block's 288 contiguous
+// bytes, the warp a contiguous run of about five block rows) and the six x values of the column node
+// through the read-only path.  No cross-lane reduction, four blocks in flight per thread.
+constexpr int SPMV_NODES_PER_WARP = 5;
 __global__ void __launch_bounds__(SPMM_THREADS)
 k_spmv1(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
         const uint8_t* __restrict__ fixed, const double* __restrict__ kspring, const double* __restrict__ x,
         double* __restrict__ y) {
     const int lane = threadIdx.x & 31;
+    const int g = lane / 6, r = lane - 6 * g;
+    if (g >= SPMV_NODES_PER_WARP) return;
     const int wglobal = (blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
     const int nw = (gridDim.x * SPMM_THREADS) >> 5;
-    for (int row = wglobal; row < n_nodes; row += nw) {
+    for (int row = wglobal * SPMV_NODES_PER_WARP + g; row < n_nodes; row += nw * SPMV_NODES_PER_WARP) {
         const int kb = rowptr[row], ke = rowptr[row + 1];
-        double acc[6] = {0, 0, 0, 0, 0, 0};
-        const int total = (ke - kb) * 36;
-        const double* base = vals + (size_t)kb * 36;
-        for (int v = lane; v < total; v += 32) {
-            const int k = v / 36, rem = v - k * 36, r = rem / 6, c = rem - r * 6;
-            const double t = __ldg(base + v) * __ldg(x + (size_t)__ldg(colidx + kb + k) * 6 + c);
+        double acc = 0.0;
+        for (int k0 = kb; k0 < ke; k0 += 4) {
+            double2 a[4][3], xv[4][3];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) acc[q] += (q == r) ? t : 0.0;
+            for (int u = 0; u < 4; ++u) {
+                const int k = min(k0 + u, ke - 1);
+                const int col = __ldg(colidx + k);
+                const double2* ap = reinterpret_cast<const double2*>(vals + (size_t)k * 36 + r * 6);
+                const double2* xp = reinterpret_cast<const double2*>(x + (size_t)col * 6);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { a[u][q] = __ldcs(ap + q); xv[u][q] = __ldg(xp + q); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k0 + u < ke) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { acc = fma(a[u][q].x, xv[u][q].x, acc); acc = fma(a[u][q].y, xv[u][q].y, acc); }
+                }
+            }
         }
-#pragma unroll
-        for (int q = 0; q < 6; ++q)
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_xor_sync(FULL, acc[q], off);
-        if (lane < 6) {
-            double out = 0.0;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) out = (q == lane) ? acc[q] : out;
-            const size_t d = (size_t)row * 6 + lane;
-            if (fixed != nullptr && fixed[d]) out = 0.0;
-            else if (kspring != nullptr) out = fma(kspring[d], x[d], out);
-            y[d] = out;
-        }
+        const size_t d = (size_t)row * 6 + r;
+        if (fixed != nullptr && fixed[d]) acc = 0.0;
+        else if (kspring != nullptr) acc = fma(kspring[d], x[d], acc);
+        y[d] = acc;
     }
 }
 
@@ -904,8 +913,8 @@ int fers_b200_spmm(int n_nodes, int nrhs, const int* rowptr, const int* colidx, 
     cudaStream_t st = as_stream(stream);
     if (n_nodes <= 0) return 0;
     if (nrhs == 1) {
-        int grid = (n_nodes + SPMM_WARPS - 1) / SPMM_WARPS;
-        int cap = sm_count() * 8;
+        int grid = (n_nodes + SPMM_WARPS * SPMV_NODES_PER_WARP - 1) / (SPMM_WARPS * SPMV_NODES_PER_WARP);
+        int cap = sm_count() * 32;
         if (grid > cap) grid = cap;
         k_spmv1<<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y);
         FERS_LAUNCH_CHECK();

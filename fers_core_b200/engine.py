@@ -24,12 +24,14 @@ from .results import ResultArrays, SECTION_FRACS, results_to_wire
 
 DENSE_MAX_DOF = 8192          # models up to this many DOFs use the dense Cholesky path
 SOLVERS = ("auto", "dense", "cholesky", "pcg")   # auto: dense up to DENSE_MAX_DOF, sparse Cholesky above
-CHOL_REFINE_STEPS = 1         # iterative-refinement passes after the direct substitution
+CHOL_REFINE_STEPS = 2         # at most this many iterative-refinement passes after the direct substitution
+CHOL_REFINE_TOL = 1e-12       # refine while the relative residual max_c ||f_c - K u_c|| / ||f_c|| exceeds this
 CHOL_RESIDUAL_LIMIT = 1e-8    # relative residual above which the direct solve is reported as failed
 PCG_TOL = 1e-12               # relative residual ||r|| / ||b|| per right-hand side
 PCG_MAX_ITER = 200000
 PCG_ALLOW_UNCONVERGED = False  # profiling captures only (bench.py --profile-iters)
 NR_CHOICES = (8, 16, 32, 64)
+ASSEMBLY_GATHER = 4           # assembly_variant: 4 = gather kernel (default); 0-3 = atomic scatter-add variants
 
 
 class EngineError(RuntimeError):
@@ -63,7 +65,7 @@ class SolveStats:
 class Engine:
     """One model resident on one GPU."""
 
-    def __init__(self, model: wire.ModelArrays, device=None, assembly_variant: int = 0, solver: str = "auto"):
+    def __init__(self, model: wire.ModelArrays, device=None, assembly_variant: int = ASSEMBLY_GATHER, solver: str = "auto"):
         if solver not in SOLVERS:
             raise EngineError(f"solver must be one of {SOLVERS}, got {solver!r}")
         self.solver = solver
@@ -135,6 +137,10 @@ class Engine:
         code = np.where(unilateral, wire.BC_FIXED, m.bc_code).astype(np.uint8)
         self.has_springs = bool((code == wire.BC_SPRING).any())
         self.d_bc_code = self._t(code.reshape(-1), np.uint8)
+        # nodes with all six DOFs restrained by supports: left out of the sparse factorisation
+        self.h_node_restrained = (code.reshape(-1, 6) == wire.BC_FIXED).all(axis=1)
+        if self.h_node_restrained.all():
+            self.h_node_restrained = None
         self.d_bc_k = self._t(m.bc_k.reshape(-1), np.float64)
         self.d_supported = self._t((m.node_support_id >= 0).astype(np.uint8), np.uint8)
         self.d_p_nodes = self._t(m.p_nodes, np.int32) if m.n_plates else None
@@ -171,6 +177,16 @@ class Engine:
         self.stats.nnzb = self.nnzb
         self.d_colidx = self.d_colidx[: self.nnzb]
         self.d_vals = self._empty(self.nnzb * 36)
+        # gather map of the default assembly kernel (half-members grouped by the block row they write)
+        self.d_hm_ptr = self._empty(nn + 1, torch.int32)
+        self.d_hm_list = self._empty(max(2 * nm, 1), torch.int32)
+        gws_bytes = lib.fers_b200_gather_map_workspace(nn, nm)
+        gws = self._empty(gws_bytes, torch.uint8)
+        n_dup = C.c_int()
+        _lib.check(lib.fers_b200_gather_map_build(
+            nn, nm, self.nnzb, _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_slot), _lib.ptr(self.d_hm_ptr),
+            _lib.ptr(self.d_hm_list), C.byref(n_dup), _lib.ptr(gws), gws_bytes, self.stream), "gather_map_build")
+        self.n_dup_half_members = n_dup.value
         nd = m.n_dof
         self.d_fixed = self._empty(nd, torch.uint8)
         self.d_free_index = self._empty(nd, torch.int32)
@@ -183,13 +199,26 @@ class Engine:
         """Element stiffness + assembly + boundary conditions for one geometry / state."""
         m, lib, st = self.model, self.lib, self.stream
         self._k_version += 1
-        _lib.check(lib.fers_b200_zero(_lib.ptr(self.d_vals), self.d_vals.numel() * 8, st), "zero")
-        _lib.check(lib.fers_b200_assemble_beams(
-            m.n_members, _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_prop),
-            _lib.ptr(self.d_type), _lib.ptr(self.d_roll), _lib.ptr(d_scale), _lib.ptr(self.d_rel_idx),
-            _lib.ptr(self.d_prop), self.n_prop, _lib.ptr(self.d_rel), 0 if self.d_rel is None else self.d_rel.shape[0],
-            _lib.ptr(d_axial), kg_mode, kg_suppress, _lib.ptr(self.d_m_slot), _lib.ptr(self.d_vals),
-            self.assembly_variant, st), "assemble_beams")
+        n_rel = 0 if self.d_rel is None else self.d_rel.shape[0]
+        if self.assembly_variant == ASSEMBLY_GATHER:
+            # gather kernel: every block a member touches is written exactly once (no atomics, no zero pass);
+            # blocks coupled only by plates are zeroed first
+            if m.n_plates:
+                _lib.check(lib.fers_b200_zero(_lib.ptr(self.d_vals), self.d_vals.numel() * 8, st), "zero")
+            _lib.check(lib.fers_b200_assemble_beams_gather(
+                m.n_nodes, m.n_members, _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_prop),
+                _lib.ptr(self.d_type), _lib.ptr(self.d_roll), _lib.ptr(d_scale), _lib.ptr(self.d_rel_idx),
+                _lib.ptr(self.d_prop), self.n_prop, _lib.ptr(self.d_rel), n_rel, _lib.ptr(d_axial), kg_mode, kg_suppress,
+                _lib.ptr(self.d_m_slot), _lib.ptr(self.d_hm_ptr), _lib.ptr(self.d_hm_list), self.n_dup_half_members,
+                _lib.ptr(self.d_diag_slot), _lib.ptr(self.d_vals), st), "assemble_beams_gather")
+        else:
+            _lib.check(lib.fers_b200_zero(_lib.ptr(self.d_vals), self.d_vals.numel() * 8, st), "zero")
+            _lib.check(lib.fers_b200_assemble_beams(
+                m.n_members, _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_prop),
+                _lib.ptr(self.d_type), _lib.ptr(self.d_roll), _lib.ptr(d_scale), _lib.ptr(self.d_rel_idx),
+                _lib.ptr(self.d_prop), self.n_prop, _lib.ptr(self.d_rel), n_rel,
+                _lib.ptr(d_axial), kg_mode, kg_suppress, _lib.ptr(self.d_m_slot), _lib.ptr(self.d_vals),
+                self.assembly_variant, st), "assemble_beams")
         if m.n_plates:
             _lib.check(lib.fers_b200_assemble_plates(
                 m.n_plates, _lib.ptr(d_xyz), _lib.ptr(self.d_p_nodes), _lib.ptr(self.d_p_data), _lib.ptr(self.d_p_flags),
@@ -290,7 +319,7 @@ class Engine:
             t0 = time.perf_counter()
             rowptr = self.d_rowptr.cpu().numpy()
             colidx = self.d_colidx.cpu().numpy()
-            plan = chol.CholPlan(rowptr, colidx, m.xyz)
+            plan = chol.CholPlan(rowptr, colidx, m.xyz, node_restrained=self.h_node_restrained)
             self._chol = chol.CholSolver(plan, self.dev, max_nrhs=64)
             self.timings["chol_plan_ms"] = (time.perf_counter() - t0) * 1e3
         sol = self._chol
@@ -306,21 +335,25 @@ class Engine:
         ku = self._empty((nd, nr))
         norms = self._empty((2, nr))
         relres = float("nan")
-        for step in range(CHOL_REFINE_STEPS + 1):
+        steps = 0
+        while True:
+            # true residual of the assembled K (block-CSR SpMM), all columns at once
             _lib.check(lib.fers_b200_spmm(m.n_nodes, nr, _lib.ptr(self.d_rowptr), _lib.ptr(self.d_colidx),
                                           _lib.ptr(self.d_vals), _lib.ptr(self.d_fixed), _lib.ptr(self.d_ks), _lib.ptr(u),
                                           _lib.ptr(ku), st), "spmm")
             _lib.check(lib.fers_b200_residual(nd, nr, _lib.ptr(d_f), _lib.ptr(ku), _lib.ptr(self.d_fixed), _lib.ptr(r),
                                               _lib.ptr(norms), st), "residual")
-            if step == CHOL_REFINE_STEPS:
+            nh = norms.cpu().numpy()
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rel = np.sqrt(np.where(nh[1] > 0, nh[0] / np.where(nh[1] > 0, nh[1], 1.0), 0.0))
+            relres = float(rel.max())
+            # iterative refinement only while it is needed (same target as the PCG path) and still pays
+            if relres <= CHOL_REFINE_TOL or steps >= CHOL_REFINE_STEPS or not np.isfinite(relres):
                 break
             sol.solve(r, u, self.d_fixed, accumulate=True)
-        nh = norms.cpu().numpy()
-        with np.errstate(divide="ignore", invalid="ignore"):
-            rel = np.sqrt(np.where(nh[1] > 0, nh[0] / np.where(nh[1] > 0, nh[1], 1.0), 0.0))
-        relres = float(rel.max())
+            steps += 1
         self.stats.method = "cholesky"
-        self.stats.iterations = CHOL_REFINE_STEPS
+        self.stats.iterations = steps
         self.stats.relres = relres
         if not (relres <= CHOL_RESIDUAL_LIMIT):
             raise EngineError(f"sparse Cholesky solve failed: relative residual {relres:.3e} after refinement")
@@ -410,7 +443,7 @@ class Engine:
 
 
 # ---------------------------------------------------------------------------------------------
-def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_variant: int = 0,
+def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_variant: int = ASSEMBLY_GATHER,
             stats_out: dict | None = None, solver: str = "auto") -> ResultArrays:
     """Full analysis of one document on the GPU (twin of oracle.fers_oracle.analyze)."""
     t_start = time.perf_counter()

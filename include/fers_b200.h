@@ -85,6 +85,23 @@ int fers_b200_assemble_beams(int n_members, const double* xyz, const int* m_n1, 
                              const double* m_scale, const int* m_rel, const double* prop, int n_prop,
                              const double* rel, int n_rel, const double* m_axial, int kg_mode, int kg_suppress,
                              const int* m_slot, double* vals, int variant, void* stream);
+/* Gather formulation of the same assembly (default of the engine): no atomics and no zero pass, every
+ * value of K is written exactly once and the result is bit-reproducible.  The map lists the
+ * "half-members" (member, end) sorted by the slot of their off-diagonal block, i.e. grouped by the
+ * block row they write: hm_ptr[n_nodes+1] (CSR over nodes), hm_list[2*n_members] = member<<2 | dup<<1 | end
+ * (dup: another member joins the same node pair; *n_dup_out [host] = how many are flagged).  Built once per
+ * pattern from m_slot; synchronises the stream. */
+size_t fers_b200_gather_map_workspace(int n_nodes, int n_members);
+int fers_b200_gather_map_build(int n_nodes, int n_members, int nnzb, const int* m_n1, const int* m_n2, const int* m_slot,
+                               int* hm_ptr, int* hm_list, int* n_dup_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Writes every diagonal block and every off-diagonal block that has a member (blocks coupled only by
+ * plates are not touched: zero vals first when the model has plates, then add the plates). */
+int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xyz, const int* m_n1, const int* m_n2,
+                                    const int* m_prop, const int* m_type, const double* m_roll, const double* m_scale,
+                                    const int* m_rel, const double* prop, int n_prop, const double* rel, int n_rel,
+                                    const double* m_axial, int kg_mode, int kg_suppress, const int* m_slot,
+                                    const int* hm_ptr, const int* hm_list, int n_dup, const int* diag_slot, double* vals,
+                                    void* stream);
 /* TRI3 shell elements: CST membrane + DSG3 Mindlin bending (pydantic_models.py:1700-1726). */
 int fers_b200_assemble_plates(int n_plates, const double* xyz, const int* p_nodes, const double* p_data,
                               const int* p_flags, const int* p_slot, double* vals, void* stream);
@@ -155,15 +172,19 @@ int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* b
  * Analysis phase, host only (no CUDA call): nested dissection on the node coordinates, front tree,
  * symbolic factorisation.  rowptr/colidx [host]: the block-CSR node pattern (structurally symmetric,
  * diagonal present, columns sorted); xyz [host][n_nodes*3].  leaf_nodes: largest undivided node set.
+ * node_restrained [host][n_nodes] or NULL: non-zero = all six DOFs of the node are restrained by supports
+ * for the lifetime of the plan; such nodes are left out of the elimination (their rows of the solution
+ * are 0), which shrinks every front they would sit in.  The `fixed` mask given to the numeric calls must
+ * restrain all their DOFs.
  * *plan_out receives an opaque host handle (free with fers_b200_chol_plan_destroy). */
 int fers_b200_chol_plan_create(int n_nodes, const int* rowptr, const int* colidx, const double* xyz, int leaf_nodes,
-                               void** plan_out);
+                               const uint8_t* node_restrained, void** plan_out);
 void fers_b200_chol_plan_destroy(void* plan);
 /* [host] out[12]: fronts, levels, largest front (nodes), factor doubles, Schur arena doubles (even
  * levels, odd levels), front-local rhs rows, index bytes, factorisation Mflop, nnz(L), K blocks
  * scattered, root separator nodes. */
 int fers_b200_chol_plan_info(void* plan, long long* out, int n_out);
-/* [host] perm_out[n_nodes]: elimination position -> node. */
+/* [host] perm_out[n_nodes]: elimination position -> node (-1 past the number of eliminated nodes). */
 int fers_b200_chol_plan_perm(void* plan, int* perm_out);
 /* [host] out[level*4 + {0,1,2,3}] = fronts, max own nodes, max front nodes, Mflop of the level. */
 int fers_b200_chol_plan_levels(void* plan, long long* out, int n_levels_cap);
@@ -198,7 +219,8 @@ int fers_b200_residual(long long n_dof, int nrhs, const double* f, const double*
  * spans and the two totals (a few events per tree level: cheap enough for a timed region); 0 = off. */
 int fers_b200_chol_set_profile(int on);
 /* Tile shape of the factorisation GEMMs: bit 0 = panel updates, bit 1 = Schur update; bit set =
- * 128x128 tile with one CTA per SM, clear (default) = 128x64 tile with two CTAs per SM. */
+ * 128x128 tile with one CTA per SM, clear (default) = 128x64 tile with two CTAs per SM; bit 2 set = no
+ * look-ahead (the update of all later columns is then not overlapped with the next block's panel chain). */
 int fers_b200_chol_set_variant(int variant);
 /* n_out >= 16 additionally returns sums since the last fers_b200_chol_set_profile call: out[10..12] = ms
  * of the Schur updates, of whole factorisations, of whole substitutions; out[13..15] = factorisations,

@@ -8,16 +8,17 @@ from tests.test_chol_plan import _pattern, _random_spd_blocks
 pytestmark = pytest.mark.gpu
 
 
-def _solver_for(rowptr, colidx, xyz, leaf, max_nrhs=64):
+def _solver_for(rowptr, colidx, xyz, leaf, max_nrhs=64, node_restrained=None):
     import torch
     from fers_core_b200 import chol
-    plan = chol.CholPlan(rowptr, colidx, xyz, leaf_nodes=leaf)
+    plan = chol.CholPlan(rowptr, colidx, xyz, leaf_nodes=leaf, node_restrained=node_restrained)
     return plan, chol.CholSolver(plan, torch.device("cuda", 0), max_nrhs=max_nrhs)
 
 
+@pytest.mark.parametrize("drop", [False, True])
 @pytest.mark.parametrize("shape,leaf,nrhs", [((3, 2, 2), 4, 8), ((4, 4, 3), 6, 64), ((6, 5, 2), 8, 2),
                                              ((9, 8, 5), 48, 16), ((1, 1, 40), 3, 64)])
-def test_chol_random_spd_matches_dense(shape, leaf, nrhs):
+def test_chol_random_spd_matches_dense(shape, leaf, nrhs, drop):
     import torch
     from fers_core_b200 import synth
     m = synth.grid_frame(*shape, n_combos=1)
@@ -29,7 +30,8 @@ def test_chol_random_spd_matches_dense(shape, leaf, nrhs):
     kspring = np.where(rng.random(len(fixed)) < 0.05, rng.uniform(1.0, 50.0, len(fixed)), 0.0)
     b = rng.standard_normal((6 * m.n_nodes, nrhs))
     diag_slot = np.array([rowptr[i] + np.searchsorted(colidx[rowptr[i]:rowptr[i + 1]], i) for i in range(m.n_nodes)], np.int32)
-    plan, sol = _solver_for(rowptr, colidx, m.xyz, leaf)
+    restrained = (m.bc_code != 0).all(axis=1) if drop else None      # base nodes left out of the elimination
+    plan, sol = _solver_for(rowptr, colidx, m.xyz, leaf, node_restrained=restrained)
     dev = sol.dev
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
     d_fixed = t(fixed, np.uint8)

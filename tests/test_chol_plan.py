@@ -93,3 +93,28 @@ def test_plan_statistics_scale():
     assert lv[:, 0].sum() == plan.info.n_fronts
     assert plan.info.nnz_l > len(colidx) * 18
     assert plan.info.root_nodes <= 13 * 9
+
+
+def test_plan_leaves_fully_restrained_nodes_out():
+    """Nodes whose six DOFs are restrained by supports are not eliminated: smaller fronts, same solution."""
+    m = synth.grid_frame(5, 4, 3, n_combos=1)
+    rowptr, colidx = _pattern(m.n_nodes, m.m_n1, m.m_n2)
+    restrained = (m.bc_code != 0).all(axis=1)
+    assert restrained.sum() == 6 * 5
+    full = chol.CholPlan(rowptr, colidx, m.xyz, leaf_nodes=6)
+    plan = chol.CholPlan(rowptr, colidx, m.xyz, leaf_nodes=6, node_restrained=restrained)
+    perm = plan.perm()
+    n_act = m.n_nodes - int(restrained.sum())
+    assert sorted(perm[:n_act].tolist()) == np.nonzero(~restrained)[0].tolist() and np.all(perm[n_act:] == -1)
+    assert plan.info.flops < full.info.flops and plan.info.nnz_l < full.info.nnz_l
+    ex = plan.export()
+    assert int(ex["fronts"]["n1"].sum()) == n_act
+    assert not np.isin(ex["nodes"], np.nonzero(restrained)[0]).any()
+    rng = np.random.default_rng(9)
+    vals = _random_spd_blocks(rowptr, colidx, rng)
+    fixed = (m.bc_code.reshape(-1) != 0).astype(np.uint8)
+    fixed[rng.integers(0, len(fixed), 5)] = 1
+    b = rng.standard_normal((6 * m.n_nodes, 3))
+    x = chol_emulator.factor_solve(ex, rowptr, colidx, vals, fixed, b)
+    want = np.linalg.solve(chol_emulator.expand_masked(rowptr, colidx, vals, fixed), np.where(fixed[:, None] != 0, 0.0, b))
+    assert np.abs(x - want).max() <= 1e-10 * np.abs(want).max()

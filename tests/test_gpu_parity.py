@@ -66,15 +66,47 @@ def _bsr_to_scipy(eng, n_nodes):
     return sp.bsr_matrix((vals, eng.d_colidx.cpu().numpy(), eng.d_rowptr.cpu().numpy()), shape=(6 * n_nodes, 6 * n_nodes))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_assembled_values_match_oracle(engine_mod, variant):
-    """Every assembly variant (aggregated/plain atomics x TMA-staged/global section table)."""
+    """Every assembly variant (aggregated/plain atomics x TMA-staged/global section table; 4 = gather)."""
     model = synth.grid_frame(5, 4, 3, timoshenko=True)
     eng = engine_mod.Engine(model, assembly_variant=variant)
     eng.assemble(eng.d_xyz0)
     K = _bsr_to_scipy(eng, model.n_nodes).toarray()
     want = fers_oracle.Assembly(model).K_elastic().toarray()
     assert np.abs(K - want).max() <= 1e-13 * np.abs(want).max()
+
+
+def test_gather_assembly_general_paths_match_scatter(engine_mod):
+    """Gather kernel against the atomic scatter-add kernel on a model with duplicate members between
+    the same node pair, end releases and geometric stiffness (the dense-local-matrix path); the gather
+    result is bit-reproducible."""
+    import torch
+    model = synth.grid_frame(7, 5, 4, timoshenko=True)
+    nm = model.n_members
+    dup = np.arange(0, nm, 9)                                  # every 9th member doubled (same nodes, other section)
+    for name in ("m_n1", "m_n2", "m_type", "m_roll", "m_prop", "m_rel"):
+        a = getattr(model, name)
+        setattr(model, name, np.concatenate([a, a[dup]]))
+    model.m_prop[nm:] = (model.m_prop[nm:] + 1) % max(model.prop.shape[0], 1)
+    rng = np.random.default_rng(5)
+    model.rel = np.full((3, 12), -1.0)
+    model.rel[0, 5] = 0.0; model.rel[1, 11] = 2.5e5; model.rel[2, [4, 10]] = 0.0
+    model.m_rel = np.where(rng.random(model.n_members) < 0.2, rng.integers(0, 3, model.n_members), -1).astype(np.int32)
+    vals = {}
+    for variant in (1, 4):
+        eng = engine_mod.Engine(model, assembly_variant=variant)
+        axial = torch.from_numpy(rng.normal(size=model.n_members) * 1e5).to(eng.dev) if variant == 1 else axial
+        out = []
+        for kg_mode, sup in ((0, 0), (1, 0), (2, 2)):
+            eng.assemble(eng.d_xyz0, d_axial=axial if kg_mode else None, kg_mode=kg_mode, kg_suppress=sup)
+            out.append(eng.d_vals.cpu().numpy().copy())
+        vals[variant] = out
+        if variant == 4:
+            eng.assemble(eng.d_xyz0, d_axial=axial, kg_mode=2, kg_suppress=2)
+            assert np.array_equal(eng.d_vals.cpu().numpy(), out[2])
+    for a, b in zip(vals[1], vals[4]):
+        assert np.abs(a - b).max() <= 1e-13 * np.abs(a).max()
 
 
 @pytest.mark.parametrize("nrhs,variant", [(1, 0), (8, 0), (16, 0), (32, 0), (64, 0), (64, 1), (64, 2)])

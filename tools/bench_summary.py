@@ -14,7 +14,11 @@ for line in sys.stdin:
           f"iters={cfg.get('pcg_iterations')} resid={cfg.get('max_rel_residual')} launches={d.get('gpu_launches')}")
     roof = d.get("roofline") or {}
     for k in roof.get("kernels", []):
-        print(f"    {k['kernel']:24s} {k['ms']:.4f} ms  {k['GB/s']:.0f} GB/s  frac={k['frac']:.3f}  share={k['share_of_step']:.3f}")
+        rate = f"{k['GB/s']:.0f} GB/s" if "GB/s" in k else f"{k['TFLOP/s']:.2f} TFLOP/s"
+        print(f"    {k['kernel'][:60]:60s} {k['ms']:.4f} ms  {rate}  frac={k['frac']:.3f}  share={k['share_of_step']:.4f}")
+    for key in ("factor_ms", "substitution_ms", "factor_tflops_all_kernels", "class_ms_profiled_step"):
+        if key in roof:
+            print(f"    {key}: {roof[key]}")
     if d.get("e2e"):
         print("    e2e", d["e2e"])
     if d.get("cpu_baseline"):

@@ -1,7 +1,8 @@
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py > gpurun_out/r1f_bench.json 2> gpurun_out/r1f_bench.err; echo "bench rc $?"
-tail -c 3000 gpurun_out/r1f_bench.err
-cat gpurun_out/r1f_bench.json | head -c 6000
-ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/r1f_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/r1f_ncu_l.log 2>&1; echo "ncu list rc $?"
-ncu --set full --clock-control none --import-source on -k regex:k_syrk --launch-skip 9 --launch-count 1 -o gpurun_out/r1f_syrk -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/r1f_ncu_syrk.log 2>&1; echo "ncu syrk rc $?"
+python tools/kernel_probe.py 2>&1 | tail -12
+CHOL_VARIANTS=4,0,4,0 python tools/chol_bench.py 60 60 30 2>&1 | tail -16
+python bench.py --no-cpu-baseline > gpurun_out/r1h_bench.json 2> gpurun_out/r1h_bench.err; echo "bench rc $?"
+tail -c 2000 gpurun_out/r1h_bench.err
+python tools/bench_summary.py r1h < gpurun_out/r1h_bench.json
+ncu --set full --clock-control none --import-source on -k regex:'k_assemble_gather|k_spmv1' --launch-skip 2 --launch-count 2 -o gpurun_out/r1h_hbm -f python tools/kernel_probe.py > gpurun_out/r1h_ncu.log 2>&1; echo "ncu rc $?"
