@@ -426,7 +426,8 @@ k_fwd_diag(SolveCtx S, int s) {
     G44::store<true>(acc, S.Y + (size_t)(6 * f.pad0 + c0) * nr, (size_t)nr, nr, nb);
 }
 
-// forward, rows below step s:  w_rest -= L[rest, s] y_s
+// forward, own rows below step s:  w[c0+nb .. k1) -= L[.., s] y_s.  The boundary rows are updated once
+// per front by k_fwd_bnd (one product over all own columns) instead of once per step.
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 k_fwd_update(SolveCtx S, int s) {
     extern __shared__ __align__(16) double smem[];
@@ -436,11 +437,27 @@ k_fwd_update(SolveCtx S, int s) {
     if (c0 >= k1) return;
     const int nb = min(NB, k1 - c0), nr = S.nrhs;
     const int r0 = c0 + nb + blockIdx.x * G48::BN;
-    if (r0 >= m) return;
+    if (r0 >= k1) return;
     const double* A = S.Y + (size_t)(6 * f.pad0 + c0) * nr;
     const double* B = S.factor + f.panel_off + (size_t)c0 * m + r0;
     G48::Acc acc;
-    G48::mainloop(acc, smem, A, nr, nr, B, m, m - r0, nb);
+    G48::mainloop(acc, smem, A, nr, nr, B, m, k1 - r0, nb);
+    G48::store<false>(acc, S.W + (size_t)(f.rhs_off + r0) * nr, (size_t)nr, nr, k1 - r0);
+}
+
+// forward, boundary rows:  w_bnd -= L21 y_own   (K = all own columns)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_fwd_bnd(SolveCtx S) {
+    extern __shared__ __align__(16) double smem[];
+    const FrontDev f = S.fronts[S.level_fronts[blockIdx.y]];
+    const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
+    const int r0 = k1 + blockIdx.x * G48::BN;
+    if (r0 >= m) return;
+    const int nr = S.nrhs;
+    const double* A = S.Y + (size_t)(6 * f.pad0) * nr;
+    const double* B = S.factor + f.panel_off + r0;
+    G48::Acc acc;
+    G48::mainloop(acc, smem, A, nr, nr, B, m, m - r0, k1);
     G48::store<false>(acc, S.W + (size_t)(f.rhs_off + r0) * nr, (size_t)nr, nr, m - r0);
 }
 
@@ -563,6 +580,7 @@ static int set_smem_attrs() {
     FERS_CK(cudaFuncSetAttribute(k_syrk<G86>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G86::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_fwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_fwd_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G48::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_fwd_bnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G48::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_bwd_bnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_bwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_bwd_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G48N::SMEM));
@@ -812,12 +830,17 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
         for (int s = 0; s < steps; ++s) {
             k_fwd_diag<<<nf, GEMM_THREADS, G44::SMEM, st>>>(S, s);
             ++launches;
-            const int rows_below = max_m - s * NB;
+            const int rows_below = max_k1 - (s + 1) * NB;     // own rows after this step
             if (rows_below > 0) {
                 dim3 grid(cdiv(rows_below, G48::BN), nf);
                 k_fwd_update<<<grid, GEMM_THREADS, G48::SMEM, st>>>(S, s);
                 ++launches;
             }
+        }
+        if (l + 1 < P.n_levels) {                              // the root level has no boundary
+            dim3 grid(cdiv(max_m, G48::BN), nf);
+            k_fwd_bnd<<<grid, GEMM_THREADS, G48::SMEM, st>>>(S);
+            ++launches;
         }
         FERS_LAUNCH_CHECK();
     }

@@ -9,7 +9,10 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
 
 #include "chol.cuh"
 #include "common.cuh"
@@ -128,6 +131,14 @@ struct Dissector {
 
 static int build_plan(int n_nodes, const int* rp, const int* ci, const double* xyz, int leaf_nodes, const uint8_t* drop,
                       CholPlanHost& P) {
+    const bool timing = getenv("FERS_PLAN_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "chol_plan %-22s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     Dissector D;
     D.n = n_nodes; D.rp = rp; D.ci = ci; D.xyz = xyz; D.leaf = leaf_nodes < 1 ? 1 : leaf_nodes;
     D.part.assign(n_nodes, 0);
@@ -141,6 +152,7 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
         P.n_active = (int)all.size();
         D.dissect(std::move(all), -1);
     }
+    lap("dissection");
     std::vector<FrontBuild>& B = D.fronts;
     const int nf = (int)B.size();
     // post-order (children before parents), iterative
@@ -184,6 +196,7 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
     }
     if ((int)P.perm.size() != P.n_active) { set_error("chol_plan: ordering lost nodes"); return 3; }
 
+    lap("ordering");
     // symbolic factorisation: boundaries in post-order
     std::vector<std::vector<int>> bnd(nf);
     std::vector<int> stamp(n_nodes, -1);
@@ -204,6 +217,7 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
         P.fronts[i].n2 = (int)out.size();
     }
 
+    lap("boundaries");
     // node lists, child lists and inverse maps
     P.nodes.clear(); P.inv.clear();
     std::vector<int> loc(n_nodes, -1);
@@ -249,6 +263,7 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
     P.factor_doubles = factor;
     P.rhs_rows = rhs_rows;
 
+    lap("node lists / inv maps");
     // levels: deepest depth first; the parent of a front of level l is in level l + 1
     P.n_levels = max_depth + 1;
     P.level_ptr.assign(P.n_levels + 1, 0);
@@ -274,6 +289,7 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
         P.schur_doubles[l & 1] = std::max(P.schur_doubles[l & 1], s);
     }
 
+    lap("levels");
     // K blocks of the lower triangle (in elimination order) -> panel positions, grouped by level
     std::vector<int> front_of_node(n_nodes, -1);
     for (int i = 0; i < nf; ++i)
@@ -314,6 +330,7 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
         }
     }
 
+    lap("k scatter list");
     // device index buffer layout
     size_t o = 0;
     auto place = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes); return at; };

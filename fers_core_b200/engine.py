@@ -16,7 +16,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from . import _lib, chol, wire
+from . import _lib, chol, unity, wire
 from .hostlogic import (
     INACTIVE_SCALE, imperfect_coordinates, pdelta_suppressed_axes, rhs_plan, rigid_property_row,
 )
@@ -456,9 +456,12 @@ def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_
     second_order = opts.order == "NONLINEAR"
     unilateral = np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE))
     span = eng.span_tables()
+    if model.unity_checks and detail:
+        out.unity = unity.UnityAccumulator(model, plan, eng.dev)      # envelopes folded batch by batch in _store
     for grp in plan.groups:
         xyz = imperfect_coordinates(model, grp.imperfection) if grp.imperfection is not None else model.xyz
         d_xyz = eng._t(xyz, np.float64) if grp.imperfection is not None else eng.d_xyz0
+        out.unity_xyz = eng.d_xyz0          # deflected positions are reported on the undeformed coordinates
         cols = list(grp.columns)
         fac = plan.factors[cols]
         if not (second_order or unilateral.any()):
@@ -562,6 +565,9 @@ def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:
         a = a.reshape(shape + (a.shape[-1],))
         return np.moveaxis(a, -1, 0)[:n]
 
+    if out.unity:
+        out.unity.accumulate([int(c) for c in cols], out.unity_xyz, d_u, rec,
+                             torch.cuda.current_stream(d_u.device).cuda_stream)
     out.U[cols] = host(d_u, (nn, 6))
     out.R[cols] = host(rec["R"], (nn, 6))
     if nm:

@@ -44,6 +44,8 @@ class ResultArrays:
     method: str = "Linear"
     solve_ms: float | None = None
     warnings: list = field(default_factory=list)
+    unity: object = None             # unity.UnityAccumulator while the analysis runs (None: no checks)
+    unity_xyz: object = None
 
     @classmethod
     def empty(cls, model, plan) -> "ResultArrays":
@@ -72,7 +74,8 @@ def _disp(v) -> dict:
 def results_to_wire(model, res: ResultArrays) -> dict:
     """``ResultsBundle`` dict (pydantic_models.py:2171-2185) from result arrays."""
     plan = res.plan
-    bundle = {"loadcases": {}, "loadcombinations": {}, "unity_check_results": []}
+    bundle = {"loadcases": {}, "loadcombinations": {},
+              "unity_check_results": res.unity.results() if res.unity is not None else []}
     sup_nodes = np.nonzero(model.node_support_id >= 0)[0]
     node_keys = [str(int(i)) for i in model.node_ids]
     mem_keys = [str(int(i)) for i in model.m_ids]

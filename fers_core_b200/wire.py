@@ -121,6 +121,17 @@ class ModelArrays:
     member_sets: dict             # id -> [member index]
     options: Options
     warnings: list = field(default_factory=list)
+    # unity checks (pydantic_models.py:2202-2220): raw definitions + what their quantities read
+    unity_checks: list = field(default_factory=list)
+    combo_limit_state: list = field(default_factory=list)      # per combination: "SLS" | "ULS" | ... | None
+    m_classification: list = field(default_factory=list)       # per member: classification string or None
+    m_section_raw: list = field(default_factory=list)          # per member: (section dict, material dict) or None
+
+    def member_raw(self, m: int):
+        """(section dict, material dict) of member index m as they came over the wire."""
+        if m < len(self.m_section_raw) and self.m_section_raw[m] is not None:
+            return self.m_section_raw[m]
+        return ({}, {})
 
     @property
     def n_nodes(self) -> int:
@@ -261,6 +272,7 @@ def parse_document(doc: dict) -> ModelArrays:
     prop_rows: list = []
     prop_rho_a: list = []
     sec_row: dict = {}
+    sec_raw: dict = {}
     for sid, s in secs.items():
         mid = s.get("material")
         if isinstance(mid, dict):
@@ -269,6 +281,7 @@ def parse_document(doc: dict) -> ModelArrays:
             if int(mid) not in mats:
                 raise WireError(f"section {sid}: unknown material {mid}")
             mat = mats[int(mid)]
+        sec_raw[sid] = (s, mat)
         E, G = float(mat["e_mod"]), float(mat["g_mod"])
         A, Iy, Iz, J = float(s["area"]), float(s["i_y"]), float(s["i_z"]), float(s["j"])
         asy = s.get("a_sy") if opts.include_shear_deformation else None
@@ -311,6 +324,8 @@ def parse_document(doc: dict) -> ModelArrays:
     m_prop = np.full(nm, -1, np.int32)
     m_rel = np.full(nm, -1, np.int32)
     rel_rows: list = []
+    m_classification = [m.get("classification") for m in members]
+    m_section_raw = [sec_raw.get(int(m["section"])) if m.get("section") is not None else None for m in members]
     for i, m in enumerate(members):
         try:
             m_n1[i] = node_index[int(m["start_node_id"])]
@@ -484,6 +499,9 @@ def parse_document(doc: dict) -> ModelArrays:
         load_cases=load_cases, combo_ids=combo_ids, combo_names=combo_names, combo_factors=combo_factors,
         imperfections=list(analysis.get("imperfection_cases") or []), member_sets=member_sets,
         options=opts, warnings=warnings,
+        unity_checks=list(analysis.get("unity_checks") or []),
+        combo_limit_state=[c.get("limit_state") for c in combos],
+        m_classification=m_classification, m_section_raw=m_section_raw,
     )
 
 

@@ -253,6 +253,25 @@ int fers_b200_reactions(int n_nodes, int nrhs, const int* rowptr, const int* col
 int fers_b200_recover_plates(int n_plates, int nrhs, const double* xyz, const int* p_nodes, const double* p_data,
                              const int* p_flags, const double* u, double* p_res, double* p_nodal, double* p_cd,
                              void* stream);
+/* ---- unity checks (pydantic_models.py: GenericSpec 2136-2151, UnityCheckDefinition
+ *      2202-2220, EntityUnityResult 1472-1489) --------------------------------------------------------
+ * Evaluates one compiled Generic check for every (entity, column) and keeps, per entity, the column with
+ * the largest utilisation = demand / capacity among the columns with col_mask != 0:
+ *   out[n_ent][4] = utilisation, demand, capacity, column (-1: no column applies).
+ * Entities are member chains: ent_ptr/ent_members (CSR, chain order), ent_node_ptr/ent_nodes (their nodes,
+ * start to end), frames[n_ent][9] = local axes of the first member.  Variables var_desc[n_vars][4] =
+ * (kind, a, b, c): 0 per-entity constant ctab[e][a]; 1 member force component a (N Vy Vz Mx My Mz) with
+ * aggregation b (0 MaxAbs 1 Max 2 Min 3 Start 4 End 5 station c of 0, 1/4, 1/2, 3/4, 1); 2 postfix
+ * program code[a .. a+b); 3 / 4 displacement / deflected position of the start (a = 0) or end node,
+ * component b (6 = translation magnitude); 5 chord-relative deflection, component a (local y, local z,
+ * magnitude), aggregation b.  code = (op, arg) pairs: 0 push consts[arg], 1 push variable arg, 2 + 3 -
+ * 4 * 5 / 6 pow 7 neg 8 abs 9 sqrt 10 min 11 max.  Result arrays in the layout of the recovery calls. */
+int fers_b200_unity_generic(int n_ent, int nrhs, int n_vars, int n_ct, const uint8_t* col_mask, const int* ent_ptr,
+                            const int* ent_members, const int* ent_node_ptr, const int* ent_nodes,
+                            const int* var_desc, const int* code, const double* consts, const double* ctab,
+                            int demand_off, int demand_len, int cap_off, int cap_len, const double* xyz,
+                            const double* u, const double* f_local, const double* sec, const double* lmax,
+                            const double* lmin, const double* frames, double* out, void* stream);
 /* axial[n_members][nrhs] = f_local[m][6][rhs] (tension +), used between P-Delta iterations. */
 int fers_b200_member_axial(int n_members, int nrhs, const double* f_local, double* axial, void* stream);
 

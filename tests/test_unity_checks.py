@@ -1,0 +1,189 @@
+"""Unity checks: expression compiler and check compilation on the CPU, device
+evaluation against the oracle restatement (oracle/unity_oracle.py) and against the one numeric statement
+the reference makes (example 100: chord-relative sag == global mid-span deflection on rigid supports)."""
+import copy
+import json
+import math
+
+import numpy as np
+import pytest
+
+from fers_core_b200 import unity, wire
+from oracle import unity_oracle
+from tests import helpers
+
+
+def _run_postfix(code, consts, vals):
+    st = []
+    for op, arg in code:
+        if op == 0: st.append(consts[arg])
+        elif op == 1: st.append(vals[arg])
+        elif op == 7: st[-1] = -st[-1]
+        elif op == 8: st[-1] = abs(st[-1])
+        elif op == 9: st[-1] = math.sqrt(st[-1])
+        else:
+            b = st.pop(); a = st.pop()
+            st.append({2: a + b, 3: a - b, 4: a * b, 5: a / b if b else math.inf, 6: a ** b, 10: min(a, b), 11: max(a, b)}[op])
+    assert len(st) == 1
+    return st[0]
+
+
+@pytest.mark.parametrize("text", [
+    "M * c / I", "abs(d)", "-a ^ 2 + b", "(a + b) * (c - d) / 2.5e-1", "max(a, b, c) - min(d, a)", "sqrt(a*a + b*b) / (c + 1)",
+    "a - b - c", "a / b / c", "2 ^ 3 ^ 2", "-(a - -b)", "pow(a, 2) + .5 * c", "y_ref - y_self", "1e3*a+B2_x",
+])
+def test_expression_compiler_matches_python(text):
+    names = {"M": 3.5, "c": 0.11, "I": 2.0e-3, "d": -4.0, "a": 1.7, "b": -2.25, "y_ref": 4.0, "y_self": 3.1, "B2_x": 9.0}
+    idx = {n: i for i, n in enumerate(names)}
+    consts = []
+    code = unity.compile_expression(text, idx, consts)
+    got = _run_postfix(code, consts, list(names.values()))
+    want = unity_oracle._eval(text, names)
+    assert got == pytest.approx(want, rel=1e-15, abs=0.0)
+
+
+@pytest.mark.parametrize("text", ["a +", "foo(a)", "a b", "(a", "unknown * 2"])
+def test_expression_compiler_rejects(text):
+    with pytest.raises(unity.UnityError):
+        unity.compile_expression(text, {"a": 0, "b": 1}, [])
+
+
+def _beam_doc():
+    """Example 100 (fers_core/examples/100_Unity_Check_Beam_Deflection_SLS.py:30-88): simply supported 6 m beam
+    of two half-members, 5 kN at mid-span, SLS deflection check on the member set."""
+    doc = copy.deepcopy(helpers.golden("cantilever_end_load")["doc"])
+    pin = {k: {"condition_type": "Fixed", "stiffness": None} for k in ("X", "Y", "Z", "RX")}
+    pin.update({k: {"condition_type": "Free", "stiffness": None} for k in ("RY", "RZ")})
+    m = doc["model"]
+    m["nodes"] = [{"id": 1, "X": 0, "Y": 0, "Z": 0, "nodal_support": 1}, {"id": 2, "X": 3.0, "Y": 0, "Z": 0, "nodal_support": None},
+                  {"id": 3, "X": 6.0, "Y": 0, "Z": 0, "nodal_support": 1}]
+    m["nodal_supports"] = [dict(id=1, classification=None, warping_condition=None, **pin)]
+    base = m["members"][0]
+    m["members"] = [dict(base, id=1, start_node_id=1, end_node_id=2, classification="Beam"),
+                    dict(base, id=2, start_node_id=2, end_node_id=3, classification="Beam")]
+    m["member_sets"] = [{"id": 7, "classification": "Beam", "member_ids": [1, 2], "buckling_restraints": []}]
+    m["sections"][0].update(h=0.18, b=0.091, wel_z=1.46e-4)
+    a = doc["analysis"]
+    a["options"]["order"] = "LINEAR"
+    a["load_cases"] = [dict(a["load_cases"][0], id=1, name="SLS", nodal_loads=[
+        {"id": 1, "node": 2, "magnitude": -5000.0, "direction": [0, 1, 0], "load_type": "force"}])]
+    a["load_combinations"] = [
+        {"id": 11, "name": "SLS-combo", "check": "ALL", "situation": "SLS", "limit_state": "SLS",
+         "load_case_factors": [{"load_case_id": 1, "factor": 1.0}]},
+        {"id": 12, "name": "ULS-combo", "check": "ALL", "situation": "ULS", "limit_state": "ULS",
+         "load_case_factors": [{"load_case_id": 1, "factor": 1.5}]}]
+    q = lambda kind, **kw: {"Quantity": {kind: kw}}
+    a["unity_checks"] = [
+        {"id": "sls_beam", "name": "Beam mid-span deflection", "applies_to": {"type": "MemberSets", "ids": [7]},
+         "limit_state": "SLS", "thresholds": [0.8, 0.95, 1.0],
+         "spec": {"Generic": {"demand": "abs(d)", "capacity": "limit", "variables": [
+             {"name": "d", "source": q("MemberDeflection", component="Magnitude", aggregation={"type": "MaxAbs"})},
+             {"name": "limit", "source": {"Quantity": {"Constant": 6.0 / 250.0}}}]}}},
+        {"id": "bending", "name": "Bending stress", "applies_to": {"type": "AllMembers"}, "limit_state": "ULS",
+         "spec": {"Generic": {"demand": "M * c / I", "capacity": "fy / 1.0", "variables": [
+             {"name": "c", "source": {"Expression": "h / 2"}},
+             {"name": "M", "source": q("MemberForce", component="Mz", aggregation={"type": "MaxAbs"})},
+             {"name": "h", "source": q("Section", property="H")},
+             {"name": "I", "source": q("Section", property="Iz")},
+             {"name": "fy", "source": q("Material", property="Fy")}]}}},
+        {"id": "shear_end", "name": "End shear", "applies_to": {"type": "Members", "ids": [2]}, "load_combination_ids": [12],
+         "spec": {"Generic": {"demand": "max(abs(V0), abs(V1), abs(Vq))", "capacity": "0.58 * fy * A / L ^ 0", "variables": [
+             {"name": "V0", "source": q("MemberForce", component="Vy", aggregation={"type": "Start"})},
+             {"name": "V1", "source": q("MemberForce", component="Vy", aggregation={"type": "End"})},
+             {"name": "Vq", "source": q("MemberForce", component="Vy", aggregation={"type": "AtFraction", "fraction": 0.25})},
+             {"name": "A", "source": q("Section", property="Area")},
+             {"name": "L", "source": q("Geometry", property="Length")},
+             {"name": "fy", "source": q("Material", property="Fy")}]}}},
+        {"id": "clear", "name": "Deflected position", "applies_to": {"type": "Members", "ids": [1]},
+         "spec": {"Generic": {"demand": "0.0 - y_end", "capacity": "0.05 + dx0", "variables": [
+             {"name": "y_end", "source": q("NodePosition", at="End", axis="Y")},
+             {"name": "dx0", "source": q("NodeDisplacement", at="Start", component="Magnitude")}]}}},
+        {"id": "ec3", "name": "EC3", "applies_to": {"type": "AllMembers"}, "spec": {"Ec3Steel": {"gamma_m0": 1.0}}},
+    ]
+    return doc
+
+
+def test_check_compilation_tables():
+    model = wire.parse_document(_beam_doc())
+    cs = [unity.compile_check(model, d) for d in model.unity_checks]
+    sls, bend, shear, clear, ec3 = cs
+    assert sls.entities == [{"type": "MemberSet", "memberset_id": 7}]
+    assert sls.ent_members.tolist() == [0, 1] and sls.ent_nodes.tolist() == [0, 1, 2]
+    assert sls.combo_ids == {11} and bend.combo_ids == {12} and shear.combo_ids == {12} and clear.combo_ids is None
+    assert len(bend.entities) == 2 and bend.var_names[-1] == "c"          # the expression moves after what it names
+    assert bend.var_desc[bend.var_names.index("M")].tolist() == [unity.V_FORCE, 5, 0, 0]
+    assert shear.var_desc[shear.var_names.index("Vq")].tolist() == [unity.V_FORCE, 1, 5, 1]
+    assert ec3.skipped is not None and "Ec3Steel" in ec3.skipped
+    assert unity._status(0.5, None) == "Green" and unity._status(0.9, None) == "Yellow"
+    assert unity._status(0.97, None) == "Orange" and unity._status(1.2, None) == "Red"
+
+
+def test_fold_envelope_rules():
+    best = np.array([[-np.inf, 0, 0, -1], [0.5, 1, 2, 3], [0.5, 1, 2, 3], [np.nan, 0, 0, 2]], float)
+    got = np.array([[0.1, 1, 10, 4], [0.5, 1, 2, 1], [0.4, 9, 9, 0], [0.2, 1, 5, 7]], float)
+    unity.fold_envelope(best, got)
+    assert best[:, 0].tolist() == [0.1, 0.5, 0.5, 0.2] and best[:, 3].tolist() == [4, 1, 3, 7]
+
+
+@pytest.mark.gpu
+def test_unity_checks_match_oracle_and_example_100():
+    import fers_calculations
+    from fers_core_b200 import engine
+    from oracle import fers_oracle
+    doc = _beam_doc()
+    out = json.loads(fers_calculations.calculate_from_json(json.dumps(doc)))["results"]
+    ucs = {u["check_id"]: u for u in out["unity_check_results"]}
+    assert set(ucs) == {"sls_beam", "bending", "shear_end", "clear", "ec3"}
+    # example 100: chord-relative sag == global mid-span |Dy| on rigid supports == P L^3 / (48 E Iz)
+    gov = ucs["sls_beam"]["governing"]
+    dy_mid = abs(out["loadcombinations"]["SLS-combo"]["displacement_nodes"]["2"]["dy"])
+    assert abs(gov["demand"] - dy_mid) < 1e-9 * dy_mid
+    assert gov["demand"] == pytest.approx(5000.0 * 6.0 ** 3 / (48 * 210e9 * 1.321e-5), rel=1e-9)
+    assert gov["governing_combination_id"] == 11 and gov["entity"] == {"type": "MemberSet", "memberset_id": 7}
+    assert ucs["sls_beam"]["status"] == unity._status(gov["demand"] / 0.024, None)
+    # bending: M = 1.5 * P L / 4 at mid-span (ULS only), sigma = M (h/2) / Iz
+    b = ucs["bending"]["governing"]
+    assert b["demand"] == pytest.approx(1.5 * 5000 * 6 / 4 * 0.09 / 1.321e-5, rel=1e-9) and b["capacity"] == 235e6
+    assert b["governing_combination_id"] == 12
+    assert ucs["ec3"]["per_entity"] == [] and "not evaluated" in ucs["ec3"]["message"]
+    # every check against the oracle restatement on the oracle's own results
+    model = wire.parse_document(doc)
+    want = {w["check_id"]: w for w in unity_oracle.evaluate(
+        _generic_only(model), fers_oracle.analyze(model))}
+    for cid, w in want.items():
+        for pe, pw in zip(ucs[cid]["per_entity"], w["per_entity"]):
+            assert pe["entity"] == pw["entity"] and pe["governing_combination_id"] == pw["governing_combination_id"]
+            for k in ("utilization", "demand", "capacity"):
+                assert pe[k] == pytest.approx(pw[k], rel=1e-9, abs=1e-300), (cid, k)
+
+
+def _generic_only(model):
+    model.unity_checks = [d for d in model.unity_checks if "Generic" in d["spec"]]
+    return model
+
+
+@pytest.mark.gpu
+def test_unity_envelope_over_many_combinations_on_frame():
+    """72 combinations (two batches of device columns) on a 3D frame: the governing combination and
+    utilisation of every member equal the oracle's."""
+    from fers_core_b200 import engine, synth
+    from oracle import fers_oracle
+    model = synth.grid_frame(4, 3, 3, n_combos=72, solve_loadcases=True)
+    q = lambda kind, **kw: {"Quantity": {kind: kw}}
+    model.unity_checks = [{
+        "id": "axial_bending", "name": "N/A + M/W", "applies_to": {"type": "AllMembers"},
+        "spec": {"Generic": {"demand": "abs(N) / A + max(abs(My), abs(Mz)) / W", "capacity": "fy", "variables": [
+            {"name": "N", "source": q("MemberForce", component="N", aggregation={"type": "MaxAbs"})},
+            {"name": "My", "source": q("MemberForce", component="My", aggregation={"type": "Max"})},
+            {"name": "Mz", "source": q("MemberForce", component="Mz", aggregation={"type": "Min"})},
+            {"name": "A", "source": {"Quantity": {"Constant": 0.0149}}},
+            {"name": "W", "source": {"Quantity": {"Constant": 1.3e-3}}},
+            {"name": "fy", "source": {"Quantity": {"Constant": 355e6}}}]}}}]
+    got = engine.analyze(model, device="cuda:0")
+    res = got.unity.results()[0]
+    want = unity_oracle.evaluate(model, fers_oracle.analyze(model))[0]
+    assert len(res["per_entity"]) == model.n_members
+    for pe, pw in zip(res["per_entity"], want["per_entity"]):
+        assert pe["governing_combination_id"] == pw["governing_combination_id"]
+        assert pe["utilization"] == pytest.approx(pw["utilization"], rel=1e-9)
+    assert res["max_utilization"] == pytest.approx(want["max_utilization"], rel=1e-9)
