@@ -32,7 +32,7 @@ SIGNATURES = {
     "fers_b200_gather_map_workspace": (_sz, [_i, _i]),
     "fers_b200_gather_map_build": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _ip, _vp, _sz, _vp]),
     "fers_b200_assemble_beams_gather": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i,
-                                             _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+                                             _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "fers_b200_load_case": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_combine": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),

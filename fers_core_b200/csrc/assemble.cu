@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_beams(BeamArgs A) {
 // of them.  Element arithmetic is the same as in k_assemble_beams (each member is formed twice, two
 // blocks each time, instead of once with four blocks).
 constexpr int GA_THREADS = 128;
-constexpr int GA_NODES = 16;
+constexpr int GA_NODES = 20;      // 20 nodes x up to 6 members = 120 half-members: one chunk of GA_THREADS on a 3D grid frame
 constexpr int GA_STRIDE = 37;
 constexpr int GA_PAIRS = (GA_NODES * 36 + GA_THREADS - 1) / GA_THREADS;
 
@@ -223,7 +223,67 @@ struct GatherArgs {
     const int* hm_ptr;     // [n_nodes + 1]
     const int* hm_list;    // [2 * n_members]  member << 2 | dup << 1 | end
     const int* diag_slot;  // [n_nodes]
+    double* cache;         // [n_members][MC_DOUBLES] frames + coefficients written by k_member_cache, or NULL
 };
+
+// Per-member invariants of one assembly pass: local frame (9), length, closed-form coefficients (12).
+// Formed once per member by k_member_cache and read by both of its half-members in k_assemble_gather
+// (64 MB at configs[3]: stays in the 126 MB L2 between the two kernels).
+constexpr int MC_DOUBLES = 24;
+
+__global__ void __launch_bounds__(256) k_member_cache(BeamArgs A, double* __restrict__ cache) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_prop = reinterpret_cast<double*>(smem_raw);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_prop + (size_t)(A.use_tma ? A.n_prop : 0) * NPROP);
+    if (A.use_tma) {          // section / material table: one TMA bulk copy per CTA, overlapped with the coordinate loads
+        if (threadIdx.x == 0) mbar_init(s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t prop_bytes = (uint32_t)A.n_prop * NPROP * sizeof(double);
+            mbar_expect_tx(s_bar, prop_bytes);
+            tma_bulk_g2s(s_prop, A.prop, prop_bytes, s_bar);
+        }
+    }
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = m < A.n_members;
+    Frame f;
+    int mtype = 0, pi = 0;
+    double scale = 1.0;
+    if (valid) {
+        const int a = A.n1[m], b = A.n2[m];
+        double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
+        double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+        f = member_frame(pa, pb, A.m_roll[m]);
+        mtype = A.m_type[m];
+        pi = A.m_prop[m];
+        if (A.m_scale) scale = A.m_scale[m];
+    }
+    if (A.use_tma) mbar_wait(s_bar, 0);
+    if (!valid) return;
+    const double* P = (A.use_tma ? s_prop : A.prop) + (size_t)pi * NPROP;
+    double Pr[NPROP];
+#pragma unroll
+    for (int i = 0; i < NPROP; ++i) Pr[i] = P[i];
+    const BeamCoef c = beam_coef(Pr, f.L, mtype, scale);
+    double* o = cache + (size_t)m * MC_DOUBLES;
+    st_global_v4(o, f.r[0][0], f.r[0][1], f.r[0][2], f.r[1][0]);
+    st_global_v4(o + 4, f.r[1][1], f.r[1][2], f.r[2][0], f.r[2][1]);
+    st_global_v4(o + 8, f.r[2][2], f.L, c.a, c.t);
+    st_global_v4(o + 12, c.z12, c.z6, c.z4, c.z2);
+    st_global_v4(o + 16, c.y12, c.y6, c.y4, c.y2);
+    st_global_v4(o + 20, c.phi_y, c.phi_z, 0.0, 0.0);
+}
+
+__device__ __forceinline__ void load_member_cache(const double* __restrict__ cache, int m, Frame& f, BeamCoef& c) {
+    const double2* p = reinterpret_cast<const double2*>(cache + (size_t)m * MC_DOUBLES);
+    double2 v[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) v[i] = __ldg(p + i);
+    f.r[0][0] = v[0].x; f.r[0][1] = v[0].y; f.r[0][2] = v[1].x; f.r[1][0] = v[1].y; f.r[1][1] = v[2].x; f.r[1][2] = v[2].y;
+    f.r[2][0] = v[3].x; f.r[2][1] = v[3].y; f.r[2][2] = v[4].x; f.L = v[4].y;
+    c.a = v[5].x; c.t = v[5].y; c.z12 = v[6].x; c.z6 = v[6].y; c.z4 = v[7].x; c.z2 = v[7].y;
+    c.y12 = v[8].x; c.y6 = v[8].y; c.y4 = v[9].x; c.y2 = v[9].y; c.phi_y = v[10].x; c.phi_z = v[10].y;
+}
 
 // one 6x6 block (bi, bj) of member m, self-contained (duplicate-member path)
 template <bool GENERAL>
@@ -260,8 +320,8 @@ __device__ __noinline__ void member_block(const BeamArgs& A, const double* prop_
     }
 }
 
-template <bool GENERAL>
-__global__ void __launch_bounds__(GA_THREADS, GENERAL ? 1 : 4) k_assemble_gather(GatherArgs G) {
+template <bool GENERAL, bool CACHED>
+__global__ void __launch_bounds__(GA_THREADS, GENERAL ? 1 : 5) k_assemble_gather(GatherArgs G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const BeamArgs& A = G.B;
     double* s_stage = reinterpret_cast<double*>(smem_raw);
@@ -270,7 +330,7 @@ __global__ void __launch_bounds__(GA_THREADS, GENERAL ? 1 : 4) k_assemble_gather
     __shared__ int s_hp[GA_NODES + 1];
 
     const int tid = threadIdx.x;
-    if (A.use_tma) {
+    if (A.use_tma) {          // (host: only when the member cache is off -- the cache kernel reads the table)
         if (tid == 0) mbar_init(s_bar, 1);
         __syncthreads();
         if (tid == 0) {
@@ -298,22 +358,30 @@ __global__ void __launch_bounds__(GA_THREADS, GENERAL ? 1 : 4) k_assemble_gather
             const int code = G.hm_list[h];
             const int m = code >> 2, end = code & 1;
             const bool dup = (code & 2) != 0;
-            const int a = A.n1[m], b = A.n2[m];
-            double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
-            double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
-            const Frame f = member_frame(pa, pb, A.m_roll[m]);
-            const int mtype = A.m_type[m];
-            const int pi = A.m_prop[m];
-            const double scale = A.m_scale ? A.m_scale[m] : 1.0;
-            const int ri = A.m_rel ? A.m_rel[m] : -1;
-            const double axial = (A.m_axial && A.kg_mode) ? A.m_axial[m] : 0.0;
+            const int ri = (GENERAL && A.m_rel) ? A.m_rel[m] : -1;
+            const double axial = (GENERAL && A.m_axial && A.kg_mode) ? A.m_axial[m] : 0.0;
             const int4 slots = reinterpret_cast<const int4*>(A.m_slot)[m];
             const int off_slot = end ? slots.z : slots.y, dg_slot = end ? slots.w : slots.x;
-            if (!prop_ready) { mbar_wait(s_bar, 0); prop_ready = true; }
-            double Pr[NPROP];
+            Frame f;
+            BeamCoef c;
+            int mtype = 0;
+            if (CACHED) {
+                load_member_cache(G.cache, m, f, c);
+                if (GENERAL) mtype = A.m_type[m];
+            } else {
+                const int a = A.n1[m], b = A.n2[m];
+                double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
+                double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+                f = member_frame(pa, pb, A.m_roll[m]);
+                mtype = A.m_type[m];
+                const int pi = A.m_prop[m];
+                const double scale = A.m_scale ? A.m_scale[m] : 1.0;
+                if (!prop_ready) { mbar_wait(s_bar, 0); prop_ready = true; }
+                double Pr[NPROP];
 #pragma unroll
-            for (int i = 0; i < NPROP; ++i) Pr[i] = prop_tab[(size_t)pi * NPROP + i];
-            const BeamCoef c = beam_coef(Pr, f.L, mtype, scale);
+                for (int i = 0; i < NPROP; ++i) Pr[i] = prop_tab[(size_t)pi * NPROP + i];
+                c = beam_coef(Pr, f.L, mtype, scale);
+            }
             const bool general = GENERAL && ((ri >= 0) || (axial != 0.0));
             double kE[GENERAL ? 144 : 1], kG[GENERAL ? 144 : 1];
             if (GENERAL && general) {
@@ -560,8 +628,8 @@ int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xy
                                     const int* m_prop, const int* m_type, const double* m_roll, const double* m_scale,
                                     const int* m_rel, const double* prop, int n_prop, const double* rel, int n_rel,
                                     const double* m_axial, int kg_mode, int kg_suppress, const int* m_slot,
-                                    const int* hm_ptr, const int* hm_list, int n_dup, const int* diag_slot, double* vals,
-                                    void* stream) {
+                                    const int* hm_ptr, const int* hm_list, int n_dup, const int* diag_slot,
+                                    double* member_cache, double* vals, void* stream) {
     (void)n_rel;
     FERS_REQUIRE(n_nodes > 0 && hm_ptr && diag_slot && vals, "assemble_beams_gather: bad arguments");
     FERS_REQUIRE(n_members <= 0 || (n_prop > 0 && hm_list && m_slot), "assemble_beams_gather: empty property table or missing maps");
@@ -572,19 +640,35 @@ int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xy
     A.m_axial = m_axial; A.kg_mode = kg_mode; A.kg_suppress = kg_suppress; A.m_slot = m_slot; A.vals = vals;
     A.aggregate = 0;
     A.use_tma = (n_members > 0 && n_prop <= MAX_PROP_SMEM_ROWS && (((uintptr_t)prop) & 15) == 0) ? 1 : 0;
-    G.n_nodes = n_nodes; G.hm_ptr = hm_ptr; G.hm_list = hm_list; G.diag_slot = diag_slot;
-    const size_t smem = (size_t)GA_THREADS * GA_STRIDE * sizeof(double) + (A.use_tma ? (size_t)n_prop * NPROP * sizeof(double) : 0) + 16;
+    G.n_nodes = n_nodes; G.hm_ptr = hm_ptr; G.hm_list = hm_list; G.diag_slot = diag_slot; G.cache = member_cache;
+    const bool cached = member_cache != nullptr && n_members > 0;
+    const size_t prop_smem = A.use_tma ? (size_t)n_prop * NPROP * sizeof(double) : 0;
     static bool attr_set = false;
     if (!attr_set) {
         const int max_smem = (int)((size_t)GA_THREADS * GA_STRIDE * 8 + MAX_PROP_SMEM_ROWS * NPROP * 8 + 16);
-        FERS_CK(cudaFuncSetAttribute(k_assemble_gather<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        FERS_CK(cudaFuncSetAttribute(k_assemble_gather<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        FERS_CK(cudaFuncSetAttribute(k_assemble_gather<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        FERS_CK(cudaFuncSetAttribute(k_assemble_gather<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        FERS_CK(cudaFuncSetAttribute(k_assemble_gather<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        FERS_CK(cudaFuncSetAttribute(k_assemble_gather<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
     }
+    if (cached) {
+        FERS_REQUIRE((((uintptr_t)member_cache) & 31) == 0, "assemble_beams_gather: member_cache must be 32-byte aligned");
+        k_member_cache<<<(n_members + 255) / 256, 256, prop_smem + 16, as_stream(stream)>>>(A, member_cache);
+        FERS_LAUNCH_CHECK();
+        count_launches(1);
+        A.use_tma = 0;       // the gather kernel reads frames and coefficients from the cache
+    }
+    const size_t smem = (size_t)GA_THREADS * GA_STRIDE * sizeof(double) + (A.use_tma ? prop_smem : 0) + 16;
     const int grid = (n_nodes + GA_NODES - 1) / GA_NODES;
     const bool general = (m_rel != nullptr) || (m_axial != nullptr && kg_mode != 0);
-    if (general) k_assemble_gather<true><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
-    else k_assemble_gather<false><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
+    if (cached) {
+        if (general) k_assemble_gather<true, true><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
+        else k_assemble_gather<false, true><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
+    } else {
+        if (general) k_assemble_gather<true, false><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
+        else k_assemble_gather<false, false><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
+    }
     FERS_LAUNCH_CHECK();
     count_launches(1);
     if (n_dup > 0 && n_members > 0) {

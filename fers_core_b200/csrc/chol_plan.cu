@@ -13,6 +13,8 @@
 #include <string.h>
 
 #include <chrono>
+#include <mutex>
+#include <thread>
 
 #include "chol.cuh"
 #include "common.cuh"
@@ -23,6 +25,8 @@ namespace {
 struct FrontBuild {
     int parent = -1;
     int depth = 0;
+    unsigned long long key = 0;   // path from the root of the recursion (1 bit per split): orders siblings
+    int key_bits = 0;
     std::vector<int> own;
     std::vector<int> children;
 };
@@ -35,12 +39,15 @@ struct Dissector {
     int leaf;
     std::vector<uint8_t> part;
     std::vector<FrontBuild> fronts;
+    std::mutex mu;                 // the two halves of the upper splits are dissected by different threads
 
-    int new_front(int parent, std::vector<int>&& own) {
+    int new_front(int parent, std::vector<int>&& own, unsigned long long key, int key_bits) {
         FrontBuild f;
         f.parent = parent;
-        f.depth = parent < 0 ? 0 : fronts[parent].depth + 1;
         f.own = std::move(own);
+        f.key = key; f.key_bits = key_bits;
+        std::lock_guard<std::mutex> lock(mu);
+        f.depth = parent < 0 ? 0 : fronts[parent].depth + 1;
         fronts.push_back(std::move(f));
         const int id = (int)fronts.size() - 1;
         if (parent >= 0) fronts[parent].children.push_back(id);
@@ -65,6 +72,8 @@ struct Dissector {
     }
 
     // one-sided boundary layers of the cut (part: 1 = a, 2 = b)
+    // (part[] is shared between threads: a thread only writes the entries of its own node set, and the only
+    // foreign entries it reads belong to separators of ancestors, which are final and 0)
     void separators(const std::vector<int>& a, const std::vector<int>& b, std::vector<int>& sa, std::vector<int>& sb) {
         for (int v : a) part[v] = 1;
         for (int v : b) part[v] = 2;
@@ -79,9 +88,23 @@ struct Dissector {
         for (int v : b) part[v] = 0;
     }
 
-    void dissect(std::vector<int>&& nodes, int parent) {
-        if ((int)nodes.size() <= leaf) {
-            if (!nodes.empty()) new_front(parent, std::move(nodes));
+    static constexpr int PAR_BITS = 3;            // splits whose halves go to separate threads (8-way)
+    static constexpr size_t PAR_MIN_NODES = 4096;
+
+    void both(std::vector<int>&& a, std::vector<int>&& b, int parent, unsigned long long key, int bits) {
+        if (bits < PAR_BITS && a.size() + b.size() >= PAR_MIN_NODES) {
+            std::thread other([&, parent, key, bits]() { dissect(std::move(a), parent, key << 1, bits + 1); });
+            dissect(std::move(b), parent, (key << 1) | 1ull, bits + 1);
+            other.join();
+        } else {
+            dissect(std::move(a), parent, key << 1, bits + 1);
+            dissect(std::move(b), parent, (key << 1) | 1ull, bits + 1);
+        }
+    }
+
+    void dissect(std::vector<int>&& nodes, int parent, unsigned long long key = 1, int bits = 0) {
+        if ((int)nodes.size() <= leaf || bits >= 62) {
+            if (!nodes.empty()) new_front(parent, std::move(nodes), key, bits);
             return;
         }
         std::vector<int> best_a, best_b, best_sep;
@@ -112,8 +135,7 @@ struct Dissector {
         }
         nodes.clear(); nodes.shrink_to_fit();
         if (best_sep.empty()) {   // the two halves are not connected: no separator front
-            dissect(std::move(best_a), parent);
-            dissect(std::move(best_b), parent);
+            both(std::move(best_a), std::move(best_b), parent, key, bits);
             return;
         }
         // remove the separator from the side it was taken from
@@ -121,9 +143,8 @@ struct Dissector {
         std::vector<int>& side = best_from_a ? best_a : best_b;
         side.erase(std::remove_if(side.begin(), side.end(), [&](int v) { return part[v] == 3; }), side.end());
         for (int v : best_sep) part[v] = 0;
-        const int f = new_front(parent, std::move(best_sep));
-        dissect(std::move(best_a), f);
-        dissect(std::move(best_b), f);
+        const int f = new_front(parent, std::move(best_sep), key, bits);
+        both(std::move(best_a), std::move(best_b), f, key, bits);
     }
 };
 
@@ -155,12 +176,23 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
     lap("dissection");
     std::vector<FrontBuild>& B = D.fronts;
     const int nf = (int)B.size();
+    // front ids depend on thread timing; the recursion path does not: order siblings and roots by it
+    auto path_less = [&](int x, int y) {
+        const FrontBuild &fx = B[x], &fy = B[y];
+        const int sx = 63 - fx.key_bits, sy = 63 - fy.key_bits;     // left-align the paths
+        const unsigned long long kx = fx.key << sx, ky = fy.key << sy;
+        return kx != ky ? kx < ky : fx.key_bits < fy.key_bits;
+    };
+    for (FrontBuild& fb : B) std::sort(fb.children.begin(), fb.children.end(), path_less);
+    std::vector<int> roots;
+    for (int r = 0; r < nf; ++r)
+        if (B[r].parent < 0) roots.push_back(r);
+    std::sort(roots.begin(), roots.end(), path_less);
     // post-order (children before parents), iterative
     std::vector<int> order; order.reserve(nf);
     {
         std::vector<std::pair<int, int>> stack;
-        for (int r = 0; r < nf; ++r) {
-            if (B[r].parent >= 0) continue;
+        for (int r : roots) {
             stack.push_back({r, 0});
             while (!stack.empty()) {
                 auto& top = stack.back();

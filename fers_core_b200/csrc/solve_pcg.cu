@@ -470,47 +470,61 @@ static int spmm_variant() {
     return g_spmm_variant;
 }
 
-// single right-hand side: one thread per scalar row.  Lanes 6g..6g+5 of a warp own the six DOF rows of
-// one node (five nodes per warp, two lanes idle); a thread streams its 48-byte row of every 6x6 block
-// of the node's block row (three 16-byte streaming loads; a group reads the block's 288 contiguous
-// bytes, the warp a contiguous run of about five block rows) and the six x values of the column node
-// through the read-only path.  No cross-lane reduction, four blocks in flight per thread.
+// single right-hand side.  Lanes 6g..6g+5 of a warp own one node (five nodes per warp, two lanes idle).
+// Per 6x6 block the six lanes of a group issue three 16-byte streaming loads that each cover 96
+// CONTIGUOUS bytes of the block (every 32-byte sector is requested exactly once per block: the L2 -> L1
+// traffic equals the matrix size), which leaves lane r = 3 rr + cc with the entries (row 2q + rr,
+// columns 2cc, 2cc+1), q = 0..2: three partial row sums per lane, combined over cc by two shuffles
+// per block ROW.  x of the column node comes through the read-only path (one 16-byte load per block).
 constexpr int SPMV_NODES_PER_WARP = 5;
-__global__ void __launch_bounds__(SPMM_THREADS)
+constexpr int SPMV_THREADS = 64;     // small CTAs: short tail on the last wave
+__global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv1(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
         const uint8_t* __restrict__ fixed, const double* __restrict__ kspring, const double* __restrict__ x,
         double* __restrict__ y) {
     const int lane = threadIdx.x & 31;
-    const int g = lane / 6, r = lane - 6 * g;
-    if (g >= SPMV_NODES_PER_WARP) return;
-    const int wglobal = (blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
-    const int nw = (gridDim.x * SPMM_THREADS) >> 5;
-    for (int row = wglobal * SPMV_NODES_PER_WARP + g; row < n_nodes; row += nw * SPMV_NODES_PER_WARP) {
-        const int kb = rowptr[row], ke = rowptr[row + 1];
-        double acc = 0.0;
+    const int g = lane / 6, r = lane - 6 * g, rr = r / 3, cc = r - 3 * rr;
+    const int wglobal = (blockIdx.x * SPMV_THREADS + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * SPMV_THREADS) >> 5;
+    for (int base = wglobal * SPMV_NODES_PER_WARP; base < n_nodes; base += nw * SPMV_NODES_PER_WARP) {
+        const int row = base + g;
+        const bool valid = g < SPMV_NODES_PER_WARP && row < n_nodes;
+        const int kb = valid ? rowptr[row] : 0, ke = valid ? rowptr[row + 1] : 0;
+        double acc[3] = {0.0, 0.0, 0.0};
         for (int k0 = kb; k0 < ke; k0 += 4) {
-            double2 a[4][3], xv[4][3];
+            double2 a[4][3], xv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int k = min(k0 + u, ke - 1);
                 const int col = __ldg(colidx + k);
-                const double2* ap = reinterpret_cast<const double2*>(vals + (size_t)k * 36 + r * 6);
-                const double2* xp = reinterpret_cast<const double2*>(x + (size_t)col * 6);
+                const double2* ap = reinterpret_cast<const double2*>(vals + (size_t)k * 36) + r;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) { a[u][q] = __ldcs(ap + q); xv[u][q] = __ldg(xp + q); }
+                for (int q = 0; q < 3; ++q) a[u][q] = __ldcs(ap + 6 * q);
+                xv[u] = __ldg(reinterpret_cast<const double2*>(x + (size_t)col * 6) + cc);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (k0 + u < ke) {
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) { acc = fma(a[u][q].x, xv[u][q].x, acc); acc = fma(a[u][q].y, xv[u][q].y, acc); }
+                    for (int q = 0; q < 3; ++q) acc[q] = fma(a[u][q].y, xv[u].y, fma(a[u][q].x, xv[u].x, acc[q]));
                 }
             }
         }
-        const size_t d = (size_t)row * 6 + r;
-        if (fixed != nullptr && fixed[d]) acc = 0.0;
-        else if (kspring != nullptr) acc = fma(kspring[d], x[d], acc);
-        y[d] = acc;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double s1 = __shfl_down_sync(FULL, acc[q], 1), s2 = __shfl_down_sync(FULL, acc[q], 2);
+            acc[q] += s1 + s2;                                    // complete on the cc == 0 lanes
+        }
+        if (valid && cc == 0) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const size_t d = (size_t)row * 6 + 2 * q + rr;
+                double out = acc[q];
+                if (fixed != nullptr && fixed[d]) out = 0.0;
+                else if (kspring != nullptr) out = fma(kspring[d], x[d], out);
+                y[d] = out;
+            }
+        }
     }
 }
 
@@ -913,10 +927,9 @@ int fers_b200_spmm(int n_nodes, int nrhs, const int* rowptr, const int* colidx, 
     cudaStream_t st = as_stream(stream);
     if (n_nodes <= 0) return 0;
     if (nrhs == 1) {
-        int grid = (n_nodes + SPMM_WARPS * SPMV_NODES_PER_WARP - 1) / (SPMM_WARPS * SPMV_NODES_PER_WARP);
-        int cap = sm_count() * 32;
-        if (grid > cap) grid = cap;
-        k_spmv1<<<grid, SPMM_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y);
+        const int per_cta = (SPMV_THREADS / 32) * SPMV_NODES_PER_WARP;
+        const int grid = (n_nodes + per_cta - 1) / per_cta;
+        k_spmv1<<<grid, SPMV_THREADS, 0, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y);
         FERS_LAUNCH_CHECK();
         count_launches(1);
         return 0;

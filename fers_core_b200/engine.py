@@ -187,6 +187,10 @@ class Engine:
             nn, nm, self.nnzb, _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_slot), _lib.ptr(self.d_hm_ptr),
             _lib.ptr(self.d_hm_list), C.byref(n_dup), _lib.ptr(gws), gws_bytes, self.stream), "gather_map_build")
         self.n_dup_half_members = n_dup.value
+        # optional scratch of the gather kernel (frames + coefficients formed once per member): measured slower
+        # than forming them per half-member at configs[3] (132 us against 106 us: the kernel is latency-bound, not
+        # instruction-bound), so it is off by default
+        self.d_member_cache = None
         nd = m.n_dof
         self.d_fixed = self._empty(nd, torch.uint8)
         self.d_free_index = self._empty(nd, torch.int32)
@@ -210,7 +214,8 @@ class Engine:
                 _lib.ptr(self.d_type), _lib.ptr(self.d_roll), _lib.ptr(d_scale), _lib.ptr(self.d_rel_idx),
                 _lib.ptr(self.d_prop), self.n_prop, _lib.ptr(self.d_rel), n_rel, _lib.ptr(d_axial), kg_mode, kg_suppress,
                 _lib.ptr(self.d_m_slot), _lib.ptr(self.d_hm_ptr), _lib.ptr(self.d_hm_list), self.n_dup_half_members,
-                _lib.ptr(self.d_diag_slot), _lib.ptr(self.d_vals), st), "assemble_beams_gather")
+                _lib.ptr(self.d_diag_slot), _lib.ptr(self.d_member_cache), _lib.ptr(self.d_vals), st),
+                "assemble_beams_gather")
         else:
             _lib.check(lib.fers_b200_zero(_lib.ptr(self.d_vals), self.d_vals.numel() * 8, st), "zero")
             _lib.check(lib.fers_b200_assemble_beams(

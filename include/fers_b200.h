@@ -95,13 +95,16 @@ size_t fers_b200_gather_map_workspace(int n_nodes, int n_members);
 int fers_b200_gather_map_build(int n_nodes, int n_members, int nnzb, const int* m_n1, const int* m_n2, const int* m_slot,
                                int* hm_ptr, int* hm_list, int* n_dup_out, void* workspace, size_t workspace_bytes, void* stream);
 /* Writes every diagonal block and every off-diagonal block that has a member (blocks coupled only by
- * plates are not touched: zero vals first when the model has plates, then add the plates). */
+ * plates are not touched: zero vals first when the model has plates, then add the plates).
+ * member_cache: scratch of n_members * 24 doubles (32-byte aligned) or NULL.  With it the local frame and
+ * the stiffness coefficients of a member are formed once (k_member_cache) and read by both of its ends;
+ * without it every half-member forms them itself. */
 int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xyz, const int* m_n1, const int* m_n2,
                                     const int* m_prop, const int* m_type, const double* m_roll, const double* m_scale,
                                     const int* m_rel, const double* prop, int n_prop, const double* rel, int n_rel,
                                     const double* m_axial, int kg_mode, int kg_suppress, const int* m_slot,
-                                    const int* hm_ptr, const int* hm_list, int n_dup, const int* diag_slot, double* vals,
-                                    void* stream);
+                                    const int* hm_ptr, const int* hm_list, int n_dup, const int* diag_slot,
+                                    double* member_cache, double* vals, void* stream);
 /* TRI3 shell elements: CST membrane + DSG3 Mindlin bending (pydantic_models.py:1700-1726). */
 int fers_b200_assemble_plates(int n_plates, const double* xyz, const int* p_nodes, const double* p_data,
                               const int* p_flags, const int* p_slot, double* vals, void* stream);

@@ -1,2 +1,2 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "full_size or gather" 2>&1 | tail -5

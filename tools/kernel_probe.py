@@ -48,7 +48,7 @@ P = _lib.ptr
 report("k_assemble_gather", nm * 64 + nnzb * 288, timed(lambda: _lib.check(lib.fers_b200_assemble_beams_gather(
     nn, nm, P(eng.d_xyz0), P(eng.d_n1), P(eng.d_n2), P(eng.d_m_prop), P(eng.d_type), P(eng.d_roll), None, None, P(eng.d_prop),
     eng.n_prop, None, 0, None, 0, 0, P(eng.d_m_slot), P(eng.d_hm_ptr), P(eng.d_hm_list), eng.n_dup_half_members,
-    P(eng.d_diag_slot), P(eng.d_vals), eng.stream), "gather")))
+    P(eng.d_diag_slot), P(eng.d_member_cache), P(eng.d_vals), eng.stream), "gather")))
 for nr in (64, 1):
     x = torch.randn((nd, nr), dtype=torch.float64, device=dev)
     y = torch.empty_like(x)
