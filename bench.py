@@ -407,10 +407,27 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             t_e2e.append(time.perf_counter() - t0)
             h2d = eng.h2d_bytes
             del out
+        # one more pass with a synchronisation after every phase: where the end-to-end time goes (diagnostic only)
+        del eng
+        torch.cuda.synchronize(dev)
+        marks = [time.perf_counter()]
+
+        def mark():
+            torch.cuda.synchronize(dev)
+            marks.append(time.perf_counter())
+        eng = engine.Engine(model, dev, args.assembly_variant, args.solver); mark()
+        out = eng.run_linear(factors); mark()
+        h_u.copy_(out["U"], non_blocking=True); h_r.copy_(out["R"], non_blocking=True)
+        h_f.copy_(out["f_local"], non_blocking=True); mark()
+        del out
+        phases = {"engine_setup_ms (H2D of the model, pattern, gather map)": 1e3 * (marks[1] - marks[0]),
+                  "run_linear_ms (incl. factorisation plan on the host)": 1e3 * (marks[2] - marks[1]),
+                  "of which chol_plan_ms (host)": eng.timings.get("chol_plan_ms"),
+                  "d2h_ms": 1e3 * (marks[3] - marks[2])}
         te = fdist.max_over_ranks(min(t_e2e), dev)
         e2e = {"value": world * units / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(h_u.numel() * 8 + h_r.numel() * 8 + h_f.numel() * 8),
-               "ms_per_step": 1e3 * te,
+               "ms_per_step": 1e3 * te, "phases_of_a_synchronised_pass": phases,
                "api": "fers_core_b200.engine.Engine(model_arrays).run_linear(factors) + D2H of U, R, f_local"}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------

@@ -495,19 +495,22 @@ k_spmv1(int n_nodes, const int* __restrict__ rowptr, const int* __restrict__ col
             double2 a[4][3], xv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int k = min(k0 + u, ke - 1);
-                const int col = __ldg(colidx + k);
-                const double2* ap = reinterpret_cast<const double2*>(vals + (size_t)k * 36) + r;
+                const int k = k0 + u;
+                xv[u] = make_double2(0.0, 0.0);
 #pragma unroll
-                for (int q = 0; q < 3; ++q) a[u][q] = __ldcs(ap + 6 * q);
-                xv[u] = __ldg(reinterpret_cast<const double2*>(x + (size_t)col * 6) + cc);
+                for (int q = 0; q < 3; ++q) a[u][q] = make_double2(0.0, 0.0);
+                if (k < ke) {                       // predicated: nothing is fetched past the end of the row
+                    const int col = __ldg(colidx + k);
+                    const double2* ap = reinterpret_cast<const double2*>(vals + (size_t)k * 36) + r;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) a[u][q] = __ldcs(ap + 6 * q);
+                    xv[u] = __ldg(reinterpret_cast<const double2*>(x + (size_t)col * 6) + cc);
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (k0 + u < ke) {
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) acc[q] = fma(a[u][q].y, xv[u].y, fma(a[u][q].x, xv[u].x, acc[q]));
-                }
+                for (int q = 0; q < 3; ++q) acc[q] = fma(a[u][q].y, xv[u].y, fma(a[u][q].x, xv[u].x, acc[q]));
             }
         }
 #pragma unroll

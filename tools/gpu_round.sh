@@ -1,2 +1,3 @@
 set -x
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "full_size or gather" 2>&1 | tail -5
+python tools/kernel_probe.py 2>&1 | tail -9
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
