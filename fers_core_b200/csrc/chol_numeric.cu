@@ -132,7 +132,8 @@ k_scatter_k(LevelCtx L, const KScatter* __restrict__ ks, long long n_entries, co
 
 // ---- diagonal tile: Cholesky + explicit inverse of the factor --------------------------------------
 constexpr int NB = CHOL_NB;
-constexpr int CHOL_OUTER = 4;           // 64-column steps per outer block of the two-level blocked panel update
+// 64-column steps per outer block of the two-level blocked panel update (FERS_CHOL_OUTER / fers_b200_chol_set_outer)
+static int g_chol_outer = getenv("FERS_CHOL_OUTER") ? atoi(getenv("FERS_CHOL_OUTER")) : 4;
 constexpr int TP = NB + 1;
 constexpr size_t POTRF_SMEM = 2 * NB * TP * sizeof(double);
 
@@ -710,6 +711,7 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
             }
             // two-level blocking: inner update inside the current OUTER-column block, outer update once per block
             const int cbeg = (s + 1) * NB;
+            const int CHOL_OUTER = g_chol_outer < 1 ? 1 : g_chol_outer;
             const int blk_end = (s / CHOL_OUTER + 1) * CHOL_OUTER * NB;
             const int in_end = std::min(blk_end, max_k1);
             if (cbeg < in_end) {
@@ -963,6 +965,12 @@ int fers_b200_residual(long long n_dof, int nrhs, const double* f, const double*
 int fers_b200_chol_set_variant(int variant) {
     FERS_REQUIRE(variant >= 0 && variant <= 7, "chol_set_variant: bit 0 = panel updates, bit 1 = Schur update use the 128x128 tile, bit 2 = no look-ahead");
     g_chol_variant = variant;
+    return 0;
+}
+
+int fers_b200_chol_set_outer(int steps) {
+    FERS_REQUIRE(steps >= 1 && steps <= 64, "chol_set_outer: 1..64 steps of 64 columns per outer block");
+    g_chol_outer = steps;
     return 0;
 }
 

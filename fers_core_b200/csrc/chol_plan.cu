@@ -22,6 +22,18 @@
 namespace fers {
 namespace {
 
+// run fn(thread, begin, end) over [0, n) split into contiguous chunks, one std::thread per chunk
+template <class F>
+void parallel_chunks(int n, int max_threads, F fn) {
+    const int t = std::max(1, std::min(max_threads, n / 8));
+    if (t == 1) { fn(0, 0, n); return; }
+    std::vector<std::thread> pool;
+    for (int k = 0; k < t; ++k)
+        pool.emplace_back([&, k]() { fn(k, (int)((long long)n * k / t), (int)((long long)n * (k + 1) / t)); });
+    for (auto& th : pool) th.join();
+}
+constexpr int PLAN_THREADS = 8;
+
 struct FrontBuild {
     int parent = -1;
     int depth = 0;
@@ -231,66 +243,102 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
     lap("ordering");
     // symbolic factorisation: boundaries in post-order
     std::vector<std::vector<int>> bnd(nf);
-    std::vector<int> stamp(n_nodes, -1);
     P.child.clear(); P.inv_off.clear();
-    for (int i = 0; i < nf; ++i) {
-        const FrontBuild& fb = B[order[i]];
-        const int first = P.front_first[i], last = first + P.fronts[i].n1;
-        std::vector<int>& out = bnd[i];
-        for (int v : fb.own)
-            for (int k = rp[v]; k < rp[v + 1]; ++k) {
-                const int w = ci[k];
-                if (P.pos[w] >= last && stamp[w] != i) { stamp[w] = i; out.push_back(w); }
-            }
-        for (int c : fb.children)
-            for (int w : bnd[new_id[c]])
-                if (P.pos[w] >= last && stamp[w] != i) { stamp[w] = i; out.push_back(w); }
-        std::sort(out.begin(), out.end(), [&](int x, int y) { return P.pos[x] < P.pos[y]; });
-        P.fronts[i].n2 = (int)out.size();
+    {
+        // children before parents: fronts of equal depth are independent (deepest first), chunks of a depth on threads
+        std::vector<std::vector<int>> by_depth(max_depth + 1);
+        for (int i = 0; i < nf; ++i) by_depth[B[order[i]].depth].push_back(i);
+        std::vector<std::vector<int>> stamps(PLAN_THREADS, std::vector<int>(n_nodes, -1));
+        for (int d = max_depth; d >= 0; --d) {
+            const std::vector<int>& ids = by_depth[d];
+            parallel_chunks((int)ids.size(), PLAN_THREADS, [&](int t, int b0, int b1) {
+                std::vector<int>& stamp = stamps[t];
+                for (int q = b0; q < b1; ++q) {
+                    const int i = ids[q];
+                    const FrontBuild& fb = B[order[i]];
+                    const int last = P.front_first[i] + P.fronts[i].n1;
+                    std::vector<int>& out = bnd[i];
+                    for (int v : fb.own)
+                        for (int k = rp[v]; k < rp[v + 1]; ++k) {
+                            const int w = ci[k];
+                            if (P.pos[w] >= last && stamp[w] != i) { stamp[w] = i; out.push_back(w); }
+                        }
+                    for (int c : fb.children)
+                        for (int w : bnd[new_id[c]])
+                            if (P.pos[w] >= last && stamp[w] != i) { stamp[w] = i; out.push_back(w); }
+                    std::sort(out.begin(), out.end(), [&](int x, int y) { return P.pos[x] < P.pos[y]; });
+                    P.fronts[i].n2 = (int)out.size();
+                }
+            });
+        }
     }
 
     lap("boundaries");
     // node lists, child lists and inverse maps
-    P.nodes.clear(); P.inv.clear();
-    std::vector<int> loc(n_nodes, -1);
     long long factor = 0, rhs_rows = 0;
     P.flops = 0; P.nnz_l = 0; P.max_front_nodes = 0;
     std::vector<int> depth_of(nf);
-    for (int i = 0; i < nf; ++i) {
-        FrontDev& f = P.fronts[i];
-        const FrontBuild& fb = B[order[i]];
-        depth_of[i] = fb.depth;
-        f.nodes_off = (int)P.nodes.size();
-        for (int v : fb.own) P.nodes.push_back(v);
-        for (int v : bnd[i]) P.nodes.push_back(v);
-        const int nt = f.n1 + f.n2;
-        P.max_front_nodes = std::max(P.max_front_nodes, nt);
-        for (int q = 0; q < nt; ++q) loc[P.nodes[f.nodes_off + q]] = q;
-        f.child_begin = (int)P.child.size();
-        for (int c : fb.children) {
-            const int cid = new_id[c];
-            P.child.push_back(cid);
-            P.inv_off.push_back((long long)P.inv.size());
-            const size_t base = P.inv.size();
-            P.inv.resize(base + nt, -1);
-            const std::vector<int>& cb = bnd[cid];
-            for (int q = 0; q < (int)cb.size(); ++q) {
-                const int l = loc[cb[q]];
-                if (l < 0) { set_error("chol_plan: child boundary node missing from parent front"); return 3; }
-                P.inv[base + l] = q;
+    std::vector<long long> inv_base(nf, 0);
+    {
+        // offsets first (sequential, cheap), then the node lists and inverse maps of the fronts on threads
+        long long n_nodes_list = 0, n_inv = 0;
+        for (int i = 0; i < nf; ++i) {
+            FrontDev& f = P.fronts[i];
+            const FrontBuild& fb = B[order[i]];
+            depth_of[i] = fb.depth;
+            const int nt = f.n1 + f.n2;
+            f.nodes_off = (int)n_nodes_list;
+            n_nodes_list += nt;
+            P.max_front_nodes = std::max(P.max_front_nodes, nt);
+            f.child_begin = (int)P.child.size();
+            inv_base[i] = n_inv;
+            for (int c : fb.children) {
+                P.child.push_back(new_id[c]);
+                P.inv_off.push_back(n_inv);
+                n_inv += nt;
             }
+            f.child_end = (int)P.child.size();
+            const long long m = 6LL * nt, k1 = 6LL * f.n1, m2 = 6LL * f.n2;
+            f.panel_off = factor;
+            factor += m * k1;
+            f.dinv_off = factor;
+            factor += ((k1 + CHOL_NB - 1) / CHOL_NB) * (long long)(CHOL_NB * CHOL_NB);
+            f.rhs_off = rhs_rows;
+            rhs_rows += m;
+            P.flops += (double)k1 * k1 * k1 / 3.0 + (double)k1 * k1 * m2 + (double)k1 * m2 * m2;
+            P.nnz_l += k1 * (k1 + 1) / 2 + m2 * k1;
         }
-        f.child_end = (int)P.child.size();
-        for (int q = 0; q < nt; ++q) loc[P.nodes[f.nodes_off + q]] = -1;
-        const long long m = 6LL * nt, k1 = 6LL * f.n1, m2 = 6LL * f.n2;
-        f.panel_off = factor;
-        factor += m * k1;
-        f.dinv_off = factor;
-        factor += ((k1 + CHOL_NB - 1) / CHOL_NB) * (long long)(CHOL_NB * CHOL_NB);
-        f.rhs_off = rhs_rows;
-        rhs_rows += m;
-        P.flops += (double)k1 * k1 * k1 / 3.0 + (double)k1 * k1 * m2 + (double)k1 * m2 * m2;
-        P.nnz_l += k1 * (k1 + 1) / 2 + m2 * k1;
+        if (n_nodes_list >= (1LL << 31)) { set_error("chol_plan: front node lists exceed 32-bit indexing"); return 3; }
+        P.nodes.assign((size_t)n_nodes_list, 0);
+        P.inv.assign((size_t)n_inv, -1);
+        std::vector<int> failed(PLAN_THREADS, 0);
+        std::vector<std::vector<int>> locs(PLAN_THREADS, std::vector<int>(n_nodes, -1));
+        parallel_chunks(nf, PLAN_THREADS, [&](int t, int b0, int b1) {
+            std::vector<int>& loc = locs[t];
+            for (int i = b0; i < b1; ++i) {
+                const FrontDev& f = P.fronts[i];
+                const FrontBuild& fb = B[order[i]];
+                int* nd = P.nodes.data() + f.nodes_off;
+                int q = 0;
+                for (int v : fb.own) nd[q++] = v;
+                for (int v : bnd[i]) nd[q++] = v;
+                const int nt = f.n1 + f.n2;
+                for (int k = 0; k < nt; ++k) loc[nd[k]] = k;
+                long long base = inv_base[i];
+                for (int c : fb.children) {
+                    const std::vector<int>& cb = bnd[new_id[c]];
+                    for (int k = 0; k < (int)cb.size(); ++k) {
+                        const int l = loc[cb[k]];
+                        if (l < 0) { failed[t] = 1; continue; }
+                        P.inv[(size_t)base + l] = k;
+                    }
+                    base += nt;
+                }
+                for (int k = 0; k < nt; ++k) loc[nd[k]] = -1;
+            }
+        });
+        for (int f : failed)
+            if (f) { set_error("chol_plan: child boundary node missing from parent front"); return 3; }
     }
     P.factor_doubles = factor;
     P.rhs_rows = rhs_rows;
@@ -323,42 +371,62 @@ static int build_plan(int n_nodes, const int* rp, const int* ci, const double* x
 
     lap("levels");
     // K blocks of the lower triangle (in elimination order) -> panel positions, grouped by level
-    std::vector<int> front_of_node(n_nodes, -1);
-    for (int i = 0; i < nf; ++i)
-        for (int q = 0; q < P.fronts[i].n1; ++q) front_of_node[P.nodes[P.fronts[i].nodes_off + q]] = i;
     std::vector<int> level_of(nf);
     for (int l = 0; l < P.n_levels; ++l)
         for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; ++q) level_of[P.level_fronts[q]] = l;
+    // per-front entry counts, then offsets (fronts of a level in index order), then the entries -- on threads
+    std::vector<long long> front_cnt(nf, 0), front_off(nf, 0);
+    parallel_chunks(nf, PLAN_THREADS, [&](int, int b0, int b1) {
+        for (int i = b0; i < b1; ++i) {
+            const FrontDev& f = P.fronts[i];
+            long long n = 0;
+            for (int q = 0; q < f.n1; ++q) {
+                const int c = P.nodes[f.nodes_off + q];
+                for (int k = rp[c]; k < rp[c + 1]; ++k)
+                    if (P.pos[ci[k]] >= P.pos[c]) ++n;
+            }
+            front_cnt[i] = n;
+        }
+    });
     std::vector<long long> cnt(P.n_levels + 1, 0);
-    for (int v = 0; v < n_nodes; ++v) {
-        if (P.pos[v] < 0) continue;
-        for (int k = rp[v]; k < rp[v + 1]; ++k)
-            if (P.pos[ci[k]] >= 0 && P.pos[v] >= P.pos[ci[k]]) cnt[level_of[front_of_node[ci[k]]] + 1]++;
-    }
+    for (int i = 0; i < nf; ++i) cnt[level_of[i] + 1] += front_cnt[i];
     for (int l = 0; l < P.n_levels; ++l) cnt[l + 1] += cnt[l];
+    {
+        std::vector<long long> cur(cnt.begin(), cnt.end() - 1);
+        for (int i = 0; i < nf; ++i) { front_off[i] = cur[level_of[i]]; cur[level_of[i]] += front_cnt[i]; }
+    }
     P.kscatter_ptr = cnt;
     P.kscatter.assign((size_t)cnt[P.n_levels], KScatter{});
     {
-        std::vector<long long> cur(cnt.begin(), cnt.end() - 1);
-        // local index of a node inside a front: own nodes by position, boundary nodes by search
-        for (int i = 0; i < nf; ++i) {
-            const FrontDev& f = P.fronts[i];
-            const int nt = f.n1 + f.n2;
-            for (int q = 0; q < nt; ++q) loc[P.nodes[f.nodes_off + q]] = q;
-            for (int q = 0; q < f.n1; ++q) {
-                const int c = P.nodes[f.nodes_off + q];          // column node (own)
-                for (int k = rp[c]; k < rp[c + 1]; ++k) {
-                    const int r = ci[k];                          // row node; block (r, c) = transpose slot of (c, r)
-                    if (P.pos[r] < P.pos[c]) continue;
-                    if (loc[r] < 0) { set_error("chol_plan: matrix entry outside its front"); return 3; }
-                    // we need the block stored at row r, column c: find it in row r
-                    const int* b = std::lower_bound(ci + rp[r], ci + rp[r + 1], c);
-                    if (b == ci + rp[r + 1] || *b != c) { set_error("chol_plan: pattern is not structurally symmetric"); return 3; }
-                    KScatter e; e.front = i; e.k = (int)(b - ci); e.bi = loc[r]; e.bj = q;
-                    P.kscatter[(size_t)cur[level_of[i]]++] = e;
+        std::vector<int> failed(PLAN_THREADS, 0);
+        std::vector<std::vector<int>> locs(PLAN_THREADS, std::vector<int>(n_nodes, -1));
+        // local index of a node inside a front: own nodes by position, boundary nodes through the front's node list
+        parallel_chunks(nf, PLAN_THREADS, [&](int t, int b0, int b1) {
+            std::vector<int>& loc = locs[t];
+            for (int i = b0; i < b1; ++i) {
+                const FrontDev& f = P.fronts[i];
+                const int nt = f.n1 + f.n2;
+                size_t at = (size_t)front_off[i];
+                for (int q = 0; q < nt; ++q) loc[P.nodes[f.nodes_off + q]] = q;
+                for (int q = 0; q < f.n1; ++q) {
+                    const int c = P.nodes[f.nodes_off + q];          // column node (own)
+                    for (int k = rp[c]; k < rp[c + 1]; ++k) {
+                        const int r = ci[k];                          // row node; block (r, c) = transpose slot of (c, r)
+                        if (P.pos[r] < P.pos[c]) continue;
+                        // we need the block stored at row r, column c: find it in row r
+                        const int* b = std::lower_bound(ci + rp[r], ci + rp[r + 1], c);
+                        if (loc[r] < 0) { failed[t] |= 1; continue; }
+                        if (b == ci + rp[r + 1] || *b != c) { failed[t] |= 2; continue; }
+                        KScatter e; e.front = i; e.k = (int)(b - ci); e.bi = loc[r]; e.bj = q;
+                        P.kscatter[at++] = e;
+                    }
                 }
+                for (int q = 0; q < nt; ++q) loc[P.nodes[f.nodes_off + q]] = -1;
             }
-            for (int q = 0; q < nt; ++q) loc[P.nodes[f.nodes_off + q]] = -1;
+        });
+        for (int f : failed) {
+            if (f & 1) { set_error("chol_plan: matrix entry outside its front"); return 3; }
+            if (f & 2) { set_error("chol_plan: pattern is not structurally symmetric"); return 3; }
         }
     }
 

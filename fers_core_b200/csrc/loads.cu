@@ -113,9 +113,46 @@ __global__ void k_load_members(LoadArgs A) {
     }
 }
 
-// out[row][rhs] = sum_l fac[rhs][l] * in[l][row]
-__global__ void k_combine(int n_rows, int n_cases, int nrhs, const double* __restrict__ in,
-                          const double* __restrict__ fac, double* __restrict__ out) {
+// out[row][rhs] = sum_l fac[rhs][l] * in[l][row].  A group of nrhs/2 lanes owns one row (two columns per lane,
+// one 16-byte store: a warp writes 512 contiguous bytes), the row's case values are loaded once per group
+// as broadcasts, four rows in flight per group.
+__global__ void __launch_bounds__(256)
+k_combine(long long n_rows, int n_cases, int nrhs, const double* __restrict__ in, const double* __restrict__ fac,
+          double* __restrict__ out) {
+    extern __shared__ double s_fac[];          // [n_cases][nrhs] (transposed: conflict-free column pairs)
+    for (int i = threadIdx.x; i < nrhs * n_cases; i += blockDim.x) {
+        const int r = i / n_cases, l = i - r * n_cases;
+        s_fac[l * nrhs + r] = fac[i];
+    }
+    __syncthreads();
+    const int cp = nrhs / 2;                   // lanes per row
+    const int lane_in_row = threadIdx.x % cp;
+    const long long groups = (long long)gridDim.x * (blockDim.x / cp);
+    const long long g0 = (long long)blockIdx.x * (blockDim.x / cp) + threadIdx.x / cp;
+    for (long long row0 = g0 * 4; row0 < n_rows; row0 += groups * 4) {
+        double2 acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = make_double2(0.0, 0.0);
+        for (int l = 0; l < n_cases; ++l) {
+            const double2 f = *reinterpret_cast<const double2*>(s_fac + l * nrhs + 2 * lane_in_row);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long row = row0 + u;
+                const double v = row < n_rows ? __ldg(in + (size_t)l * n_rows + row) : 0.0;
+                acc[u].x = fma(f.x, v, acc[u].x); acc[u].y = fma(f.y, v, acc[u].y);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long row = row0 + u;
+            if (row < n_rows) reinterpret_cast<double2*>(out + (size_t)row * nrhs)[lane_in_row] = acc[u];
+        }
+    }
+}
+
+// general shape (odd nrhs or nrhs/2 not dividing 256): one thread per output value
+__global__ void k_combine_any(int n_rows, int n_cases, int nrhs, const double* __restrict__ in,
+                              const double* __restrict__ fac, double* __restrict__ out) {
     extern __shared__ double s_fac[];
     for (int i = threadIdx.x; i < nrhs * n_cases; i += blockDim.x) s_fac[i] = fac[i];
     __syncthreads();
@@ -170,11 +207,21 @@ int fers_b200_combine(int n_rows, int n_cases, int nrhs, const double* in, const
     if (n_rows <= 0 || nrhs <= 0) return 0;
     FERS_REQUIRE((size_t)nrhs * n_cases * 8 <= 48 * 1024, "combine: factor table exceeds shared memory");
     const int T = 256;
-    size_t total = (size_t)n_rows * nrhs;
-    int grid = (int)((total + T - 1) / T);
-    int cap = sm_count() * 16;
-    if (grid > cap) grid = cap;
-    k_combine<<<grid, T, (size_t)nrhs * n_cases * 8, as_stream(stream)>>>(n_rows, n_cases, nrhs, in, factors, out);
+    const size_t smem = (size_t)nrhs * n_cases * 8;
+    const int cp = nrhs / 2;
+    if (nrhs % 2 == 0 && cp >= 1 && T % cp == 0 && (((uintptr_t)out) & 15) == 0) {
+        const long long rows_per_cta = (long long)(T / cp) * 4;
+        long long grid = (n_rows + rows_per_cta - 1) / rows_per_cta;
+        const long long cap = (long long)sm_count() * 16;
+        if (grid > cap) grid = cap;
+        k_combine<<<(unsigned)grid, T, smem, as_stream(stream)>>>(n_rows, n_cases, nrhs, in, factors, out);
+    } else {
+        size_t total = (size_t)n_rows * nrhs;
+        int grid = (int)((total + T - 1) / T);
+        int cap = sm_count() * 16;
+        if (grid > cap) grid = cap;
+        k_combine_any<<<grid, T, smem, as_stream(stream)>>>(n_rows, n_cases, nrhs, in, factors, out);
+    }
     FERS_LAUNCH_CHECK();
     count_launches(1);
     return 0;

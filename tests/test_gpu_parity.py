@@ -237,6 +237,24 @@ def test_full_size_frame_properties(engine_mod):
     assert torch.equal(u1, u2)
 
 
+@pytest.mark.parametrize("nrhs,n_cases,n_rows", [(64, 8, 1000), (8, 3, 77), (16, 1, 5), (3, 4, 33), (32, 8, 4099)])
+def test_combine_matches_numpy(engine_mod, nrhs, n_cases, n_rows):
+    """Factor matrix x per-case vectors (LoadCombination, pydantic_models.py:491-505) through the C ABI."""
+    import torch
+    from fers_core_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(nrhs + n_rows)
+    per_case = rng.normal(size=(n_cases, n_rows))
+    fac = rng.normal(size=(nrhs, n_cases))
+    dev = torch.device("cuda", 0)
+    d_in, d_fac = torch.from_numpy(per_case).to(dev), torch.from_numpy(fac).to(dev)
+    d_out = torch.empty((n_rows, nrhs), dtype=torch.float64, device=dev)
+    _lib.check(lib.fers_b200_combine(n_rows, n_cases, nrhs, _lib.ptr(d_in), _lib.ptr(d_fac), _lib.ptr(d_out),
+                                     torch.cuda.current_stream(dev).cuda_stream), "combine")
+    want = per_case.T @ fac.T
+    assert np.abs(d_out.cpu().numpy() - want).max() <= 1e-14 * np.abs(want).max()
+
+
 def test_dense_cholesky_batched(engine_mod):
     """Batched dense factor/solve used for batches of small frames (configs[4])."""
     import torch

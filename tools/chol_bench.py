@@ -54,9 +54,15 @@ for it in range(3):
     print(f"refine {it}: max relres {np.sqrt(nh[0]/nh[1]).max():.3e}  |u|max {float(u.abs().max()):.6e}", flush=True)
     sol.solve(r, u, eng.d_fixed, accumulate=True)
 lib.fers_b200_chol_set_profile(0)
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-sol.factorize(eng.d_vals, eng.d_diag_slot, eng.d_fixed, eng.d_ks, check=False)
-sol.solve(d_f, u, eng.d_fixed)
-torch.cuda.synchronize()
-print(f"unprofiled factor+solve {(time.perf_counter()-t0)*1e3:.1f} ms", flush=True)
+for outer in [int(v) for v in os.environ.get("CHOL_OUTERS", "4").split(",")]:
+    lib.fers_b200_chol_set_outer(outer)
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sol.factorize(eng.d_vals, eng.d_diag_slot, eng.d_fixed, eng.d_ks, check=False)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        sol.solve(d_f, u, eng.d_fixed)
+        torch.cuda.synchronize()
+        print(f"outer {outer}: unprofiled factor {(t1-t0)*1e3:.1f} ms ({plan.info.flops/(t1-t0)/1e12:.2f} TF/s) solve {(time.perf_counter()-t1)*1e3:.1f} ms", flush=True)
+lib.fers_b200_chol_set_outer(4)
