@@ -70,7 +70,7 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_chol_set_profile": (_i, [_i]),
     "fers_b200_chol_set_variant": (_i, [_i]),
-    "fers_b200_chol_set_outer": (_i, [_i]),
+    "fers_b200_chol_set_outer": (_i, [_i, _i]),
     "fers_b200_chol_profile": (_i, [_dp, _i]),
 }
 

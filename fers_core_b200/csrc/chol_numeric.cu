@@ -134,6 +134,8 @@ k_scatter_k(LevelCtx L, const KScatter* __restrict__ ks, long long n_entries, co
 constexpr int NB = CHOL_NB;
 // 64-column steps per outer block of the two-level blocked panel update (FERS_CHOL_OUTER / fers_b200_chol_set_outer)
 static int g_chol_outer = getenv("FERS_CHOL_OUTER") ? atoi(getenv("FERS_CHOL_OUTER")) : 4;
+// outer blocks per group of the third blocking level (FERS_CHOL_GROUP / fers_b200_chol_set_outer); 1 = two levels only
+static int g_chol_group = getenv("FERS_CHOL_GROUP") ? atoi(getenv("FERS_CHOL_GROUP")) : 1;
 constexpr int TP = NB + 1;
 constexpr size_t POTRF_SMEM = 2 * NB * TP * sizeof(double);
 
@@ -289,22 +291,56 @@ using G44N = GemmMma<64, 64, 2, 4, true, 16>;
 using G48N = GemmMma<64, 128, 2, 4, true, 16>;
 #endif
 
-// rows below the diagonal tile of step s:  X = B * inv(D)^T   (in place)
+// rows below the diagonal tile of step s, inside the current outer block only (rows < min(rend, k1)):
+// X = B * inv(D)^T (in place).  The rows below the block are handled once per block by k_row_panel.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_trsm(LevelCtx L, int s) {
+k_trsm(LevelCtx L, int s, int rend) {
     extern __shared__ __align__(16) double smem[];
     const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
     const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
     const int c0 = s * NB;
     if (c0 >= k1) return;
     const int nb = min(NB, k1 - c0);
+    const int row_end = min(min(rend, k1), m);
     const int r0 = c0 + nb + blockIdx.x * G84::BM;
-    if (r0 >= m) return;
+    if (r0 >= row_end) return;
     double* A = L.factor + f.panel_off + (size_t)c0 * m + r0;
     const double* B = L.factor + f.dinv_off + (size_t)s * NB * NB;
     G84::Acc acc;
-    G84::mainloop(acc, smem, A, m, m - r0, B, NB, nb, nb);
-    G84::store<true>(acc, A, (size_t)m, m - r0, nb);
+    G84::mainloop(acc, smem, A, m, row_end - r0, B, NB, nb, nb);
+    G84::store<true>(acc, A, (size_t)m, row_end - r0, nb);
+}
+
+// Rows below an outer block [bs, be) (be clipped to the front's own columns): X = B * L_bb^-T by forward
+// substitution over the block's 64-column sub-blocks, entirely inside the CTA that owns the 64-row tile:
+//   X_j = (B_j - [X_0 .. X_{j-1}] * L_bb[j, 0..j)^T) * inv(D_j)^T
+// -- one product with K = 64 j and one with K = 64 per sub-block instead of a trsm launch plus an inner-update
+// launch per 64-column step over all the rows of the front.
+using GRP = G44;     // tile of the row-panel kernel: 64 rows x 64 columns (128 x 64 measured no faster)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_row_panel(LevelCtx L, int bs, int be) {
+    extern __shared__ __align__(16) double smem[];
+    const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
+    const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
+    if (bs >= k1) return;
+    be = min(be, k1);
+    const int r0 = be + blockIdx.x * GRP::BM;
+    if (r0 >= m) return;
+    const int mrem = m - r0;
+    double* panel = L.factor + f.panel_off;
+    for (int cj = bs; cj < be; cj += NB) {
+        const int nb = min(NB, be - cj);
+        double* C = panel + (size_t)cj * m + r0;
+        GRP::Acc acc;
+        if (cj > bs) {
+            GRP::mainloop(acc, smem, panel + (size_t)bs * m + r0, m, mrem, panel + (size_t)bs * m + cj, m, nb, cj - bs);
+            GRP::store<false>(acc, C, (size_t)m, mrem, nb);
+            __syncthreads();                    // the tile just written is the operand of the next product
+        }
+        GRP::mainloop(acc, smem, C, m, mrem, L.factor + f.dinv_off + (size_t)(cj / NB) * NB * NB, NB, nb, nb);
+        GRP::store<true>(acc, C, (size_t)m, mrem, nb);
+        __syncthreads();
+    }
 }
 
 // panel update: columns [cbeg, min(cend, k1)) of the panel, rows >= column, get C -= X X^T with
@@ -313,18 +349,19 @@ k_trsm(LevelCtx L, int s) {
 // (kw = 256), so that most of the trailing matrix is read and written once per 256 eliminated columns.
 template <class G>
 __global__ void __launch_bounds__(GEMM_THREADS, G::MIN_CTAS)
-k_update(LevelCtx L, int kc0, int kw, int cbeg, int cend) {
+k_update(LevelCtx L, int kc0, int kw, int cbeg, int cend, int rend) {
     extern __shared__ __align__(16) double smem[];
     const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
     const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
     if (cend > k1) cend = k1;
     if (cbeg >= cend) return;
+    const int row_end = rend >= (1 << 30) ? m : min(min(rend, k1), m);   // inner updates stay inside the outer block
     const int r = cbeg + blockIdx.x * G::BM, c = cbeg + blockIdx.y * G::BN;
-    if (r >= m || c >= cend || c >= r + G::BM) return;       // outside the panel or entirely above the diagonal
+    if (r >= row_end || c >= cend || c >= r + G::BM) return;  // outside the panel or entirely above the diagonal
     const double* X = L.factor + f.panel_off + (size_t)kc0 * m;
     typename G::Acc acc;
-    G::mainloop(acc, smem, X + r, m, m - r, X + c, m, cend - c, kw);
-    G::template store<false>(acc, L.factor + f.panel_off + (size_t)c * m + r, (size_t)m, m - r, cend - c);
+    G::mainloop(acc, smem, X + r, m, row_end - r, X + c, m, cend - c, kw);
+    G::template store<false>(acc, L.factor + f.panel_off + (size_t)c * m + r, (size_t)m, row_end - r, cend - c);
 }
 
 // Schur complement: F22 -= L21 L21^T on the lower tiles
@@ -575,6 +612,7 @@ static int set_smem_attrs() {
     if (done) return 0;
     FERS_CK(cudaFuncSetAttribute(k_potrf_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
     FERS_CK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G84::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_row_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRP::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_update<G88>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G88::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_syrk<G88>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G88::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_update<G86>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G86::SMEM));
@@ -701,60 +739,79 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
             e0 = span_begin(2);
             k_potrf_inv<<<nf, 256, POTRF_SMEM, st>>>(L, s, info_dev);
             span_end(2, e0);
-            const int rows_below = max_m - s * NB;          // upper bound on rows below the diagonal tile
-            if (rows_below > 0) {
-                e0 = span_begin(3);
-                dim3 grid(cdiv(rows_below, G84::BM), 1, nf);
-                k_trsm<<<grid, GEMM_THREADS, G84::SMEM, st>>>(L, s);
-                span_end(3, e0);
-                ++launches;
-            }
-            // two-level blocking: inner update inside the current OUTER-column block, outer update once per block
+            // blocking: inside the current outer block (OUTER steps of 64 columns) the trsm and the inner update of
+            // every step touch only the rows of the block; the rows below it are brought up to date once per block
+            // by k_row_panel; the outer update then reaches all later columns
             const int cbeg = (s + 1) * NB;
             const int CHOL_OUTER = g_chol_outer < 1 ? 1 : g_chol_outer;
             const int blk_end = (s / CHOL_OUTER + 1) * CHOL_OUTER * NB;
             const int in_end = std::min(blk_end, max_k1);
             if (cbeg < in_end) {
+                e0 = span_begin(3);
+                dim3 grid(cdiv(in_end - cbeg, G84::BM), 1, nf);
+                k_trsm<<<grid, GEMM_THREADS, G84::SMEM, st>>>(L, s, blk_end);
+                span_end(3, e0);
+                ++launches;
                 e0 = span_begin(4);
                 if (g_chol_variant & 1) {
-                    dim3 grid(cdiv(max_m - cbeg, G88::BM), cdiv(in_end - cbeg, G88::BN), nf);
-                    k_update<G88><<<grid, GEMM_THREADS, G88::SMEM, st>>>(L, s * NB, NB, cbeg, blk_end);
+                    dim3 grid2(cdiv(in_end - cbeg, G88::BM), cdiv(in_end - cbeg, G88::BN), nf);
+                    k_update<G88><<<grid2, GEMM_THREADS, G88::SMEM, st>>>(L, s * NB, NB, cbeg, blk_end, blk_end);
                 } else {
-                    dim3 grid(cdiv(max_m - cbeg, G86::BM), cdiv(in_end - cbeg, G86::BN), nf);
-                    k_update<G86><<<grid, GEMM_THREADS, G86::SMEM, st>>>(L, s * NB, NB, cbeg, blk_end);
+                    dim3 grid2(cdiv(in_end - cbeg, G86::BM), cdiv(in_end - cbeg, G86::BN), nf);
+                    k_update<G86><<<grid2, GEMM_THREADS, G86::SMEM, st>>>(L, s * NB, NB, cbeg, blk_end, blk_end);
                 }
                 span_end(4, e0);
                 ++launches;
             }
+            if (cbeg >= in_end || s == steps - 1) {          // block finished: rows below it
+                const int bs = blk_end - CHOL_OUTER * NB;
+                if (max_m > bs) {
+                    e0 = span_begin(3);
+                    dim3 grid(cdiv(max_m - bs, GRP::BM), 1, nf);
+                    k_row_panel<<<grid, GEMM_THREADS, GRP::SMEM, st>>>(L, bs, blk_end);
+                    span_end(3, e0);
+                    ++launches;
+                }
+            }
             if (cbeg == blk_end && blk_end < max_k1) {
-                const int kc0 = blk_end - CHOL_OUTER * NB, kw = CHOL_OUTER * NB;
+                // third level: blocks are gathered in groups of g_chol_group; inside a group a finished block updates
+                // only the rest of its group (K = block width), a finished group updates all later columns at once
+                // (K = group width: fewer passes over the trailing panel, longer GEMM main loops)
+                const int blk_w = CHOL_OUTER * NB;
+                const int grp_w = (g_chol_group < 1 ? 1 : g_chol_group) * blk_w;
+                const int grp_end = ((blk_end - 1) / grp_w + 1) * grp_w;
+                const bool at_group_end = blk_end == grp_end;
+                const int kw = at_group_end ? grp_w : blk_w;
+                const int kc0 = blk_end - kw;
+                const int lim = at_group_end ? max_k1 : std::min(grp_end, max_k1);     // columns [blk_end, lim) are updated
+                const int lim_arg = at_group_end ? (1 << 30) : grp_end;
                 auto outer = [&](cudaStream_t q, int c_from, int c_to_grid, int c_to) {
                     if (g_chol_variant & 1) {
                         dim3 grid(cdiv(max_m - c_from, G88::BM), cdiv(c_to_grid - c_from, G88::BN), nf);
-                        k_update<G88><<<grid, GEMM_THREADS, G88::SMEM, q>>>(L, kc0, kw, c_from, c_to);
+                        k_update<G88><<<grid, GEMM_THREADS, G88::SMEM, q>>>(L, kc0, kw, c_from, c_to, 1 << 30);
                     } else {
                         dim3 grid(cdiv(max_m - c_from, G86::BM), cdiv(c_to_grid - c_from, G86::BN), nf);
-                        k_update<G86><<<grid, GEMM_THREADS, G86::SMEM, q>>>(L, kc0, kw, c_from, c_to);
+                        k_update<G86><<<grid, GEMM_THREADS, G86::SMEM, q>>>(L, kc0, kw, c_from, c_to, 1 << 30);
                     }
                     ++launches;
                 };
                 if (!lookahead) {
                     e0 = span_begin(4);
-                    outer(st, blk_end, max_k1, 1 << 30);
+                    outer(st, blk_end, lim, lim_arg);
                     span_end(4, e0);
                 } else {
-                    // look-ahead: the columns of the next outer block are updated first, on the main stream, so
-                    // that its chain of diagonal tiles / trsm / inner updates overlaps the update of all later
-                    // columns, which runs on the side stream.  Both touch disjoint columns; successive side
-                    // updates are ordered by the side stream, and the urgent update of block b+1 waits for the
-                    // side update of block b (same columns).
-                    const int next_end = std::min(blk_end + kw, max_k1);
+                    // look-ahead: the columns of the next block are updated first, on the main stream, so that its
+                    // chain of diagonal tiles / trsm / inner updates overlaps the update of the remaining columns,
+                    // which runs on the side stream.  Both touch disjoint columns; successive side updates are
+                    // ordered by the side stream, and the urgent update of block b+1 waits for the side update of
+                    // block b (same columns).
+                    const int next_end = std::min(blk_end + blk_w, lim);
                     if (side_pending) { FERS_CK(cudaStreamWaitEvent(st, ev_side, 0)); side_pending = false; }
                     outer(st, blk_end, next_end, next_end);
-                    if (next_end < max_k1) {
+                    if (next_end < lim) {
                         FERS_CK(cudaEventRecord(ev_main, st));
                         FERS_CK(cudaStreamWaitEvent(g_side_stream, ev_main, 0));
-                        outer(g_side_stream, next_end, max_k1, 1 << 30);
+                        outer(g_side_stream, next_end, lim, lim_arg);
                         FERS_CK(cudaEventRecord(ev_side, g_side_stream));
                         side_pending = true;
                     }
@@ -968,9 +1025,11 @@ int fers_b200_chol_set_variant(int variant) {
     return 0;
 }
 
-int fers_b200_chol_set_outer(int steps) {
+int fers_b200_chol_set_outer(int steps, int group) {
     FERS_REQUIRE(steps >= 1 && steps <= 64, "chol_set_outer: 1..64 steps of 64 columns per outer block");
+    FERS_REQUIRE(group >= 1 && group <= 64, "chol_set_outer: 1..64 outer blocks per group");
     g_chol_outer = steps;
+    g_chol_group = group;
     return 0;
 }
 

@@ -225,8 +225,10 @@ int fers_b200_chol_set_profile(int on);
  * 128x128 tile with one CTA per SM, clear (default) = 128x64 tile with two CTAs per SM; bit 2 set = no
  * look-ahead (the update of all later columns is then not overlapped with the next block's panel chain). */
 int fers_b200_chol_set_variant(int variant);
-/* Width of the outer block of the two-level blocked panel update in 64-column steps (default 4 = 256 columns). */
-int fers_b200_chol_set_outer(int steps);
+/* Blocking of the panel updates: `steps` 64-column steps per outer block (default 4 = 256 columns) and `group`
+ * outer blocks per group (default 1; measured: 4 x 1 is the fastest of 2 x 1, 4 x 1, 8 x 1, 4 x 2, 4 x 4, 4 x 8 at
+ * configs[3]).  A finished block updates the rest of its group, a finished group all later columns. */
+int fers_b200_chol_set_outer(int steps, int group);
 /* n_out >= 16 additionally returns sums since the last fers_b200_chol_set_profile call: out[10..12] = ms
  * of the Schur updates, of whole factorisations, of whole substitutions; out[13..15] = factorisations,
  * substitutions, Schur-update launches. */

@@ -54,8 +54,9 @@ for it in range(3):
     print(f"refine {it}: max relres {np.sqrt(nh[0]/nh[1]).max():.3e}  |u|max {float(u.abs().max()):.6e}", flush=True)
     sol.solve(r, u, eng.d_fixed, accumulate=True)
 lib.fers_b200_chol_set_profile(0)
-for outer in [int(v) for v in os.environ.get("CHOL_OUTERS", "4").split(",")]:
-    lib.fers_b200_chol_set_outer(outer)
+for spec in os.environ.get("CHOL_OUTERS", "4x1").split(","):
+    outer, group = (int(v) for v in spec.split("x"))
+    lib.fers_b200_chol_set_outer(outer, group)
     for rep in range(2):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -64,5 +65,5 @@ for outer in [int(v) for v in os.environ.get("CHOL_OUTERS", "4").split(",")]:
         t1 = time.perf_counter()
         sol.solve(d_f, u, eng.d_fixed)
         torch.cuda.synchronize()
-        print(f"outer {outer}: unprofiled factor {(t1-t0)*1e3:.1f} ms ({plan.info.flops/(t1-t0)/1e12:.2f} TF/s) solve {(time.perf_counter()-t1)*1e3:.1f} ms", flush=True)
-lib.fers_b200_chol_set_outer(4)
+        print(f"outer {outer} group {group}: unprofiled factor {(t1-t0)*1e3:.1f} ms ({plan.info.flops/(t1-t0)/1e12:.2f} TF/s) solve {(time.perf_counter()-t1)*1e3:.1f} ms", flush=True)
+lib.fers_b200_chol_set_outer(4, 1)
