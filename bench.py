@@ -168,7 +168,7 @@ def run_reference(args, rank: int, world: int) -> None:
     value = units / (ms / 1e3)
     sample = (f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} frame ({model.n_dof} DOF) x {args.combos} combinations, "
               "full pipeline (assembly, SuperLU factor, 64-RHS solve, recovery) per step")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -457,7 +457,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                          "combinations, oracle (numpy assembly + scipy SuperLU factor + 64-RHS solve + recovery; sequential code), once"}
 
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
@@ -501,7 +501,7 @@ def run_cfg5(args, rank: int, world: int, local_rank: int) -> None:
     dt = fdist.max_over_ranks((time.perf_counter() - t0) / args.steps, dev)
     summ = fdist.gather_summary(torch.from_numpy(np.abs(res.U[0]).reshape(args.frames, -1).max(axis=1)).to(dev))
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": world * units / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -516,7 +516,26 @@ def run_cfg5(args, rank: int, world: int, local_rank: int) -> None:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(obj: dict) -> None:
+    """The one JSON line of this run, on the process's ORIGINAL stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+    # chatter) is sent to stderr by pointing fd 1 at fd 2 and keeping a private copy of the real stdout
+    global _JSON_FD
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
