@@ -33,6 +33,8 @@ from __future__ import annotations
 
 import time
 
+import os
+
 import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
@@ -499,6 +501,9 @@ def constrain(K, model, extra_fixed=None):
     return Ks[free][:, free].tocsc(), free, dead
 
 
+SOLVE_THREADS = max(1, os.cpu_count() or 1)      # host threads of the multi-right-hand-side substitution
+
+
 def solve_sym(Kff, B):
     """Direct solve of K_ff X = B (B [n,nrhs])."""
     if Kff.shape[0] == 0:
@@ -512,7 +517,21 @@ def solve_sym(Kff, B):
         except np.linalg.LinAlgError:
             return np.linalg.solve(A, B)
     lu = spla.splu(Kff, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
-    return lu.solve(B)
+    nrhs = B.shape[1] if B.ndim == 2 else 1
+    threads = min(SOLVE_THREADS, nrhs)
+    if threads <= 1 or B.ndim != 2:
+        return lu.solve(B)
+    # SuperLU substitutes one column at a time and releases the GIL: independent column chunks on host threads
+    # (the factorisation itself is sequential).  Same arithmetic per column as the single call.
+    from concurrent.futures import ThreadPoolExecutor
+    bounds = [nrhs * k // threads for k in range(threads + 1)]
+    X = np.empty_like(B)
+
+    def work(k):
+        X[:, bounds[k]:bounds[k + 1]] = lu.solve(np.ascontiguousarray(B[:, bounds[k]:bounds[k + 1]]))
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
+    return X
 
 
 def recover_members(asm: Assembly, U, peq, kg_local=None):
