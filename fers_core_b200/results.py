@@ -44,6 +44,7 @@ class ResultArrays:
     method: str = "Linear"
     solve_ms: float | None = None
     warnings: list = field(default_factory=list)
+    bw: np.ndarray = None            # [nrhs,Nm,2] bimoment at the member ends (nodal force at the warping DOF)
     unity: object = None             # unity.UnityAccumulator while the analysis runs (None: no checks)
     unity_xyz: object = None
 
@@ -56,7 +57,7 @@ class ResultArrays:
                    u_local=z((n, nm, 12)), sec=z((n, nm, ns, 6)), lmax=z((n, nm, 6)), lmin=z((n, nm, 6)),
                    gmax=z((n, nm, 6)), gmin=z((n, nm, 6)), p_res=z((n, npl, 8)), p_nodal=z((n, npl, 3, 6)),
                    p_cdg=z((n, npl, 6)), p_cdl=z((n, npl, 6)), p_centroid=z((npl, 3)),
-                   iterations=np.full(n, -1, np.int64), converged=np.ones(n, bool), residual=z(n))
+                   iterations=np.full(n, -1, np.int64), converged=np.ones(n, bool), residual=z(n), bw=z((n, nm, 2)))
 
 
 def _forces(v, bw=0.0) -> dict:
@@ -76,17 +77,27 @@ def results_to_wire(model, res: ResultArrays) -> dict:
     plan = res.plan
     bundle = {"loadcases": {}, "loadcombinations": {},
               "unity_check_results": res.unity.results() if res.unity is not None else []}
-    sup_nodes = np.nonzero(model.node_support_id >= 0)[0]
+    n_real = model.n_real
+    sup_nodes = np.nonzero(model.node_support_id[:n_real] >= 0)[0]
     node_keys = [str(int(i)) for i in model.node_ids]
+    warp_node = model.warp_node if len(model.warp_node) == n_real else np.full(n_real, -1)
+
+    def warp_of(arr, col, i):
+        """Value at the warping DOF of real node i (DOF 0 of its auxiliary node), 0 without one."""
+        a = int(warp_node[i])
+        return float(arr[col, a, 0]) if a >= 0 else 0.0
     mem_keys = [str(int(i)) for i in model.m_ids]
     warn = [{"code": c, "message": m} for c, m in (list(model.warnings) + list(res.warnings))]
     for col in range(plan.n_rhs):
-        disp = {node_keys[i]: _disp(res.U[col, i]) for i in range(model.n_nodes)}
+        disp = {}
+        for i in range(n_real):
+            disp[node_keys[i]] = _disp(res.U[col, i])
+            disp[node_keys[i]]["warp"] = warp_of(res.U, col, i)
         reac = {}
         for i in sup_nodes:
             reac[node_keys[i]] = {
                 "location": {"X": float(model.xyz[i, 0]), "Y": float(model.xyz[i, 1]), "Z": float(model.xyz[i, 2])},
-                "nodal_forces": _forces(res.R[col, i]),
+                "nodal_forces": _forces(res.R[col, i], warp_of(res.R, col, i)),
                 "support_id": int(model.node_support_id[i]),
             }
         members = {}
@@ -95,10 +106,11 @@ def results_to_wire(model, res: ResultArrays) -> dict:
             sec = [{"x_frac": float(x), "forces": _forces(res.sec[col, m, si])} for si, x in enumerate(SECTION_FRACS)]
             series = ([{"x_frac": 0.0, "forces": _forces(fl[0:6])}] + sec
                       + [{"x_frac": 1.0, "forces": _forces(-fl[6:12])}])
+            b1, b2 = (float(res.bw[col, m, 0]), float(res.bw[col, m, 1])) if res.bw is not None else (0.0, 0.0)
             members[mem_keys[m]] = {
-                "start_node_forces": _forces(fg[0:6]), "end_node_forces": _forces(fg[6:12]),
+                "start_node_forces": _forces(fg[0:6], b1), "end_node_forces": _forces(fg[6:12], b2),
                 "maximums": _forces(res.gmax[col, m]), "minimums": _forces(res.gmin[col, m]),
-                "local_start_forces": _forces(fl[0:6]), "local_end_forces": _forces(fl[6:12]),
+                "local_start_forces": _forces(fl[0:6], b1), "local_end_forces": _forces(fl[6:12], b2),
                 "local_maximums": _forces(res.lmax[col, m]), "local_minimums": _forces(res.lmin[col, m]),
                 "local_displacement_start_node": _disp(ul[0:6]), "local_displacement_end_node": _disp(ul[6:12]),
                 "section_forces": sec, "internal_force_series": series,
@@ -107,7 +119,7 @@ def results_to_wire(model, res: ResultArrays) -> dict:
             "name": plan.names[col],
             "result_type": {plan.kinds[col]: int(plan.ids[col])},
             "displacement_nodes": disp, "reaction_nodes": reac, "member_results": members,
-            "summary": {"total_displacements": model.n_nodes, "total_member_forces": model.n_members,
+            "summary": {"total_displacements": n_real, "total_member_forces": model.n_members,
                         "total_reaction_forces": int(len(sup_nodes))},
             "errors_and_warnings": {"errors": [], "warnings": warn},
             "solver_diagnostics": {

@@ -126,6 +126,12 @@ class ModelArrays:
     combo_limit_state: list = field(default_factory=list)      # per combination: "SLS" | "ULS" | ... | None
     m_classification: list = field(default_factory=list)       # per member: classification string or None
     m_section_raw: list = field(default_factory=list)          # per member: (section dict, material dict) or None
+    # warping torsion (7th nodal DOF of the reference, pydantic_models.py:1384-1387): the warping DOF psi of a real
+    # node lives in DOF 0 of an auxiliary node appended after the real ones (its other five DOFs are restrained)
+    n_real_nodes: int = -1                                       # -1: no auxiliary nodes (n_nodes real nodes)
+    warp_node: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))   # [n_real] aux node or -1
+    w_member: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))    # [Nw] members with warping
+    w_aux: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), np.int32))  # [Nw,2] aux nodes of start / end
 
     def member_raw(self, m: int):
         """(section dict, material dict) of member index m as they came over the wire."""
@@ -135,7 +141,12 @@ class ModelArrays:
 
     @property
     def n_nodes(self) -> int:
+        """Nodes of the stiffness matrix: real nodes followed by the auxiliary warping nodes."""
         return int(self.node_ids.shape[0])
+
+    @property
+    def n_real(self) -> int:
+        return self.n_nodes if self.n_real_nodes < 0 else int(self.n_real_nodes)
 
     @property
     def n_members(self) -> int:
@@ -228,6 +239,7 @@ def parse_document(doc: dict) -> ModelArrays:
     bc_code = np.zeros((nn, 6), np.uint8)
     bc_k = np.zeros((nn, 6), np.float64)
     node_support_id = np.full(nn, -1, np.int64)
+    warp_fixed = np.zeros(nn, bool)         # support restrains the warping DOF (NodalSupport.warping_condition)
     for i, n in enumerate(nodes):
         sid = n.get("nodal_support")
         if sid is None:
@@ -240,6 +252,9 @@ def parse_document(doc: dict) -> ModelArrays:
                 raise WireError(f"node {n['id']}: unknown nodal_support {sid}")
             sup = supports[sid]
         node_support_id[i] = sid
+        wc = sup.get("warping_condition")
+        if isinstance(wc, dict):
+            warp_fixed[i] = _norm_enum(wc.get("condition_type", "Free")) == "fixed"
         for d, name in enumerate(DOF_NAMES):
             cond = sup.get(name)
             if cond is None:
@@ -286,14 +301,15 @@ def parse_document(doc: dict) -> ModelArrays:
         A, Iy, Iz, J = float(s["area"]), float(s["i_y"]), float(s["i_z"]), float(s["j"])
         asy = s.get("a_sy") if opts.include_shear_deformation else None
         asz = s.get("a_sz") if opts.include_shear_deformation else None
+        eiw = E * float(s["i_w"]) if (opts.include_warping and s.get("i_w")) else 0.0
         row = [E * A, E * Iy, E * Iz, G * J,
                G * float(asy) if asy else 0.0, G * float(asz) if asz else 0.0,
-               float(s.get("wpl_y") or 0.0), 0.0]
+               float(s.get("wpl_y") or 0.0), eiw]
         sec_row[sid] = len(prop_rows)
         prop_rows.append(row)
         prop_rho_a.append(float(mat.get("density") or 0.0) * A)
-        if s.get("i_w") and opts.include_warping:
-            warnings.append(("W_WARPING_IGNORED", f"section {sid}: warping DOF not modelled (St-Venant torsion only)"))
+        if eiw and (s.get("y_s") or s.get("z_s")) and opts.include_shear_center_coupling:
+            warnings.append(("W_SHEAR_CENTRE_IGNORED", f"section {sid}: shear-centre offset not coupled to bending"))
     prop = np.array(prop_rows, np.float64).reshape(len(prop_rows), NPROP)
 
     # ---- hinges (pydantic_models.py:2062-2087; release fields are spring stiffnesses) ----
@@ -491,7 +507,29 @@ def parse_document(doc: dict) -> ModelArrays:
                 raise WireError(f"combination {c['id']}: unknown load case {lid}")
             combo_factors[ci, lc_index[lid]] += float(f["factor"])
 
+    # ---- warping torsion: auxiliary nodes carrying psi ---------------------------
+    n_real = nn
+    warp_node = np.full(nn, -1, np.int32)
+    w_member = np.zeros(0, np.int32)
+    w_aux = np.zeros((0, 2), np.int32)
+    has_w = (m_prop >= 0) & ~np.isin(m_type, (MT_TRUSS, MT_RIGID))
+    has_w &= np.where(m_prop >= 0, prop[np.maximum(m_prop, 0), 7] if len(prop) else 0.0, 0.0) > 0.0
+    if has_w.any():
+        w_member = np.nonzero(has_w)[0].astype(np.int32)
+        touched = np.unique(np.concatenate([m_n1[w_member], m_n2[w_member]]))
+        warp_node[touched] = nn + np.arange(len(touched), dtype=np.int32)
+        w_aux = np.stack([warp_node[m_n1[w_member]], warp_node[m_n2[w_member]]], axis=1).astype(np.int32)
+        na = len(touched)
+        node_ids = np.concatenate([node_ids, -1 - node_ids[touched]])        # aux ids are negative: never on the wire
+        xyz = np.concatenate([xyz, xyz[touched]])
+        node_support_id = np.concatenate([node_support_id, node_support_id[touched]])
+        aux_code = np.full((na, 6), BC_FIXED, np.uint8)
+        aux_code[:, 0] = np.where(warp_fixed[touched], BC_FIXED, BC_FREE)
+        bc_code = np.concatenate([bc_code, aux_code])
+        bc_k = np.concatenate([bc_k, np.zeros((na, 6))])
+
     return ModelArrays(
+        n_real_nodes=n_real, warp_node=warp_node, w_member=w_member, w_aux=w_aux,
         node_ids=node_ids, xyz=xyz, node_support_id=node_support_id, bc_code=bc_code, bc_k=bc_k,
         m_ids=m_ids, m_n1=m_n1, m_n2=m_n2, m_type=m_type, m_roll=m_roll, m_prop=m_prop, m_rel=m_rel,
         prop=prop, prop_rho_a=np.array(prop_rho_a, np.float64), rel=rel,

@@ -100,7 +100,9 @@ def local_stiffness(P, L, mtype):
     phi_y, phi_z = shear_phis(P, L, mtype)
     axial_only = mtype == wire.MT_TRUSS
     a = EA / L
-    t = np.where(axial_only, 0.0, GJ / L)
+    # linear St-Venant torsion GJ/L plus the theta_x part 12 EIw / L^3 of the cubic-Hermite warping matrix
+    EIw = P[:, 7] if P.shape[1] > 7 else np.zeros(nm)
+    t = np.where(axial_only, 0.0, GJ / L + 12.0 * EIw / L**3)
     for (i, j, s) in ((0, 0, 1), (0, 6, -1), (6, 0, -1), (6, 6, 1)):
         k[:, i, j] = s * a
     for (i, j, s) in ((3, 3, 1), (3, 9, -1), (9, 3, -1), (9, 9, 1)):
@@ -348,6 +350,35 @@ class Assembly:
         self.plates = plate_stiffness_global(model, self.xyz) if model.n_plates else []
         self.edof = np.concatenate([6 * model.m_n1[:, None] + np.arange(6), 6 * model.m_n2[:, None] + np.arange(6)], 1) if nm else np.zeros((0, 12), np.int64)
 
+    def warping_coefficients(self):
+        """Per warping member: (theta_x direction lx [Nw,3], c6 = 6 EIw / L^2, c4 = 4 EIw / L, c2 = 2 EIw / L), scaled."""
+        model = self.model
+        w = model.w_member
+        L = self.L[w]
+        eiw = self.P[w, 7] * self.m_scale[w]
+        return self.R[w, 0, :], 6.0 * eiw / L**2, 4.0 * eiw / L, 2.0 * eiw / L
+
+    def warping_triplets(self):
+        """Coupling of the warping DOFs psi (DOF 0 of the auxiliary nodes) with the twist of the member ends:
+        cubic-Hermite matrix EIw/L^3 [[12,6L,-12,6L],[6L,4L^2,-6L,2L^2],[-12,-6L,12,-6L],[6L,2L^2,-6L,4L^2]] on
+        (theta_x1, psi1, theta_x2, psi2); its theta-theta part sits in the 12x12 torsion term."""
+        model = self.model
+        w = model.w_member
+        lx, c6, c4, c2 = self.warping_coefficients()
+        s, e = model.m_n1[w], model.m_n2[w]
+        p1, p2 = 6 * model.w_aux[:, 0].astype(np.int64), 6 * model.w_aux[:, 1].astype(np.int64)
+        rows, cols, vals = [], [], []
+
+        def add(r, c, v):
+            rows.extend([r, c]); cols.extend([c, r]); vals.extend([v, v])
+        for i in range(3):
+            t1, t2 = 6 * s.astype(np.int64) + 3 + i, 6 * e.astype(np.int64) + 3 + i
+            add(t1, p1, c6 * lx[:, i]); add(t1, p2, c6 * lx[:, i])
+            add(t2, p1, -c6 * lx[:, i]); add(t2, p2, -c6 * lx[:, i])
+        add(p1, p2, c2)
+        rows.extend([p1, p2]); cols.extend([p1, p2]); vals.extend([c4, c4])
+        return np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+
     def K_elastic(self, kg_local=None):
         """Global stiffness (no supports, no springs) as CSR [Ndof,Ndof]."""
         model = self.model
@@ -364,6 +395,9 @@ class Assembly:
         for e, (kge, *_rest) in enumerate(self.plates):
             ed = (6 * model.p_nodes[e][:, None] + np.arange(6)).reshape(-1)
             rows.append(np.repeat(ed, 18)); cols.append(np.tile(ed, 18)); vals.append(kge.reshape(-1))
+        if len(model.w_member):
+            r_, c_, v_ = self.warping_triplets()
+            rows.append(r_); cols.append(c_); vals.append(v_)
         if not rows:
             return sp.csr_matrix((nd, nd))
         K = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nd, nd))
@@ -545,7 +579,7 @@ def recover_members(asm: Assembly, U, peq, kg_local=None):
     if nm == 0:
         z = lambda *s: np.zeros((nrhs, 0) + s)
         return dict(f_local=z(12), f_global=z(12), u_local=z(12), sec=z(len(SECTION_FRACS), 6),
-                    lmax=z(6), lmin=z(6), gmax=z(6), gmin=z(6))
+                    lmax=z(6), lmin=z(6), gmax=z(6), gmin=z(6), bw=z(2))
     ue = U[:, asm.edof]                                   # [nrhs,Nm,12]
     ul = np.einsum("mij,rmj->rmi", asm.T, ue)
     kl = asm.k_cond
@@ -554,8 +588,19 @@ def recover_members(asm: Assembly, U, peq, kg_local=None):
         fl = np.einsum("rmij,rmj->rmi", kl, ul) - peq
     else:
         fl = np.einsum("mij,rmj->rmi", kl, ul) - peq
+    bw = np.zeros((nrhs, nm, 2))
+    if len(model.w_member):
+        # warping members: psi-coupling of the end torques and the bimoments (nodal force k u at the psi DOF)
+        w = model.w_member
+        _, c6, c4, c2 = asm.warping_coefficients()
+        psi1, psi2 = U[:, 6 * model.w_aux[:, 0]], U[:, 6 * model.w_aux[:, 1]]      # [nrhs,Nw]
+        th1, th2 = ul[:, w, 3], ul[:, w, 9]
+        fl[:, w, 3] += c6 * (psi1 + psi2)
+        fl[:, w, 9] -= c6 * (psi1 + psi2)
+        bw[:, w, 0] = c6 * (th1 - th2) + c4 * psi1 + c2 * psi2
+        bw[:, w, 1] = c6 * (th1 - th2) + c2 * psi1 + c4 * psi2
     fg = np.einsum("mji,rmj->rmi", asm.T, fl)
-    out["f_local"], out["f_global"], out["u_local"] = fl, fg, ul
+    out["f_local"], out["f_global"], out["u_local"], out["bw"] = fl, fg, ul, bw
     return out
 
 
@@ -793,6 +838,7 @@ def _store(out: ResultArrays, asm, model, cols, U, F, peq, K, kg, spans, fac, it
     out.R[cols] = Rn
     rec = recover_members(asm, U, peq, kg)
     out.f_local[cols] = rec["f_local"]; out.f_global[cols] = rec["f_global"]; out.u_local[cols] = rec["u_local"]
+    out.bw[cols] = rec["bw"]
     if model.n_members and detail:
         span_by_rhs = [[(fac[r, li], spans[li]) for li in range(fac.shape[1])] for r in range(len(cols))]
         sec = section_forces(asm, rec["f_local"], span_by_rhs)

@@ -10,7 +10,7 @@ Section, NodalSupport, loads, imperfections, plates ...), serialised by ``FERS.t
 ``fers_calculations.calculate_from_json`` -- plus the expectations the reference's tests hold
 for that model: closed-form beam theory (tests/common_functions.py:90-246,
 tests/beam_equation_checks/test_beam_equations.py, tests/functionality/test_functionality.py)
-and the NAFEMS known-answer numbers (tests/nafems/benchmarks/LE1_result.json, LE6_result.json).
+and the NAFEMS known-answer numbers (tests/nafems/benchmarks/LE1_result.json, LE5_result.json, LE6_result.json).
 The GPU box has no /root/reference, so the documents travel as this fixture.
 """
 import gzip
@@ -380,6 +380,18 @@ for (n, val, tol) in ((8, 396102.7, 0.06), (32, 741737.1, 0.06)):
     reset()
     calc = LE6_build.build(n)
     nafems_emit(f"nafems_LE6_{n}x{n}", calc, "LE6", LE6_build.E_CENTRE, LE6_build.T, val, tol)
+
+# 16 NAFEMS LE5 (Z-section cantilever, restrained-warping torsion through the 7th nodal DOF): the reference's own
+# builder and its known answer (tests/nafems/benchmarks/LE5_result.json: 107 643 284.3 Pa, printed to 0.1 Pa)
+import LE5_build  # noqa: E402
+
+reset()
+calc, _nodes = LE5_build.build(4)
+d = calc.to_dict(include_results=False)
+d["results"] = None
+CASES.append({"name": "nafems_LE5_4el", "doc": d,
+              "expect": [{"nafems": "LE5", "omega": LE5_build.OMEGA_TIP, "cw": LE5_build.CW, "value": 107643284.3,
+                          "abs": 0.06, "rel": 0.0}]})
 
 out = os.path.join(HERE, "wire_cases.json.gz")
 with gzip.open(out, "wt", encoding="utf-8") as fh:

@@ -49,6 +49,12 @@ def lookup(results: dict, path: str):
 def nafems_value(results: dict, spec: dict) -> float:
     """Stress extraction of the reference's NAFEMS builders (tests/nafems/benchmarks/LE1_build.py:123-135,
     LE6_build.py:109-123): plate whose centroid is nearest the target point."""
+    if spec["nafems"] == "LE5":
+        # tests/nafems/benchmarks/LE5_build.py:70-100: warping stress from the bimoment at x = 2.5 m (end of member 1 /
+        # start of member 2): sigma = 0.5 (|bw1| + |bw2|) omega_tip / C_w
+        mr = results["loadcases"]["Torque"]["member_results"]
+        bw = 0.5 * (abs(mr["1"]["end_node_forces"]["bw"]) + abs(mr["2"]["start_node_forces"]["bw"]))
+        return bw * spec["omega"] / spec["cw"]
     case = "Edge" if spec["nafems"] == "LE1" else "P"
     pr = results["loadcases"][case]["plate_results"]
     best, bestd = None, 1e9

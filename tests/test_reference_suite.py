@@ -19,6 +19,7 @@ SUITES = [
     "tests/functionality/test_functionality.py",
     "tests/functionality/test_plate_results.py",
     "tests/nafems/test_nafems_benchmarks.py::test_LE1_elliptic_membrane_converges",
+    "tests/nafems/test_nafems_benchmarks.py::test_LE5_zsection_warping_beam",
     "tests/nafems/test_nafems_benchmarks.py::test_LE6_skew_plate_converges",
 ]
 
