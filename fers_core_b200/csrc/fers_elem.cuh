@@ -21,7 +21,7 @@
 namespace fers {
 
 enum MemberType { MT_NORMAL = 0, MT_TRUSS = 1, MT_TENSION = 2, MT_COMPRESSION = 3, MT_RIGID = 4, MT_CABLE = 5 };
-enum { P_EA = 0, P_EIY = 1, P_EIZ = 2, P_GJ = 3, P_GASY = 4, P_GASZ = 5, NPROP = 8 };
+enum { P_EA = 0, P_EIY = 1, P_EIZ = 2, P_GJ = 3, P_GASY = 4, P_GASZ = 5, P_EIW = 7, NPROP = 8 };
 
 // Local frame of a member: R rows = local x, y, z expressed in global coordinates.
 struct Frame {
@@ -76,7 +76,8 @@ FERS_HD BeamCoef beam_coef(const double* P, double L, int mtype, double scale) {
     c.phi_z = (GAsy > 0.0) ? 12.0 * EIy / (GAsy * L2) : 0.0;
     bool axial_only = (mtype == MT_TRUSS);
     c.a = scale * (EA / L);
-    c.t = axial_only ? 0.0 : scale * (GJ / L);
+    // torsion: St-Venant GJ/L plus the theta_x part 12 EIw / L^3 of the Hermite warping matrix (warping.cu; 0 without)
+    c.t = axial_only ? 0.0 : scale * (GJ / L + 12.0 * P[P_EIW] / L3);
     double bz = axial_only ? 0.0 : EIz / (1.0 + c.phi_y);
     double by = axial_only ? 0.0 : EIy / (1.0 + c.phi_z);
     c.z12 = scale * (12.0 * bz / L3); c.z6 = scale * (6.0 * bz / L2);

@@ -160,17 +160,32 @@ class Engine:
     def _build_pattern(self) -> None:
         m, lib = self.model, self.lib
         nn, nm, npl = m.n_nodes, m.n_members, m.n_plates
-        cap = nn + 2 * nm + 6 * npl
+        # warping members couple the member ends with the auxiliary warping nodes: five extra node pairs each,
+        # appended after the members for the pattern build only (their m_slot rows are the kernel's slot table)
+        nw = self.n_warp = int(len(m.w_member))
+        d_pn1, d_pn2, n_pairs = self.d_n1, self.d_n2, nm
+        if nw:
+            s_, e_ = m.m_n1[m.w_member], m.m_n2[m.w_member]
+            a1, a2 = m.w_aux[:, 0], m.w_aux[:, 1]
+            x1 = np.stack([s_, s_, e_, e_, a1], axis=1).reshape(-1)
+            x2 = np.stack([a1, a2, a1, a2, a2], axis=1).reshape(-1)
+            d_pn1 = self._t(np.concatenate([m.m_n1, x1]), np.int32)
+            d_pn2 = self._t(np.concatenate([m.m_n2, x2]), np.int32)
+            n_pairs = nm + 5 * nw
+            self.d_w_member = self._t(m.w_member, np.int32)
+            self.d_w_aux = self._t(m.w_aux, np.int32)
+        cap = nn + 2 * n_pairs + 6 * npl
         self.d_rowptr = self._empty(nn + 1, torch.int32)
         self.d_colidx = self._empty(cap, torch.int32)
-        self.d_m_slot = self._empty(max(nm, 1) * 4, torch.int32)
+        self.d_m_slot = self._empty(max(n_pairs, 1) * 4, torch.int32)
+        self.d_w_slot = self.d_m_slot[4 * nm:] if nw else None
         self.d_p_slot = self._empty(max(npl, 1) * 9, torch.int32)
         self.d_diag_slot = self._empty(nn, torch.int32)
-        ws_bytes = lib.fers_b200_pattern_workspace(nn, nm, npl)
+        ws_bytes = lib.fers_b200_pattern_workspace(nn, n_pairs, npl)
         ws = self._empty(ws_bytes, torch.uint8)
         nnzb = C.c_int()
         _lib.check(lib.fers_b200_pattern_build(
-            nn, nm, _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), npl, _lib.ptr(self.d_p_nodes),
+            nn, n_pairs, _lib.ptr(d_pn1), _lib.ptr(d_pn2), npl, _lib.ptr(self.d_p_nodes),
             _lib.ptr(self.d_rowptr), _lib.ptr(self.d_colidx), cap, _lib.ptr(self.d_m_slot), _lib.ptr(self.d_p_slot),
             _lib.ptr(self.d_diag_slot), C.byref(nnzb), _lib.ptr(ws), ws_bytes, self.stream), "pattern_build")
         self.nnzb = nnzb.value
@@ -207,7 +222,7 @@ class Engine:
         if self.assembly_variant == ASSEMBLY_GATHER:
             # gather kernel: every block a member touches is written exactly once (no atomics, no zero pass);
             # blocks coupled only by plates are zeroed first
-            if m.n_plates:
+            if m.n_plates or self.n_warp:
                 _lib.check(lib.fers_b200_zero(_lib.ptr(self.d_vals), self.d_vals.numel() * 8, st), "zero")
             _lib.check(lib.fers_b200_assemble_beams_gather(
                 m.n_nodes, m.n_members, _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2), _lib.ptr(self.d_m_prop),
@@ -224,6 +239,11 @@ class Engine:
                 _lib.ptr(self.d_prop), self.n_prop, _lib.ptr(self.d_rel), n_rel,
                 _lib.ptr(d_axial), kg_mode, kg_suppress, _lib.ptr(self.d_m_slot), _lib.ptr(self.d_vals),
                 self.assembly_variant, st), "assemble_beams")
+        if self.n_warp:
+            _lib.check(lib.fers_b200_assemble_warping(
+                self.n_warp, _lib.ptr(self.d_w_member), _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2),
+                _lib.ptr(self.d_m_prop), _lib.ptr(d_scale), _lib.ptr(self.d_prop), _lib.ptr(self.d_w_slot),
+                _lib.ptr(self.d_vals), st), "assemble_warping")
         if m.n_plates:
             _lib.check(lib.fers_b200_assemble_plates(
                 m.n_plates, _lib.ptr(d_xyz), _lib.ptr(self.d_p_nodes), _lib.ptr(self.d_p_data), _lib.ptr(self.d_p_flags),
@@ -384,6 +404,13 @@ class Engine:
                 _lib.ptr(self.d_prop), _lib.ptr(self.d_rel), _lib.ptr(d_axial_rhs), kg_mode, kg_suppress,
                 _lib.ptr(d_u), _lib.ptr(d_peq), _lib.ptr(fl), _lib.ptr(fg), _lib.ptr(ul), st), "recover_members")
             out.update(f_local=fl, f_global=fg, u_local=ul)
+            if self.n_warp:
+                bw = self._empty((self.n_warp, 2, nr))
+                _lib.check(lib.fers_b200_recover_warping(
+                    self.n_warp, nr, _lib.ptr(self.d_w_member), _lib.ptr(self.d_w_aux), _lib.ptr(d_xyz), _lib.ptr(self.d_n1),
+                    _lib.ptr(self.d_n2), _lib.ptr(self.d_m_prop), _lib.ptr(d_scale), _lib.ptr(self.d_prop), _lib.ptr(d_u),
+                    _lib.ptr(fl), _lib.ptr(fg), _lib.ptr(bw), st), "recover_warping")
+                out["bw"] = bw
             if detail:
                 sp_ptr, sp_rows = span
                 sec = self._empty((nm, 18, nr))
@@ -577,6 +604,8 @@ def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:
     out.R[cols] = host(rec["R"], (nn, 6))
     if nm:
         out.f_local[cols] = host(rec["f_local"], (nm, 12))
+        if "bw" in rec:
+            out.bw[np.asarray(cols)[:, None], model.w_member[None, :]] = host(rec["bw"], (len(model.w_member), 2))
         out.f_global[cols] = host(rec["f_global"], (nm, 12))
         out.u_local[cols] = host(rec["u_local"], (nm, 12))
         if "sec" in rec:

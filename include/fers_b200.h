@@ -105,6 +105,14 @@ int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xy
                                     const double* m_axial, int kg_mode, int kg_suppress, const int* m_slot,
                                     const int* hm_ptr, const int* hm_list, int n_dup, const int* diag_slot,
                                     double* member_cache, double* vals, void* stream);
+/* Restrained-warping torsion (7th nodal DOF of the reference's beam: pydantic_models.py:1366-1369, 1384-1387;
+ * formulation SURVEY.md A.11, pinned by NAFEMS LE5).  The warping DOF psi of a node is DOF 0 of an auxiliary node;
+ * prop[.][7] = E*Iw (its theta-theta part 12 EIw/L^3 is already in the member's torsion coefficient).  Adds the
+ * psi couplings of n_w warping members to vals: w_member[n_w] member indices, w_slot[n_w][5][4] = the m_slot rows
+ * of the node pairs (s,s'), (s,e'), (e,s'), (e,e'), (s',e') (s', e' = auxiliary nodes of start / end). */
+int fers_b200_assemble_warping(int n_w, const int* w_member, const double* xyz, const int* m_n1, const int* m_n2,
+                               const int* m_prop, const double* m_scale, const double* prop, const int* w_slot, double* vals,
+                               void* stream);
 /* TRI3 shell elements: CST membrane + DSG3 Mindlin bending (pydantic_models.py:1700-1726). */
 int fers_b200_assemble_plates(int n_plates, const double* xyz, const int* p_nodes, const double* p_data,
                               const int* p_flags, const int* p_slot, double* vals, void* stream);
@@ -244,6 +252,13 @@ int fers_b200_recover_members(int n_members, int nrhs, const double* xyz, const 
                               const double* m_axial_rhs, int kg_mode, int kg_suppress,
                               const double* u, const double* peq,
                               double* f_local, double* f_global, double* u_local, void* stream);
+/* Warping members: adds the psi coupling to the end torques of f_local / f_global (f_global may be NULL) and
+ * writes the bimoments bw[n_w][2][nrhs] (nodal force at the warping DOF of the start / end node, the `bw` of
+ * NodeForces, pydantic_models.py:642-649).  w_aux[n_w][2]: auxiliary nodes of the member ends.  Call after
+ * fers_b200_recover_members. */
+int fers_b200_recover_warping(int n_w, int nrhs, const int* w_member, const int* w_aux, const double* xyz, const int* m_n1,
+                              const int* m_n2, const int* m_prop, const double* m_scale, const double* prop, const double* u,
+                              double* f_local, double* f_global, double* bw, void* stream);
 /* Interior section forces at x_frac 0.25/0.5/0.75 and per-component extrema:
  *   sec [n_members][18][nrhs]; lmax,lmin,gmax,gmin [n_members][6][nrhs].
  * Span loads are given per load case as CSR over members (sp_ptr[n_cases*(n_members+1)] into

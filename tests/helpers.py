@@ -84,12 +84,12 @@ def check_expectations(results: dict, expect: list) -> None:
 
 
 RESULT_FIELDS = ("U", "R", "f_local", "f_global", "u_local", "sec", "lmax", "lmin", "gmax", "gmin",
-                 "p_res", "p_nodal", "p_cdg", "p_cdl")
+                 "p_res", "p_nodal", "p_cdg", "p_cdl", "bw")
 
 
 # fields that are derived from the member end forces share their scale: an extremum or a section
 # force that is analytically zero carries round-off of the size eps * |f_local|
-_SCALE_OF = {"sec": "f_local", "lmax": "f_local", "lmin": "f_local", "gmax": "f_local", "gmin": "f_local",
+_SCALE_OF = {"bw": "f_local", "sec": "f_local", "lmax": "f_local", "lmin": "f_local", "gmax": "f_local", "gmin": "f_local",
              "f_global": "f_local", "u_local": "U", "p_cdg": "U", "p_cdl": "U"}
 
 
