@@ -255,6 +255,24 @@ def test_combine_matches_numpy(engine_mod, nrhs, n_cases, n_rows):
     assert np.abs(d_out.cpu().numpy() - want).max() <= 1e-14 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("name", ["space_frame_3d", "portal_pdelta_consistent", "hinge_spring"])
+def test_warping_sections_match_oracle(engine_mod, name):
+    """Golden frames with a warping constant on every section (7th nodal DOF active on all members, non-collinear
+    joints, releases, P-Delta): GPU against the oracle, including warping displacements and bimoments."""
+    import copy
+    doc = copy.deepcopy(helpers.golden(name)["doc"])
+    for sec in doc["model"]["sections"]:
+        sec["i_w"] = 40.0 * float(sec["i_y"]) * 1e-2          # same order as a rolled I-section: Iw ~ Iy h^2 / 4
+    doc["analysis"]["options"]["include_warping"] = True
+    model = wire.parse_document(doc)
+    assert len(model.w_member) and model.n_nodes > model.n_real
+    want = fers_oracle.analyze(model)
+    got = engine_mod.analyze(wire.parse_document(doc))
+    if "hinge" not in name:          # the hinge case carries no torsion
+        assert np.abs(want.bw).max() > 0 and np.abs(want.U[:, model.n_real:, 0]).max() > 0
+    helpers.assert_results_close(got, want, 1e-7 if "hinge" in name else RTOL, label=name + "+warping")
+
+
 def test_dense_cholesky_batched(engine_mod):
     """Batched dense factor/solve used for batches of small frames (configs[4])."""
     import torch
