@@ -23,7 +23,6 @@ Ec3Steel checks and reference-member quantities are reported as not evaluated (s
 """
 from __future__ import annotations
 
-import ctypes as C
 import re
 from dataclasses import dataclass, field
 

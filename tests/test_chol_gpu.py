@@ -63,14 +63,14 @@ def test_chol_reports_indefinite_matrix():
     assert sol.factorize(t(vals, np.float64), t(diag_slot, np.int32), t(fixed, np.uint8)) > 0
 
 
-@pytest.mark.parametrize("shape", [(8, 7, 5), (14, 12, 9)])
+@pytest.mark.parametrize("shape", [(8, 7, 5), (14, 12, 9), (20, 20, 12)])
 def test_chol_frame_stiffness_matches_oracle(shape):
     """Real frame stiffness (element kernels + assembly + BC on the GPU) solved by the sparse
     Cholesky against the oracle's SuperLU solve of the same model, 1e-9 relative."""
     import torch
     from fers_core_b200 import engine, synth
     from oracle import fers_oracle
-    model = synth.grid_frame(*shape, n_combos=8)
+    model = synth.grid_frame(*shape, n_combos=64 if shape[0] == 20 else 8)     # 20x20x12: 34 398 DOF, 64 columns
     stats = {}
     got = engine.analyze(model, device="cuda:0", detail=False, stats_out=stats, solver="cholesky")
     assert stats["method"] == "cholesky"
