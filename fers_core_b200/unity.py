@@ -19,7 +19,11 @@ Semantics where the closed engine is the only definition (stated, unpinned):
     (example 100: equals the global mid-span deflection on rigid supports);
   * applicable combinations: ``load_combination_ids`` when given, else the combinations whose
     ``limit_state`` equals the check's (all combinations when either side has none).
-Ec3Steel checks and reference-member quantities are reported as not evaluated (status message).
+  * ``of: ReferenceMember`` / ``ReferenceMember*`` node references follow ``Member.reference_member`` /
+    ``reference_node`` of the entity's first member (example 101); an entity without one evaluates to NaN;
+  * ``Displacement`` = largest absolute value of the component over the entity's nodes.
+Ec3Steel checks and plate quantities are reported as not evaluated (status message).  Every entity result carries a
+trace with the value of each variable at its governing combination.
 """
 from __future__ import annotations
 
@@ -31,7 +35,8 @@ import numpy as np
 from . import _lib
 
 OPS = {"PUSHC": 0, "PUSHV": 1, "+": 2, "-": 3, "*": 4, "/": 5, "^": 6, "NEG": 7, "abs": 8, "sqrt": 9, "min": 10, "max": 11}
-V_CONST, V_FORCE, V_EXPR, V_NODE_DISP, V_NODE_POS, V_DEFLECTION = range(6)
+V_CONST, V_FORCE, V_EXPR, V_NODE_DISP, V_NODE_POS, V_DEFLECTION, V_FORCE_REF, V_ENTITY_DISP = range(8)
+NODE_REF = {"Start": 0, "End": 1, "ReferenceMemberStart": 2, "ReferenceMemberEnd": 3, "ReferenceNode": 4}
 AGG = {"MaxAbs": 0, "Max": 1, "Min": 2, "Start": 3, "End": 4, "AtFraction": 5}
 FORCE_COMP = {"N": 0, "Vy": 1, "Vz": 2, "Mx": 3, "My": 4, "Mz": 5}
 DISP_COMP = {"Dx": 0, "Dy": 1, "Dz": 2, "Rx": 3, "Ry": 4, "Rz": 5, "Magnitude": 6}
@@ -191,6 +196,7 @@ class CompiledCheck:
     ent_node_ptr: np.ndarray
     ent_nodes: np.ndarray
     frames: np.ndarray                 # [n_ent, 9]
+    ent_ref: np.ndarray                # [n_ent, 4] reference member, its start / end node, reference node (-1 none)
     var_names: list
     var_desc: np.ndarray               # [n_vars, 4] int32
     code: np.ndarray                   # [n_code, 2] int32
@@ -281,6 +287,7 @@ def compile_check(model, definition: dict) -> CompiledCheck:
     spec = definition.get("spec") or {}
     empty = dict(entities=[], ent_ptr=np.zeros(1, np.int32), ent_members=np.zeros(0, np.int32),
                  ent_node_ptr=np.zeros(1, np.int32), ent_nodes=np.zeros(0, np.int32), frames=np.zeros((0, 9)),
+                 ent_ref=np.zeros((0, 4), np.int32),
                  var_names=[], var_desc=np.zeros((0, 4), np.int32), code=np.zeros((0, 2), np.int32), consts=np.zeros(1),
                  ctab=np.zeros((0, 1)), demand=(0, 0), capacity=(0, 0), combo_ids=None)
     if "Generic" not in spec:
@@ -302,6 +309,13 @@ def compile_check(model, definition: dict) -> CompiledCheck:
     ent_members = np.array([m for ms, _ in chains for m in ms], np.int32)
     ent_nodes = np.array([n for _, ns in chains for n in ns], np.int32)
     frames = np.array([_member_frame(model, ms[0]) for ms, _ in chains]).reshape(n_ent, 9)
+    ent_ref = np.full((n_ent, 4), -1, np.int32)
+    for i, (ms, _) in enumerate(chains):
+        rm = int(model.m_ref_member[ms[0]]) if len(model.m_ref_member) else -1
+        rn = int(model.m_ref_node[ms[0]]) if len(model.m_ref_node) else -1
+        if rm >= 0:
+            ent_ref[i, :3] = (rm, model.m_n1[rm], model.m_n2[rm])
+        ent_ref[i, 3] = rn
 
     variables = g.get("variables") or []
     if len(variables) > MAX_VARS:
@@ -326,9 +340,12 @@ def compile_check(model, definition: dict) -> CompiledCheck:
             continue
         q = src.get("Quantity") or {}
         (qk, qv), = q.items() if len(q) == 1 else [("?", None)]
-        if isinstance(qv, dict) and qv.get("of") not in (None, "SelfEntity"):
-            return CompiledCheck(definition=definition, skipped="reference-member quantities are not evaluated by this engine",
-                                 **empty)
+        of_ref = isinstance(qv, dict) and qv.get("of") not in (None, "SelfEntity")
+        if of_ref and qv.get("of") != "ReferenceMember":
+            raise UnityError(f"unity check {definition.get('id')}: unknown target {qv.get('of')!r}")
+
+        def target(i):      # member whose properties a constant quantity reads for entity i (-1: no reference member)
+            return int(ent_ref[i, 0]) if of_ref else chains[i][0][0]
         if qk == "Constant":
             ct_cols.append(np.full(n_ent, float(qv)))
             desc[new] = (V_CONST, len(ct_cols) - 1, 0, 0)
@@ -341,8 +358,8 @@ def compile_check(model, definition: dict) -> CompiledCheck:
             if fld is None:
                 raise UnityError(f"unity check {definition.get('id')}: unknown {qk} property {qv.get('property')!r}")
             col = np.full(n_ent, np.nan)
-            for i, (ms, _) in enumerate(chains):
-                raw = model.member_raw(ms[0])[0 if qk == "Section" else 1]
+            for i in range(n_ent):
+                raw = model.member_raw(target(i))[0 if qk == "Section" else 1] if target(i) >= 0 else None
                 val = raw.get(fld) if raw else None
                 col[i] = np.nan if val is None else float(val)
             ct_cols.append(col)
@@ -350,7 +367,9 @@ def compile_check(model, definition: dict) -> CompiledCheck:
         elif qk == "Geometry":
             col = np.zeros(n_ent)
             for i, (ms, _) in enumerate(chains):
-                col[i] = sum(float(np.linalg.norm(model.xyz[model.m_n2[m]] - model.xyz[model.m_n1[m]])) for m in ms)
+                group = ([target(i)] if target(i) >= 0 else []) if of_ref else ms
+                col[i] = sum(float(np.linalg.norm(model.xyz[model.m_n2[m]] - model.xyz[model.m_n1[m]])) for m in group) \
+                    if group else np.nan
             ct_cols.append(col)
             desc[new] = (V_CONST, len(ct_cols) - 1, 0, 0)
         elif qk == "MemberForce":
@@ -368,23 +387,24 @@ def compile_check(model, definition: dict) -> CompiledCheck:
                 raise UnityError(f"unity check {definition.get('id')}: unknown aggregation {agg!r}")
             station = 0
             if at == AGG["AtFraction"]:
-                if multi:
+                if multi and not of_ref:
                     return CompiledCheck(definition=definition, **empty,
                                          skipped="AtFraction member forces on member-set entities are not evaluated")
                 frac = float(agg.get("fraction", 0.5))
                 station = int(round(frac * 4))
                 if abs(station / 4 - frac) > 1e-12:
                     warnings.append(f"AtFraction {frac}: nearest of the stations 0, 1/4, 1/2, 3/4, 1 used")
-            desc[new] = (V_FORCE, FORCE_COMP[comp], at, station)
+            desc[new] = (V_FORCE_REF if of_ref else V_FORCE, FORCE_COMP[comp], at, station)
         elif qk in ("NodeDisplacement", "NodePosition"):
             at = qv.get("at")
-            if at not in ("Start", "End"):
-                return CompiledCheck(definition=definition, skipped=f"node reference {at!r} is not evaluated by this engine",
-                                     **empty)
+            if at not in NODE_REF:
+                raise UnityError(f"unity check {definition.get('id')}: unknown node reference {at!r}")
             if qk == "NodeDisplacement":
-                desc[new] = (V_NODE_DISP, 0 if at == "Start" else 1, DISP_COMP[qv.get("component")], 0)
+                desc[new] = (V_NODE_DISP, NODE_REF[at], DISP_COMP[qv.get("component")], 0)
             else:
-                desc[new] = (V_NODE_POS, 0 if at == "Start" else 1, AXIS[qv.get("axis")], 0)
+                desc[new] = (V_NODE_POS, NODE_REF[at], AXIS[qv.get("axis")], 0)
+        elif qk == "Displacement":
+            desc[new] = (V_ENTITY_DISP, DISP_COMP[qv.get("component", "Magnitude")], 0, 0)
         elif qk == "MemberDeflection":
             agg = (qv.get("aggregation") or {"type": "MaxAbs"}).get("type")
             if agg == "AtFraction":
@@ -408,7 +428,8 @@ def compile_check(model, definition: dict) -> CompiledCheck:
             combo_ids = {int(model.combo_ids[i]) for i, x in enumerate(ls) if x is None or x == definition["limit_state"]}
     return CompiledCheck(
         definition=definition, entities=[ref for ref, _ in ents], ent_ptr=ent_ptr, ent_members=ent_members,
-        ent_node_ptr=ent_node_ptr, ent_nodes=ent_nodes, frames=frames, var_names=[names[o] for o in order], var_desc=desc,
+        ent_node_ptr=ent_node_ptr, ent_nodes=ent_nodes, frames=frames, ent_ref=ent_ref,
+        var_names=[names[o] for o in order], var_desc=desc,
         code=np.array(code, np.int32).reshape(-1, 2), consts=np.array(consts, np.float64), ctab=np.ascontiguousarray(ctab),
         demand=demand, capacity=capacity, combo_ids=combo_ids, warnings=warnings)
 
@@ -444,6 +465,7 @@ class UnityAccumulator:
         self.lib = _lib.load()
         self.checks = [compile_check(model, d) for d in (model.unity_checks or [])]
         self.best = [np.full((len(c.entities), 4), [-np.inf, 0.0, 0.0, -1.0]) for c in self.checks]
+        self.trace = [np.zeros((len(c.entities), max(len(c.var_names), 1))) for c in self.checks]
         self._dev = {}
 
     def __bool__(self):
@@ -457,7 +479,8 @@ class UnityAccumulator:
                                  ent_node_ptr=t(c.ent_node_ptr), ent_nodes=t(c.ent_nodes if len(c.ent_nodes) else np.zeros(1, np.int32)),
                                  var_desc=t(c.var_desc if len(c.var_desc) else np.zeros((1, 4), np.int32)),
                                  code=t(c.code if len(c.code) else np.zeros((1, 2), np.int32)), consts=t(c.consts),
-                                 ctab=t(c.ctab), frames=t(c.frames))
+                                 ctab=t(c.ctab), frames=t(c.frames),
+                                 ent_ref=t(c.ent_ref if len(c.ent_ref) else np.full((1, 4), -1, np.int32)))
         return self._dev[ci]
 
     def accumulate(self, cols: list, d_xyz, d_u, rec: dict, stream: int) -> None:
@@ -479,29 +502,34 @@ class UnityAccumulator:
             T = self._tensors(ci)
             d_mask = torch.from_numpy(mask).to(self.dev)
             out = torch.empty((len(c.entities), 4), dtype=torch.float64, device=self.dev)
+            vars_out = torch.zeros((len(c.entities), max(len(c.var_names), 1)), dtype=torch.float64, device=self.dev)
             P = _lib.ptr
             _lib.check(self.lib.fers_b200_unity_generic(
                 len(c.entities), nr, len(c.var_desc), c.ctab.shape[1], P(d_mask), P(T["ent_ptr"]), P(T["ent_members"]),
                 P(T["ent_node_ptr"]), P(T["ent_nodes"]), P(T["var_desc"]), P(T["code"]), P(T["consts"]), P(T["ctab"]),
                 c.demand[0], c.demand[1], c.capacity[0], c.capacity[1], P(d_xyz), P(d_u), P(rec["f_local"]), P(rec["sec"]),
-                P(rec["lmax"]), P(rec["lmin"]), P(T["frames"]), P(out), stream), "unity_generic")
+                P(rec["lmax"]), P(rec["lmin"]), P(T["frames"]), P(T["ent_ref"]), P(out), P(vars_out), stream),
+                "unity_generic")
             got = out.cpu().numpy()
             have = got[:, 3] >= 0
             got[have, 3] = np.asarray(cols, np.float64)[got[have, 3].astype(np.int64)]     # batch column -> plan column
-            fold_envelope(self.best[ci], got)
+            taken = fold_envelope(self.best[ci], got)
+            self.trace[ci][taken] = vars_out.cpu().numpy()[taken]
 
     def results(self) -> list:
-        return [check_result(self.model, self.plan, c, b) for c, b in zip(self.checks, self.best)]
+        return [check_result(self.model, self.plan, c, b, t) for c, b, t in zip(self.checks, self.best, self.trace)]
 
 
-def fold_envelope(best: np.ndarray, got: np.ndarray) -> None:
-    """best[e] <- got[e] where got has a column and a larger utilisation (ties: lower plan column)."""
+def fold_envelope(best: np.ndarray, got: np.ndarray) -> np.ndarray:
+    """best[e] <- got[e] where got has a column and a larger utilisation (ties: lower plan column); returns the mask
+    of the entities that were replaced."""
     have = got[:, 3] >= 0
     none = best[:, 3] < 0
     bu, gu = best[:, 0], got[:, 0]
     better = (np.isnan(bu) & ~np.isnan(gu)) | (~np.isnan(gu) & ~np.isnan(bu) & ((gu > bu) | ((gu == bu) & (got[:, 3] < best[:, 3]))))
     take = have & (none | better)
     best[take] = got[take]
+    return take
 
 
 def _status(u: float, thresholds) -> str:
@@ -514,7 +542,26 @@ def _status(u: float, thresholds) -> str:
     return "Red"
 
 
-def check_result(model, plan, c: CompiledCheck, best: np.ndarray) -> dict:
+def _trace(c: CompiledCheck, values, u, dem, cap) -> list:
+    """CalcStep rows (pydantic_models.py:146-153): one per variable at the governing combination, then the verdict."""
+    g = c.definition["spec"]["Generic"]
+    src = {v["name"]: v["source"] for v in g.get("variables") or []}
+
+    def formula(name):
+        s_ = src.get(name, {})
+        if "Expression" in s_:
+            return str(s_["Expression"])
+        q = s_.get("Quantity") or {}
+        return next(iter(q), "")
+    steps = [{"label": n, "formula": formula(n), "substituted": "", "unit": "", "value": float(x)}
+             for n, x in zip(c.var_names, values)]
+    steps.append({"label": "Demand", "formula": str(g["demand"]), "substituted": "", "unit": "", "value": float(dem)})
+    steps.append({"label": "Capacity", "formula": str(g["capacity"]), "substituted": "", "unit": "", "value": float(cap)})
+    steps.append({"label": "Utilization", "formula": "Demand / Capacity", "substituted": "", "unit": "", "value": float(u)})
+    return steps
+
+
+def check_result(model, plan, c: CompiledCheck, best: np.ndarray, trace: np.ndarray | None = None) -> dict:
     d = c.definition
     base = {"check_id": str(d.get("id")), "name": str(d.get("name", d.get("id"))), "limit_state": d.get("limit_state")}
     if c.skipped is not None or not len(c.entities):
@@ -532,6 +579,7 @@ def check_result(model, plan, c: CompiledCheck, best: np.ndarray) -> dict:
         uu = float(u) if np.isfinite(u) else float("inf")
         per.append({"entity": ref, "demand": float(dem), "capacity": float(cap), "utilization": uu,
                     "status": _status(u, d.get("thresholds")), "governing_combination_id": int(plan.ids[int(col)]),
-                    "location_x_frac": None, "message": "; ".join(c.warnings) or None, "trace": []})
+                    "location_x_frac": None, "message": "; ".join(c.warnings) or None,
+                    "trace": _trace(c, trace[i], uu, dem, cap) if trace is not None else []})
     gov = max(per, key=lambda r: r["utilization"])
     return {**base, "max_utilization": gov["utilization"], "status": gov["status"], "governing": gov, "per_entity": per}

@@ -126,6 +126,8 @@ class ModelArrays:
     combo_limit_state: list = field(default_factory=list)      # per combination: "SLS" | "ULS" | ... | None
     m_classification: list = field(default_factory=list)       # per member: classification string or None
     m_section_raw: list = field(default_factory=list)          # per member: (section dict, material dict) or None
+    m_ref_member: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))   # [Nm] reference member index or -1
+    m_ref_node: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))     # [Nm] reference node index or -1
     # warping torsion (7th nodal DOF of the reference, pydantic_models.py:1384-1387): the warping DOF psi of a real
     # node lives in DOF 0 of an auxiliary node appended after the real ones (its other five DOFs are restrained)
     n_real_nodes: int = -1                                       # -1: no auxiliary nodes (n_nodes real nodes)
@@ -368,6 +370,17 @@ def parse_document(doc: dict) -> ModelArrays:
         if m.get("start_offset") or m.get("end_offset"):
             warnings.append(("W_OFFSET_IGNORED", f"member {m['id']}: end offsets not modelled"))
     rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), 12)
+    # Member.reference_member / reference_node (unity checks across members, fers_core/examples/101_...py:61-67)
+    m_ref_member = np.full(nm, -1, np.int32)
+    m_ref_node = np.full(nm, -1, np.int32)
+    for i, m in enumerate(members):
+        rm, rn = m.get("reference_member"), m.get("reference_node")
+        rm = rm.get("id") if isinstance(rm, dict) else rm
+        rn = rn.get("id") if isinstance(rn, dict) else rn
+        if rm is not None and int(rm) in member_index:
+            m_ref_member[i] = member_index[int(rm)]
+        if rn is not None and int(rn) in node_index:
+            m_ref_node[i] = node_index[int(rn)]
     member_sets = {}
     for ms in (model.get("member_sets") or []):
         idx = []
@@ -540,6 +553,7 @@ def parse_document(doc: dict) -> ModelArrays:
         unity_checks=list(analysis.get("unity_checks") or []),
         combo_limit_state=[c.get("limit_state") for c in combos],
         m_classification=m_classification, m_section_raw=m_section_raw,
+        m_ref_member=m_ref_member, m_ref_node=m_ref_node,
     )
 
 

@@ -286,14 +286,19 @@ int fers_b200_recover_plates(int n_plates, int nrhs, const double* xyz, const in
  * aggregation b (0 MaxAbs 1 Max 2 Min 3 Start 4 End 5 station c of 0, 1/4, 1/2, 3/4, 1); 2 postfix
  * program code[a .. a+b); 3 / 4 displacement / deflected position of the start (a = 0) or end node,
  * component b (6 = translation magnitude); 5 chord-relative deflection, component a (local y, local z,
- * magnitude), aggregation b.  code = (op, arg) pairs: 0 push consts[arg], 1 push variable arg, 2 + 3 -
+ * magnitude), aggregation b; 6 member force of the entity's REFERENCE member (ent_ref[e][0]); 7 largest |displacement
+ * component a| over the entity's nodes.  Node selector a of kinds 3 / 4: 0 start, 1 end, 2 / 3 start / end of the
+ * reference member, 4 reference node (ent_ref[n_ent][4] = reference member, its start node, its end node, reference
+ * node; -1 = none -> NaN).  vars_out[n_ent][n_vars] (or NULL) receives the variable values at the governing
+ * column (the calculation trace).  code = (op, arg) pairs: 0 push consts[arg], 1 push variable arg, 2 + 3 -
  * 4 * 5 / 6 pow 7 neg 8 abs 9 sqrt 10 min 11 max.  Result arrays in the layout of the recovery calls. */
 int fers_b200_unity_generic(int n_ent, int nrhs, int n_vars, int n_ct, const uint8_t* col_mask, const int* ent_ptr,
                             const int* ent_members, const int* ent_node_ptr, const int* ent_nodes,
                             const int* var_desc, const int* code, const double* consts, const double* ctab,
                             int demand_off, int demand_len, int cap_off, int cap_len, const double* xyz,
                             const double* u, const double* f_local, const double* sec, const double* lmax,
-                            const double* lmin, const double* frames, double* out, void* stream);
+                            const double* lmin, const double* frames, const int* ent_ref, double* out, double* vars_out,
+                            void* stream);
 /* axial[n_members][nrhs] = f_local[m][6][rhs] (tension +), used between P-Delta iterations. */
 int fers_b200_member_axial(int n_members, int nrhs, const double* f_local, double* axial, void* stream);
 

@@ -64,6 +64,9 @@ def _entities(model, sel):
         return [({"type": "Member", "member_id": int(i)}, [idx[int(i)]]) for i in sel["ids"]]
     if kind == "MemberSets":
         return [({"type": "MemberSet", "memberset_id": int(i)}, list(model.member_sets[int(i)])) for i in sel["ids"]]
+    if kind == "MemberClassification":
+        return [({"type": "Member", "member_id": int(model.m_ids[k])}, [k]) for k in range(model.n_members)
+                if model.m_classification[k] == sel["value"]]
     raise ValueError(kind)
 
 
@@ -128,6 +131,12 @@ def evaluate(model, res) -> list:
 
 def _quantity(model, res, c, members, nodes, q) -> float:
     (kind, v), = q.items()
+    if isinstance(v, dict) and v.get("of") == "ReferenceMember":
+        # the member the entity's first member points at (Member.reference_member, example 101)
+        rm = int(model.m_ref_member[members[0]])
+        if rm < 0:
+            return math.nan
+        members, nodes = [rm], [int(model.m_n1[rm]), int(model.m_n2[rm])]
     if kind == "Constant":
         return float(v)
     if kind == "DimensionedConstant":
@@ -155,8 +164,22 @@ def _quantity(model, res, c, members, nodes, q) -> float:
         hi = max(float(res.lmax[c, m, k]) for m in members)
         lo = min(float(res.lmin[c, m, k]) for m in members)
         return hi if t == "Max" else lo if t == "Min" else max(abs(hi), abs(lo))
+    if kind == "Displacement":
+        comp = v.get("component", "Magnitude")
+        if comp == "Magnitude":
+            return max(float(np.linalg.norm(res.U[c, n, :3])) for n in nodes)
+        return max(abs(float(res.U[c, n, DISP[comp]])) for n in nodes)
     if kind in ("NodeDisplacement", "NodePosition"):
-        node = nodes[0] if v["at"] == "Start" else nodes[-1]
+        at = v["at"]
+        if at in ("Start", "End"):
+            node = nodes[0] if at == "Start" else nodes[-1]
+        elif at == "ReferenceNode":
+            node = int(model.m_ref_node[members[0]])
+        else:
+            rm = int(model.m_ref_member[members[0]])
+            node = -1 if rm < 0 else int(model.m_n1[rm] if at == "ReferenceMemberStart" else model.m_n2[rm])
+        if node < 0:
+            return math.nan
         if kind == "NodePosition":
             a = "XYZ".index(v["axis"])
             return float(model.xyz[node, a] + res.U[c, node, a])

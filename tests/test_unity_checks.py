@@ -157,6 +157,72 @@ def test_unity_checks_match_oracle_and_example_100():
                 assert pe[k] == pytest.approx(pw[k], rel=1e-9, abs=1e-300), (cid, k)
 
 
+def _clearance_doc():
+    """Example 101 (fers_core/examples/101_Unity_Check_Reference_Member_Clearance.py:44-108): a loaded rail cantilever
+    that references the beam above it; one check composes quantities of both members."""
+    doc = copy.deepcopy(helpers.golden("cantilever_end_load")["doc"])
+    m = doc["model"]
+    m["nodes"] = [{"id": 1, "X": 0, "Y": 0.5, "Z": 0, "nodal_support": 1}, {"id": 2, "X": 4.0, "Y": 0.5, "Z": 0, "nodal_support": None},
+                  {"id": 3, "X": 0, "Y": 0.0, "Z": 0, "nodal_support": 1}, {"id": 4, "X": 4.0, "Y": 0.0, "Z": 0, "nodal_support": None}]
+    base = m["members"][0]
+    m["members"] = [dict(base, id=1, start_node_id=1, end_node_id=2, classification="Beam"),
+                    dict(base, id=2, start_node_id=3, end_node_id=4, classification="Rail", reference_member=1, reference_node=2)]
+    m["member_sets"] = [{"id": 1, "classification": "Beam", "member_ids": [1], "buckling_restraints": []},
+                        {"id": 2, "classification": "Rail", "member_ids": [2], "buckling_restraints": []}]
+    a = doc["analysis"]
+    a["options"]["order"] = "LINEAR"
+    a["load_cases"] = [dict(a["load_cases"][0], id=1, name="SLS", nodal_loads=[
+        {"id": 1, "node": 4, "magnitude": -3000.0, "direction": [0, 1, 0], "load_type": "force"},
+        {"id": 2, "node": 2, "magnitude": -100.0, "direction": [0, 1, 0], "load_type": "force"}])]
+    a["load_combinations"] = [{"id": 5, "name": "SLS-combo", "check": "ALL", "situation": "SLS",
+                               "load_case_factors": [{"load_case_id": 1, "factor": 1.0}]}]
+    q = lambda kind, **kw: {"Quantity": {kind: kw}}
+    a["unity_checks"] = [{
+        "id": "rail_clearance", "name": "Rail-to-beam vertical clearance", "applies_to": {"type": "MemberClassification", "value": "Rail"},
+        "spec": {"Generic": {"demand": "gap_min", "capacity": "y_ref - y_self", "variables": [
+            {"name": "y_self", "source": q("NodePosition", at="End", axis="Y")},
+            {"name": "y_ref", "source": q("NodePosition", at="ReferenceMemberEnd", axis="Y")},
+            {"name": "d_self", "source": q("NodeDisplacement", at="End", component="Dy")},
+            {"name": "d_ref", "source": q("NodeDisplacement", at="ReferenceMemberEnd", component="Dy")},
+            {"name": "d_node", "source": q("NodeDisplacement", at="ReferenceNode", component="Dy")},
+            {"name": "Lb", "source": q("Geometry", property="Length", of="ReferenceMember")},
+            {"name": "Vb", "source": q("MemberForce", component="Vy", aggregation={"type": "MaxAbs"}, of="ReferenceMember")},
+            {"name": "Ab", "source": q("Section", property="Area", of="ReferenceMember")},
+            {"name": "dmax", "source": q("Displacement", component="Magnitude")},
+            {"name": "gap_min", "source": {"Quantity": {"Constant": 0.40}}}]}}},
+        {"id": "no_ref", "name": "members without a reference", "applies_to": {"type": "Members", "ids": [1]},
+         "spec": {"Generic": {"demand": "abs(d)", "capacity": "1", "variables": [
+             {"name": "d", "source": q("NodeDisplacement", at="ReferenceMemberEnd", component="Dy")}]}}}]
+    return doc
+
+
+@pytest.mark.gpu
+def test_reference_member_quantities_and_trace():
+    import fers_calculations
+    from oracle import fers_oracle
+    doc = _clearance_doc()
+    out = json.loads(fers_calculations.calculate_from_json(json.dumps(doc)))["results"]
+    ucs = {u["check_id"]: u for u in out["unity_check_results"]}
+    gov = ucs["rail_clearance"]["governing"]
+    assert gov["entity"] == {"type": "Member", "member_id": 2}
+    tr = {s["label"]: s["value"] for s in gov["trace"]}
+    EI = 210e9 * 1.321e-5
+    assert tr["d_self"] == pytest.approx(-3000.0 * 4 ** 3 / (3 * EI), rel=1e-9)        # rail tip: P L^3 / 3 E I
+    assert tr["d_ref"] == pytest.approx(-100.0 * 4 ** 3 / (3 * EI), rel=1e-9) and tr["d_node"] == tr["d_ref"]
+    assert tr["y_self"] == pytest.approx(0.0 + tr["d_self"], rel=1e-12) and tr["y_ref"] == pytest.approx(0.5 + tr["d_ref"], rel=1e-12)
+    assert tr["Lb"] == 4.0 and tr["Vb"] == pytest.approx(100.0, rel=1e-9) and tr["Ab"] == 0.00196
+    assert tr["dmax"] == pytest.approx(abs(tr["d_self"]), rel=1e-9)
+    assert gov["utilization"] == pytest.approx(0.40 / (tr["y_ref"] - tr["y_self"]), rel=1e-12)
+    assert tr["Utilization"] == gov["utilization"]
+    lone = ucs["no_ref"]["per_entity"][0]
+    assert lone["status"] == "Red" and not math.isfinite(lone["utilization"])           # no reference member: NaN -> Red
+    model = wire.parse_document(doc)
+    want = unity_oracle.evaluate(model, fers_oracle.analyze(model))[0]
+    pe, pw = ucs["rail_clearance"]["per_entity"][0], want["per_entity"][0]
+    for k in ("utilization", "demand", "capacity"):
+        assert pe[k] == pytest.approx(pw[k], rel=1e-9)
+
+
 def _generic_only(model):
     model.unity_checks = [d for d in model.unity_checks if "Generic" in d["spec"]]
     return model
