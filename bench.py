@@ -34,6 +34,8 @@ if ROOT not in sys.path:
 METRIC = "solved_dof_x_load_combinations_per_second"
 UNIT = "DOF*combos/s"
 CPU_SAMPLE = (20, 20, 12)          # bays x bays x storeys of the bounded CPU sample (34 398 DOF)
+if os.environ.get("FERS_BENCH_CPU_SAMPLE"):      # tests shrink the sample (tests/test_bench_contract.py)
+    CPU_SAMPLE = tuple(int(v) for v in os.environ["FERS_BENCH_CPU_SAMPLE"].split(","))
 
 
 def parse_args():
