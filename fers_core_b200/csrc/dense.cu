@@ -192,6 +192,143 @@ __global__ void __launch_bounds__(NB* NB) k_subst_update(const double* __restric
     }
 }
 
+// ---- small matrices (n <= SMALL_MAX_N): one CTA factorises one matrix in a single launch ----------------
+// Right-looking with 32-column panels.  The panel (all rows below the diagonal tile x 32 columns) sits in
+// shared memory: diagonal tile factorised in place, one thread per row below solves its 32 entries against
+// it in registers, the panel is written back, and the trailing matrix (L2-resident, row-major) gets
+// A -= P P^T in 64x64 macro-tiles, a 4x4 micro-tile per thread.  configs[4]: 1 024 frames x 270 DOF.
+constexpr int SMALL_MAX_N = 512;
+constexpr int SMALL_THREADS = 256;
+
+__global__ void __launch_bounds__(SMALL_THREADS) k_chol_small(double* __restrict__ a_all, int n, int* __restrict__ info) {
+    extern __shared__ double ps[];                       // [n][NBP] panel
+    double* a = a_all + (size_t)blockIdx.x * n * n;
+    const int tid = threadIdx.x;
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = 0;
+    for (int j0 = 0; j0 < n; j0 += NB) {
+        const int nb = min(NB, n - j0), rows = n - j0;
+        for (int t = tid; t < rows * NB; t += SMALL_THREADS) {
+            const int r = t / NB, c = t - r * NB;
+            ps[r * NBP + c] = (c < nb && (r >= nb || c <= r)) ? a[(size_t)(j0 + r) * n + j0 + c] : 0.0;
+        }
+        __syncthreads();
+        // diagonal tile: thread (tr, c) owns rows tr, tr + 8, tr + 16, tr + 24 of column c
+        {
+            const int c = tid & 31, tr = tid >> 5;
+            for (int k = 0; k < nb; ++k) {
+                if (tid == 0) {
+                    double d = ps[k * NBP + k];
+                    if (!(d > 0.0)) { if (s_bad == 0) s_bad = j0 + k + 1; d = 1.0; }
+                    ps[k * NBP + k] = sqrt(d);
+                }
+                __syncthreads();
+                const double dk = ps[k * NBP + k];
+                if (c == k)
+                    for (int r = tr; r < nb; r += 8)
+                        if (r > k) ps[r * NBP + k] /= dk;
+                __syncthreads();
+                if (c > k && c < nb)
+                    for (int r = tr; r < nb; r += 8)
+                        if (r >= c) ps[r * NBP + c] -= ps[r * NBP + k] * ps[c * NBP + k];
+                __syncthreads();
+            }
+        }
+        // rows below: x L_jj^T = p, one thread per row, the row in registers
+        for (int r = nb + tid; r < rows; r += SMALL_THREADS) {
+            double x[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) x[c] = ps[r * NBP + c];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c < nb) {
+                    double v = x[c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) v = fma(-x[q], ps[c * NBP + q], v);
+                    x[c] = v / ps[c * NBP + c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c) ps[r * NBP + c] = x[c];
+        }
+        __syncthreads();
+        for (int t = tid; t < rows * NB; t += SMALL_THREADS) {
+            const int r = t / NB, c = t - r * NB;
+            if (c < nb && (r >= nb || c <= r)) a[(size_t)(j0 + r) * n + j0 + c] = ps[r * NBP + c];
+        }
+        // trailing update: rows / columns j0 + nb .. n - 1 (panel rows nb .. rows - 1), lower macro-tiles of 64 x 64
+        const int rem = rows - nb;
+        if (rem > 0) {
+            const int tx = tid & 15, ty = tid >> 4;
+            const int nt = (rem + 63) / 64;
+            for (int ti = 0; ti < nt; ++ti)
+                for (int tk = 0; tk <= ti; ++tk) {
+                    const int i0 = nb + 64 * ti + 4 * ty, k0 = nb + 64 * tk + 4 * tx;     // panel-row indices
+                    if (i0 >= rows || k0 >= rows || k0 > i0 + 3) continue;
+                    double acc[4][4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+                    for (int q = 0; q < nb; ++q) {
+                        double pi[4], pk[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            pi[u] = (i0 + u < rows) ? ps[(i0 + u) * NBP + q] : 0.0;
+                            pk[u] = (k0 + u < rows) ? ps[(k0 + u) * NBP + q] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) acc[u][v] = fma(pi[u], pk[v], acc[u][v]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            if (i0 + u < rows && k0 + v <= i0 + u) a[(size_t)(j0 + i0 + u) * n + j0 + k0 + v] -= acc[u][v];
+                }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && info != nullptr) info[blockIdx.x] = s_bad;
+}
+
+// single right-hand side, small matrices: one WARP per matrix.  Forward: row-oriented dot products (the row of
+// L is contiguous: coalesced, five shuffles per row); backward: x_k = y_k / L_kk, then y[0:k) -= L[k][0:k) x_k
+// (again along the contiguous row of L), x / y in the warp's shared-memory slice.
+constexpr int SOLVE1_WARPS = 8;
+__global__ void __launch_bounds__(32 * SOLVE1_WARPS) k_solve_small1(const double* __restrict__ a_all, double* __restrict__ bx_all,
+                                                                   int n, int batch) {
+    extern __shared__ double xs_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x * SOLVE1_WARPS + warp;
+    if (f >= batch) return;
+    double* xs = xs_all + (size_t)warp * n;
+    const double* a = a_all + (size_t)f * n * n;
+    double* bx = bx_all + (size_t)f * n;
+    for (int i = lane; i < n; i += 32) xs[i] = bx[i];
+    __syncwarp();
+    for (int i = 0; i < n; ++i) {
+        const double* row = a + (size_t)i * n;
+        double s = 0.0;
+        for (int k = lane; k < i; k += 32) s = fma(row[k], xs[k], s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
+        if (lane == 0) xs[i] = (xs[i] - s) / row[i];
+        __syncwarp();
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        const double* row = a + (size_t)k * n;
+        const double xk = xs[k] / row[k];
+        __syncwarp();
+        if (lane == 0) xs[k] = xk;
+        for (int i = lane; i < k; i += 32) xs[i] = fma(-row[i], xk, xs[i]);
+        __syncwarp();
+    }
+    for (int i = lane; i < n; i += 32) bx[i] = xs[i];
+}
+
 }  // namespace fers
 
 using namespace fers;
@@ -237,8 +374,19 @@ int fers_b200_dense_expand_batched(int nodes_per_frame, int batch, const int* ro
 int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* info_out, void* stream) {
     cudaStream_t st = as_stream(stream);
     FERS_REQUIRE(n > 0 && batch > 0, "dense_cholesky: empty problem");
-    FERS_REQUIRE(batch <= 65535, "dense_cholesky: batch exceeds gridDim.z");
+    FERS_REQUIRE(batch <= 65535 || n <= SMALL_MAX_N, "dense_cholesky: batch exceeds gridDim.z");
     if (info_dev) FERS_CK(cudaMemsetAsync(info_dev, 0, sizeof(int) * batch, st));
+    if (n <= SMALL_MAX_N) {                       // one CTA per matrix, one launch
+        const size_t smem = (size_t)n * NBP * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            FERS_CK(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)SMALL_MAX_N * NBP * sizeof(double))));
+            attr_set = true;
+        }
+        k_chol_small<<<batch, SMALL_THREADS, smem, st>>>(a, n, info_dev);
+        count_launches(1);
+    } else
     for (int j0 = 0; j0 < n; j0 += NB) {
         k_potrf_diag<<<dim3(1, 1, batch), NB * NB, 0, st>>>(a, n, j0, info_dev);
         count_launches(1);
@@ -261,6 +409,13 @@ int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* in
 int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* bx, void* stream) {
     cudaStream_t st = as_stream(stream);
     FERS_REQUIRE(n > 0 && nrhs > 0 && batch > 0, "dense_solve: empty problem");
+    if (nrhs == 1 && n <= 768) {                  // one warp per matrix (8 warps x n doubles of shared memory <= 48 KB)
+        k_solve_small1<<<(batch + SOLVE1_WARPS - 1) / SOLVE1_WARPS, 32 * SOLVE1_WARPS, (size_t)SOLVE1_WARPS * n * sizeof(double), st>>>(
+            a, bx, n, batch);
+        FERS_LAUNCH_CHECK();
+        count_launches(1);
+        return 0;
+    }
     const int nc = (nrhs + NB - 1) / NB;
     for (int j0 = 0; j0 < n; j0 += NB) {
         k_trsv_diag<<<dim3(nc, 1, batch), NB * NB, 0, st>>>(a, bx, n, nrhs, j0, 0);

@@ -273,13 +273,14 @@ def test_warping_sections_match_oracle(engine_mod, name):
     helpers.assert_results_close(got, want, 1e-7 if "hinge" in name else RTOL, label=name + "+warping")
 
 
-def test_dense_cholesky_batched(engine_mod):
-    """Batched dense factor/solve used for batches of small frames (configs[4])."""
+@pytest.mark.parametrize("batch,n,nrhs", [(5, 77, 3), (9, 270, 1), (3, 33, 1), (2, 512, 1), (2, 600, 2), (40, 64, 1)])
+def test_dense_cholesky_batched(engine_mod, batch, n, nrhs):
+    """Batched dense factor/solve used for batches of small frames (configs[4]): the single-launch small-matrix
+    kernel (n <= 512), the warp-per-matrix substitution (one right-hand side) and the tiled general path."""
     import torch
     from fers_core_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(0)
-    batch, n, nrhs = 5, 77, 3
     A = rng.normal(size=(batch, n, n)); A = A @ A.transpose(0, 2, 1) + n * np.eye(n)
     B = rng.normal(size=(batch, n, nrhs))
     dev = torch.device("cuda", 0)
@@ -293,6 +294,22 @@ def test_dense_cholesky_batched(engine_mod):
     X = dB.cpu().numpy()
     want = np.linalg.solve(A, B)
     assert np.abs(X - want).max() <= 1e-11 * np.abs(want).max()
+
+
+def test_dense_cholesky_reports_the_failing_minor(engine_mod):
+    import torch
+    from fers_core_b200 import _lib
+    lib = _lib.load()
+    n, batch = 50, 3
+    A = np.stack([np.eye(n) * 4.0] * batch)
+    A[1, 17, 17] = -1.0                                  # second matrix: leading minor 18 is not positive definite
+    dev = torch.device("cuda", 0)
+    dA = torch.from_numpy(A.copy()).to(dev)
+    info_dev = torch.zeros(batch, dtype=torch.int32, device=dev)
+    info = (C.c_int * batch)()
+    _lib.check(lib.fers_b200_dense_cholesky(n, batch, _lib.ptr(dA), _lib.ptr(info_dev), info,
+                                            torch.cuda.current_stream(dev).cuda_stream), "chol")
+    assert list(info) == [0, 18, 0]
 
 
 def test_frame_batch_pdelta_matches_per_frame_oracle(engine_mod):

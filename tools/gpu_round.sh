@@ -1,2 +1,3 @@
-set -x
-python -m pytest tests/test_unity_checks.py tests/test_abi_symbols.py -m gpu -x -q 2>&1 | tail -12
+python bench.py --workload cfg5 --steps 5 --warmup 3 > gpurun_out/r1p_bench_cfg5.json 2> gpurun_out/r1p_cfg5.err
+cut -c1-900 gpurun_out/r1p_bench_cfg5.json
+python bench.py --workload cfg5 --steps 5 --warmup 3 2>/dev/null | cut -c1-200
