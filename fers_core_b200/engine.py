@@ -18,7 +18,8 @@ import torch
 
 from . import _lib, chol, unity, wire
 from .hostlogic import (
-    INACTIVE_SCALE, imperfect_coordinates, pdelta_suppressed_axes, rhs_plan, rigid_property_row,
+    INACTIVE_SCALE, effective_bc, imperfect_coordinates, pdelta_suppressed_axes, rhs_plan, rigid_property_row,
+    unilateral_dofs, unilateral_update,
 )
 from .results import ResultArrays, SECTION_FRACS, results_to_wire
 
@@ -131,17 +132,17 @@ class Engine:
         self.has_rel = bool(np.any(m.m_rel >= 0))
         self.d_rel_idx = self._t(m.m_rel, np.int32) if self.has_rel else None
         self.d_rel = self._t(m.rel, np.float64) if self.has_rel else None
-        unilateral = np.isin(m.bc_code, (wire.BC_POS_ONLY, wire.BC_NEG_ONLY))
-        if unilateral.any():
-            m.warnings.append(("W_UNILATERAL_SUPPORT", "Positive/Negative-only supports treated as fixed"))
-        code = np.where(unilateral, wire.BC_FIXED, m.bc_code).astype(np.uint8)
-        self.has_springs = bool((code == wire.BC_SPRING).any())
+        # unilateral supports (PositiveOnly / NegativeOnly) start closed; engine._solve_nonlinear iterates their active set
+        self.n_unilateral = int(len(unilateral_dofs(m)[0]))
+        code, kk = effective_bc(m, np.ones(self.n_unilateral, bool))
+        code = code.astype(np.uint8)
+        self.has_springs = bool((code == wire.BC_SPRING).any()) or bool((unilateral_dofs(m)[2] > 0).any())
         self.d_bc_code = self._t(code.reshape(-1), np.uint8)
-        # nodes with all six DOFs restrained by supports: left out of the sparse factorisation
-        self.h_node_restrained = (code.reshape(-1, 6) == wire.BC_FIXED).all(axis=1)
+        self.d_bc_k = self._t(kk.reshape(-1), np.float64)
+        # nodes with all six DOFs restrained by PERMANENT supports: left out of the sparse factorisation
+        self.h_node_restrained = (m.bc_code.reshape(-1, 6) == wire.BC_FIXED).all(axis=1)
         if self.h_node_restrained.all():
             self.h_node_restrained = None
-        self.d_bc_k = self._t(m.bc_k.reshape(-1), np.float64)
         self.d_supported = self._t((m.node_support_id >= 0).astype(np.uint8), np.uint8)
         self.d_p_nodes = self._t(m.p_nodes, np.int32) if m.n_plates else None
         self.d_p_data = self._t(m.p_data, np.float64) if m.n_plates else None
@@ -214,6 +215,12 @@ class Engine:
         self._bc_ws = self._empty(self._bc_ws_bytes, torch.uint8)
 
     # ---- stages ----------------------------------------------------------------------------
+    def set_unilateral(self, active: np.ndarray) -> None:
+        """Support codes for the given active set of the unilateral supports (picked up by the next assemble())."""
+        code, kk = effective_bc(self.model, active)
+        self.d_bc_code = self._t(code.astype(np.uint8).reshape(-1), np.uint8)
+        self.d_bc_k = self._t(kk.reshape(-1), np.float64)
+
     def assemble(self, d_xyz, d_scale=None, d_axial=None, kg_mode=0, kg_suppress=0) -> None:
         """Element stiffness + assembly + boundary conditions for one geometry / state."""
         m, lib, st = self.model, self.lib, self.stream
@@ -496,7 +503,7 @@ def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_
         out.unity_xyz = eng.d_xyz0          # deflected positions are reported on the undeformed coordinates
         cols = list(grp.columns)
         fac = plan.factors[cols]
-        if not (second_order or unilateral.any()):
+        if not (second_order or unilateral.any() or eng.n_unilateral):
             f_case, peq_case = eng.load_cases(d_xyz)
             eng.assemble(d_xyz)
             for c0 in range(0, len(cols), 64):
@@ -537,7 +544,10 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
     total_it, conv, resn = 0, True, 0.0
     d_axial = None
     rec = None
-    for _outer in range(max(1, 2 * len(uni) + 2)):
+    sup_active = np.ones(eng.n_unilateral, bool)
+    for _outer in range(max(1, 2 * (len(uni) + eng.n_unilateral) + 2)):
+        if eng.n_unilateral:
+            eng.set_unilateral(sup_active)
         d_scale = eng._t(scale, np.float64) if len(uni) else None
         f_case, peq_case = eng.load_cases(d_xyz, d_scale)
         d_f = eng.combine(f_case, fac, nr)
@@ -563,7 +573,16 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
                 if resn < opts.tolerance:
                     conv = True
                     break
+        changed = False
+        if eng.n_unilateral:
+            # reactions of the current state decide which unilateral supports stay closed
+            r_now = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, d_scale, d_axial, kg_mode, sup, detail=False)["R"]
+            new_active = unilateral_update(model, sup_active, d_u[:, 0].cpu().numpy(), r_now[:, 0].cpu().numpy())
+            changed = not np.array_equal(new_active, sup_active)
+            sup_active = new_active
         if len(uni) == 0:
+            if changed:
+                continue
             break
         # elongation decides the active set
         u = d_u[:, 0].cpu().numpy().reshape(model.n_nodes, 6)
@@ -574,7 +593,7 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
         want = np.where(tens, elong >= 0.0, elong <= 0.0)
         new_scale = scale.copy()
         new_scale[uni] = np.where(want, 1.0, INACTIVE_SCALE)
-        if np.array_equal(new_scale, scale):
+        if np.array_equal(new_scale, scale) and not changed:
             break
         scale = new_scale
     d_scale = eng._t(scale, np.float64) if len(uni) else None

@@ -132,3 +132,39 @@ def pdelta_suppressed_axes(model: wire.ModelArrays) -> tuple:
         ext = np.ptp(model.xyz, axis=0)
         return (int(np.argmin(ext)),)
     return tuple("XYZ".index(a) for a in o.pdelta_suppress_axes if a in ("X", "Y", "Z"))
+
+
+# ---- unilateral supports (SupportConditionType PositiveOnly / NegativeOnly, fers_core/supports/supportcondition.py:25-32:
+#      "unilateral (contact-like) ... a spring active only in the allowed direction; if omitted ... an ideal unilateral
+#      constraint").  Convention used here (the engine that defines it is closed): a PositiveOnly support can only push
+#      the structure in the + direction of its DOF (reaction >= 0), i.e. it resists negative displacements and lets the
+#      node lift off in the + direction; NegativeOnly is the mirror image.
+def unilateral_dofs(model: wire.ModelArrays):
+    """(flat DOF indices, sign +1 / -1, spring stiffness or 0 for an ideal constraint)."""
+    code = model.bc_code.reshape(-1)
+    idx = np.nonzero(np.isin(code, (wire.BC_POS_ONLY, wire.BC_NEG_ONLY)))[0]
+    sign = np.where(code[idx] == wire.BC_POS_ONLY, 1.0, -1.0)
+    return idx, sign, model.bc_k.reshape(-1)[idx].copy()
+
+
+def effective_bc(model: wire.ModelArrays, active: np.ndarray):
+    """bc_code / bc_k with every unilateral DOF replaced by Fixed (ideal) or Spring (with stiffness) when it is active
+    and by Free when it is not."""
+    idx, _, k = unilateral_dofs(model)
+    code = model.bc_code.reshape(-1).copy()
+    kk = model.bc_k.reshape(-1).copy()
+    code[idx] = np.where(active, np.where(k > 0.0, wire.BC_SPRING, wire.BC_FIXED), wire.BC_FREE)
+    kk[idx] = np.where(active & (k > 0.0), k, 0.0)
+    return code.reshape(model.bc_code.shape), kk.reshape(model.bc_k.shape)
+
+
+def unilateral_update(model: wire.ModelArrays, active: np.ndarray, u: np.ndarray, r: np.ndarray) -> np.ndarray:
+    """Next active set from the displacements u and reactions r (force of the support on the structure) at all DOFs:
+    an active support stays while its reaction has the allowed sign, an inactive one closes when the node has moved
+    against it."""
+    idx, sign, k = unilateral_dofs(model)
+    uu, rr = u.reshape(-1)[idx] * sign, r.reshape(-1)[idx] * sign
+    tol_r = 1e-9 * max(float(np.abs(r).max()) if r.size else 0.0, 1e-300)
+    keep = np.where(k > 0.0, uu <= 0.0, rr >= -tol_r)
+    close = uu < 0.0
+    return np.where(active, keep, close)

@@ -277,6 +277,8 @@ def parse_document(doc: dict) -> ModelArrays:
                     else:
                         raise WireError(f"support {sid}.{name}: Spring without stiffness")
                 bc_k[i, d] = float(k)
+            elif ctype in (BC_POS_ONLY, BC_NEG_ONLY) and cond.get("stiffness"):
+                bc_k[i, d] = float(cond["stiffness"])        # unilateral spring (supportcondition.py:25-32)
     if opts.dimensionality == "2D":
         # out-of-plane DOFs restrained for every node (reference builders.py:108-110)
         for d in (2, 3, 4):

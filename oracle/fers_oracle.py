@@ -43,6 +43,7 @@ from fers_core_b200 import wire
 from fers_core_b200.results import ResultArrays, SECTION_FRACS
 from fers_core_b200.hostlogic import (
     rhs_plan, imperfect_coordinates, rigid_property_row, pdelta_suppressed_axes, INACTIVE_SCALE,
+    unilateral_dofs, effective_bc, unilateral_update,
 )
 
 GAUSS3_X = np.array([-np.sqrt(3.0 / 5.0), 0.0, np.sqrt(3.0 / 5.0)])
@@ -518,11 +519,12 @@ def load_vectors(asm: Assembly):
 # --------------------------------------------------------------------------------------
 # solve + recovery
 # --------------------------------------------------------------------------------------
-def constrain(K, model, extra_fixed=None):
-    """Add support springs, eliminate fixed DOFs. Returns (K_ff factor-ready csc, free idx)."""
+def constrain(K, model, extra_fixed=None, bc=None):
+    """Add support springs, eliminate fixed DOFs. Returns (K_ff factor-ready csc, free idx).
+    bc = (code, k) overrides the model's support codes (active set of the unilateral supports)."""
     nd = model.n_dof
-    code = model.bc_code.reshape(-1)
-    kspring = np.where(code == wire.BC_SPRING, model.bc_k.reshape(-1), 0.0)
+    code = (model.bc_code if bc is None else bc[0]).reshape(-1)
+    kspring = np.where(code == wire.BC_SPRING, (model.bc_k if bc is None else bc[1]).reshape(-1), 0.0)
     fixed = code == wire.BC_FIXED
     if extra_fixed is not None:
         fixed = fixed | extra_fixed
@@ -736,7 +738,7 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
         F = fac @ F_lc
         peq = np.einsum("rl,lmk->rmk", fac, peq_lc)
         cols = list(grp.columns)
-        needs_own = second_order or np.any(unilateral_members)
+        needs_own = second_order or np.any(unilateral_members) or len(unilateral_dofs(model)[0]) > 0
         if not needs_own:
             # ---- linear: one factorisation, all right-hand sides
             K = asm.K_elastic()
@@ -771,9 +773,12 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
     asm = asm0
     total_it, conv, resn = 0, True, 0.0
     suppressed = pdelta_suppressed_axes(model)
-    for _outer in range(max(1, 2 * len(uni) + 2)):
+    sup_idx = unilateral_dofs(model)[0]
+    sup_active = np.ones(len(sup_idx), bool)            # unilateral supports start closed
+    for _outer in range(max(1, 2 * (len(uni) + len(sup_idx)) + 2)):
+        bc = effective_bc(model, sup_active) if len(sup_idx) else None
         K0 = asm.K_elastic()
-        Kff, free, _ = constrain(K0, model)
+        Kff, free, _ = constrain(K0, model, bc=bc)
         U = np.zeros(nd); U[free] = solve_sym(Kff, F[free][:, None])[:, 0]
         kg = None
         K = K0
@@ -784,7 +789,7 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
                 kg = geometric_stiffness(N, asm.L, opts.pdelta_formulation, model.m_type)
                 kg = _suppress_kg(asm, kg, suppressed)
                 K = asm.K_elastic(kg)
-                Kff, free, _ = constrain(K, model)
+                Kff, free, _ = constrain(K, model, bc=bc)
                 Un = np.zeros(nd); Un[free] = solve_sym(Kff, F[free][:, None])[:, 0]
                 total_it += 1
                 den = np.linalg.norm(Un)
@@ -795,7 +800,14 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
                     break
             # geometric stiffness consistent with the converged displacement
             N = _axial_forces(asm, U, peq, kg)
+        changed = False
+        if len(sup_idx):
+            new_active = unilateral_update(model, sup_active, U, K @ U - F)
+            changed = not np.array_equal(new_active, sup_active)
+            sup_active = new_active
         if len(uni) == 0:
+            if changed:
+                continue
             break
         N = _axial_forces(asm, U, peq, kg)
         # elongation decides re-activation of inactive members
@@ -806,7 +818,7 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
         want_active = np.where(tens, elong >= 0.0, elong <= 0.0)
         new_scale = scale.copy()
         new_scale[uni] = np.where(want_active, 1.0, INACTIVE_SCALE)
-        if np.array_equal(new_scale, scale):
+        if np.array_equal(new_scale, scale) and not changed:
             break
         scale = new_scale
         asm = Assembly(model, asm0.xyz, scale)
