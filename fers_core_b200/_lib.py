@@ -69,7 +69,7 @@ SIGNATURES = {
     "fers_b200_chol_solve": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]),
     "fers_b200_residual": (_i, [C.c_longlong, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_unity_generic": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp,
-                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_chol_set_profile": (_i, [_i]),
     "fers_b200_chol_set_variant": (_i, [_i]),
     "fers_b200_chol_set_outer": (_i, [_i, _i]),

@@ -18,7 +18,7 @@
 namespace fers {
 
 enum UnityOp { U_PUSHC = 0, U_PUSHV, U_ADD, U_SUB, U_MUL, U_DIV, U_POW, U_NEG, U_ABS, U_SQRT, U_MIN, U_MAX };
-enum UnityVar { V_CONST = 0, V_FORCE, V_EXPR, V_NODE_DISP, V_NODE_POS, V_DEFLECTION, V_FORCE_REF, V_ENTITY_DISP };
+enum UnityVar { V_CONST = 0, V_FORCE, V_EXPR, V_NODE_DISP, V_NODE_POS, V_DEFLECTION, V_FORCE_REF, V_ENTITY_DISP, V_PLATE };
 enum UnityAgg { A_MAXABS = 0, A_MAX, A_MIN, A_START, A_END, A_STATION };
 
 constexpr int UNITY_MAX_VARS = 32;
@@ -43,6 +43,8 @@ struct UnityArgs {
     const double* lmax;          // [n_members][6][nrhs]
     const double* lmin;
     const double* frames;        // [n_ent][9] local axes of the entity's first member (deflection components)
+    const double* p_res;         // [n_plates][8][nrhs] plate resultants nx ny nxy mx my mxy qx qy (plate entities), or NULL
+    const double* p_data;        // [n_plates][4] thickness, E, nu, spare
     const int* ent_ref;          // [n_ent][4]: reference member, its start node, its end node, reference node (-1: none)
     double* out;                 // [n_ent][4]: utilisation, demand, capacity, column (as double; -1 none)
     double* vars_out;            // [n_ent][n_vars] variable values at the governing column, or NULL
@@ -138,6 +140,24 @@ __device__ void unity_eval_vars(const UnityArgs& A, int ent, int col, double* va
                 }
                 x = fmax(x, val);
             }
+        } else if (kind == V_PLATE) {                           // a = 0 von Mises, 1 largest principal, 2 smallest principal
+            // plate entities: ent_members lists the TRI3 rows of the plate; surface stresses sigma = n / t +- 6 m / t^2
+            // at the centroid of every row, both surfaces, enveloped (max for 0 and 1, min for 2)
+            double best = (a == 2) ? INFINITY : -INFINITY;
+            for (int q = mb; q < me && A.p_res != nullptr; ++q) {
+                const size_t e = A.ent_members[q];
+                const double t = A.p_data[e * 4];
+                const double* r = A.p_res + (e * 8) * (size_t)nr + col;
+                for (int side = -1; side <= 1; side += 2) {
+                    const double sx = r[0] / t + side * 6.0 * r[3 * (size_t)nr] / (t * t);
+                    const double sy = r[(size_t)nr] / t + side * 6.0 * r[4 * (size_t)nr] / (t * t);
+                    const double txy = r[2 * (size_t)nr] / t + side * 6.0 * r[5 * (size_t)nr] / (t * t);
+                    const double mean = 0.5 * (sx + sy), rad = sqrt(0.25 * (sx - sy) * (sx - sy) + txy * txy);
+                    const double val = a == 0 ? sqrt(sx * sx - sx * sy + sy * sy + 3.0 * txy * txy) : a == 1 ? mean + rad : mean - rad;
+                    best = (a == 2) ? fmin(best, val) : fmax(best, val);
+                }
+            }
+            x = isfinite(best) ? best : NAN;
         } else if (kind == V_DEFLECTION) {                      // a = 0 local y, 1 local z, 2 magnitude; b = aggregation
             // displacement of the entity's nodes relative to the chord between its end nodes
             const size_t n0 = A.ent_nodes[nb], n1 = A.ent_nodes[ne - 1];
@@ -220,8 +240,8 @@ extern "C" int fers_b200_unity_generic(int n_ent, int nrhs, int n_vars, int n_ct
                                        const int* var_desc, const int* code, const double* consts, const double* ctab,
                                        int demand_off, int demand_len, int cap_off, int cap_len, const double* xyz,
                                        const double* u, const double* f_local, const double* sec, const double* lmax,
-                                       const double* lmin, const double* frames, const int* ent_ref, double* out,
-                                       double* vars_out, void* stream) {
+                                       const double* lmin, const double* frames, const int* ent_ref, const double* p_res,
+                                       const double* p_data, double* out, double* vars_out, void* stream) {
     if (n_ent <= 0) return 0;
     FERS_REQUIRE(n_vars >= 0 && n_vars <= UNITY_MAX_VARS, "unity_generic: at most 32 variables per check");
     FERS_REQUIRE(col_mask && ent_ptr && ent_members && ent_node_ptr && ent_nodes && code && consts && ent_ref && out,
@@ -232,7 +252,8 @@ extern "C" int fers_b200_unity_generic(int n_ent, int nrhs, int n_vars, int n_ct
     A.ent_members = ent_members; A.ent_node_ptr = ent_node_ptr; A.ent_nodes = ent_nodes; A.var_desc = var_desc;
     A.code = code; A.consts = consts; A.ctab = ctab; A.demand_off = demand_off; A.demand_len = demand_len;
     A.cap_off = cap_off; A.cap_len = cap_len; A.xyz = xyz; A.U = u; A.f_local = f_local; A.sec = sec; A.lmax = lmax;
-    A.lmin = lmin; A.frames = frames; A.ent_ref = ent_ref; A.out = out; A.vars_out = vars_out;
+    A.lmin = lmin; A.frames = frames; A.ent_ref = ent_ref; A.p_res = p_res; A.p_data = p_data; A.out = out;
+    A.vars_out = vars_out;
     const long long threads = (long long)n_ent * 32;
     k_unity_generic<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(A);
     FERS_LAUNCH_CHECK();

@@ -22,7 +22,9 @@ Semantics where the closed engine is the only definition (stated, unpinned):
   * ``of: ReferenceMember`` / ``ReferenceMember*`` node references follow ``Member.reference_member`` /
     ``reference_node`` of the entity's first member (example 101); an entity without one evaluates to NaN;
   * ``Displacement`` = largest absolute value of the component over the entity's nodes.
-Ec3Steel checks and plate quantities are reported as not evaluated (status message).  Every entity result carries a
+  * plate entities (``AllPlates`` / ``PlateElements``): ``PlateStress`` = surface stress n/t +- 6m/t^2 at the element
+    centroid, both surfaces, enveloped; QUAD4 elements (two TRI3 rows) envelope both halves.
+Ec3Steel checks are reported as not evaluated (status message).  Every entity result carries a
 trace with the value of each variable at its governing combination.
 """
 from __future__ import annotations
@@ -35,7 +37,8 @@ import numpy as np
 from . import _lib
 
 OPS = {"PUSHC": 0, "PUSHV": 1, "+": 2, "-": 3, "*": 4, "/": 5, "^": 6, "NEG": 7, "abs": 8, "sqrt": 9, "min": 10, "max": 11}
-V_CONST, V_FORCE, V_EXPR, V_NODE_DISP, V_NODE_POS, V_DEFLECTION, V_FORCE_REF, V_ENTITY_DISP = range(8)
+V_CONST, V_FORCE, V_EXPR, V_NODE_DISP, V_NODE_POS, V_DEFLECTION, V_FORCE_REF, V_ENTITY_DISP, V_PLATE = range(9)
+PLATE_MEASURE = {"VonMises": 0, "PrincipalMax": 1, "PrincipalMin": 2}
 NODE_REF = {"Start": 0, "End": 1, "ReferenceMemberStart": 2, "ReferenceMemberEnd": 3, "ReferenceNode": 4}
 AGG = {"MaxAbs": 0, "Max": 1, "Min": 2, "Start": 3, "End": 4, "AtFraction": 5}
 FORCE_COMP = {"N": 0, "Vy": 1, "Vz": 2, "Mx": 3, "My": 4, "Mz": 5}
@@ -206,6 +209,7 @@ class CompiledCheck:
     capacity: tuple
     combo_ids: set | None              # applicable combination ids (None = all)
     skipped: str | None = None         # reason when the check is not evaluated
+    plates: bool = False               # entities are plate elements (ent_members = TRI3 rows)
     warnings: list = field(default_factory=list)
 
 
@@ -280,6 +284,15 @@ def _select_entities(model, sel: dict):
         want = sel.get("value")
         return [({"type": "Member", "member_id": int(model.m_ids[k])}, [k]) for k in range(model.n_members)
                 if model.m_classification[k] == want]
+    if kind in ("AllPlates", "PlateElements"):
+        rows_of = {}
+        for row, pid in enumerate(model.p_ids):
+            rows_of.setdefault(int(pid), []).append(row)
+        ids = list(rows_of) if kind == "AllPlates" else [int(i) for i in sel.get("ids") or []]
+        for i in ids:
+            if i not in rows_of:
+                raise UnityError(f"unity check: unknown plate element {i}")
+        return [({"type": "PlateElement", "plate_element_id": i}, rows_of[i]) for i in ids]
     raise UnityError(f"unity check: entity selector {kind!r} is not supported")
 
 
@@ -300,7 +313,11 @@ def compile_check(model, definition: dict) -> CompiledCheck:
         return CompiledCheck(definition=definition, skipped=str(e), **empty)
     ents = [(ref, ms) for ref, ms in ents if ms]
     n_ent = len(ents)
-    chains = [_chain(model, ms) for _, ms in ents]
+    plates = bool(ents) and ents[0][0]["type"] == "PlateElement"
+    if plates:      # "members" = TRI3 rows of the plate, nodes = its corner nodes
+        chains = [(ms, list(dict.fromkeys(int(n) for r in ms for n in model.p_nodes[r]))) for _, ms in ents]
+    else:
+        chains = [_chain(model, ms) for _, ms in ents]
     ent_ptr = np.zeros(n_ent + 1, np.int32)
     ent_node_ptr = np.zeros(n_ent + 1, np.int32)
     for i, (ms, ns) in enumerate(chains):
@@ -308,9 +325,10 @@ def compile_check(model, definition: dict) -> CompiledCheck:
         ent_node_ptr[i + 1] = ent_node_ptr[i] + len(ns)
     ent_members = np.array([m for ms, _ in chains for m in ms], np.int32)
     ent_nodes = np.array([n for _, ns in chains for n in ns], np.int32)
-    frames = np.array([_member_frame(model, ms[0]) for ms, _ in chains]).reshape(n_ent, 9)
+    frames = (np.zeros((n_ent, 9)) if plates else
+              np.array([_member_frame(model, ms[0]) for ms, _ in chains]).reshape(n_ent, 9))
     ent_ref = np.full((n_ent, 4), -1, np.int32)
-    for i, (ms, _) in enumerate(chains):
+    for i, (ms, _) in enumerate(chains if not plates else []):
         rm = int(model.m_ref_member[ms[0]]) if len(model.m_ref_member) else -1
         rn = int(model.m_ref_node[ms[0]]) if len(model.m_ref_node) else -1
         if rm >= 0:
@@ -340,6 +358,11 @@ def compile_check(model, definition: dict) -> CompiledCheck:
             continue
         q = src.get("Quantity") or {}
         (qk, qv), = q.items() if len(q) == 1 else [("?", None)]
+        if plates and qk not in ("Constant", "DimensionedConstant", "PlateStress", "Displacement"):
+            return CompiledCheck(definition=definition, skipped=f"quantity {qk!r} is not defined for plate entities", **empty)
+        if not plates and qk == "PlateStress":
+            return CompiledCheck(definition=definition, skipped="PlateStress needs a plate selector (AllPlates / PlateElements)",
+                                 **empty)
         of_ref = isinstance(qv, dict) and qv.get("of") not in (None, "SelfEntity")
         if of_ref and qv.get("of") != "ReferenceMember":
             raise UnityError(f"unity check {definition.get('id')}: unknown target {qv.get('of')!r}")
@@ -405,6 +428,10 @@ def compile_check(model, definition: dict) -> CompiledCheck:
                 desc[new] = (V_NODE_POS, NODE_REF[at], AXIS[qv.get("axis")], 0)
         elif qk == "Displacement":
             desc[new] = (V_ENTITY_DISP, DISP_COMP[qv.get("component", "Magnitude")], 0, 0)
+        elif qk == "PlateStress":
+            if qv.get("measure", "VonMises") not in PLATE_MEASURE:
+                raise UnityError(f"unity check {definition.get('id')}: unknown plate stress measure {qv.get('measure')!r}")
+            desc[new] = (V_PLATE, PLATE_MEASURE[qv.get("measure", "VonMises")], 0, 0)
         elif qk == "MemberDeflection":
             agg = (qv.get("aggregation") or {"type": "MaxAbs"}).get("type")
             if agg == "AtFraction":
@@ -428,7 +455,7 @@ def compile_check(model, definition: dict) -> CompiledCheck:
             combo_ids = {int(model.combo_ids[i]) for i, x in enumerate(ls) if x is None or x == definition["limit_state"]}
     return CompiledCheck(
         definition=definition, entities=[ref for ref, _ in ents], ent_ptr=ent_ptr, ent_members=ent_members,
-        ent_node_ptr=ent_node_ptr, ent_nodes=ent_nodes, frames=frames, ent_ref=ent_ref,
+        ent_node_ptr=ent_node_ptr, ent_nodes=ent_nodes, frames=frames, ent_ref=ent_ref, plates=plates,
         var_names=[names[o] for o in order], var_desc=desc,
         code=np.array(code, np.int32).reshape(-1, 2), consts=np.array(consts, np.float64), ctab=np.ascontiguousarray(ctab),
         demand=demand, capacity=capacity, combo_ids=combo_ids, warnings=warnings)
@@ -483,6 +510,13 @@ class UnityAccumulator:
                                  ent_ref=t(c.ent_ref if len(c.ent_ref) else np.full((1, 4), -1, np.int32)))
         return self._dev[ci]
 
+    def _p_data(self):
+        if self.model.n_plates == 0:
+            return None
+        if "p_data" not in self._dev:
+            self._dev["p_data"] = self.torch.from_numpy(np.ascontiguousarray(self.model.p_data, np.float64)).to(self.dev)
+        return self._dev["p_data"]
+
     def accumulate(self, cols: list, d_xyz, d_u, rec: dict, stream: int) -> None:
         """cols: plan column of each of the first len(cols) device columns of this batch."""
         torch = self.torch
@@ -496,9 +530,12 @@ class UnityAccumulator:
                     mask[j] = 1
             if not mask.any():
                 continue
-            for key in ("f_local", "sec", "lmax", "lmin"):
-                if key not in rec:
-                    raise UnityError("unity checks need the detailed member recovery (detail=True)")
+            if c.plates and "p_res" not in rec:
+                raise UnityError("plate unity checks need the plate recovery")
+            if not c.plates:
+                for key in ("f_local", "sec", "lmax", "lmin"):
+                    if key not in rec:
+                        raise UnityError("unity checks need the detailed member recovery (detail=True)")
             T = self._tensors(ci)
             d_mask = torch.from_numpy(mask).to(self.dev)
             out = torch.empty((len(c.entities), 4), dtype=torch.float64, device=self.dev)
@@ -507,8 +544,9 @@ class UnityAccumulator:
             _lib.check(self.lib.fers_b200_unity_generic(
                 len(c.entities), nr, len(c.var_desc), c.ctab.shape[1], P(d_mask), P(T["ent_ptr"]), P(T["ent_members"]),
                 P(T["ent_node_ptr"]), P(T["ent_nodes"]), P(T["var_desc"]), P(T["code"]), P(T["consts"]), P(T["ctab"]),
-                c.demand[0], c.demand[1], c.capacity[0], c.capacity[1], P(d_xyz), P(d_u), P(rec["f_local"]), P(rec["sec"]),
-                P(rec["lmax"]), P(rec["lmin"]), P(T["frames"]), P(T["ent_ref"]), P(out), P(vars_out), stream),
+                c.demand[0], c.demand[1], c.capacity[0], c.capacity[1], P(d_xyz), P(d_u), P(rec.get("f_local")),
+                P(rec.get("sec")), P(rec.get("lmax")), P(rec.get("lmin")), P(T["frames"]), P(T["ent_ref"]), P(rec.get("p_res")),
+                P(self._p_data()), P(out), P(vars_out), stream),
                 "unity_generic")
             got = out.cpu().numpy()
             have = got[:, 3] >= 0

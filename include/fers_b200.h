@@ -287,7 +287,9 @@ int fers_b200_recover_plates(int n_plates, int nrhs, const double* xyz, const in
  * program code[a .. a+b); 3 / 4 displacement / deflected position of the start (a = 0) or end node,
  * component b (6 = translation magnitude); 5 chord-relative deflection, component a (local y, local z,
  * magnitude), aggregation b; 6 member force of the entity's REFERENCE member (ent_ref[e][0]); 7 largest |displacement
- * component a| over the entity's nodes.  Node selector a of kinds 3 / 4: 0 start, 1 end, 2 / 3 start / end of the
+ * component a| over the entity's nodes; 8 plate stress at the centroid surfaces (a = 0 von Mises, 1 / 2 largest /
+ * smallest principal) of plate entities (ent_members = TRI3 rows, p_res / p_data as in fers_b200_recover_plates /
+ * fers_b200_assemble_plates; NULL without plates).  Node selector a of kinds 3 / 4: 0 start, 1 end, 2 / 3 start / end of the
  * reference member, 4 reference node (ent_ref[n_ent][4] = reference member, its start node, its end node, reference
  * node; -1 = none -> NaN).  vars_out[n_ent][n_vars] (or NULL) receives the variable values at the governing
  * column (the calculation trace).  code = (op, arg) pairs: 0 push consts[arg], 1 push variable arg, 2 + 3 -
@@ -297,8 +299,8 @@ int fers_b200_unity_generic(int n_ent, int nrhs, int n_vars, int n_ct, const uin
                             const int* var_desc, const int* code, const double* consts, const double* ctab,
                             int demand_off, int demand_len, int cap_off, int cap_len, const double* xyz,
                             const double* u, const double* f_local, const double* sec, const double* lmax,
-                            const double* lmin, const double* frames, const int* ent_ref, double* out, double* vars_out,
-                            void* stream);
+                            const double* lmin, const double* frames, const int* ent_ref, const double* p_res,
+                            const double* p_data, double* out, double* vars_out, void* stream);
 /* axial[n_members][nrhs] = f_local[m][6][rhs] (tension +), used between P-Delta iterations. */
 int fers_b200_member_axial(int n_members, int nrhs, const double* f_local, double* axial, void* stream);
 

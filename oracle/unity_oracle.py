@@ -67,6 +67,10 @@ def _entities(model, sel):
     if kind == "MemberClassification":
         return [({"type": "Member", "member_id": int(model.m_ids[k])}, [k]) for k in range(model.n_members)
                 if model.m_classification[k] == sel["value"]]
+    if kind in ("AllPlates", "PlateElements"):
+        ids = list(dict.fromkeys(int(i) for i in model.p_ids)) if kind == "AllPlates" else [int(i) for i in sel["ids"]]
+        return [({"type": "PlateElement", "plate_element_id": i}, [r for r, pid in enumerate(model.p_ids) if int(pid) == i])
+                for i in ids]
     raise ValueError(kind)
 
 
@@ -93,7 +97,10 @@ def evaluate(model, res) -> list:
             cols = [c for c in cols if ls[int(plan.ids[c])] in (None, d["limit_state"])]
         per = []
         for ref, members in _entities(model, d.get("applies_to") or {"type": "AllMembers"}):
-            nodes = _nodes_along(model, members)
+            if ref["type"] == "PlateElement":
+                nodes = list(dict.fromkeys(int(n) for r in members for n in model.p_nodes[r]))
+            else:
+                nodes = _nodes_along(model, members)
             best = None
             for c in cols:
                 env = {}
@@ -164,6 +171,18 @@ def _quantity(model, res, c, members, nodes, q) -> float:
         hi = max(float(res.lmax[c, m, k]) for m in members)
         lo = min(float(res.lmin[c, m, k]) for m in members)
         return hi if t == "Max" else lo if t == "Min" else max(abs(hi), abs(lo))
+    if kind == "PlateStress":
+        # surface stresses n / t +- 6 m / t^2 at the centroid of every TRI3 row of the plate, both surfaces
+        vals = []
+        for row in members:
+            nx, ny, nxy, mx, my, mxy = (float(x) for x in res.p_res[c, row, :6])
+            t = float(model.p_data[row, 0])
+            for side in (-1.0, 1.0):
+                sx, sy, txy = nx / t + side * 6 * mx / t**2, ny / t + side * 6 * my / t**2, nxy / t + side * 6 * mxy / t**2
+                mean, rad = 0.5 * (sx + sy), math.sqrt(0.25 * (sx - sy) ** 2 + txy ** 2)
+                vals.append({"VonMises": math.sqrt(sx * sx - sx * sy + sy * sy + 3 * txy * txy), "PrincipalMax": mean + rad,
+                             "PrincipalMin": mean - rad}[v.get("measure", "VonMises")])
+        return min(vals) if v.get("measure") == "PrincipalMin" else max(vals)
     if kind == "Displacement":
         comp = v.get("component", "Magnitude")
         if comp == "Magnitude":

@@ -223,6 +223,39 @@ def test_reference_member_quantities_and_trace():
         assert pe[k] == pytest.approx(pw[k], rel=1e-9)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["plate_strip_surface_load", "nafems_LE6_8x8"])
+def test_plate_stress_checks_match_oracle(name):
+    """PlateStress quantities on plate entities (all plates / listed plate elements) against the oracle."""
+    from fers_core_b200 import engine
+    from oracle import fers_oracle
+    doc = copy.deepcopy(helpers.golden(name)["doc"])
+    a = doc["analysis"]
+    lc_id = a["load_cases"][0]["id"]
+    a["load_combinations"] = [{"id": 3, "name": "C1", "check": "ALL", "load_case_factors": [{"load_case_id": lc_id, "factor": 1.0}]},
+                              {"id": 4, "name": "C2", "check": "ALL", "load_case_factors": [{"load_case_id": lc_id, "factor": -1.5}]}]
+    q = lambda kind, **kw: {"Quantity": {kind: kw}}
+    first = int(doc["model"]["plate_elements"][0]["id"])
+    a["unity_checks"] = [
+        {"id": "vm", "name": "von Mises", "applies_to": {"type": "AllPlates"},
+         "spec": {"Generic": {"demand": "s", "capacity": "fy / 1.1", "variables": [
+             {"name": "s", "source": q("PlateStress", measure="VonMises")}, {"name": "fy", "source": {"Quantity": {"Constant": 235e6}}}]}}},
+        {"id": "principal", "name": "principal range", "applies_to": {"type": "PlateElements", "ids": [first]},
+         "spec": {"Generic": {"demand": "max(abs(s1), abs(s2)) + 0 * d", "capacity": "235e6", "variables": [
+             {"name": "s1", "source": q("PlateStress", measure="PrincipalMax")},
+             {"name": "s2", "source": q("PlateStress", measure="PrincipalMin")},
+             {"name": "d", "source": q("Displacement", component="Magnitude")}]}}}]
+    model = wire.parse_document(doc)
+    got = engine.analyze(wire.parse_document(doc)).unity.results()
+    want = unity_oracle.evaluate(model, fers_oracle.analyze(model))
+    assert len(got[0]["per_entity"]) == len({int(i) for i in model.p_ids}) and len(got[1]["per_entity"]) == 1
+    for g, w in zip(got, want):
+        assert g["max_utilization"] > 0
+        for pe, pw in zip(g["per_entity"], w["per_entity"]):
+            assert pe["entity"] == pw["entity"] and pe["governing_combination_id"] == pw["governing_combination_id"]
+            assert pe["utilization"] == pytest.approx(pw["utilization"], rel=1e-8)
+
+
 def _generic_only(model):
     model.unity_checks = [d for d in model.unity_checks if "Generic" in d["spec"]]
     return model
