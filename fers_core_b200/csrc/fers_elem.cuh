@@ -366,6 +366,25 @@ FERS_HD void span_point_resultant(const Frame& f, const double* row, double x, d
 }
 
 // ---- TRI3 shell: CST membrane + DSG3 Mindlin bending --------
+// Per-plate record (NPDATA doubles): thickness, E, nu, then the stiffness modifiers of PlateElement.stiffness_modifiers
+// (membrane, bending, shear; pydantic_models.py:801-807).  flags: bit0 membrane, bit1 bending, bit2 plane strain
+// (PlateElement.plane_state, 1712-1715: in-plane constitutive law of the membrane part).
+enum { PD_T = 0, PD_E = 1, PD_NU = 2, PD_MODM = 3, PD_MODB = 4, PD_MODS = 5, NPDATA = 8 };
+
+// in-plane constitutive matrix: plane stress, or plane strain when asked for (membrane part only)
+FERS_HD void plate_D(double E, double nu, bool plane_strain, double D[3][3]) {
+    double d11, d12, d33;
+    if (plane_strain) {
+        const double f = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
+        d11 = f * (1.0 - nu); d12 = f * nu; d33 = f * (1.0 - 2.0 * nu) / 2.0;
+    } else {
+        const double f = E / (1.0 - nu * nu);
+        d11 = f; d12 = f * nu; d33 = f * (1.0 - nu) / 2.0;
+    }
+    D[0][0] = d11; D[0][1] = d12; D[0][2] = 0.0;
+    D[1][0] = d12; D[1][1] = d11; D[1][2] = 0.0;
+    D[2][0] = 0.0; D[2][1] = 0.0; D[2][2] = d33;
+}
 struct PlateGeom {
     double r[3][3];     // rows = local x, y, z
     double xl[3][2];    // local corner coordinates (corner 0 at origin)
@@ -433,22 +452,23 @@ FERS_HD void plate_B(const PlateGeom& g, double Bm[3][18], double Bb[3][18], dou
     }
 }
 
-// 18x18 local stiffness (row-major).  data = thickness, E, nu ; flags bit0 membrane bit1 bending.
+// 18x18 local stiffness (row-major).  data = plate record (NPDATA doubles); flags bit0 membrane bit1 bending bit2 plane strain.
 FERS_HD void plate_local_k(const PlateGeom& g, const double* data, int flags, double* k /*324*/) {
     double Bm[3][18], Bb[3][18], Bs[2][18];
     plate_B(g, Bm, Bb, Bs);
-    double t = data[0], E = data[1], nu = data[2];
+    double t = data[PD_T], E = data[PD_E], nu = data[PD_NU];
     double A = fabs(g.A);
-    double dm = E / (1.0 - nu * nu);
-    double D[3][3] = {{dm, dm * nu, 0.0}, {dm * nu, dm, 0.0}, {0.0, 0.0, dm * (1.0 - nu) / 2.0}};
-    double cm = (flags & 1) ? t * A : 0.0;
-    double cb = (flags & 2) ? A * t * t * t / 12.0 : 0.0;
-    double cs = (flags & 2) ? A * (5.0 / 6.0) * (E / (2.0 * (1.0 + nu))) * t : 0.0;
+    double Dm[3][3], D[3][3];
+    plate_D(E, nu, (flags & 4) != 0, Dm);
+    plate_D(E, nu, false, D);
+    double cm = (flags & 1) ? data[PD_MODM] * t * A : 0.0;
+    double cb = (flags & 2) ? data[PD_MODB] * A * t * t * t / 12.0 : 0.0;
+    double cs = (flags & 2) ? data[PD_MODS] * A * (5.0 / 6.0) * (E / (2.0 * (1.0 + nu))) * t : 0.0;
     for (int i = 0; i < 18; ++i)
         for (int j = 0; j < 18; ++j) {
             double sm = 0.0, sb = 0.0;
             for (int a = 0; a < 3; ++a) {
-                double dmj = D[a][0] * Bm[0][j] + D[a][1] * Bm[1][j] + D[a][2] * Bm[2][j];
+                double dmj = Dm[a][0] * Bm[0][j] + Dm[a][1] * Bm[1][j] + Dm[a][2] * Bm[2][j];
                 double dbj = D[a][0] * Bb[0][j] + D[a][1] * Bb[1][j] + D[a][2] * Bb[2][j];
                 sm += Bm[a][i] * dmj;
                 sb += Bb[a][i] * dbj;

@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_plates(int n_plates, in
     const int e = blockIdx.x * REC_WARPS + warp;
     if (e >= n_plates) return;
     const int nd[3] = {pn[3 * e], pn[3 * e + 1], pn[3 * e + 2]};
-    const double t = pdata[4 * (size_t)e], E = pdata[4 * (size_t)e + 1], nu = pdata[4 * (size_t)e + 2];
+    const double* pd = pdata + NPDATA * (size_t)e;
+    const double t = pd[PD_T], E = pd[PD_E], nu = pd[PD_NU];
     const int flags = pflags[e];
     if (lane == 0) {
         double p0[3] = {xyz[3 * nd[0]], xyz[3 * nd[0] + 1], xyz[3 * nd[0] + 2]};
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_plates(int n_plates, in
         double p2[3] = {xyz[3 * nd[2]], xyz[3 * nd[2] + 1], xyz[3 * nd[2] + 2]};
         PlateGeom g = plate_geom(p0, p1, p2);
         double kl[324];
-        plate_local_k(g, pdata + 4 * (size_t)e, flags, kl);
+        plate_local_k(g, pd, flags, kl);
         double blk[36];
         for (int bi = 0; bi < 3; ++bi)
             for (int bj = 0; bj < 3; ++bj) {
@@ -274,11 +275,12 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_plates(int n_plates, in
         for (int i = 0; i < 9; ++i) s_r[warp][i] = g.r[i / 3][i % 3];
     }
     __syncwarp();
-    const double dm = E / (1.0 - nu * nu);
-    const double D[3][3] = {{dm, dm * nu, 0.0}, {dm * nu, dm, 0.0}, {0.0, 0.0, dm * (1.0 - nu) / 2.0}};
-    const double cm = (flags & 1) ? t : 0.0;
-    const double cb = (flags & 2) ? -t * t * t / 12.0 : 0.0;
-    const double cs = (flags & 2) ? (5.0 / 6.0) * (E / (2.0 * (1.0 + nu))) * t : 0.0;
+    double Dm[3][3], D[3][3];
+    plate_D(E, nu, (flags & 4) != 0, Dm);       // membrane: plane stress or plane strain
+    plate_D(E, nu, false, D);                   // bending: plate theory (plane stress)
+    const double cm = (flags & 1) ? pd[PD_MODM] * t : 0.0;
+    const double cb = (flags & 2) ? -pd[PD_MODB] * t * t * t / 12.0 : 0.0;
+    const double cs = (flags & 2) ? pd[PD_MODS] * (5.0 / 6.0) * (E / (2.0 * (1.0 + nu))) * t : 0.0;
     for (int col = lane; col < nrhs; col += 32) {
         double ug[18], ul[18];
         for (int n = 0; n < 3; ++n)
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_plates(int n_plates, in
         }
         double out[8];
         for (int i = 0; i < 3; ++i) {
-            out[i] = cm * (D[i][0] * st[0] + D[i][1] * st[1] + D[i][2] * st[2]);
+            out[i] = cm * (Dm[i][0] * st[0] + Dm[i][1] * st[1] + Dm[i][2] * st[2]);
             out[3 + i] = cb * (D[i][0] * st[3] + D[i][1] * st[4] + D[i][2] * st[5]);
         }
         out[6] = cs * st[6];

@@ -44,7 +44,7 @@ struct UnityArgs {
     const double* lmin;
     const double* frames;        // [n_ent][9] local axes of the entity's first member (deflection components)
     const double* p_res;         // [n_plates][8][nrhs] plate resultants nx ny nxy mx my mxy qx qy (plate entities), or NULL
-    const double* p_data;        // [n_plates][4] thickness, E, nu, spare
+    const double* p_data;        // [n_plates][NPDATA] plate records (thickness first)
     const int* ent_ref;          // [n_ent][4]: reference member, its start node, its end node, reference node (-1: none)
     double* out;                 // [n_ent][4]: utilisation, demand, capacity, column (as double; -1 none)
     double* vars_out;            // [n_ent][n_vars] variable values at the governing column, or NULL
@@ -146,7 +146,7 @@ __device__ void unity_eval_vars(const UnityArgs& A, int ent, int col, double* va
             double best = (a == 2) ? INFINITY : -INFINITY;
             for (int q = mb; q < me && A.p_res != nullptr; ++q) {
                 const size_t e = A.ent_members[q];
-                const double t = A.p_data[e * 4];
+                const double t = A.p_data[e * NPDATA + PD_T];
                 const double* r = A.p_res + (e * 8) * (size_t)nr + col;
                 for (int side = -1; side <= 1; side += 2) {
                     const double sx = r[0] / t + side * 6.0 * r[3 * (size_t)nr] / (t * t);

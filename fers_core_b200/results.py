@@ -127,7 +127,7 @@ def results_to_wire(model, res: ResultArrays) -> dict:
                 "converged": bool(res.converged[col]),
                 "iterations": None if res.iterations[col] < 0 else int(res.iterations[col]),
                 "residual_norm": None if res.iterations[col] < 0 else float(res.residual[col]),
-                "solve_time_ms": None,
+                "solve_time_ms": None if res.solve_ms is None else float(res.solve_ms),
             },
         }
         if model.n_plates:

@@ -36,6 +36,7 @@ DOF_NAMES = ("X", "Y", "Z", "RX", "RY", "RZ")
 # columns of the per-section property table (one row per distinct section x option set)
 P_EA, P_EIY, P_EIZ, P_GJ, P_GASY, P_GASZ, P_WPL, P_SPARE = range(8)
 NPROP = 8
+NPDATA = 8          # doubles per plate record (csrc/fers_elem.cuh PD_*)
 # local release order = local DOF order [u v w rx ry rz]
 _HINGE_FIELDS = (
     "translational_release_vx", "translational_release_vy", "translational_release_vz",
@@ -111,8 +112,8 @@ class ModelArrays:
     # plates (TRI3): node indices, thickness, E, nu, behaviour code
     p_ids: np.ndarray             # int64 [Npl]
     p_nodes: np.ndarray           # int32 [Npl,3]
-    p_data: np.ndarray            # f64   [Npl,4]  thickness, E, nu, spare
-    p_flags: np.ndarray           # int32 [Npl]    bit0 membrane, bit1 bending
+    p_data: np.ndarray            # f64   [Npl,8]  thickness, E, nu, modifiers (membrane, bending, shear), 2 spare
+    p_flags: np.ndarray           # int32 [Npl]    bit0 membrane, bit1 bending, bit2 plane strain
     load_cases: list              # [LoadCaseArrays]
     combo_ids: np.ndarray         # int64 [Nc]
     combo_names: list
@@ -404,6 +405,15 @@ def parse_document(doc: dict) -> ModelArrays:
         nu = E / (2.0 * G) - 1.0
         beh = _norm_enum(p.get("behavior") or "Shell")
         flags = {"shell": 3, "membrane": 1, "plate": 2, "bending": 2}.get(beh, 3)
+        if _norm_enum(p.get("plane_state") or "PlaneStress") == "planestrain":
+            flags |= 4
+        sm = p.get("stiffness_modifiers") or {}
+        mods = [1.0 if sm.get(k) is None else float(sm[k]) for k in ("membrane", "bending", "shear")]
+        for key, code in (("offset", "W_PLATE_OFFSET_IGNORED"), ("local_x_direction", "W_PLATE_LOCAL_X_IGNORED")):
+            if p.get(key):
+                warnings.append((code, f"plate {p['id']}: {key} not modelled"))
+        if mat.get("orthotropic_plate"):
+            warnings.append(("W_ORTHOTROPIC_IGNORED", f"plate {p['id']}: orthotropic plate material treated as isotropic"))
         tris = [nids] if len(nids) == 3 else [[nids[0], nids[1], nids[2]], [nids[0], nids[2], nids[3]]]
         if len(nids) == 4:
             warnings.append(("W_QUAD_SPLIT", f"plate {p['id']}: QUAD4 split into two TRI3"))
@@ -413,11 +423,11 @@ def parse_document(doc: dict) -> ModelArrays:
             except KeyError as e:
                 raise WireError(f"plate {p['id']}: unknown node {e}") from None
             p_ids_l.append(int(p["id"]))
-            p_data_l.append([float(p["thickness"]), E, nu, 0.0])
+            p_data_l.append([float(p["thickness"]), E, nu, mods[0], mods[1], mods[2], 0.0, 0.0])
             p_flags_l.append(flags)
     p_ids = np.array(p_ids_l, np.int64)
     p_nodes = np.array(p_nodes_l, np.int32).reshape(len(p_ids_l), 3)
-    p_data = np.array(p_data_l, np.float64).reshape(len(p_ids_l), 4)
+    p_data = np.array(p_data_l, np.float64).reshape(len(p_ids_l), NPDATA)
     p_flags = np.array(p_flags_l, np.int32)
     plate_index = {}
     for i, pid in enumerate(p_ids_l):
@@ -493,7 +503,13 @@ def parse_document(doc: dict) -> ModelArrays:
                 sid_ = int(tgt["surface_id"])
                 ids += [i for i, p in enumerate(plates_flat_surface(plates, p_ids_l)) if p == sid_]
             for i in ids:
-                pp_plate.append(i); pp_vec.append(float(pp["magnitude"]) * d)
+                w = 1.0
+                if pp.get("projected"):      # pressure on the area projected onto `direction` (e.g. snow, 1733-1736)
+                    x3 = xyz[p_nodes[i]]
+                    nrm = np.cross(x3[1] - x3[0], x3[2] - x3[0])
+                    dn = np.linalg.norm(d)
+                    w = abs(float(nrm @ d)) / (np.linalg.norm(nrm) * dn) if dn > 0 else 0.0
+                pp_plate.append(i); pp_vec.append(w * float(pp["magnitude"]) * d)
         for sl in (c.get("surface_loads") or []):
             _surface_load_to_plates(sl, xyz, p_nodes, pp_plate, pp_vec, warnings)
         lca.nod_node = np.array(nod_node, np.int32)

@@ -222,7 +222,7 @@ def plate_frame(x3):
     return np.stack([ex, ey, ez])
 
 
-def plate_local_matrices(xl, t, E, nu, flags):
+def plate_local_matrices(xl, t, E, nu, flags, mods=(1.0, 1.0, 1.0)):
     """18x18 local stiffness of a TRI3 shell, plus (Bm, Bb, Bs, Dm, Db, Ds, area).
 
     Local DOFs per node [u v w rx ry rz]; DSG3 uses (w, bx, by) with bx = +ry, by = -rx
@@ -242,7 +242,11 @@ def plate_local_matrices(xl, t, E, nu, flags):
     Bm[2, 0::2] = cc
     Bm[2, 1::2] = bb
     Bm /= twoA
-    Dm = E / (1.0 - nu * nu) * np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]])
+    if flags & 4:      # plane strain (PlateElement.plane_state, pydantic_models.py:1712-1715)
+        Dm = E / ((1 + nu) * (1 - 2 * nu)) * np.array([[1 - nu, nu, 0], [nu, 1 - nu, 0], [0, 0, (1 - 2 * nu) / 2]])
+    else:
+        Dm = E / (1.0 - nu * nu) * np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]])
+    Dm = mods[0] * Dm                                  # PlateElement.stiffness_modifiers (801-807)
     mdof = np.array([0, 1, 6, 7, 12, 13])
     if flags & 1:
         km = t * abs(A) * Bm.T @ Dm @ Bm
@@ -253,9 +257,9 @@ def plate_local_matrices(xl, t, E, nu, flags):
                    [0, d_ - a_, b_ - c_, 0, -d_, c_, 0, a_, -b_]]) / twoA
     Bs = np.array([[b_ - c_, A, 0, c_, a_ * c_ / 2, b_ * c_ / 2, -b_, -b_ * d_ / 2, -b_ * c_ / 2],
                    [d_ - a_, 0, A, -d_, -a_ * d_ / 2, -b_ * d_ / 2, a_, a_ * d_ / 2, a_ * c_ / 2]]) / twoA
-    Db = E * t**3 / (12.0 * (1.0 - nu * nu)) * np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]])
+    Db = mods[1] * E * t**3 / (12.0 * (1.0 - nu * nu)) * np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]])
     G = E / (2.0 * (1.0 + nu))
-    Ds = (5.0 / 6.0) * G * t * np.eye(2)
+    Ds = mods[2] * (5.0 / 6.0) * G * t * np.eye(2)
     if flags & 2:
         kb = abs(A) * (Bb.T @ Db @ Bb + Bs.T @ Ds @ Bs)
         # map (w, bx, by) -> (w, rx, ry): bx = ry, by = -rx
@@ -279,8 +283,8 @@ def plate_stiffness_global(model, xyz):
         x3 = xyz[model.p_nodes[e]]
         R = plate_frame(x3)
         xl = (x3 - x3[0]) @ R.T
-        t, E, nu, _ = model.p_data[e]
-        k, mats = plate_local_matrices(xl[:, :2], t, E, nu, int(model.p_flags[e]))
+        t, E, nu = model.p_data[e, :3]
+        k, mats = plate_local_matrices(xl[:, :2], t, E, nu, int(model.p_flags[e]), tuple(model.p_data[e, 3:6]))
         T = np.zeros((18, 18))
         for b in range(6):
             T[3 * b:3 * b + 3, 3 * b:3 * b + 3] = R

@@ -99,7 +99,7 @@ def test_beam_equivalent_loads_and_span(elem_host, case):
         bc_k=np.zeros((2, 6)), m_ids=np.array([1]), m_n1=np.array([0], np.int32), m_n2=np.array([1], np.int32),
         m_type=np.array([mtype], np.int32), m_roll=np.array([roll]), m_prop=np.array([0], np.int32),
         m_rel=np.array([-1], np.int32), prop=P[None, :].copy(), prop_rho_a=np.zeros(1), rel=np.zeros((0, 12)),
-        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 4)),
+        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 8)),
         p_flags=np.zeros(0, np.int32), load_cases=[], combo_ids=np.zeros(0, np.int64), combo_names=[],
         combo_factors=np.zeros((0, 0)), imperfections=[], member_sets={}, options=wire.Options())
     lc = wire.LoadCaseArrays(id=1, name="x")
@@ -127,11 +127,14 @@ def test_plate_global_stiffness(elem_host):
             p[:, 2] = 0.3           # XY-plane plate: local = global (every pinned case)
         if t == 4:
             p[:, 0] = 1.0           # normal along X: alternate reference branch
-        data = np.array([0.02, 210e9, 0.3, 0.0])
-        for flags in (1, 2, 3):
+        # plate record: thickness, E, nu, stiffness modifiers (membrane, bending, shear), 2 spare
+        data = np.array([0.02, 210e9, 0.3, 1.0, 1.0, 1.0, 0.0, 0.0])
+        if t % 3 == 1:
+            data[3:6] = (0.35, 0.6, 1.7)
+        for flags in (1, 2, 3, 5, 7):           # bit2 = plane strain
             R = fo.plate_frame(p)
             xl = (p - p[0]) @ R.T
-            k, _ = fo.plate_local_matrices(xl[:, :2], data[0], data[1], data[2], flags)
+            k, _ = fo.plate_local_matrices(xl[:, :2], data[0], data[1], data[2], flags, tuple(data[3:6]))
             T = np.zeros((18, 18))
             for bq in range(6):
                 T[3 * bq:3 * bq + 3, 3 * bq:3 * bq + 3] = R

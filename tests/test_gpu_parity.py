@@ -273,6 +273,25 @@ def test_warping_sections_match_oracle(engine_mod, name):
     helpers.assert_results_close(got, want, 1e-7 if "hinge" in name else RTOL, label=name + "+warping")
 
 
+@pytest.mark.parametrize("name", ["plate_strip_surface_load", "nafems_LE1_24x4"])
+def test_plate_modifiers_and_plane_strain_match_oracle(engine_mod, name):
+    """PlateElement.stiffness_modifiers and plane_state = PlaneStrain on the GPU path against the oracle."""
+    import copy
+    doc = copy.deepcopy(helpers.golden(name)["doc"])
+    for i, pl in enumerate(doc["model"]["plate_elements"]):
+        if i % 2 == 0:
+            pl["stiffness_modifiers"] = {"membrane": 0.6, "bending": 0.35, "shear": 1.4}
+        if i % 3 == 0:
+            pl["plane_state"] = "PlaneStrain"
+    model = wire.parse_document(doc)
+    assert (model.p_flags & 4).any() and (model.p_data[:, 3] != 1.0).any()
+    want = fers_oracle.analyze(model)
+    base = fers_oracle.analyze(wire.parse_document(helpers.golden(name)["doc"]))
+    assert np.abs(want.U - base.U).max() > 1e-3 * np.abs(base.U).max()        # the options do change the answer
+    got = engine_mod.analyze(wire.parse_document(doc))
+    helpers.assert_results_close(got, want, RTOL, label=name + "+plate options")
+
+
 @pytest.mark.parametrize("batch,n,nrhs", [(5, 77, 3), (9, 270, 1), (3, 33, 1), (2, 512, 1), (2, 600, 2), (40, 64, 1)])
 def test_dense_cholesky_batched(engine_mod, batch, n, nrhs):
     """Batched dense factor/solve used for batches of small frames (configs[4]): the single-launch small-matrix

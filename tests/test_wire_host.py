@@ -123,6 +123,37 @@ def test_plate_documents_split_quads_and_resolve_pressures():
     assert len(lc.pp_plate) > 0 and lc.pp_vec.shape == (len(lc.pp_plate), 3)
     le6 = wire.parse_document(_doc("nafems_LE6_8x8"))
     assert le6.n_plates == 2 * 8 * 8 and (le6.p_flags != 0).all()
+    assert le6.p_data.shape == (le6.n_plates, wire.NPDATA) and (le6.p_data[:, 3:6] == 1.0).all()
+
+
+def test_plate_options_modifiers_plane_strain_projected_pressure():
+    d = _doc("plate_strip_surface_load")
+    pl = d["model"]["plate_elements"][0]
+    pl["stiffness_modifiers"] = {"membrane": 0.5, "bending": 0.25, "shear": None}
+    pl["plane_state"] = "PlaneStrain"
+    m = wire.parse_document(d)
+    rows = np.nonzero(m.p_ids == int(pl["id"]))[0]
+    assert all(m.p_data[r, 3:6].tolist() == [0.5, 0.25, 1.0] and m.p_flags[r] & 4 for r in rows)
+    others = np.nonzero(m.p_ids != int(pl["id"]))[0]
+    assert (m.p_data[others, 3:6] == 1.0).all() and not (m.p_flags[others] & 4).any()
+    # projected pressure: force scales with |n . d|; the strip lies in a coordinate plane, so an oblique direction at
+    # 60 degrees from the normal halves the load of the same magnitude
+    base = wire.parse_document(_doc("plate_strip_surface_load")).load_cases[0]
+    d2 = _doc("plate_strip_surface_load")
+    lc = d2["analysis"]["load_cases"][0]
+    if lc.get("plate_pressures"):
+        x3 = m.xyz[m.p_nodes[0]]
+        n = np.cross(x3[1] - x3[0], x3[2] - x3[0]); n /= np.linalg.norm(n)
+        tang = (x3[1] - x3[0]) / np.linalg.norm(x3[1] - x3[0])
+        direction = 0.5 * n + np.sqrt(0.75) * tang
+        for pp in lc["plate_pressures"]:
+            pp["direction"] = direction.tolist(); pp["projected"] = True
+        proj = wire.parse_document(d2).load_cases[0]
+        for pp in lc["plate_pressures"]:
+            pp["projected"] = False
+        full = wire.parse_document(d2).load_cases[0]
+        np.testing.assert_allclose(proj.pp_vec, 0.5 * full.pp_vec, rtol=1e-12)
+        assert len(base.pp_plate) == len(full.pp_plate)
 
 
 def test_warping_sections_get_auxiliary_nodes():

@@ -1,1 +1,1 @@
-python -m pytest tests/test_unity_checks.py -m gpu -x -q 2>&1 | tail -8
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6
