@@ -236,6 +236,8 @@ def parse_document(doc: dict) -> ModelArrays:
     node_ids = np.fromiter((int(n["id"]) for n in nodes), np.int64, nn)
     xyz = np.array([[float(n["X"]), float(n["Y"]), float(n["Z"])] for n in nodes], np.float64).reshape(nn, 3)
     node_index = _index_map(node_ids, "node")
+    if not np.isfinite(xyz).all():
+        raise WireError(f"node {int(node_ids[np.nonzero(~np.isfinite(xyz).all(axis=1))[0][0]])}: non-finite coordinate")
 
     # ---- supports (pydantic_models.py:2104-2115; default all-Fixed nodalsupport.py:29-41) --
     supports = {int(s["id"]): s for s in (model.get("nodal_supports") or [])}
@@ -304,6 +306,9 @@ def parse_document(doc: dict) -> ModelArrays:
         sec_raw[sid] = (s, mat)
         E, G = float(mat["e_mod"]), float(mat["g_mod"])
         A, Iy, Iz, J = float(s["area"]), float(s["i_y"]), float(s["i_z"]), float(s["j"])
+        for what, v in (("e_mod", E), ("g_mod", G), ("area", A), ("i_y", Iy), ("i_z", Iz), ("j", J)):
+            if not (np.isfinite(v) and v > 0.0):          # PositiveFloat in the schema (pydantic_models.py:1052-1114, 1497-1504)
+                raise WireError(f"section {sid}: {what} must be a positive number, got {v!r}")
         asy = s.get("a_sy") if opts.include_shear_deformation else None
         asz = s.get("a_sz") if opts.include_shear_deformation else None
         eiw = E * float(s["i_w"]) if (opts.include_warping and s.get("i_w")) else 0.0
@@ -373,6 +378,10 @@ def parse_document(doc: dict) -> ModelArrays:
         if m.get("start_offset") or m.get("end_offset"):
             warnings.append(("W_OFFSET_IGNORED", f"member {m['id']}: end offsets not modelled"))
     rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), 12)
+    if nm:
+        length = np.linalg.norm(xyz[m_n2] - xyz[m_n1], axis=1)
+        if (length <= 0.0).any():
+            raise WireError(f"member {int(m_ids[np.nonzero(length <= 0.0)[0][0]])}: zero length (start and end node coincide)")
     # Member.reference_member / reference_node (unity checks across members, fers_core/examples/101_...py:61-67)
     m_ref_member = np.full(nm, -1, np.int32)
     m_ref_node = np.full(nm, -1, np.int32)
@@ -403,6 +412,9 @@ def parse_document(doc: dict) -> ModelArrays:
             raise WireError(f"plate {p['id']}: unknown material")
         E, G = float(mat["e_mod"]), float(mat["g_mod"])
         nu = E / (2.0 * G) - 1.0
+        th = float(p["thickness"])
+        if not (np.isfinite([E, G, th]).all() and E > 0.0 and G > 0.0 and th > 0.0):
+            raise WireError(f"plate {p['id']}: e_mod, g_mod and thickness must be positive numbers")
         beh = _norm_enum(p.get("behavior") or "Shell")
         flags = {"shell": 3, "membrane": 1, "plate": 2, "bending": 2}.get(beh, 3)
         if _norm_enum(p.get("plane_state") or "PlaneStress") == "planestrain":
@@ -429,6 +441,11 @@ def parse_document(doc: dict) -> ModelArrays:
     p_nodes = np.array(p_nodes_l, np.int32).reshape(len(p_ids_l), 3)
     p_data = np.array(p_data_l, np.float64).reshape(len(p_ids_l), NPDATA)
     p_flags = np.array(p_flags_l, np.int32)
+    if len(p_ids):
+        x3 = xyz[p_nodes]
+        area2 = np.linalg.norm(np.cross(x3[:, 1] - x3[:, 0], x3[:, 2] - x3[:, 0]), axis=1)
+        if (area2 <= 0.0).any():
+            raise WireError(f"plate {int(p_ids[np.nonzero(area2 <= 0.0)[0][0]])}: degenerate element (zero area)")
     plate_index = {}
     for i, pid in enumerate(p_ids_l):
         plate_index.setdefault(pid, []).append(i)
@@ -520,6 +537,9 @@ def parse_document(doc: dict) -> ModelArrays:
         lca.pl_data = np.array(pl_data, np.float64).reshape(len(pl_member), 8)
         lca.pp_plate = np.array(pp_plate, np.int32)
         lca.pp_vec = np.array(pp_vec, np.float64).reshape(len(pp_plate), 3)
+        for arr in (lca.nod_vec, lca.dl_data, lca.pl_data, lca.pp_vec):
+            if not np.isfinite(arr).all():
+                raise WireError(f"load case {lca.id}: non-finite load value")
         load_cases.append(lca)
 
     # ---- combinations (pydantic_models.py:491-505) --------------------------------------

@@ -37,6 +37,11 @@ def test_minimal_document_arrays():
     (lambda d: d["model"]["sections"][0].update(material=9), "material"),
     (lambda d: d["model"]["members"][0].update(start_hinge=3), "hinge"),
     (lambda d: d["model"]["nodal_supports"][0]["X"].update(condition_type="Spring", stiffness=None), "stiffness"),
+    (lambda d: d["model"]["nodes"][1].update(X=0.0, Y=0.0, Z=0.0), "zero length"),
+    (lambda d: d["model"]["nodes"][1].update(X=float("nan")), "non-finite coordinate"),
+    (lambda d: d["model"]["materials"][0].update(e_mod=-1.0), "e_mod must be a positive"),
+    (lambda d: d["model"]["sections"][0].update(i_z=0.0), "i_z must be a positive"),
+    (lambda d: d["analysis"]["load_cases"][0]["nodal_loads"][0].update(magnitude=float("inf")), "non-finite load"),
 ])
 def test_malformed_documents_raise(mutate, msg):
     d = _doc()
@@ -154,6 +159,18 @@ def test_plate_options_modifiers_plane_strain_projected_pressure():
         full = wire.parse_document(d2).load_cases[0]
         np.testing.assert_allclose(proj.pp_vec, 0.5 * full.pp_vec, rtol=1e-12)
         assert len(base.pp_plate) == len(full.pp_plate)
+
+
+def test_degenerate_plates_raise():
+    d = _doc("plate_strip_surface_load")
+    pl = d["model"]["plate_elements"][0]
+    pl["node_ids"] = [pl["node_ids"][0], pl["node_ids"][1], pl["node_ids"][0]]
+    with pytest.raises(wire.WireError, match="degenerate"):
+        wire.parse_document(d)
+    d = _doc("plate_strip_surface_load")
+    d["model"]["plate_elements"][0]["thickness"] = 0.0
+    with pytest.raises(wire.WireError, match="thickness"):
+        wire.parse_document(d)
 
 
 def test_warping_sections_get_auxiliary_nodes():
