@@ -27,8 +27,15 @@ const char* fers_b200_version(void) { return "fers_b200 0.1.0 (sm_100a, abi 1)";
 const char* fers_b200_last_error(void) { return fers::g_error.c_str(); }
 
 int fers_b200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
-    cudaDeviceProp p;
-    FERS_CK(cudaGetDeviceProperties(&p, device));
+    // cudaGetDeviceProperties costs milliseconds: query once per device (an Engine is built per analysis)
+    static cudaDeviceProp cache[64];
+    static bool have[64] = {false};
+    FERS_REQUIRE(device >= 0 && device < 64, "device_info: device index out of range");
+    if (!have[device]) {
+        FERS_CK(cudaGetDeviceProperties(&cache[device], device));
+        have[device] = true;
+    }
+    const cudaDeviceProp& p = cache[device];
     if (sm_count) *sm_count = p.multiProcessorCount;
     if (cc_major) *cc_major = p.major;
     if (cc_minor) *cc_minor = p.minor;

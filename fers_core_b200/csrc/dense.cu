@@ -193,70 +193,81 @@ __global__ void __launch_bounds__(NB* NB) k_subst_update(const double* __restric
 }
 
 // ---- small matrices (n <= SMALL_MAX_N): one CTA factorises one matrix in a single launch ----------------
-// Right-looking with 32-column panels.  The panel (all rows below the diagonal tile x 32 columns) sits in
-// shared memory: diagonal tile factorised in place, one thread per row below solves its 32 entries against
-// it in registers, the panel is written back, and the trailing matrix (L2-resident, row-major) gets
-// A -= P P^T in 64x64 macro-tiles, a 4x4 micro-tile per thread.  configs[4]: 1 024 frames x 270 DOF.
+// Right-looking with 32-column panels.  The panel (all rows from the diagonal tile down x 32 columns) sits in
+// shared memory TRANSPOSED (pT[c][r], rows contiguous, zero-padded to whole 64-row macro-tiles) so that every
+// access of the three phases is conflict-free and the trailing update can use unguarded 16-byte loads:
+//   diagonal tile   one warp, lane = row, the row in registers, column broadcasts by shuffle (no barriers);
+//   rows below      one thread per row solves its 32 entries against the tile (reciprocal diagonal from the
+//                   tile phase: no divisions);
+//   trailing matrix (L2-resident, row-major) A -= P P^T in 64x64 macro-tiles, a 4x4 micro-tile per thread,
+//                   four 16-byte shared loads per 16 DFMA.
+// configs[4]: 1 024 frames x 270 DOF -- the kernel is instruction-issue bound (ncu, profiles/r1q_*).
 constexpr int SMALL_MAX_N = 512;
 constexpr int SMALL_THREADS = 256;
 
-__global__ void __launch_bounds__(SMALL_THREADS) k_chol_small(double* __restrict__ a_all, int n, int* __restrict__ info) {
-    extern __shared__ double ps[];                       // [n][NBP] panel
+// padded panel rows: 32 + whole 64-row macro-tiles + 2 (16-byte aligned columns, stride == 2 mod 16); a template
+// parameter so that every shared-memory address of the unrolled phases is an immediate offset
+template <int MAXN> struct SmallLdp { static constexpr int value = NB + ((MAXN - NB + 63) / 64) * 64 + 2; };
+
+template <int LDP>
+__global__ void __launch_bounds__(SMALL_THREADS, 2) k_chol_small(double* __restrict__ a_all, int n, int* __restrict__ info) {
+    extern __shared__ __align__(16) double pT[];         // [NB][LDP] transposed panel, then rinv[NB]
+    double* rinv = pT + NB * LDP;
     double* a = a_all + (size_t)blockIdx.x * n * n;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool even = (n & 1) == 0;
     __shared__ int s_bad;
     if (tid == 0) s_bad = 0;
     for (int j0 = 0; j0 < n; j0 += NB) {
         const int nb = min(NB, n - j0), rows = n - j0;
-        for (int t = tid; t < rows * NB; t += SMALL_THREADS) {
-            const int r = t / NB, c = t - r * NB;
-            ps[r * NBP + c] = (c < nb && (r >= nb || c <= r)) ? a[(size_t)(j0 + r) * n + j0 + c] : 0.0;
+        const int used = NB + ((max(rows - NB, 0) + 63) / 64) * 64;      // rows the trailing update may read
+        // panel -> shared (coalesced along the 32 columns of a row; padding rows and the tile's upper triangle = 0)
+        for (int r = warp; r < used; r += SMALL_THREADS / 32) {
+            double v = 0.0;
+            if (r < rows && lane < nb && (r >= nb || lane <= r)) v = a[(size_t)(j0 + r) * n + j0 + lane];
+            pT[lane * LDP + r] = v;
         }
         __syncthreads();
-        // diagonal tile: thread (tr, c) owns rows tr, tr + 8, tr + 16, tr + 24 of column c
-        {
-            const int c = tid & 31, tr = tid >> 5;
-            for (int k = 0; k < nb; ++k) {
-                if (tid == 0) {
-                    double d = ps[k * NBP + k];
-                    if (!(d > 0.0)) { if (s_bad == 0) s_bad = j0 + k + 1; d = 1.0; }
-                    ps[k * NBP + k] = sqrt(d);
+        if (warp == 0) {                                  // diagonal tile, left-looking, lane = row
+            for (int k = 0; k < NB; ++k) {
+                double s = pT[k * LDP + lane];
+#pragma unroll 4
+                for (int q = 0; q < k; ++q) s = fma(-pT[q * LDP + lane], pT[q * LDP + k], s);
+                double skk = __shfl_sync(FULL, s, k);
+                double rd = 0.0;
+                if (k < nb) {
+                    if (!(skk > 0.0)) {
+                        if (lane == 0 && s_bad == 0) s_bad = j0 + k + 1;
+                        skk = 1.0;
+                    }
+                    rd = rsqrt(skk);
                 }
-                __syncthreads();
-                const double dk = ps[k * NBP + k];
-                if (c == k)
-                    for (int r = tr; r < nb; r += 8)
-                        if (r > k) ps[r * NBP + k] /= dk;
-                __syncthreads();
-                if (c > k && c < nb)
-                    for (int r = tr; r < nb; r += 8)
-                        if (r >= c) ps[r * NBP + c] -= ps[r * NBP + k] * ps[c * NBP + k];
-                __syncthreads();
+                pT[k * LDP + lane] = (lane == k) ? skk * rd : (lane > k ? s * rd : 0.0);
+                if (lane == k) rinv[k] = rd;              // columns past nb: zero
+                __syncwarp();
             }
         }
+        __syncthreads();
         // rows below: x L_jj^T = p, one thread per row, the row in registers
         for (int r = nb + tid; r < rows; r += SMALL_THREADS) {
             double x[NB];
 #pragma unroll
-            for (int c = 0; c < NB; ++c) x[c] = ps[r * NBP + c];
+            for (int c = 0; c < NB; ++c) x[c] = pT[c * LDP + r];
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
-                if (c < nb) {
-                    double v = x[c];
+                double v = x[c];
 #pragma unroll
-                    for (int q = 0; q < c; ++q) v = fma(-x[q], ps[c * NBP + q], v);
-                    x[c] = v / ps[c * NBP + c];
-                }
+                for (int q = 0; q < c; ++q) v = fma(-x[q], pT[q * LDP + c], v);
+                x[c] = v * rinv[c];
             }
 #pragma unroll
-            for (int c = 0; c < NB; ++c) ps[r * NBP + c] = x[c];
+            for (int c = 0; c < NB; ++c) pT[c * LDP + r] = x[c];
         }
         __syncthreads();
-        for (int t = tid; t < rows * NB; t += SMALL_THREADS) {
-            const int r = t / NB, c = t - r * NB;
-            if (c < nb && (r >= nb || c <= r)) a[(size_t)(j0 + r) * n + j0 + c] = ps[r * NBP + c];
-        }
-        // trailing update: rows / columns j0 + nb .. n - 1 (panel rows nb .. rows - 1), lower macro-tiles of 64 x 64
+        for (int r = warp; r < rows; r += SMALL_THREADS / 32)
+            if (lane < nb && (r >= nb || lane <= r)) a[(size_t)(j0 + r) * n + j0 + lane] = pT[lane * LDP + r];
+        // trailing update: rows / columns j0 + nb .. n - 1 (panel rows nb .. rows - 1), lower macro-tiles of 64 x 64;
+        // the C micro-tile is fetched before the product so that its L2 latency hides behind the 512 DFMA
         const int rem = rows - nb;
         if (rem > 0) {
             const int tx = tid & 15, ty = tid >> 4;
@@ -265,28 +276,46 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_chol_small(double* __restrict
                 for (int tk = 0; tk <= ti; ++tk) {
                     const int i0 = nb + 64 * ti + 4 * ty, k0 = nb + 64 * tk + 4 * tx;     // panel-row indices
                     if (i0 >= rows || k0 >= rows || k0 > i0 + 3) continue;
+                    const bool full = even && i0 + 3 < rows && k0 + 3 <= i0;             // whole 4x4 inside the triangle
+                    double* cp = a + (size_t)(j0 + i0) * n + j0 + k0;
+                    double2 c0[4][2];
+                    if (full) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            c0[u][0] = *reinterpret_cast<const double2*>(cp + (size_t)u * n);
+                            c0[u][1] = *reinterpret_cast<const double2*>(cp + (size_t)u * n + 2);
+                        }
+                    }
                     double acc[4][4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
 #pragma unroll
                         for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-                    for (int q = 0; q < nb; ++q) {
-                        double pi[4], pk[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            pi[u] = (i0 + u < rows) ? ps[(i0 + u) * NBP + q] : 0.0;
-                            pk[u] = (k0 + u < rows) ? ps[(k0 + u) * NBP + q] : 0.0;
-                        }
+#pragma unroll 8
+                    for (int q = 0; q < NB; ++q) {
+                        const double2 pa = *reinterpret_cast<const double2*>(pT + q * LDP + i0);
+                        const double2 pb = *reinterpret_cast<const double2*>(pT + q * LDP + i0 + 2);
+                        const double2 ka = *reinterpret_cast<const double2*>(pT + q * LDP + k0);
+                        const double2 kb = *reinterpret_cast<const double2*>(pT + q * LDP + k0 + 2);
+                        const double pi[4] = {pa.x, pa.y, pb.x, pb.y}, pk[4] = {ka.x, ka.y, kb.x, kb.y};
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
 #pragma unroll
                             for (int v = 0; v < 4; ++v) acc[u][v] = fma(pi[u], pk[v], acc[u][v]);
                     }
+                    if (full) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                        for (int u = 0; u < 4; ++u) {
+                            *reinterpret_cast<double2*>(cp + (size_t)u * n) = make_double2(c0[u][0].x - acc[u][0], c0[u][0].y - acc[u][1]);
+                            *reinterpret_cast<double2*>(cp + (size_t)u * n + 2) = make_double2(c0[u][1].x - acc[u][2], c0[u][1].y - acc[u][3]);
+                        }
+                    } else {
 #pragma unroll
-                        for (int v = 0; v < 4; ++v)
-                            if (i0 + u < rows && k0 + v <= i0 + u) a[(size_t)(j0 + i0 + u) * n + j0 + k0 + v] -= acc[u][v];
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int v = 0; v < 4; ++v)
+                                if (i0 + u < rows && k0 + v <= i0 + u) cp[(size_t)u * n + v] -= acc[u][v];
+                    }
                 }
         }
         __syncthreads();
@@ -294,39 +323,82 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_chol_small(double* __restrict
     if (tid == 0 && info != nullptr) info[blockIdx.x] = s_bad;
 }
 
-// single right-hand side, small matrices: one WARP per matrix.  Forward: row-oriented dot products (the row of
-// L is contiguous: coalesced, five shuffles per row); backward: x_k = y_k / L_kk, then y[0:k) -= L[k][0:k) x_k
-// (again along the contiguous row of L), x / y in the warp's shared-memory slice.
-constexpr int SOLVE1_WARPS = 8;
-__global__ void __launch_bounds__(32 * SOLVE1_WARPS) k_solve_small1(const double* __restrict__ a_all, double* __restrict__ bx_all,
-                                                                   int n, int batch) {
-    extern __shared__ double xs_all[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.x * SOLVE1_WARPS + warp;
+template <int MAXN>
+static int launch_chol_small(double* a, int n, int batch, int* info_dev, cudaStream_t st) {
+    constexpr int LDP = SmallLdp<MAXN>::value;
+    constexpr size_t smem = ((size_t)NB * LDP + NB) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        FERS_CK(cudaFuncSetAttribute(k_chol_small<LDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_chol_small<LDP><<<batch, SMALL_THREADS, smem, st>>>(a, n, info_dev);
+    return 0;
+}
+
+// single right-hand side, small matrices: one CTA per matrix, blocked by 32 rows.  Per block the diagonal tile
+// goes to shared memory and one warp substitutes through it (lane = row, shuffles, reciprocal diagonal); the other
+// rows (forward) / columns (backward) are then updated by one thread each with 32 independent loads of L.
+constexpr int SOLVE1_THREADS = 256;
+__global__ void __launch_bounds__(SOLVE1_THREADS) k_solve_small1(const double* __restrict__ a_all, double* __restrict__ bx_all,
+                                                                 int n, int batch) {
+    extern __shared__ double xs[];                       // [n]
+    __shared__ double tile[NB][NBP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x;
     if (f >= batch) return;
-    double* xs = xs_all + (size_t)warp * n;
     const double* a = a_all + (size_t)f * n * n;
     double* bx = bx_all + (size_t)f * n;
-    for (int i = lane; i < n; i += 32) xs[i] = bx[i];
-    __syncwarp();
-    for (int i = 0; i < n; ++i) {
-        const double* row = a + (size_t)i * n;
-        double s = 0.0;
-        for (int k = lane; k < i; k += 32) s = fma(row[k], xs[k], s);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
-        if (lane == 0) xs[i] = (xs[i] - s) / row[i];
-        __syncwarp();
+    for (int i = tid; i < n; i += SOLVE1_THREADS) xs[i] = bx[i];
+    for (int j0 = 0; j0 < n; j0 += NB) {                  // forward: L y = b
+        const int nb = min(NB, n - j0);
+        for (int r = warp; r < nb; r += SOLVE1_THREADS / 32)
+            if (lane < nb) tile[r][lane] = a[(size_t)(j0 + r) * n + j0 + lane];
+        __syncthreads();
+        if (warp == 0) {
+            double xr = lane < nb ? xs[j0 + lane] : 0.0;
+            const double rd = lane < nb ? 1.0 / tile[lane][lane] : 0.0;
+            for (int k = 0; k < nb; ++k) {
+                const double xk = __shfl_sync(FULL, xr * rd, k);
+                if (lane == k) xr = xk;
+                else if (lane > k && lane < nb) xr = fma(-tile[lane][k], xk, xr);
+            }
+            if (lane < nb) xs[j0 + lane] = xr;
+        }
+        __syncthreads();
+        for (int r = j0 + nb + tid; r < n; r += SOLVE1_THREADS) {
+            const double* row = a + (size_t)r * n + j0;
+            double s = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < NB; ++c) s = fma(row[c], xs[j0 + c], s);     // nb == NB whenever rows remain below
+            xs[r] -= s;
+        }
+        __syncthreads();
     }
-    for (int k = n - 1; k >= 0; --k) {
-        const double* row = a + (size_t)k * n;
-        const double xk = xs[k] / row[k];
-        __syncwarp();
-        if (lane == 0) xs[k] = xk;
-        for (int i = lane; i < k; i += 32) xs[i] = fma(-row[i], xk, xs[i]);
-        __syncwarp();
+    for (int j0 = ((n - 1) / NB) * NB; j0 >= 0; j0 -= NB) {   // backward: L^T x = y
+        const int nb = min(NB, n - j0);
+        for (int r = warp; r < nb; r += SOLVE1_THREADS / 32)
+            if (lane < nb) tile[r][lane] = a[(size_t)(j0 + r) * n + j0 + lane];
+        __syncthreads();
+        if (warp == 0) {
+            double xr = lane < nb ? xs[j0 + lane] : 0.0;
+            const double rd = lane < nb ? 1.0 / tile[lane][lane] : 0.0;
+            for (int k = nb - 1; k >= 0; --k) {
+                const double xk = __shfl_sync(FULL, xr * rd, k);
+                if (lane == k) xr = xk;
+                else if (lane < k) xr = fma(-tile[k][lane], xk, xr);
+            }
+            if (lane < nb) xs[j0 + lane] = xr;
+        }
+        __syncthreads();
+        for (int c = tid; c < j0; c += SOLVE1_THREADS) {
+            double s = 0.0;
+            for (int i = 0; i < nb; ++i) s = fma(a[(size_t)(j0 + i) * n + c], xs[j0 + i], s);
+            xs[c] -= s;
+        }
+        __syncthreads();
     }
-    for (int i = lane; i < n; i += 32) bx[i] = xs[i];
+    for (int i = tid; i < n; i += SOLVE1_THREADS) bx[i] = xs[i];
 }
 
 }  // namespace fers
@@ -377,14 +449,12 @@ int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* in
     FERS_REQUIRE(batch <= 65535 || n <= SMALL_MAX_N, "dense_cholesky: batch exceeds gridDim.z");
     if (info_dev) FERS_CK(cudaMemsetAsync(info_dev, 0, sizeof(int) * batch, st));
     if (n <= SMALL_MAX_N) {                       // one CTA per matrix, one launch
-        const size_t smem = (size_t)n * NBP * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-            FERS_CK(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((size_t)SMALL_MAX_N * NBP * sizeof(double))));
-            attr_set = true;
-        }
-        k_chol_small<<<batch, SMALL_THREADS, smem, st>>>(a, n, info_dev);
+        int rc;
+        if (n <= 96) rc = launch_chol_small<96>(a, n, batch, info_dev, st);
+        else if (n <= 160) rc = launch_chol_small<160>(a, n, batch, info_dev, st);
+        else if (n <= 288) rc = launch_chol_small<288>(a, n, batch, info_dev, st);
+        else rc = launch_chol_small<SMALL_MAX_N>(a, n, batch, info_dev, st);
+        if (rc) return rc;
         count_launches(1);
     } else
     for (int j0 = 0; j0 < n; j0 += NB) {
@@ -409,9 +479,8 @@ int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* in
 int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* bx, void* stream) {
     cudaStream_t st = as_stream(stream);
     FERS_REQUIRE(n > 0 && nrhs > 0 && batch > 0, "dense_solve: empty problem");
-    if (nrhs == 1 && n <= 768) {                  // one warp per matrix (8 warps x n doubles of shared memory <= 48 KB)
-        k_solve_small1<<<(batch + SOLVE1_WARPS - 1) / SOLVE1_WARPS, 32 * SOLVE1_WARPS, (size_t)SOLVE1_WARPS * n * sizeof(double), st>>>(
-            a, bx, n, batch);
+    if (nrhs == 1 && n <= 4096) {                 // one CTA per matrix (n doubles of shared memory <= 32 KB)
+        k_solve_small1<<<batch, SOLVE1_THREADS, (size_t)n * sizeof(double), st>>>(a, bx, n, batch);
         FERS_LAUNCH_CHECK();
         count_launches(1);
         return 0;

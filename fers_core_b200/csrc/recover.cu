@@ -36,10 +36,15 @@ struct RecArgs {
     double* u_local;
 };
 
+// G lanes per member (a power of two): 32 in general; with few right-hand sides and no member releases a warp
+// takes 32 / G members so that the lanes are not idle (P-Delta loops recover one or two columns per pass)
+template <int G, bool REL>
 __global__ void __launch_bounds__(REC_THREADS) k_recover_members(RecArgs A) {
-    __shared__ double s_k[REC_WARPS][144];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int m = blockIdx.x * REC_WARPS + warp;
+    static_assert(!REL || G == 32, "released members need the whole warp");
+    __shared__ double s_k[REL ? REC_WARPS : 1][144];
+    const int warp = threadIdx.x >> 5;
+    const int lane = (threadIdx.x & 31) % G;
+    const int m = (blockIdx.x * REC_WARPS + warp) * (32 / G) + (threadIdx.x & 31) / G;
     if (m >= A.n_members) return;
     const int a = A.n1[m], b = A.n2[m];
     double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
@@ -48,16 +53,17 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_members(RecArgs A) {
     const int mtype = A.m_type[m];
     const double scale = A.m_scale ? A.m_scale[m] : 1.0;
     const BeamCoef c = beam_coef(A.prop + (size_t)A.m_prop[m] * NPROP, f.L, mtype, scale);
-    const int ri = A.m_rel ? A.m_rel[m] : -1;
+    const int ri = REL ? A.m_rel[m] : -1;
+    const int kw = REL ? warp : 0;
     if (ri >= 0) {
         if (lane == 0) {
-            beam_local_k(c, s_k[warp]);
-            beam_condense(s_k[warp], A.rel + 12 * (size_t)ri, nullptr, 0);
+            beam_local_k(c, s_k[kw]);
+            beam_condense(s_k[kw], A.rel + 12 * (size_t)ri, nullptr, 0);
         }
         __syncwarp();
     }
     const int nr = A.nrhs;
-    for (int col = lane; col < nr; col += 32) {
+    for (int col = lane; col < nr; col += G) {
         double ug[12], ul[12], fl[12], fg[12];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_members(RecArgs A) {
         if (ri < 0) {
             beam_k_times_u(c, ul, fl);
         } else {
-            const double* k = s_k[warp];
+            const double* k = s_k[kw];
 #pragma unroll
             for (int i = 0; i < 12; ++i) {
                 double s = 0.0;
@@ -331,8 +337,25 @@ int fers_b200_recover_members(int n_members, int nrhs, const double* xyz, const 
     A.m_roll = m_roll; A.m_scale = m_scale; A.m_rel = m_rel; A.prop = prop; A.rel = rel; A.m_axial_rhs = m_axial_rhs;
     A.kg_mode = kg_mode; A.kg_suppress = kg_suppress; A.u = u; A.peq = peq; A.f_local = f_local; A.f_global = f_global;
     A.u_local = u_local;
-    int grid = (n_members + REC_WARPS - 1) / REC_WARPS;
-    k_recover_members<<<grid, REC_THREADS, 0, as_stream(stream)>>>(A);
+    int g = 32;
+    if (m_rel == nullptr) {
+        g = 1;
+        while (g < nrhs && g < 32) g *= 2;
+    }
+    const int per_cta = REC_WARPS * (32 / g);
+    const int grid = (n_members + per_cta - 1) / per_cta;
+    cudaStream_t st = as_stream(stream);
+    switch (g) {
+        case 1: k_recover_members<1, false><<<grid, REC_THREADS, 0, st>>>(A); break;
+        case 2: k_recover_members<2, false><<<grid, REC_THREADS, 0, st>>>(A); break;
+        case 4: k_recover_members<4, false><<<grid, REC_THREADS, 0, st>>>(A); break;
+        case 8: k_recover_members<8, false><<<grid, REC_THREADS, 0, st>>>(A); break;
+        case 16: k_recover_members<16, false><<<grid, REC_THREADS, 0, st>>>(A); break;
+        default:
+            if (m_rel == nullptr) k_recover_members<32, false><<<grid, REC_THREADS, 0, st>>>(A);
+            else k_recover_members<32, true><<<grid, REC_THREADS, 0, st>>>(A);
+            break;
+    }
     FERS_LAUNCH_CHECK();
     count_launches(1);
     return 0;

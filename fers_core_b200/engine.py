@@ -606,35 +606,46 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
 
 
 def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:
-    """Device results [.., nr] -> host result arrays for the given rhs columns."""
+    """Device results [.., nr] -> host result arrays for the given rhs columns.  The column-major device layout is
+    transposed on the device and copied straight into the destination rows (one D2H per field, no host-side
+    gather) when the columns are consecutive."""
     n = len(cols)
     cols = np.asarray(cols)
     nn, nm = model.n_nodes, model.n_members
+    c0 = int(cols[0]) if n else 0
+    consecutive = n > 0 and bool(np.array_equal(cols, np.arange(c0, c0 + n)))
+
+    def dev(t, shape):
+        return t.view(shape + (t.shape[-1],)).movedim(-1, 0)[:n]
 
     def host(t, shape):
-        a = t.cpu().numpy()
-        a = a.reshape(shape + (a.shape[-1],))
-        return np.moveaxis(a, -1, 0)[:n]
+        return dev(t, shape).contiguous().cpu().numpy()
+
+    def put(dst, t, shape):
+        if consecutive and dst[c0:c0 + n].flags.c_contiguous:
+            torch.from_numpy(dst[c0:c0 + n]).copy_(dev(t, shape))
+        else:
+            dst[cols] = host(t, shape)
 
     if out.unity:
         out.unity.accumulate([int(c) for c in cols], out.unity_xyz, d_u, rec,
                              torch.cuda.current_stream(d_u.device).cuda_stream)
-    out.U[cols] = host(d_u, (nn, 6))
-    out.R[cols] = host(rec["R"], (nn, 6))
+    put(out.U, d_u, (nn, 6))
+    put(out.R, rec["R"], (nn, 6))
     if nm:
-        out.f_local[cols] = host(rec["f_local"], (nm, 12))
+        put(out.f_local, rec["f_local"], (nm, 12))
         if "bw" in rec:
             out.bw[np.asarray(cols)[:, None], model.w_member[None, :]] = host(rec["bw"], (len(model.w_member), 2))
-        out.f_global[cols] = host(rec["f_global"], (nm, 12))
-        out.u_local[cols] = host(rec["u_local"], (nm, 12))
+        put(out.f_global, rec["f_global"], (nm, 12))
+        put(out.u_local, rec["u_local"], (nm, 12))
         if "sec" in rec:
-            out.sec[cols] = host(rec["sec"], (nm, len(SECTION_FRACS), 6))
-            out.lmax[cols] = host(rec["lmax"], (nm, 6)); out.lmin[cols] = host(rec["lmin"], (nm, 6))
-            out.gmax[cols] = host(rec["gmax"], (nm, 6)); out.gmin[cols] = host(rec["gmin"], (nm, 6))
+            put(out.sec, rec["sec"], (nm, len(SECTION_FRACS), 6))
+            put(out.lmax, rec["lmax"], (nm, 6)); put(out.lmin, rec["lmin"], (nm, 6))
+            put(out.gmax, rec["gmax"], (nm, 6)); put(out.gmin, rec["gmin"], (nm, 6))
     if model.n_plates:
         npl = model.n_plates
-        out.p_res[cols] = host(rec["p_res"], (npl, 8))
-        out.p_nodal[cols] = host(rec["p_nodal"], (npl, 3, 6))
+        put(out.p_res, rec["p_res"], (npl, 8))
+        put(out.p_nodal, rec["p_nodal"], (npl, 3, 6))
         cd = host(rec["p_cd"], (npl, 12))
         out.p_cdg[cols] = cd[..., :6]; out.p_cdl[cols] = cd[..., 6:]
         out.p_centroid = xyz[model.p_nodes].mean(axis=1)
@@ -680,7 +691,7 @@ def analyze_frame_batch(model: wire.ModelArrays, nodes_per_frame: int, device=No
             nodes_per_frame, nf, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
             _lib.ptr(eng.d_ks), _lib.ptr(a), _lib.ptr(flag), st), "dense_expand_batched")
         _lib.check(lib.fers_b200_dense_cholesky(n, nf, _lib.ptr(a), _lib.ptr(info_dev), info, st), "dense_cholesky")
-        bad = [i for i in range(nf) if info[i] != 0]
+        bad = np.nonzero(np.ctypeslib.as_array(info))[0].tolist()
         if bad:
             raise EngineError(f"{len(bad)} frame(s) of the batch are not positive definite (first: frame {bad[0]}): "
                               "buckled under the applied load or insufficiently supported")

@@ -292,10 +292,10 @@ def test_plate_modifiers_and_plane_strain_match_oracle(engine_mod, name):
     helpers.assert_results_close(got, want, RTOL, label=name + "+plate options")
 
 
-@pytest.mark.parametrize("batch,n,nrhs", [(5, 77, 3), (9, 270, 1), (3, 33, 1), (2, 512, 1), (2, 600, 2), (40, 64, 1)])
+@pytest.mark.parametrize("batch,n,nrhs", [(5, 77, 3), (9, 270, 1), (3, 33, 1), (2, 512, 1), (2, 600, 2), (40, 64, 1), (4, 271, 1), (2, 1000, 1), (3, 17, 1)])
 def test_dense_cholesky_batched(engine_mod, batch, n, nrhs):
     """Batched dense factor/solve used for batches of small frames (configs[4]): the single-launch small-matrix
-    kernel (n <= 512), the warp-per-matrix substitution (one right-hand side) and the tiled general path."""
+    kernel (n <= 512), the CTA-per-matrix blocked substitution (one right-hand side) and the tiled general path."""
     import torch
     from fers_core_b200 import _lib
     lib = _lib.load()

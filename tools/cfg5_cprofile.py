@@ -12,5 +12,5 @@ engine.analyze_frame_batch(big, synth.PORTAL_NODES, dev)
 torch.cuda.synchronize()
 pr.disable()
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(22)
 print(s.getvalue()[:6000])

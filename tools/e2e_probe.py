@@ -38,3 +38,19 @@ for rep in range(3):
     torch.cuda.synchronize(dev)
     print(f"  engine {1e3 * (t1 - t0):.1f} ms, run_linear {1e3 * (time.perf_counter() - t1):.1f} ms, plan {eng.timings.get('chol_plan_ms'):.1f} ms", flush=True)
     del eng, out
+
+# where the constructor's time outside the three stages goes
+import cProfile, pstats
+for rep in range(2):
+    pr = cProfile.Profile()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    pr.enable()
+    eng = engine.Engine(model, dev)
+    torch.cuda.synchronize(dev)
+    pr.disable()
+    print(f"constructor under cProfile: {(time.perf_counter() - t0) * 1e3:.1f} ms")
+    pstats.Stats(pr).sort_stats("tottime").print_stats(8)
+    out = eng.run_linear(model.combo_factors)
+    torch.cuda.synchronize(dev)
+    del eng, out
