@@ -26,7 +26,8 @@ from .results import ResultArrays, SECTION_FRACS, results_to_wire
 DENSE_MAX_DOF = 8192          # models up to this many DOFs use the dense Cholesky path
 SOLVERS = ("auto", "dense", "cholesky", "pcg")   # auto: dense up to DENSE_MAX_DOF, sparse Cholesky above
 CHOL_REFINE_STEPS = 2         # at most this many iterative-refinement passes after the direct substitution
-CHOL_REFINE_TOL = 1e-12       # refine while the relative residual max_c ||f_c - K u_c|| / ||f_c|| exceeds this
+CHOL_REFINE_TOL = 1e-12
+STAGE_MAX_BYTES = 256 << 20   # result fields up to this size travel through pinned staging buffers       # refine while the relative residual max_c ||f_c - K u_c|| / ||f_c|| exceeds this
 CHOL_RESIDUAL_LIMIT = 1e-8    # relative residual above which the direct solve is reported as failed
 PCG_TOL = 1e-12               # relative residual ||r|| / ||b|| per right-hand side
 PCG_MAX_ITER = 200000
@@ -621,11 +622,30 @@ def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:
     def host(t, shape):
         return dev(t, shape).contiguous().cpu().numpy()
 
+    pending = []
+
     def put(dst, t, shape):
-        if consecutive and dst[c0:c0 + n].flags.c_contiguous:
-            torch.from_numpy(dst[c0:c0 + n]).copy_(dev(t, shape))
+        # D2H through pinned staging (torch's caching host allocator makes it cheap after the first pass), all
+        # fields in flight at once, one synchronisation; pageable destinations would serialise at a few GB/s
+        src = dev(t, shape).contiguous()
+        if src.numel() * 8 <= STAGE_MAX_BYTES:
+            stage = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            stage.copy_(src, non_blocking=True)
+            pending.append((dst, stage))
+        elif consecutive and dst[c0:c0 + n].flags.c_contiguous:
+            torch.from_numpy(dst[c0:c0 + n]).copy_(src)
         else:
-            dst[cols] = host(t, shape)
+            dst[cols] = src.cpu().numpy()
+
+    def flush():
+        if pending:
+            torch.cuda.current_stream(d_u.device).synchronize()
+        for dst, stage in pending:
+            if consecutive:
+                dst[c0:c0 + n] = stage.numpy()
+            else:
+                dst[cols] = stage.numpy()
+        pending.clear()
 
     if out.unity:
         out.unity.accumulate([int(c) for c in cols], out.unity_xyz, d_u, rec,
@@ -649,6 +669,7 @@ def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:
         cd = host(rec["p_cd"], (npl, 12))
         out.p_cdg[cols] = cd[..., :6]; out.p_cdl[cols] = cd[..., 6:]
         out.p_centroid = xyz[model.p_nodes].mean(axis=1)
+    flush()
 
 
 def analyze_frame_batch(model: wire.ModelArrays, nodes_per_frame: int, device=None, detail: bool = False,
