@@ -36,6 +36,12 @@ struct GemmTile {
     static constexpr int B_STAGE = B_KMAJOR ? BN * GEMM_BKP : GEMM_BK * BN;        // doubles
     static constexpr size_t SMEM = (size_t)GEMM_STAGES * (A_STAGE + B_STAGE) * sizeof(double);
     struct Acc { double v[TM][TN]; };
+    __device__ static __forceinline__ void clear(Acc& acc) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc.v[i][j] = 0.0;
+    }
 
     // stage loader: k-tile kt (columns kt*BK .. ) of A (mrem x K, lda) and B into ring slot `slot`
     __device__ static __forceinline__ void load_stage(double* smem, int slot, int kt, const double* __restrict__ A, int lda,
@@ -76,14 +82,17 @@ struct GemmTile {
     }
 
     // acc += A(mrem x K) * op(B)(K x nrem) for this CTA's tile (pointers at the tile origin)
+    template <bool CLEAR = true>
     __device__ static __forceinline__ void mainloop(Acc& acc_, double* smem, const double* __restrict__ A, int lda,
                                                     int mrem, const double* __restrict__ B, int ldb, int nrem, int K) {
         const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
         double (&acc)[TM][TN] = acc_.v;
+        if (CLEAR) {
 #pragma unroll
-        for (int i = 0; i < TM; ++i)
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
+                for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
+        }
         const int nk = (K + GEMM_BK - 1) / GEMM_BK;
 #pragma unroll
         for (int s = 0; s < GEMM_STAGES - 1; ++s) {
@@ -192,6 +201,12 @@ struct GemmMma {
     static constexpr int KSTEPS = BK / 4;
     static_assert((BK * BM / 2) % GEMM_THREADS == 0 && (BK * BN / 2) % GEMM_THREADS == 0, "whole chunks per thread");
     struct Acc { double v[NT][MT][2]; };
+    __device__ static __forceinline__ void clear(Acc& acc) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int i = 0; i < MT; ++i) acc.v[j][i][0] = acc.v[j][i][1] = 0.0;
+    }
 
     // chunk `q` (0 .. A_CHUNKS + B_CHUNKS - 1) of this thread for k-tile kt -> ring slot
     __device__ static __forceinline__ void load_chunk(int q, uint32_t stage_addr, int k0, const double* __restrict__ A, int lda,
@@ -220,15 +235,19 @@ struct GemmMma {
         }
     }
 
+    // CLEAR = false continues an accumulation started by an earlier call (same tile, next K range)
+    template <bool CLEAR = true>
     __device__ static __forceinline__ void mainloop(Acc& acc, double* smem, const double* __restrict__ A, int lda, int mrem,
                                                     const double* __restrict__ B, int ldb, int nrem, int K) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int wm0 = (warp % WARPS_M) * (MT * 8), wn0 = (warp / WARPS_M) * (NT * 8);
         const int lk = lane & 3, lr = lane >> 2;
+        if (CLEAR) {
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
+            for (int j = 0; j < NT; ++j)
 #pragma unroll
-            for (int i = 0; i < MT; ++i) acc.v[j][i][0] = acc.v[j][i][1] = 0.0;
+                for (int i = 0; i < MT; ++i) acc.v[j][i][0] = acc.v[j][i][1] = 0.0;
+        }
         const int nk = (K + BK - 1) / BK;
         const uint32_t smem_addr = (uint32_t)__cvta_generic_to_shared(smem);
         constexpr uint32_t STAGE_BYTES = (A_STAGE + B_STAGE) * 8u;

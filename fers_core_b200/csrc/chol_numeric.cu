@@ -549,6 +549,125 @@ k_bwd_update(SolveCtx S, int s) {
     G48N::store<false>(acc, S.Y + (size_t)(6 * f.pad0 + c) * nr, (size_t)nr, nr, c0 - c);
 }
 
+// ---- wavefront substitution through the own columns of every front of a level: ONE launch per level and
+// direction instead of two per 64-column step.  A CTA owns one 64-row block of one front; it draws a ticket
+// (dispatch order), so the blocks it waits for always hold smaller tickets and are running or done.  Forward
+// (left-looking): w_i -= L[i, 0:i) y[0:i) accumulated in registers block column by block column as the
+// per-front counter `done` announces them, then y_i = inv(D_i) w_i and done = i + 1.  Backward mirrors it from
+// the last block up.  The K order of every accumulation is fixed (block by block), so results do not depend on
+// timing.  Cross-CTA data goes through L2 only (st + __threadfence / cp.async.cg).
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// the 64 x 64 tile at `t` (column stride ld doubles) -> L2, one 128-byte line per thread (GEMM_THREADS == 256)
+__device__ __forceinline__ void prefetch_tile(const double* t, size_t ld) {
+    prefetch_l2(t + (size_t)(threadIdx.x >> 2) * ld + 16 * (threadIdx.x & 3));
+}
+
+// ctr[0] = ticket, ctr[1 + front-of-level] = finished blocks of that front
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_fwd_wave(SolveCtx S, int nf, int* __restrict__ ctr) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_v;
+    if (threadIdx.x == 0) s_v = atomicAdd(ctr, 1);
+    __syncthreads();
+    const int t = s_v;
+    const int i = t / nf, fi = t - i * nf;
+    const FrontDev f = S.fronts[S.level_fronts[fi]];
+    const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
+    const int c0 = i * NB;
+    if (c0 >= k1) return;
+    const int nb = min(NB, k1 - c0), nr = S.nrhs;
+    int* done = ctr + 1 + fi;
+    const double* panel = S.factor + f.panel_off;
+    double* Yf = S.Y + (size_t)(6 * f.pad0) * nr;
+    double* Wi = S.W + (size_t)(f.rhs_off + c0) * nr;
+    // the tiles of the last step of the chain (inverse of the diagonal tile, newest block column) come from HBM:
+    // fetch them into L2 while waiting
+    prefetch_tile(S.factor + f.dinv_off + (size_t)i * NB * NB, NB);
+    if (i > 0) prefetch_tile(panel + (size_t)(i - 1) * NB * m + c0, m);
+    if (i > 1) prefetch_tile(panel + (size_t)(i - 2) * NB * m + c0, m);
+    G44::Acc acc;
+    G44::clear(acc);
+    int have = 0;
+    while (have < i) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int d;
+            while ((d = ld_acquire_gpu(done)) <= have) __nanosleep(40);
+            s_v = d;
+        }
+        __syncthreads();
+        const int upto = min(s_v, i);
+        G44::mainloop<false>(acc, smem, Yf + (size_t)have * NB * nr, nr, nr, panel + (size_t)have * NB * m + c0, m, nb, (upto - have) * NB);
+        have = upto;
+    }
+    if (i > 0) {
+        G44::store<false>(acc, Wi, (size_t)nr, nr, nb);
+        __threadfence();
+        __syncthreads();
+    }
+    G44::mainloop(acc, smem, Wi, nr, nr, S.factor + f.dinv_off + (size_t)i * NB * NB, NB, nb, nb);
+    G44::store<true>(acc, Yf + (size_t)c0 * nr, (size_t)nr, nr, nb);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(done, i + 1);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_bwd_wave(SolveCtx S, int nf, int* __restrict__ ctr) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_v;
+    if (threadIdx.x == 0) s_v = atomicAdd(ctr, 1);
+    __syncthreads();
+    const int t = s_v;
+    const int ib = t / nf, fi = t - ib * nf;            // ib counts blocks from the last one
+    const FrontDev f = S.fronts[S.level_fronts[fi]];
+    const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
+    const int steps = (k1 + NB - 1) / NB;
+    if (ib >= steps) return;
+    const int i = steps - 1 - ib, c0 = i * NB;
+    const int nb = min(NB, k1 - c0), nr = S.nrhs;
+    int* done = ctr + 1 + fi;
+    const double* panel = S.factor + f.panel_off;
+    double* Yf = S.Y + (size_t)(6 * f.pad0) * nr;
+    prefetch_tile(S.factor + f.dinv_off + (size_t)i * NB * NB, NB);
+    if (ib > 0) prefetch_tile(panel + (size_t)c0 * m + c0 + NB, m);
+    if (ib > 1) prefetch_tile(panel + (size_t)c0 * m + c0 + 2 * NB, m);
+    G44N::Acc acc;
+    G44N::clear(acc);
+    for (int jb = 0; jb < ib; ++jb) {                   // source blocks steps-1, steps-2, .. i+1, always in this order
+        if (jb >= s_v || jb == 0) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int d;
+                while ((d = ld_acquire_gpu(done)) <= jb) __nanosleep(40);
+                s_v = d;
+            }
+            __syncthreads();
+        }
+        const int j = steps - 1 - jb, r0 = j * NB;
+        G44N::mainloop<false>(acc, smem, Yf + (size_t)r0 * nr, nr, nr, panel + (size_t)c0 * m + r0, m, nb, min(NB, k1 - r0));
+    }
+    if (ib > 0) {
+        G44N::store<false>(acc, Yf + (size_t)c0 * nr, (size_t)nr, nr, nb);
+        __threadfence();
+        __syncthreads();
+    }
+    G44N::mainloop(acc, smem, Yf + (size_t)c0 * nr, nr, nr, S.factor + f.dinv_off + (size_t)i * NB * NB, NB, nb, nb);
+    G44N::store<true>(acc, Yf + (size_t)c0 * nr, (size_t)nr, nr, nb);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(done, ib + 1);
+}
+
 // r = mask (f - Kx); norms2[0][c] += r_c . r_c, norms2[1][c] += (mask f_c) . (mask f_c)  (diagnostics)
 __global__ void __launch_bounds__(256)
 k_chol_residual(long long n_dof, int nr, const double* __restrict__ f, const double* __restrict__ kx,
@@ -623,6 +742,8 @@ static int set_smem_attrs() {
     FERS_CK(cudaFuncSetAttribute(k_bwd_bnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_bwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_bwd_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G48N::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_fwd_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44::SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_bwd_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
     done = true;
     return 0;
 }
@@ -653,9 +774,13 @@ static IndexPtrs index_ptrs(const CholPlanHost& P, const void* index_dev) {
     return I;
 }
 
+// counters of the wavefront substitution: per level and direction one ticket + one progress counter per front
+static size_t wave_counter_ints(const CholPlanHost& P) { return 2 * ((size_t)P.level_ptr[P.n_levels] + (size_t)P.n_levels); }
+static size_t wave_counter_bytes(const CholPlanHost& P) { return align_up(wave_counter_ints(P) * sizeof(int)) + 256; }
+
 static size_t chol_work_bytes(const CholPlanHost& P, int nrhs) {
     const size_t schur = (size_t)(P.schur_doubles[0] + P.schur_doubles[1]) * 8 + 512;
-    const size_t solve = ((size_t)P.rhs_rows + 6 * (size_t)P.n_nodes) * (size_t)nrhs * 8 + 512;
+    const size_t solve = ((size_t)P.rhs_rows + 6 * (size_t)P.n_nodes) * (size_t)nrhs * 8 + 512 + wave_counter_bytes(P);
     return align_up(schur > solve ? schur : solve) + 256;
 }
 
@@ -874,6 +999,11 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
     const bool prof = g_chol_profile_on != 0;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     if (prof) { cudaEventCreate(&ev_begin); cudaEventCreate(&ev_end); cudaEventRecord(ev_begin, st); }
+    const bool wave = !(g_chol_variant & 8);
+    int* ctr = reinterpret_cast<int*>(
+        (reinterpret_cast<uintptr_t>(S.Y + (size_t)6 * P.n_nodes * nrhs) + 255) & ~(uintptr_t)255);
+    const size_t ctr_half = (size_t)P.level_ptr[P.n_levels] + (size_t)P.n_levels;
+    if (wave) FERS_CK(cudaMemsetAsync(ctr, 0, wave_counter_ints(P) * sizeof(int), st));
     for (int l = 0; l < P.n_levels; ++l) {                // forward: children -> parents
         const int nf = P.level_ptr[l + 1] - P.level_ptr[l];
         if (nf == 0) continue;
@@ -886,6 +1016,10 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
             ++launches;
         }
         const int steps = cdiv(max_k1, NB);
+        if (wave) {
+            k_fwd_wave<<<nf * steps, GEMM_THREADS, G44::SMEM, st>>>(S, nf, ctr + P.level_ptr[l] + l);
+            ++launches;
+        } else
         for (int s = 0; s < steps; ++s) {
             k_fwd_diag<<<nf, GEMM_THREADS, G44::SMEM, st>>>(S, s);
             ++launches;
@@ -917,6 +1051,10 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
             launches += 2;
         }
         const int steps = cdiv(max_k1, NB);
+        if (wave) {
+            k_bwd_wave<<<nf * steps, GEMM_THREADS, G44N::SMEM, st>>>(S, nf, ctr + ctr_half + P.level_ptr[l] + l);
+            ++launches;
+        } else
         for (int s = steps - 1; s >= 0; --s) {
             k_bwd_diag<<<nf, GEMM_THREADS, G44N::SMEM, st>>>(S, s);
             ++launches;
@@ -1020,7 +1158,7 @@ int fers_b200_residual(long long n_dof, int nrhs, const double* f, const double*
 }
 
 int fers_b200_chol_set_variant(int variant) {
-    FERS_REQUIRE(variant >= 0 && variant <= 7, "chol_set_variant: bit 0 = panel updates, bit 1 = Schur update use the 128x128 tile, bit 2 = no look-ahead");
+    FERS_REQUIRE(variant >= 0 && variant <= 15, "chol_set_variant: bit 0 = panel updates, bit 1 = Schur update use the 128x128 tile, bit 2 = no look-ahead, bit 3 = per-step substitution kernels instead of the wavefront");
     g_chol_variant = variant;
     return 0;
 }

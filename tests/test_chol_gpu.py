@@ -78,3 +78,35 @@ def test_chol_frame_stiffness_matches_oracle(shape):
     for name in ("U", "R", "f_local"):
         a, b = getattr(got, name), getattr(want, name)
         assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max(), name
+
+
+@pytest.mark.parametrize("shape,leaf,nrhs", [((9, 8, 5), 48, 16), ((1, 1, 40), 3, 64), ((14, 14, 6), 512, 64)])
+def test_wavefront_substitution_is_deterministic_and_matches_per_step_kernels(shape, leaf, nrhs):
+    """One-launch-per-level wavefront substitution (default) against the per-step kernels (variant bit 3): same
+    answer to rounding, and bit-identical from run to run although its CTAs synchronise through flags."""
+    import torch
+    from fers_core_b200 import _lib, synth
+    lib = _lib.load()
+    m = synth.grid_frame(*shape, n_combos=1)
+    rowptr, colidx = _pattern(m.n_nodes, m.m_n1, m.m_n2)
+    rng = np.random.default_rng(5)
+    vals = _random_spd_blocks(rowptr, colidx, rng)
+    fixed = (m.bc_code.reshape(-1) != 0).astype(np.uint8)
+    b = rng.standard_normal((6 * m.n_nodes, nrhs))
+    diag_slot = np.array([rowptr[i] + np.searchsorted(colidx[rowptr[i]:rowptr[i + 1]], i) for i in range(m.n_nodes)], np.int32)
+    plan, sol = _solver_for(rowptr, colidx, m.xyz, leaf)
+    dev = sol.dev
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
+    d_fixed, d_b = t(fixed, np.uint8), t(b, np.float64)
+    assert sol.factorize(t(vals, np.float64), t(diag_slot, np.int32), d_fixed, None) == 0
+    xs = []
+    try:
+        for variant in (0, 0, 8):
+            _lib.check(lib.fers_b200_chol_set_variant(variant), "set_variant")
+            d_x = torch.empty((6 * m.n_nodes, nrhs), dtype=torch.float64, device=dev)
+            sol.solve(d_b, d_x, d_fixed)
+            xs.append(d_x.cpu().numpy())
+    finally:
+        lib.fers_b200_chol_set_variant(0)
+    assert np.array_equal(xs[0], xs[1])
+    assert np.abs(xs[0] - xs[2]).max() <= 1e-12 * np.abs(xs[2]).max()
