@@ -306,6 +306,77 @@ struct GemmMma {
         __syncthreads();
     }
 
+    // ---- helpers of the wavefront substitution (square 64 x 64 tiles: BM == BN == K) ----------------------
+    static constexpr int SQ_LD = BN + 4;                     // padded row of a resident 64 x 64 operand tile
+    static constexpr size_t SQ_BYTES = (size_t)BN * SQ_LD * sizeof(double);
+
+    // acc = -C (tile origin C, column stride ldc; entries outside mrem x nrem are zero)
+    __device__ static __forceinline__ void load_neg(Acc& acc, const double* __restrict__ C, size_t ldc, int mrem, int nrem) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int wm0 = (warp % WARPS_M) * (MT * 8), wn0 = (warp / WARPS_M) * (NT * 8);
+        const int lk = lane & 3, lr = lane >> 2;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int col = wn0 + 8 * j + lr;
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const int row = wm0 + 8 * i + 2 * lk;
+                double2 v = make_double2(0.0, 0.0);
+                if (col < nrem && row < mrem) v = __ldcg(reinterpret_cast<const double2*>(C + (size_t)col * ldc + row));
+                acc.v[j][i][0] = -v.x; acc.v[j][i][1] = -v.y;
+            }
+        }
+    }
+
+    // the accumulator tile as the A operand of a following product: as[n * SQ_LD + m] (n = tile column = K index)
+    __device__ static __forceinline__ void acc_to_operand(const Acc& acc, double* __restrict__ as) {
+        static_assert(BM == BN, "square tiles only");
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int wm0 = (warp % WARPS_M) * (MT * 8), wn0 = (warp / WARPS_M) * (NT * 8);
+        const int lk = lane & 3, lr = lane >> 2;
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+                *reinterpret_cast<double2*>(as + (wn0 + 8 * j + lr) * SQ_LD + wm0 + 8 * i + 2 * lk) =
+                    make_double2(acc.v[j][i][0], acc.v[j][i][1]);
+    }
+
+    // a 64 x 64 tile (column stride ld in global memory) -> resident operand rows of SQ_LD doubles (one commit group)
+    __device__ static __forceinline__ void load_square(double* __restrict__ bs, const double* __restrict__ B, int ld) {
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bs);
+#pragma unroll
+        for (int q = 0; q < BN * BN / 2 / GEMM_THREADS; ++q) {
+            const int c = threadIdx.x + q * GEMM_THREADS;
+            const int k = c / (BN / 2), j = 2 * (c % (BN / 2));
+            cp_async16(addr + (uint32_t)(k * SQ_LD + j) * 8u, B + (size_t)k * ld + j, true);
+        }
+        cp_async_commit();
+    }
+
+    // out[n][m] = sum_k as[k][m] * (BT ? bs[n][k] : bs[k][n]),  k = 0 .. BN - 1, both operands resident
+    template <bool BT>
+    __device__ static __forceinline__ void square_product(Acc& out, const double* __restrict__ as, const double* __restrict__ bs) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int wm0 = (warp % WARPS_M) * (MT * 8), wn0 = (warp / WARPS_M) * (NT * 8);
+        const int lk = lane & 3, lr = lane >> 2;
+        clear(out);
+        const double* ap = as + lk * SQ_LD + wm0 + lr;
+        const double* bp = BT ? bs + (wn0 + lr) * SQ_LD + lk : bs + lk * SQ_LD + wn0 + lr;
+#pragma unroll 4
+        for (int ks = 0; ks < BN / 4; ++ks) {
+            double am[MT], bn[NT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) am[i] = ap[4 * ks * SQ_LD + 8 * i];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bn[j] = BT ? bp[8 * j * SQ_LD + 4 * ks] : bp[4 * ks * SQ_LD + 8 * j];
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int i = 0; i < MT; ++i) dmma884(out.v[j][i], bn[j], am[i]);
+        }
+    }
+
     template <bool SET>
     __device__ static __forceinline__ void store(const Acc& acc, double* __restrict__ C, size_t ldc, int mrem, int nrem) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

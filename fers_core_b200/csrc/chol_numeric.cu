@@ -14,6 +14,7 @@
 // right-hand-side index as the contiguous dimension.  No atomics anywhere: results are deterministic.
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "chol.cuh"
@@ -668,6 +669,78 @@ k_bwd_wave(SolveCtx S, int nf, int* __restrict__ ctr) {
     if (threadIdx.x == 0) st_release_gpu(done, ib + 1);
 }
 
+#ifndef FERS_CHOL_DFMA
+// Second version of the wavefront kernels (default): the dependent step stays on chip.  The accumulator starts as
+// -w_i (loaded before any waiting), so after the left-looking products it holds -(w_i - L y); that tile goes to
+// shared memory as the operand of the product with the inverted diagonal tile, which has been resident since the
+// kernel started.  No round trip of w_i through L2, one fence per step instead of two.
+constexpr size_t wave_max(size_t a, size_t b) { return a > b ? a : b; }
+constexpr size_t WAVE_RING = wave_max(wave_max(G44::SMEM, G44N::SMEM), G44::SQ_BYTES);   // cp.async ring, later the operand tile
+constexpr size_t WAVE_SMEM = WAVE_RING + G44::SQ_BYTES;
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+k_wave2(SolveCtx S, int nf, int* __restrict__ ctr) {
+    using G = typename std::conditional<BACKWARD, G44N, G44>::type;
+    extern __shared__ __align__(16) double smem[];
+    double* dt = smem + WAVE_RING / sizeof(double);                        // inverted diagonal tile
+    __shared__ int s_v;
+    if (threadIdx.x == 0) s_v = atomicAdd(ctr, 1);
+    __syncthreads();
+    const int t = s_v;
+    const int ib = t / nf, fi = t - ib * nf;            // ib = blocks finished before this one
+    const FrontDev f = S.fronts[S.level_fronts[fi]];
+    const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
+    const int steps = (k1 + NB - 1) / NB;
+    if (ib >= steps) return;
+    const int i = BACKWARD ? steps - 1 - ib : ib, c0 = i * NB;
+    const int nb = min(NB, k1 - c0), nr = S.nrhs;
+    int* done = ctr + 1 + fi;
+    const double* panel = S.factor + f.panel_off;
+    double* Yf = S.Y + (size_t)(6 * f.pad0) * nr;
+    G::load_square(dt, S.factor + f.dinv_off + (size_t)i * NB * NB, NB);
+    typename G::Acc acc;
+    // forward: the right-hand side rows of the block; backward: the forward solution after the boundary coupling
+    G::load_neg(acc, BACKWARD ? Yf + (size_t)c0 * nr : S.W + (size_t)(f.rhs_off + c0) * nr, (size_t)nr, nr, nb);
+    if (ib > 0) prefetch_tile(BACKWARD ? panel + (size_t)c0 * m + c0 + NB : panel + (size_t)(i - 1) * NB * m + c0, m);
+    int have = 0;
+    while (have < ib) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int d;
+            while ((d = ld_acquire_gpu(done)) <= have) __nanosleep(40);
+            s_v = d;
+        }
+        __syncthreads();
+        const int upto = min(s_v, ib);
+        if (!BACKWARD) {
+            G::template mainloop<false>(acc, smem, Yf + (size_t)have * NB * nr, nr, nr, panel + (size_t)have * NB * m + c0, m, nb,
+                                        (upto - have) * NB);
+        } else {
+            for (int jb = have; jb < upto; ++jb) {        // fixed order, one source block at a time
+                const int r0 = (steps - 1 - jb) * NB;
+                G::template mainloop<false>(acc, smem, Yf + (size_t)r0 * nr, nr, nr, panel + (size_t)c0 * m + r0, m, nb, min(NB, k1 - r0));
+            }
+        }
+        have = upto;
+    }
+    cp_async_wait<0>();
+    __syncthreads();                                     // ring idle, inverse tile landed
+    G::acc_to_operand(acc, smem);
+    __syncthreads();
+    typename G::Acc out;
+    G::template square_product<BACKWARD>(out, smem, dt);
+#pragma unroll
+    for (int a = 0; a < G::NT; ++a)
+#pragma unroll
+        for (int b = 0; b < G::MT; ++b) { out.v[a][b][0] = -out.v[a][b][0]; out.v[a][b][1] = -out.v[a][b][1]; }
+    G::template store<true>(out, Yf + (size_t)c0 * nr, (size_t)nr, nr, nb);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(done, ib + 1);
+}
+#endif
+
 // r = mask (f - Kx); norms2[0][c] += r_c . r_c, norms2[1][c] += (mask f_c) . (mask f_c)  (diagnostics)
 __global__ void __launch_bounds__(256)
 k_chol_residual(long long n_dof, int nr, const double* __restrict__ f, const double* __restrict__ kx,
@@ -743,6 +816,10 @@ static int set_smem_attrs() {
     FERS_CK(cudaFuncSetAttribute(k_bwd_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_bwd_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G48N::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_fwd_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44::SMEM));
+#ifndef FERS_CHOL_DFMA
+    FERS_CK(cudaFuncSetAttribute(k_wave2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WAVE_SMEM));
+    FERS_CK(cudaFuncSetAttribute(k_wave2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WAVE_SMEM));
+#endif
     FERS_CK(cudaFuncSetAttribute(k_bwd_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
     done = true;
     return 0;
@@ -1017,6 +1094,10 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
         }
         const int steps = cdiv(max_k1, NB);
         if (wave) {
+#ifndef FERS_CHOL_DFMA
+            if (!(g_chol_variant & 16)) k_wave2<false><<<nf * steps, GEMM_THREADS, WAVE_SMEM, st>>>(S, nf, ctr + P.level_ptr[l] + l);
+            else
+#endif
             k_fwd_wave<<<nf * steps, GEMM_THREADS, G44::SMEM, st>>>(S, nf, ctr + P.level_ptr[l] + l);
             ++launches;
         } else
@@ -1052,6 +1133,10 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
         }
         const int steps = cdiv(max_k1, NB);
         if (wave) {
+#ifndef FERS_CHOL_DFMA
+            if (!(g_chol_variant & 16)) k_wave2<true><<<nf * steps, GEMM_THREADS, WAVE_SMEM, st>>>(S, nf, ctr + ctr_half + P.level_ptr[l] + l);
+            else
+#endif
             k_bwd_wave<<<nf * steps, GEMM_THREADS, G44N::SMEM, st>>>(S, nf, ctr + ctr_half + P.level_ptr[l] + l);
             ++launches;
         } else
@@ -1158,7 +1243,7 @@ int fers_b200_residual(long long n_dof, int nrhs, const double* f, const double*
 }
 
 int fers_b200_chol_set_variant(int variant) {
-    FERS_REQUIRE(variant >= 0 && variant <= 15, "chol_set_variant: bit 0 = panel updates, bit 1 = Schur update use the 128x128 tile, bit 2 = no look-ahead, bit 3 = per-step substitution kernels instead of the wavefront");
+    FERS_REQUIRE(variant >= 0 && variant <= 31, "chol_set_variant: bit 0 = panel updates, bit 1 = Schur update use the 128x128 tile, bit 2 = no look-ahead, bit 3 = per-step substitution kernels instead of the wavefront, bit 4 = first wavefront version");
     g_chol_variant = variant;
     return 0;
 }
