@@ -199,12 +199,13 @@ int fers_b200_bc_build(int n_nodes, const uint8_t* bc_code, const double* bc_k, 
     FERS_CK(cub::DeviceScan::ExclusiveSum(w, tmp_bytes, flag, scan, n_dof, st));
     k_bc_number<<<grid, T, 0, st>>>(n_dof, fixed, scan, free_index);
     FERS_LAUNCH_CHECK();
+    count_launches(2 + 2);
+    if (n_free_out == nullptr && n_dead_out == nullptr) return 0;      // re-assembly inside an iteration: no host sync
     int last_scan = 0, last_flag = 0, dead = 0;
     FERS_CK(cudaMemcpyAsync(&last_scan, scan + n_dof - 1, 4, cudaMemcpyDeviceToHost, st));
     FERS_CK(cudaMemcpyAsync(&last_flag, flag + n_dof - 1, 4, cudaMemcpyDeviceToHost, st));
     FERS_CK(cudaMemcpyAsync(&dead, d_cnt, 4, cudaMemcpyDeviceToHost, st));
     FERS_CK(cudaStreamSynchronize(st));
-    count_launches(2 + 2);
     if (n_free_out) *n_free_out = last_scan + last_flag;
     if (n_dead_out) *n_dead_out = dead;
     return 0;

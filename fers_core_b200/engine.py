@@ -222,7 +222,7 @@ class Engine:
         self.d_bc_code = self._t(code.astype(np.uint8).reshape(-1), np.uint8)
         self.d_bc_k = self._t(kk.reshape(-1), np.float64)
 
-    def assemble(self, d_xyz, d_scale=None, d_axial=None, kg_mode=0, kg_suppress=0) -> None:
+    def assemble(self, d_xyz, d_scale=None, d_axial=None, kg_mode=0, kg_suppress=0, count: bool = True) -> None:
         """Element stiffness + assembly + boundary conditions for one geometry / state."""
         m, lib, st = self.model, self.lib, self.stream
         self._k_version += 1
@@ -256,12 +256,14 @@ class Engine:
             _lib.check(lib.fers_b200_assemble_plates(
                 m.n_plates, _lib.ptr(d_xyz), _lib.ptr(self.d_p_nodes), _lib.ptr(self.d_p_data), _lib.ptr(self.d_p_flags),
                 _lib.ptr(self.d_p_slot), _lib.ptr(self.d_vals), st), "assemble_plates")
+        # count=False (re-assemblies inside an iteration): the free / dead DOF counts are not read back, no host sync
         n_free, n_dead = C.c_int(), C.c_int()
         _lib.check(lib.fers_b200_bc_build(
             m.n_nodes, _lib.ptr(self.d_bc_code), _lib.ptr(self.d_bc_k), _lib.ptr(self.d_vals), _lib.ptr(self.d_diag_slot),
-            _lib.ptr(self.d_fixed), _lib.ptr(self.d_free_index), _lib.ptr(self.d_kspring), C.byref(n_free),
-            C.byref(n_dead), _lib.ptr(self._bc_ws), self._bc_ws_bytes, st), "bc_build")
-        self.stats.n_free, self.stats.n_dead = n_free.value, n_dead.value
+            _lib.ptr(self.d_fixed), _lib.ptr(self.d_free_index), _lib.ptr(self.d_kspring), C.byref(n_free) if count else None,
+            C.byref(n_dead) if count else None, _lib.ptr(self._bc_ws), self._bc_ws_bytes, st), "bc_build")
+        if count:
+            self.stats.n_free, self.stats.n_dead = n_free.value, n_dead.value
 
     def load_cases(self, d_xyz, d_scale=None):
         """Per load case: nodal load vector [Nlc,Ndof] and local equivalent loads [Nlc,Nm*12]."""
@@ -704,21 +706,26 @@ def analyze_frame_batch(model: wire.ModelArrays, nodes_per_frame: int, device=No
     a = eng._empty((nf, n, n))
     flag = eng._zeros(1, torch.int32)
     info_dev = eng._zeros(nf, torch.int32)
-    info = (C.c_int * nf)()
-    free = (1 - eng.d_fixed.to(torch.float64))[:, None]
+    bad_dev = torch.zeros(nf, dtype=torch.bool, device=eng.dev)
 
     def factor_solve():
+        # asynchronous: failed pivots are collected on the device and looked at where the host synchronises anyway
         _lib.check(lib.fers_b200_dense_expand_batched(
             nodes_per_frame, nf, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
             _lib.ptr(eng.d_ks), _lib.ptr(a), _lib.ptr(flag), st), "dense_expand_batched")
-        _lib.check(lib.fers_b200_dense_cholesky(n, nf, _lib.ptr(a), _lib.ptr(info_dev), info, st), "dense_cholesky")
-        bad = np.nonzero(np.ctypeslib.as_array(info))[0].tolist()
+        _lib.check(lib.fers_b200_dense_cholesky(n, nf, _lib.ptr(a), _lib.ptr(info_dev), None, st), "dense_cholesky")
+        bad_dev.logical_or_(info_dev != 0)
+        u = (d_f * (1 - eng.d_fixed.to(torch.float64))[:, None]).contiguous()      # d_fixed is (re)built by assemble()
+        _lib.check(lib.fers_b200_dense_solve(n, 1, nf, _lib.ptr(a), _lib.ptr(u), st), "dense_solve")
+        return u
+
+    def raise_if_bad():
+        if int(flag.item()) != 0:
+            raise EngineError("analyze_frame_batch: a member connects two frames; the model is not a batch of independent frames")
+        bad = torch.nonzero(bad_dev).reshape(-1).cpu().tolist()
         if bad:
             raise EngineError(f"{len(bad)} frame(s) of the batch are not positive definite (first: frame {bad[0]}): "
                               "buckled under the applied load or insufficiently supported")
-        u = (d_f * ((1 - eng.d_fixed.to(torch.float64))[:, None])).contiguous()
-        _lib.check(lib.fers_b200_dense_solve(n, 1, nf, _lib.ptr(a), _lib.ptr(u), st), "dense_solve")
-        return u
 
     second_order = opts.order == "NONLINEAR"
     kg_mode = (1 if opts.pdelta_formulation == "CONSISTENT" else 2) if second_order else 0
@@ -741,7 +748,7 @@ def analyze_frame_batch(model: wire.ModelArrays, nodes_per_frame: int, device=No
                 am = active.repeat_interleave(nmf)[:, None]
                 ax_new = torch.where(am, ax_new, d_axial).contiguous()
             d_axial = ax_new
-            eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup)
+            eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup, count=False)
             d_un = factor_solve()
             un_f, u_f = d_un.view(nf, n), d_u.view(nf, n)
             den = torch.linalg.norm(un_f, dim=1)
@@ -750,10 +757,14 @@ def analyze_frame_batch(model: wire.ModelArrays, nodes_per_frame: int, device=No
             resid = torch.where(active, r, resid)
             d_u = torch.where(active.repeat_interleave(n)[:, None], d_un, d_u).contiguous()
             active = active & ~(r < opts.tolerance)
-            if not bool(active.any()):
+            go_on, bad = torch.stack([active.any(), bad_dev.any()]).cpu().tolist()       # the one sync of the iteration
+            if bad:
+                raise_if_bad()
+            if not go_on:
                 break
         # the matrix in eng.d_vals must be the tangent of the frozen state for the reactions
-        eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup)
+        eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup, count=False)
+    raise_if_bad()
     span = eng.span_tables() if detail else None
     rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, None, d_axial, kg_mode, sup, detail=detail)
     _store(out, model, [0], d_u, rec, xyz)

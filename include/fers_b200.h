@@ -65,7 +65,8 @@ int fers_b200_pattern_build(int n_nodes, int n_members, const int* m_n1, const i
 /* bc_code[n_dof] (0 free, 1 fixed, 2 spring) -> fixed[n_dof] (uint8 0/1) and
  * free_index[n_dof] (running number of free DOFs, -1 when constrained).  DOFs whose diagonal
  * stiffness (vals + spring) is exactly zero are restrained too ("dead" DOFs, e.g. rotations of
- * truss-only nodes).  *n_free_out, *n_dead_out [host] (synchronises the stream). */
+ * truss-only nodes).  *n_free_out, *n_dead_out [host] (synchronises the stream); pass both as NULL to skip
+ * the read-back and stay asynchronous (re-assemblies inside an iteration). */
 size_t fers_b200_bc_workspace(int n_dof);
 int fers_b200_bc_build(int n_nodes, const uint8_t* bc_code, const double* bc_k, const double* vals,
                        const int* diag_slot, uint8_t* fixed, int* free_index, double* kspring,

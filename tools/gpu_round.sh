@@ -1,2 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 2>gpurun_out/r1s_bench_n8.err | tail -1 > gpurun_out/r1s_bench_n8.json; cut -c1-300 gpurun_out/r1s_bench_n8.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --workload cfg5 2>gpurun_out/r1s_bench_cfg5_n8.err | tail -1 > gpurun_out/r1s_bench_cfg5_n8.json; cut -c1-300 gpurun_out/r1s_bench_cfg5_n8.json
+python -m pytest tests/test_gpu_parity.py tests/test_unilateral_supports.py tests/test_edge_cases.py -q -x -m gpu 2>&1 | tail -3
+python bench.py --workload cfg5 2>/dev/null | tail -1 | cut -c1-200
+python tools/cfg5_cprofile.py 2>&1 | grep -v Warning | head -18
