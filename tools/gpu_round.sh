@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_parity.py tests/test_unilateral_supports.py tests/test_edge_cases.py -q -x -m gpu 2>&1 | tail -3
-python bench.py --workload cfg5 2>/dev/null | tail -1 | cut -c1-200
-python tools/cfg5_cprofile.py 2>&1 | grep -v Warning | head -18
+python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > /dev/null 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file gpurun_out/r1s_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_l.log 2>&1
+tail -2 gpurun_out/ncu_l.log | cut -c1-200
