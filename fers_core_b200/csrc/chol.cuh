@@ -66,7 +66,6 @@ struct CholPlanHost {
     // device index buffer layout (bytes), filled by layout()
     size_t off_fronts = 0, off_nodes = 0, off_child = 0, off_inv_off = 0, off_inv = 0, off_level_fronts = 0,
            off_kscatter = 0, off_pos = 0, index_bytes = 0;
-    std::vector<unsigned char> staging;   // serialised index buffer (filled on first upload)
 };
 
 }  // namespace fers

@@ -1192,12 +1192,23 @@ size_t fers_b200_chol_work_bytes(void* plan, int nrhs) {
 int fers_b200_chol_upload(void* plan, void* index_dev, void* stream) {
     FERS_REQUIRE(plan && index_dev, "chol_upload: bad arguments");
     CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
-    if (P.staging.size() != P.index_bytes) {
-        P.staging.assign(P.index_bytes, 0);
-        chol_plan_serialise(P, P.staging.data());
-    }
-    FERS_CK(cudaMemcpyAsync(index_dev, P.staging.data(), P.index_bytes, cudaMemcpyHostToDevice, as_stream(stream)));
-    FERS_CK(cudaStreamSynchronize(as_stream(stream)));
+    // section by section straight from the plan's arrays (no zero-filled staging copy of the tens of MB of maps)
+    cudaStream_t st = as_stream(stream);
+    unsigned char* d = static_cast<unsigned char*>(index_dev);
+    auto put = [&](size_t off, const void* src, size_t bytes) -> int {
+        if (bytes == 0) return 0;
+        FERS_CK(cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    };
+    if (put(P.off_fronts, P.fronts.data(), sizeof(FrontDev) * P.fronts.size())) return 1;
+    if (put(P.off_nodes, P.nodes.data(), sizeof(int) * P.nodes.size())) return 1;
+    if (put(P.off_child, P.child.data(), sizeof(int) * P.child.size())) return 1;
+    if (put(P.off_inv_off, P.inv_off.data(), sizeof(long long) * P.inv_off.size())) return 1;
+    if (put(P.off_inv, P.inv.data(), sizeof(int) * P.inv.size())) return 1;
+    if (put(P.off_level_fronts, P.level_fronts.data(), sizeof(int) * P.level_fronts.size())) return 1;
+    if (put(P.off_kscatter, P.kscatter.data(), sizeof(KScatter) * P.kscatter.size())) return 1;
+    if (put(P.off_pos, P.pos.data(), sizeof(int) * P.pos.size())) return 1;
+    FERS_CK(cudaStreamSynchronize(st));
     return 0;
 }
 

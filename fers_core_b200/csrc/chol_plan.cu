@@ -87,6 +87,10 @@ struct Dissector {
     // (part[] is shared between threads: a thread only writes the entries of its own node set, and the only
     // foreign entries it reads belong to separators of ancestors, which are final and 0)
     void separators(const std::vector<int>& a, const std::vector<int>& b, std::vector<int>& sa, std::vector<int>& sb) {
+        separators(a, b, sa, sb, part);
+    }
+    void separators(const std::vector<int>& a, const std::vector<int>& b, std::vector<int>& sa, std::vector<int>& sb,
+                    std::vector<uint8_t>& part) const {
         for (int v : a) part[v] = 1;
         for (int v : b) part[v] = 2;
         sa.clear(); sb.clear();
@@ -100,7 +104,8 @@ struct Dissector {
         for (int v : b) part[v] = 0;
     }
 
-    static constexpr int PAR_BITS = 3;            // splits whose halves go to separate threads (8-way)
+    static constexpr int PAR_BITS = 4;            // splits whose halves go to separate threads (16-way); the three
+                                                  // candidate axes of these splits are evaluated concurrently too
     static constexpr size_t PAR_MIN_NODES = 4096;
 
     void both(std::vector<int>&& a, std::vector<int>&& b, int parent, unsigned long long key, int bits) {
@@ -123,9 +128,30 @@ struct Dissector {
         bool have = false, best_from_a = true;
         double best_score = 0.0;
         std::vector<int> a, b, sa, sb;
+        // upper splits: one thread per candidate axis (own scratch marks); the choice below is taken in axis order
+        // from the finished candidates, so the ordering does not depend on the threading
+        const bool par_axes = bits < PAR_BITS && nodes.size() >= PAR_MIN_NODES;
+        struct Candidate { bool ok = false; std::vector<int> a, b, sa, sb; };
+        Candidate cand[3];
+        if (par_axes) {
+            auto eval = [&](int axis) {
+                Candidate& c = cand[axis];
+                std::vector<uint8_t> marks((size_t)n, 0);
+                c.ok = split_axis(nodes, axis, c.a, c.b);
+                if (c.ok) separators(c.a, c.b, c.sa, c.sb, marks);
+            };
+            std::thread t1(eval, 1), t2(eval, 2);
+            eval(0);
+            t1.join(); t2.join();
+        }
         for (int axis = 0; axis < 3; ++axis) {
-            if (!split_axis(nodes, axis, a, b)) continue;
-            separators(a, b, sa, sb);
+            if (par_axes) {
+                if (!cand[axis].ok) continue;
+                a.swap(cand[axis].a); b.swap(cand[axis].b); sa.swap(cand[axis].sa); sb.swap(cand[axis].sb);
+            } else {
+                if (!split_axis(nodes, axis, a, b)) continue;
+                separators(a, b, sa, sb);
+            }
             const bool from_a = sa.size() <= sb.size();
             const std::vector<int>& sep = from_a ? sa : sb;
             // balance guard: a median split is balanced unless many nodes share the median coordinate
