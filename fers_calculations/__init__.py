@@ -12,7 +12,9 @@ on ``PYTHONPATH`` ahead of the PyPI wheel and ``FERS.run_analysis()`` runs on th
 Errors surface as exceptions, which the caller wraps in ``RuntimeError("Failed to run
 calculation: ...")`` (fers.py:301-302).
 """
-from fers_core_b200.engine import calculate_from_file, calculate_from_json, solve_document  # noqa: F401
+from fers_core_b200.engine import calculate_from_file, calculate_from_json, solve_document, solve_lazy  # noqa: F401
 
-__all__ = ["calculate_from_json", "calculate_from_file", "solve_document"]
+# beyond the reference's two functions: dict in / dict out without the JSON round trip (solve_document) and a lazy
+# ResultsBundle view over the result arrays for large models (solve_lazy)
+__all__ = ["calculate_from_json", "calculate_from_file", "solve_document", "solve_lazy"]
 __version__ = "0.2.43+b200"

@@ -21,7 +21,7 @@ from .hostlogic import (
     INACTIVE_SCALE, effective_bc, imperfect_coordinates, pdelta_suppressed_axes, rhs_plan, rigid_property_row,
     unilateral_dofs, unilateral_update,
 )
-from .results import ResultArrays, SECTION_FRACS, results_to_wire
+from .results import ResultArrays, SECTION_FRACS, lazy_bundle, results_to_wire
 
 DENSE_MAX_DOF = 8192          # models up to this many DOFs use the dense Cholesky path
 SOLVERS = ("auto", "dense", "cholesky", "pcg")   # auto: dense up to DENSE_MAX_DOF, sparse Cholesky above
@@ -789,6 +789,13 @@ def solve_document(doc: dict, device=None) -> dict:
     out = dict(doc)
     out["results"] = results_to_wire(model, res)
     return out
+
+
+def solve_lazy(doc: dict, device=None):
+    """dict in -> lazy ``ResultsBundle`` view over the result arrays (results.lazy_bundle): for models whose JSON
+    results would not fit anywhere.  Same keys and numbers as ``solve_document(doc)["results"]``."""
+    model = wire.parse_document(doc)
+    return lazy_bundle(model, analyze(model, device))
 
 
 def calculate_from_json(input_json: str) -> str:

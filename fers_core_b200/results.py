@@ -9,6 +9,7 @@ reactions for every supported node with all six components; member end forces in
 """
 from __future__ import annotations
 
+from collections.abc import Mapping
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -72,87 +73,182 @@ def _disp(v) -> dict:
     return d
 
 
-def results_to_wire(model, res: ResultArrays) -> dict:
-    """``ResultsBundle`` dict (pydantic_models.py:2171-2185) from result arrays."""
-    plan = res.plan
-    bundle = {"loadcases": {}, "loadcombinations": {},
-              "unity_check_results": res.unity.results() if res.unity is not None else []}
-    n_real = model.n_real
-    sup_nodes = np.nonzero(model.node_support_id[:n_real] >= 0)[0]
-    node_keys = [str(int(i)) for i in model.node_ids]
-    warp_node = model.warp_node if len(model.warp_node) == n_real else np.full(n_real, -1)
+class _Context:
+    """What every column of a result bundle shares: keys, supported nodes, warnings, plate rows per plate id."""
 
-    def warp_of(arr, col, i):
+    def __init__(self, model, res: ResultArrays):
+        self.model, self.res, self.plan = model, res, res.plan
+        self.n_real = model.n_real
+        self.sup_nodes = np.nonzero(model.node_support_id[:self.n_real] >= 0)[0]
+        self.node_keys = [str(int(i)) for i in model.node_ids]
+        self.mem_keys = [str(int(i)) for i in model.m_ids]
+        self.warp_node = model.warp_node if len(model.warp_node) == self.n_real else np.full(self.n_real, -1)
+        self.warn = [{"code": c, "message": m} for c, m in (list(model.warnings) + list(res.warnings))]
+        self.plate_rows: dict = {}                       # plate id key -> TRI3 rows (a split QUAD4 has two)
+        for e in range(model.n_plates):
+            self.plate_rows.setdefault(str(int(model.p_ids[e])), []).append(e)
+
+
+class _Column:
+    """One load case / combination: every wire sub-document is built from the result arrays on request."""
+
+    def __init__(self, ctx: _Context, col: int):
+        self.c, self.col = ctx, col
+
+    def _warp(self, arr, i) -> float:
         """Value at the warping DOF of real node i (DOF 0 of its auxiliary node), 0 without one."""
-        a = int(warp_node[i])
-        return float(arr[col, a, 0]) if a >= 0 else 0.0
-    mem_keys = [str(int(i)) for i in model.m_ids]
-    warn = [{"code": c, "message": m} for c, m in (list(model.warnings) + list(res.warnings))]
-    for col in range(plan.n_rhs):
-        disp = {}
-        for i in range(n_real):
-            disp[node_keys[i]] = _disp(res.U[col, i])
-            disp[node_keys[i]]["warp"] = warp_of(res.U, col, i)
-        reac = {}
-        for i in sup_nodes:
-            reac[node_keys[i]] = {
-                "location": {"X": float(model.xyz[i, 0]), "Y": float(model.xyz[i, 1]), "Z": float(model.xyz[i, 2])},
-                "nodal_forces": _forces(res.R[col, i], warp_of(res.R, col, i)),
-                "support_id": int(model.node_support_id[i]),
-            }
-        members = {}
-        for m in range(model.n_members):
-            fl, fg, ul = res.f_local[col, m], res.f_global[col, m], res.u_local[col, m]
-            sec = [{"x_frac": float(x), "forces": _forces(res.sec[col, m, si])} for si, x in enumerate(SECTION_FRACS)]
-            series = ([{"x_frac": 0.0, "forces": _forces(fl[0:6])}] + sec
-                      + [{"x_frac": 1.0, "forces": _forces(-fl[6:12])}])
-            b1, b2 = (float(res.bw[col, m, 0]), float(res.bw[col, m, 1])) if res.bw is not None else (0.0, 0.0)
-            members[mem_keys[m]] = {
-                "start_node_forces": _forces(fg[0:6], b1), "end_node_forces": _forces(fg[6:12], b2),
-                "maximums": _forces(res.gmax[col, m]), "minimums": _forces(res.gmin[col, m]),
-                "local_start_forces": _forces(fl[0:6], b1), "local_end_forces": _forces(fl[6:12], b2),
-                "local_maximums": _forces(res.lmax[col, m]), "local_minimums": _forces(res.lmin[col, m]),
-                "local_displacement_start_node": _disp(ul[0:6]), "local_displacement_end_node": _disp(ul[6:12]),
-                "section_forces": sec, "internal_force_series": series,
-            }
+        a = int(self.c.warp_node[i])
+        return float(arr[self.col, a, 0]) if a >= 0 else 0.0
+
+    def node_disp(self, i: int) -> dict:
+        d = _disp(self.c.res.U[self.col, i])
+        d["warp"] = self._warp(self.c.res.U, i)
+        return d
+
+    def reaction(self, i: int) -> dict:
+        model, res = self.c.model, self.c.res
+        return {
+            "location": {"X": float(model.xyz[i, 0]), "Y": float(model.xyz[i, 1]), "Z": float(model.xyz[i, 2])},
+            "nodal_forces": _forces(res.R[self.col, i], self._warp(res.R, i)),
+            "support_id": int(model.node_support_id[i]),
+        }
+
+    def member(self, m: int) -> dict:
+        res, col = self.c.res, self.col
+        fl, fg, ul = res.f_local[col, m], res.f_global[col, m], res.u_local[col, m]
+        sec = [{"x_frac": float(x), "forces": _forces(res.sec[col, m, si])} for si, x in enumerate(SECTION_FRACS)]
+        series = ([{"x_frac": 0.0, "forces": _forces(fl[0:6])}] + sec
+                  + [{"x_frac": 1.0, "forces": _forces(-fl[6:12])}])
+        b1, b2 = (float(res.bw[col, m, 0]), float(res.bw[col, m, 1])) if res.bw is not None else (0.0, 0.0)
+        return {
+            "start_node_forces": _forces(fg[0:6], b1), "end_node_forces": _forces(fg[6:12], b2),
+            "maximums": _forces(res.gmax[col, m]), "minimums": _forces(res.gmin[col, m]),
+            "local_start_forces": _forces(fl[0:6], b1), "local_end_forces": _forces(fl[6:12], b2),
+            "local_maximums": _forces(res.lmax[col, m]), "local_minimums": _forces(res.lmin[col, m]),
+            "local_displacement_start_node": _disp(ul[0:6]), "local_displacement_end_node": _disp(ul[6:12]),
+            "section_forces": sec, "internal_force_series": series,
+        }
+
+    def plate(self, key: str) -> dict:
+        model, res, col = self.c.model, self.c.res, self.col
+        rows = self.c.plate_rows[key]
+        e0 = rows[0]
+        nodal: dict = {}
+        for e in rows:                                   # second half of a split QUAD4: corner forces accumulate
+            for k, n in enumerate(model.p_nodes[e]):
+                f = _forces(res.p_nodal[col, e, k])
+                nk = self.c.node_keys[int(n)]
+                if nk in nodal:
+                    for comp in f:
+                        nodal[nk][comp] += f[comp]
+                else:
+                    nodal[nk] = f
+        c = res.p_centroid[e0]
+        return {
+            "plate_id": int(model.p_ids[e0]),
+            "centroid": {"X": float(c[0]), "Y": float(c[1]), "Z": float(c[2])},
+            "centroid_displacement_global": _disp(res.p_cdg[col, e0]),
+            "centroid_displacement_local": _disp(res.p_cdl[col, e0]),
+            "nodal_forces_global": nodal,
+            "resultants": {k: float(v) for k, v in zip(_PR, res.p_res[col, e0])},
+        }
+
+    def summary(self) -> dict:
+        s = {"total_displacements": self.c.n_real, "total_member_forces": self.c.model.n_members,
+             "total_reaction_forces": int(len(self.c.sup_nodes))}
+        if self.c.model.n_plates:
+            s["total_plate_forces"] = len(self.c.plate_rows)
+        return s
+
+    def diagnostics(self) -> dict:
+        res, col = self.c.res, self.col
+        return {
+            "analysis_method": res.method,
+            "converged": bool(res.converged[col]),
+            "iterations": None if res.iterations[col] < 0 else int(res.iterations[col]),
+            "residual_norm": None if res.iterations[col] < 0 else float(res.residual[col]),
+            "solve_time_ms": None if res.solve_ms is None else float(res.solve_ms),
+        }
+
+    def document(self, mapping=None) -> dict:
+        """The wire ``Results`` document of this column; ``mapping(keys, items, getter)`` builds the per-entity maps
+        (plain dicts by default, :class:`LazyMap` for :func:`lazy_bundle`)."""
+        c, plan, col = self.c, self.c.plan, self.col
+        if mapping is None:
+            def mapping(keys, items, get):
+                return {k: get(i) for k, i in zip(keys, items)}
+        nodes = range(c.n_real)
         r = {
             "name": plan.names[col],
             "result_type": {plan.kinds[col]: int(plan.ids[col])},
-            "displacement_nodes": disp, "reaction_nodes": reac, "member_results": members,
-            "summary": {"total_displacements": n_real, "total_member_forces": model.n_members,
-                        "total_reaction_forces": int(len(sup_nodes))},
-            "errors_and_warnings": {"errors": [], "warnings": warn},
-            "solver_diagnostics": {
-                "analysis_method": res.method,
-                "converged": bool(res.converged[col]),
-                "iterations": None if res.iterations[col] < 0 else int(res.iterations[col]),
-                "residual_norm": None if res.iterations[col] < 0 else float(res.residual[col]),
-                "solve_time_ms": None if res.solve_ms is None else float(res.solve_ms),
-            },
+            "displacement_nodes": mapping([c.node_keys[i] for i in nodes], nodes, self.node_disp),
+            "reaction_nodes": mapping([c.node_keys[i] for i in c.sup_nodes], c.sup_nodes, self.reaction),
+            "member_results": mapping(c.mem_keys, range(c.model.n_members), self.member),
+            "summary": self.summary(),
+            "errors_and_warnings": {"errors": [], "warnings": c.warn},
+            "solver_diagnostics": self.diagnostics(),
         }
-        if model.n_plates:
-            plates = {}
-            for e in range(model.n_plates):
-                key = str(int(model.p_ids[e]))
-                nod = {node_keys[int(n)]: _forces(res.p_nodal[col, e, k]) for k, n in enumerate(model.p_nodes[e])}
-                if key in plates:   # second half of a split QUAD4: accumulate corner forces
-                    for nk, f in nod.items():
-                        if nk in plates[key]["nodal_forces_global"]:
-                            for c in f:
-                                plates[key]["nodal_forces_global"][nk][c] += f[c]
-                        else:
-                            plates[key]["nodal_forces_global"][nk] = f
-                    continue
-                c = res.p_centroid[e]
-                plates[key] = {
-                    "plate_id": int(model.p_ids[e]),
-                    "centroid": {"X": float(c[0]), "Y": float(c[1]), "Z": float(c[2])},
-                    "centroid_displacement_global": _disp(res.p_cdg[col, e]),
-                    "centroid_displacement_local": _disp(res.p_cdl[col, e]),
-                    "nodal_forces_global": nod,
-                    "resultants": {k: float(v) for k, v in zip(_PR, res.p_res[col, e])},
-                }
-            r["plate_results"] = plates
-            r["summary"]["total_plate_forces"] = len(plates)
-        bundle["loadcases" if plan.kinds[col] == "Loadcase" else "loadcombinations"][plan.names[col]] = r
+        if c.model.n_plates:
+            keys = list(c.plate_rows)
+            r["plate_results"] = mapping(keys, keys, self.plate)
+        return r
+
+
+def results_to_wire(model, res: ResultArrays) -> dict:
+    """``ResultsBundle`` dict (pydantic_models.py:2171-2185) from result arrays."""
+    plan = res.plan
+    ctx = _Context(model, res)
+    bundle = {"loadcases": {}, "loadcombinations": {},
+              "unity_check_results": res.unity.results() if res.unity is not None else []}
+    for col in range(plan.n_rhs):
+        bundle["loadcases" if plan.kinds[col] == "Loadcase" else "loadcombinations"][plan.names[col]] = _Column(ctx, col).document()
     return bundle
+
+
+class LazyMap(Mapping):
+    """Read-only mapping whose values are built on access (one node / member / plate / column at a time)."""
+
+    def __init__(self, keys, items, get):
+        self._index = {k: i for k, i in zip(keys, items)}
+        self._get = get
+
+    def __getitem__(self, key):
+        return self._get(self._index[key])
+
+    def __iter__(self):
+        return iter(self._index)
+
+    def __len__(self):
+        return len(self._index)
+
+    def to_dict(self) -> dict:
+        return {k: _plain(v) for k, v in self.items()}
+
+
+def _plain(v):
+    if isinstance(v, LazyMap):
+        return v.to_dict()
+    if isinstance(v, dict):
+        return {k: _plain(x) for k, x in v.items()}
+    if isinstance(v, list):
+        return [_plain(x) for x in v]
+    return v
+
+
+def lazy_bundle(model, res: ResultArrays) -> LazyMap:
+    """The same ``ResultsBundle`` document as :func:`results_to_wire`, as nested read-only mappings over the
+    result arrays: ``bundle["loadcombinations"][name]["member_results"]["17"]["maximums"]["mz"]`` touches one
+    member of one column.  configs[3] would be ~70 GB as JSON; the arrays are 10 GB and a
+    view costs nothing until it is read.  ``.to_dict()`` materialises any level."""
+    plan = res.plan
+    ctx = _Context(model, res)
+
+    def column(col):
+        return _Column(ctx, col).document(mapping=LazyMap)
+    groups = {}
+    for kind, name in (("Loadcase", "loadcases"), ("Loadcombination", "loadcombinations")):
+        cols = [c for c in range(plan.n_rhs) if plan.kinds[c] == kind]
+        groups[name] = LazyMap([plan.names[c] for c in cols], cols, column)
+    unity = res.unity.results() if res.unity is not None else []
+    top = {"loadcases": groups["loadcases"], "loadcombinations": groups["loadcombinations"], "unity_check_results": unity}
+    return LazyMap(list(top), list(top), top.__getitem__)
