@@ -274,6 +274,7 @@ k_potrf_inv(LevelCtx L, int s, int* __restrict__ info) {
 }
 
 // ---- tile GEMM kernels of the factorisation --------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifdef FERS_CHOL_DFMA     // vector-FMA tile core (kept for A/B measurements)
 using G88 = GemmTile<8, 8, false>;
 using G86 = GemmTile<8, 8, false>;
@@ -329,6 +330,14 @@ k_row_panel(LevelCtx L, int bs, int be) {
     if (r0 >= m) return;
     const int mrem = m - r0;
     double* panel = L.factor + f.panel_off;
+    // the CTA's 64-row strip of the block and the inverted diagonal tiles come from HBM and are touched sub-block by
+    // sub-block: ask for all of them now (64 rows = 4 lines per column)
+    for (int q = threadIdx.x; q < 4 * (be - bs); q += GEMM_THREADS) {
+        const int col = q >> 2, seg = q & 3;
+        if (16 * seg < mrem) prefetch_l2(panel + (size_t)(bs + col) * m + r0 + 16 * seg);
+    }
+    for (int q = threadIdx.x; q < (be - bs) * NB / 16; q += GEMM_THREADS)
+        prefetch_l2(L.factor + f.dinv_off + (size_t)(bs / NB) * NB * NB + 16 * (size_t)q);
     for (int cj = bs; cj < be; cj += NB) {
         const int nb = min(NB, be - cj);
         double* C = panel + (size_t)cj * m + r0;
@@ -360,9 +369,21 @@ k_update(LevelCtx L, int kc0, int kw, int cbeg, int cend, int rend) {
     const int r = cbeg + blockIdx.x * G::BM, c = cbeg + blockIdx.y * G::BN;
     if (r >= row_end || c >= cend || c >= r + G::BM) return;  // outside the panel or entirely above the diagonal
     const double* X = L.factor + f.panel_off + (size_t)kc0 * m;
+    double* C = L.factor + f.panel_off + (size_t)c * m + r;
     typename G::Acc acc;
+    // K is short here (64 .. 256 columns) and the C tile comes from HBM: ask for it now so that the epilogue's loads
+    // find it in L2.  (Seeding the accumulator with -C would hide the latency completely, but it replaces the blocked
+    // summation C - (sum of products) by a running one: relative residual of configs[3] 5e-13 -> 3e-12, measured.)
+    {
+        const int tr = threadIdx.x & 7, tc = threadIdx.x >> 3;               // 8 lines per column, 32 columns per pass
+#pragma unroll
+        for (int q = 0; q < G::BN / 32; ++q) {
+            const int cc = tc + 32 * q;
+            if (cc < cend - c && 16 * tr < row_end - r) prefetch_l2(C + (size_t)cc * m + 16 * tr);
+        }
+    }
     G::mainloop(acc, smem, X + r, m, row_end - r, X + c, m, cend - c, kw);
-    G::template store<false>(acc, L.factor + f.panel_off + (size_t)c * m + r, (size_t)m, row_end - r, cend - c);
+    G::template store<false>(acc, C, (size_t)m, row_end - r, cend - c);
 }
 
 // Schur complement: F22 -= L21 L21^T on the lower tiles
@@ -566,7 +587,6 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // the 64 x 64 tile at `t` (column stride ld doubles) -> L2, one 128-byte line per thread (GEMM_THREADS == 256)
 __device__ __forceinline__ void prefetch_tile(const double* t, size_t ld) {
     prefetch_l2(t + (size_t)(threadIdx.x >> 2) * ld + 16 * (threadIdx.x & 3));

@@ -1,2 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 4 2>gpurun_out/r1s_bench_n4.err | tail -1 > gpurun_out/r1s_bench_n4.json; cut -c1-260 gpurun_out/r1s_bench_n4.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 2 2>gpurun_out/r1s_bench_n2.err | tail -1 > gpurun_out/r1s_bench_n2.json; cut -c1-260 gpurun_out/r1s_bench_n2.json
+timeout 600 python -m pytest tests/test_chol_gpu.py -q -x 2>&1 | tail -2
+CHOL_VARIANTS=0 CHOL_OUTERS=4x1,4x1 timeout 600 python tools/chol_bench.py 60 60 30 2>&1 | grep -E "refine 0|unprofiled|update_ms" | cut -c1-150
