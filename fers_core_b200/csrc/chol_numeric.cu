@@ -25,6 +25,8 @@ namespace fers {
 
 void chol_plan_serialise(const CholPlanHost& P, unsigned char* out);
 
+constexpr int LEVEL_SMALL_FRONTS = 8;
+
 struct LevelCtx {
     const FrontDev* fronts;
     const int* level_fronts;   // fronts of this level
@@ -35,7 +37,17 @@ struct LevelCtx {
     double* factor;
     double* schur_cur;         // arena of this level
     const double* schur_child; // arena of the children's level
+    // levels with few fronts (the top of the tree, where every CTA start is on a dependent chain or repeats
+    // thousands of times): the front records travel in the kernel parameters (constant bank) instead of two
+    // dependent global loads at the start of every CTA
+    int n_small;
+    FrontDev small_fronts[LEVEL_SMALL_FRONTS];
 };
+
+__device__ __forceinline__ FrontDev level_front(const LevelCtx& L, int z) {
+    if (L.n_small) return L.small_fronts[z];
+    return L.fronts[L.level_fronts[z]];
+}
 
 // ---- front initialisation: children's Schur complements -> panel + F22 (lower triangle) -----------
 // One thread owns two consecutive rows (the even/odd DOF pair of one node: 16-byte loads and stores
@@ -46,8 +58,8 @@ constexpr int INIT_ROWS = 2 * INIT_THREADS;
 constexpr int INIT_COLS = 24;
 
 __global__ void __launch_bounds__(INIT_THREADS)
-k_front_init(LevelCtx L) {
-    const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
+k_front_init(const __grid_constant__ LevelCtx L) {
+    const FrontDev f = level_front(L, blockIdx.z);
     const int nt = f.n1 + f.n2, m = 6 * nt, k1 = 6 * f.n1, m2 = 6 * f.n2;
     const int r0 = blockIdx.x * INIT_ROWS, c0 = blockIdx.y * INIT_COLS;
     if (r0 >= m || c0 >= m || c0 > r0 + INIT_ROWS - 1) return;
@@ -145,9 +157,8 @@ constexpr size_t POTRF_SMEM = 2 * NB * TP * sizeof(double);
 // threads apply the rank-8 update to the trailing columns.  The inverse is built block row by block
 // row, one thread per column with 8 independent accumulators (a thread only re-reads its own column).
 __global__ void __launch_bounds__(256)
-k_potrf_inv(LevelCtx L, int s, int* __restrict__ info) {
-    const int fid = L.level_fronts[blockIdx.x];
-    const FrontDev f = L.fronts[fid];
+k_potrf_inv(const __grid_constant__ LevelCtx L, int s, int* __restrict__ info) {
+    const FrontDev f = level_front(L, blockIdx.x);
     const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
     const int c0 = s * NB;
     if (c0 >= k1) return;
@@ -296,9 +307,9 @@ using G48N = GemmMma<64, 128, 2, 4, true, 16>;
 // rows below the diagonal tile of step s, inside the current outer block only (rows < min(rend, k1)):
 // X = B * inv(D)^T (in place).  The rows below the block are handled once per block by k_row_panel.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_trsm(LevelCtx L, int s, int rend) {
+k_trsm(const __grid_constant__ LevelCtx L, int s, int rend) {
     extern __shared__ __align__(16) double smem[];
-    const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
+    const FrontDev f = level_front(L, blockIdx.z);
     const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
     const int c0 = s * NB;
     if (c0 >= k1) return;
@@ -320,9 +331,9 @@ k_trsm(LevelCtx L, int s, int rend) {
 // launch per 64-column step over all the rows of the front.
 using GRP = G44;     // tile of the row-panel kernel: 64 rows x 64 columns (128 x 64 measured no faster)
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-k_row_panel(LevelCtx L, int bs, int be) {
+k_row_panel(const __grid_constant__ LevelCtx L, int bs, int be) {
     extern __shared__ __align__(16) double smem[];
-    const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
+    const FrontDev f = level_front(L, blockIdx.z);
     const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
     if (bs >= k1) return;
     be = min(be, k1);
@@ -359,9 +370,9 @@ k_row_panel(LevelCtx L, int bs, int be) {
 // (kw = 256), so that most of the trailing matrix is read and written once per 256 eliminated columns.
 template <class G>
 __global__ void __launch_bounds__(GEMM_THREADS, G::MIN_CTAS)
-k_update(LevelCtx L, int kc0, int kw, int cbeg, int cend, int rend) {
+k_update(const __grid_constant__ LevelCtx L, int kc0, int kw, int cbeg, int cend, int rend) {
     extern __shared__ __align__(16) double smem[];
-    const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
+    const FrontDev f = level_front(L, blockIdx.z);
     const int k1 = 6 * f.n1, m = 6 * (f.n1 + f.n2);
     if (cend > k1) cend = k1;
     if (cbeg >= cend) return;
@@ -389,9 +400,9 @@ k_update(LevelCtx L, int kc0, int kw, int cbeg, int cend, int rend) {
 // Schur complement: F22 -= L21 L21^T on the lower tiles
 template <class G>
 __global__ void __launch_bounds__(GEMM_THREADS, G::MIN_CTAS)
-k_syrk(LevelCtx L) {
+k_syrk(const __grid_constant__ LevelCtx L) {
     extern __shared__ __align__(16) double smem[];
-    const FrontDev f = L.fronts[L.level_fronts[blockIdx.z]];
+    const FrontDev f = level_front(L, blockIdx.z);
     const int k1 = 6 * f.n1, m2 = 6 * f.n2, m = k1 + m2;
     const int r = blockIdx.x * G::BM, c = blockIdx.y * G::BN;
     if (r >= m2 || c >= m2 || c >= r + G::BM) return;
@@ -939,6 +950,8 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
         L.fronts = I.fronts; L.level_fronts = I.level_fronts + P.level_ptr[l]; L.nodes = I.nodes; L.child = I.child;
         L.inv_off = I.inv_off; L.inv = I.inv; L.factor = factor;
         L.schur_cur = arena[l & 1]; L.schur_child = arena[(l & 1) ^ 1];
+        L.n_small = nf <= LEVEL_SMALL_FRONTS ? nf : 0;
+        for (int q = 0; q < L.n_small; ++q) L.small_fronts[q] = P.fronts[P.level_fronts[P.level_ptr[l] + q]];
         const int max_m = 6 * P.level_max_n[l], max_k1 = 6 * P.level_max_n1[l];
         cudaEvent_t e0 = span_begin(0);
         {
