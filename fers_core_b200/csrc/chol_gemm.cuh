@@ -32,6 +32,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int TM, int TN, bool B_KMAJOR>
 struct GemmTile {
     static constexpr int BM = 16 * TM, BN = 16 * TN;
+    static constexpr int MIN_CTAS = 1;
     static constexpr int A_STAGE = GEMM_BK * BM;                                   // doubles
     static constexpr int B_STAGE = B_KMAJOR ? BN * GEMM_BKP : GEMM_BK * BN;        // doubles
     static constexpr size_t SMEM = (size_t)GEMM_STAGES * (A_STAGE + B_STAGE) * sizeof(double);
