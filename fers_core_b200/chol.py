@@ -37,6 +37,24 @@ class PlanInfo:
     root_nodes: int
 
 
+def host_pattern(n_nodes: int, p1: np.ndarray, p2: np.ndarray, p_nodes: np.ndarray | None = None):
+    """(rowptr, colidx) of the block-CSR node pattern on the host -- integer for integer what
+    fers_b200_pattern_build leaves on the device (tests/test_gpu_parity.py checks it)."""
+    lib = _lib.load()
+    a = np.ascontiguousarray(p1, np.int32)
+    b = np.ascontiguousarray(p2, np.int32)
+    pn = np.zeros(0, np.int32) if p_nodes is None else np.ascontiguousarray(p_nodes, np.int32).reshape(-1)
+    npl = len(pn) // 3
+    cap = n_nodes + 2 * len(a) + 6 * npl
+    rowptr = np.empty(n_nodes + 1, np.int32)
+    colidx = np.empty(max(cap, 1), np.int32)
+    nnzb = C.c_int()
+    _lib.check(lib.fers_b200_host_pattern(n_nodes, len(a), a.ctypes.data if len(a) else None, b.ctypes.data if len(b) else None,
+                                          npl, pn.ctypes.data if npl else None, rowptr.ctypes.data, colidx.ctypes.data, cap,
+                                          C.byref(nnzb)), "host_pattern")
+    return rowptr, colidx[: nnzb.value]
+
+
 class CholPlan:
     """Nested-dissection ordering + symbolic factorisation of a block-CSR node pattern."""
 

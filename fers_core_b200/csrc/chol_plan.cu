@@ -490,6 +490,57 @@ int fers_b200_chol_plan_create(int n_nodes, const int* rowptr, const int* colidx
 
 void fers_b200_chol_plan_destroy(void* plan) { delete static_cast<CholPlanHost*>(plan); }
 
+/* [host] the block-CSR pattern fers_b200_pattern_build produces on the device (sorted unique (row, col) pairs of every
+ * diagonal, both orientations of every node pair, the six ordered pairs of every TRI3 plate), built on the host so
+ * that the factorisation plan can start before the device pattern has been copied back. */
+int fers_b200_host_pattern(int n_nodes, int n_pairs, const int* p1, const int* p2, int n_plates, const int* p_nodes,
+                           int* rowptr, int* colidx, int cap, int* nnzb_out) {
+    FERS_REQUIRE(n_nodes > 0 && rowptr && colidx && nnzb_out, "host_pattern: bad arguments");
+    FERS_REQUIRE(n_pairs == 0 || (p1 && p2), "host_pattern: node pairs missing");
+    FERS_REQUIRE(n_plates == 0 || p_nodes, "host_pattern: plate nodes missing");
+    std::vector<int> cnt((size_t)n_nodes + 1, 0);
+    auto ok = [&](int v) { return v >= 0 && v < n_nodes; };
+    for (int i = 0; i < n_pairs; ++i) {
+        FERS_REQUIRE(ok(p1[i]) && ok(p2[i]), "host_pattern: node index out of range");
+        ++cnt[p1[i] + 1]; ++cnt[p2[i] + 1];
+    }
+    for (int e = 0; e < 3 * n_plates; ++e) {
+        FERS_REQUIRE(ok(p_nodes[e]), "host_pattern: plate node index out of range");
+        cnt[p_nodes[e] + 1] += 2;
+    }
+    for (int i = 0; i < n_nodes; ++i) cnt[i + 1] += cnt[i] + 1;          // + the diagonal
+    std::vector<int> raw((size_t)cnt[n_nodes]);
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+    for (int i = 0; i < n_nodes; ++i) raw[fill[i]++] = i;
+    for (int i = 0; i < n_pairs; ++i) { raw[fill[p1[i]]++] = p2[i]; raw[fill[p2[i]]++] = p1[i]; }
+    for (int e = 0; e < n_plates; ++e)
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                if (a != b) raw[fill[p_nodes[3 * e + a]]++] = p_nodes[3 * e + b];
+    // sort + unique per row (rows are short), in parallel chunks; compact afterwards
+    std::vector<int> len((size_t)n_nodes);
+    parallel_chunks(n_nodes, PLAN_THREADS, [&](int, int b0, int b1) {
+        for (int i = b0; i < b1; ++i) {
+            int* lo = raw.data() + cnt[i];
+            int* hi = raw.data() + cnt[i + 1];
+            std::sort(lo, hi);
+            len[i] = (int)(std::unique(lo, hi) - lo);
+        }
+    });
+    long long nnzb = 0;
+    for (int i = 0; i < n_nodes; ++i) nnzb += len[i];
+    FERS_REQUIRE(nnzb <= cap, "host_pattern: colidx capacity too small");
+    int o = 0;
+    for (int i = 0; i < n_nodes; ++i) {
+        rowptr[i] = o;
+        std::copy(raw.data() + cnt[i], raw.data() + cnt[i] + len[i], colidx + o);
+        o += len[i];
+    }
+    rowptr[n_nodes] = o;
+    *nnzb_out = o;
+    return 0;
+}
+
 int fers_b200_chol_plan_info(void* plan, long long* out, int n_out) {
     FERS_REQUIRE(plan && out && n_out >= 12, "chol_plan_info: need 12 outputs");
     const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import threading
 import time
 from dataclasses import dataclass
 
@@ -67,7 +68,8 @@ class SolveStats:
 class Engine:
     """One model resident on one GPU."""
 
-    def __init__(self, model: wire.ModelArrays, device=None, assembly_variant: int = ASSEMBLY_GATHER, solver: str = "auto"):
+    def __init__(self, model: wire.ModelArrays, device=None, assembly_variant: int = ASSEMBLY_GATHER, solver: str = "auto",
+                 plan_ahead: bool = False):
         if solver not in SOLVERS:
             raise EngineError(f"solver must be one of {SOLVERS}, got {solver!r}")
         self.solver = solver
@@ -86,9 +88,51 @@ class Engine:
         self.stats = SolveStats()
         self.timings: dict = {}
         self.h2d_bytes = 0
+        # nodes with all six DOFs restrained by PERMANENT supports: left out of the sparse factorisation
+        self.h_node_restrained = (model.bc_code.reshape(-1, 6) == wire.BC_FIXED).all(axis=1)
+        if self.h_node_restrained.all():
+            self.h_node_restrained = None
+        self._plan_thread = None
+        self._plan_result = None
+        if plan_ahead and self._wants_sparse_cholesky():
+            # optional: the ordering / symbolic phase of the sparse direct solve (host, ~18 ms at configs[3]) starts now,
+            # on a host thread, from a host-built copy of the pattern, and overlaps the uploads and the device set-up.
+            # Off by default: the plan already uses every host core, so on the 16-core bench host the overlapped plan
+            # took 29 ms instead of 17 and the set-up 12-19 ms instead of 5 -- no net gain (tools/e2e_probe.py).
+            self._plan_thread = threading.Thread(target=self._plan_worker, daemon=True)
+            self._plan_thread.start()
         self._upload_static()
         self._upload_load_cases()
         self._build_pattern()
+
+    # ---- factorisation plan on a host thread ---------------------------------------------------
+    def _wants_sparse_cholesky(self) -> bool:
+        m = self.model
+        if self.solver == "cholesky":
+            return True
+        return self.solver == "auto" and m.n_dof > DENSE_MAX_DOF
+
+    def _pattern_pairs(self):
+        """Node pairs of the pattern: members, then the five extra pairs of every warping member (see _build_pattern)."""
+        m = self.model
+        p1, p2 = m.m_n1, m.m_n2
+        if len(m.w_member):
+            s_, e_ = m.m_n1[m.w_member], m.m_n2[m.w_member]
+            a1, a2 = m.w_aux[:, 0], m.w_aux[:, 1]
+            p1 = np.concatenate([p1, np.stack([s_, s_, e_, e_, a1], axis=1).reshape(-1)])
+            p2 = np.concatenate([p2, np.stack([a1, a2, a1, a2, a2], axis=1).reshape(-1)])
+        return p1, p2
+
+    def _plan_worker(self) -> None:
+        try:
+            m = self.model
+            t0 = time.perf_counter()
+            p1, p2 = self._pattern_pairs()
+            rowptr, colidx = chol.host_pattern(m.n_nodes, p1, p2, m.p_nodes if m.n_plates else None)
+            plan = chol.CholPlan(rowptr, colidx, m.xyz, node_restrained=self.h_node_restrained)
+            self._plan_result = (plan, len(colidx), (time.perf_counter() - t0) * 1e3)
+        except Exception as e:                      # surfaced by _solve_cholesky, which falls back to the inline plan
+            self._plan_result = e
 
     # ---- helpers ---------------------------------------------------------------------------
     @property
@@ -140,10 +184,6 @@ class Engine:
         self.has_springs = bool((code == wire.BC_SPRING).any()) or bool((unilateral_dofs(m)[2] > 0).any())
         self.d_bc_code = self._t(code.reshape(-1), np.uint8)
         self.d_bc_k = self._t(kk.reshape(-1), np.float64)
-        # nodes with all six DOFs restrained by PERMANENT supports: left out of the sparse factorisation
-        self.h_node_restrained = (m.bc_code.reshape(-1, 6) == wire.BC_FIXED).all(axis=1)
-        if self.h_node_restrained.all():
-            self.h_node_restrained = None
         self.d_supported = self._t((m.node_support_id >= 0).astype(np.uint8), np.uint8)
         self.d_p_nodes = self._t(m.p_nodes, np.int32) if m.n_plates else None
         self.d_p_data = self._t(m.p_data, np.float64) if m.n_plates else None
@@ -352,11 +392,20 @@ class Engine:
         nd, nr = d_f.shape
         if self._chol is None:
             t0 = time.perf_counter()
-            rowptr = self.d_rowptr.cpu().numpy()
-            colidx = self.d_colidx.cpu().numpy()
-            plan = chol.CholPlan(rowptr, colidx, m.xyz, node_restrained=self.h_node_restrained)
+            plan = None
+            if self._plan_thread is not None:
+                self._plan_thread.join()
+                self._plan_thread = None
+                res, self._plan_result = self._plan_result, None
+                if isinstance(res, tuple) and res[1] == self.nnzb:       # same pattern size as the device's
+                    plan = res[0]
+                    self.timings["chol_plan_thread_ms"] = res[2]
+            if plan is None:
+                rowptr = self.d_rowptr.cpu().numpy()
+                colidx = self.d_colidx.cpu().numpy()
+                plan = chol.CholPlan(rowptr, colidx, m.xyz, node_restrained=self.h_node_restrained)
             self._chol = chol.CholSolver(plan, self.dev, max_nrhs=64)
-            self.timings["chol_plan_ms"] = (time.perf_counter() - t0) * 1e3
+            self.timings["chol_plan_ms"] = (time.perf_counter() - t0) * 1e3          # what the pass waited for
         sol = self._chol
         if self._chol_version != self._k_version:
             info = sol.factorize(self.d_vals, self.d_diag_slot, self.d_fixed, self.d_ks)

@@ -194,6 +194,11 @@ int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* b
 int fers_b200_chol_plan_create(int n_nodes, const int* rowptr, const int* colidx, const double* xyz, int leaf_nodes,
                                const uint8_t* node_restrained, void** plan_out);
 void fers_b200_chol_plan_destroy(void* plan);
+/* [host] the same block-CSR pattern fers_b200_pattern_build leaves on the device (rowptr[n_nodes+1], colidx[cap >=
+ * n_nodes + 2 n_pairs + 6 n_plates], *nnzb_out), built from the host copies of the connectivity: lets the plan of the
+ * factorisation start on a host thread while the device is still being set up. */
+int fers_b200_host_pattern(int n_nodes, int n_pairs, const int* p1, const int* p2, int n_plates, const int* p_nodes,
+                           int* rowptr, int* colidx, int cap, int* nnzb_out);
 /* [host] out[12]: fronts, levels, largest front (nodes), factor doubles, Schur arena doubles (even
  * levels, odd levels), front-local rhs rows, index bytes, factorisation Mflop, nnz(L), K blocks
  * scattered, root separator nodes. */

@@ -110,3 +110,27 @@ def test_wavefront_substitution_is_deterministic_and_matches_per_step_kernels(sh
         lib.fers_b200_chol_set_variant(0)
     assert np.array_equal(xs[0], xs[1])
     assert np.abs(xs[0] - xs[2]).max() <= 1e-12 * np.abs(xs[2]).max()
+
+
+@pytest.mark.parametrize("name", ["portal_2d_combinations", "plate_strip_surface_load", "nafems_LE5_4el", "nafems_LE6_8x8"])
+def test_host_pattern_equals_the_device_pattern(name):
+    """The plan thread starts from a host-built pattern (engine._plan_worker): it must be the device's, integer for
+    integer, including the extra node pairs of warping members and the plate pairs."""
+    from fers_core_b200 import chol, engine, wire
+    from tests import helpers
+    m = wire.parse_document(helpers.golden(name)["doc"])
+    eng = engine.Engine(m, "cuda:0", solver="cholesky", plan_ahead=True)
+    p1, p2 = eng._pattern_pairs()
+    rowptr, colidx = chol.host_pattern(m.n_nodes, p1, p2, m.p_nodes if m.n_plates else None)
+    assert np.array_equal(rowptr, eng.d_rowptr.cpu().numpy()) and np.array_equal(colidx, eng.d_colidx.cpu().numpy())
+    # the solve picks up the plan the host thread built from that pattern, and agrees with the inline plan bit for bit
+    f_case, _ = eng.load_cases(eng.d_xyz0)
+    fac = np.ones((1, max(len(m.load_cases), 1)))
+    eng.assemble(eng.d_xyz0)
+    u_thread = eng.solve(eng.combine(f_case, fac, 8)).cpu().numpy()
+    assert "chol_plan_thread_ms" in eng.timings
+    ref = engine.Engine(m, "cuda:0", solver="cholesky")
+    f_case, _ = ref.load_cases(ref.d_xyz0)
+    ref.assemble(ref.d_xyz0)
+    u_inline = ref.solve(ref.combine(f_case, fac, 8)).cpu().numpy()
+    assert "chol_plan_thread_ms" not in ref.timings and np.array_equal(u_thread, u_inline)

@@ -118,3 +118,34 @@ def test_plan_leaves_fully_restrained_nodes_out():
     x = chol_emulator.factor_solve(ex, rowptr, colidx, vals, fixed, b)
     want = np.linalg.solve(chol_emulator.expand_masked(rowptr, colidx, vals, fixed), np.where(fixed[:, None] != 0, 0.0, b))
     assert np.abs(x - want).max() <= 1e-10 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("name", ["portal_2d_combinations", "plate_strip_surface_load", "hinge_spring"])
+def test_host_pattern_equals_the_oracle_pattern(name):
+    """fers_b200_host_pattern (the copy of the device pattern the plan thread starts from) against the oracle's
+    block pattern: members, plates and the extra pairs of warping members."""
+    from fers_core_b200 import chol, wire
+    from oracle import fers_oracle
+    from tests import helpers
+    m = wire.parse_document(helpers.golden(name)["doc"])
+    p1, p2 = m.m_n1, m.m_n2
+    if len(m.w_member):
+        s_, e_ = m.m_n1[m.w_member], m.m_n2[m.w_member]
+        a1, a2 = m.w_aux[:, 0], m.w_aux[:, 1]
+        p1 = np.concatenate([p1, np.stack([s_, s_, e_, e_, a1], axis=1).reshape(-1)])
+        p2 = np.concatenate([p2, np.stack([a1, a2, a1, a2, a2], axis=1).reshape(-1)])
+    rowptr, colidx = chol.host_pattern(m.n_nodes, p1, p2, m.p_nodes if m.n_plates else None)
+    want_rp, want_ci = fers_oracle.bsr_pattern(m)
+    assert np.array_equal(rowptr, want_rp) and np.array_equal(colidx, want_ci)
+
+
+def test_host_pattern_grid_frame_and_errors():
+    from fers_core_b200 import chol, synth, _lib
+    m = synth.grid_frame(5, 4, 3, n_combos=1)
+    rowptr, colidx = chol.host_pattern(m.n_nodes, m.m_n1, m.m_n2)
+    rp, ci = _pattern(m.n_nodes, m.m_n1, m.m_n2)
+    assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
+    dup = chol.host_pattern(m.n_nodes, np.concatenate([m.m_n1, m.m_n1]), np.concatenate([m.m_n2, m.m_n2]))
+    assert np.array_equal(dup[0], rp) and np.array_equal(dup[1], ci)          # parallel members do not add blocks
+    with pytest.raises(_lib.FersB200Error):
+        chol.host_pattern(3, np.array([0, 7]), np.array([1, 2]))

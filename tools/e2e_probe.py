@@ -36,7 +36,7 @@ for rep in range(3):
     t1 = time.perf_counter()
     out = eng.run_linear(model.combo_factors)
     torch.cuda.synchronize(dev)
-    print(f"  engine {1e3 * (t1 - t0):.1f} ms, run_linear {1e3 * (time.perf_counter() - t1):.1f} ms, plan {eng.timings.get('chol_plan_ms'):.1f} ms", flush=True)
+    print(f"  engine {1e3 * (t1 - t0):.1f} ms, run_linear {1e3 * (time.perf_counter() - t1):.1f} ms, plan waited {eng.timings.get('chol_plan_ms'):.1f} ms, plan thread {eng.timings.get('chol_plan_thread_ms', -1):.1f} ms", flush=True)
     del eng, out
 
 # where the constructor's time outside the three stages goes
