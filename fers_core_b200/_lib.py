@@ -24,6 +24,8 @@ SIGNATURES = {
     "fers_b200_pattern_workspace": (_sz, [_i, _i, _i]),
     "fers_b200_pattern_build": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _ip, _vp, _sz, _vp]),
     "fers_b200_bc_workspace": (_sz, [_i]),
+    "fers_b200_json_records_bound": (_sz, [_sz, _i, C.c_longlong, _sz]),
+    "fers_b200_json_records": (_i, [C.c_char_p, _sz, _i, C.c_longlong, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     "fers_b200_host_pattern": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _ip]),
     "fers_b200_bc_build": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip, _ip, _vp, _sz, _vp]),
     "fers_b200_assemble_beams": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i,

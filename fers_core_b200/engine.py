@@ -22,7 +22,7 @@ from .hostlogic import (
     INACTIVE_SCALE, effective_bc, imperfect_coordinates, pdelta_suppressed_axes, rhs_plan, rigid_property_row,
     unilateral_dofs, unilateral_update,
 )
-from .results import ResultArrays, SECTION_FRACS, lazy_bundle, results_to_wire
+from .results import ResultArrays, SECTION_FRACS, lazy_bundle, results_to_json, results_to_wire
 
 DENSE_MAX_DOF = 8192          # models up to this many DOFs use the dense Cholesky path
 SOLVERS = ("auto", "dense", "cholesky", "pcg")   # auto: dense up to DENSE_MAX_DOF, sparse Cholesky above
@@ -848,8 +848,14 @@ def solve_lazy(doc: dict, device=None):
 
 
 def calculate_from_json(input_json: str) -> str:
-    """Drop-in for ``fers_calculations.calculate_from_json`` (fers_core/fers/fers.py:300)."""
-    return json.dumps(solve_document(json.loads(input_json)))
+    """Drop-in for ``fers_calculations.calculate_from_json`` (fers_core/fers/fers.py:300).  The result document is
+    written as text straight from the result arrays (results.results_to_json): same document as
+    ``json.dumps(solve_document(doc))``, several times faster once a model has a few thousand members."""
+    doc = json.loads(input_json)
+    model = wire.parse_document(doc)
+    res = analyze(model)
+    head = json.dumps({k: v for k, v in doc.items() if k != "results"})
+    return head[:-1] + (', ' if len(head) > 2 else '') + '"results": ' + results_to_json(model, res) + "}"
 
 
 def calculate_from_file(file_path: str) -> str:

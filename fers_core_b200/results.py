@@ -252,3 +252,91 @@ def lazy_bundle(model, res: ResultArrays) -> LazyMap:
     unity = res.unity.results() if res.unity is not None else []
     top = {"loadcases": groups["loadcases"], "loadcombinations": groups["loadcombinations"], "unity_check_results": unity}
     return LazyMap(list(top), list(top), top.__getitem__)
+
+
+# ---- JSON text straight from the arrays (the boundary of fers_core/fers/fers.py:300 returns a string) -------------
+_SLOT, _ISLOT = "\x01", "\x02"           # number / integer slots of fers_b200_json_records templates
+_F_T = "{" + ",".join(f'"{k}":{_SLOT}' for k in _F + ("bw",)) + "}"
+_D_T = "{" + ",".join(f'"{k}":{_SLOT}' for k in _D + ("warp",)) + "}"
+_MEMBER_T = ("{" + ",".join(f'"{k}":{_F_T}' for k in (
+    "start_node_forces", "end_node_forces", "maximums", "minimums", "local_start_forces", "local_end_forces",
+    "local_maximums", "local_minimums"))
+    + f',"local_displacement_start_node":{_D_T},"local_displacement_end_node":{_D_T}'
+    + ',"section_forces":[' + ",".join(f'{{"x_frac":{float(x)!r},"forces":{_F_T}}}' for x in SECTION_FRACS) + "]"
+    + ',"internal_force_series":[' + ",".join(f'{{"x_frac":{float(x)!r},"forces":{_F_T}}}' for x in (0.0,) + SECTION_FRACS + (1.0,))
+    + "]}")
+_REACTION_T = f'{{"location":{{"X":{_SLOT},"Y":{_SLOT},"Z":{_SLOT}}},"nodal_forces":{_F_T},"support_id":{_ISLOT}}}'
+
+
+def _json_records(template: str, keys_blob: bytes, values: np.ndarray) -> str:
+    """One '{"key": record, ...}' map through the library's writer (shortest round-trip numbers)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    vals = np.ascontiguousarray(values, np.float64)
+    n, slots = vals.shape
+    t = template.encode()
+    bound = lib.fers_b200_json_records_bound(len(t), slots, n, len(keys_blob))
+    out = np.empty(bound, np.uint8)
+    written = C.c_size_t()
+    _lib.check(lib.fers_b200_json_records(t, len(t), slots, n, keys_blob, vals.ctypes.data, out.ctypes.data, bound,
+                                          C.byref(written)), "json_records")
+    return out[: written.value].tobytes().decode()
+
+
+def results_to_json(model, res: ResultArrays) -> str:
+    """The ``ResultsBundle`` document of :func:`results_to_wire` as JSON text, written from the arrays without the
+    intermediate dicts: ``json.loads(results_to_json(m, r)) == results_to_wire(m, r)``."""
+    import json
+    plan = res.plan
+    ctx = _Context(model, res)
+    n_real, nm = ctx.n_real, model.n_members
+    blob = lambda keys: ("\0".join(keys) + "\0").encode() if keys else b""     # noqa: E731
+    node_blob = blob(ctx.node_keys[:n_real])
+    sup_blob = blob([ctx.node_keys[i] for i in ctx.sup_nodes])
+    mem_blob = blob(ctx.mem_keys)
+    wn = np.asarray(ctx.warp_node[:n_real], np.int64)
+    has_w = wn >= 0
+
+    def warp(arr, col, nodes):
+        w = np.zeros(len(nodes))
+        sel = has_w[nodes]
+        w[sel] = arr[col, wn[nodes][sel], 0]
+        return w[:, None]
+    all_nodes = np.arange(n_real)
+    groups = {"loadcases": [], "loadcombinations": []}
+    for col in range(plan.n_rhs):
+        v = _Column(ctx, col)
+        disp = _json_records(_D_T, node_blob, np.hstack([res.U[col, :n_real], warp(res.U, col, all_nodes)])) if n_real else "{}"
+        sup = ctx.sup_nodes
+        if len(sup):
+            reac = _json_records(_REACTION_T, sup_blob,
+                                 np.hstack([model.xyz[sup], res.R[col, sup], warp(res.R, col, sup),
+                                            model.node_support_id[sup][:, None].astype(np.float64)]))
+        else:
+            reac = "{}"
+        if nm:
+            fl, fg, ul, sec = res.f_local[col], res.f_global[col], res.u_local[col], res.sec[col]
+            z = np.zeros((nm, 1))
+            bw = res.bw[col] if res.bw is not None else np.zeros((nm, 2))
+            b1, b2 = bw[:, :1], bw[:, 1:2]
+            secs = [x for si in range(len(SECTION_FRACS)) for x in (sec[:, si], z)]
+            mv = np.hstack([fg[:, 0:6], b1, fg[:, 6:12], b2, res.gmax[col], z, res.gmin[col], z,
+                            fl[:, 0:6], b1, fl[:, 6:12], b2, res.lmax[col], z, res.lmin[col], z,
+                            ul[:, 0:6], z, ul[:, 6:12], z] + secs + [fl[:, 0:6], z] + secs + [-fl[:, 6:12], z])
+            mem = _json_records(_MEMBER_T, mem_blob, mv)
+        else:
+            mem = "{}"
+        parts = [f'"name":{json.dumps(plan.names[col])}',
+                 f'"result_type":{json.dumps({plan.kinds[col]: int(plan.ids[col])})}',
+                 f'"displacement_nodes":{disp}', f'"reaction_nodes":{reac}', f'"member_results":{mem}',
+                 f'"summary":{json.dumps(v.summary())}',
+                 f'"errors_and_warnings":{json.dumps({"errors": [], "warnings": ctx.warn})}',
+                 f'"solver_diagnostics":{json.dumps(v.diagnostics())}']
+        if model.n_plates:
+            parts.append('"plate_results":' + json.dumps({k: v.plate(k) for k in ctx.plate_rows}))
+        groups["loadcases" if plan.kinds[col] == "Loadcase" else "loadcombinations"].append(
+            json.dumps(plan.names[col]) + ":{" + ",".join(parts) + "}")
+    unity = res.unity.results() if res.unity is not None else []
+    return ('{"loadcases":{' + ",".join(groups["loadcases"]) + '},"loadcombinations":{' + ",".join(groups["loadcombinations"])
+            + '},"unity_check_results":' + json.dumps(unity) + "}")

@@ -43,6 +43,15 @@ int fers_b200_set_device(int device);
 /* Number of kernels this library has launched in this process (monotonic). */
 long long fers_b200_launch_count(void);
 
+/* ---- [host] bulk JSON writer of the result document (fers_core/fers/fers.py:300-311: the boundary returns text) ----
+ * '{' "key_r": <tmpl with every byte 0x01 (number) / 0x02 (integer) replaced by values[r][slot]> , ... '}' for n_records
+ * equally-shaped records.
+ * keys: n_records NUL-terminated strings back to back; numbers in shortest round-trip form, integers as "5.0", non-finite
+ * values as NaN / Infinity / -Infinity (Python's json spelling).  out_cap >= fers_b200_json_records_bound(...). */
+size_t fers_b200_json_records_bound(size_t template_len, int n_slots, long long n_records, size_t keys_bytes);
+int fers_b200_json_records(const char* tmpl, size_t template_len, int n_slots, long long n_records, const char* keys,
+                           const double* values, char* out, size_t out_cap, size_t* written_out);
+
 /* Live fp64 roofline denominators (bench.py): register-resident throughput of the fp64 tensor pipe
  * (DMMA.8x8x4) and of the vector pipe (DFMA) in TFLOP/s, each the best of bursts lasting at least
  * min_ms.  scratch: device buffer of >= 8 * 1024 * SM-count bytes.  Synchronises the stream. */
