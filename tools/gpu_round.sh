@@ -1,1 +1,1 @@
-python -m pytest tests/test_results_json.py tests/test_lazy_bundle.py tests/test_edge_cases.py tests/test_gpu_parity.py -q -x -m gpu 2>&1 | tail -3
+CHOL_VARIANTS=0 CHOL_OUTERS=4x1 timeout 600 python tools/chol_bench.py 60 60 30 2>&1 | grep -E "refine 0|unprofiled|update_ms" | cut -c1-170
