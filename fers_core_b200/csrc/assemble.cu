@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_beams(BeamArgs A) {
             beam_add_kg(kG, axial, f.L, A.kg_mode == 1, mtype);
         }
         // releases condense the elastic part only (K_g is added un-condensed, as the oracle does)
-        if (ri >= 0) beam_condense(kE, A.rel + (size_t)ri * 12, nullptr, 0);
+        if (ri >= 0) beam_modify(kE, A.rel + (size_t)ri * REL_STRIDE, nullptr, 0);
     }
 
     double* stage = s_stage + warp * STAGE_DOUBLES;
@@ -304,7 +304,7 @@ __device__ __noinline__ void member_block(const BeamArgs& A, const double* prop_
     if (GENERAL && ((ri >= 0) || (axial != 0.0))) {
         double kE[144];
         beam_local_k(c, kE);
-        if (ri >= 0) beam_condense(kE, A.rel + (size_t)ri * 12, nullptr, 0);
+        if (ri >= 0) beam_modify(kE, A.rel + (size_t)ri * REL_STRIDE, nullptr, 0);
         beam_rotate_block(kE, f, bi, bj, blk);
         if (axial != 0.0) {
             for (int i = 0; i < 144; ++i) kE[i] = 0.0;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(GA_THREADS, GENERAL ? 1 : 5) k_assemble_gather
                     for (int i = 0; i < 144; ++i) kG[i] = 0.0;
                     beam_add_kg(kG, axial, f.L, A.kg_mode == 1, mtype);
                 }
-                if (ri >= 0) beam_condense(kE, A.rel + (size_t)ri * 12, nullptr, 0);
+                if (ri >= 0) beam_modify(kE, A.rel + (size_t)ri * REL_STRIDE, nullptr, 0);
             }
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {          // 0: diagonal contribution, 1: off-diagonal block

@@ -145,6 +145,33 @@ FERS_HD void beam_condense(double* k /*144*/, const double* rel /*12*/, double* 
     }
 }
 
+// Shear-centre eccentricity (pydantic_models.py:1106-1111 `y_s`, `z_s`; toggle `include_shear_center_coupling`
+// 1358-1361, "T^T.K.T transformation"; `mirror` negates both, 1521-1524).  The element's transverse
+// displacements and its twist are those of the shear-centre axis, the nodes sit on the centroid axis:
+//   v_sc = v - z_s * theta_x ,  w_sc = w + y_s * theta_x     (rigid section, both ends)
+// so  k <- S^T k S,  p <- S^T p  with  S = I + E,  E[v][rx] = -z_s, E[w][rx] = y_s per end.
+FERS_HD void beam_shear_centre(double* k /*144*/, double ys, double zs, double* p, int np) {
+    if (ys == 0.0 && zs == 0.0) return;
+    for (int e = 0; e < 2; ++e) {
+        const int v = 6 * e + 1, w = 6 * e + 2, t = 6 * e + 3;
+        for (int i = 0; i < 12; ++i) k[i * 12 + t] += ys * k[i * 12 + w] - zs * k[i * 12 + v];   // k S
+    }
+    for (int e = 0; e < 2; ++e) {
+        const int v = 6 * e + 1, w = 6 * e + 2, t = 6 * e + 3;
+        for (int j = 0; j < 12; ++j) k[t * 12 + j] += ys * k[w * 12 + j] - zs * k[v * 12 + j];   // S^T (k S)
+        for (int q = 0; q < np; ++q) p[q * 12 + t] += ys * p[q * 12 + w] - zs * p[q * 12 + v];
+    }
+}
+
+// Per-member modifier record (REL_STRIDE doubles, one row of the `rel` table): [0..11] end-release springs,
+// [12] y_s, [13] z_s.  Applied to the dense local stiffness in this order: eccentricity, then condensation
+// (the releases sit between the node and the member end, i.e. on the centroid-axis DOFs).
+enum { REL_YS = 12, REL_ZS = 13, REL_STRIDE = 14 };
+FERS_HD void beam_modify(double* k /*144*/, const double* rec /*REL_STRIDE*/, double* p, int np) {
+    beam_shear_centre(k, rec[REL_YS], rec[REL_ZS], p, np);
+    beam_condense(k, rec, p, np);
+}
+
 // G = T^T k T for one 6x6 node block (bi, bj in {0,1}) of the 12x12 local matrix.
 // out[36] row-major.  T = blockdiag(R,R,R,R).
 FERS_HD void beam_rotate_block(const double* k /*144*/, const Frame& f, int bi, int bj, double* out /*36*/) {

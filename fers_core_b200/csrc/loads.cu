@@ -99,7 +99,7 @@ __global__ void k_load_members(LoadArgs A) {
             BeamCoef c = beam_coef(A.prop + (size_t)A.m_prop[m] * NPROP, f.L, A.m_type[m], scale);
             double k[144];
             beam_local_k(c, k);
-            beam_condense(k, A.rel + 12 * (size_t)ri, p, 1);
+            beam_modify(k, A.rel + REL_STRIDE * (size_t)ri, p, 1);
             for (int i = 0; i < 12; ++i) A.peq_case[12 * (size_t)m + i] = p[i];
         }
         const int nd[2] = {A.n1[m], A.n2[m]};

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_members(RecArgs A) {
     if (ri >= 0) {
         if (lane == 0) {
             beam_local_k(c, s_k[kw]);
-            beam_condense(s_k[kw], A.rel + 12 * (size_t)ri, nullptr, 0);
+            beam_modify(s_k[kw], A.rel + REL_STRIDE * (size_t)ri, nullptr, 0);
         }
         __syncwarp();
     }

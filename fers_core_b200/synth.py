@@ -110,7 +110,7 @@ def grid_frame(nx: int, nz: int, ny: int, bay: float = 6.0, storey: float = 3.5,
         bc_code=bc_code, bc_k=np.zeros((nn, 6)),
         m_ids=np.arange(1, nm + 1, dtype=np.int64), m_n1=n1.astype(np.int32), m_n2=n2.astype(np.int32),
         m_type=np.zeros(nm, np.int32), m_roll=np.zeros(nm), m_prop=m_prop, m_rel=np.full(nm, -1, np.int32),
-        prop=prop, prop_rho_a=np.array([RHO_STEEL * HEB300[0], RHO_STEEL * IPE400[0]]), rel=np.zeros((0, 12)),
+        prop=prop, prop_rho_a=np.array([RHO_STEEL * HEB300[0], RHO_STEEL * IPE400[0]]), rel=np.zeros((0, wire.REL_STRIDE)),
         p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 8)),
         p_flags=np.zeros(0, np.int32), load_cases=cases,
         combo_ids=np.arange(1, n_combos + 1, dtype=np.int64),
@@ -245,7 +245,7 @@ def portal_frame(bay: float, storey: float, col_sec: int, beam_sec: int, gravity
         node_ids=np.arange(1, nn + 1, dtype=np.int64), xyz=xyz, node_support_id=sup, bc_code=bc, bc_k=np.zeros((nn, 6)),
         m_ids=np.arange(1, nm + 1, dtype=np.int64), m_n1=n1.astype(np.int32), m_n2=n2.astype(np.int32),
         m_type=np.zeros(nm, np.int32), m_roll=np.zeros(nm), m_prop=m_prop, m_rel=np.full(nm, -1, np.int32), prop=prop,
-        prop_rho_a=np.array([RHO_STEEL * s[0] for s in BATCH_SECTIONS]), rel=np.zeros((0, 12)),
+        prop_rho_a=np.array([RHO_STEEL * s[0] for s in BATCH_SECTIONS]), rel=np.zeros((0, wire.REL_STRIDE)),
         p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 8)),
         p_flags=np.zeros(0, np.int32), load_cases=[lc], combo_ids=np.array([1], np.int64), combo_names=["ULS"],
         combo_factors=np.ones((1, 1)), imperfections=imp, member_sets={}, options=opts)

@@ -43,6 +43,8 @@ _HINGE_FIELDS = (
     "rotational_release_mx", "rotational_release_my", "rotational_release_mz",
 )
 RIGID_RELEASE = -1.0  # sentinel: DOF rigidly connected (no hinge spring)
+# one row of ModelArrays.rel (csrc/fers_elem.cuh REL_*): 12 release springs, then the shear-centre offset
+REL_YS, REL_ZS, REL_STRIDE = 12, 13, 14
 
 
 class WireError(ValueError):
@@ -108,7 +110,8 @@ class ModelArrays:
     m_rel: np.ndarray             # int32 [Nm]      row of `rel` or -1
     prop: np.ndarray              # f64   [Np,8]    EA EIy EIz GJ GAsy GAsz Wpl spare
     prop_rho_a: np.ndarray        # f64   [Np]      density*area (self weight)
-    rel: np.ndarray               # f64   [Nr,12]   hinge spring stiffness per local end DOF (-1 rigid)
+    rel: np.ndarray               # f64   [Nr,REL_STRIDE] member modifier records: [0:12] hinge spring stiffness per
+                                  #                 local end DOF (-1 rigid), [12] y_s, [13] z_s (shear-centre offset)
     # plates (TRI3): node indices, thickness, E, nu, behaviour code
     p_ids: np.ndarray             # int64 [Npl]
     p_nodes: np.ndarray           # int32 [Npl,3]
@@ -318,8 +321,6 @@ def parse_document(doc: dict) -> ModelArrays:
         sec_row[sid] = len(prop_rows)
         prop_rows.append(row)
         prop_rho_a.append(float(mat.get("density") or 0.0) * A)
-        if eiw and (s.get("y_s") or s.get("z_s")) and opts.include_shear_center_coupling:
-            warnings.append(("W_SHEAR_CENTRE_IGNORED", f"section {sid}: shear-centre offset not coupled to bending"))
     prop = np.array(prop_rows, np.float64).reshape(len(prop_rows), NPROP)
 
     # ---- hinges (pydantic_models.py:2062-2087; release fields are spring stiffnesses) ----
@@ -370,14 +371,22 @@ def parse_document(doc: dict) -> ModelArrays:
             m_prop[i] = sec_row[int(sid)]
         elif t != MT_RIGID:
             raise WireError(f"member {m['id']}: non-rigid member without section")
-        if m.get("start_hinge") is not None or m.get("end_hinge") is not None:
+        # shear-centre eccentricity (pydantic_models.py:1106-1111; toggle 1358-1361; `mirror` negates it, 1521-1524)
+        ys = zs = 0.0
+        if sid is not None and opts.include_shear_center_coupling and t not in (MT_TRUSS, MT_RIGID):
+            s_raw = sec_raw[int(sid)][0]
+            sgn = -1.0 if m.get("mirror") else 1.0
+            ys, zs = sgn * float(s_raw.get("y_s") or 0.0), sgn * float(s_raw.get("z_s") or 0.0)
+            if not (np.isfinite(ys) and np.isfinite(zs)):
+                raise WireError(f"section {sid}: y_s / z_s must be finite")
+        if m.get("start_hinge") is not None or m.get("end_hinge") is not None or ys != 0.0 or zs != 0.0:
             m_rel[i] = len(rel_rows)
-            rel_rows.append(np.concatenate([hinge_row(m.get("start_hinge")), hinge_row(m.get("end_hinge"))]))
+            rel_rows.append(np.concatenate([hinge_row(m.get("start_hinge")), hinge_row(m.get("end_hinge")), [ys, zs]]))
         if t == MT_CABLE:
             warnings.append(("W_CABLE_AS_TENSION", f"member {m['id']}: cable treated as tension-only straight member"))
         if m.get("start_offset") or m.get("end_offset"):
             warnings.append(("W_OFFSET_IGNORED", f"member {m['id']}: end offsets not modelled"))
-    rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), 12)
+    rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), REL_STRIDE)
     if nm:
         length = np.linalg.norm(xyz[m_n2] - xyz[m_n1], axis=1)
         if (length <= 0.0).any():

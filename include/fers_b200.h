@@ -85,7 +85,9 @@ int fers_b200_bc_build(int n_nodes, const uint8_t* bc_code, const double* bc_k, 
 /* Beam members: 12x12 local stiffness (Euler-Bernoulli / Timoshenko), optional end-release
  * condensation and geometric stiffness, T^T k T, scatter-add into vals[nnzb*36].
  *   m_scale  : per-member stiffness multiplier or NULL (active-set switch of tension-only members)
- *   m_rel    : per-member row of rel[n_rel*12] or -1; NULL = no releases
+ *   m_rel    : per-member row of rel[n_rel*14] or -1; NULL = none.  One record = 12 end-release spring
+ *              stiffnesses in local DOF order (< 0: rigid) followed by the shear-centre offset y_s, z_s
+ *              (pydantic_models.py:1106-1111, 1358-1361): k <- S^T k S before the condensation
  *   m_axial  : per-member axial force (tension +) for K_g or NULL; kg_mode 0 none, 1 consistent,
  *              2 simplified; kg_suppress = bit mask of global axes removed from K_g (bit0 X..)
  *   variant  : 0 = warp-aggregated atomic scatter-add, 1 = plain atomic scatter-add

@@ -189,6 +189,26 @@ def condense_releases(k, p, rel):
     return k, p
 
 
+def shear_centre_transform(k, p, ys, zs):
+    """Shear-centre eccentricity coupling (pydantic_models.py:1106-1111 `y_s`/`z_s`, toggle 1358-1361:
+    "T^T.K.T transformation").  The beam's transverse displacements and twist are those of its shear-centre
+    axis; the nodes are on the centroid axis.  For a rigid cross-section rotating by theta_x the point
+    (y_s, z_s) moves by theta_x * (-z_s, +y_s), so per end  v_sc = v - z_s rx,  w_sc = w + y_s rx:
+    k <- S^T k S and p <- S^T p (rows of ``p`` [nrhs,12]).  Parity unpinned (no reference number)."""
+    S = np.eye(12)
+    for e in (0, 6):
+        S[e + 1, e + 3] = -zs
+        S[e + 2, e + 3] = ys
+    return S.T @ k @ S, (p @ S if p.size else p.copy())
+
+
+def member_modifiers(k, p, rec):
+    """One row of ``ModelArrays.rel``: eccentricity first, then the end-release condensation."""
+    if len(rec) > 12 and (rec[12] != 0.0 or rec[13] != 0.0):
+        k, p = shear_centre_transform(k, p, rec[12], rec[13])
+    return condense_releases(k, p, rec[:12])
+
+
 def expand_T(R):
     """[Nm,12,12] block-diagonal transformation from R [Nm,3,3]."""
     nm = R.shape[0]
@@ -351,7 +371,7 @@ class Assembly:
         self.T = expand_T(self.R)
         self.k_cond = self.k_local.copy()       # after release condensation
         for i in np.nonzero(model.m_rel >= 0)[0]:
-            self.k_cond[i], _ = condense_releases(self.k_local[i], np.zeros((0, 12)), model.rel[model.m_rel[i]])
+            self.k_cond[i], _ = member_modifiers(self.k_local[i], np.zeros((0, 12)), model.rel[model.m_rel[i]])
         self.plates = plate_stiffness_global(model, self.xyz) if model.n_plates else []
         self.edof = np.concatenate([6 * model.m_n1[:, None] + np.arange(6), 6 * model.m_n2[:, None] + np.arange(6)], 1) if nm else np.zeros((0, 12), np.int64)
 
@@ -508,7 +528,7 @@ def load_vectors(asm: Assembly):
             F[li, 6 * n:6 * n + 6] += v
         p = equivalent_loads(asm, lc)
         for i in np.nonzero(model.m_rel >= 0)[0]:
-            _, pc = condense_releases(asm.k_local[i], p[i][None, :], model.rel[model.m_rel[i]])
+            _, pc = member_modifiers(asm.k_local[i], p[i][None, :], model.rel[model.m_rel[i]])
             p[i] = pc[0]
         p *= 1.0  # member scale does not apply to loads
         peq[li] = p

@@ -6,14 +6,14 @@ using namespace fers;
 extern "C" {
 // global 12x12 via the closed-form block path (mode 0) or dense local k + rotation (mode 1)
 void h_beam_ke(const double* a, const double* b, double roll, const double* P, int mtype, double scale,
-               const double* rel /*12 or null*/, int mode, double* out /*144*/) {
+               const double* rel /*REL_STRIDE or null*/, int mode, double* out /*144*/) {
     Frame f = member_frame(a, b, roll);
     BeamCoef c = beam_coef(P, f.L, mtype, scale);
     double blk[36];
     double k[144];
     if (mode == 1) {
         beam_local_k(c, k);
-        if (rel) beam_condense(k, rel, nullptr, 0);
+        if (rel) beam_modify(k, rel, nullptr, 0);
     }
     for (int bi = 0; bi < 2; ++bi)
         for (int bj = 0; bj < 2; ++bj) {
@@ -42,7 +42,7 @@ void h_beam_loads(const double* a, const double* b, double roll, const double* P
     if (rel) {
         double k[144];
         beam_local_k(c, k);
-        beam_condense(k, rel, p, 1);
+        beam_modify(k, rel, p, 1);
     }
 }
 void h_span(const double* a, const double* b, double roll, const double* dl_rows, int ndl, const double* pl_rows,

@@ -80,7 +80,7 @@ def test_shear_areas_follow_the_option():
 
 def test_hinges_rigid_links_and_member_types():
     m = wire.parse_document(_doc("hinge_spring"))
-    assert (m.m_rel >= 0).any() and m.rel.shape[1] == 12
+    assert (m.m_rel >= 0).any() and m.rel.shape[1] == wire.REL_STRIDE
     r = m.rel[m.m_rel[m.m_rel >= 0][0]]
     assert (r >= 0).any() and (r == -1).any()                         # released / spring DOFs and rigid ones
     rigid = wire.parse_document(_doc("rigid_link"))
