@@ -53,7 +53,7 @@ SIGNATURES = {
     "fers_b200_dense_solve": (_i, [_i, _i, _i, _vp, _vp, _vp]),
     "fers_b200_recover_members": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),
-    "fers_b200_recover_sections": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+    "fers_b200_recover_sections": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp]),
     "fers_b200_reactions": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_recover_plates": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -123,11 +123,12 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_beams(BeamArgs A) {
         const int a = A.n1[m], b = A.n2[m];
         double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
         double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+        if (GENERAL && A.m_rel) ri = A.m_rel[m];
+        if (GENERAL && ri >= 0) rec_offset_points(A.rel + (size_t)ri * REL_STRIDE, pa, pb);
         f = member_frame(pa, pb, A.m_roll[m]);
         mtype = A.m_type[m];
         pi = A.m_prop[m];
         if (A.m_scale) scale = A.m_scale[m];
-        if (A.m_rel) ri = A.m_rel[m];
         if (A.m_axial && A.kg_mode) axial = A.m_axial[m];
         slots = reinterpret_cast<const int4*>(A.m_slot)[m];
         general = GENERAL && ((ri >= 0) || (axial != 0.0));
@@ -149,8 +150,12 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_beams(BeamArgs A) {
             for (int i = 0; i < 144; ++i) kG[i] = 0.0;
             beam_add_kg(kG, axial, f.L, A.kg_mode == 1, mtype);
         }
-        // releases condense the elastic part only (K_g is added un-condensed, as the oracle does)
-        if (ri >= 0) beam_modify(kE, A.rel + (size_t)ri * REL_STRIDE, nullptr, 0);
+        // releases condense the elastic part only (K_g is added un-condensed, as the oracle does); the rigid arms
+        // of the end offsets carry both
+        if (ri >= 0) {
+            beam_modify(kE, A.rel + (size_t)ri * REL_STRIDE, f, nullptr, 0);
+            if (have_g) beam_arms(kG, A.rel + (size_t)ri * REL_STRIDE, f, nullptr, 0);
+        }
     }
 
     double* stage = s_stage + warp * STAGE_DOUBLES;
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(256) k_member_cache(BeamArgs A, double* __rest
         const int a = A.n1[m], b = A.n2[m];
         double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
         double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+        if (A.m_rel && A.m_rel[m] >= 0) rec_offset_points(A.rel + (size_t)A.m_rel[m] * REL_STRIDE, pa, pb);
         f = member_frame(pa, pb, A.m_roll[m]);
         mtype = A.m_type[m];
         pi = A.m_prop[m];
@@ -291,10 +297,11 @@ __device__ __noinline__ void member_block(const BeamArgs& A, const double* prop_
     const int a = A.n1[m], b = A.n2[m];
     double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
     double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+    const int ri = A.m_rel ? A.m_rel[m] : -1;
+    if (ri >= 0) rec_offset_points(A.rel + (size_t)ri * REL_STRIDE, pa, pb);
     const Frame f = member_frame(pa, pb, A.m_roll[m]);
     const int mtype = A.m_type[m];
     const double scale = A.m_scale ? A.m_scale[m] : 1.0;
-    const int ri = A.m_rel ? A.m_rel[m] : -1;
     const double axial = (A.m_axial && A.kg_mode) ? A.m_axial[m] : 0.0;
     double Pr[NPROP];
     const double* P = prop_tab + (size_t)A.m_prop[m] * NPROP;
@@ -304,11 +311,12 @@ __device__ __noinline__ void member_block(const BeamArgs& A, const double* prop_
     if (GENERAL && ((ri >= 0) || (axial != 0.0))) {
         double kE[144];
         beam_local_k(c, kE);
-        if (ri >= 0) beam_modify(kE, A.rel + (size_t)ri * REL_STRIDE, nullptr, 0);
+        if (ri >= 0) beam_modify(kE, A.rel + (size_t)ri * REL_STRIDE, f, nullptr, 0);
         beam_rotate_block(kE, f, bi, bj, blk);
         if (axial != 0.0) {
             for (int i = 0; i < 144; ++i) kE[i] = 0.0;
             beam_add_kg(kE, axial, f.L, A.kg_mode == 1, mtype);
+            if (ri >= 0) beam_arms(kE, A.rel + (size_t)ri * REL_STRIDE, f, nullptr, 0);
             double g[36];
             beam_rotate_block(kE, f, bi, bj, g);
             if (A.kg_suppress) suppress_block(g, A.kg_suppress);
@@ -372,6 +380,7 @@ __global__ void __launch_bounds__(GA_THREADS, GENERAL ? 1 : 5) k_assemble_gather
                 const int a = A.n1[m], b = A.n2[m];
                 double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
                 double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+                if (GENERAL && ri >= 0) rec_offset_points(A.rel + (size_t)ri * REL_STRIDE, pa, pb);
                 f = member_frame(pa, pb, A.m_roll[m]);
                 mtype = A.m_type[m];
                 const int pi = A.m_prop[m];
@@ -390,7 +399,10 @@ __global__ void __launch_bounds__(GA_THREADS, GENERAL ? 1 : 5) k_assemble_gather
                     for (int i = 0; i < 144; ++i) kG[i] = 0.0;
                     beam_add_kg(kG, axial, f.L, A.kg_mode == 1, mtype);
                 }
-                if (ri >= 0) beam_modify(kE, A.rel + (size_t)ri * REL_STRIDE, nullptr, 0);
+                if (ri >= 0) {
+                    beam_modify(kE, A.rel + (size_t)ri * REL_STRIDE, f, nullptr, 0);
+                    if (axial != 0.0) beam_arms(kG, A.rel + (size_t)ri * REL_STRIDE, f, nullptr, 0);
+                }
             }
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {          // 0: diagonal contribution, 1: off-diagonal block

@@ -145,6 +145,14 @@ FERS_HD void beam_condense(double* k /*144*/, const double* rel /*12*/, double* 
     }
 }
 
+// local = R * global (each 3-vector of a 6-vector pair) and its transpose
+FERS_HD void rot_to_local(const Frame& f, const double* g, double* l) {
+    for (int i = 0; i < 3; ++i) l[i] = f.r[i][0] * g[0] + f.r[i][1] * g[1] + f.r[i][2] * g[2];
+}
+FERS_HD void rot_to_global(const Frame& f, const double* l, double* g) {
+    for (int i = 0; i < 3; ++i) g[i] = f.r[0][i] * l[0] + f.r[1][i] * l[1] + f.r[2][i] * l[2];
+}
+
 // Shear-centre eccentricity (pydantic_models.py:1106-1111 `y_s`, `z_s`; toggle `include_shear_center_coupling`
 // 1358-1361, "T^T.K.T transformation"; `mirror` negates both, 1521-1524).  The element's transverse
 // displacements and its twist are those of the shear-centre axis, the nodes sit on the centroid axis:
@@ -164,12 +172,69 @@ FERS_HD void beam_shear_centre(double* k /*144*/, double ys, double zs, double* 
 }
 
 // Per-member modifier record (REL_STRIDE doubles, one row of the `rel` table): [0..11] end-release springs,
-// [12] y_s, [13] z_s.  Applied to the dense local stiffness in this order: eccentricity, then condensation
-// (the releases sit between the node and the member end, i.e. on the centroid-axis DOFs).
-enum { REL_YS = 12, REL_ZS = 13, REL_STRIDE = 14 };
-FERS_HD void beam_modify(double* k /*144*/, const double* rec /*REL_STRIDE*/, double* p, int np) {
+// [12] y_s, [13] z_s, [14..16] start offset, [17..19] end offset (global X Y Z; MemberEndOffset,
+// pydantic_models.py:525-531, Member.start_offset / end_offset 1541 / 1518).
+enum { REL_YS = 12, REL_ZS = 13, REL_O1 = 14, REL_O2 = 17, REL_STRIDE = 20 };
+
+// End offsets: the elastic axis runs from (start node + start offset) to (end node + end offset).
+FERS_HD void rec_offset_points(const double* rec, double pa[3], double pb[3]) {
+    for (int c = 0; c < 3; ++c) { pa[c] += rec[REL_O1 + c]; pb[c] += rec[REL_O2 + c]; }
+}
+FERS_HD bool rec_has_offsets(const double* rec) {
+    bool any = false;
+    for (int c = 0; c < 6; ++c) any |= (rec[REL_O1 + c] != 0.0);
+    return any;
+}
+// Rigid arms between the nodes and the ends of the elastic axis:  u_end = u_node + theta_node x o  (o = the end's
+// offset in LOCAL axes), i.e. u_axis = E u_node.  arm_fwd: u <- E u;  arm_bwd: f <- E^T f  (m_node = m_axis + o x f).
+FERS_HD void arm_local(const double* rec, const Frame& f, double o[6]) {
+    rot_to_local(f, rec + REL_O1, o);
+    rot_to_local(f, rec + REL_O2, o + 3);
+}
+FERS_HD void arm_fwd(const double o[6], double* u /*12*/) {
+    for (int e = 0; e < 2; ++e) {
+        const double* a = o + 3 * e;
+        double* t = u + 6 * e;
+        const double tx = t[3], ty = t[4], tz = t[5];
+        t[0] += ty * a[2] - tz * a[1];
+        t[1] += tz * a[0] - tx * a[2];
+        t[2] += tx * a[1] - ty * a[0];
+    }
+}
+FERS_HD void arm_bwd(const double o[6], double* g /*12*/) {
+    for (int e = 0; e < 2; ++e) {
+        const double* a = o + 3 * e;
+        double* t = g + 6 * e;
+        const double fx = t[0], fy = t[1], fz = t[2];
+        t[3] += a[1] * fz - a[2] * fy;
+        t[4] += a[2] * fx - a[0] * fz;
+        t[5] += a[0] * fy - a[1] * fx;
+    }
+}
+// k <- E^T k E,  p <- E^T p  (dense local 12x12, row-major)
+FERS_HD void beam_arms(double* k /*144*/, const double* rec, const Frame& f, double* p, int np) {
+    if (!rec_has_offsets(rec)) return;
+    double o[6];
+    arm_local(rec, f, o);
+    for (int i = 0; i < 12; ++i) {            // rows of k E = E^T applied to each row (k symmetric in structure only)
+        double* row = k + i * 12;
+        arm_bwd(o, row);
+    }
+    for (int j = 0; j < 12; ++j) {            // columns of E^T (k E)
+        double col[12];
+        for (int i = 0; i < 12; ++i) col[i] = k[i * 12 + j];
+        arm_bwd(o, col);
+        for (int i = 0; i < 12; ++i) k[i * 12 + j] = col[i];
+    }
+    for (int q = 0; q < np; ++q) arm_bwd(o, p + q * 12);
+}
+
+// The whole record applied to the dense local stiffness in this order: shear-centre eccentricity, release
+// condensation (the releases sit at the ends of the elastic axis), rigid arms to the nodes.
+FERS_HD void beam_modify(double* k /*144*/, const double* rec /*REL_STRIDE*/, const Frame& f, double* p, int np) {
     beam_shear_centre(k, rec[REL_YS], rec[REL_ZS], p, np);
     beam_condense(k, rec, p, np);
+    beam_arms(k, rec, f, p, np);
 }
 
 // G = T^T k T for one 6x6 node block (bi, bj in {0,1}) of the 12x12 local matrix.
@@ -261,13 +326,6 @@ FERS_HD void beam_kg_times_u(double N, double L, int consistent, int mtype, cons
     }
 }
 
-// local = R * global (each 3-vector of a 6-vector pair) and its transpose
-FERS_HD void rot_to_local(const Frame& f, const double* g, double* l) {
-    for (int i = 0; i < 3; ++i) l[i] = f.r[i][0] * g[0] + f.r[i][1] * g[1] + f.r[i][2] * g[2];
-}
-FERS_HD void rot_to_global(const Frame& f, const double* l, double* g) {
-    for (int i = 0; i < 3; ++i) g[i] = f.r[0][i] * l[0] + f.r[1][i] * l[1] + f.r[2][i] * l[2];
-}
 
 // ---- Timoshenko-exact shape functions (phi = 0: Hermite cubics) ----------------------
 FERS_HD void shape_n(double xi, double phi, double L, double n[4]) {

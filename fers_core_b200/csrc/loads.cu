@@ -42,6 +42,7 @@ __device__ __forceinline__ Frame load_frame(const LoadArgs& A, int m) {
     const int a = A.n1[m], b = A.n2[m];
     double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
     double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+    if (A.m_rel && A.m_rel[m] >= 0) rec_offset_points(A.rel + REL_STRIDE * (size_t)A.m_rel[m], pa, pb);
     return member_frame(pa, pb, A.m_roll[m]);
 }
 
@@ -99,7 +100,7 @@ __global__ void k_load_members(LoadArgs A) {
             BeamCoef c = beam_coef(A.prop + (size_t)A.m_prop[m] * NPROP, f.L, A.m_type[m], scale);
             double k[144];
             beam_local_k(c, k);
-            beam_modify(k, A.rel + REL_STRIDE * (size_t)ri, p, 1);
+            beam_modify(k, A.rel + REL_STRIDE * (size_t)ri, f, p, 1);
             for (int i = 0; i < 12; ++i) A.peq_case[12 * (size_t)m + i] = p[i];
         }
         const int nd[2] = {A.n1[m], A.n2[m]};

@@ -49,16 +49,22 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_members(RecArgs A) {
     const int a = A.n1[m], b = A.n2[m];
     double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
     double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+    const int ri = REL ? A.m_rel[m] : -1;
+    const double* rec = (ri >= 0) ? A.rel + REL_STRIDE * (size_t)ri : nullptr;
+    if (rec) rec_offset_points(rec, pa, pb);
     const Frame f = member_frame(pa, pb, A.m_roll[m]);
     const int mtype = A.m_type[m];
     const double scale = A.m_scale ? A.m_scale[m] : 1.0;
     const BeamCoef c = beam_coef(A.prop + (size_t)A.m_prop[m] * NPROP, f.L, mtype, scale);
-    const int ri = REL ? A.m_rel[m] : -1;
     const int kw = REL ? warp : 0;
+    // rigid arms of the end offsets (local axes): K_g acts on the displacements of the elastic axis, u_axis = E u_node
+    double arm[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const bool armed = REL && rec && rec_has_offsets(rec);
+    if (armed) arm_local(rec, f, arm);
     if (ri >= 0) {
         if (lane == 0) {
             beam_local_k(c, s_k[kw]);
-            beam_modify(s_k[kw], A.rel + REL_STRIDE * (size_t)ri, nullptr, 0);
+            beam_modify(s_k[kw], rec, f, nullptr, 0);
         }
         __syncwarp();
     }
@@ -87,8 +93,17 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_members(RecArgs A) {
         if (A.m_axial_rhs != nullptr && A.kg_mode != 0) {
             const double N = A.m_axial_rhs[(size_t)m * nr + col];
             if (N != 0.0) {
-                if (A.kg_suppress == 0) {
+                if (A.kg_suppress == 0 && !armed) {
                     beam_kg_times_u(N, f.L, A.kg_mode == 1, mtype, ul, fl);
+                } else if (A.kg_suppress == 0) {
+                    double ua[12], g[12];
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) { ua[q] = ul[q]; g[q] = 0.0; }
+                    arm_fwd(arm, ua);
+                    beam_kg_times_u(N, f.L, A.kg_mode == 1, mtype, ua, g);
+                    arm_bwd(arm, g);
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) fl[q] += g[q];
                 } else {
                     // K_g with suppressed global translations: S (T^T k_g T) S applied to u
                     double us[12], uls[12], g[12], gg[12], gl[12];
@@ -101,7 +116,9 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_members(RecArgs A) {
                     for (int q = 0; q < 4; ++q) rot_to_local(f, us + 3 * q, uls + 3 * q);
 #pragma unroll
                     for (int q = 0; q < 12; ++q) g[q] = 0.0;
+                    if (armed) arm_fwd(arm, uls);
                     beam_kg_times_u(N, f.L, A.kg_mode == 1, mtype, uls, g);
+                    if (armed) arm_bwd(arm, g);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) rot_to_global(f, g + 3 * q, gg + 3 * q);
 #pragma unroll
@@ -141,6 +158,8 @@ struct SecArgs {
     const double* factors;
     const double* f_local;
     const double* f_global;
+    const int* m_rel;         // member modifier records (end offsets) or nullptr
+    const double* rel;
     double* sec;
     double* lmax;
     double* lmin;
@@ -155,7 +174,13 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_sections(SecArgs A) {
     const int a = A.n1[m], b = A.n2[m];
     double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
     double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+    const double* rec = (A.m_rel && A.m_rel[m] >= 0) ? A.rel + REL_STRIDE * (size_t)A.m_rel[m] : nullptr;
+    if (rec) rec_offset_points(rec, pa, pb);
     const Frame f = member_frame(pa, pb, A.m_roll[m]);
+    // start of the elastic axis of an offset member: m_axis = m_node - o x f
+    double arm[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const bool armed = rec && rec_has_offsets(rec);
+    if (armed) arm_local(rec, f, arm);
     const int nr = A.nrhs;
     const double xs[3] = {0.25, 0.5, 0.75};
     for (int col0 = 0; col0 < nr; col0 += 32) {
@@ -199,6 +224,13 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_sections(SecArgs A) {
         for (int q = 0; q < 6; ++q) {
             mxl[q] = fmax(fl[q], fl[6 + q]); mnl[q] = fmin(fl[q], fl[6 + q]);
             mxg[q] = fmax(fg[q], fg[6 + q]); mng[q] = fmin(fg[q], fg[6 + q]);
+        }
+#pragma unroll
+        if (armed) {
+            const double fx = fl[0], fy = fl[1], fz = fl[2];
+            fl[3] -= arm[1] * fz - arm[2] * fy;
+            fl[4] -= arm[2] * fx - arm[0] * fz;
+            fl[5] -= arm[0] * fy - arm[1] * fx;
         }
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
@@ -363,13 +395,14 @@ int fers_b200_recover_members(int n_members, int nrhs, const double* xyz, const 
 
 int fers_b200_recover_sections(int n_members, int nrhs, int n_cases, const double* xyz, const int* m_n1,
                                const int* m_n2, const double* m_roll, const int* sp_ptr, const double* sp_rows,
-                               const double* factors, const double* f_local, const double* f_global, double* sec,
+                               const double* factors, const double* f_local, const double* f_global,
+                               const int* m_rel, const double* rel, double* sec,
                                double* lmax, double* lmin, double* gmax, double* gmin, void* stream) {
     if (n_members <= 0 || nrhs <= 0) return 0;
     SecArgs A;
     A.n_members = n_members; A.nrhs = nrhs; A.n_cases = n_cases; A.xyz = xyz; A.n1 = m_n1; A.n2 = m_n2;
     A.m_roll = m_roll; A.sp_ptr = sp_ptr; A.sp_rows = sp_rows; A.factors = factors; A.f_local = f_local;
-    A.f_global = f_global; A.sec = sec; A.lmax = lmax; A.lmin = lmin; A.gmax = gmax; A.gmin = gmin;
+    A.f_global = f_global; A.m_rel = m_rel; A.rel = rel; A.sec = sec; A.lmax = lmax; A.lmin = lmin; A.gmax = gmax; A.gmin = gmin;
     int grid = (n_members + REC_WARPS - 1) / REC_WARPS;
     k_recover_sections<<<grid, REC_THREADS, 0, as_stream(stream)>>>(A);
     FERS_LAUNCH_CHECK();

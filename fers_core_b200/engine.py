@@ -480,7 +480,7 @@ class Engine:
                 _lib.check(lib.fers_b200_recover_sections(
                     nm, nr, factors_pad.shape[1], _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2),
                     _lib.ptr(self.d_roll), _lib.ptr(sp_ptr), _lib.ptr(sp_rows), _lib.ptr(d_fac), _lib.ptr(fl), _lib.ptr(fg),
-                    _lib.ptr(sec), _lib.ptr(mm[0]), _lib.ptr(mm[1]), _lib.ptr(mm[2]), _lib.ptr(mm[3]), st),
+                    _lib.ptr(self.d_rel_idx), _lib.ptr(self.d_rel), _lib.ptr(sec), _lib.ptr(mm[0]), _lib.ptr(mm[1]), _lib.ptr(mm[2]), _lib.ptr(mm[3]), st),
                     "recover_sections")
                 out.update(sec=sec, lmax=mm[0], lmin=mm[1], gmax=mm[2], gmin=mm[3])
         if m.n_plates:

@@ -34,7 +34,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import _lib
+from . import _lib, wire
 
 OPS = {"PUSHC": 0, "PUSHV": 1, "+": 2, "-": 3, "*": 4, "/": 5, "^": 6, "NEG": 7, "abs": 8, "sqrt": 9, "min": 10, "max": 11}
 V_CONST, V_FORCE, V_EXPR, V_NODE_DISP, V_NODE_POS, V_DEFLECTION, V_FORCE_REF, V_ENTITY_DISP, V_PLATE = range(9)
@@ -249,8 +249,8 @@ def _chain(model, members: list):
 
 def _member_frame(model, m: int) -> np.ndarray:
     """Local axes of member m (rows x, y, z), rule of fers_core/members/member.py:309-354."""
-    a, b = model.xyz[model.m_n1[m]], model.xyz[model.m_n2[m]]
-    lx = (b - a) / np.linalg.norm(b - a)
+    d = wire.member_axis(model, m)
+    lx = d / np.linalg.norm(d)
     ref = np.array([0.0, 1.0, 0.0]) if abs(lx[1]) <= 1.0 - 1e-6 else np.array([0.0, 0.0, 1.0])
     lz = np.cross(lx, ref); lz /= np.linalg.norm(lz)
     ly = np.cross(lz, lx); ly /= np.linalg.norm(ly)
@@ -391,7 +391,7 @@ def compile_check(model, definition: dict) -> CompiledCheck:
             col = np.zeros(n_ent)
             for i, (ms, _) in enumerate(chains):
                 group = ([target(i)] if target(i) >= 0 else []) if of_ref else ms
-                col[i] = sum(float(np.linalg.norm(model.xyz[model.m_n2[m]] - model.xyz[model.m_n1[m]])) for m in group) \
+                col[i] = sum(float(np.linalg.norm(wire.member_axis(model, m))) for m in group) \
                     if group else np.nan
             ct_cols.append(col)
             desc[new] = (V_CONST, len(ct_cols) - 1, 0, 0)

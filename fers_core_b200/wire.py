@@ -43,8 +43,9 @@ _HINGE_FIELDS = (
     "rotational_release_mx", "rotational_release_my", "rotational_release_mz",
 )
 RIGID_RELEASE = -1.0  # sentinel: DOF rigidly connected (no hinge spring)
-# one row of ModelArrays.rel (csrc/fers_elem.cuh REL_*): 12 release springs, then the shear-centre offset
-REL_YS, REL_ZS, REL_STRIDE = 12, 13, 14
+# one row of ModelArrays.rel (csrc/fers_elem.cuh REL_*): 12 release springs, the shear-centre offset, the two end
+# offsets (global X Y Z of start_offset, end_offset)
+REL_YS, REL_ZS, REL_O1, REL_O2, REL_STRIDE = 12, 13, 14, 17, 20
 
 
 class WireError(ValueError):
@@ -111,7 +112,8 @@ class ModelArrays:
     prop: np.ndarray              # f64   [Np,8]    EA EIy EIz GJ GAsy GAsz Wpl spare
     prop_rho_a: np.ndarray        # f64   [Np]      density*area (self weight)
     rel: np.ndarray               # f64   [Nr,REL_STRIDE] member modifier records: [0:12] hinge spring stiffness per
-                                  #                 local end DOF (-1 rigid), [12] y_s, [13] z_s (shear-centre offset)
+                                  #                 local end DOF (-1 rigid), [12] y_s, [13] z_s (shear-centre offset),
+                                  #                 [14:17] start_offset, [17:20] end_offset (global axes)
     # plates (TRI3): node indices, thickness, E, nu, behaviour code
     p_ids: np.ndarray             # int64 [Npl]
     p_nodes: np.ndarray           # int32 [Npl,3]
@@ -379,18 +381,29 @@ def parse_document(doc: dict) -> ModelArrays:
             ys, zs = sgn * float(s_raw.get("y_s") or 0.0), sgn * float(s_raw.get("z_s") or 0.0)
             if not (np.isfinite(ys) and np.isfinite(zs)):
                 raise WireError(f"section {sid}: y_s / z_s must be finite")
-        if m.get("start_hinge") is not None or m.get("end_hinge") is not None or ys != 0.0 or zs != 0.0:
+        # end offsets (MemberEndOffset, pydantic_models.py:525-531, global X Y Z): the elastic axis runs between the
+        # offset points, each tied to its node by a rigid arm
+        offs = np.zeros(6)
+        for e, key in enumerate(("start_offset", "end_offset")):
+            o = m.get(key)
+            if o:
+                offs[3 * e:3 * e + 3] = [float(o.get(ax) or 0.0) for ax in ("X", "Y", "Z")]
+        if not np.isfinite(offs).all():
+            raise WireError(f"member {m['id']}: end offsets must be finite")
+        if m.get("start_hinge") is not None or m.get("end_hinge") is not None or ys != 0.0 or zs != 0.0 or offs.any():
             m_rel[i] = len(rel_rows)
-            rel_rows.append(np.concatenate([hinge_row(m.get("start_hinge")), hinge_row(m.get("end_hinge")), [ys, zs]]))
+            rel_rows.append(np.concatenate([hinge_row(m.get("start_hinge")), hinge_row(m.get("end_hinge")), [ys, zs], offs]))
         if t == MT_CABLE:
             warnings.append(("W_CABLE_AS_TENSION", f"member {m['id']}: cable treated as tension-only straight member"))
-        if m.get("start_offset") or m.get("end_offset"):
-            warnings.append(("W_OFFSET_IGNORED", f"member {m['id']}: end offsets not modelled"))
     rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), REL_STRIDE)
     if nm:
-        length = np.linalg.norm(xyz[m_n2] - xyz[m_n1], axis=1)
+        axis = xyz[m_n2] - xyz[m_n1]
+        with_rec = np.nonzero(m_rel >= 0)[0]
+        if len(with_rec):
+            axis[with_rec] += rel[m_rel[with_rec], REL_O2:REL_O2 + 3] - rel[m_rel[with_rec], REL_O1:REL_O1 + 3]
+        length = np.linalg.norm(axis, axis=1)
         if (length <= 0.0).any():
-            raise WireError(f"member {int(m_ids[np.nonzero(length <= 0.0)[0][0]])}: zero length (start and end node coincide)")
+            raise WireError(f"member {int(m_ids[np.nonzero(length <= 0.0)[0][0]])}: zero length (start and end of the member axis coincide)")
     # Member.reference_member / reference_node (unity checks across members, fers_core/examples/101_...py:61-67)
     m_ref_member = np.full(nm, -1, np.int32)
     m_ref_node = np.full(nm, -1, np.int32)
@@ -576,6 +589,9 @@ def parse_document(doc: dict) -> ModelArrays:
     has_w &= np.where(m_prop >= 0, prop[np.maximum(m_prop, 0), 7] if len(prop) else 0.0, 0.0) > 0.0
     if has_w.any():
         w_member = np.nonzero(has_w)[0].astype(np.int32)
+        for i in w_member:
+            if m_rel[i] >= 0 and rel[m_rel[i], REL_O1:REL_O2 + 3].any():
+                warnings.append(("W_WARPING_OFFSET", f"member {int(m_ids[i])}: warping couplings follow the node-to-node axis, not the offset axis"))
         touched = np.unique(np.concatenate([m_n1[w_member], m_n2[w_member]]))
         warp_node[touched] = nn + np.arange(len(touched), dtype=np.int32)
         w_aux = np.stack([warp_node[m_n1[w_member]], warp_node[m_n2[w_member]]], axis=1).astype(np.int32)
@@ -602,6 +618,15 @@ def parse_document(doc: dict) -> ModelArrays:
         m_classification=m_classification, m_section_raw=m_section_raw,
         m_ref_member=m_ref_member, m_ref_node=m_ref_node,
     )
+
+
+def member_axis(model, m: int) -> np.ndarray:
+    """Vector from the start to the end of member m's elastic axis (end offsets included)."""
+    d = model.xyz[model.m_n2[m]] - model.xyz[model.m_n1[m]]
+    r = int(model.m_rel[m])
+    if r >= 0:
+        d = d + model.rel[r, REL_O2:REL_O2 + 3] - model.rel[r, REL_O1:REL_O1 + 3]
+    return d
 
 
 def plates_flat_surface(plates, p_ids_l):

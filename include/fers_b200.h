@@ -85,9 +85,11 @@ int fers_b200_bc_build(int n_nodes, const uint8_t* bc_code, const double* bc_k, 
 /* Beam members: 12x12 local stiffness (Euler-Bernoulli / Timoshenko), optional end-release
  * condensation and geometric stiffness, T^T k T, scatter-add into vals[nnzb*36].
  *   m_scale  : per-member stiffness multiplier or NULL (active-set switch of tension-only members)
- *   m_rel    : per-member row of rel[n_rel*14] or -1; NULL = none.  One record = 12 end-release spring
- *              stiffnesses in local DOF order (< 0: rigid) followed by the shear-centre offset y_s, z_s
- *              (pydantic_models.py:1106-1111, 1358-1361): k <- S^T k S before the condensation
+ *   m_rel    : per-member row of rel[n_rel*20] or -1; NULL = none.  One record = 12 end-release spring
+ *              stiffnesses in local DOF order (< 0: rigid), the shear-centre offset y_s, z_s
+ *              (pydantic_models.py:1106-1111, 1358-1361: k <- S^T k S before the condensation) and the
+ *              start / end offsets in global X Y Z (MemberEndOffset, 525-531: the elastic axis runs between
+ *              the offset points, tied to the nodes by rigid arms, k <- E^T k E after the condensation)
  *   m_axial  : per-member axial force (tension +) for K_g or NULL; kg_mode 0 none, 1 consistent,
  *              2 simplified; kg_suppress = bit mask of global axes removed from K_g (bit0 X..)
  *   variant  : 0 = warp-aggregated atomic scatter-add, 1 = plain atomic scatter-add
@@ -281,10 +283,13 @@ int fers_b200_recover_warping(int n_w, int nrhs, const int* w_member, const int*
 /* Interior section forces at x_frac 0.25/0.5/0.75 and per-component extrema:
  *   sec [n_members][18][nrhs]; lmax,lmin,gmax,gmin [n_members][6][nrhs].
  * Span loads are given per load case as CSR over members (sp_ptr[n_cases*(n_members+1)] into
- * rows sp_rows[*][9] = kind(0 dist,1 point) + 8 data); factors [nrhs][n_cases]. */
+ * rows sp_rows[*][9] = kind(0 dist,1 point) + 8 data); factors [nrhs][n_cases].
+ * m_rel / rel: the member modifier records of fers_b200_assemble_beams (end offsets: stations are fractions of the
+ * elastic axis, transport starts from the forces at its start) or NULL. */
 int fers_b200_recover_sections(int n_members, int nrhs, int n_cases, const double* xyz, const int* m_n1,
                                const int* m_n2, const double* m_roll, const int* sp_ptr, const double* sp_rows,
                                const double* factors, const double* f_local, const double* f_global,
+                               const int* m_rel, const double* rel,
                                double* sec, double* lmax, double* lmin, double* gmax, double* gmin, void* stream);
 /* r[n_dof][nrhs] = supported(node) ? (K u - f) : 0, K WITHOUT support springs. */
 int fers_b200_reactions(int n_nodes, int nrhs, const int* rowptr, const int* colidx, const double* vals,

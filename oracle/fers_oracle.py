@@ -53,9 +53,35 @@ GAUSS3_W = np.array([5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0])
 # --------------------------------------------------------------------------------------
 # element geometry  (fers_core/members/member.py:309-354)
 # --------------------------------------------------------------------------------------
-def member_frames(xyz, n1, n2, roll):
-    """Rotation matrices R [Nm,3,3] (rows = local x,y,z in global coordinates) and lengths."""
+def member_offsets(model):
+    """Per-member end offsets [Nm,2,3] in global axes (MemberEndOffset, pydantic_models.py:525-531; Member.start_offset /
+    end_offset 1541 / 1518), taken from the member modifier records; zero for members without a record."""
+    off = np.zeros((model.n_members, 2, 3))
+    rows = np.nonzero(model.m_rel >= 0)[0]
+    if len(rows) and model.rel.shape[1] >= 20:
+        off[rows] = model.rel[model.m_rel[rows], 14:20].reshape(-1, 2, 3)
+    return off
+
+
+def rigid_arm_matrix(o1, o2):
+    """E [12,12] of  u_end = u_node + theta_node x o  at both member ends (o in LOCAL axes):  the elastic axis runs
+    between the offset points, each tied to its node by a rigid arm.  k_node = E^T k E,  p_node = E^T p.
+    Semantics stated here, not pinned by any reference test (no solver source in the reference tree)."""
+    E = np.eye(12)
+    for e, o in ((0, o1), (6, o2)):
+        # (theta x o) = [ty oz - tz oy,  tz ox - tx oz,  tx oy - ty ox]
+        E[e + 0, e + 4] = o[2]; E[e + 0, e + 5] = -o[1]
+        E[e + 1, e + 5] = o[0]; E[e + 1, e + 3] = -o[2]
+        E[e + 2, e + 3] = o[1]; E[e + 2, e + 4] = -o[0]
+    return E
+
+
+def member_frames(xyz, n1, n2, roll, offsets=None):
+    """Rotation matrices R [Nm,3,3] (rows = local x,y,z in global coordinates) and lengths.  With end offsets the
+    axis runs from (start node + start offset) to (end node + end offset)."""
     d = xyz[n2] - xyz[n1]
+    if offsets is not None:
+        d = d + offsets[:, 1] - offsets[:, 0]
     L = np.sqrt((d * d).sum(1))
     if np.any(L < 1e-12):
         raise ValueError("zero-length member")
@@ -360,7 +386,8 @@ class Assembly:
         nm = model.n_members
         self.m_scale = np.ones(nm) if m_scale is None else m_scale
         if nm:
-            self.R, self.L = member_frames(self.xyz, model.m_n1, model.m_n2, model.m_roll)
+            self.offsets = member_offsets(model)
+            self.R, self.L = member_frames(self.xyz, model.m_n1, model.m_n2, model.m_roll, self.offsets)
             self.P = member_props(model)
             # the per-member multiplier (active-set switch) scales the stiffness BEFORE release condensation
             self.k_local = local_stiffness(self.P, self.L, model.m_type) * self.m_scale[:, None, None]
@@ -372,6 +399,13 @@ class Assembly:
         self.k_cond = self.k_local.copy()       # after release condensation
         for i in np.nonzero(model.m_rel >= 0)[0]:
             self.k_cond[i], _ = member_modifiers(self.k_local[i], np.zeros((0, 12)), model.rel[model.m_rel[i]])
+        # rigid arms of the end offsets: E per member (local axes), applied after the release condensation
+        self.arms = {}
+        if nm:
+            for i in np.nonzero(np.abs(self.offsets).reshape(nm, -1).max(1) > 0.0)[0]:
+                E = rigid_arm_matrix(self.R[i] @ self.offsets[i, 0], self.R[i] @ self.offsets[i, 1])
+                self.arms[int(i)] = E
+                self.k_cond[i] = E.T @ self.k_cond[i] @ E
         self.plates = plate_stiffness_global(model, self.xyz) if model.n_plates else []
         self.edof = np.concatenate([6 * model.m_n1[:, None] + np.arange(6), 6 * model.m_n2[:, None] + np.arange(6)], 1) if nm else np.zeros((0, 12), np.int64)
 
@@ -530,6 +564,8 @@ def load_vectors(asm: Assembly):
         for i in np.nonzero(model.m_rel >= 0)[0]:
             _, pc = member_modifiers(asm.k_local[i], p[i][None, :], model.rel[model.m_rel[i]])
             p[i] = pc[0]
+        for i, E in asm.arms.items():
+            p[i] = E.T @ p[i]
         p *= 1.0  # member scale does not apply to loads
         peq[li] = p
         if model.n_members:
@@ -683,6 +719,12 @@ def section_forces(asm: Assembly, fl, span_by_rhs):
     nrhs, nm = fl.shape[:2]
     ns = len(SECTION_FRACS)
     sec = np.zeros((nrhs, nm, ns, 6))
+    if asm.arms:
+        # forces at the start of the elastic axis from the forces at the node: m_axis = m_node - o x f
+        fl = fl.copy()
+        for i in asm.arms:
+            o = asm.R[i] @ asm.offsets[i, 0]
+            fl[:, i, 3:6] -= np.cross(o[None, :], fl[:, i, 0:3])
     for si, x in enumerate(SECTION_FRACS):
         d = x * asm.L
         sec[:, :, si, 0:3] = fl[:, :, 0:3]
@@ -811,6 +853,8 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
             for it in range(max(1, opts.max_iterations)):
                 N = _axial_forces(asm, U, peq, kg)
                 kg = geometric_stiffness(N, asm.L, opts.pdelta_formulation, model.m_type)
+                for i, E in asm.arms.items():
+                    kg[i] = E.T @ kg[i] @ E
                 kg = _suppress_kg(asm, kg, suppressed)
                 K = asm.K_elastic(kg)
                 Kff, free, _ = constrain(K, model, bc=bc)

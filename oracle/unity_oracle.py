@@ -155,7 +155,9 @@ def _quantity(model, res, c, members, nodes, q) -> float:
         x = model.member_raw(members[0])[1].get(MATERIAL[v["property"]])
         return math.nan if x is None else float(x)
     if kind == "Geometry":
-        return float(sum(np.linalg.norm(model.xyz[model.m_n2[m]] - model.xyz[model.m_n1[m]]) for m in members))
+        from oracle.fers_oracle import member_offsets
+        off = member_offsets(model)
+        return float(sum(np.linalg.norm(model.xyz[model.m_n2[m]] - model.xyz[model.m_n1[m]] + off[m, 1] - off[m, 0]) for m in members))
     if kind == "MemberForce":
         k = FORCE[v["component"]]
         agg = (v.get("aggregation") or {"type": "MaxAbs"})

@@ -7,13 +7,15 @@ extern "C" {
 // global 12x12 via the closed-form block path (mode 0) or dense local k + rotation (mode 1)
 void h_beam_ke(const double* a, const double* b, double roll, const double* P, int mtype, double scale,
                const double* rel /*REL_STRIDE or null*/, int mode, double* out /*144*/) {
-    Frame f = member_frame(a, b, roll);
+    double pa[3] = {a[0], a[1], a[2]}, pb[3] = {b[0], b[1], b[2]};
+    if (rel) rec_offset_points(rel, pa, pb);
+    Frame f = member_frame(pa, pb, roll);
     BeamCoef c = beam_coef(P, f.L, mtype, scale);
     double blk[36];
     double k[144];
     if (mode == 1) {
         beam_local_k(c, k);
-        if (rel) beam_modify(k, rel, nullptr, 0);
+        if (rel) beam_modify(k, rel, f, nullptr, 0);
     }
     for (int bi = 0; bi < 2; ++bi)
         for (int bj = 0; bj < 2; ++bj) {
@@ -34,7 +36,9 @@ void h_beam_local(const double* a, const double* b, double roll, const double* P
 }
 void h_beam_loads(const double* a, const double* b, double roll, const double* P, int mtype,
                   const double* dl_rows, int ndl, const double* pl_rows, int npl, const double* rel, double* p /*12*/) {
-    Frame f = member_frame(a, b, roll);
+    double pa[3] = {a[0], a[1], a[2]}, pb[3] = {b[0], b[1], b[2]};
+    if (rel) rec_offset_points(rel, pa, pb);
+    Frame f = member_frame(pa, pb, roll);
     BeamCoef c = beam_coef(P, f.L, mtype, 1.0);
     for (int i = 0; i < 12; ++i) p[i] = 0.0;
     for (int i = 0; i < ndl; ++i) beam_dist_load(f, c, mtype, dl_rows + 8 * i, p);
@@ -42,7 +46,7 @@ void h_beam_loads(const double* a, const double* b, double roll, const double* P
     if (rel) {
         double k[144];
         beam_local_k(c, k);
-        beam_modify(k, rel, p, 1);
+        beam_modify(k, rel, f, p, 1);
     }
 }
 void h_span(const double* a, const double* b, double roll, const double* dl_rows, int ndl, const double* pl_rows,

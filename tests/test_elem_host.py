@@ -66,7 +66,7 @@ def test_beam_global_stiffness(elem_host, case):
 def test_beam_releases_and_kg(elem_host, case):
     a, b, roll, P, mtype = case
     R, L, k, T = _oracle_member(a, b, roll, P, mtype)
-    rel = np.full(14, -1.0)
+    rel = np.full(wire.REL_STRIDE, -1.0)
     rel[5] = 0.0
     rel[10] = 2.5e4
     rel[12:] = 0.0
@@ -99,7 +99,7 @@ def test_beam_equivalent_loads_and_span(elem_host, case):
         node_ids=np.array([1, 2]), xyz=xyz, node_support_id=np.array([-1, -1]), bc_code=np.zeros((2, 6), np.uint8),
         bc_k=np.zeros((2, 6)), m_ids=np.array([1]), m_n1=np.array([0], np.int32), m_n2=np.array([1], np.int32),
         m_type=np.array([mtype], np.int32), m_roll=np.array([roll]), m_prop=np.array([0], np.int32),
-        m_rel=np.array([-1], np.int32), prop=P[None, :].copy(), prop_rho_a=np.zeros(1), rel=np.zeros((0, 14)),
+        m_rel=np.array([-1], np.int32), prop=P[None, :].copy(), prop_rho_a=np.zeros(1), rel=np.zeros((0, wire.REL_STRIDE)),
         p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 8)),
         p_flags=np.zeros(0, np.int32), load_cases=[], combo_ids=np.zeros(0, np.int64), combo_names=[],
         combo_factors=np.zeros((0, 0)), imperfections=[], member_sets={}, options=wire.Options())

@@ -48,8 +48,8 @@ def _section_numbers(doc):
 def test_parser_builds_modifier_records():
     m = wire.parse_document(_doc())
     assert m.rel.shape == (1, wire.REL_STRIDE) and m.m_rel.tolist() == [0]
-    assert (m.rel[0, :12] == wire.RIGID_RELEASE).all() and m.rel[0, 12:].tolist() == [YS, ZS]
-    assert wire.parse_document(_doc(mirror=True)).rel[0, 12:].tolist() == [-YS, -ZS]
+    assert (m.rel[0, :12] == wire.RIGID_RELEASE).all() and m.rel[0, 12:14].tolist() == [YS, ZS]
+    assert wire.parse_document(_doc(mirror=True)).rel[0, 12:14].tolist() == [-YS, -ZS]
     off = wire.parse_document(_doc(coupling=False))
     assert off.rel.shape == (0, wire.REL_STRIDE) and off.m_rel.tolist() == [-1]
     assert not [w for w in m.warnings if w[0] == "W_SHEAR_CENTRE_IGNORED"]
@@ -83,7 +83,8 @@ def test_element_code_matches_oracle(elem_host, case):
     rec = np.full(wire.REL_STRIDE, -1.0)
     rec[5] = 0.0
     rec[9] = 4.0e3
-    rec[12:] = (YS, ZS)
+    rec[12:14] = (YS, ZS)
+    rec[14:] = 0.0
     p = np.arange(1.0, 13.0)[None, :] * 17.0
     kc, pc = fo.member_modifiers(k, p, rec)
     out = np.zeros(144)
@@ -106,7 +107,8 @@ def test_element_loads_match_oracle(elem_host):
     R, L, k, T = _oracle_member(a, b, roll, Pp, mtype)
     rec = np.full(wire.REL_STRIDE, -1.0)
     rec[11] = 0.0
-    rec[12:] = (YS, ZS)
+    rec[12:14] = (YS, ZS)
+    rec[14:] = 0.0
     dl = np.array([[0.0, -1200.0, 300.0, 0.0, -400.0, 100.0, 0.1, 0.9]])
     p0 = np.zeros(12)
     elem_host.h_beam_loads(_p(a), _p(b), C.c_double(roll), _p(Pp), mtype, _p(dl), 1, None, 0, None, _p(p0))
