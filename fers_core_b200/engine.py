@@ -20,7 +20,7 @@ import torch
 from . import _lib, chol, unity, wire
 from .hostlogic import (
     INACTIVE_SCALE, effective_bc, imperfect_coordinates, pdelta_suppressed_axes, rhs_plan, rigid_property_row,
-    unilateral_dofs, unilateral_update,
+    unilateral_dofs, unilateral_update, curve_stiffness, curves_converged,
 )
 from .results import ResultArrays, SECTION_FRACS, lazy_bundle, results_to_json, results_to_wire
 
@@ -181,6 +181,7 @@ class Engine:
         self.d_rel = self._t(m.rel, np.float64) if self.has_rel else None
         # unilateral supports (PositiveOnly / NegativeOnly) start closed; engine._solve_nonlinear iterates their active set
         self.n_unilateral = int(len(unilateral_dofs(m)[0]))
+        self.n_curves = len(m.support_curves)
         code, kk = effective_bc(m, np.ones(self.n_unilateral, bool))
         code = code.astype(np.uint8)
         self.has_springs = bool((code == wire.BC_SPRING).any()) or bool((unilateral_dofs(m)[2] > 0).any())
@@ -258,9 +259,10 @@ class Engine:
         self._bc_ws = self._empty(self._bc_ws_bytes, torch.uint8)
 
     # ---- stages ----------------------------------------------------------------------------
-    def set_unilateral(self, active: np.ndarray) -> None:
-        """Support codes for the given active set of the unilateral supports (picked up by the next assemble())."""
-        code, kk = effective_bc(self.model, active)
+    def set_unilateral(self, active: np.ndarray, curve_k: np.ndarray | None = None) -> None:
+        """Support codes for the given active set of the unilateral supports and the current stiffness of the
+        load-dependent springs (picked up by the next assemble())."""
+        code, kk = effective_bc(self.model, active, curve_k)
         self.d_bc_code = self._t(code.astype(np.uint8).reshape(-1), np.uint8)
         self.d_bc_k = self._t(kk.reshape(-1), np.float64)
 
@@ -557,7 +559,7 @@ def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_
         out.unity_xyz = eng.d_xyz0          # deflected positions are reported on the undeformed coordinates
         cols = list(grp.columns)
         fac = plan.factors[cols]
-        if not (second_order or unilateral.any() or eng.n_unilateral):
+        if not (second_order or unilateral.any() or eng.n_unilateral or eng.n_curves):
             f_case, peq_case = eng.load_cases(d_xyz)
             eng.assemble(d_xyz)
             for c0 in range(0, len(cols), 64):
@@ -599,9 +601,10 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
     d_axial = None
     rec = None
     sup_active = np.ones(eng.n_unilateral, bool)
-    for _outer in range(max(1, 2 * (len(uni) + eng.n_unilateral) + 2)):
-        if eng.n_unilateral:
-            eng.set_unilateral(sup_active)
+    curve_k = curve_stiffness(model, None)              # load-dependent springs start at their zero-force stiffness
+    for _outer in range(max(1, 2 * (len(uni) + eng.n_unilateral) + 2 + (max(opts.max_iterations, 20) if eng.n_curves else 0))):
+        if eng.n_unilateral or eng.n_curves:
+            eng.set_unilateral(sup_active, curve_k)
         d_scale = eng._t(scale, np.float64) if len(uni) else None
         f_case, peq_case = eng.load_cases(d_xyz, d_scale)
         d_f = eng.combine(f_case, fac, nr)
@@ -628,12 +631,19 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
                     conv = True
                     break
         changed = False
-        if eng.n_unilateral:
-            # reactions of the current state decide which unilateral supports stay closed
+        if eng.n_unilateral or eng.n_curves:
+            # reactions of the current state decide which unilateral supports stay closed and how stiff the
+            # load-dependent springs are in the next pass
             r_now = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, d_scale, d_axial, kg_mode, sup, detail=False)["R"]
-            new_active = unilateral_update(model, sup_active, d_u[:, 0].cpu().numpy(), r_now[:, 0].cpu().numpy())
-            changed = not np.array_equal(new_active, sup_active)
-            sup_active = new_active
+            r_host = r_now[:, 0].cpu().numpy()
+            if eng.n_unilateral:
+                new_active = unilateral_update(model, sup_active, d_u[:, 0].cpu().numpy(), r_host)
+                changed = not np.array_equal(new_active, sup_active)
+                sup_active = new_active
+            if eng.n_curves:
+                new_k = curve_stiffness(model, r_host)
+                changed = changed or not curves_converged(new_k, curve_k, opts.tolerance)
+                curve_k = new_k
         if len(uni) == 0:
             if changed:
                 continue

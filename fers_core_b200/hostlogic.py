@@ -147,12 +147,32 @@ def unilateral_dofs(model: wire.ModelArrays):
     return idx, sign, model.bc_k.reshape(-1)[idx].copy()
 
 
-def effective_bc(model: wire.ModelArrays, active: np.ndarray):
+# ---- load-dependent support springs (SupportStiffnessCurve, pydantic_models.py:1249-1265; supportcondition.py:19-23:
+#      "the curve overrides the constant value and the solver re-evaluates the stiffness each iteration based on the
+#      specified ... component").  The driver is the global reaction component `depends_on` AT THE SAME NODE (force of
+#      the support on the structure, K u - F), its absolute value unless `signed`; between the points the stiffness is
+#      interpolated linearly, outside it keeps the end values (fers_core/examples/131_...py:126-139 `interpolate_k`).
+def curve_stiffness(model: wire.ModelArrays, r: np.ndarray | None) -> np.ndarray:
+    """Stiffness of every curve-driven support DOF for the reactions r [Ndof] (None: zero force)."""
+    k = np.zeros(len(model.support_curves))
+    for j, (_dof, drv, pts, signed) in enumerate(model.support_curves):
+        f = 0.0 if r is None else float(r.reshape(-1)[drv])
+        k[j] = np.interp(f if signed else abs(f), pts[:, 0], pts[:, 1])
+    return k
+
+
+def curves_converged(k_new: np.ndarray, k_old: np.ndarray, tol: float) -> bool:
+    return bool(np.all(np.abs(k_new - k_old) <= max(tol, 1e-12) * np.abs(k_old)))
+
+
+def effective_bc(model: wire.ModelArrays, active: np.ndarray, curve_k: np.ndarray | None = None):
     """bc_code / bc_k with every unilateral DOF replaced by Fixed (ideal) or Spring (with stiffness) when it is active
-    and by Free when it is not."""
+    and by Free when it is not; curve-driven springs take the stiffness ``curve_k`` of the current iteration."""
     idx, _, k = unilateral_dofs(model)
     code = model.bc_code.reshape(-1).copy()
     kk = model.bc_k.reshape(-1).copy()
+    if curve_k is not None and len(model.support_curves):
+        kk[[c[0] for c in model.support_curves]] = curve_k
     code[idx] = np.where(active, np.where(k > 0.0, wire.BC_SPRING, wire.BC_FIXED), wire.BC_FREE)
     kk[idx] = np.where(active & (k > 0.0), k, 0.0)
     return code.reshape(model.bc_code.shape), kk.reshape(model.bc_k.shape)

@@ -32,6 +32,7 @@ _BC_TYPES = {
     "negativeonly": BC_NEG_ONLY, "negative-only": BC_NEG_ONLY,
 }
 DOF_NAMES = ("X", "Y", "Z", "RX", "RY", "RZ")
+_SUPPORT_FORCE = {"Fx": 0, "Fy": 1, "Fz": 2, "Mx": 3, "My": 4, "Mz": 5}      # SupportForceComponent, pydantic_models.py:1240-1246
 
 # columns of the per-section property table (one row per distinct section x option set)
 P_EA, P_EIY, P_EIZ, P_GJ, P_GASY, P_GASZ, P_WPL, P_SPARE = range(8)
@@ -127,6 +128,9 @@ class ModelArrays:
     member_sets: dict             # id -> [member index]
     options: Options
     warnings: list = field(default_factory=list)
+    # load-dependent support springs (SupportStiffnessCurve, pydantic_models.py:1249-1265): one entry per DOF,
+    # (flat DOF, flat DOF of the driving reaction component at the same node, points [n,2] sorted by force, signed)
+    support_curves: list = field(default_factory=list)
     # unity checks (pydantic_models.py:2202-2220): raw definitions + what their quantities read
     unity_checks: list = field(default_factory=list)
     combo_limit_state: list = field(default_factory=list)      # per combination: "SLS" | "ULS" | ... | None
@@ -250,6 +254,7 @@ def parse_document(doc: dict) -> ModelArrays:
     bc_k = np.zeros((nn, 6), np.float64)
     node_support_id = np.full(nn, -1, np.int64)
     warp_fixed = np.zeros(nn, bool)         # support restrains the warping DOF (NodalSupport.warping_condition)
+    support_curves: list = []
     for i, n in enumerate(nodes):
         sid = n.get("nodal_support")
         if sid is None:
@@ -277,13 +282,19 @@ def parse_document(doc: dict) -> ModelArrays:
             bc_code[i, d] = ctype
             if ctype == BC_SPRING:
                 k = cond.get("stiffness")
-                if k is None:
-                    curve = cond.get("stiffness_curve")
-                    if curve and curve.get("points"):
-                        k = curve["points"][0][1]
-                        warnings.append(("W_SUPPORT_CURVE", f"support {sid}.{name}: stiffness curve linearised at first point"))
-                    else:
-                        raise WireError(f"support {sid}.{name}: Spring without stiffness")
+                curve = cond.get("stiffness_curve")
+                if curve and curve.get("points"):
+                    # the curve overrides the constant value (supportcondition.py:19-23); start from the stiffness at zero force
+                    pts = np.array([[float(p[0]), float(p[1])] for p in curve["points"]], np.float64)
+                    comp = _SUPPORT_FORCE.get(str(curve.get("depends_on")))
+                    if comp is None:
+                        raise WireError(f"support {sid}.{name}: stiffness_curve.depends_on must be Fx/Fy/Fz/Mx/My/Mz, got {curve.get('depends_on')!r}")
+                    if len(pts) < 2 or (np.diff(pts[:, 0]) < 0.0).any() or not (pts[:, 1] > 0.0).all() or not np.isfinite(pts).all():
+                        raise WireError(f"support {sid}.{name}: stiffness_curve needs >= 2 points sorted by force with positive stiffness")
+                    support_curves.append((6 * i + d, 6 * i + comp, pts, bool(curve.get("signed"))))
+                    k = float(np.interp(0.0, pts[:, 0], pts[:, 1]))
+                elif k is None:
+                    raise WireError(f"support {sid}.{name}: Spring without stiffness")
                 bc_k[i, d] = float(k)
             elif ctype in (BC_POS_ONLY, BC_NEG_ONLY) and cond.get("stiffness"):
                 bc_k[i, d] = float(cond["stiffness"])        # unilateral spring (supportcondition.py:25-32)
@@ -612,7 +623,7 @@ def parse_document(doc: dict) -> ModelArrays:
         p_ids=p_ids, p_nodes=p_nodes, p_data=p_data, p_flags=p_flags,
         load_cases=load_cases, combo_ids=combo_ids, combo_names=combo_names, combo_factors=combo_factors,
         imperfections=list(analysis.get("imperfection_cases") or []), member_sets=member_sets,
-        options=opts, warnings=warnings,
+        options=opts, warnings=warnings, support_curves=support_curves,
         unity_checks=list(analysis.get("unity_checks") or []),
         combo_limit_state=[c.get("limit_state") for c in combos],
         m_classification=m_classification, m_section_raw=m_section_raw,

@@ -43,7 +43,7 @@ from fers_core_b200 import wire
 from fers_core_b200.results import ResultArrays, SECTION_FRACS
 from fers_core_b200.hostlogic import (
     rhs_plan, imperfect_coordinates, rigid_property_row, pdelta_suppressed_axes, INACTIVE_SCALE,
-    unilateral_dofs, effective_bc, unilateral_update,
+    unilateral_dofs, effective_bc, unilateral_update, curve_stiffness, curves_converged,
 )
 
 GAUSS3_X = np.array([-np.sqrt(3.0 / 5.0), 0.0, np.sqrt(3.0 / 5.0)])
@@ -804,7 +804,7 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
         F = fac @ F_lc
         peq = np.einsum("rl,lmk->rmk", fac, peq_lc)
         cols = list(grp.columns)
-        needs_own = second_order or np.any(unilateral_members) or len(unilateral_dofs(model)[0]) > 0
+        needs_own = second_order or np.any(unilateral_members) or len(unilateral_dofs(model)[0]) > 0 or len(model.support_curves) > 0
         if not needs_own:
             # ---- linear: one factorisation, all right-hand sides
             K = asm.K_elastic()
@@ -841,8 +841,10 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
     suppressed = pdelta_suppressed_axes(model)
     sup_idx = unilateral_dofs(model)[0]
     sup_active = np.ones(len(sup_idx), bool)            # unilateral supports start closed
-    for _outer in range(max(1, 2 * (len(uni) + len(sup_idx)) + 2)):
-        bc = effective_bc(model, sup_active) if len(sup_idx) else None
+    n_curves = len(model.support_curves)
+    curve_k = curve_stiffness(model, None)              # load-dependent springs start at their zero-force stiffness
+    for _outer in range(max(1, 2 * (len(uni) + len(sup_idx)) + 2 + (max(opts.max_iterations, 20) if n_curves else 0))):
+        bc = effective_bc(model, sup_active, curve_k) if (len(sup_idx) or n_curves) else None
         K0 = asm.K_elastic()
         Kff, free, _ = constrain(K0, model, bc=bc)
         U = np.zeros(nd); U[free] = solve_sym(Kff, F[free][:, None])[:, 0]
@@ -873,6 +875,10 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
             new_active = unilateral_update(model, sup_active, U, K @ U - F)
             changed = not np.array_equal(new_active, sup_active)
             sup_active = new_active
+        if n_curves:
+            new_k = curve_stiffness(model, K @ U - F)
+            changed = changed or not curves_converged(new_k, curve_k, opts.tolerance)
+            curve_k = new_k
         if len(uni) == 0:
             if changed:
                 continue
