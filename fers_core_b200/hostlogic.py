@@ -125,6 +125,63 @@ def rigid_property_row(prop: np.ndarray) -> np.ndarray:
     return row
 
 
+def member_frames_host(model: wire.ModelArrays, members: np.ndarray | None = None):
+    """Local axes R [n,3,3] (rows x, y, z in global coordinates), axis lengths L [n] and end offsets [n,2,3] of the
+    given member rows (all by default) on the host: the rule of fers_core/members/member.py:309-354 over the elastic
+    axis (end offsets included).  Host-side post-processing only (deflected-shape stations); the kernels form their
+    own frames."""
+    members = np.arange(model.n_members) if members is None else np.asarray(members)
+    xyz, m_rel = model.xyz, model.m_rel[members]
+    off = np.zeros((len(members), 2, 3))
+    rows = np.nonzero(m_rel >= 0)[0]
+    if len(rows):
+        off[rows] = model.rel[m_rel[rows], wire.REL_O1:wire.REL_O1 + 6].reshape(-1, 2, 3)
+    d = xyz[model.m_n2[members]] - xyz[model.m_n1[members]] + off[:, 1] - off[:, 0]
+    L = np.linalg.norm(d, axis=1)
+    lx = d / L[:, None]
+    ref = np.where((np.abs(lx[:, 1]) > 1.0 - 1e-6)[:, None], np.array([0.0, 0.0, 1.0]), np.array([0.0, 1.0, 0.0]))
+    lz = np.cross(lx, ref)
+    lz /= np.linalg.norm(lz, axis=1)[:, None]
+    ly = np.cross(lz, lx)
+    ly /= np.linalg.norm(ly, axis=1)[:, None]
+    c, s = np.cos(model.m_roll[members])[:, None], np.sin(model.m_roll[members])[:, None]
+    return np.stack([lx, c * ly + s * lz, -s * ly + c * lz], axis=1), L, off
+
+
+DEFLECTED_STATIONS = 11      # x_frac = 0, 0.1 .. 1 (the count is the closed engine's choice; stated here, unpinned)
+
+
+def member_deflected_shape(model: wire.ModelArrays, u_nodes: np.ndarray, members: np.ndarray | None = None) -> np.ndarray:
+    """MemberResult.member_displacements (pydantic_models.py:1622-1625): global displacement [n, stations, 3] at
+    evenly spaced stations of the given member rows (all by default), "the end-DOF homogeneous cubic": Hermite
+    interpolation of the end translations and rotations in the member's local axes, the reconstruction of
+    fers_core/fers/deformation_utils.py:46-114 (pinned on it: tests/golden/hermite_cases.json); linear for truss
+    members, whose ends are pinned.  ``u_nodes`` [Nn,6] are the global node displacements of one result column."""
+    members = np.arange(model.n_members) if members is None else np.asarray(members)
+    nm = len(members)
+    xi = np.linspace(0.0, 1.0, DEFLECTED_STATIONS)
+    if nm == 0:
+        return np.zeros((0, len(xi), 3))
+    R, L, off = member_frames_host(model, members)
+    ends = []
+    for e, nodes in enumerate((model.m_n1[members], model.m_n2[members])):
+        t, r = u_nodes[nodes, 0:3], u_nodes[nodes, 3:6]
+        t = t + np.cross(r, off[:, e])                       # end of the elastic axis: rigid arm from the node
+        ends.append((np.einsum("mij,mj->mi", R, t), np.einsum("mij,mj->mi", R, r)))
+    (t1, r1), (t2, r2) = ends
+    x2, x3 = xi * xi, xi * xi * xi
+    n1, n2, n3, n4 = 1 - 3 * x2 + 2 * x3, xi - 2 * x2 + x3, 3 * x2 - 2 * x3, -x2 + x3
+    Lc = L[:, None]
+    loc = np.empty((nm, len(xi), 3))
+    loc[:, :, 0] = t1[:, 0:1] * (1 - xi) + t2[:, 0:1] * xi
+    loc[:, :, 1] = t1[:, 1:2] * n1 + Lc * r1[:, 2:3] * n2 + t2[:, 1:2] * n3 + Lc * r2[:, 2:3] * n4
+    loc[:, :, 2] = t1[:, 2:3] * n1 - Lc * r1[:, 1:2] * n2 + t2[:, 2:3] * n3 - Lc * r2[:, 1:2] * n4
+    truss = model.m_type[members] == wire.MT_TRUSS
+    if truss.any():
+        loc[truss] = t1[truss][:, None, :] * (1 - xi)[None, :, None] + t2[truss][:, None, :] * xi[None, :, None]
+    return np.einsum("mji,msj->msi", R, loc)
+
+
 def pdelta_suppressed_axes(model: wire.ModelArrays) -> tuple:
     """Global translational axes (0,1,2) excluded from P-Delta (pydantic_models.py:1374-1384)."""
     o = model.options

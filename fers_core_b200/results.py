@@ -14,7 +14,10 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+from .hostlogic import DEFLECTED_STATIONS, member_deflected_shape
+
 SECTION_FRACS = (0.25, 0.5, 0.75)
+_STATIONS = tuple(float(x) for x in np.linspace(0.0, 1.0, DEFLECTED_STATIONS))
 _F = ("fx", "fy", "fz", "mx", "my", "mz")
 _D = ("dx", "dy", "dz", "rx", "ry", "rz")
 _PR = ("nx", "ny", "nxy", "mx", "my", "mxy", "qx", "qy")
@@ -94,6 +97,13 @@ class _Column:
 
     def __init__(self, ctx: _Context, col: int):
         self.c, self.col = ctx, col
+        self._shape = None
+
+    def deflected_shape(self) -> np.ndarray:
+        """[Nm, stations, 3] global displacements along every member of this column (built once, on first use)."""
+        if self._shape is None:
+            self._shape = member_deflected_shape(self.c.model, self.c.res.U[self.col])
+        return self._shape
 
     def _warp(self, arr, i) -> float:
         """Value at the warping DOF of real node i (DOF 0 of its auxiliary node), 0 without one."""
@@ -120,13 +130,19 @@ class _Column:
         series = ([{"x_frac": 0.0, "forces": _forces(fl[0:6])}] + sec
                   + [{"x_frac": 1.0, "forces": _forces(-fl[6:12])}])
         b1, b2 = (float(res.bw[col, m, 0]), float(res.bw[col, m, 1])) if res.bw is not None else (0.0, 0.0)
+        extra = {}
+        if self.c.model.options.include_member_deflected_shape:
+            # whole table when a document is being built eagerly, this member alone under the lazy view
+            shape = self._shape[m] if self._shape is not None else member_deflected_shape(self.c.model, res.U[col], [m])[0]
+            extra["member_displacements"] = [{"x_frac": float(x), "displacement": [float(v) for v in d]}
+                                             for x, d in zip(_STATIONS, shape)]
         return {
             "start_node_forces": _forces(fg[0:6], b1), "end_node_forces": _forces(fg[6:12], b2),
             "maximums": _forces(res.gmax[col, m]), "minimums": _forces(res.gmin[col, m]),
             "local_start_forces": _forces(fl[0:6], b1), "local_end_forces": _forces(fl[6:12], b2),
             "local_maximums": _forces(res.lmax[col, m]), "local_minimums": _forces(res.lmin[col, m]),
             "local_displacement_start_node": _disp(ul[0:6]), "local_displacement_end_node": _disp(ul[6:12]),
-            "section_forces": sec, "internal_force_series": series,
+            "section_forces": sec, "internal_force_series": series, **extra,
         }
 
     def plate(self, key: str) -> dict:
@@ -175,6 +191,9 @@ class _Column:
         (plain dicts by default, :class:`LazyMap` for :func:`lazy_bundle`)."""
         c, plan, col = self.c, self.c.plan, self.col
         if mapping is None:
+            if c.model.options.include_member_deflected_shape:
+                self.deflected_shape()
+
             def mapping(keys, items, get):
                 return {k: get(i) for k, i in zip(keys, items)}
         nodes = range(c.n_real)
@@ -265,6 +284,7 @@ _MEMBER_T = ("{" + ",".join(f'"{k}":{_F_T}' for k in (
     + ',"section_forces":[' + ",".join(f'{{"x_frac":{float(x)!r},"forces":{_F_T}}}' for x in SECTION_FRACS) + "]"
     + ',"internal_force_series":[' + ",".join(f'{{"x_frac":{float(x)!r},"forces":{_F_T}}}' for x in (0.0,) + SECTION_FRACS + (1.0,))
     + "]}")
+_SHAPE_T = (',"member_displacements":[' + ",".join(f'{{"x_frac":{float(x)!r},"displacement":[{_SLOT},{_SLOT},{_SLOT}]}}' for x in _STATIONS) + "]}")
 _REACTION_T = f'{{"location":{{"X":{_SLOT},"Y":{_SLOT},"Z":{_SLOT}}},"nodal_forces":{_F_T},"support_id":{_ISLOT}}}'
 
 
@@ -324,7 +344,11 @@ def results_to_json(model, res: ResultArrays) -> str:
             mv = np.hstack([fg[:, 0:6], b1, fg[:, 6:12], b2, res.gmax[col], z, res.gmin[col], z,
                             fl[:, 0:6], b1, fl[:, 6:12], b2, res.lmax[col], z, res.lmin[col], z,
                             ul[:, 0:6], z, ul[:, 6:12], z] + secs + [fl[:, 0:6], z] + secs + [-fl[:, 6:12], z])
-            mem = _json_records(_MEMBER_T, mem_blob, mv)
+            template = _MEMBER_T
+            if model.options.include_member_deflected_shape:
+                template = _MEMBER_T[:-1] + _SHAPE_T
+                mv = np.hstack([mv, v.deflected_shape().reshape(nm, -1)])
+            mem = _json_records(template, mem_blob, mv)
         else:
             mem = "{}"
         parts = [f'"name":{json.dumps(plan.names[col])}',

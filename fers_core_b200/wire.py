@@ -88,6 +88,7 @@ class Options:
     include_shear_deformation: bool = True
     include_warping: bool = True
     include_shear_center_coupling: bool = True
+    include_member_deflected_shape: bool = False      # MemberResult.member_displacements (pydantic_models.py:1350-1353)
     solve_loadcases: bool = True
     enable_self_weight: bool = False
     gravity_direction: tuple = (0.0, -1.0, 0.0)
@@ -203,7 +204,7 @@ def parse_options(raw: dict | None) -> Options:
     if raw.get("axial_slack") is not None:
         o.axial_slack = float(raw["axial_slack"])
     for k in ("include_shear_deformation", "include_warping", "include_shear_center_coupling",
-              "solve_loadcases", "enable_self_weight"):
+              "include_member_deflected_shape", "solve_loadcases", "enable_self_weight"):
         if raw.get(k) is not None:
             setattr(o, k, bool(raw[k]))
     if raw.get("gravity_direction") is not None:

@@ -32,3 +32,19 @@ def test_reference_suite_against_oracle(suite):
     p = subprocess.run([sys.executable, "-m", "pytest", "-p", "no:cacheprovider", "-x", "-q", suite], cwd=REFERENCE,
                        env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+
+
+def test_reference_example_104_deflected_shape(tmp_path):
+    """examples/104_visual_member_deflected_shape.py up to its plotting step (pyvista is absent): the reference front
+    end sets include_member_deflected_shape, ingests ``member_displacements`` through its pydantic gate and runs its own
+    consistency assertions (:85-93) on the stations the oracle engine returns."""
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "refshim"), REFERENCE, ROOT])
+    env["FERS_SHIM_BACKEND"] = "oracle"
+    example = os.path.join(REFERENCE, "fers_core", "examples", "104_visual_member_deflected_shape.py")
+    code = ("src = open(%r).read().split('# Step 5: Visualise')[0]\n"
+            "exec(compile(src, 'example_104', 'exec'))\n"
+            "assert len(samples) == 11\n" % example)
+    p = subprocess.run([sys.executable, "-c", code], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert "Engine returned 11 deflected-shape stations" in p.stdout
