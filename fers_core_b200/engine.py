@@ -20,7 +20,7 @@ import torch
 from . import _lib, chol, unity, wire
 from .hostlogic import (
     INACTIVE_SCALE, effective_bc, imperfect_coordinates, pdelta_suppressed_axes, rhs_plan, rigid_property_row,
-    unilateral_dofs, unilateral_update, curve_stiffness, curves_converged,
+    unilateral_dofs, unilateral_update, curve_stiffness, curves_converged, hinge_curve_stiffness, rel_with_hinge_curves,
 )
 from .results import ResultArrays, SECTION_FRACS, lazy_bundle, results_to_json, results_to_wire
 
@@ -182,6 +182,7 @@ class Engine:
         # unilateral supports (PositiveOnly / NegativeOnly) start closed; engine._solve_nonlinear iterates their active set
         self.n_unilateral = int(len(unilateral_dofs(m)[0]))
         self.n_curves = len(m.support_curves)
+        self.n_hinge_curves = len(m.hinge_curves)
         code, kk = effective_bc(m, np.ones(self.n_unilateral, bool))
         code = code.astype(np.uint8)
         self.has_springs = bool((code == wire.BC_SPRING).any()) or bool((unilateral_dofs(m)[2] > 0).any())
@@ -265,6 +266,13 @@ class Engine:
         code, kk = effective_bc(self.model, active, curve_k)
         self.d_bc_code = self._t(code.astype(np.uint8).reshape(-1), np.uint8)
         self.d_bc_k = self._t(kk.reshape(-1), np.float64)
+
+    def set_rel(self, rel: np.ndarray) -> None:
+        """Member modifier records for the current stiffness of the load-dependent hinge springs (picked up by the
+        next load_cases() / assemble() / recover())."""
+        if rel.shape != self.model.rel.shape:
+            raise EngineError(f"set_rel: expected {self.model.rel.shape}, got {rel.shape}")
+        self.d_rel.copy_(torch.from_numpy(np.ascontiguousarray(rel, np.float64)))
 
     def assemble(self, d_xyz, d_scale=None, d_axial=None, kg_mode=0, kg_suppress=0, count: bool = True) -> None:
         """Element stiffness + assembly + boundary conditions for one geometry / state."""
@@ -559,7 +567,7 @@ def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_
         out.unity_xyz = eng.d_xyz0          # deflected positions are reported on the undeformed coordinates
         cols = list(grp.columns)
         fac = plan.factors[cols]
-        if not (second_order or unilateral.any() or eng.n_unilateral or eng.n_curves):
+        if not (second_order or unilateral.any() or eng.n_unilateral or eng.n_curves or eng.n_hinge_curves):
             f_case, peq_case = eng.load_cases(d_xyz)
             eng.assemble(d_xyz)
             for c0 in range(0, len(cols), 64):
@@ -602,7 +610,11 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
     rec = None
     sup_active = np.ones(eng.n_unilateral, bool)
     curve_k = curve_stiffness(model, None)              # load-dependent springs start at their zero-force stiffness
-    for _outer in range(max(1, 2 * (len(uni) + eng.n_unilateral) + 2 + (max(opts.max_iterations, 20) if eng.n_curves else 0))):
+    hinge_k = hinge_curve_stiffness(model, None)        # = the values model.rel carries
+    if eng.n_hinge_curves:
+        eng.set_rel(model.rel)                          # the previous column left its own state on the device
+    for _outer in range(max(1, 2 * (len(uni) + eng.n_unilateral) + 2
+                            + (max(opts.max_iterations, 20) if eng.n_curves or eng.n_hinge_curves else 0))):
         if eng.n_unilateral or eng.n_curves:
             eng.set_unilateral(sup_active, curve_k)
         d_scale = eng._t(scale, np.float64) if len(uni) else None
@@ -631,11 +643,11 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
                     conv = True
                     break
         changed = False
-        if eng.n_unilateral or eng.n_curves:
-            # reactions of the current state decide which unilateral supports stay closed and how stiff the
-            # load-dependent springs are in the next pass
-            r_now = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, d_scale, d_axial, kg_mode, sup, detail=False)["R"]
-            r_host = r_now[:, 0].cpu().numpy()
+        if eng.n_unilateral or eng.n_curves or eng.n_hinge_curves:
+            # reactions and member end forces of the current state decide which unilateral supports stay closed and
+            # how stiff the load-dependent springs (supports, hinges) are in the next pass
+            now = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, d_scale, d_axial, kg_mode, sup, detail=False)
+            r_host = now["R"][:, 0].cpu().numpy()
             if eng.n_unilateral:
                 new_active = unilateral_update(model, sup_active, d_u[:, 0].cpu().numpy(), r_host)
                 changed = not np.array_equal(new_active, sup_active)
@@ -644,6 +656,12 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
                 new_k = curve_stiffness(model, r_host)
                 changed = changed or not curves_converged(new_k, curve_k, opts.tolerance)
                 curve_k = new_k
+            if eng.n_hinge_curves:
+                new_k = hinge_curve_stiffness(model, now["f_local"].view(nm, 12, -1)[:, :, 0].cpu().numpy())
+                if not curves_converged(new_k, hinge_k, opts.tolerance):
+                    changed = True
+                    eng.set_rel(rel_with_hinge_curves(model, new_k))
+                hinge_k = new_k
         if len(uni) == 0:
             if changed:
                 continue

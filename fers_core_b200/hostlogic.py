@@ -222,6 +222,33 @@ def curves_converged(k_new: np.ndarray, k_old: np.ndarray, tol: float) -> bool:
     return bool(np.all(np.abs(k_new - k_old) <= max(tol, 1e-12) * np.abs(k_old)))
 
 
+# ---- load-dependent hinge springs (MemberHinge.stiffness_curve_*; MemberStiffnessCurve pydantic_models.py:1638-1652:
+#      "which member-local force component the stiffness depends on", |force| unless `signed`).  The member-side twin
+#      of the support curves, same interpolation and the same outer iteration.  The driver is the member's own local
+#      internal force at the END THE HINGE SITS ON, positive-face convention: what the member beyond the cut exerts on
+#      the +x face, i.e. +local_end_forces at the end and -local_start_forces at the start (stiffness-sign end forces,
+#      SURVEY A.6), so N is tension-positive ("Axial force (tension-positive)", pydantic_models.py:644) and every
+#      component has one sign along an unloaded member.  Only `signed` curves see the sign.  The engine that defines
+#      the convention is closed: stated, unpinned.
+def hinge_curve_stiffness(model: wire.ModelArrays, f_local: np.ndarray | None) -> np.ndarray:
+    """Stiffness of every curve-driven hinge spring for the local member end forces f_local [Nm,12] (None: zero force)."""
+    k = np.zeros(len(model.hinge_curves))
+    for j, (m, _row, slot, comp, pts, signed) in enumerate(model.hinge_curves):
+        f = 0.0
+        if f_local is not None:
+            f = -float(f_local[m, comp]) if slot < 6 else float(f_local[m, 6 + comp])
+        k[j] = np.interp(f if signed else abs(f), pts[:, 0], pts[:, 1])
+    return k
+
+
+def rel_with_hinge_curves(model: wire.ModelArrays, k: np.ndarray) -> np.ndarray:
+    """Member modifier records with the curve-driven release springs at the stiffness ``k`` of the current iteration."""
+    rel = model.rel.copy()
+    for (_m, row, slot, _comp, _pts, _signed), kj in zip(model.hinge_curves, k):
+        rel[row, slot] = kj
+    return rel
+
+
 def effective_bc(model: wire.ModelArrays, active: np.ndarray, curve_k: np.ndarray | None = None):
     """bc_code / bc_k with every unilateral DOF replaced by Fixed (ideal) or Spring (with stiffness) when it is active
     and by Free when it is not; curve-driven springs take the stiffness ``curve_k`` of the current iteration."""

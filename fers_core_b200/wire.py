@@ -43,6 +43,9 @@ _HINGE_FIELDS = (
     "translational_release_vx", "translational_release_vy", "translational_release_vz",
     "rotational_release_mx", "rotational_release_my", "rotational_release_mz",
 )
+_HINGE_CURVES = ("stiffness_curve_vx", "stiffness_curve_vy", "stiffness_curve_vz",
+                 "stiffness_curve_mx", "stiffness_curve_my", "stiffness_curve_mz")
+_MEMBER_FORCE = {"N": 0, "Vy": 1, "Vz": 2, "Mx": 3, "My": 4, "Mz": 5}       # MemberStiffnessCurveDriver, pydantic_models.py:583-589
 RIGID_RELEASE = -1.0  # sentinel: DOF rigidly connected (no hinge spring)
 # one row of ModelArrays.rel (csrc/fers_elem.cuh REL_*): 12 release springs, the shear-centre offset, the two end
 # offsets (global X Y Z of start_offset, end_offset)
@@ -132,6 +135,10 @@ class ModelArrays:
     # load-dependent support springs (SupportStiffnessCurve, pydantic_models.py:1249-1265): one entry per DOF,
     # (flat DOF, flat DOF of the driving reaction component at the same node, points [n,2] sorted by force, signed)
     support_curves: list = field(default_factory=list)
+    # load-dependent hinge springs (MemberHinge.stiffness_curve_*, MemberStiffnessCurve pydantic_models.py:1638-1652):
+    # one entry per member end DOF, (member row, rel row, slot 0..11 of the release springs, driving local force
+    # component 0..5 = N Vy Vz Mx My Mz at the same end, points [n,2] sorted by force, signed)
+    hinge_curves: list = field(default_factory=list)
     # unity checks (pydantic_models.py:2202-2220): raw definitions + what their quantities read
     unity_checks: list = field(default_factory=list)
     combo_limit_state: list = field(default_factory=list)      # per combination: "SLS" | "ULS" | ... | None
@@ -351,7 +358,23 @@ def parse_document(doc: dict) -> ModelArrays:
             v = h.get(f)
             if v is not None:
                 r[d] = max(float(v), 0.0)
+        for d, f in enumerate(_HINGE_CURVES):
+            curve = h.get(f)
+            if curve and curve.get("points"):
+                # like the support curves, the curve overrides the constant; start from the stiffness at zero force
+                r[d] = float(np.interp(0.0, *hinge_curve(int(hid), f, curve)[1].T))
         return r
+
+    def hinge_curve(hid, name, curve):
+        pts = np.array([[float(p[0]), float(p[1])] for p in curve["points"]], np.float64)
+        comp = _MEMBER_FORCE.get(str(curve.get("depends_on")))
+        if comp is None:
+            raise WireError(f"member hinge {hid}.{name}: depends_on must be N/Vy/Vz/Mx/My/Mz, got {curve.get('depends_on')!r}")
+        if len(pts) < 2 or (np.diff(pts[:, 0]) < 0.0).any() or not (pts[:, 1] > 0.0).all() or not np.isfinite(pts).all():
+            raise WireError(f"member hinge {hid}.{name}: stiffness curve needs >= 2 points sorted by force with positive stiffness")
+        return comp, pts, bool(curve.get("signed"))
+
+    hinge_curves: list = []
 
     # ---- members (pydantic_models.py:1507-1549) ----------------------------------------
     members = model.get("members") or []
@@ -405,6 +428,11 @@ def parse_document(doc: dict) -> ModelArrays:
         if m.get("start_hinge") is not None or m.get("end_hinge") is not None or ys != 0.0 or zs != 0.0 or offs.any():
             m_rel[i] = len(rel_rows)
             rel_rows.append(np.concatenate([hinge_row(m.get("start_hinge")), hinge_row(m.get("end_hinge")), [ys, zs], offs]))
+            for e, key in enumerate(("start_hinge", "end_hinge")):
+                h = hinges.get(int(m[key])) if m.get(key) is not None else None
+                for d, f in enumerate(_HINGE_CURVES if h else ()):
+                    if h.get(f) and h[f].get("points"):
+                        hinge_curves.append((i, int(m_rel[i]), 6 * e + d) + hinge_curve(int(m[key]), f, h[f]))
         if t == MT_CABLE:
             warnings.append(("W_CABLE_AS_TENSION", f"member {m['id']}: cable treated as tension-only straight member"))
     rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), REL_STRIDE)
@@ -624,7 +652,7 @@ def parse_document(doc: dict) -> ModelArrays:
         p_ids=p_ids, p_nodes=p_nodes, p_data=p_data, p_flags=p_flags,
         load_cases=load_cases, combo_ids=combo_ids, combo_names=combo_names, combo_factors=combo_factors,
         imperfections=list(analysis.get("imperfection_cases") or []), member_sets=member_sets,
-        options=opts, warnings=warnings, support_curves=support_curves,
+        options=opts, warnings=warnings, support_curves=support_curves, hinge_curves=hinge_curves,
         unity_checks=list(analysis.get("unity_checks") or []),
         combo_limit_state=[c.get("limit_state") for c in combos],
         m_classification=m_classification, m_section_raw=m_section_raw,

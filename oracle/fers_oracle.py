@@ -31,6 +31,7 @@ Pinning status: pinned against the reference's closed-form test-suite
 """
 from __future__ import annotations
 
+import dataclasses
 import time
 
 import os
@@ -44,6 +45,7 @@ from fers_core_b200.results import ResultArrays, SECTION_FRACS
 from fers_core_b200.hostlogic import (
     rhs_plan, imperfect_coordinates, rigid_property_row, pdelta_suppressed_axes, INACTIVE_SCALE,
     unilateral_dofs, effective_bc, unilateral_update, curve_stiffness, curves_converged,
+    hinge_curve_stiffness, rel_with_hinge_curves,
 )
 
 GAUSS3_X = np.array([-np.sqrt(3.0 / 5.0), 0.0, np.sqrt(3.0 / 5.0)])
@@ -804,7 +806,8 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
         F = fac @ F_lc
         peq = np.einsum("rl,lmk->rmk", fac, peq_lc)
         cols = list(grp.columns)
-        needs_own = second_order or np.any(unilateral_members) or len(unilateral_dofs(model)[0]) > 0 or len(model.support_curves) > 0
+        needs_own = (second_order or np.any(unilateral_members) or len(unilateral_dofs(model)[0]) > 0
+                     or len(model.support_curves) > 0 or len(model.hinge_curves) > 0)
         if not needs_own:
             # ---- linear: one factorisation, all right-hand sides
             K = asm.K_elastic()
@@ -814,11 +817,12 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
             _store(out, asm, model, cols, U, F, peq, K, None, spans, fac, iters=None, detail=detail)
         else:
             for ci, col in enumerate(cols):
-                U1, K1, kg1, scale1, it, conv, resn = _solve_nonlinear(asm, model, F[ci], peq[ci], second_order)
-                asm_c = asm
-                if scale1 is not None:
-                    asm_c = Assembly(model, xyz, scale1)
-                _store(out, asm_c, model, [col], U1[None], F[ci:ci + 1], peq[ci:ci + 1], K1,
+                def reload(asm_it, row=fac[ci]):
+                    # equivalent loads of released members depend on the hinge stiffness of the iteration
+                    F_it, peq_it = load_vectors(asm_it)
+                    return row @ F_it, np.einsum("l,lmk->mk", row, peq_it)
+                U1, K1, kg1, scale1, it, conv, resn, asm_c, F1, peq1 = _solve_nonlinear(asm, model, F[ci], peq[ci], second_order, reload)
+                _store(out, asm_c, model, [col], U1[None], F1[None], peq1[None], K1,
                        None if kg1 is None else kg1[None], spans, fac[ci:ci + 1], iters=(it, conv, resn), detail=detail)
     if timings is not None:
         timings["total_s"] = time.perf_counter() - t0
@@ -830,8 +834,10 @@ def _axial_forces(asm, U, peq, kg_local=None):
     return rec["f_local"][0][:, 6]
 
 
-def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
-    """Active-set (tension/compression-only) outer loop around the P-Delta fixed point."""
+def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order, reload=None):
+    """Active-set (tension/compression-only members, unilateral supports) and load-dependent springs (support and hinge
+    stiffness curves) in one outer loop around the P-Delta fixed point.  ``reload(asm) -> (F, peq)`` re-forms the
+    column's loads for a new state of the hinge springs.  Returns the assembly, loads of the final state as well."""
     opts = model.options
     nd = model.n_dof
     uni = np.nonzero(np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)))[0]
@@ -843,7 +849,10 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
     sup_active = np.ones(len(sup_idx), bool)            # unilateral supports start closed
     n_curves = len(model.support_curves)
     curve_k = curve_stiffness(model, None)              # load-dependent springs start at their zero-force stiffness
-    for _outer in range(max(1, 2 * (len(uni) + len(sup_idx)) + 2 + (max(opts.max_iterations, 20) if n_curves else 0))):
+    n_hinge = len(model.hinge_curves)
+    hinge_k = hinge_curve_stiffness(model, None)        # = the values model.rel carries
+    model_it = model
+    for _outer in range(max(1, 2 * (len(uni) + len(sup_idx)) + 2 + (max(opts.max_iterations, 20) if n_curves or n_hinge else 0))):
         bc = effective_bc(model, sup_active, curve_k) if (len(sup_idx) or n_curves) else None
         K0 = asm.K_elastic()
         Kff, free, _ = constrain(K0, model, bc=bc)
@@ -879,8 +888,19 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
             new_k = curve_stiffness(model, K @ U - F)
             changed = changed or not curves_converged(new_k, curve_k, opts.tolerance)
             curve_k = new_k
+        hinges_moved = False
+        if n_hinge:
+            f_local = recover_members(asm, U[None], peq[None], None if kg is None else kg[None])["f_local"][0]
+            new_k = hinge_curve_stiffness(model, f_local)
+            hinges_moved = not curves_converged(new_k, hinge_k, opts.tolerance)
+            changed = changed or hinges_moved
+            hinge_k = new_k
         if len(uni) == 0:
             if changed:
+                if hinges_moved:
+                    model_it = dataclasses.replace(model, rel=rel_with_hinge_curves(model, hinge_k))
+                    asm = Assembly(model_it, asm0.xyz, scale)
+                    F, peq = reload(asm)
                 continue
             break
         N = _axial_forces(asm, U, peq, kg)
@@ -895,8 +915,12 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order):
         if np.array_equal(new_scale, scale) and not changed:
             break
         scale = new_scale
-        asm = Assembly(model, asm0.xyz, scale)
-    return U, K, kg, (scale if len(uni) else None), (total_it if second_order else None), conv, resn
+        if hinges_moved:
+            model_it = dataclasses.replace(model, rel=rel_with_hinge_curves(model, hinge_k))
+        asm = Assembly(model_it, asm0.xyz, scale)
+        if hinges_moved:
+            F, peq = reload(asm)
+    return U, K, kg, (scale if len(uni) else None), (total_it if second_order else None), conv, resn, asm, F, peq
 
 
 def _suppress_kg(asm, kg, suppressed):
