@@ -45,6 +45,8 @@ _HINGE_FIELDS = (
 )
 _HINGE_CURVES = ("stiffness_curve_vx", "stiffness_curve_vy", "stiffness_curve_vz",
                  "stiffness_curve_mx", "stiffness_curve_my", "stiffness_curve_mz")
+_HINGE_CAPACITIES = ("max_tension_vx", "max_tension_vy", "max_tension_vz", "max_moment_mx", "max_moment_my",
+                     "max_moment_mz", "max_bimoment_warp")
 _MEMBER_FORCE = {"N": 0, "Vy": 1, "Vz": 2, "Mx": 3, "My": 4, "Mz": 5}       # MemberStiffnessCurveDriver, pydantic_models.py:583-589
 RIGID_RELEASE = -1.0  # sentinel: DOF rigidly connected (no hinge spring)
 # one row of ModelArrays.rel (csrc/fers_elem.cuh REL_*): 12 release springs, the shear-centre offset, the two end
@@ -339,6 +341,10 @@ def parse_document(doc: dict) -> ModelArrays:
         row = [E * A, E * Iy, E * Iz, G * J,
                G * float(asy) if asy else 0.0, G * float(asz) if asz else 0.0,
                float(s.get("wpl_y") or 0.0), eiw]
+        if float(s.get("i_yz") or 0.0) != 0.0 or float(s.get("principal_axis_angle") or 0.0) != 0.0:
+            # pydantic_models.py:1078-1090: the engine rotates the bending block between principal and centroidal axes
+            warnings.append(("W_PRINCIPAL_AXES_IGNORED", f"section {sid}: i_yz / principal_axis_angle not applied; "
+                             "i_y and i_z are used about the member's local y and z axes as given"))
         sec_row[sid] = len(prop_rows)
         prop_rows.append(row)
         prop_rho_a.append(float(mat.get("density") or 0.0) * A)
@@ -358,6 +364,10 @@ def parse_document(doc: dict) -> ModelArrays:
             v = h.get(f)
             if v is not None:
                 r[d] = max(float(v), 0.0)
+        if hid not in capacity_warned and any(h.get(f) is not None for f in _HINGE_CAPACITIES):
+            capacity_warned.add(hid)
+            warnings.append(("W_HINGE_CAPACITY_IGNORED", f"member hinge {hid}: max_tension_* / max_moment_* capacities "
+                             "are not enforced; the hinge keeps its elastic spring"))
         for d, f in enumerate(_HINGE_CURVES):
             curve = h.get(f)
             if curve and curve.get("points"):
@@ -375,6 +385,7 @@ def parse_document(doc: dict) -> ModelArrays:
         return comp, pts, bool(curve.get("signed"))
 
     hinge_curves: list = []
+    capacity_warned: set = set()
 
     # ---- members (pydantic_models.py:1507-1549) ----------------------------------------
     members = model.get("members") or []
@@ -466,6 +477,13 @@ def parse_document(doc: dict) -> ModelArrays:
 
     # ---- plate elements (pydantic_models.py:1700-1726) ---------------------------------
     plates = model.get("plate_elements") or []
+    meshed = {p.get("source_surface_id") for p in plates}
+    for surf in (model.get("plate_surfaces") or []):
+        if surf.get("id") not in meshed:
+            # PlateSurface (pydantic_models.py: boundary_node_ids + mesh settings) is meshed by the reference engine;
+            # here only surfaces that arrive with their plate elements take part
+            warnings.append(("W_SURFACE_NOT_MESHED", f"plate surface {surf.get('id')}: no plate elements reference it "
+                             "(server-side meshing is not implemented); the surface is ignored"))
     p_ids_l, p_nodes_l, p_data_l, p_flags_l = [], [], [], []
     for p in plates:
         nids = [nid["id"] if isinstance(nid, dict) else nid for nid in p["node_ids"]]

@@ -200,3 +200,20 @@ def test_unity_check_inputs_travel_with_the_model():
     assert len(m.unity_checks) == 1 and m.combo_limit_state[0] == "ULS"
     sec, mat = m.member_raw(0)
     assert sec["area"] > 0 and mat["e_mod"] > 0 and len(m.m_classification) == m.n_members
+
+
+def test_inputs_that_are_read_but_not_acted_on_are_reported():
+    """Nothing on the wire is dropped silently: hinge capacities, principal-axis data and unmeshed surfaces each leave a
+    warning in ``errors_and_warnings`` (pydantic_models.py:1877-1880)."""
+    import copy
+    doc = copy.deepcopy(helpers.golden("hinge_spring")["doc"])
+    assert not [w for w in wire.parse_document(doc).warnings if w[0].startswith(("W_HINGE", "W_PRINCIPAL", "W_SURFACE_NOT"))]
+    doc["model"]["member_hinges"][0]["max_moment_mz"] = 1.0e4
+    doc["model"]["sections"][0]["i_yz"] = 1.0e-7
+    doc["model"]["plate_surfaces"] = [{"id": 7, "boundary_node_ids": [1, 2, 3], "material": 1, "thickness": 0.01}]
+    codes = [w[0] for w in wire.parse_document(doc).warnings]
+    assert codes.count("W_HINGE_CAPACITY_IGNORED") == 1
+    assert codes.count("W_PRINCIPAL_AXES_IGNORED") == 1
+    assert codes.count("W_SURFACE_NOT_MESHED") == 1
+    doc["model"]["sections"][0].update(i_yz=0.0, principal_axis_angle=12.0)
+    assert "W_PRINCIPAL_AXES_IGNORED" in [w[0] for w in wire.parse_document(doc).warnings]
