@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_plates(int n_plates, c
         double p0[3] = {xyz[3 * a], xyz[3 * a + 1], xyz[3 * a + 2]};
         double p1[3] = {xyz[3 * b], xyz[3 * b + 1], xyz[3 * b + 2]};
         double p2[3] = {xyz[3 * c], xyz[3 * c + 1], xyz[3 * c + 2]};
-        g = plate_geom(p0, p1, p2);
+        g = plate_geom(p0, p1, p2, pdata[NPDATA * (size_t)e + PD_THETA]);
         plate_local_k(g, pdata + NPDATA * (size_t)e, pflags[e], k);
     }
     double* stage = s_stage + warp * STAGE_DOUBLES;

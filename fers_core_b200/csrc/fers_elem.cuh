@@ -454,7 +454,7 @@ FERS_HD void span_point_resultant(const Frame& f, const double* row, double x, d
 // Per-plate record (NPDATA doubles): thickness, E, nu, then the stiffness modifiers of PlateElement.stiffness_modifiers
 // (membrane, bending, shear; pydantic_models.py:801-807).  flags: bit0 membrane, bit1 bending, bit2 plane strain
 // (PlateElement.plane_state, 1712-1715: in-plane constitutive law of the membrane part).
-enum { PD_T = 0, PD_E = 1, PD_NU = 2, PD_MODM = 3, PD_MODB = 4, PD_MODS = 5, NPDATA = 8 };
+enum { PD_T = 0, PD_E = 1, PD_NU = 2, PD_MODM = 3, PD_MODB = 4, PD_MODS = 5, PD_THETA = 6, NPDATA = 8 };
 
 // in-plane constitutive matrix: plane stress, or plane strain when asked for (membrane part only)
 FERS_HD void plate_D(double E, double nu, bool plane_strain, double D[3][3]) {
@@ -476,7 +476,9 @@ struct PlateGeom {
     double A;           // signed area
 };
 
-FERS_HD PlateGeom plate_geom(const double p0[3], const double p1[3], const double p2[3]) {
+// theta: in-plane angle of local x from the default frame (PlateElement.local_x_direction, pydantic_models.py:1703,
+// resolved on the host by wire.plate_local_x_angle); 0 keeps the default frame bit for bit.
+FERS_HD PlateGeom plate_geom(const double p0[3], const double p1[3], const double p2[3], double theta = 0.0) {
     PlateGeom g;
     double e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
     double e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
@@ -490,6 +492,14 @@ FERS_HD PlateGeom plate_geom(const double p0[3], const double p1[3], const doubl
     double en = 1.0 / sqrt(ex[0] * ex[0] + ex[1] * ex[1] + ex[2] * ex[2]);
     ex[0] *= en; ex[1] *= en; ex[2] *= en;
     double ey[3] = {ez[1] * ex[2] - ez[2] * ex[1], ez[2] * ex[0] - ez[0] * ex[2], ez[0] * ex[1] - ez[1] * ex[0]};
+    if (theta != 0.0) {
+        const double ct = cos(theta), st = sin(theta);
+        for (int c = 0; c < 3; ++c) {
+            const double x0 = ex[c], y0 = ey[c];
+            ex[c] = ct * x0 + st * y0;
+            ey[c] = -st * x0 + ct * y0;
+        }
+    }
     for (int c = 0; c < 3; ++c) { g.r[0][c] = ex[c]; g.r[1][c] = ey[c]; g.r[2][c] = ez[c]; }
     g.xl[0][0] = 0.0; g.xl[0][1] = 0.0;
     g.xl[1][0] = e1[0] * ex[0] + e1[1] * ex[1] + e1[2] * ex[2];

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_plates(int n_plates, in
         double p0[3] = {xyz[3 * nd[0]], xyz[3 * nd[0] + 1], xyz[3 * nd[0] + 2]};
         double p1[3] = {xyz[3 * nd[1]], xyz[3 * nd[1] + 1], xyz[3 * nd[1] + 2]};
         double p2[3] = {xyz[3 * nd[2]], xyz[3 * nd[2] + 1], xyz[3 * nd[2] + 2]};
-        PlateGeom g = plate_geom(p0, p1, p2);
+        PlateGeom g = plate_geom(p0, p1, p2, pd[PD_THETA]);
         double kl[324];
         plate_local_k(g, pd, flags, kl);
         double blk[36];

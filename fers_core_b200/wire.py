@@ -38,6 +38,7 @@ _SUPPORT_FORCE = {"Fx": 0, "Fy": 1, "Fz": 2, "Mx": 3, "My": 4, "Mz": 5}      # S
 P_EA, P_EIY, P_EIZ, P_GJ, P_GASY, P_GASZ, P_WPL, P_SPARE = range(8)
 NPROP = 8
 NPDATA = 8          # doubles per plate record (csrc/fers_elem.cuh PD_*)
+PD_THETA = 6        # in-plane angle of local x from the default plate frame (local_x_direction), radians
 # local release order = local DOF order [u v w rx ry rz]
 _HINGE_FIELDS = (
     "translational_release_vx", "translational_release_vy", "translational_release_vz",
@@ -124,7 +125,7 @@ class ModelArrays:
     # plates (TRI3): node indices, thickness, E, nu, behaviour code
     p_ids: np.ndarray             # int64 [Npl]
     p_nodes: np.ndarray           # int32 [Npl,3]
-    p_data: np.ndarray            # f64   [Npl,8]  thickness, E, nu, modifiers (membrane, bending, shear), 2 spare
+    p_data: np.ndarray            # f64   [Npl,8]  thickness, E, nu, modifiers (membrane, bending, shear), local-x angle, 1 spare
     p_flags: np.ndarray           # int32 [Npl]    bit0 membrane, bit1 bending, bit2 plane strain
     load_cases: list              # [LoadCaseArrays]
     combo_ids: np.ndarray         # int64 [Nc]
@@ -501,9 +502,9 @@ def parse_document(doc: dict) -> ModelArrays:
             flags |= 4
         sm = p.get("stiffness_modifiers") or {}
         mods = [1.0 if sm.get(k) is None else float(sm[k]) for k in ("membrane", "bending", "shear")]
-        for key, code in (("offset", "W_PLATE_OFFSET_IGNORED"), ("local_x_direction", "W_PLATE_LOCAL_X_IGNORED")):
-            if p.get(key):
-                warnings.append((code, f"plate {p['id']}: {key} not modelled"))
+        if p.get("offset"):
+            warnings.append(("W_PLATE_OFFSET_IGNORED", f"plate {p['id']}: offset not modelled"))
+        lx_dir = _vec3(p["local_x_direction"], "plate.local_x_direction") if p.get("local_x_direction") else None
         if mat.get("orthotropic_plate"):
             warnings.append(("W_ORTHOTROPIC_IGNORED", f"plate {p['id']}: orthotropic plate material treated as isotropic"))
         tris = [nids] if len(nids) == 3 else [[nids[0], nids[1], nids[2]], [nids[0], nids[2], nids[3]]]
@@ -515,7 +516,14 @@ def parse_document(doc: dict) -> ModelArrays:
             except KeyError as e:
                 raise WireError(f"plate {p['id']}: unknown node {e}") from None
             p_ids_l.append(int(p["id"]))
-            p_data_l.append([float(p["thickness"]), E, nu, mods[0], mods[1], mods[2], 0.0, 0.0])
+            theta = 0.0
+            if lx_dir is not None:
+                theta = plate_local_x_angle(xyz[p_nodes_l[-1]], lx_dir)
+                if theta is None:
+                    theta = 0.0
+                    warnings.append(("W_PLATE_LOCAL_X_NORMAL", f"plate {p['id']}: local_x_direction is normal to the "
+                                     "plate (or zero); default local axes kept"))
+            p_data_l.append([float(p["thickness"]), E, nu, mods[0], mods[1], mods[2], theta, 0.0])
             p_flags_l.append(flags)
     p_ids = np.array(p_ids_l, np.int64)
     p_nodes = np.array(p_nodes_l, np.int32).reshape(len(p_ids_l), 3)
@@ -685,6 +693,28 @@ def member_axis(model, m: int) -> np.ndarray:
     if r >= 0:
         d = d + model.rel[r, REL_O2:REL_O2 + 3] - model.rel[r, REL_O1:REL_O1 + 3]
     return d
+
+
+def plate_local_x_angle(x3: np.ndarray, direction: np.ndarray):
+    """PlateElement.local_x_direction (pydantic_models.py:1703) as the angle that turns the default plate frame (local z =
+    normal over the node order, local x = global X projected into the plane, global Y when the normal is along X;
+    csrc/fers_elem.cuh plate_geom) about the normal so that local x is the projection of ``direction`` into the plane.
+    None when the direction has no in-plane part."""
+    n = np.cross(x3[1] - x3[0], x3[2] - x3[0])
+    nn = np.linalg.norm(n)
+    if not nn > 0.0:
+        return 0.0                          # degenerate plates are rejected further down
+    ez = n / nn
+    gx = np.array([0.0, 1.0, 0.0]) if abs(ez[0]) > 1.0 - 1e-6 else np.array([1.0, 0.0, 0.0])
+    ex = gx - (gx @ ez) * ez
+    ex /= np.linalg.norm(ex)
+    ey = np.cross(ez, ex)
+    d = np.asarray(direction, np.float64)
+    a, b = float(d @ ex), float(d @ ey)
+    if not np.hypot(a, b) > 1e-9 * max(np.linalg.norm(d), 1e-300):
+        return None
+    theta = float(np.arctan2(b, a))
+    return 0.0 if abs(theta) < 1e-15 else theta
 
 
 def plates_flat_surface(plates, p_ids_l):

@@ -128,7 +128,7 @@ int fers_b200_assemble_warping(int n_w, const int* w_member, const double* xyz, 
                                const int* m_prop, const double* m_scale, const double* prop, const int* w_slot, double* vals,
                                void* stream);
 /* TRI3 shell elements: CST membrane + DSG3 Mindlin bending (pydantic_models.py:1700-1726).
- * p_data[n_plates][8] = thickness, E, nu, stiffness modifiers (membrane, bending, shear), 2 spare;
+ * p_data[n_plates][8] = thickness, E, nu, stiffness modifiers (membrane, bending, shear), in-plane angle (rad) of local x from the default frame (PlateElement.local_x_direction, pydantic_models.py:1703), 1 spare;
  * p_flags bit0 membrane, bit1 bending, bit2 plane strain (membrane part). */
 int fers_b200_assemble_plates(int n_plates, const double* xyz, const int* p_nodes, const double* p_data,
                               const int* p_flags, const int* p_slot, double* vals, void* stream);

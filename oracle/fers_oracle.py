@@ -249,8 +249,9 @@ def expand_T(R):
 # --------------------------------------------------------------------------------------
 # plate element: CST membrane + DSG3 Mindlin bending
 # --------------------------------------------------------------------------------------
-def plate_frame(x3):
-    """Local frame of a flat triangle: rows = local x,y,z.  x3 [3,3] corner coordinates.
+def plate_frame(x3, theta=0.0):
+    """Local frame of a flat triangle: rows = local x,y,z.  x3 [3,3] corner coordinates.  ``theta`` turns local x, y
+    about the normal from the default frame (PlateElement.local_x_direction, resolved to an angle by the parser).
 
     local z = normal (right-hand rule over the wire node order); local x = global X projected
     into the plane (global Y when the normal is parallel to X), so an XY-plane plate has local =
@@ -267,6 +268,9 @@ def plate_frame(x3):
     ex = gx - (gx @ ez) * ez
     ex /= np.linalg.norm(ex)
     ey = np.cross(ez, ex)
+    if theta != 0.0:
+        c, s = np.cos(theta), np.sin(theta)
+        ex, ey = c * ex + s * ey, -s * ex + c * ey
     return np.stack([ex, ey, ez])
 
 
@@ -329,7 +333,7 @@ def plate_stiffness_global(model, xyz):
     out = []
     for e in range(model.n_plates):
         x3 = xyz[model.p_nodes[e]]
-        R = plate_frame(x3)
+        R = plate_frame(x3, float(model.p_data[e, wire.PD_THETA]))
         xl = (x3 - x3[0]) @ R.T
         t, E, nu = model.p_data[e, :3]
         k, mats = plate_local_matrices(xl[:, :2], t, E, nu, int(model.p_flags[e]), tuple(model.p_data[e, 3:6]))

@@ -57,7 +57,7 @@ void h_span(const double* a, const double* b, double roll, const double* dl_rows
     for (int i = 0; i < npl; ++i) span_point_resultant(f, pl_rows + 8 * i, x, 1.0, s);
 }
 void h_plate_ke(const double* p0, const double* p1, const double* p2, const double* data, int flags, double* out /*324*/) {
-    PlateGeom g = plate_geom(p0, p1, p2);
+    PlateGeom g = plate_geom(p0, p1, p2, data[PD_THETA]);
     double k[324], blk[36];
     plate_local_k(g, data, flags, k);
     for (int bi = 0; bi < 3; ++bi)

@@ -122,3 +122,58 @@ def test_gpu_boundary_errors_are_loud():
         d = _base()
         d["model"]["nodes"][1].update(X=0.0, Y=0.0, Z=0.0)
         fers_calculations.calculate_from_json(json.dumps(d))
+
+
+# ---- PlateElement.local_x_direction (pydantic_models.py:1703): the axes the plate resultants are reported in ----------
+def _plate_doc(direction):
+    import copy
+    doc = copy.deepcopy(helpers.golden("plate_strip_surface_load")["doc"])
+    for p in doc["model"]["plate_elements"]:
+        p["local_x_direction"] = direction
+    return doc
+
+
+def _rotate_resultants(res, theta):
+    """nx ny nxy | mx my mxy | qx qy of axes turned by theta about the normal."""
+    c, s = np.cos(theta), np.sin(theta)
+    out = np.empty_like(res)
+    for o in (0, 3):
+        xx, yy, xy = res[..., o], res[..., o + 1], res[..., o + 2]
+        out[..., o] = c * c * xx + s * s * yy + 2 * s * c * xy
+        out[..., o + 1] = s * s * xx + c * c * yy - 2 * s * c * xy
+        out[..., o + 2] = -s * c * xx + s * c * yy + (c * c - s * s) * xy
+    out[..., 6] = c * res[..., 6] + s * res[..., 7]
+    out[..., 7] = -s * res[..., 6] + c * res[..., 7]
+    return out
+
+
+def test_plate_local_x_direction_turns_the_reported_axes_only():
+    from oracle import fers_oracle
+    base_doc = _plate_doc(None)
+    base = fers_oracle.analyze(wire.parse_document(base_doc))
+    same = wire.parse_document(_plate_doc([1, 0, 0]))
+    assert not same.p_data[:, wire.PD_THETA].any() and not [w for w in same.warnings if "LOCAL_X" in w[0]]
+    model = wire.parse_document(_plate_doc([1.0, 1.0, 5.0]))           # out-of-plane part is projected away
+    theta = model.p_data[:, wire.PD_THETA]
+    np.testing.assert_allclose(np.abs(theta), np.pi / 4, rtol=1e-14)
+    res = fers_oracle.analyze(model)
+    np.testing.assert_allclose(res.U, base.U, rtol=1e-9, atol=1e-14)             # isotropic: the answer does not move
+    scale = np.abs(base.p_res).max(axis=(0, 1))
+    for e in range(model.n_plates):
+        want = _rotate_resultants(base.p_res[:, e], theta[e])
+        np.testing.assert_allclose(res.p_res[:, e], want, rtol=1e-8, atol=1e-9 * scale.max())
+    np.testing.assert_allclose(res.p_cdg, base.p_cdg, rtol=1e-9, atol=1e-14)
+    # the strip lies in a global plane: a direction along its normal cannot define local x
+    n = np.cross(model.xyz[model.p_nodes[0, 1]] - model.xyz[model.p_nodes[0, 0]], model.xyz[model.p_nodes[0, 2]] - model.xyz[model.p_nodes[0, 0]])
+    normal = wire.parse_document(_plate_doc([float(v) for v in n]))
+    assert "W_PLATE_LOCAL_X_NORMAL" in [w[0] for w in normal.warnings] and not normal.p_data[:, wire.PD_THETA].any()
+
+
+@pytest.mark.gpu
+def test_gpu_plate_local_x_direction_matches_oracle():
+    from fers_core_b200 import engine
+    from oracle import fers_oracle
+    model = wire.parse_document(_plate_doc([1.0, 1.0, 5.0]))
+    want = fers_oracle.analyze(model)
+    got = engine.analyze(model)
+    helpers.assert_results_close(got, want, 1e-9, label="plate local x")
