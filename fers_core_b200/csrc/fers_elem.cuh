@@ -173,8 +173,8 @@ FERS_HD void beam_shear_centre(double* k /*144*/, double ys, double zs, double* 
 
 // Per-member modifier record (REL_STRIDE doubles, one row of the `rel` table): [0..11] end-release springs,
 // [12] y_s, [13] z_s, [14..16] start offset, [17..19] end offset (global X Y Z; MemberEndOffset,
-// pydantic_models.py:525-531, Member.start_offset / end_offset 1541 / 1518).
-enum { REL_YS = 12, REL_ZS = 13, REL_O1 = 14, REL_O2 = 17, REL_STRIDE = 20 };
+// pydantic_models.py:525-531, Member.start_offset / end_offset 1541 / 1518), [20] E*I_yz (Section.i_yz, 1078-1082).
+enum { REL_YS = 12, REL_ZS = 13, REL_O1 = 14, REL_O2 = 17, REL_EIYZ = 20, REL_STRIDE = 21 };
 
 // End offsets: the elastic axis runs from (start node + start offset) to (end node + end offset).
 FERS_HD void rec_offset_points(const double* rec, double pa[3], double pb[3]) {
@@ -229,9 +229,27 @@ FERS_HD void beam_arms(double* k /*144*/, const double* rec, const Frame& f, dou
     for (int q = 0; q < np; ++q) arm_bwd(o, p + q * 12);
 }
 
-// The whole record applied to the dense local stiffness in this order: shear-centre eccentricity, release
-// condensation (the releases sit at the ends of the elastic axis), rigid arms to the nodes.
+// Product of inertia: E I_yz int v'' w'' dx couples the two bending planes (Euler-Bernoulli).  v over (v1, rz1, v2, rz2)
+// with the Hermite cubics, w over (w1, ry1, w2, ry2) with ry = -w'; equivalent loads do not depend on the stiffness.
+FERS_HD void beam_product_inertia(double* k /*144*/, double eiyz, double L) {
+    if (eiyz == 0.0) return;
+    const double c = eiyz / (L * L * L);
+    const double B[4][4] = {{12.0, 6.0 * L, -12.0, 6.0 * L}, {6.0 * L, 4.0 * L * L, -6.0 * L, 2.0 * L * L},
+                            {-12.0, -6.0 * L, 12.0, -6.0 * L}, {6.0 * L, 2.0 * L * L, -6.0 * L, 4.0 * L * L}};
+    const int vs[4] = {1, 5, 7, 11}, ws[4] = {2, 4, 8, 10};
+    const double sw[4] = {1.0, -1.0, 1.0, -1.0};
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            const double x = B[i][j] * c * sw[j];
+            k[vs[i] * 12 + ws[j]] += x;
+            k[ws[j] * 12 + vs[i]] += x;
+        }
+}
+
+// The whole record applied to the dense local stiffness in this order: product of inertia, shear-centre eccentricity,
+// release condensation (the releases sit at the ends of the elastic axis), rigid arms to the nodes.
 FERS_HD void beam_modify(double* k /*144*/, const double* rec /*REL_STRIDE*/, const Frame& f, double* p, int np) {
+    beam_product_inertia(k, rec[REL_EIYZ], f.L);
     beam_shear_centre(k, rec[REL_YS], rec[REL_ZS], p, np);
     beam_condense(k, rec, p, np);
     beam_arms(k, rec, f, p, np);

@@ -177,7 +177,7 @@ class Engine:
         self.has_rel = bool(np.any(m.m_rel >= 0))
         self.d_rel_idx = self._t(m.m_rel, np.int32) if self.has_rel else None
         if self.has_rel and (m.rel.ndim != 2 or m.rel.shape[1] != wire.REL_STRIDE):
-            raise EngineError(f"ModelArrays.rel must be [Nr,{wire.REL_STRIDE}] (12 release springs, y_s, z_s), got {m.rel.shape}")
+            raise EngineError(f"ModelArrays.rel must be [Nr,{wire.REL_STRIDE}] (12 release springs, y_s, z_s, end offsets, E*I_yz), got {m.rel.shape}")
         self.d_rel = self._t(m.rel, np.float64) if self.has_rel else None
         # unilateral supports (PositiveOnly / NegativeOnly) start closed; engine._solve_nonlinear iterates their active set
         self.n_unilateral = int(len(unilateral_dofs(m)[0]))

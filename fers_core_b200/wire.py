@@ -52,7 +52,7 @@ _MEMBER_FORCE = {"N": 0, "Vy": 1, "Vz": 2, "Mx": 3, "My": 4, "Mz": 5}       # Me
 RIGID_RELEASE = -1.0  # sentinel: DOF rigidly connected (no hinge spring)
 # one row of ModelArrays.rel (csrc/fers_elem.cuh REL_*): 12 release springs, the shear-centre offset, the two end
 # offsets (global X Y Z of start_offset, end_offset)
-REL_YS, REL_ZS, REL_O1, REL_O2, REL_STRIDE = 12, 13, 14, 17, 20
+REL_YS, REL_ZS, REL_O1, REL_O2, REL_EIYZ, REL_STRIDE = 12, 13, 14, 17, 20, 21
 
 
 class WireError(ValueError):
@@ -121,7 +121,7 @@ class ModelArrays:
     prop_rho_a: np.ndarray        # f64   [Np]      density*area (self weight)
     rel: np.ndarray               # f64   [Nr,REL_STRIDE] member modifier records: [0:12] hinge spring stiffness per
                                   #                 local end DOF (-1 rigid), [12] y_s, [13] z_s (shear-centre offset),
-                                  #                 [14:17] start_offset, [17:20] end_offset (global axes)
+                                  #                 [14:17] start_offset, [17:20] end_offset (global axes), [20] E*I_yz
     # plates (TRI3): node indices, thickness, E, nu, behaviour code
     p_ids: np.ndarray             # int64 [Npl]
     p_nodes: np.ndarray           # int32 [Npl,3]
@@ -322,6 +322,7 @@ def parse_document(doc: dict) -> ModelArrays:
     prop_rho_a: list = []
     sec_row: dict = {}
     sec_raw: dict = {}
+    sec_eiyz: dict = {}
     for sid, s in secs.items():
         mid = s.get("material")
         if isinstance(mid, dict):
@@ -342,10 +343,16 @@ def parse_document(doc: dict) -> ModelArrays:
         row = [E * A, E * Iy, E * Iz, G * J,
                G * float(asy) if asy else 0.0, G * float(asz) if asz else 0.0,
                float(s.get("wpl_y") or 0.0), eiw]
-        if float(s.get("i_yz") or 0.0) != 0.0 or float(s.get("principal_axis_angle") or 0.0) != 0.0:
-            # pydantic_models.py:1078-1090: the engine rotates the bending block between principal and centroidal axes
-            warnings.append(("W_PRINCIPAL_AXES_IGNORED", f"section {sid}: i_yz / principal_axis_angle not applied; "
-                             "i_y and i_z are used about the member's local y and z axes as given"))
+        # product of inertia / principal axes (pydantic_models.py:1078-1090)
+        Iy, Iz, Iyz, note = section_bending_inertias(Iy, Iz, s.get("i_yz"), s.get("principal_axis_angle"))
+        if not Iy * Iz > Iyz * Iyz:
+            raise WireError(f"section {sid}: i_yz^2 must be smaller than i_y * i_z")
+        row[1], row[2] = E * Iy, E * Iz
+        sec_eiyz[sid] = E * Iyz
+        if Iyz != 0.0 and (asy or asz):
+            note = (note + "; " if note else "") + "the y-z bending coupling is Euler-Bernoulli (shear areas act about local y, z only)"
+        if note:
+            warnings.append(("W_PRINCIPAL_AXES", f"section {sid}: {note}"))
         sec_row[sid] = len(prop_rows)
         prop_rows.append(row)
         prop_rho_a.append(float(mat.get("density") or 0.0) * A)
@@ -428,6 +435,8 @@ def parse_document(doc: dict) -> ModelArrays:
             ys, zs = sgn * float(s_raw.get("y_s") or 0.0), sgn * float(s_raw.get("z_s") or 0.0)
             if not (np.isfinite(ys) and np.isfinite(zs)):
                 raise WireError(f"section {sid}: y_s / z_s must be finite")
+        # y-z bending coupling of sections with a product of inertia (bending members only)
+        eiyz = sec_eiyz.get(int(sid), 0.0) if (sid is not None and t == MT_NORMAL) else 0.0
         # end offsets (MemberEndOffset, pydantic_models.py:525-531, global X Y Z): the elastic axis runs between the
         # offset points, each tied to its node by a rigid arm
         offs = np.zeros(6)
@@ -437,9 +446,9 @@ def parse_document(doc: dict) -> ModelArrays:
                 offs[3 * e:3 * e + 3] = [float(o.get(ax) or 0.0) for ax in ("X", "Y", "Z")]
         if not np.isfinite(offs).all():
             raise WireError(f"member {m['id']}: end offsets must be finite")
-        if m.get("start_hinge") is not None or m.get("end_hinge") is not None or ys != 0.0 or zs != 0.0 or offs.any():
+        if m.get("start_hinge") is not None or m.get("end_hinge") is not None or ys != 0.0 or zs != 0.0 or offs.any() or eiyz != 0.0:
             m_rel[i] = len(rel_rows)
-            rel_rows.append(np.concatenate([hinge_row(m.get("start_hinge")), hinge_row(m.get("end_hinge")), [ys, zs], offs]))
+            rel_rows.append(np.concatenate([hinge_row(m.get("start_hinge")), hinge_row(m.get("end_hinge")), [ys, zs], offs, [eiyz]]))
             for e, key in enumerate(("start_hinge", "end_hinge")):
                 h = hinges.get(int(m[key])) if m.get(key) is not None else None
                 for d, f in enumerate(_HINGE_CURVES if h else ()):
@@ -693,6 +702,37 @@ def member_axis(model, m: int) -> np.ndarray:
     if r >= 0:
         d = d + model.rel[r, REL_O2:REL_O2 + 3] - model.rel[r, REL_O1:REL_O1 + 3]
     return d
+
+
+def section_bending_inertias(i_y: float, i_z: float, i_yz, angle_deg):
+    """(I_y, I_z, I_yz) about the member's local y and z axes, and a note for the warnings (or None).
+
+    Section.i_yz / principal_axis_angle (pydantic_models.py:1078-1090).  I_z = int y^2, I_y = int z^2, I_yz = int y z dA in
+    the member's local axes, so the bending energy is E/2 int (I_z v''^2 + I_y w''^2 + 2 I_yz v'' w'') dx.
+    * i_yz given, no angle (or an angle that agrees with the triple: tan 2a = 2 I_yz / (I_z - I_y) to 1 degree):
+      i_y / i_z are centroidal values, used with the coupling as they are;
+    * angle given with i_yz absent or zero -- or inconsistent with the triple: i_y / i_z are principal values; the principal
+      axes are the local axes turned by the angle in the sense of `rotation_angle` (y_p = c y + s z), which gives
+      I_z = c^2 I_1 + s^2 I_2,  I_y = s^2 I_1 + c^2 I_2,  I_yz = s c (I_1 - I_2)  with I_1 = i_z, I_2 = i_y.
+    The engine that defines the signs is closed: convention stated, unpinned."""
+    iyz = float(i_yz or 0.0)
+    ang = float(angle_deg or 0.0)
+    if not (np.isfinite(iyz) and np.isfinite(ang)):
+        raise WireError("section: i_yz / principal_axis_angle must be finite")
+    if iyz != 0.0:
+        if ang == 0.0:
+            return i_y, i_z, iyz, None
+        implied = 0.5 * np.degrees(np.arctan2(2.0 * iyz, i_z - i_y))
+        diff = (ang - implied + 45.0) % 90.0 - 45.0          # principal directions repeat every 90 degrees
+        if abs(diff) <= 1.0:
+            return i_y, i_z, iyz, None
+        note = "principal_axis_angle does not match i_y, i_z, i_yz: i_y / i_z taken as principal values, i_yz ignored"
+    elif ang == 0.0:
+        return i_y, i_z, 0.0, None
+    else:
+        note = None
+    c, s_ = np.cos(np.radians(ang)), np.sin(np.radians(ang))
+    return s_ * s_ * i_z + c * c * i_y, c * c * i_z + s_ * s_ * i_y, s_ * c * (i_z - i_y), note
 
 
 def plate_local_x_angle(x3: np.ndarray, direction: np.ndarray):

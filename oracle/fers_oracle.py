@@ -230,8 +230,25 @@ def shear_centre_transform(k, p, ys, zs):
     return S.T @ k @ S, (p @ S if p.size else p.copy())
 
 
-def member_modifiers(k, p, rec):
-    """One row of ``ModelArrays.rel``: eccentricity first, then the end-release condensation."""
+def product_inertia_coupling(eiyz, L):
+    """E I_yz int v'' w'' dx between the bending planes of an Euler-Bernoulli member (Section.i_yz,
+    pydantic_models.py:1078-1082; wire.section_bending_inertias): v over (v1, rz1, v2, rz2) with the Hermite cubics,
+    w over (w1, ry1, w2, ry2) with ry = -w'."""
+    B = np.array([[12.0, 6 * L, -12.0, 6 * L], [6 * L, 4 * L * L, -6 * L, 2 * L * L],
+                  [-12.0, -6 * L, 12.0, -6 * L], [6 * L, 2 * L * L, -6 * L, 4 * L * L]]) * (eiyz / L ** 3)
+    vs, ws, sw = (1, 5, 7, 11), (2, 4, 8, 10), (1.0, -1.0, 1.0, -1.0)
+    k = np.zeros((12, 12))
+    for i in range(4):
+        for j in range(4):
+            k[vs[i], ws[j]] += B[i, j] * sw[j]
+            k[ws[j], vs[i]] += B[i, j] * sw[j]
+    return k
+
+
+def member_modifiers(k, p, rec, L=None):
+    """One row of ``ModelArrays.rel``: product of inertia, eccentricity, then the end-release condensation."""
+    if len(rec) > 20 and rec[20] != 0.0:
+        k = k + product_inertia_coupling(rec[20], L)
     if len(rec) > 12 and (rec[12] != 0.0 or rec[13] != 0.0):
         k, p = shear_centre_transform(k, p, rec[12], rec[13])
     return condense_releases(k, p, rec[:12])
@@ -404,7 +421,7 @@ class Assembly:
         self.T = expand_T(self.R)
         self.k_cond = self.k_local.copy()       # after release condensation
         for i in np.nonzero(model.m_rel >= 0)[0]:
-            self.k_cond[i], _ = member_modifiers(self.k_local[i], np.zeros((0, 12)), model.rel[model.m_rel[i]])
+            self.k_cond[i], _ = member_modifiers(self.k_local[i], np.zeros((0, 12)), model.rel[model.m_rel[i]], self.L[i])
         # rigid arms of the end offsets: E per member (local axes), applied after the release condensation
         self.arms = {}
         if nm:
@@ -568,7 +585,7 @@ def load_vectors(asm: Assembly):
             F[li, 6 * n:6 * n + 6] += v
         p = equivalent_loads(asm, lc)
         for i in np.nonzero(model.m_rel >= 0)[0]:
-            _, pc = member_modifiers(asm.k_local[i], p[i][None, :], model.rel[model.m_rel[i]])
+            _, pc = member_modifiers(asm.k_local[i], p[i][None, :], model.rel[model.m_rel[i]], asm.L[i])
             p[i] = pc[0]
         for i, E in asm.arms.items():
             p[i] = E.T @ p[i]

@@ -67,6 +67,7 @@ def test_beam_releases_and_kg(elem_host, case):
     a, b, roll, P, mtype = case
     R, L, k, T = _oracle_member(a, b, roll, P, mtype)
     rel = np.full(wire.REL_STRIDE, -1.0)
+    rel[wire.REL_EIYZ] = 0.0
     rel[5] = 0.0
     rel[10] = 2.5e4
     rel[12:] = 0.0

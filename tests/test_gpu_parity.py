@@ -91,8 +91,10 @@ def test_gather_assembly_general_paths_match_scatter(engine_mod):
     model.m_prop[nm:] = (model.m_prop[nm:] + 1) % max(model.prop.shape[0], 1)
     rng = np.random.default_rng(5)
     model.rel = np.full((3, wire.REL_STRIDE), -1.0)
+    model.rel[:, wire.REL_EIYZ] = 0.0
     model.rel[:, 12:] = 0.0
-    model.rel[2, 14:] = (0.2, -0.1, 0.05, 0.0, 0.15, -0.1)   # end offsets on top of a double release
+    model.rel[2, 14:20] = (0.2, -0.1, 0.05, 0.0, 0.15, -0.1)   # end offsets on top of a double release
+    model.rel[0, wire.REL_EIYZ] = 3.0e5                        # product of inertia on top of a release
     model.rel[1, 12:14] = (0.031, -0.012)      # shear-centre offset on top of a release spring
     model.rel[0, 5] = 0.0; model.rel[1, 11] = 2.5e5; model.rel[2, [4, 10]] = 0.0
     model.m_rel = np.where(rng.random(model.n_members) < 0.2, rng.integers(0, 3, model.n_members), -1).astype(np.int32)

@@ -37,7 +37,7 @@ def _doc(start=None, end=None, load_dir=(0, -1, 0)):
 def test_parser_builds_offset_records():
     m = wire.parse_document(_doc(start=(0.5, 0.0, 0.0), end=(0.0, 0.1, -0.2)))
     assert m.rel.shape == (1, wire.REL_STRIDE) and m.m_rel.tolist() == [0]
-    assert m.rel[0, wire.REL_O1:].tolist() == [0.5, 0.0, 0.0, 0.0, 0.1, -0.2]
+    assert m.rel[0, wire.REL_O1:wire.REL_O1 + 6].tolist() == [0.5, 0.0, 0.0, 0.0, 0.1, -0.2] and m.rel[0, wire.REL_EIYZ] == 0.0
     assert (m.rel[0, :12] == wire.RIGID_RELEASE).all() and m.rel[0, 12:14].tolist() == [0.0, 0.0]
     assert not [w for w in m.warnings if "OFFSET" in w[0]]
     assert wire.parse_document(_doc()).m_rel.tolist() == [-1]
@@ -74,17 +74,18 @@ def test_oracle_eccentric_axial_load():
 def test_element_code_matches_oracle(elem_host, case):
     a, b, roll, Pp, mtype = case
     rec = np.full(wire.REL_STRIDE, -1.0)
+    rec[wire.REL_EIYZ] = 0.3 * np.sqrt(Pp[1] * Pp[2])      # product of inertia on top of everything else
     rec[4] = 0.0
     rec[11] = 7.0e3
     rec[12:14] = (0.02, -0.03)
-    rec[14:] = (0.3, -0.2, 0.1, -0.15, 0.05, 0.25)
-    off = rec[14:].reshape(1, 2, 3)
+    rec[14:20] = (0.3, -0.2, 0.1, -0.15, 0.05, 0.25)
+    off = rec[14:20].reshape(1, 2, 3)
     xyz = np.stack([a, b])
     R, L = fo.member_frames(xyz, np.array([0]), np.array([1]), np.array([roll]), off)
     k = fo.local_stiffness(Pp[None, :], L, np.array([mtype]))[0]
     T = fo.expand_T(R)[0]
     p = np.arange(1.0, 13.0)[None, :] * 13.0
-    kc, pc = fo.member_modifiers(k, p, rec)
+    kc, pc = fo.member_modifiers(k, p, rec, L[0])
     Em = fo.rigid_arm_matrix(R[0] @ off[0, 0], R[0] @ off[0, 1])
     want = T.T @ (Em.T @ kc @ Em) @ T
     out = np.zeros(144)
@@ -103,10 +104,11 @@ def test_element_loads_match_oracle(elem_host):
     a, b, roll, Pp, _ = CASES[3]
     mtype = 0
     rec = np.full(wire.REL_STRIDE, -1.0)
+    rec[wire.REL_EIYZ] = 0.0
     rec[5] = 0.0
     rec[12:14] = 0.0
-    rec[14:] = (0.3, -0.2, 0.1, -0.15, 0.05, 0.25)
-    off = rec[14:].reshape(1, 2, 3)
+    rec[14:20] = (0.3, -0.2, 0.1, -0.15, 0.05, 0.25)
+    off = rec[14:20].reshape(1, 2, 3)
     R, L = fo.member_frames(np.stack([a, b]), np.array([0]), np.array([1]), np.array([roll]), off)
     k = fo.local_stiffness(Pp[None, :], L, np.array([mtype]))[0]
     dl = np.array([[0.0, -1200.0, 300.0, 0.0, -400.0, 100.0, 0.1, 0.9]])

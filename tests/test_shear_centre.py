@@ -81,10 +81,11 @@ def test_element_code_matches_oracle(elem_host, case):
     a, b, roll, Pp, mtype = case
     R, L, k, T = _oracle_member(a, b, roll, Pp, mtype)
     rec = np.full(wire.REL_STRIDE, -1.0)
+    rec[wire.REL_EIYZ] = 0.0
     rec[5] = 0.0
     rec[9] = 4.0e3
     rec[12:14] = (YS, ZS)
-    rec[14:] = 0.0
+    rec[14:20] = 0.0
     p = np.arange(1.0, 13.0)[None, :] * 17.0
     kc, pc = fo.member_modifiers(k, p, rec)
     out = np.zeros(144)
@@ -106,9 +107,10 @@ def test_element_loads_match_oracle(elem_host):
     mtype = 0
     R, L, k, T = _oracle_member(a, b, roll, Pp, mtype)
     rec = np.full(wire.REL_STRIDE, -1.0)
+    rec[wire.REL_EIYZ] = 0.0
     rec[11] = 0.0
     rec[12:14] = (YS, ZS)
-    rec[14:] = 0.0
+    rec[14:20] = 0.0
     dl = np.array([[0.0, -1200.0, 300.0, 0.0, -400.0, 100.0, 0.1, 0.9]])
     p0 = np.zeros(12)
     elem_host.h_beam_loads(_p(a), _p(b), C.c_double(roll), _p(Pp), mtype, _p(dl), 1, None, 0, None, _p(p0))

@@ -203,7 +203,7 @@ def test_unity_check_inputs_travel_with_the_model():
 
 
 def test_inputs_that_are_read_but_not_acted_on_are_reported():
-    """Nothing on the wire is dropped silently: hinge capacities, principal-axis data and unmeshed surfaces each leave a
+    """Nothing on the wire is dropped silently: hinge capacities, contradictory principal-axis data and unmeshed surfaces each leave a
     warning in ``errors_and_warnings`` (pydantic_models.py:1877-1880)."""
     import copy
     doc = copy.deepcopy(helpers.golden("hinge_spring")["doc"])
@@ -213,7 +213,8 @@ def test_inputs_that_are_read_but_not_acted_on_are_reported():
     doc["model"]["plate_surfaces"] = [{"id": 7, "boundary_node_ids": [1, 2, 3], "material": 1, "thickness": 0.01}]
     codes = [w[0] for w in wire.parse_document(doc).warnings]
     assert codes.count("W_HINGE_CAPACITY_IGNORED") == 1
-    assert codes.count("W_PRINCIPAL_AXES_IGNORED") == 1
+    assert not [c for c in codes if c.startswith("W_PRINCIPAL")]      # applied (tests/test_product_inertia.py), not ignored
     assert codes.count("W_SURFACE_NOT_MESHED") == 1
-    doc["model"]["sections"][0].update(i_yz=0.0, principal_axis_angle=12.0)
-    assert "W_PRINCIPAL_AXES_IGNORED" in [w[0] for w in wire.parse_document(doc).warnings]
+    # an angle that contradicts the (i_y, i_z, i_yz) triple is resolved in favour of the angle, with a note
+    doc["model"]["sections"][0].update(i_yz=1.0e-7, principal_axis_angle=40.0)
+    assert "W_PRINCIPAL_AXES" in [w[0] for w in wire.parse_document(doc).warnings]
