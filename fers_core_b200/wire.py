@@ -344,7 +344,10 @@ def parse_document(doc: dict) -> ModelArrays:
                G * float(asy) if asy else 0.0, G * float(asz) if asz else 0.0,
                float(s.get("wpl_y") or 0.0), eiw]
         # product of inertia / principal axes (pydantic_models.py:1078-1090)
-        Iy, Iz, Iyz, note = section_bending_inertias(Iy, Iz, s.get("i_yz"), s.get("principal_axis_angle"))
+        iyz_m4, unit_note = i_yz_metres4(Iy, Iz, s.get("i_yz"))
+        if unit_note:
+            warnings.append(("W_IYZ_UNITS", f"section {sid}: {unit_note}"))
+        Iy, Iz, Iyz, note = section_bending_inertias(Iy, Iz, iyz_m4, s.get("principal_axis_angle"))
         if not Iy * Iz > Iyz * Iyz:
             raise WireError(f"section {sid}: i_yz^2 must be smaller than i_y * i_z")
         row[1], row[2] = E * Iy, E * Iz
@@ -702,6 +705,23 @@ def member_axis(model, m: int) -> np.ndarray:
     if r >= 0:
         d = d + model.rel[r, REL_O2:REL_O2 + 3] - model.rel[r, REL_O1:REL_O1 + 3]
     return d
+
+
+def i_yz_metres4(i_y: float, i_z: float, i_yz):
+    """Section.i_yz in m^4, and a note for the warnings (or None).
+
+    The schema states the unit of this one field as "mm^4 in JSON, scaled to m^4 by solver" (pydantic_models.py:1078-1082)
+    while i_y / i_z travel in m^4 on the same record.  Any real section has I_yz^2 < I_y I_z, and a value in mm^4 is 1e12
+    times its value in m^4, so the two readings never both pass that bound for a physical section: a value that breaks the
+    bound as m^4 is mm^4 (the schema's reading, scaled by 1e-12); a value that already satisfies it in the units of
+    i_y / i_z is used as it is, with a note."""
+    v = float(i_yz or 0.0)
+    if v == 0.0 or not np.isfinite(v):
+        return v, None
+    if v * v >= i_y * i_z:
+        return v * 1.0e-12, None
+    return v, ("i_yz is consistent with i_y / i_z as given (m^4) and is used unscaled; the schema states mm^4 for this field "
+               "(that reading would make it 1e-12 of this value)")
 
 
 def section_bending_inertias(i_y: float, i_z: float, i_yz, angle_deg):

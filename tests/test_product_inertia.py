@@ -71,9 +71,14 @@ def test_parser_builds_coupling_record():
     assert m.rel[0, wire.REL_EIYZ] == pytest.approx(E * 1.5e-6) and (m.rel[0, :12] == wire.RIGID_RELEASE).all()
     assert m.prop[0, 1] == pytest.approx(E * Iy) and m.prop[0, 2] == pytest.approx(E * Iz)
     assert not [w for w in m.warnings if w[0] == "W_PRINCIPAL_AXES_IGNORED"]
+    assert [w[0] for w in m.warnings].count("W_IYZ_UNITS") == 1     # m^4 like i_y / i_z, the schema says mm^4
+    # the schema's unit for this one field (mm^4, pydantic_models.py:1080): same record, no note
+    mm = wire.parse_document(_doc(i_yz=1.5e6))
+    assert mm.rel[0, wire.REL_EIYZ] == pytest.approx(E * 1.5e-6, rel=1e-12) and "W_IYZ_UNITS" not in [w[0] for w in mm.warnings]
+    assert wire.i_yz_metres4(Iy, Iz, None) == (0.0, None) and wire.i_yz_metres4(Iy, Iz, -2.0e6)[0] == pytest.approx(-2.0e-6)
     assert wire.parse_document(_doc()).m_rel.tolist() == [-1]
-    with pytest.raises(wire.WireError):                  # I_yz^2 < I_y I_z for any real section
-        wire.parse_document(_doc(i_yz=1.0e-5))
+    with pytest.raises(wire.WireError):                  # I_yz^2 < I_y I_z for any real section, in either unit
+        wire.parse_document(_doc(i_yz=1.0e7))
     truss = _doc(i_yz=1.5e-6)
     truss["model"]["members"][0]["member_type"] = "Truss"
     assert wire.parse_document(truss).m_rel.tolist() == [-1]      # no bending, no coupling
