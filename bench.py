@@ -350,16 +350,13 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                         "timing": "profiled extra step (events around every launch, look-ahead off: the timed steps overlap "
                                   "the panel chain with the trailing updates)"})
         traffic, traffic_note = None, "no ncu --set full capture under profiles/"
-        cap = os.path.join(ROOT, "profiles", "r1l_ncu_summary.json")
+        cap = os.path.join(ROOT, "profiles", "r1z_syrk_ncu_summary.json")
         if os.path.exists(cap):
-            for row in json.load(open(cap)):
-                if "k_syrk" in row.get("Kernel Name", ""):
-                    gb = sum(float(row[k]) * (1e9 if "Gbyte" in k else 1e6) for k in row
-                             if k.startswith("dram__bytes_read.sum [") or k.startswith("dram__bytes_write.sum ["))
-                    traffic = gb
-                    traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of the captured launch (tree level 9: 8 fronts, "
-                                    "2.38 Tflop, i.e. 25 flop per DRAM byte) in profiles/r1l_ncu_summary.json")
-                    break
+            summ = json.load(open(cap))
+            traffic = float(summ["dram_bytes_per_launch"])
+            traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum summed over the {summ['launches_per_factorisation']} "
+                            "Schur-update launches of one factorisation, divided by their number (per launch, like `achieved`); "
+                            "profiles/r1z_syrk_ncu_summary.json has every launch")
         roofline = {"bound": "tensor", "kernel": kern[0]["kernel"], "achieved": tf, "peak": dmma.value, "unit": "TFLOP/s",
                     "frac": kern[0]["frac"], "traffic": traffic, "traffic_note": traffic_note,
                     "peak_source": "fp64 tensor pipe (DMMA.8x8x4) measured live by fers_b200_fp64_peak on this device, "
