@@ -572,12 +572,12 @@ int fers_b200_assemble_beams(int n_members, const double* xyz, const int* m_n1, 
     A.use_tma = ((variant & 2) == 0 && n_prop <= MAX_PROP_SMEM_ROWS && (((uintptr_t)prop) & 15) == 0) ? 1 : 0;
     size_t smem = (size_t)ASM_WARPS * STAGE_DOUBLES * sizeof(double) +
                   (A.use_tma ? (size_t)n_prop * NPROP * sizeof(double) : 0) + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.needed()) {
         const int max_smem = (int)((size_t)ASM_WARPS * STAGE_DOUBLES * 8 + MAX_PROP_SMEM_ROWS * NPROP * 8 + 16);
         FERS_CK(cudaFuncSetAttribute(k_assemble_beams<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         FERS_CK(cudaFuncSetAttribute(k_assemble_beams<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set = true;
+        attr_set.done();
     }
     int grid = (n_members + ASM_THREADS - 1) / ASM_THREADS;
     const bool general = (m_rel != nullptr) || (m_axial != nullptr && kg_mode != 0);
@@ -655,14 +655,14 @@ int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xy
     G.n_nodes = n_nodes; G.hm_ptr = hm_ptr; G.hm_list = hm_list; G.diag_slot = diag_slot; G.cache = member_cache;
     const bool cached = member_cache != nullptr && n_members > 0;
     const size_t prop_smem = A.use_tma ? (size_t)n_prop * NPROP * sizeof(double) : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.needed()) {
         const int max_smem = (int)((size_t)GA_THREADS * GA_STRIDE * 8 + MAX_PROP_SMEM_ROWS * NPROP * 8 + 16);
         FERS_CK(cudaFuncSetAttribute(k_assemble_gather<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         FERS_CK(cudaFuncSetAttribute(k_assemble_gather<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         FERS_CK(cudaFuncSetAttribute(k_assemble_gather<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         FERS_CK(cudaFuncSetAttribute(k_assemble_gather<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set = true;
+        attr_set.done();
     }
     if (cached) {
         FERS_REQUIRE((((uintptr_t)member_cache) & 31) == 0, "assemble_beams_gather: member_cache must be 32-byte aligned");

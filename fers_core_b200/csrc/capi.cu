@@ -10,14 +10,14 @@ void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_rel
 long long launches_total() { return g_launches.load(std::memory_order_relaxed); }
 void set_error(const std::string& msg) { g_error = msg; }
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-        if (cached <= 0) cached = 148;
+    static int cached[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (cached[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
     }
-    return cached;
+    return cached[dev];
 }
 }  // namespace fers
 

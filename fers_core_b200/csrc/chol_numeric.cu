@@ -14,6 +14,7 @@
 // right-hand-side index as the contiguous dimension.  No atomics anywhere: results are deterministic.
 #include <stdlib.h>
 
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -809,8 +810,15 @@ static CholProfile g_chol_profile;
 // tile-shape selection (A/B measurements): bit 0 = panel updates, bit 1 = Schur update;
 // set = 128x128 tile, one CTA per SM; clear = 128x64 tile, two CTAs per SM.  FERS_CHOL_VARIANT overrides.
 static int g_chol_variant = getenv("FERS_CHOL_VARIANT") ? atoi(getenv("FERS_CHOL_VARIANT")) : 0;
-static cudaStream_t g_side_stream = nullptr;   // low-priority stream of the overlapped (look-ahead) panel updates
-static cudaStream_t g_main_stream = nullptr;   // high-priority stream of the factorisation when look-ahead is on
+// internal streams and events of the look-ahead, one set per device (created on first use on that device)
+struct LookaheadState {
+    cudaStream_t side = nullptr;   // low-priority stream of the overlapped (look-ahead) panel updates
+    cudaStream_t main = nullptr;   // high-priority stream of the factorisation when look-ahead is on
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_fork = nullptr;
+};
+static LookaheadState g_lookahead[MAX_DEVICES];
+// per-launch profiling (fers_b200_chol_set_profile) keeps process-wide state: one profiled call at a time
+static std::mutex g_profile_mutex;
 static int g_chol_profile_on = 0;      // 0 off, 1 every kernel class, 2 Schur-update spans + totals only
 
 struct EventPool {
@@ -831,8 +839,8 @@ struct Timed {
 static Timed g_timed;
 
 static int set_smem_attrs() {
-    static bool done = false;
-    if (done) return 0;
+    static PerDeviceOnce once;
+    if (!once.needed()) return 0;
     FERS_CK(cudaFuncSetAttribute(k_potrf_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
     FERS_CK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G84::SMEM));
     FERS_CK(cudaFuncSetAttribute(k_row_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRP::SMEM));
@@ -852,7 +860,7 @@ static int set_smem_attrs() {
     FERS_CK(cudaFuncSetAttribute(k_wave2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WAVE_SMEM));
 #endif
     FERS_CK(cudaFuncSetAttribute(k_bwd_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G44N::SMEM));
-    done = true;
+    once.done();
     return 0;
 }
 
@@ -903,22 +911,25 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
     arena[1] = arena[0] + P.schur_doubles[0];
     const bool prof = g_chol_profile_on != 0;
     const bool prof_all = g_chol_profile_on == 1;
-    if (prof) { g_pool.reset(); g_timed.clear(); }
+    std::unique_lock<std::mutex> prof_lock(g_profile_mutex, std::defer_lock);
+    if (prof) { prof_lock.lock(); g_pool.reset(); g_timed.clear(); }
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     if (prof) { ev_begin = g_pool.get(); cudaEventRecord(ev_begin, caller); }
     // look-ahead needs two internal streams (high priority: the panel chain and everything else; low priority:
     // the overlapped panel updates); per-class profiling (mode 1) keeps everything on the caller's stream
     const bool lookahead = !(g_chol_variant & 4) && !prof_all;
-    static cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_fork = nullptr;
-    if (lookahead && g_side_stream == nullptr) {
+    LookaheadState& LA = g_lookahead[current_device()];
+    if (lookahead && LA.side == nullptr) {
         int lo = 0, hi = 0;
         FERS_CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        FERS_CK(cudaStreamCreateWithPriority(&g_side_stream, cudaStreamNonBlocking, lo));
-        FERS_CK(cudaStreamCreateWithPriority(&g_main_stream, cudaStreamNonBlocking, hi));
-        FERS_CK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
-        FERS_CK(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
-        FERS_CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        FERS_CK(cudaStreamCreateWithPriority(&LA.side, cudaStreamNonBlocking, lo));
+        FERS_CK(cudaStreamCreateWithPriority(&LA.main, cudaStreamNonBlocking, hi));
+        FERS_CK(cudaEventCreateWithFlags(&LA.ev_main, cudaEventDisableTiming));
+        FERS_CK(cudaEventCreateWithFlags(&LA.ev_side, cudaEventDisableTiming));
+        FERS_CK(cudaEventCreateWithFlags(&LA.ev_fork, cudaEventDisableTiming));
     }
+    cudaStream_t const g_side_stream = LA.side, g_main_stream = LA.main;
+    cudaEvent_t const ev_main = LA.ev_main, ev_side = LA.ev_side, ev_fork = LA.ev_fork;
     cudaStream_t st = caller;
     if (lookahead) {
         FERS_CK(cudaEventRecord(ev_fork, caller));
@@ -1107,6 +1118,8 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
     S.nrhs = nrhs;
     long long launches = 0;
     const bool prof = g_chol_profile_on != 0;
+    std::unique_lock<std::mutex> prof_lock(g_profile_mutex, std::defer_lock);
+    if (prof) prof_lock.lock();
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     if (prof) { cudaEventCreate(&ev_begin); cudaEventCreate(&ev_end); cudaEventRecord(ev_begin, st); }
     const bool wave = !(g_chol_variant & 8);

@@ -37,6 +37,21 @@ inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 int sm_count();   // SMs of the current device (cached)
 void count_launches(long long n);   // bookkeeping for fers_b200_launch_count()
 
+// One-time set-up that CUDA keeps per device (cudaFuncSetAttribute, streams, events) is keyed by the CURRENT device,
+// so engines on several GPUs of one process each get theirs.  Doing the set-up twice is harmless (two host threads
+// racing on the same device both set the same attribute).
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
+struct PerDeviceOnce {
+    volatile bool flag[MAX_DEVICES] = {};
+    bool needed() const { return !flag[current_device()]; }
+    void done() { flag[current_device()] = true; }
+};
+
 constexpr unsigned FULL = 0xffffffffu;
 
 // 128-bit read-only load of two doubles

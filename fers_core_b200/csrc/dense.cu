@@ -327,10 +327,10 @@ template <int MAXN>
 static int launch_chol_small(double* a, int n, int batch, int* info_dev, cudaStream_t st) {
     constexpr int LDP = SmallLdp<MAXN>::value;
     constexpr size_t smem = ((size_t)NB * LDP + NB) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.needed()) {
         FERS_CK(cudaFuncSetAttribute(k_chol_small<LDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set.done();
     }
     k_chol_small<LDP><<<batch, SMALL_THREADS, smem, st>>>(a, n, info_dev);
     return 0;

@@ -764,11 +764,11 @@ template <int NR>
 static int launch_spmm_dot(int n_nodes, const int* rowptr, const int* colidx, const double* vals, const uint8_t* fixed,
                            const double* kspring, const double* x, double* y, double* partial, cudaStream_t st) {
     if (NR == 64 && spmm_variant() == 2) {
-        static bool attr = false;
-        if (!attr) {
+        static PerDeviceOnce attr;
+        if (attr.needed()) {
             cudaFuncSetAttribute(k_spmm64_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
             cudaFuncSetAttribute(k_spmm64_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
-            attr = true;
+            attr.done();
         }
         int grid = sm_count() * 2;
         const int need = (n_nodes + WS_CONSUMERS - 1) / WS_CONSUMERS;
@@ -777,11 +777,11 @@ static int launch_spmm_dot(int n_nodes, const int* rowptr, const int* colidx, co
         return grid;
     }
     if (NR == 64 && spmm_variant() == 1) {
-        static bool attr = false;
-        if (!attr) {
+        static PerDeviceOnce attr;
+        if (attr.needed()) {
             cudaFuncSetAttribute(k_spmm64_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
             cudaFuncSetAttribute(k_spmm64_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
-            attr = true;
+            attr.done();
         }
         int grid = sm_count() * 2;
         const int need = (n_nodes + SPMM_WARPS - 1) / SPMM_WARPS;
@@ -800,20 +800,20 @@ static int run_spmm(int n_nodes, const int* rowptr, const int* colidx, const dou
     if (dot) {
         launch_spmm_dot<NR>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial, st);
     } else if (NR == 64 && spmm_variant() == 2) {
-        static bool attr = false;
-        if (!attr) {
+        static PerDeviceOnce attr;
+        if (attr.needed()) {
             cudaFuncSetAttribute(k_spmm64_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
-            attr = true;
+            attr.done();
         }
         int grid = sm_count() * 2;
         const int need = (n_nodes + WS_CONSUMERS - 1) / WS_CONSUMERS;
         if (grid > need) grid = need;
         k_spmm64_ws<false><<<grid, WS_THREADS, WS_SMEM, st>>>(n_nodes, rowptr, colidx, vals, fixed, kspring, x, y, partial);
     } else if (NR == 64 && spmm_variant() == 1) {
-        static bool attr = false;
-        if (!attr) {
+        static PerDeviceOnce attr;
+        if (attr.needed()) {
             cudaFuncSetAttribute(k_spmm64_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM);
-            attr = true;
+            attr.done();
         }
         int grid = sm_count() * 2;
         const int need = (n_nodes + SPMM_WARPS - 1) / SPMM_WARPS;

@@ -27,8 +27,8 @@ from .results import ResultArrays, SECTION_FRACS, lazy_bundle, results_to_json, 
 DENSE_MAX_DOF = 8192          # models up to this many DOFs use the dense Cholesky path
 SOLVERS = ("auto", "dense", "cholesky", "pcg")   # auto: dense up to DENSE_MAX_DOF, sparse Cholesky above
 CHOL_REFINE_STEPS = 2         # at most this many iterative-refinement passes after the direct substitution
-CHOL_REFINE_TOL = 1e-12
-STAGE_MAX_BYTES = 256 << 20   # result fields up to this size travel through pinned staging buffers       # refine while the relative residual max_c ||f_c - K u_c|| / ||f_c|| exceeds this
+CHOL_REFINE_TOL = 1e-12       # refine while the relative residual max_c ||f_c - K u_c|| / ||f_c|| exceeds this
+STAGE_MAX_BYTES = 256 << 20   # result fields up to this size travel through pinned staging buffers
 CHOL_RESIDUAL_LIMIT = 1e-8    # relative residual above which the direct solve is reported as failed
 PCG_TOL = 1e-12               # relative residual ||r|| / ||b|| per right-hand side
 PCG_MAX_ITER = 200000
@@ -45,6 +45,10 @@ def _require_cuda(device=None) -> torch.device:
     if not torch.cuda.is_available():
         raise EngineError("fers_core_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise EngineError(f"fers_core_b200 runs on CUDA devices only, got {dev}")
+    if dev.index is None:            # "cuda" without an index: the library must be set to the device torch is on
+        dev = torch.device("cuda", torch.cuda.current_device())
     return dev
 
 
@@ -80,9 +84,9 @@ class Engine:
         self.dev = _require_cuda(device)
         self.lib = _lib.load()
         torch.cuda.set_device(self.dev)
-        _lib.check(self.lib.fers_b200_set_device(self.dev.index or 0), "set_device")
+        _lib.check(self.lib.fers_b200_set_device(self.dev.index), "set_device")
         sm, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
-        _lib.check(self.lib.fers_b200_device_info(self.dev.index or 0, C.byref(sm), C.byref(maj), C.byref(mnr),
+        _lib.check(self.lib.fers_b200_device_info(self.dev.index, C.byref(sm), C.byref(maj), C.byref(mnr),
                                                   C.byref(mem)), "device_info")
         self.assembly_variant = assembly_variant
         self.stats = SolveStats()
@@ -143,6 +147,10 @@ class Engine:
 
     @property
     def stream(self) -> int:
+        # read before every launch: also makes this engine's GPU the current one (the library launches on the current
+        # device; another Engine of the same process may have switched it)
+        if torch.cuda.current_device() != self.dev.index:
+            torch.cuda.set_device(self.dev)
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def _t(self, a: np.ndarray, dtype) -> torch.Tensor:
@@ -613,6 +621,7 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
     hinge_k = hinge_curve_stiffness(model, None)        # = the values model.rel carries
     if eng.n_hinge_curves:
         eng.set_rel(model.rel)                          # the previous column left its own state on the device
+    settled = False
     for _outer in range(max(1, 2 * (len(uni) + eng.n_unilateral) + 2
                             + (max(opts.max_iterations, 20) if eng.n_curves or eng.n_hinge_curves else 0))):
         if eng.n_unilateral or eng.n_curves:
@@ -665,6 +674,7 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
         if len(uni) == 0:
             if changed:
                 continue
+            settled = True
             break
         # elongation decides the active set
         u = d_u[:, 0].cpu().numpy().reshape(model.n_nodes, 6)
@@ -676,14 +686,22 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
         new_scale = scale.copy()
         new_scale[uni] = np.where(want, 1.0, INACTIVE_SCALE)
         if np.array_equal(new_scale, scale) and not changed:
+            settled = True
             break
         scale = new_scale
+    if not settled:
+        # the bound of the outer loop was reached with the active set (tension / compression-only members, unilateral
+        # supports) or a stiffness curve still changing: the stored state is the last iterate, flagged as such
+        conv = False
+        out.converged[col] = False
+        out.warnings.append(("W_ACTIVE_SET_NOT_CONVERGED", f"result column {col}: the active set / stiffness curves did not "
+                             f"settle within {_outer + 1} outer iterations; the last iterate is reported"))
     d_scale = eng._t(scale, np.float64) if len(uni) else None
     rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, d_scale, d_axial, kg_mode, sup, detail=detail)
     _store(out, model, [col], d_u, rec, xyz)
     if second_order:
         out.iterations[col] = total_it
-        out.converged[col] = bool(conv)
+        out.converged[col] = bool(conv) and settled
         out.residual[col] = resn
 
 

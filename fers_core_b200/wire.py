@@ -249,6 +249,12 @@ def parse_document(doc: dict) -> ModelArrays:
     model, analysis = doc["model"], doc["analysis"]
     opts = parse_options(analysis.get("options"))
     warnings: list = []
+    if opts.rigid_strategy == "LinearMpc" and any(
+            _norm_enum(m.get("member_type", "Normal")) == "rigid" for m in (model.get("members") or [])):
+        # RigidStrategy.LinearMpc (pydantic_models.py:1047-1049): the rigid link as a constraint transformation is not
+        # implemented; rigid members are stiff members (hostlogic.rigid_property_row) under either strategy
+        warnings.append(("W_LINEAR_MPC_AS_RIGID_MEMBER", "rigid_strategy=LinearMpc: rigid members are modelled as stiff "
+                         "members (RigidMember strategy), not as multi-point constraints"))
 
     # ---- nodes (pydantic_models.py:Node; wire order = DOF numbering order) ----------------
     nodes = model.get("nodes") or []
@@ -514,6 +520,11 @@ def parse_document(doc: dict) -> ModelArrays:
             flags |= 4
         sm = p.get("stiffness_modifiers") or {}
         mods = [1.0 if sm.get(k) is None else float(sm[k]) for k in ("membrane", "bending", "shear")]
+        if _norm_enum(p.get("theory") or "Auto") == "kirchhoff" and flags & 2:
+            # PlateTheory (pydantic_models.py:816-819, field 1723): Auto / Mindlin -> DSG3; the thin-plate DKT element
+            # ("currently unreliable", tests/nafems/reference_examples.py:16-18) is not implemented
+            warnings.append(("W_PLATE_THEORY_IGNORED", f"plate {p['id']}: theory=Kirchhoff solved with the Mindlin (DSG3) "
+                             "element"))
         if p.get("offset"):
             warnings.append(("W_PLATE_OFFSET_IGNORED", f"plate {p['id']}: offset not modelled"))
         lx_dir = _vec3(p["local_x_direction"], "plate.local_x_direction") if p.get("local_x_direction") else None

@@ -941,6 +941,8 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order, reload=None):
         asm = Assembly(model_it, asm0.xyz, scale)
         if hinges_moved:
             F, peq = reload(asm)
+    else:
+        conv = False        # outer bound reached with the active set / stiffness curves still changing (engine: W_ACTIVE_SET_NOT_CONVERGED)
     return U, K, kg, (scale if len(uni) else None), (total_it if second_order else None), conv, resn, asm, F, peq
 
 
