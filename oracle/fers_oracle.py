@@ -623,8 +623,14 @@ def constrain(K, model, extra_fixed=None, bc=None):
 SOLVE_THREADS = max(1, os.cpu_count() or 1)      # host threads of the multi-right-hand-side substitution
 
 
-def solve_sym(Kff, B):
-    """Direct solve of K_ff X = B (B [n,nrhs])."""
+class NotPositiveDefinite(RuntimeError):
+    """The tangent matrix K + K_g of a second-order iteration is not positive definite: the structure has buckled
+    under the applied load (the engine raises EngineError "... not positive definite ..." at the same point)."""
+
+
+def solve_sym(Kff, B, require_pd=False):
+    """Direct solve of K_ff X = B (B [n,nrhs]).  require_pd: refuse an indefinite matrix (second-order iterations)
+    instead of solving it by LU."""
     if Kff.shape[0] == 0:
         return np.zeros_like(B)
     if Kff.shape[0] <= 3000:
@@ -634,8 +640,12 @@ def solve_sym(Kff, B):
             c = sla.cho_factor(A, lower=True, check_finite=False)
             return sla.cho_solve(c, B, check_finite=False)
         except np.linalg.LinAlgError:
+            if require_pd:
+                raise NotPositiveDefinite("stiffness matrix is not positive definite: buckled under the applied load") from None
             return np.linalg.solve(A, B)
     lu = spla.splu(Kff, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    if require_pd and not (lu.U.diagonal() > 0.0).all():      # no pivoting: U carries the pivots of the LDL^T
+        raise NotPositiveDefinite("stiffness matrix is not positive definite: buckled under the applied load")
     nrhs = B.shape[1] if B.ndim == 2 else 1
     threads = min(SOLVE_THREADS, nrhs)
     if threads <= 1 or B.ndim != 2:
@@ -890,7 +900,7 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order, reload=None):
                 kg = _suppress_kg(asm, kg, suppressed)
                 K = asm.K_elastic(kg)
                 Kff, free, _ = constrain(K, model, bc=bc)
-                Un = np.zeros(nd); Un[free] = solve_sym(Kff, F[free][:, None])[:, 0]
+                Un = np.zeros(nd); Un[free] = solve_sym(Kff, F[free][:, None], require_pd=True)[:, 0]
                 total_it += 1
                 den = np.linalg.norm(Un)
                 resn = np.linalg.norm(Un - U) / den if den > 0 else 0.0

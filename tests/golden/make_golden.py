@@ -320,6 +320,195 @@ for variant in ("consistent", "simplified_suppress_z"):
             o["pdelta_formulation"] = "SIMPLIFIED"; o["pdelta_suppress_axes"] = ["Z"]
     emit("portal_pdelta_" + variant, c, [], mut)
 
+# 12b P-Delta pinned on closed forms ("unpinned at any tolerance: geometric stiffness / P-Delta iteration,
+# imperfection application").  The expected numbers come from the self-contained plane beam-column solver below
+# (textbook element matrices, its own fixed-point loop, perturbed coordinates formed HERE) and from the classical
+# beam-column formulas -- nothing of fers_core_b200 / oracle is imported by this generator.
+import numpy as _np  # noqa: E402
+
+
+def plane_pdelta(xy, EI, EA, loads, formulation="CONSISTENT", tol=1e-15, max_it=200):
+    """Cantilever chain of plane frame elements through the points xy [n+1,2] (node 0 clamped), nodal loads
+    {node: (Fx, Fy, Mz)}.  P-Delta fixed point u <- (K_e + K_g(N(u)))^-1 f with N from the axial strain of the
+    previous iterate.  Returns (u [n+1,3], N [n], iterations); the reaction K u - f of the clamped node is left in
+    ``plane_pdelta.base_reaction`` (Fx, Fy, Mz)."""
+    xy = _np.asarray(xy, float)
+    n = len(xy) - 1
+    nd = 3 * (n + 1)
+    f = _np.zeros(nd)
+    for node, (fx, fy, mz) in loads.items():
+        f[3 * node:3 * node + 3] += (fx, fy, mz)
+    d = xy[1:] - xy[:-1]
+    L = _np.hypot(d[:, 0], d[:, 1])
+    c, s_ = d[:, 0] / L, d[:, 1] / L
+
+    def element(e, N):
+        l = L[e]
+        k = _np.zeros((6, 6))
+        a = EA / l
+        k[0, 0] = k[3, 3] = a; k[0, 3] = k[3, 0] = -a
+        b = EI / l ** 3
+        kb = b * _np.array([[12, 6 * l, -12, 6 * l], [6 * l, 4 * l * l, -6 * l, 2 * l * l],
+                            [-12, -6 * l, 12, -6 * l], [6 * l, 2 * l * l, -6 * l, 4 * l * l]])
+        if formulation == "CONSISTENT":
+            kg = N / (30 * l) * _np.array([[36, 3 * l, -36, 3 * l], [3 * l, 4 * l * l, -3 * l, -l * l],
+                                           [-36, -3 * l, 36, -3 * l], [3 * l, -l * l, -3 * l, 4 * l * l]])
+        else:
+            kg = N / l * _np.array([[1, 0, -1, 0], [0, 0, 0, 0], [-1, 0, 1, 0], [0, 0, 0, 0.0]])
+        idx = [1, 2, 4, 5]
+        k[_np.ix_(idx, idx)] += kb + kg
+        T = _np.zeros((6, 6))
+        for o in (0, 3):
+            T[o, o] = c[e]; T[o, o + 1] = s_[e]; T[o + 1, o] = -s_[e]; T[o + 1, o + 1] = c[e]; T[o + 2, o + 2] = 1.0
+        return T.T @ k @ T, T
+
+    N = _np.zeros(n)
+    u = _np.zeros(nd)
+    for it in range(max_it):
+        K = _np.zeros((nd, nd))
+        for e in range(n):
+            ke, _ = element(e, N[e])
+            sl = slice(3 * e, 3 * e + 6)
+            K[sl, sl] += ke
+        un = _np.zeros(nd)
+        un[3:] = _np.linalg.solve(K[3:, 3:], f[3:])
+        Nn = _np.zeros(n)
+        for e in range(n):
+            _, T = element(e, 0.0)
+            ul = T @ un[3 * e:3 * e + 6]
+            Nn[e] = EA / L[e] * (ul[3] - ul[0])
+        den = _np.linalg.norm(un)
+        done = it > 0 and _np.linalg.norm(un - u) <= tol * den
+        u, N = un, Nn
+        plane_pdelta.base_reaction = (K @ un - f)[:3]
+        if done:
+            break
+    return u.reshape(n + 1, 3), N, it + 1
+
+
+PD_L, PD_N = 4.0, 8
+PD_I = IY                         # doubly symmetric section (i_y = i_z): the local-axis rule cannot matter
+PD_EI, PD_EA = E * PD_I, E * A
+PD_PCR = math.pi ** 2 * PD_EI / (4 * PD_L ** 2)        # Euler load of the cantilever
+PD_H = 100.0
+PD_PHI = 1.0 / 200.0
+
+
+def pd_column(n_el, formulation, P, H, lean=0.0, sway=None, order_linear=False, name_lc="PH"):
+    """Vertical cantilever column along +Y (n_el members), tip loads P (down) and H (+X); optional sway imperfection."""
+    reset()
+    from fers_core import ImperfectionCase, SwayImperfection
+    c = FERS(); mat = steel()
+    s = Section(name="SYM", material=mat, i_y=PD_I, i_z=PD_I, j=J, area=A)
+    nodes = [Node(0.0, PD_L * i / n_el, 0.0) for i in range(n_el + 1)]
+    nodes[0].nodal_support = NodalSupport()
+    mem = [Member(start_node=nodes[i], end_node=nodes[i + 1], section=s) for i in range(n_el)]
+    c.add_member_set(MemberSet(members=mem))
+    lc = c.create_load_case(name=name_lc)
+    if P:
+        NodalLoad(node=nodes[-1], load_case=lc, magnitude=P, direction=(0, -1, 0))
+    if H:
+        NodalLoad(node=nodes[-1], load_case=lc, magnitude=H, direction=(1, 0, 0))
+    combo = c.create_load_combination(name="C", load_cases_factors={lc: 1.0}, situation="ULS", check="ALL")
+    if sway is not None:
+        imp = ImperfectionCase(loadcombinations=[combo])
+        imp.add_sway_imperfection(SwayImperfection(magnitude=sway, axis=(0, 0, 1), height_direction=(0, 1, 0),
+                                                   reference_point=(0, 0, 0)))
+        c.add_imperfection_case(imp)
+
+    def mut(d):
+        o = d["analysis"]["options"]
+        o["order"] = "NONLINEAR"; o["nonlinear_method"] = "P_DELTA"; o["tolerance"] = 1e-12; o["max_iterations"] = 50
+        o["pdelta_formulation"] = formulation
+        o["include_shear_deformation"] = False
+    return c, mut, len(nodes)
+
+
+def amplification(P):
+    """Tip deflection of the cantilever beam-column over H L^3 / 3 EI: 3 (tan kL - kL) / (kL)^3, k^2 = P / EI."""
+    kl = math.sqrt(P / PD_EI) * PD_L
+    return 3.0 * (math.tan(kl) - kl) / kl ** 3
+
+
+# (a) consistent K_g, 8 elements, P = 0.5 P_cr: the plane solver to 1e-9, the beam-column formula to 1e-5
+P = 0.5 * PD_PCR
+xy = [(0.0, PD_L * i / PD_N) for i in range(PD_N + 1)]
+u, Nax, _ = plane_pdelta(xy, PD_EI, PD_EA, {PD_N: (PD_H, -P, 0.0)})
+c, mut, ntip = pd_column(PD_N, "CONSISTENT", P, PD_H)
+d_exact = PD_H * PD_L ** 3 / (3 * PD_EI) * amplification(P)
+assert abs(u[-1, 0] / d_exact - 1.0) < 2e-6, (u[-1, 0], d_exact)
+emit("pdelta_beam_column_consistent", c, [
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", float(u[-1, 0]), 0.0, 1e-9),
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", d_exact, 0.0, 1e-5),
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dy", float(u[-1, 1]), 0.0, 1e-9),
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/rz", float(u[-1, 2]), 0.0, 1e-9),
+    # equilibrium in the displaced position: M_base = H L + P delta
+    X("loadcombinations/C/reaction_nodes/1/nodal_forces/mz", PD_H * PD_L + P * float(u[-1, 0]), 0.0, 1e-9),
+    X("loadcombinations/C/reaction_nodes/1/nodal_forces/fx", -PD_H, 0.0, 1e-9),
+    X("loadcombinations/C/reaction_nodes/1/nodal_forces/fy", P, 0.0, 1e-9),
+    X("loadcombinations/C/member_results/1/local_start_forces/fx", P, 0.0, 1e-9),      # compression: +P at the start face (stiffness sign)
+], mut)
+
+# (b) simplified K_g ("P/L-only diagonal terms"), ONE element: delta = H / (3 EI / L^3 - P / L) exactly
+P = 0.3 * PD_PCR
+c, mut, ntip = pd_column(1, "SIMPLIFIED", P, PD_H)
+d_simpl = PD_H / (3 * PD_EI / PD_L ** 3 - P / PD_L)
+u1, _, _ = plane_pdelta([(0.0, 0.0), (0.0, PD_L)], PD_EI, PD_EA, {1: (PD_H, -P, 0.0)}, "SIMPLIFIED")
+assert abs(u1[-1, 0] / d_simpl - 1.0) < 1e-12
+emit("pdelta_simplified_one_element", c, [
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", d_simpl, 0.0, 1e-9),
+    X("loadcombinations/C/reaction_nodes/1/nodal_forces/mz", PD_H * PD_L + P * d_simpl, 0.0, 1e-9),
+], mut)
+# (b') the same column with the consistent matrix: one element, closed form of the 2x2 system
+c, mut, ntip = pd_column(1, "CONSISTENT", P, PD_H)
+k11 = 12 * PD_EI / PD_L ** 3 - 6 * P / (5 * PD_L); k12 = -6 * PD_EI / PD_L ** 2 + P / 10
+k22 = 4 * PD_EI / PD_L - 2 * P * PD_L / 15
+d_cons = PD_H / (k11 - k12 * k12 / k22)
+assert d_simpl < d_cons < PD_H * PD_L ** 3 / (3 * PD_EI) * amplification(P)      # simplified < consistent < exact
+emit("pdelta_consistent_one_element", c, [
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", d_cons, 0.0, 1e-9),
+], mut)
+
+# (c) sway imperfection phi about Z (lean towards -X: axis x height_direction = Z x Y = -X), vertical load only.
+# Expected from the plane solver on coordinates perturbed HERE (x = -phi y); and the notional-load twin H = phi P.
+P = 0.5 * PD_PCR
+xy_lean = [(-PD_PHI * PD_L * i / PD_N, PD_L * i / PD_N) for i in range(PD_N + 1)]
+ul, _, _ = plane_pdelta(xy_lean, PD_EI, PD_EA, {PD_N: (0.0, -P, 0.0)})
+r_lean = plane_pdelta.base_reaction.copy()
+c, mut, ntip = pd_column(PD_N, "CONSISTENT", P, 0.0, sway=PD_PHI)
+d_lean_exact = -PD_PHI * P * PD_L ** 3 / (3 * PD_EI) * amplification(P)          # notional load phi P on the straight column
+assert abs(ul[-1, 0] / d_lean_exact - 1.0) < 2e-4, (ul[-1, 0], d_lean_exact)
+emit("pdelta_sway_imperfection", c, [
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", float(ul[-1, 0]), 0.0, 1e-9),
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", d_lean_exact, 0.0, 2e-4),
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dy", float(ul[-1, 1]), 0.0, 1e-9),
+    # base moment: the plane solver's own reaction; = -P x (lean + deflection) up to the second-order terms the
+    # linearised theory drops (the load sits phi L - dx to the left of the base)
+    X("loadcombinations/C/reaction_nodes/1/nodal_forces/mz", float(r_lean[2]), 0.0, 1e-9),
+    X("loadcombinations/C/reaction_nodes/1/nodal_forces/mz", -P * (PD_PHI * PD_L - float(ul[-1, 0])), 0.0, 1e-4),
+    # the load case alone is solved on the PERFECT geometry (imperfections attach to combinations): no sway
+    X(f"loadcases/PH/displacement_nodes/{ntip}/dx", 0.0, 1e-15, 0.0),
+], mut)
+un, _, _ = plane_pdelta(xy, PD_EI, PD_EA, {PD_N: (-PD_PHI * P, -P, 0.0)})
+c, mut, ntip = pd_column(PD_N, "CONSISTENT", P, -PD_PHI * P)
+emit("pdelta_notional_load", c, [
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", float(un[-1, 0]), 0.0, 1e-9),
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", float(ul[-1, 0]), 0.0, 2e-4),     # = the sway imperfection
+], mut)
+
+# (d) above the Euler load the tangent matrix is indefinite: the engine must refuse, not return a number
+c, mut, ntip = pd_column(PD_N, "CONSISTENT", 1.05 * PD_PCR, PD_H)
+CASES.append({"name": "pdelta_above_euler_load", "doc": (lambda d: (mut(d), d.__setitem__("results", None), d)[-1])(c.to_dict()),
+              "expect": [], "expect_error": "positive definite"})
+# just below it the deflection follows the formula (amplification ~ 1 / (1 - P / P_cr) = 20)
+P = 0.95 * PD_PCR
+u95, _, _ = plane_pdelta(xy, PD_EI, PD_EA, {PD_N: (PD_H, -P, 0.0)})
+c, mut, ntip = pd_column(PD_N, "CONSISTENT", P, PD_H)
+emit("pdelta_near_euler_load", c, [
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", float(u95[-1, 0]), 0.0, 1e-8),
+    X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", PD_H * PD_L ** 3 / (3 * PD_EI) * amplification(P), 0.0, 1e-4),
+], mut)
+
 # 13 spring support + truss members (auto-restrained rotations)
 reset()
 c = FERS(); linear(c); mat = steel(); s = ipe180(mat)

@@ -19,10 +19,15 @@ def golden_cases() -> list:
 
 
 def golden_names(small_only: bool = False) -> list:
-    names = [c["name"] for c in golden_cases()]
+    """Cases that are expected to solve (cases that must be refused: golden_error_names)."""
+    names = [c["name"] for c in golden_cases() if "expect_error" not in c]
     if small_only:
         names = [n for n in names if n not in ("nafems_LE1_72x8", "nafems_LE6_32x32")]
     return names
+
+
+def golden_error_names() -> list:
+    return [c["name"] for c in golden_cases() if "expect_error" in c]
 
 
 def golden(name: str) -> dict:

@@ -18,6 +18,13 @@ SUITES = [
     "tests/beam_equation_checks/test_beam_equations.py",
     "tests/functionality/test_functionality.py",
     "tests/functionality/test_plate_results.py",
+    "tests/functionality/test_create_beam.py",
+    "tests/functionality/test_analysis_options.py",
+    "tests/functionality/test_new_schema_features.py",
+    "tests/functionality/test_plate_surfaces.py",
+    "tests/functionality/test_stiffness_curve.py",
+    "tests/functionality/test_surface_loads.py",
+    "tests/functionality/test_unity_checks.py",
     "tests/nafems/test_nafems_benchmarks.py::test_LE1_elliptic_membrane_converges",
     "tests/nafems/test_nafems_benchmarks.py::test_LE5_zsection_warping_beam",
     "tests/nafems/test_nafems_benchmarks.py::test_LE6_skew_plate_converges",
@@ -29,7 +36,9 @@ def test_reference_suite_against_oracle(suite):
     env = dict(os.environ)
     env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "refshim"), REFERENCE, ROOT])
     env["FERS_SHIM_BACKEND"] = "oracle"
-    p = subprocess.run([sys.executable, "-m", "pytest", "-p", "no:cacheprovider", "-x", "-q", suite], cwd=REFERENCE,
+    # Section.from_name needs the absent `sectionproperties` package (fers_core/members/section.py:315)
+    deselect = ["--deselect", "tests/functionality/test_create_beam.py::test_named_section_and_schema_gate"]
+    p = subprocess.run([sys.executable, "-m", "pytest", "-p", "no:cacheprovider", "-x", "-q", *deselect, suite], cwd=REFERENCE,
                        env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
 
