@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import glob
 import json
 import os
 import subprocess
@@ -31,11 +32,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+SYRK_KERNEL_ID = "k_syrk<G86>"          # Schur-update kernel of the default path; ncu captures under profiles/ name the one they saw
 METRIC = "solved_dof_x_load_combinations_per_second"
 UNIT = "DOF*combos/s"
-CPU_SAMPLE = (20, 20, 12)          # bays x bays x storeys of the bounded CPU sample (34 398 DOF)
-if os.environ.get("FERS_BENCH_CPU_SAMPLE"):      # tests shrink the sample (tests/test_bench_contract.py)
-    CPU_SAMPLE = tuple(int(v) for v in os.environ["FERS_BENCH_CPU_SAMPLE"].split(","))
 
 
 def parse_args():
@@ -147,35 +146,79 @@ def pin_model(model):
     return model
 
 
+def workload_name(args, n_comb: int) -> str:
+    return (f"configs[3] synthetic 3D space frame {args.nx}x{args.nz} bays x {args.ny} storeys, linear static, "
+            f"{n_comb} combinations per GPU")
+
+
+def cpu_pass(args):
+    """The CPU path on THIS run's workload (same frame, same combinations): oracle/cpu_frame -- C++ / OpenMP restatement
+    of the oracle with a multifrontal Cholesky on BLAS-3 (OpenBLAS), every host thread.  Returns (CpuFrame, model)."""
+    from fers_core_b200 import synth
+    from oracle import cpu_frame
+    model = synth.grid_frame(args.nx, args.nz, args.ny, n_combos=args.combos)
+    return cpu_frame.CpuFrame(model), model
+
+
+CPU_KIND_NOTE = ("C++ / OpenMP restatement of the reference path (oracle/cpu_frame.cpp): element stiffness, assembly, load "
+                 "vectors, multifrontal Cholesky with OpenBLAS dpotrf / dtrsm / dsyrk / dgemm on all host threads, 64-RHS "
+                 "substitution, member forces and reactions; the reference's own engine is a closed Rust wheel absent from "
+                 "the reference tree")
+
+
 def run_reference(args, rank: int, world: int) -> None:
-    """CPU arm: the reference's engine is a closed Rust wheel that cannot be installed here, so the
-    CPU restatement (oracle/fers_oracle.py, numpy + scipy SuperLU) is timed on the host cores."""
+    """CPU arm: the reference's engine (closed Rust wheel fers_calculations==0.2.43) cannot be installed here, so the CPU
+    restatement of the path is timed on the host cores -- on the SAME workload as the GPU arm (configs[3] itself).  One
+    step = one full pass.  A pass takes tens of seconds, so the number of timed steps is capped by a wall budget
+    (FERS_REF_BUDGET_S, default 240 s; 0 = run exactly --steps): the line reports the steps actually timed."""
     if rank != 0:
         return
-    from fers_core_b200 import synth
-    from oracle import fers_oracle
-    # the oracle's factorisation (scipy SuperLU) and numpy element loops are sequential; the 64-column substitution
-    # runs on every host thread (oracle.fers_oracle.SOLVE_THREADS)
-    cores = fers_oracle.SOLVE_THREADS
-    model = synth.grid_frame(*CPU_SAMPLE, n_combos=args.combos)
-    units = model.n_dof * args.combos
-    times = []
-    for i in range(args.warmup + args.steps):
+    from oracle import cpu_frame
+    cf, model = cpu_pass(args)
+    factors = model.combo_factors
+    units = model.n_dof * factors.shape[0]
+    budget = float(os.environ.get("FERS_REF_BUDGET_S", "240"))
+    t_begin = time.perf_counter()
+    times, phases = [], {}
+
+    def one_pass(timed: bool) -> float:
         t0 = time.perf_counter()
-        fers_oracle.analyze(model, detail=False)
+        cf.run_linear(factors)
         dt = time.perf_counter() - t0
-        if i >= args.warmup:
+        if timed:
             times.append(dt)
+            for k, v in cf.timings.items():
+                phases[k] = phases.get(k, 0.0) + v
+        return dt
+    # the first pass (symbolic plan, page faults) is a warm-up pass unless --warmup 0 asks for none; its duration sizes
+    # the rest of the run against the wall budget
+    t_first = one_pass(timed=args.warmup == 0)
+    warm, steps = args.warmup, args.steps
+    if budget > 0:
+        room = max(budget - t_first, 0.0)
+        afford = int(room // max(t_first, 1e-9))                     # further passes the budget allows
+        steps = max(1, min(args.steps, afford + (1 if args.warmup == 0 else 0)))
+        warm = 0 if args.warmup == 0 else max(1, min(args.warmup, afford - steps + 1))
+    for _ in range(max(warm - 1, 0)):
+        one_pass(False)
+    while len(times) < steps:
+        one_pass(True)
+    phases = {k: v / steps for k, v in phases.items()}
     ms = 1e3 * float(np.mean(times))
     value = units / (ms / 1e3)
-    sample = (f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} frame ({model.n_dof} DOF) x {args.combos} combinations, "
-              "full pipeline (assembly, SuperLU factor [1 thread], 64-RHS solve [all host threads], recovery) per step")
+    cores = cpu_frame.threads()
+    sample = (f"the workload itself: {args.nx}x{args.nz}x{args.ny} frame ({model.n_dof} DOF) x {factors.shape[0]} combinations, one full "
+              f"pass per step on {cores} host threads; {steps} timed step(s) after {warm} warm-up pass(es) "
+              f"(requested {args.steps} / {args.warmup}; wall budget {budget:g} s, FERS_REF_BUDGET_S)")
     emit(({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[3] 3D space frame, linear static, 64 combinations (bounded CPU sample)",
-                   "sample": sample, "frame": list(CPU_SAMPLE), "dof": model.n_dof, "combinations": args.combos},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, factors.shape[0]), "nodes": model.n_nodes, "members": model.n_members,
+                   "dof": model.n_dof, "load_cases": len(model.load_cases), "combinations_per_gpu": int(factors.shape[0]),
+                   "sample": sample, "cpu_path": CPU_KIND_NOTE, "max_rel_residual": cf.relres,
+                   "phase_seconds": {k: round(v, 4) for k, v in phases.items()},
+                   "factor_gflops": cf.flops / 1e9 / phases["factor_s"], "wall_s": time.perf_counter() - t_begin},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "host_cores": os.cpu_count() or 1, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -349,14 +392,18 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                         "TFLOP/s_effective_with_lookahead": upd_flops / (um_eff * 1e-3) / 1e12 if um_eff > 0 else None,
                         "timing": "profiled extra step (events around every launch, look-ahead off: the timed steps overlap "
                                   "the panel chain with the trailing updates)"})
-        traffic, traffic_note = None, "no ncu --set full capture under profiles/"
-        cap = os.path.join(ROOT, "profiles", "r1z_syrk_ncu_summary.json")
-        if os.path.exists(cap):
+        # DRAM traffic comes from a committed ncu --set full capture, not from this run: it is reported only when the
+        # capture was taken on the same problem and the same Schur-update kernel (else null until re-captured)
+        traffic, traffic_note = None, "no matching ncu --set full capture under profiles/ (captured value, never measured live)"
+        for cap in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_syrk_ncu_summary.json")), reverse=True):
             summ = json.load(open(cap))
-            traffic = float(summ["dram_bytes_per_launch"])
-            traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum summed over the {summ['launches_per_factorisation']} "
-                            "Schur-update launches of one factorisation, divided by their number (per launch, like `achieved`); "
-                            "profiles/r1z_syrk_ncu_summary.json has every launch")
+            cc = summ.get("captured_config") or {}
+            if cc.get("dof") == n_dof and cc.get("nrhs") == nr and cc.get("kernel_id") == SYRK_KERNEL_ID:
+                traffic = float(summ["dram_bytes_per_launch"])
+                traffic_note = (f"CAPTURED, not live: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
+                                f"{summ['launches_per_factorisation']} Schur-update launches of one factorisation, divided by their "
+                                f"number (per launch, like `achieved`); {os.path.relpath(cap, ROOT)} (commit {cc.get('commit')}) has every launch")
+                break
         roofline = {"bound": "tensor", "kernel": kern[0]["kernel"], "achieved": tf, "peak": dmma.value, "unit": "TFLOP/s",
                     "frac": kern[0]["frac"], "traffic": traffic, "traffic_note": traffic_note,
                     "peak_source": "fp64 tensor pipe (DMMA.8x8x4) measured live by fers_b200_fp64_peak on this device, "
@@ -440,29 +487,29 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                "ms_per_step": 1e3 * te, "phases_of_a_synchronised_pass": phases,
                "api": "fers_core_b200.engine.Engine(model_arrays).run_linear(factors) + D2H of U, R, f_local"}
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------
+    # ---- CPU baseline: ONE full pass of the same workload on the host cores (rank 0, N=1 only) ------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from fers_core_b200 import synth
-        from oracle import fers_oracle
-        sm_model = synth.grid_frame(*CPU_SAMPLE, n_combos=args.combos)
+        from oracle import cpu_frame
+        del eng
+        torch.cuda.empty_cache()
+        cf, cpu_model = cpu_pass(args)
         t0 = time.perf_counter()
-        fers_oracle.analyze(sm_model, detail=False)
+        cf.run_linear(cpu_model.combo_factors)
         dt = time.perf_counter() - t0
-        cpu = {"value": sm_model.n_dof * args.combos / dt, "unit": UNIT, "cores": fers_oracle.SOLVE_THREADS,
-               "host_cores": os.cpu_count() or 1,
-               "kind": "port",
-               "seconds": dt,
-               "sample": f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} frame ({sm_model.n_dof} DOF) x {args.combos} "
-                         "combinations, oracle (numpy assembly + scipy SuperLU factor [1 thread] + 64-RHS solve [all host threads] + recovery), once"}
+        cpu = {"value": cpu_model.n_dof * args.combos / dt, "unit": UNIT, "cores": cpu_frame.threads(),
+               "host_cores": os.cpu_count() or 1, "kind": "port", "seconds": dt,
+               "phase_seconds": {k: round(v, 4) for k, v in cf.timings.items()},
+               "factor_gflops": cf.flops / 1e9 / cf.timings["factor_s"], "max_rel_residual": cf.relres,
+               "sample": f"the workload itself ({args.nx}x{args.nz}x{args.ny} frame, {cpu_model.n_dof} DOF x {args.combos} combinations), "
+                         "one cold pass including the symbolic plan; " + CPU_KIND_NOTE}
 
     if rank == 0:
         emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"configs[3] synthetic 3D space frame {args.nx}x{args.nz} bays x {args.ny} storeys, "
-                                   f"linear static, {n_comb} combinations per GPU",
+            "config": {"workload": workload_name(args, n_comb),
                        "nodes": model.n_nodes, "members": model.n_members, "dof": n_dof, "free_dof": eng.stats.n_free,
                        "nnz_blocks": nnzb, "load_cases": len(model.load_cases), "combinations_per_gpu": n_comb,
                        **solver_cfg, "max_rel_residual": resid, "parallelism": f"combination batches x{world}",

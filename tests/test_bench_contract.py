@@ -8,6 +8,9 @@ import sys
 from tests.conftest import ROOT
 
 
+SMALL = ["--nx", "4", "--nz", "4", "--ny", "3", "--combos", "8"]
+
+
 def _run(args, env_extra=None, timeout=600):
     env = dict(os.environ)
     env.update(env_extra or {})
@@ -16,7 +19,7 @@ def _run(args, env_extra=None, timeout=600):
 
 
 def test_reference_arm_prints_one_json_line():
-    p = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], {"FERS_BENCH_CPU_SAMPLE": "4,4,3"})
+    p = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", *SMALL])
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -28,11 +31,22 @@ def test_reference_arm_prints_one_json_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # same workload as the GPU arm would report for these arguments (the driver compares the two config.workload strings)
+    assert d["config"]["workload"].startswith("configs[3] synthetic 3D space frame 4x4 bays x 3 storeys")
+    assert d["config"]["dof"] == 6 * 5 * 5 * 4 and d["config"]["max_rel_residual"] < 1e-10
+
+
+def test_reference_arm_honours_steps_and_the_wall_budget():
+    p = _run(["--impl", "reference", "--steps", "3", "--warmup", "2", *SMALL])
+    d = json.loads(p.stdout.strip())
+    assert (d["steps"], d["warmup"]) == (3, 2)
+    p = _run(["--impl", "reference", "--steps", "50", "--warmup", "5", *SMALL], {"FERS_REF_BUDGET_S": "0.0001"})
+    d = json.loads(p.stdout.strip())
+    assert d["steps"] == 1 and d["warmup"] == 1 and d["steps_requested"] == 50 and d["warmup_requested"] == 5
 
 
 def test_other_ranks_of_the_reference_arm_stay_silent():
-    p = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], {"FERS_BENCH_CPU_SAMPLE": "4,4,3", "RANK": "1",
-                                                                        "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    p = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", *SMALL], {"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert p.returncode == 0 and p.stdout.strip() == ""
 
 
