@@ -491,8 +491,6 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_frame
-        del eng
-        torch.cuda.empty_cache()
         cf, cpu_model = cpu_pass(args)
         t0 = time.perf_counter()
         cf.run_linear(cpu_model.combo_factors)

@@ -77,6 +77,9 @@ SIGNATURES = {
     "fers_b200_chol_set_variant": (_i, [_i]),
     "fers_b200_chol_set_outer": (_i, [_i, _i]),
     "fers_b200_chol_profile": (_i, [_dp, _i]),
+    "fers_b200_chol_set_ozaki": (_i, [_i, _i]),
+    "fers_b200_oz_syrk_work_bytes": (_sz, [_i, _i, _i]),
+    "fers_b200_oz_syrk": (_i, [_vp, C.c_longlong, _vp, C.c_longlong, _i, _i, _i, _vp, _sz, _vp]),
 }
 
 

@@ -7,6 +7,7 @@
 // node coordinates; every tree node ("front") owns a set of nodes and a boundary (the later-eliminated
 // nodes its Schur complement touches).
 #pragma once
+#include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -67,5 +68,9 @@ struct CholPlanHost {
     size_t off_fronts = 0, off_nodes = 0, off_child = 0, off_inv_off = 0, off_inv = 0, off_level_fronts = 0,
            off_kscatter = 0, off_pos = 0, index_bytes = 0;
 };
+
+// fp64-equivalent Schur update on the int8 tensor cores (ozaki_syrk.cu): C (m2 x m2, lower) -= A A^T, A m2 x k1
+size_t oz_work_bytes(int m2, int k1, int S);
+int oz_syrk(const double* A, long long lda, double* C, long long ldc, int m2, int k1, int S, void* work, cudaStream_t st);
 
 }  // namespace fers

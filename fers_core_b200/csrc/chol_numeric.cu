@@ -820,6 +820,11 @@ static LookaheadState g_lookahead[MAX_DEVICES];
 // per-launch profiling (fers_b200_chol_set_profile) keeps process-wide state: one profiled call at a time
 static std::mutex g_profile_mutex;
 static int g_chol_profile_on = 0;      // 0 off, 1 every kernel class, 2 Schur-update spans + totals only
+// Schur updates of the upper tree levels on the int8 tensor cores (ozaki_syrk.cu): digit planes per operand (0 = off,
+// 6..8; 8 = fp64 grade) and the smallest own-column count of a level that takes that path.  FERS_CHOL_OZAKI /
+// FERS_CHOL_OZAKI_MIN_K / fers_b200_chol_set_ozaki.
+static int g_chol_ozaki = getenv("FERS_CHOL_OZAKI") ? atoi(getenv("FERS_CHOL_OZAKI")) : 8;
+static int g_chol_ozaki_min_k = getenv("FERS_CHOL_OZAKI_MIN_K") ? atoi(getenv("FERS_CHOL_OZAKI_MIN_K")) : 1024;
 
 struct EventPool {
     std::vector<cudaEvent_t> ev;
@@ -1068,7 +1073,31 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
         }
         if (side_pending) { FERS_CK(cudaStreamWaitEvent(st, ev_side, 0)); side_pending = false; }
         const int max_m2 = max_m;   // upper bound on 6 * n2
-        if (l + 1 < P.n_levels) {
+        // levels whose fronts all have many own columns: every front on its own through the int8 tensor-core kernel (the
+        // digit planes live in the children's Schur arena, free since this level's extend-add)
+        bool ozaki = false;
+        if (l + 1 < P.n_levels && g_chol_ozaki >= 5 && nf <= 64) {
+            ozaki = true;
+            const size_t room = (size_t)P.schur_doubles[(l & 1) ^ 1] * 8;
+            for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; ++q) {
+                const FrontDev& f = P.fronts[P.level_fronts[q]];
+                if (6 * f.n1 < g_chol_ozaki_min_k || 6 * f.n1 >= 65536 || 6 * f.n2 < 1024 ||
+                    oz_work_bytes(6 * f.n2, 6 * f.n1, g_chol_ozaki) > room)
+                    ozaki = false;
+            }
+        }
+        if (ozaki) {
+            e0 = span_begin(5);
+            for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; ++q) {
+                const FrontDev& f = P.fronts[P.level_fronts[q]];
+                const int k1 = 6 * f.n1, m2 = 6 * f.n2, m = k1 + m2;
+                if (oz_syrk(factor + f.panel_off + k1, m, L.schur_cur + f.schur_off, m2, m2, k1, g_chol_ozaki,
+                            arena[(l & 1) ^ 1], st))
+                    return 1;
+                launches += 3;
+            }
+            span_end(5, e0);
+        } else if (l + 1 < P.n_levels) {
             e0 = span_begin(5);
             if (g_chol_variant & 2) {
                 dim3 grid(cdiv(max_m2, G88::BM), cdiv(max_m2, G88::BN), nf);
@@ -1310,6 +1339,14 @@ int fers_b200_chol_set_outer(int steps, int group) {
     FERS_REQUIRE(group >= 1 && group <= 64, "chol_set_outer: 1..64 outer blocks per group");
     g_chol_outer = steps;
     g_chol_group = group;
+    return 0;
+}
+
+int fers_b200_chol_set_ozaki(int slices, int min_k) {
+    FERS_REQUIRE(slices == 0 || (slices >= 5 && slices <= 8), "chol_set_ozaki: slices 0 (off) or 5..8");
+    FERS_REQUIRE(min_k >= 64, "chol_set_ozaki: min_k >= 64");
+    g_chol_ozaki = slices;
+    g_chol_ozaki_min_k = min_k;
     return 0;
 }
 

@@ -1,0 +1,385 @@
+// ozaki_syrk.cu -- fp64 Schur update F22 -= L21 L21^T of the multifrontal Cholesky on the 5th-generation tensor cores
+// (tcgen05.mma kind::i8, int32 accumulators in TMEM) by integer slicing of the fp64 operand (Ozaki scheme I).
+//
+// tcgen05 has no fp64 kind; the fp64 tensor path of sm_100a is mma.sync (DMMA), 37 TFLOP/s.  The int8 path runs at more
+// than a hundred times that rate, so a product of fp64 matrices split into S signed 7-bit digit planes, with the S(S+1)/2
+// significant digit-plane products formed exactly in int32, is an fp64-equivalent GEMM whose accuracy is set by S:
+//
+//   row i of A = L21:   a_ik = 2^E_i * sum_{p<S} q_p[i,k] 2^(-6-7p),   q_p in [-64, 64],   2^E_i > max_k |a_ik|
+//   (A A^T)_ij = 2^(E_i+E_j) * sum_{d<S} 2^(-12-7d) * ( sum_{p+q=d} Q_p Q_q^T )_ij  +  O(S 2^(-6-7S)) |a_i||a_j|
+//
+// Every bracket is an int8 x int8 -> int32 GEMM chain accumulated in ONE TMEM accumulator per digit-plane diagonal d
+// (exact: |q_p q_q| <= 2^12, (d+1) K 2^12 < 2^31 for K < 65 536).  S = 8 carries 55 bits (fp64 grade), S = 7 48 bits.
+//
+// Kernels:
+//   k_oz_rowscale   E_i per row of L21 (exponent of the row maximum)
+//   k_oz_split      fp64 -> S int8 digit planes, written in the shared-memory image the tensor cores read (K-major core
+//                   matrices, 8 rows x 16 B), so that ONE bulk copy (cp.async.bulk, TMA engine) per plane and K-chunk
+//                   brings a whole operand tile; no tensor maps, any front shape
+//   k_oz_syrk       persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane,
+//                   tcgen05.mma.cta_group::1.kind::i8, 128 x 64 x 32 per instruction), warps 2-5 = epilogue
+//                   (tcgen05.ld, int32 -> fp64, scaling, C -= ...).  Ring of shared-memory stages with full / empty
+//                   mbarriers, tcgen05.commit releases a stage when the MMAs that read it have retired.
+//
+// Reference row: SURVEY.md 8a A10 (the factorisation the reference describes at fers_core/types/pydantic_models.py:1216-1219).
+#include <algorithm>
+
+#include "chol.cuh"
+#include "common.cuh"
+
+namespace fers {
+
+constexpr int OZ_M = 128;                 // rows of an output tile (TMEM lanes)
+constexpr int OZ_N = 64;                  // columns of an output tile (TMEM columns per accumulator)
+constexpr int OZ_KC = 64;                 // K bytes per shared-memory stage (two MMAs of K = 32 per digit-plane pair)
+constexpr int OZ_MAX_S = 8;               // digit planes (8 accumulators x 64 columns = all 512 TMEM columns)
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_BAND = 12;               // row blocks per band of the tile order (L2 reuse of the operand tiles)
+constexpr uint32_t OZ_SPIN_LIMIT = 1u << 28;   // a barrier that never completes traps instead of hanging the device
+
+__host__ __device__ inline size_t oz_stage_bytes(int S) { return (size_t)S * (OZ_M + OZ_N) * OZ_KC; }
+__host__ __device__ inline int oz_stages(int S) { return (int)((200 * 1024) / oz_stage_bytes(S)); }
+
+// digit planes of one front: plane p at p * plane_bytes; inside a plane [k chunk][8-row group][16-byte K piece][8 rows][16 B]
+struct OzFront {
+    const double* A;        // L21: m2 x k1, column-major, leading dimension lda
+    double* C;              // F22: m2 x m2, column-major, leading dimension ldc (lower triangle)
+    int8_t* planes;
+    double* rowscale;       // [m2_pad] 2^E_i
+    long long lda, ldc;
+    int m2, k1;
+    int m2_pad, k1_pad;     // multiples of OZ_M / OZ_KC
+};
+
+__host__ __device__ inline size_t oz_plane_bytes(int m2_pad, int k1_pad) { return (size_t)m2_pad * k1_pad; }
+
+// ---- row exponents ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_oz_rowscale(OzFront f) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= f.m2_pad) return;
+    double mx = 0.0;
+    if (r < f.m2)
+        for (int k = 0; k < f.k1; ++k) mx = fmax(mx, fabs(f.A[(size_t)k * f.lda + r]));
+    int e = 0;
+    if (mx > 0.0) { frexp(mx, &e); }           // mx = m 2^e, 0.5 <= m < 1  ->  |a| < 2^e
+    f.rowscale[r] = ldexp(1.0, e);
+}
+
+// ---- fp64 -> digit planes ---------------------------------------------------------------------------------------------------
+// thread = (row, 16-byte K piece): reads 16 doubles of its row (coalesced across the rows of a warp), writes 16 B per plane
+template <int S>
+__global__ void __launch_bounds__(256)
+k_oz_split(OzFront f) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    const int piece = blockIdx.y;                       // 16 K values
+    if (r >= f.m2_pad) return;
+    const int k0 = piece * 16;
+    const double inv = (r < f.m2) ? 64.0 / f.rowscale[r] : 0.0;
+    uint32_t w[S][4];
+#pragma unroll
+    for (int p = 0; p < S; ++p) w[p][0] = w[p][1] = w[p][2] = w[p][3] = 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int k = k0 + j;
+        double t = 0.0;
+        if (r < f.m2 && k < f.k1) t = f.A[(size_t)k * f.lda + r] * inv;       // |t| < 64, exact scaling
+#pragma unroll
+        for (int p = 0; p < S; ++p) {
+            const double q = rint(t);
+            t = (t - q) * 128.0;                                              // exact: |t - q| <= 1/2
+            w[p][j >> 2] |= ((uint32_t)(int)q & 0xffu) << (8 * (j & 3));
+        }
+    }
+    const size_t plane = oz_plane_bytes(f.m2_pad, f.k1_pad);
+    const int chunk = k0 / OZ_KC, kc16 = (k0 % OZ_KC) / 16;
+    const size_t off = (size_t)chunk * f.m2_pad * OZ_KC + (size_t)(r >> 3) * (OZ_KC * 8) + (size_t)kc16 * 128 + (size_t)(r & 7) * 16;
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+        *reinterpret_cast<uint4*>(f.planes + p * plane + off) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+}
+
+// ---- PTX helpers ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t oz_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void oz_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > OZ_SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void oz_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void oz_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void oz_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void oz_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void oz_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 contiguous bytes);
+// LBO = distance of the two core matrices an MMA spans along K, SBO = distance of consecutive 8-row groups
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version of sm_100
+    return d;                                     // base offset 0, layout type 0 (no swizzle)
+}
+// instruction descriptor of kind::i8: D = S32, A = B = signed 8 bit, both K-major, M = 128, N = 64
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(OZ_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void oz_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// tile t of the lower triangle in band order: bands of OZ_BAND row blocks; inside a band column block by column block,
+// so that the ~148 tiles in flight share about a dozen row-block and a dozen column-block operand streams in L2
+__device__ __forceinline__ bool oz_tile(int t, int nbi, int nbj, int& bi, int& bj) {
+    for (int b0 = 0; b0 < nbi; b0 += OZ_BAND) {
+        const int b1 = min(b0 + OZ_BAND, nbi);
+        // column block bj is present in row block r when bj <= 2 r + 1
+        const int maxbj = min(2 * (b1 - 1) + 1, nbj - 1);
+        for (int j = 0; j <= maxbj; ++j) {
+            const int rmin = max(b0, j / 2);                     // smallest r with 2 r + 1 >= j
+            const int cnt = b1 - rmin;
+            if (cnt <= 0) continue;
+            if (t < cnt) { bi = rmin + t; bj = j; return true; }
+            t -= cnt;
+        }
+    }
+    return false;
+}
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+k_oz_syrk(OzFront f, int n_tiles) {
+    extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
+    constexpr int STAGES = (200 * 1024) / (S * (OZ_M + OZ_N) * OZ_KC);
+    constexpr uint32_t STAGE_BYTES = S * (OZ_M + OZ_N) * OZ_KC;
+    constexpr uint32_t A_BYTES = OZ_M * OZ_KC, B_BYTES = OZ_N * OZ_KC;
+    static_assert(STAGES >= 2, "ring too shallow");
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 2];
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ring = oz_smem(oz_smem_raw);
+    const uint32_t bar_full = oz_smem(&bars[0]), bar_empty = oz_smem(&bars[STAGES]);
+    const uint32_t bar_acc_full = oz_smem(&bars[2 * STAGES]), bar_acc_empty = oz_smem(&bars[2 * STAGES + 1]);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { oz_mbar_init(bar_full + 8u * i, 1); oz_mbar_init(bar_empty + 8u * i, 1); }
+        oz_mbar_init(bar_acc_full, 1);
+        oz_mbar_init(bar_acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                    // the MMA warp owns the tensor memory: all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem(&s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    oz_fence_before();
+    __syncthreads();
+    oz_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int nbi = f.m2_pad / OZ_M, nbj = (f.m2 + OZ_N - 1) / OZ_N;
+    const int nkc = f.k1_pad / OZ_KC;
+    const size_t plane = oz_plane_bytes(f.m2_pad, f.k1_pad);
+    const size_t chunk_bytes = (size_t)f.m2_pad * OZ_KC;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                int bi, bj;
+                if (!oz_tile(t, nbi, nbj, bi, bj)) break;
+                const int8_t* a0 = f.planes + (size_t)bi * OZ_M * OZ_KC;
+                const int8_t* b0 = f.planes + (size_t)bj * OZ_N * OZ_KC;
+                for (int c = 0; c < nkc; ++c, ++it) {
+                    const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
+                    oz_mbar_wait(bar_empty + 8u * st, ph ^ 1u);
+                    const uint32_t full = bar_full + 8u * st;
+                    oz_mbar_expect_tx(full, STAGE_BYTES);
+                    const uint32_t dst = ring + st * STAGE_BYTES;
+#pragma unroll
+                    for (int p = 0; p < S; ++p) {
+                        oz_bulk_g2s(dst + p * A_BYTES, a0 + p * plane + (size_t)c * chunk_bytes, A_BYTES, full);
+                        oz_bulk_g2s(dst + S * A_BYTES + p * B_BYTES, b0 + p * plane + (size_t)c * chunk_bytes, B_BYTES, full);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t it = 0, tile_i = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+                int bi, bj;
+                if (!oz_tile(t, nbi, nbj, bi, bj)) break;
+                oz_mbar_wait(bar_acc_empty, (tile_i & 1u) ^ 1u);
+                oz_fence_after();
+                for (int c = 0; c < nkc; ++c, ++it) {
+                    const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
+                    oz_mbar_wait(bar_full + 8u * st, ph);
+                    oz_fence_after();
+                    const uint32_t sa = ring + st * STAGE_BYTES, sb = sa + S * A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < OZ_KC / 32; ++kk) {
+#pragma unroll
+                        for (int p = 0; p < S; ++p) {
+                            const uint64_t da = oz_desc(sa + p * A_BYTES + kk * 256, 128, OZ_KC * 8);
+#pragma unroll
+                            for (int q = 0; q + p < S; ++q) {
+                                const uint64_t db = oz_desc(sb + q * B_BYTES + kk * 256, 128, OZ_KC * 8);
+                                // the first product of a digit-plane diagonal d = p + q overwrites its accumulator
+                                const uint32_t acc = (c > 0 || kk > 0 || p > 0) ? 1u : 0u;
+                                oz_mma(tmem + (uint32_t)(p + q) * OZ_N, da, db, acc);
+                            }
+                        }
+                    }
+                    oz_commit(bar_empty + 8u * st);          // the stage is free once these MMAs have read it
+                }
+                oz_commit(bar_acc_full);                     // all accumulators of the tile are final
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> fp64 -> C -= 2^(E_i + E_j) sum_d 2^(-12 - 7 d) acc_d =====
+        const int quad = warp & 3;                           // the TMEM lanes this warp may read: 32 quad .. 32 quad + 31
+        uint32_t tile_i = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+            int bi, bj;
+            if (!oz_tile(t, nbi, nbj, bi, bj)) break;
+            oz_mbar_wait(bar_acc_full, tile_i & 1u);
+            oz_fence_after();
+            const int r = bi * OZ_M + 32 * quad + lane;
+            const int c0 = bj * OZ_N;
+            const double rs = f.rowscale[min(r, f.m2_pad - 1)];
+            const uint32_t lane_addr = tmem + ((uint32_t)(32 * quad) << 16);
+#pragma unroll 1
+            for (int cb = 0; cb < OZ_N; cb += 8) {
+                double sum[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sum[j] = 0.0;
+                double wgt = ldexp(1.0, -12 - 7 * (S - 1));
+#pragma unroll
+                for (int d = S - 1; d >= 0; --d) {           // smallest weights first
+                    int v[8];
+                    oz_tmem_ld8(lane_addr + (uint32_t)(d * OZ_N + cb), v);
+                    oz_tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sum[j] = fma((double)v[j], wgt, sum[j]);
+                    wgt *= 128.0;
+                }
+                if (r < f.m2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = c0 + cb + j;
+                        if (col <= r && col < f.m2) {
+                            double* dst = f.C + (size_t)col * f.ldc + r;
+                            *dst -= sum[j] * rs * f.rowscale[col];
+                        }
+                    }
+                }
+            }
+            oz_fence_before();
+            __syncwarp();
+            if (lane == 0) oz_mbar_arrive(bar_acc_empty);
+        }
+    }
+    oz_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+static int oz_tile_count(int m2, int m2_pad) {
+    const int nbi = m2_pad / OZ_M, nbj = (m2 + OZ_N - 1) / OZ_N;
+    long long n = 0;
+    for (int r = 0; r < nbi; ++r) n += std::min(2 * r + 2, nbj);
+    return (int)n;
+}
+
+size_t oz_work_bytes(int m2, int k1, int S) {
+    const int m2_pad = (m2 + OZ_M - 1) / OZ_M * OZ_M, k1_pad = (k1 + OZ_KC - 1) / OZ_KC * OZ_KC;
+    return align_up((size_t)S * oz_plane_bytes(m2_pad, k1_pad)) + align_up((size_t)m2_pad * sizeof(double)) + 256;
+}
+
+template <int S>
+static int oz_launch(OzFront f, cudaStream_t st) {
+    static PerDeviceOnce once;
+    const size_t smem = (size_t)oz_stages(S) * oz_stage_bytes(S);
+    if (once.needed()) {
+        FERS_CK(cudaFuncSetAttribute(k_oz_syrk<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        once.done();
+    }
+    k_oz_rowscale<<<(f.m2_pad + 255) / 256, 256, 0, st>>>(f);
+    dim3 grid((f.m2_pad + 255) / 256, f.k1_pad / 16);
+    k_oz_split<S><<<grid, 256, 0, st>>>(f);
+    const int n_tiles = oz_tile_count(f.m2, f.m2_pad);
+    const int ctas = std::min(n_tiles, sm_count());
+    k_oz_syrk<S><<<ctas, OZ_THREADS, smem, st>>>(f, n_tiles);
+    FERS_LAUNCH_CHECK();
+    count_launches(3);
+    return 0;
+}
+
+// C (m2 x m2, lower) -= A A^T with A m2 x k1, both column-major fp64; `work` holds the digit planes and row scales
+int oz_syrk(const double* A, long long lda, double* C, long long ldc, int m2, int k1, int S, void* work, cudaStream_t st) {
+    OzFront f;
+    f.A = A; f.C = C; f.lda = lda; f.ldc = ldc; f.m2 = m2; f.k1 = k1;
+    f.m2_pad = (m2 + OZ_M - 1) / OZ_M * OZ_M;
+    f.k1_pad = (k1 + OZ_KC - 1) / OZ_KC * OZ_KC;
+    f.planes = static_cast<int8_t*>(work);
+    f.rowscale = reinterpret_cast<double*>(static_cast<uint8_t*>(work) + align_up((size_t)S * oz_plane_bytes(f.m2_pad, f.k1_pad)));
+    switch (S) {
+        case 5: return oz_launch<5>(f, st);
+        case 6: return oz_launch<6>(f, st);
+        case 7: return oz_launch<7>(f, st);
+        case 8: return oz_launch<8>(f, st);
+    }
+    set_error("oz_syrk: 5 <= slices <= 8");
+    return 2;
+}
+
+}  // namespace fers
+
+extern "C" {
+
+size_t fers_b200_oz_syrk_work_bytes(int m2, int k1, int slices) { return fers::oz_work_bytes(m2, k1, slices); }
+
+int fers_b200_oz_syrk(const double* A, long long lda, double* C, long long ldc, int m2, int k1, int slices, void* work,
+                      size_t work_bytes, void* stream) {
+    FERS_REQUIRE(A && C && work && m2 > 0 && k1 > 0 && lda >= m2 && ldc >= m2, "oz_syrk: bad arguments");
+    FERS_REQUIRE(k1 < 65536, "oz_syrk: K must stay below 65 536 for exact int32 accumulation");
+    FERS_REQUIRE(work_bytes >= fers::oz_work_bytes(m2, k1, slices), "oz_syrk: workspace too small");
+    return fers::oz_syrk(A, lda, C, ldc, m2, k1, slices, work, fers::as_stream(stream));
+}
+
+}  // extern "C"
