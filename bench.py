@@ -360,13 +360,26 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         dmma, dfma = C.c_double(), C.c_double()
         _lib.check(lib.fers_b200_fp64_peak(50.0, C.byref(dmma), C.byref(dfma), _lib.ptr(scratch), scratch.numel(),
                                            eng.stream), "fp64_peak")
-        fr = eng._chol.plan.export()["fronts"]
+        ex = eng._chol.plan.export()
+        fr = ex["fronts"]
         k1 = 6.0 * fr["n1"].astype(np.float64)
         m2 = 6.0 * fr["n2"].astype(np.float64)
-        cls_flops = {"potrf": float((k1 ** 3 / 3).sum()), "panel": float((k1 * k1 * m2).sum()),
-                     "syrk": float((k1 * m2 * (m2 + 1)).sum())}
         n_fac = max(timed_prof["n_factor"], 1.0)
+        # which fronts' Schur updates went through the int8 tensor-core kernel: the library's rule (chol_numeric.cu), level by level
+        oz_S, oz_min_k = int(timed_prof["oz_setting"]) // 100000, int(timed_prof["oz_setting"]) % 100000
+        on_oz = np.zeros(len(fr), bool)
+        lp, lf = ex["level_ptr"], ex["level_fronts"]
+        for l in range(len(lp) - 2):                      # the root level has no Schur complement
+            ids = lf[lp[l]:lp[l + 1]]
+            if oz_S >= 4 and 0 < len(ids) <= 64 and (k1[ids] >= oz_min_k).all() and (m2[ids] >= 1024).all():
+                on_oz[ids] = True
+        if abs(on_oz.sum() * n_fac - timed_prof["n_oz_fronts"]) > 0.5:
+            raise RuntimeError(f"bench: {timed_prof['n_oz_fronts'] / n_fac} fronts took the int8 path, expected {on_oz.sum()}")
+        syrk_fl = k1 * m2 * (m2 + 1)
+        cls_flops = {"potrf": float((k1 ** 3 / 3).sum()), "panel": float((k1 * k1 * m2).sum()),
+                     "syrk": float(syrk_fl[~on_oz].sum()), "syrk_int8": float(syrk_fl[on_oz].sum())}
         syrk_ms_per_fac = timed_prof["syrk_sum_ms"] / n_fac
+        oz_ms_per_fac = timed_prof["oz_sum_ms"] / n_fac
         syrk_launches = max(timed_prof["n_syrk_launches"], 1.0)
         tf = cls_flops["syrk"] / (syrk_ms_per_fac * 1e-3) / 1e12 if syrk_ms_per_fac > 0 else 0.0
         # one more step with events around every kernel class (outside the timed region) for the breakdown
@@ -374,52 +387,83 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         eng.run_linear(factors)
         full = eng._chol.profile()
         lib.fers_b200_chol_set_profile(0)
-        breakdown = {k: full[k] for k in ("init_ms", "scatter_ms", "potrf_ms", "trsm_ms", "update_ms", "syrk_ms",
+        breakdown = {k: full[k] for k in ("init_ms", "scatter_ms", "potrf_ms", "trsm_ms", "update_ms", "syrk_ms", "oz_ms",
                                            "factor_ms", "solve_ms", "factor_launches", "solve_launches")}
         upd_flops = cls_flops["panel"] + cls_flops["potrf"]
-        kern.insert(0, {"kernel": "k_syrk<128x64 DMMA> (Schur complement F22 -= L21 L21^T)", "bound": "tensor",
-                        "algorithmic_flops": cls_flops["syrk"], "ms": syrk_ms_per_fac, "TFLOP/s": tf,
-                        "frac": tf / dmma.value if dmma.value > 0 else None,
-                        "share_of_step": syrk_ms_per_fac / ms_step})
+        pairs = oz_S * (oz_S + 1) // 2
+        int8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        if oz_ms_per_fac > 0:
+            tf_oz = cls_flops["syrk_int8"] / (oz_ms_per_fac * 1e-3) / 1e12
+            kern.insert(0, {"kernel": f"k_oz_syrk<{oz_S} digit planes> + k_oz_split + k_oz_rowscale (Schur complements of the upper tree "
+                                      f"levels, own columns >= {oz_min_k}: tcgen05.mma kind::i8, {pairs} digit-plane products per fp64 product)",
+                            "bound": "tensor", "algorithmic_flops_fp64": cls_flops["syrk_int8"],
+                            "algorithmic_int8_ops": pairs * cls_flops["syrk_int8"], "ms": oz_ms_per_fac,
+                            "fp64_equivalent_TFLOP/s": tf_oz, "vs_fp64_tensor_pipe_peak": tf_oz / dmma.value if dmma.value > 0 else None,
+                            "int8_TOP/s": pairs * tf_oz, "frac": pairs * tf_oz / int8_peak, "fronts_per_factorisation": int(on_oz.sum()),
+                            "share_of_step": oz_ms_per_fac / ms_step})
+        kern.insert(1 if oz_ms_per_fac > 0 else 0,
+                    {"kernel": "k_syrk<128x64 DMMA> (Schur complements of the other levels, F22 -= L21 L21^T)", "bound": "tensor",
+                     "algorithmic_flops": cls_flops["syrk"], "ms": syrk_ms_per_fac, "TFLOP/s": tf,
+                     "frac": tf / dmma.value if dmma.value > 0 else None,
+                     "share_of_step": syrk_ms_per_fac / ms_step})
         um = full["update_ms"] + full["trsm_ms"] + full["potrf_ms"]
         # with look-ahead (the timed steps) the panel chain overlaps the trailing updates: effective panel time =
         # timed factorisation - timed Schur updates - extend-add / scatter of the profiled step
-        um_eff = timed_prof["factor_sum_ms"] / n_fac - syrk_ms_per_fac - full["init_ms"] - full["scatter_ms"]
-        kern.insert(1, {"kernel": "panel factorisation (k_potrf_inv + k_trsm + k_update<128x64 DMMA>)", "bound": "tensor",
-                        "algorithmic_flops": upd_flops, "ms": um, "TFLOP/s": upd_flops / (um * 1e-3) / 1e12 if um > 0 else 0.0,
-                        "frac": upd_flops / (um * 1e-3) / 1e12 / dmma.value if um > 0 and dmma.value > 0 else None,
-                        "share_of_step": um_eff / ms_step, "ms_effective_with_lookahead": um_eff,
-                        "TFLOP/s_effective_with_lookahead": upd_flops / (um_eff * 1e-3) / 1e12 if um_eff > 0 else None,
-                        "timing": "profiled extra step (events around every launch, look-ahead off: the timed steps overlap "
-                                  "the panel chain with the trailing updates)"})
+        um_eff = timed_prof["factor_sum_ms"] / n_fac - syrk_ms_per_fac - oz_ms_per_fac - full["init_ms"] - full["scatter_ms"]
+        kern.insert(2 if oz_ms_per_fac > 0 else 1,
+                    {"kernel": "panel factorisation (k_potrf_inv + k_trsm + k_update<128x64 DMMA>)", "bound": "tensor",
+                     "algorithmic_flops": upd_flops, "ms": um, "TFLOP/s": upd_flops / (um * 1e-3) / 1e12 if um > 0 else 0.0,
+                     "frac": upd_flops / (um * 1e-3) / 1e12 / dmma.value if um > 0 and dmma.value > 0 else None,
+                     "share_of_step": um_eff / ms_step, "ms_effective_with_lookahead": um_eff,
+                     "TFLOP/s_effective_with_lookahead": upd_flops / (um_eff * 1e-3) / 1e12 if um_eff > 0 else None,
+                     "timing": "profiled extra step (events around every launch, look-ahead off: the timed steps overlap "
+                               "the panel chain with the trailing updates)"})
+        dom_int8 = oz_ms_per_fac > 0 and oz_ms_per_fac >= syrk_ms_per_fac
+        kernel_id = f"k_oz_syrk<S={oz_S}>" if dom_int8 else SYRK_KERNEL_ID
         # DRAM traffic comes from a committed ncu --set full capture, not from this run: it is reported only when the
         # capture was taken on the same problem and the same Schur-update kernel (else null until re-captured)
         traffic, traffic_note = None, "no matching ncu --set full capture under profiles/ (captured value, never measured live)"
         for cap in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_syrk_ncu_summary.json")), reverse=True):
             summ = json.load(open(cap))
             cc = summ.get("captured_config") or {}
-            if cc.get("dof") == n_dof and cc.get("nrhs") == nr and cc.get("kernel_id") == SYRK_KERNEL_ID:
+            if cc.get("dof") == n_dof and cc.get("nrhs") == nr and cc.get("kernel_id") == kernel_id:
                 traffic = float(summ["dram_bytes_per_launch"])
                 traffic_note = (f"CAPTURED, not live: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
-                                f"{summ['launches_per_factorisation']} Schur-update launches of one factorisation, divided by their "
+                                f"{summ['launches_per_factorisation']} launches of this kernel in one factorisation, divided by their "
                                 f"number (per launch, like `achieved`); {os.path.relpath(cap, ROOT)} (commit {cc.get('commit')}) has every launch")
                 break
-        roofline = {"bound": "tensor", "kernel": kern[0]["kernel"], "achieved": tf, "peak": dmma.value, "unit": "TFLOP/s",
-                    "frac": kern[0]["frac"], "traffic": traffic, "traffic_note": traffic_note,
-                    "peak_source": "fp64 tensor pipe (DMMA.8x8x4) measured live by fers_b200_fp64_peak on this device, "
-                                   f">=50 ms bursts (DFMA vector pipe: {dfma.value:.2f} TFLOP/s); MEASURED_PEAKS.json holds "
-                                   "no fp64 figure",
-                    "algorithmic_flops_per_launch": cls_flops["syrk"] / (syrk_launches / n_fac),
-                    "ms_per_launch": timed_prof["syrk_sum_ms"] / syrk_launches,
-                    "launches_per_step": syrk_launches / n_fac,
-                    "timing": "CUDA events on the launch stream around every Schur-update launch of the "
-                              f"{int(n_fac)} factorisations inside the timed region",
-                    "factor_tflops_all_kernels": float(sum(cls_flops.values())) / (timed_prof["factor_sum_ms"] / n_fac * 1e-3) / 1e12,
-                    "factor_ms": timed_prof["factor_sum_ms"] / n_fac,
-                    "substitution_ms": timed_prof["solve_sum_ms"] / max(timed_prof["n_solve"], 1.0),
-                    "substitutions_per_step": timed_prof["n_solve"] / n_fac,
-                    "class_ms_profiled_step": breakdown, "hbm_peak": peak, "kernels": kern}
-        solver_cfg = {"solver": "sparse multifrontal Cholesky (nested dissection, fp64 DMMA tile GEMMs) + "
+        common = {"traffic": traffic, "traffic_note": traffic_note,
+                  "factor_tflops_all_kernels": float(sum(cls_flops.values())) / (timed_prof["factor_sum_ms"] / n_fac * 1e-3) / 1e12,
+                  "factor_ms": timed_prof["factor_sum_ms"] / n_fac,
+                  "substitution_ms": timed_prof["solve_sum_ms"] / max(timed_prof["n_solve"], 1.0),
+                  "substitutions_per_step": timed_prof["n_solve"] / n_fac,
+                  "fp64_tensor_pipe_peak_tflops": dmma.value, "fp64_vector_pipe_peak_tflops": dfma.value,
+                  "class_ms_profiled_step": breakdown, "hbm_peak": peak, "kernels": kern}
+        if dom_int8:
+            n_oz = max(timed_prof["n_oz_fronts"], 1.0)
+            roofline = {"bound": "tensor", "kernel": kern[0]["kernel"], "achieved": kern[0]["int8_TOP/s"], "peak": int8_peak,
+                        "unit": "TOP/s", "frac": kern[0]["frac"],
+                        "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (" + peaks["_source"] + "): kind::i8 issues 8192 MAC/clk/SM, twice "
+                                       "kind::f16; the file holds no int8 figure (nominal dense int8: 4500 TOP/s)",
+                        "fp64_equivalent_tflops": kern[0]["fp64_equivalent_TFLOP/s"],
+                        "vs_fp64_tensor_pipe_peak": kern[0]["vs_fp64_tensor_pipe_peak"],
+                        "algorithmic_ops_per_launch": pairs * cls_flops["syrk_int8"] / (n_oz / n_fac),
+                        "ms_per_launch": timed_prof["oz_sum_ms"] / n_oz, "launches_per_step": n_oz / n_fac,
+                        "launch": "one front: k_oz_rowscale + k_oz_split + k_oz_syrk, timed together",
+                        "timing": "CUDA events on the launch stream around the int8 Schur updates of every tree level of the "
+                                  f"{int(n_fac)} factorisations inside the timed region", **common}
+        else:
+            roofline = {"bound": "tensor", "kernel": kern[0]["kernel"], "achieved": tf, "peak": dmma.value, "unit": "TFLOP/s",
+                        "frac": kern[0]["frac"],
+                        "peak_source": "fp64 tensor pipe (DMMA.8x8x4) measured live by fers_b200_fp64_peak on this device, "
+                                       f">=50 ms bursts (DFMA vector pipe: {dfma.value:.2f} TFLOP/s); MEASURED_PEAKS.json holds "
+                                       "no fp64 figure",
+                        "algorithmic_flops_per_launch": cls_flops["syrk"] / (syrk_launches / n_fac),
+                        "ms_per_launch": timed_prof["syrk_sum_ms"] / syrk_launches, "launches_per_step": syrk_launches / n_fac,
+                        "timing": "CUDA events on the launch stream around every Schur-update launch of the "
+                                  f"{int(n_fac)} factorisations inside the timed region", **common}
+        solver_cfg = {"solver": "sparse multifrontal Cholesky (nested dissection; fp64 DMMA tile GEMMs, Schur complements of the "
+                                "upper levels as int8 digit-plane products on tcgen05) + "
                                 f"residual check, iterative refinement while rel. residual > {engine.CHOL_REFINE_TOL:g} "
                                 f"({refine_passes} pass(es) taken), 64 RHS",
                       "fronts": int(len(fr)), "factor_gb": eng._chol.plan.info.factor_doubles * 8 / 1e9,
@@ -518,9 +562,75 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         dist.destroy_process_group()
 
 
+CFG5_WORKLOAD = ("configs[4] batch of {n} parametric 3D frames per GPU (2x2 bays x 4 storeys, 45 nodes, 270 DOF each), sway "
+                 "imperfection 1/200, second-order P-Delta (consistent K_g), tolerance 1e-8")
+
+
+def _cfg5_cpu_worker(job):
+    """Oracle (numpy / scipy) on frames [i0, i1) of the batch drawn with `seed`; returns seconds of pure analysis."""
+    i0, i1, seed, total = job
+    from fers_core_b200 import synth
+    from oracle import fers_oracle
+    params = synth.portal_params(total, seed)[i0:i1]
+    t0 = time.perf_counter()
+    for p in params:
+        fers_oracle.analyze(synth.portal_frame(tolerance=1e-8, **p), detail=False)
+    return time.perf_counter() - t0
+
+
+def cfg5_cpu_sample(frames: int, seed: int, n_sample: int):
+    """The CPU path (oracle, one frame at a time as the reference engine would) on the first n_sample frames of the batch,
+    spread over every host core.  Returns (DOF*combos/s, seconds, cores, sample description)."""
+    import multiprocessing as mp
+    from fers_core_b200 import synth
+    cores = os.cpu_count() or 1
+    n_sample = max(1, min(n_sample, frames))
+    chunk = (n_sample + cores - 1) // cores
+    jobs = [(i, min(i + chunk, n_sample), seed, frames) for i in range(0, n_sample, chunk)]
+    ctx = mp.get_context("spawn")                   # never fork a process that may hold a CUDA context
+    with ctx.Pool(min(cores, len(jobs))) as pool:
+        pool.map(_cfg5_cpu_worker, [(0, 1, seed, frames)] * min(cores, len(jobs)))       # imports / first-call costs
+        t0 = time.perf_counter()
+        pool.map(_cfg5_cpu_worker, jobs)
+        dt = time.perf_counter() - t0
+    sample = (f"the first {n_sample} of the {frames} frames of the batch, oracle/fers_oracle.py (numpy assembly, dense Cholesky, "
+              f"P-Delta loop, recovery) one frame at a time on {min(cores, len(jobs))} host processes")
+    return n_sample * 6 * synth.PORTAL_NODES / dt, dt, min(cores, len(jobs)), sample
+
+
+def run_cfg5_reference(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    from fers_core_b200 import synth
+    n_sample = int(os.environ.get("FERS_CFG5_CPU_SAMPLE", "256"))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, cores, sample = cfg5_cpu_sample(args.frames, synth.BATCH_SEED, n_sample)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    emit(({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([d for _, d in vals])), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": CFG5_WORKLOAD.format(n=args.frames), "frames_per_gpu": args.frames, "dof_per_frame": 270,
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "host_cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def run_cfg5(args, rank: int, world: int, local_rank: int) -> None:
-    """BASELINE.json configs[4]: batch of parametric 3D frames (45 nodes, 270 DOF each), sway
-    imperfection 1/200, second-order P-Delta (consistent K_g, tolerance 1e-8); frames sharded over GPUs."""
+    """BASELINE.json configs[4]: batch of parametric 3D frames (45 nodes, 270 DOF each), sway imperfection 1/200,
+    second-order P-Delta (consistent K_g, tolerance 1e-8); frames sharded over GPUs, no data-path collective."""
+    # CPU baseline first (rank 0, N = 1): before this process touches CUDA
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from fers_core_b200 import synth as _synth
+        v, dt, cores, sample = cfg5_cpu_sample(args.frames, _synth.BATCH_SEED, int(os.environ.get("FERS_CFG5_CPU_SAMPLE", "256")))
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "host_cores": os.cpu_count() or 1, "kind": "port", "seconds": dt,
+               "sample": sample}
     import torch
     import torch.distributed as dist
     from fers_core_b200 import _lib, engine, synth
@@ -531,31 +641,122 @@ def run_cfg5(args, rank: int, world: int, local_rank: int) -> None:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     big, _ = synth.portal_batch(args.frames, seed=synth.BATCH_SEED + rank)
+    big = pin_model(big)
     units = big.n_dof
-    stats = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident steps: the batch lives on the GPU, one step = one whole P-Delta analysis of every frame -------
+    fb = engine.FrameBatch(big, synth.PORTAL_NODES, dev)
     for _ in range(max(args.warmup, 1)):
-        engine.analyze_frame_batch(big, synth.PORTAL_NODES, dev, stats_out=stats)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
+        rec = fb.solve()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
     l0 = lib.fers_b200_launch_count()
-    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(args.steps):
-        res = engine.analyze_frame_batch(big, synth.PORTAL_NODES, dev, stats_out=stats)
-    torch.cuda.synchronize(dev)
-    dt = fdist.max_over_ranks((time.perf_counter() - t0) / args.steps, dev)
-    summ = fdist.gather_summary(torch.from_numpy(np.abs(res.U[0]).reshape(args.frames, -1).max(axis=1)).to(dev))
+        rec = fb.solve()
+    e1.record()
+    barrier()
+    launches = lib.fers_b200_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = fdist.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    res = fb.results(rec)
+    it_frames = fb.frame_iterations
+    enq = fb.stats["iterations_enqueued"]
+    summ = fdist.gather_summary(rec["U"].view(args.frames, -1).abs().amax(dim=1))       # per-frame max |u| over NVLink
+
+    # ---- kernels on their own (events around dedicated launches) -------------------------------------------------------
+    n, nf = fb.n, fb.nf
+    st = fb.eng.stream
+
+    def timed(fn, pre=None, reps=5):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out = []
+        for _ in range(reps):
+            if pre is not None:
+                pre()
+            a0.record(); fn(); a1.record()
+            torch.cuda.synchronize(dev)
+            out.append(a0.elapsed_time(a1))
+        return float(np.median(out))
+
+    def expand():
+        _lib.check(lib.fers_b200_dense_expand_batched(
+            synth.PORTAL_NODES, nf, _lib.ptr(fb.eng.d_rowptr), _lib.ptr(fb.eng.d_colidx), _lib.ptr(fb.eng.d_vals),
+            _lib.ptr(fb.eng.d_fixed), _lib.ptr(fb.eng.d_ks), _lib.ptr(fb.a), _lib.ptr(fb.flag), st), "dense_expand_batched")
+    chol_ms = timed(lambda: _lib.check(lib.fers_b200_dense_cholesky(n, nf, _lib.ptr(fb.a), _lib.ptr(fb.info_dev), None, st),
+                                       "dense_cholesky"), pre=expand)
+    expand_ms = timed(expand)
+    u_tmp = torch.ones((big.n_dof, 1), dtype=torch.float64, device=dev)
+    solve_ms = timed(lambda: _lib.check(lib.fers_b200_dense_solve(n, 1, nf, _lib.ptr(fb.a), _lib.ptr(u_tmp), st), "dense_solve"))
+    scratch = torch.empty(8 * 1024 * 160, dtype=torch.uint8, device=dev)
+    dmma, dfma = C.c_double(), C.c_double()
+    _lib.check(lib.fers_b200_fp64_peak(50.0, C.byref(dmma), C.byref(dfma), _lib.ptr(scratch), scratch.numel(), st), "fp64_peak")
+    peaks = measured_peaks()
+    chol_flops = nf * (n ** 3 / 3.0 + n * n / 2.0)
+    chol_bytes = 2.0 * nf * n * n * 8
+    n_fact = enq + 1                                            # factorisations per step (linear start + one per iteration)
+    tf = chol_flops / (chol_ms * 1e-3) / 1e12
+    kern = [{"kernel": "k_chol_small (one CTA factorises one 270 x 270 frame matrix in shared-memory panels, DFMA)", "bound": "fp64 vector pipe",
+             "algorithmic_flops": chol_flops, "algorithmic_bytes": chol_bytes, "ms": chol_ms, "TFLOP/s": tf, "frac": tf / dfma.value,
+             "GB/s": chol_bytes / (chol_ms * 1e-3) / 1e9, "frac_of_hbm": chol_bytes / (chol_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]),
+             "launches_per_step": n_fact, "share_of_step": n_fact * chol_ms / ms_step},
+            {"kernel": "k_dense_expand_batched (block-CSR -> dense frame matrices)", "bound": "hbm", "algorithmic_bytes": chol_bytes / 2,
+             "ms": expand_ms, "GB/s": chol_bytes / 2 / (expand_ms * 1e-3) / 1e9,
+             "frac": chol_bytes / 2 / (expand_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]), "launches_per_step": n_fact,
+             "share_of_step": n_fact * expand_ms / ms_step},
+            {"kernel": "k_solve_small1 (forward + backward substitution, one CTA per frame)", "bound": "hbm", "algorithmic_bytes": chol_bytes / 2,
+             "ms": solve_ms, "GB/s": chol_bytes / 2 / (solve_ms * 1e-3) / 1e9,
+             "frac": chol_bytes / 2 / (solve_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]), "launches_per_step": n_fact,
+             "share_of_step": n_fact * solve_ms / ms_step}]
+    roofline = {"bound": "tensor", "kernel": kern[0]["kernel"], "achieved": tf, "peak": dfma.value, "unit": "TFLOP/s", "frac": tf / dfma.value,
+                "traffic": None, "peak_source": "fp64 vector pipe (DFMA) measured live by fers_b200_fp64_peak on this device (the kernel is "
+                "a chain of 270 dependent pivot steps per matrix, latency-bound: neither the fp64 pipe nor HBM is near its limit; "
+                f"fp64 tensor pipe {dmma.value:.1f} TFLOP/s); MEASURED_PEAKS.json holds no fp64 figure",
+                "algorithmic_flops_per_launch": chol_flops, "ms_per_launch": chol_ms, "launches_per_step": n_fact,
+                "timing": "CUDA events around dedicated launches on freshly expanded matrices, median of 5", "kernels": kern}
+
+    # ---- end to end: host arrays in, host arrays out, every step (engine construction, H2D, analysis, D2H) ---------------
+    e2e = None
+    if not args.no_e2e:
+        del fb, rec
+        barrier()
+        ts = []
+        h2d = d2h = 0
+        for _ in range(max(args.steps, 2)):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            fb2 = engine.FrameBatch(big, synth.PORTAL_NODES, dev)
+            out = fb2.results(fb2.solve())
+            torch.cuda.synchronize(dev)
+            ts.append(time.perf_counter() - t0)
+            h2d = fb2.eng.h2d_bytes
+            d2h = sum(getattr(out, f).nbytes for f in ("U", "R", "f_local", "f_global", "u_local"))
+            del fb2
+        te = fdist.max_over_ranks(float(np.median(ts)), dev)
+        e2e = {"value": world * units / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * te,
+               "api": "fers_core_b200.engine.analyze_frame_batch == FrameBatch(model, nodes_per_frame).solve() -> .results() "
+                      "(model upload, pattern, analysis, D2H of U, R, member end forces and displacements)"}
     if rank == 0:
         emit(({
-            "metric": METRIC, "value": world * units / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": world * units / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"configs[4] batch of {args.frames} parametric frames per GPU (270 DOF each), sway "
-                                   "imperfection, P-Delta consistent, tol 1e-8, host buffers in and out (e2e timing)",
-                       "frames_per_gpu": args.frames, "dof_per_frame": 270, "pdelta_iterations_max": int(stats["frame_iterations"].max()),
-                       "pdelta_iterations_mean": float(stats["frame_iterations"].mean()), "frames_total": int(summ.shape[0])},
-            "gpu_launches": int(lib.fers_b200_launch_count() - l0),
-            "frames_x_iterations_per_s": world * float(stats["frame_iterations"].sum()) / dt,
+            "config": {"workload": CFG5_WORKLOAD.format(n=args.frames), "frames_per_gpu": args.frames, "dof_per_frame": 270,
+                       "pdelta_iterations_max": int(it_frames.max()), "pdelta_iterations_mean": float(it_frames.mean()),
+                       "pdelta_iterations_enqueued": int(enq), "converged": bool(res.converged[0]),
+                       "frames_total": int(summ.shape[0]), "parallelism": f"frame batches x{world}",
+                       "cache": "597 MB of frame matrices per factorisation >> 126 MB L2; no flush needed"},
+            "clocks": clocks, "gpu_launches": int(launches), "frames_x_iterations_per_s": world * float(it_frames.sum()) / (ms_step / 1e3),
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -586,7 +787,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.workload == "cfg5":
+            run_cfg5_reference(args, rank, world)
+        else:
+            run_reference(args, rank, world)
         return
     if args.workload == "cfg5":
         run_cfg5(args, rank, world, local_rank)

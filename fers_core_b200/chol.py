@@ -176,9 +176,9 @@ class CholSolver:
             d_x.data_ptr(), 1 if accumulate else 0, self.work.data_ptr(), self.work_bytes, self.stream), "chol_solve")
 
     def profile(self) -> dict:
-        out = (C.c_double * 16)()
-        _lib.check(self.lib.fers_b200_chol_profile(out, 16), "chol_profile")
+        out = (C.c_double * 20)()
+        _lib.check(self.lib.fers_b200_chol_profile(out, 20), "chol_profile")
         keys = ["init_ms", "scatter_ms", "potrf_ms", "trsm_ms", "update_ms", "syrk_ms", "factor_ms", "solve_ms",
                 "factor_launches", "solve_launches", "syrk_sum_ms", "factor_sum_ms", "solve_sum_ms", "n_factor",
-                "n_solve", "n_syrk_launches"]
+                "n_solve", "n_syrk_launches", "oz_ms", "oz_sum_ms", "n_oz_fronts", "oz_setting"]
         return dict(zip(keys, out[:]))

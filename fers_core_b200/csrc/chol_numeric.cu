@@ -800,11 +800,12 @@ k_chol_residual(long long n_dof, int nr, const double* __restrict__ f, const dou
 struct CholProfile {
     // ms per kernel class of the last profiled factorisation / substitution
     double init = 0, scatter = 0, potrf = 0, trsm = 0, update = 0, syrk = 0, factor_total = 0;
+    double oz = 0;           // Schur updates that went through the int8 tensor-core kernel (not part of `syrk`)
     double solve_total = 0;
     long long launches_factor = 0, launches_solve = 0;
     // accumulated since the last fers_b200_chol_set_profile call
-    double syrk_sum = 0, factor_sum = 0, solve_sum = 0;
-    long long n_factor = 0, n_solve = 0, n_syrk_launches = 0;
+    double syrk_sum = 0, factor_sum = 0, solve_sum = 0, oz_sum = 0;
+    long long n_factor = 0, n_solve = 0, n_syrk_launches = 0, n_oz_fronts = 0;
 };
 static CholProfile g_chol_profile;
 // tile-shape selection (A/B measurements): bit 0 = panel updates, bit 1 = Schur update;
@@ -823,7 +824,7 @@ static int g_chol_profile_on = 0;      // 0 off, 1 every kernel class, 2 Schur-u
 // Schur updates of the upper tree levels on the int8 tensor cores (ozaki_syrk.cu): digit planes per operand (0 = off,
 // 6..8; 8 = fp64 grade) and the smallest own-column count of a level that takes that path.  FERS_CHOL_OZAKI /
 // FERS_CHOL_OZAKI_MIN_K / fers_b200_chol_set_ozaki.
-static int g_chol_ozaki = getenv("FERS_CHOL_OZAKI") ? atoi(getenv("FERS_CHOL_OZAKI")) : 8;
+static int g_chol_ozaki = getenv("FERS_CHOL_OZAKI") ? atoi(getenv("FERS_CHOL_OZAKI")) : 7;
 static int g_chol_ozaki_min_k = getenv("FERS_CHOL_OZAKI_MIN_K") ? atoi(getenv("FERS_CHOL_OZAKI_MIN_K")) : 1024;
 
 struct EventPool {
@@ -838,7 +839,7 @@ struct EventPool {
 static EventPool g_pool;
 
 struct Timed {
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[6];
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[7];      // 6 = int8 tensor-core Schur updates
     void clear() { for (auto& s : spans) s.clear(); }
 };
 static Timed g_timed;
@@ -944,7 +945,7 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
     bool side_pending = false;
     long long launches = 0;
     auto span_begin = [&](int cls) -> cudaEvent_t {
-        if (!prof || !(prof_all || cls == 5)) return nullptr;
+        if (!prof || !(prof_all || cls >= 5)) return nullptr;
         cudaEvent_t e = g_pool.get();
         cudaEventRecord(e, st);
         return e;
@@ -1076,18 +1077,18 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
         // levels whose fronts all have many own columns: every front on its own through the int8 tensor-core kernel (the
         // digit planes live in the children's Schur arena, free since this level's extend-add)
         bool ozaki = false;
-        if (l + 1 < P.n_levels && g_chol_ozaki >= 5 && nf <= 64) {
+        if (l + 1 < P.n_levels && g_chol_ozaki >= 4 && nf <= 64) {
             ozaki = true;
             const size_t room = (size_t)P.schur_doubles[(l & 1) ^ 1] * 8;
             for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; ++q) {
                 const FrontDev& f = P.fronts[P.level_fronts[q]];
-                if (6 * f.n1 < g_chol_ozaki_min_k || 6 * f.n1 >= 65536 || 6 * f.n2 < 1024 ||
+                if (6 * f.n1 < g_chol_ozaki_min_k || 6 * f.n1 >= 16384 || 6 * f.n2 < 1024 ||
                     oz_work_bytes(6 * f.n2, 6 * f.n1, g_chol_ozaki) > room)
                     ozaki = false;
             }
         }
         if (ozaki) {
-            e0 = span_begin(5);
+            e0 = span_begin(6);
             for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; ++q) {
                 const FrontDev& f = P.fronts[P.level_fronts[q]];
                 const int k1 = 6 * f.n1, m2 = 6 * f.n2, m = k1 + m2;
@@ -1095,8 +1096,9 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
                             arena[(l & 1) ^ 1], st))
                     return 1;
                 launches += 3;
+                if (prof) g_chol_profile.n_oz_fronts += 1;
             }
-            span_end(5, e0);
+            span_end(6, e0);
         } else if (l + 1 < P.n_levels) {
             e0 = span_begin(5);
             if (g_chol_variant & 2) {
@@ -1119,13 +1121,14 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
     count_launches(launches);
     if (prof) {
         FERS_CK(cudaStreamSynchronize(caller));
-        double t[6] = {0, 0, 0, 0, 0, 0};
-        for (int c = 0; c < 6; ++c)
+        double t[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < 7; ++c)
             for (auto& sp : g_timed.spans[c]) { float ms = 0; cudaEventElapsedTime(&ms, sp.first, sp.second); t[c] += ms; }
         float tot = 0;
         cudaEventElapsedTime(&tot, ev_begin, ev_end);
         g_chol_profile.init = t[0]; g_chol_profile.scatter = t[1]; g_chol_profile.potrf = t[2];
-        g_chol_profile.trsm = t[3]; g_chol_profile.update = t[4]; g_chol_profile.syrk = t[5];
+        g_chol_profile.trsm = t[3]; g_chol_profile.update = t[4]; g_chol_profile.syrk = t[5]; g_chol_profile.oz = t[6];
+        g_chol_profile.oz_sum += t[6];
         g_chol_profile.factor_total = tot;
         g_chol_profile.launches_factor = launches;
         g_chol_profile.syrk_sum += t[5]; g_chol_profile.factor_sum += tot; g_chol_profile.n_factor += 1;
@@ -1343,7 +1346,7 @@ int fers_b200_chol_set_outer(int steps, int group) {
 }
 
 int fers_b200_chol_set_ozaki(int slices, int min_k) {
-    FERS_REQUIRE(slices == 0 || (slices >= 5 && slices <= 8), "chol_set_ozaki: slices 0 (off) or 5..8");
+    FERS_REQUIRE(slices == 0 || (slices >= 4 && slices <= 8), "chol_set_ozaki: slices 0 (off) or 4..8");
     FERS_REQUIRE(min_k >= 64, "chol_set_ozaki: min_k >= 64");
     g_chol_ozaki = slices;
     g_chol_ozaki_min_k = min_k;
@@ -1352,13 +1355,14 @@ int fers_b200_chol_set_ozaki(int slices, int min_k) {
 
 int fers_b200_chol_set_profile(int on) {
     g_chol_profile_on = on < 0 ? 0 : (on > 2 ? 1 : on);
-    g_chol_profile.syrk_sum = g_chol_profile.factor_sum = g_chol_profile.solve_sum = 0;
-    g_chol_profile.n_factor = g_chol_profile.n_solve = g_chol_profile.n_syrk_launches = 0;
+    g_chol_profile.syrk_sum = g_chol_profile.factor_sum = g_chol_profile.solve_sum = g_chol_profile.oz_sum = 0;
+    g_chol_profile.n_factor = g_chol_profile.n_solve = g_chol_profile.n_syrk_launches = g_chol_profile.n_oz_fronts = 0;
     return 0;
 }
 
 /* out[10]: ms of init, scatter, potrf, trsm, update, syrk, factor total, solve total; launches factor, solve;
- * n_out >= 16 adds sums since the last set_profile: syrk ms, factor ms, solve ms, factorisations, substitutions, syrk launches */
+ * n_out >= 16 adds sums since the last set_profile: syrk ms, factor ms, solve ms, factorisations, substitutions, syrk launches;
+ * n_out >= 20 adds the int8 tensor-core Schur updates: ms (last), ms (sum), fronts (sum), slices * 100000 + min_k */
 int fers_b200_chol_profile(double* out, int n_out) {
     FERS_REQUIRE(out && n_out >= 10, "chol_profile: need 10 outputs");
     const CholProfile& p = g_chol_profile;
@@ -1367,6 +1371,9 @@ int fers_b200_chol_profile(double* out, int n_out) {
     if (n_out >= 16) {
         out[10] = p.syrk_sum; out[11] = p.factor_sum; out[12] = p.solve_sum;
         out[13] = (double)p.n_factor; out[14] = (double)p.n_solve; out[15] = (double)p.n_syrk_launches;
+    }
+    if (n_out >= 20) {      // int8 tensor-core Schur updates: ms of the last profiled factorisation, ms and fronts since set_profile, settings
+        out[16] = p.oz; out[17] = p.oz_sum; out[18] = (double)p.n_oz_fronts; out[19] = (double)(g_chol_ozaki * 100000 + g_chol_ozaki_min_k);
     }
     return 0;
 }

@@ -5,11 +5,13 @@
 // than a hundred times that rate, so a product of fp64 matrices split into S signed 7-bit digit planes, with the S(S+1)/2
 // significant digit-plane products formed exactly in int32, is an fp64-equivalent GEMM whose accuracy is set by S:
 //
-//   row i of A = L21:   a_ik = 2^E_i * sum_{p<S} q_p[i,k] 2^(-6-7p),   q_p in [-64, 64],   2^E_i > max_k |a_ik|
-//   (A A^T)_ij = 2^(E_i+E_j) * sum_{d<S} 2^(-12-7d) * ( sum_{p+q=d} Q_p Q_q^T )_ij  +  O(S 2^(-6-7S)) |a_i||a_j|
+//   row i of A = L21:   a_ik = 2^E_i * sum_{p<S} q_p[i,k] 2^(-6-Bp),   2^E_i > max_k |a_ik|,   B = 8 bits per digit plane:
+//                       q_0 in [-65, 65], q_p in [-128, 127] (signed digits, carries normalised)
+//   (A A^T)_ij = 2^(E_i+E_j) * sum_{d<S} 2^(-12-Bd) * ( sum_{p+q=d} Q_p Q_q^T )_ij  +  O(S 2^(2-BS)) |a_i||a_j|
 //
 // Every bracket is an int8 x int8 -> int32 GEMM chain accumulated in ONE TMEM accumulator per digit-plane diagonal d
-// (exact: |q_p q_q| <= 2^12, (d+1) K 2^12 < 2^31 for K < 65 536).  S = 8 carries 55 bits (fp64 grade), S = 7 48 bits.
+// (exact: |q_p q_q| <= 2^14, (d+1) K 2^14 < 2^31 for K < 16 384 with S <= 8).  S = 7 carries 6 + 6*8 = 54 bits (fp64 grade),
+// S = 6 46 bits.  (7-bit digits, the textbook choice, need S = 8 planes and 36 instead of 28 products for the same bits.)
 //
 // Kernels:
 //   k_oz_rowscale   E_i per row of L21 (exponent of the row maximum)
@@ -22,6 +24,8 @@
 //                   mbarriers, tcgen05.commit releases a stage when the MMAs that read it have retired.
 //
 // Reference row: SURVEY.md 8a A10 (the factorisation the reference describes at fers_core/types/pydantic_models.py:1216-1219).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "chol.cuh"
@@ -31,8 +35,9 @@ namespace fers {
 
 constexpr int OZ_M = 128;                 // rows of an output tile (TMEM lanes)
 constexpr int OZ_N = 64;                  // columns of an output tile (TMEM columns per accumulator)
-constexpr int OZ_KC = 64;                 // K bytes per shared-memory stage (two MMAs of K = 32 per digit-plane pair)
-constexpr int OZ_MAX_S = 8;               // digit planes (8 accumulators x 64 columns = all 512 TMEM columns)
+constexpr int OZ_KC = 32;                 // K bytes per shared-memory stage (one MMA of K = 32 per digit-plane pair): small stages, deep ring
+constexpr int OZ_DIGIT_BITS = 8;          // bits per digit plane after the first (6 bits)
+constexpr double OZ_BASE = 256.0;         // 2^OZ_DIGIT_BITS
 constexpr int OZ_THREADS = 192;
 constexpr int OZ_BAND = 12;               // row blocks per band of the tile order (L2 reuse of the operand tiles)
 constexpr uint32_t OZ_SPIN_LIMIT = 1u << 28;   // a barrier that never completes traps instead of hanging the device
@@ -84,12 +89,18 @@ k_oz_split(OzFront f) {
         const int k = k0 + j;
         double t = 0.0;
         if (r < f.m2 && k < f.k1) t = f.A[(size_t)k * f.lda + r] * inv;       // |t| < 64, exact scaling
+        int q[S];
 #pragma unroll
         for (int p = 0; p < S; ++p) {
-            const double q = rint(t);
-            t = (t - q) * 128.0;                                              // exact: |t - q| <= 1/2
-            w[p][j >> 2] |= ((uint32_t)(int)q & 0xffu) << (8 * (j & 3));
+            const double qd = rint(t);
+            t = (t - qd) * OZ_BASE;                                           // exact: |t - qd| <= 1/2
+            q[p] = (int)qd;                                                   // p > 0: in [-128, 128]
         }
+#pragma unroll
+        for (int p = S - 1; p > 0; --p)                                       // signed digits in [-128, 127]: +128 carries upwards
+            if (q[p] >= 128) { q[p] -= 256; q[p - 1] += 1; }
+#pragma unroll
+        for (int p = 0; p < S; ++p) w[p][j >> 2] |= ((uint32_t)q[p] & 0xffu) << (8 * (j & 3));
     }
     const size_t plane = oz_plane_bytes(f.m2_pad, f.k1_pad);
     const int chunk = k0 / OZ_KC, kc16 = (k0 % OZ_KC) / 16;
@@ -128,6 +139,13 @@ __device__ __forceinline__ void oz_bulk_g2s(uint32_t dst, const void* src, uint3
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+// one lane of a CONVERGED warp; the code under it may use warp-uniform operands without a divergence loop
+__device__ __forceinline__ bool oz_elect() {
+    uint32_t pred;
+    __syncwarp();           // the lanes may leave a barrier-wait loop at different iterations: reconverge before electing
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void oz_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void oz_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void oz_commit(uint32_t bar) {
@@ -135,13 +153,11 @@ __device__ __forceinline__ void oz_commit(uint32_t bar) {
 }
 // shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 contiguous bytes);
 // LBO = distance of the two core matrices an MMA spans along K, SBO = distance of consecutive 8-row groups
-__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
-    d |= (uint64_t)1 << 46;                       // descriptor version of sm_100
-    return d;                                     // base offset 0, layout type 0 (no swizzle)
+// (shared-memory addresses are below 256 KB, so address >> 4 fits the 14-bit field and tile offsets can simply be added to it)
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr16, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint32_t lo = saddr16 | ((lbo_bytes >> 4) << 16);
+    const uint32_t hi = (sbo_bytes >> 4) | (1u << 14);      // descriptor version of sm_100 at bit 46; base offset 0, no swizzle
+    return ((uint64_t)hi << 32) | lo;
 }
 // instruction descriptor of kind::i8: D = S32, A = B = signed 8 bit, both K-major, M = 128, N = 64
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
@@ -161,15 +177,15 @@ __device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, int (&v)[8]) {
 }
 __device__ __forceinline__ void oz_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// tile t of the lower triangle in band order: bands of OZ_BAND row blocks; inside a band column block by column block,
-// so that the ~148 tiles in flight share about a dozen row-block and a dozen column-block operand streams in L2
+// Tile t of the lower triangle in band order: bands of OZ_BAND row blocks; inside a band column block by column block, so that
+// the ~148 tiles in flight share about a dozen row-block and a dozen column-block operand streams in L2.  Column block bj
+// exists in row block r when bj <= 2 r + 1.
 __device__ __forceinline__ bool oz_tile(int t, int nbi, int nbj, int& bi, int& bj) {
     for (int b0 = 0; b0 < nbi; b0 += OZ_BAND) {
         const int b1 = min(b0 + OZ_BAND, nbi);
-        // column block bj is present in row block r when bj <= 2 r + 1
         const int maxbj = min(2 * (b1 - 1) + 1, nbj - 1);
         for (int j = 0; j <= maxbj; ++j) {
-            const int rmin = max(b0, j / 2);                     // smallest r with 2 r + 1 >= j
+            const int rmin = max(b0, j / 2);                    // smallest r with 2 r + 1 >= j
             const int cnt = b1 - rmin;
             if (cnt <= 0) continue;
             if (t < cnt) { bi = rmin + t; bj = j; return true; }
@@ -179,6 +195,8 @@ __device__ __forceinline__ bool oz_tile(int t, int nbi, int nbj, int& bi, int& b
     return false;
 }
 
+// (Thread-block clusters with TMA multicast of the row-block operand were measured and dropped: 2 CTAs per cluster changed
+// nothing -- L2 already serves the dozen CTAs that stream the same tile -- and 4 per cluster strand SMs: half the throughput.)
 template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_oz_syrk(OzFront f, int n_tiles) {
@@ -207,23 +225,24 @@ k_oz_syrk(OzFront f, int n_tiles) {
     __syncthreads();
     oz_fence_after();
     const uint32_t tmem = s_tmem;
+    const int unit0 = blockIdx.x, unit_stride = gridDim.x;
     const int nbi = f.m2_pad / OZ_M, nbj = (f.m2 + OZ_N - 1) / OZ_N;
     const int nkc = f.k1_pad / OZ_KC;
     const size_t plane = oz_plane_bytes(f.m2_pad, f.k1_pad);
     const size_t chunk_bytes = (size_t)f.m2_pad * OZ_KC;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                int bi, bj;
-                if (!oz_tile(t, nbi, nbj, bi, bj)) break;
-                const int8_t* a0 = f.planes + (size_t)bi * OZ_M * OZ_KC;
-                const int8_t* b0 = f.planes + (size_t)bj * OZ_N * OZ_KC;
-                for (int c = 0; c < nkc; ++c, ++it) {
-                    const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
-                    oz_mbar_wait(bar_empty + 8u * st, ph ^ 1u);
+        // ===== TMA producer (the whole warp walks the loop, one elected lane issues) =====
+        uint32_t it = 0;
+        for (int t = unit0; t < n_tiles; t += unit_stride) {
+            int bi, bj;
+            if (!oz_tile(t, nbi, nbj, bi, bj)) break;
+            const int8_t* a0 = f.planes + (size_t)bi * OZ_M * OZ_KC;
+            const int8_t* b0 = f.planes + (size_t)bj * OZ_N * OZ_KC;
+            for (int c = 0; c < nkc; ++c, ++it) {
+                const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
+                oz_mbar_wait(bar_empty + 8u * st, ph ^ 1u);
+                if (oz_elect()) {
                     const uint32_t full = bar_full + 8u * st;
                     oz_mbar_expect_tx(full, STAGE_BYTES);
                     const uint32_t dst = ring + st * STAGE_BYTES;
@@ -233,46 +252,48 @@ k_oz_syrk(OzFront f, int n_tiles) {
                         oz_bulk_g2s(dst + S * A_BYTES + p * B_BYTES, b0 + p * plane + (size_t)c * chunk_bytes, B_BYTES, full);
                     }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            uint32_t it = 0, tile_i = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
-                int bi, bj;
-                if (!oz_tile(t, nbi, nbj, bi, bj)) break;
-                oz_mbar_wait(bar_acc_empty, (tile_i & 1u) ^ 1u);
+        // ===== MMA issuer (whole warp in the loop, one elected lane issues the MMAs of a stage) =====
+        uint32_t it = 0, tile_i = 0;
+        for (int t = unit0; t < n_tiles; t += unit_stride, ++tile_i) {
+            int bi, bj;
+            if (!oz_tile(t, nbi, nbj, bi, bj)) break;
+            oz_mbar_wait(bar_acc_empty, (tile_i & 1u) ^ 1u);
+            oz_fence_after();
+            for (int c = 0; c < nkc; ++c, ++it) {
+                const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
+                oz_mbar_wait(bar_full + 8u * st, ph);
                 oz_fence_after();
-                for (int c = 0; c < nkc; ++c, ++it) {
-                    const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
-                    oz_mbar_wait(bar_full + 8u * st, ph);
-                    oz_fence_after();
-                    const uint32_t sa = ring + st * STAGE_BYTES, sb = sa + S * A_BYTES;
+                if (oz_elect()) {
+                    const uint32_t sa = (ring + st * STAGE_BYTES) >> 4, sb = sa + ((S * A_BYTES) >> 4);
 #pragma unroll
                     for (int kk = 0; kk < OZ_KC / 32; ++kk) {
 #pragma unroll
                         for (int p = 0; p < S; ++p) {
-                            const uint64_t da = oz_desc(sa + p * A_BYTES + kk * 256, 128, OZ_KC * 8);
+                            const uint64_t da = oz_desc(sa + ((p * A_BYTES + kk * 256) >> 4), 128, OZ_KC * 8);
 #pragma unroll
                             for (int q = 0; q + p < S; ++q) {
-                                const uint64_t db = oz_desc(sb + q * B_BYTES + kk * 256, 128, OZ_KC * 8);
+                                const uint64_t db = oz_desc(sb + ((q * B_BYTES + kk * 256) >> 4), 128, OZ_KC * 8);
                                 // the first product of a digit-plane diagonal d = p + q overwrites its accumulator
                                 const uint32_t acc = (c > 0 || kk > 0 || p > 0) ? 1u : 0u;
                                 oz_mma(tmem + (uint32_t)(p + q) * OZ_N, da, db, acc);
                             }
                         }
                     }
-                    oz_commit(bar_empty + 8u * st);          // the stage is free once these MMAs have read it
+                    oz_commit(bar_empty + 8u * st);                  // the stage is free once these MMAs have read it
+                    if (c == nkc - 1) oz_commit(bar_acc_full);       // all accumulators of the tile are final
                 }
-                oz_commit(bar_acc_full);                     // all accumulators of the tile are final
+                __syncwarp();
             }
         }
     } else {
         // ===== epilogue: TMEM -> fp64 -> C -= 2^(E_i + E_j) sum_d 2^(-12 - 7 d) acc_d =====
         const int quad = warp & 3;                           // the TMEM lanes this warp may read: 32 quad .. 32 quad + 31
         uint32_t tile_i = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+        for (int t = unit0; t < n_tiles; t += unit_stride, ++tile_i) {
             int bi, bj;
             if (!oz_tile(t, nbi, nbj, bi, bj)) break;
             oz_mbar_wait(bar_acc_full, tile_i & 1u);
@@ -286,15 +307,16 @@ k_oz_syrk(OzFront f, int n_tiles) {
                 double sum[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) sum[j] = 0.0;
-                double wgt = ldexp(1.0, -12 - 7 * (S - 1));
+                int v[S][8];
+#pragma unroll
+                for (int d = 0; d < S; ++d) oz_tmem_ld8(lane_addr + (uint32_t)(d * OZ_N + cb), v[d]);
+                oz_tmem_wait_ld();
+                double wgt = ldexp(1.0, -12 - OZ_DIGIT_BITS * (S - 1));
 #pragma unroll
                 for (int d = S - 1; d >= 0; --d) {           // smallest weights first
-                    int v[8];
-                    oz_tmem_ld8(lane_addr + (uint32_t)(d * OZ_N + cb), v);
-                    oz_tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) sum[j] = fma((double)v[j], wgt, sum[j]);
-                    wgt *= 128.0;
+                    for (int j = 0; j < 8; ++j) sum[j] = fma((double)v[d][j], wgt, sum[j]);
+                    wgt *= OZ_BASE;
                 }
                 if (r < f.m2) {
 #pragma unroll
@@ -343,8 +365,7 @@ static int oz_launch(OzFront f, cudaStream_t st) {
     dim3 grid((f.m2_pad + 255) / 256, f.k1_pad / 16);
     k_oz_split<S><<<grid, 256, 0, st>>>(f);
     const int n_tiles = oz_tile_count(f.m2, f.m2_pad);
-    const int ctas = std::min(n_tiles, sm_count());
-    k_oz_syrk<S><<<ctas, OZ_THREADS, smem, st>>>(f, n_tiles);
+    k_oz_syrk<S><<<std::min(n_tiles, sm_count()), OZ_THREADS, smem, st>>>(f, n_tiles);      // persistent: one CTA per SM
     FERS_LAUNCH_CHECK();
     count_launches(3);
     return 0;
@@ -359,12 +380,13 @@ int oz_syrk(const double* A, long long lda, double* C, long long ldc, int m2, in
     f.planes = static_cast<int8_t*>(work);
     f.rowscale = reinterpret_cast<double*>(static_cast<uint8_t*>(work) + align_up((size_t)S * oz_plane_bytes(f.m2_pad, f.k1_pad)));
     switch (S) {
+        case 4: return oz_launch<4>(f, st);
         case 5: return oz_launch<5>(f, st);
         case 6: return oz_launch<6>(f, st);
         case 7: return oz_launch<7>(f, st);
         case 8: return oz_launch<8>(f, st);
     }
-    set_error("oz_syrk: 5 <= slices <= 8");
+    set_error("oz_syrk: 4 <= slices <= 8");
     return 2;
 }
 
@@ -374,10 +396,12 @@ extern "C" {
 
 size_t fers_b200_oz_syrk_work_bytes(int m2, int k1, int slices) { return fers::oz_work_bytes(m2, k1, slices); }
 
+
+
 int fers_b200_oz_syrk(const double* A, long long lda, double* C, long long ldc, int m2, int k1, int slices, void* work,
                       size_t work_bytes, void* stream) {
     FERS_REQUIRE(A && C && work && m2 > 0 && k1 > 0 && lda >= m2 && ldc >= m2, "oz_syrk: bad arguments");
-    FERS_REQUIRE(k1 < 65536, "oz_syrk: K must stay below 65 536 for exact int32 accumulation");
+    FERS_REQUIRE(k1 < 16384, "oz_syrk: K must stay below 16 384 for exact int32 accumulation");
     FERS_REQUIRE(work_bytes >= fers::oz_work_bytes(m2, k1, slices), "oz_syrk: workspace too small");
     return fers::oz_syrk(A, lda, C, ldc, m2, k1, slices, work, fers::as_stream(stream));
 }

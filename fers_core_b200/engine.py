@@ -771,110 +771,154 @@ def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:
     flush()
 
 
-def analyze_frame_batch(model: wire.ModelArrays, nodes_per_frame: int, device=None, detail: bool = False,
-                        stats_out: dict | None = None) -> ResultArrays:
-    """BASELINE.json configs[4]: a batch of independent equal-sized frames (one concatenated,
-    block-diagonal model, nodes numbered frame by frame), one combination, linear or P-Delta.
-    Every frame is factorised by the batched dense Cholesky; the P-Delta fixed point runs for all
-    frames at once and each frame stops at ITS OWN convergence (converged frames are frozen), so the
-    result equals analysing the frames one by one."""
-    eng = Engine(model, device)
-    opts = model.options
-    plan = rhs_plan(model)
-    if plan.n_rhs != 1:
-        raise EngineError("analyze_frame_batch expects exactly one right-hand side (one combination, no load cases)")
-    if model.n_nodes % nodes_per_frame or model.n_plates:
-        raise EngineError("analyze_frame_batch: model is not a batch of equal-sized beam frames")
-    nf = model.n_nodes // nodes_per_frame
-    n = 6 * nodes_per_frame
-    nm = model.n_members
-    if nm % nf:
-        raise EngineError("analyze_frame_batch: members are not evenly distributed over the frames")
-    nmf = nm // nf
-    out = ResultArrays.empty(model, plan)
-    grp = plan.groups[0]
-    xyz = imperfect_coordinates(model, grp.imperfection) if grp.imperfection is not None else model.xyz
-    d_xyz = eng._t(xyz, np.float64) if grp.imperfection is not None else eng.d_xyz0
-    lib, st = eng.lib, eng.stream
-    fac = plan.factors[[0]]
-    f_case, peq_case = eng.load_cases(d_xyz)
-    d_f = eng.combine(f_case, fac, 1)
-    d_peq = eng.combine(peq_case, fac, 1)
-    a = eng._empty((nf, n, n))
-    flag = eng._zeros(1, torch.int32)
-    info_dev = eng._zeros(nf, torch.int32)
-    bad_dev = torch.zeros(nf, dtype=torch.bool, device=eng.dev)
+class FrameBatch:
+    """BASELINE.json configs[4]: a batch of independent equal-sized frames (one concatenated, block-diagonal model, nodes
+    numbered frame by frame), one combination, linear or P-Delta, resident on one GPU.
 
-    def factor_solve():
-        # asynchronous: failed pivots are collected on the device and looked at where the host synchronises anyway
+    Every frame is factorised by the batched dense Cholesky; the P-Delta fixed point runs for all frames at once and each
+    frame stops at ITS OWN convergence (converged frames are frozen on the device), so the result equals analysing the
+    frames one by one.  The host never waits inside the loop: the "any frame still active" flag of iteration i travels to
+    pinned memory asynchronously and is looked at after iteration i + 1 has been enqueued -- at most one iteration is
+    enqueued in vain, and it changes nothing because every frame is frozen by then."""
+
+    def __init__(self, model: wire.ModelArrays, nodes_per_frame: int, device=None):
+        self.eng = eng = Engine(model, device)
+        self.model = model
+        self.plan = rhs_plan(model)
+        if self.plan.n_rhs != 1:
+            raise EngineError("FrameBatch expects exactly one right-hand side (one combination, no load cases)")
+        if model.n_nodes % nodes_per_frame or model.n_plates:
+            raise EngineError("FrameBatch: model is not a batch of equal-sized beam frames")
+        self.nodes_per_frame = nodes_per_frame
+        self.nf = model.n_nodes // nodes_per_frame
+        self.n = 6 * nodes_per_frame
+        if model.n_members % self.nf:
+            raise EngineError("FrameBatch: members are not evenly distributed over the frames")
+        self.nmf = model.n_members // self.nf
+        grp = self.plan.groups[0]
+        self.xyz = imperfect_coordinates(model, grp.imperfection) if grp.imperfection is not None else model.xyz
+        self.d_xyz = eng._t(self.xyz, np.float64) if grp.imperfection is not None else eng.d_xyz0
+        opts = model.options
+        self.second_order = opts.order == "NONLINEAR"
+        self.kg_mode = (1 if opts.pdelta_formulation == "CONSISTENT" else 2) if self.second_order else 0
+        self.sup = 0
+        for ax in pdelta_suppressed_axes(model):
+            self.sup |= 1 << ax
+        self.fac = self.plan.factors[[0]]
+        self.facp = np.zeros((1, self.fac.shape[1])); self.facp[0] = self.fac[0]
+        nf, n = self.nf, self.n
+        self.a = eng._empty((nf, n, n))
+        self.flag = eng._zeros(1, torch.int32)
+        self.info_dev = eng._zeros(nf, torch.int32)
+        self.bad_dev = torch.zeros(nf, dtype=torch.bool, device=eng.dev)
+        self.h_flags = torch.zeros((max(opts.max_iterations, 1) + 2, 2), dtype=torch.bool).pin_memory()
+        self.stats: dict = {}
+
+    # asynchronous: failed pivots are collected on the device and looked at where the host synchronises anyway
+    def _factor_solve(self, d_f):
+        eng, lib, st = self.eng, self.eng.lib, self.eng.stream
         _lib.check(lib.fers_b200_dense_expand_batched(
-            nodes_per_frame, nf, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
-            _lib.ptr(eng.d_ks), _lib.ptr(a), _lib.ptr(flag), st), "dense_expand_batched")
-        _lib.check(lib.fers_b200_dense_cholesky(n, nf, _lib.ptr(a), _lib.ptr(info_dev), None, st), "dense_cholesky")
-        bad_dev.logical_or_(info_dev != 0)
+            self.nodes_per_frame, self.nf, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
+            _lib.ptr(eng.d_ks), _lib.ptr(self.a), _lib.ptr(self.flag), st), "dense_expand_batched")
+        _lib.check(lib.fers_b200_dense_cholesky(self.n, self.nf, _lib.ptr(self.a), _lib.ptr(self.info_dev), None, st), "dense_cholesky")
+        self.bad_dev.logical_or_(self.info_dev != 0)
         u = (d_f * (1 - eng.d_fixed.to(torch.float64))[:, None]).contiguous()      # d_fixed is (re)built by assemble()
-        _lib.check(lib.fers_b200_dense_solve(n, 1, nf, _lib.ptr(a), _lib.ptr(u), st), "dense_solve")
+        _lib.check(lib.fers_b200_dense_solve(self.n, 1, self.nf, _lib.ptr(self.a), _lib.ptr(u), st), "dense_solve")
         return u
 
-    def raise_if_bad():
-        if int(flag.item()) != 0:
-            raise EngineError("analyze_frame_batch: a member connects two frames; the model is not a batch of independent frames")
-        bad = torch.nonzero(bad_dev).reshape(-1).cpu().tolist()
+    def _raise_if_bad(self):
+        if int(self.flag.item()) != 0:
+            raise EngineError("FrameBatch: a member connects two frames; the model is not a batch of independent frames")
+        bad = torch.nonzero(self.bad_dev).reshape(-1).cpu().tolist()
         if bad:
             raise EngineError(f"{len(bad)} frame(s) of the batch are not positive definite (first: frame {bad[0]}): "
                               "buckled under the applied load or insufficiently supported")
 
-    second_order = opts.order == "NONLINEAR"
-    kg_mode = (1 if opts.pdelta_formulation == "CONSISTENT" else 2) if second_order else 0
-    sup = 0
-    for ax in pdelta_suppressed_axes(model):
-        sup |= 1 << ax
-    facp = np.zeros((1, fac.shape[1])); facp[0] = fac[0]
-    eng.assemble(d_xyz)
-    d_u = factor_solve()
-    d_axial = None
-    iters = torch.zeros(nf, dtype=torch.int64, device=eng.dev)
-    resid = torch.zeros(nf, dtype=torch.float64, device=eng.dev)
-    active = torch.ones(nf, dtype=torch.bool, device=eng.dev)
-    if second_order and nm:
-        for _it in range(max(1, opts.max_iterations)):
-            rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, None, None, d_axial, kg_mode, sup, detail=False)
-            ax_new = eng._empty((nm, 1))
-            _lib.check(lib.fers_b200_member_axial(nm, 1, _lib.ptr(rec["f_local"]), _lib.ptr(ax_new), st), "member_axial")
-            if d_axial is not None:      # frozen frames keep the axial forces of their last iteration
-                am = active.repeat_interleave(nmf)[:, None]
-                ax_new = torch.where(am, ax_new, d_axial).contiguous()
-            d_axial = ax_new
+    def solve(self, detail: bool = False) -> dict:
+        """Device work of one analysis: load vectors, assembly, factorisations, P-Delta loop, recovery.  Returns the
+        result tensors (device) of Engine.recover plus "U"; self.stats holds iteration counts / residuals (device)."""
+        eng, model, lib = self.eng, self.model, self.eng.lib
+        opts = model.options
+        nf, n, nm, nmf = self.nf, self.n, model.n_members, self.nmf
+        d_xyz, kg_mode, sup = self.d_xyz, self.kg_mode, self.sup
+        self.flag.zero_(); self.bad_dev.zero_()
+        f_case, peq_case = eng.load_cases(d_xyz)
+        d_f = eng.combine(f_case, self.fac, 1)
+        d_peq = eng.combine(peq_case, self.fac, 1)
+        eng.assemble(d_xyz)
+        d_u = self._factor_solve(d_f)
+        d_axial = None
+        iters = torch.zeros(nf, dtype=torch.int64, device=eng.dev)
+        resid = torch.zeros(nf, dtype=torch.float64, device=eng.dev)
+        active = torch.ones(nf, dtype=torch.bool, device=eng.dev)
+        enqueued = 0
+        if self.second_order and nm:
+            events = []
+            max_it = max(1, opts.max_iterations)
+            for it in range(max_it):
+                rec = eng.recover(d_xyz, d_u, d_f, d_peq, self.facp, None, None, d_axial, kg_mode, sup, detail=False)
+                ax_new = eng._empty((nm, 1))
+                _lib.check(lib.fers_b200_member_axial(nm, 1, _lib.ptr(rec["f_local"]), _lib.ptr(ax_new), eng.stream), "member_axial")
+                if d_axial is not None:      # frozen frames keep the axial forces of their last iteration
+                    am = active.repeat_interleave(nmf)[:, None]
+                    ax_new = torch.where(am, ax_new, d_axial).contiguous()
+                d_axial = ax_new
+                eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup, count=False)
+                d_un = self._factor_solve(d_f)
+                un_f, u_f = d_un.view(nf, n), d_u.view(nf, n)
+                den = torch.linalg.norm(un_f, dim=1)
+                r = torch.where(den > 0, torch.linalg.norm(un_f - u_f, dim=1) / den, torch.zeros_like(den))
+                iters += active.to(torch.int64)
+                resid = torch.where(active, r, resid)
+                d_u = torch.where(active.repeat_interleave(n)[:, None], d_un, d_u).contiguous()
+                active = active & ~(r < opts.tolerance)
+                # (go on, bad pivot) of this iteration -> pinned memory, no host wait here
+                self.h_flags[it].copy_(torch.stack([active.any(), self.bad_dev.any()]), non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(eng.dev)); events.append(ev)
+                enqueued = it + 1
+                if it >= 1:                  # look at the PREVIOUS iteration's flags (normally landed by now)
+                    events[it - 1].synchronize()
+                    go_on, bad = self.h_flags[it - 1].tolist()
+                    if bad:
+                        self._raise_if_bad()
+                    if not go_on:
+                        break
+            else:
+                events[-1].synchronize()
+            # the matrix in eng.d_vals must be the tangent of the frozen state for the reactions
             eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup, count=False)
-            d_un = factor_solve()
-            un_f, u_f = d_un.view(nf, n), d_u.view(nf, n)
-            den = torch.linalg.norm(un_f, dim=1)
-            r = torch.where(den > 0, torch.linalg.norm(un_f - u_f, dim=1) / den, torch.zeros_like(den))
-            iters += active.to(torch.int64)
-            resid = torch.where(active, r, resid)
-            d_u = torch.where(active.repeat_interleave(n)[:, None], d_un, d_u).contiguous()
-            active = active & ~(r < opts.tolerance)
-            go_on, bad = torch.stack([active.any(), bad_dev.any()]).cpu().tolist()       # the one sync of the iteration
-            if bad:
-                raise_if_bad()
-            if not go_on:
-                break
-        # the matrix in eng.d_vals must be the tangent of the frozen state for the reactions
-        eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup, count=False)
-    raise_if_bad()
-    span = eng.span_tables() if detail else None
-    rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, None, d_axial, kg_mode, sup, detail=detail)
-    _store(out, model, [0], d_u, rec, xyz)
-    out.method = "Linear" if not second_order else "P_DELTA"
-    it_host = iters.cpu().numpy()
-    out.iterations[0] = int(it_host.max()) if second_order else -1
-    out.converged[0] = not bool(active.any()) if second_order else True
-    out.residual[0] = float(resid.max()) if second_order else 0.0
+        span = eng.span_tables() if detail else None
+        rec = eng.recover(d_xyz, d_u, d_f, d_peq, self.facp, span, None, d_axial, kg_mode, sup, detail=detail)
+        rec["U"] = d_u
+        self.stats = {"iters": iters, "resid": resid, "active": active, "iterations_enqueued": enqueued}
+        return rec
+
+    def results(self, rec: dict) -> ResultArrays:
+        """Host result arrays of one solve() (D2H of every field) + the convergence record."""
+        model = self.model
+        self._raise_if_bad()
+        out = ResultArrays.empty(model, self.plan)
+        _store(out, model, [0], rec["U"], rec, self.xyz)
+        out.method = "Linear" if not self.second_order else "P_DELTA"
+        it_host = self.stats["iters"].cpu().numpy()
+        out.iterations[0] = int(it_host.max()) if self.second_order else -1
+        out.converged[0] = not bool(self.stats["active"].any()) if self.second_order else True
+        out.residual[0] = float(self.stats["resid"].max()) if self.second_order else 0.0
+        self.frame_iterations = it_host
+        return out
+
+
+def analyze_frame_batch(model: wire.ModelArrays, nodes_per_frame: int, device=None, detail: bool = False,
+                        stats_out: dict | None = None) -> ResultArrays:
+    """One batch of frames, host arrays in and out (FrameBatch: upload, solve, download)."""
+    fb = FrameBatch(model, nodes_per_frame, device)
+    out = fb.results(fb.solve(detail=detail))
     if stats_out is not None:
-        stats_out.update(vars(eng.stats))
-        stats_out["frame_iterations"] = it_host
-        stats_out["frame_residual"] = resid.cpu().numpy()
-        stats_out["frames"] = nf
+        stats_out.update(vars(fb.eng.stats))
+        stats_out["frame_iterations"] = fb.frame_iterations
+        stats_out["frame_residual"] = fb.stats["resid"].cpu().numpy()
+        stats_out["frames"] = fb.nf
+        stats_out["iterations_enqueued"] = fb.stats["iterations_enqueued"]
     return out
 
 

@@ -265,11 +265,11 @@ int fers_b200_chol_profile(double* out, int n_out);
 
 /* ---- fp64-equivalent Schur update on the int8 tensor cores (tcgen05.mma kind::i8, Ozaki splitting) -------------
  * C (m2 x m2, lower triangle, column-major, leading dimension ldc) -= A A^T with A m2 x k1 (column-major, lda), both
- * fp64 on the device.  A is cut into `slices` (5..8) signed 7-bit digit planes per row exponent; the digit-plane products
- * are exact in int32 (k1 < 65 536) and are summed back in fp64: 8 slices carry 55 bits, 7 carry 48.
+ * fp64 on the device.  A is cut into `slices` (4..8) signed digit planes per row exponent (6 bits, then 8 bits each); the
+ * digit-plane products are exact in int32 (k1 < 16 384) and are summed back in fp64: 7 slices carry 54 bits, 6 carry 46.
  * work: >= fers_b200_oz_syrk_work_bytes(m2, k1, slices) device bytes (digit planes + row scales). */
 /* The sparse factorisation sends the Schur updates of tree levels whose fronts all have >= min_k own columns through this
- * kernel (slices = 0 switches it off: fp64 tensor pipe everywhere; default 8 slices, min_k 1024; FERS_CHOL_OZAKI,
+ * kernel (slices = 0 switches it off: fp64 tensor pipe everywhere; default 7 slices, min_k 1024; FERS_CHOL_OZAKI,
  * FERS_CHOL_OZAKI_MIN_K).  The solve checks the residual of every column afterwards and refines while it exceeds 1e-12. */
 int fers_b200_chol_set_ozaki(int slices, int min_k);
 size_t fers_b200_oz_syrk_work_bytes(int m2, int k1, int slices);
