@@ -21,7 +21,7 @@ enum UnityOp { U_PUSHC = 0, U_PUSHV, U_ADD, U_SUB, U_MUL, U_DIV, U_POW, U_NEG, U
 enum UnityVar { V_CONST = 0, V_FORCE, V_EXPR, V_NODE_DISP, V_NODE_POS, V_DEFLECTION, V_FORCE_REF, V_ENTITY_DISP, V_PLATE };
 enum UnityAgg { A_MAXABS = 0, A_MAX, A_MIN, A_START, A_END, A_STATION };
 
-constexpr int UNITY_MAX_VARS = 32;
+constexpr int UNITY_MAX_VARS = 96;       // the EN 1993-1-1 program (fers_core_b200/ec3.py) binds about 70 names
 constexpr int UNITY_STACK = 16;
 
 struct UnityArgs {
@@ -243,7 +243,7 @@ extern "C" int fers_b200_unity_generic(int n_ent, int nrhs, int n_vars, int n_ct
                                        const double* lmin, const double* frames, const int* ent_ref, const double* p_res,
                                        const double* p_data, double* out, double* vars_out, void* stream) {
     if (n_ent <= 0) return 0;
-    FERS_REQUIRE(n_vars >= 0 && n_vars <= UNITY_MAX_VARS, "unity_generic: at most 32 variables per check");
+    FERS_REQUIRE(n_vars >= 0 && n_vars <= UNITY_MAX_VARS, "unity_generic: at most 96 variables per check");
     FERS_REQUIRE(col_mask && ent_ptr && ent_members && ent_node_ptr && ent_nodes && code && consts && ent_ref && out,
                  "unity_generic: bad arguments");
     FERS_REQUIRE(nrhs >= 1, "unity_generic: no columns");

@@ -24,8 +24,9 @@ Semantics where the closed engine is the only definition (stated, unpinned):
   * ``Displacement`` = largest absolute value of the component over the entity's nodes.
   * plate entities (``AllPlates`` / ``PlateElements``): ``PlateStress`` = surface stress n/t +- 6m/t^2 at the element
     centroid, both surfaces, enveloped; QUAD4 elements (two TRI3 rows) envelope both halves.
-Ec3Steel checks are reported as not evaluated (status message).  Every entity result carries a
-trace with the value of each variable at its governing combination.
+Ec3Steel checks are compiled into the same postfix programs (ec3.py: EN 1993-1-1 6.2 cross-section rules, 6.3.1 flexural
+buckling, 6.3.2 lateral-torsional buckling, linear 6.3.3 interaction).  Every entity result carries a trace with the value
+of each variable (Ec3Steel: each rule under its clause label) at its governing combination.
 """
 from __future__ import annotations
 
@@ -34,7 +35,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import _lib, wire
+from . import _lib, ec3, wire
 
 OPS = {"PUSHC": 0, "PUSHV": 1, "+": 2, "-": 3, "*": 4, "/": 5, "^": 6, "NEG": 7, "abs": 8, "sqrt": 9, "min": 10, "max": 11}
 V_CONST, V_FORCE, V_EXPR, V_NODE_DISP, V_NODE_POS, V_DEFLECTION, V_FORCE_REF, V_ENTITY_DISP, V_PLATE = range(9)
@@ -48,7 +49,7 @@ DEFL_COMP = {"LocalY": 0, "LocalZ": 1, "Magnitude": 2}
 SECTION_FIELD = {"Area": "area", "Iy": "i_y", "Iz": "i_z", "J": "j", "Iw": "i_w", "WelY": "wel_y", "WelZ": "wel_z",
                  "WplY": "wpl_y", "WplZ": "wpl_z", "H": "h", "B": "b", "Asy": "a_sy", "Asz": "a_sz"}
 MATERIAL_FIELD = {"E": "e_mod", "G": "g_mod", "Fy": "yield_stress", "Density": "density"}
-MAX_VARS = 32
+MAX_VARS = 96
 MAX_STACK = 16
 STATUS = ("Green", "Yellow", "Orange", "Red")
 
@@ -211,6 +212,8 @@ class CompiledCheck:
     skipped: str | None = None         # reason when the check is not evaluated
     plates: bool = False               # entities are plate elements (ent_members = TRI3 rows)
     warnings: list = field(default_factory=list)
+    spec: dict | None = None           # the Generic specification that was compiled (generated for Ec3Steel checks)
+    labels: dict | None = None         # variable name -> trace label; None: every variable under its own name
 
 
 def _chain(model, members: list):
@@ -303,10 +306,9 @@ def compile_check(model, definition: dict) -> CompiledCheck:
                  ent_ref=np.zeros((0, 4), np.int32),
                  var_names=[], var_desc=np.zeros((0, 4), np.int32), code=np.zeros((0, 2), np.int32), consts=np.zeros(1),
                  ctab=np.zeros((0, 1)), demand=(0, 0), capacity=(0, 0), combo_ids=None)
-    if "Generic" not in spec:
+    if "Generic" not in spec and "Ec3Steel" not in spec:
         kind = next(iter(spec), "?")
         return CompiledCheck(definition=definition, skipped=f"{kind} checks are not evaluated by this engine", **empty)
-    g = spec["Generic"]
     try:
         ents = _select_entities(model, definition.get("applies_to") or {"type": "AllMembers"})
     except UnityError as e:
@@ -314,6 +316,22 @@ def compile_check(model, definition: dict) -> CompiledCheck:
     ents = [(ref, ms) for ref, ms in ents if ms]
     n_ent = len(ents)
     plates = bool(ents) and ents[0][0]["type"] == "PlateElement"
+    labels = None
+    entity_consts: dict = {}
+    ec3_notes: list = []
+    if "Ec3Steel" in spec:
+        # EN 1993-1-1 member check: the rules become a Generic program over per-entity section constants (ec3.py)
+        if plates:
+            return CompiledCheck(definition=definition, skipped="Ec3Steel checks apply to members, not plates", **empty)
+        ents = [(ref, ms) for ref, ms in ents if model.member_raw(ms[0])[0]]          # rigid links carry no section
+        n_ent = len(ents)
+        per = [ec3.entity_constants(model, spec["Ec3Steel"] or {}, _chain(model, ms)[0]) for _, ms in ents]
+        entity_consts = {n: np.array([c[n] for c, _ in per], np.float64) for n in ec3.CONST_NAMES}
+        ec3_notes = sorted({note for _, notes in per for note in notes})
+        g = ec3.program(ec3.CONST_NAMES)
+        labels = ec3.LABELS
+    else:
+        g = spec["Generic"]
     if plates:      # "members" = TRI3 rows of the plate, nodes = its corner nodes
         chains = [(ms, list(dict.fromkeys(int(n) for r in ms for n in model.p_nodes[r]))) for _, ms in ents]
     else:
@@ -369,7 +387,10 @@ def compile_check(model, definition: dict) -> CompiledCheck:
 
         def target(i):      # member whose properties a constant quantity reads for entity i (-1: no reference member)
             return int(ent_ref[i, 0]) if of_ref else chains[i][0][0]
-        if qk == "Constant":
+        if qk == "_EntityConstant":          # bound by the Ec3Steel program: one value per entity
+            ct_cols.append(entity_consts[qv] if n_ent else np.zeros(0))
+            desc[new] = (V_CONST, len(ct_cols) - 1, 0, 0)
+        elif qk == "Constant":
             ct_cols.append(np.full(n_ent, float(qv)))
             desc[new] = (V_CONST, len(ct_cols) - 1, 0, 0)
         elif qk == "DimensionedConstant":
@@ -411,8 +432,12 @@ def compile_check(model, definition: dict) -> CompiledCheck:
             station = 0
             if at == AGG["AtFraction"]:
                 if multi and not of_ref:
-                    return CompiledCheck(definition=definition, **empty,
-                                         skipped="AtFraction member forces on member-set entities are not evaluated")
+                    if labels is not None:       # Ec3Steel on a member set: quarter points of the FIRST member (noted)
+                        if "C1 of a member-set entity uses the quarter points of its first member" not in warnings:
+                            warnings.append("C1 of a member-set entity uses the quarter points of its first member")
+                    else:
+                        return CompiledCheck(definition=definition, **empty,
+                                             skipped="AtFraction member forces on member-set entities are not evaluated")
                 frac = float(agg.get("fraction", 0.5))
                 station = int(round(frac * 4))
                 if abs(station / 4 - frac) > 1e-12:
@@ -458,7 +483,7 @@ def compile_check(model, definition: dict) -> CompiledCheck:
         ent_node_ptr=ent_node_ptr, ent_nodes=ent_nodes, frames=frames, ent_ref=ent_ref, plates=plates,
         var_names=[names[o] for o in order], var_desc=desc,
         code=np.array(code, np.int32).reshape(-1, 2), consts=np.array(consts, np.float64), ctab=np.ascontiguousarray(ctab),
-        demand=demand, capacity=capacity, combo_ids=combo_ids, warnings=warnings)
+        demand=demand, capacity=capacity, combo_ids=combo_ids, warnings=warnings + ec3_notes, spec=g, labels=labels)
 
 
 def _evaluation_order(variables: list, var_index: dict) -> list:
@@ -582,8 +607,14 @@ def _status(u: float, thresholds) -> str:
 
 def _trace(c: CompiledCheck, values, u, dem, cap) -> list:
     """CalcStep rows (pydantic_models.py:146-153): one per variable at the governing combination, then the verdict."""
-    g = c.definition["spec"]["Generic"]
+    g = c.spec if c.spec is not None else c.definition["spec"]["Generic"]
     src = {v["name"]: v["source"] for v in g.get("variables") or []}
+    if c.labels is not None:
+        # generated program (Ec3Steel): the rule utilisations and a few intermediate values under their code-clause labels
+        steps = [{"label": c.labels[n], "formula": str(src[n].get("Expression", "")), "substituted": "", "unit": "", "value": float(x)}
+                 for n, x in zip(c.var_names, values) if n in c.labels and n != "gov"]
+        steps.append({"label": "Governing", "formula": "max of the rules above", "substituted": "", "unit": "", "value": float(u)})
+        return steps
 
     def formula(name):
         s_ = src.get(name, {})

@@ -144,6 +144,7 @@ class ModelArrays:
     hinge_curves: list = field(default_factory=list)
     # unity checks (pydantic_models.py:2202-2220): raw definitions + what their quantities read
     unity_checks: list = field(default_factory=list)
+    member_sets_raw: list = field(default_factory=list)        # raw member_sets records (buckling lengths of the EC3 check)
     combo_limit_state: list = field(default_factory=list)      # per combination: "SLS" | "ULS" | ... | None
     m_classification: list = field(default_factory=list)       # per member: classification string or None
     m_section_raw: list = field(default_factory=list)          # per member: (section dict, material dict) or None
@@ -702,7 +703,7 @@ def parse_document(doc: dict) -> ModelArrays:
         load_cases=load_cases, combo_ids=combo_ids, combo_names=combo_names, combo_factors=combo_factors,
         imperfections=list(analysis.get("imperfection_cases") or []), member_sets=member_sets,
         options=opts, warnings=warnings, support_curves=support_curves, hinge_curves=hinge_curves,
-        unity_checks=list(analysis.get("unity_checks") or []),
+        unity_checks=list(analysis.get("unity_checks") or []), member_sets_raw=list(model.get("member_sets") or []),
         combo_limit_state=[c.get("limit_state") for c in combos],
         m_classification=m_classification, m_section_raw=m_section_raw,
         m_ref_member=m_ref_member, m_ref_node=m_ref_node,

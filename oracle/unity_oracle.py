@@ -87,7 +87,8 @@ def evaluate(model, res) -> list:
     plan = res.plan
     out = []
     for d in model.unity_checks:
-        g = d["spec"]["Generic"]
+        is_ec3 = "Ec3Steel" in d["spec"]
+        g = None if is_ec3 else d["spec"]["Generic"]
         cols = [c for c in range(plan.n_rhs) if plan.kinds[c] == "Loadcombination"]
         ids = [int(i) for i in (d.get("load_combination_ids") or [])]
         if ids:
@@ -102,6 +103,26 @@ def evaluate(model, res) -> list:
             else:
                 nodes = _nodes_along(model, members)
             best = None
+            if is_ec3:
+                from oracle import ec3_oracle
+                if not model.member_raw(members[0])[0]:
+                    continue                                          # rigid links carry no section
+                cst = ec3_oracle.constants(model, d["spec"]["Ec3Steel"] or {}, members)
+                mf = lambda comp, agg, c, **kw: _quantity(model, res, c, members, nodes, {"MemberForce": {   # noqa: E731
+                    "component": comp, "aggregation": dict(type=agg, **kw)}})
+                rows = None
+                for c in cols:
+                    f = dict(Nmax=mf("N", "Max", c), Nmin=mf("N", "Min", c), Vy=mf("Vy", "MaxAbs", c), Vz=mf("Vz", "MaxAbs", c),
+                             My=mf("My", "MaxAbs", c), Mz=mf("Mz", "MaxAbs", c), Ma=mf("Mz", "AtFraction", c, fraction=0.25),
+                             Mb=mf("Mz", "AtFraction", c, fraction=0.5), Mc=mf("Mz", "AtFraction", c, fraction=0.75))
+                    r = ec3_oracle.rules(cst, f)
+                    if best is None or r["gov"] > best[0]:
+                        best, rows = (r["gov"], r["gov"], 1.0, c), r
+                per.append({"entity": ref, "utilization": 0.0, "demand": 0.0, "capacity": None, "governing_combination_id": None}
+                           if best is None else
+                           {"entity": ref, "utilization": best[0], "demand": best[1], "capacity": best[2],
+                            "governing_combination_id": int(plan.ids[best[3]]), "rules": rows})
+                continue
             for c in cols:
                 env = {}
                 pending = list(g.get("variables") or [])

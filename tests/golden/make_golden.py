@@ -509,6 +509,21 @@ emit("pdelta_near_euler_load", c, [
     X(f"loadcombinations/C/displacement_nodes/{ntip}/dx", PD_H * PD_L ** 3 / (3 * PD_EI) * amplification(P), 0.0, 1e-4),
 ], mut)
 
+# 12c EN 1993-1-1 member check: the reference's own check_beam builder (fers_core/builders.py:152-250) on the model of its
+# acceptance test (tests/functionality/test_check_beam.py:25-45): IPE300, 6 m, S235, simply supported, UDL 10 kN/m x 1.35.
+# Named sections come from the catalogue file the reference ships (tests/refshim reads it where `sectionproperties` is absent).
+from fers_core import check_beam  # noqa: E402
+
+reset()
+cb = check_beam(6.0, "IPE300", material="S235", support="simply_supported", udl=10000.0)
+emit("ec3_check_beam_ipe300", cb, [
+    X("loadcombinations/ULS/member_results/1/section_forces/1/forces/mz", -60750.0, 1e-6, 1e-9),      # M_Ed = 1.35 q L^2 / 8 (sagging)
+    X("unity_check_results/0/governing/trace/label=Bending z (6.2.5)/value", 60.75 / 147.6, 0.0, 0.03),                   # "Bending z (6.2.5)" hand calculation
+])
+reset()
+cb = check_beam(4.0, "HEA200", material="S355", support="fixed", udl=20000.0)
+emit("ec3_check_beam_hea200_fixed", cb, [])
+
 # 13 spring support + truss members (auto-restrained rotations)
 reset()
 c = FERS(); linear(c); mat = steel(); s = ipe180(mat)

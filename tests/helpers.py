@@ -44,7 +44,10 @@ def lookup(results: dict, path: str):
     for i, p in enumerate(parts):
         if p == "__sum_reaction_fz":
             return abs(sum(n["nodal_forces"]["fz"] for n in cur["reaction_nodes"].values()))
-        if isinstance(cur, list):
+        if isinstance(cur, list) and "=" in p:          # "label=Bending z (6.2.5)": the record whose field has that value
+            key, val = p.split("=", 1)
+            cur = next(item for item in cur if str(item.get(key)) == val)
+        elif isinstance(cur, list):
             cur = cur[int(p)]
         else:
             cur = cur[p]

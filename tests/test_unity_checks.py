@@ -113,7 +113,9 @@ def test_check_compilation_tables():
     assert len(bend.entities) == 2 and bend.var_names[-1] == "c"          # the expression moves after what it names
     assert bend.var_desc[bend.var_names.index("M")].tolist() == [unity.V_FORCE, 5, 0, 0]
     assert shear.var_desc[shear.var_names.index("Vq")].tolist() == [unity.V_FORCE, 1, 5, 1]
-    assert ec3.skipped is not None and "Ec3Steel" in ec3.skipped
+    # Ec3Steel: compiled into the same tables from the generated program (fers_core_b200/ec3.py); this section has no wel / wpl
+    assert ec3.skipped is None and ec3.labels is not None and len(ec3.entities) == 2
+    assert any("no wel / wpl" in w for w in ec3.warnings) and len(ec3.var_names) <= unity.MAX_VARS
     assert unity._status(0.5, None) == "Green" and unity._status(0.9, None) == "Yellow"
     assert unity._status(0.97, None) == "Orange" and unity._status(1.2, None) == "Red"
 
@@ -145,7 +147,7 @@ def test_unity_checks_match_oracle_and_example_100():
     b = ucs["bending"]["governing"]
     assert b["demand"] == pytest.approx(1.5 * 5000 * 6 / 4 * 0.09 / 1.321e-5, rel=1e-9) and b["capacity"] == 235e6
     assert b["governing_combination_id"] == 12
-    assert ucs["ec3"]["per_entity"] == [] and "not evaluated" in ucs["ec3"]["message"]
+    assert len(ucs["ec3"]["per_entity"]) == 2 and ucs["ec3"]["governing"]["trace"][-1]["label"] == "Governing"
     # every check against the oracle restatement on the oracle's own results
     model = wire.parse_document(doc)
     want = {w["check_id"]: w for w in unity_oracle.evaluate(
@@ -257,8 +259,7 @@ def test_plate_stress_checks_match_oracle(name):
 
 
 def _generic_only(model):
-    model.unity_checks = [d for d in model.unity_checks if "Generic" in d["spec"]]
-    return model
+    return model          # the oracle evaluates Ec3Steel checks as well (oracle/ec3_oracle.py)
 
 
 @pytest.mark.gpu
