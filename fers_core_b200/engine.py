@@ -530,6 +530,12 @@ class Engine:
         rec["U"] = d_u
         return rec
 
+    def run_linear_sharded(self, factors: np.ndarray, gather=("U", "R", "f_local"), detail: bool = False) -> dict:
+        """run_linear for all ranks of the default torch.distributed group at once: combinations sharded over the ranks,
+        result tensors gathered with one all_gather each (fers_core_b200.dist.run_linear_sharded)."""
+        from . import dist as _dist
+        return _dist.run_linear_sharded(self, factors, gather, detail)
+
     def span_tables(self):
         """Span loads per load case as CSR over members: (sp_ptr [Nlc*(Nm+1)] int32, sp_rows [*,9])."""
         m = self.model
@@ -937,6 +943,15 @@ def solve_lazy(doc: dict, device=None):
     results would not fit anywhere.  Same keys and numbers as ``solve_document(doc)["results"]``."""
     model = wire.parse_document(doc)
     return lazy_bundle(model, analyze(model, device))
+
+
+def solve_fers(calc, device=None, lazy: bool = True):
+    """Input fast path of the drop-in boundary: a reference ``FERS`` object in, results out, without the document round trip
+    of ``FERS.run_analysis`` (wire.from_fers: the object graph straight to arrays).  Returns the lazy ``ResultsBundle`` view
+    (results.lazy_bundle) or, with lazy=False, the result document as a dict (``results`` key of calculate_from_json)."""
+    model = wire.from_fers(calc)
+    res = analyze(model, device)
+    return lazy_bundle(model, res) if lazy else results_to_wire(model, res)
 
 
 def calculate_from_json(input_json: str) -> str:

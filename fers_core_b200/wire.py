@@ -243,38 +243,185 @@ def _index_map(ids: np.ndarray, what: str) -> dict:
     return m
 
 
+# ---- column records of the two big entity lists ------------------------------------------------------------------
+# The wire document and the reference's object graph are read into the same column records (one list / array per field);
+# everything after that is shared, so `from_fers(calc)` equals `parse_document(calc.to_dict())` by construction.
+@dataclass
+class NodeColumns:
+    ids: np.ndarray               # int64 [Nn]
+    xyz: np.ndarray               # f64 [Nn,3]
+    support: list                 # per node: None | support id | inline support dict
+
+
+@dataclass
+class MemberColumns:
+    ids: np.ndarray               # int64 [Nm]
+    start: np.ndarray             # int64 [Nm] node ids
+    end: np.ndarray
+    mtype: list                   # member_type spellings
+    rotation: np.ndarray          # f64 [Nm] degrees
+    section: list                 # section id or None
+    mirror: list
+    start_hinge: list
+    end_hinge: list
+    start_offset: list            # {X, Y, Z} or None
+    end_offset: list
+    classification: list
+    ref_member: list
+    ref_node: list
+    weight: list
+
+
+def node_columns(nodes: list) -> NodeColumns:
+    nn = len(nodes)
+    ids = np.fromiter((int(n["id"]) for n in nodes), np.int64, nn)
+    xyz = np.array([[float(n["X"]), float(n["Y"]), float(n["Z"])] for n in nodes], np.float64).reshape(nn, 3)
+    return NodeColumns(ids, xyz, [n.get("nodal_support") for n in nodes])
+
+
+def member_columns(members: list) -> MemberColumns:
+    nm = len(members)
+    g = lambda k: [m.get(k) for m in members]          # noqa: E731
+    return MemberColumns(
+        ids=np.fromiter((int(m["id"]) for m in members), np.int64, nm),
+        start=np.fromiter((int(m["start_node_id"]) for m in members), np.int64, nm),
+        end=np.fromiter((int(m["end_node_id"]) for m in members), np.int64, nm),
+        mtype=[m.get("member_type", "Normal") for m in members],
+        rotation=np.fromiter((float(m.get("rotation_angle") or 0.0) for m in members), np.float64, nm),
+        section=g("section"), mirror=g("mirror"), start_hinge=g("start_hinge"), end_hinge=g("end_hinge"),
+        start_offset=g("start_offset"), end_offset=g("end_offset"), classification=g("classification"),
+        ref_member=g("reference_member"), ref_node=g("reference_node"), weight=g("weight"))
+
+
 def parse_document(doc: dict) -> ModelArrays:
     """Flatten a wire document (dict) into :class:`ModelArrays`."""
     if not isinstance(doc, dict) or "model" not in doc or "analysis" not in doc:
         raise WireError("document must contain 'model' and 'analysis'")
     model, analysis = doc["model"], doc["analysis"]
+    return build_model_arrays(node_columns(model.get("nodes") or []), member_columns(model.get("members") or []), model, analysis)
+
+
+def from_fers(calc) -> ModelArrays:
+    """Input fast path: the reference's FERS object graph straight to :class:`ModelArrays`, without
+    the ``to_dict`` -> pydantic gate -> ``json.dumps`` -> ``json.loads`` round trip of ``FERS.run_analysis``
+    (fers_core/fers/fers.py:275-313; ~8 s at configs[3]).  Entities are collected the way ``FERS.to_dict`` collects them
+    (fers.py:315-361: ``get_all_nodes`` / ``get_all_members`` order, fers.py:899-973, defines the DOF numbering); the
+    two big lists (nodes, members) and the two big load lists (nodal, distributed) are read attribute by attribute into
+    the column records the wire parser produces, the small tables go through their own ``to_dict``.  Everything after the
+    columns is the code ``parse_document`` runs, so the result equals ``parse_document(calc.to_dict())`` field for field
+    (tests/test_from_fers.py)."""
+    members = calc.get_all_members()
+    nodes = calc.get_all_nodes()
+    nn, nm = len(nodes), len(members)
+    ncols = NodeColumns(ids=np.fromiter((int(n.id) for n in nodes), np.int64, nn),
+                        xyz=np.array([[float(n.X), float(n.Y), float(n.Z)] for n in nodes], np.float64).reshape(nn, 3),
+                        support=[n.nodal_support.id if n.nodal_support else None for n in nodes])
+    oid = lambda o: o.id if o else None          # noqa: E731
+    mcols = MemberColumns(
+        ids=np.fromiter((int(m.id) for m in members), np.int64, nm),
+        start=np.fromiter((int(m.start_node.id) for m in members), np.int64, nm),
+        end=np.fromiter((int(m.end_node.id) for m in members), np.int64, nm),
+        mtype=[m.member_type.value for m in members],
+        rotation=np.fromiter((float(m.rotation_angle or 0.0) for m in members), np.float64, nm),
+        section=[m.section.id if m.section is not None else None for m in members],
+        mirror=[m.mirror for m in members], start_hinge=[oid(m.start_hinge) for m in members],
+        end_hinge=[oid(m.end_hinge) for m in members], start_offset=[m.start_offset for m in members],
+        end_offset=[m.end_offset for m in members], classification=[m.classification for m in members],
+        ref_member=[oid(m.reference_member) for m in members], ref_node=[oid(m.reference_node) for m in members],
+        weight=[0.0] * nm)                         # Member.to_dict emits weight 0.0 (members/member.py:186-193)
+    settings = calc.settings.to_dict()
+    model = {
+        "member_sets": [ms.to_dict() for ms in calc.member_sets],
+        "materials": [m.to_dict() for m in calc.get_unique_materials_from_all_member_sets()],
+        "sections": [s_.to_dict() for s_ in calc.get_unique_sections_from_all_member_sets()],
+        "nodal_supports": [ns.to_dict() for ns in calc.get_unique_nodal_support_from_all_member_sets()],
+        "member_hinges": [h.to_dict() for h in calc.get_unique_member_hinges_from_all_member_sets()],
+        "plate_surfaces": [ps.to_dict() for ps in calc.plate_surfaces],
+        "plate_elements": [p.to_dict() for p in calc.plates],
+    }
+
+    def vec(v):
+        return (v["X"], v["Y"], v["Z"]) if isinstance(v, dict) else tuple(v)
+    cases = []
+    for lc in calc.load_cases:
+        cols = {}
+        for key, items in (("nodal_loads", lc.nodal_loads), ("nodal_moments", lc.nodal_moments)):
+            n = len(items)
+            cols[key] = {"node": np.fromiter((int(x.node.id) for x in items), np.int64, n),
+                         "magnitude": np.fromiter((float(x.magnitude) for x in items), np.float64, n),
+                         "direction": np.array([vec(x.direction) for x in items], np.float64).reshape(n, 3)}
+        dls = lc.distributed_loads
+        n = len(dls)
+        cols["distributed_loads"] = {
+            "member": np.fromiter((int(x.member.id) for x in dls), np.int64, n),
+            "magnitude": np.fromiter((float(x.magnitude) for x in dls), np.float64, n),
+            "end_magnitude": np.fromiter((float(x.magnitude if x.end_magnitude is None else x.end_magnitude) for x in dls), np.float64, n),
+            "direction": np.array([vec(x.direction) for x in dls], np.float64).reshape(n, 3),
+            "start_frac": np.fromiter((float(x.start_frac or 0.0) for x in dls), np.float64, n),
+            "end_frac": np.fromiter((float(1.0 if x.end_frac is None else x.end_frac) for x in dls), np.float64, n)}
+        cases.append({"id": lc.id, "name": lc.name, "_columns": cols,
+                      "surface_loads": [x.to_dict() for x in lc.surface_loads],
+                      "member_point_loads": [x.to_dict() for x in lc.member_point_loads],
+                      "member_point_moments": [x.to_dict() for x in lc.member_point_moments],
+                      "plate_pressures": [x.to_dict() for x in lc.plate_pressures]})
+    analysis = {"options": settings.get("analysis_options"),
+                "load_cases": cases,
+                "load_combinations": [c.to_dict() for c in calc.load_combinations],
+                "imperfection_cases": [c.to_dict() for c in calc.imperfection_cases],
+                "unity_checks": [c.to_dict() if hasattr(c, "to_dict") else c for c in calc.unity_checks]}
+    return build_model_arrays(ncols, mcols, model, analysis)
+
+
+def build_model_arrays(ncols: NodeColumns, mcols: MemberColumns, model: dict, analysis: dict) -> ModelArrays:
+    """Everything after the two big lists were read into columns; ``model`` / ``analysis`` carry the small tables (supports,
+    materials, sections, hinges, member sets, plates, load cases, combinations, imperfections, unity checks)."""
     opts = parse_options(analysis.get("options"))
     warnings: list = []
-    if opts.rigid_strategy == "LinearMpc" and any(
-            _norm_enum(m.get("member_type", "Normal")) == "rigid" for m in (model.get("members") or [])):
+    if opts.rigid_strategy == "LinearMpc" and any(_norm_enum(t) == "rigid" for t in mcols.mtype):
         # RigidStrategy.LinearMpc (pydantic_models.py:1047-1049): the rigid link as a constraint transformation is not
         # implemented; rigid members are stiff members (hostlogic.rigid_property_row) under either strategy
         warnings.append(("W_LINEAR_MPC_AS_RIGID_MEMBER", "rigid_strategy=LinearMpc: rigid members are modelled as stiff "
                          "members (RigidMember strategy), not as multi-point constraints"))
+    nd = _parse_nodes(ncols, model, opts)
+    sc = _parse_sections(model, opts, warnings)
+    mats = {int(m["id"]): m for m in (model.get("materials") or [])}
+    mb = _parse_members(mcols, nd, sc, model, opts, warnings)
+    pl = _parse_plates(model, mats, nd, warnings)
+    load_cases = _parse_load_cases(analysis, opts, nd, mb, sc, pl, mcols, warnings)
+    combos = analysis.get("load_combinations") or []
+    combo_ids, combo_names, combo_factors = _parse_combinations(combos, load_cases)
+    wp = _warping_nodes(nd, mb, sc, warnings)
+    return ModelArrays(
+        n_real_nodes=wp["n_real"], warp_node=wp["warp_node"], w_member=wp["w_member"], w_aux=wp["w_aux"],
+        node_ids=wp["node_ids"], xyz=wp["xyz"], node_support_id=wp["node_support_id"], bc_code=wp["bc_code"], bc_k=wp["bc_k"],
+        m_ids=mcols.ids, m_n1=mb["m_n1"], m_n2=mb["m_n2"], m_type=mb["m_type"], m_roll=mb["m_roll"], m_prop=mb["m_prop"],
+        m_rel=mb["m_rel"], prop=sc["prop"], prop_rho_a=np.array(sc["prop_rho_a"], np.float64), rel=mb["rel"],
+        p_ids=pl["p_ids"], p_nodes=pl["p_nodes"], p_data=pl["p_data"], p_flags=pl["p_flags"],
+        load_cases=load_cases, combo_ids=combo_ids, combo_names=combo_names, combo_factors=combo_factors,
+        imperfections=list(analysis.get("imperfection_cases") or []), member_sets=mb["member_sets"],
+        options=opts, warnings=warnings, support_curves=nd["support_curves"], hinge_curves=mb["hinge_curves"],
+        unity_checks=list(analysis.get("unity_checks") or []), member_sets_raw=list(model.get("member_sets") or []),
+        combo_limit_state=[c.get("limit_state") for c in combos],
+        m_classification=list(mcols.classification), m_section_raw=mb["m_section_raw"],
+        m_ref_member=mb["m_ref_member"], m_ref_node=mb["m_ref_node"],
+    )
 
-    # ---- nodes (pydantic_models.py:Node; wire order = DOF numbering order) ----------------
-    nodes = model.get("nodes") or []
-    nn = len(nodes)
-    node_ids = np.fromiter((int(n["id"]) for n in nodes), np.int64, nn)
-    xyz = np.array([[float(n["X"]), float(n["Y"]), float(n["Z"])] for n in nodes], np.float64).reshape(nn, 3)
+
+def _parse_nodes(ncols: NodeColumns, model: dict, opts: Options) -> dict:
+    """Nodes (pydantic_models.py:Node; wire order = DOF numbering order) and supports (2104-2115; default all-Fixed
+    nodalsupport.py:29-41)."""
+    node_ids, xyz = ncols.ids, ncols.xyz
+    nn = len(node_ids)
     node_index = _index_map(node_ids, "node")
     if not np.isfinite(xyz).all():
         raise WireError(f"node {int(node_ids[np.nonzero(~np.isfinite(xyz).all(axis=1))[0][0]])}: non-finite coordinate")
-
-    # ---- supports (pydantic_models.py:2104-2115; default all-Fixed nodalsupport.py:29-41) --
     supports = {int(s["id"]): s for s in (model.get("nodal_supports") or [])}
     bc_code = np.zeros((nn, 6), np.uint8)
     bc_k = np.zeros((nn, 6), np.float64)
     node_support_id = np.full(nn, -1, np.int64)
     warp_fixed = np.zeros(nn, bool)         # support restrains the warping DOF (NodalSupport.warping_condition)
     support_curves: list = []
-    for i, n in enumerate(nodes):
-        sid = n.get("nodal_support")
+    for i, sid in enumerate(ncols.support):
         if sid is None:
             continue
         if isinstance(sid, dict):
@@ -282,7 +429,7 @@ def parse_document(doc: dict) -> ModelArrays:
         else:
             sid = int(sid)
             if sid not in supports:
-                raise WireError(f"node {n['id']}: unknown nodal_support {sid}")
+                raise WireError(f"node {int(node_ids[i])}: unknown nodal_support {sid}")
             sup = supports[sid]
         node_support_id[i] = sid
         wc = sup.get("warping_condition")
@@ -321,8 +468,12 @@ def parse_document(doc: dict) -> ModelArrays:
         for d in (2, 3, 4):
             free = bc_code[:, d] == BC_FREE
             bc_code[free, d] = BC_FIXED
+    return dict(node_ids=node_ids, xyz=xyz, node_index=node_index, bc_code=bc_code, bc_k=bc_k, node_support_id=node_support_id,
+                warp_fixed=warp_fixed, support_curves=support_curves)
 
-    # ---- materials / sections -> property table ---------------------------------------
+
+def _parse_sections(model: dict, opts: Options, warnings: list) -> dict:
+    """materials / sections -> property table (pydantic_models.py:1052-1114, 1497-1504)."""
     mats = {int(m["id"]): m for m in (model.get("materials") or [])}
     secs = {int(s["id"]): s for s in (model.get("sections") or [])}
     prop_rows: list = []
@@ -367,9 +518,26 @@ def parse_document(doc: dict) -> ModelArrays:
         prop_rows.append(row)
         prop_rho_a.append(float(mat.get("density") or 0.0) * A)
     prop = np.array(prop_rows, np.float64).reshape(len(prop_rows), NPROP)
+    return dict(prop=prop, prop_rho_a=prop_rho_a, sec_row=sec_row, sec_raw=sec_raw, sec_eiyz=sec_eiyz)
 
-    # ---- hinges (pydantic_models.py:2062-2087; release fields are spring stiffnesses) ----
+
+def _parse_members(mc: MemberColumns, nd: dict, sc: dict, model: dict, opts: Options, warnings: list) -> dict:
+    """Members (pydantic_models.py:1507-1549), hinges (2062-2087; release fields are spring stiffnesses), member sets.
+    The common case (no hinge, no end offset, a section without shear-centre offset or product of inertia) is vectorised;
+    members that need a modifier record are visited one by one, in wire order."""
     hinges = {int(h["id"]): h for h in (model.get("member_hinges") or [])}
+    sec_row, sec_raw, sec_eiyz = sc["sec_row"], sc["sec_raw"], sc["sec_eiyz"]
+    node_index, xyz = nd["node_index"], nd["xyz"]
+    capacity_warned: set = set()
+
+    def hinge_curve(hid, name, curve):
+        pts = np.array([[float(p[0]), float(p[1])] for p in curve["points"]], np.float64)
+        comp = _MEMBER_FORCE.get(str(curve.get("depends_on")))
+        if comp is None:
+            raise WireError(f"member hinge {hid}.{name}: depends_on must be N/Vy/Vz/Mx/My/Mz, got {curve.get('depends_on')!r}")
+        if len(pts) < 2 or (np.diff(pts[:, 0]) < 0.0).any() or not (pts[:, 1] > 0.0).all() or not np.isfinite(pts).all():
+            raise WireError(f"member hinge {hid}.{name}: stiffness curve needs >= 2 points sorted by force with positive stiffness")
+        return comp, pts, bool(curve.get("signed"))
 
     def hinge_row(hid) -> np.ndarray:
         r = np.full(6, RIGID_RELEASE)
@@ -393,55 +561,56 @@ def parse_document(doc: dict) -> ModelArrays:
                 r[d] = float(np.interp(0.0, *hinge_curve(int(hid), f, curve)[1].T))
         return r
 
-    def hinge_curve(hid, name, curve):
-        pts = np.array([[float(p[0]), float(p[1])] for p in curve["points"]], np.float64)
-        comp = _MEMBER_FORCE.get(str(curve.get("depends_on")))
-        if comp is None:
-            raise WireError(f"member hinge {hid}.{name}: depends_on must be N/Vy/Vz/Mx/My/Mz, got {curve.get('depends_on')!r}")
-        if len(pts) < 2 or (np.diff(pts[:, 0]) < 0.0).any() or not (pts[:, 1] > 0.0).all() or not np.isfinite(pts).all():
-            raise WireError(f"member hinge {hid}.{name}: stiffness curve needs >= 2 points sorted by force with positive stiffness")
-        return comp, pts, bool(curve.get("signed"))
-
-    hinge_curves: list = []
-    capacity_warned: set = set()
-
-    # ---- members (pydantic_models.py:1507-1549) ----------------------------------------
-    members = model.get("members") or []
-    nm = len(members)
-    m_ids = np.fromiter((int(m["id"]) for m in members), np.int64, nm)
+    nm = len(mc.ids)
+    m_ids = mc.ids
     member_index = _index_map(m_ids, "member")
-    m_n1 = np.zeros(nm, np.int32)
-    m_n2 = np.zeros(nm, np.int32)
-    m_type = np.zeros(nm, np.int32)
-    m_roll = np.zeros(nm, np.float64)
+    try:
+        m_n1 = np.fromiter((node_index[int(v)] for v in mc.start), np.int32, nm)
+        m_n2 = np.fromiter((node_index[int(v)] for v in mc.end), np.int32, nm)
+    except KeyError:
+        for i in range(nm):
+            for v in (mc.start[i], mc.end[i]):
+                if int(v) not in node_index:
+                    raise WireError(f"member {int(m_ids[i])}: unknown node {int(v)!r}") from None
+        raise
+    type_code = {}
+    for t in set(mc.mtype):
+        code = _MEMBER_TYPES.get(_norm_enum(t))
+        if code is None:
+            bad = mc.mtype.index(t)
+            raise WireError(f"member {int(m_ids[bad])}: unknown member_type {t!r}")
+        type_code[t] = code
+    m_type = np.fromiter((type_code[t] for t in mc.mtype), np.int32, nm)
+    m_roll = np.radians(mc.rotation)
     m_prop = np.full(nm, -1, np.int32)
-    m_rel = np.full(nm, -1, np.int32)
-    rel_rows: list = []
-    m_classification = [m.get("classification") for m in members]
-    m_section_raw = [sec_raw.get(int(m["section"])) if m.get("section") is not None else None for m in members]
-    for i, m in enumerate(members):
-        try:
-            m_n1[i] = node_index[int(m["start_node_id"])]
-            m_n2[i] = node_index[int(m["end_node_id"])]
-        except KeyError as e:
-            raise WireError(f"member {m['id']}: unknown node {e}") from None
-        t = _MEMBER_TYPES.get(_norm_enum(m.get("member_type", "Normal")))
-        if t is None:
-            raise WireError(f"member {m['id']}: unknown member_type {m.get('member_type')!r}")
-        m_type[i] = t
-        m_roll[i] = np.radians(float(m.get("rotation_angle") or 0.0))
-        sid = m.get("section")
+    for i, sid in enumerate(mc.section):
         if sid is not None:
             if int(sid) not in sec_row:
-                raise WireError(f"member {m['id']}: unknown section {sid}")
+                raise WireError(f"member {int(m_ids[i])}: unknown section {sid}")
             m_prop[i] = sec_row[int(sid)]
-        elif t != MT_RIGID:
-            raise WireError(f"member {m['id']}: non-rigid member without section")
+        elif m_type[i] != MT_RIGID:
+            raise WireError(f"member {int(m_ids[i])}: non-rigid member without section")
+    m_section_raw = [sec_raw.get(int(sid)) if sid is not None else None for sid in mc.section]
+    # sections that send their members to the modifier path: shear-centre offset (coupling on) or a product of inertia
+    sec_special = set()
+    for sid, (s_raw, _mat) in sec_raw.items():
+        if (opts.include_shear_center_coupling and (float(s_raw.get("y_s") or 0.0) != 0.0 or float(s_raw.get("z_s") or 0.0) != 0.0)) \
+                or sec_eiyz.get(sid, 0.0) != 0.0 or not np.isfinite(float(s_raw.get("y_s") or 0.0) + float(s_raw.get("z_s") or 0.0)):
+            sec_special.add(sid)
+    m_rel = np.full(nm, -1, np.int32)
+    rel_rows: list = []
+    hinge_curves: list = []
+    for i in range(nm):
+        sid = mc.section[i]
+        if mc.start_hinge[i] is None and mc.end_hinge[i] is None and not mc.start_offset[i] and not mc.end_offset[i] \
+                and (sid is None or int(sid) not in sec_special):
+            continue
+        t = int(m_type[i])
         # shear-centre eccentricity (pydantic_models.py:1106-1111; toggle 1358-1361; `mirror` negates it, 1521-1524)
         ys = zs = 0.0
         if sid is not None and opts.include_shear_center_coupling and t not in (MT_TRUSS, MT_RIGID):
             s_raw = sec_raw[int(sid)][0]
-            sgn = -1.0 if m.get("mirror") else 1.0
+            sgn = -1.0 if mc.mirror[i] else 1.0
             ys, zs = sgn * float(s_raw.get("y_s") or 0.0), sgn * float(s_raw.get("z_s") or 0.0)
             if not (np.isfinite(ys) and np.isfinite(zs)):
                 raise WireError(f"section {sid}: y_s / z_s must be finite")
@@ -450,22 +619,21 @@ def parse_document(doc: dict) -> ModelArrays:
         # end offsets (MemberEndOffset, pydantic_models.py:525-531, global X Y Z): the elastic axis runs between the
         # offset points, each tied to its node by a rigid arm
         offs = np.zeros(6)
-        for e, key in enumerate(("start_offset", "end_offset")):
-            o = m.get(key)
+        for e, o in enumerate((mc.start_offset[i], mc.end_offset[i])):
             if o:
                 offs[3 * e:3 * e + 3] = [float(o.get(ax) or 0.0) for ax in ("X", "Y", "Z")]
         if not np.isfinite(offs).all():
-            raise WireError(f"member {m['id']}: end offsets must be finite")
-        if m.get("start_hinge") is not None or m.get("end_hinge") is not None or ys != 0.0 or zs != 0.0 or offs.any() or eiyz != 0.0:
+            raise WireError(f"member {int(m_ids[i])}: end offsets must be finite")
+        if mc.start_hinge[i] is not None or mc.end_hinge[i] is not None or ys != 0.0 or zs != 0.0 or offs.any() or eiyz != 0.0:
             m_rel[i] = len(rel_rows)
-            rel_rows.append(np.concatenate([hinge_row(m.get("start_hinge")), hinge_row(m.get("end_hinge")), [ys, zs], offs, [eiyz]]))
-            for e, key in enumerate(("start_hinge", "end_hinge")):
-                h = hinges.get(int(m[key])) if m.get(key) is not None else None
+            rel_rows.append(np.concatenate([hinge_row(mc.start_hinge[i]), hinge_row(mc.end_hinge[i]), [ys, zs], offs, [eiyz]]))
+            for e, hid in enumerate((mc.start_hinge[i], mc.end_hinge[i])):
+                h = hinges.get(int(hid)) if hid is not None else None
                 for d, f in enumerate(_HINGE_CURVES if h else ()):
                     if h.get(f) and h[f].get("points"):
-                        hinge_curves.append((i, int(m_rel[i]), 6 * e + d) + hinge_curve(int(m[key]), f, h[f]))
-        if t == MT_CABLE:
-            warnings.append(("W_CABLE_AS_TENSION", f"member {m['id']}: cable treated as tension-only straight member"))
+                        hinge_curves.append((i, int(m_rel[i]), 6 * e + d) + hinge_curve(int(hid), f, h[f]))
+    for i in np.nonzero(m_type == MT_CABLE)[0]:
+        warnings.append(("W_CABLE_AS_TENSION", f"member {int(m_ids[i])}: cable treated as tension-only straight member"))
     rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), REL_STRIDE)
     if nm:
         axis = xyz[m_n2] - xyz[m_n1]
@@ -478,8 +646,10 @@ def parse_document(doc: dict) -> ModelArrays:
     # Member.reference_member / reference_node (unity checks across members, fers_core/examples/101_...py:61-67)
     m_ref_member = np.full(nm, -1, np.int32)
     m_ref_node = np.full(nm, -1, np.int32)
-    for i, m in enumerate(members):
-        rm, rn = m.get("reference_member"), m.get("reference_node")
+    for i in range(nm):
+        rm, rn = mc.ref_member[i], mc.ref_node[i]
+        if rm is None and rn is None:
+            continue
         rm = rm.get("id") if isinstance(rm, dict) else rm
         rn = rn.get("id") if isinstance(rn, dict) else rn
         if rm is not None and int(rm) in member_index:
@@ -494,16 +664,21 @@ def parse_document(doc: dict) -> ModelArrays:
             if int(mid) in member_index:
                 idx.append(member_index[int(mid)])
         member_sets[int(ms["id"])] = idx
+    return dict(m_n1=m_n1, m_n2=m_n2, m_type=m_type, m_roll=m_roll, m_prop=m_prop, m_rel=m_rel, rel=rel, member_index=member_index,
+                member_ids=m_ids,
+                hinge_curves=hinge_curves, m_section_raw=m_section_raw, m_ref_member=m_ref_member, m_ref_node=m_ref_node,
+                member_sets=member_sets)
 
-    # ---- plate elements (pydantic_models.py:1700-1726) ---------------------------------
-    plates = model.get("plate_elements") or []
+
+def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:
+    """Plate elements (pydantic_models.py:1700-1726); plate surfaces that arrive without elements are meshed here
+    (`mesh_plate_surfaces`: ear clipping over the boundary nodes, the reference's own client-side rule)."""
+    node_index, xyz = nd["node_index"], nd["xyz"]
+    plates = list(model.get("plate_elements") or [])
     meshed = {p.get("source_surface_id") for p in plates}
-    for surf in (model.get("plate_surfaces") or []):
-        if surf.get("id") not in meshed:
-            # PlateSurface (pydantic_models.py: boundary_node_ids + mesh settings) is meshed by the reference engine;
-            # here only surfaces that arrive with their plate elements take part
-            warnings.append(("W_SURFACE_NOT_MESHED", f"plate surface {surf.get('id')}: no plate elements reference it "
-                             "(server-side meshing is not implemented); the surface is ignored"))
+    todo = [surf for surf in (model.get("plate_surfaces") or []) if surf.get("id") not in meshed]
+    if todo:
+        plates += mesh_plate_surfaces(todo, plates, nd, warnings)
     p_ids_l, p_nodes_l, p_data_l, p_flags_l = [], [], [], []
     for p in plates:
         nids = [nid["id"] if isinstance(nid, dict) else nid for nid in p["node_ids"]]
@@ -561,8 +736,21 @@ def parse_document(doc: dict) -> ModelArrays:
     plate_index = {}
     for i, pid in enumerate(p_ids_l):
         plate_index.setdefault(pid, []).append(i)
+    return dict(plates=plates, p_ids=p_ids, p_ids_l=p_ids_l, p_nodes=p_nodes, p_data=p_data, p_flags=p_flags, plate_index=plate_index)
 
-    # ---- load cases (pydantic_models.py:2048-2059) -------------------------------------
+
+def _load_records(c: dict, key: str):
+    """One load list of a load case: the wire records, or columns prepared by from_fers (``_columns`` entry)."""
+    cols = (c.get("_columns") or {}).get(key)
+    return cols if cols is not None else list(c.get(key) or [])
+
+
+def _parse_load_cases(analysis: dict, opts: Options, nd: dict, mb: dict, sc: dict, pl: dict, mcols: MemberColumns,
+                      warnings: list) -> list:
+    """Load cases (pydantic_models.py:2048-2059)."""
+    node_index, member_index, xyz = nd["node_index"], mb["member_index"], nd["xyz"]
+    m_prop, m_type = mb["m_prop"], mb["m_type"]
+    plates, p_ids_l, p_nodes, plate_index = pl["plates"], pl["p_ids_l"], pl["p_nodes"], pl["plate_index"]
     load_cases = []
     raw_cases = list(analysis.get("load_cases") or [])
     sw_case_id = None
@@ -574,45 +762,65 @@ def parse_document(doc: dict) -> ModelArrays:
     for c in raw_cases:
         lca = LoadCaseArrays(id=int(c["id"]), name=str(c.get("name", c["id"])))
         nod_node, nod_vec = [], []
-        for nl in (c.get("nodal_loads") or []):
-            v = np.zeros(6)
-            v[:3] = float(nl["magnitude"]) * _vec3(nl["direction"], "nodal_load.direction")
-            nod_node.append(_node_of(nl, node_index)); nod_vec.append(v)
-        for nmo in (c.get("nodal_moments") or []):
-            v = np.zeros(6)
-            v[3:] = float(nmo["magnitude"]) * _vec3(nmo["direction"], "nodal_moment.direction")
-            nod_node.append(_node_of(nmo, node_index)); nod_vec.append(v)
+        for key, lo in (("nodal_loads", 0), ("nodal_moments", 3)):
+            recs = _load_records(c, key)
+            if isinstance(recs, dict):                     # columns: node ids, magnitudes, directions [n,3]
+                n = len(recs["node"])
+                v = np.zeros((n, 6))
+                v[:, lo:lo + 3] = recs["magnitude"][:, None] * recs["direction"]
+                try:
+                    nod_node += [node_index[int(i)] for i in recs["node"]]
+                except KeyError as e:
+                    raise WireError(f"load case {lca.id}: nodal load on unknown node {e}") from None
+                nod_vec += list(v)
+                continue
+            for nl in recs:
+                v = np.zeros(6)
+                v[lo:lo + 3] = float(nl["magnitude"]) * _vec3(nl["direction"], key[:-1] + ".direction")
+                nod_node.append(_node_of(nl, node_index)); nod_vec.append(v)
         dl_member, dl_data = [], []
-        for dl in (c.get("distributed_loads") or []):
-            mi = _member_of(dl, member_index)
-            d = _vec3(dl["direction"], "distributed_load.direction")
-            q1 = float(dl["magnitude"])
-            q2 = float(dl["end_magnitude"]) if dl.get("end_magnitude") is not None else q1
-            a = float(dl.get("start_frac", 0.0) or 0.0)
-            b = float(dl.get("end_frac", 1.0) if dl.get("end_frac") is not None else 1.0)
-            if not (0.0 <= a <= b <= 1.0):
-                raise WireError(f"distributed load {dl.get('id')}: need 0<=start_frac<=end_frac<=1")
-            dl_member.append(mi)
-            dl_data.append(np.concatenate([q1 * d, q2 * d, [a, b]]))
+        recs = _load_records(c, "distributed_loads")
+        if isinstance(recs, dict):                         # columns: member ids, q1, q2, directions [n,3], a, b
+            a, b = recs["start_frac"], recs["end_frac"]
+            if not ((0.0 <= a) & (a <= b) & (b <= 1.0)).all():
+                raise WireError(f"load case {lca.id}: distributed load needs 0<=start_frac<=end_frac<=1")
+            try:
+                dl_member += [member_index[int(i)] for i in recs["member"]]
+            except KeyError as e:
+                raise WireError(f"load case {lca.id}: distributed load on unknown member {e}") from None
+            dl_data += list(np.concatenate([recs["magnitude"][:, None] * recs["direction"],
+                                            recs["end_magnitude"][:, None] * recs["direction"], a[:, None], b[:, None]], axis=1))
+        else:
+            for dl in recs:
+                mi = _member_of(dl, member_index)
+                d = _vec3(dl["direction"], "distributed_load.direction")
+                q1 = float(dl["magnitude"])
+                q2 = float(dl["end_magnitude"]) if dl.get("end_magnitude") is not None else q1
+                a = float(dl.get("start_frac", 0.0) or 0.0)
+                b = float(dl.get("end_frac", 1.0) if dl.get("end_frac") is not None else 1.0)
+                if not (0.0 <= a <= b <= 1.0):
+                    raise WireError(f"distributed load {dl.get('id')}: need 0<=start_frac<=end_frac<=1")
+                dl_member.append(mi)
+                dl_data.append(np.concatenate([q1 * d, q2 * d, [a, b]]))
         if opts.enable_self_weight and int(c["id"]) == sw_case_id:
             g = np.asarray(opts.gravity_direction, np.float64)
             g = g / (np.linalg.norm(g) or 1.0)
-            for i, m in enumerate(members):
+            for i in range(len(mcols.ids)):
                 if m_prop[i] < 0 or m_type[i] == MT_CABLE:
                     continue
-                w = float(m.get("weight") or 0.0)
+                w = float(mcols.weight[i] or 0.0)
                 if w == 0.0:
-                    w = prop_rho_a[m_prop[i]] * abs(opts.gravity_factor)
+                    w = sc["prop_rho_a"][m_prop[i]] * abs(opts.gravity_factor)
                 if w != 0.0:
                     dl_member.append(i)
                     dl_data.append(np.concatenate([w * g, w * g, [0.0, 1.0]]))
         pl_member, pl_data = [], []
-        for pl in (c.get("member_point_loads") or []):
+        for pl_ in (c.get("member_point_loads") or []):
             row = np.zeros(8)
-            row[:3] = float(pl["magnitude"]) * _vec3(pl["direction"], "member_point_load.direction")
-            row[6] = float(pl["position"])
-            row[7] = 1.0 if _norm_enum(pl.get("axes") or "global") == "local" else 0.0
-            pl_member.append(_member_of(pl, member_index)); pl_data.append(row)
+            row[:3] = float(pl_["magnitude"]) * _vec3(pl_["direction"], "member_point_load.direction")
+            row[6] = float(pl_["position"])
+            row[7] = 1.0 if _norm_enum(pl_.get("axes") or "global") == "local" else 0.0
+            pl_member.append(_member_of(pl_, member_index)); pl_data.append(row)
         for pm_ in (c.get("member_point_moments") or []):
             row = np.zeros(8)
             row[3:6] = float(pm_["magnitude"]) * _vec3(pm_["direction"], "member_point_moment.direction")
@@ -640,7 +848,10 @@ def parse_document(doc: dict) -> ModelArrays:
                     w = abs(float(nrm @ d)) / (np.linalg.norm(nrm) * dn) if dn > 0 else 0.0
                 pp_plate.append(i); pp_vec.append(w * float(pp["magnitude"]) * d)
         for sl in (c.get("surface_loads") or []):
-            _surface_load_to_plates(sl, xyz, p_nodes, pp_plate, pp_vec, warnings)
+            if p_nodes.shape[0]:
+                _surface_load_to_plates(sl, xyz, p_nodes, pp_plate, pp_vec, warnings)
+            else:
+                _surface_load_to_members(sl, xyz, mb, dl_member, dl_data, warnings)
         lca.nod_node = np.array(nod_node, np.int32)
         lca.nod_vec = np.array(nod_vec, np.float64).reshape(len(nod_node), 6)
         lca.dl_member = np.array(dl_member, np.int32)
@@ -653,10 +864,12 @@ def parse_document(doc: dict) -> ModelArrays:
             if not np.isfinite(arr).all():
                 raise WireError(f"load case {lca.id}: non-finite load value")
         load_cases.append(lca)
+    return load_cases
 
-    # ---- combinations (pydantic_models.py:491-505) --------------------------------------
+
+def _parse_combinations(combos: list, load_cases: list):
+    """Combinations (pydantic_models.py:491-505)."""
     lc_index = {lc.id: i for i, lc in enumerate(load_cases)}
-    combos = analysis.get("load_combinations") or []
     combo_ids = np.fromiter((int(c["id"]) for c in combos), np.int64, len(combos))
     combo_names = [str(c.get("name", c["id"])) for c in combos]
     combo_factors = np.zeros((len(combos), len(load_cases)), np.float64)
@@ -669,9 +882,14 @@ def parse_document(doc: dict) -> ModelArrays:
             if lid not in lc_index:
                 raise WireError(f"combination {c['id']}: unknown load case {lid}")
             combo_factors[ci, lc_index[lid]] += float(f["factor"])
+    return combo_ids, combo_names, combo_factors
 
-    # ---- warping torsion: auxiliary nodes carrying psi ---------------------------
-    n_real = nn
+
+def _warping_nodes(nd: dict, mb: dict, sc: dict, warnings: list) -> dict:
+    """Warping torsion: auxiliary nodes carrying psi."""
+    node_ids, xyz, node_support_id, bc_code, bc_k = nd["node_ids"], nd["xyz"], nd["node_support_id"], nd["bc_code"], nd["bc_k"]
+    m_prop, m_type, m_rel, rel, m_n1, m_n2, prop = mb["m_prop"], mb["m_type"], mb["m_rel"], mb["rel"], mb["m_n1"], mb["m_n2"], sc["prop"]
+    nn = len(node_ids)
     warp_node = np.full(nn, -1, np.int32)
     w_member = np.zeros(0, np.int32)
     w_aux = np.zeros((0, 2), np.int32)
@@ -681,7 +899,7 @@ def parse_document(doc: dict) -> ModelArrays:
         w_member = np.nonzero(has_w)[0].astype(np.int32)
         for i in w_member:
             if m_rel[i] >= 0 and rel[m_rel[i], REL_O1:REL_O2 + 3].any():
-                warnings.append(("W_WARPING_OFFSET", f"member {int(m_ids[i])}: warping couplings follow the node-to-node axis, not the offset axis"))
+                warnings.append(("W_WARPING_OFFSET", f"member {int(mb['member_ids'][i])}: warping couplings follow the node-to-node axis, not the offset axis"))
         touched = np.unique(np.concatenate([m_n1[w_member], m_n2[w_member]]))
         warp_node[touched] = nn + np.arange(len(touched), dtype=np.int32)
         w_aux = np.stack([warp_node[m_n1[w_member]], warp_node[m_n2[w_member]]], axis=1).astype(np.int32)
@@ -690,24 +908,11 @@ def parse_document(doc: dict) -> ModelArrays:
         xyz = np.concatenate([xyz, xyz[touched]])
         node_support_id = np.concatenate([node_support_id, node_support_id[touched]])
         aux_code = np.full((na, 6), BC_FIXED, np.uint8)
-        aux_code[:, 0] = np.where(warp_fixed[touched], BC_FIXED, BC_FREE)
+        aux_code[:, 0] = np.where(nd["warp_fixed"][touched], BC_FIXED, BC_FREE)
         bc_code = np.concatenate([bc_code, aux_code])
         bc_k = np.concatenate([bc_k, np.zeros((na, 6))])
-
-    return ModelArrays(
-        n_real_nodes=n_real, warp_node=warp_node, w_member=w_member, w_aux=w_aux,
-        node_ids=node_ids, xyz=xyz, node_support_id=node_support_id, bc_code=bc_code, bc_k=bc_k,
-        m_ids=m_ids, m_n1=m_n1, m_n2=m_n2, m_type=m_type, m_roll=m_roll, m_prop=m_prop, m_rel=m_rel,
-        prop=prop, prop_rho_a=np.array(prop_rho_a, np.float64), rel=rel,
-        p_ids=p_ids, p_nodes=p_nodes, p_data=p_data, p_flags=p_flags,
-        load_cases=load_cases, combo_ids=combo_ids, combo_names=combo_names, combo_factors=combo_factors,
-        imperfections=list(analysis.get("imperfection_cases") or []), member_sets=member_sets,
-        options=opts, warnings=warnings, support_curves=support_curves, hinge_curves=hinge_curves,
-        unity_checks=list(analysis.get("unity_checks") or []), member_sets_raw=list(model.get("member_sets") or []),
-        combo_limit_state=[c.get("limit_state") for c in combos],
-        m_classification=m_classification, m_section_raw=m_section_raw,
-        m_ref_member=m_ref_member, m_ref_node=m_ref_node,
-    )
+    return dict(n_real=nn, warp_node=warp_node, w_member=w_member, w_aux=w_aux, node_ids=node_ids, xyz=xyz,
+                node_support_id=node_support_id, bc_code=bc_code, bc_k=bc_k)
 
 
 def member_axis(model, m: int) -> np.ndarray:
@@ -795,6 +1000,96 @@ def plates_flat_surface(plates, p_ids_l):
     return [(-1 if by_id[pid] is None else int(by_id[pid])) for pid in p_ids_l]
 
 
+# ---- plate surfaces that arrive without elements -------------------------------------------------------------------
+def mesh_plate_surfaces(surfaces: list, plates: list, nd: dict, warnings: list) -> list:
+    """PlateSurface records (pydantic_models.py:1752-1790) -> TRI3 plate-element records, the rule of the reference's
+    client-side mesher (fers_core/plates/mesh.py:12-31, :106-148; fers/fers.py:1071-1086): the boundary polygon is
+    projected into its plane, oriented counter-clockwise and ear-clipped; element ids continue after the largest plate
+    id.  Only the boundary nodes are used: interior refinement (`mesh.target_size`) and openings are noted, not meshed."""
+    node_index, xyz = nd["node_index"], nd["xyz"]
+    next_id = max([int(p["id"]) for p in plates], default=0) + 1
+    out = []
+    for surf in surfaces:
+        nids = [int(v["id"] if isinstance(v, dict) else v) for v in surf.get("boundary_node_ids") or []]
+        for v in nids:
+            if v not in node_index:
+                raise WireError(f"plate surface {surf.get('id')}: unknown boundary node {v}")
+        pts = xyz[[node_index[v] for v in nids]]
+        if len(nids) > 1 and np.linalg.norm(pts[0] - pts[-1]) <= 1e-9:
+            nids, pts = nids[:-1], pts[:-1]
+        if len(nids) < 3:
+            raise WireError(f"plate surface {surf.get('id')}: needs at least three boundary nodes")
+        tris = ear_clip_polygon(pts, f"plate surface {surf.get('id')}")
+        if (surf.get("mesh") or {}).get("target_size") or (surf.get("mesh") or {}).get("divisions"):
+            warnings.append(("W_SURFACE_MESH_BOUNDARY_ONLY", f"plate surface {surf.get('id')}: meshed over its boundary nodes only "
+                             "(no interior refinement to the requested size)"))
+        if surf.get("openings"):
+            warnings.append(("W_SURFACE_OPENINGS_IGNORED", f"plate surface {surf.get('id')}: openings are not cut out of the mesh"))
+        for (i, j, k) in tris:
+            out.append({"id": next_id, "node_ids": [nids[i], nids[j], nids[k]], "material": surf["material"],
+                        "thickness": surf["thickness"], "behavior": surf.get("behavior"), "theory": surf.get("theory"),
+                        "plane_state": surf.get("plane_state"), "offset": surf.get("offset"),
+                        "stiffness_modifiers": surf.get("stiffness_modifiers"), "local_x_direction": surf.get("local_x_direction"),
+                        "source_surface_id": surf.get("id"), "classification": surf.get("classification")})
+            next_id += 1
+    return out
+
+
+def ear_clip_polygon(pts: np.ndarray, what: str = "polygon") -> list:
+    """Triangles (index triples into ``pts`` [n,3]) of a simple planar polygon by ear clipping, counter-clockwise about the
+    polygon normal (fers_core/plates/mesh.py:47-66 plane basis, :106-148 ear clipping, tolerance 1e-9)."""
+    tol = 1e-9
+    o = pts[0]
+    u = nrm = None
+    for i in range(1, len(pts) - 1):
+        ea, eb = pts[i] - o, pts[i + 1] - o
+        if u is None and np.linalg.norm(ea) > tol:
+            u = ea / np.linalg.norm(ea)
+        c = np.cross(ea, eb)
+        if np.linalg.norm(c) > tol:
+            nrm = c / np.linalg.norm(c)
+            break
+    if u is None or nrm is None:
+        raise WireError(f"{what}: degenerate polygon")
+    if (np.abs((pts - o) @ nrm) > 1e-7).any():
+        raise WireError(f"{what}: polygon must be planar")
+    v = np.cross(nrm, u)
+    v /= np.linalg.norm(v)
+    p2 = np.stack([(pts - o) @ u, (pts - o) @ v], axis=1)
+    idx = list(range(len(pts)))
+    area = 0.5 * sum(p2[i, 0] * p2[(i + 1) % len(pts), 1] - p2[(i + 1) % len(pts), 0] * p2[i, 1] for i in range(len(pts)))
+    if area < 0.0:
+        idx.reverse()
+
+    def cross2(a, b):
+        return a[0] * b[1] - a[1] * b[0]
+
+    def inside(p, a, b, c):
+        v0, v1, v2 = c - a, b - a, p - a
+        d00, d01, d02, d11, d12 = v0 @ v0, v0 @ v1, v0 @ v2, v1 @ v1, v1 @ v2
+        den = d00 * d11 - d01 * d01
+        if abs(den) <= tol:
+            return False
+        uu, vv = (d11 * d02 - d01 * d12) / den, (d00 * d12 - d01 * d02) / den
+        return uu >= -tol and vv >= -tol and uu + vv <= 1.0 + tol
+    tris = []
+    while len(idx) > 3:
+        for off, cur in enumerate(idx):
+            prev, nxt = idx[off - 1], idx[(off + 1) % len(idx)]
+            a, b, c = p2[prev], p2[cur], p2[nxt]
+            if cross2(b - a, c - b) <= tol:
+                continue
+            if any(q not in (prev, cur, nxt) and inside(p2[q], a, b, c) for q in idx):
+                continue
+            tris.append((prev, cur, nxt))
+            del idx[off]
+            break
+        else:
+            raise WireError(f"{what}: polygon could not be triangulated (use a simple, non-self-intersecting polygon)")
+    tris.append((idx[0], idx[1], idx[2]))
+    return tris
+
+
 def _node_of(item: dict, node_index: dict) -> int:
     nid = item.get("node")
     nid = nid["id"] if isinstance(nid, dict) else nid
@@ -850,3 +1145,97 @@ def _surface_load_to_plates(sl, xyz, p_nodes, pp_plate, pp_vec, warnings):
     inside &= off <= 1e-6 * span + 1e-9
     for i in np.nonzero(inside)[0]:
         pp_plate.append(int(i)); pp_vec.append(q * d)
+
+
+def _surface_load_to_members(sl, xyz, mb, dl_member, dl_data, warnings):
+    """SurfaceLoad on a model without plates (pydantic_models.py:1962-1967): the area load travels one way to the members
+    that lie in the polygon's plane along ``distribution_direction`` (fers_core/loads/surfaceload.py:24-45; the only
+    in-repo model, tests/functionality/test_surface_loads.py:8-37, has two members along X under a polygon with
+    distribution_direction = X).  Every such member line takes the strip of the polygon between the mid-lines to its
+    neighbours (the polygon edge beyond the outermost lines); along the member the strip width is piecewise linear, so
+    the load becomes trapezoid member loads between the break points (polygon vertices and strip-boundary crossings).
+    Total applied force = magnitude x polygon area when the members span the polygon.  Semantics stated, unpinned."""
+    poly = np.array([_vec3(v, "surface_load.polygon") for v in sl["polygon"]])
+    if len(poly) < 3:
+        raise WireError(f"surface load {sl.get('id')}: polygon needs at least three vertices")
+    d = _vec3(sl["direction"], "surface_load.direction")
+    q = float(sl["magnitude"])
+    dd = sl.get("distribution_direction")
+    o = poly[0]
+    nrm = np.zeros(3)
+    for i in range(len(poly)):
+        nrm += np.cross(poly[i] - o, poly[(i + 1) % len(poly)] - o)
+    if np.linalg.norm(nrm) == 0.0:
+        raise WireError(f"surface load {sl.get('id')}: degenerate polygon")
+    nrm /= np.linalg.norm(nrm)
+    m_n1, m_n2 = mb["m_n1"], mb["m_n2"]
+    span = max(np.ptp(poly, axis=0).max(), 1e-12)
+    tolp = 1e-6 * span + 1e-9
+    in_plane = (np.abs((xyz[m_n1] - o) @ nrm) <= tolp) & (np.abs((xyz[m_n2] - o) @ nrm) <= tolp) if len(m_n1) else np.zeros(0, bool)
+    if dd is None:
+        # no direction given: the direction most in-plane members follow
+        cand = np.nonzero(in_plane)[0]
+        if len(cand):
+            ax = xyz[m_n2[cand]] - xyz[m_n1[cand]]
+            ax /= np.linalg.norm(ax, axis=1)[:, None]
+            ref = ax[0]
+            dd = ref
+    if dd is None:
+        warnings.append(("W_SURFACE_LOAD_NO_PLATES", f"surface load {sl.get('id')}: no plate elements and no members in its plane"))
+        return
+    e_s = _vec3(dd, "surface_load.distribution_direction")
+    e_s = e_s - (e_s @ nrm) * nrm
+    if np.linalg.norm(e_s) == 0.0:
+        raise WireError(f"surface load {sl.get('id')}: distribution_direction is normal to the polygon")
+    e_s /= np.linalg.norm(e_s)
+    e_t = np.cross(nrm, e_s)
+    P = np.stack([(poly - o) @ e_s, (poly - o) @ e_t], axis=1)                  # polygon in (s, t)
+    axis = xyz[m_n2] - xyz[m_n1] if len(m_n1) else np.zeros((0, 3))
+    L = np.linalg.norm(axis, axis=1)
+    par = in_plane & (np.abs(np.abs((axis / np.maximum(L, 1e-300)[:, None]) @ e_s) - 1.0) <= 1e-6)
+    members = np.nonzero(par)[0]
+    if len(members) == 0:
+        warnings.append(("W_SURFACE_LOAD_NO_PLATES", f"surface load {sl.get('id')}: no plate elements and no members along its "
+                         "distribution direction"))
+        return
+    t_of = ((xyz[m_n1[members]] - o) @ e_t)
+    lines = np.unique(np.round(t_of / tolp).astype(np.int64))                       # distinct member lines
+    t_lines = np.array([t_of[np.round(t_of / tolp).astype(np.int64) == k].mean() for k in lines])
+    t_min, t_max = P[:, 1].min(), P[:, 1].max()
+    bounds = np.concatenate([[min(t_min, t_lines[0])], 0.5 * (t_lines[1:] + t_lines[:-1]), [max(t_max, t_lines[-1])]])
+
+    def width(sv, lo, hi):
+        """Length of {t in [lo, hi] : (sv, t) inside the polygon} (even-odd rule over the crossings of the line s = sv)."""
+        ts = []
+        n = len(P)
+        for i in range(n):
+            (s1, t1), (s2, t2) = P[i], P[(i + 1) % n]
+            if (s1 > sv) != (s2 > sv):
+                ts.append(t1 + (sv - s1) * (t2 - t1) / (s2 - s1))
+        ts.sort()
+        return sum(max(0.0, min(b, hi) - max(a, lo)) for a, b in zip(ts[0::2], ts[1::2]))
+    for li, tl in enumerate(t_lines):
+        lo, hi = bounds[li], bounds[li + 1]
+        # break points along s: polygon vertices and the crossings of the polygon edges with the strip boundaries
+        brk = list(P[:, 0])
+        n = len(P)
+        for i in range(n):
+            (s1, t1), (s2, t2) = P[i], P[(i + 1) % n]
+            for tb in (lo, hi):
+                if (t1 > tb) != (t2 > tb):
+                    brk.append(s1 + (tb - t1) * (s2 - s1) / (t2 - t1))
+        on_line = members[np.abs(t_of - tl) <= 2 * tolp]
+        for m in on_line:
+            s_a, s_b = float((xyz[m_n1[m]] - o) @ e_s), float((xyz[m_n2[m]] - o) @ e_s)
+            s_lo, s_hi = min(s_a, s_b), max(s_a, s_b)
+            cuts = sorted({s_lo, s_hi, *[b for b in brk if s_lo < b < s_hi]})
+            for c0, c1 in zip(cuts[:-1], cuts[1:]):
+                eps = 1e-9 * (c1 - c0)
+                w0, w1 = width(c0 + eps, lo, hi), width(c1 - eps, lo, hi)
+                if w0 == 0.0 and w1 == 0.0:
+                    continue
+                f0, f1 = (c0 - s_a) / (s_b - s_a), (c1 - s_a) / (s_b - s_a)
+                if f0 > f1:                                                  # member runs against e_s
+                    f0, f1, w0, w1 = f1, f0, w1, w0
+                dl_member.append(int(m))
+                dl_data.append(np.concatenate([q * w0 * d, q * w1 * d, [f0, f1]]))

@@ -35,8 +35,21 @@ def _worker(rank, world, port, q):
     local = torch.from_numpy(mine.sum(axis=1, keepdims=True).copy())
     allv = fdist.gather_summary(local, counts)
     t = fdist.max_over_ranks(float(rank + 1), torch.device("cpu"))
+    # result tensors [rows, 12, columns]: every rank contributes its own columns (with padding columns behind them)
+    full = torch.arange(5 * 12 * 11, dtype=torch.float64).reshape(5, 12, 11)
+    lo, hi = fdist.shard_range(11, world, rank)
+    local = torch.full((5, 12, 8), -1.0, dtype=torch.float64)
+    local[..., : hi - lo] = full[..., lo:hi]
+    got_cols = fdist.gather_columns(local, counts)
+
+    class FakeEngine:                                  # run_linear of a stand-in engine: U[:, c] = factors[c].sum()
+        def run_linear(self, fac, detail=False):
+            u = torch.zeros((4, 8), dtype=torch.float64)
+            u[:, : fac.shape[0]] = torch.from_numpy(fac.sum(axis=1))[None, :]
+            return {"U": u}
+    sh = fdist.run_linear_sharded(FakeEngine(), factors, gather=("U", "R"))
     if rank == 0:
-        q.put((allv.numpy().reshape(-1).tolist(), t))
+        q.put((allv.numpy().reshape(-1).tolist(), t, bool(torch.equal(got_cols, full)), sh["U"][0].tolist(), sh["columns"]))
     dist.destroy_process_group()
 
 
@@ -49,10 +62,11 @@ def test_two_rank_gather_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got, tmax = q.get(timeout=120)
+    got, tmax, cols_ok, sharded_u, my_cols = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     want = np.arange(11 * 3, dtype=np.float64).reshape(11, 3).sum(axis=1)
     assert np.allclose(got, want)
     assert tmax == 2.0
+    assert cols_ok and np.allclose(sharded_u, want) and my_cols == (0, 6)

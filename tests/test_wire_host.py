@@ -203,18 +203,24 @@ def test_unity_check_inputs_travel_with_the_model():
 
 
 def test_inputs_that_are_read_but_not_acted_on_are_reported():
-    """Nothing on the wire is dropped silently: hinge capacities, contradictory principal-axis data and unmeshed surfaces each leave a
+    """Nothing on the wire is dropped silently: hinge capacities, contradictory principal-axis data and mesh requests that are not honoured each leave a
     warning in ``errors_and_warnings`` (pydantic_models.py:1877-1880)."""
     import copy
     doc = copy.deepcopy(helpers.golden("hinge_spring")["doc"])
     assert not [w for w in wire.parse_document(doc).warnings if w[0].startswith(("W_HINGE", "W_PRINCIPAL", "W_SURFACE_NOT"))]
     doc["model"]["member_hinges"][0]["max_moment_mz"] = 1.0e4
     doc["model"]["sections"][0]["i_yz"] = 1.0e-7
+    # (nodes 1, 2, 3 of this model are collinear: a surface over them is rejected, one with an opening is meshed and noted)
     doc["model"]["plate_surfaces"] = [{"id": 7, "boundary_node_ids": [1, 2, 3], "material": 1, "thickness": 0.01}]
+    with pytest.raises(wire.WireError, match="degenerate"):
+        wire.parse_document(doc)
+    doc["model"]["nodes"].append({"id": 99, "X": 1.0, "Y": 1.0, "Z": 0.5, "nodal_support": None})
+    doc["model"]["plate_surfaces"] = [{"id": 7, "boundary_node_ids": [1, 2, 99], "material": 1, "thickness": 0.01,
+                                       "openings": [{"id": 1, "boundary_node_ids": [1, 2, 99]}]}]
     codes = [w[0] for w in wire.parse_document(doc).warnings]
     assert codes.count("W_HINGE_CAPACITY_IGNORED") == 1
     assert not [c for c in codes if c.startswith("W_PRINCIPAL")]      # applied (tests/test_product_inertia.py), not ignored
-    assert codes.count("W_SURFACE_NOT_MESHED") == 1
+    assert codes.count("W_SURFACE_OPENINGS_IGNORED") == 1 and wire.parse_document(doc).n_plates == 1
     # an angle that contradicts the (i_y, i_z, i_yz) triple is resolved in favour of the angle, with a note
     doc["model"]["sections"][0].update(i_yz=1.0e-7, principal_axis_angle=40.0)
     assert "W_PRINCIPAL_AXES" in [w[0] for w in wire.parse_document(doc).warnings]
