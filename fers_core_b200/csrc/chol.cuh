@@ -71,6 +71,8 @@ struct CholPlanHost {
 
 // fp64-equivalent Schur update on the int8 tensor cores (ozaki_syrk.cu): C (m2 x m2, lower) -= A A^T, A m2 x k1
 size_t oz_work_bytes(int m2, int k1, int S);
-int oz_syrk(const double* A, long long lda, double* C, long long ldc, int m2, int k1, int S, void* work, cudaStream_t st);
+// ncols: only the first ncols columns of C (0: all); persistent: one CTA per SM walking the tiles, else one CTA per tile
+int oz_syrk(const double* A, long long lda, double* C, long long ldc, int m2, int k1, int S, void* work, cudaStream_t st,
+            int ncols = 0, bool persistent = true);
 
 }  // namespace fers

@@ -826,6 +826,9 @@ static int g_chol_profile_on = 0;      // 0 off, 1 every kernel class, 2 Schur-u
 // FERS_CHOL_OZAKI_MIN_K / fers_b200_chol_set_ozaki.
 static int g_chol_ozaki = getenv("FERS_CHOL_OZAKI") ? atoi(getenv("FERS_CHOL_OZAKI")) : 7;
 static int g_chol_ozaki_min_k = getenv("FERS_CHOL_OZAKI_MIN_K") ? atoi(getenv("FERS_CHOL_OZAKI_MIN_K")) : 1024;
+// the outer panel updates (K = one 256-column block) of levels whose fronts have at least this many own columns take the same
+// kernel, one CTA per tile on the low-priority stream of the look-ahead (0 = off); FERS_CHOL_OZAKI_PANEL_K
+static int g_chol_ozaki_panel_k = getenv("FERS_CHOL_OZAKI_PANEL_K") ? atoi(getenv("FERS_CHOL_OZAKI_PANEL_K")) : 2048;
 
 struct EventPool {
     std::vector<cudaEvent_t> ev;
@@ -1037,7 +1040,25 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
                 const int kc0 = blk_end - kw;
                 const int lim = at_group_end ? max_k1 : std::min(grp_end, max_k1);     // columns [blk_end, lim) are updated
                 const int lim_arg = at_group_end ? (1 << 30) : grp_end;
+                // fronts with many own columns: the update of all later columns as int8 digit-plane products (ozaki_syrk.cu),
+                // front by front; digit planes in the children's arena (the Schur update of the level reuses it afterwards)
+                const bool oz_panel = g_chol_ozaki >= 4 && g_chol_ozaki_panel_k > 0 && nf <= 8 && kw < 16384 &&
+                                      6 * P.level_max_n1[l] >= g_chol_ozaki_panel_k &&
+                                      oz_work_bytes(max_m, kw, g_chol_ozaki) <= (size_t)P.schur_doubles[(l & 1) ^ 1] * 8;
                 auto outer = [&](cudaStream_t q, int c_from, int c_to_grid, int c_to) {
+                    if (oz_panel && q != st) {
+                        for (int z = P.level_ptr[l]; z < P.level_ptr[l + 1]; ++z) {
+                            const FrontDev& f = P.fronts[P.level_fronts[z]];
+                            const int fk1 = 6 * f.n1, fm = 6 * (f.n1 + f.n2);
+                            const int hi = std::min(c_to, fk1);
+                            if (c_from >= hi) continue;
+                            double* panel = factor + f.panel_off;
+                            oz_syrk(panel + (size_t)kc0 * fm + c_from, fm, panel + (size_t)c_from * fm + c_from, fm, fm - c_from, kw,
+                                    g_chol_ozaki, arena[(l & 1) ^ 1], q, hi - c_from, false);
+                            launches += 3;
+                        }
+                        return;
+                    }
                     if (g_chol_variant & 1) {
                         dim3 grid(cdiv(max_m - c_from, G88::BM), cdiv(c_to_grid - c_from, G88::BN), nf);
                         k_update<G88><<<grid, GEMM_THREADS, G88::SMEM, q>>>(L, kc0, kw, c_from, c_to, 1 << 30);

@@ -54,6 +54,7 @@ struct OzFront {
     long long lda, ldc;
     int m2, k1;
     int m2_pad, k1_pad;     // multiples of OZ_M / OZ_KC
+    int ncols;              // only columns < ncols of C are updated (ncols = m2: the whole lower triangle)
 };
 
 __host__ __device__ inline size_t oz_plane_bytes(int m2_pad, int k1_pad) { return (size_t)m2_pad * k1_pad; }
@@ -226,7 +227,7 @@ k_oz_syrk(OzFront f, int n_tiles) {
     oz_fence_after();
     const uint32_t tmem = s_tmem;
     const int unit0 = blockIdx.x, unit_stride = gridDim.x;
-    const int nbi = f.m2_pad / OZ_M, nbj = (f.m2 + OZ_N - 1) / OZ_N;
+    const int nbi = f.m2_pad / OZ_M, nbj = (f.ncols + OZ_N - 1) / OZ_N;
     const int nkc = f.k1_pad / OZ_KC;
     const size_t plane = oz_plane_bytes(f.m2_pad, f.k1_pad);
     const size_t chunk_bytes = (size_t)f.m2_pad * OZ_KC;
@@ -322,7 +323,7 @@ k_oz_syrk(OzFront f, int n_tiles) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int col = c0 + cb + j;
-                        if (col <= r && col < f.m2) {
+                        if (col <= r && col < f.ncols) {
                             double* dst = f.C + (size_t)col * f.ldc + r;
                             *dst -= sum[j] * rs * f.rowscale[col];
                         }
@@ -341,8 +342,8 @@ k_oz_syrk(OzFront f, int n_tiles) {
     }
 }
 
-static int oz_tile_count(int m2, int m2_pad) {
-    const int nbi = m2_pad / OZ_M, nbj = (m2 + OZ_N - 1) / OZ_N;
+static int oz_tile_count(int ncols, int m2_pad) {
+    const int nbi = m2_pad / OZ_M, nbj = (ncols + OZ_N - 1) / OZ_N;
     long long n = 0;
     for (int r = 0; r < nbi; ++r) n += std::min(2 * r + 2, nbj);
     return (int)n;
@@ -354,7 +355,7 @@ size_t oz_work_bytes(int m2, int k1, int S) {
 }
 
 template <int S>
-static int oz_launch(OzFront f, cudaStream_t st) {
+static int oz_launch(OzFront f, cudaStream_t st, bool persistent) {
     static PerDeviceOnce once;
     const size_t smem = (size_t)oz_stages(S) * oz_stage_bytes(S);
     if (once.needed()) {
@@ -364,27 +365,31 @@ static int oz_launch(OzFront f, cudaStream_t st) {
     k_oz_rowscale<<<(f.m2_pad + 255) / 256, 256, 0, st>>>(f);
     dim3 grid((f.m2_pad + 255) / 256, f.k1_pad / 16);
     k_oz_split<S><<<grid, 256, 0, st>>>(f);
-    const int n_tiles = oz_tile_count(f.m2, f.m2_pad);
-    k_oz_syrk<S><<<std::min(n_tiles, sm_count()), OZ_THREADS, smem, st>>>(f, n_tiles);      // persistent: one CTA per SM
+    const int n_tiles = oz_tile_count(f.ncols, f.m2_pad);
+    // persistent: one CTA per SM walks the tile list (long K: the Schur updates).  Otherwise one CTA per tile, so that SMs
+    // come free every few microseconds for the kernels of a higher-priority stream (the panel chain of the look-ahead)
+    k_oz_syrk<S><<<persistent ? std::min(n_tiles, sm_count()) : n_tiles, OZ_THREADS, smem, st>>>(f, n_tiles);
     FERS_LAUNCH_CHECK();
     count_launches(3);
     return 0;
 }
 
 // C (m2 x m2, lower) -= A A^T with A m2 x k1, both column-major fp64; `work` holds the digit planes and row scales
-int oz_syrk(const double* A, long long lda, double* C, long long ldc, int m2, int k1, int S, void* work, cudaStream_t st) {
+int oz_syrk(const double* A, long long lda, double* C, long long ldc, int m2, int k1, int S, void* work, cudaStream_t st,
+            int ncols, bool persistent) {
     OzFront f;
     f.A = A; f.C = C; f.lda = lda; f.ldc = ldc; f.m2 = m2; f.k1 = k1;
+    f.ncols = (ncols <= 0 || ncols > m2) ? m2 : ncols;
     f.m2_pad = (m2 + OZ_M - 1) / OZ_M * OZ_M;
     f.k1_pad = (k1 + OZ_KC - 1) / OZ_KC * OZ_KC;
     f.planes = static_cast<int8_t*>(work);
     f.rowscale = reinterpret_cast<double*>(static_cast<uint8_t*>(work) + align_up((size_t)S * oz_plane_bytes(f.m2_pad, f.k1_pad)));
     switch (S) {
-        case 4: return oz_launch<4>(f, st);
-        case 5: return oz_launch<5>(f, st);
-        case 6: return oz_launch<6>(f, st);
-        case 7: return oz_launch<7>(f, st);
-        case 8: return oz_launch<8>(f, st);
+        case 4: return oz_launch<4>(f, st, persistent);
+        case 5: return oz_launch<5>(f, st, persistent);
+        case 6: return oz_launch<6>(f, st, persistent);
+        case 7: return oz_launch<7>(f, st, persistent);
+        case 8: return oz_launch<8>(f, st, persistent);
     }
     set_error("oz_syrk: 4 <= slices <= 8");
     return 2;
@@ -403,7 +408,7 @@ int fers_b200_oz_syrk(const double* A, long long lda, double* C, long long ldc, 
     FERS_REQUIRE(A && C && work && m2 > 0 && k1 > 0 && lda >= m2 && ldc >= m2, "oz_syrk: bad arguments");
     FERS_REQUIRE(k1 < 16384, "oz_syrk: K must stay below 16 384 for exact int32 accumulation");
     FERS_REQUIRE(work_bytes >= fers::oz_work_bytes(m2, k1, slices), "oz_syrk: workspace too small");
-    return fers::oz_syrk(A, lda, C, ldc, m2, k1, slices, work, fers::as_stream(stream));
+    return fers::oz_syrk(A, lda, C, ldc, m2, k1, slices, work, fers::as_stream(stream), m2, true);
 }
 
 }  // extern "C"
