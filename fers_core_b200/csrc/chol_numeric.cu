@@ -827,8 +827,11 @@ static int g_chol_profile_on = 0;      // 0 off, 1 every kernel class, 2 Schur-u
 static int g_chol_ozaki = getenv("FERS_CHOL_OZAKI") ? atoi(getenv("FERS_CHOL_OZAKI")) : 7;
 static int g_chol_ozaki_min_k = getenv("FERS_CHOL_OZAKI_MIN_K") ? atoi(getenv("FERS_CHOL_OZAKI_MIN_K")) : 1024;
 // the outer panel updates (K = one 256-column block) of levels whose fronts have at least this many own columns take the same
-// kernel, one CTA per tile on the low-priority stream of the look-ahead (0 = off); FERS_CHOL_OZAKI_PANEL_K
-static int g_chol_ozaki_panel_k = getenv("FERS_CHOL_OZAKI_PANEL_K") ? atoi(getenv("FERS_CHOL_OZAKI_PANEL_K")) : 2048;
+// kernel, one CTA per tile on the low-priority stream of the look-ahead (0 = off, the default: measured gain 1 % with 2048-column groups, a loss with shorter K); FERS_CHOL_OZAKI_PANEL_K
+static int g_chol_ozaki_panel_k = getenv("FERS_CHOL_OZAKI_PANEL_K") ? atoi(getenv("FERS_CHOL_OZAKI_PANEL_K")) : 0;
+// ... and only updates whose K (block or group width) is at least this long: a 256-column update spends as long in the
+// tile prologue / epilogue as in its 8 MMA steps (measured: factorisation 385 -> 535 ms with K = 256)
+static int g_chol_ozaki_panel_kw = getenv("FERS_CHOL_OZAKI_PANEL_KW") ? atoi(getenv("FERS_CHOL_OZAKI_PANEL_KW")) : 1024;
 
 struct EventPool {
     std::vector<cudaEvent_t> ev;
@@ -1043,6 +1046,7 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
                 // fronts with many own columns: the update of all later columns as int8 digit-plane products (ozaki_syrk.cu),
                 // front by front; digit planes in the children's arena (the Schur update of the level reuses it afterwards)
                 const bool oz_panel = g_chol_ozaki >= 4 && g_chol_ozaki_panel_k > 0 && nf <= 8 && kw < 16384 &&
+                                      kw >= g_chol_ozaki_panel_kw &&
                                       6 * P.level_max_n1[l] >= g_chol_ozaki_panel_k &&
                                       oz_work_bytes(max_m, kw, g_chol_ozaki) <= (size_t)P.schur_doubles[(l & 1) ^ 1] * 8;
                 auto outer = [&](cudaStream_t q, int c_from, int c_to_grid, int c_to) {

@@ -784,8 +784,9 @@ class FrameBatch:
     Every frame is factorised by the batched dense Cholesky; the P-Delta fixed point runs for all frames at once and each
     frame stops at ITS OWN convergence (converged frames are frozen on the device), so the result equals analysing the
     frames one by one.  The host never waits inside the loop: the "any frame still active" flag of iteration i travels to
-    pinned memory asynchronously and is looked at after iteration i + 1 has been enqueued -- at most one iteration is
-    enqueued in vain, and it changes nothing because every frame is frozen by then."""
+    pinned memory asynchronously and is looked at after the cheap first half of iteration i + 1 (axial forces, tangent
+    matrix) has been enqueued -- at most that half is enqueued in vain, and it changes nothing because every frame is frozen
+    by then; the factorisations are only enqueued once the flags say they are needed."""
 
     def __init__(self, model: wire.ModelArrays, nodes_per_frame: int, device=None):
         self.eng = eng = Engine(model, device)
@@ -862,6 +863,9 @@ class FrameBatch:
             events = []
             max_it = max(1, opts.max_iterations)
             for it in range(max_it):
+                # first half of the iteration (cheap kernels): axial forces of the current state, tangent matrix.  It is
+                # enqueued BEFORE the host looks at the convergence flags of the previous iteration, so the GPU is never idle
+                # while the flags travel; if every frame had already converged it changes nothing (all frames frozen)
                 rec = eng.recover(d_xyz, d_u, d_f, d_peq, self.facp, None, None, d_axial, kg_mode, sup, detail=False)
                 ax_new = eng._empty((nm, 1))
                 _lib.check(lib.fers_b200_member_axial(nm, 1, _lib.ptr(rec["f_local"]), _lib.ptr(ax_new), eng.stream), "member_axial")
@@ -870,6 +874,14 @@ class FrameBatch:
                     ax_new = torch.where(am, ax_new, d_axial).contiguous()
                 d_axial = ax_new
                 eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup, count=False)
+                if it >= 1:                  # flags of the PREVIOUS iteration (in flight since its second half was enqueued)
+                    events[it - 1].synchronize()
+                    go_on, bad = self.h_flags[it - 1].tolist()
+                    if bad:
+                        self._raise_if_bad()
+                    if not go_on:
+                        break
+                # second half (the expensive kernels): factorisation, substitution, convergence test
                 d_un = self._factor_solve(d_f)
                 un_f, u_f = d_un.view(nf, n), d_u.view(nf, n)
                 den = torch.linalg.norm(un_f, dim=1)
@@ -882,15 +894,10 @@ class FrameBatch:
                 self.h_flags[it].copy_(torch.stack([active.any(), self.bad_dev.any()]), non_blocking=True)
                 ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(eng.dev)); events.append(ev)
                 enqueued = it + 1
-                if it >= 1:                  # look at the PREVIOUS iteration's flags (normally landed by now)
-                    events[it - 1].synchronize()
-                    go_on, bad = self.h_flags[it - 1].tolist()
-                    if bad:
-                        self._raise_if_bad()
-                    if not go_on:
-                        break
             else:
                 events[-1].synchronize()
+                if self.h_flags[max_it - 1].tolist()[1]:
+                    self._raise_if_bad()
             # the matrix in eng.d_vals must be the tangent of the frozen state for the reactions
             eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup, count=False)
         span = eng.span_tables() if detail else None
