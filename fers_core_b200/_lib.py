@@ -31,6 +31,7 @@ SIGNATURES = {
     "fers_b200_assemble_beams": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i,
                                       _vp, _vp, _i, _vp]),
     "fers_b200_assemble_plates": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fers_b200_assemble_set_gather_kernel": (_i, [_i]),
     "fers_b200_zero": (_i, [_vp, _sz, _vp]),
     "fers_b200_assemble_warping": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_recover_warping": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

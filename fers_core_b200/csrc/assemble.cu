@@ -453,6 +453,141 @@ __global__ void __launch_bounds__(GA_THREADS, GENERAL ? 1 : 5) k_assemble_gather
     }
 }
 
+// ---- gather assembly of plain members (no modifier record, no K_g): element-lane kernel -----------------------------------
+// Every 6x6 block of an un-released member is +- one of four 3x3 matrices (x, y, z = rows of the member frame):
+//   TT = a x x^T + z12 y y^T + y12 z z^T     R4 = t x x^T + y4 y y^T + z4 z z^T     R2 = -t x x^T + y2 y y^T + z2 z z^T
+//   TR = z6 y z^T - y6 z y^T                 (TT, R4, R2 symmetric: 6 + 6 + 6 + 9 = 27 values per member)
+//   K_ss = [TT TR; TR^T R4]   K_se = [-TT TR; -TR^T R2]   K_es = [-TT -TR; TR^T R2]   K_ee = [TT -TR; -TR^T R4]
+// Phase A: one thread per half-member forms the 27 values in shared memory (a third of the arithmetic of two full blocks,
+// 40 registers instead of 96).  Phase B: groups of 36 lanes, one lane per entry of a 6x6 block, stream the off-diagonal
+// blocks out (consecutive half-members of the list own consecutive slots: 8-byte stores coalesce into whole 288-byte
+// blocks) and sum the diagonal contributions of the CTA's nodes in list order (same order as k_assemble_gather: no atomics,
+// bit-reproducible).  Same arithmetic per entry as beam_block_closed.
+constexpr int GP_GROUPS = 4;
+constexpr int GP_THREADS = 36 * GP_GROUPS;        // 144
+constexpr int GP_NODES = 24;                      // 24 nodes x 6 members = 144 half-members: one chunk on a 3D grid frame
+constexpr int GP_VALS = 27;
+constexpr int GP_QS = GP_NODES / GP_GROUPS;       // diagonal entries per lane
+static_assert(GP_NODES % GP_GROUPS == 0 && GP_NODES + 1 <= GP_THREADS, "plain gather kernel geometry");
+
+__device__ __forceinline__ int gp_sym6(int r, int q) {
+    const int lo = min(r, q), hi = max(r, q);
+    return lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
+}
+
+__global__ void __launch_bounds__(GP_THREADS, 5) k_assemble_gather_plain(GatherArgs G) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const BeamArgs& A = G.B;
+    double* s_val = reinterpret_cast<double*>(smem_raw);                 // [GP_THREADS][GP_VALS]
+    double* s_prop = s_val + GP_THREADS * GP_VALS;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_prop + (size_t)(A.use_tma ? A.n_prop : 0) * NPROP);
+    __shared__ int s_hp[GP_NODES + 1];
+    __shared__ int s_off[GP_THREADS];          // slot of the off-diagonal block, -1: not written here (duplicate pair / self pair)
+    __shared__ int s_end[GP_THREADS];
+
+    const int tid = threadIdx.x;
+    if (A.use_tma) {
+        if (tid == 0) mbar_init(s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t prop_bytes = (uint32_t)A.n_prop * NPROP * sizeof(double);
+            mbar_expect_tx(s_bar, prop_bytes);
+            tma_bulk_g2s(s_prop, A.prop, prop_bytes, s_bar);
+        }
+    }
+    const int node_a = blockIdx.x * GP_NODES;
+    const int nn = min(GP_NODES, G.n_nodes - node_a);
+    if (tid <= nn) s_hp[tid] = G.hm_ptr[node_a + tid];
+    __syncthreads();
+    const int h_begin = s_hp[0], h_end = s_hp[nn];
+    const double* prop_tab = A.use_tma ? s_prop : A.prop;
+    bool prop_ready = !A.use_tma;
+
+    const int g = tid / 36, e = tid - 36 * g;
+    double acc[GP_QS];
+#pragma unroll
+    for (int k = 0; k < GP_QS; ++k) acc[k] = 0.0;
+
+    for (int chunk0 = h_begin; chunk0 < h_end; chunk0 += GP_THREADS) {
+        const int h = chunk0 + tid;
+        if (h < h_end) {
+            const int code = G.hm_list[h];
+            const int m = code >> 2, end = code & 1;
+            const int4 slots = reinterpret_cast<const int4*>(A.m_slot)[m];
+            const int off_slot = end ? slots.z : slots.y, dg_slot = end ? slots.w : slots.x;
+            const int a = A.n1[m], b = A.n2[m];
+            const double roll = A.m_roll[m];
+            const int mtype = A.m_type[m], pi = A.m_prop[m];
+            const double scale = A.m_scale ? A.m_scale[m] : 1.0;
+            const double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
+            const double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
+            const Frame f = member_frame(pa, pb, roll);
+            if (!prop_ready) { mbar_wait(s_bar, 0); prop_ready = true; }
+            double Pr[NPROP];
+#pragma unroll
+            for (int i = 0; i < NPROP; ++i) Pr[i] = prop_tab[(size_t)pi * NPROP + i];
+            const BeamCoef c = beam_coef(Pr, f.L, mtype, scale);
+            const double* x = f.r[0];
+            const double* y = f.r[1];
+            const double* z = f.r[2];
+            double* o = s_val + tid * GP_VALS;
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = i; j < 3; ++j, ++k) {
+                    o[k] = c.a * x[i] * x[j] + c.z12 * y[i] * y[j] + c.y12 * z[i] * z[j];
+                    o[6 + k] = c.t * x[i] * x[j] + c.y4 * y[i] * y[j] + c.z4 * z[i] * z[j];
+                    o[12 + k] = -c.t * x[i] * x[j] + c.y2 * y[i] * y[j] + c.z2 * z[i] * z[j];
+                }
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) o[18 + 3 * i + j] = c.z6 * y[i] * z[j] + (-c.y6) * z[i] * y[j];
+            s_off[tid] = ((code & 2) || off_slot == dg_slot) ? -1 : off_slot;     // duplicated node pairs: k_gather_dups
+            s_end[tid] = end;
+        }
+        __syncthreads();
+        // the entry of a 6x6 block this lane owns: where it sits in the 27 values and with which sign per block kind
+        const int R = e / 6, C = e - 6 * R, sr = R >= 3, sc = C >= 3, r = R - 3 * sr, q = C - 3 * sc;
+        int idx_dg, idx_off;
+        double sg_se, sg_es, sg_ee;                    // K_ss carries no sign
+        if (!sr && !sc) { idx_dg = idx_off = gp_sym6(r, q); sg_se = sg_es = -1.0; sg_ee = 1.0; }
+        else if (sr && sc) { idx_dg = 6 + gp_sym6(r, q); idx_off = 12 + gp_sym6(r, q); sg_se = sg_es = sg_ee = 1.0; }
+        else if (!sr) { idx_dg = idx_off = 18 + 3 * r + q; sg_se = 1.0; sg_es = sg_ee = -1.0; }       // translation row, rotation column
+        else { idx_dg = idx_off = 18 + 3 * q + r; sg_es = 1.0; sg_se = sg_ee = -1.0; }                // rotation row, translation column
+        const int cnt = min(GP_THREADS, h_end - chunk0);
+#pragma unroll 4
+        for (int i = g; i < cnt; i += GP_GROUPS) {
+            const int slot = s_off[i];
+            if (slot >= 0) {
+                const double v = s_val[i * GP_VALS + idx_off];
+                A.vals[(size_t)slot * 36 + e] = (s_end[i] ? sg_es : sg_se) * v;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < GP_QS; ++k) {
+            const int nl = g + GP_GROUPS * k;
+            if (nl < nn) {
+                const int lo = max(s_hp[nl], chunk0) - chunk0, hi = min(s_hp[nl + 1], chunk0 + GP_THREADS) - chunk0;
+                for (int i = lo; i < hi; ++i) {
+                    const double v = s_val[i * GP_VALS + idx_dg];
+                    acc[k] += s_end[i] ? sg_ee * v : v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!prop_ready) mbar_wait(s_bar, 0);     // never leave the CTA with a bulk copy in flight
+#pragma unroll
+    for (int k = 0; k < GP_QS; ++k) {
+        const int nl = g + GP_GROUPS * k;
+        if (nl < nn) A.vals[(size_t)G.diag_slot[node_a + nl] * 36 + e] = acc[k];
+    }
+}
+
+static int g_gather_kernel = 0;      // 0: element-lane kernel for plain models (default); 1: always k_assemble_gather
+
 // Off-diagonal blocks shared by several members (flagged dup): the first half-member of each run of
 // equal slots forms every contribution of the run and stores the sum.  Launched only when the map has
 // duplicates.
@@ -662,6 +797,8 @@ int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xy
         FERS_CK(cudaFuncSetAttribute(k_assemble_gather<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         FERS_CK(cudaFuncSetAttribute(k_assemble_gather<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         FERS_CK(cudaFuncSetAttribute(k_assemble_gather<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        FERS_CK(cudaFuncSetAttribute(k_assemble_gather_plain, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)GP_THREADS * GP_VALS * 8 + MAX_PROP_SMEM_ROWS * NPROP * 8 + 16)));
         attr_set.done();
     }
     if (cached) {
@@ -674,7 +811,10 @@ int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xy
     const size_t smem = (size_t)GA_THREADS * GA_STRIDE * sizeof(double) + (A.use_tma ? prop_smem : 0) + 16;
     const int grid = (n_nodes + GA_NODES - 1) / GA_NODES;
     const bool general = (m_rel != nullptr) || (m_axial != nullptr && kg_mode != 0);
-    if (cached) {
+    if (!general && !cached && g_gather_kernel == 0 && n_members > 0) {
+        const size_t smem_p = (size_t)GP_THREADS * GP_VALS * sizeof(double) + prop_smem + 16;
+        k_assemble_gather_plain<<<(n_nodes + GP_NODES - 1) / GP_NODES, GP_THREADS, smem_p, as_stream(stream)>>>(G);
+    } else if (cached) {
         if (general) k_assemble_gather<true, true><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
         else k_assemble_gather<false, true><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
     } else {
@@ -690,6 +830,12 @@ int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xy
         FERS_LAUNCH_CHECK();
         count_launches(1);
     }
+    return 0;
+}
+
+int fers_b200_assemble_set_gather_kernel(int kind) {
+    FERS_REQUIRE(kind == 0 || kind == 1, "assemble_set_gather_kernel: 0 = element-lane kernel for plain models, 1 = per-half-member kernel");
+    g_gather_kernel = kind;
     return 0;
 }
 

@@ -40,6 +40,7 @@ constexpr int OZ_DIGIT_BITS = 8;          // bits per digit plane after the firs
 constexpr double OZ_BASE = 256.0;         // 2^OZ_DIGIT_BITS
 constexpr int OZ_THREADS = 192;
 constexpr int OZ_BAND = 12;               // row blocks per band of the tile order (L2 reuse of the operand tiles)
+constexpr int OZ_TS_DEFAULT = 0;          // A operand through tensor memory unless FERS_OZ_TS says otherwise
 constexpr uint32_t OZ_SPIN_LIMIT = 1u << 28;   // a barrier that never completes traps instead of hanging the device
 
 __host__ __device__ inline size_t oz_stage_bytes(int S) { return (size_t)S * (OZ_M + OZ_N) * OZ_KC; }
@@ -170,6 +171,19 @@ __device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(OZ_IDESC), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory (128 lanes x K / 4 columns): the tile is copied there once per digit plane and K chunk
+// (tcgen05.cp, 128 rows x 256 bits) and read by every product of that plane, instead of S - p reads of shared memory
+__device__ __forceinline__ void oz_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(OZ_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void oz_cp_a(uint32_t tmem_a, uint64_t da) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_a), "l"(da) : "memory");
+}
 __device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, int (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -198,9 +212,12 @@ __device__ __forceinline__ bool oz_tile(int t, int nbi, int nbj, int& bi, int& b
 
 // (Thread-block clusters with TMA multicast of the row-block operand were measured and dropped: 2 CTAs per cluster changed
 // nothing -- L2 already serves the dozen CTAs that stream the same tile -- and 4 per cluster strand SMs: half the throughput.)
-template <int S>
+// TS: the A tile of a digit plane goes through tensor memory (columns S * OZ_N ..: 8 per plane; S <= 7).  tcgen05.cp and
+// tcgen05.mma of one thread execute in issue order, so the copies of the next K chunk wait for the products of this one.
+template <int S, bool TS>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_oz_syrk(OzFront f, int n_tiles) {
+    static_assert(!TS || (S * OZ_N + S * (OZ_KC / 4) <= 512 && OZ_KC == 32), "A staging does not fit the tensor memory");
     extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
     constexpr int STAGES = (200 * 1024) / (S * (OZ_M + OZ_N) * OZ_KC);
     constexpr uint32_t STAGE_BYTES = S * (OZ_M + OZ_N) * OZ_KC;
@@ -270,6 +287,18 @@ k_oz_syrk(OzFront f, int n_tiles) {
                 oz_fence_after();
                 if (oz_elect()) {
                     const uint32_t sa = (ring + st * STAGE_BYTES) >> 4, sb = sa + ((S * A_BYTES) >> 4);
+                    if (TS) {
+#pragma unroll
+                        for (int p = 0; p < S; ++p)
+                            oz_cp_a(tmem + (uint32_t)(S * OZ_N + 8 * p), oz_desc(sa + ((p * A_BYTES) >> 4), 128, OZ_KC * 8));
+#pragma unroll
+                        for (int p = 0; p < S; ++p)
+#pragma unroll
+                            for (int q = 0; q + p < S; ++q) {
+                                const uint64_t db = oz_desc(sb + ((q * B_BYTES) >> 4), 128, OZ_KC * 8);
+                                oz_mma_ts(tmem + (uint32_t)(p + q) * OZ_N, tmem + (uint32_t)(S * OZ_N + 8 * p), db, (c > 0 || p > 0) ? 1u : 0u);
+                            }
+                    } else
 #pragma unroll
                     for (int kk = 0; kk < OZ_KC / 32; ++kk) {
 #pragma unroll
@@ -354,12 +383,20 @@ size_t oz_work_bytes(int m2, int k1, int S) {
     return align_up((size_t)S * oz_plane_bytes(m2_pad, k1_pad)) + align_up((size_t)m2_pad * sizeof(double)) + 256;
 }
 
+static int g_oz_ts = -1;      // A operand through tensor memory (S <= 7); FERS_OZ_TS=0 keeps both operands in shared memory
+
 template <int S>
 static int oz_launch(OzFront f, cudaStream_t st, bool persistent) {
     static PerDeviceOnce once;
+    constexpr bool TS_OK = (S <= 7);
     const size_t smem = (size_t)oz_stages(S) * oz_stage_bytes(S);
+    if (g_oz_ts < 0) {
+        const char* e = getenv("FERS_OZ_TS");
+        g_oz_ts = e ? atoi(e) : OZ_TS_DEFAULT;
+    }
     if (once.needed()) {
-        FERS_CK(cudaFuncSetAttribute(k_oz_syrk<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FERS_CK(cudaFuncSetAttribute(k_oz_syrk<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FERS_CK(cudaFuncSetAttribute(k_oz_syrk<S, TS_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         once.done();
     }
     k_oz_rowscale<<<(f.m2_pad + 255) / 256, 256, 0, st>>>(f);
@@ -368,7 +405,9 @@ static int oz_launch(OzFront f, cudaStream_t st, bool persistent) {
     const int n_tiles = oz_tile_count(f.ncols, f.m2_pad);
     // persistent: one CTA per SM walks the tile list (long K: the Schur updates).  Otherwise one CTA per tile, so that SMs
     // come free every few microseconds for the kernels of a higher-priority stream (the panel chain of the look-ahead)
-    k_oz_syrk<S><<<persistent ? std::min(n_tiles, sm_count()) : n_tiles, OZ_THREADS, smem, st>>>(f, n_tiles);
+    const int n_cta = persistent ? std::min(n_tiles, sm_count()) : n_tiles;
+    if (TS_OK && g_oz_ts) k_oz_syrk<S, TS_OK><<<n_cta, OZ_THREADS, smem, st>>>(f, n_tiles);
+    else k_oz_syrk<S, false><<<n_cta, OZ_THREADS, smem, st>>>(f, n_tiles);
     FERS_LAUNCH_CHECK();
     count_launches(3);
     return 0;

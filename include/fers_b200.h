@@ -119,6 +119,10 @@ int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xy
                                     const double* m_axial, int kg_mode, int kg_suppress, const int* m_slot,
                                     const int* hm_ptr, const int* hm_list, int n_dup, const int* diag_slot,
                                     double* member_cache, double* vals, void* stream);
+/* Which kernel the gather assembly runs for plain models (no modifier records, no K_g, no member cache): 0 (default) = the
+ * element-lane kernel k_assemble_gather_plain (27 values per half-member in shared memory, one lane per entry of a 6x6
+ * block), 1 = the per-half-member kernel k_assemble_gather that also serves the general case.  Same K either way. */
+int fers_b200_assemble_set_gather_kernel(int kind);
 /* Restrained-warping torsion (7th nodal DOF of the reference's beam: pydantic_models.py:1366-1369, 1384-1387;
  * formulation SURVEY.md A.11, pinned by NAFEMS LE5).  The warping DOF psi of a node is DOF 0 of an auxiliary node;
  * prop[.][7] = E*Iw (its theta-theta part 12 EIw/L^3 is already in the member's torsion coefficient).  Adds the

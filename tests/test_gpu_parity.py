@@ -77,6 +77,42 @@ def test_assembled_values_match_oracle(engine_mod, variant):
     assert np.abs(K - want).max() <= 1e-13 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("dims,dup", [((5, 4, 3), False), ((7, 6, 5), True), ((1, 1, 1), False)])
+def test_plain_gather_kernel_matches_half_member_kernel(engine_mod, dims, dup):
+    """The element-lane kernel for plain models (27 values per half-member, one lane per block entry) writes the K of
+    the per-half-member kernel: same arithmetic per entry, same summation order on the diagonal -> equal to round-off of
+    the compiler's contraction choices (1e-15), duplicate members between a node pair left to k_gather_dups, trusses and
+    rolled members included."""
+    import torch
+    from fers_core_b200 import _lib
+    model = synth.grid_frame(*dims, timoshenko=True)
+    rng = np.random.default_rng(5)
+    model.m_roll = np.where(rng.random(model.n_members) < 0.3, rng.normal(size=model.n_members), 0.0)
+    model.m_type = np.where(rng.random(model.n_members) < 0.2, 1, model.m_type).astype(np.int32)
+    if dup:                                     # a second member on some node pairs
+        k = model.n_members // 7
+        for name in ("m_n1", "m_n2", "m_prop", "m_type", "m_roll", "m_rel"):
+            a = getattr(model, name)
+            setattr(model, name, np.concatenate([a, a[:k]]))
+        model.m_ids = np.arange(1, len(model.m_n1) + 1, dtype=np.int64)
+    lib = _lib.load()
+    out = []
+    try:
+        for kind in (1, 0):
+            _lib.check(lib.fers_b200_assemble_set_gather_kernel(kind), "set_gather_kernel")
+            eng = engine_mod.Engine(model)
+            eng.d_vals.fill_(float("nan"))
+            eng.assemble(eng.d_xyz0)
+            out.append(eng.d_vals.cpu().numpy().copy())
+    finally:
+        lib.fers_b200_assemble_set_gather_kernel(0)
+    assert np.isfinite(out[1]).all()
+    assert np.abs(out[0] - out[1]).max() <= 1e-15 * np.abs(out[0]).max()
+    K = _bsr_to_scipy(eng, model.n_nodes).toarray()
+    want = fers_oracle.Assembly(model).K_elastic().toarray()
+    assert np.abs(K - want).max() <= 1e-13 * np.abs(want).max()
+
+
 def test_gather_assembly_general_paths_match_scatter(engine_mod):
     """Gather kernel against the atomic scatter-add kernel on a model with duplicate members between
     the same node pair, end releases and geometric stiffness (the dense-local-matrix path); the gather
