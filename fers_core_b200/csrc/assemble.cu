@@ -458,32 +458,48 @@ __global__ void __launch_bounds__(GA_THREADS, GENERAL ? 1 : 5) k_assemble_gather
 //   TT = a x x^T + z12 y y^T + y12 z z^T     R4 = t x x^T + y4 y y^T + z4 z z^T     R2 = -t x x^T + y2 y y^T + z2 z z^T
 //   TR = z6 y z^T - y6 z y^T                 (TT, R4, R2 symmetric: 6 + 6 + 6 + 9 = 27 values per member)
 //   K_ss = [TT TR; TR^T R4]   K_se = [-TT TR; -TR^T R2]   K_es = [-TT -TR; TR^T R2]   K_ee = [TT -TR; -TR^T R4]
-// Phase A: one thread per half-member forms the 27 values in shared memory (a third of the arithmetic of two full blocks,
-// 40 registers instead of 96).  Phase B: groups of 36 lanes, one lane per entry of a 6x6 block, stream the off-diagonal
-// blocks out (consecutive half-members of the list own consecutive slots: 8-byte stores coalesce into whole 288-byte
-// blocks) and sum the diagonal contributions of the CTA's nodes in list order (same order as k_assemble_gather: no atomics,
-// bit-reproducible).  Same arithmetic per entry as beam_block_closed.
-constexpr int GP_GROUPS = 4;
-constexpr int GP_THREADS = 36 * GP_GROUPS;        // 144
+// Phase A: one thread per half-member forms the 27 values in shared memory: frame and coefficients on one reciprocal
+// square root of the length (the rule of member_frame / beam_coef, equal to them to a few ulp; the fp64 divisions of the
+// shared functions were two thirds of the instructions of this kernel).  Phase B: groups of 18 lanes, one lane per pair of
+// neighbouring entries of a 6x6 block, stream the off-diagonal blocks out (consecutive half-members of the list own
+// consecutive slots: 16-byte stores coalesce into whole 288-byte blocks; signs are applied to the high word) and sum the
+// diagonal contributions of the CTA's nodes in list order (the order of k_assemble_gather: no atomics, bit-reproducible).
+constexpr int GP_GROUPS = 8;                      // groups of 18 lanes: a lane owns two neighbouring entries of a 6x6 block
+constexpr int GP_LANES = 18;
+constexpr int GP_THREADS = GP_LANES * GP_GROUPS;  // 144
 constexpr int GP_NODES = 24;                      // 24 nodes x 6 members = 144 half-members: one chunk on a 3D grid frame
 constexpr int GP_VALS = 27;
-constexpr int GP_QS = GP_NODES / GP_GROUPS;       // diagonal entries per lane
+constexpr int GP_QS = GP_NODES / GP_GROUPS;       // nodes per group
 static_assert(GP_NODES % GP_GROUPS == 0 && GP_NODES + 1 <= GP_THREADS, "plain gather kernel geometry");
 
 __device__ __forceinline__ int gp_sym6(int r, int q) {
     const int lo = min(r, q), hi = max(r, q);
     return lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
 }
+// where entry (R, C) of a 6x6 block sits in the 27 values (diagonal kinds K_ss / K_ee and off-diagonal kinds K_se / K_es)
+// and its sign per kind as a mask on the high word: bit 0 of `sg` = K_se, bit 1 = K_es, bit 2 = K_ee (K_ss carries none)
+__device__ __forceinline__ void gp_entry(int R, int C, int& idx_dg, int& idx_off, int& sg) {
+    const int sr = R >= 3, sc = C >= 3, r = R - 3 * sr, q = C - 3 * sc;
+    if (!sr && !sc) { idx_dg = idx_off = gp_sym6(r, q); sg = 1 | 2; }
+    else if (sr && sc) { idx_dg = 6 + gp_sym6(r, q); idx_off = 12 + gp_sym6(r, q); sg = 0; }
+    else if (!sr) { idx_dg = idx_off = 18 + 3 * r + q; sg = 2 | 4; }       // translation row, rotation column: sign of the row end
+    else { idx_dg = idx_off = 18 + 3 * q + r; sg = 1 | 4; }                // rotation row, translation column: sign of the column end
+}
+__device__ __forceinline__ double gp_flip(double v, unsigned mask) {
+    return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
+}
+__device__ __forceinline__ void st_global_v2(double* p, double a, double b) {
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
 
-__global__ void __launch_bounds__(GP_THREADS, 5) k_assemble_gather_plain(GatherArgs G) {
+__global__ void __launch_bounds__(GP_THREADS, 6) k_assemble_gather_plain(GatherArgs G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const BeamArgs& A = G.B;
     double* s_val = reinterpret_cast<double*>(smem_raw);                 // [GP_THREADS][GP_VALS]
     double* s_prop = s_val + GP_THREADS * GP_VALS;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_prop + (size_t)(A.use_tma ? A.n_prop : 0) * NPROP);
     __shared__ int s_hp[GP_NODES + 1];
-    __shared__ int s_off[GP_THREADS];          // slot of the off-diagonal block, -1: not written here (duplicate pair / self pair)
-    __shared__ int s_end[GP_THREADS];
+    __shared__ int s_meta[GP_THREADS];         // slot of the off-diagonal block << 2 | not written here << 1 | end
 
     const int tid = threadIdx.x;
     if (A.use_tma) {
@@ -503,10 +519,10 @@ __global__ void __launch_bounds__(GP_THREADS, 5) k_assemble_gather_plain(GatherA
     const double* prop_tab = A.use_tma ? s_prop : A.prop;
     bool prop_ready = !A.use_tma;
 
-    const int g = tid / 36, e = tid - 36 * g;
-    double acc[GP_QS];
+    const int g = tid / GP_LANES, pr = tid - GP_LANES * g;
+    double acc[GP_QS][2];
 #pragma unroll
-    for (int k = 0; k < GP_QS; ++k) acc[k] = 0.0;
+    for (int k = 0; k < GP_QS; ++k) acc[k][0] = acc[k][1] = 0.0;
 
     for (int chunk0 = h_begin; chunk0 < h_end; chunk0 += GP_THREADS) {
         const int h = chunk0 + tid;
@@ -519,50 +535,79 @@ __global__ void __launch_bounds__(GP_THREADS, 5) k_assemble_gather_plain(GatherA
             const double roll = A.m_roll[m];
             const int mtype = A.m_type[m], pi = A.m_prop[m];
             const double scale = A.m_scale ? A.m_scale[m] : 1.0;
-            const double pa[3] = {A.xyz[3 * a], A.xyz[3 * a + 1], A.xyz[3 * a + 2]};
-            const double pb[3] = {A.xyz[3 * b], A.xyz[3 * b + 1], A.xyz[3 * b + 2]};
-            const Frame f = member_frame(pa, pb, roll);
-            if (!prop_ready) { mbar_wait(s_bar, 0); prop_ready = true; }
-            double Pr[NPROP];
+            // local frame (the rule of member_frame) and closed-form coefficients (those of beam_coef) on one reciprocal
+            // of the length: the divisions of the shared functions cost more than everything else in this kernel
+            const double dx = A.xyz[3 * b] - A.xyz[3 * a], dy = A.xyz[3 * b + 1] - A.xyz[3 * a + 1], dz = A.xyz[3 * b + 2] - A.xyz[3 * a + 2];
+            const double iL = rsqrt(dx * dx + dy * dy + dz * dz);
+            double x[3] = {dx * iL, dy * iL, dz * iL}, y[3], z[3];
+            {
+                double rf1 = 1.0, rf2 = 0.0;
+                if (fabs(x[1]) > 1.0 - 1e-6) { rf1 = 0.0; rf2 = 1.0; }
+                z[0] = x[1] * rf2 - x[2] * rf1; z[1] = -x[0] * rf2; z[2] = x[0] * rf1;
+                const double zn = rsqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
+                z[0] *= zn; z[1] *= zn; z[2] *= zn;
+                y[0] = z[1] * x[2] - z[2] * x[1]; y[1] = z[2] * x[0] - z[0] * x[2]; y[2] = z[0] * x[1] - z[1] * x[0];
+                const double yn = rsqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+                y[0] *= yn; y[1] *= yn; y[2] *= yn;
+                if (roll != 0.0) {
+                    const double cr = cos(roll), sn = sin(roll);
 #pragma unroll
-            for (int i = 0; i < NPROP; ++i) Pr[i] = prop_tab[(size_t)pi * NPROP + i];
-            const BeamCoef c = beam_coef(Pr, f.L, mtype, scale);
-            const double* x = f.r[0];
-            const double* y = f.r[1];
-            const double* z = f.r[2];
+                    for (int i = 0; i < 3; ++i) {
+                        const double ny = cr * y[i] + sn * z[i], nz = -sn * y[i] + cr * z[i];
+                        y[i] = ny; z[i] = nz;
+                    }
+                }
+            }
+            if (!prop_ready) { mbar_wait(s_bar, 0); prop_ready = true; }
+            const double* P = prop_tab + (size_t)pi * NPROP;
+            const double iL2 = iL * iL, iL3 = iL2 * iL;
+            const bool axial_only = (mtype == MT_TRUSS);
+            double bz = 0.0, by = 0.0, phi_y = 0.0, phi_z = 0.0;
+            if (!axial_only) {
+                bz = P[P_EIZ]; by = P[P_EIY];
+                if (P[P_GASZ] > 0.0) { phi_y = 12.0 * bz * iL2 / P[P_GASZ]; bz = bz / (1.0 + phi_y); }
+                if (P[P_GASY] > 0.0) { phi_z = 12.0 * by * iL2 / P[P_GASY]; by = by / (1.0 + phi_z); }
+            }
+            const double ca = scale * (P[P_EA] * iL);
+            const double ct = axial_only ? 0.0 : scale * (P[P_GJ] * iL + 12.0 * P[P_EIW] * iL3);
+            const double z12 = scale * (12.0 * bz * iL3), z6 = scale * (6.0 * bz * iL2);
+            const double z4 = scale * ((4.0 + phi_y) * bz * iL), z2 = scale * ((2.0 - phi_y) * bz * iL);
+            const double y12 = scale * (12.0 * by * iL3), y6 = scale * (6.0 * by * iL2);
+            const double y4 = scale * ((4.0 + phi_z) * by * iL), y2 = scale * ((2.0 - phi_z) * by * iL);
             double* o = s_val + tid * GP_VALS;
             int k = 0;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = i; j < 3; ++j, ++k) {
-                    o[k] = c.a * x[i] * x[j] + c.z12 * y[i] * y[j] + c.y12 * z[i] * z[j];
-                    o[6 + k] = c.t * x[i] * x[j] + c.y4 * y[i] * y[j] + c.z4 * z[i] * z[j];
-                    o[12 + k] = -c.t * x[i] * x[j] + c.y2 * y[i] * y[j] + c.z2 * z[i] * z[j];
+                    const double xx = x[i] * x[j], yy = y[i] * y[j], zz = z[i] * z[j];
+                    o[k] = ca * xx + z12 * yy + y12 * zz;
+                    o[6 + k] = ct * xx + y4 * yy + z4 * zz;
+                    o[12 + k] = -ct * xx + y2 * yy + z2 * zz;
                 }
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) o[18 + 3 * i + j] = c.z6 * y[i] * z[j] + (-c.y6) * z[i] * y[j];
-            s_off[tid] = ((code & 2) || off_slot == dg_slot) ? -1 : off_slot;     // duplicated node pairs: k_gather_dups
-            s_end[tid] = end;
+                for (int j = 0; j < 3; ++j) o[18 + 3 * i + j] = z6 * y[i] * z[j] - y6 * z[i] * y[j];
+            // duplicated node pairs are left to k_gather_dups
+            s_meta[tid] = (off_slot << 2) | ((((code & 2) != 0) || off_slot == dg_slot) ? 2 : 0) | end;
         }
         __syncthreads();
-        // the entry of a 6x6 block this lane owns: where it sits in the 27 values and with which sign per block kind
-        const int R = e / 6, C = e - 6 * R, sr = R >= 3, sc = C >= 3, r = R - 3 * sr, q = C - 3 * sc;
-        int idx_dg, idx_off;
-        double sg_se, sg_es, sg_ee;                    // K_ss carries no sign
-        if (!sr && !sc) { idx_dg = idx_off = gp_sym6(r, q); sg_se = sg_es = -1.0; sg_ee = 1.0; }
-        else if (sr && sc) { idx_dg = 6 + gp_sym6(r, q); idx_off = 12 + gp_sym6(r, q); sg_se = sg_es = sg_ee = 1.0; }
-        else if (!sr) { idx_dg = idx_off = 18 + 3 * r + q; sg_se = 1.0; sg_es = sg_ee = -1.0; }       // translation row, rotation column
-        else { idx_dg = idx_off = 18 + 3 * q + r; sg_es = 1.0; sg_se = sg_ee = -1.0; }                // rotation row, translation column
+        // the two neighbouring entries (R, C0), (R, C0 + 1) of a 6x6 block this lane owns
+        const int R = pr / 3, C0 = 2 * (pr - 3 * R);
+        int idg0, iof0, sg0, idg1, iof1, sg1;
+        gp_entry(R, C0, idg0, iof0, sg0);
+        gp_entry(R, C0 + 1, idg1, iof1, sg1);
         const int cnt = min(GP_THREADS, h_end - chunk0);
+        double* const out = A.vals + 2 * pr;
 #pragma unroll 4
         for (int i = g; i < cnt; i += GP_GROUPS) {
-            const int slot = s_off[i];
-            if (slot >= 0) {
-                const double v = s_val[i * GP_VALS + idx_off];
-                A.vals[(size_t)slot * 36 + e] = (s_end[i] ? sg_es : sg_se) * v;
+            const int meta = s_meta[i];
+            if (!(meta & 2)) {
+                const int bit = 1 << (meta & 1);                     // K_se for a start end, K_es for an end end
+                const double* v = s_val + i * GP_VALS;
+                st_global_v2(out + (size_t)(meta >> 2) * 36, gp_flip(v[iof0], (sg0 & bit) ? 0x80000000u : 0u),
+                             gp_flip(v[iof1], (sg1 & bit) ? 0x80000000u : 0u));
             }
         }
 #pragma unroll
@@ -571,8 +616,10 @@ __global__ void __launch_bounds__(GP_THREADS, 5) k_assemble_gather_plain(GatherA
             if (nl < nn) {
                 const int lo = max(s_hp[nl], chunk0) - chunk0, hi = min(s_hp[nl + 1], chunk0 + GP_THREADS) - chunk0;
                 for (int i = lo; i < hi; ++i) {
-                    const double v = s_val[i * GP_VALS + idx_dg];
-                    acc[k] += s_end[i] ? sg_ee * v : v;
+                    const unsigned ee = (s_meta[i] & 1) ? 4u : 0u;   // K_ee for an end end, K_ss (no sign) for a start end
+                    const double* v = s_val + i * GP_VALS;
+                    acc[k][0] += gp_flip(v[idg0], (sg0 & ee) ? 0x80000000u : 0u);
+                    acc[k][1] += gp_flip(v[idg1], (sg1 & ee) ? 0x80000000u : 0u);
                 }
             }
         }
@@ -582,7 +629,7 @@ __global__ void __launch_bounds__(GP_THREADS, 5) k_assemble_gather_plain(GatherA
 #pragma unroll
     for (int k = 0; k < GP_QS; ++k) {
         const int nl = g + GP_GROUPS * k;
-        if (nl < nn) A.vals[(size_t)G.diag_slot[node_a + nl] * 36 + e] = acc[k];
+        if (nl < nn) st_global_v2(A.vals + (size_t)G.diag_slot[node_a + nl] * 36 + 2 * pr, acc[k][0], acc[k][1]);
     }
 }
 

@@ -149,7 +149,7 @@ constexpr int NB = CHOL_NB;
 // 64-column steps per outer block of the two-level blocked panel update (FERS_CHOL_OUTER / fers_b200_chol_set_outer)
 static int g_chol_outer = getenv("FERS_CHOL_OUTER") ? atoi(getenv("FERS_CHOL_OUTER")) : 4;
 // outer blocks per group of the third blocking level (FERS_CHOL_GROUP / fers_b200_chol_set_outer); 1 = two levels only
-static int g_chol_group = getenv("FERS_CHOL_GROUP") ? atoi(getenv("FERS_CHOL_GROUP")) : 1;
+static int g_chol_group = getenv("FERS_CHOL_GROUP") ? atoi(getenv("FERS_CHOL_GROUP")) : 6;
 constexpr int TP = NB + 1;
 constexpr size_t POTRF_SMEM = 2 * NB * TP * sizeof(double);
 
@@ -825,13 +825,17 @@ static int g_chol_profile_on = 0;      // 0 off, 1 every kernel class, 2 Schur-u
 // 6..8; 8 = fp64 grade) and the smallest own-column count of a level that takes that path.  FERS_CHOL_OZAKI /
 // FERS_CHOL_OZAKI_MIN_K / fers_b200_chol_set_ozaki.
 static int g_chol_ozaki = getenv("FERS_CHOL_OZAKI") ? atoi(getenv("FERS_CHOL_OZAKI")) : 7;
-static int g_chol_ozaki_min_k = getenv("FERS_CHOL_OZAKI_MIN_K") ? atoi(getenv("FERS_CHOL_OZAKI_MIN_K")) : 1024;
-// the outer panel updates (K = one 256-column block) of levels whose fronts have at least this many own columns take the same
-// kernel, one CTA per tile on the low-priority stream of the look-ahead (0 = off, the default: measured gain 1 % with 2048-column groups, a loss with shorter K); FERS_CHOL_OZAKI_PANEL_K
-static int g_chol_ozaki_panel_k = getenv("FERS_CHOL_OZAKI_PANEL_K") ? atoi(getenv("FERS_CHOL_OZAKI_PANEL_K")) : 0;
+static int g_chol_ozaki_min_k = getenv("FERS_CHOL_OZAKI_MIN_K") ? atoi(getenv("FERS_CHOL_OZAKI_MIN_K")) : 768;
+// the group updates of the panel factorisation (K = one group of 256-column blocks) of levels whose fronts have at least
+// this many own columns take the same kernel, one CTA per tile on the low-priority stream of the look-ahead (0 = off).
+// Measured at configs[3] with the 128 x 128 two-pass kernel: 379.6 -> 364.0 ms per pass with groups of 6 blocks
+// (1536 columns); 370.6 with 1024, 366.1 with 2048, 365.1 with 3072; a loss with K = 512.  FERS_CHOL_OZAKI_PANEL_K
+static int g_chol_ozaki_panel_k = getenv("FERS_CHOL_OZAKI_PANEL_K") ? atoi(getenv("FERS_CHOL_OZAKI_PANEL_K")) : 2048;
+// ... on levels of at most this many fronts (FERS_CHOL_OZAKI_PANEL_NF)
+static int g_chol_ozaki_panel_nf = getenv("FERS_CHOL_OZAKI_PANEL_NF") ? atoi(getenv("FERS_CHOL_OZAKI_PANEL_NF")) : 8;
 // ... and only updates whose K (block or group width) is at least this long: a 256-column update spends as long in the
 // tile prologue / epilogue as in its 8 MMA steps (measured: factorisation 385 -> 535 ms with K = 256)
-static int g_chol_ozaki_panel_kw = getenv("FERS_CHOL_OZAKI_PANEL_KW") ? atoi(getenv("FERS_CHOL_OZAKI_PANEL_KW")) : 1024;
+static int g_chol_ozaki_panel_kw = getenv("FERS_CHOL_OZAKI_PANEL_KW") ? atoi(getenv("FERS_CHOL_OZAKI_PANEL_KW")) : 1536;
 
 struct EventPool {
     std::vector<cudaEvent_t> ev;
@@ -1045,7 +1049,7 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
                 const int lim_arg = at_group_end ? (1 << 30) : grp_end;
                 // fronts with many own columns: the update of all later columns as int8 digit-plane products (ozaki_syrk.cu),
                 // front by front; digit planes in the children's arena (the Schur update of the level reuses it afterwards)
-                const bool oz_panel = g_chol_ozaki >= 4 && g_chol_ozaki_panel_k > 0 && nf <= 8 && kw < 16384 &&
+                const bool oz_panel = g_chol_ozaki >= 4 && g_chol_ozaki_panel_k > 0 && nf <= g_chol_ozaki_panel_nf && kw < 16384 &&
                                       kw >= g_chol_ozaki_panel_kw &&
                                       6 * P.level_max_n1[l] >= g_chol_ozaki_panel_k &&
                                       oz_work_bytes(max_m, kw, g_chol_ozaki) <= (size_t)P.schur_doubles[(l & 1) ^ 1] * 8;

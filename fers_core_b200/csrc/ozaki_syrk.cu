@@ -40,6 +40,7 @@ constexpr int OZ_DIGIT_BITS = 8;          // bits per digit plane after the firs
 constexpr double OZ_BASE = 256.0;         // 2^OZ_DIGIT_BITS
 constexpr int OZ_THREADS = 192;
 constexpr int OZ_BAND = 12;               // row blocks per band of the tile order (L2 reuse of the operand tiles)
+constexpr int OZ_WIDE_DEFAULT = 1;
 constexpr int OZ_TS_DEFAULT = 0;          // A operand through tensor memory unless FERS_OZ_TS says otherwise
 constexpr uint32_t OZ_SPIN_LIMIT = 1u << 28;   // a barrier that never completes traps instead of hanging the device
 
@@ -371,6 +372,242 @@ k_oz_syrk(OzFront f, int n_tiles) {
     }
 }
 
+// ---- wide tiles: 128 x 128 per CTA, two passes over K -----------------------------------------------------------------------
+// Measured on B200 (tools/micro/mma_rate.cu): a tcgen05.mma with both operands in shared memory takes
+// max(N / 2, (4096 + 32 N) / 128) cycles at M = 128, K = 32 bytes -- the tensor core reads its operands at 128 B per cycle.
+// N = 64 costs 48 cycles (2/3 of the int8 rate), N = 128 costs 64 (full rate).  S accumulators of 128 columns do not fit the
+// 512 columns of tensor memory, so a tile is done in two passes over K: first the low-order diagonals d >= 4 (all S planes,
+// S - 4 accumulators), then d < 4 (planes 0..3, 4 accumulators); each pass ends with its own C -= ... (small terms first).
+// The operand bytes per product are the same as with 128 x 64 tiles (11 plane loads of 256 rows against 7 of 192 for half
+// the tile), the products run twice as wide.
+constexpr int OZW_N = 128;
+constexpr int OZW_EPI_WARPS = 8;
+constexpr int OZW_THREADS = 64 + 32 * OZW_EPI_WARPS;
+constexpr uint32_t OZW_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZW_N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
+__device__ __forceinline__ void oz_mma_w(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(OZW_IDESC), "r"(accumulate)
+        : "memory");
+}
+// tile t of the lower triangle of 128 x 128 blocks, bands of OZ_BAND row blocks, column by column inside a band
+__device__ __forceinline__ bool ozw_tile(int t, int nb, int nbj, int& bi, int& bj) {
+    for (int b0 = 0; b0 < nb; b0 += OZ_BAND) {
+        const int b1 = min(b0 + OZ_BAND, nb);
+        const int maxbj = min(b1 - 1, nbj - 1);
+        for (int j = 0; j <= maxbj; ++j) {
+            const int rmin = max(b0, j);
+            const int cnt = b1 - rmin;
+            if (t < cnt) { bi = rmin + t; bj = j; return true; }
+            t -= cnt;
+        }
+    }
+    return false;
+}
+
+// DS: diagonals d >= DS in the first pass (all S planes), d < DS in the second (planes 0 .. DS - 1)
+template <int S, int DS>
+__global__ void __launch_bounds__(OZW_THREADS, 1)
+k_oz_syrk_wide(OzFront f, int n_tiles) {
+    extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
+    constexpr uint32_t T_BYTES = OZ_M * OZ_KC;                      // one 128-row tile of one plane and K chunk
+    constexpr uint32_t STAGE_BYTES = 2 * S * T_BYTES;               // A planes, then B planes
+    constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+    constexpr int NPASS = S > DS ? 2 : 1;
+    static_assert(STAGES >= 2 && OZ_KC == 32 && (S - DS) * OZW_N <= 512 && DS * OZW_N <= 512, "wide int8 tile geometry");
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 2];
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ring = oz_smem(oz_smem_raw);
+    const uint32_t bar_full = oz_smem(&bars[0]), bar_empty = oz_smem(&bars[STAGES]);
+    const uint32_t bar_acc_full = oz_smem(&bars[2 * STAGES]), bar_acc_empty = oz_smem(&bars[2 * STAGES + 1]);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { oz_mbar_init(bar_full + 8u * i, 1); oz_mbar_init(bar_empty + 8u * i, 1); }
+        oz_mbar_init(bar_acc_full, 1);
+        oz_mbar_init(bar_acc_empty, OZW_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem(&s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    oz_fence_before();
+    __syncthreads();
+    oz_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int unit0 = blockIdx.x, unit_stride = gridDim.x;
+    const int nb = f.m2_pad / OZ_M, nbj = (f.ncols + OZW_N - 1) / OZW_N;
+    const int nkc = f.k1_pad / OZ_KC;
+    const size_t plane = oz_plane_bytes(f.m2_pad, f.k1_pad);
+    const size_t chunk_bytes = (size_t)f.m2_pad * OZ_KC;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        uint32_t it = 0;
+        for (int t = unit0; t < n_tiles; t += unit_stride) {
+            int bi, bj;
+            if (!ozw_tile(t, nb, nbj, bi, bj)) break;
+            const int8_t* a0 = f.planes + (size_t)bi * T_BYTES;
+            const int8_t* b0 = f.planes + (size_t)bj * T_BYTES;
+            for (int pass = 0; pass < NPASS; ++pass) {
+                const int np = (NPASS == 2 && pass == 0) ? S : (S < DS ? S : DS);
+                for (int c = 0; c < nkc; ++c, ++it) {
+                    const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
+                    oz_mbar_wait(bar_empty + 8u * st, ph ^ 1u);
+                    if (oz_elect()) {
+                        const uint32_t full = bar_full + 8u * st;
+                        oz_mbar_expect_tx(full, 2u * np * T_BYTES);
+                        const uint32_t dst = ring + st * STAGE_BYTES;
+                        for (int p = 0; p < np; ++p) {
+                            oz_bulk_g2s(dst + p * T_BYTES, a0 + p * plane + (size_t)c * chunk_bytes, T_BYTES, full);
+                            oz_bulk_g2s(dst + (S + p) * T_BYTES, b0 + p * plane + (size_t)c * chunk_bytes, T_BYTES, full);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        uint32_t it = 0, acc_i = 0;
+        for (int t = unit0; t < n_tiles; t += unit_stride) {
+            int bi, bj;
+            if (!ozw_tile(t, nb, nbj, bi, bj)) break;
+            for (int pass = 0; pass < NPASS; ++pass, ++acc_i) {
+                const bool low = (NPASS == 2 && pass == 0);         // diagonals d >= DS
+                oz_mbar_wait(bar_acc_empty, (acc_i & 1u) ^ 1u);
+                oz_fence_after();
+                for (int c = 0; c < nkc; ++c, ++it) {
+                    const uint32_t st = it % STAGES, ph = (it / STAGES) & 1u;
+                    oz_mbar_wait(bar_full + 8u * st, ph);
+                    oz_fence_after();
+                    if (oz_elect()) {
+                        const uint32_t sa = (ring + st * STAGE_BYTES) >> 4, sb = sa + ((S * T_BYTES) >> 4);
+                        if (low) {
+#pragma unroll
+                            for (int p = 0; p < S; ++p) {
+                                const uint64_t da = oz_desc(sa + ((p * T_BYTES) >> 4), 128, OZ_KC * 8);
+#pragma unroll
+                                for (int q = 0; q + p < S; ++q) {
+                                    if (p + q < DS) continue;
+                                    const uint64_t db = oz_desc(sb + ((q * T_BYTES) >> 4), 128, OZ_KC * 8);
+                                    oz_mma_w(tmem + (uint32_t)(p + q - DS) * OZW_N, da, db, (c > 0 || p > 0) ? 1u : 0u);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int p = 0; p < S && p < DS; ++p) {
+                                const uint64_t da = oz_desc(sa + ((p * T_BYTES) >> 4), 128, OZ_KC * 8);
+#pragma unroll
+                                for (int q = 0; q + p < S && q + p < DS; ++q) {
+                                    const uint64_t db = oz_desc(sb + ((q * T_BYTES) >> 4), 128, OZ_KC * 8);
+                                    oz_mma_w(tmem + (uint32_t)(p + q) * OZW_N, da, db, (c > 0 || p > 0) ? 1u : 0u);
+                                }
+                            }
+                        }
+                        oz_commit(bar_empty + 8u * st);
+                        if (c == nkc - 1) oz_commit(bar_acc_full);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: 8 warps, warp w reads TMEM lanes 32 (w % 4) .., columns 64 (w / 4) .. of every accumulator =====
+        const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+        uint32_t acc_i = 0;
+        for (int t = unit0; t < n_tiles; t += unit_stride) {
+            int bi, bj;
+            if (!ozw_tile(t, nb, nbj, bi, bj)) break;
+            const int r = bi * OZ_M + 32 * quad + lane;
+            const int c0 = bj * OZW_N + 64 * half;
+            const double rs = f.rowscale[min(r, f.m2_pad - 1)];
+            const uint32_t lane_addr = tmem + ((uint32_t)(32 * quad) << 16) + (uint32_t)(64 * half);
+            for (int pass = 0; pass < NPASS; ++pass, ++acc_i) {
+                const bool low = (NPASS == 2 && pass == 0);
+                oz_mbar_wait(bar_acc_full, acc_i & 1u);
+                oz_fence_after();
+                if (low) {
+                    constexpr int ND = S > DS ? S - DS : 1;
+#pragma unroll 1
+                    for (int cb = 0; cb < 64; cb += 8) {
+                        double sum[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sum[j] = 0.0;
+                        int v[ND][8];
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) oz_tmem_ld8(lane_addr + (uint32_t)(d * OZW_N + cb), v[d]);
+                        oz_tmem_wait_ld();
+                        double wgt = ldexp(1.0, -12 - OZ_DIGIT_BITS * (S - 1));
+#pragma unroll
+                        for (int d = ND - 1; d >= 0; --d) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) sum[j] = fma((double)v[d][j], wgt, sum[j]);
+                            wgt *= OZ_BASE;
+                        }
+                        if (r < f.m2) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int col = c0 + cb + j;
+                                if (col <= r && col < f.ncols) {
+                                    double* dst = f.C + (size_t)col * f.ldc + r;
+                                    *dst -= sum[j] * rs * f.rowscale[col];
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    constexpr int ND = S < DS ? S : DS;
+#pragma unroll 1
+                    for (int cb = 0; cb < 64; cb += 8) {
+                        double sum[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sum[j] = 0.0;
+                        int v[ND][8];
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) oz_tmem_ld8(lane_addr + (uint32_t)(d * OZW_N + cb), v[d]);
+                        oz_tmem_wait_ld();
+                        double wgt = ldexp(1.0, -12 - OZ_DIGIT_BITS * (ND - 1));
+#pragma unroll
+                        for (int d = ND - 1; d >= 0; --d) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) sum[j] = fma((double)v[d][j], wgt, sum[j]);
+                            wgt *= OZ_BASE;
+                        }
+                        if (r < f.m2) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int col = c0 + cb + j;
+                                if (col <= r && col < f.ncols) {
+                                    double* dst = f.C + (size_t)col * f.ldc + r;
+                                    *dst -= sum[j] * rs * f.rowscale[col];
+                                }
+                            }
+                        }
+                    }
+                }
+                oz_fence_before();
+                __syncwarp();
+                if (lane == 0) oz_mbar_arrive(bar_acc_empty);
+            }
+        }
+    }
+    oz_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+static int ozw_tile_count(int ncols, int m2_pad) {
+    const int nb = m2_pad / OZ_M, nbj = (ncols + OZW_N - 1) / OZW_N;
+    long long n = 0;
+    for (int r = 0; r < nb; ++r) n += std::min(r + 1, nbj);
+    return (int)n;
+}
+
 static int oz_tile_count(int ncols, int m2_pad) {
     const int nbi = m2_pad / OZ_M, nbj = (ncols + OZ_N - 1) / OZ_N;
     long long n = 0;
@@ -383,6 +620,8 @@ size_t oz_work_bytes(int m2, int k1, int S) {
     return align_up((size_t)S * oz_plane_bytes(m2_pad, k1_pad)) + align_up((size_t)m2_pad * sizeof(double)) + 256;
 }
 
+static int g_oz_dsplit = 3;
+static int g_oz_wide = -1;    // 128 x 128 tiles in two passes over K (S <= 7); FERS_OZ_WIDE=0 keeps the 128 x 64 single-pass kernel
 static int g_oz_ts = -1;      // A operand through tensor memory (S <= 7); FERS_OZ_TS=0 keeps both operands in shared memory
 
 template <int S>
@@ -402,6 +641,29 @@ static int oz_launch(OzFront f, cudaStream_t st, bool persistent) {
     k_oz_rowscale<<<(f.m2_pad + 255) / 256, 256, 0, st>>>(f);
     dim3 grid((f.m2_pad + 255) / 256, f.k1_pad / 16);
     k_oz_split<S><<<grid, 256, 0, st>>>(f);
+    if (g_oz_wide < 0) {
+        const char* e = getenv("FERS_OZ_WIDE");
+        g_oz_wide = e ? atoi(e) : OZ_WIDE_DEFAULT;
+        const char* d = getenv("FERS_OZ_DSPLIT");
+        g_oz_dsplit = d ? atoi(d) : 3;
+    }
+    if (g_oz_wide) {
+        static PerDeviceOnce once_w;
+        constexpr size_t smem_w = (size_t)((200 * 1024) / (2 * S * OZ_M * OZ_KC)) * (2 * S * OZ_M * OZ_KC);
+        constexpr int DS_ALT = (S - 3) * OZW_N <= 512 ? 3 : 4;       // split at d = 3 (default): one plane load less per K chunk than at d = 4
+        if (once_w.needed()) {
+            FERS_CK(cudaFuncSetAttribute(k_oz_syrk_wide<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            FERS_CK(cudaFuncSetAttribute(k_oz_syrk_wide<S, DS_ALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            once_w.done();
+        }
+        const int n_w = ozw_tile_count(f.ncols, f.m2_pad);
+        const int n_cta_w = persistent ? std::min(n_w, sm_count()) : n_w;
+        if (g_oz_dsplit == 3) k_oz_syrk_wide<S, DS_ALT><<<n_cta_w, OZW_THREADS, smem_w, st>>>(f, n_w);
+        else k_oz_syrk_wide<S, 4><<<n_cta_w, OZW_THREADS, smem_w, st>>>(f, n_w);
+        FERS_LAUNCH_CHECK();
+        count_launches(3);
+        return 0;
+    }
     const int n_tiles = oz_tile_count(f.ncols, f.m2_pad);
     // persistent: one CTA per SM walks the tile list (long K: the Schur updates).  Otherwise one CTA per tile, so that SMs
     // come free every few microseconds for the kernels of a higher-priority stream (the panel chain of the look-ahead)

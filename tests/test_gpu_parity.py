@@ -80,9 +80,9 @@ def test_assembled_values_match_oracle(engine_mod, variant):
 @pytest.mark.parametrize("dims,dup", [((5, 4, 3), False), ((7, 6, 5), True), ((1, 1, 1), False)])
 def test_plain_gather_kernel_matches_half_member_kernel(engine_mod, dims, dup):
     """The element-lane kernel for plain models (27 values per half-member, one lane per block entry) writes the K of
-    the per-half-member kernel: same arithmetic per entry, same summation order on the diagonal -> equal to round-off of
-    the compiler's contraction choices (1e-15), duplicate members between a node pair left to k_gather_dups, trusses and
-    rolled members included."""
+    the per-half-member kernel: same closed forms per entry (on a reciprocal length instead of divisions), same summation
+    order on the diagonal -> equal to a few ulp, duplicate members between a node pair left to k_gather_dups, trusses
+    and rolled members included."""
     import torch
     from fers_core_b200 import _lib
     model = synth.grid_frame(*dims, timoshenko=True)
@@ -107,7 +107,7 @@ def test_plain_gather_kernel_matches_half_member_kernel(engine_mod, dims, dup):
     finally:
         lib.fers_b200_assemble_set_gather_kernel(0)
     assert np.isfinite(out[1]).all()
-    assert np.abs(out[0] - out[1]).max() <= 1e-15 * np.abs(out[0]).max()
+    assert np.abs(out[0] - out[1]).max() <= 2e-14 * np.abs(out[0]).max()
     K = _bsr_to_scipy(eng, model.n_nodes).toarray()
     want = fers_oracle.Assembly(model).K_elastic().toarray()
     assert np.abs(K - want).max() <= 1e-13 * np.abs(want).max()

@@ -34,7 +34,9 @@ def _update(m2, k1, S, seed, spread=3.0):
     bound = k1 * amax[:, None] * amax[None, :]                 # scale of the digit-plane truncation: K max|a_i| max|a_j|
     low = torch.triu(torch.ones_like(C, dtype=torch.bool))     # view[col, row] with row >= col
     err = (((Z - ref).abs() / bound)[low]).max().item()
-    assert torch.equal(C[low], (C0 + Z)[low])                  # same products, one rounding of the subtraction
+    # same products; the wide kernel subtracts the low-order diagonals and the high-order ones in two steps (two roundings
+    # of C, each half an ulp), the 128 x 64 kernel in one
+    assert bool(((C - (C0 + Z)).abs()[low] <= 2.0 ** -51 * torch.maximum(C0.abs(), (C0 + Z).abs())[low]).all())
     upper_same = bool((torch.tril(C, -1) == torch.tril(C0, -1)).all()) and bool((torch.tril(Z, -1) == 0).all())
     return err, upper_same
 

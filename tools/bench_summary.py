@@ -14,7 +14,8 @@ for line in sys.stdin:
           f"iters={cfg.get('pcg_iterations')} resid={cfg.get('max_rel_residual')} launches={d.get('gpu_launches')}")
     roof = d.get("roofline") or {}
     for k in roof.get("kernels", []):
-        rate = f"{k['GB/s']:.0f} GB/s" if "GB/s" in k else f"{k['TFLOP/s']:.2f} TFLOP/s"
+        rate = (f"{k['GB/s']:.0f} GB/s" if "GB/s" in k else f"{k['TFLOP/s']:.2f} TFLOP/s" if "TFLOP/s" in k
+                else f"{k.get('int8_TOP/s', 0.0):.0f} TOP/s")
         print(f"    {k['kernel'][:60]:60s} {k['ms']:.4f} ms  {rate}  frac={k['frac']:.3f}  share={k['share_of_step']:.4f}")
     for key in ("factor_ms", "substitution_ms", "factor_tflops_all_kernels", "class_ms_profiled_step"):
         if key in roof:
