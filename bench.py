@@ -415,8 +415,9 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         int8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
         if oz_ms_per_fac > 0:
             tf_oz = cls_flops["syrk_int8"] / (oz_ms_per_fac * 1e-3) / 1e12
-            kern.insert(0, {"kernel": f"k_oz_syrk<{oz_S} digit planes> + k_oz_split + k_oz_rowscale (Schur complements of the upper tree "
-                                      f"levels, own columns >= {oz_min_k}: tcgen05.mma kind::i8, {pairs} digit-plane products per fp64 product)",
+            kern.insert(0, {"kernel": f"k_oz_syrk_wide<{oz_S} digit planes, 128x128 tiles in two passes over K> + k_oz_split + k_oz_rowmax (Schur "
+                                      f"complements of the upper tree levels, own columns >= {oz_min_k}: tcgen05.mma kind::i8 M=128 N=128, "
+                                      f"{pairs} digit-plane products per fp64 product)",
                             "bound": "tensor", "algorithmic_flops_fp64": cls_flops["syrk_int8"],
                             "algorithmic_int8_ops": pairs * cls_flops["syrk_int8"], "ms": oz_ms_per_fac,
                             "fp64_equivalent_TFLOP/s": tf_oz, "vs_fp64_tensor_pipe_peak": tf_oz / dmma.value if dmma.value > 0 else None,
@@ -470,7 +471,12 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                         "vs_fp64_tensor_pipe_peak": kern[0]["vs_fp64_tensor_pipe_peak"],
                         "algorithmic_ops_per_launch": pairs * cls_flops["syrk_int8"] / (n_oz / n_fac),
                         "ms_per_launch": timed_prof["oz_sum_ms"] / n_oz, "launches_per_step": n_oz / n_fac,
-                        "launch": "one front: k_oz_rowscale + k_oz_split + k_oz_syrk, timed together",
+                        "launch": "one front: k_oz_rowmax + k_oz_split + k_oz_syrk_wide, timed together",
+                        "int8_mma_issue_peak_TOPs": 4576.0,
+                        "frac_of_int8_mma_issue_peak": kern[0]["int8_TOP/s"] / 4576.0,
+                        "int8_mma_issue_peak_source": "tools/micro/mma_rate.cu on this pool's B200 (profiles/r2o_mma_rate.txt): kind::i8 M=128 N=256, "
+                                                      "operands resident in shared memory, 148 SMs, 128 cycles per MMA",
+
                         "timing": "CUDA events on the launch stream around the int8 Schur updates of every tree level of the "
                                   f"{int(n_fac)} factorisations inside the timed region", **common}
         else:

@@ -14,7 +14,7 @@
 // S = 6 46 bits.  (7-bit digits, the textbook choice, need S = 8 planes and 36 instead of 28 products for the same bits.)
 //
 // Kernels:
-//   k_oz_rowscale   E_i per row of L21 (exponent of the row maximum)
+//   k_oz_rowmax     max_k |a_ik| per row of L21 (E_i = its exponent)
 //   k_oz_split      fp64 -> S int8 digit planes, written in the shared-memory image the tensor cores read (K-major core
 //                   matrices, 8 rows x 16 B), so that ONE bulk copy (cp.async.bulk, TMA engine) per plane and K-chunk
 //                   brings a whole operand tile; no tensor maps, any front shape
@@ -53,6 +53,7 @@ struct OzFront {
     double* C;              // F22: m2 x m2, column-major, leading dimension ldc (lower triangle)
     int8_t* planes;
     double* rowscale;       // [m2_pad] 2^E_i
+    double* rowmax;         // [m2_pad] max_k |a_ik| (scratch of k_oz_rowmax)
     long long lda, ldc;
     int m2, k1;
     int m2_pad, k1_pad;     // multiples of OZ_M / OZ_KC
@@ -62,16 +63,30 @@ struct OzFront {
 __host__ __device__ inline size_t oz_plane_bytes(int m2_pad, int k1_pad) { return (size_t)m2_pad * k1_pad; }
 
 // ---- row exponents ---------------------------------------------------------------------------------------------------------
+// row maxima by a 2D grid (rows x slices of K; one thread per row alone is a chain of k1 dependent fmax over 50 CTAs:
+// 17.6 ms per factorisation at configs[3]); non-negative doubles order like their bit patterns, so the slices meet in an
+// integer atomicMax.  k_oz_split turns the maximum into 2^E_i.
 __global__ void __launch_bounds__(256)
-k_oz_rowscale(OzFront f) {
+k_oz_rowmax(OzFront f, int k_per_slice) {
     const int r = blockIdx.x * 256 + threadIdx.x;
-    if (r >= f.m2_pad) return;
-    double mx = 0.0;
-    if (r < f.m2)
-        for (int k = 0; k < f.k1; ++k) mx = fmax(mx, fabs(f.A[(size_t)k * f.lda + r]));
+    if (r >= f.m2) return;
+    const int k0 = blockIdx.y * k_per_slice, k1 = min(k0 + k_per_slice, f.k1);
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {
+        m0 = fmax(m0, fabs(f.A[(size_t)k * f.lda + r]));
+        m1 = fmax(m1, fabs(f.A[(size_t)(k + 1) * f.lda + r]));
+        m2 = fmax(m2, fabs(f.A[(size_t)(k + 2) * f.lda + r]));
+        m3 = fmax(m3, fabs(f.A[(size_t)(k + 3) * f.lda + r]));
+    }
+    for (; k < k1; ++k) m0 = fmax(m0, fabs(f.A[(size_t)k * f.lda + r]));
+    const double mx = fmax(fmax(m0, m1), fmax(m2, m3));
+    if (mx > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(f.rowmax + r), (unsigned long long)__double_as_longlong(mx));
+}
+__device__ __forceinline__ double oz_rowscale_of(double mx) {
     int e = 0;
     if (mx > 0.0) { frexp(mx, &e); }           // mx = m 2^e, 0.5 <= m < 1  ->  |a| < 2^e
-    f.rowscale[r] = ldexp(1.0, e);
+    return ldexp(1.0, e);
 }
 
 // ---- fp64 -> digit planes ---------------------------------------------------------------------------------------------------
@@ -83,7 +98,9 @@ k_oz_split(OzFront f) {
     const int piece = blockIdx.y;                       // 16 K values
     if (r >= f.m2_pad) return;
     const int k0 = piece * 16;
-    const double inv = (r < f.m2) ? 64.0 / f.rowscale[r] : 0.0;
+    const double rs = (r < f.m2) ? oz_rowscale_of(f.rowmax[r]) : 1.0;
+    if (piece == 0) f.rowscale[r] = rs;
+    const double inv = (r < f.m2) ? 64.0 / rs : 0.0;
     uint32_t w[S][4];
 #pragma unroll
     for (int p = 0; p < S; ++p) w[p][0] = w[p][1] = w[p][2] = w[p][3] = 0u;
@@ -617,7 +634,7 @@ static int oz_tile_count(int ncols, int m2_pad) {
 
 size_t oz_work_bytes(int m2, int k1, int S) {
     const int m2_pad = (m2 + OZ_M - 1) / OZ_M * OZ_M, k1_pad = (k1 + OZ_KC - 1) / OZ_KC * OZ_KC;
-    return align_up((size_t)S * oz_plane_bytes(m2_pad, k1_pad)) + align_up((size_t)m2_pad * sizeof(double)) + 256;
+    return align_up((size_t)S * oz_plane_bytes(m2_pad, k1_pad)) + 2 * align_up((size_t)m2_pad * sizeof(double)) + 256;
 }
 
 static int g_oz_dsplit = 3;
@@ -638,7 +655,13 @@ static int oz_launch(OzFront f, cudaStream_t st, bool persistent) {
         FERS_CK(cudaFuncSetAttribute(k_oz_syrk<S, TS_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         once.done();
     }
-    k_oz_rowscale<<<(f.m2_pad + 255) / 256, 256, 0, st>>>(f);
+    FERS_CK(cudaMemsetAsync(f.rowmax, 0, (size_t)f.m2_pad * sizeof(double), st));
+    {
+        const int row_blocks = (f.m2_pad + 255) / 256;
+        const int slices = std::max(1, std::min((f.k1 + 63) / 64, (4 * sm_count() + row_blocks - 1) / row_blocks));
+        const int k_per_slice = (f.k1 + slices - 1) / slices;
+        k_oz_rowmax<<<dim3(row_blocks, (f.k1 + k_per_slice - 1) / k_per_slice), 256, 0, st>>>(f, k_per_slice);
+    }
     dim3 grid((f.m2_pad + 255) / 256, f.k1_pad / 16);
     k_oz_split<S><<<grid, 256, 0, st>>>(f);
     if (g_oz_wide < 0) {
@@ -685,6 +708,7 @@ int oz_syrk(const double* A, long long lda, double* C, long long ldc, int m2, in
     f.k1_pad = (k1 + OZ_KC - 1) / OZ_KC * OZ_KC;
     f.planes = static_cast<int8_t*>(work);
     f.rowscale = reinterpret_cast<double*>(static_cast<uint8_t*>(work) + align_up((size_t)S * oz_plane_bytes(f.m2_pad, f.k1_pad)));
+    f.rowmax = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(f.rowscale) + align_up((size_t)f.m2_pad * sizeof(double)));
     switch (S) {
         case 4: return oz_launch<4>(f, st, persistent);
         case 5: return oz_launch<5>(f, st, persistent);

@@ -20,6 +20,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!done && ++spins > (1u << 26)) __trap();
     }
 }
+__device__ __forceinline__ bool elect() {
+    uint32_t pred;
+    __syncwarp();
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
@@ -27,12 +33,6 @@ __device__ __forceinline__ uint64_t desc(uint32_t saddr16, uint32_t lbo, uint32_
     const uint32_t lo = saddr16 | ((lbo >> 4) << 16);
     const uint32_t hi = (sbo >> 4) | (1u << 14);
     return ((uint64_t)hi << 32) | lo;
-}
-__device__ __forceinline__ bool elect() {
-    uint32_t pred;
-    __syncwarp();
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
 }
 template <int KIND>     // 0 = i8, 1 = f16
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -64,19 +64,23 @@ __global__ void __launch_bounds__(128) k_rate(int n_mma, int n_acc, int n_a, int
     const uint32_t tmem = s_tmem;
     // i8: D = S32 (2), A = B = S8 (1); f16: D = F32 (1), A = B = F16 (0)
     const uint32_t idesc = (KIND == 0 ? ((2u << 4) | (1u << 7) | (1u << 10)) : (1u << 4)) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    if (threadIdx.x == 0) {
+    if (warp == 0) {               // converged warp, elected lane (a lone thread 0 makes the compiler wrap every MMA in a
+                                   // divergence loop that moves its operands to uniform registers: 84 cycles per MMA, seen in r2o)
         const uint32_t sa0 = smem_u32(tiles) >> 4, sb0 = sa0 + ((n_a * A_BYTES) >> 4);
         const long long t0 = clock64();
         int ia = 0, ib = 0, ic = 0;
         for (int i = 0; i < n_mma; ++i) {
-            mma_ss<KIND>(tmem + (uint32_t)ic * N, desc(sa0 + ((ia * A_BYTES) >> 4), 128, 256), desc(sb0 + ((ib * B_BYTES) >> 4), 128, 256), idesc, i >= n_acc ? 1u : 0u);
+            if (elect())
+                mma_ss<KIND>(tmem + (uint32_t)ic * N, desc(sa0 + ((ia * A_BYTES) >> 4), 128, 256), desc(sb0 + ((ib * B_BYTES) >> 4), 128, 256), idesc, i >= n_acc ? 1u : 0u);
+            __syncwarp();
             if (++ia == n_a) ia = 0;
             if (++ib == n_b) ib = 0;
             if (++ic == n_acc) ic = 0;
         }
-        commit(smem_u32(&bar));
+        if (elect()) commit(smem_u32(&bar));
+        __syncwarp();
         mbar_wait(smem_u32(&bar), 0);
-        cycles[blockIdx.x] = clock64() - t0;
+        if ((threadIdx.x & 31) == 0) cycles[blockIdx.x] = clock64() - t0;
     }
     fence_before();
     __syncthreads();
