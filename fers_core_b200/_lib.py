@@ -52,6 +52,9 @@ SIGNATURES = {
     "fers_b200_dense_expand_batched": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_dense_cholesky": (_i, [_i, _i, _vp, _vp, _ip, _vp]),
     "fers_b200_dense_solve": (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    "fers_b200_frame_batch_factor_solve": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fers_b200_frame_batch_step": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp]),
+    "fers_b200_member_axial_masked": (_i, [_i, _i, _vp, _vp, _vp, _vp]),
     "fers_b200_recover_members": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_recover_sections": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

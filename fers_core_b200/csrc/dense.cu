@@ -39,12 +39,14 @@ __global__ void k_dense_expand(int n_nodes, const int* __restrict__ rowptr, cons
 // (numbered frame by frame); frame f is expanded into its own dense matrix a[f][n][n], n = 6*npf
 __global__ void k_dense_expand_batched(int npf, int batch, const int* __restrict__ rowptr, const int* __restrict__ colidx,
                                        const double* __restrict__ vals, const uint8_t* __restrict__ fixed,
-                                       const double* __restrict__ kspring, double* __restrict__ a, int* __restrict__ bad) {
+                                       const double* __restrict__ kspring, double* __restrict__ a, int* __restrict__ bad,
+                                       const uint8_t* __restrict__ active) {
     const int n = 6 * npf;
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= npf * batch) return;
     const int f = row / npf, lr = row - f * npf;
+    if (active != nullptr && !active[f]) return;           // frozen frame of a P-Delta batch: its matrix is not needed again
     double* af = a + (size_t)f * n * n;
     for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) {
         const int col = colidx[k];
@@ -210,8 +212,10 @@ constexpr int SMALL_THREADS = 256;
 template <int MAXN> struct SmallLdp { static constexpr int value = NB + ((MAXN - NB + 63) / 64) * 64 + 2; };
 
 template <int LDP>
-__global__ void __launch_bounds__(SMALL_THREADS, 2) k_chol_small(double* __restrict__ a_all, int n, int* __restrict__ info) {
+__global__ void __launch_bounds__(SMALL_THREADS, 2) k_chol_small(double* __restrict__ a_all, int n, int* __restrict__ info,
+                                                                 const uint8_t* __restrict__ active) {
     extern __shared__ __align__(16) double pT[];         // [NB][LDP] transposed panel, then rinv[NB]
+    if (active != nullptr && !active[blockIdx.x]) return;
     double* rinv = pT + NB * LDP;
     double* a = a_all + (size_t)blockIdx.x * n * n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -324,7 +328,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 2) k_chol_small(double* __restr
 }
 
 template <int MAXN>
-static int launch_chol_small(double* a, int n, int batch, int* info_dev, cudaStream_t st) {
+static int launch_chol_small(double* a, int n, int batch, int* info_dev, cudaStream_t st, const uint8_t* active = nullptr) {
     constexpr int LDP = SmallLdp<MAXN>::value;
     constexpr size_t smem = ((size_t)NB * LDP + NB) * sizeof(double);
     static PerDeviceOnce attr_set;
@@ -332,7 +336,7 @@ static int launch_chol_small(double* a, int n, int batch, int* info_dev, cudaStr
         FERS_CK(cudaFuncSetAttribute(k_chol_small<LDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set.done();
     }
-    k_chol_small<LDP><<<batch, SMALL_THREADS, smem, st>>>(a, n, info_dev);
+    k_chol_small<LDP><<<batch, SMALL_THREADS, smem, st>>>(a, n, info_dev, active);
     return 0;
 }
 
@@ -341,12 +345,13 @@ static int launch_chol_small(double* a, int n, int batch, int* info_dev, cudaStr
 // rows (forward) / columns (backward) are then updated by one thread each with 32 independent loads of L.
 constexpr int SOLVE1_THREADS = 256;
 __global__ void __launch_bounds__(SOLVE1_THREADS) k_solve_small1(const double* __restrict__ a_all, double* __restrict__ bx_all,
-                                                                 int n, int batch) {
+                                                                 int n, int batch, const uint8_t* __restrict__ active) {
     extern __shared__ double xs[];                       // [n]
     __shared__ double tile[NB][NBP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.x;
     if (f >= batch) return;
+    if (active != nullptr && !active[f]) return;
     const double* a = a_all + (size_t)f * n * n;
     double* bx = bx_all + (size_t)f * n;
     for (int i = tid; i < n; i += SOLVE1_THREADS) xs[i] = bx[i];
@@ -407,6 +412,41 @@ using namespace fers;
 
 static inline int rem_count(int n, int j0) { return (n - j0 - NB) > 0 ? 2 : 1; }
 
+// One CTA per frame: relative change r = |un - u| / |un| of this P-Delta iteration.  An active frame takes the new
+// displacements, counts the iteration and freezes once r < tol; frozen frames keep everything.  flags[0] |= some frame is
+// still active, flags[1] |= some frame hit a non-positive pivot (bad[] remembers which).
+__global__ void __launch_bounds__(128) k_frame_batch_step(int n, const double* __restrict__ un_all, double* __restrict__ u_all,
+                                                          uint8_t* __restrict__ active, long long* __restrict__ iters,
+                                                          double* __restrict__ resid, double tol, const int* __restrict__ info,
+                                                          uint8_t* __restrict__ bad, int* __restrict__ flags) {
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (!active[f]) return;
+    const double* un = un_all + (size_t)f * n;
+    double* u = u_all + (size_t)f * n;
+    double num = 0.0, den = 0.0;
+    for (int i = tid; i < n; i += 128) {
+        const double a = un[i], d = a - u[i];
+        num += d * d; den += a * a;
+    }
+    __shared__ double s_num[4], s_den[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { num += __shfl_xor_sync(0xffffffffu, num, o); den += __shfl_xor_sync(0xffffffffu, den, o); }
+    if ((tid & 31) == 0) { s_num[tid >> 5] = num; s_den[tid >> 5] = den; }
+    __syncthreads();
+    num = (s_num[0] + s_num[1]) + (s_num[2] + s_num[3]);
+    den = (s_den[0] + s_den[1]) + (s_den[2] + s_den[3]);
+    for (int i = tid; i < n; i += 128) u[i] = un[i];
+    if (tid == 0) {
+        const double r = den > 0.0 ? sqrt(num) / sqrt(den) : 0.0;
+        iters[f] += 1;
+        resid[f] = r;
+        const bool go_on = !(r < tol);
+        active[f] = go_on ? 1 : 0;
+        if (go_on) atomicOr(flags, 1);
+        if (info[f] != 0) { bad[f] = 1; atomicOr(flags + 1, 1); }
+    }
+}
+
 extern "C" {
 
 int fers_b200_dense_expand(int n_nodes, const int* rowptr, const int* colidx, const double* vals,
@@ -433,7 +473,7 @@ int fers_b200_dense_expand_batched(int nodes_per_frame, int batch, const int* ro
     const int T = 256;
     const long long rows = (long long)nodes_per_frame * batch;
     int grid = (int)((rows * 32 + T - 1) / T);
-    k_dense_expand_batched<<<grid, T, 0, st>>>(nodes_per_frame, batch, rowptr, colidx, vals, fixed, kspring, a, flag_dev);
+    k_dense_expand_batched<<<grid, T, 0, st>>>(nodes_per_frame, batch, rowptr, colidx, vals, fixed, kspring, a, flag_dev, nullptr);
     FERS_LAUNCH_CHECK();
     count_launches(1);
     int bad = 0;
@@ -476,11 +516,46 @@ int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* in
     return 0;
 }
 
+// ---- batch of frames in a P-Delta fixed point (configs[4]): masked, asynchronous ------------------------------------------
+int fers_b200_frame_batch_factor_solve(int nodes_per_frame, int batch, const int* rowptr, const int* colidx, const double* vals,
+                                       const uint8_t* fixed, const double* kspring, double* a, const uint8_t* active,
+                                       int* info_dev, int* flag_dev, double* bx, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    const int n = 6 * nodes_per_frame;
+    FERS_REQUIRE(nodes_per_frame > 0 && batch > 0 && a && info_dev && flag_dev && bx, "frame_batch_factor_solve: bad arguments");
+    FERS_REQUIRE(n <= SMALL_MAX_N, "frame_batch_factor_solve: frames of at most 512 DOF (one CTA per frame)");
+    FERS_CK(cudaMemsetAsync(a, 0, (size_t)batch * n * n * sizeof(double), st));
+    FERS_CK(cudaMemsetAsync(info_dev, 0, sizeof(int) * batch, st));
+    const int T = 256;
+    const long long rows = (long long)nodes_per_frame * batch;
+    k_dense_expand_batched<<<(int)((rows * 32 + T - 1) / T), T, 0, st>>>(nodes_per_frame, batch, rowptr, colidx, vals, fixed, kspring,
+                                                                         a, flag_dev, active);
+    int rc;
+    if (n <= 96) rc = launch_chol_small<96>(a, n, batch, info_dev, st, active);
+    else if (n <= 160) rc = launch_chol_small<160>(a, n, batch, info_dev, st, active);
+    else if (n <= 288) rc = launch_chol_small<288>(a, n, batch, info_dev, st, active);
+    else rc = launch_chol_small<SMALL_MAX_N>(a, n, batch, info_dev, st, active);
+    if (rc) return rc;
+    k_solve_small1<<<batch, SOLVE1_THREADS, (size_t)n * sizeof(double), st>>>(a, bx, n, batch, active);
+    FERS_LAUNCH_CHECK();
+    count_launches(3);
+    return 0;
+}
+
+int fers_b200_frame_batch_step(int batch, int n, const double* un, double* u, uint8_t* active, long long* iters, double* resid,
+                               double tol, const int* info_dev, uint8_t* bad, int* flags, void* stream) {
+    FERS_REQUIRE(batch > 0 && n > 0 && un && u && active && iters && resid && info_dev && bad && flags, "frame_batch_step: bad arguments");
+    k_frame_batch_step<<<batch, 128, 0, as_stream(stream)>>>(n, un, u, active, iters, resid, tol, info_dev, bad, flags);
+    FERS_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
 int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* bx, void* stream) {
     cudaStream_t st = as_stream(stream);
     FERS_REQUIRE(n > 0 && nrhs > 0 && batch > 0, "dense_solve: empty problem");
     if (nrhs == 1 && n <= 4096) {                 // one CTA per matrix (n doubles of shared memory <= 32 KB)
-        k_solve_small1<<<batch, SOLVE1_THREADS, (size_t)n * sizeof(double), st>>>(a, bx, n, batch);
+        k_solve_small1<<<batch, SOLVE1_THREADS, (size_t)n * sizeof(double), st>>>(a, bx, n, batch, nullptr);
         FERS_LAUNCH_CHECK();
         count_launches(1);
         return 0;

@@ -274,6 +274,13 @@ __global__ void k_member_axial(size_t total, int nrhs, const double* __restrict_
     }
 }
 
+// one right-hand side, members numbered frame by frame: frozen frames of a P-Delta batch keep their axial forces
+__global__ void k_member_axial_masked(int n_members, int members_per_frame, const double* __restrict__ f_local,
+                                      const uint8_t* __restrict__ active, double* __restrict__ axial) {
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n_members; m += gridDim.x * blockDim.x)
+        if (active == nullptr || active[m / members_per_frame]) axial[m] = f_local[(size_t)m * 12 + 6];
+}
+
 // plates: one warp per element; lane 0 builds B matrices and the global stiffness in shared memory
 __global__ void __launch_bounds__(REC_THREADS) k_recover_plates(int n_plates, int nrhs, const double* __restrict__ xyz,
                                                                 const int* __restrict__ pn, const double* __restrict__ pdata,
@@ -444,6 +451,17 @@ int fers_b200_member_axial(int n_members, int nrhs, const double* f_local, doubl
     size_t g = (total + T - 1) / T;
     size_t cap = (size_t)sm_count() * 16;
     k_member_axial<<<(int)(g < cap ? g : cap), T, 0, as_stream(stream)>>>(total, nrhs, f_local, axial);
+    FERS_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int fers_b200_member_axial_masked(int n_members, int members_per_frame, const double* f_local, const uint8_t* active,
+                                  double* axial, void* stream) {
+    FERS_REQUIRE(n_members > 0 && members_per_frame > 0 && f_local && axial, "member_axial_masked: bad arguments");
+    const int T = 256;
+    const int g = (n_members + T - 1) / T, cap = sm_count() * 16;
+    k_member_axial_masked<<<g < cap ? g : cap, T, 0, as_stream(stream)>>>(n_members, members_per_frame, f_local, active, axial);
     FERS_LAUNCH_CHECK();
     count_launches(1);
     return 0;

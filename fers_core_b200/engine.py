@@ -818,19 +818,18 @@ class FrameBatch:
         self.flag = eng._zeros(1, torch.int32)
         self.info_dev = eng._zeros(nf, torch.int32)
         self.bad_dev = torch.zeros(nf, dtype=torch.bool, device=eng.dev)
-        self.h_flags = torch.zeros((max(opts.max_iterations, 1) + 2, 2), dtype=torch.bool).pin_memory()
+        self.h_flags_i32 = torch.zeros((max(opts.max_iterations, 1) + 2, 2), dtype=torch.int32).pin_memory()
         self.stats: dict = {}
 
-    # asynchronous: failed pivots are collected on the device and looked at where the host synchronises anyway
-    def _factor_solve(self, d_f):
+    # asynchronous: no host synchronisation; frames whose `active` flag is 0 are skipped; failed pivots and members that
+    # cross frames are collected on the device and looked at where the host synchronises anyway
+    def _factor_solve(self, rhs, active=None):
         eng, lib, st = self.eng, self.eng.lib, self.eng.stream
-        _lib.check(lib.fers_b200_dense_expand_batched(
+        u = rhs.clone()
+        _lib.check(lib.fers_b200_frame_batch_factor_solve(
             self.nodes_per_frame, self.nf, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
-            _lib.ptr(eng.d_ks), _lib.ptr(self.a), _lib.ptr(self.flag), st), "dense_expand_batched")
-        _lib.check(lib.fers_b200_dense_cholesky(self.n, self.nf, _lib.ptr(self.a), _lib.ptr(self.info_dev), None, st), "dense_cholesky")
-        self.bad_dev.logical_or_(self.info_dev != 0)
-        u = (d_f * (1 - eng.d_fixed.to(torch.float64))[:, None]).contiguous()      # d_fixed is (re)built by assemble()
-        _lib.check(lib.fers_b200_dense_solve(self.n, 1, self.nf, _lib.ptr(self.a), _lib.ptr(u), st), "dense_solve")
+            _lib.ptr(eng.d_ks), _lib.ptr(self.a), _lib.ptr(active), _lib.ptr(self.info_dev), _lib.ptr(self.flag), _lib.ptr(u), st),
+            "frame_batch_factor_solve")
         return u
 
     def _raise_if_bad(self):
@@ -853,7 +852,9 @@ class FrameBatch:
         d_f = eng.combine(f_case, self.fac, 1)
         d_peq = eng.combine(peq_case, self.fac, 1)
         eng.assemble(d_xyz)
-        d_u = self._factor_solve(d_f)
+        rhs = (d_f * (1 - eng.d_fixed.to(torch.float64))[:, None]).contiguous()      # the mask assemble() builds does not change
+        d_u = self._factor_solve(rhs)
+        self.bad_dev.logical_or_(self.info_dev != 0)
         d_axial = None
         iters = torch.zeros(nf, dtype=torch.int64, device=eng.dev)
         resid = torch.zeros(nf, dtype=torch.float64, device=eng.dev)
@@ -862,44 +863,41 @@ class FrameBatch:
         if self.second_order and nm:
             events = []
             max_it = max(1, opts.max_iterations)
+            d_axial = eng._empty((nm, 1))
+            d_flags = torch.zeros((max_it, 2), dtype=torch.int32, device=eng.dev)
+            h_flags = self.h_flags_i32
+            h_flags.zero_()
             for it in range(max_it):
-                # first half of the iteration (cheap kernels): axial forces of the current state, tangent matrix.  It is
-                # enqueued BEFORE the host looks at the convergence flags of the previous iteration, so the GPU is never idle
-                # while the flags travel; if every frame had already converged it changes nothing (all frames frozen)
-                rec = eng.recover(d_xyz, d_u, d_f, d_peq, self.facp, None, None, d_axial, kg_mode, sup, detail=False)
-                ax_new = eng._empty((nm, 1))
-                _lib.check(lib.fers_b200_member_axial(nm, 1, _lib.ptr(rec["f_local"]), _lib.ptr(ax_new), eng.stream), "member_axial")
-                if d_axial is not None:      # frozen frames keep the axial forces of their last iteration
-                    am = active.repeat_interleave(nmf)[:, None]
-                    ax_new = torch.where(am, ax_new, d_axial).contiguous()
-                d_axial = ax_new
-                eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup, count=False)
-                if it >= 1:                  # flags of the PREVIOUS iteration (in flight since its second half was enqueued)
-                    events[it - 1].synchronize()
-                    go_on, bad = self.h_flags[it - 1].tolist()
+                # The host runs one iteration ahead of the flags it reads: iteration `it` is enqueued as soon as the flags of
+                # iteration it - 2 are known, so the GPU never waits for the host.  An iteration enqueued after every frame
+                # has frozen costs a few empty launches: every kernel of the loop skips frozen frames.
+                if it >= 2:
+                    events[it - 2].synchronize()
+                    go_on, bad = (int(v) for v in h_flags[it - 2])
                     if bad:
                         self._raise_if_bad()
                     if not go_on:
                         break
-                # second half (the expensive kernels): factorisation, substitution, convergence test
-                d_un = self._factor_solve(d_f)
-                un_f, u_f = d_un.view(nf, n), d_u.view(nf, n)
-                den = torch.linalg.norm(un_f, dim=1)
-                r = torch.where(den > 0, torch.linalg.norm(un_f - u_f, dim=1) / den, torch.zeros_like(den))
-                iters += active.to(torch.int64)
-                resid = torch.where(active, r, resid)
-                d_u = torch.where(active.repeat_interleave(n)[:, None], d_un, d_u).contiguous()
-                active = active & ~(r < opts.tolerance)
-                # (go on, bad pivot) of this iteration -> pinned memory, no host wait here
-                self.h_flags[it].copy_(torch.stack([active.any(), self.bad_dev.any()]), non_blocking=True)
+                # axial forces of the current state (frozen frames keep theirs), tangent matrix, factorisation, substitution
+                rec = eng.recover(d_xyz, d_u, d_f, d_peq, self.facp, None, None, d_axial if it else None, kg_mode, sup, detail=False)
+                _lib.check(lib.fers_b200_member_axial_masked(nm, nmf, _lib.ptr(rec["f_local"]), _lib.ptr(active) if it else None,
+                                                             _lib.ptr(d_axial), eng.stream), "member_axial_masked")
+                eng.assemble(d_xyz, None, d_axial[:, 0], kg_mode, sup, count=False)
+                d_un = self._factor_solve(rhs, active)
+                # convergence test, new state of the active frames, (go on, bad pivot) of this iteration -> pinned memory
+                _lib.check(lib.fers_b200_frame_batch_step(nf, n, _lib.ptr(d_un), _lib.ptr(d_u), _lib.ptr(active), _lib.ptr(iters),
+                                                          _lib.ptr(resid), float(opts.tolerance), _lib.ptr(self.info_dev),
+                                                          _lib.ptr(self.bad_dev), _lib.ptr(d_flags[it]), eng.stream), "frame_batch_step")
+                h_flags[it].copy_(d_flags[it], non_blocking=True)
                 ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(eng.dev)); events.append(ev)
                 enqueued = it + 1
-            else:
-                events[-1].synchronize()
-                if self.h_flags[max_it - 1].tolist()[1]:
+            # flags not looked at yet (the last one or two iterations enqueued)
+            for j in range(max(0, enqueued - 2), enqueued):
+                events[j].synchronize()
+                if int(h_flags[j][1]):
                     self._raise_if_bad()
             # the matrix in eng.d_vals must be the tangent of the frozen state for the reactions
-            eng.assemble(d_xyz, None, d_axial[:, 0].contiguous(), kg_mode, sup, count=False)
+            eng.assemble(d_xyz, None, d_axial[:, 0], kg_mode, sup, count=False)
         span = eng.span_tables() if detail else None
         rec = eng.recover(d_xyz, d_u, d_f, d_peq, self.facp, span, None, d_axial, kg_mode, sup, detail=detail)
         rec["U"] = d_u

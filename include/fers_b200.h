@@ -196,6 +196,23 @@ int fers_b200_dense_expand_batched(int nodes_per_frame, int batch, const int* ro
                                    int* flag_dev, void* stream);
 int fers_b200_dense_cholesky(int n, int batch, double* a, int* info_dev, int* info_out, void* stream);
 int fers_b200_dense_solve(int n, int nrhs, int batch, const double* a, double* bx, void* stream);
+/* Batch of frames inside a P-Delta fixed point (BASELINE.json configs[4]; reference: the per-model iteration of
+ * pydantic_models.py:1370-1398 run for every frame of the batch).  All three calls are asynchronous (no host
+ * synchronisation) and skip the frames whose active[f] is 0 (NULL: every frame):
+ *  frame_batch_factor_solve: zero a, expand the block-CSR matrix of every active frame (fers_b200_dense_expand_batched
+ *    without its check-and-synchronise: *flag_dev is OR-ed when a block couples two frames, the caller zeroes and reads
+ *    it), factorise (one CTA per frame, n = 6 nodes_per_frame <= 512; info_dev[f] = failing minor or 0) and substitute
+ *    bx[f][n] in place;
+ *  frame_batch_step: r = |un - u| / |un| per active frame; it takes un, counts the iteration, records r and freezes
+ *    when r < tol; flags[0] |= a frame is still active, flags[1] |= a frame had a non-positive pivot (bad[f] = 1);
+ *  member_axial_masked: axial[m] = f_local[m][6] (one right-hand side) for the members of active frames. */
+int fers_b200_frame_batch_factor_solve(int nodes_per_frame, int batch, const int* rowptr, const int* colidx, const double* vals,
+                                       const uint8_t* fixed, const double* kspring, double* a, const uint8_t* active,
+                                       int* info_dev, int* flag_dev, double* bx, void* stream);
+int fers_b200_frame_batch_step(int batch, int n, const double* un, double* u, uint8_t* active, long long* iters, double* resid,
+                               double tol, const int* info_dev, uint8_t* bad, int* flags, void* stream);
+int fers_b200_member_axial_masked(int n_members, int members_per_frame, const double* f_local, const uint8_t* active,
+                                  double* axial, void* stream);
 
 /* ---- sparse direct solve: multifrontal Cholesky (the reference engine's
  *      "batch first-order solve that shares one factorization across many load cases",
