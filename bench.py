@@ -59,6 +59,9 @@ def parse_args():
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                    help="weak = every GPU solves its own batch of --combos combinations (default, the driver's scaling run); strong = ONE "
                         "model x --combos combinations split over the GPUs (replicated factorisation, result tensors all-gathered)")
+    p.add_argument("--detail", action="store_true",
+                   help="cfg4: the timed step also recovers section forces along the members and their extrema "
+                        "(run_linear(detail=True)); default: member end forces, displacements and reactions only")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--profile-iters", type=int, default=0,
@@ -151,7 +154,8 @@ def pin_model(model):
 
 def workload_name(args, n_comb: int) -> str:
     return (f"configs[3] synthetic 3D space frame {args.nx}x{args.nz} bays x {args.ny} storeys, linear static, "
-            f"{n_comb} combinations per GPU")
+            f"{n_comb} combinations per GPU"
+            + (", section forces along the members and their extrema recovered in the timed step" if getattr(args, "detail", False) else ""))
 
 
 def cpu_pass(args):
@@ -268,7 +272,13 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             out = e.run_linear_sharded(factors, gather=("U", "R", "f_local"))
             return {"U": out["U"], "R": out["R"], "f_local": out["f_local"]}
     else:
+        span_cache = {}
+
         def step_with(e):
+            if args.detail:
+                if id(e) not in span_cache:
+                    span_cache[id(e)] = e.span_tables()
+                return e.run_linear(factors, detail=True, span=span_cache[id(e)])
             return e.run_linear(factors)
 
     def one_step():
@@ -328,16 +338,22 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
     kern = []
 
     def timed_launches(fn, reps=5, pre=None):
+        # events around a burst of 8 back-to-back launches (one launch alone carries ~10 us of host launch gap between the
+        # first event and the kernel: asm_probe, r2x); kernels with a preparation pass are timed one launch at a time.
+        # fn(i): launch i of the burst works on copy i % 3 of the matrix values, so that no launch finds the lines of the
+        # previous one in the 126 MB L2 (three copies of K = 0.67 GB at configs[3])
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        burst = 1 if pre is not None else 8
         out = []
         for _ in range(reps):
             if pre is not None:
                 pre()
             a0.record()
-            fn()
+            for _b in range(burst):
+                fn(_b)
             a1.record()
             torch.cuda.synchronize(dev)
-            out.append(a0.elapsed_time(a1))
+            out.append(a0.elapsed_time(a1) / burst)
         return float(np.median(out))
 
     def hbm_row(name, b, ms, launches_per_step):
@@ -346,17 +362,18 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                 "share_of_step": ms * launches_per_step / ms_step if ms_step > 0 else 0.0}
 
     # assembly and SpMM kernels timed on their own (few launches per step): events around dedicated launches
+    vals_rot = [eng.d_vals, eng.d_vals.clone(), eng.d_vals.clone()]
     if args.assembly_variant == engine.ASSEMBLY_GATHER:
-        am = timed_launches(lambda: _lib.check(lib.fers_b200_assemble_beams_gather(
+        am = timed_launches(lambda i: _lib.check(lib.fers_b200_assemble_beams_gather(
             model.n_nodes, model.n_members, _lib.ptr(eng.d_xyz0), _lib.ptr(eng.d_n1), _lib.ptr(eng.d_n2),
             _lib.ptr(eng.d_m_prop), _lib.ptr(eng.d_type), _lib.ptr(eng.d_roll), None, None, _lib.ptr(eng.d_prop), eng.n_prop,
             None, 0, None, 0, 0, _lib.ptr(eng.d_m_slot), _lib.ptr(eng.d_hm_ptr), _lib.ptr(eng.d_hm_list),
-            eng.n_dup_half_members, _lib.ptr(eng.d_diag_slot), _lib.ptr(eng.d_member_cache), _lib.ptr(eng.d_vals), eng.stream), "assemble_gather"))
+            eng.n_dup_half_members, _lib.ptr(eng.d_diag_slot), _lib.ptr(eng.d_member_cache), _lib.ptr(vals_rot[i % 3]), eng.stream), "assemble_gather"))
         asm_name = "k_assemble_gather"
         # unique bytes: member records in, every block of K out once (the gather kernel has no zero pass, no atomics)
         asm_bytes = model.n_members * 64 + nnzb * 36 * 8
     else:
-        am = timed_launches(lambda: _lib.check(lib.fers_b200_assemble_beams(
+        am = timed_launches(lambda i: _lib.check(lib.fers_b200_assemble_beams(
             model.n_members, _lib.ptr(eng.d_xyz0), _lib.ptr(eng.d_n1), _lib.ptr(eng.d_n2), _lib.ptr(eng.d_m_prop),
             _lib.ptr(eng.d_type), _lib.ptr(eng.d_roll), None, None, _lib.ptr(eng.d_prop), eng.n_prop, None, 0, None, 0, 0,
             _lib.ptr(eng.d_m_slot), _lib.ptr(eng.d_vals), args.assembly_variant, eng.stream), "assemble"),
@@ -364,14 +381,14 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         asm_name = "k_assemble_beams (atomic scatter-add)"
         asm_bytes = model.n_members * (64 + 4 * 36 * 8)      # 4 blocks per member, RMW not counted
     if direct:
-        sm = timed_launches(lambda: _lib.check(lib.fers_b200_spmm(
-            model.n_nodes, nr, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
+        sm = timed_launches(lambda i: _lib.check(lib.fers_b200_spmm(
+            model.n_nodes, nr, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(vals_rot[i % 3]), _lib.ptr(eng.d_fixed),
             _lib.ptr(eng.d_ks), _lib.ptr(rec["U"]), _lib.ptr(ku), eng.stream), "spmm"))
         kern.append(hbm_row("k_spmm64_tma (64 RHS; residual check / refinement)", spmm_bytes, sm, refine_passes + 1))
         x1 = rec["U"][:, 0].contiguous()
         y1 = torch.empty_like(x1)
-        sv = timed_launches(lambda: _lib.check(lib.fers_b200_spmm(
-            model.n_nodes, 1, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(eng.d_vals), _lib.ptr(eng.d_fixed),
+        sv = timed_launches(lambda i: _lib.check(lib.fers_b200_spmm(
+            model.n_nodes, 1, _lib.ptr(eng.d_rowptr), _lib.ptr(eng.d_colidx), _lib.ptr(vals_rot[i % 3]), _lib.ptr(eng.d_fixed),
             _lib.ptr(eng.d_ks), _lib.ptr(x1), _lib.ptr(y1), eng.stream), "spmv"))
         spmv_bytes = nnzb * (36 * 8 + 4) + (nn + 1) * 4 + 2 * n_dof * 8 + n_dof      # BSR-6 values + indices, x, y, BC mask
         kern.append(hbm_row("k_spmv (1 RHS, not on the step path)", spmv_bytes, sv, 0))

@@ -29,10 +29,13 @@ for kind in (1, 0):
     _lib.check(lib.fers_b200_assemble_set_gather_kernel(kind), "kind")
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ts = []
-    for _ in range(7):
-        a0.record(); launch(); a1.record()
+    for _ in range(7):              # 10 launches per event pair: one launch alone carries ~10 us of host launch gap
+        a0.record()
+        for _ in range(10):
+            launch()
+        a1.record()
         torch.cuda.synchronize(dev)
-        ts.append(a0.elapsed_time(a1) * 1e3)
+        ts.append(a0.elapsed_time(a1) * 1e2)
     out[kind] = eng.d_vals.clone()
     med = float(np.median(ts))
     print(f"kind {kind}: {med:7.1f} us (best {min(ts):7.1f})  {nbytes / med / 1e3:6.0f} GB/s", flush=True)
