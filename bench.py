@@ -535,7 +535,8 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         del rec, ku, d_f, f_case
         nm = model.n_members
         h_u = torch.empty((n_dof, nr), dtype=torch.float64).pin_memory()
-        h_r = torch.empty((n_dof, nr), dtype=torch.float64).pin_memory()
+        n_sup = len(eng.sup_nodes)
+        h_r = torch.empty((n_sup, 6, nr), dtype=torch.float64).pin_memory()      # reactions: rows of the supported nodes
         barrier()
         t_e2e = []
         h2d = 0
@@ -545,7 +546,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             t0 = time.perf_counter()
             eng = engine.Engine(model, dev, args.assembly_variant, args.solver)   # H2D of the model + symbolic pattern / plan
             out = step_with(eng)
-            h_u.copy_(out["U"], non_blocking=True); h_r.copy_(out["R"], non_blocking=True)
+            h_u.copy_(out["U"], non_blocking=True); h_r.copy_(eng.reactions_at_supports(out["R"])[1], non_blocking=True)
             torch.cuda.synchronize(dev)
             t_e2e.append(time.perf_counter() - t0)
             h2d = eng.h2d_bytes
@@ -561,7 +562,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             marks.append(time.perf_counter())
         eng = engine.Engine(model, dev, args.assembly_variant, args.solver); mark()
         out = step_with(eng); mark()
-        h_u.copy_(out["U"], non_blocking=True); h_r.copy_(out["R"], non_blocking=True); mark()
+        h_u.copy_(out["U"], non_blocking=True); h_r.copy_(eng.reactions_at_supports(out["R"])[1], non_blocking=True); mark()
         h_f = torch.empty(tuple(out["f_local"].shape), dtype=torch.float64).pin_memory()
         torch.cuda.synchronize(dev)
         t_f0 = time.perf_counter()
@@ -581,7 +582,8 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
                "d2h_bytes_per_step": int(h_u.numel() * 8 + h_r.numel() * 8),
                "ms_per_step": 1e3 * te, "phases_of_a_synchronised_pass": phases,
                "api": "fers_core_b200.engine.Engine(model_arrays)." + ("run_linear_sharded" if strong else "run_linear")
-                      + "(factors) + D2H of the displacements U and reactions R of every combination (member end forces stay on the "
+                      + "(factors) + D2H of the displacements U of every combination and of the reactions R at the "
+                        "supported nodes (Engine.reactions_at_supports: R is exactly zero elsewhere; member end forces stay on the "
                         "device until asked for: optional_d2h_* in the phases)"}
 
     # ---- CPU baseline: ONE full pass of the same workload on the host cores (rank 0, N=1 only) ------------------

@@ -78,6 +78,9 @@ SIGNATURES = {
     "fers_b200_unity_generic": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_chol_set_profile": (_i, [_i]),
+    "fers_b200_chol_plan_partition": (_i, [_vp, _i, _i, C.POINTER(C.c_longlong), _i]),
+    "fers_b200_chol_factor_levels": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _vp]),
+    "fers_b200_chol_solve_phase": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _sz, _i, _i, _i, _vp]),
     "fers_b200_chol_set_variant": (_i, [_i]),
     "fers_b200_chol_set_outer": (_i, [_i, _i]),
     "fers_b200_chol_profile": (_i, [_dp, _i]),

@@ -182,3 +182,97 @@ class CholSolver:
                 "factor_launches", "solve_launches", "syrk_sum_ms", "factor_sum_ms", "solve_sum_ms", "n_factor",
                 "n_solve", "n_syrk_launches", "oz_ms", "oz_sum_ms", "n_oz_fronts", "oz_setting"]
         return dict(zip(keys, out[:]))
+
+
+class TreeParallelSolver(CholSolver):
+    """The sparse direct solve of ONE model on two GPUs (strong scaling; SURVEY.md 8e only asks for sharding by
+    combinations -- the reference describes a single shared factorisation, pydantic_models.py:1216-1219).
+
+    The root front of the nested dissection has two children: rank r factorises the subtree under child r
+    (fers_b200_chol_plan_partition drops the other fronts from this rank's level lists; every offset stays that of the whole
+    plan), rank 1 sends the Schur complement of its top front to rank 0 over NVLink (NCCL send / recv; gloo in tests), rank 0
+    extend-adds both and factorises the root.  The substitution mirrors it: forward on the two subtrees, rank 1's boundary
+    right-hand side to rank 0, root forward + backward on rank 0, root solution to rank 1, backward on the subtrees, the two
+    halves of the permuted solution exchanged -- both ranks end with the whole solution.  What crosses the link per
+    factorisation: one [6 n2]^2 Schur complement (0.96 GB at configs[3]); per substitution: 2 x 5.6 MB + the two halves of
+    the solution."""
+
+    def __init__(self, plan: CholPlan, device, rank: int, world: int, group=None, max_nrhs: int = 64):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank, self.peer = int(rank), 1 - int(rank)
+        fronts = plan.export()["fronts"].copy()          # the whole plan, before this rank's fronts are selected
+        out = (C.c_longlong * 12)()
+        _lib.check(plan.lib.fers_b200_chol_plan_partition(plan.handle, int(rank), int(world), out, 12), "chol_plan_partition")
+        self.root, self.c0, self.c1, self.ls = (int(out[i]) for i in range(4))
+        self.sub = ((int(out[4]), int(out[5])), (int(out[6]), int(out[7])))
+        self.root_pos = (int(out[8]), int(out[8] + out[9]))
+        self.fronts_kept, self.k_blocks_kept = int(out[10]), int(out[11])
+        f1 = fronts[self.c1]
+        m2 = 6 * int(f1["n2"])
+        arena = plan.info.schur_doubles[0] if ((self.ls - 1) & 1) else 0
+        self._schur = (arena + int(f1["schur_off"]), m2 * m2)                     # doubles into the work buffer
+        self._rhs_c1 = (int(f1["rhs_off"]), 6 * int(f1["n1"] + f1["n2"]))         # rows of the front-local store W
+        self._rhs_rows = int(plan.info.rhs_rows)
+        super().__init__(plan, device, max_nrhs)
+        self.wk = self.work[: (self.work_bytes // 8) * 8].view(self.torch.float64)
+        self.link_bytes = {"factor": 8 * self._schur[1]}
+
+    def _send(self, t):
+        self.dist.send(t, self.peer, group=self.group)
+
+    def _recv(self, t):
+        self.dist.recv(t, self.peer, group=self.group)
+
+    def factorize(self, d_vals, d_diag_slot, d_fixed, d_kspring=None, check: bool = True) -> int:
+        ks = None if d_kspring is None else d_kspring.data_ptr()
+
+        def levels(lo, hi):
+            _lib.check(self.lib.fers_b200_chol_factor_levels(
+                self.plan.handle, self.index.data_ptr(), d_vals.data_ptr(), d_diag_slot.data_ptr(), d_fixed.data_ptr(), ks,
+                self.factor.data_ptr(), self.work.data_ptr(), self.work_bytes, self.info_dev.data_ptr(), lo, hi, self.stream),
+                "chol_factor_levels")
+        levels(0, self.ls)
+        off, n = self._schur
+        if self.rank == 1:
+            self._send(self.wk[off: off + n])
+        else:
+            self._recv(self.wk[off: off + n])
+            levels(self.ls, self.ls + 1)
+        self.factored = True
+        if not check:
+            return 0
+        info = self.info_dev.clone()
+        self.dist.all_reduce(info, op=self.dist.ReduceOp.MAX, group=self.group)
+        return int(info.item())
+
+    def solve(self, d_b, d_x, d_fixed, accumulate: bool = False) -> None:
+        nrhs = int(d_b.shape[1])
+
+        def phase(bits, lo, hi):
+            _lib.check(self.lib.fers_b200_chol_solve_phase(
+                self.plan.handle, self.index.data_ptr(), self.factor.data_ptr(), d_fixed.data_ptr(), nrhs, d_b.data_ptr(),
+                d_x.data_ptr(), 1 if accumulate else 0, self.work.data_ptr(), self.work_bytes, bits, lo, hi, self.stream),
+                "chol_solve_phase")
+        y0 = self._rhs_rows * nrhs                                         # the permuted solution Y follows W
+        rows = lambda a, b: self.wk[y0 + 6 * a * nrhs: y0 + 6 * b * nrhs]
+        w_c1 = self.wk[self._rhs_c1[0] * nrhs: (self._rhs_c1[0] + self._rhs_c1[1]) * nrhs]
+        phase(1, 0, self.ls)
+        if self.rank == 1:
+            self._send(w_c1)
+            self._recv(rows(*self.root_pos))
+        else:
+            self._recv(w_c1)
+            phase(3, self.ls, self.ls + 1)
+            self._send(rows(*self.root_pos))
+        phase(2, 0, self.ls)
+        mine, theirs = rows(*self.sub[self.rank]), rows(*self.sub[self.peer])
+        ops = [self.dist.P2POp(self.dist.isend, mine, self.peer, group=self.group),
+               self.dist.P2POp(self.dist.irecv, theirs, self.peer, group=self.group)]
+        if self.rank == 1:
+            ops.reverse()
+        for r in self.dist.batch_isend_irecv(ops):
+            r.wait()
+        phase(4, 0, self.ls + 1)
+        self.link_bytes["solve"] = 8 * (w_c1.numel() + rows(*self.root_pos).numel() + mine.numel() + theirs.numel())

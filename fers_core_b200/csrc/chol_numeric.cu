@@ -916,9 +916,11 @@ static size_t chol_work_bytes(const CholPlanHost& P, int nrhs) {
     return align_up(schur > solve ? schur : solve) + 256;
 }
 
+// levels [l_begin, l_end) of the front tree (the whole factorisation: 0 .. n_levels); the row scales and the pivot flag
+// are set up by the call that starts at level 0
 static int chol_factor(const CholPlanHost& P, const void* index_dev, const double* vals, const int* diag_slot,
                        const uint8_t* fixed, const double* kspring, double* factor, void* work, int* info_dev,
-                       cudaStream_t caller) {
+                       cudaStream_t caller, int l_begin = 0, int l_end = 1 << 30) {
     if (set_smem_attrs()) return 1;
     const IndexPtrs I = index_ptrs(P, index_dev);
     double* sc = factor + P.factor_doubles;
@@ -966,11 +968,13 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
         cudaEventRecord(e, st);
         g_timed.spans[cls].push_back({b, e});
     };
-    FERS_CK(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
-    k_chol_scale<<<cdiv(6 * P.n_nodes, 256), 256, 0, st>>>(P.n_nodes, vals, diag_slot, fixed, kspring, sc);
-    FERS_LAUNCH_CHECK();
-    ++launches;
-    for (int l = 0; l < P.n_levels; ++l) {
+    if (l_begin <= 0) {
+        FERS_CK(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
+        k_chol_scale<<<cdiv(6 * P.n_nodes, 256), 256, 0, st>>>(P.n_nodes, vals, diag_slot, fixed, kspring, sc);
+        FERS_LAUNCH_CHECK();
+        ++launches;
+    }
+    for (int l = std::max(l_begin, 0); l < std::min(l_end, P.n_levels); ++l) {
         const int nf = P.level_ptr[l + 1] - P.level_ptr[l];
         if (nf == 0) continue;
         LevelCtx L;
@@ -1166,8 +1170,13 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
     return 0;
 }
 
+// phases: 1 = forward substitution over levels [l_begin, l_end), 2 = backward over the same levels (top down),
+// 4 = permuted solution -> x; the whole substitution is 7 over 0 .. n_levels
 static int chol_solve(const CholPlanHost& P, const void* index_dev, const double* factor, const uint8_t* fixed, int nrhs,
-                      const double* b, double* x, int accumulate, void* work, cudaStream_t st) {
+                      const double* b, double* x, int accumulate, void* work, cudaStream_t st, int phases = 7, int l_begin = 0,
+                      int l_end = 1 << 30) {
+    l_begin = std::max(l_begin, 0);
+    l_end = std::min(l_end, P.n_levels);
     if (set_smem_attrs()) return 1;
     const IndexPtrs I = index_ptrs(P, index_dev);
     const double* sc = factor + P.factor_doubles;
@@ -1187,8 +1196,8 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
     int* ctr = reinterpret_cast<int*>(
         (reinterpret_cast<uintptr_t>(S.Y + (size_t)6 * P.n_nodes * nrhs) + 255) & ~(uintptr_t)255);
     const size_t ctr_half = (size_t)P.level_ptr[P.n_levels] + (size_t)P.n_levels;
-    if (wave) FERS_CK(cudaMemsetAsync(ctr, 0, wave_counter_ints(P) * sizeof(int), st));
-    for (int l = 0; l < P.n_levels; ++l) {                // forward: children -> parents
+    if (wave && (phases & 1) && l_begin == 0) FERS_CK(cudaMemsetAsync(ctr, 0, wave_counter_ints(P) * sizeof(int), st));
+    for (int l = l_begin; (phases & 1) && l < l_end; ++l) {                // forward: children -> parents
         const int nf = P.level_ptr[l + 1] - P.level_ptr[l];
         if (nf == 0) continue;
         S.level_fronts = I.level_fronts + P.level_ptr[l];
@@ -1225,7 +1234,7 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
         }
         FERS_LAUNCH_CHECK();
     }
-    for (int l = P.n_levels - 1; l >= 0; --l) {           // backward: parents -> children
+    for (int l = l_end - 1; (phases & 2) && l >= l_begin; --l) {           // backward: parents -> children
         const int nf = P.level_ptr[l + 1] - P.level_ptr[l];
         if (nf == 0) continue;
         S.level_fronts = I.level_fronts + P.level_ptr[l];
@@ -1258,7 +1267,7 @@ static int chol_solve(const CholPlanHost& P, const void* index_dev, const double
         }
         FERS_LAUNCH_CHECK();
     }
-    {
+    if (phases & 4) {
         const long long total = (long long)P.n_nodes * 6 * nrhs;
         k_chol_unpermute<<<(unsigned)std::min<long long>((total + 255) / 256, 65535), 256, 0, st>>>(
             P.n_nodes, nrhs, I.pos, fixed, sc, S.Y, x, accumulate);
@@ -1332,6 +1341,27 @@ int fers_b200_chol_factor(void* plan, const void* index_dev, const double* vals,
         FERS_CK(cudaStreamSynchronize(as_stream(stream)));
     }
     return 0;
+}
+
+int fers_b200_chol_factor_levels(void* plan, const void* index_dev, const double* vals, const int* diag_slot,
+                                 const uint8_t* fixed, const double* kspring, double* factor, void* work, size_t work_bytes,
+                                 int* info_dev, int l_begin, int l_end, void* stream) {
+    FERS_REQUIRE(plan && index_dev && vals && diag_slot && fixed && factor && work && info_dev, "chol_factor_levels: bad arguments");
+    const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    FERS_REQUIRE(work_bytes >= chol_work_bytes(P, 1), "chol_factor_levels: workspace too small");
+    FERS_REQUIRE(0 <= l_begin && l_begin <= l_end, "chol_factor_levels: bad level range");
+    return chol_factor(P, index_dev, vals, diag_slot, fixed, kspring, factor, work, info_dev, as_stream(stream), l_begin, l_end);
+}
+
+int fers_b200_chol_solve_phase(void* plan, const void* index_dev, const double* factor, const uint8_t* fixed, int nrhs,
+                               const double* b, double* x, int accumulate, void* work, size_t work_bytes, int phases,
+                               int l_begin, int l_end, void* stream) {
+    FERS_REQUIRE(plan && index_dev && factor && fixed && b && x && work, "chol_solve_phase: bad arguments");
+    FERS_REQUIRE(nrhs >= 2 && nrhs <= 64 && (nrhs % 2) == 0, "chol_solve_phase: nrhs must be even and in 2..64");
+    FERS_REQUIRE(phases > 0 && phases < 8 && 0 <= l_begin && l_begin <= l_end, "chol_solve_phase: bad phases / level range");
+    const CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    FERS_REQUIRE(work_bytes >= chol_work_bytes(P, nrhs), "chol_solve_phase: workspace too small");
+    return chol_solve(P, index_dev, factor, fixed, nrhs, b, x, accumulate, work, as_stream(stream), phases, l_begin, l_end);
 }
 
 int fers_b200_chol_solve(void* plan, const void* index_dev, const double* factor, const uint8_t* fixed, int nrhs,

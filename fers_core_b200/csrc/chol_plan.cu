@@ -587,6 +587,66 @@ int fers_b200_chol_plan_levels(void* plan, long long* out, int n_levels_cap) {
     return 0;
 }
 
+/* Tree-parallel factorisation on two GPUs (strong scaling of ONE model): the root front has two children; rank r keeps the
+ * fronts of the subtree under child r (rank 0 also the root) and drops the others from the level lists and from the
+ * scatter list of the K blocks.  Offsets into the factor store, the Schur arenas and the right-hand-side stores are those
+ * of the whole plan, so what one rank computes can be copied to the same place on the other.  Call before chol_upload.
+ * out[12] = root front, child 0, child 1, root level, first / one-past-last elimination position of subtree 0, the same of
+ * subtree 1, first position and node count of the root, fronts kept, K blocks kept. */
+int fers_b200_chol_plan_partition(void* plan, int rank, int world, long long* out, int n_out) {
+    FERS_REQUIRE(plan && out && n_out >= 12, "chol_plan_partition: bad arguments");
+    FERS_REQUIRE(world == 2 && (rank == 0 || rank == 1), "chol_plan_partition: two ranks (the two subtrees under the root front)");
+    CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
+    FERS_REQUIRE(P.n_levels >= 2, "chol_plan_partition: the front tree has a single level");
+    const int ls = P.n_levels - 1;
+    FERS_REQUIRE(P.level_ptr[ls + 1] - P.level_ptr[ls] == 1, "chol_plan_partition: the top level holds more than one front");
+    const int root = P.level_fronts[P.level_ptr[ls]];
+    const FrontDev& R = P.fronts[root];
+    FERS_REQUIRE(R.child_end - R.child_begin == 2, "chol_plan_partition: the root front does not have exactly two children");
+    const int c[2] = {P.child[R.child_begin], P.child[R.child_begin + 1]};
+    std::vector<int> owner(P.n_fronts, -1);
+    owner[root] = 0;
+    for (int f = 0; f < P.n_fronts; ++f) {
+        if (f == root) continue;
+        int a = f;
+        while (P.fronts[a].parent != root && P.fronts[a].parent >= 0) a = P.fronts[a].parent;
+        FERS_REQUIRE(P.fronts[a].parent == root, "chol_plan_partition: a front is not under the root (forest)");
+        owner[f] = (a == c[0]) ? 0 : 1;
+    }
+    long long lo[2] = {1LL << 60, 1LL << 60}, hi[2] = {0, 0}, cnt[2] = {0, 0};
+    for (int f = 0; f < P.n_fronts; ++f) {
+        if (f == root) continue;
+        const int o = owner[f];
+        lo[o] = std::min<long long>(lo[o], P.fronts[f].pad0);
+        hi[o] = std::max<long long>(hi[o], (long long)P.fronts[f].pad0 + P.fronts[f].n1);
+        cnt[o] += P.fronts[f].n1;
+    }
+    FERS_REQUIRE(hi[0] - lo[0] == cnt[0] && hi[1] - lo[1] == cnt[1], "chol_plan_partition: a subtree is not contiguous in the elimination order");
+    std::vector<int> lf, lp(P.n_levels + 1, 0);
+    std::vector<KScatter> ks;
+    std::vector<long long> kp(P.n_levels + 1, 0);
+    for (int l = 0; l < P.n_levels; ++l) {
+        int mx1 = 0, mx = 0;
+        for (int q = P.level_ptr[l]; q < P.level_ptr[l + 1]; ++q) {
+            const int f = P.level_fronts[q];
+            if (owner[f] != rank) continue;
+            lf.push_back(f);
+            mx1 = std::max(mx1, P.fronts[f].n1);
+            mx = std::max(mx, P.fronts[f].n1 + P.fronts[f].n2);
+        }
+        lp[l + 1] = (int)lf.size();
+        P.level_max_n1[l] = mx1; P.level_max_n[l] = mx;
+        for (long long q = P.kscatter_ptr[l]; q < P.kscatter_ptr[l + 1]; ++q)
+            if (owner[P.kscatter[q].front] == rank) ks.push_back(P.kscatter[q]);
+        kp[l + 1] = (long long)ks.size();
+    }
+    P.level_fronts.swap(lf); P.level_ptr.swap(lp); P.kscatter.swap(ks); P.kscatter_ptr.swap(kp);
+    out[0] = root; out[1] = c[0]; out[2] = c[1]; out[3] = ls;
+    out[4] = lo[0]; out[5] = hi[0]; out[6] = lo[1]; out[7] = hi[1];
+    out[8] = R.pad0; out[9] = R.n1; out[10] = (long long)P.level_fronts.size(); out[11] = (long long)P.kscatter.size();
+    return 0;
+}
+
 }  // extern "C"
 
 namespace fers {

@@ -73,10 +73,13 @@ class Engine:
     """One model resident on one GPU."""
 
     def __init__(self, model: wire.ModelArrays, device=None, assembly_variant: int = ASSEMBLY_GATHER, solver: str = "auto",
-                 plan_ahead: bool = False):
+                 plan_ahead: bool = False, tree_parallel=None):
         if solver not in SOLVERS:
             raise EngineError(f"solver must be one of {SOLVERS}, got {solver!r}")
         self.solver = solver
+        # (rank, world[, group]) of a torch.distributed group of two GPUs that hold the SAME model: the sparse factorisation
+        # is split by the two subtrees under the root front (chol.TreeParallelSolver); every other stage runs on both
+        self.tree_parallel = tree_parallel
         self._chol = None
         self._k_version = 0
         self._chol_version = -1
@@ -197,6 +200,9 @@ class Engine:
         self.d_bc_code = self._t(code.reshape(-1), np.uint8)
         self.d_bc_k = self._t(kk.reshape(-1), np.float64)
         self.d_supported = self._t((m.node_support_id >= 0).astype(np.uint8), np.uint8)
+        # reactions are exactly zero off the supported nodes (k_reaction_finish): only their rows travel to the host
+        self.sup_nodes = np.nonzero(m.node_support_id >= 0)[0]
+        self.d_sup_nodes = torch.from_numpy(self.sup_nodes.astype(np.int64)).to(self.dev)
         self.d_p_nodes = self._t(m.p_nodes, np.int32) if m.n_plates else None
         self.d_p_data = self._t(m.p_data, np.float64) if m.n_plates else None
         self.d_p_flags = self._t(m.p_flags, np.int32) if m.n_plates else None
@@ -424,7 +430,10 @@ class Engine:
                 rowptr = self.d_rowptr.cpu().numpy()
                 colidx = self.d_colidx.cpu().numpy()
                 plan = chol.CholPlan(rowptr, colidx, m.xyz, node_restrained=self.h_node_restrained)
-            self._chol = chol.CholSolver(plan, self.dev, max_nrhs=64)
+            if self.tree_parallel is not None:
+                self._chol = chol.TreeParallelSolver(plan, self.dev, *self.tree_parallel, max_nrhs=64)
+            else:
+                self._chol = chol.CholSolver(plan, self.dev, max_nrhs=64)
             self.timings["chol_plan_ms"] = (time.perf_counter() - t0) * 1e3          # what the pass waited for
         sol = self._chol
         if self._chol_version != self._k_version:
@@ -475,6 +484,7 @@ class Engine:
                                            _lib.ptr(self.d_vals), _lib.ptr(self.d_supported), _lib.ptr(d_u),
                                            _lib.ptr(d_f), _lib.ptr(r), st), "reactions")
         out["R"] = r
+        out["sup_nodes"] = (self.sup_nodes, self.d_sup_nodes)
         if nm:
             fl = self._empty((nm, 12, nr)); fg = self._empty((nm, 12, nr)); ul = self._empty((nm, 12, nr))
             _lib.check(lib.fers_b200_recover_members(
@@ -529,6 +539,12 @@ class Engine:
         rec = self.recover(self.d_xyz0, d_u, d_f, d_peq, facp, span, detail=detail)
         rec["U"] = d_u
         return rec
+
+    def reactions_at_supports(self, r: torch.Tensor):
+        """(supported node indices [ns] on the host, reactions [ns, 6, nr] on the device): the rows of the reaction
+        multi-vector that are not identically zero -- what a caller downloads instead of the whole [Ndof, nr] array."""
+        nr = r.shape[-1]
+        return self.sup_nodes, r.view(self.model.n_nodes, 6, nr).index_select(0, self.d_sup_nodes)
 
     def run_linear_sharded(self, factors: np.ndarray, gather=("U", "R", "f_local"), detail: bool = False) -> dict:
         """run_linear for all ranks of the default torch.distributed group at once: combinations sharded over the ranks,
@@ -756,7 +772,16 @@ def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:
         out.unity.accumulate([int(c) for c in cols], out.unity_xyz, d_u, rec,
                              torch.cuda.current_stream(d_u.device).cuda_stream)
     put(out.U, d_u, (nn, 6))
-    put(out.R, rec["R"], (nn, 6))
+    sup_pending = None
+    if "sup_nodes" in rec and 2 * len(rec["sup_nodes"][0]) < nn:
+        # reactions: only the rows of the supported nodes are downloaded (the rest of out.R is, and stays, zero)
+        sup_host, sup_dev = rec["sup_nodes"]
+        src = rec["R"].view(nn, 6, rec["R"].shape[-1]).index_select(0, sup_dev).movedim(-1, 0)[:n].contiguous()
+        stage_r = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+        stage_r.copy_(src, non_blocking=True)
+        sup_pending = (sup_host, stage_r)
+    else:
+        put(out.R, rec["R"], (nn, 6))
     if nm:
         put(out.f_local, rec["f_local"], (nm, 12))
         if "bw" in rec:
@@ -775,6 +800,10 @@ def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:
         out.p_cdg[cols] = cd[..., :6]; out.p_cdl[cols] = cd[..., 6:]
         out.p_centroid = xyz[model.p_nodes].mean(axis=1)
     flush()
+    if sup_pending is not None:
+        torch.cuda.current_stream(d_u.device).synchronize()
+        sup_host, stage_r = sup_pending
+        out.R[np.asarray(cols)[:, None], sup_host[None, :]] = stage_r.numpy()
 
 
 class FrameBatch:

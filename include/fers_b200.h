@@ -274,6 +274,23 @@ int fers_b200_chol_set_profile(int on);
 /* Tile shape of the factorisation GEMMs: bit 0 = panel updates, bit 1 = Schur update; bit set =
  * 128x128 tile with one CTA per SM, clear (default) = 128x64 tile with two CTAs per SM; bit 2 set = no
  * look-ahead (the update of all later columns is then not overlapped with the next block's panel chain). */
+/* Tree-parallel use of the sparse direct solve on two GPUs (strong scaling of ONE model; SURVEY.md 8e asks for sharding
+ * by combinations only -- this goes further).  chol_plan_partition (before chol_upload): rank r keeps the fronts of the
+ * subtree under child r of the root front (rank 0 also the root); all offsets stay those of the whole plan.
+ * out[12] = root front, child 0, child 1, root level, [first, one past last) elimination position of subtree 0, of
+ * subtree 1, first position and node count of the root, fronts kept, K blocks kept.
+ * chol_factor_levels: levels [l_begin, l_end) of the numeric factorisation, asynchronous (level 0 starts a factorisation).
+ * chol_solve_phase: phases (bit 0 forward, bit 1 backward, bit 2 un-permute into x) over levels [l_begin, l_end).
+ * Between the calls the caller moves, rank to rank: the Schur complement of child 1 (arena of its level parity at its
+ * schur_off), its front-local right-hand side rows, the root rows and the subtree rows of the permuted solution
+ * (fers_core_b200.chol.TreeParallelSolver does, with torch.distributed send / recv over NVLink). */
+int fers_b200_chol_plan_partition(void* plan, int rank, int world, long long* out, int n_out);
+int fers_b200_chol_factor_levels(void* plan, const void* index_dev, const double* vals, const int* diag_slot,
+                                 const uint8_t* fixed, const double* kspring, double* factor, void* work, size_t work_bytes,
+                                 int* info_dev, int l_begin, int l_end, void* stream);
+int fers_b200_chol_solve_phase(void* plan, const void* index_dev, const double* factor, const uint8_t* fixed, int nrhs,
+                               const double* b, double* x, int accumulate, void* work, size_t work_bytes, int phases,
+                               int l_begin, int l_end, void* stream);
 int fers_b200_chol_set_variant(int variant);
 /* Blocking of the panel updates: `steps` 64-column steps per outer block (default 4 = 256 columns) and `group`
  * outer blocks per group (default 1; measured: 4 x 1 is the fastest of 2 x 1, 4 x 1, 8 x 1, 4 x 2, 4 x 4, 4 x 8 at
