@@ -185,45 +185,68 @@ class CholSolver:
 
 
 class TreeParallelSolver(CholSolver):
-    """The sparse direct solve of ONE model on two GPUs (strong scaling; SURVEY.md 8e only asks for sharding by
+    """The sparse direct solve of ONE model on 2^k GPUs (strong scaling; SURVEY.md 8e only asks for sharding by
     combinations -- the reference describes a single shared factorisation, pydantic_models.py:1216-1219).
 
-    The root front of the nested dissection has two children: rank r factorises the subtree under child r
-    (fers_b200_chol_plan_partition drops the other fronts from this rank's level lists; every offset stays that of the whole
-    plan), rank 1 sends the Schur complement of its top front to rank 0 over NVLink (NCCL send / recv; gloo in tests), rank 0
-    extend-adds both and factorises the root.  The substitution mirrors it: forward on the two subtrees, rank 1's boundary
-    right-hand side to rank 0, root forward + backward on rank 0, root solution to rank 1, backward on the subtrees, the two
-    halves of the permuted solution exchanged -- both ranks end with the whole solution.  What crosses the link per
-    factorisation: one [6 n2]^2 Schur complement (0.96 GB at configs[3]); per substitution: 2 x 5.6 MB + the two halves of
-    the solution."""
+    The top k levels of the nested-dissection front tree are a binary tree.  Rank s factorises the subtree under its s-th
+    depth-k front; an upper front (depth d, index j) belongs to the leftmost rank below it, j << (k - d)
+    (fers_b200_chol_plan_partition drops everything else from this rank's level lists; every offset stays that of the whole
+    plan).  Going up, the owner of a right child sends its Schur complement to the owner of the parent -- which holds the left
+    child -- over NVLink (NCCL send / recv; gloo in tests); the parent is extend-added and factorised there.  The
+    substitution mirrors it: forward on the subtrees, boundary right-hand sides up the tree, backward from the root with the
+    solution of the ancestors handed down to the right children, and one all_gather of the rows each rank owns -- every rank
+    ends with the whole solution.  Across the links per factorisation: one [6 n2]^2 Schur complement per upper front
+    (0.96 GB for the root of configs[3])."""
 
     def __init__(self, plan: CholPlan, device, rank: int, world: int, group=None, max_nrhs: int = 64):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
-        self.rank, self.peer = int(rank), 1 - int(rank)
+        self.rank, self.world = int(rank), int(world)
         fronts = plan.export()["fronts"].copy()          # the whole plan, before this rank's fronts are selected
-        out = (C.c_longlong * 12)()
-        _lib.check(plan.lib.fers_b200_chol_plan_partition(plan.handle, int(rank), int(world), out, 12), "chol_plan_partition")
-        self.root, self.c0, self.c1, self.ls = (int(out[i]) for i in range(4))
-        self.sub = ((int(out[4]), int(out[5])), (int(out[6]), int(out[7])))
-        self.root_pos = (int(out[8]), int(out[8] + out[9]))
-        self.fronts_kept, self.k_blocks_kept = int(out[10]), int(out[11])
-        f1 = fronts[self.c1]
-        m2 = 6 * int(f1["n2"])
-        arena = plan.info.schur_doubles[0] if ((self.ls - 1) & 1) else 0
-        self._schur = (arena + int(f1["schur_off"]), m2 * m2)                     # doubles into the work buffer
-        self._rhs_c1 = (int(f1["rhs_off"]), 6 * int(f1["n1"] + f1["n2"]))         # rows of the front-local store W
+        n_out = 4 + 4 * self.world
+        out = (C.c_longlong * n_out)()
+        _lib.check(plan.lib.fers_b200_chol_plan_partition(plan.handle, self.rank, self.world, out, n_out), "chol_plan_partition")
+        k = self.k = int(out[0])
+        self.ls = int(out[1])
+        self.fronts_kept, self.k_blocks_kept = int(out[2]), int(out[3])
+        n_top = (2 << k) - 1
+        ids = [int(out[4 + t]) for t in range(n_top)]
+        self.top = [[ids[(1 << d) - 1 + j] for j in range(1 << d)] for d in range(k + 1)]     # top[d][j] = front id
+        lo = [int(out[4 + n_top + s]) for s in range(self.world)]
+        self._f = fronts
+        sd0 = int(plan.info.schur_doubles[0])
         self._rhs_rows = int(plan.info.rhs_rows)
+
+        def own(fid):                                    # [first, one past last) elimination position of a front's own nodes
+            return int(fronts[fid]["pad0"]), int(fronts[fid]["pad0"] + fronts[fid]["n1"])
+        self._own = own
+        # rows of the permuted solution each rank owns: its subtree and the upper fronts it factorises
+        self.owned = []
+        for r in range(self.world):
+            rng = [(lo[r], own(self.top[k][r])[1])]
+            for d in range(k):
+                for j in range(1 << d):
+                    if self.owner(d, j) == r:
+                        rng.append(own(self.top[d][j]))
+            self.owned.append(rng)
+        self._sd0 = sd0
         super().__init__(plan, device, max_nrhs)
         self.wk = self.work[: (self.work_bytes // 8) * 8].view(self.torch.float64)
-        self.link_bytes = {"factor": 8 * self._schur[1]}
+        self.link_bytes = {"factor": 0, "solve": 0}
 
-    def _send(self, t):
-        self.dist.send(t, self.peer, group=self.group)
+    def owner(self, d: int, j: int) -> int:
+        return j << (self.k - d)
 
-    def _recv(self, t):
-        self.dist.recv(t, self.peer, group=self.group)
+    def _schur(self, fid: int, depth: int):
+        """The Schur complement of front `fid` (tree depth `depth`) inside the work buffer, as a flat tensor."""
+        m2 = 6 * int(self._f[fid]["n2"])
+        off = (self._sd0 if ((self.ls - depth) & 1) else 0) + int(self._f[fid]["schur_off"])
+        return self.wk[off: off + m2 * m2]
+
+    def _merge_pairs(self, d: int):
+        """(front of the right child, its owner, owner of the parent) for the upper fronts of depth d."""
+        return [(self.top[d + 1][2 * j + 1], self.owner(d + 1, 2 * j + 1), self.owner(d, j)) for j in range(1 << d)]
 
     def factorize(self, d_vals, d_diag_slot, d_fixed, d_kspring=None, check: bool = True) -> int:
         ks = None if d_kspring is None else d_kspring.data_ptr()
@@ -233,13 +256,18 @@ class TreeParallelSolver(CholSolver):
                 self.plan.handle, self.index.data_ptr(), d_vals.data_ptr(), d_diag_slot.data_ptr(), d_fixed.data_ptr(), ks,
                 self.factor.data_ptr(), self.work.data_ptr(), self.work_bytes, self.info_dev.data_ptr(), lo, hi, self.stream),
                 "chol_factor_levels")
-        levels(0, self.ls)
-        off, n = self._schur
-        if self.rank == 1:
-            self._send(self.wk[off: off + n])
-        else:
-            self._recv(self.wk[off: off + n])
-            levels(self.ls, self.ls + 1)
+        levels(0, self.ls - self.k + 1)
+        sent = 0
+        for d in range(self.k - 1, -1, -1):
+            for fid, src, dst in self._merge_pairs(d):
+                if self.rank == src:
+                    t = self._schur(fid, d + 1)
+                    self.dist.send(t, dst, group=self.group)
+                    sent += 8 * t.numel()
+                elif self.rank == dst:
+                    self.dist.recv(self._schur(fid, d + 1), src, group=self.group)
+            levels(self.ls - d, self.ls - d + 1)
+        self.link_bytes["factor"] = sent
         self.factored = True
         if not check:
             return 0
@@ -248,6 +276,7 @@ class TreeParallelSolver(CholSolver):
         return int(info.item())
 
     def solve(self, d_b, d_x, d_fixed, accumulate: bool = False) -> None:
+        torch = self.torch
         nrhs = int(d_b.shape[1])
 
         def phase(bits, lo, hi):
@@ -256,23 +285,57 @@ class TreeParallelSolver(CholSolver):
                 d_x.data_ptr(), 1 if accumulate else 0, self.work.data_ptr(), self.work_bytes, bits, lo, hi, self.stream),
                 "chol_solve_phase")
         y0 = self._rhs_rows * nrhs                                         # the permuted solution Y follows W
-        rows = lambda a, b: self.wk[y0 + 6 * a * nrhs: y0 + 6 * b * nrhs]
-        w_c1 = self.wk[self._rhs_c1[0] * nrhs: (self._rhs_c1[0] + self._rhs_c1[1]) * nrhs]
-        phase(1, 0, self.ls)
-        if self.rank == 1:
-            self._send(w_c1)
-            self._recv(rows(*self.root_pos))
-        else:
-            self._recv(w_c1)
-            phase(3, self.ls, self.ls + 1)
-            self._send(rows(*self.root_pos))
-        phase(2, 0, self.ls)
-        mine, theirs = rows(*self.sub[self.rank]), rows(*self.sub[self.peer])
-        ops = [self.dist.P2POp(self.dist.isend, mine, self.peer, group=self.group),
-               self.dist.P2POp(self.dist.irecv, theirs, self.peer, group=self.group)]
-        if self.rank == 1:
-            ops.reverse()
-        for r in self.dist.batch_isend_irecv(ops):
-            r.wait()
-        phase(4, 0, self.ls + 1)
-        self.link_bytes["solve"] = 8 * (w_c1.numel() + rows(*self.root_pos).numel() + mine.numel() + theirs.numel())
+
+        def rows(a, b):
+            return self.wk[y0 + 6 * a * nrhs: y0 + 6 * b * nrhs]
+
+        def w_block(fid):                                                   # front-local right-hand side rows of a front
+            f = self._f[fid]
+            return self.wk[int(f["rhs_off"]) * nrhs: (int(f["rhs_off"]) + 6 * int(f["n1"] + f["n2"])) * nrhs]
+        k, ls, sent = self.k, self.ls, 0
+        phase(1, 0, ls - k + 1)
+        for d in range(k - 1, -1, -1):                                      # forward: boundary right-hand sides up the tree
+            for fid, src, dst in self._merge_pairs(d):
+                if self.rank == src:
+                    self.dist.send(w_block(fid), dst, group=self.group)
+                    sent += 8 * w_block(fid).numel()
+                elif self.rank == dst:
+                    self.dist.recv(w_block(fid), src, group=self.group)
+            phase(1, ls - d, ls - d + 1)
+        for d in range(k):                                                  # backward: the ancestors' solution down the tree
+            phase(2, ls - d, ls - d + 1)
+            for j in range(1 << d):
+                src, dst = self.owner(d, j), self.owner(d + 1, 2 * j + 1)
+                if self.rank not in (src, dst):
+                    continue
+                chain = [self._own(self.top[dd][j >> (d - dd)]) for dd in range(d, -1, -1)]     # this front and its ancestors
+                if self.rank == src:
+                    buf = torch.cat([rows(a, b) for a, b in chain])
+                    self.dist.send(buf, dst, group=self.group)
+                    sent += 8 * buf.numel()
+                else:
+                    buf = torch.empty(sum(6 * (b - a) * nrhs for a, b in chain), dtype=torch.float64, device=self.wk.device)
+                    self.dist.recv(buf, src, group=self.group)
+                    o = 0
+                    for a, b in chain:
+                        n = 6 * (b - a) * nrhs
+                        rows(a, b).copy_(buf[o: o + n]); o += n
+        phase(2, 0, ls - k + 1)
+        # every rank gets the rows the others own: one all_gather of equally padded blocks
+        width = max(sum(6 * (b - a) for a, b in rng) for rng in self.owned) * nrhs
+        mine = torch.zeros(width, dtype=torch.float64, device=self.wk.device)
+        o = 0
+        for a, b in self.owned[self.rank]:
+            n = 6 * (b - a) * nrhs
+            mine[o: o + n] = rows(a, b); o += n
+        allb = torch.empty(self.world * width, dtype=torch.float64, device=self.wk.device)
+        self.dist.all_gather_into_tensor(allb, mine, group=self.group)
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            o = r * width
+            for a, b in self.owned[r]:
+                n = 6 * (b - a) * nrhs
+                rows(a, b).copy_(allb[o: o + n]); o += n
+        phase(4, 0, ls + 1)
+        self.link_bytes["solve"] = sent + 8 * (self.world - 1) * width

@@ -587,41 +587,66 @@ int fers_b200_chol_plan_levels(void* plan, long long* out, int n_levels_cap) {
     return 0;
 }
 
-/* Tree-parallel factorisation on two GPUs (strong scaling of ONE model): the root front has two children; rank r keeps the
- * fronts of the subtree under child r (rank 0 also the root) and drops the others from the level lists and from the
- * scatter list of the K blocks.  Offsets into the factor store, the Schur arenas and the right-hand-side stores are those
- * of the whole plan, so what one rank computes can be copied to the same place on the other.  Call before chol_upload.
- * out[12] = root front, child 0, child 1, root level, first / one-past-last elimination position of subtree 0, the same of
- * subtree 1, first position and node count of the root, fronts kept, K blocks kept. */
+/* Tree-parallel factorisation on 2^k GPUs (strong scaling of ONE model).  The top k levels of the front tree must be a
+ * complete binary tree; its fronts are numbered (depth d, index j) from the root (0, 0) by the order of the child lists.
+ * Rank s keeps the subtree under front (k, s); an upper front (d, j) belongs to the leftmost rank below it, j << (k - d).
+ * Everything else is dropped from this rank's level lists and from its scatter list of the K blocks; offsets into the
+ * factor store, the Schur arenas and the right-hand-side stores stay those of the whole plan, so what one rank computes can
+ * be copied to the same place on another.  Call before chol_upload.
+ * out: [0] k, [1] level of the root, [2] fronts kept, [3] K blocks kept, then the 2^(k+1) - 1 upper fronts depth by depth,
+ * then the first elimination position of each of the 2^k subtrees (its last is that of its top front). */
 int fers_b200_chol_plan_partition(void* plan, int rank, int world, long long* out, int n_out) {
-    FERS_REQUIRE(plan && out && n_out >= 12, "chol_plan_partition: bad arguments");
-    FERS_REQUIRE(world == 2 && (rank == 0 || rank == 1), "chol_plan_partition: two ranks (the two subtrees under the root front)");
+    FERS_REQUIRE(plan && out, "chol_plan_partition: bad arguments");
+    int k = 0;
+    while ((1 << k) < world) ++k;
+    FERS_REQUIRE(world >= 2 && world <= 64 && (1 << k) == world && rank >= 0 && rank < world,
+                 "chol_plan_partition: the number of ranks must be a power of two (2 .. 64)");
+    const int n_top = (2 << k) - 1;
+    FERS_REQUIRE(n_out >= 4 + n_top + world, "chol_plan_partition: output too small");
     CholPlanHost& P = *static_cast<CholPlanHost*>(plan);
-    FERS_REQUIRE(P.n_levels >= 2, "chol_plan_partition: the front tree has a single level");
+    FERS_REQUIRE(P.n_levels > k, "chol_plan_partition: the front tree is shallower than the rank tree");
     const int ls = P.n_levels - 1;
     FERS_REQUIRE(P.level_ptr[ls + 1] - P.level_ptr[ls] == 1, "chol_plan_partition: the top level holds more than one front");
-    const int root = P.level_fronts[P.level_ptr[ls]];
-    const FrontDev& R = P.fronts[root];
-    FERS_REQUIRE(R.child_end - R.child_begin == 2, "chol_plan_partition: the root front does not have exactly two children");
-    const int c[2] = {P.child[R.child_begin], P.child[R.child_begin + 1]};
-    std::vector<int> owner(P.n_fronts, -1);
-    owner[root] = 0;
+    std::vector<int> top(n_top, -1), owner(P.n_fronts, -1);
+    top[0] = P.level_fronts[P.level_ptr[ls]];
+    for (int d = 0; d < k; ++d)
+        for (int j = 0; j < (1 << d); ++j) {
+            const FrontDev& F = P.fronts[top[(1 << d) - 1 + j]];
+            FERS_REQUIRE(F.child_end - F.child_begin == 2, "chol_plan_partition: an upper front does not have exactly two children");
+            top[(2 << d) - 1 + 2 * j] = P.child[F.child_begin];
+            top[(2 << d) - 1 + 2 * j + 1] = P.child[F.child_begin + 1];
+        }
+    for (int d = 0; d <= k; ++d)
+        for (int j = 0; j < (1 << d); ++j) owner[top[(1 << d) - 1 + j]] = j << (k - d);
+    // every other front belongs to the rank of the depth-k front above it (fronts are in post-order: the climb from an
+    // unresolved front passes unresolved fronts only, until it meets an upper front)
+    std::vector<char> is_leaf_top(P.n_fronts, 0);
+    for (int j = 0; j < world; ++j) is_leaf_top[top[world - 1 + j]] = 1;
+    std::vector<int> under(P.n_fronts, -1);
     for (int f = 0; f < P.n_fronts; ++f) {
-        if (f == root) continue;
-        int a = f;
-        while (P.fronts[a].parent != root && P.fronts[a].parent >= 0) a = P.fronts[a].parent;
-        FERS_REQUIRE(P.fronts[a].parent == root, "chol_plan_partition: a front is not under the root (forest)");
-        owner[f] = (a == c[0]) ? 0 : 1;
+        if (owner[f] >= 0) continue;
+        int a = f, hops = 0;
+        while (owner[a] < 0 && P.fronts[a].parent >= 0 && hops++ < P.n_fronts) a = P.fronts[a].parent;
+        FERS_REQUIRE(owner[a] >= 0 && is_leaf_top[a], "chol_plan_partition: a front does not hang under one of the 2^k subtree tops");
+        under[f] = owner[a];
     }
-    long long lo[2] = {1LL << 60, 1LL << 60}, hi[2] = {0, 0}, cnt[2] = {0, 0};
+    for (int f = 0; f < P.n_fronts; ++f)
+        if (owner[f] < 0) owner[f] = under[f];
+    std::vector<long long> lo(world, 1LL << 60), hi(world, 0), cnt(world, 0);
+    std::vector<char> is_top(P.n_fronts, 0);
+    for (int t = 0; t < world - 1; ++t) is_top[top[t]] = 1;          // depths 0 .. k-1
     for (int f = 0; f < P.n_fronts; ++f) {
-        if (f == root) continue;
+        if (is_top[f]) continue;
         const int o = owner[f];
         lo[o] = std::min<long long>(lo[o], P.fronts[f].pad0);
         hi[o] = std::max<long long>(hi[o], (long long)P.fronts[f].pad0 + P.fronts[f].n1);
         cnt[o] += P.fronts[f].n1;
     }
-    FERS_REQUIRE(hi[0] - lo[0] == cnt[0] && hi[1] - lo[1] == cnt[1], "chol_plan_partition: a subtree is not contiguous in the elimination order");
+    for (int o = 0; o < world; ++o) {
+        FERS_REQUIRE(hi[o] - lo[o] == cnt[o], "chol_plan_partition: a subtree is not contiguous in the elimination order");
+        const FrontDev& T = P.fronts[top[world - 1 + o]];
+        FERS_REQUIRE(hi[o] == (long long)T.pad0 + T.n1, "chol_plan_partition: a subtree does not end with its top front");
+    }
     std::vector<int> lf, lp(P.n_levels + 1, 0);
     std::vector<KScatter> ks;
     std::vector<long long> kp(P.n_levels + 1, 0);
@@ -641,9 +666,9 @@ int fers_b200_chol_plan_partition(void* plan, int rank, int world, long long* ou
         kp[l + 1] = (long long)ks.size();
     }
     P.level_fronts.swap(lf); P.level_ptr.swap(lp); P.kscatter.swap(ks); P.kscatter_ptr.swap(kp);
-    out[0] = root; out[1] = c[0]; out[2] = c[1]; out[3] = ls;
-    out[4] = lo[0]; out[5] = hi[0]; out[6] = lo[1]; out[7] = hi[1];
-    out[8] = R.pad0; out[9] = R.n1; out[10] = (long long)P.level_fronts.size(); out[11] = (long long)P.kscatter.size();
+    out[0] = k; out[1] = ls; out[2] = (long long)P.level_fronts.size(); out[3] = (long long)P.kscatter.size();
+    for (int t = 0; t < n_top; ++t) out[4 + t] = top[t];
+    for (int o = 0; o < world; ++o) out[4 + n_top + o] = lo[o];
     return 0;
 }
 

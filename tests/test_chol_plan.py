@@ -151,24 +151,28 @@ def test_host_pattern_grid_frame_and_errors():
         chol.host_pattern(3, np.array([0, 7]), np.array([1, 2]))
 
 
-def test_tree_partition_splits_the_fronts_between_two_ranks():
-    """fers_b200_chol_plan_partition: the two subtrees under the root front go to the two ranks, the root to rank 0; the
-    kept fronts are disjoint and cover the tree, the subtrees are contiguous ranges of the elimination order, and every
-    offset of the whole plan survives (what one rank computes can be copied to the same place on the other)."""
+@pytest.mark.parametrize("world", [2, 4])
+def test_tree_partition_splits_the_fronts_between_the_ranks(world):
+    """fers_b200_chol_plan_partition: rank s keeps the subtree under the s-th depth-k front, an upper front goes to the
+    leftmost rank below it; the kept fronts are disjoint and cover the tree, every subtree is a contiguous range of the
+    elimination order that ends with its top front, and every offset of the whole plan survives (what one rank computes
+    can be copied to the same place on another)."""
     import ctypes as C
     from fers_core_b200 import _lib, chol, synth
     model = synth.grid_frame(9, 8, 6)
     rowptr, colidx = chol.host_pattern(model.n_nodes, model.m_n1, model.m_n2)
+    k = world.bit_length() - 1
+    n_top, n_out = (2 << k) - 1, 4 + 4 * world
     kept, infos, fronts_full = [], [], None
-    for rank in (0, 1):
+    for rank in range(world):
         plan = chol.CholPlan(rowptr, colidx, model.xyz)
         full = plan.export()
         if fronts_full is None:
             fronts_full = full["fronts"].copy()
             nf = plan.info.n_fronts
             lv_full = [set(full["level_fronts"][full["level_ptr"][l]:full["level_ptr"][l + 1]].tolist()) for l in range(plan.info.n_levels)]
-        out = (C.c_longlong * 12)()
-        _lib.check(plan.lib.fers_b200_chol_plan_partition(plan.handle, rank, 2, out, 12), "partition")
+        out = (C.c_longlong * n_out)()
+        _lib.check(plan.lib.fers_b200_chol_plan_partition(plan.handle, rank, world, out, n_out), "partition")
         part = plan.export()
         assert np.array_equal(part["fronts"], fronts_full)                      # offsets untouched
         lp = part["level_ptr"]
@@ -177,20 +181,27 @@ def test_tree_partition_splits_the_fronts_between_two_ranks():
             lv = set(part["level_fronts"][lp[l]:lp[l + 1]].tolist())
             assert lv <= lv_full[l]
             mine |= lv
-        assert len(mine) == out[10] and set(np.unique(part["kscatter"]["front"][: out[11]]).tolist()) <= mine
+        assert len(mine) == out[2] and set(np.unique(part["kscatter"]["front"][: out[3]]).tolist()) <= mine
         kept.append(mine)
         infos.append([int(v) for v in out])
         plan.close()
-    root, c0, c1, ls = infos[0][:4]
-    assert infos[0][:10] == infos[1][:10]
-    assert kept[0] & kept[1] == set() and kept[0] | kept[1] == set(range(nf))
-    assert root in kept[0] and c0 in kept[0] and c1 in kept[1]
-    (a0, b0), (a1, b1), r0 = infos[0][4:6], infos[0][6:8], infos[0][8]
-    assert b0 == a1 or b1 == a0                                                  # the subtrees are neighbours ...
-    assert max(b0, b1) == r0                                                     # ... and the root comes last
-    for rank, (a, b) in enumerate(((a0, b0), (a1, b1))):
-        pos = [range(int(fronts_full[f]["pad0"]), int(fronts_full[f]["pad0"] + fronts_full[f]["n1"])) for f in kept[rank] if f != root]
-        assert sorted(p for r in pos for p in r) == list(range(a, b))
+    assert all(i[:2] == infos[0][:2] and i[4:] == infos[0][4:] for i in infos) and infos[0][0] == k
+    top = infos[0][4:4 + n_top]
+    lo = infos[0][4 + n_top:4 + n_top + world]
+    assert set().union(*kept) == set(range(nf)) and sum(len(s) for s in kept) == nf
+    for d in range(k + 1):
+        for j in range(1 << d):
+            f = top[(1 << d) - 1 + j]
+            assert f in kept[j << (k - d)]
+            if d < k:                                                            # children in the order of the child list
+                assert fronts_full[top[(2 << d) - 1 + 2 * j]]["parent"] == f and fronts_full[top[(2 << d) - 1 + 2 * j + 1]]["parent"] == f
+    upper = set(top[: world - 1])
+    for r in range(world):
+        t = top[world - 1 + r]
+        hi = int(fronts_full[t]["pad0"] + fronts_full[t]["n1"])
+        pos = sorted(p for f in kept[r] if f not in upper
+                     for p in range(int(fronts_full[f]["pad0"]), int(fronts_full[f]["pad0"] + fronts_full[f]["n1"])))
+        assert pos == list(range(lo[r], hi))
     with pytest.raises(Exception):
         plan = chol.CholPlan(rowptr, colidx, model.xyz)
-        _lib.check(plan.lib.fers_b200_chol_plan_partition(plan.handle, 0, 4, (C.c_longlong * 12)(), 12), "partition")
+        _lib.check(plan.lib.fers_b200_chol_plan_partition(plan.handle, 0, 3, (C.c_longlong * 64)(), 64), "partition")

@@ -19,7 +19,7 @@ local = int(os.environ.get("LOCAL_RANK", 0))
 dev = torch.device("cuda", local)
 torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
-assert world == 2
+assert world >= 2 and (world & (world - 1)) == 0
 model = synth.grid_frame(nx, nz, ny, n_combos=64)
 factors = model.combo_factors[:64]
 
