@@ -56,9 +56,11 @@ def parse_args():
     p.add_argument("--spmm-variant", type=int, default=-1, help="0 register/LDG, 1 TMA-staged, 2 TMA warp-specialised (default: library default)")
     p.add_argument("--solver", default="auto", choices=["auto", "cholesky", "pcg"],
                    help="auto = sparse multifrontal Cholesky above 8 192 DOF (default); pcg = block-Jacobi PCG")
-    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong", "tree"],
                    help="weak = every GPU solves its own batch of --combos combinations (default, the driver's scaling run); strong = ONE "
-                        "model x --combos combinations split over the GPUs (replicated factorisation, result tensors all-gathered)")
+                        "model x --combos combinations split over the GPUs (replicated factorisation, result tensors all-gathered); "
+                        "tree = ONE model x --combos combinations, the sparse factorisation itself split over 2^k GPUs by the "
+                        "subtrees of the front tree (Schur complements over NVLink; chol.TreeParallelSolver)")
     p.add_argument("--detail", action="store_true",
                    help="cfg4: the timed step also recovers section forces along the members and their extrema "
                         "(run_linear(detail=True)); default: member end forces, displacements and reactions only")
@@ -619,6 +621,104 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         dist.destroy_process_group()
 
 
+def run_tree(args, rank: int, world: int, local_rank: int) -> None:
+    """--scaling tree: ONE model x --combos combinations on 2^k GPUs, the factorisation split by the subtrees of the front
+    tree (strong scaling of the headline problem; every rank ends with all results)."""
+    import torch
+    import torch.distributed as dist
+    from fers_core_b200 import _lib, dist as fdist, engine
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
+    dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    model = pin_model(build_model(args, 0))                 # the same model and combinations on every rank
+    factors = model.combo_factors
+    n_dof, n_comb = model.n_dof, factors.shape[0]
+
+    def make():
+        return engine.Engine(model, dev, args.assembly_variant, "cholesky", tree_parallel=(rank, world))
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+    eng = make()
+    for _ in range(args.warmup):
+        rec = eng.run_linear(factors)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.fers_b200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        rec = eng.run_linear(factors)
+    e1.record()
+    barrier()
+    launches = lib.fers_b200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = fdist.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    value = n_dof * n_comb / (ms_step / 1e3)
+    sol = eng._chol
+    flops = float(sol.plan.info.flops)
+    link = dict(sol.link_bytes)
+    resid = float(eng.stats.relres)
+    dmma, dfma = C.c_double(), C.c_double()
+    scratch = torch.empty(8 * 1024 * 160, dtype=torch.uint8, device=dev)
+    _lib.check(lib.fers_b200_fp64_peak(50.0, C.byref(dmma), C.byref(dfma), _lib.ptr(scratch), scratch.numel(), eng.stream), "fp64_peak")
+    # end to end with host buffers: model upload, pattern, plan + partition, pass, D2H of U and of the reactions at the supports
+    nr = rec["U"].shape[1]
+    h_u = torch.empty((n_dof, nr), dtype=torch.float64).pin_memory()
+    h_r = torch.empty((len(eng.sup_nodes), 6, nr), dtype=torch.float64).pin_memory()
+    del rec
+    t_e2e = []
+    h2d = 0
+    for _ in range(2):
+        del eng
+        barrier()
+        t0 = time.perf_counter()
+        eng = make()
+        out = eng.run_linear(factors)
+        if rank == 0:
+            h_u.copy_(out["U"], non_blocking=True); h_r.copy_(eng.reactions_at_supports(out["R"])[1], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        t_e2e.append(time.perf_counter() - t0)
+        h2d = eng.h2d_bytes
+        del out
+    te = fdist.max_over_ranks(min(t_e2e), dev)
+    if rank == 0:
+        tf = flops / (ms_step * 1e-3) / 1e12
+        emit({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args, n_comb).replace("per GPU", f"in total on {world} GPUs (strong scaling, tree-parallel factorisation)"),
+                       "nodes": model.n_nodes, "members": model.n_members, "dof": n_dof, "combinations": n_comb,
+                       "solver": "sparse multifrontal Cholesky split over the ranks by the subtrees of the front tree (chol.TreeParallelSolver)",
+                       "fronts_kept_rank0": sol.fronts_kept, "max_rel_residual": resid,
+                       "parallelism": f"one model on {world} GPUs: rank s factorises the s-th subtree of depth {sol.k}, upper fronts on the leftmost rank "
+                                      "below them; Schur complements / boundary right-hand sides up the tree over NVLink (NCCL send / recv), "
+                                      "ancestors' solution down, one all_gather of the solution rows; every other stage replicated",
+                       "link_bytes_rank0": link,
+                       "cache": "factor (16 GB over the ranks) and multi-vectors (354 MB each) >> 126 MB L2; no flush needed"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "whole factorisation + substitution (the kernels of the N = 1 line: k_oz_syrk_wide int8, DMMA tile GEMMs)",
+                         "achieved": tf, "peak": world * dmma.value, "unit": "TFLOP/s", "frac": tf / (world * dmma.value) if dmma.value > 0 else None,
+                         "traffic": None,
+                         "peak_source": f"{world} x the fp64 tensor-pipe peak measured live by fers_b200_fp64_peak (fp64-equivalent flops of one "
+                                        "factorisation over the time of a whole pass; the int8 digit-plane path runs above the fp64 pipe's rate, "
+                                        "the upper fronts of the tree run on one rank each while the others wait)",
+                         "algorithmic_flops_per_step": flops},
+            "e2e": {"value": n_dof * n_comb / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(h_u.numel() * 8 + h_r.numel() * 8), "ms_per_step": 1e3 * te,
+                    "api": "fers_core_b200.engine.Engine(model_arrays, tree_parallel=(rank, world)).run_linear(factors) on every rank + D2H of "
+                           "U and of the reactions at the supported nodes on rank 0"},
+            "cpu_baseline": None,
+        })
+    dist.destroy_process_group()
+
+
 CFG5_WORKLOAD = ("configs[4] batch of {n} parametric 3D frames per GPU (2x2 bays x 4 storeys, 45 nodes, 270 DOF each), sway "
                  "imperfection 1/200, second-order P-Delta (consistent K_g), tolerance 1e-8")
 
@@ -851,6 +951,9 @@ def main():
         return
     if args.workload == "cfg5":
         run_cfg5(args, rank, world, local_rank)
+        return
+    if args.scaling == "tree" and world > 1:
+        run_tree(args, rank, world, local_rank)
         return
     run_b200(args, rank, world, local_rank)
 
