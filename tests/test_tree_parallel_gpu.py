@@ -23,8 +23,8 @@ def _worker(rank, world, port, out):
         fac = model.combo_factors[:8]
         tp = engine.Engine(model, dev, solver="cholesky", tree_parallel=(rank, world))
         u_tp = tp.run_linear(fac)["U"].clone()
-        u_tp2 = tp.run_linear(fac)["U"]                       # a second pass re-uses the plan and the buffers
-        assert torch.equal(u_tp, u_tp2)
+        u_tp2 = tp.run_linear(fac)["U"]                       # a second pass re-uses the plan and the buffers (the load
+        assert float((u_tp - u_tp2).abs().max() / u_tp.abs().max()) < 1e-12      # vectors are summed with atomics: round-off)
         one = engine.Engine(model, dev, solver="cholesky")
         u_1 = one.run_linear(fac)["U"]
         out[rank] = (float((u_tp - u_1).abs().max() / u_1.abs().max()), float(tp.stats.relres), float(one.stats.relres),
