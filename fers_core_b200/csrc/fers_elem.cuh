@@ -472,7 +472,33 @@ FERS_HD void span_point_resultant(const Frame& f, const double* row, double x, d
 // Per-plate record (NPDATA doubles): thickness, E, nu, then the stiffness modifiers of PlateElement.stiffness_modifiers
 // (membrane, bending, shear; pydantic_models.py:801-807).  flags: bit0 membrane, bit1 bending, bit2 plane strain
 // (PlateElement.plane_state, 1712-1715: in-plane constitutive law of the membrane part).
-enum { PD_T = 0, PD_E = 1, PD_NU = 2, PD_MODM = 3, PD_MODB = 4, PD_MODS = 5, PD_THETA = 6, NPDATA = 8 };
+// Orthotropic plate material (OrthotropicPlateMaterial, pydantic_models.py:663-681; material axes = the plate's local x, y):
+// PD_ORTHO != 0 -> E_x, E_y, G_xy, nu_xy (nu_yx from E_x nu_yx = E_y nu_xy) for membrane and bending, G_xz / G_yz for the
+// transverse shear of the Mindlin part.
+enum { PD_T = 0, PD_E = 1, PD_NU = 2, PD_MODM = 3, PD_MODB = 4, PD_MODS = 5, PD_THETA = 6, PD_ORTHO = 7,
+       PD_EX = 8, PD_EY = 9, PD_GXY = 10, PD_NUXY = 11, PD_GXZ = 12, PD_GYZ = 13, PD_OFFSET = 14, NPDATA = 16 };
+
+// Plate offset (PlateElement.offset, pydantic_models.py:1711-1714: "distance from the reference surface along the local
+// plate normal"): the mid-surface sits at local z = o from the nodes, every node carries it on a rigid arm,
+//   u_mid = u + o ry,  v_mid = v - o rx   (local axes; w and the rotations are shared),   u_mid = E u_node.
+// plate_offset_fwd: local nodal displacements -> mid-surface displacements (18 values in place); the stiffness is E^T k E.
+FERS_HD void plate_offset_fwd(double o, double* u /*18*/) {
+    if (o == 0.0) return;
+    for (int n = 0; n < 3; ++n) { u[6 * n] += o * u[6 * n + 4]; u[6 * n + 1] -= o * u[6 * n + 3]; }
+}
+FERS_HD void plate_offset_k(double o, double* k /*324*/) {
+    if (o == 0.0) return;
+    for (int i = 0; i < 18; ++i)              // k E: columns of ry take o x the u column, columns of rx take -o x the v column
+        for (int n = 0; n < 3; ++n) {
+            k[i * 18 + 6 * n + 4] += o * k[i * 18 + 6 * n];
+            k[i * 18 + 6 * n + 3] -= o * k[i * 18 + 6 * n + 1];
+        }
+    for (int j = 0; j < 18; ++j)              // E^T (k E): the same on the rows
+        for (int n = 0; n < 3; ++n) {
+            k[(6 * n + 4) * 18 + j] += o * k[(6 * n) * 18 + j];
+            k[(6 * n + 3) * 18 + j] -= o * k[(6 * n + 1) * 18 + j];
+        }
+}
 
 // in-plane constitutive matrix: plane stress, or plane strain when asked for (membrane part only)
 FERS_HD void plate_D(double E, double nu, bool plane_strain, double D[3][3]) {
@@ -487,6 +513,23 @@ FERS_HD void plate_D(double E, double nu, bool plane_strain, double D[3][3]) {
     D[0][0] = d11; D[0][1] = d12; D[0][2] = 0.0;
     D[1][0] = d12; D[1][1] = d11; D[1][2] = 0.0;
     D[2][0] = 0.0; D[2][1] = 0.0; D[2][2] = d33;
+}
+// membrane (Dm) and bending (Db) in-plane constitutive matrices and the two transverse shear moduli of one plate record
+FERS_HD void plate_constitutive(const double* data, int flags, double Dm[3][3], double Db[3][3], double Gs[2]) {
+    if (data[PD_ORTHO] != 0.0) {
+        const double ex = data[PD_EX], ey = data[PD_EY], nxy = data[PD_NUXY];
+        const double nyx = nxy * ey / ex, den = 1.0 - nxy * nyx;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Dm[i][j] = 0.0;
+        Dm[0][0] = ex / den; Dm[1][1] = ey / den; Dm[0][1] = Dm[1][0] = nxy * ey / den; Dm[2][2] = data[PD_GXY];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Db[i][j] = Dm[i][j];
+        Gs[0] = data[PD_GXZ]; Gs[1] = data[PD_GYZ];
+    } else {
+        plate_D(data[PD_E], data[PD_NU], (flags & 4) != 0, Dm);      // membrane: plane stress or plane strain
+        plate_D(data[PD_E], data[PD_NU], false, Db);                 // bending: plate theory (plane stress)
+        Gs[0] = Gs[1] = data[PD_E] / (2.0 * (1.0 + data[PD_NU]));
+    }
 }
 struct PlateGeom {
     double r[3][3];     // rows = local x, y, z
@@ -569,14 +612,13 @@ FERS_HD void plate_B(const PlateGeom& g, double Bm[3][18], double Bb[3][18], dou
 FERS_HD void plate_local_k(const PlateGeom& g, const double* data, int flags, double* k /*324*/) {
     double Bm[3][18], Bb[3][18], Bs[2][18];
     plate_B(g, Bm, Bb, Bs);
-    double t = data[PD_T], E = data[PD_E], nu = data[PD_NU];
+    double t = data[PD_T], E = data[PD_E];
     double A = fabs(g.A);
-    double Dm[3][3], D[3][3];
-    plate_D(E, nu, (flags & 4) != 0, Dm);
-    plate_D(E, nu, false, D);
+    double Dm[3][3], D[3][3], Gs[2];
+    plate_constitutive(data, flags, Dm, D, Gs);
     double cm = (flags & 1) ? data[PD_MODM] * t * A : 0.0;
     double cb = (flags & 2) ? data[PD_MODB] * A * t * t * t / 12.0 : 0.0;
-    double cs = (flags & 2) ? data[PD_MODS] * A * (5.0 / 6.0) * (E / (2.0 * (1.0 + nu))) * t : 0.0;
+    double cs = (flags & 2) ? data[PD_MODS] * A * (5.0 / 6.0) * t : 0.0;
     for (int i = 0; i < 18; ++i)
         for (int j = 0; j < 18; ++j) {
             double sm = 0.0, sb = 0.0;
@@ -586,11 +628,12 @@ FERS_HD void plate_local_k(const PlateGeom& g, const double* data, int flags, do
                 sm += Bm[a][i] * dmj;
                 sb += Bb[a][i] * dbj;
             }
-            double ss = Bs[0][i] * Bs[0][j] + Bs[1][i] * Bs[1][j];
+            double ss = Gs[0] * Bs[0][i] * Bs[0][j] + Gs[1] * Bs[1][i] * Bs[1][j];
             k[i * 18 + j] = cm * sm + cb * sb + cs * ss;
         }
     double kd = 1e-6 * E * t * A;     // drilling stabilisation
     for (int n = 0; n < 3; ++n) k[(6 * n + 5) * 18 + 6 * n + 5] += kd;
+    plate_offset_k(data[PD_OFFSET], k);
 }
 
 // Global 6x6 block (node bi, node bj) of T^T k T for a plate.

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_plates(int n_plates, in
     if (e >= n_plates) return;
     const int nd[3] = {pn[3 * e], pn[3 * e + 1], pn[3 * e + 2]};
     const double* pd = pdata + NPDATA * (size_t)e;
-    const double t = pd[PD_T], E = pd[PD_E], nu = pd[PD_NU];
+    const double t = pd[PD_T];
     const int flags = pflags[e];
     if (lane == 0) {
         double p0[3] = {xyz[3 * nd[0]], xyz[3 * nd[0] + 1], xyz[3 * nd[0] + 2]};
@@ -320,12 +320,11 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_plates(int n_plates, in
         for (int i = 0; i < 9; ++i) s_r[warp][i] = g.r[i / 3][i % 3];
     }
     __syncwarp();
-    double Dm[3][3], D[3][3];
-    plate_D(E, nu, (flags & 4) != 0, Dm);       // membrane: plane stress or plane strain
-    plate_D(E, nu, false, D);                   // bending: plate theory (plane stress)
+    double Dm[3][3], D[3][3], Gs[2];
+    plate_constitutive(pd, flags, Dm, D, Gs);
     const double cm = (flags & 1) ? pd[PD_MODM] * t : 0.0;
     const double cb = (flags & 2) ? -pd[PD_MODB] * t * t * t / 12.0 : 0.0;
-    const double cs = (flags & 2) ? pd[PD_MODS] * (5.0 / 6.0) * (E / (2.0 * (1.0 + nu))) * t : 0.0;
+    const double cs = (flags & 2) ? pd[PD_MODS] * (5.0 / 6.0) * t : 0.0;
     for (int col = lane; col < nrhs; col += 32) {
         double ug[18], ul[18];
         for (int n = 0; n < 3; ++n)
@@ -334,18 +333,23 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_plates(int n_plates, in
             for (int i = 0; i < 3; ++i)
                 ul[3 * b + i] = s_r[warp][3 * i] * ug[3 * b] + s_r[warp][3 * i + 1] * ug[3 * b + 1] + s_r[warp][3 * i + 2] * ug[3 * b + 2];
         double st[8];
-        for (int i = 0; i < 8; ++i) {
-            double s = 0.0;
-            for (int j = 0; j < 18; ++j) s = fma(s_b[warp][i][j], ul[j], s);
-            st[i] = s;
+        {
+            double um[18];                                  // strains are those of the mid-surface (plate offset)
+            for (int j = 0; j < 18; ++j) um[j] = ul[j];
+            plate_offset_fwd(pd[PD_OFFSET], um);
+            for (int i = 0; i < 8; ++i) {
+                double s = 0.0;
+                for (int j = 0; j < 18; ++j) s = fma(s_b[warp][i][j], um[j], s);
+                st[i] = s;
+            }
         }
         double out[8];
         for (int i = 0; i < 3; ++i) {
             out[i] = cm * (Dm[i][0] * st[0] + Dm[i][1] * st[1] + Dm[i][2] * st[2]);
             out[3 + i] = cb * (D[i][0] * st[3] + D[i][1] * st[4] + D[i][2] * st[5]);
         }
-        out[6] = cs * st[6];
-        out[7] = cs * st[7];
+        out[6] = cs * Gs[0] * st[6];
+        out[7] = cs * Gs[1] * st[7];
         for (int i = 0; i < 8; ++i) p_res[((size_t)e * 8 + i) * nrhs + col] = out[i];
         for (int i = 0; i < 18; ++i) {
             double s = 0.0;

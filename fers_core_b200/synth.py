@@ -111,7 +111,7 @@ def grid_frame(nx: int, nz: int, ny: int, bay: float = 6.0, storey: float = 3.5,
         m_ids=np.arange(1, nm + 1, dtype=np.int64), m_n1=n1.astype(np.int32), m_n2=n2.astype(np.int32),
         m_type=np.zeros(nm, np.int32), m_roll=np.zeros(nm), m_prop=m_prop, m_rel=np.full(nm, -1, np.int32),
         prop=prop, prop_rho_a=np.array([RHO_STEEL * HEB300[0], RHO_STEEL * IPE400[0]]), rel=np.zeros((0, wire.REL_STRIDE)),
-        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 8)),
+        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, wire.NPDATA)),
         p_flags=np.zeros(0, np.int32), load_cases=cases,
         combo_ids=np.arange(1, n_combos + 1, dtype=np.int64),
         combo_names=[f"C{c + 1:02d}" for c in range(n_combos)], combo_factors=factors,
@@ -246,7 +246,7 @@ def portal_frame(bay: float, storey: float, col_sec: int, beam_sec: int, gravity
         m_ids=np.arange(1, nm + 1, dtype=np.int64), m_n1=n1.astype(np.int32), m_n2=n2.astype(np.int32),
         m_type=np.zeros(nm, np.int32), m_roll=np.zeros(nm), m_prop=m_prop, m_rel=np.full(nm, -1, np.int32), prop=prop,
         prop_rho_a=np.array([RHO_STEEL * s[0] for s in BATCH_SECTIONS]), rel=np.zeros((0, wire.REL_STRIDE)),
-        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 8)),
+        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, wire.NPDATA)),
         p_flags=np.zeros(0, np.int32), load_cases=[lc], combo_ids=np.array([1], np.int64), combo_names=["ULS"],
         combo_factors=np.ones((1, 1)), imperfections=imp, member_sets={}, options=opts)
 
@@ -291,7 +291,7 @@ def concat_models(models: list) -> wire.ModelArrays:
         m_ids=np.arange(1, nf * nm + 1, dtype=np.int64), m_n1=cat("m_n1", node_offset=True).astype(np.int32),
         m_n2=cat("m_n2", node_offset=True).astype(np.int32), m_type=cat("m_type"), m_roll=cat("m_roll"),
         m_prop=cat("m_prop"), m_rel=cat("m_rel"), prop=m0.prop.copy(), prop_rho_a=m0.prop_rho_a.copy(), rel=m0.rel.copy(),
-        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 8)),
+        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, wire.NPDATA)),
         p_flags=np.zeros(0, np.int32), load_cases=cases, combo_ids=m0.combo_ids.copy(), combo_names=list(m0.combo_names),
         combo_factors=m0.combo_factors.copy(), imperfections=list(m0.imperfections), member_sets={}, options=m0.options)
 

@@ -37,8 +37,11 @@ _SUPPORT_FORCE = {"Fx": 0, "Fy": 1, "Fz": 2, "Mx": 3, "My": 4, "Mz": 5}      # S
 # columns of the per-section property table (one row per distinct section x option set)
 P_EA, P_EIY, P_EIZ, P_GJ, P_GASY, P_GASZ, P_WPL, P_SPARE = range(8)
 NPROP = 8
-NPDATA = 8          # doubles per plate record (csrc/fers_elem.cuh PD_*)
+NPDATA = 16         # doubles per plate record (csrc/fers_elem.cuh PD_*)
 PD_THETA = 6        # in-plane angle of local x from the default plate frame (local_x_direction), radians
+PD_ORTHO = 7        # != 0: orthotropic plate material in slots 8..13 (E_x, E_y, G_xy, nu_xy, G_xz, G_yz)
+PD_EX, PD_EY, PD_GXY, PD_NUXY, PD_GXZ, PD_GYZ = 8, 9, 10, 11, 12, 13
+PD_OFFSET = 14      # distance of the mid-surface from the nodes along the local plate normal (PlateElement.offset)
 # local release order = local DOF order [u v w rx ry rz]
 _HINGE_FIELDS = (
     "translational_release_vx", "translational_release_vy", "translational_release_vz",
@@ -701,11 +704,25 @@ def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:
             # ("currently unreliable", tests/nafems/reference_examples.py:16-18) is not implemented
             warnings.append(("W_PLATE_THEORY_IGNORED", f"plate {p['id']}: theory=Kirchhoff solved with the Mindlin (DSG3) "
                              "element"))
-        if p.get("offset"):
-            warnings.append(("W_PLATE_OFFSET_IGNORED", f"plate {p['id']}: offset not modelled"))
+        offset = float(p.get("offset") or 0.0)
+        if not np.isfinite(offset):
+            raise WireError(f"plate {p['id']}: offset must be a number")
         lx_dir = _vec3(p["local_x_direction"], "plate.local_x_direction") if p.get("local_x_direction") else None
-        if mat.get("orthotropic_plate"):
-            warnings.append(("W_ORTHOTROPIC_IGNORED", f"plate {p['id']}: orthotropic plate material treated as isotropic"))
+        ortho = [0.0] * 7
+        op = mat.get("orthotropic_plate")
+        if op:
+            # OrthotropicPlateMaterial (pydantic_models.py:663-681): E_x, E_y along the plate's local x / y, G_xy, nu_xy
+            # ("nu_yx is derived from e_x nu_yx = e_y nu_xy"); the transverse shear moduli of the Mindlin part default
+            # to G_xy when omitted (the engine that defines the default is closed: stated)
+            ex, ey, gxy, nxy = (float(op[k]) for k in ("e_x", "e_y", "g_xy", "nu_xy"))
+            gxz = float(op["g_xz"]) if op.get("g_xz") is not None else gxy
+            gyz = float(op["g_yz"]) if op.get("g_yz") is not None else gxy
+            if not (np.isfinite([ex, ey, gxy, nxy, gxz, gyz]).all() and min(ex, ey, gxy, gxz, gyz) > 0.0 and nxy * nxy * ey / ex < 1.0):
+                raise WireError(f"plate {p['id']}: orthotropic plate material needs positive moduli and nu_xy^2 e_y / e_x < 1")
+            ortho = [1.0, ex, ey, gxy, nxy, gxz, gyz]
+            if flags & 4:
+                warnings.append(("W_ORTHOTROPIC_PLANE_STRAIN", f"plate {p['id']}: plane strain with an orthotropic plate material "
+                                 "needs out-of-plane constants the schema does not carry; the plane-stress law is used"))
         tris = [nids] if len(nids) == 3 else [[nids[0], nids[1], nids[2]], [nids[0], nids[2], nids[3]]]
         if len(nids) == 4:
             warnings.append(("W_QUAD_SPLIT", f"plate {p['id']}: QUAD4 split into two TRI3"))
@@ -722,7 +739,7 @@ def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:
                     theta = 0.0
                     warnings.append(("W_PLATE_LOCAL_X_NORMAL", f"plate {p['id']}: local_x_direction is normal to the "
                                      "plate (or zero); default local axes kept"))
-            p_data_l.append([float(p["thickness"]), E, nu, mods[0], mods[1], mods[2], theta, 0.0])
+            p_data_l.append([float(p["thickness"]), E, nu, mods[0], mods[1], mods[2], theta] + ortho + [offset, 0.0])
             p_flags_l.append(flags)
     p_ids = np.array(p_ids_l, np.int64)
     p_nodes = np.array(p_nodes_l, np.int32).reshape(len(p_ids_l), 3)

@@ -295,8 +295,24 @@ def plate_frame(x3, theta=0.0):
     return np.stack([ex, ey, ez])
 
 
-def plate_local_matrices(xl, t, E, nu, flags, mods=(1.0, 1.0, 1.0)):
+def plate_offset_matrix(offset: float) -> np.ndarray:
+    """E with u_mid = E u_node for a plate whose mid-surface sits `offset` above its nodes along the local normal
+    (PlateElement.offset, pydantic_models.py:1711-1714): a point at height z of a rotating normal moves by theta x (0,0,z),
+    i.e. (+z ry, -z rx, 0) in local axes."""
+    E = np.eye(18)
+    for n in range(3):
+        arm = np.array([0.0, 0.0, offset])
+        for c in range(3):                                   # unit rotation about local axis c at node n
+            rot = np.zeros(3); rot[c] = 1.0
+            E[6 * n:6 * n + 3, 6 * n + 3 + c] = np.cross(rot, arm)
+    return E
+
+
+def plate_local_matrices(xl, t, E, nu, flags, mods=(1.0, 1.0, 1.0), ortho=None):
     """18x18 local stiffness of a TRI3 shell, plus (Bm, Bb, Bs, Dm, Db, Ds, area).
+
+    ortho = (E_x, E_y, G_xy, nu_xy, G_xz, G_yz): OrthotropicPlateMaterial (pydantic_models.py:663-681), material axes =
+    local x, y; the compliance form is inverted here (the CUDA path writes the stiffness form out).
 
     Local DOFs per node [u v w rx ry rz]; DSG3 uses (w, bx, by) with bx = +ry, by = -rx
     (SURVEY.md B.3 note).  Drilling rz gets a small stabilising stiffness.
@@ -319,6 +335,12 @@ def plate_local_matrices(xl, t, E, nu, flags, mods=(1.0, 1.0, 1.0)):
         Dm = E / ((1 + nu) * (1 - 2 * nu)) * np.array([[1 - nu, nu, 0], [nu, 1 - nu, 0], [0, 0, (1 - 2 * nu) / 2]])
     else:
         Dm = E / (1.0 - nu * nu) * np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]])
+    D_ortho = None
+    if ortho is not None:
+        ex, ey, gxy, nxy, gxz, gyz = ortho
+        compliance = np.array([[1.0 / ex, -nxy / ex, 0.0], [-nxy / ex, 1.0 / ey, 0.0], [0.0, 0.0, 1.0 / gxy]])   # eps = C sigma
+        D_ortho = np.linalg.inv(compliance)
+        Dm = D_ortho.copy()
     Dm = mods[0] * Dm                                  # PlateElement.stiffness_modifiers (801-807)
     mdof = np.array([0, 1, 6, 7, 12, 13])
     if flags & 1:
@@ -333,6 +355,9 @@ def plate_local_matrices(xl, t, E, nu, flags, mods=(1.0, 1.0, 1.0)):
     Db = mods[1] * E * t**3 / (12.0 * (1.0 - nu * nu)) * np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]])
     G = E / (2.0 * (1.0 + nu))
     Ds = mods[2] * (5.0 / 6.0) * G * t * np.eye(2)
+    if ortho is not None:
+        Db = mods[1] * t**3 / 12.0 * D_ortho
+        Ds = mods[2] * (5.0 / 6.0) * t * np.diag([ortho[4], ortho[5]])
     if flags & 2:
         kb = abs(A) * (Bb.T @ Db @ Bb + Bs.T @ Ds @ Bs)
         # map (w, bx, by) -> (w, rx, ry): bx = ry, by = -rx
@@ -357,7 +382,12 @@ def plate_stiffness_global(model, xyz):
         R = plate_frame(x3, float(model.p_data[e, wire.PD_THETA]))
         xl = (x3 - x3[0]) @ R.T
         t, E, nu = model.p_data[e, :3]
-        k, mats = plate_local_matrices(xl[:, :2], t, E, nu, int(model.p_flags[e]), tuple(model.p_data[e, 3:6]))
+        ortho = tuple(model.p_data[e, 8:14]) if model.p_data.shape[1] > 8 and model.p_data[e, 7] != 0.0 else None
+        k, mats = plate_local_matrices(xl[:, :2], t, E, nu, int(model.p_flags[e]), tuple(model.p_data[e, 3:6]), ortho)
+        off = float(model.p_data[e, 14]) if model.p_data.shape[1] > 14 else 0.0
+        if off != 0.0:                                       # nodes on the reference surface, element on the mid-surface
+            Eo = plate_offset_matrix(off)
+            k = Eo.T @ k @ Eo
         T = np.zeros((18, 18))
         for b in range(6):
             T[3 * b:3 * b + 3, 3 * b:3 * b + 3] = R
@@ -805,6 +835,9 @@ def recover_plates(asm: Assembly, U):
         for r in range(nrhs):
             ug = U[r, ed]
             ul = T @ ug
+            off = float(model.p_data[e, 14]) if model.p_data.shape[1] > 14 else 0.0
+            ue = plate_offset_matrix(off) @ ul if off != 0.0 else ul      # mid-surface displacements
+            ul_nodes, ul = ul, ue
             um = ul[[0, 1, 6, 7, 12, 13]]
             ub = np.zeros(9)
             for n in range(3):
@@ -816,7 +849,7 @@ def recover_plates(asm: Assembly, U):
             res[r, e] = np.concatenate([Nm_, Mb, Qs])
             nod[r, e] = (kge @ ug).reshape(3, 6)
             cdg[r, e] = ug.reshape(3, 6).mean(0)
-            cdl[r, e] = ul.reshape(3, 6).mean(0)
+            cdl[r, e] = ul_nodes.reshape(3, 6).mean(0)
     return dict(p_res=res, p_nodal=nod, p_cdg=cdg, p_cdl=cdl, p_centroid=cen)
 
 

@@ -101,7 +101,7 @@ def test_beam_equivalent_loads_and_span(elem_host, case):
         bc_k=np.zeros((2, 6)), m_ids=np.array([1]), m_n1=np.array([0], np.int32), m_n2=np.array([1], np.int32),
         m_type=np.array([mtype], np.int32), m_roll=np.array([roll]), m_prop=np.array([0], np.int32),
         m_rel=np.array([-1], np.int32), prop=P[None, :].copy(), prop_rho_a=np.zeros(1), rel=np.zeros((0, wire.REL_STRIDE)),
-        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, 8)),
+        p_ids=np.zeros(0, np.int64), p_nodes=np.zeros((0, 3), np.int32), p_data=np.zeros((0, wire.NPDATA)),
         p_flags=np.zeros(0, np.int32), load_cases=[], combo_ids=np.zeros(0, np.int64), combo_names=[],
         combo_factors=np.zeros((0, 0)), imperfections=[], member_sets={}, options=wire.Options())
     lc = wire.LoadCaseArrays(id=1, name="x")
@@ -130,13 +130,26 @@ def test_plate_global_stiffness(elem_host):
         if t == 4:
             p[:, 0] = 1.0           # normal along X: alternate reference branch
         # plate record: thickness, E, nu, stiffness modifiers (membrane, bending, shear), 2 spare
-        data = np.array([0.02, 210e9, 0.3, 1.0, 1.0, 1.0, 0.0, 0.0])
+        data = np.zeros(wire.NPDATA)
+        data[:7] = (0.02, 210e9, 0.3, 1.0, 1.0, 1.0, 0.0)
         if t % 3 == 1:
             data[3:6] = (0.35, 0.6, 1.7)
+        ortho = None
+        if t % 4 == 2:              # orthotropic plate material: E_x, E_y, G_xy, nu_xy, G_xz, G_yz
+            ortho = (11.0e9, 0.7e9, 0.65e9, 0.35, 0.6e9, 0.05e9)
+            data[wire.PD_ORTHO] = 1.0
+            data[wire.PD_EX:wire.PD_GYZ + 1] = ortho
+        if t % 5 == 3:
+            data[wire.PD_OFFSET] = 0.07 * (-1) ** t          # mid-surface off the nodes
         for flags in (1, 2, 3, 5, 7):           # bit2 = plane strain
+            if ortho is not None and flags & 4:
+                continue                        # orthotropic: plane-stress law only (wire warns)
             R = fo.plate_frame(p)
             xl = (p - p[0]) @ R.T
-            k, _ = fo.plate_local_matrices(xl[:, :2], data[0], data[1], data[2], flags, tuple(data[3:6]))
+            k, _ = fo.plate_local_matrices(xl[:, :2], data[0], data[1], data[2], flags, tuple(data[3:6]), ortho)
+            if data[wire.PD_OFFSET] != 0.0:
+                Eo = fo.plate_offset_matrix(data[wire.PD_OFFSET])
+                k = Eo.T @ k @ Eo
             T = np.zeros((18, 18))
             for bq in range(6):
                 T[3 * bq:3 * bq + 3, 3 * bq:3 * bq + 3] = R

@@ -1,6 +1,6 @@
 """Summarise the raw page of an `ncu --set full` capture of the k_oz_syrk launches of one factorisation
 (ncu -i X.ncu-rep --page raw --csv > raw.csv) into the capture summary bench.py reads for roofline.traffic:
-python tools/oz_ncu_raw_summary.py raw.csv "<ncu command>" <commit> [launches per factorisation in bench.py] > profiles/rNN_oz_syrk_ncu_summary.json"""
+python tools/oz_ncu_raw_summary.py raw.csv "<ncu command>" <commit> "<note>" > profiles/rNN_oz_syrk_ncu_summary.json"""
 import csv
 import json
 import sys
@@ -25,9 +25,11 @@ def val(r, name):
 
 
 launches = []
+kernels = set()
 for r in data:
     if "k_oz_syrk" not in r[col("Kernel Name")]:
         continue
+    kernels.add(r[col("Kernel Name")].split("(")[0])
     ms = val(r, "gpu__time_duration.sum")
     l2sm = val(r, "l1tex__m_xbar2l1tex_read_bytes.sum")
     launches.append({
@@ -40,15 +42,15 @@ for r in data:
         "sm_throughput_pct": val(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed")})
 tot = sum(x["dram_read_GB"] + x["dram_write_GB"] for x in launches) * 1e9
 ms = sum(x["ms"] for x in launches)
+note = sys.argv[4] if len(sys.argv) > 4 else ""
+name = launches_kernel = "k_oz_syrk"
 print(json.dumps({
-    "kernel": "k_oz_syrk<7> (tcgen05.mma kind::i8 Schur updates of tree levels 9-11 of one factorisation of configs[3])",
+    "kernel": "int8 Schur / panel-group updates (tcgen05.mma kind::i8) of one factorisation of configs[3]: " + ", ".join(sorted(kernels)),
     "commands": [sys.argv[2]],
-    "note": "one launch per front; the fronts of level 8 (16 launches of 1-3 ms in bench.py's factorisation, "
-            + (sys.argv[4] if len(sys.argv) > 4 else "30") + " launches in all) are not in this capture (tools/factor_once.py "
-            "keeps them on the DMMA path), so dram_bytes_per_launch is the average over the 14 large fronts.  Tensor pipe 27-43 % "
-            "active with the shared-memory data banks at 26-33 % (reads) / 7-8 % (writes) and L2 -> SM at 4.5-5.7 TB/s: neither DRAM "
-            "(0.4-0.6 TB/s, L2 hit 85-92 %) nor shared-memory bandwidth is near its limit",
+    "note": note,
     "launches_per_factorisation": len(launches), "dram_bytes_total": tot, "dram_bytes_per_launch": tot / max(len(launches), 1),
     "duration_ms_total": ms, "dram_GBps_average": tot / 1e9 / (ms * 1e-3) if ms else None,
+    "tensor_pipe_active_pct_time_weighted": sum(x["tensor_pipe_active_pct"] * x["ms"] for x in launches) / ms if ms else None,
+    "l2_to_sm_TBps_time_weighted": sum(x["l2_to_sm_TBps"] * x["ms"] for x in launches) / ms if ms else None,
     "captured_config": {"dof": 692106, "nrhs": 64, "frame": [60, 60, 30], "kernel_id": "k_oz_syrk<S=7>", "commit": sys.argv[3] if len(sys.argv) > 3 else ""},
     "launches": launches}, indent=1))
