@@ -133,4 +133,8 @@ def test_host_pattern_equals_the_device_pattern(name):
     f_case, _ = ref.load_cases(ref.d_xyz0)
     ref.assemble(ref.d_xyz0)
     u_inline = ref.solve(ref.combine(f_case, fac, 8)).cpu().numpy()
-    assert "chol_plan_thread_ms" not in ref.timings and np.array_equal(u_thread, u_inline)
+    assert "chol_plan_thread_ms" not in ref.timings
+    if m.n_plates:      # plate stiffness and plate pressures are summed with atomics: equal to round-off, not bit for bit
+        assert np.abs(u_thread - u_inline).max() <= 1e-11 * np.abs(u_inline).max(), np.abs(u_thread - u_inline).max() / np.abs(u_inline).max()
+    else:
+        assert np.array_equal(u_thread, u_inline), np.abs(u_thread - u_inline).max() / np.abs(u_inline).max()

@@ -17,7 +17,7 @@ ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Met
 marks = [i for i, r in enumerate(rows) if "k_chol_scale" in r[ik]]
 if len(marks) < 2:
     sys.exit("need two k_chol_scale launches (two passes) in the list")
-seg = rows[marks[-2]:marks[-1]]
+seg = [r for r in rows[marks[-2]:marks[-1]] if "k_peak_" not in r[ik]]      # the live fp64-peak measurement is not part of a pass
 scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0}
 agg = collections.defaultdict(lambda: [0, 0.0])
 for r in seg:

@@ -21,7 +21,10 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "
 
 def val(r, name):
     i = col(name)
-    return float(r[i].replace(",", "")) * SCALE.get(units[i].strip(), 1.0) if r[i] else None
+    try:
+        return float(r[i].replace(",", "")) * SCALE.get(units[i].strip(), 1.0) if r[i] else None
+    except ValueError:              # "no data" for a counter ncu could not collect on that launch
+        return None
 
 
 launches = []
@@ -50,7 +53,8 @@ print(json.dumps({
     "note": note,
     "launches_per_factorisation": len(launches), "dram_bytes_total": tot, "dram_bytes_per_launch": tot / max(len(launches), 1),
     "duration_ms_total": ms, "dram_GBps_average": tot / 1e9 / (ms * 1e-3) if ms else None,
-    "tensor_pipe_active_pct_time_weighted": sum(x["tensor_pipe_active_pct"] * x["ms"] for x in launches) / ms if ms else None,
+    "tensor_pipe_active_pct_time_weighted": (sum(x["tensor_pipe_active_pct"] * x["ms"] for x in launches if x["tensor_pipe_active_pct"] is not None)
+                                             / max(sum(x["ms"] for x in launches if x["tensor_pipe_active_pct"] is not None), 1e-30)),
     "l2_to_sm_TBps_time_weighted": sum(x["l2_to_sm_TBps"] * x["ms"] for x in launches) / ms if ms else None,
     "captured_config": {"dof": 692106, "nrhs": 64, "frame": [60, 60, 30], "kernel_id": "k_oz_syrk<S=7>", "commit": sys.argv[3] if len(sys.argv) > 3 else ""},
     "launches": launches}, indent=1))
