@@ -542,6 +542,17 @@ k_oz_syrk_wide(OzFront f, int n_tiles) {
             const int c0 = bj * OZW_N + 64 * half;
             const double rs = f.rowscale[min(r, f.m2_pad - 1)];
             const uint32_t lane_addr = tmem + ((uint32_t)(32 * quad) << 16) + (uint32_t)(64 * half);
+            // the C tile is read-modify-written from DRAM (a front's F22 is gigabytes): ask for it in L2 now, while the
+            // products of this tile run, so that the epilogue -- which the next pass waits for -- finds it there.  A warp's
+            // 32 rows of one column are one 256-byte run: every fourth lane asks for its 32-byte sector.
+            if (r < f.m2 && (lane & 3) == 0) {
+#pragma unroll 4
+                for (int j = 0; j < 64; ++j) {
+                    const int col = c0 + j;
+                    if (col <= r + 3 && col < f.ncols)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(f.C + (size_t)col * f.ldc + r));
+                }
+            }
             for (int pass = 0; pass < NPASS; ++pass, ++acc_i) {
                 const bool low = (NPASS == 2 && pass == 0);
                 oz_mbar_wait(bar_acc_full, acc_i & 1u);
