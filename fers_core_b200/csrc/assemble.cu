@@ -488,11 +488,14 @@ __device__ __forceinline__ void gp_entry(int R, int C, int& idx_dg, int& idx_off
 __device__ __forceinline__ double gp_flip(double v, unsigned mask) {
     return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
 }
+// rolled members are rare: the double-precision sin / cos (whose slow path owns a stack frame) stays out of line
+__device__ __noinline__ double2 gp_cos_sin(double roll) { return make_double2(cos(roll), sin(roll)); }
 __device__ __forceinline__ void st_global_v2(double* p, double a, double b) {
     asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
-__global__ void __launch_bounds__(GP_THREADS, 6) k_assemble_gather_plain(GatherArgs G) {
+template <int MINB>
+__global__ void __launch_bounds__(GP_THREADS, MINB) k_assemble_gather_plain(GatherArgs G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const BeamArgs& A = G.B;
     double* s_val = reinterpret_cast<double*>(smem_raw);                 // [GP_THREADS][GP_VALS]
@@ -520,9 +523,12 @@ __global__ void __launch_bounds__(GP_THREADS, 6) k_assemble_gather_plain(GatherA
     bool prop_ready = !A.use_tma;
 
     const int g = tid / GP_LANES, pr = tid - GP_LANES * g;
-    double acc[GP_QS][2];
-#pragma unroll
-    for (int k = 0; k < GP_QS; ++k) acc[k][0] = acc[k][1] = 0.0;
+    // diagonal sums: written straight out when the CTA's half-members fit one chunk (always, on frames with up to six members
+    // per node); carried from chunk to chunk in shared memory otherwise -- no accumulator lives across the register-heavy phase A
+    __shared__ double s_acc[GP_NODES * 36];
+    const bool one_chunk = h_end - h_begin <= GP_THREADS;
+    if (!one_chunk)
+        for (int i = tid; i < GP_NODES * 36; i += GP_THREADS) s_acc[i] = 0.0;
 
     for (int chunk0 = h_begin; chunk0 < h_end; chunk0 += GP_THREADS) {
         const int h = chunk0 + tid;
@@ -550,10 +556,10 @@ __global__ void __launch_bounds__(GP_THREADS, 6) k_assemble_gather_plain(GatherA
                 const double yn = rsqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
                 y[0] *= yn; y[1] *= yn; y[2] *= yn;
                 if (roll != 0.0) {
-                    const double cr = cos(roll), sn = sin(roll);
+                    const double2 cs = gp_cos_sin(roll);
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
-                        const double ny = cr * y[i] + sn * z[i], nz = -sn * y[i] + cr * z[i];
+                        const double ny = cs.x * y[i] + cs.y * z[i], nz = -cs.y * y[i] + cs.x * z[i];
                         y[i] = ny; z[i] = nz;
                     }
                 }
@@ -615,21 +621,27 @@ __global__ void __launch_bounds__(GP_THREADS, 6) k_assemble_gather_plain(GatherA
             const int nl = g + GP_GROUPS * k;
             if (nl < nn) {
                 const int lo = max(s_hp[nl], chunk0) - chunk0, hi = min(s_hp[nl + 1], chunk0 + GP_THREADS) - chunk0;
+                double a0 = one_chunk ? 0.0 : s_acc[nl * 36 + 2 * pr], a1 = one_chunk ? 0.0 : s_acc[nl * 36 + 2 * pr + 1];
                 for (int i = lo; i < hi; ++i) {
                     const unsigned ee = (s_meta[i] & 1) ? 4u : 0u;   // K_ee for an end end, K_ss (no sign) for a start end
                     const double* v = s_val + i * GP_VALS;
-                    acc[k][0] += gp_flip(v[idg0], (sg0 & ee) ? 0x80000000u : 0u);
-                    acc[k][1] += gp_flip(v[idg1], (sg1 & ee) ? 0x80000000u : 0u);
+                    a0 += gp_flip(v[idg0], (sg0 & ee) ? 0x80000000u : 0u);
+                    a1 += gp_flip(v[idg1], (sg1 & ee) ? 0x80000000u : 0u);
                 }
+                if (one_chunk || chunk0 + GP_THREADS >= h_end)        // the node's list is complete
+                    st_global_v2(A.vals + (size_t)G.diag_slot[node_a + nl] * 36 + 2 * pr, a0, a1);
+                else { s_acc[nl * 36 + 2 * pr] = a0; s_acc[nl * 36 + 2 * pr + 1] = a1; }
             }
         }
         __syncthreads();
     }
     if (!prop_ready) mbar_wait(s_bar, 0);     // never leave the CTA with a bulk copy in flight
+    if (h_begin >= h_end) {                   // nodes without members: zero diagonal blocks
 #pragma unroll
-    for (int k = 0; k < GP_QS; ++k) {
-        const int nl = g + GP_GROUPS * k;
-        if (nl < nn) st_global_v2(A.vals + (size_t)G.diag_slot[node_a + nl] * 36 + 2 * pr, acc[k][0], acc[k][1]);
+        for (int k = 0; k < GP_QS; ++k) {
+            const int nl = g + GP_GROUPS * k;
+            if (nl < nn) st_global_v2(A.vals + (size_t)G.diag_slot[node_a + nl] * 36 + 2 * pr, 0.0, 0.0);
+        }
     }
 }
 
@@ -844,7 +856,9 @@ int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xy
         FERS_CK(cudaFuncSetAttribute(k_assemble_gather<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         FERS_CK(cudaFuncSetAttribute(k_assemble_gather<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         FERS_CK(cudaFuncSetAttribute(k_assemble_gather<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        FERS_CK(cudaFuncSetAttribute(k_assemble_gather_plain, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        FERS_CK(cudaFuncSetAttribute(k_assemble_gather_plain<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)GP_THREADS * GP_VALS * 8 + MAX_PROP_SMEM_ROWS * NPROP * 8 + 16)));
+        FERS_CK(cudaFuncSetAttribute(k_assemble_gather_plain<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((size_t)GP_THREADS * GP_VALS * 8 + MAX_PROP_SMEM_ROWS * NPROP * 8 + 16)));
         attr_set.done();
     }
@@ -860,7 +874,11 @@ int fers_b200_assemble_beams_gather(int n_nodes, int n_members, const double* xy
     const bool general = (m_rel != nullptr) || (m_axial != nullptr && kg_mode != 0);
     if (!general && !cached && g_gather_kernel == 0 && n_members > 0) {
         const size_t smem_p = (size_t)GP_THREADS * GP_VALS * sizeof(double) + prop_smem + 16;
-        k_assemble_gather_plain<<<(n_nodes + GP_NODES - 1) / GP_NODES, GP_THREADS, smem_p, as_stream(stream)>>>(G);
+        // 5 CTAs per SM at 72 registers beat 6 at 64 (73 against 79 us at configs[3]: the spills of the tighter budget go
+        // through local memory, which misses L1 under this kernel's shared-memory carve-out); FERS_GATHER_MINB=6 for the other
+        static const int minb = getenv("FERS_GATHER_MINB") ? atoi(getenv("FERS_GATHER_MINB")) : 5;
+        if (minb == 5) k_assemble_gather_plain<5><<<(n_nodes + GP_NODES - 1) / GP_NODES, GP_THREADS, smem_p, as_stream(stream)>>>(G);
+        else k_assemble_gather_plain<6><<<(n_nodes + GP_NODES - 1) / GP_NODES, GP_THREADS, smem_p, as_stream(stream)>>>(G);
     } else if (cached) {
         if (general) k_assemble_gather<true, true><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
         else k_assemble_gather<false, true><<<grid, GA_THREADS, smem, as_stream(stream)>>>(G);
