@@ -184,6 +184,35 @@ class CholSolver:
         return dict(zip(keys, out[:]))
 
 
+def tree_owner(k: int, d: int, j: int) -> int:
+    """Rank that owns the upper front (depth d, index j) of a 2^k-rank tree: the leftmost rank below it."""
+    return j << (k - d)
+
+
+def tree_schedule(k: int, ls: int, top: list) -> dict:
+    """The order of work and messages of the tree-parallel solve, the same on every rank (a rank skips the messages it is not
+    part of; level calls on levels where it owns nothing are empty).  ``top[d][j]`` = front id of the upper front (d, j).
+    Steps: ("levels" | "fwd" | "bwd", first level, one past last level); ("schur" | "w", front, depth, src, dst): the Schur
+    complement / the front-local right-hand side of a right child to the owner of its parent; ("anc", [fronts], src, dst): the
+    solution rows of an upper front and of its ancestors to the owner of its right child; ("gather",): every rank's own rows
+    to everyone; ("unpermute",)."""
+    factor, solve = [("levels", 0, ls - k + 1)], [("fwd", 0, ls - k + 1)]
+    for d in range(k - 1, -1, -1):
+        for j in range(1 << d):
+            fid, src, dst = top[d + 1][2 * j + 1], tree_owner(k, d + 1, 2 * j + 1), tree_owner(k, d, j)
+            factor.append(("schur", fid, d + 1, src, dst))
+            solve.append(("w", fid, d + 1, src, dst))
+        factor.append(("levels", ls - d, ls - d + 1))
+        solve.append(("fwd", ls - d, ls - d + 1))
+    for d in range(k):
+        solve.append(("bwd", ls - d, ls - d + 1))
+        for j in range(1 << d):
+            chain = [top[dd][j >> (d - dd)] for dd in range(d, -1, -1)]
+            solve.append(("anc", chain, tree_owner(k, d, j), tree_owner(k, d + 1, 2 * j + 1)))
+    solve += [("bwd", 0, ls - k + 1), ("gather",), ("unpermute",)]
+    return {"factor": factor, "solve": solve}
+
+
 class TreeParallelSolver(CholSolver):
     """The sparse direct solve of ONE model on 2^k GPUs (strong scaling; SURVEY.md 8e only asks for sharding by
     combinations -- the reference describes a single shared factorisation, pydantic_models.py:1216-1219).
@@ -236,7 +265,7 @@ class TreeParallelSolver(CholSolver):
         self.link_bytes = {"factor": 0, "solve": 0}
 
     def owner(self, d: int, j: int) -> int:
-        return j << (self.k - d)
+        return tree_owner(self.k, d, j)
 
     def _schur(self, fid: int, depth: int):
         """The Schur complement of front `fid` (tree depth `depth`) inside the work buffer, as a flat tensor."""
@@ -244,29 +273,23 @@ class TreeParallelSolver(CholSolver):
         off = (self._sd0 if ((self.ls - depth) & 1) else 0) + int(self._f[fid]["schur_off"])
         return self.wk[off: off + m2 * m2]
 
-    def _merge_pairs(self, d: int):
-        """(front of the right child, its owner, owner of the parent) for the upper fronts of depth d."""
-        return [(self.top[d + 1][2 * j + 1], self.owner(d + 1, 2 * j + 1), self.owner(d, j)) for j in range(1 << d)]
-
     def factorize(self, d_vals, d_diag_slot, d_fixed, d_kspring=None, check: bool = True) -> int:
         ks = None if d_kspring is None else d_kspring.data_ptr()
-
-        def levels(lo, hi):
-            _lib.check(self.lib.fers_b200_chol_factor_levels(
-                self.plan.handle, self.index.data_ptr(), d_vals.data_ptr(), d_diag_slot.data_ptr(), d_fixed.data_ptr(), ks,
-                self.factor.data_ptr(), self.work.data_ptr(), self.work_bytes, self.info_dev.data_ptr(), lo, hi, self.stream),
-                "chol_factor_levels")
-        levels(0, self.ls - self.k + 1)
         sent = 0
-        for d in range(self.k - 1, -1, -1):
-            for fid, src, dst in self._merge_pairs(d):
+        for step in tree_schedule(self.k, self.ls, self.top)["factor"]:
+            if step[0] == "levels":
+                _lib.check(self.lib.fers_b200_chol_factor_levels(
+                    self.plan.handle, self.index.data_ptr(), d_vals.data_ptr(), d_diag_slot.data_ptr(), d_fixed.data_ptr(), ks,
+                    self.factor.data_ptr(), self.work.data_ptr(), self.work_bytes, self.info_dev.data_ptr(), step[1], step[2],
+                    self.stream), "chol_factor_levels")
+            else:
+                _, fid, depth, src, dst = step
                 if self.rank == src:
-                    t = self._schur(fid, d + 1)
+                    t = self._schur(fid, depth)
                     self.dist.send(t, dst, group=self.group)
                     sent += 8 * t.numel()
                 elif self.rank == dst:
-                    self.dist.recv(self._schur(fid, d + 1), src, group=self.group)
-            levels(self.ls - d, self.ls - d + 1)
+                    self.dist.recv(self._schur(fid, depth), src, group=self.group)
         self.link_bytes["factor"] = sent
         self.factored = True
         if not check:
@@ -292,23 +315,25 @@ class TreeParallelSolver(CholSolver):
         def w_block(fid):                                                   # front-local right-hand side rows of a front
             f = self._f[fid]
             return self.wk[int(f["rhs_off"]) * nrhs: (int(f["rhs_off"]) + 6 * int(f["n1"] + f["n2"])) * nrhs]
-        k, ls, sent = self.k, self.ls, 0
-        phase(1, 0, ls - k + 1)
-        for d in range(k - 1, -1, -1):                                      # forward: boundary right-hand sides up the tree
-            for fid, src, dst in self._merge_pairs(d):
+        sent = 0
+        for step in tree_schedule(self.k, self.ls, self.top)["solve"]:
+            kind = step[0]
+            if kind == "fwd":
+                phase(1, step[1], step[2])
+            elif kind == "bwd":
+                phase(2, step[1], step[2])
+            elif kind == "w":                                               # boundary right-hand sides up the tree
+                _, fid, _depth, src, dst = step
                 if self.rank == src:
                     self.dist.send(w_block(fid), dst, group=self.group)
                     sent += 8 * w_block(fid).numel()
                 elif self.rank == dst:
                     self.dist.recv(w_block(fid), src, group=self.group)
-            phase(1, ls - d, ls - d + 1)
-        for d in range(k):                                                  # backward: the ancestors' solution down the tree
-            phase(2, ls - d, ls - d + 1)
-            for j in range(1 << d):
-                src, dst = self.owner(d, j), self.owner(d + 1, 2 * j + 1)
+            elif kind == "anc":                                             # the ancestors' solution down the tree
+                _, chain_fronts, src, dst = step
                 if self.rank not in (src, dst):
                     continue
-                chain = [self._own(self.top[dd][j >> (d - dd)]) for dd in range(d, -1, -1)]     # this front and its ancestors
+                chain = [self._own(fid) for fid in chain_fronts]
                 if self.rank == src:
                     buf = torch.cat([rows(a, b) for a, b in chain])
                     self.dist.send(buf, dst, group=self.group)
@@ -320,22 +345,23 @@ class TreeParallelSolver(CholSolver):
                     for a, b in chain:
                         n = 6 * (b - a) * nrhs
                         rows(a, b).copy_(buf[o: o + n]); o += n
-        phase(2, 0, ls - k + 1)
-        # every rank gets the rows the others own: one all_gather of equally padded blocks
-        width = max(sum(6 * (b - a) for a, b in rng) for rng in self.owned) * nrhs
-        mine = torch.zeros(width, dtype=torch.float64, device=self.wk.device)
-        o = 0
-        for a, b in self.owned[self.rank]:
-            n = 6 * (b - a) * nrhs
-            mine[o: o + n] = rows(a, b); o += n
-        allb = torch.empty(self.world * width, dtype=torch.float64, device=self.wk.device)
-        self.dist.all_gather_into_tensor(allb, mine, group=self.group)
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            o = r * width
-            for a, b in self.owned[r]:
-                n = 6 * (b - a) * nrhs
-                rows(a, b).copy_(allb[o: o + n]); o += n
-        phase(4, 0, ls + 1)
-        self.link_bytes["solve"] = sent + 8 * (self.world - 1) * width
+            elif kind == "gather":                                          # one all_gather of equally padded blocks
+                width = max(sum(6 * (b - a) for a, b in rng) for rng in self.owned) * nrhs
+                mine = torch.zeros(width, dtype=torch.float64, device=self.wk.device)
+                o = 0
+                for a, b in self.owned[self.rank]:
+                    n = 6 * (b - a) * nrhs
+                    mine[o: o + n] = rows(a, b); o += n
+                allb = torch.empty(self.world * width, dtype=torch.float64, device=self.wk.device)
+                self.dist.all_gather_into_tensor(allb, mine, group=self.group)
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    o = r * width
+                    for a, b in self.owned[r]:
+                        n = 6 * (b - a) * nrhs
+                        rows(a, b).copy_(allb[o: o + n]); o += n
+                sent += 8 * (self.world - 1) * width
+            else:
+                phase(4, 0, self.ls + 1)
+        self.link_bytes["solve"] = sent

@@ -21,18 +21,32 @@ def expand_masked(rowptr, colidx, vals, fixed, kspring=None):
     return a
 
 
-def factor_solve(plan_export, rowptr, colidx, vals, fixed, b, kspring=None):
-    """Multifrontal LL^T + substitution following the plan; returns x (same shape as b [n_dof, nrhs])."""
-    ex = plan_export
-    fronts, nodes, child, inv_off, inv = ex["fronts"], ex["nodes"], ex["child"], ex["inv_off"], ex["inv"]
-    nf = len(fronts)
-    fx = fixed.astype(bool)
-    panels = [None] * nf
-    schur = [None] * nf
-    dofs = [None] * nf
-    for l in range(len(ex["level_ptr"]) - 1):
-        for q in range(ex["level_ptr"][l], ex["level_ptr"][l + 1]):
-            i = ex["level_fronts"][q]
+class Emulator:
+    """The numeric phase front by front: factor(fronts) -> forward(fronts) -> backward(fronts) on a global right-hand-side
+    array, so that a caller can run any subset of the tree (the whole of it: factor_solve; a rank's share of it: the
+    tree-parallel protocol test)."""
+
+    def __init__(self, plan_export, rowptr, colidx, vals, fixed, kspring=None):
+        self.ex, self.rowptr, self.colidx, self.vals, self.kspring = plan_export, rowptr, colidx, vals, kspring
+        self.fx = fixed.astype(bool)
+        nf = len(plan_export["fronts"])
+        self.panels, self.schur, self.dofs = [None] * nf, [None] * nf, [None] * nf
+        ex = plan_export
+        self.level_of = {}
+        for l in range(len(ex["level_ptr"]) - 1):
+            for q in range(ex["level_ptr"][l], ex["level_ptr"][l + 1]):
+                self.level_of[int(ex["level_fronts"][q])] = l
+
+    def fronts_in_order(self):
+        ex = self.ex
+        return [int(ex["level_fronts"][q]) for q in range(ex["level_ptr"][-1])]
+
+    def factor(self, front_ids):
+        ex, fx, kspring, rowptr, colidx, vals = self.ex, self.fx, self.kspring, self.rowptr, self.colidx, self.vals
+        fronts, nodes, child, inv_off, inv = ex["fronts"], ex["nodes"], ex["child"], ex["inv_off"], ex["inv"]
+        schur = self.schur
+        for i in front_ids:
+            l = self.level_of[i]
             f = fronts[i]
             n1, n2 = int(f["n1"]), int(f["n2"])
             nt = n1 + n2
@@ -45,6 +59,7 @@ def factor_solve(plan_export, rowptr, colidx, vals, fixed, b, kspring=None):
                 assert len(sel) == fronts[c]["n2"] and np.all(np.diff(src) > 0), "inverse map is not a monotone bijection"
                 rows = (6 * sel[:, None] + np.arange(6)).reshape(-1)
                 srows = (6 * src[:, None] + np.arange(6)).reshape(-1)
+                assert schur[c] is not None, f"front {i} needs the Schur complement of its child {c}"
                 F[np.ix_(rows, rows)] += schur[c][np.ix_(srows, srows)]
                 schur[c] = None
             ks = ex["kscatter"][ex["kscatter_ptr"][l]:ex["kscatter_ptr"][l + 1]]
@@ -67,25 +82,40 @@ def factor_solve(plan_export, rowptr, colidx, vals, fixed, b, kspring=None):
             L11 = np.linalg.cholesky(F[:k1, :k1])
             L21 = np.linalg.solve(L11, F[:k1, k1:]).T if n2 else np.zeros((0, k1))
             schur[i] = F[k1:, k1:] - L21 @ L21.T
-            panels[i] = (L11, L21)
+            self.panels[i] = (L11, L21)
             nd = nodes[f["nodes_off"]:f["nodes_off"] + nt]
-            dofs[i] = (6 * nd[:, None] + np.arange(6)).reshape(-1)
-    x = np.where(fx[:, None], 0.0, b).astype(np.float64)
-    order = [ex["level_fronts"][q] for q in range(nf)]
-    for i in order:                          # forward
-        L11, L21 = panels[i]
-        k1 = L11.shape[0]
-        d = dofs[i]
-        y = np.linalg.solve(L11, x[d[:k1]])
-        x[d[:k1]] = y
-        if len(d) > k1:
-            x[d[k1:]] -= L21 @ y
-    for i in reversed(order):                # backward
-        L11, L21 = panels[i]
-        k1 = L11.shape[0]
-        d = dofs[i]
-        y = x[d[:k1]]
-        if len(d) > k1:
-            y = y - L21.T @ x[d[k1:]]
-        x[d[:k1]] = np.linalg.solve(L11.T, y)
+            self.dofs[i] = (6 * nd[:, None] + np.arange(6)).reshape(-1)
+
+    def start(self, b):
+        return np.where(self.fx[:, None], 0.0, b).astype(np.float64)
+
+    def forward(self, x, front_ids):
+        for i in front_ids:
+            L11, L21 = self.panels[i]
+            k1 = L11.shape[0]
+            d = self.dofs[i]
+            y = np.linalg.solve(L11, x[d[:k1]])
+            x[d[:k1]] = y
+            if len(d) > k1:
+                x[d[k1:]] -= L21 @ y
+
+    def backward(self, x, front_ids):
+        for i in reversed(list(front_ids)):
+            L11, L21 = self.panels[i]
+            k1 = L11.shape[0]
+            d = self.dofs[i]
+            y = x[d[:k1]]
+            if len(d) > k1:
+                y = y - L21.T @ x[d[k1:]]
+            x[d[:k1]] = np.linalg.solve(L11.T, y)
+
+
+def factor_solve(plan_export, rowptr, colidx, vals, fixed, b, kspring=None):
+    """Multifrontal LL^T + substitution following the plan; returns x (same shape as b [n_dof, nrhs])."""
+    em = Emulator(plan_export, rowptr, colidx, vals, fixed, kspring)
+    order = em.fronts_in_order()
+    em.factor(order)
+    x = em.start(b)
+    em.forward(x, order)
+    em.backward(x, order)
     return x
