@@ -157,7 +157,8 @@ def pin_model(model):
 def workload_name(args, n_comb: int) -> str:
     return (f"configs[3] synthetic 3D space frame {args.nx}x{args.nz} bays x {args.ny} storeys, linear static, "
             f"{n_comb} combinations per GPU"
-            + (", section forces along the members and their extrema recovered in the timed step" if getattr(args, "detail", False) else ""))
+            + (", section forces along the members, their extrema and a Generic unity check on every member evaluated in the timed step"
+               if getattr(args, "detail", False) else ""))
 
 
 def cpu_pass(args):
@@ -275,12 +276,32 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
             return {"U": out["U"], "R": out["R"], "f_local": out["f_local"]}
     else:
         span_cache = {}
+        unity_acc = {}
+        if args.detail:
+            # a Generic unity check on every member (N / N_Rd + |Mz| / M_Rd with constant resistances), evaluated on the
+            # device over all combinations inside the timed step (row A13): the check is compiled once, its envelope reset per step
+            from fers_core_b200 import hostlogic, unity
+            q = lambda kind, **kw: {"Quantity": {kind: kw}}
+            model.unity_checks = [{"id": "nm", "name": "N + M interaction", "applies_to": {"type": "AllMembers"},
+                                   "spec": {"Generic": {"demand": "abs(N) / NRd + M / MRd", "capacity": "1", "variables": [
+                                       {"name": "N", "source": q("MemberForce", component="N", aggregation={"type": "MaxAbs"})},
+                                       {"name": "M", "source": q("MemberForce", component="Mz", aggregation={"type": "MaxAbs"})},
+                                       {"name": "NRd", "source": {"Quantity": {"Constant": 3.5e6}}},
+                                       {"name": "MRd", "source": {"Quantity": {"Constant": 4.6e5}}}]}}}]
+            unity_plan = hostlogic.rhs_plan(model)
 
         def step_with(e):
             if args.detail:
                 if id(e) not in span_cache:
                     span_cache[id(e)] = e.span_tables()
-                return e.run_linear(factors, detail=True, span=span_cache[id(e)])
+                    unity_acc[id(e)] = unity.UnityAccumulator(model, unity_plan, e.dev)
+                rec_ = e.run_linear(factors, detail=True, span=span_cache[id(e)])
+                acc = unity_acc[id(e)]
+                for b_ in acc.best:
+                    b_[:] = [-np.inf, 0.0, 0.0, -1.0]
+                acc.accumulate(list(range(factors.shape[0])), e.d_xyz0, rec_["U"], rec_, e.stream)
+                rec_["unity_max_utilisation"] = float(np.nanmax(acc.best[0][:, 0]))
+                return rec_
             return e.run_linear(factors)
 
     def one_step():
