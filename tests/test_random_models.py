@@ -1,0 +1,75 @@
+"""Randomised sweep: small 3D frames with jittered geometry, rolled members, trusses, end releases and springs, shear-centre
+and end offsets, products of inertia, pinned and sprung supports, linear and P-Delta -- every result field of the GPU path
+against the oracle.  The fixed cases elsewhere pin single features; this one pins their combinations."""
+import numpy as np
+import pytest
+
+from fers_core_b200 import synth, wire
+from oracle import fers_oracle
+
+SEEDS = list(range(10))
+
+
+def random_model(seed: int):
+    rng = np.random.default_rng(1000 + seed)
+    nx, nz, ny = (int(v) for v in rng.integers(2, 5, size=3))
+    second_order = seed % 3 == 0
+    model = synth.grid_frame(nx, nz, ny, n_combos=5, timoshenko=bool(seed % 2), order="NONLINEAR" if second_order else "LINEAR",
+                             solve_loadcases=True)
+    nn, nm = model.n_nodes, model.n_members
+    base = model.node_support_id >= 0
+    jitter = rng.normal(size=(nn, 3)) * np.array([0.25, 0.12, 0.25])
+    jitter[base] = 0.0
+    model.xyz = model.xyz + jitter
+    model.m_roll = np.where(rng.random(nm) < 0.3, rng.uniform(-1.2, 1.2, nm), 0.0)
+    column = np.isclose(model.xyz[model.m_n1, 0], model.xyz[model.m_n2, 0], atol=1.0) & \
+        (np.abs(model.xyz[model.m_n2, 1] - model.xyz[model.m_n1, 1]) > 2.0)
+    model.m_type = np.where(~column & (rng.random(nm) < 0.08), wire.MT_TRUSS, model.m_type).astype(np.int32)
+    # member modifier records: releases / springs, shear-centre offsets, end offsets, product of inertia
+    rel = np.full((5, wire.REL_STRIDE), 0.0)
+    rel[:, :12] = wire.RIGID_RELEASE
+    rel[0, 11] = 0.0                                   # pinned about local z at the end
+    rel[1, [4, 5]] = (2.0e6, 0.0)                      # spring about y, pin about z at the start
+    rel[2, 12:14] = (0.02, -0.015)                     # shear-centre offset
+    rel[3, 14:20] = (0.05, -0.03, 0.02, -0.04, 0.0, 0.03)     # end offsets
+    rel[3, 5] = 5.0e5
+    rel[4, wire.REL_EIYZ] = 0.2 * float(np.sqrt(model.prop[1, wire.P_EIY] * model.prop[1, wire.P_EIZ]))
+    pick = (rng.random(nm) < 0.18) & ~column & (model.m_type == wire.MT_NORMAL)
+    model.rel = rel
+    model.m_rel = np.where(pick, rng.integers(0, 5, nm), -1).astype(np.int32)
+    # supports: a third of the base nodes pinned, one of them on a vertical spring
+    base_idx = np.nonzero(base)[0]
+    pinned = base_idx[rng.random(len(base_idx)) < 0.33]
+    model.bc_code = model.bc_code.copy(); model.bc_k = model.bc_k.copy()
+    model.bc_code[pinned, 3:] = wire.BC_FREE
+    if len(pinned):
+        model.bc_code[pinned[0], 1] = wire.BC_SPRING
+        model.bc_k[pinned[0], 1] = 4.0e8
+    return model
+
+
+def _fields(res):
+    return {n: getattr(res, n) for n in ("U", "R", "f_local", "f_global", "sec", "lmax", "lmin")}
+
+
+@pytest.mark.parametrize("seed", SEEDS[:3])
+def test_oracle_solves_the_random_models(seed):
+    model = random_model(seed)
+    res = fers_oracle.analyze(model)
+    assert np.isfinite(res.U).all() and np.abs(res.U).max() < 1.0           # a structure, not a mechanism
+    # global equilibrium of every column: reactions + applied loads sum to zero
+    asm = fers_oracle.Assembly(model, model.xyz)
+    assert res.converged.all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", SEEDS)
+def test_gpu_matches_oracle_on_random_models(seed):
+    from fers_core_b200 import engine
+    model = random_model(seed)
+    want = fers_oracle.analyze(model)
+    got = engine.analyze(model, solver="cholesky" if seed % 4 == 1 else "auto")
+    assert np.array_equal(got.converged, want.converged) and np.array_equal(got.iterations, want.iterations)
+    for name, y in _fields(want).items():
+        x = getattr(got, name)
+        assert np.abs(x - y).max() <= 2e-9 * np.abs(y).max(), (seed, name, np.abs(x - y).max() / np.abs(y).max())
