@@ -45,11 +45,42 @@ def random_model(seed: int):
     if len(pinned):
         model.bc_code[pinned[0], 1] = wire.BC_SPRING
         model.bc_k[pinned[0], 1] = 4.0e8
+    if seed % 2 and not second_order:
+        # a floor slab on the top storey of some bays: two triangles per bay, random thickness, behaviour, local-x angle,
+        # orthotropic material and offset; uniform pressure in the gravity case
+        px, pz = nx + 1, nz + 1
+        nid = lambda i, k, j: i + px * (k + pz * j)
+        tris, data, flags = [], [], []
+        for i in range(nx):
+            for k in range(nz):
+                if rng.random() < 0.6:
+                    a, b, c, d = nid(i, k, ny), nid(i + 1, k, ny), nid(i + 1, k + 1, ny), nid(i, k + 1, ny)
+                    for t3 in ((a, b, c), (a, c, d)):
+                        rec = np.zeros(wire.NPDATA)
+                        E = 30e9
+                        rec[:7] = (rng.uniform(0.12, 0.3), E, 0.2, 1.0, rng.uniform(0.5, 1.0), 1.0, rng.uniform(-1.0, 1.0))
+                        if rng.random() < 0.5:
+                            rec[wire.PD_ORTHO] = 1.0
+                            rec[wire.PD_EX:wire.PD_GYZ + 1] = (E, 0.4 * E, 0.2 * E, 0.15, 0.25 * E, 0.1 * E)
+                        if rng.random() < 0.5:
+                            rec[wire.PD_OFFSET] = rng.uniform(-0.15, 0.15)
+                        tris.append(t3); data.append(rec); flags.append(int(rng.choice([1, 2, 3])))
+        if tris:
+            model.p_ids = np.arange(1, len(tris) + 1, dtype=np.int64)
+            model.p_nodes = np.array(tris, np.int32)
+            model.p_data = np.array(data)
+            model.p_flags = np.array(flags, np.int32)
+            lc = model.load_cases[0]
+            lc.pp_plate = np.arange(len(tris), dtype=np.int32)
+            lc.pp_vec = np.tile(np.array([0.0, -4.0e3, 0.0]), (len(tris), 1))
     return model
 
 
 def _fields(res):
-    return {n: getattr(res, n) for n in ("U", "R", "f_local", "f_global", "sec", "lmax", "lmin")}
+    out = {n: getattr(res, n) for n in ("U", "R", "f_local", "f_global", "sec", "lmax", "lmin")}
+    if res.p_res.size:
+        out.update(p_res=res.p_res, p_nodal=res.p_nodal)
+    return out
 
 
 @pytest.mark.parametrize("seed", SEEDS[:3])
