@@ -853,7 +853,7 @@ def recover_plates(asm: Assembly, U):
     return dict(p_res=res, p_nodal=nod, p_cdg=cdg, p_cdl=cdl, p_centroid=cen)
 
 
-def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool = True) -> ResultArrays:
+def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool = True, exact_mpc: bool = False) -> ResultArrays:
     """Full analysis of one document: the oracle twin of fers_core_b200.engine.analyze.
     detail=False skips interior section forces / extrema (as the engine's detail=False)."""
     opts = model.options
@@ -876,7 +876,12 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
         cols = list(grp.columns)
         needs_own = (second_order or np.any(unilateral_members) or len(unilateral_dofs(model)[0]) > 0
                      or len(model.support_curves) > 0 or len(model.hinge_curves) > 0)
-        if not needs_own:
+        if not needs_own and exact_mpc and mpc_applies(model):
+            # ---- linear with the rigid members as exact constraints (master-slave elimination): NOT what the product does
+            # (it solves stiff members under either RigidStrategy and says so); kept to measure the error of that choice
+            U, links, asm0, K0 = solve_linear_mpc(model, xyz, F)
+            _store(out, asm0, model, cols, U, F, peq, K0, None, spans, fac, iters=None, detail=detail, links=links)
+        elif not needs_own:
             # ---- linear: one factorisation, all right-hand sides
             K = asm.K_elastic()
             Kff, free, dead = constrain(K, model)
@@ -895,6 +900,128 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
     if timings is not None:
         timings["total_s"] = time.perf_counter() - t0
     return out
+
+
+def mpc_applies(model) -> bool:
+    """The exact-constraint solve (analyze(exact_mpc=True)) covers first-order analyses whose rigid members carry no member
+    loads."""
+    if not np.any(model.m_type == wire.MT_RIGID):
+        return False
+    rigid = set(np.nonzero(model.m_type == wire.MT_RIGID)[0].tolist())
+    for lc in model.load_cases:
+        if rigid & set(np.asarray(lc.dl_member).tolist()) or rigid & set(np.asarray(lc.pl_member).tolist()):
+            return False
+    return True
+
+
+def mpc_forest(model):
+    """The rigid members as a forest over the nodes: (parent node or -1, rigid member to the parent or -1, root) per node.
+    The root of a cluster is its supported node when it has one, else its lowest node index."""
+    nn = model.n_nodes
+    rigid = np.nonzero(model.m_type == wire.MT_RIGID)[0]
+    adj = {}
+    for m in rigid:
+        a, b = int(model.m_n1[m]), int(model.m_n2[m])
+        adj.setdefault(a, []).append((b, int(m))); adj.setdefault(b, []).append((a, int(m)))
+    parent = np.full(nn, -1); via = np.full(nn, -1); root = np.arange(nn)
+    seen = set()
+    for start in sorted(adj):
+        if start in seen:
+            continue
+        comp, stack = [], [start]
+        seen.add(start)
+        while stack:
+            v = stack.pop(); comp.append(v)
+            for w, _m in adj[v]:
+                if w not in seen:
+                    seen.add(w); stack.append(w)
+        supported = [v for v in sorted(comp) if model.node_support_id[v] >= 0]
+        if len(supported) > 1:
+            raise ValueError("LinearMpc: a rigid cluster with more than one supported node is over-constrained")
+        r0 = supported[0] if supported else min(comp)
+        order, stack, done = [], [r0], {r0}
+        while stack:
+            v = stack.pop(); order.append(v)
+            for w, m in adj[v]:
+                if w not in done:
+                    done.add(w); parent[w] = v; via[w] = m; stack.append(w)
+        if len(done) != len(comp):
+            raise ValueError("LinearMpc: rigid members form a loop")
+        for v in comp:
+            root[v] = r0
+    return parent, via, root
+
+
+def solve_linear_mpc(model, xyz, F):
+    """First-order solve with the rigid members as exact kinematic constraints  u_s = u_m + theta_m x (x_s - x_m),
+    theta_s = theta_m  (master m = root of the rigid cluster): u = T u_red, (T^T K0 T) u_red = T^T f with K0 the structure
+    WITHOUT its rigid members.  Returns U [ncols, nd], (reactions carried through the links [ncols, nd], rigid member rows,
+    their global end forces [ncols, n_rigid, 12] in the stiffness sign), the assembly without the links and K0."""
+    nd, nn = model.n_dof, model.n_nodes
+    rigid = np.nonzero(model.m_type == wire.MT_RIGID)[0]
+    asm0 = Assembly(model, xyz, m_scale=np.where(model.m_type == wire.MT_RIGID, 0.0, 1.0))
+    K0 = asm0.K_elastic()
+    parent, via, root = mpc_forest(model)
+    slaves = np.nonzero(root != np.arange(nn))[0]
+    code = model.bc_code.reshape(nn, 6)
+    if np.any(code[slaves] != wire.BC_FREE):
+        raise ValueError("LinearMpc: a support on a slave node of a rigid cluster")
+    rows, colsT, vals = list(range(nd)), list(range(nd)), [1.0] * nd
+    T = sp.lil_matrix((nd, nd))
+    T.setdiag(1.0)
+    for s_ in slaves:
+        m_ = int(root[s_])
+        r = xyz[s_] - xyz[m_]
+        T[6 * s_:6 * s_ + 6, 6 * s_:6 * s_ + 6] = 0.0
+        for c in range(3):
+            T[6 * s_ + c, 6 * m_ + c] = 1.0
+            T[6 * s_ + 3 + c, 6 * m_ + 3 + c] = 1.0
+        # u_s = u_m + theta x r  ->  -[r]_x theta
+        T[6 * s_ + 0, 6 * m_ + 4] = r[2];  T[6 * s_ + 0, 6 * m_ + 5] = -r[1]
+        T[6 * s_ + 1, 6 * m_ + 3] = -r[2]; T[6 * s_ + 1, 6 * m_ + 5] = r[0]
+        T[6 * s_ + 2, 6 * m_ + 3] = r[1];  T[6 * s_ + 2, 6 * m_ + 4] = -r[0]
+    T = T.tocsr()
+    kspring = np.where(model.bc_code.reshape(-1) == wire.BC_SPRING, model.bc_k.reshape(-1), 0.0)
+    Kr = (T.T @ (K0 + sp.diags(kspring)) @ T).tocsr()
+    Fr = (T.T @ F.T).T
+    fixed = model.bc_code.reshape(-1) == wire.BC_FIXED
+    slave_dof = np.zeros(nd, bool)
+    slave_dof[(6 * slaves[:, None] + np.arange(6)).reshape(-1)] = True
+    diag = Kr.diagonal()
+    dead = (~fixed) & ((diag == 0.0) | slave_dof)
+    free = np.nonzero(~(fixed | dead))[0]
+    Ur = np.zeros((F.shape[0], nd))
+    Ur[:, free] = solve_sym(Kr[free][:, free].tocsc(), Fr[:, free].T).T
+    U = (T @ Ur.T).T
+    # what the links must supply at every node: rho = K0 u - f (springs are supports, excluded as everywhere)
+    rho = (K0 @ U.T).T - F                                       # [ncols, nd]
+    R_links = (T.T @ rho.T).T                                    # the whole cluster's demand arrives at its root
+    # end forces of the links: the demand of the subtree beyond a link, carried to its far node
+    depth = np.zeros(nn, int)
+    for v in range(nn):
+        d, w = 0, v
+        while parent[w] >= 0:
+            w = parent[w]; d += 1
+        depth[v] = d
+    sub = rho.reshape(F.shape[0], nn, 6).copy()                  # accumulated demand at each node, about that node
+    fg = np.zeros((F.shape[0], len(rigid), 12))
+    row_of = {int(m): i for i, m in enumerate(rigid)}
+    for v in sorted(np.nonzero(parent >= 0)[0], key=lambda n: -depth[n]):
+        p_, m_ = int(parent[v]), int(via[v])
+        Fv, Mv = sub[:, v, :3], sub[:, v, 3:]
+        # K_rigid u = f - K0 u = -rho: in the stiffness sign (forces of the nodes on the member ends) the far node acts on the
+        # link with minus the demand of its subtree, the near node with that demand carried over the arm (link in equilibrium)
+        arm = xyz[v] - xyz[p_]
+        at_v = np.concatenate([-Fv, -Mv], 1)
+        at_p = np.concatenate([Fv, Mv + np.cross(arm[None, :], Fv)], 1)
+        i = row_of[m_]
+        if int(model.m_n2[m_]) == v:
+            fg[:, i, 6:] = at_v; fg[:, i, :6] = at_p
+        else:
+            fg[:, i, :6] = at_v; fg[:, i, 6:] = at_p
+        sub[:, p_, :3] += Fv
+        sub[:, p_, 3:] += Mv + np.cross(arm[None, :], Fv)
+    return U, (R_links, rigid, fg), asm0, K0
 
 
 def _axial_forces(asm, U, peq, kg_local=None):
@@ -1006,17 +1133,22 @@ def _suppress_kg(asm, kg, suppressed):
     return np.einsum("mij,mjk,mlk->mil", asm.T, kgg, asm.T)
 
 
-def _store(out: ResultArrays, asm, model, cols, U, F, peq, K, kg, spans, fac, iters, detail=True):
-    """Fill result arrays for the given rhs columns."""
+def _store(out: ResultArrays, asm, model, cols, U, F, peq, K, kg, spans, fac, iters, detail=True, links=None):
+    """Fill result arrays for the given rhs columns.  links = (R_full [ncols, nd], member rows, f_global [ncols, n, 12]) of a
+    LinearMpc solve: the reactions carried through the rigid links and the end forces of the links themselves."""
     nn = model.n_nodes
     cols = np.asarray(cols)
     out.U[cols] = U.reshape(len(cols), nn, 6)
     # reactions R = K u - F at supported nodes (SURVEY.md A.3); springs excluded from K
-    Rfull = (K @ U.T).T - F
+    Rfull = (K @ U.T).T - F if links is None else links[0]
     sup = model.node_support_id >= 0
     Rn = Rfull.reshape(len(cols), nn, 6) * sup[None, :, None]
     out.R[cols] = Rn
     rec = recover_members(asm, U, peq, kg)
+    if links is not None:
+        rows, fg = links[1], links[2]
+        rec["f_global"][:, rows] += fg
+        rec["f_local"][:, rows] += np.einsum("mij,cmj->cmi", asm.T[rows], fg)
     out.f_local[cols] = rec["f_local"]; out.f_global[cols] = rec["f_global"]; out.u_local[cols] = rec["u_local"]
     out.bw[cols] = rec["bw"]
     if model.n_members and detail:
