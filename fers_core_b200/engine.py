@@ -19,7 +19,8 @@ import torch
 
 from . import _lib, chol, unity, wire
 from .hostlogic import (
-    INACTIVE_SCALE, effective_bc, imperfect_coordinates, pdelta_suppressed_axes, rhs_plan, rigid_property_row,
+    INACTIVE_SCALE, effective_bc, imperfect_coordinates, member_frames_host, mpc_transform, pdelta_suppressed_axes, rhs_plan,
+    rigid_property_row,
     unilateral_dofs, unilateral_update, curve_stiffness, curves_converged, hinge_curve_stiffness, rel_with_hinge_curves,
 )
 from .results import ResultArrays, SECTION_FRACS, lazy_bundle, results_to_json, results_to_wire
@@ -473,7 +474,7 @@ class Engine:
         return u
 
     def recover(self, d_xyz, d_u, d_f, d_peq, factors_pad, span, d_scale=None, d_axial_rhs=None, kg_mode=0,
-                kg_suppress=0, detail=True) -> dict:
+                kg_suppress=0, detail=True, link_forces=None) -> dict:
         """All recovery kernels for displacement columns d_u [Ndof,nr]."""
         m, lib, st = self.model, self.lib, self.stream
         nr = d_u.shape[1]
@@ -492,6 +493,21 @@ class Engine:
                 _lib.ptr(self.d_type), _lib.ptr(self.d_roll), _lib.ptr(d_scale), _lib.ptr(self.d_rel_idx),
                 _lib.ptr(self.d_prop), _lib.ptr(self.d_rel), _lib.ptr(d_axial_rhs), kg_mode, kg_suppress,
                 _lib.ptr(d_u), _lib.ptr(d_peq), _lib.ptr(fl), _lib.ptr(fg), _lib.ptr(ul), st), "recover_members")
+            sec_tables = (self.d_n1, self.d_n2, self.d_rel_idx, self.d_rel)
+            if link_forces is not None:
+                # LinearMpc (engine._MpcDevice): end forces of the rigid links; end forces of the members that sat on a slave
+                # node carried from the master back to that node.  The section forces below are then formed on the ORIGINAL
+                # connectivity and offsets (report tables), from these node forces.
+                rows, lam_l, lam_g, ends, sec_tables = link_forces
+                fl.index_copy_(0, rows, lam_l)
+                fg.index_copy_(0, rows, lam_g)
+                if ends is not None:
+                    e_rows, e_end, e_arm, e_R = ends                     # member rows, 0 / 1, arm x_slave - x_master, member frames
+                    g = fg.view(nm, 2, 6, nr)
+                    F = g[e_rows, e_end, :3]
+                    M = g[e_rows, e_end, 3:] - _MpcDevice._cross(e_arm, F)
+                    g[e_rows, e_end, 3:] = M
+                    fl.view(nm, 2, 2, 3, nr)[e_rows, e_end, 1] = torch.einsum("mij,mjr->mir", e_R, M)
             out.update(f_local=fl, f_global=fg, u_local=ul)
             if self.n_warp:
                 bw = self._empty((self.n_warp, 2, nr))
@@ -506,9 +522,9 @@ class Engine:
                 mm = [self._empty((nm, 6, nr)) for _ in range(4)]
                 d_fac = self._t(factors_pad, np.float64)
                 _lib.check(lib.fers_b200_recover_sections(
-                    nm, nr, factors_pad.shape[1], _lib.ptr(d_xyz), _lib.ptr(self.d_n1), _lib.ptr(self.d_n2),
+                    nm, nr, factors_pad.shape[1], _lib.ptr(d_xyz), _lib.ptr(sec_tables[0]), _lib.ptr(sec_tables[1]),
                     _lib.ptr(self.d_roll), _lib.ptr(sp_ptr), _lib.ptr(sp_rows), _lib.ptr(d_fac), _lib.ptr(fl), _lib.ptr(fg),
-                    _lib.ptr(self.d_rel_idx), _lib.ptr(self.d_rel), _lib.ptr(sec), _lib.ptr(mm[0]), _lib.ptr(mm[1]), _lib.ptr(mm[2]), _lib.ptr(mm[3]), st),
+                    _lib.ptr(sec_tables[2]), _lib.ptr(sec_tables[3]), _lib.ptr(sec), _lib.ptr(mm[0]), _lib.ptr(mm[1]), _lib.ptr(mm[2]), _lib.ptr(mm[3]), st),
                     "recover_sections")
                 out.update(sec=sec, lmax=mm[0], lmin=mm[1], gmax=mm[2], gmin=mm[3])
         if m.n_plates:
@@ -580,10 +596,18 @@ def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_
             stats_out: dict | None = None, solver: str = "auto") -> ResultArrays:
     """Full analysis of one document on the GPU (twin of oracle.fers_oracle.analyze)."""
     t_start = time.perf_counter()
-    eng = Engine(model, device, assembly_variant, solver)
+    # RigidStrategy.LinearMpc: the engine solves the transformed model (slaves on rigid arms of their master, hostlogic.
+    # mpc_transform) and reports on the original one; where the transformation does not apply the rigid members are stiff
+    # members and the result says so
+    model_t, mpc = mpc_transform(model)
+    eng = Engine(model if model_t is None else model_t, device, assembly_variant, solver)
     opts = model.options
     plan = rhs_plan(model)
     out = ResultArrays.empty(model, plan)
+    if model_t is None and opts.rigid_strategy == "LinearMpc" and np.any(model.m_type == wire.MT_RIGID):
+        out.warnings.append(("W_LINEAR_MPC_AS_RIGID_MEMBER", f"rigid_strategy=LinearMpc not applied ({mpc}): rigid members are "
+                             "modelled as stiff members (RigidMember strategy)"))
+    mpc_dev = _MpcDevice(eng, model, mpc) if model_t is not None else None
     if plan.n_rhs == 0:
         return out
     second_order = opts.order == "NONLINEAR"
@@ -607,7 +631,10 @@ def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_
                 d_f = eng.combine(f_case, fac[c0:c0 + 64], nr)
                 d_peq = eng.combine(peq_case, fac[c0:c0 + 64], nr)
                 d_u = eng.solve(d_f)
-                rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, detail=detail)
+                links = None
+                if mpc_dev is not None:
+                    links = mpc_dev.finish(d_u, eng.recover(d_xyz, d_u, d_f, d_peq, facp, None, detail=False), facp)
+                rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, detail=detail, link_forces=links)
                 _store(out, model, sub, d_u, rec, xyz)
         else:
             for ci, col in enumerate(cols):
@@ -621,6 +648,77 @@ def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_
     if stats_out is not None:
         stats_out.update(vars(eng.stats))
     return out
+
+
+class _MpcDevice:
+    """Device side of RigidStrategy.LinearMpc after the solve of the transformed model: displacements of the slave nodes from
+    their masters, end forces of the rigid links from the equilibrium of the slave nodes (the elastic members that sat on a
+    slave report their end forces at the master; carried back over the arm they, minus the nodal loads of the slave, are what
+    the link must hold)."""
+
+    def __init__(self, eng: Engine, model, info):
+        dev = eng.dev
+        t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+        self.info = info
+        self.slaves, self.master = t(info.slaves, torch.int64), t(info.master, torch.int64)
+        self.arm = t(info.arm)
+        self.att_member, self.att_end, self.att_slave = (t(a, torch.int64) for a in (info.att_member, info.att_end, info.att_slave))
+        self.ext = t(info.ext)                                               # [ns, 6, Nlc]
+        self.slave_pos = {int(s): i for i, s in enumerate(info.slaves)}
+        rows = np.array([m for m, _, _ in info.links], np.int64)
+        self.rows = t(rows, torch.int64)
+        R, _, _ = member_frames_host(model, rows)                           # frames of the links (original geometry)
+        self.R = t(R)
+        self.far_is_end = [int(model.m_n2[m]) == far for m, _, far in info.links]
+        self.link_arm = t(np.array([model.xyz[far] - model.xyz[near] for _, near, far in info.links]).reshape(-1, 3))
+        # report tables: connectivity and modifier records of the ORIGINAL model for the section-force kernel
+        has_rel = bool(np.any(model.m_rel >= 0))
+        self.sec_tables = (t(model.m_n1, torch.int32), t(model.m_n2, torch.int32),
+                           t(model.m_rel, torch.int32) if has_rel else None, t(model.rel) if has_rel else None)
+        self.ends = None
+        if len(info.att_member):
+            Ra, _, _ = member_frames_host(model, info.att_member)
+            self.ends = (self.att_member, self.att_end, self.arm.index_select(0, self.att_slave), t(Ra))
+
+    @staticmethod
+    def _cross(a, b):
+        """a [3] or [n,3] (constant over the columns) x b [.., 3, nr]."""
+        ax, ay, az = a[..., 0, None], a[..., 1, None], a[..., 2, None]
+        return torch.stack([ay * b[..., 2, :] - az * b[..., 1, :], az * b[..., 0, :] - ax * b[..., 2, :],
+                            ax * b[..., 1, :] - ay * b[..., 0, :]], dim=-2)
+
+    def finish(self, d_u, rec, facp):
+        nr = d_u.shape[1]
+        info = self.info
+        ns = len(info.slaves)
+        # displacements of the slaves: theta_s = theta_m, u_s = u_m + theta_m x arm
+        um = d_u.view(-1, 6, nr).index_select(0, self.master)
+        us = um.clone()
+        us[:, :3] += self._cross(-self.arm, um[:, 3:])                      # theta x r = -(r x theta)
+        d_u.view(-1, 6, nr).index_copy_(0, self.slaves, us)
+        # demand at the slave nodes
+        rho = torch.zeros((ns, 6, nr), dtype=torch.float64, device=d_u.device)
+        if len(info.att_member):
+            ends = rec["f_global"].view(-1, 2, 6, nr)[self.att_member, self.att_end]          # at the master node
+            F = ends[:, :3]
+            M = ends[:, 3:] - self._cross(self.arm.index_select(0, self.att_slave), F)         # carried to the slave
+            rho.index_add_(0, self.att_slave, torch.cat([F, M], dim=1))
+        fac = torch.from_numpy(np.ascontiguousarray(facp, np.float64)).to(d_u.device)          # [nr, Nlc]
+        rho -= torch.einsum("sql,rl->sqr", self.ext[:, :, : fac.shape[1]], fac)
+        # up the forest, deepest link first
+        sub = {s: rho[i].clone() for s, i in self.slave_pos.items()}
+        lam_g = torch.zeros((len(info.links), 12, nr), dtype=torch.float64, device=d_u.device)
+        for li, (_m, near, far) in enumerate(info.links):
+            D = sub[far]
+            carried = torch.cat([D[:3], D[3:] + self._cross(self.link_arm[li], D[:3])], dim=0)
+            if self.far_is_end[li]:
+                lam_g[li, :6], lam_g[li, 6:] = carried, -D
+            else:
+                lam_g[li, :6], lam_g[li, 6:] = -D, carried
+            if near in sub:
+                sub[near] = sub[near] + carried
+        lam_l = torch.einsum("mij,mbjr->mbir", self.R, lam_g.view(-1, 4, 3, nr)).reshape(-1, 12, nr)
+        return self.rows, lam_l, lam_g, self.ends, self.sec_tables
 
 
 def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second_order, detail):

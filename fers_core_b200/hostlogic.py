@@ -6,6 +6,7 @@ on (imperfection cases, pydantic_models.py:2036-2040) and a few scalar conventio
 """
 from __future__ import annotations
 
+import dataclasses
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -180,6 +181,135 @@ def member_deflected_shape(model: wire.ModelArrays, u_nodes: np.ndarray, members
     if truss.any():
         loc[truss] = t1[truss][:, None, :] * (1 - xi)[None, :, None] + t2[truss][:, None, :] * xi[None, :, None]
     return np.einsum("mji,msj->msi", R, loc)
+
+
+# ---- RigidStrategy.LinearMpc (pydantic_models.py:1047-1049): rigid members as exact kinematic constraints -------------------
+@dataclass
+class MpcInfo:
+    """What engine.analyze needs after solving the transformed model (mpc_transform)."""
+    slaves: np.ndarray          # [ns] node indices carried by a master
+    master: np.ndarray          # [ns] root node of each slave's rigid cluster
+    arm: np.ndarray             # [ns,3] x_slave - x_master
+    links: list                 # rigid members far node first: (member row, near node, far node), deepest first
+    att_member: np.ndarray      # [na] elastic member ends that sat on a slave node: member row ...
+    att_end: np.ndarray         # [na] ... 0 start / 1 end ...
+    att_slave: np.ndarray       # [na] ... index into `slaves`
+    ext: np.ndarray             # [ns,6,Nlc] nodal loads that sat on the slave nodes, per load case
+
+
+def mpc_transform(model: wire.ModelArrays):
+    """(transformed model, MpcInfo), or (None, reason) when the rigid members stay stiff members.
+
+    Every node of a cluster of rigid members rides on the cluster's root (its supported node, else its lowest index):
+    u_s = u_m + theta_m x (x_s - x_m), theta_s = theta_m.  In the transformed model the elastic members that ended on a slave
+    end on the master instead, with the arm added to their end offset (the rigid arms of Member.start_offset / end_offset do
+    exactly this kinematics, csrc/fers_elem.cuh beam_arms); nodal loads on slaves move to the master with their moment
+    r x F; slave nodes are held (their displacements follow from the master afterwards) and the rigid members get a
+    zero-stiffness section.  Nothing is approximated: the matrix that is factorised is T^T K0 T written member by member."""
+    opts = model.options
+    rigid = np.nonzero(model.m_type == wire.MT_RIGID)[0]
+    if opts.rigid_strategy != "LinearMpc" or not len(rigid):
+        return None, "not requested"
+    if opts.order != "LINEAR":
+        return None, "second-order analysis"
+    if model.imperfections or len(model.support_curves) or len(model.hinge_curves):
+        return None, "imperfection cases or load-dependent springs"
+    if np.isin(model.bc_code, (wire.BC_POS_ONLY, wire.BC_NEG_ONLY)).any() or \
+            np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)).any():
+        return None, "unilateral supports or members"
+    nn = model.n_nodes
+    adj: dict = {}
+    for m in rigid:
+        a, b = int(model.m_n1[m]), int(model.m_n2[m])
+        adj.setdefault(a, []).append((b, int(m))); adj.setdefault(b, []).append((a, int(m)))
+    loaded = set()
+    for lc in model.load_cases:
+        loaded.update(np.asarray(lc.dl_member).tolist()); loaded.update(np.asarray(lc.pl_member).tolist())
+    if loaded & set(rigid.tolist()):
+        return None, "a rigid member carries a member load"
+    master = np.arange(nn)
+    depth = np.zeros(nn, np.int64)
+    links = []
+    seen: set = set()
+    for start in sorted(adj):
+        if start in seen:
+            continue
+        comp, stack = [], [start]
+        seen.add(start)
+        while stack:
+            v = stack.pop(); comp.append(v)
+            for w, _ in adj[v]:
+                if w not in seen:
+                    seen.add(w); stack.append(w)
+        supported = [v for v in sorted(comp) if model.node_support_id[v] >= 0]
+        if len(supported) > 1:
+            return None, "a rigid cluster with more than one supported node"
+        root = supported[0] if supported else min(comp)
+        done, stack, n_links = {root}, [root], 0
+        while stack:
+            v = stack.pop()
+            for w, m in adj[v]:
+                if w not in done:
+                    done.add(w); depth[w] = depth[v] + 1; links.append((m, v, w)); stack.append(w); n_links += 1
+        if n_links != sum(len(adj[v]) for v in comp) // 2:
+            return None, "rigid members form a loop"
+        for v in comp:
+            master[v] = root
+    slaves = np.nonzero(master != np.arange(nn))[0]
+    if (model.bc_code[slaves] != wire.BC_FREE).any():
+        return None, "a support on a slave node"
+    is_slave = np.zeros(nn, bool); is_slave[slaves] = True
+    if model.n_plates and is_slave[model.p_nodes].any():
+        return None, "a plate on a slave node"
+    if len(model.w_member) and (is_slave[model.m_n1[model.w_member]].any() or is_slave[model.m_n2[model.w_member]].any()):
+        return None, "a warping member on a slave node"
+    elastic = model.m_type != wire.MT_RIGID
+    if (elastic & (master[model.m_n1] == master[model.m_n2])).any():
+        return None, "an elastic member with both ends in one rigid cluster"
+    slave_pos = {int(s): i for i, s in enumerate(slaves)}
+    arm = model.xyz[slaves] - model.xyz[master[slaves]]
+    # ---- the transformed model
+    m_n1, m_n2, m_rel = model.m_n1.copy(), model.m_n2.copy(), model.m_rel.copy()
+    rel = [r for r in model.rel]
+    att_m, att_e, att_s = [], [], []
+    for end, nodes in ((0, m_n1), (1, m_n2)):
+        for m in np.nonzero(elastic & is_slave[nodes])[0]:
+            s_i = slave_pos[int(nodes[m])]
+            if m_rel[m] < 0:
+                row = np.zeros(wire.REL_STRIDE); row[:12] = wire.RIGID_RELEASE
+            else:
+                row = rel[m_rel[m]].copy()                      # records may be shared between members: copy on write
+            m_rel[m] = len(rel)
+            o = wire.REL_O1 if end == 0 else wire.REL_O2
+            row[o:o + 3] += arm[s_i]
+            rel.append(row)
+            nodes[m] = master[nodes[m]]
+            att_m.append(int(m)); att_e.append(end); att_s.append(s_i)
+    prop = np.vstack([model.prop, np.zeros((1, model.prop.shape[1]))]) if model.prop.size else np.zeros((1, wire.NPROP))
+    m_prop, m_type = model.m_prop.copy(), model.m_type.copy()
+    m_prop[rigid] = prop.shape[0] - 1
+    m_type[rigid] = wire.MT_NORMAL
+    bc_code = model.bc_code.copy()
+    bc_code[slaves] = wire.BC_FIXED
+    nlc = len(model.load_cases)
+    ext = np.zeros((len(slaves), 6, max(nlc, 1)))
+    cases = []
+    for li, lc in enumerate(model.load_cases):
+        node, vec = np.asarray(lc.nod_node).copy(), np.asarray(lc.nod_vec, np.float64).copy()
+        for k in np.nonzero(is_slave[node])[0] if len(node) else []:
+            s_i = slave_pos[int(node[k])]
+            ext[s_i, :, li] += vec[k]
+            vec[k, 3:] += np.cross(arm[s_i], vec[k, :3])
+            node[k] = master[node[k]]
+        cases.append(dataclasses.replace(lc, nod_node=node, nod_vec=vec))
+    rho = model.prop_rho_a
+    if rho is not None and len(rho) == model.prop.shape[0]:
+        rho = np.concatenate([rho, [0.0]])
+    model_t = dataclasses.replace(model, m_n1=m_n1, m_n2=m_n2, m_rel=m_rel, rel=np.array(rel).reshape(len(rel), wire.REL_STRIDE),
+                                  prop=prop, prop_rho_a=rho, m_prop=m_prop, m_type=m_type, bc_code=bc_code, load_cases=cases)
+    links.sort(key=lambda t: -depth[t[2]])
+    return model_t, MpcInfo(slaves, master[slaves], arm, links, np.array(att_m, np.int64), np.array(att_e, np.int64),
+                            np.array(att_s, np.int64), ext)
 
 
 def pdelta_suppressed_axes(model: wire.ModelArrays) -> tuple:

@@ -380,11 +380,8 @@ def build_model_arrays(ncols: NodeColumns, mcols: MemberColumns, model: dict, an
     materials, sections, hinges, member sets, plates, load cases, combinations, imperfections, unity checks)."""
     opts = parse_options(analysis.get("options"))
     warnings: list = []
-    if opts.rigid_strategy == "LinearMpc" and any(_norm_enum(t) == "rigid" for t in mcols.mtype):
-        # RigidStrategy.LinearMpc (pydantic_models.py:1047-1049): the rigid link as a constraint transformation is not
-        # implemented; rigid members are stiff members (hostlogic.rigid_property_row) under either strategy
-        warnings.append(("W_LINEAR_MPC_AS_RIGID_MEMBER", "rigid_strategy=LinearMpc: rigid members are modelled as stiff "
-                         "members (RigidMember strategy), not as multi-point constraints"))
+    # RigidStrategy.LinearMpc (pydantic_models.py:1047-1049): applied by engine.analyze where hostlogic.mpc_transform can (first-
+    # order analyses, slaves without supports / plates); elsewhere the result carries W_LINEAR_MPC_AS_RIGID_MEMBER
     nd = _parse_nodes(ncols, model, opts)
     sc = _parse_sections(model, opts, warnings)
     mats = {int(m["id"]): m for m in (model.get("materials") or [])}

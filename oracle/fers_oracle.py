@@ -853,7 +853,7 @@ def recover_plates(asm: Assembly, U):
     return dict(p_res=res, p_nodal=nod, p_cdg=cdg, p_cdl=cdl, p_centroid=cen)
 
 
-def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool = True, exact_mpc: bool = False) -> ResultArrays:
+def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool = True, exact_mpc: bool | None = None) -> ResultArrays:
     """Full analysis of one document: the oracle twin of fers_core_b200.engine.analyze.
     detail=False skips interior section forces / extrema (as the engine's detail=False)."""
     opts = model.options
@@ -865,6 +865,14 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
     second_order = opts.order == "NONLINEAR"
     unilateral_members = np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE))
     t0 = time.perf_counter()
+    # RigidStrategy.LinearMpc (pydantic_models.py:1047-1049): exact constraints where mpc_applies, else stiff members + a note;
+    # exact_mpc=True / False forces either (tests measure the stiff member against the constraint)
+    wants_mpc = opts.rigid_strategy == "LinearMpc" and bool(np.any(model.m_type == wire.MT_RIGID))
+    use_mpc = mpc_applies(model) if exact_mpc is None else (bool(exact_mpc) and mpc_applies(model))
+    if exact_mpc is None and not wants_mpc:
+        use_mpc = False
+    if wants_mpc and not use_mpc:
+        out.warnings.append(("W_LINEAR_MPC_AS_RIGID_MEMBER", "rigid members solved as stiff members (RigidMember strategy)"))
     for grp in plan.groups:
         xyz = imperfect_coordinates(model, grp.imperfection) if grp.imperfection is not None else model.xyz
         asm = Assembly(model, xyz)
@@ -876,9 +884,8 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
         cols = list(grp.columns)
         needs_own = (second_order or np.any(unilateral_members) or len(unilateral_dofs(model)[0]) > 0
                      or len(model.support_curves) > 0 or len(model.hinge_curves) > 0)
-        if not needs_own and exact_mpc and mpc_applies(model):
-            # ---- linear with the rigid members as exact constraints (master-slave elimination): NOT what the product does
-            # (it solves stiff members under either RigidStrategy and says so); kept to measure the error of that choice
+        if not needs_own and use_mpc:
+            # ---- linear with RigidStrategy.LinearMpc: the rigid members as exact constraints (master-slave elimination)
             U, links, asm0, K0 = solve_linear_mpc(model, xyz, F)
             _store(out, asm0, model, cols, U, F, peq, K0, None, spans, fac, iters=None, detail=detail, links=links)
         elif not needs_own:
@@ -903,15 +910,34 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
 
 
 def mpc_applies(model) -> bool:
-    """The exact-constraint solve (analyze(exact_mpc=True)) covers first-order analyses whose rigid members carry no member
-    loads."""
-    if not np.any(model.m_type == wire.MT_RIGID):
+    """Where the rigid members can be exact constraints: a first-order analysis on the perfect geometry without unilateral
+    parts or load-dependent springs; rigid members free of member loads, forming trees with at most one supported node each;
+    slave nodes (every node of a tree but its root) without supports, plates or warping members; no elastic member with
+    both ends in one tree.  (The product states the same conditions in hostlogic.mpc_transform; tests hold the two together.)"""
+    o = model.options
+    if not np.any(model.m_type == wire.MT_RIGID) or o.order != "LINEAR" or model.imperfections:
+        return False
+    if len(model.support_curves) or len(model.hinge_curves) or len(unilateral_dofs(model)[0]):
+        return False
+    if np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)).any():
         return False
     rigid = set(np.nonzero(model.m_type == wire.MT_RIGID)[0].tolist())
     for lc in model.load_cases:
         if rigid & set(np.asarray(lc.dl_member).tolist()) or rigid & set(np.asarray(lc.pl_member).tolist()):
             return False
-    return True
+    try:
+        _parent, _via, root = mpc_forest(model)
+    except ValueError:
+        return False
+    slave = root != np.arange(model.n_nodes)
+    if (model.bc_code.reshape(model.n_nodes, 6)[slave] != wire.BC_FREE).any():
+        return False
+    if model.n_plates and slave[model.p_nodes].any():
+        return False
+    if len(model.w_member) and (slave[model.m_n1[model.w_member]].any() or slave[model.m_n2[model.w_member]].any()):
+        return False
+    elastic = model.m_type != wire.MT_RIGID
+    return not bool((elastic & (root[model.m_n1] == root[model.m_n2])).any())
 
 
 def mpc_forest(model):
