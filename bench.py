@@ -415,6 +415,14 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> None:
         spmv_bytes = nnzb * (36 * 8 + 4) + (nn + 1) * 4 + 2 * n_dof * 8 + n_dof      # BSR-6 values + indices, x, y, BC mask
         kern.append(hbm_row("k_spmv (1 RHS, not on the step path)", spmv_bytes, sv, 0))
         kern.append(hbm_row(asm_name, asm_bytes, am, 1))
+        if args.assembly_variant == engine.ASSEMBLY_GATHER:
+            # SURVEY.md 8(d) counts the assembly's algorithmic bytes per MEMBER: 64 B read + four 6x6 blocks written (1 152 B),
+            # atomics' read-modify-write not counted -- 0.403 GB at configs[3].  The gather kernel sums the diagonal blocks on
+            # chip and writes every block of K once (0.245 GB, the figure `frac` above uses); both are reported.
+            survey_bytes = model.n_members * (64 + 4 * 36 * 8)
+            kern[-1].update({"survey_8d_algorithmic_bytes": int(survey_bytes),
+                             "GB/s_survey_8d": survey_bytes / (am * 1e-3) / 1e9 if am > 0 else 0.0,
+                             "frac_survey_8d": survey_bytes / (am * 1e-3) / 1e9 / peak if am > 0 else 0.0})
         # fp64 pipe peak measured live by the library (register-resident DMMA.8x8x4 / DFMA bursts)
         scratch = torch.empty(8 * 1024 * 160, dtype=torch.uint8, device=dev)
         dmma, dfma = C.c_double(), C.c_double()
