@@ -34,6 +34,8 @@ SIGNATURES = {
     "fers_b200_assemble_set_gather_kernel": (_i, [_i]),
     "fers_b200_zero": (_i, [_vp, _sz, _vp]),
     "fers_b200_assemble_warping": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fers_b200_assemble_cables": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "fers_b200_cable_rhs": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "fers_b200_recover_warping": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fers_b200_gather_map_workspace": (_sz, [_i, _i]),
     "fers_b200_gather_map_build": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _ip, _vp, _sz, _vp]),

@@ -64,9 +64,15 @@ def _plane(d: np.ndarray, q: np.ndarray):
 def _spans(H, p0, w, l0, ea):
     p1 = p0 - w * l0
     t0, t1 = np.hypot(H, p0), np.hypot(H, p1)
-    A = (np.arcsinh(p0 / H) - np.arcsinh(p1 / H)) / w
+    # differences written without cancellation (a taut cable has t0 ~ t1 >> w l0):
+    #   t0 - t1 = (p0^2 - p1^2) / (t0 + t1);  asinh(x0) - asinh(x1) = asinh(x0 sqrt(1 + x1^2) - x1 sqrt(1 + x0^2)), whose
+    #   argument is H^2 (p0^2 - p1^2) / (p0 t1 + p1 t0) / H^2 when p0 and p1 have the same sign (no cancellation in the sum)
+    dt = w * l0 * (p0 + p1) / (t0 + t1)
+    same = p0 * p1 > 0.0
+    den = np.where(same, p0 * t1 + p1 * t0, 1.0)
+    A = np.where(same, np.arcsinh(w * l0 * (p0 + p1) / den), np.arcsinh(p0 / H) - np.arcsinh(p1 / H)) / w
     l = H * (l0 / ea + A)
-    h = (p0 * l0 - 0.5 * w * l0 * l0) / ea + (t0 - t1) / w
+    h = (p0 * l0 - 0.5 * w * l0 * l0) / ea + dt / w
     return l, h, p1, t0, t1, A
 
 
@@ -117,6 +123,8 @@ def end_tension(d: np.ndarray, q: np.ndarray, l0: np.ndarray, ea: np.ndarray):
             det = fhh * fqq - fhq * fhq
             dH = (fqq * r1 - fhq * r2) / det
             dp = (fhh * r2 - fhq * r1) / det
+            if (np.maximum(np.abs(dH), np.abs(dp)) <= 1e-14 * np.hypot(H, p0)).all():
+                break                                  # the step is below the resolution of the unknowns
             # damping: H stays positive and the residual must not grow
             step = np.ones_like(H)
             neg = H + dH <= 0.0

@@ -9,6 +9,7 @@ without the built library every entry point raises.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 import json
 import threading
 import time
@@ -17,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from . import _lib, chol, unity, wire
+from . import _lib, cable, chol, unity, wire
 from .hostlogic import (
     INACTIVE_SCALE, effective_bc, imperfect_coordinates, member_frames_host, mpc_transform, pdelta_suppressed_axes, rhs_plan,
     rigid_property_row,
@@ -36,6 +37,10 @@ PCG_MAX_ITER = 200000
 PCG_ALLOW_UNCONVERGED = False  # profiling captures only (bench.py --profile-iters)
 NR_CHOICES = (8, 16, 32, 64)
 ASSEMBLY_GATHER = 4           # assembly_variant: 4 = gather kernel (default); 0-3 = atomic scatter-add variants
+
+
+CABLE_TOL = 1.0e-9          # relative change of the displacements between two Newton steps of the cable state
+CABLE_MAX_ITER = 60
 
 
 class EngineError(RuntimeError):
@@ -208,6 +213,9 @@ class Engine:
         self.d_p_data = self._t(m.p_data, np.float64) if m.n_plates else None
         self.d_p_flags = self._t(m.p_flags, np.int32) if m.n_plates else None
         self.d_xyz0 = self._t(m.xyz, np.float64)
+        # catenary cables (cable.py): member rows; their tangents / right-hand-side corrections arrive per Newton step
+        self.n_cables = int(len(m.c_member))
+        self.d_c_member = self._t(m.c_member, np.int32) if self.n_cables else None
 
     def _upload_load_cases(self) -> None:
         """Load records of every case, resident on the device (inputs of fers_b200_load_case)."""
@@ -289,8 +297,9 @@ class Engine:
             raise EngineError(f"set_rel: expected {self.model.rel.shape}, got {rel.shape}")
         self.d_rel.copy_(torch.from_numpy(np.ascontiguousarray(rel, np.float64)))
 
-    def assemble(self, d_xyz, d_scale=None, d_axial=None, kg_mode=0, kg_suppress=0, count: bool = True) -> None:
-        """Element stiffness + assembly + boundary conditions for one geometry / state."""
+    def assemble(self, d_xyz, d_scale=None, d_axial=None, kg_mode=0, kg_suppress=0, count: bool = True, cable_g=None) -> None:
+        """Element stiffness + assembly + boundary conditions for one geometry / state.  ``cable_g`` [Ncable,3,3]: tangents of
+        the catenary cables at the current state (their member rows carry scale 0 in ``d_scale``)."""
         m, lib, st = self.model, self.lib, self.stream
         self._k_version += 1
         n_rel = 0 if self.d_rel is None else self.d_rel.shape[0]
@@ -323,6 +332,9 @@ class Engine:
             _lib.check(lib.fers_b200_assemble_plates(
                 m.n_plates, _lib.ptr(d_xyz), _lib.ptr(self.d_p_nodes), _lib.ptr(self.d_p_data), _lib.ptr(self.d_p_flags),
                 _lib.ptr(self.d_p_slot), _lib.ptr(self.d_vals), st), "assemble_plates")
+        if cable_g is not None and self.n_cables:
+            _lib.check(lib.fers_b200_assemble_cables(self.n_cables, _lib.ptr(self.d_c_member), _lib.ptr(cable_g),
+                                                     _lib.ptr(self.d_m_slot), _lib.ptr(self.d_vals), st), "assemble_cables")
         # count=False (re-assemblies inside an iteration): the free / dead DOF counts are not read back, no host sync
         n_free, n_dead = C.c_int(), C.c_int()
         _lib.check(lib.fers_b200_bc_build(
@@ -474,7 +486,7 @@ class Engine:
         return u
 
     def recover(self, d_xyz, d_u, d_f, d_peq, factors_pad, span, d_scale=None, d_axial_rhs=None, kg_mode=0,
-                kg_suppress=0, detail=True, link_forces=None) -> dict:
+                kg_suppress=0, detail=True, link_forces=None, cables=None) -> dict:
         """All recovery kernels for displacement columns d_u [Ndof,nr]."""
         m, lib, st = self.model, self.lib, self.stream
         nr = d_u.shape[1]
@@ -508,6 +520,10 @@ class Engine:
                     M = g[e_rows, e_end, 3:] - _MpcDevice._cross(e_arm, F)
                     g[e_rows, e_end, 3:] = M
                     fl.view(nm, 2, 2, 3, nr)[e_rows, e_end, 1] = torch.einsum("mij,mjr->mir", e_R, M)
+            if cables is not None:
+                # catenary cables: end forces of the converged state, formed on the host (_cable_report)
+                fl.index_copy_(0, cables["rows"], cables["f_local"].expand(-1, -1, nr).contiguous())
+                fg.index_copy_(0, cables["rows"], cables["f_global"].expand(-1, -1, nr).contiguous())
             out.update(f_local=fl, f_global=fg, u_local=ul)
             if self.n_warp:
                 bw = self._empty((self.n_warp, 2, nr))
@@ -526,6 +542,9 @@ class Engine:
                     _lib.ptr(self.d_roll), _lib.ptr(sp_ptr), _lib.ptr(sp_rows), _lib.ptr(d_fac), _lib.ptr(fl), _lib.ptr(fg),
                     _lib.ptr(sec_tables[2]), _lib.ptr(sec_tables[3]), _lib.ptr(sec), _lib.ptr(mm[0]), _lib.ptr(mm[1]), _lib.ptr(mm[2]), _lib.ptr(mm[3]), st),
                     "recover_sections")
+                if cables is not None:
+                    for dst, key in ((sec, "sec"), (mm[0], "lmax"), (mm[1], "lmin"), (mm[2], "gmax"), (mm[3], "gmin")):
+                        dst.index_copy_(0, cables["rows"], cables[key].expand(-1, -1, nr).contiguous())
                 out.update(sec=sec, lmax=mm[0], lmin=mm[1], gmax=mm[2], gmin=mm[3])
         if m.n_plates:
             npl = m.n_plates
@@ -541,6 +560,8 @@ class Engine:
         load vectors -> element stiffness + assembly + BC -> multi-RHS solve -> recovery.
         Everything stays on the device; returns the result tensors (layout [.., nr])."""
         nr = _pad_nr(factors.shape[0])
+        if self.n_cables:
+            raise EngineError("run_linear: models with cables need the iteration of engine.analyze")
         if factors.shape[0] > 64:
             raise EngineError("run_linear handles at most 64 right-hand sides per pass")
         f_case, peq_case = self.load_cases(self.d_xyz0)
@@ -596,6 +617,10 @@ def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_
             stats_out: dict | None = None, solver: str = "auto") -> ResultArrays:
     """Full analysis of one document on the GPU (twin of oracle.fers_oracle.analyze)."""
     t_start = time.perf_counter()
+    if len(model.c_member):
+        # catenary cables: outside their own element (cable.py) the member rows behave as pin-ended bars without stiffness
+        # (loads the catenary cannot take -- partial / point loads -- go to the end nodes as on a truss member)
+        model = dataclasses.replace(model, m_type=np.where(model.m_type == wire.MT_CABLE, wire.MT_TRUSS, model.m_type).astype(np.int32))
     # RigidStrategy.LinearMpc: the engine solves the transformed model (slaves on rigid arms of their master, hostlogic.
     # mpc_transform) and reports on the original one; where the transformation does not apply the rigid members are stiff
     # members and the result says so
@@ -611,7 +636,7 @@ def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_
     if plan.n_rhs == 0:
         return out
     second_order = opts.order == "NONLINEAR"
-    unilateral = np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE))
+    unilateral = np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION)) | (len(model.c_member) > 0)
     span = eng.span_tables()
     if model.unity_checks and detail:
         out.unity = unity.UnityAccumulator(model, plan, eng.dev)      # envelopes folded batch by batch in _store
@@ -725,8 +750,17 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
     """Active-set (tension/compression-only members) around the P-Delta fixed point, one column."""
     opts = model.options
     nm = model.n_members
-    uni = np.nonzero(np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)))[0]
+    uni = np.nonzero(np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION)))[0]
     scale = np.ones(nm)
+    n_cab = eng.n_cables
+    if n_cab:
+        # catenary cables live outside the beam assembly (their member rows carry no stiffness); load per unstretched length
+        # of this column: own weight + the uniform member loads of the combination
+        scale[model.c_member] = 0.0
+        cab_q = model.c_w + sum(fac[0, li] * lc.cab_q for li, lc in enumerate(model.load_cases))
+        c_i, c_j = model.m_n1[model.c_member], model.m_n2[model.c_member]
+    u_host = np.zeros((model.n_nodes, 6))
+    d_cab_g = None
     kg_mode = (1 if opts.pdelta_formulation == "CONSISTENT" else 2) if second_order else 0
     sup = 0
     for ax in pdelta_suppressed_axes(model):
@@ -743,14 +777,23 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
         eng.set_rel(model.rel)                          # the previous column left its own state on the device
     settled = False
     for _outer in range(max(1, 2 * (len(uni) + eng.n_unilateral) + 2
-                            + (max(opts.max_iterations, 20) if eng.n_curves or eng.n_hinge_curves else 0))):
+                            + (max(opts.max_iterations, 20) if eng.n_curves or eng.n_hinge_curves else 0)
+                            + (CABLE_MAX_ITER if n_cab else 0))):
         if eng.n_unilateral or eng.n_curves:
             eng.set_unilateral(sup_active, curve_k)
-        d_scale = eng._t(scale, np.float64) if len(uni) else None
+        d_scale = eng._t(scale, np.float64) if (len(uni) or n_cab) else None
         f_case, peq_case = eng.load_cases(d_xyz, d_scale)
         d_f = eng.combine(f_case, fac, nr)
         d_peq = eng.combine(peq_case, fac, nr)
-        eng.assemble(d_xyz, d_scale)
+        if n_cab:
+            # Newton step in total form: (K + Kc) u = f - p(u_k) + Kc u_k, the cable state (p, G) from the host
+            p_c, g_c, _a = cable.element_state(xyz[c_i] + u_host[c_i, :3], xyz[c_j] + u_host[c_j, :3], cab_q, model.c_l0, model.c_ea)
+            gu = np.einsum("cij,cj->ci", g_c, u_host[c_i, :3] - u_host[c_j, :3])
+            corr = np.concatenate([gu, -gu], axis=1) - p_c
+            d_cab_g = eng._t(g_c, np.float64)
+            _lib.check(eng.lib.fers_b200_cable_rhs(n_cab, _lib.ptr(eng.d_c_member), _lib.ptr(eng.d_n1), _lib.ptr(eng.d_n2),
+                                                   _lib.ptr(eng._t(corr, np.float64)), _lib.ptr(d_f), nr, 0, eng.stream), "cable_rhs")
+        eng.assemble(d_xyz, d_scale, cable_g=d_cab_g)
         d_u = eng.solve(d_f)
         d_axial = None
         if second_order and nm:
@@ -762,7 +805,7 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
                            "member_axial")
                 d_axial = ax_rhs
                 d_ax1 = ax_rhs[:, 0].contiguous()
-                eng.assemble(d_xyz, d_scale, d_ax1, kg_mode, sup)
+                eng.assemble(d_xyz, d_scale, d_ax1, kg_mode, sup, cable_g=d_cab_g)
                 d_un = eng.solve(d_f)
                 total_it += 1
                 den = float(torch.linalg.norm(d_un[:, 0]))
@@ -772,6 +815,11 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
                     conv = True
                     break
         changed = False
+        if n_cab:
+            u_new = d_u[:, 0].cpu().numpy().reshape(model.n_nodes, 6)
+            den = float(np.linalg.norm(u_new))
+            changed = bool(den > 0.0 and float(np.linalg.norm(u_new - u_host)) > CABLE_TOL * den)
+            u_host = u_new
         if eng.n_unilateral or eng.n_curves or eng.n_hinge_curves:
             # reactions and member end forces of the current state decide which unilateral supports stay closed and
             # how stiff the load-dependent springs (supports, hinges) are in the next pass
@@ -816,13 +864,39 @@ def _solve_nonlinear(eng: Engine, out, model, d_xyz, xyz, col, fac, span, second
         out.converged[col] = False
         out.warnings.append(("W_ACTIVE_SET_NOT_CONVERGED", f"result column {col}: the active set / stiffness curves did not "
                              f"settle within {_outer + 1} outer iterations; the last iterate is reported"))
-    d_scale = eng._t(scale, np.float64) if len(uni) else None
-    rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, d_scale, d_axial, kg_mode, sup, detail=detail)
+    d_scale = eng._t(scale, np.float64) if (len(uni) or n_cab) else None
+    cab = _cable_report(eng, model, xyz, u_host, cab_q) if n_cab else None
+    rec = eng.recover(d_xyz, d_u, d_f, d_peq, facp, span, d_scale, d_axial, kg_mode, sup, detail=detail, cables=cab)
     _store(out, model, [col], d_u, rec, xyz)
     if second_order:
         out.iterations[col] = total_it
         out.converged[col] = bool(conv) and settled
         out.residual[col] = resn
+
+
+def _cable_report(eng: Engine, model, xyz, u, cab_q) -> dict:
+    """Results of the catenary cables at the node displacements u [Nn,6] (one column): end forces in the stiffness sign
+    (-a at the start, a - q L0 at the end), the start force carried along the unstretched length at the report stations
+    (q s - a, no moments) and the extrema over {ends, stations}, as device tensors [Ncable, ., 1] for Engine.recover."""
+    cm = model.c_member
+    ni, nj = model.m_n1[cm], model.m_n2[cm]
+    _p, _g, a = cable.element_state(xyz[ni] + u[ni, :3], xyz[nj] + u[nj, :3], cab_q, model.c_l0, model.c_ea)
+    R, _, _ = member_frames_host(dataclasses.replace(model, xyz=xyz), cm)
+    nc = len(cm)
+    fg = np.zeros((nc, 12))
+    fg[:, 0:3] = -a
+    fg[:, 6:9] = a - cab_q * model.c_l0[:, None]
+    fl = np.zeros((nc, 12))
+    fl[:, 0:3] = np.einsum("mij,mj->mi", R, fg[:, 0:3])
+    fl[:, 6:9] = np.einsum("mij,mj->mi", R, fg[:, 6:9])
+    tg = -cable.tension_along(a, cab_q, model.c_l0, SECTION_FRACS)                # [nc, ns, 3] global
+    sec_g = np.zeros((nc, len(SECTION_FRACS), 6)); sec_g[:, :, 0:3] = tg
+    sec = np.zeros_like(sec_g); sec[:, :, 0:3] = np.einsum("mij,msj->msi", R, tg)
+    loc = np.concatenate([fl[:, None, 0:6], fl[:, None, 6:12], sec], axis=1)
+    glo = np.concatenate([fg[:, None, 0:6], fg[:, None, 6:12], sec_g], axis=1)
+    t = lambda x: eng._t(np.ascontiguousarray(x).reshape(nc, -1, 1), np.float64)          # noqa: E731
+    return dict(rows=eng.d_c_member.to(torch.int64), f_local=t(fl), f_global=t(fg), sec=t(sec), lmax=t(loc.max(1)),
+                lmin=t(loc.min(1)), gmax=t(glo.max(1)), gmin=t(glo.min(1)))
 
 
 def _store(out: ResultArrays, model, cols, d_u, rec, xyz) -> None:

@@ -215,8 +215,8 @@ def mpc_transform(model: wire.ModelArrays):
     if model.imperfections or len(model.support_curves) or len(model.hinge_curves):
         return None, "imperfection cases or load-dependent springs"
     if np.isin(model.bc_code, (wire.BC_POS_ONLY, wire.BC_NEG_ONLY)).any() or \
-            np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)).any():
-        return None, "unilateral supports or members"
+            np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)).any() or len(model.c_member):
+        return None, "unilateral supports or members, cables"
     nn = model.n_nodes
     adj: dict = {}
     for m in rigid:

@@ -73,6 +73,7 @@ class LoadCaseArrays:
     # distributed (trapezoid) member loads, global direction; row = [q1(3), q2(3), a, b]
     dl_member: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
     dl_data: np.ndarray = field(default_factory=lambda: np.zeros((0, 8)))
+    cab_q: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))     # [Ncable,3] uniform load per unstretched length on the cables
     # member point loads / moments; row = [F(3), M(3), position, is_local]
     pl_member: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
     pl_data: np.ndarray = field(default_factory=lambda: np.zeros((0, 8)))
@@ -159,6 +160,12 @@ class ModelArrays:
     warp_node: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))   # [n_real] aux node or -1
     w_member: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))    # [Nw] members with warping
     w_aux: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), np.int32))  # [Nw,2] aux nodes of start / end
+    # MemberType.Cable (pydantic_models.py:592-598): elastic catenary elements (fers_core_b200/cable.py); LoadCaseArrays.cab_q
+    # carries their uniform member loads in the same order
+    c_member: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))    # [Ncable] member rows
+    c_l0: np.ndarray = field(default_factory=lambda: np.zeros(0))                  # [Ncable] unstretched length
+    c_ea: np.ndarray = field(default_factory=lambda: np.zeros(0))                  # [Ncable] axial stiffness
+    c_w: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))              # [Ncable,3] own weight per unstretched length
 
     def member_raw(self, m: int):
         """(section dict, material dict) of member index m as they came over the wire."""
@@ -273,6 +280,8 @@ class MemberColumns:
     ref_member: list
     ref_node: list
     weight: list
+    pretension: list = None        # Cable members (pydantic_models.py:1525-1528)
+    unstretched_length: list = None  # Cable members (pydantic_models.py:1542-1545)
 
 
 def node_columns(nodes: list) -> NodeColumns:
@@ -293,7 +302,8 @@ def member_columns(members: list) -> MemberColumns:
         rotation=np.fromiter((float(m.get("rotation_angle") or 0.0) for m in members), np.float64, nm),
         section=g("section"), mirror=g("mirror"), start_hinge=g("start_hinge"), end_hinge=g("end_hinge"),
         start_offset=g("start_offset"), end_offset=g("end_offset"), classification=g("classification"),
-        ref_member=g("reference_member"), ref_node=g("reference_node"), weight=g("weight"))
+        ref_member=g("reference_member"), ref_node=g("reference_node"), weight=g("weight"),
+        pretension=g("pretension"), unstretched_length=g("unstretched_length"))
 
 
 def parse_document(doc: dict) -> ModelArrays:
@@ -331,7 +341,9 @@ def from_fers(calc) -> ModelArrays:
         end_hinge=[oid(m.end_hinge) for m in members], start_offset=[m.start_offset for m in members],
         end_offset=[m.end_offset for m in members], classification=[m.classification for m in members],
         ref_member=[oid(m.reference_member) for m in members], ref_node=[oid(m.reference_node) for m in members],
-        weight=[0.0] * nm)                         # Member.to_dict emits weight 0.0 (members/member.py:186-193)
+        weight=[0.0] * nm,                         # Member.to_dict emits weight 0.0 (members/member.py:186-193)
+        pretension=[getattr(m, "pretension", None) for m in members],
+        unstretched_length=[getattr(m, "unstretched_length", None) for m in members])
     settings = calc.settings.to_dict()
     model = {
         "member_sets": [ms.to_dict() for ms in calc.member_sets],
@@ -404,6 +416,7 @@ def build_model_arrays(ncols: NodeColumns, mcols: MemberColumns, model: dict, an
         combo_limit_state=[c.get("limit_state") for c in combos],
         m_classification=list(mcols.classification), m_section_raw=mb["m_section_raw"],
         m_ref_member=mb["m_ref_member"], m_ref_node=mb["m_ref_node"],
+        c_member=mb["c_member"], c_l0=mb["c_l0"], c_ea=mb["c_ea"], c_w=mb["c_w"],
     )
 
 
@@ -632,9 +645,37 @@ def _parse_members(mc: MemberColumns, nd: dict, sc: dict, model: dict, opts: Opt
                 for d, f in enumerate(_HINGE_CURVES if h else ()):
                     if h.get(f) and h[f].get("points"):
                         hinge_curves.append((i, int(m_rel[i]), 6 * e + d) + hinge_curve(int(hid), f, h[f]))
-    for i in np.nonzero(m_type == MT_CABLE)[0]:
-        warnings.append(("W_CABLE_AS_TENSION", f"member {int(m_ids[i])}: cable treated as tension-only straight member"))
     rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), REL_STRIDE)
+    # cables: elastic catenary between the end nodes; hinges, offsets and section eccentricities do not apply to them
+    c_member = np.nonzero(m_type == MT_CABLE)[0].astype(np.int32)
+    for i in c_member:
+        if m_rel[i] >= 0:
+            m_rel[i] = -1
+            warnings.append(("W_CABLE_MODIFIERS_IGNORED", f"member {int(m_ids[i])}: hinges, end offsets and shear-centre offsets "
+                             "do not apply to a cable"))
+    c_chord = np.linalg.norm(xyz[m_n2[c_member]] - xyz[m_n1[c_member]], axis=1)
+    c_ea = np.array([sc["prop"][m_prop[i]][0] for i in c_member], np.float64)
+    pre = mc.pretension if mc.pretension is not None else [None] * nm
+    given = mc.unstretched_length if mc.unstretched_length is not None else [None] * nm
+    c_l0 = c_chord.copy()
+    for j, i in enumerate(c_member):
+        # `unstretched_length` wins over `pretension`: L0 = L_chord / (1 + pretension / EA); neither: the chord
+        if given[i] is not None:
+            c_l0[j] = float(given[i])
+        elif pre[i] is not None:
+            c_l0[j] = c_chord[j] / (1.0 + float(pre[i]) / c_ea[j])
+        if not (np.isfinite(c_l0[j]) and c_l0[j] > 0.0 and c_ea[j] > 0.0):
+            raise WireError(f"member {int(m_ids[i])}: a cable needs a positive unstretched length and axial stiffness")
+    # own weight per unit length, "carried intrinsically in the catenary formulation" (1337-1340): the `weight` override when
+    # non-zero, else density * area * |gravity_factor| when self weight is enabled
+    g_dir = np.asarray(opts.gravity_direction, np.float64)
+    g_dir = g_dir / (np.linalg.norm(g_dir) or 1.0)
+    c_w = np.zeros((len(c_member), 3))
+    for j, i in enumerate(c_member):
+        w = abs(float(mc.weight[i] or 0.0))
+        if w == 0.0 and opts.enable_self_weight:
+            w = sc["prop_rho_a"][m_prop[i]] * abs(opts.gravity_factor)
+        c_w[j] = w * g_dir
     if nm:
         axis = xyz[m_n2] - xyz[m_n1]
         with_rec = np.nonzero(m_rel >= 0)[0]
@@ -667,7 +708,7 @@ def _parse_members(mc: MemberColumns, nd: dict, sc: dict, model: dict, opts: Opt
     return dict(m_n1=m_n1, m_n2=m_n2, m_type=m_type, m_roll=m_roll, m_prop=m_prop, m_rel=m_rel, rel=rel, member_index=member_index,
                 member_ids=m_ids,
                 hinge_curves=hinge_curves, m_section_raw=m_section_raw, m_ref_member=m_ref_member, m_ref_node=m_ref_node,
-                member_sets=member_sets)
+                member_sets=member_sets, c_member=c_member, c_l0=c_l0, c_ea=c_ea, c_w=c_w)
 
 
 def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:
@@ -766,6 +807,7 @@ def _parse_load_cases(analysis: dict, opts: Options, nd: dict, mb: dict, sc: dic
     m_prop, m_type = mb["m_prop"], mb["m_type"]
     plates, p_ids_l, p_nodes, plate_index = pl["plates"], pl["p_ids_l"], pl["p_nodes"], pl["plate_index"]
     load_cases = []
+    cable_row = {int(m): j for j, m in enumerate(mb["c_member"])}
     raw_cases = list(analysis.get("load_cases") or [])
     sw_case_id = None
     if opts.enable_self_weight:
@@ -866,6 +908,23 @@ def _parse_load_cases(analysis: dict, opts: Options, nd: dict, mb: dict, sc: dic
                 _surface_load_to_plates(sl, xyz, p_nodes, pp_plate, pp_vec, warnings)
             else:
                 _surface_load_to_members(sl, xyz, mb, dl_member, dl_data, warnings)
+        # uniform full-length loads on cables belong to the catenary (load per unstretched length); anything else on a cable
+        # is carried to its end nodes like on a pin-ended member
+        cab_q = np.zeros((len(cable_row), 3))
+        if cable_row and dl_member:
+            keep_m, keep_d = [], []
+            for mi, row in zip(dl_member, dl_data):
+                j = cable_row.get(int(mi))
+                if j is None:
+                    keep_m.append(mi); keep_d.append(row)
+                elif row[6] == 0.0 and row[7] == 1.0 and np.array_equal(row[0:3], row[3:6]):
+                    cab_q[j] += row[0:3]
+                else:
+                    keep_m.append(mi); keep_d.append(row)
+                    warnings.append(("W_CABLE_LOAD_LUMPED", f"load case {lca.id}: a partial or varying distributed load on cable "
+                                     f"{int(mcols.ids[mi])} is carried to its end nodes"))
+            dl_member, dl_data = keep_m, keep_d
+        lca.cab_q = cab_q
         lca.nod_node = np.array(nod_node, np.int32)
         lca.nod_vec = np.array(nod_vec, np.float64).reshape(len(nod_node), 6)
         lca.dl_member = np.array(dl_member, np.int32)

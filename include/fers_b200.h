@@ -131,6 +131,15 @@ int fers_b200_assemble_set_gather_kernel(int kind);
 int fers_b200_assemble_warping(int n_w, const int* w_member, const double* xyz, const int* m_n1, const int* m_n2,
                                const int* m_prop, const double* m_scale, const double* prop, const int* w_slot, double* vals,
                                void* stream);
+/* Elastic catenary cables (MemberType.Cable, pydantic_models.py:592-598; pretension 1525-1528, unstretched_length
+ * 1542-1545): one Newton step of the cable state, formed on the host (fers_core_b200/cable.py), into the device matrix
+ * and right-hand side.  c_member[n_cables] member rows; g[n_cables][3][3] symmetric tangent between the translations of
+ * the end nodes: K(a,a) += G, K(a,b) -= G, K(b,a) -= G, K(b,b) += G; corr[n_cables][6] added to column `col` of
+ * f[Ndof][nrhs] at the translations of (start, end). */
+int fers_b200_assemble_cables(int n_cables, const int* c_member, const double* g, const int* m_slot, double* vals,
+                              void* stream);
+int fers_b200_cable_rhs(int n_cables, const int* c_member, const int* m_n1, const int* m_n2, const double* corr, double* f,
+                        int nrhs, int col, void* stream);
 /* TRI3 shell elements: CST membrane + DSG3 Mindlin bending (pydantic_models.py:1700-1726).
  * p_data[n_plates][8] = thickness, E, nu, stiffness modifiers (membrane, bending, shear), in-plane angle (rad) of local x from the default frame (PlateElement.local_x_direction, pydantic_models.py:1703), 1 spare;
  * p_flags bit0 membrane, bit1 bending, bit2 plane strain (membrane part). */

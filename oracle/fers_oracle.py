@@ -44,6 +44,7 @@ from fers_core_b200 import wire
 from fers_core_b200.results import ResultArrays, SECTION_FRACS
 # the host-side rules (result columns, imperfect geometry, rigid members, active sets, load-dependent springs) in the oracle's
 # own restatement -- not the product's hostlogic.py (a shared helper hides its bugs from every parity test)
+from oracle import cable_oracle
 from oracle.host_oracle import (
     rhs_plan, imperfect_coordinates, rigid_property_row, pdelta_suppressed_axes,
     unilateral_dofs, effective_bc, unilateral_update, curve_stiffness, curves_converged,
@@ -856,6 +857,9 @@ def recover_plates(asm: Assembly, U):
 def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool = True, exact_mpc: bool | None = None) -> ResultArrays:
     """Full analysis of one document: the oracle twin of fers_core_b200.engine.analyze.
     detail=False skips interior section forces / extrema (as the engine's detail=False)."""
+    if len(model.c_member):
+        # catenary cables: outside their own element the member rows are pin-ended bars without stiffness
+        model = dataclasses.replace(model, m_type=np.where(model.m_type == wire.MT_CABLE, wire.MT_TRUSS, model.m_type).astype(np.int32))
     opts = model.options
     plan = rhs_plan(model)              # list of RhsGroup(imperfection case, rhs columns ...)
     nn, nm, nd = model.n_nodes, model.n_members, model.n_dof
@@ -863,7 +867,7 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
     ns = len(SECTION_FRACS)
     out = ResultArrays.empty(model, plan)
     second_order = opts.order == "NONLINEAR"
-    unilateral_members = np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE))
+    unilateral_members = np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION)) | (len(model.c_member) > 0)
     t0 = time.perf_counter()
     # RigidStrategy.LinearMpc (pydantic_models.py:1047-1049): exact constraints where mpc_applies, else stiff members + a note;
     # exact_mpc=True / False forces either (tests measure the stiff member against the constraint)
@@ -901,9 +905,14 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
                     # equivalent loads of released members depend on the hinge stiffness of the iteration
                     F_it, peq_it = load_vectors(asm_it)
                     return row @ F_it, np.einsum("l,lmk->mk", row, peq_it)
-                U1, K1, kg1, scale1, it, conv, resn, asm_c, F1, peq1 = _solve_nonlinear(asm, model, F[ci], peq[ci], second_order, reload)
+                cab_q = None
+                if len(model.c_member):
+                    # load per unstretched length of every cable in this column: own weight + the uniform member loads
+                    cab_q = model.c_w + sum(fac[ci, li] * lc.cab_q for li, lc in enumerate(model.load_cases))
+                U1, K1, kg1, scale1, it, conv, resn, asm_c, F1, peq1, cab = _solve_nonlinear(asm, model, F[ci], peq[ci], second_order,
+                                                                                           reload, cab_q)
                 _store(out, asm_c, model, [col], U1[None], F1[None], peq1[None], K1,
-                       None if kg1 is None else kg1[None], spans, fac[ci:ci + 1], iters=(it, conv, resn), detail=detail)
+                       None if kg1 is None else kg1[None], spans, fac[ci:ci + 1], iters=(it, conv, resn), detail=detail, cables=cab)
     if timings is not None:
         timings["total_s"] = time.perf_counter() - t0
     return out
@@ -919,7 +928,7 @@ def mpc_applies(model) -> bool:
         return False
     if len(model.support_curves) or len(model.hinge_curves) or len(unilateral_dofs(model)[0]):
         return False
-    if np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)).any():
+    if np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)).any() or len(model.c_member):
         return False
     rigid = set(np.nonzero(model.m_type == wire.MT_RIGID)[0].tolist())
     for lc in model.load_cases:
@@ -1050,20 +1059,53 @@ def solve_linear_mpc(model, xyz, F):
     return U, (R_links, rigid, fg), asm0, K0
 
 
+CABLE_TOL = 1.0e-9         # relative change of the displacements between two Newton steps of the cable state
+CABLE_MAX_ITER = 60
+
+
 def _axial_forces(asm, U, peq, kg_local=None):
     rec = recover_members(asm, U[None], peq[None], None if kg_local is None else kg_local[None])
     return rec["f_local"][0][:, 6]
 
 
-def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order, reload=None):
+def _cable_linearisation(model, xyz, U, cab_q):
+    """Catenary cables at the displacement state U (oracle/cable_oracle.py): sparse tangent Kc, the right-hand-side
+    correction Kc U - p (p the internal forces of the cables at U) and the state (a, q) the results are reported from."""
+    nd = model.n_dof
+    cm = model.c_member
+    ni, nj = model.m_n1[cm], model.m_n2[cm]
+    u = U.reshape(-1, 6)
+    d = (xyz[nj] + u[nj, :3]) - (xyz[ni] + u[ni, :3])
+    a, G = cable_oracle.end_tension(d, cab_q, model.c_l0, model.c_ea)
+    Kc = sp.lil_matrix((nd, nd))
+    p = np.zeros(nd)
+    for c in range(len(cm)):
+        di = np.arange(6 * ni[c], 6 * ni[c] + 3); dj = np.arange(6 * nj[c], 6 * nj[c] + 3)
+        for r_, c_, sg in ((di, di, 1.0), (di, dj, -1.0), (dj, di, -1.0), (dj, dj, 1.0)):
+            Kc[np.ix_(r_, c_)] = Kc[np.ix_(r_, c_)] + sg * G[c]
+        p[di] += -a[c]
+        p[dj] += a[c] - cab_q[c] * model.c_l0[c]
+    Kc = Kc.tocsr()
+    return Kc, Kc @ U - p, (a, np.array(cab_q, float))
+
+
+def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order, reload=None, cab_q=None):
     """Active-set (tension/compression-only members, unilateral supports) and load-dependent springs (support and hinge
     stiffness curves) in one outer loop around the P-Delta fixed point.  ``reload(asm) -> (F, peq)`` re-forms the
     column's loads for a new state of the hinge springs.  Returns the assembly, loads of the final state as well."""
     opts = model.options
     nd = model.n_dof
-    uni = np.nonzero(np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION, wire.MT_CABLE)))[0]
+    uni = np.nonzero(np.isin(model.m_type, (wire.MT_TENSION, wire.MT_COMPRESSION)))[0]
     scale = np.ones(model.n_members)
     asm = asm0
+    n_cab = 0 if cab_q is None else len(model.c_member)
+    if n_cab:
+        # cables are catenary elements outside the beam assembly: their member rows carry no stiffness
+        scale[model.c_member] = 0.0
+        asm = Assembly(model, asm0.xyz, scale)
+    F_ext = F
+    U = np.zeros(nd)
+    Kc, cab = None, None
     total_it, conv, resn = 0, True, 0.0
     suppressed = pdelta_suppressed_axes(model)
     sup_idx = unilateral_dofs(model)[0]
@@ -1073,9 +1115,16 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order, reload=None):
     n_hinge = len(model.hinge_curves)
     hinge_k = hinge_curve_stiffness(model, None)        # = the values model.rel carries
     model_it = model
-    for _outer in range(max(1, 2 * (len(uni) + len(sup_idx)) + 2 + (max(opts.max_iterations, 20) if n_curves or n_hinge else 0))):
+    for _outer in range(max(1, 2 * (len(uni) + len(sup_idx)) + 2 + (max(opts.max_iterations, 20) if n_curves or n_hinge else 0)
+                            + (CABLE_MAX_ITER if n_cab else 0))):
         bc = effective_bc(model, sup_active, curve_k) if (len(sup_idx) or n_curves) else None
         K0 = asm.K_elastic()
+        U_prev = U
+        if n_cab:
+            # Newton step in total form: (K + Kc) u = f - p(u_k) + Kc u_k
+            Kc, corr, cab = _cable_linearisation(model, asm0.xyz, U_prev, cab_q)
+            K0 = (K0 + Kc).tocsr()
+            F = F_ext + corr
         Kff, free, _ = constrain(K0, model, bc=bc)
         U = np.zeros(nd); U[free] = solve_sym(Kff, F[free][:, None])[:, 0]
         kg = None
@@ -1089,6 +1138,8 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order, reload=None):
                     kg[i] = E.T @ kg[i] @ E
                 kg = _suppress_kg(asm, kg, suppressed)
                 K = asm.K_elastic(kg)
+                if n_cab:
+                    K = (K + Kc).tocsr()
                 Kff, free, _ = constrain(K, model, bc=bc)
                 Un = np.zeros(nd); Un[free] = solve_sym(Kff, F[free][:, None], require_pd=True)[:, 0]
                 total_it += 1
@@ -1101,6 +1152,9 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order, reload=None):
             # geometric stiffness consistent with the converged displacement
             N = _axial_forces(asm, U, peq, kg)
         changed = False
+        if n_cab:
+            den = np.linalg.norm(U)
+            changed = bool(den > 0.0 and np.linalg.norm(U - U_prev) > CABLE_TOL * den)
         if len(sup_idx):
             new_active = unilateral_update(model, sup_active, U, K @ U - F)
             changed = not np.array_equal(new_active, sup_active)
@@ -1121,7 +1175,8 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order, reload=None):
                 if hinges_moved:
                     model_it = dataclasses.replace(model, rel=rel_with_hinge_curves(model, hinge_k))
                     asm = Assembly(model_it, asm0.xyz, scale)
-                    F, peq = reload(asm)
+                    F_ext, peq = reload(asm)
+                    F = F_ext
                 continue
             break
         N = _axial_forces(asm, U, peq, kg)
@@ -1140,10 +1195,16 @@ def _solve_nonlinear(asm0: Assembly, model, F, peq, second_order, reload=None):
             model_it = dataclasses.replace(model, rel=rel_with_hinge_curves(model, hinge_k))
         asm = Assembly(model_it, asm0.xyz, scale)
         if hinges_moved:
-            F, peq = reload(asm)
+            F_ext, peq = reload(asm)
+            F = F_ext
     else:
         conv = False        # outer bound reached with the active set / stiffness curves still changing (engine: W_ACTIVE_SET_NOT_CONVERGED)
-    return U, K, kg, (scale if len(uni) else None), (total_it if second_order else None), conv, resn, asm, F, peq
+    if n_cab:
+        # report from the cable state AT the final displacements: reactions K u - F then hold the cables' true end forces
+        Kc_f, corr, cab = _cable_linearisation(model, asm0.xyz, U, cab_q)
+        K = (K - Kc + Kc_f).tocsr()
+        F = F_ext + corr
+    return U, K, kg, (scale if len(uni) else None), (total_it if second_order else None), conv, resn, asm, F, peq, cab
 
 
 def _suppress_kg(asm, kg, suppressed):
@@ -1159,7 +1220,7 @@ def _suppress_kg(asm, kg, suppressed):
     return np.einsum("mij,mjk,mlk->mil", asm.T, kgg, asm.T)
 
 
-def _store(out: ResultArrays, asm, model, cols, U, F, peq, K, kg, spans, fac, iters, detail=True, links=None):
+def _store(out: ResultArrays, asm, model, cols, U, F, peq, K, kg, spans, fac, iters, detail=True, links=None, cables=None):
     """Fill result arrays for the given rhs columns.  links = (R_full [ncols, nd], member rows, f_global [ncols, n, 12]) of a
     LinearMpc solve: the reactions carried through the rigid links and the end forces of the links themselves."""
     nn = model.n_nodes
@@ -1175,11 +1236,28 @@ def _store(out: ResultArrays, asm, model, cols, U, F, peq, K, kg, spans, fac, it
         rows, fg = links[1], links[2]
         rec["f_global"][:, rows] += fg
         rec["f_local"][:, rows] += np.einsum("mij,cmj->cmi", asm.T[rows], fg)
+    if cables is not None:
+        # end forces of the catenary cables (one column): the nodes act on the cable with -a at the start, a - q L0 at the end
+        a, q = cables
+        rows = model.c_member
+        fg = np.zeros((len(rows), 12))
+        fg[:, 0:3] = -a
+        fg[:, 6:9] = a - q * model.c_l0[:, None]
+        rec["f_global"][0, rows] = fg
+        rec["f_local"][0, rows] = np.einsum("mij,mj->mi", asm.T[rows], fg)
     out.f_local[cols] = rec["f_local"]; out.f_global[cols] = rec["f_global"]; out.u_local[cols] = rec["u_local"]
     out.bw[cols] = rec["bw"]
     if model.n_members and detail:
         span_by_rhs = [[(fac[r, li], spans[li]) for li in range(fac.shape[1])] for r in range(len(cols))]
         sec = section_forces(asm, rec["f_local"], span_by_rhs)
+        if cables is not None:
+            # along a cable: the start force carried along the unstretched length, -t(s) = q s - a, no moments
+            a, q = cables
+            rows = model.c_member
+            for si, x in enumerate(SECTION_FRACS):
+                tg = q * (x * model.c_l0)[:, None] - a
+                sec[0, rows, si, 0:3] = np.einsum("mij,mj->mi", asm.R[rows], tg)
+                sec[0, rows, si, 3:6] = 0.0
         out.sec[cols] = sec
         lmax, lmin, gmax, gmin = min_max(asm, rec["f_local"], rec["f_global"], sec)
         out.lmax[cols], out.lmin[cols], out.gmax[cols], out.gmin[cols] = lmax, lmin, gmax, gmin

@@ -1,0 +1,251 @@
+"""MemberType.Cable as an elastic catenary (pydantic_models.py:592-598; `pretension` 1525-1528, `unstretched_length`
+1542-1545; own weight "carried intrinsically in the catenary formulation", 1337-1340).
+
+The reference ships no cable example, test or number (its engine is closed): the element is pinned on the classical
+catenary instead -- the inextensible closed form  L0 = (2H/w) sinh(w l / 2H),  V = w L0 / 2,  the straight-bar limit, a
+pretensioned string under a point load (scalar equilibrium solved by bisection), overall equilibrium and the work-conjugate
+tangent -- with the product's closed-form element (fers_core_b200/cable.py) held against the oracle's quadrature
+restatement (oracle/cable_oracle.py), and the GPU analysis against the oracle's."""
+import copy
+
+import numpy as np
+import pytest
+from scipy.optimize import brentq
+
+from fers_core_b200 import cable, wire
+from oracle import cable_oracle, fers_oracle
+from tests import helpers
+
+E_MOD = 210e9
+
+
+@pytest.fixture(scope="module")
+def engine_mod():
+    from fers_core_b200 import engine
+    return engine
+
+
+def cable_doc(nodes, members, loads=(), dls=(), order="LINEAR", self_weight=False, combos=()):
+    """nodes [(id, x, y, z, support id or None)]: support 1 clamps, 2 pins; members: dicts over the golden cantilever's
+    member record; loads [(case, node, magnitude, direction)]; dls [(case, member, magnitude, direction, start, end)]."""
+    doc = copy.deepcopy(helpers.golden("cantilever_end_load")["doc"])
+    m = doc["model"]
+    m["nodes"] = [{"id": i, "X": x, "Y": y, "Z": z, "nodal_support": s} for i, x, y, z, s in nodes]
+    fixed = {"condition_type": "Fixed", "stiffness": None}
+    free = {"condition_type": "Free", "stiffness": None}
+    m["nodal_supports"] = [dict(id=1, classification=None, warping_condition=None, X=fixed, Y=fixed, Z=fixed, RX=fixed, RY=fixed, RZ=fixed),
+                           dict(id=2, classification=None, warping_condition=None, X=fixed, Y=fixed, Z=fixed, RX=free, RY=free, RZ=free)]
+    base = m["members"][0]
+    m["members"] = [dict(base, **mm) for mm in members]
+    m["member_sets"] = [{"id": 1, "classification": None, "member_ids": [mm["id"] for mm in members], "buckling_restraints": []}]
+    a = doc["analysis"]
+    a["options"]["order"] = order
+    a["options"]["enable_self_weight"] = self_weight
+    lc = a["load_cases"][0]
+    cases = sorted({c for c, *_ in loads} | {c for c, *_ in dls}) or [1]
+    a["load_cases"] = [
+        dict(lc, id=c, name=f"LC{c}",
+             nodal_loads=[{"id": 100 * c + k, "node": n, "magnitude": mag, "direction": list(dr), "load_type": "force"}
+                          for k, (cc, n, mag, dr) in enumerate(loads) if cc == c],
+             distributed_loads=[{"id": 200 * c + k, "member": mm, "magnitude": mag, "end_magnitude": mag, "direction": list(dr),
+                                 "start_frac": s0, "end_frac": s1, "load_type": "force"}
+                                for k, (cc, mm, mag, dr, s0, s1) in enumerate(dls) if cc == c])
+        for c in cases]
+    a["load_combinations"] = [{"id": 10 + k, "name": f"C{k}", "load_case_factors": {str(c): f for c, f in fac.items()},
+                               "limit_state": "ULS"} for k, fac in enumerate(combos)]
+    return doc
+
+
+def _cab(i, a, b, **kw):
+    return dict(id=i, start_node_id=a, end_node_id=b, member_type="Cable", **kw)
+
+
+def _ea(doc):
+    return float(wire.parse_document(doc).prop[0][0])
+
+
+# ---- the element ---------------------------------------------------------------------------------------------------------
+def test_element_equals_the_quadrature_restatement():
+    rng = np.random.default_rng(7)
+    n = 40
+    d = rng.normal(size=(n, 3)) * 10.0
+    q = rng.normal(size=(n, 3)) * 5.0
+    L = np.linalg.norm(d, axis=1)
+    l0 = L * rng.uniform(0.9, 1.3, n)                      # taut and slack
+    ea = 10.0 ** rng.uniform(4, 8, n)
+    a, G = cable.end_tension(d, q, l0, ea)
+    a2, G2 = cable_oracle.end_tension(d, q, l0, ea)
+    assert (np.abs(a - a2).max(1) / np.abs(a2).max(1)).max() < 1e-10
+    assert (np.abs(G - G2).max((1, 2)) / np.abs(G2).max((1, 2))).max() < 1e-9
+    assert np.abs(G - G.transpose(0, 2, 1)).max() <= 1e-12 * np.abs(G).max()
+    assert (np.linalg.eigvalsh(G) > 0.0).all()             # a hanging cable is stable in every direction
+
+
+def test_tangent_is_the_derivative_of_the_end_force():
+    d = np.array([[30.0, -4.0, 7.0]]); q = np.array([[0.5, -12.0, 1.0]]); l0 = np.array([33.0]); ea = np.array([3.0e6])
+    _, G = cable.end_tension(d, q, l0, ea)
+    h = 1e-6
+    fd = np.zeros((3, 3))
+    for c in range(3):
+        e = np.zeros((1, 3)); e[0, c] = h
+        fd[:, c] = (cable.end_tension(d + e, q, l0, ea)[0] - cable.end_tension(d - e, q, l0, ea)[0])[0] / (2 * h)
+    assert np.abs(fd - G[0]).max() < 1e-7 * np.abs(G).max()
+
+
+def test_inextensible_catenary_closed_form():
+    w, span, H = 10.0, 100.0, 2000.0
+    l0 = 2 * H / w * np.sinh(w * span / (2 * H))
+    a, _ = cable.end_tension(np.array([[span, 0.0, 0.0]]), np.array([[0.0, -w, 0.0]]), np.array([l0]), np.array([1e15]))
+    assert a[0, 0] == pytest.approx(H, rel=1e-8)
+    assert a[0, 1] == pytest.approx(-w * l0 / 2, rel=1e-12)     # the start tension points down into the sagging cable
+    # sag from the tension at mid-length: T(L0/2) = H, and from the tension at the support T0 = H cosh(w l / 2H)
+    assert np.linalg.norm(a[0]) == pytest.approx(H * np.cosh(w * span / (2 * H)), rel=1e-8)
+
+
+def test_weightless_cable_is_a_bar_that_only_pulls():
+    d = np.array([[3.0, 4.0, 0.0], [3.0, 4.0, 0.0]]); l0 = np.array([4.9, 5.1]); ea = np.array([1e6, 1e6])
+    a, G = cable.end_tension(d, np.zeros((2, 3)), l0, ea)
+    assert np.allclose(a[0], 1e6 * 0.1 / 4.9 * np.array([0.6, 0.8, 0.0]))
+    assert np.allclose(a[1], 0.0) and np.abs(G[1]).max() <= 1e-8 * np.abs(G[0]).max()
+    n = np.array([0.6, 0.8, 0.0])
+    assert n @ G[0] @ n == pytest.approx(1e6 / 4.9)
+    t = np.array([-0.8, 0.6, 0.0])
+    assert t @ G[0] @ t == pytest.approx(np.linalg.norm(a[0]) / 5.0)        # string stiffness T / L across the chord
+
+
+def test_vertical_cable_hangs_on_its_upper_end():
+    w, l0, ea = 10.0, 9.99, 1e6
+    a, _ = cable.end_tension(np.array([[0.0, -10.0, 0.0]]), np.array([[0.0, -w, 0.0]]), np.array([l0]), np.array([ea]))
+    # stretched by 0.01 in total: mean tension EA * 0.01 / L0, the upper end carries half of the weight more
+    assert a[0, 1] == pytest.approx(-(ea * 0.01 / l0 + w * l0 / 2), rel=1e-9)
+    assert abs(a[0, 0]) + abs(a[0, 2]) < 1e-3
+
+
+# ---- the wire ------------------------------------------------------------------------------------------------------------
+def test_wire_reads_the_cable_fields():
+    nodes = [(1, 0, 0, 0, 2), (2, 10, 0, 0, 2), (3, 20, 0, 0, 2)]
+    doc = cable_doc(nodes, [_cab(1, 1, 2, pretension=5000.0), _cab(2, 2, 3, unstretched_length=10.5, pretension=1.0, weight=3.0)],
+                    dls=[(1, 1, 7.0, (0, -1, 0), 0.0, 1.0), (1, 2, 7.0, (0, -1, 0), 0.0, 0.5)])
+    m = wire.parse_document(doc)
+    ea = _ea(doc)
+    assert m.c_member.tolist() == [0, 1]
+    assert m.c_l0[0] == pytest.approx(10.0 / (1.0 + 5000.0 / ea)) and m.c_l0[1] == 10.5       # unstretched_length wins
+    assert np.allclose(m.c_w, [[0, 0, 0], [0, -3.0, 0]])                                      # `weight` override, along gravity
+    lc = m.load_cases[0]
+    assert np.allclose(lc.cab_q, [[0, -7.0, 0], [0, 0, 0]])               # the full-length uniform load belongs to the catenary
+    assert lc.dl_member.tolist() == [1]                                    # the partial one is carried to the end nodes
+    assert any(code == "W_CABLE_LOAD_LUMPED" for code, _ in m.warnings)
+    assert not any(code == "W_CABLE_AS_TENSION" for code, _ in m.warnings)
+    doc["analysis"]["options"]["enable_self_weight"] = True
+    m = wire.parse_document(doc)
+    assert m.c_w[0, 1] == pytest.approx(-m.prop_rho_a[0] * 9.81) and m.c_w[1, 1] == -3.0
+    sw = [lc for lc in m.load_cases if lc.name == "Self weight"]
+    assert sw and len(sw[0].dl_member) == 0                                # cables are excluded from the generated self weight
+
+
+# ---- structures, oracle --------------------------------------------------------------------------------------------------
+def _hanging(span=100.0, w=10.0, H=2000.0):
+    l0 = 2 * H / w * np.sinh(w * span / (2 * H))
+    return cable_doc([(1, 0, 0, 0, 2), (2, span, 0, 0, 2)], [_cab(1, 1, 2, weight=w, unstretched_length=l0)]), l0
+
+
+def test_hanging_cable_reactions():
+    doc, l0 = _hanging()
+    res = fers_oracle.analyze(wire.parse_document(doc))
+    R = res.R[0].reshape(-1, 6)
+    # EA = 4e8: the elastic stretch lowers H by 2.4e-4 of its inextensible value
+    assert R[0, 0] == pytest.approx(-2000.0, rel=5e-4) and R[1, 0] == pytest.approx(2000.0, rel=5e-4)
+    assert R[0, 1] == pytest.approx(10.0 * l0 / 2, rel=1e-10) and R[1, 1] == pytest.approx(10.0 * l0 / 2, rel=1e-10)
+    # tension along the cable: at mid-length it is horizontal and equal to H
+    mid = res.sec[0, 0, 1]
+    assert abs(mid[0]) == pytest.approx(abs(R[0, 0]), rel=1e-10) and abs(mid[1]) < 1e-6 and np.abs(mid[3:]).max() == 0.0
+
+
+def _string_doc(b=5.0, n0=20e3, p=3e3, order="LINEAR"):
+    nodes = [(1, 0, 0, 0, 2), (2, b, 0, 0, None), (3, 2 * b, 0, 0, 2)]
+    return cable_doc(nodes, [_cab(1, 1, 2, pretension=n0), _cab(2, 2, 3, pretension=n0)], loads=[(1, 2, p, (0, -1, 0))], order=order)
+
+
+@pytest.mark.parametrize("order", ["LINEAR", "NONLINEAR"])
+def test_pretensioned_string_under_a_point_load(order):
+    b, n0, p = 5.0, 20e3, 3e3
+    doc = _string_doc(b, n0, p, order)
+    ea = _ea(doc)
+    l0 = b / (1.0 + n0 / ea)
+
+    def unbalance(delta):
+        L = np.hypot(b, delta)
+        return 2.0 * ea * (L - l0) / l0 * delta / L - p
+    delta = brentq(unbalance, 0.0, b, xtol=1e-15)
+    res = fers_oracle.analyze(wire.parse_document(doc))
+    assert res.U[0, 1, 1] == pytest.approx(-delta, rel=1e-8)
+    T = ea * (np.hypot(b, delta) - l0) / l0
+    assert np.linalg.norm(res.f_global[0, 0, 0:3]) == pytest.approx(T, rel=1e-8)
+    assert res.R[0, 0, 1] == pytest.approx(p / 2, rel=1e-8) and res.R[0, 2, 1] == pytest.approx(p / 2, rel=1e-8)
+    assert bool(res.converged[0])
+
+
+def _mast_doc(order="LINEAR", self_weight=True):
+    """A 12 m clamped mast with two guys in its plane and one out of it, a lateral load, a uniform load on one guy; three
+    combinations."""
+    nodes = [(1, 0, 0, 0, 1), (2, 0, 6, 0, None), (3, 0, 12, 0, None), (4, -8, 0, 0, 2), (5, 8, 0, 0, 2), (6, 0, 0, 9, 2)]
+    members = [dict(id=1, start_node_id=1, end_node_id=2), dict(id=2, start_node_id=2, end_node_id=3),
+               _cab(3, 4, 3, pretension=1e3, weight=5.0), _cab(4, 5, 3, unstretched_length=14.44, weight=5.0),
+               _cab(5, 6, 3, unstretched_length=15.02, weight=5.0 if self_weight else 0.0)]
+    # (weak axis of the mast: E I = 2.1e5, Euler load of the guyed 12 m mast ~ 29 kN: the loads stay well below; the cables
+    # share the mast's section, EA = 4e8, and weigh 5 N/m through the `weight` override)
+    return cable_doc(nodes, members, loads=[(1, 3, 800.0, (1, 0, 0)), (2, 2, 500.0, (0, 0, -1)), (2, 3, 2e3, (0, -1, 0))],
+                     dls=[(2, 4, 20.0, (0, -1, 0), 0.0, 1.0)], order=order, self_weight=self_weight,
+                     combos=[{1: 1.0}, {1: 1.5, 2: 1.0}, {2: 1.35}])
+
+
+@pytest.mark.parametrize("order", ["LINEAR", "NONLINEAR"])
+def test_guyed_mast_is_in_equilibrium(order):
+    m = wire.parse_document(_mast_doc(order))
+    res = fers_oracle.analyze(m)
+    assert res.converged.all()
+    plan_cols = res.U.shape[0]
+    for col in range(plan_cols):
+        # what the cables hand to their end nodes plus what they weigh is in balance with the rest of the structure:
+        # sum of reactions + applied loads (incl. the cables' own weight and their uniform loads) = 0
+        fac = fers_oracle.rhs_plan(m).factors[col]
+        applied = np.zeros(3)
+        for li, lc in enumerate(m.load_cases):
+            applied += fac[li] * (lc.nod_vec[:, :3].sum(0) + (lc.cab_q * m.c_l0[:, None]).sum(0))
+            for mi, row in zip(lc.dl_member, lc.dl_data):
+                L = np.linalg.norm(m.xyz[m.m_n2[mi]] - m.xyz[m.m_n1[mi]])
+                applied += fac[li] * 0.5 * (row[0:3] + row[3:6]) * (row[7] - row[6]) * L
+        applied += (m.c_w * m.c_l0[:, None]).sum(0)
+        total = res.R[col, :, :3].sum(0) + applied
+        assert np.abs(total).max() < 1e-6 * max(np.abs(applied).max(), 1.0), (col, total, applied)
+    # the guys pull: start tension along the chord
+    for c, mi in enumerate(m.c_member):
+        chord = m.xyz[m.m_n2[mi]] - m.xyz[m.m_n1[mi]]
+        assert (-res.f_global[:, mi, 0:3] @ chord > 0.0).all()
+
+
+# ---- GPU -----------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hanging", "string_linear", "string_nonlinear", "mast_linear", "mast_nonlinear", "mast_no_weight"])
+def test_gpu_matches_oracle(engine_mod, name):
+    doc = {"hanging": lambda: _hanging()[0], "string_linear": lambda: _string_doc(order="LINEAR"),
+           "string_nonlinear": lambda: _string_doc(order="NONLINEAR"), "mast_linear": lambda: _mast_doc("LINEAR"),
+           "mast_nonlinear": lambda: _mast_doc("NONLINEAR"), "mast_no_weight": lambda: _mast_doc("LINEAR", False)}[name]()
+    m = wire.parse_document(doc)
+    got = engine_mod.analyze(m)
+    want = fers_oracle.analyze(m)
+    assert got.converged.all() and want.converged.all()
+    # both sides stop their Newton iteration at a relative step of 1e-9: the converged states agree far below that
+    helpers.assert_results_close(got, want, rtol=1e-8, label=name)
+
+
+@pytest.mark.gpu
+def test_gpu_pretensioned_string_closed_form(engine_mod):
+    b, n0, p = 5.0, 20e3, 3e3
+    doc = _string_doc(b, n0, p)
+    ea = _ea(doc)
+    l0 = b / (1.0 + n0 / ea)
+    delta = brentq(lambda d: 2.0 * ea * (np.hypot(b, d) - l0) / l0 * d / np.hypot(b, d) - p, 0.0, b, xtol=1e-15)
+    res = engine_mod.analyze(wire.parse_document(doc))
+    assert res.U[0, 1, 1] == pytest.approx(-delta, rel=1e-8)
+    assert res.R[0, 0, 1] == pytest.approx(p / 2, rel=1e-8)
