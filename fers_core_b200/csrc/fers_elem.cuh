@@ -608,7 +608,59 @@ FERS_HD void plate_B(const PlateGeom& g, double Bm[3][18], double Bb[3][18], dou
     }
 }
 
-// 18x18 local stiffness (row-major).  data = plate record (NPDATA doubles); flags bit0 membrane bit1 bending bit2 plane strain.
+// ---- thin plates: discrete Kirchhoff triangle (PlateTheory.Kirchhoff, pydantic_models.py:816-819, field 1723) -------------
+// Batoz, Bathe, Ho (1980): the rotations of the normal bx = +ry, by = -rx are quadratic over the element, tied to w by the
+// Kirchhoff condition at the corners and, along each side, at its mid-point (w cubic along the side); no transverse shear
+// energy.  Curvature rows kappa = [bx,x  by,y  bx,y + by,x] at the area coordinates (xi, eta) = (L2, L3), in the local shell
+// DOFs (columns w, rx, ry of every node; the others stay zero): the explicit derivatives of the paper's Hx, Hy.
+FERS_HD void plate_dkt_B(const PlateGeom& g, double xi, double eta, double Bb[3][18]) {
+    const double x1 = g.xl[0][0], y1 = g.xl[0][1], x2 = g.xl[1][0], y2 = g.xl[1][1], x3 = g.xl[2][0], y3 = g.xl[2][1];
+    const double x23 = x2 - x3, x31 = x3 - x1, x12 = x1 - x2, y23 = y2 - y3, y31 = y3 - y1, y12 = y1 - y2;
+    const double i4 = 1.0 / (x23 * x23 + y23 * y23), i5 = 1.0 / (x31 * x31 + y31 * y31), i6 = 1.0 / (x12 * x12 + y12 * y12);
+    const double P4 = -6.0 * x23 * i4, P5 = -6.0 * x31 * i5, P6 = -6.0 * x12 * i6;
+    const double t4 = -6.0 * y23 * i4, t5 = -6.0 * y31 * i5, t6 = -6.0 * y12 * i6;
+    const double q4 = 3.0 * x23 * y23 * i4, q5 = 3.0 * x31 * y31 * i5, q6 = 3.0 * x12 * y12 * i6;
+    const double r4 = 3.0 * y23 * y23 * i4, r5 = 3.0 * y31 * y31 * i5, r6 = 3.0 * y12 * y12 * i6;
+    const double a = 1.0 - 2.0 * xi, b = 1.0 - 2.0 * eta, x = xi, e = eta;
+    const double hxx[9] = {P6 * a + (P5 - P6) * e, q6 * a - (q5 + q6) * e, -4.0 + 6.0 * (x + e) + r6 * a - e * (r5 + r6),
+                           -P6 * a + e * (P4 + P6), q6 * a - e * (q6 - q4), -2.0 + 6.0 * x + r6 * a + e * (r4 - r6),
+                           -e * (P5 + P4), e * (q4 - q5), -e * (r5 - r4)};
+    const double hyx[9] = {t6 * a + e * (t5 - t6), 1.0 + r6 * a - e * (r5 + r6), -q6 * a + e * (q5 + q6),
+                           -t6 * a + e * (t4 + t6), -1.0 + r6 * a + e * (r4 - r6), -q6 * a - e * (q4 - q6),
+                           -e * (t4 + t5), e * (r4 - r5), -e * (q4 - q5)};
+    const double hxe[9] = {-P5 * b - x * (P6 - P5), q5 * b - x * (q5 + q6), -4.0 + 6.0 * (x + e) + r5 * b - x * (r5 + r6),
+                           x * (P4 + P6), x * (q4 - q6), -x * (r6 - r4),
+                           P5 * b - x * (P4 + P5), q5 * b + x * (q4 - q5), -2.0 + 6.0 * e + r5 * b + x * (r4 - r5)};
+    const double hye[9] = {-t5 * b - x * (t6 - t5), 1.0 + r5 * b - x * (r5 + r6), -q5 * b + x * (q5 + q6),
+                           x * (t4 + t6), x * (r4 - r6), -x * (q4 - q6),
+                           t5 * b - x * (t4 + t5), -1.0 + r5 * b + x * (r4 - r5), -q5 * b - x * (q4 - q5)};
+    const double i2A = 1.0 / (x31 * y12 - x12 * y31);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 18; ++j) Bb[i][j] = 0.0;
+    for (int n = 0; n < 3; ++n)
+        for (int c = 0; c < 3; ++c) {
+            const int j = 3 * n + c, col = 6 * n + 2 + c;       // (w, theta_x, theta_y) = local DOFs (w, rx, ry)
+            Bb[0][col] = (y31 * hxx[j] + y12 * hxe[j]) * i2A;
+            Bb[1][col] = (-x31 * hyx[j] - x12 * hye[j]) * i2A;
+            Bb[2][col] = (-x31 * hxx[j] - x12 * hxe[j] + y31 * hyx[j] + y12 * hye[j]) * i2A;
+        }
+}
+
+// Strain operators the results are formed from: Mindlin -> plate_B.  Kirchhoff -> curvature of the DKT element at the
+// centroid and NO shear rows: a thin plate has no transverse shear strain, its shear forces are derivatives of the moments,
+// and differentiating the curvature inside one DKT element is not a usable estimate (measured on a cantilever strip: 30 %
+// off at every mesh size; the nodal-force form has exact resultants but oscillates by several times its mean) -- the
+// result carries zeros and the analysis says so (W_KIRCHHOFF_NO_SHEAR_FORCES).
+FERS_HD bool plate_is_kirchhoff(int flags) { return (flags & 8) != 0 && (flags & 2) != 0; }
+FERS_HD void plate_B_theory(const PlateGeom& g, int flags, double Bm[3][18], double Bb[3][18], double Bs[2][18]) {
+    plate_B(g, Bm, Bb, Bs);
+    if (!plate_is_kirchhoff(flags)) return;
+    plate_dkt_B(g, 1.0 / 3.0, 1.0 / 3.0, Bb);
+    for (int j = 0; j < 18; ++j) Bs[0][j] = Bs[1][j] = 0.0;
+}
+
+// 18x18 local stiffness (row-major).  data = plate record (NPDATA doubles); flags bit0 membrane bit1 bending bit2 plane strain
+// bit3 Kirchhoff (DKT bending, three mid-side integration points, no shear part).
 FERS_HD void plate_local_k(const PlateGeom& g, const double* data, int flags, double* k /*324*/) {
     double Bm[3][18], Bb[3][18], Bs[2][18];
     plate_B(g, Bm, Bb, Bs);
@@ -619,6 +671,8 @@ FERS_HD void plate_local_k(const PlateGeom& g, const double* data, int flags, do
     double cm = (flags & 1) ? data[PD_MODM] * t * A : 0.0;
     double cb = (flags & 2) ? data[PD_MODB] * A * t * t * t / 12.0 : 0.0;
     double cs = (flags & 2) ? data[PD_MODS] * A * (5.0 / 6.0) * t : 0.0;
+    const bool dkt = plate_is_kirchhoff(flags);
+    if (dkt) cs = 0.0;
     for (int i = 0; i < 18; ++i)
         for (int j = 0; j < 18; ++j) {
             double sm = 0.0, sb = 0.0;
@@ -629,8 +683,20 @@ FERS_HD void plate_local_k(const PlateGeom& g, const double* data, int flags, do
                 sb += Bb[a][i] * dbj;
             }
             double ss = Gs[0] * Bs[0][i] * Bs[0][j] + Gs[1] * Bs[1][i] * Bs[1][j];
-            k[i * 18 + j] = cm * sm + cb * sb + cs * ss;
+            k[i * 18 + j] = cm * sm + (dkt ? 0.0 : cb * sb) + cs * ss;
         }
+    if (dkt) {
+        const double gp[3][2] = {{0.5, 0.5}, {0.0, 0.5}, {0.5, 0.0}};
+        for (int p = 0; p < 3; ++p) {
+            plate_dkt_B(g, gp[p][0], gp[p][1], Bb);
+            for (int j = 0; j < 18; ++j) {
+                double db[3];
+                for (int a = 0; a < 3; ++a) db[a] = D[a][0] * Bb[0][j] + D[a][1] * Bb[1][j] + D[a][2] * Bb[2][j];
+                for (int i = 0; i < 18; ++i)
+                    k[i * 18 + j] += (cb / 3.0) * (Bb[0][i] * db[0] + Bb[1][i] * db[1] + Bb[2][i] * db[2]);
+            }
+        }
+    }
     double kd = 1e-6 * E * t * A;     // drilling stabilisation
     for (int n = 0; n < 3; ++n) k[(6 * n + 5) * 18 + 6 * n + 5] += kd;
     plate_offset_k(data[PD_OFFSET], k);

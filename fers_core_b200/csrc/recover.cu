@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(REC_THREADS) k_recover_plates(int n_plates, in
                     for (int q = 0; q < 6; ++q) s_k[warp][(6 * bi + r) * 18 + 6 * bj + q] = blk[r * 6 + q];
             }
         double Bm[3][18], Bb[3][18], Bs[2][18];
-        plate_B(g, Bm, Bb, Bs);
+        plate_B_theory(g, flags, Bm, Bb, Bs);
         for (int j = 0; j < 18; ++j) {
             for (int i = 0; i < 3; ++i) { s_b[warp][i][j] = Bm[i][j]; s_b[warp][3 + i][j] = Bb[i][j]; }
             s_b[warp][6][j] = Bs[0][j]; s_b[warp][7][j] = Bs[1][j];

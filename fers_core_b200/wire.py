@@ -130,7 +130,7 @@ class ModelArrays:
     p_ids: np.ndarray             # int64 [Npl]
     p_nodes: np.ndarray           # int32 [Npl,3]
     p_data: np.ndarray            # f64   [Npl,8]  thickness, E, nu, modifiers (membrane, bending, shear), local-x angle, 1 spare
-    p_flags: np.ndarray           # int32 [Npl]    bit0 membrane, bit1 bending, bit2 plane strain
+    p_flags: np.ndarray           # int32 [Npl]    bit0 membrane, bit1 bending, bit2 plane strain, bit3 Kirchhoff (DKT)
     load_cases: list              # [LoadCaseArrays]
     combo_ids: np.ndarray         # int64 [Nc]
     combo_names: list
@@ -738,10 +738,13 @@ def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:
         sm = p.get("stiffness_modifiers") or {}
         mods = [1.0 if sm.get(k) is None else float(sm[k]) for k in ("membrane", "bending", "shear")]
         if _norm_enum(p.get("theory") or "Auto") == "kirchhoff" and flags & 2:
-            # PlateTheory (pydantic_models.py:816-819, field 1723): Auto / Mindlin -> DSG3; the thin-plate DKT element
-            # ("currently unreliable", tests/nafems/reference_examples.py:16-18) is not implemented
-            warnings.append(("W_PLATE_THEORY_IGNORED", f"plate {p['id']}: theory=Kirchhoff solved with the Mindlin (DSG3) "
-                             "element"))
+            # PlateTheory (pydantic_models.py:816-819, field 1723): Kirchhoff -> discrete Kirchhoff triangle (DKT, no
+            # transverse shear deformation); Auto / Mindlin -> DSG3.  The reference calls its own DKT element "currently
+            # unreliable" (tests/nafems/reference_examples.py:16-18): this one is pinned on thin-plate theory instead
+            flags |= 8
+            if not any(code == "W_KIRCHHOFF_NO_SHEAR_FORCES" for code, _ in warnings):
+                warnings.append(("W_KIRCHHOFF_NO_SHEAR_FORCES", "theory=Kirchhoff: thin-plate (DKT) elements carry no transverse shear "
+                                 "strain; their results hold zero shear forces q_x, q_y (moments and deflections are thin-plate values)"))
         offset = float(p.get("offset") or 0.0)
         if not np.isfinite(offset):
             raise WireError(f"plate {p['id']}: offset must be a number")

@@ -309,6 +309,49 @@ def plate_offset_matrix(offset: float) -> np.ndarray:
     return E
 
 
+def dkt_curvature(xl, xi: float, eta: float) -> np.ndarray:
+    """Curvature operator [3,9] of the discrete Kirchhoff triangle (PlateTheory.Kirchhoff, pydantic_models.py:816-819) at the
+    area coordinates (xi, eta) = (L2, L3), DOFs (w, bx, by) per corner, built from the element's DEFINITION rather than
+    from the published coefficient lists the CUDA path uses: the rotations of the normal are quadratic (corner + mid-side
+    values); at a corner they are the nodal ones; at the middle of a side the tangential one is minus the slope of the
+    cubic w along the side, -w,s = 3/(2l) (w_i - w_j) - (b_s,i + b_s,j)/4, the normal one the mean of the two ends."""
+    X = np.asarray(xl, float)
+    (x1, y1), (x2, y2), (x3, y3) = X
+    twoA = (x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1)
+    dLx = np.array([y2 - y3, y3 - y1, y1 - y2]) / twoA
+    dLy = np.array([x3 - x2, x1 - x3, x2 - x1]) / twoA
+    H = np.zeros((6, 2, 9))                                  # rotation (bx, by) of the six nodes in the nine DOFs
+    for i in range(3):
+        H[i, 0, 3 * i + 1] = 1.0
+        H[i, 1, 3 * i + 2] = 1.0
+    sides = [(1, 2), (2, 0), (0, 1)]
+    for k, (i, j) in enumerate(sides):
+        d = X[j] - X[i]
+        l = float(np.hypot(*d))
+        s_ = d / l
+        n_ = np.array([s_[1], -s_[0]])
+        bs = np.zeros(9); bn = np.zeros(9)
+        bs[3 * i] += 1.5 / l; bs[3 * j] -= 1.5 / l
+        for nd in (i, j):
+            bs[3 * nd + 1] -= 0.25 * s_[0]; bs[3 * nd + 2] -= 0.25 * s_[1]
+            bn[3 * nd + 1] += 0.5 * n_[0]; bn[3 * nd + 2] += 0.5 * n_[1]
+        H[3 + k, 0] = bs * s_[0] + bn * n_[0]
+        H[3 + k, 1] = bs * s_[1] + bn * n_[1]
+    L = np.array([1.0 - xi - eta, xi, eta])
+    dN = np.zeros((6, 3))                                    # dN_a / dL_i of the quadratic shape functions
+    for i in range(3):
+        dN[i, i] = 4.0 * L[i] - 1.0
+    for k, (i, j) in enumerate(sides):
+        dN[3 + k, i] = 4.0 * L[j]; dN[3 + k, j] = 4.0 * L[i]
+    nx, ny = dN @ dLx, dN @ dLy
+    B = np.zeros((3, 9))
+    for a in range(6):
+        B[0] += nx[a] * H[a, 0]
+        B[1] += ny[a] * H[a, 1]
+        B[2] += ny[a] * H[a, 0] + nx[a] * H[a, 1]
+    return B
+
+
 def plate_local_matrices(xl, t, E, nu, flags, mods=(1.0, 1.0, 1.0), ortho=None):
     """18x18 local stiffness of a TRI3 shell, plus (Bm, Bb, Bs, Dm, Db, Ds, area).
 
@@ -359,8 +402,16 @@ def plate_local_matrices(xl, t, E, nu, flags, mods=(1.0, 1.0, 1.0), ortho=None):
     if ortho is not None:
         Db = mods[1] * t**3 / 12.0 * D_ortho
         Ds = mods[2] * (5.0 / 6.0) * t * np.diag([ortho[4], ortho[5]])
-    if flags & 2:
+    if flags & 2 and flags & 8:
+        # thin plate (Kirchhoff): DKT bending, three mid-side integration points, no shear energy.  The results take the
+        # curvature at the centroid; shear forces are not formed (they are derivatives of the moments, which one DKT element
+        # does not resolve: W_KIRCHHOFF_NO_SHEAR_FORCES)
+        kb = sum(abs(A) / 3.0 * (B.T @ Db @ B) for B in (dkt_curvature(xl, *gp) for gp in ((0.5, 0.5), (0.0, 0.5), (0.5, 0.0))))
+        Bb = dkt_curvature(xl, 1.0 / 3.0, 1.0 / 3.0)
+        Bs = np.zeros((2, 9))
+    elif flags & 2:
         kb = abs(A) * (Bb.T @ Db @ Bb + Bs.T @ Ds @ Bs)
+    if flags & 2:
         # map (w, bx, by) -> (w, rx, ry): bx = ry, by = -rx
         S = np.zeros((9, 18))
         for n in range(3):

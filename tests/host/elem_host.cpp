@@ -67,4 +67,14 @@ void h_plate_ke(const double* p0, const double* p1, const double* p2, const doub
                 for (int q = 0; q < 6; ++q) out[(6 * bi + r) * 18 + 6 * bj + q] = blk[r * 6 + q];
         }
 }
+// strain operators of the plate results (rows: 3 membrane, 3 curvature, 2 shear), local DOFs
+void h_plate_B(const double* p0, const double* p1, const double* p2, const double* data, int flags, double* out /*8*18*/) {
+    PlateGeom g = plate_geom(p0, p1, p2, data[PD_THETA]);
+    double Bm[3][18], Bb[3][18], Bs[2][18];
+    plate_B_theory(g, flags, Bm, Bb, Bs);
+    for (int j = 0; j < 18; ++j) {
+        for (int i = 0; i < 3; ++i) { out[i * 18 + j] = Bm[i][j]; out[(3 + i) * 18 + j] = Bb[i][j]; }
+        out[6 * 18 + j] = Bs[0][j]; out[7 * 18 + j] = Bs[1][j];
+    }
+}
 }
