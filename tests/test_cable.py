@@ -185,6 +185,29 @@ def test_pretensioned_string_under_a_point_load(order):
     assert bool(res.converged[0])
 
 
+def _slack_doc(l0=5.5, p=100.0):
+    """Two slack cable segments (10 % longer than their chords) between pinned ends, a point load on the middle node: the
+    node drops by 2.25 m on a 10 m span -- far outside small displacements."""
+    nodes = [(1, 0, 0, 0, 2), (2, 5, 0, 0, None), (3, 10, 0, 0, 2)]
+    return cable_doc(nodes, [_cab(1, 1, 2, unstretched_length=l0, weight=10.0), _cab(2, 2, 3, unstretched_length=l0, weight=10.0)],
+                     loads=[(1, 2, p, (0, -1, 0))])
+
+
+def test_slack_cable_with_a_point_load_large_displacements():
+    l0, p, w = 5.5, 100.0, 10.0
+    m = wire.parse_document(_slack_doc(l0, p))
+    res = fers_oracle.analyze(m)
+    assert res.converged.all()
+    drop = -res.U[0, 1, 1]
+    assert 2.0 < drop < np.sqrt(l0 ** 2 - 5.0 ** 2) and abs(res.U[0, 1, 0]) < 1e-9          # below the straight-segment bound
+    # supports: half of the load and of the weight each, equal and opposite horizontal pulls
+    assert res.R[0, 0, 1] == pytest.approx((p + 2 * w * l0) / 2, rel=1e-9) and res.R[0, 2, 1] == pytest.approx((p + 2 * w * l0) / 2, rel=1e-9)
+    assert res.R[0, 0, 0] == pytest.approx(-res.R[0, 2, 0], rel=1e-9) and res.R[0, 0, 0] < 0.0
+    # the left segment in its final position is the catenary the element formulas give: support reaction = -(its pull on node 1)
+    a, _ = cable.end_tension(np.array([[5.0, -drop, 0.0]]), np.array([[0.0, -w, 0.0]]), np.array([l0]), m.c_ea[:1])
+    assert np.allclose(res.R[0, 0, :3], -a[0], rtol=1e-8, atol=1e-8 * np.abs(a).max())
+
+
 def _mast_doc(order="LINEAR", self_weight=True):
     """A 12 m clamped mast with two guys in its plane and one out of it, a lateral load, a uniform load on one guy; three
     combinations."""
@@ -226,11 +249,12 @@ def test_guyed_mast_is_in_equilibrium(order):
 
 # ---- GPU -----------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["hanging", "string_linear", "string_nonlinear", "mast_linear", "mast_nonlinear", "mast_no_weight"])
+@pytest.mark.parametrize("name", ["hanging", "string_linear", "string_nonlinear", "mast_linear", "mast_nonlinear", "mast_no_weight", "slack"])
 def test_gpu_matches_oracle(engine_mod, name):
     doc = {"hanging": lambda: _hanging()[0], "string_linear": lambda: _string_doc(order="LINEAR"),
            "string_nonlinear": lambda: _string_doc(order="NONLINEAR"), "mast_linear": lambda: _mast_doc("LINEAR"),
-           "mast_nonlinear": lambda: _mast_doc("NONLINEAR"), "mast_no_weight": lambda: _mast_doc("LINEAR", False)}[name]()
+           "mast_nonlinear": lambda: _mast_doc("NONLINEAR"), "mast_no_weight": lambda: _mast_doc("LINEAR", False),
+           "slack": _slack_doc}[name]()
     m = wire.parse_document(doc)
     got = engine_mod.analyze(m)
     want = fers_oracle.analyze(m)
