@@ -85,7 +85,19 @@ def entity_constants(model: wire.ModelArrays, spec: dict, members: list) -> tupl
             Lcr[ax] = L
     Llt = float(ms["ltb_length"]) if ms.get("ltb_length") is not None else L
     if ms.get("buckling_restraints"):
-        notes.append("buckling_restraints are not evaluated: L_cr = member length unless buckling_length_* is given")
+        # BucklingRestraint (pydantic_models.py:129-143; fers_core/members/bucklingrestraint.py:1-10: "the spacing between
+        # consecutive restraint nodes yields the unrestrained length used for the corresponding buckling check"): explicit
+        # lengths and factors win (548-566); buckling about y moves the beam along local z and the other way round; a twist
+        # restraint is a lateral-torsional restraint
+        spans = restraint_spans(model, ms, members)
+        if spans is None:
+            notes.append("buckling_restraints not evaluated: the member set is not a chain of members")
+        else:
+            for ax, held in (("y", "z"), ("z", "y")):
+                if ms.get(f"buckling_length_{ax}") is None and ms.get(f"effective_length_factor_{ax}") is None:
+                    Lcr[ax] = spans[held]
+            if ms.get("ltb_length") is None:
+                Llt = spans["t"]
     alpha = {k: ALPHA.get(str(ec3.get(f"buckling_curve_{k}") or "B").upper(), ALPHA["B"]) for k in ("y", "z", "lt")}
     for k in ("c2", "c3", "z_g"):
         if spec.get(k):
@@ -99,6 +111,56 @@ def entity_constants(model: wire.ModelArrays, spec: dict, members: list) -> tupl
              gm0=float(spec.get("gamma_m0") or 1.0), gm1=float(spec.get("gamma_m1") or 1.0),
              c1=_num(spec.get("c1"), 0.0), on_b=1.0 if buckling else 0.0, on_lt=1.0 if ltb_applies else 0.0)
     return c, notes
+
+
+def restraint_spans(model, ms: dict, members: list):
+    """Unrestrained lengths of an entity (member rows ``members``) inside the member set ``ms`` (one physical beam): per
+    restrained quantity ("y", "z": displacement along that local axis; "t": twist) the longest interval between
+    consecutive restraint points -- the two ends of the beam and the nodes of ``buckling_restraints`` that hold the
+    quantity -- that overlaps the entity.  None when the set's members do not form a chain."""
+    index = {int(i): r for r, i in enumerate(model.m_ids)}
+    try:
+        rows = [index[int(i["id"] if isinstance(i, dict) else i)] for i in (ms.get("member_ids") or ms.get("members") or [])]
+    except KeyError:
+        return None
+    if not rows:
+        return None
+    # walk the chain: station of every node along the beam
+    first = rows[0]
+    a, b = int(model.m_n1[first]), int(model.m_n2[first])
+    if len(rows) > 1:
+        nxt = {int(model.m_n1[rows[1]]), int(model.m_n2[rows[1]])}
+        if a in nxt and b not in nxt:
+            a, b = b, a
+    station = {a: 0.0}
+    span_of = {}
+    at, s_at = a, 0.0
+    for r in rows:
+        n1, n2 = int(model.m_n1[r]), int(model.m_n2[r])
+        if at not in (n1, n2):
+            return None
+        far = n2 if at == n1 else n1
+        length = float(np.linalg.norm(wire.member_axis(model, r)))
+        span_of[r] = (s_at, s_at + length)
+        s_at += length
+        station[far] = s_at
+        at = far
+    if any(m not in span_of for m in members):
+        return None
+    lo = min(span_of[m][0] for m in members)
+    hi = max(span_of[m][1] for m in members)
+    node_index = {int(i): k for k, i in enumerate(model.node_ids)}
+    out = {}
+    for key, flag in (("y", "restrains_local_y"), ("z", "restrains_local_z"), ("t", "restrains_torsion")):
+        pts = {0.0, s_at}
+        for br in ms.get("buckling_restraints") or []:
+            node = node_index.get(int(br["node_id"]["id"] if isinstance(br["node_id"], dict) else br["node_id"]))
+            if br.get(flag) and node in station:
+                pts.add(station[node])
+        pts = sorted(pts)
+        eps = 1e-9 * max(s_at, 1.0)
+        out[key] = max((q - p for p, q in zip(pts[:-1], pts[1:]) if min(q, hi) - max(p, lo) > eps), default=hi - lo)
+    return out
 
 
 def _member_set_of(model, members: list) -> dict:

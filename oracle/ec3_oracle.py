@@ -47,18 +47,47 @@ def constants(model, spec: dict, members: list) -> dict:
         if mine <= ids and not ms:
             ms = raw
 
+    def unrestrained(flag):
+        """Longest stretch between restraint points (beam ends + nodes of `buckling_restraints` with ``flag``) that the
+        entity touches (BucklingRestraint, pydantic_models.py:129-143; bucklingrestraint.py:1-10); None without restraints."""
+        if not ms.get("buckling_restraints"):
+            return None
+        row_of = {int(i): r for r, i in enumerate(model.m_ids)}
+        chain = [row_of[int(i["id"] if isinstance(i, dict) else i)] for i in (ms.get("member_ids") or ms.get("members") or [])]
+        # node sequence of the beam, tip to tail
+        seq = [int(model.m_n1[chain[0]]), int(model.m_n2[chain[0]])]
+        if len(chain) > 1 and seq[1] not in (int(model.m_n1[chain[1]]), int(model.m_n2[chain[1]])):
+            seq.reverse()
+        for r in chain[1:]:
+            a, b = int(model.m_n1[r]), int(model.m_n2[r])
+            if seq[-1] not in (a, b):
+                return None
+            seq.append(b if a == seq[-1] else a)
+        lengths = [float(np.linalg.norm(model.xyz[model.m_n2[r]] - model.xyz[model.m_n1[r]] + off[r, 1] - off[r, 0])) for r in chain]
+        x = np.concatenate([[0.0], np.cumsum(lengths)])
+        held_ids = {int(br["node_id"]) for br in ms["buckling_restraints"] if br.get(flag)}
+        cuts = [0] + [k for k in range(1, len(seq) - 1) if int(model.node_ids[seq[k]]) in held_ids] + [len(seq) - 1]
+        mine_pos = [k for k, r in enumerate(chain) if r in members]
+        best = 0.0
+        for c0, c1 in zip(cuts[:-1], cuts[1:]):
+            if any(c0 <= k < c1 for k in mine_pos):                 # member k spans nodes k .. k+1
+                best = max(best, x[c1] - x[c0])
+        return best
+
     def lcr(ax):
         if ms.get(f"buckling_length_{ax}") is not None:
             return float(ms[f"buckling_length_{ax}"])
         if ms.get(f"effective_length_factor_{ax}") is not None:
             return float(ms[f"effective_length_factor_{ax}"]) * L
-        return L
+        free = unrestrained("restrains_local_z" if ax == "y" else "restrains_local_y")      # buckling about y moves along z
+        return L if free is None else free
     Iy, Iz, J = g(sec, "i_y"), g(sec, "i_z"), g(sec, "j")
     av = lambda k: (float(sec[k]) if sec.get(k) else BIG)                               # noqa: E731
     return dict(fy=g(mat, "yield_stress"), E=g(mat, "e_mod"), G=g(mat, "g_mod"),
                 A=g(ec3, "a_eff", g(sec, "area")) if cls == 4 else g(sec, "area"), Iy=Iy, Iz=Iz, J=J, Iw=g(sec, "i_w", 0.0), L=L,
                 Wy=W("y"), Wz=W("z"), Avy=av("a_sz"), Avz=av("a_sy"), Lcry=lcr("y"), Lcrz=lcr("z"),
-                Llt=float(ms["ltb_length"]) if ms.get("ltb_length") is not None else L,
+                Llt=float(ms["ltb_length"]) if ms.get("ltb_length") is not None else (
+                    L if unrestrained("restrains_torsion") is None else unrestrained("restrains_torsion")),
                 ay=ALPHA.get(str(ec3.get("buckling_curve_y") or "B").upper(), 0.34),
                 az=ALPHA.get(str(ec3.get("buckling_curve_z") or "B").upper(), 0.34),
                 alt=ALPHA.get(str(ec3.get("buckling_curve_lt") or "B").upper(), 0.34),

@@ -103,6 +103,59 @@ def test_defaults_follow_the_catalogue_note():
     assert {k: c2[k] for k in want} == ec3_oracle.constants(m2, {"gamma_m1": 1.1, "c1": 1.0}, [0])
 
 
+def _restrained_doc():
+    """The 6 m IPE 300 beam of the reference's check cut into four members of one member set, with buckling restraints: the
+    node at 3.0 m holds local y and twist, the node at 1.5 m holds local z."""
+    doc = copy.deepcopy(helpers.golden("ec3_check_beam_ipe300")["doc"])
+    m = doc["model"]
+    n0, n1 = m["nodes"]
+    base = m["members"][0]
+    xs = [0.0, 1.5, 3.0, 4.5, 6.0]
+    m["nodes"] = [dict(n0, id=1, X=xs[0])] + [dict(n0, id=10 + k, X=xs[k], nodal_support=None) for k in (1, 2, 3)] + [dict(n1, id=2, X=xs[4])]
+    ids = [1, 11, 12, 13, 2]
+    m["members"] = [dict(base, id=k + 1, start_node_id=ids[k], end_node_id=ids[k + 1]) for k in range(4)]
+    m["member_sets"] = [dict(m["member_sets"][0], member_ids=[1, 2, 3, 4], buckling_restraints=[
+        {"node_id": 12, "restrains_local_y": True, "restrains_local_z": False, "restrains_torsion": True},
+        {"node_id": 11, "restrains_local_y": False, "restrains_local_z": True, "restrains_torsion": False}])]
+    for lc in doc["analysis"]["load_cases"]:
+        new = []
+        for dl in lc.get("distributed_loads") or []:
+            for k in range(4):
+                new.append(dict(dl, id=100 * dl["id"] + k, member=k + 1))
+        lc["distributed_loads"] = new
+    return doc
+
+
+def test_buckling_restraints_set_the_unrestrained_lengths():
+    """BucklingRestraint (pydantic_models.py:129-143; bucklingrestraint.py:1-10): spacing of consecutive restraint nodes;
+    buckling about y moves the beam along local z (held by restrains_local_z) and the other way round; twist -> LTB."""
+    model = wire.parse_document(_restrained_doc())
+    want = {(0, 1, 2, 3): (4.5, 3.0, 3.0), (0,): (1.5, 3.0, 3.0), (1,): (4.5, 3.0, 3.0), (2,): (4.5, 3.0, 3.0), (3,): (4.5, 3.0, 3.0)}
+    for members, (lcry, lcrz, llt) in want.items():
+        c, notes = ec3.entity_constants(model, {}, list(members))
+        assert (c["Lcry"], c["Lcrz"], c["Llt"]) == pytest.approx((lcry, lcrz, llt)), members
+        assert not [n for n in notes if "restraint" in n]
+        o = ec3_oracle.constants(model, {}, list(members))
+        assert (o["Lcry"], o["Lcrz"], o["Llt"]) == pytest.approx((lcry, lcrz, llt)), members
+    # explicit lengths and factors win over the restraints
+    doc = _restrained_doc()
+    doc["model"]["member_sets"][0].update(buckling_length_y=2.0, effective_length_factor_z=0.5, ltb_length=1.0)
+    m2 = wire.parse_document(doc)
+    c, _ = ec3.entity_constants(m2, {}, [0, 1, 2, 3])
+    assert (c["Lcry"], c["Lcrz"], c["Llt"]) == pytest.approx((2.0, 3.0, 1.0))
+    o = ec3_oracle.constants(m2, {}, [0, 1, 2, 3])
+    assert (o["Lcry"], o["Lcrz"], o["Llt"]) == pytest.approx((2.0, 3.0, 1.0))
+
+
+def test_restrained_beam_has_a_higher_ltb_resistance():
+    free = oracle_engine.solve_document(helpers.golden("ec3_check_beam_ipe300")["doc"])["results"]["unity_check_results"][0]
+    held = oracle_engine.solve_document(_restrained_doc())["results"]["unity_check_results"][0]
+    ltb = "LTB (6.3.2)"
+    u_free = max(_rows({"governing": p})[ltb] for p in free["per_entity"])
+    u_held = max(_rows({"governing": p})[ltb] for p in held["per_entity"])
+    assert 0.0 < u_held < u_free
+
+
 def _frame_doc():
     """Portal of the golden 2D fixture with an Ec3Steel check on every member: columns in compression, beam in bending."""
     doc = copy.deepcopy(helpers.golden("portal_2d_combinations")["doc"])
@@ -130,7 +183,7 @@ def test_oracle_frame_check_has_compression_members():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("make", [lambda: helpers.golden("ec3_check_beam_ipe300")["doc"],
-                                  lambda: helpers.golden("ec3_check_beam_hea200_fixed")["doc"], _frame_doc])
+                                  lambda: helpers.golden("ec3_check_beam_hea200_fixed")["doc"], _frame_doc, _restrained_doc])
 def test_engine_matches_oracle(make):
     from fers_core_b200 import engine
     doc = make()
