@@ -18,13 +18,13 @@ over the applicable combinations.  Rules (FERS axes: local z is the major axis o
   6.2.6           V_Ed / (A_v f_y / (sqrt 3 gM0))                               when the section carries shear areas
   6.2.1 (7)       n + m_y + m_z                                                 conservative linear N + M
   6.3.1           N_c,Ed / (chi A f_y / gM1), chi from the buckling curve (default b), L_cr = member(-set) length or override
-  6.3.2           M_z,Ed / (chi_LT W_z f_y / gM1); M_cr = C1 pi^2 E I_y / L^2 sqrt(I_w / I_y + L^2 G J / (pi^2 E I_y)),
+  6.3.2           M_z,Ed / (chi_LT W_z f_y / gM1); M_cr = C1 pi^2 E I_y / L^2 [sqrt(I_w / I_y + L^2 G J / (pi^2 E I_y) + zz^2) - zz],
+                  zz = C2 z_g - C3 z_j (load height above the shear centre, mono-symmetry z_j = Section.wagner_coeff; NCCI SN003),
                   C1 given or from the quarter-point moments 12.5 M_max / (2.5 M_max + 3 M_A + 4 M_B + 3 M_C); general case (6.56)
   6.3.3           N_c / N_b,Rd,min + M_z / M_b,Rd + M_y / M_c,Rd,y  (interaction factors k = 1: conservative; Annex A / B not evaluated)
 
 Unpinned beyond the reference's own hand calculation (test_check_beam.py:25-45: bending z = 60.75 / 147.6, LTB governs):
-the engine that defines the remaining numbers is closed.  C2 / C3 / z_g / z_j (general M_cr) are read and reported as not
-applied when non-zero."""
+the engine that defines the remaining numbers is closed."""
 from __future__ import annotations
 
 import numpy as np
@@ -99,9 +99,9 @@ def entity_constants(model: wire.ModelArrays, spec: dict, members: list) -> tupl
             if ms.get("ltb_length") is None:
                 Llt = spans["t"]
     alpha = {k: ALPHA.get(str(ec3.get(f"buckling_curve_{k}") or "B").upper(), ALPHA["B"]) for k in ("y", "z", "lt")}
-    for k in ("c2", "c3", "z_g"):
-        if spec.get(k):
-            notes.append(f"{k} is not applied: M_cr is the doubly symmetric form")
+    # general M_cr (NCCI SN003, k = k_w = 1): load height z_g above the shear centre with C2, mono-symmetry z_j (the
+    # section's `wagner_coeff`, pydantic_models.py:1092-1094) with C3; both zero -> the doubly symmetric form
+    zz = _num(spec.get("c2"), 0.0) * _num(spec.get("z_g"), 0.0) - _num(spec.get("c3"), 0.0) * _num(sec.get("wagner_coeff"), 0.0)
     ltb_applies = bool(spec.get("include_ltb", True)) and np.isfinite(Wz) and Iz > Iy and J > 0.0
     buckling = bool(spec.get("include_buckling", True))
     c = dict(fy=fy, E=E, G=G, A=A, Iy=Iy, Iz=Iz, J=J, Iw=Iw, L=L,
@@ -109,7 +109,7 @@ def entity_constants(model: wire.ModelArrays, spec: dict, members: list) -> tupl
              Avy=Avy if np.isfinite(Avy) and Avy > 0 else BIG, Avz=Avz if np.isfinite(Avz) and Avz > 0 else BIG,
              Lcry=Lcr["y"], Lcrz=Lcr["z"], Llt=Llt, ay=alpha["y"], az=alpha["z"], alt=alpha["lt"],
              gm0=float(spec.get("gamma_m0") or 1.0), gm1=float(spec.get("gamma_m1") or 1.0),
-             c1=_num(spec.get("c1"), 0.0), on_b=1.0 if buckling else 0.0, on_lt=1.0 if ltb_applies else 0.0)
+             c1=_num(spec.get("c1"), 0.0), zz=zz, on_b=1.0 if buckling else 0.0, on_lt=1.0 if ltb_applies else 0.0)
     return c, notes
 
 
@@ -211,7 +211,7 @@ def program(const_names: list) -> dict:
     # lateral-torsional buckling about the major (z) axis; C1 from the quarter-point moments unless given
     e("C1q", f"12.5 * (Mz + {TINY!r}) / (2.5 * (Mz + {TINY!r}) + 3 * abs(Ma) + 4 * abs(Mb) + 3 * abs(Mc))")
     e("C1", "max(c1, 0) + (1 - min(c1 * 1e30, 1)) * C1q")          # c1 > 0: the given value; c1 = 0: the computed one
-    e("Mcr", f"C1 * {pi2} * E * Iy / (Llt * Llt) * sqrt(Iw / Iy + Llt * Llt * G * J / ({pi2} * E * Iy))")
+    e("Mcr", f"C1 * {pi2} * E * Iy / (Llt * Llt) * (sqrt(Iw / Iy + Llt * Llt * G * J / ({pi2} * E * Iy) + zz * zz) - zz)")
     e("lamlt", "sqrt(Wz * fy / Mcr)")
     e("philt", "0.5 * (1 + alt * (lamlt - 0.2) + lamlt * lamlt)")
     e("chilt", "min(1, 1 / (philt + sqrt(max(philt * philt - lamlt * lamlt, 0))))")
@@ -222,6 +222,6 @@ def program(const_names: list) -> dict:
 
 
 CONST_NAMES = ["fy", "E", "G", "A", "Iy", "Iz", "J", "Iw", "L", "Wy", "Wz", "Avy", "Avz", "Lcry", "Lcrz", "Llt", "ay", "az", "alt",
-               "gm0", "gm1", "c1", "on_b", "on_lt"]
+               "gm0", "gm1", "c1", "zz", "on_b", "on_lt"]
 LABELS = dict(RULES, gov="Governing", C1="C1 (6.3.2)", Mcr="M_cr", chilt="chi_LT", chiy="chi_y", chiz="chi_z", lamlt="lambda_LT",
               lamy="lambda_y", lamz="lambda_z")

@@ -92,6 +92,7 @@ def constants(model, spec: dict, members: list) -> dict:
                 az=ALPHA.get(str(ec3.get("buckling_curve_z") or "B").upper(), 0.34),
                 alt=ALPHA.get(str(ec3.get("buckling_curve_lt") or "B").upper(), 0.34),
                 gm0=float(spec.get("gamma_m0") or 1.0), gm1=float(spec.get("gamma_m1") or 1.0), c1=float(spec.get("c1") or 0.0),
+                zz=float(spec.get("c2") or 0.0) * float(spec.get("z_g") or 0.0) - float(spec.get("c3") or 0.0) * float(sec.get("wagner_coeff") or 0.0),
                 on_b=1.0 if spec.get("include_buckling", True) else 0.0,
                 on_lt=1.0 if (spec.get("include_ltb", True) and W("z") < BIG and Iz > Iy and J > 0.0) else 0.0)
 
@@ -116,7 +117,10 @@ def rules(c: dict, f: dict) -> dict:
     c1 = c["c1"] if c["c1"] > 0.0 else \
         12.5 * (f["Mz"] + TINY) / (2.5 * (f["Mz"] + TINY) + 3 * abs(f["Ma"]) + 4 * abs(f["Mb"]) + 3 * abs(f["Mc"]))
     L = c["Llt"]
-    mcr = c1 * math.pi ** 2 * c["E"] * c["Iy"] / L ** 2 * math.sqrt(c["Iw"] / c["Iy"] + L * L * c["G"] * c["J"] / (math.pi ** 2 * c["E"] * c["Iy"]))
+    # general form (NCCI SN003, k = k_w = 1): zz = C2 z_g - C3 z_j, z_g load height above the shear centre, z_j = wagner_coeff
+    zz = c["zz"]
+    ncr_minor = math.pi ** 2 * c["E"] * c["Iy"] / L ** 2
+    mcr = c1 * ncr_minor * (math.sqrt(c["Iw"] / c["Iy"] + c["G"] * c["J"] / ncr_minor + zz * zz) - zz)
     out.update(C1=c1, Mcr=mcr, chilt=chi(math.sqrt(c["Wz"] * c["fy"] / mcr), c["alt"]))
     out["u_ltb"] = c["on_lt"] * f["Mz"] / (out["chilt"] * c["Wz"] * c["fy"] / c["gm1"])
     out["u_int"] = c["on_b"] * (max(out["u_by"], out["u_bz"]) + max(out["u_ltb"], out["u_mz"] * c["gm1"] / c["gm0"])

@@ -42,7 +42,8 @@ def _random_case(seed):
     c = dict(fy=235e6 * rng.uniform(1, 2), E=210e9, G=80.77e9, A=rng.uniform(2e-3, 2e-2), Iy=rng.uniform(1e-6, 1e-5),
              Iz=rng.uniform(2e-5, 2e-4), J=rng.uniform(1e-8, 1e-6), Iw=rng.uniform(0, 1e-6), L=rng.uniform(2, 9),
              Wy=rng.uniform(5e-5, 5e-4), Wz=rng.uniform(2e-4, 2e-3), Avy=rng.uniform(1e-3, 5e-3), Avz=ec3.BIG, ay=0.34, az=0.49,
-             alt=0.21, gm0=1.0, gm1=1.1, c1=float(rng.choice([0.0, 1.0, 1.35])), on_b=1.0, on_lt=1.0)
+             alt=0.21, gm0=1.0, gm1=1.1, c1=float(rng.choice([0.0, 1.0, 1.35])), on_b=1.0, on_lt=1.0,
+             zz=float(rng.choice([0.0, 0.08, -0.05])))        # C2 z_g - C3 z_j of the general M_cr
     c.update(Lcry=c["L"] * rng.uniform(0.5, 1), Lcrz=c["L"], Llt=c["L"] * rng.uniform(0.5, 1))
     m = rng.uniform(1e3, 2e5)
     f = dict(Nmax=rng.uniform(-1e5, 1e5), Nmin=rng.uniform(-3e5, 0), Vy=rng.uniform(0, 1e5), Vz=rng.uniform(0, 1e4),
@@ -101,6 +102,32 @@ def test_defaults_follow_the_catalogue_note():
     assert c2["Wz"] == sec["wel_z"] and (c2["alt"], c2["ay"], c2["az"]) == (0.21, 0.49, 0.34)
     assert (c2["Lcry"], c2["Lcrz"], c2["Llt"], c2["gm1"], c2["c1"]) == (3.0, 6.0, 2.0, 1.1, 1.0)
     assert {k: c2[k] for k in want} == ec3_oracle.constants(m2, {"gamma_m1": 1.1, "c1": 1.0}, [0])
+
+
+def test_general_mcr_load_height():
+    """NCCI SN003: a load on the top flange (z_g > 0, C2 = 0.454 for a uniform load) lowers M_cr, one below the shear centre
+    raises it; zero C2 / C3 is the doubly symmetric form; the mono-symmetry term reads Section.wagner_coeff."""
+    doc = copy.deepcopy(helpers.golden("ec3_check_beam_ipe300")["doc"])
+    model = wire.parse_document(doc)
+    base, _ = ec3.entity_constants(model, {}, [0])
+    top, notes = ec3.entity_constants(model, {"c2": 0.454, "z_g": 0.15}, [0])
+    assert base["zz"] == 0.0 and top["zz"] == pytest.approx(0.454 * 0.15) and not notes
+    assert ec3_oracle.constants(model, {"c2": 0.454, "z_g": 0.15}, [0])["zz"] == pytest.approx(top["zz"])
+    f = dict(Nmax=0.0, Nmin=0.0, Vy=0.0, Vz=0.0, My=0.0, Mz=60.75e3, Ma=45.6e3, Mb=60.75e3, Mc=45.6e3)
+    m0 = ec3_oracle.rules(ec3_oracle.constants(model, {}, [0]), f)["Mcr"]
+    m_top = ec3_oracle.rules(ec3_oracle.constants(model, {"c2": 0.454, "z_g": 0.15}, [0]), f)["Mcr"]
+    m_bot = ec3_oracle.rules(ec3_oracle.constants(model, {"c2": 0.454, "z_g": -0.15}, [0]), f)["Mcr"]
+    assert m_top < m0 < m_bot
+    # hand formula
+    c = ec3_oracle.constants(model, {"c2": 0.454, "z_g": 0.15}, [0])
+    c1 = 12.5 * 60.75 / (2.5 * 60.75 + 3 * 45.6 + 4 * 60.75 + 3 * 45.6)
+    ncr = math.pi ** 2 * c["E"] * c["Iy"] / c["Llt"] ** 2
+    zz = 0.454 * 0.15
+    assert m_top == pytest.approx(c1 * ncr * (math.sqrt(c["Iw"] / c["Iy"] + c["G"] * c["J"] / ncr + zz * zz) - zz), rel=1e-12)
+    doc["model"]["sections"][0]["wagner_coeff"] = 0.02
+    m3 = wire.parse_document(doc)
+    assert ec3.entity_constants(m3, {"c3": 0.525}, [0])[0]["zz"] == pytest.approx(-0.525 * 0.02)
+    assert ec3_oracle.constants(m3, {"c3": 0.525}, [0])["zz"] == pytest.approx(-0.525 * 0.02)
 
 
 def _restrained_doc():
