@@ -646,6 +646,14 @@ def _parse_members(mc: MemberColumns, nd: dict, sc: dict, model: dict, opts: Opt
                     if h.get(f) and h[f].get("points"):
                         hinge_curves.append((i, int(m_rel[i]), 6 * e + d) + hinge_curve(int(hid), f, h[f]))
     rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), REL_STRIDE)
+    # MemberHinge.rotational_release_warp (pydantic_models.py:2078): spring stiffness between the warping of the member end and
+    # that of its node, as the other release fields; None = continuous.  Acted on in _warping_nodes
+    m_warp_rel = np.full((nm, 2), RIGID_RELEASE)
+    for i in range(nm):
+        for e, hid in enumerate((mc.start_hinge[i], mc.end_hinge[i])):
+            h = hinges.get(int(hid)) if hid is not None else None
+            if h is not None and h.get("rotational_release_warp") is not None:
+                m_warp_rel[i, e] = max(float(h["rotational_release_warp"]), 0.0)
     # cables: elastic catenary between the end nodes; hinges, offsets and section eccentricities do not apply to them
     c_member = np.nonzero(m_type == MT_CABLE)[0].astype(np.int32)
     for i in c_member:
@@ -708,7 +716,7 @@ def _parse_members(mc: MemberColumns, nd: dict, sc: dict, model: dict, opts: Opt
     return dict(m_n1=m_n1, m_n2=m_n2, m_type=m_type, m_roll=m_roll, m_prop=m_prop, m_rel=m_rel, rel=rel, member_index=member_index,
                 member_ids=m_ids,
                 hinge_curves=hinge_curves, m_section_raw=m_section_raw, m_ref_member=m_ref_member, m_ref_node=m_ref_node,
-                member_sets=member_sets, c_member=c_member, c_l0=c_l0, c_ea=c_ea, c_w=c_w)
+                member_sets=member_sets, c_member=c_member, c_l0=c_l0, c_ea=c_ea, c_w=c_w, m_warp_rel=m_warp_rel)
 
 
 def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:
@@ -979,12 +987,29 @@ def _warping_nodes(nd: dict, mb: dict, sc: dict, warnings: list) -> dict:
         touched = np.unique(np.concatenate([m_n1[w_member], m_n2[w_member]]))
         warp_node[touched] = nn + np.arange(len(touched), dtype=np.int32)
         w_aux = np.stack([warp_node[m_n1[w_member]], warp_node[m_n2[w_member]]], axis=1).astype(np.int32)
+        # warping released at a member end (MemberHinge.rotational_release_warp = 0): that end warps freely, whatever its node
+        # does -- it gets an auxiliary node of its own (unrestrained psi: the bimoment vanishes there)
+        owner = list(touched)                       # real node every auxiliary node belongs to
+        free_psi = [False] * len(touched)
+        for k, i in enumerate(w_member):
+            for e in range(2):
+                kw = mb["m_warp_rel"][i, e]
+                if kw == 0.0:
+                    w_aux[k, e] = nn + len(owner)
+                    owner.append(int(m_n1[i] if e == 0 else m_n2[i]))
+                    free_psi.append(True)
+                elif kw > 0.0:
+                    warnings.append(("W_WARP_RELEASE_SPRING", f"member {int(mb['member_ids'][i])}: a warping release with a spring "
+                                     "stiffness is not modelled; the warping of this end stays continuous with its node"))
+        touched = np.asarray(owner, np.int64)
         na = len(touched)
-        node_ids = np.concatenate([node_ids, -1 - node_ids[touched]])        # aux ids are negative: never on the wire
+        aux_ids = -1 - node_ids[touched]
+        aux_ids[len(free_psi) - sum(free_psi):] -= (1 << 40) * (1 + np.arange(sum(free_psi)))     # private ones: unique, negative
+        node_ids = np.concatenate([node_ids, aux_ids])        # aux ids are negative: never on the wire
         xyz = np.concatenate([xyz, xyz[touched]])
         node_support_id = np.concatenate([node_support_id, node_support_id[touched]])
         aux_code = np.full((na, 6), BC_FIXED, np.uint8)
-        aux_code[:, 0] = np.where(nd["warp_fixed"][touched], BC_FIXED, BC_FREE)
+        aux_code[:, 0] = np.where(nd["warp_fixed"][touched] & ~np.asarray(free_psi), BC_FIXED, BC_FREE)
         bc_code = np.concatenate([bc_code, aux_code])
         bc_k = np.concatenate([bc_k, np.zeros((na, 6))])
     return dict(n_real=nn, warp_node=warp_node, w_member=w_member, w_aux=w_aux, node_ids=node_ids, xyz=xyz,
