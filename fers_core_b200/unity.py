@@ -22,7 +22,7 @@ Semantics where the closed engine is the only definition (stated, unpinned):
   * ``of: ReferenceMember`` / ``ReferenceMember*`` node references follow ``Member.reference_member`` /
     ``reference_node`` of the entity's first member (example 101); an entity without one evaluates to NaN;
   * ``Displacement`` = largest absolute value of the component over the entity's nodes.
-  * plate entities (``AllPlates`` / ``PlateElements``): ``PlateStress`` = surface stress n/t +- 6m/t^2 at the element
+  * plate entities (``AllPlates`` / ``PlateElements`` / ``PlateSurfaces``): ``PlateStress`` = surface stress n/t +- 6m/t^2 at the element
     centroid, both surfaces, enveloped; QUAD4 elements (two TRI3 rows) envelope both halves.
 Ec3Steel checks are compiled into the same postfix programs (ec3.py: EN 1993-1-1 6.2 cross-section rules, 6.3.1 flexural
 buckling, 6.3.2 lateral-torsional buckling, linear 6.3.3 interaction).  Every entity result carries a trace with the value
@@ -296,6 +296,16 @@ def _select_entities(model, sel: dict):
             if i not in rows_of:
                 raise UnityError(f"unity check: unknown plate element {i}")
         return [({"type": "PlateElement", "plate_element_id": i}, rows_of[i]) for i in ids]
+    if kind == "PlateSurfaces":
+        # EntitySelector6 / EntityRef4 (pydantic_models.py:314-319, 395-400): one entity per surface, made of the elements
+        # meshed from it (PlateElement.source_surface_id); the envelope runs over all of them
+        out = []
+        for i in sel.get("ids") or []:
+            rows = [int(r) for r in np.nonzero(np.asarray(model.p_surface) == int(i))[0]]
+            if not rows:
+                raise UnityError(f"unity check: plate surface {i} has no elements")
+            out.append(({"type": "PlateSurface", "plate_surface_id": int(i)}, rows))
+        return out
     raise UnityError(f"unity check: entity selector {kind!r} is not supported")
 
 
@@ -315,7 +325,7 @@ def compile_check(model, definition: dict) -> CompiledCheck:
         return CompiledCheck(definition=definition, skipped=str(e), **empty)
     ents = [(ref, ms) for ref, ms in ents if ms]
     n_ent = len(ents)
-    plates = bool(ents) and ents[0][0]["type"] == "PlateElement"
+    plates = bool(ents) and ents[0][0]["type"] in ("PlateElement", "PlateSurface")
     labels = None
     entity_consts: dict = {}
     ec3_notes: list = []
@@ -379,7 +389,7 @@ def compile_check(model, definition: dict) -> CompiledCheck:
         if plates and qk not in ("Constant", "DimensionedConstant", "PlateStress", "Displacement"):
             return CompiledCheck(definition=definition, skipped=f"quantity {qk!r} is not defined for plate entities", **empty)
         if not plates and qk == "PlateStress":
-            return CompiledCheck(definition=definition, skipped="PlateStress needs a plate selector (AllPlates / PlateElements)",
+            return CompiledCheck(definition=definition, skipped="PlateStress needs a plate selector (AllPlates / PlateElements / PlateSurfaces)",
                                  **empty)
         of_ref = isinstance(qv, dict) and qv.get("of") not in (None, "SelfEntity")
         if of_ref and qv.get("of") != "ReferenceMember":

@@ -166,6 +166,7 @@ class ModelArrays:
     c_l0: np.ndarray = field(default_factory=lambda: np.zeros(0))                  # [Ncable] unstretched length
     c_ea: np.ndarray = field(default_factory=lambda: np.zeros(0))                  # [Ncable] axial stiffness
     c_w: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))              # [Ncable,3] own weight per unstretched length
+    p_surface: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))   # [Npl] PlateElement.source_surface_id or -1
 
     def member_raw(self, m: int):
         """(section dict, material dict) of member index m as they came over the wire."""
@@ -416,7 +417,7 @@ def build_model_arrays(ncols: NodeColumns, mcols: MemberColumns, model: dict, an
         combo_limit_state=[c.get("limit_state") for c in combos],
         m_classification=list(mcols.classification), m_section_raw=mb["m_section_raw"],
         m_ref_member=mb["m_ref_member"], m_ref_node=mb["m_ref_node"],
-        c_member=mb["c_member"], c_l0=mb["c_l0"], c_ea=mb["c_ea"], c_w=mb["c_w"],
+        c_member=mb["c_member"], c_l0=mb["c_l0"], c_ea=mb["c_ea"], c_w=mb["c_w"], p_surface=pl["p_surface"],
     )
 
 
@@ -728,7 +729,7 @@ def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:
     todo = [surf for surf in (model.get("plate_surfaces") or []) if surf.get("id") not in meshed]
     if todo:
         plates += mesh_plate_surfaces(todo, plates, nd, warnings)
-    p_ids_l, p_nodes_l, p_data_l, p_flags_l = [], [], [], []
+    p_ids_l, p_nodes_l, p_data_l, p_flags_l, p_surface_l = [], [], [], [], []
     for p in plates:
         nids = [nid["id"] if isinstance(nid, dict) else nid for nid in p["node_ids"]]
         mat = mats.get(int(p["material"])) if not isinstance(p.get("material"), dict) else p["material"]
@@ -781,6 +782,7 @@ def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:
             except KeyError as e:
                 raise WireError(f"plate {p['id']}: unknown node {e}") from None
             p_ids_l.append(int(p["id"]))
+            p_surface_l.append(-1 if p.get("source_surface_id") is None else int(p["source_surface_id"]))
             theta = 0.0
             if lx_dir is not None:
                 theta = plate_local_x_angle(xyz[p_nodes_l[-1]], lx_dir)
@@ -802,7 +804,8 @@ def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:
     plate_index = {}
     for i, pid in enumerate(p_ids_l):
         plate_index.setdefault(pid, []).append(i)
-    return dict(plates=plates, p_ids=p_ids, p_ids_l=p_ids_l, p_nodes=p_nodes, p_data=p_data, p_flags=p_flags, plate_index=plate_index)
+    return dict(plates=plates, p_ids=p_ids, p_ids_l=p_ids_l, p_nodes=p_nodes, p_data=p_data, p_flags=p_flags, plate_index=plate_index,
+                p_surface=np.array(p_surface_l, np.int64))
 
 
 def _load_records(c: dict, key: str):

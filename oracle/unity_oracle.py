@@ -71,6 +71,9 @@ def _entities(model, sel):
         ids = list(dict.fromkeys(int(i) for i in model.p_ids)) if kind == "AllPlates" else [int(i) for i in sel["ids"]]
         return [({"type": "PlateElement", "plate_element_id": i}, [r for r, pid in enumerate(model.p_ids) if int(pid) == i])
                 for i in ids]
+    if kind == "PlateSurfaces":         # one entity per surface: every element meshed from it
+        return [({"type": "PlateSurface", "plate_surface_id": int(i)},
+                 [r for r in range(model.n_plates) if int(model.p_surface[r]) == int(i)]) for i in sel["ids"]]
     raise ValueError(kind)
 
 
@@ -98,7 +101,7 @@ def evaluate(model, res) -> list:
             cols = [c for c in cols if ls[int(plan.ids[c])] in (None, d["limit_state"])]
         per = []
         for ref, members in _entities(model, d.get("applies_to") or {"type": "AllMembers"}):
-            if ref["type"] == "PlateElement":
+            if ref["type"] in ("PlateElement", "PlateSurface"):
                 nodes = list(dict.fromkeys(int(n) for r in members for n in model.p_nodes[r]))
             else:
                 nodes = _nodes_along(model, members)

@@ -247,15 +247,58 @@ def test_plate_stress_checks_match_oracle(name):
              {"name": "s1", "source": q("PlateStress", measure="PrincipalMax")},
              {"name": "s2", "source": q("PlateStress", measure="PrincipalMin")},
              {"name": "d", "source": q("Displacement", component="Magnitude")}]}}}]
+    # the elements of the first half of the list belong to surface 7, the rest to surface 8: one entity per surface
+    half = len(doc["model"]["plate_elements"]) // 2
+    for k, p in enumerate(doc["model"]["plate_elements"]):
+        p["source_surface_id"] = 7 if k < half else 8
+    a["unity_checks"].append(
+        {"id": "surf", "name": "von Mises per surface", "applies_to": {"type": "PlateSurfaces", "ids": [7, 8]},
+         "spec": {"Generic": {"demand": "s", "capacity": "235e6", "variables": [{"name": "s", "source": q("PlateStress", measure="VonMises")}]}}})
     model = wire.parse_document(doc)
     got = engine.analyze(wire.parse_document(doc)).unity.results()
     want = unity_oracle.evaluate(model, fers_oracle.analyze(model))
     assert len(got[0]["per_entity"]) == len({int(i) for i in model.p_ids}) and len(got[1]["per_entity"]) == 1
+    assert [pe["entity"] for pe in got[2]["per_entity"]] == [{"type": "PlateSurface", "plate_surface_id": 7},
+                                                             {"type": "PlateSurface", "plate_surface_id": 8}]
+    # a surface is as utilised as its worst element
+    by_el = {pe["entity"]["plate_element_id"]: pe["utilization"] * (235e6 / 1.1) / 235e6 for pe in got[0]["per_entity"]}
+    ids7 = [int(p["id"]) for p in doc["model"]["plate_elements"][:half]]
+    assert got[2]["per_entity"][0]["utilization"] == pytest.approx(max(by_el[i] for i in ids7), rel=1e-9)
     for g, w in zip(got, want):
         assert g["max_utilization"] > 0
         for pe, pw in zip(g["per_entity"], w["per_entity"]):
             assert pe["entity"] == pw["entity"] and pe["governing_combination_id"] == pw["governing_combination_id"]
             assert pe["utilization"] == pytest.approx(pw["utilization"], rel=1e-8)
+
+
+def test_plate_surface_selector_on_the_oracle():
+    """EntitySelector PlateSurfaces (pydantic_models.py:395-400): one entity per surface = the elements meshed from it."""
+    from oracle import fers_oracle
+    doc = copy.deepcopy(helpers.golden("plate_strip_surface_load")["doc"])
+    els = doc["model"]["plate_elements"]
+    for k, p in enumerate(els):
+        p["source_surface_id"] = 7 if k < len(els) // 2 else 8
+    q = {"Quantity": {"PlateStress": {"measure": "VonMises"}}}
+    doc["analysis"]["unity_checks"] = [
+        {"id": "el", "name": "per element", "applies_to": {"type": "AllPlates"},
+         "spec": {"Generic": {"demand": "s", "capacity": "235e6", "variables": [{"name": "s", "source": q}]}}},
+        {"id": "surf", "name": "per surface", "applies_to": {"type": "PlateSurfaces", "ids": [8, 7]},
+         "spec": {"Generic": {"demand": "s", "capacity": "235e6", "variables": [{"name": "s", "source": q}]}}}]
+    model = wire.parse_document(doc)
+    assert sorted(set(model.p_surface.tolist())) == [7, 8]
+    out = unity_oracle.evaluate(model, fers_oracle.analyze(model))
+    by_el = {pe["entity"]["plate_element_id"]: pe["utilization"] for pe in out[0]["per_entity"]}
+    assert [pe["entity"]["plate_surface_id"] for pe in out[1]["per_entity"]] == [8, 7]
+    for pe in out[1]["per_entity"]:
+        mine = [int(p["id"]) for p in els if p["source_surface_id"] == pe["entity"]["plate_surface_id"]]
+        assert pe["utilization"] == pytest.approx(max(by_el[i] for i in mine), rel=1e-12)
+    # the product compiles the same entity table
+    c = unity.compile_check(model, doc["analysis"]["unity_checks"][1])
+    assert c.plates and [e["plate_surface_id"] for e in c.entities] == [8, 7]
+    rows = {sid: sorted(np.nonzero(model.p_surface == sid)[0].tolist()) for sid in (7, 8)}
+    assert sorted(c.ent_members[c.ent_ptr[0]:c.ent_ptr[1]].tolist()) == rows[8]
+    bad = unity.compile_check(model, dict(doc["analysis"]["unity_checks"][1], applies_to={"type": "PlateSurfaces", "ids": [99]}))
+    assert bad.skipped and "plate surface 99" in bad.skipped
 
 
 def _generic_only(model):
