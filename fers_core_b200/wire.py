@@ -483,7 +483,7 @@ def _parse_nodes(ncols: NodeColumns, model: dict, opts: Options) -> dict:
             free = bc_code[:, d] == BC_FREE
             bc_code[free, d] = BC_FIXED
     return dict(node_ids=node_ids, xyz=xyz, node_index=node_index, bc_code=bc_code, bc_k=bc_k, node_support_id=node_support_id,
-                warp_fixed=warp_fixed, support_curves=support_curves)
+                warp_fixed=warp_fixed, support_curves=support_curves, two_d=opts.dimensionality == "2D")
 
 
 def _parse_sections(model: dict, opts: Options, warnings: list) -> dict:
@@ -729,6 +729,7 @@ def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:
     todo = [surf for surf in (model.get("plate_surfaces") or []) if surf.get("id") not in meshed]
     if todo:
         plates += mesh_plate_surfaces(todo, plates, nd, warnings)
+        xyz = nd["xyz"]                                  # the mesher may have added boundary nodes
     p_ids_l, p_nodes_l, p_data_l, p_flags_l, p_surface_l = [], [], [], [], []
     for p in plates:
         nids = [nid["id"] if isinstance(nid, dict) else nid for nid in p["node_ids"]]
@@ -1105,15 +1106,61 @@ def plates_flat_surface(plates, p_ids_l):
 
 
 # ---- plate surfaces that arrive without elements -------------------------------------------------------------------
+def densify_polygon(pts: np.ndarray, size) -> np.ndarray:
+    """Boundary of a surface with its edges cut into ceil(length / size) equal segments (fers_core/plates/mesh.py:72-94, the
+    reference's ``mesh.target_size`` rule: the boundary is refined, no interior nodes are made); consecutive duplicates
+    dropped (:97-107, tolerance 1e-9)."""
+    if size is None or not (float(size) > 0.0):
+        return pts
+    out = []
+    n = len(pts)
+    for i in range(n):
+        a, b = pts[i], pts[(i + 1) % n]
+        seg = max(1, int(np.ceil(np.linalg.norm(b - a) / float(size))))
+        for k in range(seg):
+            out.append(a + (b - a) * (k / seg))
+    keep = []
+    for q in out:
+        if not keep or np.linalg.norm(q - keep[-1]) > 1e-9:
+            keep.append(q)
+    if len(keep) > 1 and np.linalg.norm(keep[0] - keep[-1]) <= 1e-9:
+        keep.pop()
+    return np.array(keep, float)
+
+
+def _append_nodes(nd: dict, ids: list, xyz: np.ndarray) -> None:
+    """Nodes made by the surface mesher join the node table after the wire nodes: unsupported, free (out-of-plane DOFs held
+    in a 2D model, as for every node)."""
+    n = len(ids)
+    first = len(nd["node_ids"])
+    nd["node_ids"] = np.concatenate([nd["node_ids"], np.asarray(ids, np.int64)])
+    nd["xyz"] = np.concatenate([nd["xyz"], np.asarray(xyz, np.float64).reshape(n, 3)])
+    code = np.zeros((n, 6), np.uint8)
+    if nd.get("two_d"):
+        code[:, 2:5] = BC_FIXED
+    nd["bc_code"] = np.concatenate([nd["bc_code"], code])
+    nd["bc_k"] = np.concatenate([nd["bc_k"], np.zeros((n, 6))])
+    nd["node_support_id"] = np.concatenate([nd["node_support_id"], np.full(n, -1, np.int64)])
+    nd["warp_fixed"] = np.concatenate([nd["warp_fixed"], np.zeros(n, bool)])
+    for k, i in enumerate(ids):
+        nd["node_index"][int(i)] = first + k
+
+
 def mesh_plate_surfaces(surfaces: list, plates: list, nd: dict, warnings: list) -> list:
     """PlateSurface records (pydantic_models.py:1752-1790) -> TRI3 plate-element records, the rule of the reference's
-    client-side mesher (fers_core/plates/mesh.py:12-31, :106-148; fers/fers.py:1071-1086): the boundary polygon is
-    projected into its plane, oriented counter-clockwise and ear-clipped; element ids continue after the largest plate
-    id.  Only the boundary nodes are used: interior refinement (`mesh.target_size`) and openings are noted, not meshed."""
-    node_index, xyz = nd["node_index"], nd["xyz"]
+    client-side mesher (fers_core/plates/mesh.py:12-31, :72-94, :106-148; plates/platesurface.py:180-237; fers/fers.py:
+    1071-1086): the boundary polygon is refined to ``mesh.target_size`` (edges cut into equal segments), projected into
+    its plane, oriented counter-clockwise and ear-clipped; a generated vertex that coincides (9 decimals) with a boundary
+    node of the surface -- or with a node generated for a surface of the same ``mesh_group_id`` -- reuses it, the others
+    become new nodes numbered after the largest node id; element ids continue after the largest plate id.  No interior
+    nodes are made (the reference makes none either); ``mesh.divisions`` and openings are noted, not meshed."""
+    node_index = nd["node_index"]
     next_id = max([int(p["id"]) for p in plates], default=0) + 1
+    next_node = int(max(nd["node_ids"].max() if len(nd["node_ids"]) else 0, 0)) + 1
+    group_cache: dict = {}
     out = []
     for surf in surfaces:
+        xyz = nd["xyz"]
         nids = [int(v["id"] if isinstance(v, dict) else v) for v in surf.get("boundary_node_ids") or []]
         for v in nids:
             if v not in node_index:
@@ -1123,14 +1170,32 @@ def mesh_plate_surfaces(surfaces: list, plates: list, nd: dict, warnings: list) 
             nids, pts = nids[:-1], pts[:-1]
         if len(nids) < 3:
             raise WireError(f"plate surface {surf.get('id')}: needs at least three boundary nodes")
-        tris = ear_clip_polygon(pts, f"plate surface {surf.get('id')}")
-        if (surf.get("mesh") or {}).get("target_size") or (surf.get("mesh") or {}).get("divisions"):
-            warnings.append(("W_SURFACE_MESH_BOUNDARY_ONLY", f"plate surface {surf.get('id')}: meshed over its boundary nodes only "
-                             "(no interior refinement to the requested size)"))
+        mesh = surf.get("mesh") or {}
+        key = lambda q: (round(float(q[0]), 9), round(float(q[1]), 9), round(float(q[2]), 9))       # noqa: E731
+        gid = surf.get("mesh_group_id")
+        cache = group_cache.setdefault(gid, {}) if gid is not None else {}
+        for v, q in zip(nids, pts):
+            cache[key(q)] = v
+        dense = densify_polygon(pts, mesh.get("target_size"))
+        ids, new_ids, new_xyz = [], [], []
+        for q in dense:
+            v = cache.get(key(q))
+            if v is None:
+                v = next_node
+                next_node += 1
+                cache[key(q)] = v
+                new_ids.append(v); new_xyz.append(q)
+            ids.append(v)
+        if new_ids:
+            _append_nodes(nd, new_ids, np.array(new_xyz))
+        tris = ear_clip_polygon(dense, f"plate surface {surf.get('id')}")
+        if mesh.get("divisions"):
+            warnings.append(("W_SURFACE_MESH_DIVISIONS_IGNORED", f"plate surface {surf.get('id')}: mesh.divisions is not applied "
+                             "(the boundary is refined to mesh.target_size only)"))
         if surf.get("openings"):
             warnings.append(("W_SURFACE_OPENINGS_IGNORED", f"plate surface {surf.get('id')}: openings are not cut out of the mesh"))
         for (i, j, k) in tris:
-            out.append({"id": next_id, "node_ids": [nids[i], nids[j], nids[k]], "material": surf["material"],
+            out.append({"id": next_id, "node_ids": [ids[i], ids[j], ids[k]], "material": surf["material"],
                         "thickness": surf["thickness"], "behavior": surf.get("behavior"), "theory": surf.get("theory"),
                         "plane_state": surf.get("plane_state"), "offset": surf.get("offset"),
                         "stiffness_modifiers": surf.get("stiffness_modifiers"), "local_x_direction": surf.get("local_x_direction"),

@@ -102,10 +102,12 @@ for poly in ([(0, 0, 0), (4, 0, 0), (4, 0, 3), (0, 0, 3)],                      
     u, v = pts[1] - pts[0], pts[2] - pts[0]
     n = np.cross(u, v); n /= np.linalg.norm(n)
     pts = pts - np.outer((pts - pts[0]) @ n, n)                                             # exactly planar
-    want = triangulate_surface_polygon([tuple(p) for p in pts])
-    got = wire.ear_clip_polygon(pts)
-    assert len(got) == len(want) == len(pts) - 2
-    for (i, j, k), tri in zip(got, want):
-        assert np.allclose(pts[[i, j, k]], np.array(tri), atol=1e-12), (poly, got, want)
+    for size in (None, 0.9, 1.5, 2.0, 10.0):                                                # mesh.target_size: refined boundary
+        want = triangulate_surface_polygon([tuple(p) for p in pts], mesh_size=size)
+        dense = wire.densify_polygon(pts, size)
+        got = wire.ear_clip_polygon(dense)
+        assert len(got) == len(want) == len(dense) - 2
+        for (i, j, k), tri in zip(got, want):
+            assert np.allclose(dense[[i, j, k]], np.array(tri), atol=1e-12), (poly, size, got, want)
 print(json.dumps({"checked": checked, "members": len(mem), "from_fers_s": t_fast, "to_dict_s": t_dict, "json_round_trip_s": t_json,
                   "parse_document_s": t_parse, "pydantic_gate_s": t_gate, "mesher_polygons": 4}))
