@@ -1,5 +1,6 @@
 """Randomised sweep: small 3D frames with jittered geometry, rolled members, trusses, end releases and springs, shear-centre
-and end offsets, products of inertia, pinned and sprung supports, linear and P-Delta -- every result field of the GPU path
+and end offsets, products of inertia, pinned and sprung supports, slabs (Mindlin / thin-plate, orthotropic, offset), pretensioned
+cable braces, linear and P-Delta -- every result field of the GPU path
 against the oracle.  The fixed cases elsewhere pin single features; this one pins their combinations."""
 import numpy as np
 import pytest
@@ -64,7 +65,10 @@ def random_model(seed: int):
                             rec[wire.PD_EX:wire.PD_GYZ + 1] = (E, 0.4 * E, 0.2 * E, 0.15, 0.25 * E, 0.1 * E)
                         if rng.random() < 0.5:
                             rec[wire.PD_OFFSET] = rng.uniform(-0.15, 0.15)
-                        tris.append(t3); data.append(rec); flags.append(int(rng.choice([1, 2, 3])))
+                        fl = int(rng.choice([1, 2, 3]))
+                        if fl & 2 and rng.random() < 0.4:
+                            fl |= 8                                   # thin-plate (DKT) bending
+                        tris.append(t3); data.append(rec); flags.append(fl)
         if tris:
             model.p_ids = np.arange(1, len(tris) + 1, dtype=np.int64)
             model.p_nodes = np.array(tris, np.int32)
@@ -73,7 +77,51 @@ def random_model(seed: int):
             lc = model.load_cases[0]
             lc.pp_plate = np.arange(len(tris), dtype=np.int32)
             lc.pp_vec = np.tile(np.array([0.0, -4.0e3, 0.0]), (len(tris), 1))
+    if seed % 5 == 3:
+        _add_cable_braces(model, rng, nx, nz, ny)
     return model
+
+
+def _add_cable_braces(model, rng, nx, nz, ny):
+    """Pretensioned cable diagonals (elastic catenaries with a little own weight) across some bays of the first storeys."""
+    px, pz = nx + 1, nz + 1
+    nid = lambda i, k, j: i + px * (k + pz * j)          # noqa: E731
+    pairs = []
+    for i in range(nx):
+        for k in range(pz):
+            if rng.random() < 0.4:
+                j = int(rng.integers(0, ny))
+                pairs.append((nid(i, k, j), nid(i + 1, k, j + 1)) if rng.random() < 0.5 else (nid(i + 1, k, j), nid(i, k, j + 1)))
+    if not pairs:
+        pairs = [(nid(0, 0, 0), nid(1, 0, 1))]
+    nc, nm = len(pairs), model.n_members
+    n1 = np.array([p[0] for p in pairs], np.int32); n2 = np.array([p[1] for p in pairs], np.int32)
+    prop_row = 0
+    model.m_ids = np.concatenate([model.m_ids, model.m_ids.max() + 1 + np.arange(nc)])
+    model.m_n1 = np.concatenate([model.m_n1, n1]).astype(np.int32)
+    model.m_n2 = np.concatenate([model.m_n2, n2]).astype(np.int32)
+    model.m_type = np.concatenate([model.m_type, np.full(nc, wire.MT_CABLE)]).astype(np.int32)
+    model.m_roll = np.concatenate([model.m_roll, np.zeros(nc)])
+    model.m_prop = np.concatenate([model.m_prop, np.full(nc, prop_row)]).astype(np.int32)
+    model.m_rel = np.concatenate([model.m_rel, np.full(nc, -1)]).astype(np.int32)
+    for name in ("m_ref_member", "m_ref_node"):
+        arr = getattr(model, name)
+        if len(arr) == nm:
+            setattr(model, name, np.concatenate([arr, np.full(nc, -1, arr.dtype)]))
+    for name in ("m_classification", "m_section_raw"):
+        lst = getattr(model, name)
+        if len(lst) == nm:
+            setattr(model, name, list(lst) + [None] * nc)
+    chord = np.linalg.norm(model.xyz[n2] - model.xyz[n1], axis=1)
+    ea = np.full(nc, 0.02 * float(model.prop[prop_row, 0]))          # a rod of 2 % of the column's axial stiffness
+    model.c_member = (nm + np.arange(nc)).astype(np.int32)
+    model.c_ea = ea
+    model.c_l0 = chord / (1.0 + rng.uniform(2e3, 3e4, nc) / ea)
+    model.c_w = np.tile(np.array([0.0, -25.0, 0.0]), (nc, 1))
+    for li, lc in enumerate(model.load_cases):
+        lc.cab_q = np.zeros((nc, 3))
+        if li == 1:
+            lc.cab_q[:, 0] = 40.0                                      # a wind-like uniform load on the cables in one case
 
 
 def _fields(res):
@@ -83,7 +131,7 @@ def _fields(res):
     return out
 
 
-@pytest.mark.parametrize("seed", SEEDS[:3])
+@pytest.mark.parametrize("seed", SEEDS[:4])
 def test_oracle_solves_the_random_models(seed):
     model = random_model(seed)
     res = fers_oracle.analyze(model)
