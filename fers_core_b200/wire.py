@@ -1177,18 +1177,21 @@ def mesh_plate_surfaces(surfaces: list, plates: list, nd: dict, warnings: list) 
         for v, q in zip(nids, pts):
             cache[key(q)] = v
         dense = densify_polygon(pts, mesh.get("target_size"))
-        ids, new_ids, new_xyz = [], [], []
-        for q in dense:
-            v = cache.get(key(q))
-            if v is None:
-                v = next_node
-                next_node += 1
-                cache[key(q)] = v
-                new_ids.append(v); new_xyz.append(q)
-            ids.append(v)
+        tris = ear_clip_polygon(dense, f"plate surface {surf.get('id')}")
+        # node ids in the order the triangles first meet a new vertex (platesurface.py:207-216)
+        ids, new_ids, new_xyz = [cache.get(key(q)) for q in dense], [], []
+        for tri in tris:
+            for i in tri:
+                if ids[i] is None:
+                    v = cache.get(key(dense[i]))
+                    if v is None:
+                        v = next_node
+                        next_node += 1
+                        cache[key(dense[i])] = v
+                        new_ids.append(v); new_xyz.append(dense[i])
+                    ids[i] = v
         if new_ids:
             _append_nodes(nd, new_ids, np.array(new_xyz))
-        tris = ear_clip_polygon(dense, f"plate surface {surf.get('id')}")
         if mesh.get("divisions"):
             warnings.append(("W_SURFACE_MESH_DIVISIONS_IGNORED", f"plate surface {surf.get('id')}: mesh.divisions is not applied "
                              "(the boundary is refined to mesh.target_size only)"))
