@@ -43,3 +43,27 @@ def test_oracle_pattern_is_sorted_unique():
     for i in range(model.n_nodes):
         row = colidx[rowptr[i]:rowptr[i + 1]]
         assert np.all(np.diff(row) > 0) and i in row
+
+
+def test_engine_result_805_is_matched_to_second_order_terms():
+    """The only full result set of the reference's own (older, corotational) engine in the repository:
+    examples/json_input_solver/805_JSON_Import_Export_with_results.json -- fixed-fixed IPE 200, 6 m, 20 kN at mid-span,
+    order Nonlinear (fixture tests/golden/engine_result_805.json, made by tests/golden/make_engine_golden.py).
+    The oracle (P-Delta; no axial force develops in this beam, so the first-order answer) agrees with the engine on the
+    deflection, the vertical reactions and the end moments to 2.5e-4; what it does not have is the catenary action of the
+    corotational formulation -- 1.12 kN of horizontal reaction from the stretching of the deflected beam between its
+    clamped ends, the source of that 2.5e-4 -- which is why the product flags corotational requests W_COROTATIONAL_AS_PDELTA."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "engine_result_805.json"), encoding="utf-8") as fh:
+        fx = json.load(fh)
+    from oracle import oracle_engine
+    out = oracle_engine.solve_document(fx["doc"])["results"]["loadcases"][fx["golden"]["loadcase"]]
+    g = fx["golden"]
+    assert out["displacement_nodes"]["2"]["dy"] == pytest.approx(g["displacement_nodes"]["2"]["dy"], rel=2.5e-4)
+    for n in ("1", "3"):
+        got, want = out["reaction_nodes"][n]["nodal_forces"], g["reaction_nodes"][n]
+        assert got["fy"] == pytest.approx(want["fy"], rel=1e-5)
+        assert got["mz"] == pytest.approx(want["mz"], rel=2.5e-4)
+        # the membrane force of the stretched beam: EA x (mean axial strain of the deflected shape) ~ 1.1 kN in the engine
+        assert abs(want["fx"]) == pytest.approx(1117.5, rel=1e-3) and abs(got["fx"]) < 1e-6
