@@ -23,6 +23,7 @@ from .hostlogic import (
     INACTIVE_SCALE, effective_bc, imperfect_coordinates, member_frames_host, mpc_transform, pdelta_suppressed_axes, rhs_plan,
     rigid_property_row,
     unilateral_dofs, unilateral_update, curve_stiffness, curves_converged, hinge_curve_stiffness, rel_with_hinge_curves,
+    hinge_capacity_notes,
 )
 from .results import ResultArrays, SECTION_FRACS, lazy_bundle, results_to_json, results_to_wire
 
@@ -669,6 +670,8 @@ def analyze(model: wire.ModelArrays, device=None, detail: bool = True, assembly_
         out.warnings.append(("W_COROTATIONAL_AS_PDELTA",
                              "corotational Newton-Raphson is not implemented; second-order effects use P-Delta"))
     torch.cuda.synchronize(eng.dev)
+    if model.hinge_caps and model.n_members:
+        out.warnings += hinge_capacity_notes(model, out.f_local, plan.names)
     out.solve_ms = (time.perf_counter() - t_start) * 1e3
     if stats_out is not None:
         stats_out.update(vars(eng.stats))

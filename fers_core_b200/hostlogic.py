@@ -402,3 +402,25 @@ def unilateral_update(model: wire.ModelArrays, active: np.ndarray, u: np.ndarray
     keep = np.where(k > 0.0, uu <= 0.0, rr >= -tol_r)
     close = uu < 0.0
     return np.where(active, keep, close)
+
+
+# ---- hinge capacities (MemberHinge.max_tension_v* / max_moment_m*, pydantic_models.py:2069-2074) -------------------------------
+HINGE_FORCE_NAMES = ("N", "Vy", "Vz", "Mx", "My", "Mz")
+
+
+def hinge_capacity_notes(model: wire.ModelArrays, f_local: np.ndarray, names: list) -> list:
+    """The schema gives the hinge capacities no behaviour in the analysis, so they are not enforced; what the analysis can
+    say is where they are exceeded.  For every capacity the largest demand over the result columns (f_local [ncols, Nm, 12],
+    member end forces in the stiffness sign): the axial one counts TENSION only ("max_tension_vx": minus the end force at the
+    start, plus at the end), the others by magnitude.  Returns W_HINGE_CAPACITY_EXCEEDED notes (code, message)."""
+    notes = []
+    for m, end, comp, cap, hid in model.hinge_caps:
+        v = f_local[:, m, 6 * end + comp]
+        demand = (-v if end == 0 else v) if comp == 0 else np.abs(v)
+        col = int(np.argmax(demand))
+        if demand[col] > cap * (1.0 + 1e-12):
+            notes.append(("W_HINGE_CAPACITY_EXCEEDED",
+                          f"member {int(model.m_ids[m])} {'start' if end == 0 else 'end'} (hinge {hid}): {HINGE_FORCE_NAMES[comp]} = "
+                          f"{demand[col]:.6g} exceeds the capacity {cap:.6g} (utilisation {demand[col] / cap:.3f}, {names[col]}); "
+                          "capacities are not enforced in the analysis"))
+    return notes

@@ -146,6 +146,10 @@ class ModelArrays:
     # one entry per member end DOF, (member row, rel row, slot 0..11 of the release springs, driving local force
     # component 0..5 = N Vy Vz Mx My Mz at the same end, points [n,2] sorted by force, signed)
     hinge_curves: list = field(default_factory=list)
+    # MemberHinge.max_tension_v* / max_moment_m* (pydantic_models.py:2069-2074): (member row, end 0 / 1, local force component
+    # 0..5 = N Vy Vz Mx My Mz, capacity, hinge id).  Not enforced in the analysis (the schema states no behaviour); the
+    # end forces are held against them afterwards (hostlogic.hinge_capacity_notes)
+    hinge_caps: list = field(default_factory=list)
     # unity checks (pydantic_models.py:2202-2220): raw definitions + what their quantities read
     unity_checks: list = field(default_factory=list)
     member_sets_raw: list = field(default_factory=list)        # raw member_sets records (buckling lengths of the EC3 check)
@@ -418,6 +422,7 @@ def build_model_arrays(ncols: NodeColumns, mcols: MemberColumns, model: dict, an
         m_classification=list(mcols.classification), m_section_raw=mb["m_section_raw"],
         m_ref_member=mb["m_ref_member"], m_ref_node=mb["m_ref_node"],
         c_member=mb["c_member"], c_l0=mb["c_l0"], c_ea=mb["c_ea"], c_w=mb["c_w"], p_surface=pl["p_surface"],
+        hinge_caps=mb["hinge_caps"],
     )
 
 
@@ -567,7 +572,8 @@ def _parse_members(mc: MemberColumns, nd: dict, sc: dict, model: dict, opts: Opt
         if hid not in capacity_warned and any(h.get(f) is not None for f in _HINGE_CAPACITIES):
             capacity_warned.add(hid)
             warnings.append(("W_HINGE_CAPACITY_IGNORED", f"member hinge {hid}: max_tension_* / max_moment_* capacities "
-                             "are not enforced; the hinge keeps its elastic spring"))
+                             "are not enforced (the hinge keeps its elastic spring); the end forces are checked against them "
+                             "after the analysis (W_HINGE_CAPACITY_EXCEEDED)"))
         for d, f in enumerate(_HINGE_CURVES):
             curve = h.get(f)
             if curve and curve.get("points"):
@@ -647,6 +653,13 @@ def _parse_members(mc: MemberColumns, nd: dict, sc: dict, model: dict, opts: Opt
                     if h.get(f) and h[f].get("points"):
                         hinge_curves.append((i, int(m_rel[i]), 6 * e + d) + hinge_curve(int(hid), f, h[f]))
     rel = np.array(rel_rows, np.float64).reshape(len(rel_rows), REL_STRIDE)
+    hinge_caps: list = []
+    for i in range(nm):
+        for e, hid in enumerate((mc.start_hinge[i], mc.end_hinge[i])):
+            h = hinges.get(int(hid)) if hid is not None else None
+            for comp, f in enumerate(_HINGE_CAPACITIES[:6] if h else ()):
+                if h.get(f) is not None and np.isfinite(float(h[f])) and float(h[f]) > 0.0:
+                    hinge_caps.append((i, e, comp, float(h[f]), int(hid)))
     # MemberHinge.rotational_release_warp (pydantic_models.py:2078): spring stiffness between the warping of the member end and
     # that of its node, as the other release fields; None = continuous.  Acted on in _warping_nodes
     m_warp_rel = np.full((nm, 2), RIGID_RELEASE)
@@ -717,7 +730,8 @@ def _parse_members(mc: MemberColumns, nd: dict, sc: dict, model: dict, opts: Opt
     return dict(m_n1=m_n1, m_n2=m_n2, m_type=m_type, m_roll=m_roll, m_prop=m_prop, m_rel=m_rel, rel=rel, member_index=member_index,
                 member_ids=m_ids,
                 hinge_curves=hinge_curves, m_section_raw=m_section_raw, m_ref_member=m_ref_member, m_ref_node=m_ref_node,
-                member_sets=member_sets, c_member=c_member, c_l0=c_l0, c_ea=c_ea, c_w=c_w, m_warp_rel=m_warp_rel)
+                member_sets=member_sets, c_member=c_member, c_l0=c_l0, c_ea=c_ea, c_w=c_w, m_warp_rel=m_warp_rel,
+                hinge_caps=hinge_caps)
 
 
 def _parse_plates(model: dict, mats: dict, nd: dict, warnings: list) -> dict:

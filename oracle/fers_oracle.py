@@ -44,7 +44,7 @@ from fers_core_b200 import wire
 from fers_core_b200.results import ResultArrays, SECTION_FRACS
 # the host-side rules (result columns, imperfect geometry, rigid members, active sets, load-dependent springs) in the oracle's
 # own restatement -- not the product's hostlogic.py (a shared helper hides its bugs from every parity test)
-from oracle import cable_oracle
+from oracle import cable_oracle, host_oracle
 from oracle.host_oracle import (
     rhs_plan, imperfect_coordinates, rigid_property_row, pdelta_suppressed_axes,
     unilateral_dofs, effective_bc, unilateral_update, curve_stiffness, curves_converged,
@@ -964,6 +964,8 @@ def analyze(model: wire.ModelArrays, timings: dict | None = None, detail: bool =
                                                                                            reload, cab_q)
                 _store(out, asm_c, model, [col], U1[None], F1[None], peq1[None], K1,
                        None if kg1 is None else kg1[None], spans, fac[ci:ci + 1], iters=(it, conv, resn), detail=detail, cables=cab)
+    if model.hinge_caps and model.n_members:
+        out.warnings += host_oracle.hinge_capacity_notes(model, out.f_local, plan.names)
     if timings is not None:
         timings["total_s"] = time.perf_counter() - t0
     return out

@@ -219,3 +219,24 @@ def rel_with_hinge_curves(model, k) -> np.ndarray:
 
 def curves_converged(k_new, k_old, tol: float) -> bool:
     return all(abs(a - b) <= max(tol, 1e-12) * abs(b) for a, b in zip(k_new, k_old))
+
+
+# ---- hinge capacities (MemberHinge.max_tension_v* / max_moment_m*, pydantic_models.py:2069-2074) ----------------------------
+def hinge_capacity_notes(model, f_local, names) -> list:
+    """Capacities are not enforced (no behaviour stated in the schema): one note per capacity whose demand -- tension for the
+    axial one, magnitude for shears and moments, largest over the result columns -- exceeds it."""
+    label = ("N", "Vy", "Vz", "Mx", "My", "Mz")
+    out = []
+    for m, end, comp, cap, hid in model.hinge_caps:
+        worst, at = -math.inf, 0
+        for col in range(f_local.shape[0]):
+            v = float(f_local[col, m, 6 * end + comp])
+            d = ((-v) if end == 0 else v) if comp == 0 else abs(v)
+            if d > worst:
+                worst, at = d, col
+        if worst > cap * (1.0 + 1e-12):
+            out.append(("W_HINGE_CAPACITY_EXCEEDED",
+                        f"member {int(model.m_ids[m])} {'start' if end == 0 else 'end'} (hinge {hid}): {label[comp]} = {worst:.6g} "
+                        f"exceeds the capacity {cap:.6g} (utilisation {worst / cap:.3f}, {names[at]}); capacities are not enforced "
+                        "in the analysis"))
+    return out

@@ -133,3 +133,35 @@ def test_gpu_matches_oracle(engine_mod, case):
     if case == "moment":
         for col, p in enumerate(LOADS):
             assert got.U[col, 2, 1] == pytest.approx(_closed_form(p, _k(CURVE_M, p * B_LEN)), rel=1e-9)
+
+
+def test_hinge_capacities_are_checked_after_the_analysis():
+    """MemberHinge.max_moment_* / max_tension_* (pydantic_models.py:2069-2074): no behaviour is stated for them, so the
+    analysis does not enforce them -- it reports where the end forces exceed them.  The joint moment is M = P b
+    (statically determinate): with a capacity of 3 kNm the load cases P = 1600 N (4.0 kNm) and 3000 N (7.5 kNm) exceed it,
+    the governing one is named, and a capacity above the largest moment stays silent."""
+    for cap, expect in ((3.0e3, True), (8.0e3, False)):
+        doc = _doc(constant=40_000.0)
+        doc["model"]["member_hinges"][0]["max_moment_mz"] = cap
+        doc["model"]["member_hinges"][0]["max_tension_vx"] = 1.0          # the cantilever carries no axial force: never exceeded
+        model = wire.parse_document(doc)
+        assert [(c[1], c[2], c[3]) for c in model.hinge_caps] == [(1, 0, 1.0), (1, 5, cap)]
+        res = fo.analyze(model)
+        notes = [msg for code, msg in res.warnings if code == "W_HINGE_CAPACITY_EXCEEDED"]
+        assert bool(notes) == expect
+        if expect:
+            assert len(notes) == 1 and "Mz = 7500" in notes[0] and f"utilisation {7500.0 / cap:.3f}" in notes[0]
+        # the product states the rule a second time (hostlogic); both read the same end forces
+        assert hostlogic.hinge_capacity_notes(model, res.f_local, fo.rhs_plan(model).names) == \
+            [(c, msg) for c, msg in res.warnings if c == "W_HINGE_CAPACITY_EXCEEDED"]
+        assert any(c == "W_HINGE_CAPACITY_IGNORED" for c, _ in model.warnings)
+
+
+@pytest.mark.gpu
+def test_gpu_reports_the_same_capacity_notes(engine_mod):
+    doc = _doc(constant=40_000.0)
+    doc["model"]["member_hinges"][0]["max_moment_mz"] = 3.0e3
+    model = wire.parse_document(doc)
+    got = [w for w in engine_mod.analyze(model).warnings if w[0] == "W_HINGE_CAPACITY_EXCEEDED"]
+    want = [w for w in fo.analyze(model).warnings if w[0] == "W_HINGE_CAPACITY_EXCEEDED"]
+    assert len(got) == 1 and got[0][1].split("=")[0] == want[0][1].split("=")[0] and "utilisation 2.500" in got[0][1]
