@@ -52,13 +52,18 @@ __device__ __forceinline__ FrontDev level_front(const LevelCtx& L, int z) {
 
 // ---- front initialisation: children's Schur complements -> panel + F22 (lower triangle) -----------
 // One thread owns two consecutive rows (the even/odd DOF pair of one node: 16-byte loads and stores
-// along the contiguous dimension of the column-major fronts) and INIT_COLS columns (four whole nodes,
+// along the contiguous dimension of the column-major fronts) and INIT_COLS columns (whole nodes: two by default,
 // so the child index of a column node is looked up once per six columns).
 constexpr int INIT_THREADS = 192;
 constexpr int INIT_ROWS = 2 * INIT_THREADS;
-constexpr int INIT_COLS = 24;
+// Columns per thread and resident CTAs per SM (FERS_INIT_COLS).  The kernel waits on its loads (long-scoreboard stalls; with
+// 24 columns = 142 registers = 2 CTAs only 12 % of the warp slots were occupied, profiles/r2P_front_init_ncu.json), so
+// occupancy is what it needs: measured per pass of configs[3] (profiles/r2Q_init_cols.txt) 24 columns 21 ms, 18 columns
+// 19.0, 12 columns (80 registers, 4 CTAs) 15.1, 6 columns (62 registers, 5 CTAs) 14.6.
+static int g_init_cols = getenv("FERS_INIT_COLS") ? atoi(getenv("FERS_INIT_COLS")) : 12;
 
-__global__ void __launch_bounds__(INIT_THREADS)
+template <int INIT_COLS, int MINB>
+__global__ void __launch_bounds__(INIT_THREADS, MINB)
 k_front_init(const __grid_constant__ LevelCtx L) {
     const FrontDev f = level_front(L, blockIdx.z);
     const int nt = f.n1 + f.n2, m = 6 * nt, k1 = 6 * f.n1, m2 = 6 * f.n2;
@@ -986,8 +991,19 @@ static int chol_factor(const CholPlanHost& P, const void* index_dev, const doubl
         const int max_m = 6 * P.level_max_n[l], max_k1 = 6 * P.level_max_n1[l];
         cudaEvent_t e0 = span_begin(0);
         {
-            dim3 grid(cdiv(max_m, INIT_ROWS), cdiv(max_m, INIT_COLS), nf);
-            k_front_init<<<grid, INIT_THREADS, 0, st>>>(L);
+            if (g_init_cols == 12) {
+                dim3 grid(cdiv(max_m, INIT_ROWS), cdiv(max_m, 12), nf);
+                k_front_init<12, 4><<<grid, INIT_THREADS, 0, st>>>(L);
+            } else if (g_init_cols == 18) {
+                dim3 grid(cdiv(max_m, INIT_ROWS), cdiv(max_m, 18), nf);
+                k_front_init<18, 3><<<grid, INIT_THREADS, 0, st>>>(L);
+            } else if (g_init_cols == 6) {
+                dim3 grid(cdiv(max_m, INIT_ROWS), cdiv(max_m, 6), nf);
+                k_front_init<6, 5><<<grid, INIT_THREADS, 0, st>>>(L);
+            } else {
+                dim3 grid(cdiv(max_m, INIT_ROWS), cdiv(max_m, 24), nf);
+                k_front_init<24, 1><<<grid, INIT_THREADS, 0, st>>>(L);
+            }
             FERS_LAUNCH_CHECK();
             ++launches;
         }
