@@ -102,6 +102,35 @@ def test_inextensible_catenary_closed_form():
     assert np.linalg.norm(a[0]) == pytest.approx(H * np.cosh(w * span / (2 * H)), rel=1e-8)
 
 
+@pytest.mark.parametrize("rise", [-30.0, 12.0, 45.0])
+def test_inclined_inextensible_catenary_closed_form(rise):
+    """Supports at different levels: an inextensible catenary of horizontal tension H over the span l with the end `rise`
+    above the start has the length  L0^2 = rise^2 + (2H/w sinh(w l / 2H))^2  (Irvine, Cable Structures, 1.2); the end forces
+    carry the weight (force balance) and balance its moment about the start (centre of gravity from the integrated shape)."""
+    w, span, H = 8.0, 120.0, 3500.0
+    l0 = np.sqrt(rise ** 2 + (2 * H / w * np.sinh(w * span / (2 * H))) ** 2)
+    d = np.array([[span, rise, 0.0]])
+    q = np.array([[0.0, -w, 0.0]])
+    a, _ = cable.end_tension(d, q, np.array([l0]), np.array([1e16]))
+    assert a[0, 0] == pytest.approx(H, rel=1e-7)
+    a2, _ = cable_oracle.end_tension(d, q, np.array([l0]), np.array([1e16]))
+    assert np.allclose(a, a2, rtol=1e-8)
+    # forces of the cable on its end nodes: +a at the start, -(a - q L0) at the end; their sum is the weight
+    f_start, f_end = a[0], -(a[0] - q[0] * l0)
+    assert np.allclose(f_start + f_end, q[0] * l0, atol=1e-9 * w * l0)
+    # moment balance about the start: the end force at (span, rise) against the weight acting at the centre of gravity, whose
+    # abscissa follows from the shape x(s) -- integrate the tangent direction t/|t| numerically
+    s = np.linspace(0.0, l0, 20001)
+    t = a[0][None, :] - q * s[:, None]
+    tx = t[:, 0] / np.linalg.norm(t, axis=1)
+    x = np.concatenate([[0.0], np.cumsum(0.5 * (tx[1:] + tx[:-1]) * np.diff(s))])
+    assert x[-1] == pytest.approx(span, rel=1e-6)
+    x_cg = float(np.sum(0.5 * (x[1:] + x[:-1]) * np.diff(s))) / l0
+    # sum of moments about the start (z component): the end node pulls the cable with -f_end at (span, rise); weight -w L0 at x_cg
+    on_cable_end = -f_end
+    assert span * on_cable_end[1] - rise * on_cable_end[0] - w * l0 * x_cg == pytest.approx(0.0, abs=2e-5 * w * l0 * span)
+
+
 def test_weightless_cable_is_a_bar_that_only_pulls():
     d = np.array([[3.0, 4.0, 0.0], [3.0, 4.0, 0.0]]); l0 = np.array([4.9, 5.1]); ea = np.array([1e6, 1e6])
     a, G = cable.end_tension(d, np.zeros((2, 3)), l0, ea)
