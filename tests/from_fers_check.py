@@ -91,6 +91,38 @@ except Exception:
 print(json.dumps({"checked": checked, "members": len(mem), "from_fers_s": t_fast, "to_dict_s": t_dict, "json_round_trip_s": t_json,
                   "parse_document_s": t_parse, "pydantic_gate_s": t_gate}))
 
+# a small guyed mast from reference objects: cables with pretension / unstretched length, a hinge with capacities and a warping
+# release, buckling restraints on the member set -- the fields the later parts of round 2 read -- through both input routes
+from fers_core import BucklingRestraint, MemberHinge, MemberType  # noqa: E402
+
+base, mid, top = Node(0, 0, 0), Node(0, 6, 0), Node(0, 12, 0)
+base.nodal_support = NodalSupport()
+anchors = [Node(-8, 0, 0), Node(8, 0, 0), Node(0, 0, 9)]
+for nd_ in anchors:
+    nd_.nodal_support = NodalSupport()
+hinge = MemberHinge(hinge_type="cap", rotational_release_mz=5.0e5, max_moment_mz=2.0e4, max_tension_vx=1.0e5, rotational_release_warp=0.0)
+mast = [Member(start_node=base, end_node=mid, section=sec), Member(start_node=mid, end_node=top, section=sec, start_hinge=hinge)]
+guys = [Member(start_node=anchors[0], end_node=top, section=sec, member_type=MemberType.CABLE, pretension=3000.0),
+        Member(start_node=anchors[1], end_node=top, section=sec, member_type=MemberType.CABLE, unstretched_length=14.44),
+        Member(start_node=anchors[2], end_node=top, section=sec, member_type=MemberType.CABLE)]
+small = FERS()
+small.add_member_set(MemberSet(members=mast, classification="Mast",
+                               buckling_restraints=[BucklingRestraint(node_id=mid.id, restrains_local_y=True, restrains_torsion=True)]))
+small.add_member_set(MemberSet(members=guys, classification="Guys"))
+lc2 = small.create_load_case(name="W")
+NodalLoad(node=top, load_case=lc2, magnitude=800.0, direction=(1, 0, 0))
+DistributedLoad(member=guys[1], load_case=lc2, magnitude=20.0, direction=(0, -1, 0))
+small.create_load_combination(name="ULS", load_cases_factors={lc2: 1.5}, situation="ULS", check="ALL")
+got = wire.from_fers(small)
+want = wire.parse_document(json.loads(json.dumps(small.to_dict(include_results=False))))
+same(got, want, "guyed mast")
+chord0 = (8.0 ** 2 + 12.0 ** 2) ** 0.5
+assert got.c_member.tolist() == [2, 3, 4] and got.c_l0[1] == 14.44 and got.c_l0[2] == 15.0
+assert abs(got.c_l0[0] - chord0 / (1.0 + 3000.0 / got.c_ea[0])) < 1e-12 and got.c_l0[0] < chord0
+assert len(got.hinge_caps) == 2 and got.member_sets_raw[0]["buckling_restraints"][0]["restrains_torsion"] is True
+assert got.load_cases[0].cab_q[1].tolist() == [0.0, -20.0, 0.0] and len(got.load_cases[0].dl_member) == 0
+checked += 1
+
 # the server-side mesher of unmeshed plate surfaces against the reference's own client-side mesher (plates/mesh.py)
 from fers_core.plates.mesh import triangulate_surface_polygon  # noqa: E402
 
