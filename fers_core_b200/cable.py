@@ -25,6 +25,11 @@ from __future__ import annotations
 
 import numpy as np
 
+class CableError(RuntimeError):
+    """The catenary equations of a cable have no solution the iteration can reach (the boundary raises RuntimeError for
+    every analysis failure, as the reference's engine does: fers_core/fers/fers.py:301-302)."""
+
+
 SLACK_STIFFNESS = 1.0e-9          # a slack weightless cable keeps this fraction of EA/L0 along its chord (K stays regular)
 NEWTON_MAX = 200
 NEWTON_TOL = 1.0e-13
@@ -138,7 +143,7 @@ def end_tension(d: np.ndarray, q: np.ndarray, l0: np.ndarray, ea: np.ndarray):
                 step[worse] *= 0.5
             H, p0 = Hn, pn
         else:
-            raise ArithmeticError("cable: the catenary equations did not converge")
+            raise CableError("cable: the catenary equations did not converge")
         _, _, fhh, fhq, fqq, fnn = _flex2(H, p0, wc, l0c, eac)
         det = fhh * fqq - fhq * fhq
         ghh, ghq, gqq = fqq / det, -fhq / det, fhh / det
