@@ -998,8 +998,8 @@ class FrameBatch:
         self.plan = rhs_plan(model)
         if self.plan.n_rhs != 1:
             raise EngineError("FrameBatch expects exactly one right-hand side (one combination, no load cases)")
-        if model.n_nodes % nodes_per_frame or model.n_plates:
-            raise EngineError("FrameBatch: model is not a batch of equal-sized beam frames")
+        if model.n_nodes % nodes_per_frame or model.n_plates or len(model.c_member):
+            raise EngineError("FrameBatch: model is not a batch of equal-sized beam frames (plates and cables take engine.analyze)")
         self.nodes_per_frame = nodes_per_frame
         self.nf = model.n_nodes // nodes_per_frame
         self.n = 6 * nodes_per_frame
