@@ -215,6 +215,9 @@ class Engine:
         self.d_p_flags = self._t(m.p_flags, np.int32) if m.n_plates else None
         self.d_xyz0 = self._t(m.xyz, np.float64)
         # catenary cables (cable.py): member rows; their tangents / right-hand-side corrections arrive per Newton step
+        if int((m.m_type == wire.MT_CABLE).sum()) not in (0, len(m.c_member)) and not len(m.c_member):
+            raise EngineError("ModelArrays: members of type Cable need the cable tables c_member / c_l0 / c_ea / c_w (wire.parse_document "
+                              "fills them)")
         self.n_cables = int(len(m.c_member))
         self.d_c_member = self._t(m.c_member, np.int32) if self.n_cables else None
 
