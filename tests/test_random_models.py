@@ -136,9 +136,20 @@ def test_oracle_solves_the_random_models(seed):
     model = random_model(seed)
     res = fers_oracle.analyze(model)
     assert np.isfinite(res.U).all() and np.abs(res.U).max() < 1.0           # a structure, not a mechanism
-    # global equilibrium of every column: reactions + applied loads sum to zero
-    asm = fers_oracle.Assembly(model, model.xyz)
     assert res.converged.all()
+    # global equilibrium of every column: support reactions (R = K u - f at the supported nodes holds the force of a support
+    # spring as well) + applied loads (the nodal load vectors of the cases, the own weight and the uniform loads of the cables)
+    # sum to zero
+    asm = fers_oracle.Assembly(model, model.xyz)
+    F_lc, _ = fers_oracle.load_vectors(asm)
+    plan = fers_oracle.rhs_plan(model)
+    for col in range(plan.n_rhs):
+        applied = (plan.factors[col] @ F_lc).reshape(-1, 6)[:, :3].sum(0)
+        if len(model.c_member):
+            q = model.c_w + sum(plan.factors[col, li] * lc.cab_q for li, lc in enumerate(model.load_cases))
+            applied = applied + (q * model.c_l0[:, None]).sum(0)
+        held = res.R[col, :, :3].sum(0)
+        assert np.abs(held + applied).max() < 1e-7 * max(np.abs(applied).max(), 1.0), (seed, col, held, applied)
 
 
 @pytest.mark.gpu
