@@ -268,6 +268,44 @@ def test_slack_cable_with_a_point_load_large_displacements():
     assert np.allclose(res.R[0, 0, :3], -a[0], rtol=1e-8, atol=1e-8 * np.abs(a).max())
 
 
+def test_chain_of_cable_segments_is_the_single_catenary():
+    """A heavy cable cut into four elements at free nodes is still ONE catenary: after the nodes have dropped (2.8 m on a 20 m
+    span -- form finding from the straight chord) the horizontal reaction equals the horizontal tension of the single elastic
+    catenary of the same total unstretched length, the nodes lie on its curve, and the net of four cables on a loaded node,
+    a stay that goes slack under uplift and a 30 % slack chain all converge."""
+    w, slack = 50.0, 1.05
+    nodes = [(1, 0, 0, 0, 2), (2, 5, 0, 0, None), (3, 10, 0, 0, None), (4, 15, 0, 0, None), (5, 20, 0, 0, 2)]
+    m = wire.parse_document(cable_doc(nodes, [_cab(i, i, i + 1, unstretched_length=5 * slack, weight=w) for i in (1, 2, 3, 4)]))
+    res = fers_oracle.analyze(m)
+    assert res.converged.all()
+    q = np.array([[0.0, -w, 0.0]])
+    a, _ = cable.end_tension(np.array([[20.0, 0.0, 0.0]]), q, np.array([20 * slack]), m.c_ea[:1])
+    assert -res.R[0, 0, 0] == pytest.approx(a[0, 0], rel=1e-9)
+    assert res.R[0, 0, 1] == pytest.approx(w * 20 * slack / 2, rel=1e-9)
+    # the middle node sits at the lowest point of the single catenary: integrate its shape to s = L0 / 2
+    s = np.linspace(0.0, 10 * slack, 200001)
+    t = a[0][None, :] - q * s[:, None]
+    tn = np.linalg.norm(t, axis=1)
+    f = t / tn[:, None] * (1.0 + tn / m.c_ea[0])[:, None]
+    mid = np.sum(0.5 * (f[1:] + f[:-1]) * np.diff(s)[:, None], axis=0)
+    assert mid[0] == pytest.approx(10.0, abs=1e-6)
+    assert res.U[0, 2, 1] == pytest.approx(mid[1], rel=1e-6) and res.U[0, 2, 1] < -2.5
+    for slack2 in (1.001, 1.3):
+        doc = cable_doc(nodes, [_cab(i, i, i + 1, unstretched_length=5 * slack2, weight=w) for i in (1, 2, 3, 4)])
+        assert fers_oracle.analyze(wire.parse_document(doc)).converged.all()
+    # four cables to a loaded node; a stay whose pretension is overcome by uplift
+    b = 6.0
+    net = [(1, -b, 0, -b, 2), (2, b, 0, -b, 2), (3, b, 0, b, 2), (4, -b, 0, b, 2), (5, 0, -1.0, 0, None)]
+    L = np.sqrt(2 * b * b + 1.0)
+    r_net = fers_oracle.analyze(wire.parse_document(cable_doc(net, [_cab(i, i, 5, unstretched_length=1.02 * L, weight=8.0) for i in (1, 2, 3, 4)],
+                                                              loads=[(1, 5, 5e3, (0, -1, 0))])))
+    assert r_net.converged.all() and r_net.R[0, :4, 1].sum() == pytest.approx(5e3 + 4 * 8.0 * 1.02 * L, rel=1e-9)
+    stay = cable_doc([(1, 0, 0, 0, 1), (2, 10, 0, 0, None), (3, 0, 6, 0, 2)],
+                     [dict(id=1, start_node_id=1, end_node_id=2), _cab(2, 3, 2, pretension=100.0)], loads=[(1, 2, 8e3, (0, 1, 0))])
+    r_stay = fers_oracle.analyze(wire.parse_document(stay))
+    assert r_stay.converged.all() and np.abs(r_stay.f_global[0, 1, :3]).max() < 1e-3      # slack: the stay carries nothing
+
+
 def _mast_doc(order="LINEAR", self_weight=True):
     """A 12 m clamped mast with two guys in its plane and one out of it, a lateral load, a uniform load on one guy; three
     combinations."""
