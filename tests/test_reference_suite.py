@@ -57,3 +57,31 @@ def test_reference_example_104_deflected_shape(tmp_path):
     p = subprocess.run([sys.executable, "-c", code], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     assert "Engine returned 11 deflected-shape stations" in p.stdout
+
+
+VALIDATING_EXAMPLES = [
+    "001_Cantilever_with_End_Load", "002_Cantilever_with_Intermediate_Load", "003_Cantilever_with_Uniform_Distributed_Load",
+    "004_Cantilever_with_Partial_Uniform_Distributed_Load", "005_Cantilever_with_Triangular_Distributed_Load",
+    "006_Cantilever_with_Partial_Triangular_Distributed_Load", "007_Cantilever_with_End_Moment",
+    "011_Simply_Supported_with_Center_Load", "012_Simply_Supported_with_Intermediate_Load",
+    "013_Simply_Supported_with_Double_symmetric_Load", "014_Simply_Supported_with_Uniform_Distributed_Load",
+    "021_Simply_Supported_Moment_at_each_Support", "022_Simply_Supported_Moment_at_start_Support",
+    "023_Simply_Supported_Moment_at_Center", "031_Fixed_Fixed_with_Center_Load", "032_Fixed_Fixed_with_Uniform_Distributed_load",
+    "041_Rigid_member", "042_Rigid_member_reversed", "051_Member_hinge_at_half", "071_Support_connection",
+    "091_Load_Combinations_Cantilever", "121_Shear_Deformation_Toggle", "122_Warping_Deformation_Toggle",
+]
+
+
+@pytest.mark.parametrize("example", VALIDATING_EXAMPLES)
+def test_reference_example_prints_only_matches(example, tmp_path):
+    """The example scripts of the reference compare the engine's answer with closed forms and print a mark per comparison
+    (fers_core/examples/0xx_*.py, e.g. 014:116-125): against the oracle backend every mark of these 23 scripts is a match.
+    (052 / 053 contradict their own load sign, 061 expects a displacement of the wrong sign: DESIGN.md section 2.)"""
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "refshim"), REFERENCE, ROOT])
+    env["FERS_SHIM_BACKEND"] = "oracle"
+    env["MPLBACKEND"] = "Agg"
+    script = os.path.join(REFERENCE, "fers_core", "examples", example + ".py")
+    p = subprocess.run([sys.executable, script], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "✅" in p.stdout and "❌" not in p.stdout, p.stdout[-3000:]
