@@ -397,6 +397,13 @@ def build_model_arrays(ncols: NodeColumns, mcols: MemberColumns, model: dict, an
     materials, sections, hinges, member sets, plates, load cases, combinations, imperfections, unity checks)."""
     opts = parse_options(analysis.get("options"))
     warnings: list = []
+    if opts.axial_slack != Options().axial_slack and any(
+            _MEMBER_TYPES.get(_norm_enum(t)) in (MT_TENSION, MT_COMPRESSION) for t in set(mcols.mtype)):
+        # AnalysisOptions.axial_slack (pydantic_models.py:1335, default 500): the reference steers the residual stiffness of a
+        # slack tension- / compression-only member with it ("slack model", tests/functionality/test_functionality.py:202-204);
+        # its meaning is stated nowhere.  Here a switched-off member keeps hostlogic.INACTIVE_SCALE of its stiffness
+        warnings.append(("W_AXIAL_SLACK_IGNORED", f"analysis option axial_slack = {opts.axial_slack:g} is not applied: inactive tension- / "
+                         "compression-only members keep a fixed 1e-9 of their stiffness"))
     # RigidStrategy.LinearMpc (pydantic_models.py:1047-1049): applied by engine.analyze where hostlogic.mpc_transform can (first-
     # order analyses, slaves without supports / plates); elsewhere the result carries W_LINEAR_MPC_AS_RIGID_MEMBER
     nd = _parse_nodes(ncols, model, opts)

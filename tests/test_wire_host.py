@@ -221,6 +221,11 @@ def test_inputs_that_are_read_but_not_acted_on_are_reported():
     assert codes.count("W_HINGE_CAPACITY_IGNORED") == 1
     assert not [c for c in codes if c.startswith("W_PRINCIPAL")]      # applied (tests/test_product_inertia.py), not ignored
     assert codes.count("W_SURFACE_OPENINGS_IGNORED") == 1 and wire.parse_document(doc).n_plates == 1
+    # a slack model other than the default on a model with tension-only members
+    t_doc = copy.deepcopy(helpers.golden("tension_only")["doc"])
+    assert "W_AXIAL_SLACK_IGNORED" not in [w[0] for w in wire.parse_document(t_doc).warnings]
+    t_doc["analysis"]["options"]["axial_slack"] = 0.1
+    assert "W_AXIAL_SLACK_IGNORED" in [w[0] for w in wire.parse_document(t_doc).warnings]
     # an angle that contradicts the (i_y, i_z, i_yz) triple is resolved in favour of the angle, with a note
     doc["model"]["sections"][0].update(i_yz=1.0e-7, principal_axis_angle=40.0)
     assert "W_PRINCIPAL_AXES" in [w[0] for w in wire.parse_document(doc).warnings]
