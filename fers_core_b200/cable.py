@@ -15,8 +15,9 @@ In the plane of d and q (e_q = q/|q|, e_h the unit vector of the part of d norma
 
 which `end_tension` solves for (H, p0) by a damped Newton iteration, all cables of the model at once.  The internal forces
 of the element (forces of the end nodes on the cable, the sign of K u = f) are  p_i = -a,  p_j = a - q L0,  and its tangent
-is [[G, -G], [-G, G]] with G = (dd/da)^-1, formed in closed form by `flexibility`.  Without a load (|q| = 0) the cable is a
-straight bar that only pulls: T = EA (|d| - L0)/L0 when positive, else slack.
+is [[G, -G], [-G, G]] with G = (dd/da)^-1, formed in closed form (`_flex2`).  Without a load (|q| = 0) the cable is a
+straight bar that only pulls: T = EA (|d| - L0)/L0 when positive, else slack.  The unstretched length itself comes from the
+wire (`unstretched_length`, else L_chord / (1 + pretension/EA), else the chord: wire._parse_members).
 
 Everything here is host-side bookkeeping of a handful of cables per model (numpy, vectorised over the cables); the global
 tangent blocks and the right-hand-side corrections it produces are assembled and solved on the device (engine.py).
@@ -33,17 +34,6 @@ class CableError(RuntimeError):
 SLACK_STIFFNESS = 1.0e-9          # a slack weightless cable keeps this fraction of EA/L0 along its chord (K stays regular)
 NEWTON_MAX = 200
 NEWTON_TOL = 1.0e-13
-
-
-def unstretched_length(chord: np.ndarray, ea: np.ndarray, pretension, given) -> np.ndarray:
-    """`unstretched_length` wins; else L0 = L_chord / (1 + pretension/EA); else the chord (pydantic_models.py:1527, 1544)."""
-    l0 = np.array(chord, float, copy=True)
-    for i in range(len(l0)):
-        if given[i] is not None:
-            l0[i] = float(given[i])
-        elif pretension[i] is not None:
-            l0[i] = chord[i] / (1.0 + float(pretension[i]) / ea[i])
-    return l0
 
 
 def _plane(d: np.ndarray, q: np.ndarray):

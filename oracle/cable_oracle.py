@@ -84,10 +84,3 @@ def end_tension(d, q, l0, ea):
     for i in range(d.shape[0]):
         a[i], G[i] = end_tension_one(d[i], np.asarray(q, float).reshape(-1, 3)[i], float(l0[i]), float(ea[i]))
     return a, G
-
-
-def unstretched_length(chord, ea, pretension, given):
-    out = []
-    for c, k, p, g in zip(chord, ea, pretension, given):
-        out.append(float(g) if g is not None else (c / (1.0 + float(p) / k) if p is not None else float(c)))
-    return np.asarray(out, float)
