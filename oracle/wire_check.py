@@ -6,8 +6,9 @@ the schema text (fers_core/types/pydantic_models.py: Node, Member 1507-1549, Sec
 NodalSupport 2104-2115 / SupportCondition 1956-1959, NodalLoad 1684-1689, NodalMoment, DistributedLoad 1434-1446,
 LoadCombination 491-505), with dictionaries and plain loops, for tests/test_wire_check.py to hold against the parser's arrays:
 coordinates, connectivity, member types and roll angles, the first six stiffnesses of every member's section, support codes
-and spring stiffnesses, nodal load vectors, distributed member loads, combination factors.  It covers the common members only
-(no hinges, offsets, plates: those have their own closed-form tests)."""
+and spring stiffnesses, hinge release springs, plate triangles with thickness / E / nu, nodal load vectors, distributed member
+loads, combination factors.  (End offsets, shear-centre offsets, products of inertia, stiffness curves and surface loads are
+left to their own closed-form tests.)"""
 from __future__ import annotations
 
 import math
@@ -79,6 +80,37 @@ def read(doc: dict) -> dict:
         stiff.append([E * float(s["area"]), E * float(s["i_y"]) if plain else math.nan, E * float(s["i_z"]) if plain else math.nan,
                       G * float(s["j"]), G * asy, G * asz])
     out["m_stiffness"] = stiff
+    # hinges: twelve release springs per member (start u v w rx ry rz, end ...), -1 = rigidly connected (MemberHinge 2062-2087:
+    # "release" fields are spring stiffnesses; a stiffness curve overrides its constant: left to the curve tests -> nan)
+    hinges = {int(h["id"]): h for h in model.get("member_hinges") or []}
+    fields = ("translational_release_vx", "translational_release_vy", "translational_release_vz",
+              "rotational_release_mx", "rotational_release_my", "rotational_release_mz")
+    curves = ("stiffness_curve_vx", "stiffness_curve_vy", "stiffness_curve_vz", "stiffness_curve_mx", "stiffness_curve_my",
+              "stiffness_curve_mz")
+    releases = []
+    for m in members:
+        if m.get("start_hinge") is None and m.get("end_hinge") is None:
+            releases.append(None)
+            continue
+        row = []
+        for hid in (m.get("start_hinge"), m.get("end_hinge")):
+            h = hinges[_id(hid)] if hid is not None else {}
+            for f, c in zip(fields, curves):
+                if h.get(c) and h[c].get("points"):
+                    row.append(math.nan)
+                else:
+                    row.append(-1.0 if h.get(f) is None else max(float(h[f]), 0.0))
+        releases.append(row)
+    out["m_release"] = releases
+    # plates: triangles (a quad is cut into (0, 1, 2) and (0, 2, 3)), thickness, E, nu = E / 2G - 1 (PlateElement 1700-1726)
+    plates = []
+    for p in model.get("plate_elements") or []:
+        ids = [_id(v) for v in p["node_ids"]]
+        mat = p["material"] if isinstance(p["material"], dict) else materials[int(p["material"])]
+        E, G = float(mat["e_mod"]), float(mat["g_mod"])
+        for tri in ([ids] if len(ids) == 3 else [[ids[0], ids[1], ids[2]], [ids[0], ids[2], ids[3]]]):
+            plates.append((int(p["id"]), [index[v] for v in tri], float(p["thickness"]), E, E / (2.0 * G) - 1.0))
+    out["plates"] = plates
     member_index = {mid: i for i, mid in enumerate(out["m_ids"])}
     cases = []
     for lc in analysis.get("load_cases") or []:

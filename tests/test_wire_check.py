@@ -39,6 +39,19 @@ def test_parser_arrays_equal_the_second_reading(name, doc):
         for c, v in enumerate(row):
             if not math.isnan(v):
                 assert got[c] == pytest.approx(v, rel=1e-15), (name, i, c)
+    for i, row in enumerate(r["m_release"]):
+        if row is None or m.m_type[i] == wire.MT_CABLE:
+            continue
+        assert m.m_rel[i] >= 0
+        got = m.rel[m.m_rel[i], :12]
+        for c, v in enumerate(row):
+            if not math.isnan(v):
+                assert got[c] == v, (name, i, c)
+    if not (doc["model"].get("plate_surfaces") and not doc["model"].get("plate_elements")):
+        assert m.n_plates == len(r["plates"])
+        for e, (pid, tri, th, E, nu) in enumerate(r["plates"]):
+            assert int(m.p_ids[e]) == pid and m.p_nodes[e].tolist() == tri
+            assert m.p_data[e, 0] == th and m.p_data[e, 1] == E and m.p_data[e, 2] == pytest.approx(nu, rel=1e-15)
     cable = set(m.c_member.tolist())
     generated = len(m.load_cases) - len(r["load_cases"])     # a self-weight case the parser may have appended
     assert generated in (0, 1)
