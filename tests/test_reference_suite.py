@@ -138,3 +138,28 @@ def test_LE1_convergence_series_of_the_reference(tmp_path):
     assert got["72x8"] == pytest.approx(ref["results"][0]["fers"], abs=0.06)
     series = {k: round(100.0 * (1.0 - v / target), 1) for k, v in got.items()}
     assert series == {"12x3": 24.0, "24x4": 14.6, "48x6": 6.4, "72x8": 2.7}, series
+
+
+def test_result_documents_pass_the_reference_schema(tmp_path):
+    """Every result document the oracle engine returns for the golden models is a valid ``ResultsBundle`` of the reference's
+    own schema (fers_core/types/pydantic_models.py:2171-2185, generated from the engine's types): names, nesting and types of
+    the whole output contract, checked by the reference's pydantic classes (the GPU path writes the same document:
+    tests/test_results_json.py, tests/test_gpu_parity.py)."""
+    code = (
+        "import sys, json, gzip\n"
+        "from fers_core.types.pydantic_models import ResultsBundle\n"
+        "from oracle import oracle_engine\n"
+        f"cases = json.load(gzip.open({os.path.join(ROOT, 'tests', 'golden', 'wire_cases.json.gz')!r}, 'rt'))\n"
+        "n = 0\n"
+        "for c in cases:\n"
+        "    if c.get('error') or c['name'] == 'pdelta_above_euler_load':\n"
+        "        continue\n"
+        "    out = oracle_engine.solve_document(c['doc'])\n"
+        "    ResultsBundle(**json.loads(json.dumps(out['results'])))\n"
+        "    n += 1\n"
+        "print('validated', n)\n")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "refshim"), REFERENCE, ROOT])
+    p = subprocess.run([sys.executable, "-c", code], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    assert int(p.stdout.strip().split()[-1]) >= 25
