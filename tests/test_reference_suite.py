@@ -163,3 +163,39 @@ def test_result_documents_pass_the_reference_schema(tmp_path):
     p = subprocess.run([sys.executable, "-c", code], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
     assert int(p.stdout.strip().split()[-1]) >= 25
+
+
+def test_results_of_the_round_2_features_pass_the_reference_schema(tmp_path):
+    """Cable members, thin plates, the restrained EC3 beam, a warping release and a PlateSurfaces unity check: their result
+    documents are valid ``ResultsBundle`` documents of the reference's schema as well."""
+    import copy
+    import json
+    from tests import helpers
+    from tests.test_cable import _mast_doc, _slack_doc
+    from tests.test_ec3 import _restrained_doc
+    from tests.test_plate_kirchhoff import plate_doc
+    from tests.test_warping_release import _doc as warp_doc
+    surf = copy.deepcopy(helpers.golden("plate_strip_surface_load")["doc"])
+    els = surf["model"]["plate_elements"]
+    for k, p_ in enumerate(els):
+        p_["source_surface_id"] = 7 if k < len(els) // 2 else 8
+    surf["analysis"]["unity_checks"] = [{"id": "surf", "name": "per surface", "applies_to": {"type": "PlateSurfaces", "ids": [8, 7]},
+                                         "spec": {"Generic": {"demand": "s", "capacity": "235e6", "variables": [
+                                             {"name": "s", "source": {"Quantity": {"PlateStress": {"measure": "VonMises"}}}}]}}}]
+    docs = {"mast": _mast_doc("LINEAR"), "slack": _slack_doc(), "dkt": plate_doc(2.0, 2.0, 4, 4, 0.2, "Kirchhoff", pressure=5e3)[0],
+            "ec3_restrained": _restrained_doc(), "warp_release": warp_doc(0.0), "plate_surfaces": surf}
+    path = tmp_path / "docs.json"
+    path.write_text(json.dumps(docs), encoding="utf-8")
+    code = (
+        "import sys, json\n"
+        "from fers_core.types.pydantic_models import ResultsBundle\n"
+        "from oracle import oracle_engine\n"
+        f"docs = json.load(open({str(path)!r}, encoding='utf-8'))\n"
+        "for name, d in docs.items():\n"
+        "    ResultsBundle(**json.loads(json.dumps(oracle_engine.solve_document(d)['results'])))\n"
+        "print('validated', len(docs))\n")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "refshim"), REFERENCE, ROOT])
+    p = subprocess.run([sys.executable, "-c", code], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    assert p.stdout.strip().endswith("validated 6")
