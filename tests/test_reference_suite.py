@@ -72,19 +72,45 @@ VALIDATING_EXAMPLES = [
 ]
 
 
-@pytest.mark.parametrize("example", VALIDATING_EXAMPLES)
-def test_reference_example_prints_only_matches(example, tmp_path):
-    """The example scripts of the reference compare the engine's answer with closed forms and print a mark per comparison
-    (fers_core/examples/0xx_*.py, e.g. 014:116-125): against the oracle backend every mark of these 23 scripts is a match.
-    (052 / 053 contradict their own load sign, 061 expects a displacement of the wrong sign: DESIGN.md section 2.)"""
+@pytest.fixture(scope="module")
+def example_outputs(tmp_path_factory):
+    """All validating example scripts in ONE interpreter (the imports of the reference's front end dominate a run): each is
+    executed as __main__ with its standard output captured; returns {example: (ok, text)}."""
+    import json
+    work = tmp_path_factory.mktemp("examples")
+    code = (
+        "import io, json, runpy, sys, traceback\n"
+        "from contextlib import redirect_stdout\n"
+        f"names = {VALIDATING_EXAMPLES!r}\n"
+        "out = {}\n"
+        "for name in names:\n"
+        "    buf = io.StringIO()\n"
+        "    ok = True\n"
+        "    try:\n"
+        "        with redirect_stdout(buf):\n"
+        f"            runpy.run_path({os.path.join(REFERENCE, 'fers_core', 'examples')!r} + '/' + name + '.py', run_name='__main__')\n"
+        "    except BaseException:\n"
+        "        ok = False\n"
+        "        buf.write(traceback.format_exc())\n"
+        "    out[name] = [ok, buf.getvalue()]\n"
+        "sys.__stdout__.write(json.dumps(out))\n")
     env = dict(os.environ)
     env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "refshim"), REFERENCE, ROOT])
     env["FERS_SHIM_BACKEND"] = "oracle"
     env["MPLBACKEND"] = "Agg"
-    script = os.path.join(REFERENCE, "fers_core", "examples", example + ".py")
-    p = subprocess.run([sys.executable, script], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
-    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
-    assert "✅" in p.stdout and "❌" not in p.stdout, p.stdout[-3000:]
+    p = subprocess.run([sys.executable, "-c", code], cwd=work, env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    return json.loads(p.stdout[p.stdout.index("{"):])
+
+
+@pytest.mark.parametrize("example", VALIDATING_EXAMPLES)
+def test_reference_example_prints_only_matches(example, example_outputs):
+    """The example scripts of the reference compare the engine's answer with closed forms and print a mark per comparison
+    (fers_core/examples/0xx_*.py, e.g. 014:116-125): against the oracle backend every mark of these 23 scripts is a match.
+    (052 / 053 contradict their own load sign, 061 expects a displacement of the wrong sign: DESIGN.md section 2.)"""
+    ok, text = example_outputs[example]
+    assert ok, text[-3000:]
+    assert "✅" in text and "❌" not in text, text[-3000:]
 
 
 def test_LE6_convergence_series_of_the_reference(tmp_path):
